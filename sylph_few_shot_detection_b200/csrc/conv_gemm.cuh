@@ -1,0 +1,302 @@
+// Implicit-GEMM convolution on the 5th-gen tensor cores (tcgen05, TF32 in / FP32 accumulate in TMEM).
+//
+// Data layout ("flat padded planes"): every activation tensor is a row-major matrix [rows][C] of fp32 where a row
+// is one pixel of a zero-bordered NHWC plane (border = `pad` pixels on every side) and the planes of all images /
+// FPN levels are concatenated, each plane starting on a multiple of 128 rows.  In that layout a k x k stride-1
+// convolution is a sum over taps of plain GEMMs whose A operand is the same matrix shifted by
+// (dy * Wp + dx) rows, so every A tile is one 2-D TMA box (zero fill outside the buffer) and the towers of all
+// FPN levels and all images run as ONE launch.  Border rows are recomputed as garbage and zeroed by the epilogue,
+// which keeps the zero-border invariant for the next layer.
+//
+// Kernel structure (persistent, one CTA per SM, 192 threads):
+//   warp 0   : TMA producer  (A box 128 x 32 fp32, B box BN x 32 fp32, 128-byte swizzle, STAGES-deep mbarrier ring)
+//   warp 1   : tcgen05.mma issuer (one thread), TMEM owner (2 accumulator buffers x BN columns)
+//   warps 2-5: epilogue: tcgen05.ld -> bias / residual / ReLU / border mask / TF32 rounding / GroupNorm partial sums
+//              -> vectorised global stores, overlapped with the next tile's MMAs through the second TMEM buffer.
+//
+// Replaces the cuDNN convolutions reached from detectron2/AdelaiDet modules at
+//   sylph/modeling/meta_arch/meta_one_stage_detector.py:180-182 (backbone), sylph/modeling/meta_fcos/fcos.py:625-664
+//   (towers, predictors), sylph/modeling/code_generator/code_generator.py:941-960 (support tower / cls conv).
+#pragma once
+#include "ptx_sm100.cuh"
+
+namespace sylph {
+
+constexpr int kBlockM = 128;
+constexpr int kBlockK = 32;   // fp32 elements = one 128-byte swizzle row
+constexpr int kUmmaK = 8;     // tf32: 32 bytes of K per tcgen05.mma
+constexpr int kMaxTaps = 16;
+constexpr int kGemmThreads = 192;
+
+// One zero-bordered plane (an image at one resolution) inside a flat buffer.
+struct Seg {
+    int row0;   // first row, multiple of 128
+    int nrows;  // Hp * Wp
+    int Wp;     // padded width  (W + 2 * pad)
+    int pad;    // border width
+    int H, W;   // interior size
+};
+
+enum EpilogueFlags : int {
+    kEpiRelu = 1,       // max(x, 0)
+    kEpiResidual = 2,   // += residual[row][col]
+    kEpiMask = 4,       // zero rows that are not interior pixels of their plane
+    kEpiRoundTf32 = 8,  // round the stored value to TF32 (the output feeds another tensor-core GEMM)
+    kEpiGnStats = 16,   // per-tile GroupNorm partial sums (32 groups of 8 channels; needs BN == 256)
+};
+
+struct GemmArgs {
+    int tile_begin;        // first output M tile (absolute index, row = tile * 128)
+    int num_m_tiles;
+    int num_n_tiles;
+    int a_row_delta;       // A row = output row + a_row_delta + tap_shift[tap]
+    int taps;
+    int kblocks_per_tap;   // K per tap / 32
+    int b_rows_per_tap;    // rows of the weight matrix per tap (Cout padded up to a multiple of BN)
+    int tap_shift[kMaxTaps];
+    const float* bias;     // [n_tiles * BN] or nullptr
+    const float* residual; // same row indexing as out, or nullptr
+    int ld_res;
+    float* out;
+    int ldc;
+    int flags;
+    const int* tile_seg;   // [absolute tile] -> segment index
+    const Seg* segs;
+    float* gn_partial;     // [absolute tile][32][2]
+};
+
+template <int BN, int STAGES>
+struct GemmSmem {
+    static constexpr int kABytes = kBlockM * kBlockK * 4;  // 16 KiB
+    static constexpr int kBBytes = BN * kBlockK * 4;
+    static constexpr int kStageBytes = kABytes + kBBytes;
+    static constexpr int kBarOffset = STAGES * kStageBytes;
+    static constexpr int kGnOffset = kBarOffset + 256;
+    static constexpr int kTotal = kGnOffset + 4 * 32 * 2 * 4 + 1024;  // + alignment slack
+};
+
+template <int BN, int STAGES>
+__global__ void __launch_bounds__(kGemmThreads, 1)
+conv_gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
+                      const GemmArgs p) {
+    using S = GemmSmem<BN, STAGES>;
+    constexpr int CH = BN < 32 ? BN : 32;                 // epilogue column chunk
+    constexpr uint32_t kTmemCols = (2 * BN < 32) ? 32 : 2 * BN;
+    constexpr uint32_t kIdesc = ptx::make_idesc_tf32(kBlockM, BN);
+
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + S::kBarOffset);
+    uint64_t* empty_bar = full_bar + STAGES;
+    uint64_t* tmem_full = empty_bar + STAGES;
+    uint64_t* tmem_empty = tmem_full + 2;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+    float* gn_smem = reinterpret_cast<float*>(smem + S::kGnOffset);
+
+    const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0);
+    const int lane = threadIdx.x & 31;
+
+    if (warp == 0 && lane == 0) {
+        ptx::prefetch_tensormap(&tmap_a);
+        ptx::prefetch_tensormap(&tmap_b);
+    }
+    if (warp == 1 && lane == 0) {
+        for (int s = 0; s < STAGES; ++s) {
+            ptx::mbar_init(&full_bar[s], 1);
+            ptx::mbar_init(&empty_bar[s], 1);
+        }
+        for (int a = 0; a < 2; ++a) {
+            ptx::mbar_init(&tmem_full[a], 1);
+            ptx::mbar_init(&tmem_empty[a], 128);
+        }
+        ptx::fence_barrier_init();
+    }
+    if (warp == 1) {
+        __syncwarp();
+        ptx::tmem_alloc(tmem_slot, kTmemCols);
+        ptx::tmem_relinquish();
+    }
+    ptx::tc_fence_before();
+    __syncthreads();
+    ptx::tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    const int total_tiles = p.num_m_tiles * p.num_n_tiles;
+    const int ksteps = p.taps * p.kblocks_per_tap;
+
+    if (warp == 0) {
+        // ------------------------------------------------------------ TMA producer
+        if (lane == 0) {
+            int stage = 0;
+            uint32_t phase = 0;
+            for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+                const int m_tile = tile / p.num_n_tiles;
+                const int n_tile = tile - m_tile * p.num_n_tiles;
+                const int a_row_base = (p.tile_begin + m_tile) * kBlockM + p.a_row_delta;
+                const int b_row_base = n_tile * BN;
+                int tap = 0, kb = 0;
+                for (int ks = 0; ks < ksteps; ++ks) {
+                    ptx::mbar_wait(&empty_bar[stage], phase ^ 1u);
+                    ptx::mbar_arrive_expect_tx(&full_bar[stage], S::kStageBytes);
+                    uint8_t* sa = smem + stage * S::kStageBytes;
+                    ptx::tma_load_2d(sa, &tmap_a, &full_bar[stage], kb * kBlockK, a_row_base + p.tap_shift[tap]);
+                    ptx::tma_load_2d(sa + S::kABytes, &tmap_b, &full_bar[stage], kb * kBlockK,
+                                     tap * p.b_rows_per_tap + b_row_base);
+                    if (++kb == p.kblocks_per_tap) { kb = 0; ++tap; }
+                    if (++stage == STAGES) { stage = 0; phase ^= 1u; }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ------------------------------------------------------------ MMA issuer
+        if (lane == 0) {
+            int stage = 0;
+            uint32_t phase = 0;
+            int acc = 0;
+            uint32_t acc_phase = 0;
+            for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+                ptx::mbar_wait(&tmem_empty[acc], acc_phase ^ 1u);
+                ptx::tc_fence_after();
+                const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(acc * BN);
+                for (int ks = 0; ks < ksteps; ++ks) {
+                    ptx::mbar_wait(&full_bar[stage], phase);
+                    ptx::tc_fence_after();
+                    const uint32_t sa = ptx::smem_u32(smem + stage * S::kStageBytes);
+                    const uint64_t da = ptx::make_sw128_kmajor_desc(sa);
+                    const uint64_t db = ptx::make_sw128_kmajor_desc(sa + S::kABytes);
+#pragma unroll
+                    for (int k = 0; k < kBlockK / kUmmaK; ++k) {
+                        // advance 32 bytes of K inside the swizzle row: +2 in the (addr >> 4) field
+                        ptx::umma_tf32(d_tmem, da + 2 * k, db + 2 * k, kIdesc, (ks | k) ? 1u : 0u);
+                    }
+                    ptx::umma_commit(&empty_bar[stage]);
+                    if (++stage == STAGES) { stage = 0; phase ^= 1u; }
+                }
+                ptx::umma_commit(&tmem_full[acc]);
+                acc ^= 1;
+                if (acc == 0) acc_phase ^= 1u;
+            }
+        }
+    } else {
+        // ------------------------------------------------------------ epilogue (warps 2..5)
+        const int quad = warp & 3;  // TMEM lane quadrant this warp may read
+        const int et = (warp - 2) * 32 + lane;  // 0..127 among epilogue threads
+        int acc = 0;
+        uint32_t acc_phase = 0;
+        for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+            const int m_tile = tile / p.num_n_tiles;
+            const int n_tile = tile - m_tile * p.num_n_tiles;
+            const int abs_tile = p.tile_begin + m_tile;
+            const int row = abs_tile * kBlockM + quad * 32 + lane;
+            bool interior = true;
+            if (p.flags & (kEpiMask | kEpiGnStats)) {
+                const Seg sg = p.segs[p.tile_seg[abs_tile]];
+                const int local = row - sg.row0;
+                const int y = local / sg.Wp;
+                const int x = local - y * sg.Wp;
+                interior = (local < sg.nrows) && (y >= sg.pad) && (y < sg.pad + sg.H) && (x >= sg.pad) &&
+                           (x < sg.pad + sg.W);
+            }
+            const bool keep = interior || !(p.flags & kEpiMask);
+            const size_t out_off = static_cast<size_t>(row) * p.ldc + static_cast<size_t>(n_tile) * BN;
+            const size_t res_off = static_cast<size_t>(row) * p.ld_res + static_cast<size_t>(n_tile) * BN;
+
+            ptx::mbar_wait(&tmem_full[acc], acc_phase);
+            ptx::tc_fence_after();
+            const uint32_t t_row = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + static_cast<uint32_t>(acc * BN);
+
+#pragma unroll 1
+            for (int c0 = 0; c0 < BN; c0 += CH) {
+                uint32_t v[CH];
+                if constexpr (CH == 32) ptx::tmem_ld_32x32b_x32(t_row + c0, v);
+                else ptx::tmem_ld_32x32b_x16(t_row + c0, v);
+                float4 r4[CH / 4];
+                if ((p.flags & kEpiResidual) && keep) {
+                    const float4* rp = reinterpret_cast<const float4*>(p.residual + res_off + c0);
+#pragma unroll
+                    for (int j = 0; j < CH / 4; ++j) r4[j] = __ldg(rp + j);
+                }
+                ptx::tmem_ld_wait();
+                float f[CH];
+#pragma unroll
+                for (int j = 0; j < CH; ++j) f[j] = __uint_as_float(v[j]);
+                if (p.bias != nullptr) {
+                    const float4* bp = reinterpret_cast<const float4*>(p.bias + n_tile * BN + c0);
+#pragma unroll
+                    for (int j = 0; j < CH / 4; ++j) {
+                        const float4 b = __ldg(bp + j);
+                        f[4 * j + 0] += b.x; f[4 * j + 1] += b.y; f[4 * j + 2] += b.z; f[4 * j + 3] += b.w;
+                    }
+                }
+                if constexpr (BN == 256) {
+                    if (p.flags & kEpiGnStats) {
+                        // 4 groups of 8 channels in this chunk; reduce over the warp's 32 rows.
+#pragma unroll
+                        for (int g = 0; g < 4; ++g) {
+                            float s = 0.f, ss = 0.f;
+                            if (interior) {
+#pragma unroll
+                                for (int j = 0; j < 8; ++j) { const float x = f[8 * g + j]; s += x; ss += x * x; }
+                            }
+#pragma unroll
+                            for (int o = 16; o > 0; o >>= 1) {
+                                s += __shfl_xor_sync(0xffffffffu, s, o);
+                                ss += __shfl_xor_sync(0xffffffffu, ss, o);
+                            }
+                            if (lane == 0) {
+                                gn_smem[(quad * 32 + (c0 >> 3) + g) * 2 + 0] = s;
+                                gn_smem[(quad * 32 + (c0 >> 3) + g) * 2 + 1] = ss;
+                            }
+                        }
+                    }
+                }
+                if ((p.flags & kEpiResidual) && keep) {
+#pragma unroll
+                    for (int j = 0; j < CH / 4; ++j) {
+                        f[4 * j + 0] += r4[j].x; f[4 * j + 1] += r4[j].y; f[4 * j + 2] += r4[j].z; f[4 * j + 3] += r4[j].w;
+                    }
+                }
+                if (p.flags & kEpiRelu) {
+#pragma unroll
+                    for (int j = 0; j < CH; ++j) f[j] = fmaxf(f[j], 0.f);
+                }
+                if (p.flags & kEpiRoundTf32) {
+#pragma unroll
+                    for (int j = 0; j < CH; ++j) f[j] = ptx::round_tf32(f[j]);
+                }
+                if (!keep) {
+#pragma unroll
+                    for (int j = 0; j < CH; ++j) f[j] = 0.f;
+                }
+                float4* op = reinterpret_cast<float4*>(p.out + out_off + c0);
+#pragma unroll
+                for (int j = 0; j < CH / 4; ++j) op[j] = make_float4(f[4 * j], f[4 * j + 1], f[4 * j + 2], f[4 * j + 3]);
+            }
+            // accumulator buffer fully read: hand it back to the MMA warp
+            ptx::tc_fence_before();
+            ptx::mbar_arrive(&tmem_empty[acc]);
+            acc ^= 1;
+            if (acc == 0) acc_phase ^= 1u;
+
+            if constexpr (BN == 256) {
+                if (p.flags & kEpiGnStats) {
+                    asm volatile("bar.sync 1, 128;" ::: "memory");
+                    if (et < 64) {
+                        const float t = gn_smem[et] + gn_smem[64 + et] + gn_smem[128 + et] + gn_smem[192 + et];
+                        p.gn_partial[static_cast<size_t>(abs_tile) * 64 + et] = t;
+                    }
+                    asm volatile("bar.sync 1, 128;" ::: "memory");
+                }
+            }
+        }
+    }
+
+    ptx::tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        __syncwarp();
+        ptx::tmem_dealloc(tmem_base, kTmemCols);
+    }
+}
+
+}  // namespace sylph

@@ -1,0 +1,81 @@
+// Host-side launcher for conv_gemm_tf32_kernel: TMA descriptor encoding (driver entry point fetched at run time,
+// so the library links against cudart only) and per-BN dispatch.
+#pragma once
+#include <cstdio>
+#include <cstring>
+#include <string>
+
+#include "conv_gemm.cuh"
+
+namespace sylph {
+
+typedef CUresult (*PFN_tmapEncodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                        const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                        CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+inline PFN_tmapEncodeTiled get_tmap_encode() {
+    static PFN_tmapEncodeTiled fn = nullptr;
+    if (fn == nullptr) {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        cudaError_t e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q);
+        if (e != cudaSuccess || q != cudaDriverEntryPointSuccess || p == nullptr) return nullptr;
+        fn = reinterpret_cast<PFN_tmapEncodeTiled>(p);
+    }
+    return fn;
+}
+
+// 2-D fp32 matrix [rows][cols] with row pitch `ld_elems`; box = [box_rows][32 cols], 128-byte swizzle, zero OOB fill.
+// `ld_elems` may be smaller than `cols` (overlapping rows) -- used by the stem convolution.
+inline int make_tmap_2d(CUtensorMap* m, const float* base, uint64_t rows, uint64_t cols, uint64_t ld_elems,
+                        uint32_t box_rows, std::string* err) {
+    PFN_tmapEncodeTiled enc = get_tmap_encode();
+    if (enc == nullptr) {
+        if (err) *err = "cuTensorMapEncodeTiled entry point unavailable";
+        return 1;
+    }
+    cuuint64_t dims[2] = {cols, rows};
+    cuuint64_t strides[1] = {ld_elems * sizeof(float)};
+    cuuint32_t box[2] = {static_cast<cuuint32_t>(kBlockK), box_rows};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(base), dims, strides, box, estr,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+        if (err) *err = "cuTensorMapEncodeTiled failed with CUresult " + std::to_string(static_cast<int>(r));
+        return 2;
+    }
+    return 0;
+}
+
+template <int BN, int STAGES>
+inline cudaError_t launch_conv_gemm_bn(const CUtensorMap& ta, const CUtensorMap& tb, const GemmArgs& args, int num_sms,
+                                       cudaStream_t stream) {
+    using S = GemmSmem<BN, STAGES>;
+    static bool configured = false;
+    if (!configured) {
+        cudaError_t e = cudaFuncSetAttribute(conv_gemm_tf32_kernel<BN, STAGES>,
+                                             cudaFuncAttributeMaxDynamicSharedMemorySize, S::kTotal);
+        if (e != cudaSuccess) return e;
+        configured = true;
+    }
+    const int total = args.num_m_tiles * args.num_n_tiles;
+    if (total <= 0) return cudaSuccess;
+    const int grid = total < num_sms ? total : num_sms;
+    conv_gemm_tf32_kernel<BN, STAGES><<<grid, kGemmThreads, S::kTotal, stream>>>(ta, tb, args);
+    return cudaGetLastError();
+}
+
+// BN in {16, 64, 128, 256}.
+inline cudaError_t launch_conv_gemm(int bn, const CUtensorMap& ta, const CUtensorMap& tb, const GemmArgs& args,
+                                    int num_sms, cudaStream_t stream) {
+    switch (bn) {
+        case 16: return launch_conv_gemm_bn<16, 8>(ta, tb, args, num_sms, stream);
+        case 64: return launch_conv_gemm_bn<64, 8>(ta, tb, args, num_sms, stream);
+        case 128: return launch_conv_gemm_bn<128, 6>(ta, tb, args, num_sms, stream);
+        case 256: return launch_conv_gemm_bn<256, 4>(ta, tb, args, num_sms, stream);
+        default: return cudaErrorInvalidValue;
+    }
+}
+
+}  // namespace sylph
