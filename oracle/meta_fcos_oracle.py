@@ -1,0 +1,299 @@
+"""ORACLE (test infrastructure only -- the product path never imports this; it must fail loudly without its CUDA
+extension instead).
+
+CPU fp32 restatement of the reference's Meta-FCOS few-shot INFERENCE path, written functionally over a flat
+state dict (keys = SURVEY.md Appendix C).  Each function cites the reference lines it follows.  The un-vendored
+upstream operators come from oracle/upstream.py.
+
+PINNING: checked against outputs of the reference's own modules (run unmodified through oracle/shims by
+oracle/make_golden.py) stored in tests/golden/*.pt -- see tests/test_oracle.py.  The reference's own tests hold no
+numeric golden vectors for this path (shapes/keys only).
+"""
+from __future__ import annotations
+
+import math
+from typing import Dict, List, Optional, Sequence, Tuple
+
+import torch
+import torch.nn.functional as F
+
+from . import upstream as up
+
+
+def _gn(x: torch.Tensor, w: torch.Tensor, b: torch.Tensor, groups: int = 32) -> torch.Tensor:
+    return F.group_norm(x, groups, w, b, 1e-5)
+
+
+class MetaFCOSOracle:
+    def __init__(self, cfg, state: Dict[str, torch.Tensor], dtype: torch.dtype = torch.float32):
+        self.cfg = cfg
+        self.dtype = dtype
+        self.sd = {k: v.detach().to(dtype) for k, v in state.items()}
+        self.backbone = up.build_fcos_resnet_fpn_backbone(cfg).to(dtype)
+        bb = {k[len("backbone."):]: v for k, v in self.sd.items() if k.startswith("backbone.")}
+        self.backbone.load_state_dict(bb, strict=True)
+        self.backbone.eval()
+        self.in_features = list(cfg.MODEL.FCOS.IN_FEATURES)
+        self.strides = list(cfg.MODEL.FCOS.FPN_STRIDES)
+        G = cfg.MODEL.META_LEARN.CODE_GENERATOR
+        self.G = G
+        self.pooler = up.ROIPooler(output_size=G.ROI_BOX.POOLER_RESOLUTION, scales=[1.0 / s for s in self.strides],
+                                   sampling_ratio=0, pooler_type=G.ROI_BOX.POOLER_TYPE)
+        p = cfg.MODEL.FCOS.PRIOR_PROB
+        self.bias_value = torch.tensor(-math.log((1 - p) / p))  # code_generator.py:422-423
+
+    # -------------------------------------------------------------------------------- images / backbone
+    def preprocess(self, images: Sequence[torch.Tensor]) -> up.ImageList:
+        """meta_one_stage_detector.py:174-178: (x - mean) / std per image, then zero-pad to a /32 batch."""
+        mean, std = self.sd["pixel_mean"], self.sd["pixel_std"]
+        normed = [(im.to(self.dtype) - mean) / std for im in images]
+        return up.ImageList.from_tensors(normed, self.backbone.size_divisibility)
+
+    @torch.no_grad()
+    def features(self, batch: torch.Tensor) -> List[torch.Tensor]:
+        """meta_one_stage_detector.py:180-182, :247-250: backbone dict -> list ordered by FCOS.IN_FEATURES."""
+        out = self.backbone(batch)
+        return [out[f] for f in self.in_features]
+
+    # -------------------------------------------------------------------------------- code generator
+    def _cg(self, name: str) -> torch.Tensor:
+        return self.sd["code_generator.code_generator_head." + name]
+
+    def _cg_tower(self, x: torch.Tensor) -> torch.Tensor:
+        """support_set_shared_tower (code_generator.py:648-688): per layer conv3x3 [+ norm] [+ act]."""
+        idx = 0
+        for norm_type, act in self.G.TOWER_LAYERS:
+            x = F.conv2d(x, self._cg(f"support_set_shared_tower.{idx}.weight"),
+                         self._cg(f"support_set_shared_tower.{idx}.bias"), padding=1)
+            idx += 1
+            if norm_type in ("GN", "NaiveGN", "LN"):
+                groups = 1 if norm_type == "LN" else 32
+                x = _gn(x, self._cg(f"support_set_shared_tower.{idx}.weight"),
+                        self._cg(f"support_set_shared_tower.{idx}.bias"), groups)
+                idx += 1
+            elif norm_type not in ("", "none", None):
+                raise NotImplementedError(norm_type)
+            if act == "ReLU":
+                x = F.relu(x)
+                idx += 1
+            elif act == "Tanh":
+                x = torch.tanh(x)
+                idx += 1
+        return x
+
+    @torch.no_grad()
+    def roi_features(self, feats: List[torch.Tensor], boxes: torch.Tensor) -> Tuple[torch.Tensor, torch.Tensor]:
+        """code_generator.py:928-930: one box per support image -> (N, 256, 7, 7); also returns level indices."""
+        box_lists = [up.Boxes(boxes[i:i + 1].to(torch.float32)) for i in range(boxes.shape[0])]
+        levels = up.assign_boxes_to_levels(box_lists, self.pooler.min_level, self.pooler.max_level,
+                                           self.pooler.canonical_box_size, self.pooler.canonical_level)
+        return self.pooler(feats, box_lists), levels
+
+    @torch.no_grad()
+    def per_shot_codes(self, roi: torch.Tensor) -> Tuple[torch.Tensor, Optional[torch.Tensor]]:
+        """code_generator.py:941-967: shared tower, cls-conv + global average pool, bias conv (+ L2 over the 49
+        positions when BIAS_L2_NORM) + pool.  Returns (N, OC, 1, 1) and (N, 1, 1, 1) or None."""
+        x = self._cg_tower(roi) if len(self.G.TOWER_LAYERS) > 0 else roi
+        w = F.conv2d(x, self._cg("support_set_cls_conv.0.weight"), self._cg("support_set_cls_conv.0.bias"), padding=1)
+        if self.G.CLS_LAYER[0] in ("GN", "NaiveGN", "LN"):
+            w = _gn(w, self._cg("support_set_cls_conv.1.weight"), self._cg("support_set_cls_conv.1.bias"),
+                    1 if self.G.CLS_LAYER[0] == "LN" else 32)
+        if self.G.CLS_LAYER[1] == "ReLU":
+            w = F.relu(w)
+        elif self.G.CLS_LAYER[1] == "Tanh":
+            w = torch.tanh(w)
+        k_s = int(self.G.CLS_LAYER[2])
+        w = F.adaptive_avg_pool2d(w, (k_s, k_s))
+        b = None
+        if len(self.G.BIAS_LAYER) == 3:
+            b = F.conv2d(x, self._cg("support_set_cls_bias.0.weight"), self._cg("support_set_cls_bias.0.bias"), padding=1)
+            if self.G.BIAS_L2_NORM:
+                shp = b.shape
+                b = F.normalize(b.reshape(shp[0], shp[1], -1), p=2, dim=2).reshape(shp)
+            b = F.adaptive_avg_pool2d(b, (1, 1))
+        return w, b
+
+    @torch.no_grad()
+    def class_code(self, support_images: Sequence[torch.Tensor], boxes: torch.Tensor) -> Dict[str, torch.Tensor]:
+        """run_type="meta_learn_test_support" (meta_one_stage_detector.py:229-254 -> code_generator.py:924-1002).
+        ALL rows of the call form ONE class (eval: num_shot = size(0), code_generator.py:790-793); uniform 1/K
+        weights (:805-806, 817); codes are returned RAW (normalisation only `if self.training`, :993-994)."""
+        il = self.preprocess(support_images)
+        feats = self.features(il.tensor)
+        roi, _ = self.roi_features(feats, boxes)
+        w, b = self.per_shot_codes(roi)
+        k = w.shape[0]
+        weight = torch.full((1, k, 1, 1, 1), 1.0 / k, dtype=w.dtype)
+        cls_conv = (weight * w.view(1, k, *w.shape[1:])).sum(dim=1)
+        if b is not None:
+            cls_bias = (weight * b.view(1, k, 1, 1, 1)).sum(dim=1)
+        else:
+            cls_bias = torch.zeros(1, 1, 1, 1, dtype=w.dtype)
+        return {"cls_conv": cls_conv, "cls_bias": cls_bias}
+
+    @torch.no_grad()
+    def normalize_code(self, cls_conv: torch.Tensor, cls_bias: torch.Tensor,
+                       cls_weight_norm: Optional[torch.Tensor] = None) -> Tuple[torch.Tensor, torch.Tensor]:
+        """run_type="meta_learn_normalize_code": code_process_module (code_generator.py:864-875):
+        post_norm GN (if present and C % 32 == 0, :838-839) -> L2 over channels (:841-842) -> x weight_norm ->
+        x conv_scale (:873); bias: flatten -> x bias_scale -> + bias_value (:853-860)."""
+        w = cls_conv
+        assert w.ndim == 4
+        if self.G.POST_NORM != "" and w.size(1) % 32 == 0:
+            w = _gn(w, self._cg("post_norm.weight"), self._cg("post_norm.bias"), 1 if self.G.POST_NORM == "LN" else 32)
+        if self.G.CONV_L2_NORM:
+            w = F.normalize(w, p=2, dim=1)
+        if cls_weight_norm is not None:
+            w = w * cls_weight_norm
+        key = "code_generator.code_generator_head.conv_scale.scale"
+        if key in self.sd:
+            w = w * self.sd[key]
+        assert cls_bias.size(0) == 1, "predicted bias should only have batch size 1"
+        b = cls_bias.reshape(cls_bias.numel())
+        key = "code_generator.code_generator_head.bias_scale.scale"
+        if key in self.sd:
+            b = b * self.sd[key]
+        b = b + self.bias_value.to(b.dtype)
+        return w, b
+
+    @staticmethod
+    def pack_codes(codes: List[Dict]) -> Dict[str, torch.Tensor]:
+        """format_class_codes_shared (sylph/evaluation/meta_learn_evaluation.py:71-103): order by
+        support_set_target, concatenate, flatten the bias."""
+        by_id = {int(c["support_set_target"]): c["class_code"] for c in codes}
+        ids = sorted(by_id)
+        return {"cls_conv": torch.cat([by_id[i]["cls_conv"] for i in ids], dim=0),
+                "cls_bias": torch.cat([by_id[i]["cls_bias"].reshape(-1) for i in ids], dim=0)}
+
+    # -------------------------------------------------------------------------------- FCOS head
+    def _head(self, name: str) -> torch.Tensor:
+        return self.sd["proposal_generator.fcos_head." + name]
+
+    def _tower(self, x: torch.Tensor, which: str, n: int) -> torch.Tensor:
+        """fcos.py:72-122: n x [conv3x3 + GN(32) + ReLU], weights shared across levels."""
+        norm = self.cfg.MODEL.FCOS.NORM
+        for i in range(n):
+            x = F.conv2d(x, self._head(f"{which}.{3 * i}.weight"), self._head(f"{which}.{3 * i}.bias"), padding=1)
+            if norm in ("GN", "NaiveGN"):
+                x = _gn(x, self._head(f"{which}.{3 * i + 1}.weight"), self._head(f"{which}.{3 * i + 1}.bias"))
+            elif norm not in ("none", None):
+                raise NotImplementedError(norm)
+            x = F.relu(x)
+        return x
+
+    @torch.no_grad()
+    def head(self, feats: List[torch.Tensor], codes: Dict[str, torch.Tensor]):
+        """MetaFCOSHead.forward (fcos.py:582-667) with CondConvBasic (head_utils.py:60-81)."""
+        C = self.cfg.MODEL.FCOS
+        k_s = int(self.G.CLS_LAYER[2])
+        w = codes["cls_conv"].to(self.dtype)
+        b = codes["cls_bias"].to(self.dtype) if self.G.USE_BIAS else None
+        logits, regs, ctrs, ious = [], [], [], []
+        for lvl, f in enumerate(feats):
+            ct = self._tower(f, "cls_tower", int(C.NUM_CLS_CONVS))
+            bt = self._tower(f, "bbox_tower", int(C.NUM_BOX_CONVS))
+            logits.append(F.conv2d(ct, w, b, stride=1, padding=k_s // 2))
+            reg = F.conv2d(bt, self._head("bbox_pred.weight"), self._head("bbox_pred.bias"), padding=1)
+            if C.USE_SCALE:
+                reg = reg * self._head(f"scales.{lvl}.scale")
+            regs.append(F.relu(reg))
+            ctrs.append(F.conv2d(bt, self._head("ctrness.weight"), self._head("ctrness.bias"), padding=1))
+            ious.append(F.conv2d(bt, self._head("iou_overlap.weight"), self._head("iou_overlap.bias"), padding=1))
+        return logits, regs, ctrs, ious
+
+    @torch.no_grad()
+    def level_candidates(self, level: int, logits: torch.Tensor, reg: torch.Tensor, ctr: torch.Tensor,
+                         iou: torch.Tensor) -> List[Dict[str, torch.Tensor]]:
+        """forward_for_single_feature_map (fcos_outputs.py:904-1008), per image of the batch.  Candidates are
+        returned in (location, class) order, i.e. the order of `nonzero()` (:967-969)."""
+        C = self.cfg.MODEL.FCOS
+        N, NC, H, W = logits.shape
+        stride = self.strides[level]
+        locations = up.compute_locations(H, W, stride, logits.device).to(self.dtype)
+        cls = logits.permute(0, 2, 3, 1).reshape(N, -1, NC).sigmoid()
+        box_reg = (reg * stride).permute(0, 2, 3, 1).reshape(N, -1, 4)  # fcos_outputs.py:786
+        ctrness = ctr.permute(0, 2, 3, 1).reshape(N, -1).sigmoid()
+        iouness = iou.permute(0, 2, 3, 1).reshape(N, -1).sigmoid()
+        quality = sorted(C.BOX_QUALITY)
+        if quality == ["ctrness"]:
+            q = ctrness
+        elif quality == ["iou"]:
+            q = iouness
+        elif quality == ["ctrness", "iou"]:
+            q = torch.sqrt(iouness * ctrness)
+        else:
+            raise NotImplementedError(quality)
+        if C.THRESH_WITH_CTR:
+            cls = cls * q[:, :, None]
+        cand = cls > C.INFERENCE_TH_TEST
+        if not C.THRESH_WITH_CTR:
+            cls = cls * q[:, :, None]
+        out = []
+        for i in range(N):
+            nz = cand[i].nonzero()
+            loc_idx, cls_idx = nz[:, 0], nz[:, 1]
+            score = cls[i][cand[i]]
+            top_n = min(int(cand[i].sum()), int(C.PRE_NMS_TOPK_TEST))
+            if score.numel() > top_n:
+                # torch.topk(sorted=False) leaves ties implementation-defined; the oracle keeps the smallest
+                # (location, class) index among equal scores and tests treat exact ties at the cut as a guard band.
+                order = torch.sort(score, descending=True, stable=True).indices[:top_n]
+                order = torch.sort(order).values
+                score, loc_idx, cls_idx = score[order], loc_idx[order], cls_idx[order]
+            r = box_reg[i][loc_idx]
+            l = locations[loc_idx]
+            boxes = torch.stack([l[:, 0] - r[:, 0], l[:, 1] - r[:, 1], l[:, 0] + r[:, 2], l[:, 1] + r[:, 3]], dim=1)
+            out.append({"boxes": boxes, "scores": torch.sqrt(score), "classes": cls_idx, "locations": l,
+                        "loc_index": loc_idx, "levels": torch.full_like(cls_idx, level)})
+        return out
+
+    @torch.no_grad()
+    def select(self, per_image: Dict[str, torch.Tensor]) -> Dict[str, torch.Tensor]:
+        """select_over_all_levels (fcos_outputs.py:1010-1028): class-aware NMS, then keep everything scoring at
+        least the POST_NMS_TOPK-th best (ties kept, `>=`)."""
+        C = self.cfg.MODEL.FCOS
+        keep = up.batched_nms(per_image["boxes"].float(), per_image["scores"].float(), per_image["classes"], C.NMS_TH)
+        res = {k: v[keep] for k, v in per_image.items()}
+        n = keep.numel()
+        topk = int(C.POST_NMS_TOPK_TEST)
+        if n > topk > 0:
+            thresh, _ = torch.kthvalue(res["scores"], n - topk + 1)
+            m = res["scores"] >= thresh
+            res = {k: v[m] for k, v in res.items()}
+        return res
+
+    @staticmethod
+    def postprocess(res: Dict[str, torch.Tensor], image_size: Tuple[int, int], out_h: int, out_w: int):
+        """detector_postprocess (meta_one_stage_detector.py:288-295, upstream A.8): rescale, clip, drop empty."""
+        sx, sy = out_w / image_size[1], out_h / image_size[0]
+        b = res["boxes"].clone()
+        b[:, 0::2] *= sx
+        b[:, 1::2] *= sy
+        b[:, 0::2] = b[:, 0::2].clamp(min=0, max=out_w)
+        b[:, 1::2] = b[:, 1::2].clamp(min=0, max=out_h)
+        ok = ((b[:, 2] - b[:, 0]) > 0) & ((b[:, 3] - b[:, 1]) > 0)
+        out = {k: v[ok] for k, v in res.items()}
+        out["boxes"] = b[ok]
+        return out
+
+    @torch.no_grad()
+    def detect(self, query_images: Sequence[torch.Tensor], codes: Dict[str, torch.Tensor],
+               out_sizes: Optional[Sequence[Tuple[int, int]]] = None, return_intermediate: bool = False):
+        """run_type="meta_learn_test_instance" (meta_one_stage_detector.py:261-296 -> fcos.py:184-268 ->
+        fcos_outputs.py:743-812)."""
+        il = self.preprocess(query_images)
+        feats = self.features(il.tensor)
+        logits, regs, ctrs, ious = self.head(feats, codes)
+        per_level = [self.level_candidates(l, logits[l], regs[l], ctrs[l], ious[l]) for l in range(len(feats))]
+        results = []
+        pre_nms = []
+        for i in range(len(query_images)):
+            merged = {k: torch.cat([per_level[l][i][k] for l in range(len(feats))], dim=0) for k in per_level[0][i]}
+            pre_nms.append(merged)
+            sel = self.select(merged)
+            h, w = out_sizes[i] if out_sizes is not None else il.image_sizes[i]
+            results.append(self.postprocess(sel, il.image_sizes[i], h, w))
+        if return_intermediate:
+            return results, {"features": feats, "logits": logits, "reg": regs, "ctr": ctrs, "iou": ious,
+                             "pre_nms": pre_nms, "image_sizes": il.image_sizes}
+        return results
