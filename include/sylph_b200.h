@@ -1,0 +1,132 @@
+/*
+ * sylph_b200 -- C ABI of the B200-native Meta-FCOS few-shot inference path.
+ *
+ * The reference (facebookresearch/sylph-few-shot-detection) is 100 % Python; its "FFI" for this path is the set of
+ * nn.Module entry points listed below.  Each function names the reference interface it replaces (file:line under
+ * /root/reference).  Plain pointers and sizes only; no torch types.  Conventions:
+ *   - every function returns 0 on success, non-zero on failure; sylph_last_error(ctx) gives the message;
+ *   - one context per device, thread-compatible (not thread-safe per context);
+ *   - "dev" pointers are CUDA device pointers owned by the caller, "host" pointers are host memory;
+ *   - all work is enqueued on the stream passed in (a cudaStream_t cast to void*; NULL = legacy default stream)
+ *     and is asynchronous unless stated otherwise;
+ *   - images are fp32 CHW, 3 channels in the order of MODEL.PIXEL_MEAN (BGR), values 0..255, NOT normalised;
+ *   - a class code row is 257 floats: 256 conv weights (cls_conv[c, :, 0, 0]) followed by the bias.
+ */
+#ifndef SYLPH_B200_H_
+#define SYLPH_B200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct sylph_ctx sylph_ctx;
+
+#define SYLPH_CODE_STRIDE 257
+#define SYLPH_NUM_LEVELS 5
+#define SYLPH_DET_STRIDE 9 /* x0, y0, x1, y1, score, class, loc_x, loc_y, level  (all stored as float) */
+
+/* Model hyper-parameters the hot path reads from the reference config ("Config / flags"). */
+typedef struct sylph_model_config {
+    int resnet_depth;          /* MODEL.RESNETS.DEPTH: 50 | 101 | 152 */
+    int num_cls_convs;         /* MODEL.FCOS.NUM_CLS_CONVS */
+    int num_box_convs;         /* MODEL.FCOS.NUM_BOX_CONVS */
+    int use_scale;             /* MODEL.FCOS.USE_SCALE */
+    int thresh_with_ctr;       /* MODEL.FCOS.THRESH_WITH_CTR */
+    int box_quality;           /* bit 0: "ctrness", bit 1: "iou"  (MODEL.FCOS.BOX_QUALITY) */
+    int pre_nms_topk;          /* MODEL.FCOS.PRE_NMS_TOPK_TEST */
+    int post_nms_topk;         /* MODEL.FCOS.POST_NMS_TOPK_TEST */
+    float inference_thresh;    /* MODEL.FCOS.INFERENCE_TH_TEST */
+    float nms_thresh;          /* MODEL.FCOS.NMS_TH */
+    float prior_prob;          /* MODEL.FCOS.PRIOR_PROB */
+    float pixel_mean[3];       /* MODEL.PIXEL_MEAN */
+    float pixel_std[3];        /* MODEL.PIXEL_STD */
+    int cg_tower_layers;       /* len(CODE_GENERATOR.TOWER_LAYERS); each layer must be ["GN","ReLU"] */
+    int cg_post_norm;          /* CODE_GENERATOR.POST_NORM == "GN" */
+    int cg_conv_l2_norm;       /* CODE_GENERATOR.CONV_L2_NORM */
+    int cg_bias_layer;         /* len(CODE_GENERATOR.BIAS_LAYER) == 3 */
+    int cg_bias_l2_norm;       /* CODE_GENERATOR.BIAS_L2_NORM */
+    int cg_use_bias;           /* CODE_GENERATOR.USE_BIAS (CondConvBasic use_bias) */
+    int cg_has_conv_scale;     /* USE_WEIGHT_SCALE and (CONV_L2_NORM or POST_NORM) */
+} sylph_model_config;
+
+/* Library / build identification (no GPU needed). */
+const char* sylph_version(void);
+
+/* Create / destroy a context bound to CUDA device `device`.  Replaces MetaOneStageDetector construction,
+ * sylph/modeling/meta_arch/meta_one_stage_detector.py:72-88 (from_config). */
+int sylph_create(sylph_ctx** ctx, int device, const sylph_model_config* cfg);
+void sylph_destroy(sylph_ctx* ctx);
+const char* sylph_last_error(const sylph_ctx* ctx);
+
+/* Stage one state-dict tensor (host fp32, contiguous) under its reference key, then
+ * finalize: fold FrozenBN into the convolutions, reorder to tap-major K-major, round to TF32, upload.
+ * Replaces DetectionCheckpointer.load into the module tree (tools/train_net.py:51-61). Synchronous. */
+int sylph_load_tensor(sylph_ctx* ctx, const char* key, const float* host_data, const int64_t* shape, int ndim);
+int sylph_finalize_weights(sylph_ctx* ctx);
+
+/* Feature slots: the context keeps NUM_SLOTS pyramids (p3..p7 for a batch of images) alive at a time. */
+#define SYLPH_SLOT_SUPPORT 0
+#define SYLPH_SLOT_QUERY 1
+#define SYLPH_NUM_SLOTS 2
+
+/* Normalise + pad to /32 + backbone.  Replaces convert_batched_inputs_to_image_list + backbone call,
+ * meta_one_stage_detector.py:174-182 (and :245-247, :272-273).  images_dev[i] is a (3, heights[i], widths[i]) fp32
+ * device tensor. */
+int sylph_extract_features(sylph_ctx* ctx, int slot, int n_images, const float* const* images_dev, const int* heights,
+                           const int* widths, void* stream);
+
+/* Plugin-level entry for features produced elsewhere (NCHW fp32 device tensors, one per level, (n, 256, H_l, W_l)):
+ * the `features` argument of CodeGenerator.forward, sylph/modeling/code_generator/code_generator.py:1037-1053. */
+int sylph_import_features(sylph_ctx* ctx, int slot, int n_images, int padded_h, int padded_w,
+                          const float* const* level_ptrs_dev, const int* level_h, const int* level_w, void* stream);
+
+/* Geometry of a slot after extract/import: level_h/level_w receive SYLPH_NUM_LEVELS entries. */
+int sylph_feature_shape(sylph_ctx* ctx, int slot, int* n_images, int* padded_h, int* padded_w, int* level_h, int* level_w);
+
+/* Copy one level of a slot out as NCHW fp32 (n, 256, H_l, W_l) -- what backbone(...)[f] returns in the reference. */
+int sylph_export_features(sylph_ctx* ctx, int slot, int level, float* out_dev, void* stream);
+
+/* Class-code generation for `n_classes` classes from the support slot.  boxes_host: (n_rois, 4) XYXY absolute pixels,
+ * roi_image[i] = index of the support image of ROI i inside the slot, class_offsets: n_classes + 1 prefix offsets
+ * into the ROI list (ROIs of a class are contiguous).  Writes RAW (un-normalised) codes, (n_classes, 257), to
+ * codes_out_dev and, if non-NULL, the FPN level index of every ROI (int64, like assign_boxes_to_levels) to
+ * levels_out_dev.  Replaces CodeGeneratorHead.forward_roi_align, code_generator.py:924-1002, called once per class
+ * by forward_class_code, meta_one_stage_detector.py:229-254. */
+int sylph_generate_codes(sylph_ctx* ctx, int slot, int n_rois, const float* boxes_host, const int* roi_image,
+                         int n_classes, const int* class_offsets, float* codes_out_dev, int64_t* levels_out_dev,
+                         void* stream);
+
+/* Copy the pooled ROI features of the last sylph_generate_codes call out as (n_rois, 256, 7, 7) fp32. */
+int sylph_export_roi_features(sylph_ctx* ctx, float* out_dev, void* stream);
+
+/* Code normalisation: GN(32) -> L2 -> x conv_scale; bias x bias_scale + prior.  In-place safe (out == in).
+ * Replaces forward_normalize_code / code_process_module, code_generator.py:864-897. */
+int sylph_normalize_codes(sylph_ctx* ctx, const float* raw_codes_dev, float* out_codes_dev, int n_classes, void* stream);
+
+/* Detection on the query slot with (n_classes, 257) normalised codes.  out_sizes: (n_images, 2) = (height, width)
+ * requested output resolution per image (detector_postprocess).  dets_out_dev: (n_images, max_dets, 9) floats,
+ * counts_out_dev: (n_images) int32; rows are in descending score order.  max_dets must be >= post_nms_topk.
+ * Replaces MetaFCOS.forward + FCOSOutputs.predict_proposals + detector_postprocess:
+ * sylph/modeling/meta_fcos/fcos.py:184-268,582-667, fcos_outputs.py:743-812,904-1028,
+ * meta_one_stage_detector.py:279-295. */
+int sylph_detect(sylph_ctx* ctx, int slot, const float* codes_dev, int n_classes, const int* out_sizes_host,
+                 float* dets_out_dev, int* counts_out_dev, int max_dets, void* stream);
+
+/* Head intermediates of the last sylph_detect call, NCHW fp32: which = 0 logits (n, n_classes, H, W),
+ * 1 bbox_reg after scale+ReLU (n, 4, H, W), 2 ctrness (n, 1, H, W), 3 iou (n, 1, H, W). */
+int sylph_export_head_output(sylph_ctx* ctx, int which, int level, float* out_dev, void* stream);
+
+/* Number of kernels this library launched on the context since creation (bench.py's gpu_launches). */
+int64_t sylph_launch_count(const sylph_ctx* ctx);
+
+/* Per-stage device time of the most recent profiled call: enable with sylph_set_profiling(ctx, 1); then
+ * sylph_get_timings fills up to `cap` (name, ms) pairs and returns how many exist. */
+int sylph_set_profiling(sylph_ctx* ctx, int enabled);
+int sylph_get_timings(sylph_ctx* ctx, char (*names)[48], float* ms, double* flops, double* bytes, int cap);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SYLPH_B200_H_ */

@@ -1,0 +1,118 @@
+"""ctypes binding of libsylph_b200.so (C ABI declared in include/sylph_b200.h) and its in-tree build recipe.
+
+The shared library is the product; this module only declares argument types.  There is no CPU fallback: if the
+library is missing it is built with nvcc for sm_100a, and if that is impossible an ImportError is raised.
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+import subprocess
+from ctypes import POINTER, Structure, c_char_p, c_double, c_float, c_int, c_int64, c_void_p
+
+_PKG = os.path.dirname(os.path.abspath(__file__))
+_CSRC = os.path.join(_PKG, "csrc")
+LIB_PATH = os.path.join(_PKG, "libsylph_b200.so")
+NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17"]
+
+CODE_STRIDE = 257
+DET_STRIDE = 9
+NUM_LEVELS = 5
+SLOT_SUPPORT, SLOT_QUERY = 0, 1
+
+
+class ModelConfig(Structure):
+    """Mirror of `sylph_model_config`."""
+    _fields_ = [
+        ("resnet_depth", c_int), ("num_cls_convs", c_int), ("num_box_convs", c_int), ("use_scale", c_int),
+        ("thresh_with_ctr", c_int), ("box_quality", c_int), ("pre_nms_topk", c_int), ("post_nms_topk", c_int),
+        ("inference_thresh", c_float), ("nms_thresh", c_float), ("prior_prob", c_float),
+        ("pixel_mean", c_float * 3), ("pixel_std", c_float * 3),
+        ("cg_tower_layers", c_int), ("cg_post_norm", c_int), ("cg_conv_l2_norm", c_int), ("cg_bias_layer", c_int),
+        ("cg_bias_l2_norm", c_int), ("cg_use_bias", c_int), ("cg_has_conv_scale", c_int),
+    ]
+
+
+def _sources():
+    return sorted(os.path.join(_CSRC, f) for f in os.listdir(_CSRC) if f.endswith((".cu", ".cuh"))) + \
+        [os.path.join(os.path.dirname(_PKG), "include", "sylph_b200.h")]
+
+
+def needs_build() -> bool:
+    if not os.path.exists(LIB_PATH):
+        return True
+    t = os.path.getmtime(LIB_PATH)
+    return any(os.path.getmtime(s) > t for s in _sources() if os.path.exists(s))
+
+
+def build(force: bool = False, verbose: bool = False) -> str:
+    """nvcc cross-compiles for sm_100a without a GPU; the .so stays in-tree (git-ignored, travels with gpurun)."""
+    if not force and not needs_build():
+        return LIB_PATH
+    nvcc = os.environ.get("NVCC", "nvcc")
+    cmd = [nvcc] + NVCC_FLAGS + ["-shared", "-Xcompiler", "-fPIC", "-o", LIB_PATH, os.path.join(_CSRC, "engine.cu")]
+    if verbose:
+        print(" ".join(cmd))
+    res = subprocess.run(cmd, capture_output=True, text=True)
+    if res.returncode != 0:
+        raise ImportError(f"building libsylph_b200.so failed:\n{res.stdout}\n{res.stderr}")
+    return LIB_PATH
+
+
+_lib = None
+
+
+def load() -> ctypes.CDLL:
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        build()
+    lib = ctypes.CDLL(LIB_PATH)
+    vp, ip, fp = c_void_p, POINTER(c_int), POINTER(c_float)
+    lib.sylph_version.restype = c_char_p
+    lib.sylph_version.argtypes = []
+    lib.sylph_create.restype = c_int
+    lib.sylph_create.argtypes = [POINTER(vp), c_int, POINTER(ModelConfig)]
+    lib.sylph_destroy.restype = None
+    lib.sylph_destroy.argtypes = [vp]
+    lib.sylph_last_error.restype = c_char_p
+    lib.sylph_last_error.argtypes = [vp]
+    lib.sylph_load_tensor.restype = c_int
+    lib.sylph_load_tensor.argtypes = [vp, c_char_p, vp, POINTER(c_int64), c_int]
+    lib.sylph_finalize_weights.restype = c_int
+    lib.sylph_finalize_weights.argtypes = [vp]
+    lib.sylph_extract_features.restype = c_int
+    lib.sylph_extract_features.argtypes = [vp, c_int, c_int, POINTER(vp), ip, ip, vp]
+    lib.sylph_import_features.restype = c_int
+    lib.sylph_import_features.argtypes = [vp, c_int, c_int, c_int, c_int, POINTER(vp), ip, ip, vp]
+    lib.sylph_feature_shape.restype = c_int
+    lib.sylph_feature_shape.argtypes = [vp, c_int, ip, ip, ip, ip, ip]
+    lib.sylph_export_features.restype = c_int
+    lib.sylph_export_features.argtypes = [vp, c_int, c_int, vp, vp]
+    lib.sylph_generate_codes.restype = c_int
+    lib.sylph_generate_codes.argtypes = [vp, c_int, c_int, fp, ip, c_int, ip, vp, vp, vp]
+    lib.sylph_export_roi_features.restype = c_int
+    lib.sylph_export_roi_features.argtypes = [vp, vp, vp]
+    lib.sylph_normalize_codes.restype = c_int
+    lib.sylph_normalize_codes.argtypes = [vp, vp, vp, c_int, vp]
+    lib.sylph_detect.restype = c_int
+    lib.sylph_detect.argtypes = [vp, c_int, vp, c_int, ip, vp, vp, c_int, vp]
+    lib.sylph_export_head_output.restype = c_int
+    lib.sylph_export_head_output.argtypes = [vp, c_int, c_int, vp, vp]
+    lib.sylph_launch_count.restype = c_int64
+    lib.sylph_launch_count.argtypes = [vp]
+    lib.sylph_set_profiling.restype = c_int
+    lib.sylph_set_profiling.argtypes = [vp, c_int]
+    lib.sylph_get_timings.restype = c_int
+    lib.sylph_get_timings.argtypes = [vp, vp, fp, POINTER(c_double), POINTER(c_double), c_int]
+    _lib = lib
+    return lib
+
+
+EXPORTED_SYMBOLS = [
+    "sylph_version", "sylph_create", "sylph_destroy", "sylph_last_error", "sylph_load_tensor",
+    "sylph_finalize_weights", "sylph_extract_features", "sylph_import_features", "sylph_feature_shape",
+    "sylph_export_features", "sylph_generate_codes", "sylph_export_roi_features", "sylph_normalize_codes",
+    "sylph_detect", "sylph_export_head_output", "sylph_launch_count", "sylph_set_profiling", "sylph_get_timings",
+]

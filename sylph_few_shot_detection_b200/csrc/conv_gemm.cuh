@@ -49,11 +49,12 @@ struct GemmArgs {
     int tile_begin;        // first output M tile (absolute index, row = tile * 128)
     int num_m_tiles;
     int num_n_tiles;
-    int a_row_delta;       // A row = output row + a_row_delta + tap_shift[tap]
+    int a_row_delta;       // A row = output row + a_row_delta + tap_dy[tap] * Wp(plane of the tile) + tap_dx[tap]
     int taps;
     int kblocks_per_tap;   // K per tap / 32
     int b_rows_per_tap;    // rows of the weight matrix per tap (Cout padded up to a multiple of BN)
-    int tap_shift[kMaxTaps];
+    signed char tap_dy[kMaxTaps];
+    signed char tap_dx[kMaxTaps];
     const float* bias;     // [n_tiles * BN] or nullptr
     const float* residual; // same row indexing as out, or nullptr
     int ld_res;
@@ -134,12 +135,15 @@ conv_gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_c
                 const int n_tile = tile - m_tile * p.num_n_tiles;
                 const int a_row_base = (p.tile_begin + m_tile) * kBlockM + p.a_row_delta;
                 const int b_row_base = n_tile * BN;
+                // planes of different FPN levels have different padded widths: the row shift of a tap is per tile
+                const int wp = p.segs[p.tile_seg[p.tile_begin + m_tile]].Wp;
                 int tap = 0, kb = 0;
                 for (int ks = 0; ks < ksteps; ++ks) {
                     ptx::mbar_wait(&empty_bar[stage], phase ^ 1u);
                     ptx::mbar_arrive_expect_tx(&full_bar[stage], S::kStageBytes);
                     uint8_t* sa = smem + stage * S::kStageBytes;
-                    ptx::tma_load_2d(sa, &tmap_a, &full_bar[stage], kb * kBlockK, a_row_base + p.tap_shift[tap]);
+                    ptx::tma_load_2d(sa, &tmap_a, &full_bar[stage], kb * kBlockK,
+                                     a_row_base + static_cast<int>(p.tap_dy[tap]) * wp + static_cast<int>(p.tap_dx[tap]));
                     ptx::tma_load_2d(sa + S::kABytes, &tmap_b, &full_bar[stage], kb * kBlockK,
                                      tap * p.b_rows_per_tap + b_row_base);
                     if (++kb == p.kblocks_per_tap) { kb = 0; ++tap; }

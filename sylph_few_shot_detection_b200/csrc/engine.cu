@@ -1,0 +1,1127 @@
+// libsylph_b200: host-side engine + C ABI (include/sylph_b200.h) of the B200-native Meta-FCOS inference path.
+// Owns the prepared weights, the flat-plane activation buffers and the launch sequence; all arithmetic runs in the
+// CUDA kernels of this directory.  There is no CPU fallback: without a CUDA device every entry point fails.
+#include <algorithm>
+#include <cmath>
+#include <cstdarg>
+#include <cstring>
+#include <map>
+#include <memory>
+#include <string>
+#include <vector>
+
+#include "../../include/sylph_b200.h"
+#include "conv_gemm_host.cuh"
+#include "kernels_detect.cuh"
+
+namespace sylph {
+
+static inline int round_up(int x, int m) { return (x + m - 1) / m * m; }
+static inline int ceil_div(long long a, long long b) { return static_cast<int>((a + b - 1) / b); }
+
+static float tf32_rne(float x) {
+    uint32_t u;
+    memcpy(&u, &x, 4);
+    if ((u & 0x7F800000u) == 0x7F800000u) return x;
+    u += 0xFFFu + ((u >> 13) & 1u);
+    u &= 0xFFFFE000u;
+    float y;
+    memcpy(&y, &u, 4);
+    return y;
+}
+
+struct HostTensor {
+    std::vector<int64_t> shape;
+    std::vector<float> data;
+};
+
+// A convolution prepared for conv_gemm: weights [taps][cout_pad][k_per_tap] (TF32-rounded), bias [cout_pad].
+struct ConvW {
+    float* w = nullptr;
+    float* bias = nullptr;
+    int taps = 0, k_per_tap = 0, cout = 0, cout_pad = 0, bn = 0, ksize = 0;
+};
+
+struct PlaneSet {
+    std::vector<Seg> segs;
+    int total_rows = 0;
+    Seg* d_segs = nullptr;
+    int* d_tile_seg = nullptr;
+};
+
+struct Buffer {
+    void* p = nullptr;
+    size_t cap = 0;
+    std::string sig;
+};
+
+struct Timing {
+    std::string name;
+    cudaEvent_t e0, e1;
+    double flops, bytes;
+};
+
+struct Slot {
+    bool valid = false;
+    int n = 0, hpad = 0, wpad = 0;
+    int lh[5] = {0}, lw[5] = {0};
+    std::vector<int> img_h, img_w;
+    PyramidGeom pg;
+    std::shared_ptr<PlaneSet> ps;  // level-major pyramid plane set
+    long long level_row0[6] = {0};
+    float* pyr = nullptr;
+};
+
+}  // namespace sylph
+
+using namespace sylph;
+
+struct sylph_ctx {
+    int device = 0;
+    int num_sms = 0;
+    sylph_model_config cfg;
+    std::string err;
+    std::map<std::string, HostTensor> staged;
+    bool finalized = false;
+    int64_t launches = 0;
+    bool profiling = false;
+    std::vector<Timing> timings;
+
+    // prepared weights
+    ConvW stem;
+    struct Block { ConvW c1, c2, c3, sc; bool has_sc = false; };
+    std::vector<std::vector<Block>> stages;
+    ConvW lat[3], outc[3], p6, p7;
+    std::vector<ConvW> cls_tower, box_tower, cg_tower;
+    std::vector<float*> cls_gn_w, cls_gn_b, box_gn_w, box_gn_b, cg_gn_w, cg_gn_b;
+    ConvW pred, cg_cls;
+    float level_scale[5] = {1, 1, 1, 1, 1};
+    float* cg_wbias = nullptr;  // [9][256]
+    float* cg_bbias = nullptr;  // [1]
+    float* post_gn_w = nullptr;
+    float* post_gn_b = nullptr;
+    float conv_scale = 1.f, bias_scale = 1.f, bias_value = 0.f;
+
+    std::map<std::string, Buffer> bufs;
+    std::map<std::string, std::shared_ptr<PlaneSet>> plane_sets;
+    Slot slots[SYLPH_NUM_SLOTS];
+    // state of the last generate_codes / detect call (for exports)
+    int last_n_rois = 0;
+    int last_detect_slot = -1, last_detect_classes = 0, last_logit_stride = 0;
+
+    int fail(const char* fmt, ...) {
+        char b[1024];
+        va_list ap;
+        va_start(ap, fmt);
+        vsnprintf(b, sizeof(b), fmt, ap);
+        va_end(ap);
+        err = b;
+        return 1;
+    }
+};
+
+#define CU_TRY(ctx, expr)                                                                            \
+    do {                                                                                             \
+        cudaError_t e__ = (expr);                                                                    \
+        if (e__ != cudaSuccess) return (ctx)->fail("%s failed: %s (%s:%d)", #expr, cudaGetErrorString(e__), __FILE__, __LINE__); \
+    } while (0)
+#define TRY(expr)              \
+    do {                       \
+        int r__ = (expr);      \
+        if (r__ != 0) return r__; \
+    } while (0)
+
+namespace sylph {
+
+// ------------------------------------------------------------------------------------------------ memory helpers
+static int ensure(sylph_ctx* c, const std::string& name, size_t bytes, const std::string& sig, void** out,
+                  cudaStream_t st, bool zero_on_change) {
+    Buffer& b = c->bufs[name];
+    bool fresh = false;
+    if (b.cap < bytes) {
+        if (b.p) {
+            CU_TRY(c, cudaDeviceSynchronize());
+            CU_TRY(c, cudaFree(b.p));
+        }
+        size_t cap = bytes + (bytes >> 3) + 65536;
+        CU_TRY(c, cudaMalloc(&b.p, cap));
+        b.cap = cap;
+        fresh = true;
+    }
+    if (zero_on_change && (fresh || b.sig != sig)) CU_TRY(c, cudaMemsetAsync(b.p, 0, b.cap, st));
+    b.sig = sig;
+    *out = b.p;
+    return 0;
+}
+
+static int upload(sylph_ctx* c, const std::vector<float>& h, float** d) {
+    CU_TRY(c, cudaMalloc(d, std::max<size_t>(h.size(), 1) * sizeof(float)));
+    CU_TRY(c, cudaMemcpy(*d, h.data(), h.size() * sizeof(float), cudaMemcpyHostToDevice));
+    return 0;
+}
+
+static int make_plane_set(sylph_ctx* c, const std::string& key, const std::vector<Seg>& segs, int total_rows,
+                          std::shared_ptr<PlaneSet>* out) {
+    auto it = c->plane_sets.find(key);
+    if (it != c->plane_sets.end()) {
+        *out = it->second;
+        return 0;
+    }
+    auto ps = std::make_shared<PlaneSet>();
+    ps->segs = segs;
+    ps->total_rows = total_rows;
+    std::vector<int> tile_seg(total_rows / kBlockM, 0);
+    for (size_t s = 0; s < segs.size(); ++s) {
+        const int t0 = segs[s].row0 / kBlockM, t1 = (segs[s].row0 + segs[s].nrows + kBlockM - 1) / kBlockM;
+        for (int t = t0; t < t1; ++t) tile_seg[t] = static_cast<int>(s);
+    }
+    CU_TRY(c, cudaMalloc(&ps->d_segs, segs.size() * sizeof(Seg)));
+    CU_TRY(c, cudaMalloc(&ps->d_tile_seg, tile_seg.size() * sizeof(int)));
+    CU_TRY(c, cudaMemcpy(ps->d_segs, segs.data(), segs.size() * sizeof(Seg), cudaMemcpyHostToDevice));
+    CU_TRY(c, cudaMemcpy(ps->d_tile_seg, tile_seg.data(), tile_seg.size() * sizeof(int), cudaMemcpyHostToDevice));
+    c->plane_sets[key] = ps;
+    *out = ps;
+    return 0;
+}
+
+// n planes of identical geometry, each starting on a 128-row boundary.
+static PlaneGeom regular_geom(int row_base, int H, int W, int pad) {
+    PlaneGeom g;
+    g.row_base = row_base;
+    g.Wp = W + 2 * pad;
+    g.pad = pad;
+    g.H = H;
+    g.W = W;
+    g.rows_per_img = round_up((H + 2 * pad) * (W + 2 * pad), kBlockM);
+    return g;
+}
+
+static std::vector<Seg> geom_segs(const PlaneGeom& g, int n) {
+    std::vector<Seg> v;
+    for (int i = 0; i < n; ++i) {
+        Seg s;
+        s.row0 = g.row_base + i * g.rows_per_img;
+        s.nrows = (g.H + 2 * g.pad) * g.Wp;
+        s.Wp = g.Wp;
+        s.pad = g.pad;
+        s.H = g.H;
+        s.W = g.W;
+        v.push_back(s);
+    }
+    return v;
+}
+
+static int grid_for(long long work_items, int threads, int num_sms) {
+    long long blocks = (work_items + threads - 1) / threads;
+    long long cap = static_cast<long long>(num_sms) * 16;
+    return static_cast<int>(std::max<long long>(1, std::min(blocks, cap)));
+}
+
+// ------------------------------------------------------------------------------------------------ weight prep
+static const HostTensor* find_t(sylph_ctx* c, const std::string& k) {
+    auto it = c->staged.find(k);
+    return it == c->staged.end() ? nullptr : &it->second;
+}
+
+static int pick_bn(int cout) {
+    if (cout <= 16) return 16;
+    if (cout <= 64) return 64;
+    if (cout <= 128) return 128;
+    return 256;
+}
+
+// OIHW conv (+ optional FrozenBN fold, + optional conv bias) -> ConvW.
+static int prep_conv(sylph_ctx* c, const std::string& prefix, bool frozen_bn, bool has_bias, ConvW* out) {
+    const HostTensor* w = find_t(c, prefix + ".weight");
+    if (!w || w->shape.size() != 4) return c->fail("missing conv weight %s.weight", prefix.c_str());
+    const int co = static_cast<int>(w->shape[0]), ci = static_cast<int>(w->shape[1]);
+    const int kh = static_cast<int>(w->shape[2]), kw = static_cast<int>(w->shape[3]);
+    if (ci % 32 != 0) return c->fail("%s: Cin=%d is not a multiple of 32", prefix.c_str(), ci);
+    std::vector<float> scale(co, 1.f), shift(co, 0.f);
+    if (frozen_bn) {
+        const HostTensor *g = find_t(c, prefix + ".norm.weight"), *b = find_t(c, prefix + ".norm.bias"),
+                         *m = find_t(c, prefix + ".norm.running_mean"), *v = find_t(c, prefix + ".norm.running_var");
+        if (!g || !b || !m || !v) return c->fail("missing FrozenBN tensors for %s", prefix.c_str());
+        for (int o = 0; o < co; ++o) {
+            // detectron2 FrozenBatchNorm2d: scale = weight * rsqrt(var + eps); bias = bias - mean * scale
+            const float s = g->data[o] * (1.0f / std::sqrt(v->data[o] + 1e-5f));
+            scale[o] = s;
+            shift[o] = b->data[o] - m->data[o] * s;
+        }
+    }
+    if (has_bias) {
+        const HostTensor* b = find_t(c, prefix + ".bias");
+        if (!b) return c->fail("missing %s.bias", prefix.c_str());
+        for (int o = 0; o < co; ++o) shift[o] += b->data[o];
+    }
+    out->taps = kh * kw;
+    out->ksize = kh;
+    out->k_per_tap = ci;
+    out->cout = co;
+    out->bn = pick_bn(co);
+    out->cout_pad = round_up(co, out->bn);
+    std::vector<float> hw(static_cast<size_t>(out->taps) * out->cout_pad * ci, 0.f), hb(out->cout_pad, 0.f);
+    for (int o = 0; o < co; ++o) {
+        hb[o] = shift[o];
+        for (int i = 0; i < ci; ++i)
+            for (int t = 0; t < out->taps; ++t)
+                hw[(static_cast<size_t>(t) * out->cout_pad + o) * ci + i] =
+                    tf32_rne(w->data[(static_cast<size_t>(o) * ci + i) * out->taps + t] * scale[o]);
+    }
+    TRY(upload(c, hw, &out->w));
+    TRY(upload(c, hb, &out->bias));
+    return 0;
+}
+
+// 7x7 / 2 stem over 3 channels -> 4 vertical taps x (4 horizontal taps x 16 space-to-depth channels).
+static int prep_stem(sylph_ctx* c, ConvW* out) {
+    const std::string prefix = "backbone.bottom_up.stem.conv1";
+    const HostTensor* w = find_t(c, prefix + ".weight");
+    if (!w || w->shape.size() != 4 || w->shape[1] != 3 || w->shape[2] != 7) return c->fail("bad stem weight");
+    const int co = static_cast<int>(w->shape[0]);
+    const HostTensor *g = find_t(c, prefix + ".norm.weight"), *b = find_t(c, prefix + ".norm.bias"),
+                     *m = find_t(c, prefix + ".norm.running_mean"), *v = find_t(c, prefix + ".norm.running_var");
+    if (!g || !b || !m || !v) return c->fail("missing stem FrozenBN");
+    out->taps = 4;
+    out->ksize = 7;
+    out->k_per_tap = 64;
+    out->cout = co;
+    out->bn = pick_bn(co);
+    out->cout_pad = round_up(co, out->bn);
+    std::vector<float> hw(static_cast<size_t>(4) * out->cout_pad * 64, 0.f), hb(out->cout_pad, 0.f);
+    for (int o = 0; o < co; ++o) {
+        const float s = g->data[o] * (1.0f / std::sqrt(v->data[o] + 1e-5f));
+        hb[o] = b->data[o] - m->data[o] * s;
+        for (int ty = 0; ty < 4; ++ty)
+            for (int tx = 0; tx < 4; ++tx)
+                for (int dy = 0; dy < 2; ++dy)
+                    for (int dx = 0; dx < 2; ++dx) {
+                        const int ky = 2 * ty + dy - 1, kx = 2 * tx + dx - 1;
+                        if (ky < 0 || ky > 6 || kx < 0 || kx > 6) continue;
+                        for (int ch = 0; ch < 3; ++ch) {
+                            const int k = tx * 16 + (dy * 2 + dx) * 3 + ch;
+                            hw[(static_cast<size_t>(ty) * out->cout_pad + o) * 64 + k] =
+                                tf32_rne(w->data[((static_cast<size_t>(o) * 3 + ch) * 7 + ky) * 7 + kx] * s);
+                        }
+                    }
+    }
+    TRY(upload(c, hw, &out->w));
+    TRY(upload(c, hb, &out->bias));
+    return 0;
+}
+
+static int upload_vec(sylph_ctx* c, const std::string& key, float** d, size_t expect) {
+    const HostTensor* t = find_t(c, key);
+    if (!t || t->data.size() != expect) return c->fail("missing or mis-sized tensor %s", key.c_str());
+    return upload(c, t->data, d);
+}
+
+static int scalar_of(sylph_ctx* c, const std::string& key, float* v) {
+    const HostTensor* t = find_t(c, key);
+    if (!t || t->data.size() != 1) return c->fail("missing scalar %s", key.c_str());
+    *v = t->data[0];
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------------ conv launch
+struct ConvCall {
+    const ConvW* W;
+    const float* A;
+    long long a_rows;   // rows of the A buffer visible to TMA
+    int a_cols, a_ld;   // inner dim / pitch (elements)
+    const PlaneSet* ps; // plane set of the OUTPUT buffer
+    int tile_begin, n_tiles;
+    int a_row_delta;
+    float* out;
+    int ldc;
+    int flags;
+    const float* residual = nullptr;
+    int ld_res = 0;
+    float* gn_partial = nullptr;
+    const float* bias_override = nullptr;
+    const float* w_override = nullptr;
+    int stem = 0;
+    const char* name = "conv";
+};
+
+static int run_conv(sylph_ctx* c, const ConvCall& k, cudaStream_t st) {
+    const ConvW& W = *k.W;
+    CUtensorMap ta, tb;
+    std::string err;
+    if (make_tmap_2d(&ta, k.A, static_cast<uint64_t>(k.a_rows), k.a_cols, k.a_ld, kBlockM, &err))
+        return c->fail("A tensor map (%s): %s", k.name, err.c_str());
+    if (make_tmap_2d(&tb, k.w_override ? k.w_override : W.w, static_cast<uint64_t>(W.taps) * W.cout_pad, W.k_per_tap,
+                     W.k_per_tap, W.bn, &err))
+        return c->fail("B tensor map (%s): %s", k.name, err.c_str());
+    GemmArgs g{};
+    g.tile_begin = k.tile_begin;
+    g.num_m_tiles = k.n_tiles;
+    g.num_n_tiles = W.cout_pad / W.bn;
+    g.a_row_delta = k.a_row_delta;
+    g.taps = W.taps;
+    g.kblocks_per_tap = W.k_per_tap / kBlockK;
+    g.b_rows_per_tap = W.cout_pad;
+    for (int t = 0; t < W.taps; ++t) {
+        if (k.stem) { g.tap_dy[t] = static_cast<signed char>(t - 2); g.tap_dx[t] = -2; }
+        else if (W.taps == 9) { g.tap_dy[t] = static_cast<signed char>(t / 3 - 1); g.tap_dx[t] = static_cast<signed char>(t % 3 - 1); }
+        else { g.tap_dy[t] = 0; g.tap_dx[t] = 0; }
+    }
+    g.bias = k.bias_override ? k.bias_override : W.bias;
+    g.residual = k.residual;
+    g.ld_res = k.ld_res;
+    g.out = k.out;
+    g.ldc = k.ldc;
+    g.flags = k.flags;
+    g.tile_seg = k.ps->d_tile_seg;
+    g.segs = k.ps->d_segs;
+    g.gn_partial = k.gn_partial;
+    Timing tm;
+    if (c->profiling) {
+        tm.name = k.name;
+        cudaEventCreate(&tm.e0);
+        cudaEventCreate(&tm.e1);
+        const double rows = static_cast<double>(k.n_tiles) * kBlockM;
+        tm.flops = 2.0 * rows * W.cout_pad * W.k_per_tap * W.taps;
+        tm.bytes = rows * (static_cast<double>(k.a_ld < k.a_cols ? k.a_ld : k.a_cols) + static_cast<double>(k.ldc < W.cout_pad ? k.ldc : W.cout_pad) *
+                           ((k.flags & kEpiResidual) ? 2.0 : 1.0)) * 4.0;
+        cudaEventRecord(tm.e0, st);
+    }
+    CU_TRY(c, launch_conv_gemm(W.bn, ta, tb, g, c->num_sms, st));
+    c->launches++;
+    if (c->profiling) {
+        cudaEventRecord(tm.e1, st);
+        c->timings.push_back(tm);
+    }
+    return 0;
+}
+
+struct StageTimer {
+    sylph_ctx* c;
+    cudaStream_t st;
+    Timing tm;
+    bool on;
+    StageTimer(sylph_ctx* c_, const char* name, cudaStream_t s, double bytes = 0) : c(c_), st(s), on(c_->profiling) {
+        if (on) {
+            tm.name = name;
+            tm.flops = 0;
+            tm.bytes = bytes;
+            cudaEventCreate(&tm.e0);
+            cudaEventCreate(&tm.e1);
+            cudaEventRecord(tm.e0, st);
+        }
+    }
+    ~StageTimer() {
+        if (on) {
+            cudaEventRecord(tm.e1, st);
+            c->timings.push_back(tm);
+        }
+    }
+};
+
+}  // namespace sylph
+
+// ================================================================================================== C ABI
+extern "C" {
+
+const char* sylph_version(void) { return "sylph_b200 0.1 (sm_100a, tcgen05 TF32 implicit-GEMM)"; }
+
+int sylph_create(sylph_ctx** out, int device, const sylph_model_config* cfg) {
+    if (!out || !cfg) return 1;
+    *out = nullptr;
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess || device >= n) return 2;  // no CPU fallback
+    cudaDeviceProp prop;
+    if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) return 2;
+    if (prop.major != 10) return 3;  // sm_100a only
+    if (cudaSetDevice(device) != cudaSuccess) return 2;
+    sylph_ctx* c = new sylph_ctx();
+    c->device = device;
+    c->num_sms = prop.multiProcessorCount;
+    c->cfg = *cfg;
+    *out = c;
+    if (cfg->pre_nms_topk * 5 > 8192) { c->fail("pre_nms_topk * 5 must be <= 8192"); }
+    return 0;
+}
+
+void sylph_destroy(sylph_ctx* c) {
+    if (!c) return;
+    cudaSetDevice(c->device);
+    cudaDeviceSynchronize();
+    for (auto& kv : c->bufs) if (kv.second.p) cudaFree(kv.second.p);
+    for (auto& kv : c->plane_sets) { cudaFree(kv.second->d_segs); cudaFree(kv.second->d_tile_seg); }
+    delete c;  // prepared weights are released with the CUDA context
+}
+
+const char* sylph_last_error(const sylph_ctx* c) { return c ? c->err.c_str() : "null context"; }
+
+int sylph_load_tensor(sylph_ctx* c, const char* key, const float* host_data, const int64_t* shape, int ndim) {
+    if (!c || !key || !host_data) return 1;
+    HostTensor t;
+    size_t n = 1;
+    for (int i = 0; i < ndim; ++i) { t.shape.push_back(shape[i]); n *= static_cast<size_t>(shape[i]); }
+    t.data.assign(host_data, host_data + n);
+    c->staged[key] = std::move(t);
+    c->finalized = false;
+    return 0;
+}
+
+int sylph_finalize_weights(sylph_ctx* c) {
+    if (!c) return 1;
+    CU_TRY(c, cudaSetDevice(c->device));
+    const sylph_model_config& f = c->cfg;
+    TRY(prep_stem(c, &c->stem));
+    int nblocks[4];
+    if (f.resnet_depth == 50) { int b[4] = {3, 4, 6, 3}; memcpy(nblocks, b, sizeof(b)); }
+    else if (f.resnet_depth == 101) { int b[4] = {3, 4, 23, 3}; memcpy(nblocks, b, sizeof(b)); }
+    else if (f.resnet_depth == 152) { int b[4] = {3, 8, 36, 3}; memcpy(nblocks, b, sizeof(b)); }
+    else return c->fail("unsupported RESNETS.DEPTH %d", f.resnet_depth);
+    c->stages.clear();
+    for (int s = 0; s < 4; ++s) {
+        std::vector<sylph_ctx::Block> blocks(nblocks[s]);
+        for (int b = 0; b < nblocks[s]; ++b) {
+            const std::string p = "backbone.bottom_up.res" + std::to_string(s + 2) + "." + std::to_string(b);
+            blocks[b].has_sc = find_t(c, p + ".shortcut.weight") != nullptr;
+            if (blocks[b].has_sc) TRY(prep_conv(c, p + ".shortcut", true, false, &blocks[b].sc));
+            TRY(prep_conv(c, p + ".conv1", true, false, &blocks[b].c1));
+            TRY(prep_conv(c, p + ".conv2", true, false, &blocks[b].c2));
+            TRY(prep_conv(c, p + ".conv3", true, false, &blocks[b].c3));
+        }
+        c->stages.push_back(std::move(blocks));
+    }
+    for (int i = 0; i < 3; ++i) {
+        TRY(prep_conv(c, "backbone.fpn_lateral" + std::to_string(i + 3), false, true, &c->lat[i]));
+        TRY(prep_conv(c, "backbone.fpn_output" + std::to_string(i + 3), false, true, &c->outc[i]));
+    }
+    TRY(prep_conv(c, "backbone.top_block.p6", false, true, &c->p6));
+    TRY(prep_conv(c, "backbone.top_block.p7", false, true, &c->p7));
+    const std::string head = "proposal_generator.fcos_head.";
+    auto prep_tower = [&](const std::string& name, int n, std::vector<ConvW>* tw, std::vector<float*>* gw,
+                          std::vector<float*>* gb) -> int {
+        tw->assign(n, ConvW());
+        gw->assign(n, nullptr);
+        gb->assign(n, nullptr);
+        for (int i = 0; i < n; ++i) {
+            TRY(prep_conv(c, name + std::to_string(3 * i), false, true, &(*tw)[i]));
+            TRY(upload_vec(c, name + std::to_string(3 * i + 1) + ".weight", &(*gw)[i], 256));
+            TRY(upload_vec(c, name + std::to_string(3 * i + 1) + ".bias", &(*gb)[i], 256));
+        }
+        return 0;
+    };
+    TRY(prep_tower(head + "cls_tower.", f.num_cls_convs, &c->cls_tower, &c->cls_gn_w, &c->cls_gn_b));
+    TRY(prep_tower(head + "bbox_tower.", f.num_box_convs, &c->box_tower, &c->box_gn_w, &c->box_gn_b));
+    {   // bbox_pred (4) + ctrness (1) + iou_overlap (1) fused into one 16-wide 3x3 convolution
+        const HostTensor *wb = find_t(c, head + "bbox_pred.weight"), *wc = find_t(c, head + "ctrness.weight"),
+                         *wi = find_t(c, head + "iou_overlap.weight"), *bb = find_t(c, head + "bbox_pred.bias"),
+                         *bc = find_t(c, head + "ctrness.bias"), *bi = find_t(c, head + "iou_overlap.bias");
+        if (!wb || !wc || !wi || !bb || !bc || !bi) return c->fail("missing FCOS predictor tensors");
+        HostTensor w, b;
+        w.shape = {6, 256, 3, 3};
+        w.data = wb->data;
+        w.data.insert(w.data.end(), wc->data.begin(), wc->data.end());
+        w.data.insert(w.data.end(), wi->data.begin(), wi->data.end());
+        b.shape = {6};
+        b.data = bb->data;
+        b.data.insert(b.data.end(), bc->data.begin(), bc->data.end());
+        b.data.insert(b.data.end(), bi->data.begin(), bi->data.end());
+        c->staged["__pred.weight"] = w;
+        c->staged["__pred.bias"] = b;
+        TRY(prep_conv(c, "__pred", false, true, &c->pred));
+    }
+    for (int l = 0; l < 5; ++l) {
+        c->level_scale[l] = 1.f;
+        if (f.use_scale) TRY(scalar_of(c, head + "scales." + std::to_string(l) + ".scale", &c->level_scale[l]));
+    }
+    const std::string cg = "code_generator.code_generator_head.";
+    c->cg_tower.assign(f.cg_tower_layers, ConvW());
+    c->cg_gn_w.assign(f.cg_tower_layers, nullptr);
+    c->cg_gn_b.assign(f.cg_tower_layers, nullptr);
+    for (int i = 0; i < f.cg_tower_layers; ++i) {
+        TRY(prep_conv(c, cg + "support_set_shared_tower." + std::to_string(3 * i), false, true, &c->cg_tower[i]));
+        TRY(upload_vec(c, cg + "support_set_shared_tower." + std::to_string(3 * i + 1) + ".weight", &c->cg_gn_w[i], 256));
+        TRY(upload_vec(c, cg + "support_set_shared_tower." + std::to_string(3 * i + 1) + ".bias", &c->cg_gn_b[i], 256));
+    }
+    TRY(prep_conv(c, cg + "support_set_cls_conv.0", false, true, &c->cg_cls));
+    if (c->cg_cls.cout != 256) return c->fail("CODE_GENERATOR.OUT_CHANNEL must be 256 on this path");
+    if (f.cg_bias_layer) {
+        const HostTensor *w = find_t(c, cg + "support_set_cls_bias.0.weight"), *b = find_t(c, cg + "support_set_cls_bias.0.bias");
+        if (!w || !b || w->data.size() != 256 * 9) return c->fail("missing support_set_cls_bias tensors");
+        std::vector<float> hw(9 * 256);
+        for (int ch = 0; ch < 256; ++ch)
+            for (int t = 0; t < 9; ++t) hw[t * 256 + ch] = w->data[ch * 9 + t];
+        TRY(upload(c, hw, &c->cg_wbias));
+        TRY(upload(c, b->data, &c->cg_bbias));
+        TRY(scalar_of(c, cg + "bias_scale.scale", &c->bias_scale));
+    } else {
+        c->bias_scale = 1.f;
+    }
+    if (f.cg_post_norm) {
+        TRY(upload_vec(c, cg + "post_norm.weight", &c->post_gn_w, 256));
+        TRY(upload_vec(c, cg + "post_norm.bias", &c->post_gn_b, 256));
+    }
+    c->conv_scale = 1.f;
+    if (f.cg_has_conv_scale) TRY(scalar_of(c, cg + "conv_scale.scale", &c->conv_scale));
+    c->bias_value = -std::log((1.f - f.prior_prob) / f.prior_prob);
+    c->staged.clear();
+    c->finalized = true;
+    return 0;
+}
+
+}  // extern "C"
+
+namespace sylph {
+
+// ------------------------------------------------------------------------------------------------ pyramid slot
+static int setup_slot(sylph_ctx* c, int slot, int n, int hpad, int wpad, const int* lh, const int* lw, cudaStream_t st) {
+    Slot& S = c->slots[slot];
+    S.n = n;
+    S.hpad = hpad;
+    S.wpad = wpad;
+    std::vector<Seg> segs;
+    int row = 0;
+    for (int l = 0; l < 5; ++l) {
+        S.lh[l] = lh[l];
+        S.lw[l] = lw[l];
+        PlaneGeom g = regular_geom(row, lh[l], lw[l], 1);
+        S.pg.lv[l] = g;
+        S.pg.scale[l] = 1.0f / static_cast<float>(8 << l);
+        S.level_row0[l] = row;
+        auto v = geom_segs(g, n);
+        segs.insert(segs.end(), v.begin(), v.end());
+        row += n * g.rows_per_img;
+    }
+    S.level_row0[5] = row;
+    std::string key = "pyr:" + std::to_string(n);
+    for (int l = 0; l < 5; ++l) key += ":" + std::to_string(lh[l]) + "x" + std::to_string(lw[l]);
+    TRY(make_plane_set(c, key, segs, row, &S.ps));
+    void* p;
+    TRY(ensure(c, "pyr" + std::to_string(slot), (static_cast<size_t>(row) + kBlockM) * 256 * 4, key, &p, st, true));
+    S.pyr = static_cast<float*>(p);
+    S.valid = true;
+    return 0;
+}
+
+static int run_backbone(sylph_ctx* c, int slot, int n, const float* const* images_dev, const int* hs, const int* ws,
+                        cudaStream_t st) {
+    const sylph_model_config& f = c->cfg;
+    int hmax = 0, wmax = 0;
+    for (int i = 0; i < n; ++i) { hmax = std::max(hmax, hs[i]); wmax = std::max(wmax, ws[i]); }
+    const int hpad = round_up(hmax, 32), wpad = round_up(wmax, 32);
+    const std::string sig = std::to_string(n) + ":" + std::to_string(hpad) + "x" + std::to_string(wpad);
+    // geometries
+    const PlaneGeom g0 = regular_geom(0, hpad / 2, wpad / 2, 2);      // space-to-depth input / stem output
+    PlaneGeom gs[4];                                                 // res2..res5
+    for (int s = 0; s < 4; ++s) gs[s] = regular_geom(0, hpad >> (s + 2), wpad >> (s + 2), 1);
+    int lh[5], lw[5];
+    for (int l = 0; l < 3; ++l) { lh[l] = gs[l + 1].H; lw[l] = gs[l + 1].W; }
+    lh[3] = (lh[2] + 1) / 2; lw[3] = (lw[2] + 1) / 2;
+    lh[4] = (lh[3] + 1) / 2; lw[4] = (lw[3] + 1) / 2;
+    TRY(setup_slot(c, slot, n, hpad, wpad, lh, lw, st));
+    Slot& S = c->slots[slot];
+    S.img_h.assign(hs, hs + n);
+    S.img_w.assign(ws, ws + n);
+
+    std::shared_ptr<PlaneSet> ps0, pss[4];
+    TRY(make_plane_set(c, "stem:" + sig, geom_segs(g0, n), n * g0.rows_per_img, &ps0));
+    for (int s = 0; s < 4; ++s)
+        TRY(make_plane_set(c, "res" + std::to_string(s + 2) + ":" + sig, geom_segs(gs[s], n), n * gs[s].rows_per_img, &pss[s]));
+
+    auto buf = [&](const std::string& name, long long rows, int ch, bool zero, float** out) -> int {
+        void* p;
+        TRY(ensure(c, name, (static_cast<size_t>(rows) + kBlockM) * ch * 4, sig, &p, st, zero));
+        *out = static_cast<float*>(p);
+        return 0;
+    };
+    const long long rows0 = static_cast<long long>(n) * g0.rows_per_img;
+    float *S0, *S1;
+    TRY(buf("bb.s0", rows0, 16, true, &S0));
+    TRY(buf("bb.s1", rows0, 64, false, &S1));
+    // ---- image descriptors
+    std::vector<ImageDesc> descs(n);
+    for (int i = 0; i < n; ++i) { descs[i].ptr = images_dev[i]; descs[i].h = hs[i]; descs[i].w = ws[i]; }
+    void* d_desc;
+    TRY(ensure(c, "bb.desc", n * sizeof(ImageDesc), "", &d_desc, st, false));
+    CU_TRY(c, cudaMemcpyAsync(d_desc, descs.data(), n * sizeof(ImageDesc), cudaMemcpyHostToDevice, st));
+    CU_TRY(c, cudaStreamSynchronize(st));  // descs is a stack-lifetime staging vector
+    {
+        StageTimer t(c, "prep_stem_input", st, static_cast<double>(n) * (3.0 * hmax * wmax + 16.0 * g0.H * g0.W) * 4);
+        prep_stem_input_kernel<<<grid_for(static_cast<long long>(n) * g0.H * g0.W, 256, c->num_sms), 256, 0, st>>>(
+            static_cast<const ImageDesc*>(d_desc), S0, g0, n, f.pixel_mean[0], f.pixel_mean[1], f.pixel_mean[2],
+            f.pixel_std[0], f.pixel_std[1], f.pixel_std[2]);
+        CU_TRY(c, cudaGetLastError());
+        c->launches++;
+    }
+    {   // stem: 7x7/2 conv + FrozenBN + ReLU as a 4-tap GEMM over overlapped 64-float rows
+        ConvCall k{};
+        k.W = &c->stem; k.A = S0; k.a_rows = rows0; k.a_cols = 64; k.a_ld = 16; k.ps = ps0.get();
+        k.tile_begin = 0; k.n_tiles = static_cast<int>(rows0 / kBlockM); k.a_row_delta = 0; k.out = S1; k.ldc = 64;
+        k.flags = kEpiRelu | kEpiMask; k.stem = 1; k.name = "stem7x7";
+        TRY(run_conv(c, k, st));
+    }
+    // ---- res2..res5
+    float* X = nullptr;  // running stage output
+    int x_ch = 64;
+    for (int s = 0; s < 4; ++s) {
+        const PlaneGeom& g = gs[s];
+        const long long rows = static_cast<long long>(n) * g.rows_per_img;
+        const int tiles = static_cast<int>(rows / kBlockM);
+        const int out_ch = 256 << s, bott = 64 << s, in_ch = x_ch;
+        float *IN, *Y, *T1, *T2;
+        const std::string sn = "bb.res" + std::to_string(s + 2);
+        TRY(buf(sn + ".in", rows, in_ch, true, &IN));
+        TRY(buf(sn + ".x", rows, out_ch, false, &Y));
+        TRY(buf(sn + ".t1", rows, bott, false, &T1));
+        TRY(buf(sn + ".t2", rows, bott, false, &T2));
+        {
+            StageTimer t(c, s == 0 ? "maxpool3x3s2" : "subsample2", st,
+                         static_cast<double>(n) * g.H * g.W * in_ch * 4 * (s == 0 ? 5.0 : 2.0));
+            const long long work = static_cast<long long>(n) * g.H * g.W * (in_ch / 4);
+            if (s == 0) maxpool3x3s2_kernel<<<grid_for(work, 256, c->num_sms), 256, 0, st>>>(S1, IN, g0, g, n, in_ch);
+            else subsample2_kernel<<<grid_for(work, 256, c->num_sms), 256, 0, st>>>(X, IN, gs[s - 1], g, n, in_ch);
+            CU_TRY(c, cudaGetLastError());
+            c->launches++;
+        }
+        const auto& blocks = c->stages[s];
+        for (size_t b = 0; b < blocks.size(); ++b) {
+            const sylph_ctx::Block& B = blocks[b];
+            const float* bin = (b == 0) ? IN : Y;
+            const int bin_ch = (b == 0) ? in_ch : out_ch;
+            ConvCall k{};
+            k.ps = pss[s].get(); k.tile_begin = 0; k.n_tiles = tiles; k.a_row_delta = 0; k.a_rows = rows;
+            if (B.has_sc) {
+                if (b != 0) return c->fail("shortcut conv on a non-first block is not supported");
+                k.W = &B.sc; k.A = bin; k.a_cols = k.a_ld = bin_ch; k.out = Y; k.ldc = out_ch; k.flags = kEpiMask;
+                k.name = "res.shortcut1x1";
+                TRY(run_conv(c, k, st));
+            } else if (b == 0) {
+                return c->fail("identity shortcut on the first block of a stage is not supported");
+            }
+            k.residual = nullptr;
+            k.W = &B.c1; k.A = bin; k.a_cols = k.a_ld = bin_ch; k.out = T1; k.ldc = bott;
+            k.flags = kEpiRelu | kEpiMask | kEpiRoundTf32; k.name = "res.conv1_1x1";
+            TRY(run_conv(c, k, st));
+            k.W = &B.c2; k.A = T1; k.a_cols = k.a_ld = bott; k.out = T2; k.ldc = bott; k.name = "res.conv2_3x3";
+            TRY(run_conv(c, k, st));
+            k.W = &B.c3; k.A = T2; k.a_cols = k.a_ld = bott; k.out = Y; k.ldc = out_ch; k.residual = Y; k.ld_res = out_ch;
+            k.flags = kEpiRelu | kEpiMask | kEpiRoundTf32 | kEpiResidual; k.name = "res.conv3_1x1";
+            TRY(run_conv(c, k, st));
+        }
+        X = Y;
+        x_ch = out_ch;
+        // lateral 1x1 for res3..res5 straight into the pyramid-indexed lateral buffer
+    }
+    // ---- FPN (top-down): lateral buffers share the pyramid row indexing
+    float* LAT;
+    {
+        void* p;
+        TRY(ensure(c, "bb.lat", (static_cast<size_t>(S.level_row0[5]) + kBlockM) * 256 * 4, S.ps ? ("pyr" + sig) : sig, &p, st, true));
+        LAT = static_cast<float*>(p);
+    }
+    for (int l = 2; l >= 0; --l) {
+        const PlaneGeom& g = S.pg.lv[l];
+        const long long rows = static_cast<long long>(n) * g.rows_per_img;
+        float* XS = static_cast<float*>(c->bufs["bb.res" + std::to_string(l + 3) + ".x"].p);
+        ConvCall k{};
+        k.W = &c->lat[l]; k.A = XS; k.a_rows = rows; k.a_cols = k.a_ld = 512 << l; k.ps = S.ps.get();
+        k.tile_begin = static_cast<int>(S.level_row0[l] / kBlockM); k.n_tiles = static_cast<int>(rows / kBlockM);
+        k.a_row_delta = -static_cast<int>(S.level_row0[l]); k.out = LAT; k.ldc = 256;
+        k.flags = kEpiMask | kEpiRoundTf32; k.name = "fpn.lateral1x1";
+        TRY(run_conv(c, k, st));
+        if (l < 2) {
+            StageTimer t(c, "fpn.upsample_add", st, static_cast<double>(n) * g.H * g.W * 256 * 4 * 2.25);
+            upsample_add_kernel<<<grid_for(static_cast<long long>(n) * g.H * g.W * 64, 256, c->num_sms), 256, 0, st>>>(
+                LAT, LAT, g, S.pg.lv[l + 1], n, 256);
+            CU_TRY(c, cudaGetLastError());
+            c->launches++;
+        }
+        k.W = &c->outc[l]; k.A = LAT; k.a_rows = S.level_row0[5]; k.a_cols = k.a_ld = 256; k.a_row_delta = 0;
+        k.out = S.pyr; k.name = "fpn.output3x3";
+        TRY(run_conv(c, k, st));
+    }
+    // ---- p6 = conv3x3/2(p5), p7 = conv3x3/2(relu(p6)): stride-1 conv, then the even positions
+    {
+        const PlaneGeom& g5 = S.pg.lv[2];
+        const long long rows5 = static_cast<long long>(n) * g5.rows_per_img;
+        float *TMP, *R6;
+        TRY(buf("bb.p6tmp", S.level_row0[5], 256, false, &TMP));
+        TRY(buf("bb.p6relu", S.level_row0[5], 256, true, &R6));
+        ConvCall k{};
+        k.W = &c->p6; k.A = S.pyr; k.a_rows = S.level_row0[5]; k.a_cols = k.a_ld = 256; k.ps = S.ps.get();
+        k.tile_begin = static_cast<int>(S.level_row0[2] / kBlockM); k.n_tiles = static_cast<int>(rows5 / kBlockM);
+        k.a_row_delta = 0; k.out = TMP; k.ldc = 256; k.flags = kEpiMask | kEpiRoundTf32; k.name = "fpn.p6_3x3";
+        TRY(run_conv(c, k, st));
+        const PlaneGeom& g6 = S.pg.lv[3];
+        subsample2_kernel<<<grid_for(static_cast<long long>(n) * g6.H * g6.W * 64, 256, c->num_sms), 256, 0, st>>>(
+            TMP, S.pyr, g5, g6, n, 256);
+        CU_TRY(c, cudaGetLastError());
+        const long long rows6 = static_cast<long long>(n) * g6.rows_per_img;
+        relu_copy_kernel<<<grid_for(rows6 * 64, 256, c->num_sms), 256, 0, st>>>(
+            reinterpret_cast<const float4*>(S.pyr + S.level_row0[3] * 256), reinterpret_cast<float4*>(R6 + S.level_row0[3] * 256),
+            rows6 * 64);
+        CU_TRY(c, cudaGetLastError());
+        c->launches += 2;
+        k.W = &c->p7; k.A = R6; k.tile_begin = static_cast<int>(S.level_row0[3] / kBlockM);
+        k.n_tiles = static_cast<int>(rows6 / kBlockM); k.name = "fpn.p7_3x3";
+        TRY(run_conv(c, k, st));
+        const PlaneGeom& g7 = S.pg.lv[4];
+        subsample2_kernel<<<grid_for(static_cast<long long>(n) * g7.H * g7.W * 64, 256, c->num_sms), 256, 0, st>>>(
+            TMP, S.pyr, g6, g7, n, 256);
+        CU_TRY(c, cudaGetLastError());
+        c->launches++;
+    }
+    return 0;
+}
+
+// conv3x3 + GroupNorm(32) + ReLU over `tiles` tiles of a plane set: conv epilogue accumulates the per-tile partial
+// sums, finalize reduces them per plane, apply normalises in place.
+static int conv_gn_relu(sylph_ctx* c, const ConvW& W, const float* gn_w, const float* gn_b, const float* in,
+                        long long a_rows, float* out, const PlaneSet* ps, int tile_begin, int tiles, int seg_begin,
+                        int n_segs, float* gn_partial, float* gn_stats, const char* name, cudaStream_t st) {
+    ConvCall k{};
+    k.W = &W; k.A = in; k.a_rows = a_rows; k.a_cols = k.a_ld = 256; k.ps = ps; k.tile_begin = tile_begin; k.n_tiles = tiles;
+    k.a_row_delta = 0; k.out = out; k.ldc = 256; k.flags = kEpiGnStats; k.gn_partial = gn_partial; k.name = name;
+    TRY(run_conv(c, k, st));
+    gn_finalize_kernel<<<ceil_div(static_cast<long long>(n_segs) * 32, 128), 128, 0, st>>>(gn_partial, ps->d_segs, seg_begin,
+                                                                                       n_segs, gn_stats);
+    CU_TRY(c, cudaGetLastError());
+    {
+        const long long rows = static_cast<long long>(tiles) * kBlockM;
+        StageTimer t(c, "gn_apply_relu", st, static_cast<double>(rows) * 256 * 4 * 2);
+        gn_apply_relu_kernel<<<grid_for(rows * 64, 256, c->num_sms), 256, 0, st>>>(
+            out, gn_stats, gn_w, gn_b, ps->d_tile_seg, ps->d_segs, tile_begin * kBlockM, rows, 1);
+        CU_TRY(c, cudaGetLastError());
+    }
+    c->launches += 2;
+    return 0;
+}
+
+}  // namespace sylph
+
+extern "C" {
+
+int sylph_extract_features(sylph_ctx* c, int slot, int n_images, const float* const* images_dev, const int* heights,
+                           const int* widths, void* stream) {
+    if (!c) return 1;
+    if (!c->finalized) return c->fail("weights not finalized");
+    if (slot < 0 || slot >= SYLPH_NUM_SLOTS || n_images <= 0) return c->fail("bad slot / image count");
+    CU_TRY(c, cudaSetDevice(c->device));
+    return run_backbone(c, slot, n_images, images_dev, heights, widths, static_cast<cudaStream_t>(stream));
+}
+
+int sylph_import_features(sylph_ctx* c, int slot, int n_images, int padded_h, int padded_w,
+                          const float* const* level_ptrs_dev, const int* level_h, const int* level_w, void* stream) {
+    if (!c) return 1;
+    if (slot < 0 || slot >= SYLPH_NUM_SLOTS || n_images <= 0) return c->fail("bad slot / image count");
+    CU_TRY(c, cudaSetDevice(c->device));
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    TRY(setup_slot(c, slot, n_images, padded_h, padded_w, level_h, level_w, st));
+    Slot& S = c->slots[slot];
+    S.img_h.assign(n_images, padded_h);
+    S.img_w.assign(n_images, padded_w);
+    for (int l = 0; l < 5; ++l) {
+        const long long work = static_cast<long long>(n_images) * 256 * level_h[l] * level_w[l];
+        import_nchw_kernel<<<grid_for(work, 256, c->num_sms), 256, 0, st>>>(level_ptrs_dev[l], S.pyr, S.pg.lv[l], n_images, 256, 1);
+        CU_TRY(c, cudaGetLastError());
+        c->launches++;
+    }
+    return 0;
+}
+
+int sylph_feature_shape(sylph_ctx* c, int slot, int* n_images, int* padded_h, int* padded_w, int* level_h, int* level_w) {
+    if (!c) return 1;
+    if (slot < 0 || slot >= SYLPH_NUM_SLOTS || !c->slots[slot].valid) return c->fail("slot %d holds no features", slot);
+    const Slot& S = c->slots[slot];
+    if (n_images) *n_images = S.n;
+    if (padded_h) *padded_h = S.hpad;
+    if (padded_w) *padded_w = S.wpad;
+    for (int l = 0; l < 5; ++l) {
+        if (level_h) level_h[l] = S.lh[l];
+        if (level_w) level_w[l] = S.lw[l];
+    }
+    return 0;
+}
+
+int sylph_export_features(sylph_ctx* c, int slot, int level, float* out_dev, void* stream) {
+    if (!c) return 1;
+    if (slot < 0 || slot >= SYLPH_NUM_SLOTS || !c->slots[slot].valid || level < 0 || level > 4) return c->fail("bad slot/level");
+    const Slot& S = c->slots[slot];
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    const long long work = static_cast<long long>(S.n) * 256 * S.lh[level] * S.lw[level];
+    export_nchw_kernel<<<grid_for(work, 256, c->num_sms), 256, 0, st>>>(S.pyr, out_dev, S.pg.lv[level], S.n, 256, 256, 0, 1.f, 0);
+    CU_TRY(c, cudaGetLastError());
+    c->launches++;
+    return 0;
+}
+
+int sylph_generate_codes(sylph_ctx* c, int slot, int n_rois, const float* boxes_host, const int* roi_image,
+                         int n_classes, const int* class_offsets, float* codes_out_dev, int64_t* levels_out_dev,
+                         void* stream) {
+    if (!c) return 1;
+    if (!c->finalized) return c->fail("weights not finalized");
+    if (slot < 0 || slot >= SYLPH_NUM_SLOTS || !c->slots[slot].valid) return c->fail("slot %d holds no features", slot);
+    if (n_rois <= 0 || n_classes <= 0) return c->fail("empty support set");  // select_a_mask raises ValueError
+    const Slot& S = c->slots[slot];
+    for (int i = 0; i < n_rois; ++i)
+        if (roi_image[i] < 0 || roi_image[i] >= S.n) return c->fail("roi_image[%d]=%d out of range", i, roi_image[i]);
+    if (class_offsets[0] != 0 || class_offsets[n_classes] != n_rois) return c->fail("class_offsets must span all ROIs");
+    for (int k = 0; k < n_classes; ++k)
+        if (class_offsets[k + 1] <= class_offsets[k]) return c->fail("class %d has no support ROI", k);
+    CU_TRY(c, cudaSetDevice(c->device));
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    const sylph_model_config& f = c->cfg;
+    const long long rows = static_cast<long long>(n_rois) * 128;
+    void *pb, *pi, *po, *r0, *r1, *r2, *gp, *gs, *sc;
+    TRY(ensure(c, "cg.boxes", n_rois * 16, "", &pb, st, false));
+    TRY(ensure(c, "cg.roi_image", n_rois * 4, "", &pi, st, false));
+    TRY(ensure(c, "cg.class_off", (n_classes + 1) * 4, "", &po, st, false));
+    TRY(ensure(c, "cg.r0", (rows + kBlockM) * 256 * 4, "roi", &r0, st, true));
+    TRY(ensure(c, "cg.r1", (rows + kBlockM) * 256 * 4, "roi", &r1, st, true));
+    TRY(ensure(c, "cg.r2", (rows + kBlockM) * 256 * 4, "roi", &r2, st, true));
+    TRY(ensure(c, "cg.gn_partial", static_cast<size_t>(n_rois) * 64 * 4, "", &gp, st, false));
+    TRY(ensure(c, "cg.gn_stats", static_cast<size_t>(n_rois) * 64 * 4, "", &gs, st, false));
+    TRY(ensure(c, "cg.shot", static_cast<size_t>(n_rois) * 257 * 4, "", &sc, st, false));
+    CU_TRY(c, cudaMemcpyAsync(pb, boxes_host, n_rois * 16, cudaMemcpyHostToDevice, st));
+    CU_TRY(c, cudaMemcpyAsync(pi, roi_image, n_rois * 4, cudaMemcpyHostToDevice, st));
+    CU_TRY(c, cudaMemcpyAsync(po, class_offsets, (n_classes + 1) * 4, cudaMemcpyHostToDevice, st));
+    // plane set of the ROI planes (one 9x9 plane = one tile per ROI); grows with the largest ROI count seen
+    std::shared_ptr<PlaneSet> ps;
+    {
+        const int cap = std::max(64, 1 << static_cast<int>(std::ceil(std::log2(static_cast<double>(n_rois)))));
+        const PlaneGeom g = regular_geom(0, 7, 7, 1);
+        TRY(make_plane_set(c, "roi:" + std::to_string(cap), geom_segs(g, cap), cap * 128, &ps));
+    }
+    {
+        StageTimer t(c, "roi_align", st, static_cast<double>(n_rois) * (50176.0 + 0.5e6));
+        roi_align_kernel<<<dim3(n_rois, 7), 256, 0, st>>>(S.pyr, S.pg, static_cast<const float*>(pb), static_cast<const int*>(pi),
+                                                         static_cast<float*>(r0), reinterpret_cast<long long*>(levels_out_dev));
+        CU_TRY(c, cudaGetLastError());
+        c->launches++;
+    }
+    c->last_n_rois = n_rois;
+    float* cur = static_cast<float*>(r0);
+    float* nxt = static_cast<float*>(r1);
+    for (int i = 0; i < f.cg_tower_layers; ++i) {
+        TRY(conv_gn_relu(c, c->cg_tower[i], c->cg_gn_w[i], c->cg_gn_b[i], cur, rows, nxt, ps.get(), 0, n_rois, 0, n_rois,
+                         static_cast<float*>(gp), static_cast<float*>(gs), "codegen.tower3x3", st));
+        cur = nxt;
+        nxt = (cur == r1) ? static_cast<float*>(r2) : static_cast<float*>(r1);
+    }
+    {
+        ConvCall k{};
+        k.W = &c->cg_cls; k.A = cur; k.a_rows = rows; k.a_cols = k.a_ld = 256; k.ps = ps.get(); k.tile_begin = 0;
+        k.n_tiles = n_rois; k.a_row_delta = 0; k.out = nxt; k.ldc = 256; k.flags = 0; k.name = "codegen.cls_conv3x3";
+        TRY(run_conv(c, k, st));
+    }
+    {
+        StageTimer t(c, "codegen.tail", st, static_cast<double>(n_rois) * 2 * 49 * 256 * 4);
+        shot_code_kernel<<<n_rois, 256, 0, st>>>(nxt, cur, c->cg_wbias, c->cg_bbias, f.cg_bias_layer, f.cg_bias_l2_norm,
+                                                 static_cast<float*>(sc));
+        CU_TRY(c, cudaGetLastError());
+        class_mean_kernel<<<n_classes, 288, 0, st>>>(static_cast<const float*>(sc), static_cast<const int*>(po), codes_out_dev);
+        CU_TRY(c, cudaGetLastError());
+        c->launches += 2;
+    }
+    CU_TRY(c, cudaStreamSynchronize(st));  // host staging arrays (boxes_host ...) belong to the caller
+    return 0;
+}
+
+int sylph_export_roi_features(sylph_ctx* c, float* out_dev, void* stream) {
+    if (!c) return 1;
+    if (c->last_n_rois <= 0) return c->fail("no ROI features: call sylph_generate_codes first");
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    export_roi_kernel<<<grid_for(static_cast<long long>(c->last_n_rois) * 256 * 49, 256, c->num_sms), 256, 0, st>>>(
+        static_cast<const float*>(c->bufs["cg.r0"].p), out_dev, c->last_n_rois);
+    CU_TRY(c, cudaGetLastError());
+    c->launches++;
+    return 0;
+}
+
+int sylph_normalize_codes(sylph_ctx* c, const float* raw_codes_dev, float* out_codes_dev, int n_classes, void* stream) {
+    if (!c) return 1;
+    if (!c->finalized) return c->fail("weights not finalized");
+    if (n_classes <= 0) return 0;  // forward_normalize_code returns an empty list unchanged
+    const sylph_model_config& f = c->cfg;
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    normalize_codes_kernel<<<n_classes, 256, 0, st>>>(raw_codes_dev, out_codes_dev, c->post_gn_w, c->post_gn_b, f.cg_post_norm,
+                                                      f.cg_conv_l2_norm, c->conv_scale, c->bias_scale, c->bias_value);
+    CU_TRY(c, cudaGetLastError());
+    c->launches++;
+    return 0;
+}
+
+int sylph_detect(sylph_ctx* c, int slot, const float* codes_dev, int n_classes, const int* out_sizes_host,
+                 float* dets_out_dev, int* counts_out_dev, int max_dets, void* stream) {
+    if (!c) return 1;
+    if (!c->finalized) return c->fail("weights not finalized");
+    if (slot < 0 || slot >= SYLPH_NUM_SLOTS || !c->slots[slot].valid) return c->fail("slot %d holds no features", slot);
+    if (n_classes <= 0) return c->fail("no class codes");
+    const sylph_model_config& f = c->cfg;
+    if (max_dets < f.post_nms_topk || max_dets > 1024) return c->fail("max_dets must be in [post_nms_topk, 1024]");
+    CU_TRY(c, cudaSetDevice(c->device));
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    const Slot& S = c->slots[slot];
+    const long long rows = S.level_row0[5];
+    const int tiles = static_cast<int>(rows / kBlockM);
+    const int n_segs = 5 * S.n;
+    // ---- code-conditioned classifier weights
+    ConvW CW;
+    CW.taps = 1; CW.ksize = 1; CW.k_per_tap = 256; CW.cout = n_classes; CW.bn = pick_bn(n_classes);
+    CW.cout_pad = round_up(n_classes, CW.bn);
+    void *cw, *cb, *ta, *tb, *lg, *pr, *gp, *gs;
+    TRY(ensure(c, "det.code_w", static_cast<size_t>(CW.cout_pad) * 256 * 4, "", &cw, st, false));
+    TRY(ensure(c, "det.code_b", static_cast<size_t>(CW.cout_pad) * 4, "", &cb, st, false));
+    TRY(ensure(c, "det.ta", (static_cast<size_t>(rows) + kBlockM) * 256 * 4, "", &ta, st, false));
+    TRY(ensure(c, "det.tb", (static_cast<size_t>(rows) + kBlockM) * 256 * 4, "", &tb, st, false));
+    TRY(ensure(c, "det.logits", (static_cast<size_t>(rows) + kBlockM) * CW.cout_pad * 4, "", &lg, st, false));
+    TRY(ensure(c, "det.pred", (static_cast<size_t>(rows) + kBlockM) * 16 * 4, "", &pr, st, false));
+    TRY(ensure(c, "det.gn_partial", static_cast<size_t>(tiles) * 64 * 4, "", &gp, st, false));
+    TRY(ensure(c, "det.gn_stats", static_cast<size_t>(n_segs) * 64 * 4, "", &gs, st, false));
+    CW.w = static_cast<float*>(cw);
+    CW.bias = static_cast<float*>(cb);
+    pack_code_weights_kernel<<<ceil_div(static_cast<long long>(CW.cout_pad) * 256, 256), 256, 0, st>>>(
+        codes_dev, n_classes, CW.cout_pad, f.cg_use_bias, CW.w, CW.bias);
+    CU_TRY(c, cudaGetLastError());
+    c->launches++;
+    auto tower = [&](const std::vector<ConvW>& tw, const std::vector<float*>& gw, const std::vector<float*>& gb,
+                     const char* name, float** result) -> int {
+        const float* cur = S.pyr;
+        float* bufs2[2] = {static_cast<float*>(ta), static_cast<float*>(tb)};
+        for (size_t i = 0; i < tw.size(); ++i) {
+            float* o = bufs2[i & 1];
+            TRY(conv_gn_relu(c, tw[i], gw[i], gb[i], cur, rows, o, S.ps.get(), 0, tiles, 0, n_segs, static_cast<float*>(gp),
+                             static_cast<float*>(gs), name, st));
+            cur = o;
+        }
+        *result = const_cast<float*>(cur);
+        return 0;
+    };
+    float* x;
+    TRY(tower(c->cls_tower, c->cls_gn_w, c->cls_gn_b, "head.cls_tower3x3", &x));
+    {
+        ConvCall k{};
+        k.W = &CW; k.A = x; k.a_rows = rows; k.a_cols = k.a_ld = 256; k.ps = S.ps.get(); k.tile_begin = 0; k.n_tiles = tiles;
+        k.a_row_delta = 0; k.out = static_cast<float*>(lg); k.ldc = CW.cout_pad; k.flags = 0; k.name = "head.cond_cls1x1";
+        TRY(run_conv(c, k, st));
+    }
+    TRY(tower(c->box_tower, c->box_gn_w, c->box_gn_b, "head.bbox_tower3x3", &x));
+    {
+        ConvCall k{};
+        k.W = &c->pred; k.A = x; k.a_rows = rows; k.a_cols = k.a_ld = 256; k.ps = S.ps.get(); k.tile_begin = 0; k.n_tiles = tiles;
+        k.a_row_delta = 0; k.out = static_cast<float*>(pr); k.ldc = 16; k.flags = 0; k.name = "head.pred3x3";
+        TRY(run_conv(c, k, st));
+    }
+    c->last_detect_slot = slot;
+    c->last_detect_classes = n_classes;
+    c->last_logit_stride = CW.cout_pad;
+    // ---- proposals
+    DetectParams P{};
+    P.pg = S.pg;
+    P.n_images = S.n;
+    P.n_classes = n_classes;
+    P.logit_stride = CW.cout_pad;
+    long long off = 0;
+    for (int l = 0; l < 5; ++l) {
+        const long long full = static_cast<long long>(S.lh[l]) * S.lw[l] * n_classes;
+        P.cap[l] = static_cast<int>(std::min<long long>(full, 1 << 22));
+        P.cand_off[l] = off;
+        off += static_cast<long long>(S.n) * P.cap[l];
+        P.level_scale[l] = c->level_scale[l];
+        P.stride[l] = 8 << l;
+    }
+    P.thresh = f.inference_thresh;
+    P.thresh_with_ctr = f.thresh_with_ctr;
+    P.box_quality = f.box_quality;
+    P.pre_topk = f.pre_nms_topk;
+    P.post_topk = f.post_nms_topk;
+    P.nms_thresh = f.nms_thresh;
+    void *cand, *cnt, *sel, *selc, *ia;
+    TRY(ensure(c, "det.cand", static_cast<size_t>(off) * 8, "", &cand, st, false));
+    TRY(ensure(c, "det.counts", static_cast<size_t>(n_segs + 1) * 4, "", &cnt, st, false));
+    TRY(ensure(c, "det.sel", static_cast<size_t>(n_segs) * P.pre_topk * 8, "", &sel, st, false));
+    TRY(ensure(c, "det.sel_count", static_cast<size_t>(n_segs) * 4, "", &selc, st, false));
+    TRY(ensure(c, "det.img_args", static_cast<size_t>(S.n) * sizeof(NmsImageArgs), "", &ia, st, false));
+    std::vector<NmsImageArgs> args(S.n);
+    for (int i = 0; i < S.n; ++i) {
+        const int oh = out_sizes_host ? out_sizes_host[2 * i] : S.img_h[i];
+        const int ow = out_sizes_host ? out_sizes_host[2 * i + 1] : S.img_w[i];
+        args[i].scale_x = static_cast<float>(static_cast<double>(ow) / S.img_w[i]);
+        args[i].scale_y = static_cast<float>(static_cast<double>(oh) / S.img_h[i]);
+        args[i].out_w = static_cast<float>(ow);
+        args[i].out_h = static_cast<float>(oh);
+    }
+    CU_TRY(c, cudaMemcpyAsync(ia, args.data(), S.n * sizeof(NmsImageArgs), cudaMemcpyHostToDevice, st));
+    CU_TRY(c, cudaMemsetAsync(cnt, 0, static_cast<size_t>(n_segs + 1) * 4, st));
+    {
+        StageTimer t(c, "proposals", st, static_cast<double>(S.n) * 22400 * (CW.cout_pad + 16) * 4);
+        long long total_px = 0;
+        for (int l = 0; l < 5; ++l) total_px += static_cast<long long>(S.n) * S.lh[l] * S.lw[l];
+        fcos_candidates_kernel<<<grid_for(total_px, 256, c->num_sms), 256, 0, st>>>(
+            static_cast<const float*>(lg), static_cast<const float*>(pr), P, static_cast<unsigned long long*>(cand),
+            static_cast<int*>(cnt), static_cast<int*>(cnt) + n_segs);
+        CU_TRY(c, cudaGetLastError());
+        fcos_select_kernel<<<n_segs, 1024, 0, st>>>(static_cast<const unsigned long long*>(cand), static_cast<const int*>(cnt), P,
+                                                    static_cast<unsigned long long*>(sel), static_cast<int*>(selc));
+        CU_TRY(c, cudaGetLastError());
+        const int n_max = 5 * P.pre_topk;
+        int sort_n = 32;
+        while (sort_n < n_max) sort_n <<= 1;
+        const size_t smem = static_cast<size_t>(sort_n) * 8 + static_cast<size_t>(n_max) * 21 + 16;
+        static bool attr_set = false;
+        if (!attr_set) {
+            CU_TRY(c, cudaFuncSetAttribute(fcos_nms_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+            attr_set = true;
+        }
+        if (smem > 200 * 1024) return c->fail("NMS shared memory budget exceeded (pre_nms_topk too large)");
+        fcos_nms_kernel<<<S.n, 1024, smem, st>>>(static_cast<const unsigned long long*>(sel), static_cast<const int*>(selc),
+                                                 static_cast<const float*>(pr), P, static_cast<const NmsImageArgs*>(ia), sort_n,
+                                                 n_max, dets_out_dev, counts_out_dev, max_dets);
+        CU_TRY(c, cudaGetLastError());
+        c->launches += 3;
+    }
+    CU_TRY(c, cudaStreamSynchronize(st));  // `args` staging vector lifetime
+    return 0;
+}
+
+int sylph_export_head_output(sylph_ctx* c, int which, int level, float* out_dev, void* stream) {
+    if (!c) return 1;
+    if (c->last_detect_slot < 0 || level < 0 || level > 4 || which < 0 || which > 3) return c->fail("no detect call to export from");
+    const Slot& S = c->slots[c->last_detect_slot];
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    const float* src = static_cast<const float*>(c->bufs[which == 0 ? "det.logits" : "det.pred"].p);
+    int C = 1, cstride = 16, coff = 0, relu = 0;
+    float scale = 1.f;
+    if (which == 0) { C = c->last_detect_classes; cstride = c->last_logit_stride; }
+    else if (which == 1) { C = 4; scale = c->level_scale[level]; relu = 1; }
+    else if (which == 2) { coff = 4; }
+    else { coff = 5; }
+    const long long work = static_cast<long long>(S.n) * C * S.lh[level] * S.lw[level];
+    export_nchw_kernel<<<grid_for(work, 256, c->num_sms), 256, 0, st>>>(src, out_dev, S.pg.lv[level], S.n, C, cstride, coff, scale, relu);
+    CU_TRY(c, cudaGetLastError());
+    c->launches++;
+    return 0;
+}
+
+int64_t sylph_launch_count(const sylph_ctx* c) { return c ? c->launches : 0; }
+
+int sylph_set_profiling(sylph_ctx* c, int enabled) {
+    if (!c) return 1;
+    for (auto& t : c->timings) { cudaEventDestroy(t.e0); cudaEventDestroy(t.e1); }
+    c->timings.clear();
+    c->profiling = enabled != 0;
+    return 0;
+}
+
+int sylph_get_timings(sylph_ctx* c, char (*names)[48], float* ms, double* flops, double* bytes, int cap) {
+    if (!c) return -1;
+    cudaDeviceSynchronize();
+    const int n = static_cast<int>(c->timings.size());
+    for (int i = 0; i < n && i < cap; ++i) {
+        strncpy(names[i], c->timings[i].name.c_str(), 47);
+        names[i][47] = 0;
+        cudaEventElapsedTime(&ms[i], c->timings[i].e0, c->timings[i].e1);
+        flops[i] = c->timings[i].flops;
+        bytes[i] = c->timings[i].bytes;
+    }
+    return n;
+}
+
+}  // extern "C"

@@ -1,0 +1,204 @@
+// Code-generation kernels around the tensor-core tower: multi-level ROIAlign gather, per-shot pooling + bias conv,
+// K-shot mean, code normalisation.  These move kilobytes per class; they are latency/HBM-bound gather and
+// warp-shuffle reduction kernels.
+#pragma once
+#include "kernels_misc.cuh"
+
+namespace sylph {
+
+struct PyramidGeom {
+    PlaneGeom lv[5];
+    float scale[5];  // 1 / stride
+};
+
+// FPN level of a box, the op sequence of detectron2 assign_boxes_to_levels:
+// floor(4 + log2(sqrt(area) / 224 + 1e-8)) clamped to [3, 7], minus 3.  Explicit _rn intrinsics keep the compiler
+// from contracting the fp32 steps.
+__device__ __forceinline__ int assign_level(float x0, float y0, float x1, float y1) {
+    const float area = __fmul_rn(__fsub_rn(x1, x0), __fsub_rn(y1, y0));
+    const float s = sqrtf(area);
+    const float t = __fadd_rn(__fdiv_rn(s, 224.f), 1e-8f);
+    float l = floorf(__fadd_rn(4.f, log2f(t)));
+    l = fminf(fmaxf(l, 3.f), 7.f);  // NaN (negative area) -> 3 like torch.clamp then cast
+    return static_cast<int>(l) - 3;
+}
+
+__device__ __forceinline__ float bilinear_tap(const float* __restrict__ feat, const PlaneGeom& g, int n, int H, int W,
+                                              float y, float x, int c) {
+    if (y < -1.f || y > static_cast<float>(H) || x < -1.f || x > static_cast<float>(W)) return 0.f;
+    y = fmaxf(y, 0.f);
+    x = fmaxf(x, 0.f);
+    int y_low = static_cast<int>(y), x_low = static_cast<int>(x), y_high, x_high;
+    if (y_low >= H - 1) { y_high = y_low = H - 1; y = static_cast<float>(y_low); } else { y_high = y_low + 1; }
+    if (x_low >= W - 1) { x_high = x_low = W - 1; x = static_cast<float>(x_low); } else { x_high = x_low + 1; }
+    const float ly = y - y_low, lx = x - x_low, hy = 1.f - ly, hx = 1.f - lx;
+    const float v1 = __ldg(feat + plane_row(g, n, y_low, x_low) * 256 + c);
+    const float v2 = __ldg(feat + plane_row(g, n, y_low, x_high) * 256 + c);
+    const float v3 = __ldg(feat + plane_row(g, n, y_high, x_low) * 256 + c);
+    const float v4 = __ldg(feat + plane_row(g, n, y_high, x_high) * 256 + c);
+    return hy * hx * v1 + hy * lx * v2 + ly * hx * v3 + ly * lx * v4;
+}
+
+// ROIAlignV2 (aligned=True, sampling_ratio=0, 7x7) over the assigned FPN level, all levels in ONE launch.
+// grid = (n_rois, 7 output rows), block = 256 threads = 256 channels (each feature tap is one coalesced 1 KiB row).
+// Output goes straight into the 9x9 zero-bordered ROI planes (128 rows per ROI) the tower GEMM reads.
+// Replaces detectron2 ROIPooler.forward (torchvision roi_align per level + nonzero + index_put_),
+// reference call site sylph/modeling/code_generator/code_generator.py:930.
+__global__ void __launch_bounds__(256)
+roi_align_kernel(const float* __restrict__ pyramid, PyramidGeom pg, const float* __restrict__ boxes,
+                 const int* __restrict__ roi_image, float* __restrict__ roi_planes, long long* __restrict__ levels_out) {
+    const int roi = blockIdx.x, ph = blockIdx.y, c = threadIdx.x;
+    const float bx0 = boxes[roi * 4 + 0], by0 = boxes[roi * 4 + 1], bx1 = boxes[roi * 4 + 2], by1 = boxes[roi * 4 + 3];
+    const int lvl = assign_level(bx0, by0, bx1, by1);
+    if (ph == 0 && c == 0 && levels_out != nullptr) levels_out[roi] = lvl;
+    const PlaneGeom g = pg.lv[lvl];
+    const float sc = pg.scale[lvl];
+    const int n = roi_image[roi];
+    const float x0 = __fsub_rn(__fmul_rn(bx0, sc), 0.5f), y0 = __fsub_rn(__fmul_rn(by0, sc), 0.5f);
+    const float x1 = __fsub_rn(__fmul_rn(bx1, sc), 0.5f), y1 = __fsub_rn(__fmul_rn(by1, sc), 0.5f);
+    const float roi_w = __fsub_rn(x1, x0), roi_h = __fsub_rn(y1, y0);
+    const float bin_h = __fdiv_rn(roi_h, 7.f), bin_w = __fdiv_rn(roi_w, 7.f);
+    const int grid_h = static_cast<int>(ceilf(__fdiv_rn(roi_h, 7.f)));
+    const int grid_w = static_cast<int>(ceilf(__fdiv_rn(roi_w, 7.f)));
+    const float count = fmaxf(static_cast<float>(grid_h * grid_w), 1.f);
+    for (int pw = 0; pw < 7; ++pw) {
+        float acc = 0.f;
+        for (int iy = 0; iy < grid_h; ++iy) {
+            const float y = __fadd_rn(__fadd_rn(y0, __fmul_rn(static_cast<float>(ph), bin_h)),
+                                      __fdiv_rn(__fmul_rn(static_cast<float>(iy) + 0.5f, bin_h), static_cast<float>(grid_h)));
+            for (int ix = 0; ix < grid_w; ++ix) {
+                const float x = __fadd_rn(__fadd_rn(x0, __fmul_rn(static_cast<float>(pw), bin_w)),
+                                          __fdiv_rn(__fmul_rn(static_cast<float>(ix) + 0.5f, bin_w), static_cast<float>(grid_w)));
+                acc += bilinear_tap(pyramid, g, n, g.H, g.W, y, x, c);
+            }
+        }
+        const size_t row = static_cast<size_t>(roi) * 128 + (ph + 1) * 9 + (pw + 1);
+        roi_planes[row * 256 + c] = ptx::round_tf32(acc / count);
+    }
+}
+
+// Per support ROI ("shot"): global average pool of the cls-conv output (GlobalAdaptiveAvgPool2d, k_s = 1) and the
+// 256 -> 1 3x3 bias convolution on the tower output, optional L2 normalisation over the 49 positions, then its pool.
+// reference: code_generator.py:954-967, utils.py:51-67.   grid = n_rois, block = 256.
+__global__ void __launch_bounds__(256)
+shot_code_kernel(const float* __restrict__ cls_raw, const float* __restrict__ tower_out,
+                 const float* __restrict__ w_bias /* [9][256] tap-major */, const float* __restrict__ b_bias,
+                 int has_bias_layer, int bias_l2_norm, float* __restrict__ shot_codes /* [n_rois][257] */) {
+    __shared__ float pix[49];
+    const int roi = blockIdx.x, t = threadIdx.x, warp = t >> 5, lane = t & 31;
+    const size_t base = static_cast<size_t>(roi) * 128;
+    float s = 0.f;
+    for (int p = 0; p < 49; ++p) {
+        const int row = (p / 7 + 1) * 9 + (p % 7 + 1);
+        s += cls_raw[(base + row) * 256 + t];
+    }
+    shot_codes[static_cast<size_t>(roi) * 257 + t] = s / 49.f;
+    if (!has_bias_layer) {
+        if (t == 0) shot_codes[static_cast<size_t>(roi) * 257 + 256] = 0.f;
+        return;
+    }
+    for (int p = warp; p < 49; p += 8) {
+        const int row = (p / 7 + 1) * 9 + (p % 7 + 1);
+        float acc = 0.f;
+#pragma unroll
+        for (int tap = 0; tap < 9; ++tap) {
+            const int r2 = row + (tap / 3 - 1) * 9 + (tap % 3 - 1);  // zero border supplies the padding
+            const float* a = tower_out + (base + r2) * 256;
+            const float* w = w_bias + tap * 256;
+#pragma unroll
+            for (int j = 0; j < 8; ++j) acc += a[lane + 32 * j] * __ldg(w + lane + 32 * j);
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+        if (lane == 0) pix[p] = acc + b_bias[0];
+    }
+    __syncthreads();
+    if (t == 0) {
+        float denom = 1.f;
+        if (bias_l2_norm) {
+            float ss = 0.f;
+            for (int p = 0; p < 49; ++p) ss += pix[p] * pix[p];
+            denom = fmaxf(sqrtf(ss), 1e-12f);  // F.normalize eps
+        }
+        float m = 0.f;
+        for (int p = 0; p < 49; ++p) m += pix[p] / denom;
+        shot_codes[static_cast<size_t>(roi) * 257 + 256] = m / 49.f;
+    }
+}
+
+// K-shot mean per class with the reference's op order: sum_k (1/K) * x_k  (compute_code, code_generator.py:805-817).
+__global__ void __launch_bounds__(288)
+class_mean_kernel(const float* __restrict__ shot_codes, const int* __restrict__ class_offsets,
+                  float* __restrict__ raw_codes) {
+    const int cls = blockIdx.x, t = threadIdx.x;
+    if (t >= 257) return;
+    const int k0 = class_offsets[cls], k1 = class_offsets[cls + 1];
+    const float w = 1.0f / static_cast<float>(k1 - k0);
+    float s = 0.f;
+    for (int k = k0; k < k1; ++k) s += w * shot_codes[static_cast<size_t>(k) * 257 + t];
+    raw_codes[static_cast<size_t>(cls) * 257 + t] = s;
+}
+
+// Code normalisation, one 256-thread block per class (code_process_module, code_generator.py:832-875):
+// GroupNorm(32, 256) on the 1x1 map (8-lane shuffles) -> L2 normalise over the 256 channels -> x conv_scale;
+// bias x bias_scale + (-log((1 - p) / p)).
+__global__ void __launch_bounds__(256)
+normalize_codes_kernel(const float* __restrict__ raw, float* __restrict__ out, const float* __restrict__ gn_w,
+                       const float* __restrict__ gn_b, int post_norm, int l2_norm, float conv_scale, float bias_scale,
+                       float bias_value) {
+    __shared__ float red[8];
+    const int cls = blockIdx.x, t = threadIdx.x, lane = t & 31, warp = t >> 5;
+    float x = raw[static_cast<size_t>(cls) * 257 + t];
+    const float b = raw[static_cast<size_t>(cls) * 257 + 256];
+    if (post_norm) {
+        float s = x;
+        s += __shfl_xor_sync(0xffffffffu, s, 1);
+        s += __shfl_xor_sync(0xffffffffu, s, 2);
+        s += __shfl_xor_sync(0xffffffffu, s, 4);
+        const float mean = s / 8.f;
+        const float d = x - mean;
+        float v = d * d;
+        v += __shfl_xor_sync(0xffffffffu, v, 1);
+        v += __shfl_xor_sync(0xffffffffu, v, 2);
+        v += __shfl_xor_sync(0xffffffffu, v, 4);
+        x = d * rsqrtf(v / 8.f + 1e-5f) * gn_w[t] + gn_b[t];
+    }
+    if (l2_norm) {
+        float ss = x * x;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
+        if (lane == 0) red[warp] = ss;
+        __syncthreads();
+        float tot = 0.f;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) tot += red[i];
+        x = x / fmaxf(sqrtf(tot), 1e-12f);
+    }
+    out[static_cast<size_t>(cls) * 257 + t] = x * conv_scale;
+    if (t == 0) out[static_cast<size_t>(cls) * 257 + 256] = b * bias_scale + bias_value;
+}
+
+// Expand (n_classes, 257) codes into the K-major weight matrix [n_pad][256] + bias [n_pad] the logits GEMM reads
+// (rows >= n_classes are zero); weights are rounded to TF32 here.
+__global__ void pack_code_weights_kernel(const float* __restrict__ codes, int n_classes, int n_pad, int use_bias,
+                                         float* __restrict__ w, float* __restrict__ bias) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_pad * 256) return;
+    const int r = i >> 8, c = i & 255;
+    w[i] = r < n_classes ? ptx::round_tf32(codes[static_cast<size_t>(r) * 257 + c]) : 0.f;
+    if (c == 0) bias[r] = (r < n_classes && use_bias) ? codes[static_cast<size_t>(r) * 257 + 256] : 0.f;
+}
+
+// (n_rois, 256, 7, 7) export of the pooled ROI planes (tests / plugin interop).
+__global__ void export_roi_kernel(const float* __restrict__ roi_planes, float* __restrict__ out, int n_rois) {
+    const long long total = static_cast<long long>(n_rois) * 256 * 49;
+    for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
+         i += static_cast<long long>(gridDim.x) * blockDim.x) {
+        const int p = static_cast<int>(i % 49);
+        const int c = static_cast<int>((i / 49) % 256);
+        const int r = static_cast<int>(i / (49 * 256));
+        out[i] = roi_planes[(static_cast<size_t>(r) * 128 + (p / 7 + 1) * 9 + (p % 7 + 1)) * 256 + c];
+    }
+}
+
+}  // namespace sylph

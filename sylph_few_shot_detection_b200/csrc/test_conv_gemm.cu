@@ -44,7 +44,7 @@ struct Case {
     int cout;             // multiple of bn
     int taps;
     int kpt;              // k-blocks per tap
-    std::vector<int> shifts;
+    std::vector<int> dys, dxs;
     int flags;
     bool bias;
 };
@@ -103,7 +103,7 @@ static int run_case(const Case& c, int num_sms) {
     g.taps = c.taps;
     g.kblocks_per_tap = c.kpt;
     g.b_rows_per_tap = c.cout;
-    for (int t = 0; t < c.taps; ++t) g.tap_shift[t] = c.shifts[t];
+    for (int t = 0; t < c.taps; ++t) { g.tap_dy[t] = c.dys[t]; g.tap_dx[t] = c.dxs[t]; }
     g.bias = c.bias ? dB : nullptr;
     g.residual = dR;
     g.ld_res = c.cout;
@@ -135,7 +135,7 @@ static int run_case(const Case& c, int num_sms) {
         for (int n = 0; n < c.cout; ++n) {
             double acc = hB[n];
             for (int t = 0; t < c.taps; ++t) {
-                long ar = static_cast<long>(r) + c.shifts[t];
+                long ar = static_cast<long>(r) + c.dys[t] * sg.Wp + c.dxs[t];
                 if (ar < 0 || ar >= static_cast<long>(a_rows_dim)) continue;
                 const float* arow = &hA[static_cast<size_t>(ar) * c.a_ld];
                 const float* wrow = &hW[(static_cast<size_t>(t) * c.cout + n) * Kt];
@@ -197,8 +197,7 @@ static void bench_shape(const char* name, int bn, int m_tiles, int cin, int cout
     CK(cudaMemset(dW, 0, static_cast<size_t>(taps) * cout * cin * 4));
     CK(cudaMemset(dB, 0, cout * 4));
     CK(cudaMemset(dTS, 0, m_tiles * 4));
-    Seg s = mk_seg(0, 1, M - 200, 1);  // one long thin plane; only used for masks
-    s.nrows = M;
+    Seg s = mk_seg(0, M / 170 - 2, 168, 1);  // p3-like plane width
     CK(cudaMemcpy(dS, &s, sizeof(Seg), cudaMemcpyHostToDevice));
     if (flags & kEpiResidual) {
         CK(cudaMalloc(&dR, static_cast<size_t>(M) * cout * 4));
@@ -212,8 +211,7 @@ static void bench_shape(const char* name, int bn, int m_tiles, int cin, int cout
     }
     GemmArgs g{};
     g.num_m_tiles = m_tiles; g.num_n_tiles = cout / bn; g.taps = taps; g.kblocks_per_tap = cin / 32; g.b_rows_per_tap = cout;
-    const int Wp = 170;
-    for (int t = 0; t < taps; ++t) g.tap_shift[t] = taps == 9 ? ((t / 3) - 1) * Wp + (t % 3) - 1 : 0;
+    for (int t = 0; t < taps; ++t) { g.tap_dy[t] = taps == 9 ? (t / 3) - 1 : 0; g.tap_dx[t] = taps == 9 ? (t % 3) - 1 : 0; }
     g.bias = dB; g.residual = dR; g.ld_res = cout; g.out = dO; g.ldc = cout; g.flags = flags; g.tile_seg = dTS; g.segs = dS; g.gn_partial = dG;
     cudaEvent_t e0, e1;
     CK(cudaEventCreate(&e0)); CK(cudaEventCreate(&e1));
@@ -243,14 +241,17 @@ int main(int argc, char** argv) {
     printf("device %s sm_%d%d SMs=%d\n", prop.name, prop.major, prop.minor, prop.multiProcessorCount);
     const int sms = prop.multiProcessorCount;
     int fails = 0;
-    std::vector<int> one = {0};
+    const std::vector<int> z1 = {0};
+    std::vector<int> dy9, dx9, dy4, dx4;
+    for (int t = 0; t < 9; ++t) { dy9.push_back(t / 3 - 1); dx9.push_back(t % 3 - 1); }
+    for (int t = 0; t < 4; ++t) { dy4.push_back(t - 2); dx4.push_back(-2); }
     {   // plain GEMM, one tap
-        Case c{"gemm_bn256_k64", 256, {mk_seg(0, 1, 638, 1)}, 640 * 3, 64, 64, 256, 1, 2, one, 0, true};
+        Case c{"gemm_bn256_k64", 256, {mk_seg(0, 1, 638, 1)}, 640 * 3, 64, 64, 256, 1, 2, z1, z1, 0, true};
         c.segs[0].nrows = c.total_rows;
         fails += run_case(c, sms);
     }
     {   // many tiles > SM count to exercise the persistent loop + phases
-        Case c{"gemm_bn256_k256_persistent", 256, {mk_seg(0, 1, 638, 1)}, 128 * 333, 256, 256, 256, 1, 8, one, kEpiRelu, true};
+        Case c{"gemm_bn256_k256_persistent", 256, {mk_seg(0, 1, 638, 1)}, 128 * 333, 256, 256, 256, 1, 8, z1, z1, kEpiRelu, true};
         c.segs[0].nrows = c.total_rows;
         fails += run_case(c, sms);
     }
@@ -258,42 +259,33 @@ int main(int argc, char** argv) {
         Seg s0 = mk_seg(0, 13, 21, 1);
         Seg s1 = mk_seg(round128(s0.nrows), 7, 11, 1);
         int total = s1.row0 + round128(s1.nrows);
-        std::vector<int> sh;
-        // NOTE: shifts depend on the plane; this case uses two planes with DIFFERENT Wp, so run them as one launch
-        // only when Wp matches.  Use same-W planes instead:
-        s1 = mk_seg(round128(s0.nrows), 9, 21, 1);
-        total = s1.row0 + round128(s1.nrows);
-        for (int t = 0; t < 9; ++t) sh.push_back(((t / 3) - 1) * s0.Wp + (t % 3) - 1);
-        Case c{"conv3x3_bn256_mask_gn", 256, {s0, s1}, total, 64, 64, 256, 9, 2, sh, kEpiMask | kEpiGnStats | kEpiRoundTf32, true};
+        // two planes with DIFFERENT padded widths in one launch (the per-tile Wp lookup of the producer)
+        Case c{"conv3x3_bn256_mask_gn", 256, {s0, s1}, total, 64, 64, 256, 9, 2, dy9, dx9, kEpiMask | kEpiGnStats | kEpiRoundTf32, true};
         fails += run_case(c, sms);
     }
     {   // BN=64 with residual + relu
-        Case c{"gemm_bn64_res_relu", 64, {mk_seg(0, 1, 638, 1)}, 128 * 7, 64, 64, 64, 1, 2, one, kEpiResidual | kEpiRelu, true};
+        Case c{"gemm_bn64_res_relu", 64, {mk_seg(0, 1, 638, 1)}, 128 * 7, 64, 64, 64, 1, 2, z1, z1, kEpiResidual | kEpiRelu, true};
         c.segs[0].nrows = c.total_rows;
         fails += run_case(c, sms);
     }
     {   // BN=128, two n tiles
-        Case c{"gemm_bn128_n256", 128, {mk_seg(0, 1, 638, 1)}, 128 * 9, 128, 128, 256, 1, 4, one, kEpiRelu, false};
+        Case c{"gemm_bn128_n256", 128, {mk_seg(0, 1, 638, 1)}, 128 * 9, 128, 128, 256, 1, 4, z1, z1, kEpiRelu, false};
         c.segs[0].nrows = c.total_rows;
         fails += run_case(c, sms);
     }
     {   // BN=256, eight n tiles (res5-like)
-        Case c{"gemm_bn256_n1024", 256, {mk_seg(0, 1, 638, 1)}, 128 * 3, 128, 128, 1024, 1, 4, one, kEpiRelu, true};
+        Case c{"gemm_bn256_n1024", 256, {mk_seg(0, 1, 638, 1)}, 128 * 3, 128, 128, 1024, 1, 4, z1, z1, kEpiRelu, true};
         c.segs[0].nrows = c.total_rows;
         fails += run_case(c, sms);
     }
     {   // BN=16 3x3 predictor-style conv
         Seg s0 = mk_seg(0, 13, 21, 1);
-        std::vector<int> sh;
-        for (int t = 0; t < 9; ++t) sh.push_back(((t / 3) - 1) * s0.Wp + (t % 3) - 1);
-        Case c{"conv3x3_bn16", 16, {s0}, round128(s0.nrows), 256, 256, 16, 9, 8, sh, kEpiMask, true};
+        Case c{"conv3x3_bn16", 16, {s0}, round128(s0.nrows), 256, 256, 16, 9, 8, dy9, dx9, kEpiMask, true};
         fails += run_case(c, sms);
     }
     {   // stem trick: 16-channel pixels, rows overlapped (pitch 16 floats, 64 visible), 4 vertical taps x K=64
         Seg s0 = mk_seg(0, 10, 12, 2);
-        std::vector<int> sh;
-        for (int t = 0; t < 4; ++t) sh.push_back((t - 2) * s0.Wp - 2);
-        Case c{"stem_overlapped_rows_bn64", 64, {s0}, round128(s0.nrows), 64, 16, 64, 4, 2, sh, kEpiMask | kEpiRelu | kEpiRoundTf32, true};
+        Case c{"stem_overlapped_rows_bn64", 64, {s0}, round128(s0.nrows), 64, 16, 64, 4, 2, dy4, dx4, kEpiMask | kEpiRelu | kEpiRoundTf32, true};
         fails += run_case(c, sms);
     }
     printf("correctness: %d failing case(s)\n", fails);

@@ -1,0 +1,339 @@
+"""Host-side mirror of the reference's plugin surface for the Meta-FCOS inference path.
+
+Same registry names, class names, `run_type` strings, argument meaning, return schema and error behaviour as
+  * `CODE_GENERATOR_REGISTRY` / `build_code_generator` .. sylph/modeling/code_generator/build.py:18-39
+  * `CodeGenerator.forward` ........................... sylph/modeling/code_generator/code_generator.py:1037-1053
+  * `MetaFCOS` (PROPOSAL_GENERATOR_REGISTRY) .......... sylph/modeling/meta_fcos/fcos.py:158-268
+  * `build_fcos_resnet_fpn_backbone` (BACKBONE_REGISTRY) configs/COCO-Detection/Meta-FCOS/Base-FCOS.yaml:3-4
+  * `MetaOneStageDetector.forward(run_type=...)` ...... sylph/modeling/meta_arch/meta_one_stage_detector.py:425-445
+so the reference's configs and runner loops (sylph/evaluation/meta_learn_evaluation.py:256-470) drive it unchanged.
+All arithmetic happens in libsylph_b200.so; these classes hold no parameters and only marshal arguments.
+"""
+from __future__ import annotations
+
+from typing import Any, Dict, List, Optional, Sequence, Tuple
+
+import numpy as np
+import torch
+from torch import nn
+
+from .runtime import CODE_STRIDE, SLOT_QUERY, SLOT_SUPPORT, Engine
+from .structures import HAVE_DETECTRON2, Boxes, Instances, Registry, ShapeSpec
+from .weights import state_spec
+
+CODE_GENERATOR_REGISTRY = Registry("CODE_GENERATOR")
+CODE_GENERATOR_REGISTRY.__doc__ = "Registry for code generator (same name as the reference's)."
+
+if HAVE_DETECTRON2:  # pragma: no cover - bind into the real registries when they exist
+    from detectron2.modeling import BACKBONE_REGISTRY, META_ARCH_REGISTRY, PROPOSAL_GENERATOR_REGISTRY  # type: ignore
+else:
+    META_ARCH_REGISTRY = Registry("META_ARCH")
+    PROPOSAL_GENERATOR_REGISTRY = Registry("PROPOSAL_GENERATOR")
+    BACKBONE_REGISTRY = Registry("BACKBONE")
+
+
+def build_code_generator(cfg, feature_channels: int, feature_levels: Optional[int], strides: Tuple[int]):
+    """reference: sylph/modeling/code_generator/build.py:29-39 (None when the name is empty)."""
+    name = cfg.MODEL.META_LEARN.CODE_GENERATOR.NAME
+    if name == "":
+        return None
+    return CODE_GENERATOR_REGISTRY.get(name)(cfg, feature_channels, feature_levels, strides)
+
+
+def select_a_mask(gt_instances: Sequence[Any], use_all_masks: bool = False) -> List[torch.Tensor]:
+    """One GT box per support image, drawn with the global NumPy RNG exactly like the reference
+    (sylph/modeling/code_generator/utils.py:27-47); empty boxes raise ValueError."""
+    out = []
+    for inst in gt_instances:
+        boxes = inst.gt_boxes.tensor
+        if len(boxes) == 0:
+            raise ValueError("support image without a ground-truth box")
+        if use_all_masks:
+            out.append(boxes)
+        else:
+            idx = np.random.choice(range(len(boxes)), 1)
+            out.append(boxes[idx])
+    return out
+
+
+class _EngineBound(nn.Module):
+    """Mixin: modules on this path share the detector's C-ABI context."""
+
+    def __init__(self):
+        super().__init__()
+        object.__setattr__(self, "_engine_ref", None)
+
+    def bind_engine(self, engine: Engine) -> None:
+        object.__setattr__(self, "_engine_ref", engine)
+
+    @property
+    def engine(self) -> Engine:
+        eng = object.__getattribute__(self, "_engine_ref")
+        if eng is None:
+            raise RuntimeError("no weights loaded: call MetaOneStageDetector.load_state_dict first "
+                               "(the B200 path has no CPU fallback)")
+        return eng
+
+
+@CODE_GENERATOR_REGISTRY.register()
+class CodeGenerator(_EngineBound):
+    """Drop-in for the reference's `CodeGenerator` (registered under the same name, same forward signature)."""
+
+    def __init__(self, cfg, feature_channels: int, feature_levels: int, strides: Tuple[int]):
+        super().__init__()
+        assert feature_channels == 256 and feature_levels == 5, "the B200 path is built for the 256-channel p3..p7 pyramid"
+        self.in_features = cfg.MODEL.FCOS.IN_FEATURES
+        self.strides = tuple(strides)
+        self.all_mask = cfg.MODEL.META_LEARN.CODE_GENERATOR.ALL_MASK
+        self.contrastive_loss = cfg.MODEL.META_LEARN.CODE_GENERATOR.CONTRASTIVE_LOSS
+        if self.all_mask:
+            raise NotImplementedError("ALL_MASK=True is not supported")
+
+    def forward(self, features: Optional[List[torch.Tensor]], target_instances=None, cls_norm: bool = False,
+                class_codes: Optional[List[Dict]] = None):
+        if not self.training and cls_norm and class_codes is not None:
+            return self.forward_normalize_code(class_codes)
+        return self.forward_roi_align(features, target_instances)
+
+    # generate mode: List[(N, 256, H_l, W_l)] NCHW features + List[Instances] -> raw code of ONE class (eval quirk:
+    # num_shot = size(0), code_generator.py:790-793)
+    def forward_roi_align(self, features: List[torch.Tensor], gt_instances: Sequence[Any]) -> Dict[str, torch.Tensor]:
+        assert not self.training, "the B200 path implements inference only"
+        total_shots = features[0].size(0)
+        assert len(gt_instances) == total_shots
+        boxes = torch.cat([b.reshape(-1, 4)[:1] for b in select_a_mask(gt_instances, self.all_mask)], dim=0)
+        h, w = features[0].shape[-2:]
+        self.engine.import_features(SLOT_SUPPORT, features, (h * self.strides[0], w * self.strides[0]))
+        return self._codes_of_one_class(boxes, list(range(total_shots)))
+
+    def _codes_of_one_class(self, boxes: torch.Tensor, roi_image: List[int]) -> Dict[str, torch.Tensor]:
+        raw = self.engine.generate_codes(SLOT_SUPPORT, boxes, roi_image, [0, len(roi_image)])
+        out = {"cls_conv": raw[:, :256].reshape(1, 256, 1, 1), "cls_bias": raw[:, 256:].reshape(1, 1, 1, 1)}
+        if self.contrastive_loss == "snnl":
+            raise NotImplementedError("CONTRASTIVE_LOSS='snnl' output is not produced on the inference path")
+        return out
+
+    # normalise mode (code_generator.py:877-897): mutates the dicts in place, returns the same list
+    def forward_normalize_code(self, codes: List[Dict]) -> List[Dict]:
+        assert not self.training, "Only support testing mode here"
+        assert codes is not None
+        if len(codes) == 0:
+            return codes
+        rows = []
+        for code in codes:
+            assert "class_code" in code, "class_code is not in code"
+            assert "cls_conv" in code["class_code"], "class_conv is not in class_code"
+            if "cls_weight_norm" in code["class_code"]:
+                raise NotImplementedError("cls_weight_norm (SCALE_LAYER) is not supported")
+            w = code["class_code"]["cls_conv"]
+            b = code["class_code"]["cls_bias"]
+            assert b.numel() == 1, "predicted bias should only have batch size 1"
+            rows.append(torch.cat([w.reshape(-1).float().cpu(), b.reshape(-1).float().cpu()]))
+        raw = torch.stack(rows).to(self.engine.device)
+        normed = self.engine.normalize_codes(raw)
+        for i, code in enumerate(codes):
+            code["class_code"]["cls_conv"] = normed[i, :256].reshape(1, 256, 1, 1)
+            code["class_code"]["cls_bias"] = normed[i, 256:].reshape(1)
+        return codes
+
+
+CODE_GENERATOR_REGISTRY._map["CodeGeneratorHead"] = CodeGenerator if not HAVE_DETECTRON2 else None  # same plugin, both names
+
+
+class _FCOSHeadHandle(nn.Module):
+    """Attribute tree the reference's freezing code touches (meta_one_stage_detector.py:117-155); no parameters."""
+
+    def __init__(self):
+        super().__init__()
+        for name in ("cls_tower", "bbox_tower", "share_tower", "cls_logits", "bbox_pred", "ctrness", "iou_overlap"):
+            self.add_module(name, nn.Sequential())
+
+
+@PROPOSAL_GENERATOR_REGISTRY.register()
+class MetaFCOS(_EngineBound):
+    """Drop-in for `MetaFCOS` (fcos.py:158-268): eval forward returns (List[Instances], {})."""
+
+    def __init__(self, cfg, input_shape: Dict[str, Any]):
+        super().__init__()
+        self.cfg = cfg
+        self.in_features = cfg.MODEL.FCOS.IN_FEATURES
+        self.fpn_strides = cfg.MODEL.FCOS.FPN_STRIDES
+        self.fcos_head = _FCOSHeadHandle()
+        self.in_channels_to_top_module = 256
+
+    def forward(self, images, features, gt_instances=None, top_module=None, support_set_per_class_code=None,
+                support_set_targets=None):
+        assert not self.training, "the B200 path implements inference only"
+        if support_set_per_class_code is None:
+            raise NotImplementedError("base-detector inference (cls_logits) is not implemented on the B200 path")
+        image_sizes = images.image_sizes if hasattr(images, "image_sizes") else images
+        if features is not None:  # NCHW features from a foreign backbone
+            feats = [features[f] for f in self.in_features]
+            h, w = feats[0].shape[-2:]
+            self.engine.import_features(SLOT_QUERY, feats, (h * self.fpn_strides[0], w * self.fpn_strides[0]))
+        return self.predict(support_set_per_class_code, image_sizes, image_sizes), {}
+
+    def predict(self, class_codes: Dict[str, torch.Tensor], image_sizes, out_sizes) -> List[Any]:
+        codes = pack_code_rows(class_codes).to(self.engine.device)
+        dets, counts = self.engine.detect(SLOT_QUERY, codes, out_sizes)
+        counts = counts.cpu().tolist()
+        results = []
+        for i, n in enumerate(counts):
+            d = dets[i, :n]
+            inst = Instances(tuple(int(v) for v in out_sizes[i]))
+            inst.pred_boxes = Boxes(d[:, 0:4])
+            inst.scores = d[:, 4]
+            inst.pred_classes = d[:, 5].to(torch.int64)
+            inst.locations = d[:, 6:8]
+            inst.fpn_levels = d[:, 8].to(torch.int64)
+            results.append(inst)
+        return results
+
+
+def pack_code_rows(class_codes: Dict[str, torch.Tensor]) -> torch.Tensor:
+    """{"cls_conv": (C, 256, 1, 1), "cls_bias": (C,)} -> (C, 257) rows of the C ABI."""
+    w = class_codes["cls_conv"]
+    assert w.dim() == 4 and w.shape[1] == 256 and w.shape[2] == 1 and w.shape[3] == 1, f"cls_conv has shape {tuple(w.shape)}"
+    b = class_codes["cls_bias"].reshape(-1, 1)
+    assert b.shape[0] == w.shape[0]
+    return torch.cat([w.reshape(w.shape[0], 256).float(), b.float().to(w.device)], dim=1).contiguous()
+
+
+class _BackboneHandle(_EngineBound):
+    """`build_fcos_resnet_fpn_backbone` stand-in: exposes `size_divisibility` / `output_shape()` and, when called with
+    a normalised (N, 3, H, W) batch, is not supported -- the fused prep+backbone entry takes raw images."""
+
+    size_divisibility = 32
+
+    def __init__(self, cfg):
+        super().__init__()
+        self._out = {f"p{3 + i}": ShapeSpec(channels=cfg.MODEL.FPN.OUT_CHANNELS, stride=8 << i) for i in range(5)}
+
+    def output_shape(self):
+        return self._out
+
+    def forward(self, x):
+        raise NotImplementedError("call MetaOneStageDetector with raw images: normalisation is fused into the stem")
+
+
+@BACKBONE_REGISTRY.register()
+def build_fcos_resnet_fpn_backbone(cfg, input_shape=None):
+    return _BackboneHandle(cfg)
+
+
+def build_backbone(cfg):
+    return BACKBONE_REGISTRY.get(cfg.MODEL.BACKBONE.NAME)(cfg, None)
+
+
+def build_proposal_generator(cfg, input_shape):
+    return PROPOSAL_GENERATOR_REGISTRY.get(cfg.MODEL.PROPOSAL_GENERATOR.NAME)(cfg, input_shape)
+
+
+@META_ARCH_REGISTRY.register()
+class MetaOneStageDetector(nn.Module):
+    """Drop-in for the reference meta-architecture in eval mode (meta_one_stage_detector.py:415-455)."""
+
+    def __init__(self, cfg):
+        super().__init__()
+        self.cfg = cfg
+        self.episodic_learning = cfg.MODEL.META_LEARN.EPISODIC_LEARNING
+        self.backbone = build_backbone(cfg)
+        self.proposal_generator = build_proposal_generator(cfg, self.backbone.output_shape())
+        shapes = [self.backbone.output_shape()[f] for f in cfg.MODEL.FCOS.IN_FEATURES]
+        self.code_generator = (build_code_generator(cfg, feature_channels=shapes[0].channels,
+                                                    feature_levels=len(shapes), strides=cfg.MODEL.FCOS.FPN_STRIDES)
+                               if self.episodic_learning else None)
+        if self.episodic_learning:
+            assert self.code_generator is not None
+        self.register_buffer("pixel_mean", torch.Tensor(cfg.MODEL.PIXEL_MEAN).view(-1, 1, 1))
+        self.register_buffer("pixel_std", torch.Tensor(cfg.MODEL.PIXEL_STD).view(-1, 1, 1))
+        self.in_features = cfg.MODEL.FCOS.IN_FEATURES
+        self._state: Dict[str, torch.Tensor] = {}
+        self._engine: Optional[Engine] = None
+        self.eval()
+
+    # ------------------------------------------------------------------ weights: reference key layout (Appendix C)
+    def load_state_dict(self, state_dict, strict: bool = True):  # type: ignore[override]
+        spec = state_spec(self.cfg)
+        missing = [k for k in spec if k not in state_dict]
+        unexpected = [k for k in state_dict if k not in spec]
+        if strict and (missing or unexpected):
+            raise RuntimeError(f"Error(s) in loading state_dict: missing {missing[:4]} unexpected {unexpected[:4]}")
+        for k, shp in spec.items():
+            if k in state_dict and tuple(state_dict[k].shape) != tuple(shp):
+                raise RuntimeError(f"size mismatch for {k}: {tuple(state_dict[k].shape)} vs {tuple(shp)}")
+        self._state = {k: state_dict[k].detach().cpu().float() for k in spec if k in state_dict}
+        dev = self.pixel_mean.device
+        index = dev.index if dev.type == "cuda" and dev.index is not None else (torch.cuda.current_device() if torch.cuda.is_available() else 0)
+        self._engine = Engine(self.cfg, index)
+        self._engine.load_state_dict(self._state)
+        for m in (self.backbone, self.proposal_generator, self.code_generator):
+            if m is not None:
+                m.bind_engine(self._engine)
+        return self
+
+    def state_dict(self, *args, **kwargs):  # type: ignore[override]
+        return dict(self._state)
+
+    @property
+    def device(self):
+        return self._engine.device if self._engine is not None else self.pixel_mean.device
+
+    @property
+    def engine(self) -> Engine:
+        if self._engine is None:
+            raise RuntimeError("no weights loaded: call load_state_dict first (the B200 path has no CPU fallback)")
+        return self._engine
+
+    # ------------------------------------------------------------------ run_type protocol
+    def forward(self, batched_inputs, class_code=None, run_type=None):
+        if self.training:
+            raise NotImplementedError("training forward is outside the B200 inference path")
+        if run_type is None:
+            raise NotImplementedError("base-detector inference (run_type=None) is not implemented on the B200 path")
+        if run_type == "meta_learn_test_support":
+            return self.forward_class_code(batched_inputs)
+        if run_type == "meta_learn_normalize_code":
+            return self.normalize_class_code(class_code)
+        if run_type == "meta_learn_test_instance":
+            return self.forward_instances(batched_inputs, class_code)
+        raise NotImplementedError(f"not support this forward type: {run_type}, class_code: {class_code}")
+
+    def forward_class_code(self, batched_inputs: List[Dict[str, Any]]) -> Dict[str, torch.Tensor]:
+        """One class per call (assert at meta_one_stage_detector.py:238)."""
+        assert not self.training, "Not for training"
+        assert len(batched_inputs) == 1, f"batched_inputs has length: {len(batched_inputs)}"
+        return self.forward_class_codes_batched(batched_inputs)[0]
+
+    def forward_class_codes_batched(self, batched_inputs: List[Dict[str, Any]]) -> List[Dict[str, torch.Tensor]]:
+        """B200-native extension: the support sets of MANY classes through one backbone batch and one code-generation
+        launch sequence; result[i] equals forward_class_code([batched_inputs[i]])."""
+        records, offsets = [], [0]
+        for item in batched_inputs:
+            records.extend(item["support_set"])
+            offsets.append(len(records))
+        boxes = torch.cat([b.reshape(-1, 4)[:1].cpu() for b in select_a_mask([r["instances"] for r in records])], dim=0)
+        self.engine.extract_features(SLOT_SUPPORT, [r["image"] for r in records])
+        raw = self.engine.generate_codes(SLOT_SUPPORT, boxes, list(range(len(records))), offsets)
+        return [{"cls_conv": raw[i:i + 1, :256].reshape(1, 256, 1, 1), "cls_bias": raw[i:i + 1, 256:].reshape(1, 1, 1, 1)}
+                for i in range(len(batched_inputs))]
+
+    def normalize_class_code(self, codes: List[Dict]):
+        assert self.episodic_learning
+        assert not self.training
+        return self.code_generator(features=None, target_instances=None, cls_norm=True, class_codes=codes)
+
+    def forward_instances(self, batched_inputs: List[Dict[str, Any]], class_codes: Dict[str, torch.Tensor]):
+        assert self.episodic_learning
+        assert not self.training, "Not for training"
+        images = [x["image"] for x in batched_inputs]
+        self.engine.extract_features(SLOT_QUERY, images)
+        sizes = [(int(im.shape[-2]), int(im.shape[-1])) for im in images]
+        out_sizes = [(int(x.get("height", s[0])), int(x.get("width", s[1]))) for x, s in zip(batched_inputs, sizes)]
+        results = self.proposal_generator.predict(class_codes, sizes, out_sizes)
+        return [{"instances": r} for r in results]
+
+
+def build_model(cfg) -> MetaOneStageDetector:
+    """`runner.build_model(cfg)` equivalent: META_ARCH_REGISTRY lookup by cfg.MODEL.META_ARCHITECTURE."""
+    return META_ARCH_REGISTRY.get(cfg.MODEL.META_ARCHITECTURE)(cfg)

@@ -1,0 +1,198 @@
+"""Thin Python handle over the C-ABI context: torch is used only for device memory and the current CUDA stream."""
+from __future__ import annotations
+
+import ctypes
+from ctypes import POINTER, byref, c_char, c_double, c_float, c_int, c_int64, c_void_p
+from typing import Dict, List, Optional, Sequence, Tuple
+
+import torch
+
+from . import _lib
+from ._lib import CODE_STRIDE, DET_STRIDE, NUM_LEVELS, SLOT_QUERY, SLOT_SUPPORT, ModelConfig
+
+
+def model_config_from_cfg(cfg) -> ModelConfig:
+    """Collect the config keys the hot path reads into the C struct."""
+    F, G = cfg.MODEL.FCOS, cfg.MODEL.META_LEARN.CODE_GENERATOR
+    if cfg.MODEL.META_LEARN.CODE_GENERATOR.NAME not in ("CodeGenerator", "CodeGeneratorHead"):
+        raise NotImplementedError("only the CodeGenerator hypernetwork is implemented on the B200 path")
+    if F.NORM != "GN" or F.USE_DEFORMABLE or F.NUM_SHARE_CONVS != 0 or list(F.IN_FEATURES) != ["p3", "p4", "p5", "p6", "p7"]:
+        raise NotImplementedError("FCOS head variant outside the shipped Meta-FCOS configs")
+    if list(F.FPN_STRIDES) != [8, 16, 32, 64, 128] or int(F.TOP_LEVELS) != 2:
+        raise NotImplementedError("only the p3..p7 pyramid (strides 8..128) is implemented")
+    if cfg.MODEL.RESNETS.NORM != "FrozenBN" or not cfg.MODEL.RESNETS.STRIDE_IN_1X1:
+        raise NotImplementedError("backbone must use FrozenBN and STRIDE_IN_1X1 (inference path)")
+    for layer in G.TOWER_LAYERS:
+        if list(layer) != ["GN", "ReLU"]:
+            raise NotImplementedError("CODE_GENERATOR.TOWER_LAYERS entries must be ['GN', 'ReLU']")
+    if list(G.CLS_LAYER) != ["", "", 1]:
+        raise NotImplementedError("CODE_GENERATOR.CLS_LAYER must be ['', '', 1]")
+    if len(G.WEIGHT_LAYER) or len(G.SCALE_LAYER) or G.COMPRESS_CODE_W_MAX or G.ROI_BOX.FPN_MULTILEVEL_FEATURE:
+        raise NotImplementedError("WEIGHT_LAYER / SCALE_LAYER / COMPRESS_CODE_W_MAX / multilevel ROI are not implemented")
+    if G.ROI_BOX.POOLER_TYPE != "ROIAlignV2" or int(G.ROI_BOX.POOLER_RESOLUTION) != 7:
+        raise NotImplementedError("ROI pooler must be ROIAlignV2 at 7x7")
+    if cfg.MODEL.PROPOSAL_GENERATOR.OWD:
+        raise NotImplementedError("OWD scoring is not implemented")
+    quality = sorted(F.BOX_QUALITY)
+    mc = ModelConfig()
+    mc.resnet_depth = int(cfg.MODEL.RESNETS.DEPTH)
+    mc.num_cls_convs, mc.num_box_convs = int(F.NUM_CLS_CONVS), int(F.NUM_BOX_CONVS)
+    mc.use_scale = int(bool(F.USE_SCALE))
+    mc.thresh_with_ctr = int(bool(F.THRESH_WITH_CTR))
+    mc.box_quality = (1 if "ctrness" in quality else 0) | (2 if "iou" in quality else 0)
+    mc.pre_nms_topk, mc.post_nms_topk = int(F.PRE_NMS_TOPK_TEST), int(F.POST_NMS_TOPK_TEST)
+    mc.inference_thresh, mc.nms_thresh, mc.prior_prob = float(F.INFERENCE_TH_TEST), float(F.NMS_TH), float(F.PRIOR_PROB)
+    for i in range(3):
+        mc.pixel_mean[i] = float(cfg.MODEL.PIXEL_MEAN[i])
+        mc.pixel_std[i] = float(cfg.MODEL.PIXEL_STD[i])
+    mc.cg_tower_layers = len(G.TOWER_LAYERS)
+    mc.cg_post_norm = int(G.POST_NORM == "GN")
+    if G.POST_NORM not in ("", "GN"):
+        raise NotImplementedError("POST_NORM must be '' or 'GN'")
+    mc.cg_conv_l2_norm = int(bool(G.CONV_L2_NORM))
+    mc.cg_bias_layer = int(len(G.BIAS_LAYER) == 3)
+    mc.cg_bias_l2_norm = int(bool(G.BIAS_L2_NORM))
+    mc.cg_use_bias = int(bool(G.USE_BIAS))
+    mc.cg_has_conv_scale = int(bool(G.USE_WEIGHT_SCALE and (G.CONV_L2_NORM or G.POST_NORM != "")))
+    return mc
+
+
+class Engine:
+    """One context per device.  Raises RuntimeError with the library's message on any non-zero status."""
+
+    def __init__(self, cfg, device: int = 0):
+        if not torch.cuda.is_available():
+            raise RuntimeError("sylph_b200 needs a CUDA device (sm_100a); there is no CPU fallback")
+        self.lib = _lib.load()
+        self.device = torch.device("cuda", device)
+        self.cfg = cfg
+        self.mc = model_config_from_cfg(cfg)
+        self.post_nms_topk = self.mc.post_nms_topk
+        h = c_void_p()
+        rc = self.lib.sylph_create(byref(h), device, byref(self.mc))
+        if rc != 0 or not h:
+            raise RuntimeError(f"sylph_create failed with status {rc} (needs an sm_100 device)")
+        self.h = h
+        self._loaded = False
+
+    def __del__(self):
+        try:
+            if getattr(self, "h", None):
+                self.lib.sylph_destroy(self.h)
+                self.h = None
+        except Exception:
+            pass
+
+    def _check(self, rc: int) -> None:
+        if rc != 0:
+            raise RuntimeError("sylph_b200: " + self.lib.sylph_last_error(self.h).decode())
+
+    @staticmethod
+    def _stream() -> c_void_p:
+        return c_void_p(torch.cuda.current_stream().cuda_stream)
+
+    # ------------------------------------------------------------------ weights
+    def load_state_dict(self, state: Dict[str, torch.Tensor]) -> None:
+        for k, v in state.items():
+            t = v.detach().to("cpu", torch.float32).contiguous()
+            shape = (c_int64 * max(t.dim(), 1))(*t.shape)
+            self._check(self.lib.sylph_load_tensor(self.h, k.encode(), c_void_p(t.data_ptr()), shape, t.dim()))
+        self._check(self.lib.sylph_finalize_weights(self.h))
+        self._loaded = True
+
+    # ------------------------------------------------------------------ features
+    def extract_features(self, slot: int, images: Sequence[torch.Tensor]) -> None:
+        imgs = [im.to(self.device, torch.float32).contiguous() for im in images]
+        n = len(imgs)
+        ptrs = (c_void_p * n)(*[im.data_ptr() for im in imgs])
+        hs = (c_int * n)(*[int(im.shape[-2]) for im in imgs])
+        ws = (c_int * n)(*[int(im.shape[-1]) for im in imgs])
+        self._check(self.lib.sylph_extract_features(self.h, slot, n, ptrs, hs, ws, self._stream()))
+        self._keep = imgs  # keep inputs alive until the stream work is done
+
+    def import_features(self, slot: int, features: Sequence[torch.Tensor], padded_hw: Tuple[int, int]) -> None:
+        feats = [f.to(self.device, torch.float32).contiguous() for f in features]
+        assert len(feats) == NUM_LEVELS and all(f.shape[1] == 256 for f in feats)
+        n = feats[0].shape[0]
+        ptrs = (c_void_p * NUM_LEVELS)(*[f.data_ptr() for f in feats])
+        lh = (c_int * NUM_LEVELS)(*[int(f.shape[2]) for f in feats])
+        lw = (c_int * NUM_LEVELS)(*[int(f.shape[3]) for f in feats])
+        self._check(self.lib.sylph_import_features(self.h, slot, n, int(padded_hw[0]), int(padded_hw[1]), ptrs, lh, lw,
+                                                   self._stream()))
+        self._keep = feats
+
+    def feature_shape(self, slot: int):
+        n, ph, pw = c_int(), c_int(), c_int()
+        lh, lw = (c_int * NUM_LEVELS)(), (c_int * NUM_LEVELS)()
+        self._check(self.lib.sylph_feature_shape(self.h, slot, byref(n), byref(ph), byref(pw), lh, lw))
+        return n.value, ph.value, pw.value, list(lh), list(lw)
+
+    def export_features(self, slot: int, level: int) -> torch.Tensor:
+        n, _, _, lh, lw = self.feature_shape(slot)
+        out = torch.empty((n, 256, lh[level], lw[level]), device=self.device, dtype=torch.float32)
+        self._check(self.lib.sylph_export_features(self.h, slot, level, c_void_p(out.data_ptr()), self._stream()))
+        return out
+
+    # ------------------------------------------------------------------ class codes
+    def generate_codes(self, slot: int, boxes: torch.Tensor, roi_image: Sequence[int], class_offsets: Sequence[int],
+                       want_levels: bool = False):
+        boxes = boxes.detach().to("cpu", torch.float32).contiguous()
+        n_rois, n_classes = boxes.shape[0], len(class_offsets) - 1
+        codes = torch.empty((n_classes, CODE_STRIDE), device=self.device, dtype=torch.float32)
+        levels = torch.empty((n_rois,), device=self.device, dtype=torch.int64) if want_levels else None
+        ri = (c_int * n_rois)(*[int(i) for i in roi_image])
+        co = (c_int * (n_classes + 1))(*[int(i) for i in class_offsets])
+        self._check(self.lib.sylph_generate_codes(
+            self.h, slot, n_rois, ctypes.cast(c_void_p(boxes.data_ptr()), POINTER(c_float)), ri, n_classes, co,
+            c_void_p(codes.data_ptr()), c_void_p(levels.data_ptr()) if want_levels else None, self._stream()))
+        return (codes, levels) if want_levels else codes
+
+    def export_roi_features(self, n_rois: int) -> torch.Tensor:
+        out = torch.empty((n_rois, 256, 7, 7), device=self.device, dtype=torch.float32)
+        self._check(self.lib.sylph_export_roi_features(self.h, c_void_p(out.data_ptr()), self._stream()))
+        return out
+
+    def normalize_codes(self, raw: torch.Tensor) -> torch.Tensor:
+        raw = raw.to(self.device, torch.float32).contiguous()
+        out = torch.empty_like(raw)
+        self._check(self.lib.sylph_normalize_codes(self.h, c_void_p(raw.data_ptr()), c_void_p(out.data_ptr()),
+                                                   raw.shape[0], self._stream()))
+        return out
+
+    # ------------------------------------------------------------------ detection
+    def detect(self, slot: int, codes: torch.Tensor, out_sizes: Optional[Sequence[Tuple[int, int]]] = None,
+               max_dets: Optional[int] = None):
+        codes = codes.to(self.device, torch.float32).contiguous()
+        n = self.feature_shape(slot)[0]
+        max_dets = max_dets or min(1024, max(self.post_nms_topk * 2, 128))
+        dets = torch.zeros((n, max_dets, DET_STRIDE), device=self.device, dtype=torch.float32)
+        counts = torch.zeros((n,), device=self.device, dtype=torch.int32)
+        sizes = None
+        if out_sizes is not None:
+            flat = [int(v) for hw in out_sizes for v in hw]
+            sizes = (c_int * len(flat))(*flat)
+        self._check(self.lib.sylph_detect(self.h, slot, c_void_p(codes.data_ptr()), codes.shape[0], sizes,
+                                          c_void_p(dets.data_ptr()), c_void_p(counts.data_ptr()), max_dets, self._stream()))
+        return dets, counts
+
+    def export_head_output(self, which: int, level: int, slot: int, n_classes: int) -> torch.Tensor:
+        n, _, _, lh, lw = self.feature_shape(slot)
+        ch = {0: n_classes, 1: 4, 2: 1, 3: 1}[which]
+        out = torch.empty((n, ch, lh[level], lw[level]), device=self.device, dtype=torch.float32)
+        self._check(self.lib.sylph_export_head_output(self.h, which, level, c_void_p(out.data_ptr()), self._stream()))
+        return out
+
+    # ------------------------------------------------------------------ instrumentation
+    def launch_count(self) -> int:
+        return int(self.lib.sylph_launch_count(self.h))
+
+    def set_profiling(self, on: bool) -> None:
+        self._check(self.lib.sylph_set_profiling(self.h, int(on)))
+
+    def timings(self, cap: int = 4096):
+        names = ((c_char * 48) * cap)()
+        ms = (c_float * cap)()
+        fl = (c_double * cap)()
+        by = (c_double * cap)()
+        n = self.lib.sylph_get_timings(self.h, names, ms, fl, by, cap)
+        return [(names[i].value.decode(), ms[i], fl[i], by[i]) for i in range(min(n, cap))]

