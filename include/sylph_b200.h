@@ -77,6 +77,10 @@ int sylph_finalize_weights(sylph_ctx* ctx);
 int sylph_extract_features(sylph_ctx* ctx, int slot, int n_images, const float* const* images_dev, const int* heights,
                            const int* widths, void* stream);
 
+/* Same, for uint8 images (what detectron2's DatasetMapper hands to the model; 4x less host-to-device traffic). */
+int sylph_extract_features_u8(sylph_ctx* ctx, int slot, int n_images, const uint8_t* const* images_dev,
+                              const int* heights, const int* widths, void* stream);
+
 /* Plugin-level entry for features produced elsewhere (NCHW fp32 device tensors, one per level, (n, 256, H_l, W_l)):
  * the `features` argument of CodeGenerator.forward, sylph/modeling/code_generator/code_generator.py:1037-1053. */
 int sylph_import_features(sylph_ctx* ctx, int slot, int n_images, int padded_h, int padded_w,

@@ -22,9 +22,11 @@ def load():
     """Returns a namespace with the reference classes needed on the hot path."""
     if not available():
         raise RuntimeError(f"reference tree not found at {REFERENCE_ROOT}")
-    for p in (_REPO, _SHIMS, REFERENCE_ROOT):
+    for p in (_REPO, _SHIMS):
         if p not in sys.path:
             sys.path.insert(0, p)
+    if REFERENCE_ROOT not in sys.path:
+        sys.path.append(REFERENCE_ROOT)  # last: the reference has its own top-level `tests` package
     # `sylph/modeling/meta_arch/__init__.py:10-11` also imports the RCNN meta-archs (out of scope, need more of
     # detectron2); register an empty package in its place and load the one-stage file by path.
     if "sylph.modeling.meta_arch" not in sys.modules:

@@ -600,8 +600,8 @@ static int setup_slot(sylph_ctx* c, int slot, int n, int hpad, int wpad, const i
     return 0;
 }
 
-static int run_backbone(sylph_ctx* c, int slot, int n, const float* const* images_dev, const int* hs, const int* ws,
-                        cudaStream_t st) {
+static int run_backbone(sylph_ctx* c, int slot, int n, const void* const* images_dev, int is_u8, const int* hs,
+                        const int* ws, cudaStream_t st) {
     const sylph_model_config& f = c->cfg;
     int hmax = 0, wmax = 0;
     for (int i = 0; i < n; ++i) { hmax = std::max(hmax, hs[i]); wmax = std::max(wmax, ws[i]); }
@@ -637,7 +637,7 @@ static int run_backbone(sylph_ctx* c, int slot, int n, const float* const* image
     TRY(buf("bb.s1", rows0, 64, false, &S1));
     // ---- image descriptors
     std::vector<ImageDesc> descs(n);
-    for (int i = 0; i < n; ++i) { descs[i].ptr = images_dev[i]; descs[i].h = hs[i]; descs[i].w = ws[i]; }
+    for (int i = 0; i < n; ++i) { descs[i].ptr = images_dev[i]; descs[i].h = hs[i]; descs[i].w = ws[i]; descs[i].is_u8 = is_u8; }
     void* d_desc;
     TRY(ensure(c, "bb.desc", n * sizeof(ImageDesc), "", &d_desc, st, false));
     CU_TRY(c, cudaMemcpyAsync(d_desc, descs.data(), n * sizeof(ImageDesc), cudaMemcpyHostToDevice, st));
@@ -804,7 +804,18 @@ int sylph_extract_features(sylph_ctx* c, int slot, int n_images, const float* co
     if (!c->finalized) return c->fail("weights not finalized");
     if (slot < 0 || slot >= SYLPH_NUM_SLOTS || n_images <= 0) return c->fail("bad slot / image count");
     CU_TRY(c, cudaSetDevice(c->device));
-    return run_backbone(c, slot, n_images, images_dev, heights, widths, static_cast<cudaStream_t>(stream));
+    return run_backbone(c, slot, n_images, reinterpret_cast<const void* const*>(images_dev), 0, heights, widths,
+                        static_cast<cudaStream_t>(stream));
+}
+
+int sylph_extract_features_u8(sylph_ctx* c, int slot, int n_images, const uint8_t* const* images_dev, const int* heights,
+                              const int* widths, void* stream) {
+    if (!c) return 1;
+    if (!c->finalized) return c->fail("weights not finalized");
+    if (slot < 0 || slot >= SYLPH_NUM_SLOTS || n_images <= 0) return c->fail("bad slot / image count");
+    CU_TRY(c, cudaSetDevice(c->device));
+    return run_backbone(c, slot, n_images, reinterpret_cast<const void* const*>(images_dev), 1, heights, widths,
+                        static_cast<cudaStream_t>(stream));
 }
 
 int sylph_import_features(sylph_ctx* c, int slot, int n_images, int padded_h, int padded_w,

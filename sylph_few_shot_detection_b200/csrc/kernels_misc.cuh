@@ -23,8 +23,9 @@ __device__ __forceinline__ size_t plane_row(const PlaneGeom& g, int n, int y, in
 // (sylph/modeling/meta_arch/meta_one_stage_detector.py:174-178), fused with the 2x2 space-to-depth re-layout that
 // turns the 7x7/2 stem convolution into a 4x4/1 convolution over 12 (padded to 16) channels.
 struct ImageDesc {
-    const float* ptr;  // (3, h, w) fp32
+    const void* ptr;  // (3, h, w) fp32 or uint8
     int h, w;
+    int is_u8;
 };
 
 __global__ void prep_stem_input_kernel(const ImageDesc* __restrict__ imgs, float* __restrict__ out, PlaneGeom g,
@@ -48,7 +49,12 @@ __global__ void prep_stem_input_kernel(const ImageDesc* __restrict__ imgs, float
 #pragma unroll
                 for (int c = 0; c < 3; ++c) {
                     float t = 0.f;
-                    if (in) t = (__ldg(im.ptr + (static_cast<size_t>(c) * im.h + iy) * im.w + ix) - mean[c]) / stdv[c];
+                    if (in) {
+                        const size_t off = (static_cast<size_t>(c) * im.h + iy) * im.w + ix;
+                        const float px = im.is_u8 ? static_cast<float>(__ldg(static_cast<const unsigned char*>(im.ptr) + off))
+                                                  : __ldg(static_cast<const float*>(im.ptr) + off);
+                        t = (px - mean[c]) / stdv[c];
+                    }
                     v[(dy * 2 + dx) * 3 + c] = ptx::round_tf32(t);
                 }
             }

@@ -137,7 +137,14 @@ class CodeGenerator(_EngineBound):
         return codes
 
 
-CODE_GENERATOR_REGISTRY._map["CodeGeneratorHead"] = CodeGenerator if not HAVE_DETECTRON2 else None  # same plugin, both names
+def _register_alias(registry, name: str, obj) -> None:
+    if hasattr(registry, "_do_register"):  # fvcore / detectron2 Registry
+        registry._do_register(name, obj)
+    else:
+        registry._map[name] = obj
+
+
+_register_alias(CODE_GENERATOR_REGISTRY, "CodeGeneratorHead", CodeGenerator)  # the reference registers both names
 
 
 class _FCOSHeadHandle(nn.Module):

@@ -1,0 +1,157 @@
+"""Meta-test orchestration: the callers of the hot path, restated for the B200 build.
+
+Mirrors, step for step, `MetaFCOSRunner._do_test_meta_learning` (sylph/runner/meta_fcos_runner.py:451-672, SURVEY.md
+section 3.2):
+  B. inference_on_support_set_dataset ........ sylph/evaluation/meta_learn_evaluation.py:256-365
+  C. _gather_class_code ...................... sylph/runner/meta_fcos_runner.py:381-439
+  D. inference_normalization ................. sylph/evaluation/meta_learn_evaluation.py:105-116
+  E. format_class_codes_shared ............... sylph/evaluation/meta_learn_evaluation.py:71-103
+  F. inference_on_dataset_with_class_codes ... sylph/evaluation/meta_learn_evaluation.py:367-470
+The reference runs B and F as batch-1 Python loops with a device synchronise per item; here all classes of a rank
+go through one backbone batch and one code-generation launch sequence, all query images through one head launch
+sequence, and the gather moves a fixed-stride (classes, 257) fp32 DEVICE buffer with one NCCL all-gather instead of
+pickled CPU tensors through all_gather_object.
+"""
+from __future__ import annotations
+
+from typing import Any, Dict, List, Optional, Sequence
+
+import torch
+import torch.distributed as dist
+
+from .config import CfgNode, get_default_cfg
+from .modeling import META_ARCH_REGISTRY, MetaOneStageDetector, build_model
+
+CODE_STRIDE = 257
+
+
+def shard_range(n_items: int, world: int, rank: int) -> range:
+    """Contiguous, balanced shards -- detectron2 `InferenceSampler._get_local_indices` (recent versions): the first
+    `n % world` ranks get one extra item.  (sylph/data/build.py:578-592 builds the support loader with it.)"""
+    base, extra = divmod(n_items, world)
+    begin = rank * base + min(rank, extra)
+    return range(begin, begin + base + (1 if rank < extra else 0))
+
+
+def inference_on_support_set(model: MetaOneStageDetector, support_items: Sequence[Dict[str, Any]]) -> List[Dict]:
+    """Step B for this rank's classes.  Each item: {"support_set": [K records], "support_set_target", "class_name"}.
+    Returns the reference's list schema (meta_learn_evaluation.py:305-326) with RAW codes on the device."""
+    if len(support_items) == 0:
+        return []
+    with torch.no_grad():
+        codes = model.forward_class_codes_batched(list(support_items))
+    out = []
+    for item, code in zip(support_items, codes):
+        out.append({"support_set_target": item["support_set_target"], "class_name": item.get("class_name", ""),
+                    "class_code": code})
+    return out
+
+
+def _target_id(t) -> int:
+    return int(t.item()) if torch.is_tensor(t) else int(t)
+
+
+def gather_class_code(sub_class_codes: List[Dict], group=None, device: Optional[torch.device] = None) -> List[Dict]:
+    """Step C: all ranks end up with the codes of ALL classes, ordered by rank then local order (what concatenating
+    the all_gather_object output gives, meta_fcos_runner.py:386-396).  One all-gather of a padded
+    [max_shard, 258] fp32 buffer (257 code floats + class id; class names travel separately only if present).
+    World size 1 short-circuits like the reference (:430-431)."""
+    if not dist.is_available() or not dist.is_initialized() or dist.get_world_size(group) == 1:
+        return sub_class_codes
+    world = dist.get_world_size(group)
+    backend = dist.get_backend(group)
+    if device is None:
+        device = torch.device("cuda", torch.cuda.current_device()) if backend == "nccl" else torch.device("cpu")
+    n_local = torch.tensor([len(sub_class_codes)], dtype=torch.int64, device=device)
+    counts = [torch.zeros_like(n_local) for _ in range(world)]
+    dist.all_gather(counts, n_local, group=group)
+    counts = [int(c) for c in counts]
+    max_n = max(max(counts), 1)
+    buf = torch.zeros((max_n, CODE_STRIDE + 1), dtype=torch.float32, device=device)
+    for i, c in enumerate(sub_class_codes):
+        buf[i, :256] = c["class_code"]["cls_conv"].reshape(-1).to(device)
+        buf[i, 256] = c["class_code"]["cls_bias"].reshape(-1)[0].to(device)
+        buf[i, 257] = float(_target_id(c["support_set_target"]))
+    gathered = torch.empty((world * max_n, CODE_STRIDE + 1), dtype=torch.float32, device=device)
+    dist.all_gather_into_tensor(gathered, buf, group=group)
+    names = [None] * world
+    dist.all_gather_object(names, [c.get("class_name", "") for c in sub_class_codes], group=group)
+    out = []
+    for r in range(world):
+        for i in range(counts[r]):
+            row = gathered[r * max_n + i]
+            out.append({"support_set_target": torch.tensor(int(row[257].item())), "class_name": names[r][i],
+                        "class_code": {"cls_conv": row[:256].reshape(1, 256, 1, 1).clone(),
+                                       "cls_bias": row[256:257].reshape(1, 1, 1, 1).clone()}})
+    return out
+
+
+def inference_normalization(model: MetaOneStageDetector, all_class_codes: List[Dict]) -> List[Dict]:
+    """Step D (meta_learn_evaluation.py:105-116)."""
+    with torch.no_grad():
+        return model(None, class_code=all_class_codes, run_type="meta_learn_normalize_code")
+
+
+def format_class_codes_shared(all_class_codes: List[Dict], device=None) -> Dict[str, torch.Tensor]:
+    """Step E (meta_learn_evaluation.py:71-103): index by support_set_target, concatenate, flatten the bias."""
+    by_id = {}
+    for c in all_class_codes:
+        by_id[_target_id(c["support_set_target"])] = c["class_code"]
+    ids = sorted(by_id)
+    conv = torch.cat([by_id[i]["cls_conv"] for i in ids], dim=0)
+    bias = torch.cat([by_id[i]["cls_bias"].reshape(-1) for i in ids], dim=0)
+    if device is not None:
+        conv, bias = conv.to(device), bias.to(device)
+    return {"cls_conv": conv, "cls_bias": bias}
+
+
+def inference_with_class_codes(model: MetaOneStageDetector, query_items: Sequence[Dict[str, Any]],
+                               class_codes: Dict[str, torch.Tensor], batch_size: int = 16) -> List[Dict]:
+    """Step F for this rank's query images: [{"instances": Instances}] per image, in input order."""
+    out: List[Dict] = []
+    with torch.no_grad():
+        for i in range(0, len(query_items), batch_size):
+            out.extend(model(list(query_items[i:i + batch_size]), class_code=class_codes, run_type="meta_learn_test_instance"))
+    return out
+
+
+def run_episode(model: MetaOneStageDetector, support_items: Sequence[Dict[str, Any]], query_items: Sequence[Dict[str, Any]],
+                group=None, shard: bool = True) -> List[Dict]:
+    """One meta-test episode (steps B-F).  With a process group and `shard=True`, classes and query images are split
+    contiguously over the ranks (InferenceSampler semantics) with ONE collective in between; each rank returns the
+    detections of its own query shard."""
+    world = dist.get_world_size(group) if (dist.is_available() and dist.is_initialized()) else 1
+    rank = dist.get_rank(group) if world > 1 else 0
+    if world > 1 and shard:
+        my_support = [support_items[i] for i in shard_range(len(support_items), world, rank)]
+        my_query = [query_items[i] for i in shard_range(len(query_items), world, rank)]
+    else:
+        my_support, my_query = list(support_items), list(query_items)
+    sub_codes = inference_on_support_set(model, my_support)
+    all_codes = gather_class_code(sub_codes, group=group) if (world > 1 and shard) else sub_codes
+    all_codes = inference_normalization(model, all_codes)
+    packed = format_class_codes_shared(all_codes, device=model.device)
+    return inference_with_class_codes(model, my_query, packed)
+
+
+class MetaFCOSRunner:
+    """The d2go-runner surface the reference CLI drives (`create_runner("sylph.runner.MetaFCOSRunner")`,
+    sylph/runner/meta_fcos_runner.py:92-114, 381-382, 674-701), reduced to the inference hot path."""
+
+    def get_default_cfg(self) -> CfgNode:
+        return get_default_cfg()
+
+    def build_model(self, cfg, eval_only: bool = True) -> MetaOneStageDetector:
+        if not eval_only:
+            raise NotImplementedError("training is outside the B200 inference path")
+        return build_model(cfg)
+
+    @classmethod
+    def _gather_class_code(cls, sub_class_codes: List[Dict], reduce: bool = False) -> List[Dict]:
+        if reduce:
+            raise NotImplementedError("reduce_class_code (base-class all-GT path) is a 'next' row, SURVEY.md 8(f)")
+        return gather_class_code(sub_class_codes)
+
+    def do_test(self, cfg, model, support_items, query_items):
+        """Episode-level equivalent of `_do_test_meta_learning` for in-memory loaders."""
+        return run_episode(model, support_items, query_items)

@@ -102,12 +102,14 @@ class Engine:
 
     # ------------------------------------------------------------------ features
     def extract_features(self, slot: int, images: Sequence[torch.Tensor]) -> None:
-        imgs = [im.to(self.device, torch.float32).contiguous() for im in images]
+        u8 = all(im.dtype == torch.uint8 for im in images)
+        imgs = [im.to(self.device, torch.uint8 if u8 else torch.float32, non_blocking=True).contiguous() for im in images]
         n = len(imgs)
         ptrs = (c_void_p * n)(*[im.data_ptr() for im in imgs])
         hs = (c_int * n)(*[int(im.shape[-2]) for im in imgs])
         ws = (c_int * n)(*[int(im.shape[-1]) for im in imgs])
-        self._check(self.lib.sylph_extract_features(self.h, slot, n, ptrs, hs, ws, self._stream()))
+        fn = self.lib.sylph_extract_features_u8 if u8 else self.lib.sylph_extract_features
+        self._check(fn(self.h, slot, n, ptrs, hs, ws, self._stream()))
         self._keep = imgs  # keep inputs alive until the stream work is done
 
     def import_features(self, slot: int, features: Sequence[torch.Tensor], padded_hw: Tuple[int, int]) -> None:

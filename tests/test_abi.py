@@ -1,0 +1,54 @@
+"""The C-ABI library builds for sm_100a, loads without a GPU and exports every symbol include/sylph_b200.h declares.
+(No compute calls here: they need a device and live in the `-m gpu` tests.)"""
+import ctypes
+import os
+import re
+
+from sylph_few_shot_detection_b200 import _lib
+
+REPO = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _declared_functions():
+    text = open(os.path.join(REPO, "include", "sylph_b200.h")).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(sylph_[a-z0-9_]+)\s*\(", text)))
+
+
+def test_header_and_binding_agree():
+    declared = _declared_functions()
+    assert len(declared) >= 18
+    assert sorted(_lib.EXPORTED_SYMBOLS) == declared
+
+
+def test_library_loads_and_exports_every_declared_symbol():
+    _lib.build()
+    lib = _lib.load()
+    for name in _declared_functions():
+        assert hasattr(lib, name), f"{name} declared in include/sylph_b200.h but not exported"
+    assert b"sm_100a" in lib.sylph_version()
+
+
+def test_model_config_struct_layout_matches_header():
+    text = open(os.path.join(REPO, "include", "sylph_b200.h")).read()
+    body = text[text.index("typedef struct sylph_model_config {"):text.index("} sylph_model_config;")]
+    body = re.sub(r"/\*.*?\*/", "", body, flags=re.S)
+    fields = re.findall(r"\b(?:int|float)\s+([a-z_0-9]+)(?:\[3\])?;", body)
+    assert fields == [f[0] for f in _lib.ModelConfig._fields_]
+    assert ctypes.sizeof(_lib.ModelConfig) == 4 * (8 + 3 + 6 + 7)
+
+
+def test_create_fails_loudly_without_a_device():
+    import torch
+    if torch.cuda.is_available():
+        return
+    lib = _lib.load()
+    h = ctypes.c_void_p()
+    mc = _lib.ModelConfig()
+    rc = lib.sylph_create(ctypes.byref(h), 0, ctypes.byref(mc))
+    assert rc != 0 and not h, "there must be no CPU fallback"
+    import pytest
+    from sylph_few_shot_detection_b200.presets import coco_meta_fcos_cfg
+    from sylph_few_shot_detection_b200.runtime import Engine
+    with pytest.raises(RuntimeError):
+        Engine(coco_meta_fcos_cfg(), 0)

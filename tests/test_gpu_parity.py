@@ -11,7 +11,7 @@ candidates whose oracle score lies within `GUARD` of a decision threshold (SURVE
 import pytest
 import torch
 
-from tests.cases import cfg_for, load_golden, rel_err
+from tests.cases import cfg_for, load_golden, rel_err, rel_l2
 
 pytestmark = pytest.mark.gpu
 
@@ -56,8 +56,8 @@ def test_episode_matches_reference_golden(case):
     ref_feats = orc.features(il.tensor)
     for l in range(5):
         got = eng.export_features(SLOT_SUPPORT, l)
-        e = rel_err(got, ref_feats[l])
-        report.append((f"support p{l + 3}", e, REL_TOL))
+        report.append((f"support p{l + 3}", rel_err(got, ref_feats[l]), REL_TOL))
+        report.append((f"support p{l + 3} (L2)", rel_l2(got, ref_feats[l]), REL_TOL))
     raw, levels = eng.generate_codes(SLOT_SUPPORT, torch.stack(boxes), roi_image, offsets, want_levels=True)
     roi_ref, lvl_ref = orc.roi_features(ref_feats, torch.stack(boxes))
     assert torch.equal(levels.cpu(), lvl_ref), "FPN level assignment must be bit-exact"
@@ -79,6 +79,8 @@ def test_episode_matches_reference_golden(case):
     n_cls = packed.shape[0]
     for l in range(5):
         report.append((f"logits p{l + 3}", rel_err(eng.export_head_output(0, l, SLOT_QUERY, n_cls), g["logits"][l]), LOGIT_TOL))
+        report.append((f"logits p{l + 3} (L2)", rel_l2(eng.export_head_output(0, l, SLOT_QUERY, n_cls), g["logits"][l]), LOGIT_TOL))
+        report.append((f"ctr p{l + 3} (L2)", rel_l2(eng.export_head_output(2, l, SLOT_QUERY, n_cls), g["ctr"][l]), LOGIT_TOL))
         report.append((f"reg p{l + 3}", rel_err(eng.export_head_output(1, l, SLOT_QUERY, n_cls), g["reg"][l]), LOGIT_TOL))
         report.append((f"ctr p{l + 3}", rel_err(eng.export_head_output(2, l, SLOT_QUERY, n_cls), g["ctr"][l]), LOGIT_TOL))
     print()

@@ -1,0 +1,55 @@
+"""The CPU oracle (oracle/meta_fcos_oracle.py) against the golden vectors produced by the REFERENCE's own modules
+(oracle/make_golden.py ran them unmodified in the build container).  fp32 on CPU on both sides: agreement is expected
+to the last bits; the tolerance only allows for a different BLAS summation order on another host."""
+import pytest
+import torch
+
+from oracle.meta_fcos_oracle import MetaFCOSOracle
+from sylph_few_shot_detection_b200 import weights as W
+from tests.cases import cfg_for, load_golden, rel_err
+
+TOL = 2e-5
+
+
+@pytest.mark.parametrize("case", ["coco_2way_2shot", "lvis_1way_3shot"])
+def test_oracle_reproduces_reference_outputs(case):
+    g = load_golden(case)
+    cfg = cfg_for(g["config"])
+    state = W.synthetic_state_dict(cfg, g["seed"])
+    orc = MetaFCOSOracle(cfg, state)
+    normed = []
+    for c, shots in enumerate(g["support"]):
+        code = orc.class_code([s["image"].float() for s in shots], torch.stack([s["box"] for s in shots]))
+        assert code["cls_conv"].shape == (1, 256, 1, 1) and code["cls_bias"].shape == (1, 1, 1, 1)
+        assert rel_err(code["cls_conv"], g["raw_codes"][c]["cls_conv"]) < TOL
+        assert rel_err(code["cls_bias"], g["raw_codes"][c]["cls_bias"]) < TOL
+        w, b = orc.normalize_code(code["cls_conv"], code["cls_bias"])
+        assert b.shape == (1,)
+        assert rel_err(w, g["norm_codes"][c]["cls_conv"]) < TOL
+        assert rel_err(b, g["norm_codes"][c]["cls_bias"]) < TOL
+        normed.append({"support_set_target": c, "class_code": {"cls_conv": w, "cls_bias": b}})
+    packed = orc.pack_codes(normed)
+    assert packed["cls_conv"].shape == g["packed"]["cls_conv"].shape
+    assert packed["cls_bias"].shape == g["packed"]["cls_bias"].shape
+    dets, inter = orc.detect([q.float() for q in g["query"]], g["packed"], return_intermediate=True)
+    for l in range(5):
+        assert rel_err(inter["logits"][l], g["logits"][l]) < TOL
+        assert rel_err(inter["reg"][l], g["reg"][l]) < TOL
+        assert rel_err(inter["ctr"][l], g["ctr"][l]) < TOL
+    for d, r in zip(dets, g["detections"]):
+        assert d["scores"].numel() == r["scores"].numel() > 0
+        assert torch.equal(d["classes"], r["classes"])
+        assert torch.equal(d["levels"], r["levels"])
+        assert torch.equal(d["locations"], r["locations"])
+        assert rel_err(d["boxes"], r["boxes"]) < TOL
+        assert rel_err(d["scores"], r["scores"]) < TOL
+
+
+def test_golden_vectors_cover_the_interesting_regimes():
+    g = load_golden("coco_2way_2shot")
+    # post-NMS top-k saturated on one image, not on the other; several FPN levels contribute
+    counts = [int(d["scores"].numel()) for d in g["detections"]]
+    assert max(counts) == 100 and min(counts) < 100
+    assert len(set(int(v) for v in g["detections"][0]["levels"])) >= 2
+    g = load_golden("lvis_1way_3shot")
+    assert len(g["support"]) == 1 and len(g["support"][0]) == 3
