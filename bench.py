@@ -279,12 +279,12 @@ def main():
             avg_ms = sum(tower) / len(tower)
             achieved = TOWER_FLOP_PER_IMAGE_LAYER * N_QUERY / (avg_ms * 1e-3) * 1e-12
             peak = float(peaks["bf16_tflops_sustained"])
-            roofline = {"kernel": "conv_gemm_tf32_kernel<256,4> (FCOS tower 3x3 256->256, all levels x 8 images)",
+            roofline = {"kernel": "conv_gemm_f16_kernel<256,4> (FCOS tower 3x3 256->256, all levels x 8 images)",
                         "bound": "tensor", "achieved": round(achieved, 1), "peak": peak, "unit": "TFLOP/s",
                         "frac": round(achieved / peak, 4), "traffic": None,
                         "avg_launch_ms": round(avg_ms, 4), "launches_timed": len(tower),
                         "peak_source": f"MEASURED_PEAKS.json bf16_tflops_sustained ({peaks['source']}); the kernel issues "
-                                       f"tcgen05.mma kind::tf32 whose dense rate is half of bf16, so frac 0.5 == TF32 peak",
+                                       f"tcgen05.mma kind::f16 (fp16 operands, fp32 accumulate), same dense rate as bf16",
                         "flop_per_launch": TOWER_FLOP_PER_IMAGE_LAYER * N_QUERY}
         if args.profile_out:
             with open(args.profile_out, "w") as f:
@@ -297,7 +297,7 @@ def main():
     if rank == 0:
         out = {"metric": "episodes/sec 5-way 5-shot Meta-FCOS R-50", "value": round(value, 3), "unit": "episodes/s",
                "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": round(ms / args.steps, 3),
-               "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "tf32",
+               "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f16",
                "data": "synthetic", "config": config,
                "e2e": {"value": round(e2e_value, 3), "unit": "episodes/s", "h2d_bytes_per_step": int(h2d),
                        "d2h_bytes_per_step": int(d2h), "ms_per_step": round(ms_e2e / args.steps, 3)},

@@ -1,0 +1,1 @@
+__sylph_shim__ = True  # stand-in package: the product must never bind to it (see structures.py)

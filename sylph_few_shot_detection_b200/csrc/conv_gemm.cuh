@@ -1,6 +1,6 @@
-// Implicit-GEMM convolution on the 5th-gen tensor cores (tcgen05, TF32 in / FP32 accumulate in TMEM).
+// Implicit-GEMM convolution on the 5th-gen tensor cores (tcgen05, FP16 operands / FP32 accumulate in TMEM).
 //
-// Data layout ("flat padded planes"): every activation tensor is a row-major matrix [rows][C] of fp32 where a row
+// Data layout ("flat padded planes"): every activation tensor is a row-major matrix [rows][C] of fp16 where a row
 // is one pixel of a zero-bordered NHWC plane (border = `pad` pixels on every side) and the planes of all images /
 // FPN levels are concatenated, each plane starting on a multiple of 128 rows.  In that layout a k x k stride-1
 // convolution is a sum over taps of plain GEMMs whose A operand is the same matrix shifted by
@@ -8,25 +8,35 @@
 // FPN levels and all images run as ONE launch.  Border rows are recomputed as garbage and zeroed by the epilogue,
 // which keeps the zero-border invariant for the next layer.
 //
-// Kernel structure (persistent, one CTA per SM, 192 threads):
-//   warp 0   : TMA producer  (A box 128 x 32 fp32, B box BN x 32 fp32, 128-byte swizzle, STAGES-deep mbarrier ring)
+// Precision: operands carry a 10-bit mantissa (fp16; the same operand precision as the TF32 path PyTorch/cuDNN use
+// by default for fp32 convolutions on GPUs), products and sums are exact/FP32 in the tensor core, every epilogue
+// (bias, residual, ReLU, GroupNorm statistics) is FP32, stores round to nearest.  Values are clamped to the finite
+// fp16 range on store.
+//
+// Kernel structure (persistent, one CTA per SM, 320 threads):
+//   warp 0   : TMA producer  (A box 128 x 64 fp16, B box BN x 64 fp16, 128-byte swizzle, STAGES-deep mbarrier ring)
 //   warp 1   : tcgen05.mma issuer (one thread), TMEM owner (2 accumulator buffers x BN columns)
-//   warps 2-5: epilogue: tcgen05.ld -> bias / residual / ReLU / border mask / TF32 rounding / GroupNorm partial sums
-//              -> vectorised global stores, overlapped with the next tile's MMAs through the second TMEM buffer.
+//   warps 2-9: epilogue, two warps per TMEM lane quadrant (each takes half of the BN columns): residual prefetch
+//              (issued before the accumulator is ready) -> tcgen05.ld -> bias / residual / ReLU / border mask /
+//              GroupNorm partial sums -> fp16 (or fp32) vector stores, overlapped with the next tile's MMAs through
+//              the second TMEM buffer.
 //
 // Replaces the cuDNN convolutions reached from detectron2/AdelaiDet modules at
 //   sylph/modeling/meta_arch/meta_one_stage_detector.py:180-182 (backbone), sylph/modeling/meta_fcos/fcos.py:625-664
 //   (towers, predictors), sylph/modeling/code_generator/code_generator.py:941-960 (support tower / cls conv).
 #pragma once
+#include <cuda_fp16.h>
+
 #include "ptx_sm100.cuh"
 
 namespace sylph {
 
 constexpr int kBlockM = 128;
-constexpr int kBlockK = 32;   // fp32 elements = one 128-byte swizzle row
-constexpr int kUmmaK = 8;     // tf32: 32 bytes of K per tcgen05.mma
+constexpr int kBlockK = 64;   // fp16 elements = one 128-byte swizzle row
+constexpr int kUmmaK = 16;    // fp16: 32 bytes of K per tcgen05.mma
 constexpr int kMaxTaps = 16;
-constexpr int kGemmThreads = 192;
+constexpr int kGemmThreads = 320;
+constexpr float kHalfMax = 65504.f;
 
 // One zero-bordered plane (an image at one resolution) inside a flat buffer.
 struct Seg {
@@ -39,9 +49,9 @@ struct Seg {
 
 enum EpilogueFlags : int {
     kEpiRelu = 1,       // max(x, 0)
-    kEpiResidual = 2,   // += residual[row][col]
+    kEpiResidual = 2,   // += residual[row][col]   (fp16)
     kEpiMask = 4,       // zero rows that are not interior pixels of their plane
-    kEpiRoundTf32 = 8,  // round the stored value to TF32 (the output feeds another tensor-core GEMM)
+    kEpiOutF32 = 8,     // store fp32 instead of fp16 (pre-GroupNorm tower outputs, logits, predictor outputs)
     kEpiGnStats = 16,   // per-tile GroupNorm partial sums (32 groups of 8 channels; needs BN == 256)
 };
 
@@ -51,14 +61,14 @@ struct GemmArgs {
     int num_n_tiles;
     int a_row_delta;       // A row = output row + a_row_delta + tap_dy[tap] * Wp(plane of the tile) + tap_dx[tap]
     int taps;
-    int kblocks_per_tap;   // K per tap / 32
+    int kblocks_per_tap;   // K per tap / 64
     int b_rows_per_tap;    // rows of the weight matrix per tap (Cout padded up to a multiple of BN)
     signed char tap_dy[kMaxTaps];
     signed char tap_dx[kMaxTaps];
     const float* bias;     // [n_tiles * BN] or nullptr
-    const float* residual; // same row indexing as out, or nullptr
+    const __half* residual;  // same row indexing as out, or nullptr
     int ld_res;
-    float* out;
+    void* out;             // __half* (default) or float* (kEpiOutF32)
     int ldc;
     int flags;
     const int* tile_seg;   // [absolute tile] -> segment index
@@ -68,22 +78,32 @@ struct GemmArgs {
 
 template <int BN, int STAGES>
 struct GemmSmem {
-    static constexpr int kABytes = kBlockM * kBlockK * 4;  // 16 KiB
-    static constexpr int kBBytes = BN * kBlockK * 4;
+    static constexpr int kABytes = kBlockM * kBlockK * 2;  // 16 KiB
+    static constexpr int kBBytes = BN * kBlockK * 2;
     static constexpr int kStageBytes = kABytes + kBBytes;
     static constexpr int kBarOffset = STAGES * kStageBytes;
     static constexpr int kGnOffset = kBarOffset + 256;
     static constexpr int kTotal = kGnOffset + 4 * 32 * 2 * 4 + 1024;  // + alignment slack
 };
 
+__device__ __forceinline__ uint32_t pack_half2(float a, float b) {
+    const __half2 h = __floats2half2_rn(fminf(fmaxf(a, -kHalfMax), kHalfMax), fminf(fmaxf(b, -kHalfMax), kHalfMax));
+    return *reinterpret_cast<const uint32_t*>(&h);
+}
+__device__ __forceinline__ float2 unpack_half2(uint32_t u) {
+    return __half22float2(*reinterpret_cast<const __half2*>(&u));
+}
+
 template <int BN, int STAGES>
 __global__ void __launch_bounds__(kGemmThreads, 1)
-conv_gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
-                      const GemmArgs p) {
+conv_gemm_f16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
+                     const GemmArgs p) {
     using S = GemmSmem<BN, STAGES>;
-    constexpr int CH = BN < 32 ? BN : 32;                 // epilogue column chunk
+    constexpr int NH = BN >= 64 ? 2 : 1;       // epilogue warps per lane quadrant (column halves)
+    constexpr int COLS = BN / NH;              // columns per epilogue warp
+    constexpr int CH = COLS < 32 ? COLS : 32;  // epilogue column chunk
     constexpr uint32_t kTmemCols = (2 * BN < 32) ? 32 : 2 * BN;
-    constexpr uint32_t kIdesc = ptx::make_idesc_tf32(kBlockM, BN);
+    constexpr uint32_t kIdesc = ptx::make_idesc_f16(kBlockM, BN);
 
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -108,7 +128,7 @@ conv_gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_c
         }
         for (int a = 0; a < 2; ++a) {
             ptx::mbar_init(&tmem_full[a], 1);
-            ptx::mbar_init(&tmem_empty[a], 128);
+            ptx::mbar_init(&tmem_empty[a], 128 * NH);
         }
         ptx::fence_barrier_init();
     }
@@ -171,7 +191,7 @@ conv_gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_c
 #pragma unroll
                     for (int k = 0; k < kBlockK / kUmmaK; ++k) {
                         // advance 32 bytes of K inside the swizzle row: +2 in the (addr >> 4) field
-                        ptx::umma_tf32(d_tmem, da + 2 * k, db + 2 * k, kIdesc, (ks | k) ? 1u : 0u);
+                        ptx::umma_f16(d_tmem, da + 2 * k, db + 2 * k, kIdesc, (ks | k) ? 1u : 0u);
                     }
                     ptx::umma_commit(&empty_bar[stage]);
                     if (++stage == STAGES) { stage = 0; phase ^= 1u; }
@@ -181,10 +201,12 @@ conv_gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_c
                 if (acc == 0) acc_phase ^= 1u;
             }
         }
-    } else {
-        // ------------------------------------------------------------ epilogue (warps 2..5)
-        const int quad = warp & 3;  // TMEM lane quadrant this warp may read
-        const int et = (warp - 2) * 32 + lane;  // 0..127 among epilogue threads
+    } else if (warp - 2 < 4 * NH) {
+        // ------------------------------------------------------------ epilogue (warps 2..2+4*NH)
+        const int quad = warp & 3;           // TMEM lane quadrant this warp may read
+        const int half_idx = (warp - 2) >> 2;  // which half of the BN columns
+        const int col_begin = half_idx * COLS;
+        const int et = (warp - 2) * 32 + lane;
         int acc = 0;
         uint32_t acc_phase = 0;
         for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
@@ -202,30 +224,34 @@ conv_gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_c
                            (x < sg.pad + sg.W);
             }
             const bool keep = interior || !(p.flags & kEpiMask);
-            const size_t out_off = static_cast<size_t>(row) * p.ldc + static_cast<size_t>(n_tile) * BN;
-            const size_t res_off = static_cast<size_t>(row) * p.ld_res + static_cast<size_t>(n_tile) * BN;
+            const size_t out_off = static_cast<size_t>(row) * p.ldc + static_cast<size_t>(n_tile) * BN + col_begin;
+
+            // residual prefetch for this warp's whole column range, issued before the accumulator is ready
+            uint4 res[COLS / 8 > 0 ? COLS / 8 : 1];
+            const bool use_res = (p.flags & kEpiResidual) && keep;
+            if (use_res) {
+                const uint4* rp = reinterpret_cast<const uint4*>(
+                    p.residual + static_cast<size_t>(row) * p.ld_res + static_cast<size_t>(n_tile) * BN + col_begin);
+#pragma unroll
+                for (int j = 0; j < COLS / 8; ++j) res[j] = __ldg(rp + j);
+            }
 
             ptx::mbar_wait(&tmem_full[acc], acc_phase);
             ptx::tc_fence_after();
-            const uint32_t t_row = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + static_cast<uint32_t>(acc * BN);
+            const uint32_t t_row = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) +
+                                   static_cast<uint32_t>(acc * BN + col_begin);
 
-#pragma unroll 1
-            for (int c0 = 0; c0 < BN; c0 += CH) {
+#pragma unroll
+            for (int c0 = 0; c0 < COLS; c0 += CH) {
                 uint32_t v[CH];
                 if constexpr (CH == 32) ptx::tmem_ld_32x32b_x32(t_row + c0, v);
                 else ptx::tmem_ld_32x32b_x16(t_row + c0, v);
-                float4 r4[CH / 4];
-                if ((p.flags & kEpiResidual) && keep) {
-                    const float4* rp = reinterpret_cast<const float4*>(p.residual + res_off + c0);
-#pragma unroll
-                    for (int j = 0; j < CH / 4; ++j) r4[j] = __ldg(rp + j);
-                }
                 ptx::tmem_ld_wait();
                 float f[CH];
 #pragma unroll
                 for (int j = 0; j < CH; ++j) f[j] = __uint_as_float(v[j]);
                 if (p.bias != nullptr) {
-                    const float4* bp = reinterpret_cast<const float4*>(p.bias + n_tile * BN + c0);
+                    const float4* bp = reinterpret_cast<const float4*>(p.bias + n_tile * BN + col_begin + c0);
 #pragma unroll
                     for (int j = 0; j < CH / 4; ++j) {
                         const float4 b = __ldg(bp + j);
@@ -248,33 +274,41 @@ conv_gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_c
                                 ss += __shfl_xor_sync(0xffffffffu, ss, o);
                             }
                             if (lane == 0) {
-                                gn_smem[(quad * 32 + (c0 >> 3) + g) * 2 + 0] = s;
-                                gn_smem[(quad * 32 + (c0 >> 3) + g) * 2 + 1] = ss;
+                                const int grp = ((col_begin + c0) >> 3) + g;
+                                gn_smem[(quad * 32 + grp) * 2 + 0] = s;
+                                gn_smem[(quad * 32 + grp) * 2 + 1] = ss;
                             }
                         }
                     }
                 }
-                if ((p.flags & kEpiResidual) && keep) {
+                if (use_res) {
 #pragma unroll
-                    for (int j = 0; j < CH / 4; ++j) {
-                        f[4 * j + 0] += r4[j].x; f[4 * j + 1] += r4[j].y; f[4 * j + 2] += r4[j].z; f[4 * j + 3] += r4[j].w;
+                    for (int j = 0; j < CH / 8; ++j) {
+                        const uint4 r = res[c0 / 8 + j];
+                        const float2 a = unpack_half2(r.x), b = unpack_half2(r.y), c = unpack_half2(r.z), d = unpack_half2(r.w);
+                        f[8 * j + 0] += a.x; f[8 * j + 1] += a.y; f[8 * j + 2] += b.x; f[8 * j + 3] += b.y;
+                        f[8 * j + 4] += c.x; f[8 * j + 5] += c.y; f[8 * j + 6] += d.x; f[8 * j + 7] += d.y;
                     }
                 }
                 if (p.flags & kEpiRelu) {
 #pragma unroll
                     for (int j = 0; j < CH; ++j) f[j] = fmaxf(f[j], 0.f);
                 }
-                if (p.flags & kEpiRoundTf32) {
-#pragma unroll
-                    for (int j = 0; j < CH; ++j) f[j] = ptx::round_tf32(f[j]);
-                }
                 if (!keep) {
 #pragma unroll
                     for (int j = 0; j < CH; ++j) f[j] = 0.f;
                 }
-                float4* op = reinterpret_cast<float4*>(p.out + out_off + c0);
+                if (p.flags & kEpiOutF32) {
+                    float4* op = reinterpret_cast<float4*>(static_cast<float*>(p.out) + out_off + c0);
 #pragma unroll
-                for (int j = 0; j < CH / 4; ++j) op[j] = make_float4(f[4 * j], f[4 * j + 1], f[4 * j + 2], f[4 * j + 3]);
+                    for (int j = 0; j < CH / 4; ++j) op[j] = make_float4(f[4 * j], f[4 * j + 1], f[4 * j + 2], f[4 * j + 3]);
+                } else {
+                    uint4* op = reinterpret_cast<uint4*>(static_cast<__half*>(p.out) + out_off + c0);
+#pragma unroll
+                    for (int j = 0; j < CH / 8; ++j)
+                        op[j] = make_uint4(pack_half2(f[8 * j], f[8 * j + 1]), pack_half2(f[8 * j + 2], f[8 * j + 3]),
+                                           pack_half2(f[8 * j + 4], f[8 * j + 5]), pack_half2(f[8 * j + 6], f[8 * j + 7]));
+                }
             }
             // accumulator buffer fully read: hand it back to the MMA warp
             ptx::tc_fence_before();
@@ -284,12 +318,12 @@ conv_gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_c
 
             if constexpr (BN == 256) {
                 if (p.flags & kEpiGnStats) {
-                    asm volatile("bar.sync 1, 128;" ::: "memory");
+                    asm volatile("bar.sync 1, 256;" ::: "memory");
                     if (et < 64) {
                         const float t = gn_smem[et] + gn_smem[64 + et] + gn_smem[128 + et] + gn_smem[192 + et];
                         p.gn_partial[static_cast<size_t>(abs_tile) * 64 + et] = t;
                     }
-                    asm volatile("bar.sync 1, 128;" ::: "memory");
+                    asm volatile("bar.sync 1, 256;" ::: "memory");
                 }
             }
         }

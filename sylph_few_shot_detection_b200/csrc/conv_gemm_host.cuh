@@ -1,4 +1,4 @@
-// Host-side launcher for conv_gemm_tf32_kernel: TMA descriptor encoding (driver entry point fetched at run time,
+// Host-side launcher for conv_gemm_f16_kernel: TMA descriptor encoding (driver entry point fetched at run time,
 // so the library links against cudart only) and per-BN dispatch.
 #pragma once
 #include <cstdio>
@@ -25,9 +25,9 @@ inline PFN_tmapEncodeTiled get_tmap_encode() {
     return fn;
 }
 
-// 2-D fp32 matrix [rows][cols] with row pitch `ld_elems`; box = [box_rows][32 cols], 128-byte swizzle, zero OOB fill.
+// 2-D fp16 matrix [rows][cols] with row pitch `ld_elems`; box = [box_rows][64 cols], 128-byte swizzle, zero OOB fill.
 // `ld_elems` may be smaller than `cols` (overlapping rows) -- used by the stem convolution.
-inline int make_tmap_2d(CUtensorMap* m, const float* base, uint64_t rows, uint64_t cols, uint64_t ld_elems,
+inline int make_tmap_2d(CUtensorMap* m, const __half* base, uint64_t rows, uint64_t cols, uint64_t ld_elems,
                         uint32_t box_rows, std::string* err) {
     PFN_tmapEncodeTiled enc = get_tmap_encode();
     if (enc == nullptr) {
@@ -35,10 +35,10 @@ inline int make_tmap_2d(CUtensorMap* m, const float* base, uint64_t rows, uint64
         return 1;
     }
     cuuint64_t dims[2] = {cols, rows};
-    cuuint64_t strides[1] = {ld_elems * sizeof(float)};
+    cuuint64_t strides[1] = {ld_elems * sizeof(__half)};
     cuuint32_t box[2] = {static_cast<cuuint32_t>(kBlockK), box_rows};
     cuuint32_t estr[2] = {1, 1};
-    CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(base), dims, strides, box, estr,
+    CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<__half*>(base), dims, strides, box, estr,
                      CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                      CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) {
@@ -54,7 +54,7 @@ inline cudaError_t launch_conv_gemm_bn(const CUtensorMap& ta, const CUtensorMap&
     using S = GemmSmem<BN, STAGES>;
     static bool configured = false;
     if (!configured) {
-        cudaError_t e = cudaFuncSetAttribute(conv_gemm_tf32_kernel<BN, STAGES>,
+        cudaError_t e = cudaFuncSetAttribute(conv_gemm_f16_kernel<BN, STAGES>,
                                              cudaFuncAttributeMaxDynamicSharedMemorySize, S::kTotal);
         if (e != cudaSuccess) return e;
         configured = true;
@@ -62,7 +62,7 @@ inline cudaError_t launch_conv_gemm_bn(const CUtensorMap& ta, const CUtensorMap&
     const int total = args.num_m_tiles * args.num_n_tiles;
     if (total <= 0) return cudaSuccess;
     const int grid = total < num_sms ? total : num_sms;
-    conv_gemm_tf32_kernel<BN, STAGES><<<grid, kGemmThreads, S::kTotal, stream>>>(ta, tb, args);
+    conv_gemm_f16_kernel<BN, STAGES><<<grid, kGemmThreads, S::kTotal, stream>>>(ta, tb, args);
     return cudaGetLastError();
 }
 
@@ -76,6 +76,27 @@ inline cudaError_t launch_conv_gemm(int bn, const CUtensorMap& ta, const CUtenso
         case 256: return launch_conv_gemm_bn<256, 4>(ta, tb, args, num_sms, stream);
         default: return cudaErrorInvalidValue;
     }
+}
+
+// IEEE fp32 -> fp16, round to nearest even, saturating to the finite range (host-side weight preparation).
+inline uint16_t float_to_half_bits(float f) {
+    uint32_t x;
+    memcpy(&x, &f, 4);
+    const uint32_t sign = (x >> 16) & 0x8000u;
+    x &= 0x7FFFFFFFu;
+    if (x >= 0x7F800000u) return static_cast<uint16_t>(sign | (x > 0x7F800000u ? 0x7E00u : 0x7BFFu));
+    if (x >= 0x477FF000u) return static_cast<uint16_t>(sign | 0x7BFFu);  // >= 65520 rounds past the largest finite half
+    if (x < 0x33000001u) return static_cast<uint16_t>(sign);              // below half of the smallest subnormal
+    int e = static_cast<int>(x >> 23) - 127;
+    uint32_t m = (x & 0x7FFFFFu) | 0x800000u;
+    int shift;
+    uint32_t base;
+    if (e < -14) { shift = 13 + (-14 - e); base = 0; }           // subnormal half
+    else { shift = 13; base = static_cast<uint32_t>(e + 15) << 10; m &= 0x7FFFFFu; }
+    const uint32_t q = m >> shift, rem = m & ((1u << shift) - 1u), halfway = 1u << (shift - 1);
+    uint32_t h = base + q;
+    if (rem > halfway || (rem == halfway && (h & 1u))) ++h;
+    return static_cast<uint16_t>(sign | h);
 }
 
 }  // namespace sylph

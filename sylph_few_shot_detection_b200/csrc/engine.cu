@@ -19,16 +19,6 @@ namespace sylph {
 static inline int round_up(int x, int m) { return (x + m - 1) / m * m; }
 static inline int ceil_div(long long a, long long b) { return static_cast<int>((a + b - 1) / b); }
 
-static float tf32_rne(float x) {
-    uint32_t u;
-    memcpy(&u, &x, 4);
-    if ((u & 0x7F800000u) == 0x7F800000u) return x;
-    u += 0xFFFu + ((u >> 13) & 1u);
-    u &= 0xFFFFE000u;
-    float y;
-    memcpy(&y, &u, 4);
-    return y;
-}
 
 struct HostTensor {
     std::vector<int64_t> shape;
@@ -37,7 +27,7 @@ struct HostTensor {
 
 // A convolution prepared for conv_gemm: weights [taps][cout_pad][k_per_tap] (TF32-rounded), bias [cout_pad].
 struct ConvW {
-    float* w = nullptr;
+    __half* w = nullptr;
     float* bias = nullptr;
     int taps = 0, k_per_tap = 0, cout = 0, cout_pad = 0, bn = 0, ksize = 0;
 };
@@ -69,7 +59,7 @@ struct Slot {
     PyramidGeom pg;
     std::shared_ptr<PlaneSet> ps;  // level-major pyramid plane set
     long long level_row0[6] = {0};
-    float* pyr = nullptr;
+    __half* pyr = nullptr;
 };
 
 }  // namespace sylph
@@ -160,6 +150,12 @@ static int upload(sylph_ctx* c, const std::vector<float>& h, float** d) {
     return 0;
 }
 
+static int upload_half(sylph_ctx* c, const std::vector<uint16_t>& h, __half** d) {
+    CU_TRY(c, cudaMalloc(d, std::max<size_t>(h.size(), 1) * sizeof(uint16_t)));
+    CU_TRY(c, cudaMemcpy(*d, h.data(), h.size() * sizeof(uint16_t), cudaMemcpyHostToDevice));
+    return 0;
+}
+
 static int make_plane_set(sylph_ctx* c, const std::string& key, const std::vector<Seg>& segs, int total_rows,
                           std::shared_ptr<PlaneSet>* out) {
     auto it = c->plane_sets.find(key);
@@ -236,7 +232,7 @@ static int prep_conv(sylph_ctx* c, const std::string& prefix, bool frozen_bn, bo
     if (!w || w->shape.size() != 4) return c->fail("missing conv weight %s.weight", prefix.c_str());
     const int co = static_cast<int>(w->shape[0]), ci = static_cast<int>(w->shape[1]);
     const int kh = static_cast<int>(w->shape[2]), kw = static_cast<int>(w->shape[3]);
-    if (ci % 32 != 0) return c->fail("%s: Cin=%d is not a multiple of 32", prefix.c_str(), ci);
+    if (ci % kBlockK != 0) return c->fail("%s: Cin=%d is not a multiple of %d", prefix.c_str(), ci, kBlockK);
     std::vector<float> scale(co, 1.f), shift(co, 0.f);
     if (frozen_bn) {
         const HostTensor *g = find_t(c, prefix + ".norm.weight"), *b = find_t(c, prefix + ".norm.bias"),
@@ -260,15 +256,16 @@ static int prep_conv(sylph_ctx* c, const std::string& prefix, bool frozen_bn, bo
     out->cout = co;
     out->bn = pick_bn(co);
     out->cout_pad = round_up(co, out->bn);
-    std::vector<float> hw(static_cast<size_t>(out->taps) * out->cout_pad * ci, 0.f), hb(out->cout_pad, 0.f);
+    std::vector<uint16_t> hw(static_cast<size_t>(out->taps) * out->cout_pad * ci, 0);
+    std::vector<float> hb(out->cout_pad, 0.f);
     for (int o = 0; o < co; ++o) {
         hb[o] = shift[o];
         for (int i = 0; i < ci; ++i)
             for (int t = 0; t < out->taps; ++t)
                 hw[(static_cast<size_t>(t) * out->cout_pad + o) * ci + i] =
-                    tf32_rne(w->data[(static_cast<size_t>(o) * ci + i) * out->taps + t] * scale[o]);
+                    float_to_half_bits(w->data[(static_cast<size_t>(o) * ci + i) * out->taps + t] * scale[o]);
     }
-    TRY(upload(c, hw, &out->w));
+    TRY(upload_half(c, hw, &out->w));
     TRY(upload(c, hb, &out->bias));
     return 0;
 }
@@ -288,7 +285,8 @@ static int prep_stem(sylph_ctx* c, ConvW* out) {
     out->cout = co;
     out->bn = pick_bn(co);
     out->cout_pad = round_up(co, out->bn);
-    std::vector<float> hw(static_cast<size_t>(4) * out->cout_pad * 64, 0.f), hb(out->cout_pad, 0.f);
+    std::vector<uint16_t> hw(static_cast<size_t>(4) * out->cout_pad * 64, 0);
+    std::vector<float> hb(out->cout_pad, 0.f);
     for (int o = 0; o < co; ++o) {
         const float s = g->data[o] * (1.0f / std::sqrt(v->data[o] + 1e-5f));
         hb[o] = b->data[o] - m->data[o] * s;
@@ -301,11 +299,11 @@ static int prep_stem(sylph_ctx* c, ConvW* out) {
                         for (int ch = 0; ch < 3; ++ch) {
                             const int k = tx * 16 + (dy * 2 + dx) * 3 + ch;
                             hw[(static_cast<size_t>(ty) * out->cout_pad + o) * 64 + k] =
-                                tf32_rne(w->data[((static_cast<size_t>(o) * 3 + ch) * 7 + ky) * 7 + kx] * s);
+                                float_to_half_bits(w->data[((static_cast<size_t>(o) * 3 + ch) * 7 + ky) * 7 + kx] * s);
                         }
                     }
     }
-    TRY(upload(c, hw, &out->w));
+    TRY(upload_half(c, hw, &out->w));
     TRY(upload(c, hb, &out->bias));
     return 0;
 }
@@ -326,20 +324,20 @@ static int scalar_of(sylph_ctx* c, const std::string& key, float* v) {
 // ------------------------------------------------------------------------------------------------ conv launch
 struct ConvCall {
     const ConvW* W;
-    const float* A;
+    const __half* A;
     long long a_rows;   // rows of the A buffer visible to TMA
     int a_cols, a_ld;   // inner dim / pitch (elements)
     const PlaneSet* ps; // plane set of the OUTPUT buffer
     int tile_begin, n_tiles;
     int a_row_delta;
-    float* out;
+    void* out;
     int ldc;
     int flags;
-    const float* residual = nullptr;
+    const __half* residual = nullptr;
     int ld_res = 0;
     float* gn_partial = nullptr;
     const float* bias_override = nullptr;
-    const float* w_override = nullptr;
+    const __half* w_override = nullptr;
     int stem = 0;
     const char* name = "conv";
 };
@@ -383,7 +381,7 @@ static int run_conv(sylph_ctx* c, const ConvCall& k, cudaStream_t st) {
         const double rows = static_cast<double>(k.n_tiles) * kBlockM;
         tm.flops = 2.0 * rows * W.cout_pad * W.k_per_tap * W.taps;
         tm.bytes = rows * (static_cast<double>(k.a_ld < k.a_cols ? k.a_ld : k.a_cols) + static_cast<double>(k.ldc < W.cout_pad ? k.ldc : W.cout_pad) *
-                           ((k.flags & kEpiResidual) ? 2.0 : 1.0)) * 4.0;
+                           ((k.flags & kEpiResidual) ? 2.0 : 1.0)) * 2.0;
         cudaEventRecord(tm.e0, st);
     }
     CU_TRY(c, launch_conv_gemm(W.bn, ta, tb, g, c->num_sms, st));
@@ -423,7 +421,7 @@ struct StageTimer {
 // ================================================================================================== C ABI
 extern "C" {
 
-const char* sylph_version(void) { return "sylph_b200 0.1 (sm_100a, tcgen05 TF32 implicit-GEMM)"; }
+const char* sylph_version(void) { return "sylph_b200 0.1 (sm_100a, tcgen05 FP16-operand / FP32-accumulate implicit-GEMM)"; }
 
 int sylph_create(sylph_ctx** out, int device, const sylph_model_config* cfg) {
     if (!out || !cfg) return 1;
@@ -594,8 +592,8 @@ static int setup_slot(sylph_ctx* c, int slot, int n, int hpad, int wpad, const i
     for (int l = 0; l < 5; ++l) key += ":" + std::to_string(lh[l]) + "x" + std::to_string(lw[l]);
     TRY(make_plane_set(c, key, segs, row, &S.ps));
     void* p;
-    TRY(ensure(c, "pyr" + std::to_string(slot), (static_cast<size_t>(row) + kBlockM) * 256 * 4, key, &p, st, true));
-    S.pyr = static_cast<float*>(p);
+    TRY(ensure(c, "pyr" + std::to_string(slot), (static_cast<size_t>(row) + kBlockM) * 256 * 2, key, &p, st, true));
+    S.pyr = static_cast<__half*>(p);
     S.valid = true;
     return 0;
 }
@@ -625,14 +623,14 @@ static int run_backbone(sylph_ctx* c, int slot, int n, const void* const* images
     for (int s = 0; s < 4; ++s)
         TRY(make_plane_set(c, "res" + std::to_string(s + 2) + ":" + sig, geom_segs(gs[s], n), n * gs[s].rows_per_img, &pss[s]));
 
-    auto buf = [&](const std::string& name, long long rows, int ch, bool zero, float** out) -> int {
+    auto buf = [&](const std::string& name, long long rows, int ch, bool zero, __half** out) -> int {
         void* p;
-        TRY(ensure(c, name, (static_cast<size_t>(rows) + kBlockM) * ch * 4, sig, &p, st, zero));
-        *out = static_cast<float*>(p);
+        TRY(ensure(c, name, (static_cast<size_t>(rows) + kBlockM) * ch * 2, sig, &p, st, zero));
+        *out = static_cast<__half*>(p);
         return 0;
     };
     const long long rows0 = static_cast<long long>(n) * g0.rows_per_img;
-    float *S0, *S1;
+    __half *S0, *S1;
     TRY(buf("bb.s0", rows0, 16, true, &S0));
     TRY(buf("bb.s1", rows0, 64, false, &S1));
     // ---- image descriptors
@@ -643,7 +641,7 @@ static int run_backbone(sylph_ctx* c, int slot, int n, const void* const* images
     CU_TRY(c, cudaMemcpyAsync(d_desc, descs.data(), n * sizeof(ImageDesc), cudaMemcpyHostToDevice, st));
     CU_TRY(c, cudaStreamSynchronize(st));  // descs is a stack-lifetime staging vector
     {
-        StageTimer t(c, "prep_stem_input", st, static_cast<double>(n) * (3.0 * hmax * wmax + 16.0 * g0.H * g0.W) * 4);
+        StageTimer t(c, "prep_stem_input", st, static_cast<double>(n) * (3.0 * hmax * wmax + 32.0 * g0.H * g0.W));
         prep_stem_input_kernel<<<grid_for(static_cast<long long>(n) * g0.H * g0.W, 256, c->num_sms), 256, 0, st>>>(
             static_cast<const ImageDesc*>(d_desc), S0, g0, n, f.pixel_mean[0], f.pixel_mean[1], f.pixel_mean[2],
             f.pixel_std[0], f.pixel_std[1], f.pixel_std[2]);
@@ -658,14 +656,14 @@ static int run_backbone(sylph_ctx* c, int slot, int n, const void* const* images
         TRY(run_conv(c, k, st));
     }
     // ---- res2..res5
-    float* X = nullptr;  // running stage output
+    __half* X = nullptr;  // running stage output
     int x_ch = 64;
     for (int s = 0; s < 4; ++s) {
         const PlaneGeom& g = gs[s];
         const long long rows = static_cast<long long>(n) * g.rows_per_img;
         const int tiles = static_cast<int>(rows / kBlockM);
         const int out_ch = 256 << s, bott = 64 << s, in_ch = x_ch;
-        float *IN, *Y, *T1, *T2;
+        __half *IN, *Y, *T1, *T2;
         const std::string sn = "bb.res" + std::to_string(s + 2);
         TRY(buf(sn + ".in", rows, in_ch, true, &IN));
         TRY(buf(sn + ".x", rows, out_ch, false, &Y));
@@ -673,8 +671,8 @@ static int run_backbone(sylph_ctx* c, int slot, int n, const void* const* images
         TRY(buf(sn + ".t2", rows, bott, false, &T2));
         {
             StageTimer t(c, s == 0 ? "maxpool3x3s2" : "subsample2", st,
-                         static_cast<double>(n) * g.H * g.W * in_ch * 4 * (s == 0 ? 5.0 : 2.0));
-            const long long work = static_cast<long long>(n) * g.H * g.W * (in_ch / 4);
+                         static_cast<double>(n) * g.H * g.W * in_ch * 2 * (s == 0 ? 5.0 : 2.0));
+            const long long work = static_cast<long long>(n) * g.H * g.W * (in_ch / 8);
             if (s == 0) maxpool3x3s2_kernel<<<grid_for(work, 256, c->num_sms), 256, 0, st>>>(S1, IN, g0, g, n, in_ch);
             else subsample2_kernel<<<grid_for(work, 256, c->num_sms), 256, 0, st>>>(X, IN, gs[s - 1], g, n, in_ch);
             CU_TRY(c, cudaGetLastError());
@@ -683,7 +681,7 @@ static int run_backbone(sylph_ctx* c, int slot, int n, const void* const* images
         const auto& blocks = c->stages[s];
         for (size_t b = 0; b < blocks.size(); ++b) {
             const sylph_ctx::Block& B = blocks[b];
-            const float* bin = (b == 0) ? IN : Y;
+            const __half* bin = (b == 0) ? IN : Y;
             const int bin_ch = (b == 0) ? in_ch : out_ch;
             ConvCall k{};
             k.ps = pss[s].get(); k.tile_begin = 0; k.n_tiles = tiles; k.a_row_delta = 0; k.a_rows = rows;
@@ -697,12 +695,12 @@ static int run_backbone(sylph_ctx* c, int slot, int n, const void* const* images
             }
             k.residual = nullptr;
             k.W = &B.c1; k.A = bin; k.a_cols = k.a_ld = bin_ch; k.out = T1; k.ldc = bott;
-            k.flags = kEpiRelu | kEpiMask | kEpiRoundTf32; k.name = "res.conv1_1x1";
+            k.flags = kEpiRelu | kEpiMask; k.name = "res.conv1_1x1";
             TRY(run_conv(c, k, st));
             k.W = &B.c2; k.A = T1; k.a_cols = k.a_ld = bott; k.out = T2; k.ldc = bott; k.name = "res.conv2_3x3";
             TRY(run_conv(c, k, st));
             k.W = &B.c3; k.A = T2; k.a_cols = k.a_ld = bott; k.out = Y; k.ldc = out_ch; k.residual = Y; k.ld_res = out_ch;
-            k.flags = kEpiRelu | kEpiMask | kEpiRoundTf32 | kEpiResidual; k.name = "res.conv3_1x1";
+            k.flags = kEpiRelu | kEpiMask | kEpiResidual; k.name = "res.conv3_1x1";
             TRY(run_conv(c, k, st));
         }
         X = Y;
@@ -710,25 +708,25 @@ static int run_backbone(sylph_ctx* c, int slot, int n, const void* const* images
         // lateral 1x1 for res3..res5 straight into the pyramid-indexed lateral buffer
     }
     // ---- FPN (top-down): lateral buffers share the pyramid row indexing
-    float* LAT;
+    __half* LAT;
     {
         void* p;
-        TRY(ensure(c, "bb.lat", (static_cast<size_t>(S.level_row0[5]) + kBlockM) * 256 * 4, S.ps ? ("pyr" + sig) : sig, &p, st, true));
-        LAT = static_cast<float*>(p);
+        TRY(ensure(c, "bb.lat", (static_cast<size_t>(S.level_row0[5]) + kBlockM) * 256 * 2, S.ps ? ("pyr" + sig) : sig, &p, st, true));
+        LAT = static_cast<__half*>(p);
     }
     for (int l = 2; l >= 0; --l) {
         const PlaneGeom& g = S.pg.lv[l];
         const long long rows = static_cast<long long>(n) * g.rows_per_img;
-        float* XS = static_cast<float*>(c->bufs["bb.res" + std::to_string(l + 3) + ".x"].p);
+        __half* XS = static_cast<__half*>(c->bufs["bb.res" + std::to_string(l + 3) + ".x"].p);
         ConvCall k{};
         k.W = &c->lat[l]; k.A = XS; k.a_rows = rows; k.a_cols = k.a_ld = 512 << l; k.ps = S.ps.get();
         k.tile_begin = static_cast<int>(S.level_row0[l] / kBlockM); k.n_tiles = static_cast<int>(rows / kBlockM);
         k.a_row_delta = -static_cast<int>(S.level_row0[l]); k.out = LAT; k.ldc = 256;
-        k.flags = kEpiMask | kEpiRoundTf32; k.name = "fpn.lateral1x1";
+        k.flags = kEpiMask; k.name = "fpn.lateral1x1";
         TRY(run_conv(c, k, st));
         if (l < 2) {
-            StageTimer t(c, "fpn.upsample_add", st, static_cast<double>(n) * g.H * g.W * 256 * 4 * 2.25);
-            upsample_add_kernel<<<grid_for(static_cast<long long>(n) * g.H * g.W * 64, 256, c->num_sms), 256, 0, st>>>(
+            StageTimer t(c, "fpn.upsample_add", st, static_cast<double>(n) * g.H * g.W * 256 * 2 * 2.25);
+            upsample_add_kernel<<<grid_for(static_cast<long long>(n) * g.H * g.W * 32, 256, c->num_sms), 256, 0, st>>>(
                 LAT, LAT, g, S.pg.lv[l + 1], n, 256);
             CU_TRY(c, cudaGetLastError());
             c->launches++;
@@ -741,29 +739,29 @@ static int run_backbone(sylph_ctx* c, int slot, int n, const void* const* images
     {
         const PlaneGeom& g5 = S.pg.lv[2];
         const long long rows5 = static_cast<long long>(n) * g5.rows_per_img;
-        float *TMP, *R6;
+        __half *TMP, *R6;
         TRY(buf("bb.p6tmp", S.level_row0[5], 256, false, &TMP));
         TRY(buf("bb.p6relu", S.level_row0[5], 256, true, &R6));
         ConvCall k{};
         k.W = &c->p6; k.A = S.pyr; k.a_rows = S.level_row0[5]; k.a_cols = k.a_ld = 256; k.ps = S.ps.get();
         k.tile_begin = static_cast<int>(S.level_row0[2] / kBlockM); k.n_tiles = static_cast<int>(rows5 / kBlockM);
-        k.a_row_delta = 0; k.out = TMP; k.ldc = 256; k.flags = kEpiMask | kEpiRoundTf32; k.name = "fpn.p6_3x3";
+        k.a_row_delta = 0; k.out = TMP; k.ldc = 256; k.flags = kEpiMask; k.name = "fpn.p6_3x3";
         TRY(run_conv(c, k, st));
         const PlaneGeom& g6 = S.pg.lv[3];
-        subsample2_kernel<<<grid_for(static_cast<long long>(n) * g6.H * g6.W * 64, 256, c->num_sms), 256, 0, st>>>(
+        subsample2_kernel<<<grid_for(static_cast<long long>(n) * g6.H * g6.W * 32, 256, c->num_sms), 256, 0, st>>>(
             TMP, S.pyr, g5, g6, n, 256);
         CU_TRY(c, cudaGetLastError());
         const long long rows6 = static_cast<long long>(n) * g6.rows_per_img;
-        relu_copy_kernel<<<grid_for(rows6 * 64, 256, c->num_sms), 256, 0, st>>>(
-            reinterpret_cast<const float4*>(S.pyr + S.level_row0[3] * 256), reinterpret_cast<float4*>(R6 + S.level_row0[3] * 256),
-            rows6 * 64);
+        relu_copy_kernel<<<grid_for(rows6 * 32, 256, c->num_sms), 256, 0, st>>>(
+            reinterpret_cast<const uint4*>(S.pyr + S.level_row0[3] * 256), reinterpret_cast<uint4*>(R6 + S.level_row0[3] * 256),
+            rows6 * 32);
         CU_TRY(c, cudaGetLastError());
         c->launches += 2;
         k.W = &c->p7; k.A = R6; k.tile_begin = static_cast<int>(S.level_row0[3] / kBlockM);
         k.n_tiles = static_cast<int>(rows6 / kBlockM); k.name = "fpn.p7_3x3";
         TRY(run_conv(c, k, st));
         const PlaneGeom& g7 = S.pg.lv[4];
-        subsample2_kernel<<<grid_for(static_cast<long long>(n) * g7.H * g7.W * 64, 256, c->num_sms), 256, 0, st>>>(
+        subsample2_kernel<<<grid_for(static_cast<long long>(n) * g7.H * g7.W * 32, 256, c->num_sms), 256, 0, st>>>(
             TMP, S.pyr, g6, g7, n, 256);
         CU_TRY(c, cudaGetLastError());
         c->launches++;
@@ -773,21 +771,21 @@ static int run_backbone(sylph_ctx* c, int slot, int n, const void* const* images
 
 // conv3x3 + GroupNorm(32) + ReLU over `tiles` tiles of a plane set: conv epilogue accumulates the per-tile partial
 // sums, finalize reduces them per plane, apply normalises in place.
-static int conv_gn_relu(sylph_ctx* c, const ConvW& W, const float* gn_w, const float* gn_b, const float* in,
-                        long long a_rows, float* out, const PlaneSet* ps, int tile_begin, int tiles, int seg_begin,
-                        int n_segs, float* gn_partial, float* gn_stats, const char* name, cudaStream_t st) {
+static int conv_gn_relu(sylph_ctx* c, const ConvW& W, const float* gn_w, const float* gn_b, const __half* in,
+                        long long a_rows, float* raw, __half* out, const PlaneSet* ps, int tile_begin, int tiles,
+                        int seg_begin, int n_segs, float* gn_partial, float* gn_stats, const char* name, cudaStream_t st) {
     ConvCall k{};
     k.W = &W; k.A = in; k.a_rows = a_rows; k.a_cols = k.a_ld = 256; k.ps = ps; k.tile_begin = tile_begin; k.n_tiles = tiles;
-    k.a_row_delta = 0; k.out = out; k.ldc = 256; k.flags = kEpiGnStats; k.gn_partial = gn_partial; k.name = name;
+    k.a_row_delta = 0; k.out = raw; k.ldc = 256; k.flags = kEpiGnStats | kEpiOutF32; k.gn_partial = gn_partial; k.name = name;
     TRY(run_conv(c, k, st));
     gn_finalize_kernel<<<ceil_div(static_cast<long long>(n_segs) * 32, 128), 128, 0, st>>>(gn_partial, ps->d_segs, seg_begin,
                                                                                        n_segs, gn_stats);
     CU_TRY(c, cudaGetLastError());
     {
         const long long rows = static_cast<long long>(tiles) * kBlockM;
-        StageTimer t(c, "gn_apply_relu", st, static_cast<double>(rows) * 256 * 4 * 2);
-        gn_apply_relu_kernel<<<grid_for(rows * 64, 256, c->num_sms), 256, 0, st>>>(
-            out, gn_stats, gn_w, gn_b, ps->d_tile_seg, ps->d_segs, tile_begin * kBlockM, rows, 1);
+        StageTimer t(c, "gn_apply_relu", st, static_cast<double>(rows) * 256 * 6);
+        gn_apply_relu_kernel<<<grid_for(rows * 32, 256, c->num_sms), 256, 0, st>>>(
+            raw, out, gn_stats, gn_w, gn_b, ps->d_tile_seg, ps->d_segs, tile_begin * kBlockM, rows, 1);
         CU_TRY(c, cudaGetLastError());
     }
     c->launches += 2;
@@ -830,7 +828,7 @@ int sylph_import_features(sylph_ctx* c, int slot, int n_images, int padded_h, in
     S.img_w.assign(n_images, padded_w);
     for (int l = 0; l < 5; ++l) {
         const long long work = static_cast<long long>(n_images) * 256 * level_h[l] * level_w[l];
-        import_nchw_kernel<<<grid_for(work, 256, c->num_sms), 256, 0, st>>>(level_ptrs_dev[l], S.pyr, S.pg.lv[l], n_images, 256, 1);
+        import_nchw_kernel<<<grid_for(work, 256, c->num_sms), 256, 0, st>>>(level_ptrs_dev[l], S.pyr, S.pg.lv[l], n_images, 256);
         CU_TRY(c, cudaGetLastError());
         c->launches++;
     }
@@ -857,7 +855,7 @@ int sylph_export_features(sylph_ctx* c, int slot, int level, float* out_dev, voi
     const Slot& S = c->slots[slot];
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     const long long work = static_cast<long long>(S.n) * 256 * S.lh[level] * S.lw[level];
-    export_nchw_kernel<<<grid_for(work, 256, c->num_sms), 256, 0, st>>>(S.pyr, out_dev, S.pg.lv[level], S.n, 256, 256, 0, 1.f, 0);
+    export_nchw_kernel<__half><<<grid_for(work, 256, c->num_sms), 256, 0, st>>>(S.pyr, out_dev, S.pg.lv[level], S.n, 256, 256, 0, 1.f, 0);
     CU_TRY(c, cudaGetLastError());
     c->launches++;
     return 0;
@@ -880,13 +878,14 @@ int sylph_generate_codes(sylph_ctx* c, int slot, int n_rois, const float* boxes_
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     const sylph_model_config& f = c->cfg;
     const long long rows = static_cast<long long>(n_rois) * 128;
-    void *pb, *pi, *po, *r0, *r1, *r2, *gp, *gs, *sc;
+    void *pb, *pi, *po, *r0, *r1, *r2, *rawp, *gp, *gs, *sc;
     TRY(ensure(c, "cg.boxes", n_rois * 16, "", &pb, st, false));
     TRY(ensure(c, "cg.roi_image", n_rois * 4, "", &pi, st, false));
     TRY(ensure(c, "cg.class_off", (n_classes + 1) * 4, "", &po, st, false));
-    TRY(ensure(c, "cg.r0", (rows + kBlockM) * 256 * 4, "roi", &r0, st, true));
-    TRY(ensure(c, "cg.r1", (rows + kBlockM) * 256 * 4, "roi", &r1, st, true));
-    TRY(ensure(c, "cg.r2", (rows + kBlockM) * 256 * 4, "roi", &r2, st, true));
+    TRY(ensure(c, "cg.r0", (rows + kBlockM) * 256 * 2, "roi", &r0, st, true));
+    TRY(ensure(c, "cg.r1", (rows + kBlockM) * 256 * 2, "roi", &r1, st, true));
+    TRY(ensure(c, "cg.r2", (rows + kBlockM) * 256 * 2, "roi", &r2, st, true));
+    TRY(ensure(c, "cg.raw", (rows + kBlockM) * 256 * 4, "roi", &rawp, st, false));
     TRY(ensure(c, "cg.gn_partial", static_cast<size_t>(n_rois) * 64 * 4, "", &gp, st, false));
     TRY(ensure(c, "cg.gn_stats", static_cast<size_t>(n_rois) * 64 * 4, "", &gs, st, false));
     TRY(ensure(c, "cg.shot", static_cast<size_t>(n_rois) * 257 * 4, "", &sc, st, false));
@@ -903,28 +902,29 @@ int sylph_generate_codes(sylph_ctx* c, int slot, int n_rois, const float* boxes_
     {
         StageTimer t(c, "roi_align", st, static_cast<double>(n_rois) * (50176.0 + 0.5e6));
         roi_align_kernel<<<dim3(n_rois, 7), 256, 0, st>>>(S.pyr, S.pg, static_cast<const float*>(pb), static_cast<const int*>(pi),
-                                                         static_cast<float*>(r0), reinterpret_cast<long long*>(levels_out_dev));
+                                                         static_cast<__half*>(r0), reinterpret_cast<long long*>(levels_out_dev));
         CU_TRY(c, cudaGetLastError());
         c->launches++;
     }
     c->last_n_rois = n_rois;
-    float* cur = static_cast<float*>(r0);
-    float* nxt = static_cast<float*>(r1);
+    __half* cur = static_cast<__half*>(r0);
+    __half* nxt = static_cast<__half*>(r1);
+    float* raw = static_cast<float*>(rawp);
     for (int i = 0; i < f.cg_tower_layers; ++i) {
-        TRY(conv_gn_relu(c, c->cg_tower[i], c->cg_gn_w[i], c->cg_gn_b[i], cur, rows, nxt, ps.get(), 0, n_rois, 0, n_rois,
+        TRY(conv_gn_relu(c, c->cg_tower[i], c->cg_gn_w[i], c->cg_gn_b[i], cur, rows, raw, nxt, ps.get(), 0, n_rois, 0, n_rois,
                          static_cast<float*>(gp), static_cast<float*>(gs), "codegen.tower3x3", st));
         cur = nxt;
-        nxt = (cur == r1) ? static_cast<float*>(r2) : static_cast<float*>(r1);
+        nxt = (cur == r1) ? static_cast<__half*>(r2) : static_cast<__half*>(r1);
     }
     {
         ConvCall k{};
         k.W = &c->cg_cls; k.A = cur; k.a_rows = rows; k.a_cols = k.a_ld = 256; k.ps = ps.get(); k.tile_begin = 0;
-        k.n_tiles = n_rois; k.a_row_delta = 0; k.out = nxt; k.ldc = 256; k.flags = 0; k.name = "codegen.cls_conv3x3";
+        k.n_tiles = n_rois; k.a_row_delta = 0; k.out = raw; k.ldc = 256; k.flags = kEpiOutF32; k.name = "codegen.cls_conv3x3";
         TRY(run_conv(c, k, st));
     }
     {
         StageTimer t(c, "codegen.tail", st, static_cast<double>(n_rois) * 2 * 49 * 256 * 4);
-        shot_code_kernel<<<n_rois, 256, 0, st>>>(nxt, cur, c->cg_wbias, c->cg_bbias, f.cg_bias_layer, f.cg_bias_l2_norm,
+        shot_code_kernel<<<n_rois, 256, 0, st>>>(raw, cur, c->cg_wbias, c->cg_bbias, f.cg_bias_layer, f.cg_bias_l2_norm,
                                                  static_cast<float*>(sc));
         CU_TRY(c, cudaGetLastError());
         class_mean_kernel<<<n_classes, 288, 0, st>>>(static_cast<const float*>(sc), static_cast<const int*>(po), codes_out_dev);
@@ -940,7 +940,7 @@ int sylph_export_roi_features(sylph_ctx* c, float* out_dev, void* stream) {
     if (c->last_n_rois <= 0) return c->fail("no ROI features: call sylph_generate_codes first");
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     export_roi_kernel<<<grid_for(static_cast<long long>(c->last_n_rois) * 256 * 49, 256, c->num_sms), 256, 0, st>>>(
-        static_cast<const float*>(c->bufs["cg.r0"].p), out_dev, c->last_n_rois);
+        static_cast<const __half*>(c->bufs["cg.r0"].p), out_dev, c->last_n_rois);
     CU_TRY(c, cudaGetLastError());
     c->launches++;
     return 0;
@@ -977,47 +977,48 @@ int sylph_detect(sylph_ctx* c, int slot, const float* codes_dev, int n_classes, 
     ConvW CW;
     CW.taps = 1; CW.ksize = 1; CW.k_per_tap = 256; CW.cout = n_classes; CW.bn = pick_bn(n_classes);
     CW.cout_pad = round_up(n_classes, CW.bn);
-    void *cw, *cb, *ta, *tb, *lg, *pr, *gp, *gs;
-    TRY(ensure(c, "det.code_w", static_cast<size_t>(CW.cout_pad) * 256 * 4, "", &cw, st, false));
+    void *cw, *cb, *ta, *tb, *rawp, *lg, *pr, *gp, *gs;
+    TRY(ensure(c, "det.code_w", static_cast<size_t>(CW.cout_pad) * 256 * 2, "", &cw, st, false));
     TRY(ensure(c, "det.code_b", static_cast<size_t>(CW.cout_pad) * 4, "", &cb, st, false));
-    TRY(ensure(c, "det.ta", (static_cast<size_t>(rows) + kBlockM) * 256 * 4, "", &ta, st, false));
-    TRY(ensure(c, "det.tb", (static_cast<size_t>(rows) + kBlockM) * 256 * 4, "", &tb, st, false));
+    TRY(ensure(c, "det.ta", (static_cast<size_t>(rows) + kBlockM) * 256 * 2, "", &ta, st, false));
+    TRY(ensure(c, "det.tb", (static_cast<size_t>(rows) + kBlockM) * 256 * 2, "", &tb, st, false));
+    TRY(ensure(c, "det.raw", (static_cast<size_t>(rows) + kBlockM) * 256 * 4, "", &rawp, st, false));
     TRY(ensure(c, "det.logits", (static_cast<size_t>(rows) + kBlockM) * CW.cout_pad * 4, "", &lg, st, false));
     TRY(ensure(c, "det.pred", (static_cast<size_t>(rows) + kBlockM) * 16 * 4, "", &pr, st, false));
     TRY(ensure(c, "det.gn_partial", static_cast<size_t>(tiles) * 64 * 4, "", &gp, st, false));
     TRY(ensure(c, "det.gn_stats", static_cast<size_t>(n_segs) * 64 * 4, "", &gs, st, false));
-    CW.w = static_cast<float*>(cw);
+    CW.w = static_cast<__half*>(cw);
     CW.bias = static_cast<float*>(cb);
     pack_code_weights_kernel<<<ceil_div(static_cast<long long>(CW.cout_pad) * 256, 256), 256, 0, st>>>(
         codes_dev, n_classes, CW.cout_pad, f.cg_use_bias, CW.w, CW.bias);
     CU_TRY(c, cudaGetLastError());
     c->launches++;
     auto tower = [&](const std::vector<ConvW>& tw, const std::vector<float*>& gw, const std::vector<float*>& gb,
-                     const char* name, float** result) -> int {
-        const float* cur = S.pyr;
-        float* bufs2[2] = {static_cast<float*>(ta), static_cast<float*>(tb)};
+                     const char* name, __half** result) -> int {
+        const __half* cur = S.pyr;
+        __half* bufs2[2] = {static_cast<__half*>(ta), static_cast<__half*>(tb)};
         for (size_t i = 0; i < tw.size(); ++i) {
-            float* o = bufs2[i & 1];
-            TRY(conv_gn_relu(c, tw[i], gw[i], gb[i], cur, rows, o, S.ps.get(), 0, tiles, 0, n_segs, static_cast<float*>(gp),
-                             static_cast<float*>(gs), name, st));
+            __half* o = bufs2[i & 1];
+            TRY(conv_gn_relu(c, tw[i], gw[i], gb[i], cur, rows, static_cast<float*>(rawp), o, S.ps.get(), 0, tiles, 0, n_segs,
+                             static_cast<float*>(gp), static_cast<float*>(gs), name, st));
             cur = o;
         }
-        *result = const_cast<float*>(cur);
+        *result = const_cast<__half*>(cur);
         return 0;
     };
-    float* x;
+    __half* x;
     TRY(tower(c->cls_tower, c->cls_gn_w, c->cls_gn_b, "head.cls_tower3x3", &x));
     {
         ConvCall k{};
         k.W = &CW; k.A = x; k.a_rows = rows; k.a_cols = k.a_ld = 256; k.ps = S.ps.get(); k.tile_begin = 0; k.n_tiles = tiles;
-        k.a_row_delta = 0; k.out = static_cast<float*>(lg); k.ldc = CW.cout_pad; k.flags = 0; k.name = "head.cond_cls1x1";
+        k.a_row_delta = 0; k.out = lg; k.ldc = CW.cout_pad; k.flags = kEpiOutF32; k.name = "head.cond_cls1x1";
         TRY(run_conv(c, k, st));
     }
     TRY(tower(c->box_tower, c->box_gn_w, c->box_gn_b, "head.bbox_tower3x3", &x));
     {
         ConvCall k{};
         k.W = &c->pred; k.A = x; k.a_rows = rows; k.a_cols = k.a_ld = 256; k.ps = S.ps.get(); k.tile_begin = 0; k.n_tiles = tiles;
-        k.a_row_delta = 0; k.out = static_cast<float*>(pr); k.ldc = 16; k.flags = 0; k.name = "head.pred3x3";
+        k.a_row_delta = 0; k.out = pr; k.ldc = 16; k.flags = kEpiOutF32; k.name = "head.pred3x3";
         TRY(run_conv(c, k, st));
     }
     c->last_detect_slot = slot;
@@ -1105,7 +1106,7 @@ int sylph_export_head_output(sylph_ctx* c, int which, int level, float* out_dev,
     else if (which == 2) { coff = 4; }
     else { coff = 5; }
     const long long work = static_cast<long long>(S.n) * C * S.lh[level] * S.lw[level];
-    export_nchw_kernel<<<grid_for(work, 256, c->num_sms), 256, 0, st>>>(src, out_dev, S.pg.lv[level], S.n, C, cstride, coff, scale, relu);
+    export_nchw_kernel<float><<<grid_for(work, 256, c->num_sms), 256, 0, st>>>(src, out_dev, S.pg.lv[level], S.n, C, cstride, coff, scale, relu);
     CU_TRY(c, cudaGetLastError());
     c->launches++;
     return 0;

@@ -23,7 +23,7 @@ __device__ __forceinline__ int assign_level(float x0, float y0, float x1, float 
     return static_cast<int>(l) - 3;
 }
 
-__device__ __forceinline__ float bilinear_tap(const float* __restrict__ feat, const PlaneGeom& g, int n, int H, int W,
+__device__ __forceinline__ float bilinear_tap(const __half* __restrict__ feat, const PlaneGeom& g, int n, int H, int W,
                                               float y, float x, int c) {
     if (y < -1.f || y > static_cast<float>(H) || x < -1.f || x > static_cast<float>(W)) return 0.f;
     y = fmaxf(y, 0.f);
@@ -32,10 +32,10 @@ __device__ __forceinline__ float bilinear_tap(const float* __restrict__ feat, co
     if (y_low >= H - 1) { y_high = y_low = H - 1; y = static_cast<float>(y_low); } else { y_high = y_low + 1; }
     if (x_low >= W - 1) { x_high = x_low = W - 1; x = static_cast<float>(x_low); } else { x_high = x_low + 1; }
     const float ly = y - y_low, lx = x - x_low, hy = 1.f - ly, hx = 1.f - lx;
-    const float v1 = __ldg(feat + plane_row(g, n, y_low, x_low) * 256 + c);
-    const float v2 = __ldg(feat + plane_row(g, n, y_low, x_high) * 256 + c);
-    const float v3 = __ldg(feat + plane_row(g, n, y_high, x_low) * 256 + c);
-    const float v4 = __ldg(feat + plane_row(g, n, y_high, x_high) * 256 + c);
+    const float v1 = __half2float(__ldg(feat + plane_row(g, n, y_low, x_low) * 256 + c));
+    const float v2 = __half2float(__ldg(feat + plane_row(g, n, y_low, x_high) * 256 + c));
+    const float v3 = __half2float(__ldg(feat + plane_row(g, n, y_high, x_low) * 256 + c));
+    const float v4 = __half2float(__ldg(feat + plane_row(g, n, y_high, x_high) * 256 + c));
     return hy * hx * v1 + hy * lx * v2 + ly * hx * v3 + ly * lx * v4;
 }
 
@@ -45,8 +45,8 @@ __device__ __forceinline__ float bilinear_tap(const float* __restrict__ feat, co
 // Replaces detectron2 ROIPooler.forward (torchvision roi_align per level + nonzero + index_put_),
 // reference call site sylph/modeling/code_generator/code_generator.py:930.
 __global__ void __launch_bounds__(256)
-roi_align_kernel(const float* __restrict__ pyramid, PyramidGeom pg, const float* __restrict__ boxes,
-                 const int* __restrict__ roi_image, float* __restrict__ roi_planes, long long* __restrict__ levels_out) {
+roi_align_kernel(const __half* __restrict__ pyramid, PyramidGeom pg, const float* __restrict__ boxes,
+                 const int* __restrict__ roi_image, __half* __restrict__ roi_planes, long long* __restrict__ levels_out) {
     const int roi = blockIdx.x, ph = blockIdx.y, c = threadIdx.x;
     const float bx0 = boxes[roi * 4 + 0], by0 = boxes[roi * 4 + 1], bx1 = boxes[roi * 4 + 2], by1 = boxes[roi * 4 + 3];
     const int lvl = assign_level(bx0, by0, bx1, by1);
@@ -73,7 +73,7 @@ roi_align_kernel(const float* __restrict__ pyramid, PyramidGeom pg, const float*
             }
         }
         const size_t row = static_cast<size_t>(roi) * 128 + (ph + 1) * 9 + (pw + 1);
-        roi_planes[row * 256 + c] = ptx::round_tf32(acc / count);
+        roi_planes[row * 256 + c] = __float2half_rn(fminf(fmaxf(acc / count, -kHalfMax), kHalfMax));
     }
 }
 
@@ -81,7 +81,7 @@ roi_align_kernel(const float* __restrict__ pyramid, PyramidGeom pg, const float*
 // 256 -> 1 3x3 bias convolution on the tower output, optional L2 normalisation over the 49 positions, then its pool.
 // reference: code_generator.py:954-967, utils.py:51-67.   grid = n_rois, block = 256.
 __global__ void __launch_bounds__(256)
-shot_code_kernel(const float* __restrict__ cls_raw, const float* __restrict__ tower_out,
+shot_code_kernel(const float* __restrict__ cls_raw, const __half* __restrict__ tower_out,
                  const float* __restrict__ w_bias /* [9][256] tap-major */, const float* __restrict__ b_bias,
                  int has_bias_layer, int bias_l2_norm, float* __restrict__ shot_codes /* [n_rois][257] */) {
     __shared__ float pix[49];
@@ -103,10 +103,10 @@ shot_code_kernel(const float* __restrict__ cls_raw, const float* __restrict__ to
 #pragma unroll
         for (int tap = 0; tap < 9; ++tap) {
             const int r2 = row + (tap / 3 - 1) * 9 + (tap % 3 - 1);  // zero border supplies the padding
-            const float* a = tower_out + (base + r2) * 256;
+            const __half* a = tower_out + (base + r2) * 256;
             const float* w = w_bias + tap * 256;
 #pragma unroll
-            for (int j = 0; j < 8; ++j) acc += a[lane + 32 * j] * __ldg(w + lane + 32 * j);
+            for (int j = 0; j < 8; ++j) acc += __half2float(a[lane + 32 * j]) * __ldg(w + lane + 32 * j);
         }
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
@@ -179,25 +179,26 @@ normalize_codes_kernel(const float* __restrict__ raw, float* __restrict__ out, c
 }
 
 // Expand (n_classes, 257) codes into the K-major weight matrix [n_pad][256] + bias [n_pad] the logits GEMM reads
-// (rows >= n_classes are zero); weights are rounded to TF32 here.
+// (rows >= n_classes are zero); weights are rounded to fp16 here.
 __global__ void pack_code_weights_kernel(const float* __restrict__ codes, int n_classes, int n_pad, int use_bias,
-                                         float* __restrict__ w, float* __restrict__ bias) {
+                                         __half* __restrict__ w, float* __restrict__ bias) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n_pad * 256) return;
     const int r = i >> 8, c = i & 255;
-    w[i] = r < n_classes ? ptx::round_tf32(codes[static_cast<size_t>(r) * 257 + c]) : 0.f;
+    const float v = r < n_classes ? codes[static_cast<size_t>(r) * 257 + c] : 0.f;
+    w[i] = __float2half_rn(fminf(fmaxf(v, -kHalfMax), kHalfMax));
     if (c == 0) bias[r] = (r < n_classes && use_bias) ? codes[static_cast<size_t>(r) * 257 + 256] : 0.f;
 }
 
 // (n_rois, 256, 7, 7) export of the pooled ROI planes (tests / plugin interop).
-__global__ void export_roi_kernel(const float* __restrict__ roi_planes, float* __restrict__ out, int n_rois) {
+__global__ void export_roi_kernel(const __half* __restrict__ roi_planes, float* __restrict__ out, int n_rois) {
     const long long total = static_cast<long long>(n_rois) * 256 * 49;
     for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
          i += static_cast<long long>(gridDim.x) * blockDim.x) {
         const int p = static_cast<int>(i % 49);
         const int c = static_cast<int>((i / 49) % 256);
         const int r = static_cast<int>(i / (49 * 256));
-        out[i] = roi_planes[(static_cast<size_t>(r) * 128 + (p / 7 + 1) * 9 + (p % 7 + 1)) * 256 + c];
+        out[i] = __half2float(roi_planes[(static_cast<size_t>(r) * 128 + (p / 7 + 1) * 9 + (p % 7 + 1)) * 256 + c]);
     }
 }
 

@@ -1,6 +1,6 @@
 // HBM-bound helper kernels around the tensor-core convolutions: image normalise/pad/space-to-depth, max-pool,
 // stride-2 gathers, FPN top-down add, GroupNorm finalize/apply, NCHW import/export.  All operate on the flat
-// zero-bordered NHWC planes described in conv_gemm.cuh; channel vectors are moved as float4 (coalesced 16-byte lanes).
+// zero-bordered NHWC fp16 planes described in conv_gemm.cuh; channel vectors move as 16-byte lanes (8 halves).
 #pragma once
 #include "conv_gemm.cuh"
 
@@ -18,6 +18,15 @@ __device__ __forceinline__ size_t plane_row(const PlaneGeom& g, int n, int y, in
            static_cast<size_t>(y + g.pad) * g.Wp + (x + g.pad);
 }
 
+__device__ __forceinline__ uint4 hmax8(uint4 a, uint4 b) {
+    uint4 r;
+    *reinterpret_cast<__half2*>(&r.x) = __hmax2(*reinterpret_cast<__half2*>(&a.x), *reinterpret_cast<__half2*>(&b.x));
+    *reinterpret_cast<__half2*>(&r.y) = __hmax2(*reinterpret_cast<__half2*>(&a.y), *reinterpret_cast<__half2*>(&b.y));
+    *reinterpret_cast<__half2*>(&r.z) = __hmax2(*reinterpret_cast<__half2*>(&a.z), *reinterpret_cast<__half2*>(&b.z));
+    *reinterpret_cast<__half2*>(&r.w) = __hmax2(*reinterpret_cast<__half2*>(&a.w), *reinterpret_cast<__half2*>(&b.w));
+    return r;
+}
+
 // ------------------------------------------------------------------------------------------------ image prep
 // Replaces (x - pixel_mean) / pixel_std + ImageList.from_tensors zero padding
 // (sylph/modeling/meta_arch/meta_one_stage_detector.py:174-178), fused with the 2x2 space-to-depth re-layout that
@@ -28,7 +37,7 @@ struct ImageDesc {
     int is_u8;
 };
 
-__global__ void prep_stem_input_kernel(const ImageDesc* __restrict__ imgs, float* __restrict__ out, PlaneGeom g,
+__global__ void prep_stem_input_kernel(const ImageDesc* __restrict__ imgs, __half* __restrict__ out, PlaneGeom g,
                                        int n_images, float m0, float m1, float m2, float s0, float s1, float s2) {
     const long long total = static_cast<long long>(n_images) * g.H * g.W;
     for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
@@ -55,99 +64,92 @@ __global__ void prep_stem_input_kernel(const ImageDesc* __restrict__ imgs, float
                                                   : __ldg(static_cast<const float*>(im.ptr) + off);
                         t = (px - mean[c]) / stdv[c];
                     }
-                    v[(dy * 2 + dx) * 3 + c] = ptx::round_tf32(t);
+                    v[(dy * 2 + dx) * 3 + c] = t;
                 }
             }
         v[12] = v[13] = v[14] = v[15] = 0.f;
-        float4* o = reinterpret_cast<float4*>(out + plane_row(g, n, y2, x2) * 16);
-        o[0] = make_float4(v[0], v[1], v[2], v[3]);
-        o[1] = make_float4(v[4], v[5], v[6], v[7]);
-        o[2] = make_float4(v[8], v[9], v[10], v[11]);
-        o[3] = make_float4(v[12], v[13], v[14], v[15]);
+        uint4* o = reinterpret_cast<uint4*>(out + plane_row(g, n, y2, x2) * 16);
+        o[0] = make_uint4(pack_half2(v[0], v[1]), pack_half2(v[2], v[3]), pack_half2(v[4], v[5]), pack_half2(v[6], v[7]));
+        o[1] = make_uint4(pack_half2(v[8], v[9]), pack_half2(v[10], v[11]), 0u, 0u);
     }
 }
 
 // ------------------------------------------------------------------------------------------------ max-pool 3x3 / 2
 // detectron2 BasicStem max_pool2d(kernel 3, stride 2, padding 1) on post-ReLU (>= 0) activations: the zero border of
 // the input plane stands in for the -inf padding.
-__global__ void maxpool3x3s2_kernel(const float* __restrict__ in, float* __restrict__ out, PlaneGeom gi, PlaneGeom go,
+__global__ void maxpool3x3s2_kernel(const __half* __restrict__ in, __half* __restrict__ out, PlaneGeom gi, PlaneGeom go,
                                     int n_images, int C) {
-    const int c4n = C / 4;
-    const long long total = static_cast<long long>(n_images) * go.H * go.W * c4n;
+    const int c8n = C / 8;
+    const long long total = static_cast<long long>(n_images) * go.H * go.W * c8n;
     for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
          i += static_cast<long long>(gridDim.x) * blockDim.x) {
-        const int c4 = static_cast<int>(i % c4n);
-        long long r = i / c4n;
+        const int c8 = static_cast<int>(i % c8n);
+        long long r = i / c8n;
         const int ox = static_cast<int>(r % go.W);
         r /= go.W;
         const int oy = static_cast<int>(r % go.H);
         const int n = static_cast<int>(r / go.H);
-        float4 m = make_float4(0.f, 0.f, 0.f, 0.f);
+        uint4 m = make_uint4(0u, 0u, 0u, 0u);
 #pragma unroll
         for (int ky = 0; ky < 3; ++ky)
 #pragma unroll
             for (int kx = 0; kx < 3; ++kx) {
                 const int iy = 2 * oy - 1 + ky, ix = 2 * ox - 1 + kx;  // >= -1: inside the zero border (pad >= 1)
-                if (iy < gi.H + gi.pad && ix < gi.W + gi.pad) {
-                    const float4 v = __ldg(reinterpret_cast<const float4*>(in + plane_row(gi, n, iy, ix) * C) + c4);
-                    m.x = fmaxf(m.x, v.x); m.y = fmaxf(m.y, v.y); m.z = fmaxf(m.z, v.z); m.w = fmaxf(m.w, v.w);
-                }
+                if (iy < gi.H + gi.pad && ix < gi.W + gi.pad)
+                    m = hmax8(m, __ldg(reinterpret_cast<const uint4*>(in + plane_row(gi, n, iy, ix) * C) + c8));
             }
-        reinterpret_cast<float4*>(out + plane_row(go, n, oy, ox) * C)[c4] = m;
+        reinterpret_cast<uint4*>(out + plane_row(go, n, oy, ox) * C)[c8] = m;
     }
 }
 
 // ------------------------------------------------------------------------------------------------ stride-2 gather
 // out(oy, ox) = in(2 oy, 2 ox): the input side of every stride-2 1x1 convolution (STRIDE_IN_1X1) and the output side
 // of the stride-2 3x3 convolutions p6/p7 (computed at stride 1).
-__global__ void subsample2_kernel(const float* __restrict__ in, float* __restrict__ out, PlaneGeom gi, PlaneGeom go,
+__global__ void subsample2_kernel(const __half* __restrict__ in, __half* __restrict__ out, PlaneGeom gi, PlaneGeom go,
                                   int n_images, int C) {
-    const int c4n = C / 4;
-    const long long total = static_cast<long long>(n_images) * go.H * go.W * c4n;
+    const int c8n = C / 8;
+    const long long total = static_cast<long long>(n_images) * go.H * go.W * c8n;
     for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
          i += static_cast<long long>(gridDim.x) * blockDim.x) {
-        const int c4 = static_cast<int>(i % c4n);
-        long long r = i / c4n;
+        const int c8 = static_cast<int>(i % c8n);
+        long long r = i / c8n;
         const int ox = static_cast<int>(r % go.W);
         r /= go.W;
         const int oy = static_cast<int>(r % go.H);
         const int n = static_cast<int>(r / go.H);
-        const float4 v = __ldg(reinterpret_cast<const float4*>(in + plane_row(gi, n, 2 * oy, 2 * ox) * C) + c4);
-        reinterpret_cast<float4*>(out + plane_row(go, n, oy, ox) * C)[c4] = v;
+        const uint4 v = __ldg(reinterpret_cast<const uint4*>(in + plane_row(gi, n, 2 * oy, 2 * ox) * C) + c8);
+        reinterpret_cast<uint4*>(out + plane_row(go, n, oy, ox) * C)[c8] = v;
     }
 }
 
 // ------------------------------------------------------------------------------------------------ FPN top-down
-// lateral(y, x) += coarser(y / 2, x / 2)  (F.interpolate(scale_factor=2, mode="nearest") + add), rounded to TF32
-// because the sum feeds the 3x3 output convolution.
-__global__ void upsample_add_kernel(float* __restrict__ fine, const float* __restrict__ coarse, PlaneGeom gf,
-                                    PlaneGeom gc, int n_images, int C) {
-    const int c4n = C / 4;
-    const long long total = static_cast<long long>(n_images) * gf.H * gf.W * c4n;
+// lateral(y, x) += coarser(y / 2, x / 2)  (F.interpolate(scale_factor=2, mode="nearest") + add), summed in fp32.
+__global__ void upsample_add_kernel(__half* fine, const __half* coarse, PlaneGeom gf, PlaneGeom gc, int n_images, int C) {
+    const int c8n = C / 8;
+    const long long total = static_cast<long long>(n_images) * gf.H * gf.W * c8n;
     for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
          i += static_cast<long long>(gridDim.x) * blockDim.x) {
-        const int c4 = static_cast<int>(i % c4n);
-        long long r = i / c4n;
+        const int c8 = static_cast<int>(i % c8n);
+        long long r = i / c8n;
         const int x = static_cast<int>(r % gf.W);
         r /= gf.W;
         const int y = static_cast<int>(r % gf.H);
         const int n = static_cast<int>(r / gf.H);
-        float4* fp = reinterpret_cast<float4*>(fine + plane_row(gf, n, y, x) * C) + c4;
-        const float4 c = __ldg(reinterpret_cast<const float4*>(coarse + plane_row(gc, n, y >> 1, x >> 1) * C) + c4);
-        float4 f = *fp;
-        f.x = ptx::round_tf32(f.x + c.x); f.y = ptx::round_tf32(f.y + c.y);
-        f.z = ptx::round_tf32(f.z + c.z); f.w = ptx::round_tf32(f.w + c.w);
-        *fp = f;
+        uint4* fp = reinterpret_cast<uint4*>(fine + plane_row(gf, n, y, x) * C) + c8;
+        const uint4 c = *(reinterpret_cast<const uint4*>(coarse + plane_row(gc, n, y >> 1, x >> 1) * C) + c8);
+        const uint4 f = *fp;
+        const float2 f0 = unpack_half2(f.x), f1 = unpack_half2(f.y), f2 = unpack_half2(f.z), f3 = unpack_half2(f.w);
+        const float2 c0 = unpack_half2(c.x), c1 = unpack_half2(c.y), c2 = unpack_half2(c.z), c3 = unpack_half2(c.w);
+        *fp = make_uint4(pack_half2(f0.x + c0.x, f0.y + c0.y), pack_half2(f1.x + c1.x, f1.y + c1.y),
+                         pack_half2(f2.x + c2.x, f2.y + c2.y), pack_half2(f3.x + c3.x, f3.y + c3.y));
     }
 }
 
-__global__ void relu_copy_kernel(const float4* __restrict__ in, float4* __restrict__ out, long long n4) {
-    for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < n4;
-         i += static_cast<long long>(gridDim.x) * blockDim.x) {
-        float4 v = __ldg(in + i);
-        v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f);
-        out[i] = v;
-    }
+__global__ void relu_copy_kernel(const uint4* __restrict__ in, uint4* __restrict__ out, long long n8) {
+    const uint4 z = make_uint4(0u, 0u, 0u, 0u);
+    for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < n8;
+         i += static_cast<long long>(gridDim.x) * blockDim.x)
+        out[i] = hmax8(__ldg(in + i), z);
 }
 
 // ------------------------------------------------------------------------------------------------ GroupNorm(32, 256)
@@ -173,46 +175,48 @@ __global__ void gn_finalize_kernel(const float* __restrict__ partial, const Seg*
     stats[(static_cast<size_t>(s) * 32 + g) * 2 + 1] = static_cast<float>(1.0 / sqrt(var + 1e-5));
 }
 
-// Apply: y = relu((x - mean) * rstd * gamma + beta) on interior pixels, 0 elsewhere, rounded to TF32; in place.
-// One thread per (row, 4 channels); C = 256 -> 64 threads per row, coalesced 1 KiB rows.
-__global__ void gn_apply_relu_kernel(float* __restrict__ x, const float* __restrict__ stats,
+// Apply: y = relu((x - mean) * rstd * gamma + beta) on interior pixels, 0 elsewhere; reads the fp32 conv output,
+// writes the fp16 activation the next convolution consumes.  One thread per (row, group of 8 channels).
+__global__ void gn_apply_relu_kernel(const float* __restrict__ x, __half* __restrict__ y, const float* __restrict__ stats,
                                      const float* __restrict__ gamma, const float* __restrict__ beta,
                                      const int* __restrict__ tile_seg, const Seg* __restrict__ segs, int row_begin,
                                      long long n_rows, int relu) {
-    const long long total = n_rows * 64;
+    const long long total = n_rows * 32;
     for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
          i += static_cast<long long>(gridDim.x) * blockDim.x) {
-        const int c4 = static_cast<int>(i & 63);
-        const long long row = row_begin + (i >> 6);
+        const int g = static_cast<int>(i & 31);
+        const long long row = row_begin + (i >> 5);
         const int s = tile_seg[row / kBlockM];
         const Seg sg = segs[s];
         const int local = static_cast<int>(row - sg.row0);
-        const int y = local / sg.Wp, xx = local - y * sg.Wp;
-        const bool interior = local < sg.nrows && y >= sg.pad && y < sg.pad + sg.H && xx >= sg.pad && xx < sg.pad + sg.W;
-        float4* p = reinterpret_cast<float4*>(x + row * 256) + c4;
-        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+        const int yy = local / sg.Wp, xx = local - yy * sg.Wp;
+        const bool interior = local < sg.nrows && yy >= sg.pad && yy < sg.pad + sg.H && xx >= sg.pad && xx < sg.pad + sg.W;
+        uint4 o = make_uint4(0u, 0u, 0u, 0u);
         if (interior) {
-            v = *p;
-            const int g = c4 >> 1;  // 8 channels per group
+            const float4* p = reinterpret_cast<const float4*>(x + row * 256) + 2 * g;
+            const float4 a = __ldg(p), b = __ldg(p + 1);
             const float mean = stats[(static_cast<size_t>(s) * 32 + g) * 2];
             const float rstd = stats[(static_cast<size_t>(s) * 32 + g) * 2 + 1];
-            const float4 ga = __ldg(reinterpret_cast<const float4*>(gamma) + c4);
-            const float4 be = __ldg(reinterpret_cast<const float4*>(beta) + c4);
-            v.x = (v.x - mean) * rstd * ga.x + be.x;
-            v.y = (v.y - mean) * rstd * ga.y + be.y;
-            v.z = (v.z - mean) * rstd * ga.z + be.z;
-            v.w = (v.w - mean) * rstd * ga.w + be.w;
-            if (relu) { v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f); }
-            v.x = ptx::round_tf32(v.x); v.y = ptx::round_tf32(v.y); v.z = ptx::round_tf32(v.z); v.w = ptx::round_tf32(v.w);
+            const float4 ga = __ldg(reinterpret_cast<const float4*>(gamma) + 2 * g), gb = __ldg(reinterpret_cast<const float4*>(gamma) + 2 * g + 1);
+            const float4 ba = __ldg(reinterpret_cast<const float4*>(beta) + 2 * g), bb = __ldg(reinterpret_cast<const float4*>(beta) + 2 * g + 1);
+            float v[8] = {(a.x - mean) * rstd * ga.x + ba.x, (a.y - mean) * rstd * ga.y + ba.y,
+                          (a.z - mean) * rstd * ga.z + ba.z, (a.w - mean) * rstd * ga.w + ba.w,
+                          (b.x - mean) * rstd * gb.x + bb.x, (b.y - mean) * rstd * gb.y + bb.y,
+                          (b.z - mean) * rstd * gb.z + bb.z, (b.w - mean) * rstd * gb.w + bb.w};
+            if (relu) {
+#pragma unroll
+                for (int j = 0; j < 8; ++j) v[j] = fmaxf(v[j], 0.f);
+            }
+            o = make_uint4(pack_half2(v[0], v[1]), pack_half2(v[2], v[3]), pack_half2(v[4], v[5]), pack_half2(v[6], v[7]));
         }
-        *p = v;
+        reinterpret_cast<uint4*>(y + row * 256)[g] = o;
     }
 }
 
 // ------------------------------------------------------------------------------------------------ NCHW <-> planes
 // (n, C, H, W) fp32 <-> plane rows; used by the plugin-level import and by tests/exports, not by the episode path.
-// `cstride` = channels per plane row, `coff` = first channel, `scale_relu`: export-time transform for bbox_reg.
-__global__ void export_nchw_kernel(const float* __restrict__ plane, float* __restrict__ out, PlaneGeom g, int n_images,
+template <typename T>
+__global__ void export_nchw_kernel(const T* __restrict__ plane, float* __restrict__ out, PlaneGeom g, int n_images,
                                    int C, int cstride, int coff, float scale, int relu) {
     const long long total = static_cast<long long>(n_images) * C * g.H * g.W;
     for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
@@ -223,14 +227,14 @@ __global__ void export_nchw_kernel(const float* __restrict__ plane, float* __res
         r /= g.H;
         const int c = static_cast<int>(r % C);
         const int n = static_cast<int>(r / C);
-        float v = plane[plane_row(g, n, y, x) * cstride + coff + c] * scale;
+        float v = static_cast<float>(plane[plane_row(g, n, y, x) * cstride + coff + c]) * scale;
         if (relu) v = fmaxf(v, 0.f);
         out[i] = v;
     }
 }
 
-__global__ void import_nchw_kernel(const float* __restrict__ in, float* __restrict__ plane, PlaneGeom g, int n_images,
-                                   int C, int round) {
+__global__ void import_nchw_kernel(const float* __restrict__ in, __half* __restrict__ plane, PlaneGeom g, int n_images,
+                                   int C) {
     const long long total = static_cast<long long>(n_images) * C * g.H * g.W;
     for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
          i += static_cast<long long>(gridDim.x) * blockDim.x) {
@@ -240,9 +244,8 @@ __global__ void import_nchw_kernel(const float* __restrict__ in, float* __restri
         r /= g.W;
         const int y = static_cast<int>(r % g.H);
         const int n = static_cast<int>(r / g.H);
-        float v = __ldg(in + ((static_cast<size_t>(n) * C + c) * g.H + y) * g.W + x);
-        if (round) v = ptx::round_tf32(v);
-        plane[plane_row(g, n, y, x) * C + c] = v;
+        const float v = __ldg(in + ((static_cast<size_t>(n) * C + c) * g.H + y) * g.W + x);
+        plane[plane_row(g, n, y, x) * C + c] = __float2half_rn(fminf(fmaxf(v, -kHalfMax), kHalfMax));
     }
 }
 

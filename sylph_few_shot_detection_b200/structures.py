@@ -12,6 +12,9 @@ from typing import Any, Dict, Tuple
 import torch
 
 try:  # pragma: no cover - exercised only where detectron2 exists
+    import detectron2 as _d2  # type: ignore
+    if getattr(_d2, "__sylph_shim__", False):  # the oracle's stand-in package is test infrastructure, not detectron2
+        raise ImportError("oracle shim on sys.path")
     from detectron2.layers import ShapeSpec  # type: ignore
     from detectron2.structures import Boxes, Instances  # type: ignore
     from detectron2.utils.registry import Registry  # type: ignore
