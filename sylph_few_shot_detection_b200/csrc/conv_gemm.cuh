@@ -13,13 +13,18 @@
 // (bias, residual, ReLU, GroupNorm statistics) is FP32, stores round to nearest.  Values are clamped to the finite
 // fp16 range on store.
 //
-// Kernel structure (persistent, one CTA per SM, 320 threads):
-//   warp 0   : TMA producer  (A box 128 x 64 fp16, B box BN x 64 fp16, 128-byte swizzle, STAGES-deep mbarrier ring)
+// Kernel structure (persistent, one CTA per SM):
+//   warp 0   : TMA producer  (A box 128 x 64 fp16, B box BN x 64 fp16, 128-byte swizzle, STAGES-deep mbarrier ring;
+//              in the TMA-epilogue variant also the residual tile of the NEXT output tile)
 //   warp 1   : tcgen05.mma issuer (one thread), TMEM owner (2 accumulator buffers x BN columns)
-//   warps 2-9: epilogue, two warps per TMEM lane quadrant (each takes half of the BN columns): residual prefetch
-//              (issued before the accumulator is ready) -> tcgen05.ld -> bias / residual / ReLU / border mask /
-//              GroupNorm partial sums -> fp16 (or fp32) vector stores, overlapped with the next tile's MMAs through
-//              the second TMEM buffer.
+//   warps 2-9: epilogue, two warps per TMEM lane quadrant (each takes half of the BN columns):
+//              tcgen05.ld -> bias / residual / ReLU / border mask / GroupNorm partial sums -> store, overlapped with
+//              the next tile's MMAs through the second TMEM buffer.
+//   direct variant (TMA_EPI = false): residual prefetched into registers, fp16 or fp32 vector stores from registers.
+//   TMA variant    (TMA_EPI = true) : for the HBM-bound bottleneck 1x1 convolutions.  The residual tile arrives in a
+//              128-byte-swizzled shared-memory tile by TMA while the previous tile is still in its epilogue, the
+//              epilogue rewrites that tile in place, and warp 10 streams it out with TMA stores: no thread ever
+//              waits on a global load and every HBM transaction is a full line.
 //
 // Replaces the cuDNN convolutions reached from detectron2/AdelaiDet modules at
 //   sylph/modeling/meta_arch/meta_one_stage_detector.py:180-182 (backbone), sylph/modeling/meta_fcos/fcos.py:625-664
@@ -35,7 +40,6 @@ constexpr int kBlockM = 128;
 constexpr int kBlockK = 64;   // fp16 elements = one 128-byte swizzle row
 constexpr int kUmmaK = 16;    // fp16: 32 bytes of K per tcgen05.mma
 constexpr int kMaxTaps = 16;
-constexpr int kGemmThreads = 320;
 constexpr float kHalfMax = 65504.f;
 
 // One zero-bordered plane (an image at one resolution) inside a flat buffer.
@@ -66,9 +70,9 @@ struct GemmArgs {
     signed char tap_dy[kMaxTaps];
     signed char tap_dx[kMaxTaps];
     const float* bias;     // [n_tiles * BN] or nullptr
-    const __half* residual;  // same row indexing as out, or nullptr
+    const __half* residual;  // same row indexing as out, or nullptr (direct variant)
     int ld_res;
-    void* out;             // __half* (default) or float* (kEpiOutF32)
+    void* out;             // __half* (default) or float* (kEpiOutF32) (direct variant)
     int ldc;
     int flags;
     const int* tile_seg;   // [absolute tile] -> segment index
@@ -76,14 +80,17 @@ struct GemmArgs {
     float* gn_partial;     // [absolute tile][32][2]
 };
 
-template <int BN, int STAGES>
+template <int BN, int STAGES, bool TMA_EPI>
 struct GemmSmem {
     static constexpr int kABytes = kBlockM * kBlockK * 2;  // 16 KiB
     static constexpr int kBBytes = BN * kBlockK * 2;
     static constexpr int kStageBytes = kABytes + kBBytes;
-    static constexpr int kBarOffset = STAGES * kStageBytes;
+    static constexpr int kEpiBytes = TMA_EPI ? kBlockM * BN * 2 : 0;  // one staged output tile, BN/64 swizzled panels
+    static constexpr int kEpiOffset = STAGES * kStageBytes;
+    static constexpr int kBarOffset = kEpiOffset + 2 * kEpiBytes;
     static constexpr int kGnOffset = kBarOffset + 256;
-    static constexpr int kTotal = kGnOffset + 4 * 32 * 2 * 4 + 1024;  // + alignment slack
+    static constexpr int kTotal = kGnOffset + (TMA_EPI ? 0 : 4 * 32 * 2 * 4) + 1024;  // + alignment slack
+    static constexpr int kThreads = TMA_EPI ? 352 : 320;
 };
 
 __device__ __forceinline__ uint32_t pack_half2(float a, float b) {
@@ -94,16 +101,18 @@ __device__ __forceinline__ float2 unpack_half2(uint32_t u) {
     return __half22float2(*reinterpret_cast<const __half2*>(&u));
 }
 
-template <int BN, int STAGES>
-__global__ void __launch_bounds__(kGemmThreads, 1)
+template <int BN, int STAGES, bool TMA_EPI>
+__global__ void __launch_bounds__(GemmSmem<BN, STAGES, TMA_EPI>::kThreads, 1)
 conv_gemm_f16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
+                     const __grid_constant__ CUtensorMap tmap_res, const __grid_constant__ CUtensorMap tmap_out,
                      const GemmArgs p) {
-    using S = GemmSmem<BN, STAGES>;
+    using S = GemmSmem<BN, STAGES, TMA_EPI>;
     constexpr int NH = BN >= 64 ? 2 : 1;       // epilogue warps per lane quadrant (column halves)
     constexpr int COLS = BN / NH;              // columns per epilogue warp
     constexpr int CH = COLS < 32 ? COLS : 32;  // epilogue column chunk
     constexpr uint32_t kTmemCols = (2 * BN < 32) ? 32 : 2 * BN;
     constexpr uint32_t kIdesc = ptx::make_idesc_f16(kBlockM, BN);
+    static_assert(!TMA_EPI || BN % 64 == 0, "TMA epilogue works on 64-column panels");
 
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -111,8 +120,12 @@ conv_gemm_f16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_co
     uint64_t* empty_bar = full_bar + STAGES;
     uint64_t* tmem_full = empty_bar + STAGES;
     uint64_t* tmem_empty = tmem_full + 2;
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+    uint64_t* res_full = tmem_empty + 2;     // TMA_EPI: residual tile landed in epi buffer b
+    uint64_t* stage_ready = res_full + 2;    // TMA_EPI: epilogue finished writing epi buffer b
+    uint64_t* epi_free = stage_ready + 2;    // TMA_EPI: TMA store finished reading epi buffer b
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(epi_free + 2);
     float* gn_smem = reinterpret_cast<float*>(smem + S::kGnOffset);
+    uint8_t* epi_smem = smem + S::kEpiOffset;
 
     const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0);
     const int lane = threadIdx.x & 31;
@@ -120,6 +133,10 @@ conv_gemm_f16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_co
     if (warp == 0 && lane == 0) {
         ptx::prefetch_tensormap(&tmap_a);
         ptx::prefetch_tensormap(&tmap_b);
+        if constexpr (TMA_EPI) {
+            ptx::prefetch_tensormap(&tmap_res);
+            ptx::prefetch_tensormap(&tmap_out);
+        }
     }
     if (warp == 1 && lane == 0) {
         for (int s = 0; s < STAGES; ++s) {
@@ -129,6 +146,9 @@ conv_gemm_f16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_co
         for (int a = 0; a < 2; ++a) {
             ptx::mbar_init(&tmem_full[a], 1);
             ptx::mbar_init(&tmem_empty[a], 128 * NH);
+            ptx::mbar_init(&res_full[a], 1);
+            ptx::mbar_init(&stage_ready[a], 128 * NH);
+            ptx::mbar_init(&epi_free[a], 1);
         }
         ptx::fence_barrier_init();
     }
@@ -144,17 +164,31 @@ conv_gemm_f16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_co
 
     const int total_tiles = p.num_m_tiles * p.num_n_tiles;
     const int ksteps = p.taps * p.kblocks_per_tap;
+    const bool use_res_tile = TMA_EPI && (p.flags & kEpiResidual);
 
     if (warp == 0) {
         // ------------------------------------------------------------ TMA producer
         if (lane == 0) {
             int stage = 0;
             uint32_t phase = 0;
-            for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+            int it = 0;
+            for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
                 const int m_tile = tile / p.num_n_tiles;
                 const int n_tile = tile - m_tile * p.num_n_tiles;
-                const int a_row_base = (p.tile_begin + m_tile) * kBlockM + p.a_row_delta;
+                const int out_row_base = (p.tile_begin + m_tile) * kBlockM;
+                const int a_row_base = out_row_base + p.a_row_delta;
                 const int b_row_base = n_tile * BN;
+                if constexpr (TMA_EPI) {
+                    if (use_res_tile) {
+                        const int buf = it & 1;
+                        ptx::mbar_wait(&epi_free[buf], ((it >> 1) & 1) ^ 1u);
+                        ptx::mbar_arrive_expect_tx(&res_full[buf], S::kEpiBytes);
+#pragma unroll
+                        for (int pn = 0; pn < BN / 64; ++pn)
+                            ptx::tma_load_2d(epi_smem + buf * S::kEpiBytes + pn * (kBlockM * 128), &tmap_res, &res_full[buf],
+                                             n_tile * BN + pn * 64, out_row_base);
+                    }
+                }
                 // planes of different FPN levels have different padded widths: the row shift of a tap is per tile
                 const int wp = p.segs[p.tile_seg[p.tile_begin + m_tile]].Wp;
                 int tap = 0, kb = 0;
@@ -207,13 +241,15 @@ conv_gemm_f16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_co
         const int half_idx = (warp - 2) >> 2;  // which half of the BN columns
         const int col_begin = half_idx * COLS;
         const int et = (warp - 2) * 32 + lane;
+        const int r_in_tile = quad * 32 + lane;
         int acc = 0;
         uint32_t acc_phase = 0;
-        for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        int it = 0;
+        for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
             const int m_tile = tile / p.num_n_tiles;
             const int n_tile = tile - m_tile * p.num_n_tiles;
             const int abs_tile = p.tile_begin + m_tile;
-            const int row = abs_tile * kBlockM + quad * 32 + lane;
+            const int row = abs_tile * kBlockM + r_in_tile;
             bool interior = true;
             if (p.flags & (kEpiMask | kEpiGnStats)) {
                 const Seg sg = p.segs[p.tile_seg[abs_tile]];
@@ -224,108 +260,191 @@ conv_gemm_f16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_co
                            (x < sg.pad + sg.W);
             }
             const bool keep = interior || !(p.flags & kEpiMask);
-            const size_t out_off = static_cast<size_t>(row) * p.ldc + static_cast<size_t>(n_tile) * BN + col_begin;
 
-            // residual prefetch for this warp's whole column range, issued before the accumulator is ready
-            uint4 res[COLS / 8 > 0 ? COLS / 8 : 1];
-            const bool use_res = (p.flags & kEpiResidual) && keep;
-            if (use_res) {
-                const uint4* rp = reinterpret_cast<const uint4*>(
-                    p.residual + static_cast<size_t>(row) * p.ld_res + static_cast<size_t>(n_tile) * BN + col_begin);
+            if constexpr (TMA_EPI) {
+                // ======================================================= staged (TMA in / TMA out) epilogue
+                const int buf = it & 1;
+                const uint32_t ph = (it >> 1) & 1;
+                uint8_t* tile_smem = epi_smem + buf * S::kEpiBytes;
+                ptx::mbar_wait(&tmem_full[acc], acc_phase);
+                if (use_res_tile) ptx::mbar_wait(&res_full[buf], ph);
+                else ptx::mbar_wait(&epi_free[buf], ph ^ 1u);
+                ptx::tc_fence_after();
+                const uint32_t t_row = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) +
+                                       static_cast<uint32_t>(acc * BN + col_begin);
 #pragma unroll
-                for (int j = 0; j < COLS / 8; ++j) res[j] = __ldg(rp + j);
-            }
-
-            ptx::mbar_wait(&tmem_full[acc], acc_phase);
-            ptx::tc_fence_after();
-            const uint32_t t_row = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) +
-                                   static_cast<uint32_t>(acc * BN + col_begin);
-
+                for (int c0 = 0; c0 < COLS; c0 += CH) {
+                    uint32_t v[CH];
+                    ptx::tmem_ld_32x32b_x32(t_row + c0, v);
+                    const int col = col_begin + c0;                 // first column of this chunk inside the tile
+                    uint8_t* panel = tile_smem + (col >> 6) * (kBlockM * 128) + r_in_tile * 128;
+                    const int ch16 = (col & 63) >> 3;               // first 16-byte chunk inside the panel row
+                    uint4 rr[CH / 8];
+                    if (use_res_tile) {
 #pragma unroll
-            for (int c0 = 0; c0 < COLS; c0 += CH) {
-                uint32_t v[CH];
-                if constexpr (CH == 32) ptx::tmem_ld_32x32b_x32(t_row + c0, v);
-                else ptx::tmem_ld_32x32b_x16(t_row + c0, v);
-                ptx::tmem_ld_wait();
-                float f[CH];
-#pragma unroll
-                for (int j = 0; j < CH; ++j) f[j] = __uint_as_float(v[j]);
-                if (p.bias != nullptr) {
-                    const float4* bp = reinterpret_cast<const float4*>(p.bias + n_tile * BN + col_begin + c0);
-#pragma unroll
-                    for (int j = 0; j < CH / 4; ++j) {
-                        const float4 b = __ldg(bp + j);
-                        f[4 * j + 0] += b.x; f[4 * j + 1] += b.y; f[4 * j + 2] += b.z; f[4 * j + 3] += b.w;
+                        for (int j = 0; j < CH / 8; ++j)
+                            rr[j] = *reinterpret_cast<const uint4*>(panel + (((ch16 + j) ^ (r_in_tile & 7)) << 4));
                     }
+                    ptx::tmem_ld_wait();
+                    float f[CH];
+#pragma unroll
+                    for (int j = 0; j < CH; ++j) f[j] = __uint_as_float(v[j]);
+                    if (p.bias != nullptr) {
+                        const float4* bp = reinterpret_cast<const float4*>(p.bias + n_tile * BN + col);
+#pragma unroll
+                        for (int j = 0; j < CH / 4; ++j) {
+                            const float4 b = __ldg(bp + j);
+                            f[4 * j + 0] += b.x; f[4 * j + 1] += b.y; f[4 * j + 2] += b.z; f[4 * j + 3] += b.w;
+                        }
+                    }
+                    if (use_res_tile) {
+#pragma unroll
+                        for (int j = 0; j < CH / 8; ++j) {
+                            const float2 a = unpack_half2(rr[j].x), b = unpack_half2(rr[j].y), c = unpack_half2(rr[j].z),
+                                         d = unpack_half2(rr[j].w);
+                            f[8 * j + 0] += a.x; f[8 * j + 1] += a.y; f[8 * j + 2] += b.x; f[8 * j + 3] += b.y;
+                            f[8 * j + 4] += c.x; f[8 * j + 5] += c.y; f[8 * j + 6] += d.x; f[8 * j + 7] += d.y;
+                        }
+                    }
+                    if (p.flags & kEpiRelu) {
+#pragma unroll
+                        for (int j = 0; j < CH; ++j) f[j] = fmaxf(f[j], 0.f);
+                    }
+                    if (!keep) {
+#pragma unroll
+                        for (int j = 0; j < CH; ++j) f[j] = 0.f;
+                    }
+#pragma unroll
+                    for (int j = 0; j < CH / 8; ++j)
+                        *reinterpret_cast<uint4*>(panel + (((ch16 + j) ^ (r_in_tile & 7)) << 4)) =
+                            make_uint4(pack_half2(f[8 * j], f[8 * j + 1]), pack_half2(f[8 * j + 2], f[8 * j + 3]),
+                                       pack_half2(f[8 * j + 4], f[8 * j + 5]), pack_half2(f[8 * j + 6], f[8 * j + 7]));
                 }
-                if constexpr (BN == 256) {
-                    if (p.flags & kEpiGnStats) {
-                        // 4 groups of 8 channels in this chunk; reduce over the warp's 32 rows.
+                ptx::tc_fence_before();
+                ptx::mbar_arrive(&tmem_empty[acc]);
+                ptx::fence_proxy_async();          // generic-proxy smem writes -> visible to the TMA store
+                ptx::mbar_arrive(&stage_ready[buf]);
+            } else {
+                // ======================================================= direct (register) epilogue
+                const size_t out_off = static_cast<size_t>(row) * p.ldc + static_cast<size_t>(n_tile) * BN + col_begin;
+                // residual prefetch for this warp's whole column range, issued before the accumulator is ready
+                uint4 res[COLS / 8 > 0 ? COLS / 8 : 1];
+                const bool use_res = (p.flags & kEpiResidual) && keep;
+                if (use_res) {
+                    const uint4* rp = reinterpret_cast<const uint4*>(
+                        p.residual + static_cast<size_t>(row) * p.ld_res + static_cast<size_t>(n_tile) * BN + col_begin);
 #pragma unroll
-                        for (int g = 0; g < 4; ++g) {
-                            float s = 0.f, ss = 0.f;
-                            if (interior) {
+                    for (int j = 0; j < COLS / 8; ++j) res[j] = __ldg(rp + j);
+                }
+                ptx::mbar_wait(&tmem_full[acc], acc_phase);
+                ptx::tc_fence_after();
+                const uint32_t t_row = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) +
+                                       static_cast<uint32_t>(acc * BN + col_begin);
 #pragma unroll
-                                for (int j = 0; j < 8; ++j) { const float x = f[8 * g + j]; s += x; ss += x * x; }
-                            }
+                for (int c0 = 0; c0 < COLS; c0 += CH) {
+                    uint32_t v[CH];
+                    if constexpr (CH == 32) ptx::tmem_ld_32x32b_x32(t_row + c0, v);
+                    else ptx::tmem_ld_32x32b_x16(t_row + c0, v);
+                    ptx::tmem_ld_wait();
+                    float f[CH];
 #pragma unroll
-                            for (int o = 16; o > 0; o >>= 1) {
-                                s += __shfl_xor_sync(0xffffffffu, s, o);
-                                ss += __shfl_xor_sync(0xffffffffu, ss, o);
-                            }
-                            if (lane == 0) {
-                                const int grp = ((col_begin + c0) >> 3) + g;
-                                gn_smem[(quad * 32 + grp) * 2 + 0] = s;
-                                gn_smem[(quad * 32 + grp) * 2 + 1] = ss;
+                    for (int j = 0; j < CH; ++j) f[j] = __uint_as_float(v[j]);
+                    if (p.bias != nullptr) {
+                        const float4* bp = reinterpret_cast<const float4*>(p.bias + n_tile * BN + col_begin + c0);
+#pragma unroll
+                        for (int j = 0; j < CH / 4; ++j) {
+                            const float4 b = __ldg(bp + j);
+                            f[4 * j + 0] += b.x; f[4 * j + 1] += b.y; f[4 * j + 2] += b.z; f[4 * j + 3] += b.w;
+                        }
+                    }
+                    if constexpr (BN == 256) {
+                        if (p.flags & kEpiGnStats) {
+                            // 4 groups of 8 channels in this chunk; reduce over the warp's 32 rows.
+#pragma unroll
+                            for (int g = 0; g < 4; ++g) {
+                                float s = 0.f, ss = 0.f;
+                                if (interior) {
+#pragma unroll
+                                    for (int j = 0; j < 8; ++j) { const float x = f[8 * g + j]; s += x; ss += x * x; }
+                                }
+#pragma unroll
+                                for (int o = 16; o > 0; o >>= 1) {
+                                    s += __shfl_xor_sync(0xffffffffu, s, o);
+                                    ss += __shfl_xor_sync(0xffffffffu, ss, o);
+                                }
+                                if (lane == 0) {
+                                    const int grp = ((col_begin + c0) >> 3) + g;
+                                    gn_smem[(quad * 32 + grp) * 2 + 0] = s;
+                                    gn_smem[(quad * 32 + grp) * 2 + 1] = ss;
+                                }
                             }
                         }
                     }
-                }
-                if (use_res) {
+                    if (use_res) {
 #pragma unroll
-                    for (int j = 0; j < CH / 8; ++j) {
-                        const uint4 r = res[c0 / 8 + j];
-                        const float2 a = unpack_half2(r.x), b = unpack_half2(r.y), c = unpack_half2(r.z), d = unpack_half2(r.w);
-                        f[8 * j + 0] += a.x; f[8 * j + 1] += a.y; f[8 * j + 2] += b.x; f[8 * j + 3] += b.y;
-                        f[8 * j + 4] += c.x; f[8 * j + 5] += c.y; f[8 * j + 6] += d.x; f[8 * j + 7] += d.y;
+                        for (int j = 0; j < CH / 8; ++j) {
+                            const uint4 r = res[c0 / 8 + j];
+                            const float2 a = unpack_half2(r.x), b = unpack_half2(r.y), c = unpack_half2(r.z), d = unpack_half2(r.w);
+                            f[8 * j + 0] += a.x; f[8 * j + 1] += a.y; f[8 * j + 2] += b.x; f[8 * j + 3] += b.y;
+                            f[8 * j + 4] += c.x; f[8 * j + 5] += c.y; f[8 * j + 6] += d.x; f[8 * j + 7] += d.y;
+                        }
+                    }
+                    if (p.flags & kEpiRelu) {
+#pragma unroll
+                        for (int j = 0; j < CH; ++j) f[j] = fmaxf(f[j], 0.f);
+                    }
+                    if (!keep) {
+#pragma unroll
+                        for (int j = 0; j < CH; ++j) f[j] = 0.f;
+                    }
+                    if (p.flags & kEpiOutF32) {
+                        float4* op = reinterpret_cast<float4*>(static_cast<float*>(p.out) + out_off + c0);
+#pragma unroll
+                        for (int j = 0; j < CH / 4; ++j) op[j] = make_float4(f[4 * j], f[4 * j + 1], f[4 * j + 2], f[4 * j + 3]);
+                    } else {
+                        uint4* op = reinterpret_cast<uint4*>(static_cast<__half*>(p.out) + out_off + c0);
+#pragma unroll
+                        for (int j = 0; j < CH / 8; ++j)
+                            op[j] = make_uint4(pack_half2(f[8 * j], f[8 * j + 1]), pack_half2(f[8 * j + 2], f[8 * j + 3]),
+                                               pack_half2(f[8 * j + 4], f[8 * j + 5]), pack_half2(f[8 * j + 6], f[8 * j + 7]));
                     }
                 }
-                if (p.flags & kEpiRelu) {
-#pragma unroll
-                    for (int j = 0; j < CH; ++j) f[j] = fmaxf(f[j], 0.f);
-                }
-                if (!keep) {
-#pragma unroll
-                    for (int j = 0; j < CH; ++j) f[j] = 0.f;
-                }
-                if (p.flags & kEpiOutF32) {
-                    float4* op = reinterpret_cast<float4*>(static_cast<float*>(p.out) + out_off + c0);
-#pragma unroll
-                    for (int j = 0; j < CH / 4; ++j) op[j] = make_float4(f[4 * j], f[4 * j + 1], f[4 * j + 2], f[4 * j + 3]);
-                } else {
-                    uint4* op = reinterpret_cast<uint4*>(static_cast<__half*>(p.out) + out_off + c0);
-#pragma unroll
-                    for (int j = 0; j < CH / 8; ++j)
-                        op[j] = make_uint4(pack_half2(f[8 * j], f[8 * j + 1]), pack_half2(f[8 * j + 2], f[8 * j + 3]),
-                                           pack_half2(f[8 * j + 4], f[8 * j + 5]), pack_half2(f[8 * j + 6], f[8 * j + 7]));
+                // accumulator buffer fully read: hand it back to the MMA warp
+                ptx::tc_fence_before();
+                ptx::mbar_arrive(&tmem_empty[acc]);
+                if constexpr (BN == 256) {
+                    if (p.flags & kEpiGnStats) {
+                        asm volatile("bar.sync 1, 256;" ::: "memory");
+                        if (et < 64) {
+                            const float t = gn_smem[et] + gn_smem[64 + et] + gn_smem[128 + et] + gn_smem[192 + et];
+                            p.gn_partial[static_cast<size_t>(abs_tile) * 64 + et] = t;
+                        }
+                        asm volatile("bar.sync 1, 256;" ::: "memory");
+                    }
                 }
             }
-            // accumulator buffer fully read: hand it back to the MMA warp
-            ptx::tc_fence_before();
-            ptx::mbar_arrive(&tmem_empty[acc]);
             acc ^= 1;
             if (acc == 0) acc_phase ^= 1u;
-
-            if constexpr (BN == 256) {
-                if (p.flags & kEpiGnStats) {
-                    asm volatile("bar.sync 1, 256;" ::: "memory");
-                    if (et < 64) {
-                        const float t = gn_smem[et] + gn_smem[64 + et] + gn_smem[128 + et] + gn_smem[192 + et];
-                        p.gn_partial[static_cast<size_t>(abs_tile) * 64 + et] = t;
-                    }
-                    asm volatile("bar.sync 1, 256;" ::: "memory");
-                }
+        }
+    } else if (TMA_EPI && warp == 2 + 4 * NH) {
+        // ------------------------------------------------------------ TMA store warp (staged epilogue only)
+        if (lane == 0) {
+            int it = 0;
+            for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
+                const int m_tile = tile / p.num_n_tiles;
+                const int n_tile = tile - m_tile * p.num_n_tiles;
+                const int out_row_base = (p.tile_begin + m_tile) * kBlockM;
+                const int buf = it & 1;
+                ptx::mbar_wait(&stage_ready[buf], (it >> 1) & 1);
+#pragma unroll
+                for (int pn = 0; pn < BN / 64; ++pn)
+                    ptx::tma_store_2d(&tmap_out, epi_smem + buf * S::kEpiBytes + pn * (kBlockM * 128), n_tile * BN + pn * 64,
+                                      out_row_base);
+                ptx::bulk_commit_group();
+                ptx::bulk_wait_read_all();
+                ptx::mbar_arrive(&epi_free[buf]);
             }
+            ptx::bulk_wait_all();
         }
     }
 

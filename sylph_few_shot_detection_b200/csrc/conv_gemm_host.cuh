@@ -48,13 +48,13 @@ inline int make_tmap_2d(CUtensorMap* m, const __half* base, uint64_t rows, uint6
     return 0;
 }
 
-template <int BN, int STAGES>
-inline cudaError_t launch_conv_gemm_bn(const CUtensorMap& ta, const CUtensorMap& tb, const GemmArgs& args, int num_sms,
-                                       cudaStream_t stream) {
-    using S = GemmSmem<BN, STAGES>;
+template <int BN, int STAGES, bool TMA_EPI>
+inline cudaError_t launch_conv_gemm_bn(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tres,
+                                       const CUtensorMap& tout, const GemmArgs& args, int num_sms, cudaStream_t stream) {
+    using S = GemmSmem<BN, STAGES, TMA_EPI>;
     static bool configured = false;
     if (!configured) {
-        cudaError_t e = cudaFuncSetAttribute(conv_gemm_f16_kernel<BN, STAGES>,
+        cudaError_t e = cudaFuncSetAttribute(conv_gemm_f16_kernel<BN, STAGES, TMA_EPI>,
                                              cudaFuncAttributeMaxDynamicSharedMemorySize, S::kTotal);
         if (e != cudaSuccess) return e;
         configured = true;
@@ -62,20 +62,27 @@ inline cudaError_t launch_conv_gemm_bn(const CUtensorMap& ta, const CUtensorMap&
     const int total = args.num_m_tiles * args.num_n_tiles;
     if (total <= 0) return cudaSuccess;
     const int grid = total < num_sms ? total : num_sms;
-    conv_gemm_f16_kernel<BN, STAGES><<<grid, kGemmThreads, S::kTotal, stream>>>(ta, tb, args);
+    conv_gemm_f16_kernel<BN, STAGES, TMA_EPI><<<grid, S::kThreads, S::kTotal, stream>>>(ta, tb, tres, tout, args);
     return cudaGetLastError();
 }
 
-// BN in {16, 64, 128, 256}.
+// Direct-epilogue variants: BN in {16, 64, 128, 256}.
 inline cudaError_t launch_conv_gemm(int bn, const CUtensorMap& ta, const CUtensorMap& tb, const GemmArgs& args,
                                     int num_sms, cudaStream_t stream) {
     switch (bn) {
-        case 16: return launch_conv_gemm_bn<16, 8>(ta, tb, args, num_sms, stream);
-        case 64: return launch_conv_gemm_bn<64, 8>(ta, tb, args, num_sms, stream);
-        case 128: return launch_conv_gemm_bn<128, 6>(ta, tb, args, num_sms, stream);
-        case 256: return launch_conv_gemm_bn<256, 4>(ta, tb, args, num_sms, stream);
+        case 16: return launch_conv_gemm_bn<16, 8, false>(ta, tb, ta, ta, args, num_sms, stream);
+        case 64: return launch_conv_gemm_bn<64, 8, false>(ta, tb, ta, ta, args, num_sms, stream);
+        case 128: return launch_conv_gemm_bn<128, 6, false>(ta, tb, ta, ta, args, num_sms, stream);
+        case 256: return launch_conv_gemm_bn<256, 4, false>(ta, tb, ta, ta, args, num_sms, stream);
         default: return cudaErrorInvalidValue;
     }
+}
+
+// Staged (TMA in / TMA out) epilogue, fp16 output, BN = 256: `tres` / `tout` are [rows][C] maps with 128 x 64 boxes.
+inline cudaError_t launch_conv_gemm_staged(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tres,
+                                           const CUtensorMap& tout, const GemmArgs& args, int num_sms,
+                                           cudaStream_t stream) {
+    return launch_conv_gemm_bn<256, 2, true>(ta, tb, tres, tout, args, num_sms, stream);
 }
 
 // IEEE fp32 -> fp16, round to nearest even, saturating to the finite range (host-side weight preparation).

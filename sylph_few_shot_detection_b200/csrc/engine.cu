@@ -75,6 +75,7 @@ struct sylph_ctx {
     bool finalized = false;
     int64_t launches = 0;
     bool profiling = false;
+    int staged_epilogue = 1;  // SYLPH_STAGED_EPILOGUE=0 falls back to the register epilogue for conv3
     std::vector<Timing> timings;
 
     // prepared weights
@@ -339,6 +340,8 @@ struct ConvCall {
     const float* bias_override = nullptr;
     const __half* w_override = nullptr;
     int stem = 0;
+    int staged = 0;          // TMA-in / TMA-out epilogue (fp16 output, BN = 256); needs out_rows
+    long long out_rows = 0;  // rows of the output (and residual) buffer, for the staged epilogue's tensor maps
     const char* name = "conv";
 };
 
@@ -384,7 +387,19 @@ static int run_conv(sylph_ctx* c, const ConvCall& k, cudaStream_t st) {
                            ((k.flags & kEpiResidual) ? 2.0 : 1.0)) * 2.0;
         cudaEventRecord(tm.e0, st);
     }
-    CU_TRY(c, launch_conv_gemm(W.bn, ta, tb, g, c->num_sms, st));
+    if (k.staged) {
+        if (W.bn != 256 || (k.flags & (kEpiOutF32 | kEpiGnStats)) || k.out_rows <= 0)
+            return c->fail("staged epilogue needs BN = 256, fp16 output and out_rows (%s)", k.name);
+        CUtensorMap tres, tout;
+        const __half* rsrc = (k.flags & kEpiResidual) ? k.residual : static_cast<const __half*>(k.out);
+        if (make_tmap_2d(&tres, rsrc, static_cast<uint64_t>(k.out_rows), (k.flags & kEpiResidual) ? k.ld_res : k.ldc,
+                         (k.flags & kEpiResidual) ? k.ld_res : k.ldc, kBlockM, &err) ||
+            make_tmap_2d(&tout, static_cast<const __half*>(k.out), static_cast<uint64_t>(k.out_rows), k.ldc, k.ldc, kBlockM, &err))
+            return c->fail("epilogue tensor maps (%s): %s", k.name, err.c_str());
+        CU_TRY(c, launch_conv_gemm_staged(ta, tb, tres, tout, g, c->num_sms, st));
+    } else {
+        CU_TRY(c, launch_conv_gemm(W.bn, ta, tb, g, c->num_sms, st));
+    }
     c->launches++;
     if (c->profiling) {
         cudaEventRecord(tm.e1, st);
@@ -436,6 +451,7 @@ int sylph_create(sylph_ctx** out, int device, const sylph_model_config* cfg) {
     c->device = device;
     c->num_sms = prop.multiProcessorCount;
     c->cfg = *cfg;
+    if (const char* e = getenv("SYLPH_STAGED_EPILOGUE")) c->staged_epilogue = atoi(e);
     *out = c;
     if (cfg->pre_nms_topk * 5 > 8192) { c->fail("pre_nms_topk * 5 must be <= 8192"); }
     return 0;
@@ -701,7 +717,9 @@ static int run_backbone(sylph_ctx* c, int slot, int n, const void* const* images
             TRY(run_conv(c, k, st));
             k.W = &B.c3; k.A = T2; k.a_cols = k.a_ld = bott; k.out = Y; k.ldc = out_ch; k.residual = Y; k.ld_res = out_ch;
             k.flags = kEpiRelu | kEpiMask | kEpiResidual; k.name = "res.conv3_1x1";
+            k.staged = c->staged_epilogue; k.out_rows = rows;
             TRY(run_conv(c, k, st));
+            k.staged = 0;
         }
         X = Y;
         x_ch = out_ch;

@@ -55,6 +55,7 @@ struct Case {
     std::vector<int> dys, dxs;
     int flags;
     bool bias;
+    bool staged = false;  // TMA-in / TMA-out epilogue, run IN PLACE (out == residual buffer) like the bottleneck conv3
 };
 
 static int run_case(const Case& c, int num_sms) {
@@ -125,7 +126,18 @@ static int run_case(const Case& c, int num_sms) {
     g.tile_seg = dTS;
     g.segs = dS;
     g.gn_partial = dG;
-    CK(launch_conv_gemm(c.bn, ta, tb, g, num_sms, 0));
+    if (c.staged) {
+        if (!hR.empty()) CK(cudaMemcpy(dO, hR.data(), hR.size() * 2, cudaMemcpyHostToDevice));  // in place: out starts as the residual
+        g.residual = static_cast<const __half*>(dO);
+        CUtensorMap tio;
+        if (make_tmap_2d(&tio, static_cast<const __half*>(dO), M, c.cout, c.cout, 128, &err)) {
+            printf("[%s] FAIL epilogue tensor map: %s\n", c.name, err.c_str());
+            return 1;
+        }
+        CK(launch_conv_gemm_staged(ta, tb, tio, tio, g, num_sms, 0));
+    } else {
+        CK(launch_conv_gemm(c.bn, ta, tb, g, num_sms, 0));
+    }
     cudaError_t e = cudaDeviceSynchronize();
     if (e != cudaSuccess) {
         printf("[%s] FAIL kernel: %s\n", c.name, cudaGetErrorString(e));
@@ -193,7 +205,7 @@ static Seg mk_seg(int row0, int H, int W, int pad) {
 }
 static int round128(int x) { return (x + 127) / 128 * 128; }
 
-static void bench_shape(const char* name, int bn, int m_tiles, int cin, int cout, int taps, int flags, int num_sms) {
+static void bench_shape(const char* name, int bn, int m_tiles, int cin, int cout, int taps, int flags, int num_sms, bool staged = false) {
     const int M = m_tiles * 128;
     const int osz = (flags & kEpiOutF32) ? 4 : 2;
     __half *dA, *dW, *dR = nullptr;
@@ -236,11 +248,17 @@ static void bench_shape(const char* name, int bn, int m_tiles, int cin, int cout
     g.bias = dB; g.residual = dR; g.ld_res = cout; g.out = dO; g.ldc = cout; g.flags = flags; g.tile_seg = dTS; g.segs = dS; g.gn_partial = dG;
     cudaEvent_t e0, e1;
     CK(cudaEventCreate(&e0)); CK(cudaEventCreate(&e1));
-    for (int i = 0; i < 3; ++i) CK(launch_conv_gemm(bn, ta, tb, g, num_sms, 0));
+    CUtensorMap tio = ta;
+    if (staged) {
+        g.residual = static_cast<const __half*>(dO);
+        if (make_tmap_2d(&tio, static_cast<const __half*>(dO), M, cout, cout, 128, &err)) { printf("tmap failed\n"); return; }
+    }
+    auto launch = [&]() { return staged ? launch_conv_gemm_staged(ta, tb, tio, tio, g, num_sms, 0) : launch_conv_gemm(bn, ta, tb, g, num_sms, 0); };
+    for (int i = 0; i < 3; ++i) CK(launch());
     CK(cudaDeviceSynchronize());
     const int iters = 10;
     CK(cudaEventRecord(e0));
-    for (int i = 0; i < iters; ++i) CK(launch_conv_gemm(bn, ta, tb, g, num_sms, 0));
+    for (int i = 0; i < iters; ++i) CK(launch());
     CK(cudaEventRecord(e1));
     CK(cudaEventSynchronize(e1));
     float ms;
@@ -310,6 +328,18 @@ int main(int argc, char** argv) {
         c.segs[0].nrows = c.total_rows;
         fails += run_case(c, sms);
     }
+    {   // staged epilogue, in place, 4 n-tiles, many tiles per CTA (buffer/phase cycling), masked borders
+        Seg s0 = mk_seg(0, 150, 168, 1);
+        Case c{"staged_inplace_res_relu_mask_n1024", 256, {s0}, round128(s0.nrows), 128, 128, 1024, 1, 2, z1, z1, kEpiRelu | kEpiResidual | kEpiMask, true};
+        c.staged = true;
+        fails += run_case(c, sms);
+    }
+    {   // staged epilogue without residual (store-only staging)
+        Case c{"staged_noresidual_n256", 256, {mk_seg(0, 1, 638, 1)}, 128 * 301, 64, 64, 256, 1, 1, z1, z1, kEpiRelu, true};
+        c.segs[0].nrows = c.total_rows;
+        c.staged = true;
+        fails += run_case(c, sms);
+    }
     {
         Seg s0 = mk_seg(0, 13, 21, 1);
         Case c{"conv3x3_bn16_f32out", 16, {s0}, round128(s0.nrows), 256, 256, 16, 9, 4, dy9, dx9, kEpiMask | kEpiOutF32, true};
@@ -325,6 +355,8 @@ int main(int argc, char** argv) {
         bench_shape("tower3x3_256_gn_f32out", 256, 1480, 256, 256, 9, kEpiMask | kEpiGnStats | kEpiOutF32, sms);
         bench_shape("tower3x3_256_plain", 256, 1480, 256, 256, 9, 0, sms);
         bench_shape("res2_conv3_1x1_64_256_res", 256, 4272, 64, 256, 1, kEpiResidual | kEpiRelu | kEpiMask, sms);
+        bench_shape("res2_conv3_1x1_64_256_res_STAGED", 256, 4272, 64, 256, 1, kEpiResidual | kEpiRelu | kEpiMask, sms, true);
+        bench_shape("res4_conv3_1x1_256_1024_res_STAGED", 256, 280, 256, 1024, 1, kEpiResidual | kEpiRelu | kEpiMask, sms, true);
         bench_shape("res2_conv1_1x1_256_64", 64, 4272, 256, 64, 1, kEpiRelu | kEpiMask, sms);
         bench_shape("res2_conv2_3x3_64_64", 64, 4272, 64, 64, 9, kEpiRelu | kEpiMask, sms);
         bench_shape("res3_conv2_3x3_128_128", 128, 1088, 128, 128, 9, kEpiRelu | kEpiMask, sms);

@@ -115,6 +115,16 @@ def inference_with_class_codes(model: MetaOneStageDetector, query_items: Sequenc
     return out
 
 
+_COPY_STREAMS: Dict[Any, Any] = {}
+
+
+def _copy_stream(device):
+    key = str(device)
+    if key not in _COPY_STREAMS:
+        _COPY_STREAMS[key] = torch.cuda.Stream(device=device)
+    return _COPY_STREAMS[key]
+
+
 def run_episode(model: MetaOneStageDetector, support_items: Sequence[Dict[str, Any]], query_items: Sequence[Dict[str, Any]],
                 group=None, shard: bool = True) -> List[Dict]:
     """One meta-test episode (steps B-F).  With a process group and `shard=True`, classes and query images are split
@@ -127,10 +137,21 @@ def run_episode(model: MetaOneStageDetector, support_items: Sequence[Dict[str, A
         my_query = [query_items[i] for i in shard_range(len(query_items), world, rank)]
     else:
         my_support, my_query = list(support_items), list(query_items)
+    # host-resident query images start their H2D copy on a side stream now, so it overlaps the support pass
+    ready = None
+    if torch.cuda.is_available() and any(not q["image"].is_cuda for q in my_query):
+        side = _copy_stream(model.device)
+        with torch.cuda.stream(side):
+            staged = [dict(q, image=q["image"].to(model.device, non_blocking=True)) for q in my_query]
+        ready = torch.cuda.Event()
+        ready.record(side)
+        my_query = staged
     sub_codes = inference_on_support_set(model, my_support)
     all_codes = gather_class_code(sub_codes, group=group) if (world > 1 and shard) else sub_codes
     all_codes = inference_normalization(model, all_codes)
     packed = format_class_codes_shared(all_codes, device=model.device)
+    if ready is not None:
+        torch.cuda.current_stream().wait_event(ready)
     return inference_with_class_codes(model, my_query, packed)
 
 
