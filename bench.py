@@ -175,11 +175,22 @@ def main():
         return
 
     import torch.distributed as dist
-    if world > 1:
-        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        # NCCL prints its version banner on stdout at the first collective; keep stdout for the ONE JSON line
+        sys.stdout.flush()
+        saved = os.dup(1)
+        os.dup2(2, 1)
+        try:
+            dist.init_process_group("nccl", device_id=dev)
+            dist.barrier()
+            torch.cuda.synchronize()
+        finally:
+            sys.stdout.flush()
+            os.dup2(saved, 1)
+            os.close(saved)
 
     from sylph_few_shot_detection_b200.modeling import build_model
     from sylph_few_shot_detection_b200.runtime import SLOT_QUERY, SLOT_SUPPORT
@@ -245,9 +256,15 @@ def main():
         support_items.append({"support_set": recs, "support_set_target": torch.tensor(c), "class_name": f"class{c}"})
     query_items = [{"image": q, "height": IMG_H, "width": IMG_W} for q in query_h]
 
+    # Every step copies one episode's images from pinned host memory (the NEXT episode's, double-buffered on a side
+    # stream while the current one computes) and reads the current episode's detections back to the host.
+    from sylph_few_shot_detection_b200.runner import EpisodePipeline
+    pipe = EpisodePipeline(model)
+    pending = [pipe.submit(support_items, query_items)]
+
     def episode_e2e():
-        from sylph_few_shot_detection_b200.runner import run_episode
-        res = run_episode(model, support_items, query_items)
+        pending.append(pipe.submit(support_items, query_items))
+        res = pipe.run(pending.pop(0))
         return [(r["instances"].pred_boxes.tensor.cpu(), r["instances"].scores.cpu()) for r in res]
 
     for _ in range(2):
@@ -308,7 +325,8 @@ def main():
                        "d2h_bytes_per_step": int(d2h), "ms_per_step": round(ms_e2e / args.steps, 3)},
                "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu,
                "episode_tflops": round(EPISODE_GFLOP * 1e-3 * value / world, 1),
-               "detections_per_image": [int(c) for c in counts.cpu().tolist()], "per_kernel": breakdown}
+               "detections_per_image": [int(c) for c in counts.cpu().tolist()],
+               "e2e_detections_per_image": [int(s.numel()) for _, s in res], "per_kernel": breakdown}
         print(json.dumps(out))
     if world > 1:
         dist.destroy_process_group()

@@ -78,17 +78,30 @@ struct GemmArgs {
     const int* tile_seg;   // [absolute tile] -> segment index
     const Seg* segs;
     float* gn_partial;     // [absolute tile][32][2]
+    int dbg_a_row_skew;    // experiment: load the A box `skew` rows early and start the MMA descriptor `skew` rows in
+    int dbg_base_offset;   // experiment: matrix-descriptor base_offset field used with the skew
 };
 
-template <int BN, int STAGES, bool TMA_EPI>
+// HALO > 0 selects the 3x3 "halo" pipeline: ONE A box of 130 rows (the 128 output rows plus one row on either side)
+// is loaded per (vertical tap, k-block) into one of HALO slots and serves the three horizontal taps -- the tensor-core
+// matrix descriptor simply starts 0, 1 or 2 rows into the swizzled tile (the 128-byte swizzle is a pure function of the
+// shared-memory address, so a row-shifted start needs no base-offset) -- while the per-tap B tiles cycle through their
+// own ring of STAGES slots.  A traffic from L2 drops 3x, which is what bounds the N <= 128 convolutions and most of
+// what bounds the N = 256 ones (profiles/r01_ncu_head_tower_kernel.md).
+template <int BN, int STAGES, int EPI_BUFS, int HALO>
 struct GemmSmem {
+    static constexpr bool TMA_EPI = EPI_BUFS > 0;          // 0: direct epilogue, 1 / 2: staged epilogue buffers
     static constexpr int kABytes = kBlockM * kBlockK * 2;  // 16 KiB
+    static constexpr int kAHaloRows = kBlockM + 2;
+    static constexpr int kAHaloTx = kAHaloRows * 128;       // bytes one halo box delivers
+    static constexpr int kAHaloBytes = 17 * 1024;           // slot size (multiple of the 1024-byte swizzle period)
     static constexpr int kBBytes = BN * kBlockK * 2;
-    static constexpr int kStageBytes = kABytes + kBBytes;
+    static constexpr int kStageBytes = HALO ? kBBytes : kABytes + kBBytes;
+    static constexpr int kRingOffset = HALO * kAHaloBytes;  // halo slots first, then the (B or A+B) stage ring
     static constexpr int kEpiBytes = TMA_EPI ? kBlockM * BN * 2 : 0;  // one staged output tile, BN/64 swizzled panels
-    static constexpr int kEpiOffset = STAGES * kStageBytes;
-    static constexpr int kBarOffset = kEpiOffset + 2 * kEpiBytes;
-    static constexpr int kGnOffset = kBarOffset + 256;
+    static constexpr int kEpiOffset = kRingOffset + STAGES * kStageBytes;
+    static constexpr int kBarOffset = kEpiOffset + EPI_BUFS * kEpiBytes;
+    static constexpr int kGnOffset = kBarOffset + 512;
     static constexpr int kTotal = kGnOffset + (TMA_EPI ? 0 : 4 * 32 * 2 * 4) + 1024;  // + alignment slack
     static constexpr int kThreads = TMA_EPI ? 352 : 320;
 };
@@ -101,12 +114,16 @@ __device__ __forceinline__ float2 unpack_half2(uint32_t u) {
     return __half22float2(*reinterpret_cast<const __half2*>(&u));
 }
 
-template <int BN, int STAGES, bool TMA_EPI>
-__global__ void __launch_bounds__(GemmSmem<BN, STAGES, TMA_EPI>::kThreads, 1)
+template <int BN, int STAGES, int EPI_BUFS, int HALO>
+__global__ void __launch_bounds__(GemmSmem<BN, STAGES, EPI_BUFS, HALO>::kThreads, 1)
 conv_gemm_f16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
                      const __grid_constant__ CUtensorMap tmap_res, const __grid_constant__ CUtensorMap tmap_out,
                      const GemmArgs p) {
-    using S = GemmSmem<BN, STAGES, TMA_EPI>;
+    using S = GemmSmem<BN, STAGES, EPI_BUFS, HALO>;
+    constexpr bool TMA_EPI = EPI_BUFS > 0;
+    constexpr int kHalo = HALO > 0 ? HALO : 1;
+    static_assert(HALO == 0 || EPI_BUFS == 0, "the halo pipeline uses the direct epilogue");
+    constexpr int kBufs = EPI_BUFS > 0 ? EPI_BUFS : 1;
     constexpr int NH = BN >= 64 ? 2 : 1;       // epilogue warps per lane quadrant (column halves)
     constexpr int COLS = BN / NH;              // columns per epilogue warp
     constexpr int CH = COLS < 32 ? COLS : 32;  // epilogue column chunk
@@ -123,7 +140,9 @@ conv_gemm_f16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_co
     uint64_t* res_full = tmem_empty + 2;     // TMA_EPI: residual tile landed in epi buffer b
     uint64_t* stage_ready = res_full + 2;    // TMA_EPI: epilogue finished writing epi buffer b
     uint64_t* epi_free = stage_ready + 2;    // TMA_EPI: TMA store finished reading epi buffer b
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(epi_free + 2);
+    uint64_t* a_full = epi_free + 2;         // HALO: halo A slot landed
+    uint64_t* a_empty = a_full + kHalo;      // HALO: all MMAs reading the halo A slot retired
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(a_empty + kHalo);
     float* gn_smem = reinterpret_cast<float*>(smem + S::kGnOffset);
     uint8_t* epi_smem = smem + S::kEpiOffset;
 
@@ -142,6 +161,10 @@ conv_gemm_f16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_co
         for (int s = 0; s < STAGES; ++s) {
             ptx::mbar_init(&full_bar[s], 1);
             ptx::mbar_init(&empty_bar[s], 1);
+        }
+        for (int a = 0; a < kHalo; ++a) {
+            ptx::mbar_init(&a_full[a], 1);
+            ptx::mbar_init(&a_empty[a], 1);
         }
         for (int a = 0; a < 2; ++a) {
             ptx::mbar_init(&tmem_full[a], 1);
@@ -171,6 +194,8 @@ conv_gemm_f16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_co
         if (lane == 0) {
             int stage = 0;
             uint32_t phase = 0;
+            int hs = 0;
+            uint32_t hphase = 0;
             int it = 0;
             for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
                 const int m_tile = tile / p.num_n_tiles;
@@ -180,8 +205,8 @@ conv_gemm_f16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_co
                 const int b_row_base = n_tile * BN;
                 if constexpr (TMA_EPI) {
                     if (use_res_tile) {
-                        const int buf = it & 1;
-                        ptx::mbar_wait(&epi_free[buf], ((it >> 1) & 1) ^ 1u);
+                        const int buf = it % kBufs;
+                        ptx::mbar_wait(&epi_free[buf], ((it / kBufs) & 1) ^ 1u);
                         ptx::mbar_arrive_expect_tx(&res_full[buf], S::kEpiBytes);
 #pragma unroll
                         for (int pn = 0; pn < BN / 64; ++pn)
@@ -191,13 +216,33 @@ conv_gemm_f16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_co
                 }
                 // planes of different FPN levels have different padded widths: the row shift of a tap is per tile
                 const int wp = p.segs[p.tile_seg[p.tile_begin + m_tile]].Wp;
+                if constexpr (HALO > 0) {
+                    for (int dyi = 0; dyi < 3; ++dyi) {
+                        for (int kb = 0; kb < p.kblocks_per_tap; ++kb) {
+                            ptx::mbar_wait(&a_empty[hs], hphase ^ 1u);
+                            ptx::mbar_arrive_expect_tx(&a_full[hs], S::kAHaloTx);
+                            ptx::tma_load_2d(smem + hs * S::kAHaloBytes, &tmap_a, &a_full[hs], kb * kBlockK,
+                                             a_row_base + (dyi - 1) * wp - 1);
+                            if (++hs == kHalo) { hs = 0; hphase ^= 1u; }
+                            for (int dxi = 0; dxi < 3; ++dxi) {
+                                ptx::mbar_wait(&empty_bar[stage], phase ^ 1u);
+                                ptx::mbar_arrive_expect_tx(&full_bar[stage], S::kBBytes);
+                                ptx::tma_load_2d(smem + S::kRingOffset + stage * S::kStageBytes, &tmap_b, &full_bar[stage],
+                                                 kb * kBlockK, (dyi * 3 + dxi) * p.b_rows_per_tap + b_row_base);
+                                if (++stage == STAGES) { stage = 0; phase ^= 1u; }
+                            }
+                        }
+                    }
+                    continue;
+                }
                 int tap = 0, kb = 0;
                 for (int ks = 0; ks < ksteps; ++ks) {
                     ptx::mbar_wait(&empty_bar[stage], phase ^ 1u);
                     ptx::mbar_arrive_expect_tx(&full_bar[stage], S::kStageBytes);
-                    uint8_t* sa = smem + stage * S::kStageBytes;
+                    uint8_t* sa = smem + S::kRingOffset + stage * S::kStageBytes;
                     ptx::tma_load_2d(sa, &tmap_a, &full_bar[stage], kb * kBlockK,
-                                     a_row_base + static_cast<int>(p.tap_dy[tap]) * wp + static_cast<int>(p.tap_dx[tap]));
+                                     a_row_base + static_cast<int>(p.tap_dy[tap]) * wp + static_cast<int>(p.tap_dx[tap]) -
+                                         p.dbg_a_row_skew);
                     ptx::tma_load_2d(sa + S::kABytes, &tmap_b, &full_bar[stage], kb * kBlockK,
                                      tap * p.b_rows_per_tap + b_row_base);
                     if (++kb == p.kblocks_per_tap) { kb = 0; ++tap; }
@@ -212,15 +257,45 @@ conv_gemm_f16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_co
             uint32_t phase = 0;
             int acc = 0;
             uint32_t acc_phase = 0;
+            int hs = 0;
+            uint32_t hphase = 0;
             for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
                 ptx::mbar_wait(&tmem_empty[acc], acc_phase ^ 1u);
                 ptx::tc_fence_after();
                 const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(acc * BN);
+                if constexpr (HALO > 0) {
+                    uint32_t first = 0;
+                    for (int g = 0; g < 3 * p.kblocks_per_tap; ++g) {
+                        ptx::mbar_wait(&a_full[hs], hphase);
+                        const uint32_t sa = ptx::smem_u32(smem + hs * S::kAHaloBytes);
+                        for (int dxi = 0; dxi < 3; ++dxi) {
+                            ptx::mbar_wait(&full_bar[stage], phase);
+                            ptx::tc_fence_after();
+                            // the tap's A tile is the halo tile started dxi rows in (address-based 128B swizzle)
+                            const uint64_t da = ptx::make_sw128_kmajor_desc(sa + dxi * 128);
+                            const uint64_t db = ptx::make_sw128_kmajor_desc(
+                                ptx::smem_u32(smem + S::kRingOffset + stage * S::kStageBytes));
+#pragma unroll
+                            for (int k = 0; k < kBlockK / kUmmaK; ++k)
+                                ptx::umma_f16(d_tmem, da + 2 * k, db + 2 * k, kIdesc, (first | k) ? 1u : 0u);
+                            first = 1;
+                            ptx::umma_commit(&empty_bar[stage]);
+                            if (++stage == STAGES) { stage = 0; phase ^= 1u; }
+                        }
+                        ptx::umma_commit(&a_empty[hs]);
+                        if (++hs == kHalo) { hs = 0; hphase ^= 1u; }
+                    }
+                    ptx::umma_commit(&tmem_full[acc]);
+                    acc ^= 1;
+                    if (acc == 0) acc_phase ^= 1u;
+                    continue;
+                }
                 for (int ks = 0; ks < ksteps; ++ks) {
                     ptx::mbar_wait(&full_bar[stage], phase);
                     ptx::tc_fence_after();
-                    const uint32_t sa = ptx::smem_u32(smem + stage * S::kStageBytes);
-                    const uint64_t da = ptx::make_sw128_kmajor_desc(sa);
+                    const uint32_t sa = ptx::smem_u32(smem + S::kRingOffset + stage * S::kStageBytes);
+                    const uint64_t da = ptx::make_sw128_kmajor_desc(sa + p.dbg_a_row_skew * 128) |
+                                        (static_cast<uint64_t>(p.dbg_base_offset & 7) << 49);
                     const uint64_t db = ptx::make_sw128_kmajor_desc(sa + S::kABytes);
 #pragma unroll
                     for (int k = 0; k < kBlockK / kUmmaK; ++k) {
@@ -263,8 +338,8 @@ conv_gemm_f16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_co
 
             if constexpr (TMA_EPI) {
                 // ======================================================= staged (TMA in / TMA out) epilogue
-                const int buf = it & 1;
-                const uint32_t ph = (it >> 1) & 1;
+                const int buf = it % kBufs;
+                const uint32_t ph = (it / kBufs) & 1;
                 uint8_t* tile_smem = epi_smem + buf * S::kEpiBytes;
                 ptx::mbar_wait(&tmem_full[acc], acc_phase);
                 if (use_res_tile) ptx::mbar_wait(&res_full[buf], ph);
@@ -434,8 +509,8 @@ conv_gemm_f16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_co
                 const int m_tile = tile / p.num_n_tiles;
                 const int n_tile = tile - m_tile * p.num_n_tiles;
                 const int out_row_base = (p.tile_begin + m_tile) * kBlockM;
-                const int buf = it & 1;
-                ptx::mbar_wait(&stage_ready[buf], (it >> 1) & 1);
+                const int buf = it % kBufs;
+                ptx::mbar_wait(&stage_ready[buf], (it / kBufs) & 1);
 #pragma unroll
                 for (int pn = 0; pn < BN / 64; ++pn)
                     ptx::tma_store_2d(&tmap_out, epi_smem + buf * S::kEpiBytes + pn * (kBlockM * 128), n_tile * BN + pn * 64,

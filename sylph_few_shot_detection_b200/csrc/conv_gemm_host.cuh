@@ -48,13 +48,13 @@ inline int make_tmap_2d(CUtensorMap* m, const __half* base, uint64_t rows, uint6
     return 0;
 }
 
-template <int BN, int STAGES, bool TMA_EPI>
+template <int BN, int STAGES, int EPI_BUFS, int HALO = 0>
 inline cudaError_t launch_conv_gemm_bn(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tres,
                                        const CUtensorMap& tout, const GemmArgs& args, int num_sms, cudaStream_t stream) {
-    using S = GemmSmem<BN, STAGES, TMA_EPI>;
+    using S = GemmSmem<BN, STAGES, EPI_BUFS, HALO>;
     static bool configured = false;
     if (!configured) {
-        cudaError_t e = cudaFuncSetAttribute(conv_gemm_f16_kernel<BN, STAGES, TMA_EPI>,
+        cudaError_t e = cudaFuncSetAttribute(conv_gemm_f16_kernel<BN, STAGES, EPI_BUFS, HALO>,
                                              cudaFuncAttributeMaxDynamicSharedMemorySize, S::kTotal);
         if (e != cudaSuccess) return e;
         configured = true;
@@ -62,18 +62,33 @@ inline cudaError_t launch_conv_gemm_bn(const CUtensorMap& ta, const CUtensorMap&
     const int total = args.num_m_tiles * args.num_n_tiles;
     if (total <= 0) return cudaSuccess;
     const int grid = total < num_sms ? total : num_sms;
-    conv_gemm_f16_kernel<BN, STAGES, TMA_EPI><<<grid, S::kThreads, S::kTotal, stream>>>(ta, tb, tres, tout, args);
+    conv_gemm_f16_kernel<BN, STAGES, EPI_BUFS, HALO><<<grid, S::kThreads, S::kTotal, stream>>>(ta, tb, tres, tout, args);
     return cudaGetLastError();
 }
+
+constexpr int kStagedTwoBufMaxKSteps = 8;
 
 // Direct-epilogue variants: BN in {16, 64, 128, 256}.
 inline cudaError_t launch_conv_gemm(int bn, const CUtensorMap& ta, const CUtensorMap& tb, const GemmArgs& args,
                                     int num_sms, cudaStream_t stream) {
     switch (bn) {
-        case 16: return launch_conv_gemm_bn<16, 8, false>(ta, tb, ta, ta, args, num_sms, stream);
-        case 64: return launch_conv_gemm_bn<64, 8, false>(ta, tb, ta, ta, args, num_sms, stream);
-        case 128: return launch_conv_gemm_bn<128, 6, false>(ta, tb, ta, ta, args, num_sms, stream);
-        case 256: return launch_conv_gemm_bn<256, 4, false>(ta, tb, ta, ta, args, num_sms, stream);
+        case 16: return launch_conv_gemm_bn<16, 8, 0>(ta, tb, ta, ta, args, num_sms, stream);
+        case 64: return launch_conv_gemm_bn<64, 8, 0>(ta, tb, ta, ta, args, num_sms, stream);
+        case 128: return launch_conv_gemm_bn<128, 6, 0>(ta, tb, ta, ta, args, num_sms, stream);
+        case 256: return launch_conv_gemm_bn<256, 4, 0>(ta, tb, ta, ta, args, num_sms, stream);
+        default: return cudaErrorInvalidValue;
+    }
+}
+
+// 3x3 halo pipeline (taps in the standard (dy, dx) row-major order): `ta` must be a map whose box has kBlockM + 2 rows.
+// <BN, B slots, 0, A halo slots>: 3 x 17 KB + 5 x 32 KB = 211 KB for BN = 256.
+inline cudaError_t launch_conv_gemm_halo(int bn, const CUtensorMap& ta, const CUtensorMap& tb, const GemmArgs& args,
+                                         int num_sms, cudaStream_t stream) {
+    switch (bn) {
+        case 16: return launch_conv_gemm_bn<16, 12, 0, 4>(ta, tb, ta, ta, args, num_sms, stream);
+        case 64: return launch_conv_gemm_bn<64, 12, 0, 4>(ta, tb, ta, ta, args, num_sms, stream);
+        case 128: return launch_conv_gemm_bn<128, 8, 0, 4>(ta, tb, ta, ta, args, num_sms, stream);
+        case 256: return launch_conv_gemm_bn<256, 5, 0, 3>(ta, tb, ta, ta, args, num_sms, stream);
         default: return cudaErrorInvalidValue;
     }
 }
@@ -81,8 +96,12 @@ inline cudaError_t launch_conv_gemm(int bn, const CUtensorMap& ta, const CUtenso
 // Staged (TMA in / TMA out) epilogue, fp16 output, BN = 256: `tres` / `tout` are [rows][C] maps with 128 x 64 boxes.
 inline cudaError_t launch_conv_gemm_staged(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tres,
                                            const CUtensorMap& tout, const GemmArgs& args, int num_sms,
-                                           cudaStream_t stream) {
-    return launch_conv_gemm_bn<256, 2, true>(ta, tb, tres, tout, args, num_sms, stream);
+                                           cudaStream_t stream, int variant = 0) {
+    // variant 1: 2 mainloop stages + 2 staging buffers (the residual of tile i+1 streams in during the epilogue of
+    // tile i); variant 2: 3 stages + 1 staging buffer for long K.  0 = pick by the number of k-steps.
+    if (variant == 0) variant = (args.taps * args.kblocks_per_tap <= kStagedTwoBufMaxKSteps) ? 1 : 2;
+    if (variant == 1) return launch_conv_gemm_bn<256, 2, 2>(ta, tb, tres, tout, args, num_sms, stream);
+    return launch_conv_gemm_bn<256, 3, 1>(ta, tb, tres, tout, args, num_sms, stream);
 }
 
 // IEEE fp32 -> fp16, round to nearest even, saturating to the finite range (host-side weight preparation).

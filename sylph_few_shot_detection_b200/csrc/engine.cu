@@ -76,6 +76,7 @@ struct sylph_ctx {
     int64_t launches = 0;
     bool profiling = false;
     int staged_epilogue = 1;  // SYLPH_STAGED_EPILOGUE=0 falls back to the register epilogue for conv3
+    int halo_pipeline = 1;    // SYLPH_HALO=0 falls back to one A box per tap for the 3x3 convolutions
     std::vector<Timing> timings;
 
     // prepared weights
@@ -349,7 +350,8 @@ static int run_conv(sylph_ctx* c, const ConvCall& k, cudaStream_t st) {
     const ConvW& W = *k.W;
     CUtensorMap ta, tb;
     std::string err;
-    if (make_tmap_2d(&ta, k.A, static_cast<uint64_t>(k.a_rows), k.a_cols, k.a_ld, kBlockM, &err))
+    const bool halo = c->halo_pipeline && W.taps == 9 && !k.stem && !k.staged;
+    if (make_tmap_2d(&ta, k.A, static_cast<uint64_t>(k.a_rows), k.a_cols, k.a_ld, halo ? kBlockM + 2 : kBlockM, &err))
         return c->fail("A tensor map (%s): %s", k.name, err.c_str());
     if (make_tmap_2d(&tb, k.w_override ? k.w_override : W.w, static_cast<uint64_t>(W.taps) * W.cout_pad, W.k_per_tap,
                      W.k_per_tap, W.bn, &err))
@@ -397,6 +399,8 @@ static int run_conv(sylph_ctx* c, const ConvCall& k, cudaStream_t st) {
             make_tmap_2d(&tout, static_cast<const __half*>(k.out), static_cast<uint64_t>(k.out_rows), k.ldc, k.ldc, kBlockM, &err))
             return c->fail("epilogue tensor maps (%s): %s", k.name, err.c_str());
         CU_TRY(c, launch_conv_gemm_staged(ta, tb, tres, tout, g, c->num_sms, st));
+    } else if (halo) {
+        CU_TRY(c, launch_conv_gemm_halo(W.bn, ta, tb, g, c->num_sms, st));
     } else {
         CU_TRY(c, launch_conv_gemm(W.bn, ta, tb, g, c->num_sms, st));
     }
@@ -452,6 +456,7 @@ int sylph_create(sylph_ctx** out, int device, const sylph_model_config* cfg) {
     c->num_sms = prop.multiProcessorCount;
     c->cfg = *cfg;
     if (const char* e = getenv("SYLPH_STAGED_EPILOGUE")) c->staged_epilogue = atoi(e);
+    if (const char* e = getenv("SYLPH_HALO")) c->halo_pipeline = atoi(e);
     *out = c;
     if (cfg->pre_nms_topk * 5 > 8192) { c->fail("pre_nms_topk * 5 must be <= 8192"); }
     return 0;
@@ -705,7 +710,9 @@ static int run_backbone(sylph_ctx* c, int slot, int n, const void* const* images
                 if (b != 0) return c->fail("shortcut conv on a non-first block is not supported");
                 k.W = &B.sc; k.A = bin; k.a_cols = k.a_ld = bin_ch; k.out = Y; k.ldc = out_ch; k.flags = kEpiMask;
                 k.name = "res.shortcut1x1";
+                k.staged = c->staged_epilogue; k.out_rows = rows;
                 TRY(run_conv(c, k, st));
+                k.staged = 0;
             } else if (b == 0) {
                 return c->fail("identity shortcut on the first block of a stage is not supported");
             }
@@ -796,8 +803,7 @@ static int conv_gn_relu(sylph_ctx* c, const ConvW& W, const float* gn_w, const f
     k.W = &W; k.A = in; k.a_rows = a_rows; k.a_cols = k.a_ld = 256; k.ps = ps; k.tile_begin = tile_begin; k.n_tiles = tiles;
     k.a_row_delta = 0; k.out = raw; k.ldc = 256; k.flags = kEpiGnStats | kEpiOutF32; k.gn_partial = gn_partial; k.name = name;
     TRY(run_conv(c, k, st));
-    gn_finalize_kernel<<<ceil_div(static_cast<long long>(n_segs) * 32, 128), 128, 0, st>>>(gn_partial, ps->d_segs, seg_begin,
-                                                                                       n_segs, gn_stats);
+    gn_finalize_kernel<<<n_segs, 256, 0, st>>>(gn_partial, ps->d_segs, seg_begin, n_segs, gn_stats);
     CU_TRY(c, cudaGetLastError());
     {
         const long long rows = static_cast<long long>(tiles) * kBlockM;

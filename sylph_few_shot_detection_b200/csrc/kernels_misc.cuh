@@ -155,24 +155,34 @@ __global__ void relu_copy_kernel(const uint4* __restrict__ in, uint4* __restrict
 // ------------------------------------------------------------------------------------------------ GroupNorm(32, 256)
 // Finalize: per (plane, group) reduce the per-tile partial sums the conv epilogue wrote, in double, in a fixed
 // order (deterministic).  stats[(seg * 32 + g) * 2] = mean, [+1] = rstd.   eps = 1e-5 (nn.GroupNorm default).
-__global__ void gn_finalize_kernel(const float* __restrict__ partial, const Seg* __restrict__ segs, int seg_begin,
-                                   int n_segs, float* __restrict__ stats) {
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n_segs * 32) return;
-    const int s = seg_begin + i / 32, g = i % 32;
+__global__ void __launch_bounds__(256)
+gn_finalize_kernel(const float* __restrict__ partial, const Seg* __restrict__ segs, int seg_begin, int n_segs,
+                   float* __restrict__ stats) {
+    // one block per plane: 32 groups x 8 lanes; each lane strides over the plane's tiles, then an 8-lane shuffle
+    // tree in a fixed order (deterministic), all in double
+    const int s = seg_begin + blockIdx.x;
+    const int g = threadIdx.x >> 3, l = threadIdx.x & 7;
     const Seg sg = segs[s];
     const int t0 = sg.row0 / kBlockM, t1 = (sg.row0 + sg.nrows + kBlockM - 1) / kBlockM;
     double sum = 0.0, sq = 0.0;
-    for (int t = t0; t < t1; ++t) {
-        sum += partial[static_cast<size_t>(t) * 64 + g * 2];
-        sq += partial[static_cast<size_t>(t) * 64 + g * 2 + 1];
+    for (int t = t0 + l; t < t1; t += 8) {
+        const float2 v = *reinterpret_cast<const float2*>(partial + static_cast<size_t>(t) * 64 + g * 2);
+        sum += v.x;
+        sq += v.y;
     }
-    const double cnt = static_cast<double>(sg.H) * sg.W * 8.0;
-    const double mean = sum / cnt;
-    double var = sq / cnt - mean * mean;
-    if (var < 0.0) var = 0.0;
-    stats[(static_cast<size_t>(s) * 32 + g) * 2] = static_cast<float>(mean);
-    stats[(static_cast<size_t>(s) * 32 + g) * 2 + 1] = static_cast<float>(1.0 / sqrt(var + 1e-5));
+#pragma unroll
+    for (int o = 1; o < 8; o <<= 1) {
+        sum += __shfl_xor_sync(0xffffffffu, sum, o);
+        sq += __shfl_xor_sync(0xffffffffu, sq, o);
+    }
+    if (l == 0) {
+        const double cnt = static_cast<double>(sg.H) * sg.W * 8.0;
+        const double mean = sum / cnt;
+        double var = sq / cnt - mean * mean;
+        if (var < 0.0) var = 0.0;
+        stats[(static_cast<size_t>(s) * 32 + g) * 2] = static_cast<float>(mean);
+        stats[(static_cast<size_t>(s) * 32 + g) * 2 + 1] = static_cast<float>(1.0 / sqrt(var + 1e-5));
+    }
 }
 
 // Apply: y = relu((x - mean) * rstd * gamma + beta) on interior pixels, 0 elsewhere; reads the fp32 conv output,

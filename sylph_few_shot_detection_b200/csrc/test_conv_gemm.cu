@@ -55,6 +55,8 @@ struct Case {
     std::vector<int> dys, dxs;
     int flags;
     bool bias;
+    int skew = 0, base_offset = 0;  // experiment: A box loaded `skew` rows early, descriptor started `skew` rows in
+    bool halo = false;    // 3x3 halo pipeline (one 130-row A box per vertical tap and k-block)
     bool staged = false;  // TMA-in / TMA-out epilogue, run IN PLACE (out == residual buffer) like the bottleneck conv3
 };
 
@@ -103,7 +105,7 @@ static int run_case(const Case& c, int num_sms) {
     const uint64_t a_rows_dim = (c.a_ld < c.cin_cols) ? static_cast<uint64_t>(M) - (c.cin_cols / c.a_ld - 1) : M;
     CUtensorMap ta, tb;
     std::string err;
-    if (make_tmap_2d(&ta, dA, a_rows_dim, c.cin_cols, c.a_ld, 128, &err) ||
+    if (make_tmap_2d(&ta, dA, a_rows_dim, c.cin_cols, c.a_ld, c.halo ? 130 : 128, &err) ||
         make_tmap_2d(&tb, dW, static_cast<uint64_t>(c.taps) * c.cout, Kt, Kt, c.bn, &err)) {
         printf("[%s] FAIL tensor map: %s\n", c.name, err.c_str());
         return 1;
@@ -126,6 +128,8 @@ static int run_case(const Case& c, int num_sms) {
     g.tile_seg = dTS;
     g.segs = dS;
     g.gn_partial = dG;
+    g.dbg_a_row_skew = c.skew;
+    g.dbg_base_offset = c.base_offset;
     if (c.staged) {
         if (!hR.empty()) CK(cudaMemcpy(dO, hR.data(), hR.size() * 2, cudaMemcpyHostToDevice));  // in place: out starts as the residual
         g.residual = static_cast<const __half*>(dO);
@@ -135,6 +139,8 @@ static int run_case(const Case& c, int num_sms) {
             return 1;
         }
         CK(launch_conv_gemm_staged(ta, tb, tio, tio, g, num_sms, 0));
+    } else if (c.halo) {
+        CK(launch_conv_gemm_halo(c.bn, ta, tb, g, num_sms, 0));
     } else {
         CK(launch_conv_gemm(c.bn, ta, tb, g, num_sms, 0));
     }
@@ -181,6 +187,7 @@ static int run_case(const Case& c, int num_sms) {
             if (!(err2 == err2)) err2 = 1e30;
             if (err2 > max_err) max_err = err2;
             if (fabs(acc) > max_ref) max_ref = fabs(acc);
+            if (c.skew && (r % 128) >= 128 - c.skew) continue;  // those rows read past the 128-row box by construction
             if (err2 > tol * (1.0 + fabs(acc)) && bad < 5) {
                 printf("  mismatch r=%d n=%d got=%g ref=%g\n", r, n, got, acc);
                 ++bad;
@@ -205,7 +212,7 @@ static Seg mk_seg(int row0, int H, int W, int pad) {
 }
 static int round128(int x) { return (x + 127) / 128 * 128; }
 
-static void bench_shape(const char* name, int bn, int m_tiles, int cin, int cout, int taps, int flags, int num_sms, bool staged = false) {
+static void bench_shape(const char* name, int bn, int m_tiles, int cin, int cout, int taps, int flags, int num_sms, int staged = 0, bool halo = false) {
     const int M = m_tiles * 128;
     const int osz = (flags & kEpiOutF32) ? 4 : 2;
     __half *dA, *dW, *dR = nullptr;
@@ -238,7 +245,7 @@ static void bench_shape(const char* name, int bn, int m_tiles, int cin, int cout
     }
     CUtensorMap ta, tb;
     std::string err;
-    if (make_tmap_2d(&ta, dA, M, cin, cin, 128, &err) || make_tmap_2d(&tb, dW, static_cast<uint64_t>(taps) * cout, cin, cin, bn, &err)) {
+    if (make_tmap_2d(&ta, dA, M, cin, cin, halo ? 130 : 128, &err) || make_tmap_2d(&tb, dW, static_cast<uint64_t>(taps) * cout, cin, cin, bn, &err)) {
         printf("[%s] tensor map failed: %s\n", name, err.c_str());
         return;
     }
@@ -253,7 +260,7 @@ static void bench_shape(const char* name, int bn, int m_tiles, int cin, int cout
         g.residual = static_cast<const __half*>(dO);
         if (make_tmap_2d(&tio, static_cast<const __half*>(dO), M, cout, cout, 128, &err)) { printf("tmap failed\n"); return; }
     }
-    auto launch = [&]() { return staged ? launch_conv_gemm_staged(ta, tb, tio, tio, g, num_sms, 0) : launch_conv_gemm(bn, ta, tb, g, num_sms, 0); };
+    auto launch = [&]() { return staged ? launch_conv_gemm_staged(ta, tb, tio, tio, g, num_sms, 0, staged) : (halo ? launch_conv_gemm_halo(bn, ta, tb, g, num_sms, 0) : launch_conv_gemm(bn, ta, tb, g, num_sms, 0)); };
     for (int i = 0; i < 3; ++i) CK(launch());
     CK(cudaDeviceSynchronize());
     const int iters = 10;
@@ -301,6 +308,15 @@ int main(int argc, char** argv) {
         c.segs[0].nrows = c.total_rows;
         fails += run_case(c, sms);
     }
+    for (int skew = 1; skew <= 3; ++skew)
+        for (int mode = 0; mode < 2; ++mode) {   // does a descriptor that starts `skew` rows into a swizzled tile work?
+            Case c{mode ? "EXPERIMENT_skew_base_offset=skew" : "EXPERIMENT_skew_base_offset=0", 256, {mk_seg(0, 1, 638, 1)}, 640, 128, 128, 256, 1, 2, z1, z1, kEpiOutF32, true};
+            c.segs[0].nrows = c.total_rows;
+            c.skew = skew;
+            c.base_offset = mode ? skew : 0;
+            printf("skew=%d ", skew);
+            run_case(c, sms);
+        }
     {
         Case c{"gemm_bn256_k256_persistent_f32out", 256, {mk_seg(0, 1, 638, 1)}, 128 * 333, 256, 256, 256, 1, 4, z1, z1, kEpiRelu | kEpiOutF32, true};
         c.segs[0].nrows = c.total_rows;
@@ -345,6 +361,25 @@ int main(int argc, char** argv) {
         Case c{"conv3x3_bn16_f32out", 16, {s0}, round128(s0.nrows), 256, 256, 16, 9, 4, dy9, dx9, kEpiMask | kEpiOutF32, true};
         fails += run_case(c, sms);
     }
+    for (int bnv : {256, 128, 64, 16}) {   // halo pipeline, every BN, two planes of different width, many tiles per CTA
+        Seg s0 = mk_seg(0, 140, 168, 1);
+        Seg s1 = mk_seg(round128(s0.nrows), 37, 41, 1);
+        int total = s1.row0 + round128(s1.nrows);
+        const int cout = bnv == 16 ? 16 : (bnv == 256 ? 512 : bnv);
+        Case c{"HALO_conv3x3", bnv, {s0, s1}, total, 128, 128, cout, 9, 2, dy9, dx9,
+               kEpiMask | (bnv == 256 ? 0 : kEpiRelu) | (bnv == 16 ? kEpiOutF32 : 0), true};
+        c.halo = true;
+        printf("bn=%d ", bnv);
+        fails += run_case(c, sms);
+    }
+    {   // halo + GroupNorm statistics + fp32 output (the tower configuration)
+        Seg s0 = mk_seg(0, 13, 21, 1);
+        Seg s1 = mk_seg(round128(s0.nrows), 7, 11, 1);
+        int total = s1.row0 + round128(s1.nrows);
+        Case c{"HALO_conv3x3_bn256_mask_gn_f32out", 256, {s0, s1}, total, 256, 256, 256, 9, 4, dy9, dx9, kEpiMask | kEpiGnStats | kEpiOutF32, true};
+        c.halo = true;
+        fails += run_case(c, sms);
+    }
     {   // stem trick: 16-channel pixels, rows overlapped (pitch 16 halves, 64 visible), 4 vertical taps x K=64
         Seg s0 = mk_seg(0, 10, 12, 2);
         Case c{"stem_overlapped_rows_bn64", 64, {s0}, round128(s0.nrows), 64, 16, 64, 4, 1, dy4, dx4, kEpiMask | kEpiRelu, true};
@@ -354,9 +389,26 @@ int main(int argc, char** argv) {
     if (argc > 1 && std::string(argv[1]) == "bench") {
         bench_shape("tower3x3_256_gn_f32out", 256, 1480, 256, 256, 9, kEpiMask | kEpiGnStats | kEpiOutF32, sms);
         bench_shape("tower3x3_256_plain", 256, 1480, 256, 256, 9, 0, sms);
+        bench_shape("tower3x3_256_gn_f32out_HALO", 256, 1480, 256, 256, 9, kEpiMask | kEpiGnStats | kEpiOutF32, sms, 0, true);
+        bench_shape("tower3x3_256_plain_HALO", 256, 1480, 256, 256, 9, 0, sms, 0, true);
+        bench_shape("res2_conv2_3x3_64_64_HALO", 64, 4272, 64, 64, 9, kEpiRelu | kEpiMask, sms, 0, true);
+        bench_shape("res3_conv2_3x3_128_128_HALO", 128, 1088, 128, 128, 9, kEpiRelu | kEpiMask, sms, 0, true);
+        bench_shape("res5_conv2_3x3_512_512_HALO", 256, 80, 512, 512, 9, kEpiRelu | kEpiMask, sms, 0, true);
+        bench_shape("pred3x3_256_16_f32out", 16, 1480, 256, 16, 9, kEpiOutF32, sms);
+        bench_shape("pred3x3_256_16_f32out_HALO", 16, 1480, 256, 16, 9, kEpiOutF32, sms, 0, true);
         bench_shape("res2_conv3_1x1_64_256_res", 256, 4272, 64, 256, 1, kEpiResidual | kEpiRelu | kEpiMask, sms);
-        bench_shape("res2_conv3_1x1_64_256_res_STAGED", 256, 4272, 64, 256, 1, kEpiResidual | kEpiRelu | kEpiMask, sms, true);
-        bench_shape("res4_conv3_1x1_256_1024_res_STAGED", 256, 280, 256, 1024, 1, kEpiResidual | kEpiRelu | kEpiMask, sms, true);
+        bench_shape("res2_conv3_1x1_64_256_res_STAGED_2x2", 256, 4272, 64, 256, 1, kEpiResidual | kEpiRelu | kEpiMask, sms, 1);
+        bench_shape("res3_conv3_1x1_128_512_res", 256, 1088, 128, 512, 1, kEpiResidual | kEpiRelu | kEpiMask, sms, 0);
+        bench_shape("res3_conv3_1x1_128_512_res_STAGED_2x2", 256, 1088, 128, 512, 1, kEpiResidual | kEpiRelu | kEpiMask, sms, 1);
+        bench_shape("res3_conv3_1x1_128_512_res_STAGED_3x1", 256, 1088, 128, 512, 1, kEpiResidual | kEpiRelu | kEpiMask, sms, 2);
+        bench_shape("res4_conv3_1x1_256_1024_res_STAGED_2x2", 256, 280, 256, 1024, 1, kEpiResidual | kEpiRelu | kEpiMask, sms, 1);
+        bench_shape("res4_conv3_1x1_256_1024_res_STAGED_3x1", 256, 280, 256, 1024, 1, kEpiResidual | kEpiRelu | kEpiMask, sms, 2);
+        bench_shape("res5_conv3_1x1_512_2048_res", 256, 80, 512, 2048, 1, kEpiResidual | kEpiRelu | kEpiMask, sms, 0);
+        bench_shape("res5_conv3_1x1_512_2048_res_STAGED_2x2", 256, 80, 512, 2048, 1, kEpiResidual | kEpiRelu | kEpiMask, sms, 1);
+        bench_shape("res5_conv3_1x1_512_2048_res_STAGED_3x1", 256, 80, 512, 2048, 1, kEpiResidual | kEpiRelu | kEpiMask, sms, 2);
+        bench_shape("res5_shortcut_1x1_1024_2048", 256, 80, 1024, 2048, 1, kEpiMask, sms, 0);
+        bench_shape("res5_shortcut_1x1_1024_2048_STAGED_2x2", 256, 80, 1024, 2048, 1, kEpiMask, sms, 1);
+        bench_shape("res5_shortcut_1x1_1024_2048_STAGED_3x1", 256, 80, 1024, 2048, 1, kEpiMask, sms, 2);
         bench_shape("res2_conv1_1x1_256_64", 64, 4272, 256, 64, 1, kEpiRelu | kEpiMask, sms);
         bench_shape("res2_conv2_3x3_64_64", 64, 4272, 64, 64, 9, kEpiRelu | kEpiMask, sms);
         bench_shape("res3_conv2_3x3_128_128", 128, 1088, 128, 128, 9, kEpiRelu | kEpiMask, sms);

@@ -155,6 +155,49 @@ def run_episode(model: MetaOneStageDetector, support_items: Sequence[Dict[str, A
     return inference_with_class_codes(model, my_query, packed)
 
 
+class EpisodePipeline:
+    """Throughput mode for a stream of episodes with HOST-resident inputs: `submit` starts the host-to-device copies
+    of an episode on a side stream, `run` executes it on the current stream once its copies have landed.  Submitting
+    episode i+1 before running episode i overlaps its H2D traffic with the compute of episode i.
+
+        h = pipe.submit(s0, q0)
+        for next_s, next_q in episodes:
+            nxt = pipe.submit(next_s, next_q)
+            results = pipe.run(h)
+            h = nxt
+    """
+
+    def __init__(self, model: MetaOneStageDetector):
+        self.model = model
+
+    def submit(self, support_items: Sequence[Dict[str, Any]], query_items: Sequence[Dict[str, Any]]):
+        dev = self.model.device
+        side = _copy_stream(dev)
+        with torch.cuda.stream(side):
+            sup = []
+            for item in support_items:
+                recs = [dict(r, image=r["image"].to(dev, non_blocking=True)) for r in item["support_set"]]
+                sup.append(dict(item, support_set=recs))
+            qry = [dict(q, image=q["image"].to(dev, non_blocking=True)) for q in query_items]
+        ev = torch.cuda.Event()
+        ev.record(side)
+        return sup, qry, ev
+
+    def run(self, handle) -> List[Dict]:
+        sup, qry, ev = handle
+        cur = torch.cuda.current_stream()
+        cur.wait_event(ev)
+        out = run_episode(self.model, sup, qry, shard=False)
+        # the staged tensors were allocated on the copy stream: tell the caching allocator they are in use on the
+        # compute stream, otherwise the next submit() could recycle their memory while kernels still read it
+        for item in sup:
+            for r in item["support_set"]:
+                r["image"].record_stream(cur)
+        for q in qry:
+            q["image"].record_stream(cur)
+        return out
+
+
 class MetaFCOSRunner:
     """The d2go-runner surface the reference CLI drives (`create_runner("sylph.runner.MetaFCOSRunner")`,
     sylph/runner/meta_fcos_runner.py:92-114, 381-382, 674-701), reduced to the inference hot path."""

@@ -1,0 +1,226 @@
+"""More GPU parity / property tests through the plugin API and the C ABI: edge cases the reference's domain has
+(no candidates, more candidates than PRE_NMS_TOPK, ragged image sizes, many classes, R-101, foreign NCHW features)
+and size-independent properties at BASELINE.json's full 800x1333 size."""
+import numpy as np
+import pytest
+import torch
+
+from tests.cases import rel_err
+
+pytestmark = pytest.mark.gpu
+
+
+def _setup(opts=None, seed=21, preset="COCO-Detection/Meta-FCOS/Meta-FCOS-finetune.yaml"):
+    from oracle.meta_fcos_oracle import MetaFCOSOracle
+    from sylph_few_shot_detection_b200 import weights as W
+    from sylph_few_shot_detection_b200.modeling import build_model
+    from sylph_few_shot_detection_b200.presets import preset_cfg
+    cfg = preset_cfg(preset, opts)
+    state = W.synthetic_state_dict(cfg, seed)
+    model = build_model(cfg)
+    model.load_state_dict(state)
+    return cfg, state, model, MetaFCOSOracle(cfg, state)
+
+
+def _images(n, h, w, seed):
+    g = torch.Generator().manual_seed(seed)
+    out = []
+    for i in range(n):
+        base = torch.rand(3, h // 8 + 2, w // 8 + 2, generator=g) * 255.0
+        img = torch.nn.functional.interpolate(base[None], size=(h, w), mode="bilinear", align_corners=False)[0]
+        out.append((img + (torch.rand(3, h, w, generator=g) - 0.5) * 40.0).clamp(0, 255).round().to(torch.uint8))
+    return out
+
+
+def _support_item(images, boxes, cls):
+    from sylph_few_shot_detection_b200.structures import Boxes, Instances
+    recs = []
+    for im, b in zip(images, boxes):
+        inst = Instances(tuple(im.shape[-2:]))
+        inst.gt_boxes = Boxes(b[None])
+        inst.gt_classes = torch.tensor([cls])
+        recs.append({"image": im, "instances": inst, "height": im.shape[-2], "width": im.shape[-1]})
+    return {"support_set": recs, "support_set_target": torch.tensor(cls), "class_name": f"c{cls}"}
+
+
+def _match(dets, ref, guard=5e-3, frac=0.1):
+    got = {(int(l), int(loc[0]), int(loc[1]), int(c)): (b, float(s)) for b, s, c, loc, l in
+           zip(dets.pred_boxes.tensor.cpu(), dets.scores.cpu(), dets.pred_classes.cpu(), dets.locations.cpu(), dets.fpn_levels.cpu())}
+    want = {(int(l), int(loc[0]), int(loc[1]), int(c)): (b, float(s)) for b, s, c, loc, l in
+            zip(ref["boxes"], ref["scores"], ref["classes"], ref["locations"], ref["levels"])}
+    common = set(got) & set(want)
+    diff = (set(got) - set(want)) | (set(want) - set(got))
+    assert len(diff) <= max(2, int(frac * max(len(want), 1))), (len(got), len(want), sorted(diff)[:6])
+    for k in common:
+        assert float((got[k][0] - want[k][0]).abs().max()) <= 0.5
+        assert abs(got[k][1] - want[k][1]) <= guard
+    return len(common), len(diff)
+
+
+def test_no_candidates_gives_empty_instances_and_codes_still_match():
+    """Reference initialisers leave every logit at the prior (sigmoid(-4.6) = 0.01 < 0.05): zero candidates."""
+    cfg, state, model, orc = _setup()
+    ims = _images(3, 160, 224, 1)
+    box = torch.tensor([[20.0, 30.0, 120.0, 140.0], [5.0, 5.0, 200.0, 150.0]])
+    code = model([_support_item(ims[:2], box, 0)], run_type="meta_learn_test_support")
+    ref = orc.class_code([i.float() for i in ims[:2]], box)
+    assert code["cls_conv"].shape == (1, 256, 1, 1) and code["cls_bias"].shape == (1, 1, 1, 1)
+    assert rel_err(code["cls_conv"], ref["cls_conv"]) < 1e-3
+    dead = {"cls_conv": torch.zeros(3, 256, 1, 1), "cls_bias": torch.full((3,), -4.59512)}
+    out = model([{"image": ims[2], "height": 160, "width": 224}], class_code=dead, run_type="meta_learn_test_instance")
+    inst = out[0]["instances"]
+    assert len(inst) == 0 and inst.pred_boxes.tensor.shape == (0, 4) and inst.pred_classes.dtype == torch.int64
+    assert inst.image_size == (160, 224)
+
+
+def test_more_candidates_than_pre_nms_topk_and_many_classes():
+    """Low threshold + small PRE_NMS_TOPK exercises the exact radix select; 20 classes exercise the 64-wide logits GEMM."""
+    cfg, state, model, orc = _setup(["MODEL.FCOS.INFERENCE_TH_TEST", 0.002, "MODEL.FCOS.PRE_NMS_TOPK_TEST", 150,
+                                     "MODEL.FCOS.POST_NMS_TOPK_TEST", 60], seed=4)
+    g = torch.Generator().manual_seed(9)
+    w = torch.nn.functional.normalize(torch.randn(20, 256, 1, 1, generator=g), dim=1) * 5.0
+    codes = {"cls_conv": w, "cls_bias": torch.randn(20, generator=g) * 0.3 - 4.0}
+    ims = _images(2, 192, 256, 3)
+    ims[1] = ims[1][:, :170, :230].contiguous()  # ragged batch: padded to the common /32 size
+    items = [{"image": im, "height": im.shape[-2], "width": im.shape[-1]} for im in ims]
+    out = model(items, class_code=codes, run_type="meta_learn_test_instance")
+    ref, inter = orc.detect([i.float() for i in ims], codes, return_intermediate=True)
+    assert max(int(p["scores"].numel()) for p in inter["pre_nms"]) >= 150 * 2, "test must overflow the per-level top-k"
+    for o, r in zip(out, ref):
+        n_common, n_diff = _match(o["instances"], r, frac=0.15)
+        assert n_common >= 40
+
+
+def test_output_rescaling_to_requested_height_width():
+    cfg, state, model, orc = _setup(seed=4)
+    g = torch.Generator().manual_seed(2)
+    codes = {"cls_conv": torch.nn.functional.normalize(torch.randn(2, 256, 1, 1, generator=g), dim=1) * 6.0,
+             "cls_bias": torch.tensor([-3.5, -3.8])}
+    im = _images(1, 160, 256, 5)[0]
+    out = model([{"image": im, "height": 320, "width": 512}], class_code=codes, run_type="meta_learn_test_instance")
+    ref = orc.detect([im.float()], codes, out_sizes=[(320, 512)])[0]
+    assert out[0]["instances"].image_size == (320, 512)
+    _match(out[0]["instances"], ref)
+    b = out[0]["instances"].pred_boxes.tensor
+    assert float(b[:, 0::2].max()) <= 512 and float(b[:, 1::2].max()) <= 320 and float(b.min()) >= 0
+
+
+def test_resnet101_backbone_features():
+    from sylph_few_shot_detection_b200.runtime import SLOT_SUPPORT
+    cfg, state, model, orc = _setup(["MODEL.RESNETS.DEPTH", 101], seed=2)
+    ims = _images(2, 128, 160, 8)
+    model.engine.extract_features(SLOT_SUPPORT, [i.cuda() for i in ims])
+    ref = orc.features(orc.preprocess([i.float() for i in ims]).tensor)
+    for l in range(5):
+        assert rel_err(model.engine.export_features(SLOT_SUPPORT, l), ref[l]) < 4e-3, l
+
+
+def test_code_generator_plugin_with_foreign_nchw_features():
+    """`CodeGenerator.forward(features, target_instances)` -- the plugin boundary -- fed with NCHW features computed
+    elsewhere (here: the CPU oracle's backbone), like tests/code_generator_roi_encoder_test.py does with synthetic
+    features in the reference."""
+    from sylph_few_shot_detection_b200.structures import Boxes, Instances
+    cfg, state, model, orc = _setup(seed=6, preset="LVISv1-Detection/Meta-FCOS/Meta-FCOS-finetune.yaml")
+    ims = _images(3, 256, 320, 12)
+    feats = orc.features(orc.preprocess([i.float() for i in ims]).tensor)
+    boxes = torch.tensor([[30.0, 40.0, 90.0, 120.0], [10.0, 10.0, 300.0, 250.0], [100.0, 60.0, 220.0, 200.0]])
+    insts = []
+    for b in boxes:
+        inst = Instances((256, 320))
+        inst.gt_boxes = Boxes(b[None])
+        insts.append(inst)
+    out = model.code_generator([f.cuda() for f in feats], insts)
+    roi, _ = orc.roi_features(feats, boxes)
+    w, b = orc.per_shot_codes(roi)
+    assert out["cls_conv"].shape == (1, 256, 1, 1) and out["cls_bias"].shape == (1, 1, 1, 1)
+    assert rel_err(out["cls_conv"].reshape(-1), w.mean(0).reshape(-1)) < 1e-3
+    assert abs(float(out["cls_bias"]) - float(b.mean())) < 1e-3
+    normed = model.normalize_class_code([{"support_set_target": 0, "class_code": dict(out)}])
+    wn, bn = orc.normalize_code(w.mean(0, keepdim=True), b.mean(0, keepdim=True))
+    assert normed[0]["class_code"]["cls_bias"].shape == (1,)
+    assert rel_err(normed[0]["class_code"]["cls_conv"], wn) < 1e-3 and rel_err(normed[0]["class_code"]["cls_bias"], bn) < 1e-3
+
+
+def test_batched_class_codes_equal_per_class_calls_and_levels_are_exact():
+    from sylph_few_shot_detection_b200.runtime import SLOT_SUPPORT
+    from oracle import upstream as up
+    cfg, state, model, orc = _setup(seed=3)
+    ims = _images(4, 480, 640, 17)
+    boxes = torch.tensor([[10.0, 10.0, 100.0, 90.0], [0.0, 0.0, 639.0, 479.0], [100.0, 100.0, 420.0, 400.0], [300.0, 200.0, 332.0, 230.0]])
+    items = [_support_item(ims[:2], boxes[:2], 0), _support_item(ims[2:], boxes[2:], 1)]
+    np.random.seed(0)
+    batched = model.forward_class_codes_batched(items)
+    single = [model([it], run_type="meta_learn_test_support") for it in items]
+    for a, b in zip(batched, single):
+        assert torch.equal(a["cls_conv"], b["cls_conv"]) and torch.equal(a["cls_bias"], b["cls_bias"])
+    model.engine.extract_features(SLOT_SUPPORT, [i.cuda() for i in ims])
+    _, levels = model.engine.generate_codes(SLOT_SUPPORT, boxes, [0, 1, 2, 3], [0, 2, 4], want_levels=True)
+    ref = up.assign_boxes_to_levels([up.Boxes(b[None]) for b in boxes], 3, 7, 224, 4)
+    assert levels.dtype == torch.int64 and torch.equal(levels.cpu(), ref)
+    assert len(set(ref.tolist())) >= 3  # boxes were chosen to land on several FPN levels
+
+
+def test_full_size_episode_properties():
+    """BASELINE configs[1] size (800x1333): no oracle run (minutes on CPU); size-independent properties instead --
+    run-to-run determinism, descending scores, boxes inside the image, post-NMS count bound, finite class codes."""
+    from sylph_few_shot_detection_b200.runner import run_episode
+    cfg, state, model, orc = _setup(seed=0)
+    g = torch.Generator().manual_seed(77)
+    ims = [torch.randint(0, 256, (3, 800, 1333), generator=g, dtype=torch.uint8) for _ in range(6)]
+    boxes = torch.tensor([[100.0, 100.0, 400.0, 500.0], [600.0, 200.0, 1300.0, 780.0], [50.0, 40.0, 120.0, 130.0], [0.0, 0.0, 1333.0, 800.0]])
+    support = [_support_item(ims[:2], boxes[:2], 0), _support_item(ims[2:4], boxes[2:], 1)]
+    query = [{"image": im, "height": 800, "width": 1333} for im in ims[4:]]
+    a = run_episode(model, support, query)
+    b = run_episode(model, support, query)
+    for ra, rb in zip(a, b):
+        ia, ib = ra["instances"], rb["instances"]
+        assert torch.equal(ia.pred_boxes.tensor, ib.pred_boxes.tensor) and torch.equal(ia.scores, ib.scores)
+        assert torch.equal(ia.pred_classes, ib.pred_classes)
+        s = ia.scores.cpu()
+        assert len(ia) <= 100 + 5 and bool((s[:-1] >= s[1:]).all()) and bool(torch.isfinite(s).all())
+        bx = ia.pred_boxes.tensor.cpu()
+        assert float(bx.min()) >= 0 and float(bx[:, 0::2].max()) <= 1333 and float(bx[:, 1::2].max()) <= 800
+        assert bool(((bx[:, 2] > bx[:, 0]) & (bx[:, 3] > bx[:, 1])).all())
+        assert int(ia.pred_classes.max()) <= 1 and int(ia.fpn_levels.max()) <= 4
+
+
+def test_many_classes_use_the_wide_logits_gemm_and_class_sweep_codes():
+    """Config-4/5 regimes at reduced size: 300 class codes (two 256-wide N tiles of the conditional classifier) and a
+    class sweep of 40 classes x 3 shots generated in ONE launch sequence from a small pool of support images."""
+    from sylph_few_shot_detection_b200.runtime import SLOT_QUERY, SLOT_SUPPORT
+    cfg, state, model, orc = _setup(seed=8)
+    g = torch.Generator().manual_seed(4)
+    n_cls = 300
+    codes = {"cls_conv": torch.nn.functional.normalize(torch.randn(n_cls, 256, 1, 1, generator=g), dim=1) * 4.0,
+             "cls_bias": torch.randn(n_cls, generator=g) * 0.2 - 4.5}
+    im = _images(1, 128, 192, 6)[0]
+    out = model([{"image": im, "height": 128, "width": 192}], class_code=codes, run_type="meta_learn_test_instance")
+    ref, inter = orc.detect([im.float()], codes, return_intermediate=True)
+    for l in range(5):
+        got = model.engine.export_head_output(0, l, SLOT_QUERY, n_cls)
+        assert got.shape == inter["logits"][l].shape
+        assert rel_err(got, inter["logits"][l]) < 3e-3, l
+    _match(out[0]["instances"], ref[0], frac=0.15)
+    assert int(out[0]["instances"].pred_classes.max()) > 255  # classes of the second N tile are reachable
+
+    pool = _images(4, 256, 320, 40)
+    n_classes, shots = 40, 3
+    boxes, roi_image, offsets = [], [], [0]
+    for c in range(n_classes):
+        for s in range(shots):
+            side = 24.0 + 5.0 * ((c * shots + s) % 40)
+            x0, y0 = float((7 * c + 3 * s) % 60), float((5 * c + 11 * s) % 40)
+            boxes.append([x0, y0, min(x0 + side * 1.2, 319.0), min(y0 + side, 255.0)])
+            roi_image.append((c + s) % 4)
+        offsets.append(len(boxes))
+    boxes = torch.tensor(boxes)
+    model.engine.extract_features(SLOT_SUPPORT, [p.cuda() for p in pool])
+    raw = model.engine.generate_codes(SLOT_SUPPORT, boxes, roi_image, offsets)
+    feats = orc.features(orc.preprocess([p.float() for p in pool]).tensor)
+    for c in (0, 17, 39):
+        idx = list(range(offsets[c], offsets[c + 1]))
+        sub = [f[[roi_image[i] for i in idx]] for f in feats]
+        roi, _ = orc.roi_features(sub, boxes[idx])
+        w, b = orc.per_shot_codes(roi)
+        assert rel_err(raw[c, :256], w.mean(0).reshape(-1)) < 1e-3
+        assert abs(float(raw[c, 256]) - float(b.mean())) < 1e-3
