@@ -95,6 +95,10 @@ struct sylph_ctx {
     float conv_scale = 1.f, bias_scale = 1.f, bias_value = 0.f;
 
     std::map<std::string, Buffer> bufs;
+    // pinned host ring for small host->device argument arrays: copies from it are truly asynchronous, so no entry
+    // point has to drain the stream (a pageable cudaMemcpyAsync synchronises the stream first)
+    uint8_t* pinned = nullptr;
+    size_t pinned_cap = 0, pinned_head = 0;
     std::map<std::string, std::shared_ptr<PlaneSet>> plane_sets;
     Slot slots[SYLPH_NUM_SLOTS];
     // state of the last generate_codes / detect call (for exports)
@@ -143,6 +147,27 @@ static int ensure(sylph_ctx* c, const std::string& name, size_t bytes, const std
     if (zero_on_change && (fresh || b.sig != sig)) CU_TRY(c, cudaMemsetAsync(b.p, 0, b.cap, st));
     b.sig = sig;
     *out = b.p;
+    return 0;
+}
+
+// Copy `bytes` of host data to device memory through the pinned ring, stream-ordered, without blocking the host.
+static int stage_h2d(sylph_ctx* c, void* dst_dev, const void* src_host, size_t bytes, cudaStream_t st) {
+    if (bytes == 0) return 0;
+    const size_t need = (bytes + 255) & ~size_t(255);
+    if (c->pinned == nullptr || need > c->pinned_cap) {
+        if (c->pinned) { CU_TRY(c, cudaDeviceSynchronize()); CU_TRY(c, cudaFreeHost(c->pinned)); }
+        c->pinned_cap = std::max<size_t>(need * 2, size_t(4) << 20);
+        CU_TRY(c, cudaMallocHost(reinterpret_cast<void**>(&c->pinned), c->pinned_cap));
+        c->pinned_head = 0;
+    }
+    if (c->pinned_head + need > c->pinned_cap) {
+        CU_TRY(c, cudaStreamSynchronize(st));  // wrap-around: earlier copies out of the ring must have executed
+        c->pinned_head = 0;
+    }
+    uint8_t* slot = c->pinned + c->pinned_head;
+    c->pinned_head += need;
+    memcpy(slot, src_host, bytes);
+    CU_TRY(c, cudaMemcpyAsync(dst_dev, slot, bytes, cudaMemcpyHostToDevice, st));
     return 0;
 }
 
@@ -467,6 +492,7 @@ void sylph_destroy(sylph_ctx* c) {
     cudaSetDevice(c->device);
     cudaDeviceSynchronize();
     for (auto& kv : c->bufs) if (kv.second.p) cudaFree(kv.second.p);
+    if (c->pinned) cudaFreeHost(c->pinned);
     for (auto& kv : c->plane_sets) { cudaFree(kv.second->d_segs); cudaFree(kv.second->d_tile_seg); }
     delete c;  // prepared weights are released with the CUDA context
 }
@@ -659,8 +685,7 @@ static int run_backbone(sylph_ctx* c, int slot, int n, const void* const* images
     for (int i = 0; i < n; ++i) { descs[i].ptr = images_dev[i]; descs[i].h = hs[i]; descs[i].w = ws[i]; descs[i].is_u8 = is_u8; }
     void* d_desc;
     TRY(ensure(c, "bb.desc", n * sizeof(ImageDesc), "", &d_desc, st, false));
-    CU_TRY(c, cudaMemcpyAsync(d_desc, descs.data(), n * sizeof(ImageDesc), cudaMemcpyHostToDevice, st));
-    CU_TRY(c, cudaStreamSynchronize(st));  // descs is a stack-lifetime staging vector
+    TRY(stage_h2d(c, d_desc, descs.data(), n * sizeof(ImageDesc), st));
     {
         StageTimer t(c, "prep_stem_input", st, static_cast<double>(n) * (3.0 * hmax * wmax + 32.0 * g0.H * g0.W));
         prep_stem_input_kernel<<<grid_for(static_cast<long long>(n) * g0.H * g0.W, 256, c->num_sms), 256, 0, st>>>(
@@ -913,9 +938,9 @@ int sylph_generate_codes(sylph_ctx* c, int slot, int n_rois, const float* boxes_
     TRY(ensure(c, "cg.gn_partial", static_cast<size_t>(n_rois) * 64 * 4, "", &gp, st, false));
     TRY(ensure(c, "cg.gn_stats", static_cast<size_t>(n_rois) * 64 * 4, "", &gs, st, false));
     TRY(ensure(c, "cg.shot", static_cast<size_t>(n_rois) * 257 * 4, "", &sc, st, false));
-    CU_TRY(c, cudaMemcpyAsync(pb, boxes_host, n_rois * 16, cudaMemcpyHostToDevice, st));
-    CU_TRY(c, cudaMemcpyAsync(pi, roi_image, n_rois * 4, cudaMemcpyHostToDevice, st));
-    CU_TRY(c, cudaMemcpyAsync(po, class_offsets, (n_classes + 1) * 4, cudaMemcpyHostToDevice, st));
+    TRY(stage_h2d(c, pb, boxes_host, static_cast<size_t>(n_rois) * 16, st));
+    TRY(stage_h2d(c, pi, roi_image, static_cast<size_t>(n_rois) * 4, st));
+    TRY(stage_h2d(c, po, class_offsets, static_cast<size_t>(n_classes + 1) * 4, st));
     // plane set of the ROI planes (one 9x9 plane = one tile per ROI); grows with the largest ROI count seen
     std::shared_ptr<PlaneSet> ps;
     {
@@ -955,7 +980,6 @@ int sylph_generate_codes(sylph_ctx* c, int slot, int n_rois, const float* boxes_
         CU_TRY(c, cudaGetLastError());
         c->launches += 2;
     }
-    CU_TRY(c, cudaStreamSynchronize(st));  // host staging arrays (boxes_host ...) belong to the caller
     return 0;
 }
 
@@ -1084,7 +1108,7 @@ int sylph_detect(sylph_ctx* c, int slot, const float* codes_dev, int n_classes, 
         args[i].out_w = static_cast<float>(ow);
         args[i].out_h = static_cast<float>(oh);
     }
-    CU_TRY(c, cudaMemcpyAsync(ia, args.data(), S.n * sizeof(NmsImageArgs), cudaMemcpyHostToDevice, st));
+    TRY(stage_h2d(c, ia, args.data(), S.n * sizeof(NmsImageArgs), st));
     CU_TRY(c, cudaMemsetAsync(cnt, 0, static_cast<size_t>(n_segs + 1) * 4, st));
     {
         StageTimer t(c, "proposals", st, static_cast<double>(S.n) * 22400 * (CW.cout_pad + 16) * 4);
@@ -1113,7 +1137,6 @@ int sylph_detect(sylph_ctx* c, int slot, const float* codes_dev, int n_classes, 
         CU_TRY(c, cudaGetLastError());
         c->launches += 3;
     }
-    CU_TRY(c, cudaStreamSynchronize(st));  // `args` staging vector lifetime
     return 0;
 }
 

@@ -224,3 +224,27 @@ def test_many_classes_use_the_wide_logits_gemm_and_class_sweep_codes():
         w, b = orc.per_shot_codes(roi)
         assert rel_err(raw[c, :256], w.mean(0).reshape(-1)) < 1e-3
         assert abs(float(raw[c, 256]) - float(b.mean())) < 1e-3
+
+
+@pytest.mark.parametrize("sizes", [[(64, 64)], [(96, 160), (80, 150)], [(160, 96)], [(257, 131), (200, 97), (31, 33)],
+                                   [(352, 480)], [(32, 512)], [(416, 64), (400, 40)]])
+def test_geometry_sweep_features_and_head_outputs(sizes):
+    """Odd, tiny, ragged and extreme-aspect images: every plane geometry (padding to /32, p6/p7 of 1-3 pixels, planes
+    narrower than a tile, batches of different sizes) against the CPU oracle."""
+    from sylph_few_shot_detection_b200.runtime import SLOT_QUERY
+    cfg, state, model, orc = _setup(seed=5)
+    ims = [_images(1, h, w, 100 + i)[0] for i, (h, w) in enumerate(sizes)]
+    g = torch.Generator().manual_seed(3)
+    codes = {"cls_conv": torch.nn.functional.normalize(torch.randn(3, 256, 1, 1, generator=g), dim=1) * 5.0,
+             "cls_bias": torch.tensor([-3.0, -3.5, -4.0])}
+    items = [{"image": im, "height": im.shape[-2], "width": im.shape[-1]} for im in ims]
+    out = model(items, class_code=codes, run_type="meta_learn_test_instance")
+    ref, inter = orc.detect([i.float() for i in ims], codes, return_intermediate=True)
+    for l in range(5):
+        got = model.engine.export_features(SLOT_QUERY, l)
+        assert got.shape == inter["features"][l].shape, (l, got.shape, inter["features"][l].shape)
+        assert rel_err(got, inter["features"][l]) < 3e-3, ("features", l)
+        assert rel_err(model.engine.export_head_output(0, l, SLOT_QUERY, 3), inter["logits"][l]) < 4e-3, ("logits", l)
+        assert rel_err(model.engine.export_head_output(1, l, SLOT_QUERY, 3), inter["reg"][l]) < 4e-3, ("reg", l)
+    for o, r in zip(out, ref):
+        _match(o["instances"], r, frac=0.15)
