@@ -301,7 +301,7 @@ def main():
             avg_ms = sum(tower) / len(tower)
             achieved = TOWER_FLOP_PER_IMAGE_LAYER * N_QUERY / (avg_ms * 1e-3) * 1e-12
             peak = float(peaks["bf16_tflops_sustained"])
-            roofline = {"kernel": "conv_gemm_f16_kernel<256,4> (FCOS tower 3x3 256->256, all levels x 8 images)",
+            roofline = {"kernel": "conv3x3_pair_kernel<3,8> -- cta_group::2 halo conv (FCOS tower 3x3 256->256, all levels x 8 images)",
                         "bound": "tensor", "achieved": round(achieved, 1), "peak": peak, "unit": "TFLOP/s",
                         "frac": round(achieved / peak, 4), "traffic": None,
                         "avg_launch_ms": round(avg_ms, 4), "launches_timed": len(tower),

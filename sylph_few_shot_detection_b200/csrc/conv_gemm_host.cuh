@@ -6,6 +6,7 @@
 #include <string>
 
 #include "conv_gemm.cuh"
+#include "conv_gemm_2cta.cuh"
 
 namespace sylph {
 
@@ -91,6 +92,23 @@ inline cudaError_t launch_conv_gemm_halo(int bn, const CUtensorMap& ta, const CU
         case 256: return launch_conv_gemm_bn<256, 5, 0, 3>(ta, tb, ta, ta, args, num_sms, stream);
         default: return cudaErrorInvalidValue;
     }
+}
+
+// CTA-pair (cta_group::2) 3x3 halo convolution, N tiles of 256: `ta` box = kBlockM + 2 rows, `tb` box = 128 rows.
+inline cudaError_t launch_conv3x3_pair(const CUtensorMap& ta, const CUtensorMap& tb, const GemmArgs& args, int num_sms,
+                                       cudaStream_t stream) {
+    using S = Gemm2Smem<3, 8>;
+    static bool configured = false;
+    if (!configured) {
+        cudaError_t e = cudaFuncSetAttribute(conv3x3_pair_kernel<3, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, S::kTotal);
+        if (e != cudaSuccess) return e;
+        configured = true;
+    }
+    const int pairs = ((args.num_m_tiles + 1) / 2) * args.num_n_tiles;
+    if (pairs <= 0) return cudaSuccess;
+    const int clusters = pairs < num_sms / 2 ? pairs : num_sms / 2;
+    conv3x3_pair_kernel<3, 8><<<clusters * 2, S::kThreads, S::kTotal, stream>>>(ta, tb, args);
+    return cudaGetLastError();
 }
 
 // Staged (TMA in / TMA out) epilogue, fp16 output, BN = 256: `tres` / `tout` are [rows][C] maps with 128 x 64 boxes.

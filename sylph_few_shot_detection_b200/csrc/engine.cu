@@ -77,6 +77,7 @@ struct sylph_ctx {
     bool profiling = false;
     int staged_epilogue = 1;  // SYLPH_STAGED_EPILOGUE=0 falls back to the register epilogue for conv3
     int halo_pipeline = 1;    // SYLPH_HALO=0 falls back to one A box per tap for the 3x3 convolutions
+    int pair_kernel = 1;      // SYLPH_PAIR=0 keeps the N = 256 3x3 convolutions on the single-CTA halo kernel
     std::vector<Timing> timings;
 
     // prepared weights
@@ -376,10 +377,11 @@ static int run_conv(sylph_ctx* c, const ConvCall& k, cudaStream_t st) {
     CUtensorMap ta, tb;
     std::string err;
     const bool halo = c->halo_pipeline && W.taps == 9 && !k.stem && !k.staged;
+    const bool pair = halo && c->pair_kernel && W.bn == 256 && !(k.flags & kEpiResidual);
     if (make_tmap_2d(&ta, k.A, static_cast<uint64_t>(k.a_rows), k.a_cols, k.a_ld, halo ? kBlockM + 2 : kBlockM, &err))
         return c->fail("A tensor map (%s): %s", k.name, err.c_str());
     if (make_tmap_2d(&tb, k.w_override ? k.w_override : W.w, static_cast<uint64_t>(W.taps) * W.cout_pad, W.k_per_tap,
-                     W.k_per_tap, W.bn, &err))
+                     W.k_per_tap, pair ? 128 : W.bn, &err))
         return c->fail("B tensor map (%s): %s", k.name, err.c_str());
     GemmArgs g{};
     g.tile_begin = k.tile_begin;
@@ -424,6 +426,8 @@ static int run_conv(sylph_ctx* c, const ConvCall& k, cudaStream_t st) {
             make_tmap_2d(&tout, static_cast<const __half*>(k.out), static_cast<uint64_t>(k.out_rows), k.ldc, k.ldc, kBlockM, &err))
             return c->fail("epilogue tensor maps (%s): %s", k.name, err.c_str());
         CU_TRY(c, launch_conv_gemm_staged(ta, tb, tres, tout, g, c->num_sms, st));
+    } else if (pair) {
+        CU_TRY(c, launch_conv3x3_pair(ta, tb, g, c->num_sms, st));
     } else if (halo) {
         CU_TRY(c, launch_conv_gemm_halo(W.bn, ta, tb, g, c->num_sms, st));
     } else {
@@ -482,6 +486,7 @@ int sylph_create(sylph_ctx** out, int device, const sylph_model_config* cfg) {
     c->cfg = *cfg;
     if (const char* e = getenv("SYLPH_STAGED_EPILOGUE")) c->staged_epilogue = atoi(e);
     if (const char* e = getenv("SYLPH_HALO")) c->halo_pipeline = atoi(e);
+    if (const char* e = getenv("SYLPH_PAIR")) c->pair_kernel = atoi(e);
     *out = c;
     if (cfg->pre_nms_topk * 5 > 8192) { c->fail("pre_nms_topk * 5 must be <= 8192"); }
     return 0;

@@ -137,7 +137,7 @@ struct NmsImageArgs {
 };
 
 // One CTA per image.  dynamic smem: keys[sort_n] (u64) | boxes[n_max] (float4) | class offset[n_max] (float) |
-// suppressed[n_max] (u8).
+// suppressed bitmap[(n_max + 31) / 32] (u32).
 __global__ void __launch_bounds__(1024)
 fcos_nms_kernel(const unsigned long long* __restrict__ sel, const int* __restrict__ sel_count,
                 const float* __restrict__ pred, DetectParams p, const NmsImageArgs* __restrict__ img_args, int sort_n,
@@ -146,7 +146,7 @@ fcos_nms_kernel(const unsigned long long* __restrict__ sel, const int* __restric
     unsigned long long* keys = reinterpret_cast<unsigned long long*>(sm);
     float4* rbox = reinterpret_cast<float4*>(sm + static_cast<size_t>(sort_n) * 8);
     float* boff = reinterpret_cast<float*>(rbox + n_max);
-    unsigned char* supp = reinterpret_cast<unsigned char*>(boff + n_max);
+    unsigned int* supp = reinterpret_cast<unsigned int*>(boff + n_max);
     __shared__ float red[32];
     __shared__ int kept_idx[1024];
     __shared__ int n_kept_s;
@@ -200,7 +200,6 @@ fcos_nms_kernel(const unsigned long long* __restrict__ sel, const int* __restric
         const float r2 = fmaxf(pr[2] * p.level_scale[l], 0.f) * st, r3 = fmaxf(pr[3] * p.level_scale[l], 0.f) * st;
         const float4 b = make_float4(lx - r0, ly - r1, lx + r2, ly + r3);
         rbox[i] = b;
-        supp[i] = 0;
         local_max = fmaxf(local_max, fmaxf(fmaxf(b.x, b.y), fmaxf(b.z, b.w)));
     }
     // block max of all coordinates (torchvision batched_nms: offsets = cls * (boxes.max() + 1))
@@ -216,6 +215,7 @@ fcos_nms_kernel(const unsigned long long* __restrict__ sel, const int* __restric
         const unsigned idx = low & 0x0FFFFFFFu;
         boff[i] = static_cast<float>(idx % p.n_classes) * off_unit;
     }
+    for (int i = tid; i < (n_max + 31) / 32; i += blockDim.x) supp[i] = 0u;
     if (tid == 0) n_kept_s = 0;
     __syncthreads();
     // ---- greedy NMS in score order; stops once POST_NMS_TOPK survivors (plus score ties, `>=`) are found
@@ -223,7 +223,11 @@ fcos_nms_kernel(const unsigned long long* __restrict__ sel, const int* __restric
     float last_score = 0.f;
     int n_kept = 0;
     for (int i = 0; i < total; ++i) {
-        if (supp[i]) continue;  // uniform: written before the last barrier
+        // next unsuppressed candidate: 32 flags per word (uniform: the bitmap was last written before a barrier)
+        const unsigned alive = ~supp[i >> 5] & (0xFFFFFFFFu << (i & 31));
+        if (alive == 0u) { i |= 31; continue; }
+        i = (i & ~31) + __ffs(alive) - 1;
+        if (i >= total) break;
         const float sc = sqrtf(__uint_as_float(static_cast<unsigned>(keys[i] >> 32)));
         if (p.post_topk > 0 && n_kept >= p.post_topk && sc < last_score) break;
         if (n_kept >= keep_cap) break;
@@ -235,7 +239,7 @@ fcos_nms_kernel(const unsigned long long* __restrict__ sel, const int* __restric
         a.x += oa; a.y += oa; a.z += oa; a.w += oa;
         const float area_a = (a.z - a.x) * (a.w - a.y);
         for (int j = i + 1 + tid; j < total; j += blockDim.x) {
-            if (supp[j]) continue;
+            if ((supp[j >> 5] >> (j & 31)) & 1u) continue;
             const float ob = boff[j];
             float4 b = rbox[j];
             b.x += ob; b.y += ob; b.z += ob; b.w += ob;
@@ -243,7 +247,7 @@ fcos_nms_kernel(const unsigned long long* __restrict__ sel, const int* __restric
             const float h = fmaxf(fminf(a.w, b.w) - fmaxf(a.y, b.y), 0.f);
             const float inter = w * h;
             const float area_b = (b.z - b.x) * (b.w - b.y);
-            if (inter / (area_a + area_b - inter) > p.nms_thresh) supp[j] = 1;
+            if (inter / (area_a + area_b - inter) > p.nms_thresh) atomicOr(&supp[j >> 5], 1u << (j & 31));
         }
         __syncthreads();
     }

@@ -56,6 +56,7 @@ struct Case {
     int flags;
     bool bias;
     int skew = 0, base_offset = 0;  // experiment: A box loaded `skew` rows early, descriptor started `skew` rows in
+    bool pair = false;    // CTA-pair (cta_group::2) halo kernel
     bool halo = false;    // 3x3 halo pipeline (one 130-row A box per vertical tap and k-block)
     bool staged = false;  // TMA-in / TMA-out epilogue, run IN PLACE (out == residual buffer) like the bottleneck conv3
 };
@@ -105,8 +106,8 @@ static int run_case(const Case& c, int num_sms) {
     const uint64_t a_rows_dim = (c.a_ld < c.cin_cols) ? static_cast<uint64_t>(M) - (c.cin_cols / c.a_ld - 1) : M;
     CUtensorMap ta, tb;
     std::string err;
-    if (make_tmap_2d(&ta, dA, a_rows_dim, c.cin_cols, c.a_ld, c.halo ? 130 : 128, &err) ||
-        make_tmap_2d(&tb, dW, static_cast<uint64_t>(c.taps) * c.cout, Kt, Kt, c.bn, &err)) {
+    if (make_tmap_2d(&ta, dA, a_rows_dim, c.cin_cols, c.a_ld, (c.halo || c.pair) ? 130 : 128, &err) ||
+        make_tmap_2d(&tb, dW, static_cast<uint64_t>(c.taps) * c.cout, Kt, Kt, c.pair ? 128 : c.bn, &err)) {
         printf("[%s] FAIL tensor map: %s\n", c.name, err.c_str());
         return 1;
     }
@@ -139,6 +140,8 @@ static int run_case(const Case& c, int num_sms) {
             return 1;
         }
         CK(launch_conv_gemm_staged(ta, tb, tio, tio, g, num_sms, 0));
+    } else if (c.pair) {
+        CK(launch_conv3x3_pair(ta, tb, g, num_sms, 0));
     } else if (c.halo) {
         CK(launch_conv_gemm_halo(c.bn, ta, tb, g, num_sms, 0));
     } else {
@@ -212,7 +215,7 @@ static Seg mk_seg(int row0, int H, int W, int pad) {
 }
 static int round128(int x) { return (x + 127) / 128 * 128; }
 
-static void bench_shape(const char* name, int bn, int m_tiles, int cin, int cout, int taps, int flags, int num_sms, int staged = 0, bool halo = false) {
+static void bench_shape(const char* name, int bn, int m_tiles, int cin, int cout, int taps, int flags, int num_sms, int staged = 0, bool halo = false, bool pair = false) {
     const int M = m_tiles * 128;
     const int osz = (flags & kEpiOutF32) ? 4 : 2;
     __half *dA, *dW, *dR = nullptr;
@@ -245,7 +248,7 @@ static void bench_shape(const char* name, int bn, int m_tiles, int cin, int cout
     }
     CUtensorMap ta, tb;
     std::string err;
-    if (make_tmap_2d(&ta, dA, M, cin, cin, halo ? 130 : 128, &err) || make_tmap_2d(&tb, dW, static_cast<uint64_t>(taps) * cout, cin, cin, bn, &err)) {
+    if (make_tmap_2d(&ta, dA, M, cin, cin, (halo || pair) ? 130 : 128, &err) || make_tmap_2d(&tb, dW, static_cast<uint64_t>(taps) * cout, cin, cin, pair ? 128 : bn, &err)) {
         printf("[%s] tensor map failed: %s\n", name, err.c_str());
         return;
     }
@@ -260,7 +263,7 @@ static void bench_shape(const char* name, int bn, int m_tiles, int cin, int cout
         g.residual = static_cast<const __half*>(dO);
         if (make_tmap_2d(&tio, static_cast<const __half*>(dO), M, cout, cout, 128, &err)) { printf("tmap failed\n"); return; }
     }
-    auto launch = [&]() { return staged ? launch_conv_gemm_staged(ta, tb, tio, tio, g, num_sms, 0, staged) : (halo ? launch_conv_gemm_halo(bn, ta, tb, g, num_sms, 0) : launch_conv_gemm(bn, ta, tb, g, num_sms, 0)); };
+    auto launch = [&]() { return staged ? launch_conv_gemm_staged(ta, tb, tio, tio, g, num_sms, 0, staged) : (pair ? launch_conv3x3_pair(ta, tb, g, num_sms, 0) : (halo ? launch_conv_gemm_halo(bn, ta, tb, g, num_sms, 0) : launch_conv_gemm(bn, ta, tb, g, num_sms, 0))); };
     for (int i = 0; i < 3; ++i) CK(launch());
     CK(cudaDeviceSynchronize());
     const int iters = 10;
@@ -372,6 +375,23 @@ int main(int argc, char** argv) {
         printf("bn=%d ", bnv);
         fails += run_case(c, sms);
     }
+    {   // CTA pair, ODD number of M tiles (phantom tile), two planes, two N tiles, masked, fp16 out
+        Seg s0 = mk_seg(0, 140, 168, 1);
+        Seg s1 = mk_seg(round128(s0.nrows), 37, 41, 1);
+        int total = s1.row0 + round128(s1.nrows);
+        if ((total / 128) % 2 == 0) total += 128;
+        Case c{"PAIR_conv3x3_n512_mask_relu", 256, {s0, s1}, total, 128, 128, 512, 9, 2, dy9, dx9, kEpiMask | kEpiRelu, true};
+        c.pair = true;
+        fails += run_case(c, sms);
+    }
+    {   // CTA pair + GroupNorm statistics + fp32 output (the tower configuration)
+        Seg s0 = mk_seg(0, 13, 21, 1);
+        Seg s1 = mk_seg(round128(s0.nrows), 7, 11, 1);
+        int total = s1.row0 + round128(s1.nrows);
+        Case c{"PAIR_conv3x3_bn256_mask_gn_f32out", 256, {s0, s1}, total, 256, 256, 256, 9, 4, dy9, dx9, kEpiMask | kEpiGnStats | kEpiOutF32, true};
+        c.pair = true;
+        fails += run_case(c, sms);
+    }
     {   // halo + GroupNorm statistics + fp32 output (the tower configuration)
         Seg s0 = mk_seg(0, 13, 21, 1);
         Seg s1 = mk_seg(round128(s0.nrows), 7, 11, 1);
@@ -391,6 +411,9 @@ int main(int argc, char** argv) {
         bench_shape("tower3x3_256_plain", 256, 1480, 256, 256, 9, 0, sms);
         bench_shape("tower3x3_256_gn_f32out_HALO", 256, 1480, 256, 256, 9, kEpiMask | kEpiGnStats | kEpiOutF32, sms, 0, true);
         bench_shape("tower3x3_256_plain_HALO", 256, 1480, 256, 256, 9, 0, sms, 0, true);
+        bench_shape("tower3x3_256_gn_f32out_PAIR", 256, 1480, 256, 256, 9, kEpiMask | kEpiGnStats | kEpiOutF32, sms, 0, false, true);
+        bench_shape("tower3x3_256_plain_PAIR", 256, 1480, 256, 256, 9, 0, sms, 0, false, true);
+        bench_shape("res5_conv2_3x3_512_512_PAIR", 256, 80, 512, 512, 9, kEpiRelu | kEpiMask, sms, 0, false, true);
         bench_shape("res2_conv2_3x3_64_64_HALO", 64, 4272, 64, 64, 9, kEpiRelu | kEpiMask, sms, 0, true);
         bench_shape("res3_conv2_3x3_128_128_HALO", 128, 1088, 128, 128, 9, kEpiRelu | kEpiMask, sms, 0, true);
         bench_shape("res5_conv2_3x3_512_512_HALO", 256, 80, 512, 512, 9, kEpiRelu | kEpiMask, sms, 0, true);
