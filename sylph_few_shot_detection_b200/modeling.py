@@ -128,8 +128,9 @@ class CodeGenerator(_EngineBound):
             w = code["class_code"]["cls_conv"]
             b = code["class_code"]["cls_bias"]
             assert b.numel() == 1, "predicted bias should only have batch size 1"
-            rows.append(torch.cat([w.reshape(-1).float().cpu(), b.reshape(-1).float().cpu()]))
-        raw = torch.stack(rows).to(self.engine.device)
+            dev = self.engine.device  # codes normally already live on the device: no host round trip, no sync
+            rows.append(torch.cat([w.reshape(-1).to(dev, torch.float32), b.reshape(-1).to(dev, torch.float32)]))
+        raw = torch.stack(rows)
         normed = self.engine.normalize_codes(raw)
         for i, code in enumerate(codes):
             code["class_code"]["cls_conv"] = normed[i, :256].reshape(1, 256, 1, 1)
