@@ -32,6 +32,7 @@
 #pragma once
 #include <cuda_fp16.h>
 
+#include "launch.cuh"
 #include "ptx_sm100.cuh"
 
 namespace sylph {
@@ -149,6 +150,7 @@ conv_gemm_f16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_co
     const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0);
     const int lane = threadIdx.x & 31;
 
+    ptx::griddep_launch();   // PDL: the next kernel may be scheduled; it parks in griddep_wait until this grid is done
     if (warp == 0 && lane == 0) {
         ptx::prefetch_tensormap(&tmap_a);
         ptx::prefetch_tensormap(&tmap_b);
@@ -184,6 +186,7 @@ conv_gemm_f16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_co
     __syncthreads();
     ptx::tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
+    ptx::griddep_wait();     // PDL: everything above overlapped the previous kernel's tail; global memory from here on
 
     const int total_tiles = p.num_m_tiles * p.num_n_tiles;
     const int ksteps = p.taps * p.kblocks_per_tap;

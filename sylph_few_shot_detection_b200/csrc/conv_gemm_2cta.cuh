@@ -124,6 +124,7 @@ conv3x3_pair_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
     const int lane = threadIdx.x & 31;
     const uint32_t rank = ptx::cluster_ctarank();
 
+    ptx::griddep_launch();
     if (warp == 0 && lane == 0) {
         ptx::prefetch_tensormap(&tmap_a);
         ptx::prefetch_tensormap(&tmap_b);
@@ -152,6 +153,7 @@ conv3x3_pair_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
     ptx::cluster_sync_all();   // barriers of BOTH CTAs are initialised before anyone signals across the pair
     ptx::tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
+    ptx::griddep_wait();
 
     const int pair_m_tiles = (p.num_m_tiles + 1) >> 1;
     const int total_pairs = pair_m_tiles * p.num_n_tiles;

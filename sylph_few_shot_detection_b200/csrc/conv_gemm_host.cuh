@@ -63,8 +63,7 @@ inline cudaError_t launch_conv_gemm_bn(const CUtensorMap& ta, const CUtensorMap&
     const int total = args.num_m_tiles * args.num_n_tiles;
     if (total <= 0) return cudaSuccess;
     const int grid = total < num_sms ? total : num_sms;
-    conv_gemm_f16_kernel<BN, STAGES, EPI_BUFS, HALO><<<grid, S::kThreads, S::kTotal, stream>>>(ta, tb, tres, tout, args);
-    return cudaGetLastError();
+    return launch_k(conv_gemm_f16_kernel<BN, STAGES, EPI_BUFS, HALO>, dim3(grid), dim3(S::kThreads), S::kTotal, stream, ta, tb, tres, tout, args);
 }
 
 constexpr int kStagedTwoBufMaxKSteps = 8;
@@ -107,16 +106,20 @@ inline cudaError_t launch_conv3x3_pair(const CUtensorMap& ta, const CUtensorMap&
     const int pairs = ((args.num_m_tiles + 1) / 2) * args.num_n_tiles;
     if (pairs <= 0) return cudaSuccess;
     const int clusters = pairs < num_sms / 2 ? pairs : num_sms / 2;
-    conv3x3_pair_kernel<3, 8><<<clusters * 2, S::kThreads, S::kTotal, stream>>>(ta, tb, args);
-    return cudaGetLastError();
+    return launch_k(conv3x3_pair_kernel<3, 8>, dim3(clusters * 2), dim3(S::kThreads), S::kTotal, stream, ta, tb, args);
 }
 
-// Staged (TMA in / TMA out) epilogue, fp16 output, BN = 256: `tres` / `tout` are [rows][C] maps with 128 x 64 boxes.
-inline cudaError_t launch_conv_gemm_staged(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tres,
+// Staged (TMA in / TMA out) epilogue, fp16 output: `tres` / `tout` are [rows][C] maps with 128 x 64 boxes.
+// Every fp16 store of the direct epilogue is a 16-byte piece of a different row (a thread owns a row), which tops out
+// near 1.3 TB/s of write bandwidth; staging the tile in swizzled shared memory and leaving by TMA writes full lines.
+inline cudaError_t launch_conv_gemm_staged(int bn, const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tres,
                                            const CUtensorMap& tout, const GemmArgs& args, int num_sms,
                                            cudaStream_t stream, int variant = 0) {
-    // variant 1: 2 mainloop stages + 2 staging buffers (the residual of tile i+1 streams in during the epilogue of
-    // tile i); variant 2: 3 stages + 1 staging buffer for long K.  0 = pick by the number of k-steps.
+    // BN = 256, variant 1: 2 mainloop stages + 2 staging buffers (the residual of tile i+1 streams in during the
+    // epilogue of tile i); variant 2: 3 stages + 1 staging buffer for long K.  0 = pick by the number of k-steps.
+    if (bn == 64) return launch_conv_gemm_bn<64, 6, 2>(ta, tb, tres, tout, args, num_sms, stream);
+    if (bn == 128) return launch_conv_gemm_bn<128, 4, 2>(ta, tb, tres, tout, args, num_sms, stream);
+    if (bn != 256) return cudaErrorInvalidValue;
     if (variant == 0) variant = (args.taps * args.kblocks_per_tap <= kStagedTwoBufMaxKSteps) ? 1 : 2;
     if (variant == 1) return launch_conv_gemm_bn<256, 2, 2>(ta, tb, tres, tout, args, num_sms, stream);
     return launch_conv_gemm_bn<256, 3, 1>(ta, tb, tres, tout, args, num_sms, stream);

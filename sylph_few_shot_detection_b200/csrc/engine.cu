@@ -417,15 +417,15 @@ static int run_conv(sylph_ctx* c, const ConvCall& k, cudaStream_t st) {
         cudaEventRecord(tm.e0, st);
     }
     if (k.staged) {
-        if (W.bn != 256 || (k.flags & (kEpiOutF32 | kEpiGnStats)) || k.out_rows <= 0)
-            return c->fail("staged epilogue needs BN = 256, fp16 output and out_rows (%s)", k.name);
+        if (W.bn < 64 || (k.flags & (kEpiOutF32 | kEpiGnStats)) || k.out_rows <= 0)
+            return c->fail("staged epilogue needs BN >= 64, fp16 output and out_rows (%s)", k.name);
         CUtensorMap tres, tout;
         const __half* rsrc = (k.flags & kEpiResidual) ? k.residual : static_cast<const __half*>(k.out);
         if (make_tmap_2d(&tres, rsrc, static_cast<uint64_t>(k.out_rows), (k.flags & kEpiResidual) ? k.ld_res : k.ldc,
                          (k.flags & kEpiResidual) ? k.ld_res : k.ldc, kBlockM, &err) ||
             make_tmap_2d(&tout, static_cast<const __half*>(k.out), static_cast<uint64_t>(k.out_rows), k.ldc, k.ldc, kBlockM, &err))
             return c->fail("epilogue tensor maps (%s): %s", k.name, err.c_str());
-        CU_TRY(c, launch_conv_gemm_staged(ta, tb, tres, tout, g, c->num_sms, st));
+        CU_TRY(c, launch_conv_gemm_staged(W.bn, ta, tb, tres, tout, g, c->num_sms, st));
     } else if (pair) {
         CU_TRY(c, launch_conv3x3_pair(ta, tb, g, c->num_sms, st));
     } else if (halo) {
@@ -693,9 +693,9 @@ static int run_backbone(sylph_ctx* c, int slot, int n, const void* const* images
     TRY(stage_h2d(c, d_desc, descs.data(), n * sizeof(ImageDesc), st));
     {
         StageTimer t(c, "prep_stem_input", st, static_cast<double>(n) * (3.0 * hmax * wmax + 32.0 * g0.H * g0.W));
-        prep_stem_input_kernel<<<grid_for(static_cast<long long>(n) * g0.H * g0.W, 256, c->num_sms), 256, 0, st>>>(
+        CU_TRY(c, launch_k(prep_stem_input_kernel, dim3(grid_for(static_cast<long long>(n) * g0.H * g0.W, 256, c->num_sms)), dim3(256), 0, st, 
             static_cast<const ImageDesc*>(d_desc), S0, g0, n, f.pixel_mean[0], f.pixel_mean[1], f.pixel_mean[2],
-            f.pixel_std[0], f.pixel_std[1], f.pixel_std[2]);
+            f.pixel_std[0], f.pixel_std[1], f.pixel_std[2]));
         CU_TRY(c, cudaGetLastError());
         c->launches++;
     }
@@ -704,6 +704,7 @@ static int run_backbone(sylph_ctx* c, int slot, int n, const void* const* images
         k.W = &c->stem; k.A = S0; k.a_rows = rows0; k.a_cols = 64; k.a_ld = 16; k.ps = ps0.get();
         k.tile_begin = 0; k.n_tiles = static_cast<int>(rows0 / kBlockM); k.a_row_delta = 0; k.out = S1; k.ldc = 64;
         k.flags = kEpiRelu | kEpiMask; k.stem = 1; k.name = "stem7x7";
+        k.staged = c->staged_epilogue; k.out_rows = rows0;
         TRY(run_conv(c, k, st));
     }
     // ---- res2..res5
@@ -724,8 +725,8 @@ static int run_backbone(sylph_ctx* c, int slot, int n, const void* const* images
             StageTimer t(c, s == 0 ? "maxpool3x3s2" : "subsample2", st,
                          static_cast<double>(n) * g.H * g.W * in_ch * 2 * (s == 0 ? 5.0 : 2.0));
             const long long work = static_cast<long long>(n) * g.H * g.W * (in_ch / 8);
-            if (s == 0) maxpool3x3s2_kernel<<<grid_for(work, 256, c->num_sms), 256, 0, st>>>(S1, IN, g0, g, n, in_ch);
-            else subsample2_kernel<<<grid_for(work, 256, c->num_sms), 256, 0, st>>>(X, IN, gs[s - 1], g, n, in_ch);
+            if (s == 0) CU_TRY(c, launch_k(maxpool3x3s2_kernel, dim3(grid_for(work, 256, c->num_sms)), dim3(256), 0, st, S1, IN, g0, g, n, in_ch));
+            else CU_TRY(c, launch_k(subsample2_kernel, dim3(grid_for(work, 256, c->num_sms)), dim3(256), 0, st, X, IN, gs[s - 1], g, n, in_ch));
             CU_TRY(c, cudaGetLastError());
             c->launches++;
         }
@@ -749,7 +750,9 @@ static int run_backbone(sylph_ctx* c, int slot, int n, const void* const* images
             k.residual = nullptr;
             k.W = &B.c1; k.A = bin; k.a_cols = k.a_ld = bin_ch; k.out = T1; k.ldc = bott;
             k.flags = kEpiRelu | kEpiMask; k.name = "res.conv1_1x1";
+            k.staged = c->staged_epilogue; k.out_rows = rows;
             TRY(run_conv(c, k, st));
+            k.staged = 0;
             k.W = &B.c2; k.A = T1; k.a_cols = k.a_ld = bott; k.out = T2; k.ldc = bott; k.name = "res.conv2_3x3";
             TRY(run_conv(c, k, st));
             k.W = &B.c3; k.A = T2; k.a_cols = k.a_ld = bott; k.out = Y; k.ldc = out_ch; k.residual = Y; k.ld_res = out_ch;
@@ -781,8 +784,8 @@ static int run_backbone(sylph_ctx* c, int slot, int n, const void* const* images
         TRY(run_conv(c, k, st));
         if (l < 2) {
             StageTimer t(c, "fpn.upsample_add", st, static_cast<double>(n) * g.H * g.W * 256 * 2 * 2.25);
-            upsample_add_kernel<<<grid_for(static_cast<long long>(n) * g.H * g.W * 32, 256, c->num_sms), 256, 0, st>>>(
-                LAT, LAT, g, S.pg.lv[l + 1], n, 256);
+            CU_TRY(c, launch_k(upsample_add_kernel, dim3(grid_for(static_cast<long long>(n) * g.H * g.W * 32, 256, c->num_sms)), dim3(256), 0, st, 
+                LAT, LAT, g, S.pg.lv[l + 1], n, 256));
             CU_TRY(c, cudaGetLastError());
             c->launches++;
         }
@@ -803,21 +806,21 @@ static int run_backbone(sylph_ctx* c, int slot, int n, const void* const* images
         k.a_row_delta = 0; k.out = TMP; k.ldc = 256; k.flags = kEpiMask; k.name = "fpn.p6_3x3";
         TRY(run_conv(c, k, st));
         const PlaneGeom& g6 = S.pg.lv[3];
-        subsample2_kernel<<<grid_for(static_cast<long long>(n) * g6.H * g6.W * 32, 256, c->num_sms), 256, 0, st>>>(
-            TMP, S.pyr, g5, g6, n, 256);
+        CU_TRY(c, launch_k(subsample2_kernel, dim3(grid_for(static_cast<long long>(n) * g6.H * g6.W * 32, 256, c->num_sms)), dim3(256), 0, st, 
+            TMP, S.pyr, g5, g6, n, 256));
         CU_TRY(c, cudaGetLastError());
         const long long rows6 = static_cast<long long>(n) * g6.rows_per_img;
-        relu_copy_kernel<<<grid_for(rows6 * 32, 256, c->num_sms), 256, 0, st>>>(
+        CU_TRY(c, launch_k(relu_copy_kernel, dim3(grid_for(rows6 * 32, 256, c->num_sms)), dim3(256), 0, st, 
             reinterpret_cast<const uint4*>(S.pyr + S.level_row0[3] * 256), reinterpret_cast<uint4*>(R6 + S.level_row0[3] * 256),
-            rows6 * 32);
+            rows6 * 32));
         CU_TRY(c, cudaGetLastError());
         c->launches += 2;
         k.W = &c->p7; k.A = R6; k.tile_begin = static_cast<int>(S.level_row0[3] / kBlockM);
         k.n_tiles = static_cast<int>(rows6 / kBlockM); k.name = "fpn.p7_3x3";
         TRY(run_conv(c, k, st));
         const PlaneGeom& g7 = S.pg.lv[4];
-        subsample2_kernel<<<grid_for(static_cast<long long>(n) * g7.H * g7.W * 32, 256, c->num_sms), 256, 0, st>>>(
-            TMP, S.pyr, g6, g7, n, 256);
+        CU_TRY(c, launch_k(subsample2_kernel, dim3(grid_for(static_cast<long long>(n) * g7.H * g7.W * 32, 256, c->num_sms)), dim3(256), 0, st, 
+            TMP, S.pyr, g6, g7, n, 256));
         CU_TRY(c, cudaGetLastError());
         c->launches++;
     }
@@ -833,13 +836,13 @@ static int conv_gn_relu(sylph_ctx* c, const ConvW& W, const float* gn_w, const f
     k.W = &W; k.A = in; k.a_rows = a_rows; k.a_cols = k.a_ld = 256; k.ps = ps; k.tile_begin = tile_begin; k.n_tiles = tiles;
     k.a_row_delta = 0; k.out = raw; k.ldc = 256; k.flags = kEpiGnStats | kEpiOutF32; k.gn_partial = gn_partial; k.name = name;
     TRY(run_conv(c, k, st));
-    gn_finalize_kernel<<<n_segs, 256, 0, st>>>(gn_partial, ps->d_segs, seg_begin, n_segs, gn_stats);
+    CU_TRY(c, launch_k(gn_finalize_kernel, dim3(n_segs), dim3(256), 0, st, gn_partial, ps->d_segs, seg_begin, n_segs, gn_stats));
     CU_TRY(c, cudaGetLastError());
     {
         const long long rows = static_cast<long long>(tiles) * kBlockM;
         StageTimer t(c, "gn_apply_relu", st, static_cast<double>(rows) * 256 * 6);
-        gn_apply_relu_kernel<<<grid_for(rows * 32, 256, c->num_sms), 256, 0, st>>>(
-            raw, out, gn_stats, gn_w, gn_b, ps->d_tile_seg, ps->d_segs, tile_begin * kBlockM, rows, 1);
+        CU_TRY(c, launch_k(gn_apply_relu_kernel, dim3(grid_for(rows * 32, 256, c->num_sms)), dim3(256), 0, st, 
+            raw, out, gn_stats, gn_w, gn_b, ps->d_tile_seg, ps->d_segs, tile_begin * kBlockM, rows, 1));
         CU_TRY(c, cudaGetLastError());
     }
     c->launches += 2;
@@ -882,7 +885,7 @@ int sylph_import_features(sylph_ctx* c, int slot, int n_images, int padded_h, in
     S.img_w.assign(n_images, padded_w);
     for (int l = 0; l < 5; ++l) {
         const long long work = static_cast<long long>(n_images) * 256 * level_h[l] * level_w[l];
-        import_nchw_kernel<<<grid_for(work, 256, c->num_sms), 256, 0, st>>>(level_ptrs_dev[l], S.pyr, S.pg.lv[l], n_images, 256);
+        CU_TRY(c, launch_k(import_nchw_kernel, dim3(grid_for(work, 256, c->num_sms)), dim3(256), 0, st, level_ptrs_dev[l], S.pyr, S.pg.lv[l], n_images, 256));
         CU_TRY(c, cudaGetLastError());
         c->launches++;
     }
@@ -909,7 +912,7 @@ int sylph_export_features(sylph_ctx* c, int slot, int level, float* out_dev, voi
     const Slot& S = c->slots[slot];
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     const long long work = static_cast<long long>(S.n) * 256 * S.lh[level] * S.lw[level];
-    export_nchw_kernel<__half><<<grid_for(work, 256, c->num_sms), 256, 0, st>>>(S.pyr, out_dev, S.pg.lv[level], S.n, 256, 256, 0, 1.f, 0);
+    CU_TRY(c, launch_k(export_nchw_kernel<__half>, dim3(grid_for(work, 256, c->num_sms)), dim3(256), 0, st, S.pyr, out_dev, S.pg.lv[level], S.n, 256, 256, 0, 1.f, 0));
     CU_TRY(c, cudaGetLastError());
     c->launches++;
     return 0;
@@ -955,8 +958,8 @@ int sylph_generate_codes(sylph_ctx* c, int slot, int n_rois, const float* boxes_
     }
     {
         StageTimer t(c, "roi_align", st, static_cast<double>(n_rois) * (50176.0 + 0.5e6));
-        roi_align_kernel<<<dim3(n_rois, 7), 256, 0, st>>>(S.pyr, S.pg, static_cast<const float*>(pb), static_cast<const int*>(pi),
-                                                         static_cast<__half*>(r0), reinterpret_cast<long long*>(levels_out_dev));
+        CU_TRY(c, launch_k(roi_align_kernel, dim3(n_rois, 7), dim3(256), 0, st, S.pyr, S.pg, static_cast<const float*>(pb), static_cast<const int*>(pi),
+                                                         static_cast<__half*>(r0), reinterpret_cast<long long*>(levels_out_dev)));
         CU_TRY(c, cudaGetLastError());
         c->launches++;
     }
@@ -978,10 +981,10 @@ int sylph_generate_codes(sylph_ctx* c, int slot, int n_rois, const float* boxes_
     }
     {
         StageTimer t(c, "codegen.tail", st, static_cast<double>(n_rois) * 2 * 49 * 256 * 4);
-        shot_code_kernel<<<n_rois, 256, 0, st>>>(raw, cur, c->cg_wbias, c->cg_bbias, f.cg_bias_layer, f.cg_bias_l2_norm,
-                                                 static_cast<float*>(sc));
+        CU_TRY(c, launch_k(shot_code_kernel, dim3(n_rois), dim3(256), 0, st, raw, cur, c->cg_wbias, c->cg_bbias, f.cg_bias_layer, f.cg_bias_l2_norm,
+                                                 static_cast<float*>(sc)));
         CU_TRY(c, cudaGetLastError());
-        class_mean_kernel<<<n_classes, 288, 0, st>>>(static_cast<const float*>(sc), static_cast<const int*>(po), codes_out_dev);
+        CU_TRY(c, launch_k(class_mean_kernel, dim3(n_classes), dim3(288), 0, st, static_cast<const float*>(sc), static_cast<const int*>(po), codes_out_dev));
         CU_TRY(c, cudaGetLastError());
         c->launches += 2;
     }
@@ -992,8 +995,8 @@ int sylph_export_roi_features(sylph_ctx* c, float* out_dev, void* stream) {
     if (!c) return 1;
     if (c->last_n_rois <= 0) return c->fail("no ROI features: call sylph_generate_codes first");
     cudaStream_t st = static_cast<cudaStream_t>(stream);
-    export_roi_kernel<<<grid_for(static_cast<long long>(c->last_n_rois) * 256 * 49, 256, c->num_sms), 256, 0, st>>>(
-        static_cast<const __half*>(c->bufs["cg.r0"].p), out_dev, c->last_n_rois);
+    CU_TRY(c, launch_k(export_roi_kernel, dim3(grid_for(static_cast<long long>(c->last_n_rois) * 256 * 49, 256, c->num_sms)), dim3(256), 0, st, 
+        static_cast<const __half*>(c->bufs["cg.r0"].p), out_dev, c->last_n_rois));
     CU_TRY(c, cudaGetLastError());
     c->launches++;
     return 0;
@@ -1005,8 +1008,8 @@ int sylph_normalize_codes(sylph_ctx* c, const float* raw_codes_dev, float* out_c
     if (n_classes <= 0) return 0;  // forward_normalize_code returns an empty list unchanged
     const sylph_model_config& f = c->cfg;
     cudaStream_t st = static_cast<cudaStream_t>(stream);
-    normalize_codes_kernel<<<n_classes, 256, 0, st>>>(raw_codes_dev, out_codes_dev, c->post_gn_w, c->post_gn_b, f.cg_post_norm,
-                                                      f.cg_conv_l2_norm, c->conv_scale, c->bias_scale, c->bias_value);
+    CU_TRY(c, launch_k(normalize_codes_kernel, dim3(n_classes), dim3(256), 0, st, raw_codes_dev, out_codes_dev, c->post_gn_w, c->post_gn_b, f.cg_post_norm,
+                                                      f.cg_conv_l2_norm, c->conv_scale, c->bias_scale, c->bias_value));
     CU_TRY(c, cudaGetLastError());
     c->launches++;
     return 0;
@@ -1042,8 +1045,8 @@ int sylph_detect(sylph_ctx* c, int slot, const float* codes_dev, int n_classes, 
     TRY(ensure(c, "det.gn_stats", static_cast<size_t>(n_segs) * 64 * 4, "", &gs, st, false));
     CW.w = static_cast<__half*>(cw);
     CW.bias = static_cast<float*>(cb);
-    pack_code_weights_kernel<<<ceil_div(static_cast<long long>(CW.cout_pad) * 256, 256), 256, 0, st>>>(
-        codes_dev, n_classes, CW.cout_pad, f.cg_use_bias, CW.w, CW.bias);
+    CU_TRY(c, launch_k(pack_code_weights_kernel, dim3(ceil_div(static_cast<long long>(CW.cout_pad) * 256, 256)), dim3(256), 0, st, 
+        codes_dev, n_classes, CW.cout_pad, f.cg_use_bias, CW.w, CW.bias));
     CU_TRY(c, cudaGetLastError());
     c->launches++;
     auto tower = [&](const std::vector<ConvW>& tw, const std::vector<float*>& gw, const std::vector<float*>& gb,
@@ -1119,12 +1122,12 @@ int sylph_detect(sylph_ctx* c, int slot, const float* codes_dev, int n_classes, 
         StageTimer t(c, "proposals", st, static_cast<double>(S.n) * 22400 * (CW.cout_pad + 16) * 4);
         long long total_px = 0;
         for (int l = 0; l < 5; ++l) total_px += static_cast<long long>(S.n) * S.lh[l] * S.lw[l];
-        fcos_candidates_kernel<<<grid_for(total_px, 256, c->num_sms), 256, 0, st>>>(
+        CU_TRY(c, launch_k(fcos_candidates_kernel, dim3(grid_for(total_px, 256, c->num_sms)), dim3(256), 0, st, 
             static_cast<const float*>(lg), static_cast<const float*>(pr), P, static_cast<unsigned long long*>(cand),
-            static_cast<int*>(cnt), static_cast<int*>(cnt) + n_segs);
+            static_cast<int*>(cnt), static_cast<int*>(cnt) + n_segs));
         CU_TRY(c, cudaGetLastError());
-        fcos_select_kernel<<<n_segs, 1024, 0, st>>>(static_cast<const unsigned long long*>(cand), static_cast<const int*>(cnt), P,
-                                                    static_cast<unsigned long long*>(sel), static_cast<int*>(selc));
+        CU_TRY(c, launch_k(fcos_select_kernel, dim3(n_segs), dim3(1024), 0, st, static_cast<const unsigned long long*>(cand), static_cast<const int*>(cnt), P,
+                                                    static_cast<unsigned long long*>(sel), static_cast<int*>(selc)));
         CU_TRY(c, cudaGetLastError());
         const int n_max = 5 * P.pre_topk;
         int sort_n = 32;
@@ -1136,9 +1139,9 @@ int sylph_detect(sylph_ctx* c, int slot, const float* codes_dev, int n_classes, 
             attr_set = true;
         }
         if (smem > 200 * 1024) return c->fail("NMS shared memory budget exceeded (pre_nms_topk too large)");
-        fcos_nms_kernel<<<S.n, 1024, smem, st>>>(static_cast<const unsigned long long*>(sel), static_cast<const int*>(selc),
+        CU_TRY(c, launch_k(fcos_nms_kernel, dim3(S.n), dim3(1024), smem, st, static_cast<const unsigned long long*>(sel), static_cast<const int*>(selc),
                                                  static_cast<const float*>(pr), P, static_cast<const NmsImageArgs*>(ia), sort_n,
-                                                 n_max, dets_out_dev, counts_out_dev, max_dets);
+                                                 n_max, dets_out_dev, counts_out_dev, max_dets));
         CU_TRY(c, cudaGetLastError());
         c->launches += 3;
     }
@@ -1158,7 +1161,7 @@ int sylph_export_head_output(sylph_ctx* c, int which, int level, float* out_dev,
     else if (which == 2) { coff = 4; }
     else { coff = 5; }
     const long long work = static_cast<long long>(S.n) * C * S.lh[level] * S.lw[level];
-    export_nchw_kernel<float><<<grid_for(work, 256, c->num_sms), 256, 0, st>>>(src, out_dev, S.pg.lv[level], S.n, C, cstride, coff, scale, relu);
+    CU_TRY(c, launch_k(export_nchw_kernel<float>, dim3(grid_for(work, 256, c->num_sms)), dim3(256), 0, st, src, out_dev, S.pg.lv[level], S.n, C, cstride, coff, scale, relu));
     CU_TRY(c, cudaGetLastError());
     c->launches++;
     return 0;

@@ -47,6 +47,8 @@ __device__ __forceinline__ float bilinear_tap(const __half* __restrict__ feat, c
 __global__ void __launch_bounds__(256)
 roi_align_kernel(const __half* __restrict__ pyramid, PyramidGeom pg, const float* __restrict__ boxes,
                  const int* __restrict__ roi_image, __half* __restrict__ roi_planes, long long* __restrict__ levels_out) {
+    ptx::griddep_launch();
+    ptx::griddep_wait();
     const int roi = blockIdx.x, ph = blockIdx.y, c = threadIdx.x;
     const float bx0 = boxes[roi * 4 + 0], by0 = boxes[roi * 4 + 1], bx1 = boxes[roi * 4 + 2], by1 = boxes[roi * 4 + 3];
     const int lvl = assign_level(bx0, by0, bx1, by1);
@@ -84,6 +86,8 @@ __global__ void __launch_bounds__(256)
 shot_code_kernel(const float* __restrict__ cls_raw, const __half* __restrict__ tower_out,
                  const float* __restrict__ w_bias /* [9][256] tap-major */, const float* __restrict__ b_bias,
                  int has_bias_layer, int bias_l2_norm, float* __restrict__ shot_codes /* [n_rois][257] */) {
+    ptx::griddep_launch();
+    ptx::griddep_wait();
     __shared__ float pix[49];
     const int roi = blockIdx.x, t = threadIdx.x, warp = t >> 5, lane = t & 31;
     const size_t base = static_cast<size_t>(roi) * 128;
@@ -130,6 +134,8 @@ shot_code_kernel(const float* __restrict__ cls_raw, const __half* __restrict__ t
 __global__ void __launch_bounds__(288)
 class_mean_kernel(const float* __restrict__ shot_codes, const int* __restrict__ class_offsets,
                   float* __restrict__ raw_codes) {
+    ptx::griddep_launch();
+    ptx::griddep_wait();
     const int cls = blockIdx.x, t = threadIdx.x;
     if (t >= 257) return;
     const int k0 = class_offsets[cls], k1 = class_offsets[cls + 1];
@@ -146,6 +152,8 @@ __global__ void __launch_bounds__(256)
 normalize_codes_kernel(const float* __restrict__ raw, float* __restrict__ out, const float* __restrict__ gn_w,
                        const float* __restrict__ gn_b, int post_norm, int l2_norm, float conv_scale, float bias_scale,
                        float bias_value) {
+    ptx::griddep_launch();
+    ptx::griddep_wait();
     __shared__ float red[8];
     const int cls = blockIdx.x, t = threadIdx.x, lane = t & 31, warp = t >> 5;
     float x = raw[static_cast<size_t>(cls) * 257 + t];
@@ -182,6 +190,8 @@ normalize_codes_kernel(const float* __restrict__ raw, float* __restrict__ out, c
 // (rows >= n_classes are zero); weights are rounded to fp16 here.
 __global__ void pack_code_weights_kernel(const float* __restrict__ codes, int n_classes, int n_pad, int use_bias,
                                          __half* __restrict__ w, float* __restrict__ bias) {
+    ptx::griddep_launch();
+    ptx::griddep_wait();
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n_pad * 256) return;
     const int r = i >> 8, c = i & 255;
@@ -192,6 +202,8 @@ __global__ void pack_code_weights_kernel(const float* __restrict__ codes, int n_
 
 // (n_rois, 256, 7, 7) export of the pooled ROI planes (tests / plugin interop).
 __global__ void export_roi_kernel(const __half* __restrict__ roi_planes, float* __restrict__ out, int n_rois) {
+    ptx::griddep_launch();
+    ptx::griddep_wait();
     const long long total = static_cast<long long>(n_rois) * 256 * 49;
     for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
          i += static_cast<long long>(gridDim.x) * blockDim.x) {

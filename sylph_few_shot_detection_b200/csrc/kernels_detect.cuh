@@ -38,6 +38,8 @@ __device__ __forceinline__ unsigned long long make_key(float score, unsigned idx
 __global__ void fcos_candidates_kernel(const float* __restrict__ logits, const float* __restrict__ pred,
                                        DetectParams p, unsigned long long* __restrict__ cand, int* __restrict__ counts,
                                        int* __restrict__ overflow) {
+    ptx::griddep_launch();
+    ptx::griddep_wait();
     long long total = 0;
     long long lvl_start[6];
     for (int l = 0; l < 5; ++l) { lvl_start[l] = total; total += static_cast<long long>(p.n_images) * p.pg.lv[l].H * p.pg.lv[l].W; }
@@ -81,6 +83,8 @@ __global__ void fcos_candidates_kernel(const float* __restrict__ logits, const f
 __global__ void __launch_bounds__(1024)
 fcos_select_kernel(const unsigned long long* __restrict__ cand, const int* __restrict__ counts, DetectParams p,
                    unsigned long long* __restrict__ sel, int* __restrict__ sel_count) {
+    ptx::griddep_launch();
+    ptx::griddep_wait();
     __shared__ int hist[256];
     __shared__ unsigned long long prefix_s;
     __shared__ int remaining_s;
@@ -142,6 +146,8 @@ __global__ void __launch_bounds__(1024)
 fcos_nms_kernel(const unsigned long long* __restrict__ sel, const int* __restrict__ sel_count,
                 const float* __restrict__ pred, DetectParams p, const NmsImageArgs* __restrict__ img_args, int sort_n,
                 int n_max, float* __restrict__ dets, int* __restrict__ det_counts, int max_dets) {
+    ptx::griddep_launch();
+    ptx::griddep_wait();
     extern __shared__ __align__(16) unsigned char sm[];
     unsigned long long* keys = reinterpret_cast<unsigned long long*>(sm);
     float4* rbox = reinterpret_cast<float4*>(sm + static_cast<size_t>(sort_n) * 8);

@@ -39,6 +39,8 @@ struct ImageDesc {
 
 __global__ void prep_stem_input_kernel(const ImageDesc* __restrict__ imgs, __half* __restrict__ out, PlaneGeom g,
                                        int n_images, float m0, float m1, float m2, float s0, float s1, float s2) {
+    ptx::griddep_launch();
+    ptx::griddep_wait();
     const long long total = static_cast<long long>(n_images) * g.H * g.W;
     for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
          i += static_cast<long long>(gridDim.x) * blockDim.x) {
@@ -79,6 +81,8 @@ __global__ void prep_stem_input_kernel(const ImageDesc* __restrict__ imgs, __hal
 // the input plane stands in for the -inf padding.
 __global__ void maxpool3x3s2_kernel(const __half* __restrict__ in, __half* __restrict__ out, PlaneGeom gi, PlaneGeom go,
                                     int n_images, int C) {
+    ptx::griddep_launch();
+    ptx::griddep_wait();
     const int c8n = C / 8;
     const long long total = static_cast<long long>(n_images) * go.H * go.W * c8n;
     for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
@@ -107,6 +111,8 @@ __global__ void maxpool3x3s2_kernel(const __half* __restrict__ in, __half* __res
 // of the stride-2 3x3 convolutions p6/p7 (computed at stride 1).
 __global__ void subsample2_kernel(const __half* __restrict__ in, __half* __restrict__ out, PlaneGeom gi, PlaneGeom go,
                                   int n_images, int C) {
+    ptx::griddep_launch();
+    ptx::griddep_wait();
     const int c8n = C / 8;
     const long long total = static_cast<long long>(n_images) * go.H * go.W * c8n;
     for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
@@ -125,6 +131,8 @@ __global__ void subsample2_kernel(const __half* __restrict__ in, __half* __restr
 // ------------------------------------------------------------------------------------------------ FPN top-down
 // lateral(y, x) += coarser(y / 2, x / 2)  (F.interpolate(scale_factor=2, mode="nearest") + add), summed in fp32.
 __global__ void upsample_add_kernel(__half* fine, const __half* coarse, PlaneGeom gf, PlaneGeom gc, int n_images, int C) {
+    ptx::griddep_launch();
+    ptx::griddep_wait();
     const int c8n = C / 8;
     const long long total = static_cast<long long>(n_images) * gf.H * gf.W * c8n;
     for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
@@ -146,6 +154,8 @@ __global__ void upsample_add_kernel(__half* fine, const __half* coarse, PlaneGeo
 }
 
 __global__ void relu_copy_kernel(const uint4* __restrict__ in, uint4* __restrict__ out, long long n8) {
+    ptx::griddep_launch();
+    ptx::griddep_wait();
     const uint4 z = make_uint4(0u, 0u, 0u, 0u);
     for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < n8;
          i += static_cast<long long>(gridDim.x) * blockDim.x)
@@ -158,6 +168,8 @@ __global__ void relu_copy_kernel(const uint4* __restrict__ in, uint4* __restrict
 __global__ void __launch_bounds__(256)
 gn_finalize_kernel(const float* __restrict__ partial, const Seg* __restrict__ segs, int seg_begin, int n_segs,
                    float* __restrict__ stats) {
+    ptx::griddep_launch();
+    ptx::griddep_wait();
     // one block per plane: 32 groups x 8 lanes; each lane strides over the plane's tiles, then an 8-lane shuffle
     // tree in a fixed order (deterministic), all in double
     const int s = seg_begin + blockIdx.x;
@@ -191,6 +203,8 @@ __global__ void gn_apply_relu_kernel(const float* __restrict__ x, __half* __rest
                                      const float* __restrict__ gamma, const float* __restrict__ beta,
                                      const int* __restrict__ tile_seg, const Seg* __restrict__ segs, int row_begin,
                                      long long n_rows, int relu) {
+    ptx::griddep_launch();
+    ptx::griddep_wait();
     const long long total = n_rows * 32;
     for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
          i += static_cast<long long>(gridDim.x) * blockDim.x) {
@@ -228,6 +242,8 @@ __global__ void gn_apply_relu_kernel(const float* __restrict__ x, __half* __rest
 template <typename T>
 __global__ void export_nchw_kernel(const T* __restrict__ plane, float* __restrict__ out, PlaneGeom g, int n_images,
                                    int C, int cstride, int coff, float scale, int relu) {
+    ptx::griddep_launch();
+    ptx::griddep_wait();
     const long long total = static_cast<long long>(n_images) * C * g.H * g.W;
     for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
          i += static_cast<long long>(gridDim.x) * blockDim.x) {
@@ -245,6 +261,8 @@ __global__ void export_nchw_kernel(const T* __restrict__ plane, float* __restric
 
 __global__ void import_nchw_kernel(const float* __restrict__ in, __half* __restrict__ plane, PlaneGeom g, int n_images,
                                    int C) {
+    ptx::griddep_launch();
+    ptx::griddep_wait();
     const long long total = static_cast<long long>(n_images) * C * g.H * g.W;
     for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
          i += static_cast<long long>(gridDim.x) * blockDim.x) {

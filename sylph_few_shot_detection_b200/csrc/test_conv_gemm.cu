@@ -139,7 +139,7 @@ static int run_case(const Case& c, int num_sms) {
             printf("[%s] FAIL epilogue tensor map: %s\n", c.name, err.c_str());
             return 1;
         }
-        CK(launch_conv_gemm_staged(ta, tb, tio, tio, g, num_sms, 0));
+        CK(launch_conv_gemm_staged(c.bn, ta, tb, tio, tio, g, num_sms, 0));
     } else if (c.pair) {
         CK(launch_conv3x3_pair(ta, tb, g, num_sms, 0));
     } else if (c.halo) {
@@ -263,7 +263,7 @@ static void bench_shape(const char* name, int bn, int m_tiles, int cin, int cout
         g.residual = static_cast<const __half*>(dO);
         if (make_tmap_2d(&tio, static_cast<const __half*>(dO), M, cout, cout, 128, &err)) { printf("tmap failed\n"); return; }
     }
-    auto launch = [&]() { return staged ? launch_conv_gemm_staged(ta, tb, tio, tio, g, num_sms, 0, staged) : (pair ? launch_conv3x3_pair(ta, tb, g, num_sms, 0) : (halo ? launch_conv_gemm_halo(bn, ta, tb, g, num_sms, 0) : launch_conv_gemm(bn, ta, tb, g, num_sms, 0))); };
+    auto launch = [&]() { return staged ? launch_conv_gemm_staged(bn, ta, tb, tio, tio, g, num_sms, 0, staged) : (pair ? launch_conv3x3_pair(ta, tb, g, num_sms, 0) : (halo ? launch_conv_gemm_halo(bn, ta, tb, g, num_sms, 0) : launch_conv_gemm(bn, ta, tb, g, num_sms, 0))); };
     for (int i = 0; i < 3; ++i) CK(launch());
     CK(cudaDeviceSynchronize());
     const int iters = 10;
@@ -405,6 +405,19 @@ int main(int argc, char** argv) {
         Case c{"stem_overlapped_rows_bn64", 64, {s0}, round128(s0.nrows), 64, 16, 64, 4, 1, dy4, dx4, kEpiMask | kEpiRelu, true};
         fails += run_case(c, sms);
     }
+    {   // staged epilogue on the stem layout (BN = 64, overlapped rows, no residual)
+        Seg s0 = mk_seg(0, 60, 70, 2);
+        Case c{"STAGED_stem_overlapped_rows_bn64", 64, {s0}, round128(s0.nrows), 64, 16, 64, 4, 1, dy4, dx4, kEpiMask | kEpiRelu, true};
+        c.staged = true;
+        fails += run_case(c, sms);
+    }
+    for (int bnv : {64, 128}) {   // staged epilogue for the narrow 1x1 convolutions (bottleneck conv1), many tiles per CTA
+        Seg s0 = mk_seg(0, 150, 168, 1);
+        Case c{"STAGED_conv1_1x1_relu_mask", bnv, {s0}, round128(s0.nrows), 256, 256, bnv, 1, 4, z1, z1, kEpiRelu | kEpiMask, true};
+        c.staged = true;
+        printf("bn=%d ", bnv);
+        fails += run_case(c, sms);
+    }
     printf("correctness: %d failing case(s)\n", fails);
     if (argc > 1 && std::string(argv[1]) == "bench") {
         bench_shape("tower3x3_256_gn_f32out", 256, 1480, 256, 256, 9, kEpiMask | kEpiGnStats | kEpiOutF32, sms);
@@ -433,6 +446,13 @@ int main(int argc, char** argv) {
         bench_shape("res5_shortcut_1x1_1024_2048_STAGED_2x2", 256, 80, 1024, 2048, 1, kEpiMask, sms, 1);
         bench_shape("res5_shortcut_1x1_1024_2048_STAGED_3x1", 256, 80, 1024, 2048, 1, kEpiMask, sms, 2);
         bench_shape("res2_conv1_1x1_256_64", 64, 4272, 256, 64, 1, kEpiRelu | kEpiMask, sms);
+        bench_shape("res2_conv1_1x1_256_64_STAGED", 64, 4272, 256, 64, 1, kEpiRelu | kEpiMask, sms, 1);
+        bench_shape("res3_conv1_1x1_512_128", 128, 1088, 512, 128, 1, kEpiRelu | kEpiMask, sms);
+        bench_shape("res3_conv1_1x1_512_128_STAGED", 128, 1088, 512, 128, 1, kEpiRelu | kEpiMask, sms, 1);
+        bench_shape("res4_conv1_1x1_1024_256", 256, 280, 1024, 256, 1, kEpiRelu | kEpiMask, sms);
+        bench_shape("res4_conv1_1x1_1024_256_STAGED", 256, 280, 1024, 256, 1, kEpiRelu | kEpiMask, sms, 2);
+        bench_shape("stemlike_k256_n64", 64, 17072, 256, 64, 1, kEpiRelu | kEpiMask, sms);
+        bench_shape("stemlike_k256_n64_STAGED", 64, 17072, 256, 64, 1, kEpiRelu | kEpiMask, sms, 1);
         bench_shape("res2_conv2_3x3_64_64", 64, 4272, 64, 64, 9, kEpiRelu | kEpiMask, sms);
         bench_shape("res3_conv2_3x3_128_128", 128, 1088, 128, 128, 9, kEpiRelu | kEpiMask, sms);
         bench_shape("res4_conv3_1x1_256_1024", 256, 280, 256, 1024, 1, kEpiResidual | kEpiRelu | kEpiMask, sms);
