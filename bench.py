@@ -10,7 +10,8 @@ classifier, proposals, NMS).  Synthetic uint8 images, synthetic "trained-like" w
   value     episodes/s with all inputs already resident in HBM, timed with CUDA events (max over ranks)
   e2e       the same through the public plugin API (MetaOneStageDetector.forward with run_type=...), inputs in pinned
             HOST memory: H2D of every image and D2H of the detections inside the timed region
-  roofline  the dominant kernel (tcgen05 implicit-GEMM conv of the FCOS tower layers), timed live with CUDA events
+  roofline  the kernel with the largest share of the step (staged 1x1 bottleneck conv, HBM-bound) and, as
+            roofline_tensor, the tensor-bound FCOS tower kernel; both timed live with CUDA events
   cpu_baseline  the CPU oracle (port of the reference forward) on this box's host cores, bounded sample (rank 0, N=1)
 
 N > 1 (torchrun, one rank per GPU): "replicas" -- every rank runs whole episodes (5 classes < 8 GPUs; the
@@ -137,7 +138,7 @@ def cpu_reference_sample(cfg, state, threads: int):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--steps", type=int, default=40)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -275,7 +276,7 @@ def main():
     d2h = sum(b.numel() * 4 + s.numel() * 4 for b, s in res) + N_WAY * 257 * 4
 
     # ---- roofline of the dominant kernel (FCOS tower layer), live CUDA events around each launch
-    roofline, breakdown = None, None
+    roofline, roofline_tensor, breakdown = None, None, None
     if rank == 0:
         peaks = {"bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0, "hbm_gbs": 6650.0, "source": "fallback"}
         try:
@@ -296,18 +297,56 @@ def main():
         breakdown = {k: {"launches": a[0], "ms": round(a[1], 4), "share": round(a[1] / total_ms, 4),
                          "tflops_padded": round(a[2] / a[1] * 1e-9, 1) if a[1] > 0 else None} for k, a in
                      sorted(agg.items(), key=lambda kv: -kv[1][1])}
+        traffic = {}
+        try:
+            with open(os.path.join(REPO, "profiles", "ncu_traffic.json")) as f:
+                traffic = json.load(f)
+        except Exception:
+            pass
+
+        def ncu_traffic(key):
+            t = traffic.get(key)
+            return float(t["bytes_per_launch"]) if t else None
+
+        # (1) the kernel with the largest share of the step: the staged-epilogue 1x1 convolution of the bottleneck
+        # blocks (conv3 + residual).  HBM-bound; algorithmic bytes = interior pixels x (Cin read + residual read +
+        # output write) x 2 B per launch, summed over the 16 launches of one backbone pass.
+        conv3 = [t for n, t, _, _ in tm if n == "res.conv3_1x1"]
+        hp, wp = (IMG_H + 31) // 32 * 32, (IMG_W + 31) // 32 * 32
+        conv3_bytes_img = sum(nb * (hp >> (s + 2)) * (wp >> (s + 2)) * ((64 << s) + 2 * (256 << s)) * 2
+                              for s, nb in enumerate([3, 4, 6, 3]))
+        if conv3:
+            tot_ms = sum(conv3)
+            n_img = N_WAY * N_SHOT + N_QUERY
+            achieved = conv3_bytes_img * n_img / (tot_ms * 1e-3) * 1e-9
+            peak = float(peaks["hbm_gbs"])
+            roofline = {"kernel": "conv_gemm_f16_kernel<256,2,2,0> -- staged TMA-in/TMA-out 1x1 conv + residual + ReLU "
+                                  "(bottleneck conv3, res2..res5), the largest share of the step",
+                        "bound": "hbm", "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s",
+                        "frac": round(achieved / peak, 4), "traffic": ncu_traffic("conv_gemm_f16_kernel<256,2,2,0>.res2_conv3"),
+                        "avg_launch_ms": round(tot_ms / len(conv3), 4), "launches_timed": len(conv3),
+                        "share_of_step": breakdown["res.conv3_1x1"]["share"],
+                        "bytes_per_launch": conv3_bytes_img * n_img / len(conv3),
+                        "peak_source": f"MEASURED_PEAKS.json hbm_gbs ({peaks['source']})",
+                        "note": "achieved = sum of algorithmic bytes / sum of launch durations over the launches of one "
+                                "episode (shapes differ per stage); traffic = ncu DRAM bytes of ONE res2 launch at 8 images "
+                                "(algorithmic for that launch: 8 x 67200 px x 1152 B = 619 MB)"}
+        # (2) the tensor-bound kernel: CTA-pair 3x3 convolution of the FCOS towers
         tower = [t for n, t, _, _ in tm if n in ("head.cls_tower3x3", "head.bbox_tower3x3")]
         if tower:
             avg_ms = sum(tower) / len(tower)
             achieved = TOWER_FLOP_PER_IMAGE_LAYER * N_QUERY / (avg_ms * 1e-3) * 1e-12
             peak = float(peaks["bf16_tflops_sustained"])
-            roofline = {"kernel": "conv3x3_pair_kernel<3,8> -- cta_group::2 halo conv (FCOS tower 3x3 256->256, all levels x 8 images)",
-                        "bound": "tensor", "achieved": round(achieved, 1), "peak": peak, "unit": "TFLOP/s",
-                        "frac": round(achieved / peak, 4), "traffic": None,
-                        "avg_launch_ms": round(avg_ms, 4), "launches_timed": len(tower),
-                        "peak_source": f"MEASURED_PEAKS.json bf16_tflops_sustained ({peaks['source']}); the kernel issues "
-                                       f"tcgen05.mma kind::f16 (fp16 operands, fp32 accumulate), same dense rate as bf16",
-                        "flop_per_launch": TOWER_FLOP_PER_IMAGE_LAYER * N_QUERY}
+            roofline_tensor = {"kernel": "conv3x3_pair_kernel<3,8> -- cta_group::2 halo conv (FCOS tower 3x3 256->256, all levels x 8 images)",
+                               "bound": "tensor", "achieved": round(achieved, 1), "peak": peak, "unit": "TFLOP/s",
+                               "frac": round(achieved / peak, 4), "traffic": ncu_traffic("conv3x3_pair_kernel.tower"),
+                               "avg_launch_ms": round(avg_ms, 4), "launches_timed": len(tower),
+                               "share_of_step": round(breakdown["head.cls_tower3x3"]["share"] + breakdown["head.bbox_tower3x3"]["share"], 4),
+                               "peak_source": f"MEASURED_PEAKS.json bf16_tflops_sustained ({peaks['source']}); the kernel issues "
+                                              f"tcgen05.mma kind::f16 (fp16 operands, fp32 accumulate), same dense rate as bf16",
+                               "flop_per_launch": TOWER_FLOP_PER_IMAGE_LAYER * N_QUERY}
+            if roofline is None:
+                roofline = roofline_tensor
         if args.profile_out:
             with open(args.profile_out, "w") as f:
                 json.dump({"per_kernel": breakdown, "episode_ms_sum_of_timed": total_ms}, f, indent=1)
@@ -323,7 +362,7 @@ def main():
                "data": "synthetic", "config": config,
                "e2e": {"value": round(e2e_value, 3), "unit": "episodes/s", "h2d_bytes_per_step": int(h2d),
                        "d2h_bytes_per_step": int(d2h), "ms_per_step": round(ms_e2e / args.steps, 3)},
-               "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu,
+               "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline, "roofline_tensor": roofline_tensor, "cpu_baseline": cpu,
                "episode_tflops": round(EPISODE_GFLOP * 1e-3 * value / world, 1),
                "detections_per_image": [int(c) for c in counts.cpu().tolist()],
                "e2e_detections_per_image": [int(s.numel()) for _, s in res], "per_kernel": breakdown}

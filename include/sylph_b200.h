@@ -109,6 +109,20 @@ int sylph_export_roi_features(sylph_ctx* ctx, float* out_dev, void* stream);
  * Replaces forward_normalize_code / code_process_module, code_generator.py:864-897. */
 int sylph_normalize_codes(sylph_ctx* ctx, const float* raw_codes_dev, float* out_codes_dev, int n_classes, void* stream);
 
+/* Base-class "all ground truths" path (MODEL.META_LEARN.USE_ALL_GTS_IN_BASE_CLASSES): a class arrives as several
+ * chunks of <= 10 support boxes.  acc[class_of(k)] += chunk_codes[k] * chunk_weight[k] for k = 0..n_chunks-1 in order,
+ * with the reference's fp32 rounding sequence (multiply, then add; no FMA).  acc_dev is [n_classes][257], zeroed by the
+ * caller before the first call; chunk_weight = (float)len / total_len.  Replaces the accumulation loop of
+ * inference_on_support_set_dataset_base, sylph/evaluation/meta_learn_evaluation.py:190-203. */
+int sylph_accumulate_codes(sylph_ctx* ctx, const float* chunk_codes_dev, int n_chunks, const int* chunk_class_host,
+                           const float* chunk_weight_host, float* acc_dev, int n_classes, void* stream);
+
+/* Sum `n_parts` partial accumulators ([n_parts][n_classes][257], one per rank, in rank order starting from 0) and
+ * divide class c by divisor_host[c] when it is non-zero (the caller sets it to the accumulated weight where
+ * |1 - acc_weight| > 1e-6, else 0).  Replaces reduce_class_code, sylph/modeling/code_generator/utils.py:397-427. */
+int sylph_reduce_codes(sylph_ctx* ctx, const float* parts_dev, int n_parts, int n_classes, const float* divisor_host,
+                       float* codes_out_dev, void* stream);
+
 /* Detection on the query slot with (n_classes, 257) normalised codes.  out_sizes: (n_images, 2) = (height, width)
  * requested output resolution per image (detector_postprocess).  dets_out_dev: (n_images, max_dets, 9) floats,
  * counts_out_dev: (n_images) int32; rows are in descending score order.  max_dets must be >= post_nms_topk.

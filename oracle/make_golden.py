@@ -125,8 +125,94 @@ def compare(tag, a, b):
     return err / (ref + 1e-30)
 
 
+def build_base_reduce_golden():
+    """Base-class all-GT path: seeded chunk codes -> weighted accumulation (restated loop) -> the REFERENCE's own
+    reduce_class_code / replace_class_code (sylph/modeling/code_generator/utils.py:376-427, imported unmodified)."""
+    import copy
+    import logging
+    from oracle import base_codes_oracle as bo
+    ns = reference_loader.load()
+    logging.getLogger(ns.cg_utils.__name__).setLevel(logging.ERROR)
+    g = torch.Generator().manual_seed(77)
+    # 6 classes; class c has total_len boxes split into chunks of <= 10; chunks are dealt round-robin to 3 "ranks";
+    # class 4 misses its last chunk (acc_weight != 1 -> rebalance), class 5 has a single full chunk
+    totals = {0: 23, 1: 10, 2: 37, 3: 4, 4: 26, 5: 10}
+    chunks = []
+    for cid, tot in totals.items():
+        n_chunks = (tot + 9) // 10
+        for j in range(n_chunks):
+            ln = min(10, tot - 10 * j)
+            if cid == 4 and j == n_chunks - 1:
+                continue
+            chunks.append({"cid": cid, "len": ln, "total_len": tot, "name": f"class{cid}",
+                           "code": {"cls_conv": torch.randn(1, 256, 1, 1, generator=g) * 0.3,
+                                    "cls_bias": torch.randn(1, 1, 1, 1, generator=g)}})
+    perm = torch.randperm(len(chunks), generator=g).tolist()
+    chunks = [chunks[i] for i in perm]
+    ranks = [chunks[r::3] for r in range(3)]
+    per_rank = [bo.accumulate_base_codes([copy.deepcopy(c["code"]) for c in rk], [c["cid"] for c in rk],
+                                         [c["len"] for c in rk], [c["total_len"] for c in rk], [c["name"] for c in rk])
+                for rk in ranks]
+    gathered = [c for rk in per_rank for c in rk]
+    # reduce_class_code's last log line reads result["class_code"]["cls_weight_norm"], which the shipped configs never
+    # produce (KeyError at utils.py:426): the reference path only runs with that log call neutralised.
+    class _Quiet:
+        def info(self, *a, **k):
+            pass
+    real_logger = ns.cg_utils.logger
+    ns.cg_utils.logger = _Quiet()
+    try:
+        try:
+            ref_reduced = ns.cg_utils.reduce_class_code(copy.deepcopy(gathered))
+            quirk = None
+        except KeyError as e:   # f-string argument is evaluated even with a quiet logger
+            quirk = f"KeyError {e} at utils.py:426 (log line needs cls_weight_norm)"
+            patched = copy.deepcopy(gathered)
+            for c in patched:
+                c["class_code"]["cls_weight_norm"] = torch.zeros(1) * 0.0
+            ref_reduced = ns.cg_utils.reduce_class_code(patched)
+            for c in ref_reduced:
+                del c["class_code"]["cls_weight_norm"]
+        few_shot = [{"support_set_target": torch.tensor(cid), "class_name": f"class{cid}",
+                     "class_code": {"cls_conv": torch.randn(1, 256, 1, 1, generator=g), "cls_bias": torch.randn(1, 1, 1, 1, generator=g)}}
+                    for cid in (0, 1, 2, 3, 4, 5, 6, 7)]
+        with contextlib.redirect_stdout(io.StringIO()), warnings_off():
+            ref_replaced = ns.cg_utils.replace_class_code(copy.deepcopy(few_shot), copy.deepcopy(ref_reduced), "cpu")
+    finally:
+        ns.cg_utils.logger = real_logger
+    mine = bo.reduce_class_code(copy.deepcopy(gathered))
+    assert [c["support_set_target"] for c in mine] == [bo._cid(c["support_set_target"]) for c in ref_reduced]
+    for a, b in zip(mine, ref_reduced):
+        assert torch.equal(a["class_code"]["cls_conv"], b["class_code"]["cls_conv"])
+        assert torch.equal(a["class_code"]["cls_bias"], b["class_code"]["cls_bias"])
+        assert "acc_weight" not in b["class_code"]
+    mine_rep = bo.replace_class_code(few_shot, mine)
+    for a, b in zip(mine_rep, ref_replaced):
+        assert torch.equal(a["class_code"]["cls_conv"], b["class_code"]["cls_conv"])
+        assert torch.equal(a["class_code"]["cls_bias"], b["class_code"]["cls_bias"])
+    print(f"[base_reduce] oracle restatement == reference reduce_class_code / replace_class_code (bit exact); quirk: {quirk}")
+    golden = {"chunks_per_rank": [[{k: c[k] for k in ("cid", "len", "total_len", "name", "code")} for c in rk] for rk in ranks],
+              "per_rank": per_rank, "reduced": ref_reduced, "few_shot": few_shot, "replaced": ref_replaced, "quirk": quirk,
+              "torch_version": torch.__version__}
+    path = os.path.join(GOLDEN_DIR, "base_reduce.pt")
+    torch.save(golden, path)
+    print(f"[base_reduce] wrote {path} ({os.path.getsize(path) / 1e3:.1f} kB)")
+
+
+@contextlib.contextmanager
+def warnings_off():
+    import warnings
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        yield
+
+
 def main():
     os.makedirs(GOLDEN_DIR, exist_ok=True)
+    if "--base-only" in sys.argv or "--all" in sys.argv or len(sys.argv) == 1:
+        build_base_reduce_golden()
+    if "--base-only" in sys.argv:
+        return
     for name in CASES:
         cfg_name, seed, support, query = build_case(name)
         cfg = load_cfg(os.path.join(reference_loader.REFERENCE_ROOT, "configs", CONFIGS[cfg_name]),

@@ -98,6 +98,10 @@ def load() -> ctypes.CDLL:
     lib.sylph_export_roi_features.argtypes = [vp, vp, vp]
     lib.sylph_normalize_codes.restype = c_int
     lib.sylph_normalize_codes.argtypes = [vp, vp, vp, c_int, vp]
+    lib.sylph_accumulate_codes.restype = c_int
+    lib.sylph_accumulate_codes.argtypes = [vp, vp, c_int, ip, fp, vp, c_int, vp]
+    lib.sylph_reduce_codes.restype = c_int
+    lib.sylph_reduce_codes.argtypes = [vp, vp, c_int, c_int, fp, vp, vp]
     lib.sylph_detect.restype = c_int
     lib.sylph_detect.argtypes = [vp, c_int, vp, c_int, ip, vp, vp, c_int, vp]
     lib.sylph_export_head_output.restype = c_int
@@ -115,6 +119,6 @@ def load() -> ctypes.CDLL:
 EXPORTED_SYMBOLS = [
     "sylph_version", "sylph_create", "sylph_destroy", "sylph_last_error", "sylph_load_tensor",
     "sylph_finalize_weights", "sylph_extract_features", "sylph_extract_features_u8", "sylph_import_features", "sylph_feature_shape",
-    "sylph_export_features", "sylph_generate_codes", "sylph_export_roi_features", "sylph_normalize_codes",
+    "sylph_export_features", "sylph_generate_codes", "sylph_export_roi_features", "sylph_normalize_codes", "sylph_accumulate_codes", "sylph_reduce_codes",
     "sylph_detect", "sylph_export_head_output", "sylph_launch_count", "sylph_set_profiling", "sylph_get_timings",
 ]

@@ -1015,6 +1015,44 @@ int sylph_normalize_codes(sylph_ctx* c, const float* raw_codes_dev, float* out_c
     return 0;
 }
 
+int sylph_accumulate_codes(sylph_ctx* c, const float* chunk_codes_dev, int n_chunks, const int* chunk_class_host,
+                           const float* chunk_weight_host, float* acc_dev, int n_classes, void* stream) {
+    if (!c) return 1;
+    if (n_chunks <= 0) return 0;
+    if (n_classes <= 0 || !chunk_codes_dev || !chunk_class_host || !chunk_weight_host || !acc_dev)
+        return c->fail("sylph_accumulate_codes: null argument or no classes");
+    for (int k = 0; k < n_chunks; ++k)
+        if (chunk_class_host[k] < 0 || chunk_class_host[k] >= n_classes)
+            return c->fail("chunk %d has class id %d outside [0, %d)", k, chunk_class_host[k], n_classes);
+    CU_TRY(c, cudaSetDevice(c->device));
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    void *pc, *pw;
+    TRY(ensure(c, "acc.chunk_class", static_cast<size_t>(n_chunks) * 4, "", &pc, st, false));
+    TRY(ensure(c, "acc.chunk_weight", static_cast<size_t>(n_chunks) * 4, "", &pw, st, false));
+    TRY(stage_h2d(c, pc, chunk_class_host, static_cast<size_t>(n_chunks) * 4, st));
+    TRY(stage_h2d(c, pw, chunk_weight_host, static_cast<size_t>(n_chunks) * 4, st));
+    CU_TRY(c, launch_k(accumulate_codes_kernel, dim3(n_classes), dim3(288), 0, st, chunk_codes_dev, static_cast<const int*>(pc),
+                       static_cast<const float*>(pw), n_chunks, acc_dev));
+    c->launches++;
+    return 0;
+}
+
+int sylph_reduce_codes(sylph_ctx* c, const float* parts_dev, int n_parts, int n_classes, const float* divisor_host,
+                       float* codes_out_dev, void* stream) {
+    if (!c) return 1;
+    if (n_classes <= 0) return 0;  // reduce_class_code returns an empty list unchanged
+    if (n_parts <= 0 || !parts_dev || !divisor_host || !codes_out_dev) return c->fail("sylph_reduce_codes: bad arguments");
+    CU_TRY(c, cudaSetDevice(c->device));
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    void* pd;
+    TRY(ensure(c, "acc.divisor", static_cast<size_t>(n_classes) * 4, "", &pd, st, false));
+    TRY(stage_h2d(c, pd, divisor_host, static_cast<size_t>(n_classes) * 4, st));
+    CU_TRY(c, launch_k(reduce_codes_kernel, dim3(n_classes), dim3(288), 0, st, parts_dev, n_parts, n_classes,
+                       static_cast<const float*>(pd), codes_out_dev));
+    c->launches++;
+    return 0;
+}
+
 int sylph_detect(sylph_ctx* c, int slot, const float* codes_dev, int n_classes, const int* out_sizes_host,
                  float* dets_out_dev, int* counts_out_dev, int max_dets, void* stream) {
     if (!c) return 1;

@@ -145,6 +145,41 @@ class_mean_kernel(const float* __restrict__ shot_codes, const int* __restrict__ 
     raw_codes[static_cast<size_t>(cls) * 257 + t] = s;
 }
 
+// Base-class "all ground truths" path: every class arrives as several chunks of <= 10 support boxes, each chunk's code
+// weighted by len / total_len and summed in arrival order (inference_on_support_set_dataset_base,
+// sylph/evaluation/meta_learn_evaluation.py:190-203).  One block per class walks the chunk list in order, so the fp32
+// rounding sequence is the reference's: acc = fl(acc + fl(code * w)) (no FMA contraction).
+__global__ void __launch_bounds__(288)
+accumulate_codes_kernel(const float* __restrict__ chunk_codes, const int* __restrict__ chunk_class,
+                        const float* __restrict__ chunk_weight, int n_chunks, float* __restrict__ acc) {
+    ptx::griddep_launch();
+    ptx::griddep_wait();
+    const int cls = blockIdx.x, t = threadIdx.x;
+    if (t >= 257) return;
+    float s = acc[static_cast<size_t>(cls) * 257 + t];
+    for (int k = 0; k < n_chunks; ++k) {
+        if (chunk_class[k] != cls) continue;
+        s = __fadd_rn(s, __fmul_rn(chunk_codes[static_cast<size_t>(k) * 257 + t], chunk_weight[k]));
+    }
+    acc[static_cast<size_t>(cls) * 257 + t] = s;
+}
+
+// reduce_class_code (sylph/modeling/code_generator/utils.py:397-427): sum the per-rank partial codes of a class in
+// rank order (functools.reduce starting from 0), then divide by the accumulated weight where it differs from 1
+// (`divisor[cls] != 0`; the host decides with the reference's |1 - acc_weight| > 1e-6 test in double precision).
+__global__ void __launch_bounds__(288)
+reduce_codes_kernel(const float* __restrict__ parts, int n_parts, int n_classes, const float* __restrict__ divisor,
+                    float* __restrict__ out) {
+    ptx::griddep_launch();
+    ptx::griddep_wait();
+    const int cls = blockIdx.x, t = threadIdx.x;
+    if (t >= 257) return;
+    float s = 0.f;
+    for (int r = 0; r < n_parts; ++r) s = __fadd_rn(s, parts[(static_cast<size_t>(r) * n_classes + cls) * 257 + t]);
+    const float d = divisor[cls];
+    out[static_cast<size_t>(cls) * 257 + t] = d != 0.f ? __fdiv_rn(s, d) : s;
+}
+
 // Code normalisation, one 256-thread block per class (code_process_module, code_generator.py:832-875):
 // GroupNorm(32, 256) on the 1x1 map (8-lane shuffles) -> L2 normalise over the 256 channels -> x conv_scale;
 // bias x bias_scale + (-log((1 - p) / p)).

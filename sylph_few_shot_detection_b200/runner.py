@@ -51,13 +51,113 @@ def _target_id(t) -> int:
     return int(t.item()) if torch.is_tensor(t) else int(t)
 
 
-def gather_class_code(sub_class_codes: List[Dict], group=None, device: Optional[torch.device] = None) -> List[Dict]:
+def inference_on_support_set_base(model: MetaOneStageDetector, chunk_items: Sequence[Dict[str, Any]],
+                                  chunks_per_batch: int = 4) -> List[Dict]:
+    """Base-class "all ground truths" path for this rank's chunks (inference_on_support_set_dataset_base,
+    sylph/evaluation/meta_learn_evaluation.py:118-254).  Every item is ONE chunk of <= 10 support records of one class
+    and carries "len" / "total_len" (sylph/data/.../meta_lvis.py:303-306); its code is weighted by len / total_len and
+    accumulated per class in arrival order.  Returns the reference's per-rank list: one entry per class id seen here,
+    `class_code` = {"cls_conv", "cls_bias", "acc_weight"}; codes stay on the device, `acc_weight` is a Python float
+    accumulated in double precision like the reference's."""
+    if len(chunk_items) == 0:
+        return []
+    eng = model.engine
+    cids = [_target_id(it["support_set_target"]) for it in chunk_items]
+    weights = [float(it["len"]) / it["total_len"] for it in chunk_items]
+    order: List[int] = []           # class ids in first-appearance order (dict insertion order in the reference)
+    names: Dict[int, str] = {}
+    acc_w: Dict[int, float] = {}
+    for cid, w, it in zip(cids, weights, chunk_items):
+        if cid not in acc_w:
+            order.append(cid)
+            acc_w[cid] = 0.0
+        acc_w[cid] += w
+        names[cid] = it.get("class_name", "")
+    slot_of = {cid: i for i, cid in enumerate(order)}
+    acc = torch.zeros((len(order), CODE_STRIDE), device=eng.device, dtype=torch.float32)
+    with torch.no_grad():
+        for i in range(0, len(chunk_items), chunks_per_batch):
+            batch = list(chunk_items[i:i + chunks_per_batch])
+            codes = model.forward_class_codes_batched(batch)
+            rows = torch.cat([torch.cat([c["cls_conv"].reshape(1, 256), c["cls_bias"].reshape(1, 1)], dim=1) for c in codes])
+            eng.accumulate_codes(rows, [slot_of[c] for c in cids[i:i + chunks_per_batch]], weights[i:i + chunks_per_batch], acc)
+    return [{"support_set_target": cid, "class_name": names[cid],
+             "class_code": {"cls_conv": acc[slot_of[cid], :256].reshape(1, 256, 1, 1),
+                            "cls_bias": acc[slot_of[cid], 256:].reshape(1, 1, 1, 1), "acc_weight": acc_w[cid]}}
+            for cid in order]
+
+
+def reduce_class_code(out_codes: List[Dict], engine=None) -> List[Dict]:
+    """`reduce_class_code` (sylph/modeling/code_generator/utils.py:397-427): merge the entries of one class id (partial
+    sums from different ranks) by adding them in list order, divide by the accumulated weight where it is not 1
+    (|1 - acc_weight| > 1e-6) and drop `acc_weight`.  Output order = first appearance of each class id.  The sums run
+    in one kernel over a dense (occurrence, class, 257) device buffer (`sylph_reduce_codes`)."""
+    if len(out_codes) == 0:
+        return out_codes
+    assert "class_code" in out_codes[0]
+    order: List[int] = []
+    occ: Dict[int, List[Dict]] = {}
+    other: Dict[int, Dict] = {}
+    for c in out_codes:
+        cid = _target_id(c["support_set_target"])
+        assert "class_code" in c
+        if cid not in occ:
+            order.append(cid)
+            occ[cid] = []
+            other[cid] = {k: v for k, v in c.items() if k != "class_code"}
+        occ[cid].append(c["class_code"])
+    dev = None
+    for c in out_codes:
+        if c["class_code"]["cls_conv"].is_cuda:
+            dev = c["class_code"]["cls_conv"].device
+            break
+    if engine is None or dev is None:
+        raise RuntimeError("reduce_class_code runs on the device: pass the model's engine and device-resident codes "
+                           "(the B200 path has no CPU fallback)")
+    n_parts = max(len(v) for v in occ.values())
+    parts = torch.zeros((n_parts, len(order), CODE_STRIDE), device=dev, dtype=torch.float32)
+    divisor = []
+    for i, cid in enumerate(order):
+        acc_weight = 0
+        for j, code in enumerate(occ[cid]):
+            parts[j, i, :256] = code["cls_conv"].reshape(-1).to(dev)
+            parts[j, i, 256] = code["cls_bias"].reshape(-1)[0].to(dev)
+            acc_weight = acc_weight + code["acc_weight"]          # functools.reduce(lambda x, y: x + y[key], lst, 0)
+        divisor.append(float(acc_weight) if abs(1.0 - acc_weight) > 1e-6 else 0.0)
+    red = engine.reduce_codes(parts, divisor)
+    results = []
+    for i, cid in enumerate(order):
+        r = dict(other[cid])
+        r["class_code"] = {"cls_conv": red[i, :256].reshape(1, 256, 1, 1), "cls_bias": red[i, 256:].reshape(1, 1, 1, 1)}
+        results.append(r)
+    return results
+
+
+def replace_class_code(support_set_class_code: List[Dict], target_class_codes: List[Dict], device) -> List[Dict]:
+    """`replace_class_code` (sylph/modeling/code_generator/utils.py:376-394): few-shot codes whose class id also has
+    an all-GT base code take that code (the first one of the id); everything ends up on `device`."""
+    target: Dict[int, Dict] = {}
+    for c in target_class_codes:
+        target.setdefault(_target_id(c["support_set_target"]), c["class_code"])
+    results = []
+    for c in support_set_class_code:
+        r = dict(c)
+        cid = _target_id(c["support_set_target"])
+        code = target[cid] if cid in target else c["class_code"]
+        r["class_code"] = {k: (v.to(device) if torch.is_tensor(v) else torch.tensor(v).to(device)) for k, v in code.items()}
+        results.append(r)
+    return results
+
+
+def gather_class_code(sub_class_codes: List[Dict], group=None, device: Optional[torch.device] = None,
+                      reduce: bool = False, engine=None) -> List[Dict]:
     """Step C: all ranks end up with the codes of ALL classes, ordered by rank then local order (what concatenating
     the all_gather_object output gives, meta_fcos_runner.py:386-396).  One all-gather of a padded
-    [max_shard, 258] fp32 buffer (257 code floats + class id; class names travel separately only if present).
-    World size 1 short-circuits like the reference (:430-431)."""
+    [max_shard, 258] fp32 buffer (257 code floats + class id; class names travel separately only if present) and,
+    for the base-class path, one of the float64 accumulated weights.  `reduce=True` then merges the entries of a
+    class id with `reduce_class_code` (:432-439).  World size 1 short-circuits like the reference (:430-431)."""
     if not dist.is_available() or not dist.is_initialized() or dist.get_world_size(group) == 1:
-        return sub_class_codes
+        return reduce_class_code(sub_class_codes, engine) if reduce else sub_class_codes
     world = dist.get_world_size(group)
     backend = dist.get_backend(group)
     if device is None:
@@ -68,22 +168,29 @@ def gather_class_code(sub_class_codes: List[Dict], group=None, device: Optional[
     counts = [int(c) for c in counts]
     max_n = max(max(counts), 1)
     buf = torch.zeros((max_n, CODE_STRIDE + 1), dtype=torch.float32, device=device)
+    wbuf = torch.full((max_n,), -1.0, dtype=torch.float64, device=device)
     for i, c in enumerate(sub_class_codes):
         buf[i, :256] = c["class_code"]["cls_conv"].reshape(-1).to(device)
         buf[i, 256] = c["class_code"]["cls_bias"].reshape(-1)[0].to(device)
         buf[i, 257] = float(_target_id(c["support_set_target"]))
+        if "acc_weight" in c["class_code"]:
+            wbuf[i] = float(c["class_code"]["acc_weight"])
     gathered = torch.empty((world * max_n, CODE_STRIDE + 1), dtype=torch.float32, device=device)
     dist.all_gather_into_tensor(gathered, buf, group=group)
+    wall = torch.empty((world * max_n,), dtype=torch.float64, device=device)
+    dist.all_gather_into_tensor(wall, wbuf, group=group)
+    wall = wall.cpu().tolist()
     names = [None] * world
     dist.all_gather_object(names, [c.get("class_name", "") for c in sub_class_codes], group=group)
     out = []
     for r in range(world):
         for i in range(counts[r]):
             row = gathered[r * max_n + i]
-            out.append({"support_set_target": torch.tensor(int(row[257].item())), "class_name": names[r][i],
-                        "class_code": {"cls_conv": row[:256].reshape(1, 256, 1, 1).clone(),
-                                       "cls_bias": row[256:257].reshape(1, 1, 1, 1).clone()}})
-    return out
+            code = {"cls_conv": row[:256].reshape(1, 256, 1, 1).clone(), "cls_bias": row[256:257].reshape(1, 1, 1, 1).clone()}
+            if wall[r * max_n + i] >= 0:
+                code["acc_weight"] = wall[r * max_n + i]
+            out.append({"support_set_target": torch.tensor(int(row[257].item())), "class_name": names[r][i], "class_code": code})
+    return reduce_class_code(out, engine) if reduce else out
 
 
 def inference_normalization(model: MetaOneStageDetector, all_class_codes: List[Dict]) -> List[Dict]:
@@ -208,13 +315,16 @@ class MetaFCOSRunner:
     def build_model(self, cfg, eval_only: bool = True) -> MetaOneStageDetector:
         if not eval_only:
             raise NotImplementedError("training is outside the B200 inference path")
-        return build_model(cfg)
+        model = build_model(cfg)
+        type(self)._model = model
+        return model
+
+    _model = None   # reduce_class_code sums on the device through the last built model's C-ABI context
 
     @classmethod
     def _gather_class_code(cls, sub_class_codes: List[Dict], reduce: bool = False) -> List[Dict]:
-        if reduce:
-            raise NotImplementedError("reduce_class_code (base-class all-GT path) is a 'next' row, SURVEY.md 8(f)")
-        return gather_class_code(sub_class_codes)
+        """meta_fcos_runner.py:381-439; `reduce=True` is the base-class all-GT path (reduce_class_code)."""
+        return gather_class_code(sub_class_codes, reduce=reduce, engine=cls._model.engine if cls._model is not None else None)
 
     def do_test(self, cfg, model, support_items, query_items):
         """Episode-level equivalent of `_do_test_meta_learning` for in-memory loaders."""

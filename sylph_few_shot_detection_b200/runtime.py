@@ -161,6 +161,29 @@ class Engine:
                                                    raw.shape[0], self._stream()))
         return out
 
+    # ------------------------------------------------------------------ base-class accumulation / reduction
+    def accumulate_codes(self, chunk_codes: torch.Tensor, chunk_class: Sequence[int], chunk_weight: Sequence[float],
+                         acc: torch.Tensor) -> torch.Tensor:
+        """acc[class_k] += chunk_codes[k] * float32(chunk_weight[k]) in chunk order (in place on the device)."""
+        chunk_codes = chunk_codes.to(self.device, torch.float32).contiguous()
+        n = chunk_codes.shape[0]
+        assert acc.is_cuda and acc.dtype == torch.float32 and acc.is_contiguous() and acc.shape[1] == CODE_STRIDE
+        cc = (c_int * n)(*[int(v) for v in chunk_class])
+        cw = (c_float * n)(*[float(v) for v in chunk_weight])
+        self._check(self.lib.sylph_accumulate_codes(self.h, c_void_p(chunk_codes.data_ptr()), n, cc, cw,
+                                                    c_void_p(acc.data_ptr()), acc.shape[0], self._stream()))
+        return acc
+
+    def reduce_codes(self, parts: torch.Tensor, divisor: Sequence[float]) -> torch.Tensor:
+        """parts (n_parts, n_classes, 257) -> (n_classes, 257): ordered sum over parts, then / divisor where != 0."""
+        parts = parts.to(self.device, torch.float32).contiguous()
+        n_parts, n_classes = parts.shape[0], parts.shape[1]
+        out = torch.empty((n_classes, CODE_STRIDE), device=self.device, dtype=torch.float32)
+        dv = (c_float * max(n_classes, 1))(*[float(v) for v in divisor])
+        self._check(self.lib.sylph_reduce_codes(self.h, c_void_p(parts.data_ptr()), n_parts, n_classes, dv,
+                                                c_void_p(out.data_ptr()), self._stream()))
+        return out
+
     # ------------------------------------------------------------------ detection
     def detect(self, slot: int, codes: torch.Tensor, out_sizes: Optional[Sequence[Tuple[int, int]]] = None,
                max_dets: Optional[int] = None):

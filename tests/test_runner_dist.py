@@ -37,6 +37,44 @@ def _worker(rank, world, port, n_classes, q):
         dist.destroy_process_group()
 
 
+def _worker_base(rank, world, port, q):
+    """Base-class path: both ranks hold a PARTIAL sum of class 7 (acc_weight 0.4 / 0.6); rank 1 also holds class 3."""
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        g = torch.Generator().manual_seed(500 + rank)
+        mine = [{"support_set_target": 7, "class_name": "seven",
+                 "class_code": {"cls_conv": torch.randn(1, 256, 1, 1, generator=g), "cls_bias": torch.randn(1, 1, 1, 1, generator=g),
+                                "acc_weight": 0.4 if rank == 0 else 0.6}}]
+        if rank == 1:
+            mine.append({"support_set_target": 3, "class_name": "three",
+                         "class_code": {"cls_conv": torch.randn(1, 256, 1, 1, generator=g),
+                                        "cls_bias": torch.randn(1, 1, 1, 1, generator=g), "acc_weight": 1.0 / 3 + 2.0 / 3}})
+        allc = gather_class_code(mine)          # reduce=False: the merge itself runs on the device (GPU tests)
+        q.put((rank, [(int(c["support_set_target"]), c["class_name"], c["class_code"]["acc_weight"],
+                       c["class_code"]["cls_conv"].clone()) for c in allc]))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_gather_carries_accumulated_weights_in_double_precision():
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker_base, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    out = sorted([q.get(timeout=120) for _ in range(2)], key=lambda t: t[0])
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    for rank, entries in out:
+        assert [(e[0], e[1]) for e in entries] == [(7, "seven"), (7, "seven"), (3, "three")]
+        assert entries[0][2] == 0.4 and entries[1][2] == 0.6 and entries[2][2] == 1.0 / 3 + 2.0 / 3   # exact doubles
+        assert torch.equal(entries[0][3], torch.randn(1, 256, 1, 1, generator=torch.Generator().manual_seed(500)))
+
+
 def _run(n_classes, world=2):
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
