@@ -49,6 +49,12 @@ typedef struct sylph_model_config {
     int cg_bias_l2_norm;       /* CODE_GENERATOR.BIAS_L2_NORM */
     int cg_use_bias;           /* CODE_GENERATOR.USE_BIAS (CondConvBasic use_bias) */
     int cg_has_conv_scale;     /* USE_WEIGHT_SCALE and (CONV_L2_NORM or POST_NORM) */
+    int generator;             /* CODE_GENERATOR.NAME: 0 = "CodeGenerator" / "CodeGeneratorHead", 1 = "ROIEncoder" */
+    int re_tok_convs;          /* ROIEncoder: CODE_GENERATOR.TOKENIZER.NUM_CONV (CONV_DIM 256, NORM "GN") */
+    int re_tok_fcs;            /* ROIEncoder: CODE_GENERATOR.TOKENIZER.NUM_FC (FC_DIM 256 = transformer d_model) */
+    int re_layers;             /* ROIEncoder: CODE_GENERATOR.TRANSFORMER_ENCODER.LAYERS (dim_feedforward = 4 x 256) */
+    int re_head_fcs;           /* ROIEncoder: CODE_GENERATOR.HEAD.NUM_FC (OUTPUT_DIM 256) */
+    int re_head_dim;           /* ROIEncoder: CODE_GENERATOR.HEAD.FC_DIM (<= 1024) */
 } sylph_model_config;
 
 /* Library / build identification (no GPU needed). */
@@ -97,7 +103,11 @@ int sylph_export_features(sylph_ctx* ctx, int slot, int level, float* out_dev, v
  * into the ROI list (ROIs of a class are contiguous).  Writes RAW (un-normalised) codes, (n_classes, 257), to
  * codes_out_dev and, if non-NULL, the FPN level index of every ROI (int64, like assign_boxes_to_levels) to
  * levels_out_dev.  Replaces CodeGeneratorHead.forward_roi_align, code_generator.py:924-1002, called once per class
- * by forward_class_code, meta_one_stage_detector.py:229-254. */
+ * by forward_class_code, meta_one_stage_detector.py:229-254.
+ * With generator == 1 the same entry runs ROIEncoder.forward (sylph/modeling/code_generator/roi_encoder.py:146-204):
+ * ROIAlign -> conv3x3+GN+ReLU -> MS_CAM context gate -> tokenizer -> transformer encoder -> class-token mean ->
+ * weight / bias hyper-network heads; a row is then the FINAL code (bias includes the -log((1-p)/p) prior) and
+ * sylph_normalize_codes is not applicable. */
 int sylph_generate_codes(sylph_ctx* ctx, int slot, int n_rois, const float* boxes_host, const int* roi_image,
                          int n_classes, const int* class_offsets, float* codes_out_dev, int64_t* levels_out_dev,
                          void* stream);

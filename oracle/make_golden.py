@@ -22,6 +22,7 @@ if REPO not in sys.path:
 
 from oracle import reference_loader, upstream as up  # noqa: E402
 from oracle.meta_fcos_oracle import MetaFCOSOracle  # noqa: E402
+from oracle.roi_encoder_oracle import build_oracle  # noqa: E402
 from sylph_few_shot_detection_b200 import weights as W  # noqa: E402
 from sylph_few_shot_detection_b200.config import load_cfg  # noqa: E402
 
@@ -29,12 +30,16 @@ GOLDEN_DIR = os.path.join(REPO, "tests", "golden")
 CONFIGS = {
     "coco": "COCO-Detection/Meta-FCOS/Meta-FCOS-finetune.yaml",
     "lvis": "LVISv1-Detection/Meta-FCOS/Meta-FCOS-finetune.yaml",
+    "lvis_roienc": "LVISv1-Detection/Meta-FCOS/Meta-FCOS-ROI-Encoder-finetune.yaml",
 }
+# extra config overrides of a case (also applied by the tests that rebuild the cfg from the preset)
+CASE_OPTS = {"lvis_roienc_2way_3shot": ["MODEL.META_LEARN.EVAL_SHOT", 3]}
 # vendored copies of the two YAML trees are NOT kept; tests rebuild the cfg from these overrides on top of defaults
 CASES = {
     # name: (config, seed, classes, shots, support (H, W) list, query (H, W) list)
     "coco_2way_2shot": ("coco", 3, 2, 2, [(256, 320), (240, 300)], [(256, 320), (200, 288)]),
     "lvis_1way_3shot": ("lvis", 5, 1, 3, [(224, 256), (256, 224), (200, 240)], [(224, 288)]),
+    "lvis_roienc_2way_3shot": ("lvis_roienc", 9, 2, 3, [(224, 256), (256, 224), (200, 240)], [(224, 288)]),
 }
 
 
@@ -91,8 +96,11 @@ def run_reference(cfg, state, support, query):
             out["raw_codes"].append({k: v.clone() for k, v in code.items()})
             codes.append({"support_set_target": torch.tensor(c), "class_name": f"class{c}",
                           "class_code": {k: v.clone() for k, v in code.items()}})
-        with contextlib.redirect_stdout(io.StringIO()):
-            codes = model(None, class_code=codes, run_type="meta_learn_normalize_code")
+        try:
+            with contextlib.redirect_stdout(io.StringIO()):
+                codes = model(None, class_code=codes, run_type="meta_learn_normalize_code")
+        except TypeError as e:   # ROIEncoder.forward has no cls_norm / class_codes keywords (reference quirk)
+            out["normalize_error"] = f"TypeError: {e}"
         out["norm_codes"] = [{k: v.clone() for k, v in c["class_code"].items()} for c in codes]
         packed = MetaFCOSOracle.pack_codes(codes)  # restates format_class_codes_shared (needs pycocotools to import)
         out["packed"] = packed
@@ -215,14 +223,16 @@ def main():
         return
     for name in CASES:
         cfg_name, seed, support, query = build_case(name)
+        if "--only" in sys.argv and name != sys.argv[sys.argv.index("--only") + 1]:
+            continue
         cfg = load_cfg(os.path.join(reference_loader.REFERENCE_ROOT, "configs", CONFIGS[cfg_name]),
-                       ["MODEL.DEVICE", "cpu"])
+                       ["MODEL.DEVICE", "cpu"] + CASE_OPTS.get(name, []))
         state = W.synthetic_state_dict(cfg, seed)
         ref = run_reference(cfg, state, support, query)
         n_det = [int(d["scores"].numel()) for d in ref["detections"]]
         print(f"[{name}] reference detections per image: {n_det}; feature |mean| {ref['feat_abs_mean']}")
         # oracle on the same inputs
-        orc = MetaFCOSOracle(cfg, state)
+        orc = build_oracle(cfg, state)
         worst = 0.0
         raw = []
         for c, shots in enumerate(support):
@@ -253,7 +263,8 @@ def main():
                 assert torch.equal(d["locations"], r["locations"])
         print(f"[{name}] worst relative deviation oracle vs reference: {worst:.3e}")
         golden = {
-            "case": name, "config": CONFIGS[cfg_name], "seed": seed,
+            "case": name, "config": CONFIGS[cfg_name], "seed": seed, "opts": CASE_OPTS.get(name, []),
+            "normalize_error": ref.get("normalize_error"),
             "support": [[{"image": s["image"].to(torch.uint8), "box": s["box"]} for s in shots] for shots in support],
             "query": [q.to(torch.uint8) for q in query],
             "raw_codes": ref["raw_codes"], "norm_codes": ref["norm_codes"], "packed": ref["packed"],

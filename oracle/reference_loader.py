@@ -36,6 +36,7 @@ def load():
         sys.modules["sylph.modeling.meta_arch"] = pkg
     import sylph.modeling.code_generator  # noqa: F401  registers CodeGenerator / CodeGeneratorHead
     import sylph.modeling.meta_fcos  # noqa: F401  registers MetaFCOS
+    importlib.import_module("sylph.modeling.code_generator.roi_encoder")  # registers ROIEncoder (meta_fcos_runner.py:70-71)
     name = "sylph.modeling.meta_arch.meta_one_stage_detector"
     if name not in sys.modules:
         spec = importlib.util.spec_from_file_location(
@@ -48,6 +49,7 @@ def load():
     ns.MetaOneStageDetector = ns.meta_arch.MetaOneStageDetector
     ns.code_generator = importlib.import_module("sylph.modeling.code_generator.code_generator")
     ns.cg_utils = importlib.import_module("sylph.modeling.code_generator.utils")
+    ns.roi_encoder = importlib.import_module("sylph.modeling.code_generator.roi_encoder")
     ns.fcos = importlib.import_module("sylph.modeling.meta_fcos.fcos")
     ns.fcos_outputs = importlib.import_module("sylph.modeling.meta_fcos.fcos_outputs")
     ns.head_utils = importlib.import_module("sylph.modeling.meta_fcos.head_utils")

@@ -13,6 +13,7 @@
 #include "../../include/sylph_b200.h"
 #include "conv_gemm_host.cuh"
 #include "kernels_detect.cuh"
+#include "kernels_roi_encoder.cuh"
 
 namespace sylph {
 
@@ -94,6 +95,18 @@ struct sylph_ctx {
     float* post_gn_w = nullptr;
     float* post_gn_b = nullptr;
     float conv_scale = 1.f, bias_scale = 1.f, bias_value = 0.f;
+    // ROIEncoder generator (cfg.generator == 1)
+    struct Dense { float* w = nullptr; float* b = nullptr; int in = 0, out = 0; };
+    struct EncLayer { Dense attn, ff1, ff2; float *n1w = nullptr, *n1b = nullptr, *n2w = nullptr, *n2b = nullptr; };
+    ConvW re_pool_conv, re_fc1;
+    float *re_pool_gn_w = nullptr, *re_pool_gn_b = nullptr;
+    std::vector<ConvW> re_tok_conv;
+    std::vector<float*> re_tok_gn_w, re_tok_gn_b;
+    MsCamWeights re_cam{};
+    std::vector<Dense> re_tok_fc;      // tokenizer fc2.. (fc1 is the tensor-core GEMM re_fc1)
+    std::vector<EncLayer> re_enc;
+    std::vector<Dense> re_whead, re_bhead;
+    float cond_scale = 1.f;            // fcos_head.cond_cls_logits.scales.0.scale (CondConvBlock, head_utils.py:121-162)
 
     std::map<std::string, Buffer> bufs;
     // pinned host ring for small host->device argument arrays: copies from it are truly asynchronous, so no entry
@@ -349,6 +362,128 @@ static int scalar_of(sylph_ctx* c, const std::string& key, float* v) {
     return 0;
 }
 
+// ------------------------------------------------------------------------------------------------ ROIEncoder weights
+static int upload_t(sylph_ctx* c, const std::string& key, float** d, size_t expect, bool transpose = false, int rows = 0,
+                    int cols = 0) {
+    const HostTensor* t = find_t(c, key);
+    if (!t || t->data.size() != expect) return c->fail("missing or mis-sized tensor %s", key.c_str());
+    if (!transpose) return upload(c, t->data, d);
+    std::vector<float> h(expect);
+    for (int r = 0; r < rows; ++r)
+        for (int q = 0; q < cols; ++q) h[static_cast<size_t>(q) * rows + r] = t->data[static_cast<size_t>(r) * cols + q];
+    return upload(c, h, d);
+}
+
+static int prep_dense(sylph_ctx* c, const std::string& prefix, int in, int out, sylph_ctx::Dense* d) {
+    d->in = in;
+    d->out = out;
+    TRY(upload_t(c, prefix + ".weight", &d->w, static_cast<size_t>(in) * out));
+    TRY(upload_t(c, prefix + ".bias", &d->b, static_cast<size_t>(out)));
+    return 0;
+}
+
+// ROIEncoder (sylph/modeling/code_generator/roi_encoder.py:206-281): FeatureFusionModuleV2 conv + MS_CAM, Tokenizer,
+// TransformerEncoder (sequence length 1 at inference: W_o W_v folded), weight / bias HyperNetworkHead.
+static int prep_roi_encoder(sylph_ctx* c) {
+    const sylph_model_config& f = c->cfg;
+    const std::string cg = "code_generator.";
+    if (f.re_tok_convs < 1 || f.re_tok_fcs < 1 || f.re_layers < 0 || f.re_head_fcs < 1 || f.re_head_dim > 1024)
+        return c->fail("unsupported ROIEncoder dimensions");
+    TRY(prep_conv(c, cg + "box_pooler.conv.0", false, true, &c->re_pool_conv));
+    TRY(upload_vec(c, cg + "box_pooler.conv.1.weight", &c->re_pool_gn_w, 256));
+    TRY(upload_vec(c, cg + "box_pooler.conv.1.bias", &c->re_pool_gn_b, 256));
+    const std::string cam = cg + "box_pooler.context_attention_module.";
+    MsCamWeights& m = c->re_cam;
+    float* p;
+    TRY(upload_t(c, cam + "local_att.0.weight", &p, 64 * 256, true, 64, 256)); m.l_w1t = p;
+    TRY(upload_t(c, cam + "local_att.0.bias", &p, 64)); m.l_b1 = p;
+    TRY(upload_t(c, cam + "local_att.1.weight", &p, 64)); m.l_g1w = p;
+    TRY(upload_t(c, cam + "local_att.1.bias", &p, 64)); m.l_g1b = p;
+    TRY(upload_t(c, cam + "local_att.3.weight", &p, 256 * 64, true, 256, 64)); m.l_w2t = p;
+    TRY(upload_t(c, cam + "local_att.3.bias", &p, 256)); m.l_b2 = p;
+    TRY(upload_t(c, cam + "local_att.4.weight", &p, 256)); m.l_g2w = p;
+    TRY(upload_t(c, cam + "local_att.4.bias", &p, 256)); m.l_g2b = p;
+    TRY(upload_t(c, cam + "global_att.1.weight", &p, 64 * 256)); m.g_w1 = p;
+    TRY(upload_t(c, cam + "global_att.1.bias", &p, 64)); m.g_b1 = p;
+    TRY(upload_t(c, cam + "global_att.2.weight", &p, 64)); m.g_g1w = p;
+    TRY(upload_t(c, cam + "global_att.2.bias", &p, 64)); m.g_g1b = p;
+    TRY(upload_t(c, cam + "global_att.4.weight", &p, 256 * 64, true, 256, 64)); m.g_w2t = p;
+    TRY(upload_t(c, cam + "global_att.4.bias", &p, 256)); m.g_b2 = p;
+    TRY(upload_t(c, cam + "global_att.5.weight", &p, 256)); m.g_g2w = p;
+    TRY(upload_t(c, cam + "global_att.5.bias", &p, 256)); m.g_g2b = p;
+    // tokenizer convolutions: Conv2d(bias = not norm) + GN + ReLU; the GEMM epilogue adds a zero bias
+    c->re_tok_conv.assign(f.re_tok_convs, ConvW());
+    c->re_tok_gn_w.assign(f.re_tok_convs, nullptr);
+    c->re_tok_gn_b.assign(f.re_tok_convs, nullptr);
+    for (int i = 0; i < f.re_tok_convs; ++i) {
+        const std::string k = cg + "tokenizer.conv" + std::to_string(i + 1);
+        TRY(prep_conv(c, k, false, false, &c->re_tok_conv[i]));
+        TRY(upload_vec(c, k + ".norm.weight", &c->re_tok_gn_w[i], 256));
+        TRY(upload_vec(c, k + ".norm.bias", &c->re_tok_gn_b[i], 256));
+    }
+    {   // fc1: (256, 256 * 49) over nn.Flatten order c * 49 + p  ->  1x1 "convolution" over K = p * 256 + c
+        const HostTensor *w = find_t(c, cg + "tokenizer.fc1.weight"), *b = find_t(c, cg + "tokenizer.fc1.bias");
+        if (!w || !b || w->data.size() != static_cast<size_t>(256) * 12544 || b->data.size() != 256)
+            return c->fail("tokenizer.fc1 must map 256 x 7 x 7 to 256 features");
+        HostTensor pw;
+        pw.shape = {256, 12544, 1, 1};
+        pw.data.resize(w->data.size());
+        for (int o = 0; o < 256; ++o)
+            for (int ch = 0; ch < 256; ++ch)
+                for (int px = 0; px < 49; ++px)
+                    pw.data[static_cast<size_t>(o) * 12544 + px * 256 + ch] = w->data[static_cast<size_t>(o) * 12544 + ch * 49 + px];
+        c->staged["__re_fc1.weight"] = std::move(pw);
+        c->staged["__re_fc1.bias"] = *b;
+        TRY(prep_conv(c, "__re_fc1", false, true, &c->re_fc1));
+    }
+    c->re_tok_fc.assign(f.re_tok_fcs - 1, sylph_ctx::Dense());
+    for (int i = 1; i < f.re_tok_fcs; ++i) TRY(prep_dense(c, cg + "tokenizer.fc" + std::to_string(i + 1), 256, 256, &c->re_tok_fc[i - 1]));
+    c->re_enc.assign(f.re_layers, sylph_ctx::EncLayer());
+    for (int l = 0; l < f.re_layers; ++l) {
+        const std::string k = cg + "transformer_encoder.layers." + std::to_string(l) + ".";
+        const HostTensor *ipw = find_t(c, k + "self_attn.in_proj_weight"), *ipb = find_t(c, k + "self_attn.in_proj_bias"),
+                         *ow = find_t(c, k + "self_attn.out_proj.weight"), *ob = find_t(c, k + "self_attn.out_proj.bias");
+        if (!ipw || !ipb || !ow || !ob || ipw->data.size() != 768 * 256 || ow->data.size() != 256 * 256)
+            return c->fail("transformer layer %d: d_model must be 256", l);
+        // sequence length 1: attention output = out_proj(v_proj(x)); fold in double precision
+        std::vector<float> wf(256 * 256), bf(256);
+        for (int o = 0; o < 256; ++o) {
+            double bacc = ob->data[o];
+            for (int j = 0; j < 256; ++j) bacc += static_cast<double>(ow->data[o * 256 + j]) * ipb->data[512 + j];
+            bf[o] = static_cast<float>(bacc);
+            for (int i = 0; i < 256; ++i) {
+                double acc = 0.0;
+                for (int j = 0; j < 256; ++j) acc += static_cast<double>(ow->data[o * 256 + j]) * ipw->data[(512 + j) * 256 + i];
+                wf[o * 256 + i] = static_cast<float>(acc);
+            }
+        }
+        sylph_ctx::EncLayer& L = c->re_enc[l];
+        L.attn.in = L.attn.out = 256;
+        TRY(upload(c, wf, &L.attn.w));
+        TRY(upload(c, bf, &L.attn.b));
+        TRY(prep_dense(c, k + "linear1", 256, 1024, &L.ff1));
+        TRY(prep_dense(c, k + "linear2", 1024, 256, &L.ff2));
+        TRY(upload_vec(c, k + "norm1.weight", &L.n1w, 256));
+        TRY(upload_vec(c, k + "norm1.bias", &L.n1b, 256));
+        TRY(upload_vec(c, k + "norm2.weight", &L.n2w, 256));
+        TRY(upload_vec(c, k + "norm2.bias", &L.n2b, 256));
+    }
+    auto prep_head = [&](const std::string& name, int out_dim, std::vector<sylph_ctx::Dense>* hd) -> int {
+        hd->assign(f.re_head_fcs, sylph_ctx::Dense());
+        int din = 256;
+        for (int i = 0; i < f.re_head_fcs; ++i) {
+            const int dout = (i == f.re_head_fcs - 1) ? out_dim : f.re_head_dim;
+            TRY(prep_dense(c, cg + name + ".fc" + std::to_string(i + 1), din, dout, &(*hd)[i]));
+            din = dout;
+        }
+        return 0;
+    };
+    TRY(prep_head("weight_head", 256, &c->re_whead));
+    TRY(prep_head("bias_head", 1, &c->re_bhead));
+    TRY(scalar_of(c, "proposal_generator.fcos_head.cond_cls_logits.scales.0.scale", &c->cond_scale));
+    return 0;
+}
+
 // ------------------------------------------------------------------------------------------------ conv launch
 struct ConvCall {
     const ConvW* W;
@@ -581,35 +716,39 @@ int sylph_finalize_weights(sylph_ctx* c) {
         c->level_scale[l] = 1.f;
         if (f.use_scale) TRY(scalar_of(c, head + "scales." + std::to_string(l) + ".scale", &c->level_scale[l]));
     }
-    const std::string cg = "code_generator.code_generator_head.";
-    c->cg_tower.assign(f.cg_tower_layers, ConvW());
-    c->cg_gn_w.assign(f.cg_tower_layers, nullptr);
-    c->cg_gn_b.assign(f.cg_tower_layers, nullptr);
-    for (int i = 0; i < f.cg_tower_layers; ++i) {
-        TRY(prep_conv(c, cg + "support_set_shared_tower." + std::to_string(3 * i), false, true, &c->cg_tower[i]));
-        TRY(upload_vec(c, cg + "support_set_shared_tower." + std::to_string(3 * i + 1) + ".weight", &c->cg_gn_w[i], 256));
-        TRY(upload_vec(c, cg + "support_set_shared_tower." + std::to_string(3 * i + 1) + ".bias", &c->cg_gn_b[i], 256));
-    }
-    TRY(prep_conv(c, cg + "support_set_cls_conv.0", false, true, &c->cg_cls));
-    if (c->cg_cls.cout != 256) return c->fail("CODE_GENERATOR.OUT_CHANNEL must be 256 on this path");
-    if (f.cg_bias_layer) {
-        const HostTensor *w = find_t(c, cg + "support_set_cls_bias.0.weight"), *b = find_t(c, cg + "support_set_cls_bias.0.bias");
-        if (!w || !b || w->data.size() != 256 * 9) return c->fail("missing support_set_cls_bias tensors");
-        std::vector<float> hw(9 * 256);
-        for (int ch = 0; ch < 256; ++ch)
-            for (int t = 0; t < 9; ++t) hw[t * 256 + ch] = w->data[ch * 9 + t];
-        TRY(upload(c, hw, &c->cg_wbias));
-        TRY(upload(c, b->data, &c->cg_bbias));
-        TRY(scalar_of(c, cg + "bias_scale.scale", &c->bias_scale));
+    if (f.generator == 1) {
+        TRY(prep_roi_encoder(c));
     } else {
-        c->bias_scale = 1.f;
+        const std::string cg = "code_generator.code_generator_head.";
+        c->cg_tower.assign(f.cg_tower_layers, ConvW());
+        c->cg_gn_w.assign(f.cg_tower_layers, nullptr);
+        c->cg_gn_b.assign(f.cg_tower_layers, nullptr);
+        for (int i = 0; i < f.cg_tower_layers; ++i) {
+            TRY(prep_conv(c, cg + "support_set_shared_tower." + std::to_string(3 * i), false, true, &c->cg_tower[i]));
+            TRY(upload_vec(c, cg + "support_set_shared_tower." + std::to_string(3 * i + 1) + ".weight", &c->cg_gn_w[i], 256));
+            TRY(upload_vec(c, cg + "support_set_shared_tower." + std::to_string(3 * i + 1) + ".bias", &c->cg_gn_b[i], 256));
+        }
+        TRY(prep_conv(c, cg + "support_set_cls_conv.0", false, true, &c->cg_cls));
+        if (c->cg_cls.cout != 256) return c->fail("CODE_GENERATOR.OUT_CHANNEL must be 256 on this path");
+        if (f.cg_bias_layer) {
+            const HostTensor *w = find_t(c, cg + "support_set_cls_bias.0.weight"), *b = find_t(c, cg + "support_set_cls_bias.0.bias");
+            if (!w || !b || w->data.size() != 256 * 9) return c->fail("missing support_set_cls_bias tensors");
+            std::vector<float> hw(9 * 256);
+            for (int ch = 0; ch < 256; ++ch)
+                for (int t = 0; t < 9; ++t) hw[t * 256 + ch] = w->data[ch * 9 + t];
+            TRY(upload(c, hw, &c->cg_wbias));
+            TRY(upload(c, b->data, &c->cg_bbias));
+            TRY(scalar_of(c, cg + "bias_scale.scale", &c->bias_scale));
+        } else {
+            c->bias_scale = 1.f;
+        }
+        if (f.cg_post_norm) {
+            TRY(upload_vec(c, cg + "post_norm.weight", &c->post_gn_w, 256));
+            TRY(upload_vec(c, cg + "post_norm.bias", &c->post_gn_b, 256));
+        }
+        c->conv_scale = 1.f;
+        if (f.cg_has_conv_scale) TRY(scalar_of(c, cg + "conv_scale.scale", &c->conv_scale));
     }
-    if (f.cg_post_norm) {
-        TRY(upload_vec(c, cg + "post_norm.weight", &c->post_gn_w, 256));
-        TRY(upload_vec(c, cg + "post_norm.bias", &c->post_gn_b, 256));
-    }
-    c->conv_scale = 1.f;
-    if (f.cg_has_conv_scale) TRY(scalar_of(c, cg + "conv_scale.scale", &c->conv_scale));
     c->bias_value = -std::log((1.f - f.prior_prob) / f.prior_prob);
     c->staged.clear();
     c->finalized = true;
@@ -849,6 +988,113 @@ static int conv_gn_relu(sylph_ctx* c, const ConvW& W, const float* gn_w, const f
     return 0;
 }
 
+static int run_linear(sylph_ctx* c, const sylph_ctx::Dense& d, const float* x, int ldx, float* y, int ldy, int T, int relu,
+                      float add_const, cudaStream_t st) {
+    if (d.in > 1024) return c->fail("linear layer wider than 1024 inputs");
+    CU_TRY(c, launch_k(linear_kernel, dim3(ceil_div(T, 8), ceil_div(d.out, 64)), dim3(256), 0, st, x, ldx,
+                       static_cast<const float*>(d.w), static_cast<const float*>(d.b), y, ldy, T, d.in, d.out, relu, add_const));
+    c->launches++;
+    return 0;
+}
+
+// ROIEncoder.forward at inference (sylph/modeling/code_generator/roi_encoder.py:146-204) after the shared ROIAlign:
+// r0 holds the pooled ROI planes; r1 / r2 are scratch planes of the same shape.
+static int roi_encoder_codes(sylph_ctx* c, const Slot& S, int n_rois, int n_classes, const int* d_roi_image,
+                             const int* d_class_off, const PlaneSet* ps, __half* r0, __half* r1, __half* r2, float* raw,
+                             float* gp, float* gs, float* codes_out_dev, cudaStream_t st) {
+    const sylph_model_config& f = c->cfg;
+    const long long rows = static_cast<long long>(n_rois) * 128;
+    const int t_pad = round_up(n_rois, kBlockM);
+    void *pctx, *ptok, *px0, *px1, *pxa, *ph, *pcls, *phd;
+    TRY(ensure(c, "re.ctx", static_cast<size_t>(n_rois) * 49 * 256 * 4, "", &pctx, st, false));
+    TRY(ensure(c, "re.tokens", (static_cast<size_t>(t_pad) + kBlockM) * 12544 * 2, "tok", &ptok, st, true));
+    TRY(ensure(c, "re.x0", static_cast<size_t>(t_pad) * 256 * 4, "", &px0, st, false));
+    TRY(ensure(c, "re.x1", static_cast<size_t>(t_pad) * 256 * 4, "", &px1, st, false));
+    TRY(ensure(c, "re.xa", static_cast<size_t>(t_pad) * 256 * 4, "", &pxa, st, false));
+    TRY(ensure(c, "re.h", static_cast<size_t>(t_pad) * 1024 * 4, "", &ph, st, false));
+    TRY(ensure(c, "re.cls", static_cast<size_t>(n_classes) * 256 * 4, "", &pcls, st, false));
+    TRY(ensure(c, "re.hd", static_cast<size_t>(n_classes) * 1024 * 4 * 2, "", &phd, st, false));
+    // FeatureFusionModuleV2: conv3x3 + GN + ReLU on the pooled features, then the MS_CAM context gate
+    TRY(conv_gn_relu(c, c->re_pool_conv, c->re_pool_gn_w, c->re_pool_gn_b, r0, rows, raw, r1, ps, 0, n_rois, 0, n_rois, gp, gs,
+                     "roienc.pool_conv3x3", st));
+    {
+        StageTimer t(c, "roienc.context_pool", st, static_cast<double>(n_rois) * 22400 * 256 * 2);
+        CU_TRY(c, launch_k(context_pool_kernel, dim3(n_rois, 49), dim3(256), 0, st, static_cast<const __half*>(S.pyr), S.pg,
+                           d_roi_image, static_cast<float*>(pctx)));
+        c->launches++;
+    }
+    {
+        static bool attr_set = false;
+        if (!attr_set) {
+            CU_TRY(c, cudaFuncSetAttribute(ms_cam_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kMsCamSmem));
+            attr_set = true;
+        }
+        StageTimer t(c, "roienc.ms_cam", st, static_cast<double>(n_rois) * 49 * 256 * 8);
+        CU_TRY(c, launch_k(ms_cam_kernel, dim3(n_rois), dim3(256), static_cast<size_t>(kMsCamSmem), st,
+                           static_cast<const float*>(pctx), static_cast<const __half*>(r1), c->re_cam, r2));
+        c->launches++;
+    }
+    // Tokenizer: NUM_CONV x (conv3x3 + GN + ReLU), flatten, fc1 (tensor-core GEMM over K = 12544), fc2.. (+ ReLU)
+    __half* cur = r2;
+    __half* nxt = r0;
+    for (int i = 0; i < f.re_tok_convs; ++i) {
+        TRY(conv_gn_relu(c, c->re_tok_conv[i], c->re_tok_gn_w[i], c->re_tok_gn_b[i], cur, rows, raw, nxt, ps, 0, n_rois, 0,
+                         n_rois, gp, gs, "roienc.tok_conv3x3", st));
+        __half* done = cur;
+        cur = nxt;
+        nxt = (done == r2) ? r1 : done;
+    }
+    CU_TRY(c, launch_k(gather_tokens_kernel, dim3(grid_for(static_cast<long long>(n_rois) * 49 * 32, 256, c->num_sms)), dim3(256),
+                       0, st, static_cast<const __half*>(cur), static_cast<__half*>(ptok), n_rois));
+    c->launches++;
+    {
+        ConvCall k{};
+        k.W = &c->re_fc1; k.A = static_cast<const __half*>(ptok); k.a_rows = t_pad; k.a_cols = k.a_ld = 12544; k.ps = ps;
+        k.tile_begin = 0; k.n_tiles = t_pad / kBlockM; k.a_row_delta = 0; k.out = px0; k.ldc = 256;
+        k.flags = kEpiRelu | kEpiOutF32; k.name = "roienc.fc1_gemm";
+        TRY(run_conv(c, k, st));
+    }
+    float* x = static_cast<float*>(px0);
+    float* y = static_cast<float*>(px1);
+    float* xa = static_cast<float*>(pxa);
+    float* h = static_cast<float*>(ph);
+    StageTimer t(c, "roienc.token_mlp", st, 0);
+    for (const auto& d : c->re_tok_fc) {
+        TRY(run_linear(c, d, x, 256, y, 256, n_rois, 1, 0.f, st));
+        std::swap(x, y);
+    }
+    // TransformerEncoder, sequence length 1 per class (see kernels_roi_encoder.cuh)
+    for (const auto& L : c->re_enc) {
+        TRY(run_linear(c, L.attn, x, 256, xa, 256, n_rois, 0, 0.f, st));
+        CU_TRY(c, launch_k(add_layernorm_kernel, dim3(ceil_div(n_rois, 8)), dim3(256), 0, st, static_cast<const float*>(x),
+                           static_cast<const float*>(xa), static_cast<const float*>(L.n1w), static_cast<const float*>(L.n1b), y, n_rois));
+        TRY(run_linear(c, L.ff1, y, 256, h, 1024, n_rois, 1, 0.f, st));
+        TRY(run_linear(c, L.ff2, h, 1024, xa, 256, n_rois, 0, 0.f, st));
+        CU_TRY(c, launch_k(add_layernorm_kernel, dim3(ceil_div(n_rois, 8)), dim3(256), 0, st, static_cast<const float*>(y),
+                           static_cast<const float*>(xa), static_cast<const float*>(L.n2w), static_cast<const float*>(L.n2b), x, n_rois));
+        c->launches += 2;
+    }
+    CU_TRY(c, launch_k(token_mean_kernel, dim3(n_classes), dim3(256), 0, st, static_cast<const float*>(x), d_class_off,
+                       static_cast<float*>(pcls)));
+    c->launches++;
+    // hyper-network heads: weights -> columns 0..255, prior + delta bias -> column 256 of the code rows
+    const float prior = -std::log((1.f - 0.01f) / 0.01f);   // roi_encoder.py:141-142 (prior_prob = 0.01, hard-coded)
+    for (int which = 0; which < 2; ++which) {
+        const auto& hd = which == 0 ? c->re_whead : c->re_bhead;
+        const float* in = static_cast<const float*>(pcls);
+        int ld = 256;
+        float* tmp[2] = {static_cast<float*>(phd), static_cast<float*>(phd) + static_cast<size_t>(n_classes) * 1024};
+        for (size_t i = 0; i < hd.size(); ++i) {
+            const bool last = i + 1 == hd.size();
+            float* out = last ? (codes_out_dev + (which == 0 ? 0 : 256)) : tmp[i & 1];
+            TRY(run_linear(c, hd[i], in, ld, out, last ? 257 : 1024, n_classes, last ? 0 : 1, (last && which == 1) ? prior : 0.f, st));
+            in = out;
+            ld = 1024;
+        }
+    }
+    return 0;
+}
+
 }  // namespace sylph
 
 extern "C" {
@@ -964,6 +1210,10 @@ int sylph_generate_codes(sylph_ctx* c, int slot, int n_rois, const float* boxes_
         c->launches++;
     }
     c->last_n_rois = n_rois;
+    if (f.generator == 1)
+        return roi_encoder_codes(c, S, n_rois, n_classes, static_cast<const int*>(pi), static_cast<const int*>(po), ps.get(),
+                                 static_cast<__half*>(r0), static_cast<__half*>(r1), static_cast<__half*>(r2),
+                                 static_cast<float*>(rawp), static_cast<float*>(gp), static_cast<float*>(gs), codes_out_dev, st);
     __half* cur = static_cast<__half*>(r0);
     __half* nxt = static_cast<__half*>(r1);
     float* raw = static_cast<float*>(rawp);
@@ -1007,6 +1257,7 @@ int sylph_normalize_codes(sylph_ctx* c, const float* raw_codes_dev, float* out_c
     if (!c->finalized) return c->fail("weights not finalized");
     if (n_classes <= 0) return 0;  // forward_normalize_code returns an empty list unchanged
     const sylph_model_config& f = c->cfg;
+    if (f.generator == 1) return c->fail("ROIEncoder codes are final: there is no code normalisation for this generator");
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     CU_TRY(c, launch_k(normalize_codes_kernel, dim3(n_classes), dim3(256), 0, st, raw_codes_dev, out_codes_dev, c->post_gn_w, c->post_gn_b, f.cg_post_norm,
                                                       f.cg_conv_l2_norm, c->conv_scale, c->bias_scale, c->bias_value));
@@ -1084,7 +1335,7 @@ int sylph_detect(sylph_ctx* c, int slot, const float* codes_dev, int n_classes, 
     CW.w = static_cast<__half*>(cw);
     CW.bias = static_cast<float*>(cb);
     CU_TRY(c, launch_k(pack_code_weights_kernel, dim3(ceil_div(static_cast<long long>(CW.cout_pad) * 256, 256)), dim3(256), 0, st, 
-        codes_dev, n_classes, CW.cout_pad, f.cg_use_bias, CW.w, CW.bias));
+        codes_dev, n_classes, CW.cout_pad, f.generator == 1 ? 1 : f.cg_use_bias, f.generator == 1 ? c->cond_scale : 1.f, CW.w, CW.bias));
     CU_TRY(c, cudaGetLastError());
     c->launches++;
     auto tower = [&](const std::vector<ConvW>& tw, const std::vector<float*>& gw, const std::vector<float*>& gb,

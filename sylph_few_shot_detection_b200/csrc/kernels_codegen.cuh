@@ -223,16 +223,18 @@ normalize_codes_kernel(const float* __restrict__ raw, float* __restrict__ out, c
 
 // Expand (n_classes, 257) codes into the K-major weight matrix [n_pad][256] + bias [n_pad] the logits GEMM reads
 // (rows >= n_classes are zero); weights are rounded to fp16 here.
-__global__ void pack_code_weights_kernel(const float* __restrict__ codes, int n_classes, int n_pad, int use_bias,
+// `scale` is the learned output scale of CondConvBlock (head_utils.py:121-162, ROIEncoder head):
+// scale * (conv(x, W) + b) = conv(x, scale * W) + scale * b; 1 for CondConvBasic.
+__global__ void pack_code_weights_kernel(const float* __restrict__ codes, int n_classes, int n_pad, int use_bias, float scale,
                                          __half* __restrict__ w, float* __restrict__ bias) {
     ptx::griddep_launch();
     ptx::griddep_wait();
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n_pad * 256) return;
     const int r = i >> 8, c = i & 255;
-    const float v = r < n_classes ? codes[static_cast<size_t>(r) * 257 + c] : 0.f;
+    const float v = r < n_classes ? codes[static_cast<size_t>(r) * 257 + c] * scale : 0.f;
     w[i] = __float2half_rn(fminf(fmaxf(v, -kHalfMax), kHalfMax));
-    if (c == 0) bias[r] = (r < n_classes && use_bias) ? codes[static_cast<size_t>(r) * 257 + 256] : 0.f;
+    if (c == 0) bias[r] = (r < n_classes && use_bias) ? codes[static_cast<size_t>(r) * 257 + 256] * scale : 0.f;
 }
 
 // (n_rois, 256, 7, 7) export of the pooled ROI planes (tests / plugin interop).

@@ -138,6 +138,47 @@ class CodeGenerator(_EngineBound):
         return codes
 
 
+@CODE_GENERATOR_REGISTRY.register()
+class ROIEncoder(_EngineBound):
+    """Drop-in for the reference's `ROIEncoder` generator (sylph/modeling/code_generator/roi_encoder.py:118-204), same
+    registry name and forward signature: ROIAlign -> FeatureFusionModuleV2 (conv + MS_CAM context gate) -> Tokenizer ->
+    TransformerEncoder -> class-token mean -> weight / bias hyper-network heads, all inside `sylph_generate_codes`.
+
+    Returns {"cls_conv": (bs, 256, 1, 1), "cls_bias": (bs,)}; the bias already contains the focal-loss prior, so the
+    codes are final.  Reference quirk: `normalize_class_code` passes `features=None, cls_norm=True, class_codes=...`
+    (meta_one_stage_detector.py:256-259), keywords `ROIEncoder.forward` does not accept -- the reference meta-test loop
+    raises TypeError there.  This class accepts them and returns the codes unchanged (there is nothing to normalise)."""
+
+    def __init__(self, cfg, feature_channels: int, feature_levels: int, strides: Tuple[int]):
+        super().__init__()
+        assert feature_channels == 256 and feature_levels == 5, "the B200 path is built for the 256-channel p3..p7 pyramid"
+        self.cfg = cfg
+        self.strides = tuple(strides)
+        self.shot = cfg.MODEL.META_LEARN.SHOT
+        self.eval_shot = cfg.MODEL.META_LEARN.EVAL_SHOT
+        self.bias_value = -float(np.log((1 - 0.01) / 0.01))   # roi_encoder.py:141-142
+
+    def forward(self, support_set_image_features: Optional[List[torch.Tensor]] = None, gt_instances=None, *,
+                features: Optional[List[torch.Tensor]] = None, target_instances=None, cls_norm: bool = False,
+                class_codes: Optional[List[Dict]] = None):
+        if cls_norm and class_codes is not None:
+            return class_codes
+        feats = support_set_image_features if support_set_image_features is not None else features
+        insts = gt_instances if gt_instances is not None else target_instances
+        assert not self.training, "the B200 path implements inference only"
+        num_shots = self.eval_shot
+        boxes = torch.cat([b.reshape(-1, 4)[:1] for b in select_a_mask(insts)], dim=0)
+        n = feats[0].shape[0]
+        assert n % num_shots == 0, f"{n} % {num_shots}"                       # roi_encoder.py:160-163
+        for lvl, f in enumerate(feats):
+            assert f.shape[0] == n, f"lvl {lvl}, {f.shape[0]} vs {n}"
+        assert len(insts) == n, f"boxes_ls {len(insts)} vs {n}"
+        h, w = feats[0].shape[-2:]
+        self.engine.import_features(SLOT_SUPPORT, feats, (h * self.strides[0], w * self.strides[0]))
+        raw = self.engine.generate_codes(SLOT_SUPPORT, boxes, list(range(n)), list(range(0, n + 1, num_shots)))
+        return {"cls_conv": raw[:, :256].reshape(-1, 256, 1, 1), "cls_bias": raw[:, 256].reshape(-1)}
+
+
 def _register_alias(registry, name: str, obj) -> None:
     if hasattr(registry, "_do_register"):  # fvcore / detectron2 Registry
         registry._do_register(name, obj)
@@ -322,7 +363,14 @@ class MetaOneStageDetector(nn.Module):
             offsets.append(len(records))
         boxes = torch.cat([b.reshape(-1, 4)[:1].cpu() for b in select_a_mask([r["instances"] for r in records])], dim=0)
         self.engine.extract_features(SLOT_SUPPORT, [r["image"] for r in records])
+        if isinstance(self.code_generator, ROIEncoder):
+            for a, b in zip(offsets[:-1], offsets[1:]):   # bs = 1 per call in the reference: N % EVAL_SHOT == 0
+                assert (b - a) % self.code_generator.eval_shot == 0 and b - a == self.code_generator.eval_shot, \
+                    f"{b - a} % {self.code_generator.eval_shot}"
         raw = self.engine.generate_codes(SLOT_SUPPORT, boxes, list(range(len(records))), offsets)
+        if isinstance(self.code_generator, ROIEncoder):
+            return [{"cls_conv": raw[i:i + 1, :256].reshape(1, 256, 1, 1), "cls_bias": raw[i, 256:].reshape(1)}
+                    for i in range(len(batched_inputs))]
         return [{"cls_conv": raw[i:i + 1, :256].reshape(1, 256, 1, 1), "cls_bias": raw[i:i + 1, 256:].reshape(1, 1, 1, 1)}
                 for i in range(len(batched_inputs))]
 

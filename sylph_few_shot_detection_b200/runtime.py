@@ -14,21 +14,29 @@ from ._lib import CODE_STRIDE, DET_STRIDE, NUM_LEVELS, SLOT_QUERY, SLOT_SUPPORT,
 def model_config_from_cfg(cfg) -> ModelConfig:
     """Collect the config keys the hot path reads into the C struct."""
     F, G = cfg.MODEL.FCOS, cfg.MODEL.META_LEARN.CODE_GENERATOR
-    if cfg.MODEL.META_LEARN.CODE_GENERATOR.NAME not in ("CodeGenerator", "CodeGeneratorHead"):
-        raise NotImplementedError("only the CodeGenerator hypernetwork is implemented on the B200 path")
+    if G.NAME not in ("CodeGenerator", "CodeGeneratorHead", "ROIEncoder"):
+        raise NotImplementedError(f"code generator {G.NAME!r} is not implemented on the B200 path")
+    roi_encoder = G.NAME == "ROIEncoder"
     if F.NORM != "GN" or F.USE_DEFORMABLE or F.NUM_SHARE_CONVS != 0 or list(F.IN_FEATURES) != ["p3", "p4", "p5", "p6", "p7"]:
         raise NotImplementedError("FCOS head variant outside the shipped Meta-FCOS configs")
     if list(F.FPN_STRIDES) != [8, 16, 32, 64, 128] or int(F.TOP_LEVELS) != 2:
         raise NotImplementedError("only the p3..p7 pyramid (strides 8..128) is implemented")
     if cfg.MODEL.RESNETS.NORM != "FrozenBN" or not cfg.MODEL.RESNETS.STRIDE_IN_1X1:
         raise NotImplementedError("backbone must use FrozenBN and STRIDE_IN_1X1 (inference path)")
-    for layer in G.TOWER_LAYERS:
-        if list(layer) != ["GN", "ReLU"]:
-            raise NotImplementedError("CODE_GENERATOR.TOWER_LAYERS entries must be ['GN', 'ReLU']")
-    if list(G.CLS_LAYER) != ["", "", 1]:
-        raise NotImplementedError("CODE_GENERATOR.CLS_LAYER must be ['', '', 1]")
-    if len(G.WEIGHT_LAYER) or len(G.SCALE_LAYER) or G.COMPRESS_CODE_W_MAX or G.ROI_BOX.FPN_MULTILEVEL_FEATURE:
-        raise NotImplementedError("WEIGHT_LAYER / SCALE_LAYER / COMPRESS_CODE_W_MAX / multilevel ROI are not implemented")
+    if roi_encoder:
+        T, E, H = G.TOKENIZER, G.TRANSFORMER_ENCODER, G.HEAD
+        if int(T.CONV_DIM) != 256 or int(T.FC_DIM) != 256 or int(H.OUTPUT_DIM) != 256 or T.NORM != "GN":
+            raise NotImplementedError("ROIEncoder: TOKENIZER.CONV_DIM / FC_DIM and HEAD.OUTPUT_DIM must be 256, TOKENIZER.NORM 'GN'")
+        if int(T.NUM_CONV) < 1 or int(T.NUM_FC) < 1 or int(H.NUM_FC) < 1 or int(H.FC_DIM) > 1024 or 256 % int(E.HEADS):
+            raise NotImplementedError("ROIEncoder: unsupported tokenizer / head depth or width")
+    else:
+        for layer in G.TOWER_LAYERS:
+            if list(layer) != ["GN", "ReLU"]:
+                raise NotImplementedError("CODE_GENERATOR.TOWER_LAYERS entries must be ['GN', 'ReLU']")
+        if list(G.CLS_LAYER) != ["", "", 1]:
+            raise NotImplementedError("CODE_GENERATOR.CLS_LAYER must be ['', '', 1]")
+        if len(G.WEIGHT_LAYER) or len(G.SCALE_LAYER) or G.COMPRESS_CODE_W_MAX or G.ROI_BOX.FPN_MULTILEVEL_FEATURE:
+            raise NotImplementedError("WEIGHT_LAYER / SCALE_LAYER / COMPRESS_CODE_W_MAX / multilevel ROI are not implemented")
     if G.ROI_BOX.POOLER_TYPE != "ROIAlignV2" or int(G.ROI_BOX.POOLER_RESOLUTION) != 7:
         raise NotImplementedError("ROI pooler must be ROIAlignV2 at 7x7")
     if cfg.MODEL.PROPOSAL_GENERATOR.OWD:
@@ -54,6 +62,11 @@ def model_config_from_cfg(cfg) -> ModelConfig:
     mc.cg_bias_l2_norm = int(bool(G.BIAS_L2_NORM))
     mc.cg_use_bias = int(bool(G.USE_BIAS))
     mc.cg_has_conv_scale = int(bool(G.USE_WEIGHT_SCALE and (G.CONV_L2_NORM or G.POST_NORM != "")))
+    mc.generator = int(roi_encoder)
+    if roi_encoder:
+        mc.re_tok_convs, mc.re_tok_fcs = int(G.TOKENIZER.NUM_CONV), int(G.TOKENIZER.NUM_FC)
+        mc.re_layers = int(G.TRANSFORMER_ENCODER.LAYERS)
+        mc.re_head_fcs, mc.re_head_dim = int(G.HEAD.NUM_FC), int(G.HEAD.FC_DIM)
     return mc
 
 

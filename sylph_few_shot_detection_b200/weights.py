@@ -89,6 +89,19 @@ def state_spec(cfg) -> "OrderedDict[str, Tuple[int, ...]]":
             spec[f"{head}.scales.{lvl}.scale"] = (1,)
 
     G = cfg.MODEL.META_LEARN.CODE_GENERATOR
+    if G.NAME == "ROIEncoder":
+        _roi_encoder_spec(cfg, spec, conv, gn)
+        spec[f"{head}.cond_cls_logits.scales.0.scale"] = (1,)   # CondConvBlock(weight_len=256), head_utils.py:131-137
+    else:
+        _code_generator_spec(cfg, spec, conv, gn, fpn_c)
+    spec["pixel_mean"] = (3, 1, 1)
+    spec["pixel_std"] = (3, 1, 1)
+    return spec
+
+
+def _code_generator_spec(cfg, spec, conv, gn, fpn_c) -> None:
+    """`CodeGenerator` / `CodeGeneratorHead` (code_generator.py:328-333, 359-374, 509-581, 648-688)."""
+    G = cfg.MODEL.META_LEARN.CODE_GENERATOR
     cg = "code_generator.code_generator_head"
     oc = _conv_out_channels(cfg)
     for lvl in range(len(cfg.MODEL.FCOS.IN_FEATURES)):
@@ -113,10 +126,53 @@ def state_spec(cfg) -> "OrderedDict[str, Tuple[int, ...]]":
         spec[f"{cg}.bias_scale.scale"] = (1,)
     if G.USE_WEIGHT_SCALE and (G.CONV_L2_NORM or G.POST_NORM != ""):
         spec[f"{cg}.conv_scale.scale"] = (1,)
-    spec["pixel_mean"] = (3, 1, 1)
-    spec["pixel_std"] = (3, 1, 1)
-    return spec
 
+
+def _roi_encoder_spec(cfg, spec, conv, gn) -> None:
+    """`ROIEncoder` (sylph/modeling/code_generator/roi_encoder.py:206-281): FeatureFusionModuleV2 with MS_CAM
+    (utils.py:70-165), Tokenizer (:26-79), nn.TransformerEncoder, two HyperNetworkHeads (:82-115)."""
+    G = cfg.MODEL.META_LEARN.CODE_GENERATOR
+    cg = "code_generator"
+    cam = f"{cg}.box_pooler.context_attention_module"
+    for branch, (i1, i2, i3, i4) in (("local_att", (0, 1, 3, 4)), ("global_att", (1, 2, 4, 5))):
+        conv(f"{cam}.{branch}.{i1}", 64, 256, 1, True)
+        gn(f"{cam}.{branch}.{i2}", 64)
+        conv(f"{cam}.{branch}.{i3}", 256, 64, 1, True)
+        gn(f"{cam}.{branch}.{i4}", 256)
+    conv(f"{cg}.box_pooler.conv.0", 256, 256, 3, True)
+    gn(f"{cg}.box_pooler.conv.1", 256)
+    T = G.TOKENIZER
+    cin = 256
+    for k in range(int(T.NUM_CONV)):
+        conv(f"{cg}.tokenizer.conv{k + 1}", int(T.CONV_DIM), cin, 3, T.NORM == "")
+        if T.NORM != "":
+            gn(f"{cg}.tokenizer.conv{k + 1}.norm", int(T.CONV_DIM))
+        cin = int(T.CONV_DIM)
+    din = cin * int(G.ROI_BOX.POOLER_RESOLUTION) ** 2
+    for k in range(int(T.NUM_FC)):
+        spec[f"{cg}.tokenizer.fc{k + 1}.weight"] = (int(T.FC_DIM), din)
+        spec[f"{cg}.tokenizer.fc{k + 1}.bias"] = (int(T.FC_DIM),)
+        din = int(T.FC_DIM)
+    d = int(T.FC_DIM)
+    for l in range(int(G.TRANSFORMER_ENCODER.LAYERS)):
+        p = f"{cg}.transformer_encoder.layers.{l}"
+        spec[f"{p}.self_attn.in_proj_weight"] = (3 * d, d)
+        spec[f"{p}.self_attn.in_proj_bias"] = (3 * d,)
+        spec[f"{p}.self_attn.out_proj.weight"] = (d, d)
+        spec[f"{p}.self_attn.out_proj.bias"] = (d,)
+        spec[f"{p}.linear1.weight"] = (4 * d, d)
+        spec[f"{p}.linear1.bias"] = (4 * d,)
+        spec[f"{p}.linear2.weight"] = (d, 4 * d)
+        spec[f"{p}.linear2.bias"] = (d,)
+        for n in ("norm1", "norm2"):
+            gn(f"{p}.{n}", d)
+    for name, out_dim in (("weight_head", int(G.HEAD.OUTPUT_DIM)), ("bias_head", 1)):
+        din = d
+        for i in range(int(G.HEAD.NUM_FC)):
+            dout = out_dim if i == int(G.HEAD.NUM_FC) - 1 else int(G.HEAD.FC_DIM)
+            spec[f"{cg}.{name}.fc{i + 1}.weight"] = (dout, din)
+            spec[f"{cg}.{name}.fc{i + 1}.bias"] = (dout,)
+            din = dout
 
 def _gen(key: str, seed: int) -> torch.Generator:
     g = torch.Generator(device="cpu")
@@ -163,6 +219,12 @@ def synthetic_tensor(cfg, key: str, shape: Tuple[int, ...], seed: int = 0) -> to
         if key.endswith("bbox_pred.bias"):
             return torch.full(shape, 1.0)
         return normal(0.02)
+    if len(shape) == 2:  # nn.Linear / attention projections of the ROIEncoder generator
+        if "bias_head" in key and shape[0] == 1:
+            return normal(0.5 * math.sqrt(1.0 / shape[1]))
+        if "weight_head" in key and shape[0] == int(cfg.MODEL.META_LEARN.CODE_GENERATOR.HEAD.OUTPUT_DIM) and shape[1] != 256:
+            return normal(0.12 * math.sqrt(1.5 / shape[1]))   # keeps |logit| < ~10: no saturated-sigmoid score ties
+        return normal(math.sqrt(1.5 / shape[1]))
     cout, cin, kh, kw = shape
     if key.startswith("backbone.bottom_up"):
         return normal(math.sqrt(2.0 / (cout * kh * kw)))
@@ -186,6 +248,12 @@ def _is_gn_key(key: str) -> bool:
             return idx % 3 == 1
         if owner in ("support_set_cls_conv",):
             return idx == 1
+        if owner == "conv" and "box_pooler" in key:
+            return idx == 1
+        if owner == "local_att":
+            return idx in (1, 4)
+        if owner == "global_att":
+            return idx in (2, 5)
     return False
 
 

@@ -11,8 +11,8 @@ GOLDEN_DIR = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
 from sylph_few_shot_detection_b200.presets import preset_cfg
 
 
-def cfg_for(config_name: str):
-    return preset_cfg(config_name, ["MODEL.DEVICE", "cpu"])
+def cfg_for(config_name: str, opts=None):
+    return preset_cfg(config_name, ["MODEL.DEVICE", "cpu"] + list(opts or []))
 
 
 def load_golden(name: str):

@@ -45,6 +45,41 @@ def test_oracle_reproduces_reference_outputs(case):
         assert rel_err(d["scores"], r["scores"]) < TOL
 
 
+def test_roi_encoder_oracle_reproduces_reference_outputs():
+    """ROIEncoder generator + CondConvBlock head against the reference's own modules."""
+    from oracle.roi_encoder_oracle import ROIEncoderOracle, build_oracle
+    g = load_golden("lvis_roienc_2way_3shot")
+    cfg = cfg_for(g["config"], g["opts"])
+    state = W.synthetic_state_dict(cfg, g["seed"])
+    orc = build_oracle(cfg, state)
+    assert isinstance(orc, ROIEncoderOracle)
+    assert g["normalize_error"].startswith("TypeError")      # the reference cannot normalise ROIEncoder codes (quirk)
+    codes = []
+    for c, shots in enumerate(g["support"]):
+        code = orc.class_code([s["image"].float() for s in shots], torch.stack([s["box"] for s in shots]))
+        assert code["cls_conv"].shape == (1, 256, 1, 1) and code["cls_bias"].shape == (1,)
+        assert rel_err(code["cls_conv"], g["raw_codes"][c]["cls_conv"]) < TOL
+        assert rel_err(code["cls_bias"], g["raw_codes"][c]["cls_bias"]) < TOL
+        codes.append({"support_set_target": c, "class_code": code})
+    packed = orc.pack_codes(codes)
+    assert torch.equal(packed["cls_conv"], g["packed"]["cls_conv"]) or rel_err(packed["cls_conv"], g["packed"]["cls_conv"]) < TOL
+    # two classes in ONE call: bs = 2 -> the transformer attends across the CLASS axis (batch_first=False), so the
+    # result differs from two bs = 1 calls; the restatement must still run and keep shapes (roi_encoder.py:176-199)
+    both = orc.class_code([s["image"].float() for shots in g["support"] for s in shots],
+                          torch.stack([s["box"] for shots in g["support"] for s in shots]))
+    assert both["cls_conv"].shape == (2, 256, 1, 1) and both["cls_bias"].shape == (2,)
+    assert rel_err(both["cls_conv"][:1], g["raw_codes"][0]["cls_conv"]) > 1e-3
+    dets, inter = orc.detect([q.float() for q in g["query"]], g["packed"], return_intermediate=True)
+    for l in range(5):
+        assert rel_err(inter["logits"][l], g["logits"][l]) < TOL
+        assert rel_err(inter["reg"][l], g["reg"][l]) < TOL
+    for d, r in zip(dets, g["detections"]):
+        assert d["scores"].numel() == r["scores"].numel() > 0
+        assert torch.equal(d["classes"], r["classes"]) and torch.equal(d["levels"], r["levels"])
+        assert torch.equal(d["locations"], r["locations"])
+        assert rel_err(d["boxes"], r["boxes"]) < TOL and rel_err(d["scores"], r["scores"]) < TOL
+
+
 def test_golden_vectors_cover_the_interesting_regimes():
     g = load_golden("coco_2way_2shot")
     # post-NMS top-k saturated on one image, not on the other; several FPN levels contribute
