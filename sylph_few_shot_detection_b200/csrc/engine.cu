@@ -1006,7 +1006,7 @@ static int roi_encoder_codes(sylph_ctx* c, const Slot& S, int n_rois, int n_clas
     const long long rows = static_cast<long long>(n_rois) * 128;
     const int t_pad = round_up(n_rois, kBlockM);
     void *pctx, *ptok, *px0, *px1, *pxa, *ph, *pcls, *phd;
-    TRY(ensure(c, "re.ctx", static_cast<size_t>(n_rois) * 49 * 256 * 4, "", &pctx, st, false));
+    TRY(ensure(c, "re.ctx", static_cast<size_t>(S.n) * 49 * 256 * 4, "", &pctx, st, false));
     TRY(ensure(c, "re.tokens", (static_cast<size_t>(t_pad) + kBlockM) * 12544 * 2, "tok", &ptok, st, true));
     TRY(ensure(c, "re.x0", static_cast<size_t>(t_pad) * 256 * 4, "", &px0, st, false));
     TRY(ensure(c, "re.x1", static_cast<size_t>(t_pad) * 256 * 4, "", &px1, st, false));
@@ -1018,9 +1018,9 @@ static int roi_encoder_codes(sylph_ctx* c, const Slot& S, int n_rois, int n_clas
     TRY(conv_gn_relu(c, c->re_pool_conv, c->re_pool_gn_w, c->re_pool_gn_b, r0, rows, raw, r1, ps, 0, n_rois, 0, n_rois, gp, gs,
                      "roienc.pool_conv3x3", st));
     {
-        StageTimer t(c, "roienc.context_pool", st, static_cast<double>(n_rois) * 22400 * 256 * 2);
-        CU_TRY(c, launch_k(context_pool_kernel, dim3(n_rois, 49), dim3(256), 0, st, static_cast<const __half*>(S.pyr), S.pg,
-                           d_roi_image, static_cast<float*>(pctx)));
+        StageTimer t(c, "roienc.context_pool", st, static_cast<double>(S.n) * 22400 * 256 * 2);
+        CU_TRY(c, launch_k(context_pool_kernel, dim3(S.n, 49), dim3(256), 0, st, static_cast<const __half*>(S.pyr), S.pg,
+                           static_cast<float*>(pctx)));
         c->launches++;
     }
     {
@@ -1031,7 +1031,7 @@ static int roi_encoder_codes(sylph_ctx* c, const Slot& S, int n_rois, int n_clas
         }
         StageTimer t(c, "roienc.ms_cam", st, static_cast<double>(n_rois) * 49 * 256 * 8);
         CU_TRY(c, launch_k(ms_cam_kernel, dim3(n_rois), dim3(256), static_cast<size_t>(kMsCamSmem), st,
-                           static_cast<const float*>(pctx), static_cast<const __half*>(r1), c->re_cam, r2));
+                           static_cast<const float*>(pctx), d_roi_image, static_cast<const __half*>(r1), c->re_cam, r2));
         c->launches++;
     }
     // Tokenizer: NUM_CONV x (conv3x3 + GN + ReLU), flatten, fc1 (tensor-core GEMM over K = 12544), fc2.. (+ ReLU)

@@ -22,16 +22,15 @@
 namespace sylph {
 
 // ------------------------------------------------------------------------------------------------ context pooling
-// grid = (n_rois, 49 bins), block = 256 channels.  ctx[roi][bin][c] = mean over the 5 levels of the adaptive-average
-// bin (torch adaptive_avg_pool2d: rows floor(i*H/7) .. ceil((i+1)*H/7) - 1) of the ROI's image.
+// grid = (n_images, 49 bins), block = 256 channels.  ctx[image][bin][c] = mean over the 5 levels of the adaptive-average
+// bin (torch adaptive_avg_pool2d: rows floor(i*H/7) .. ceil((i+1)*H/7) - 1).  The context depends on the image only, so it
+// is computed once per support image and shared by all ROIs of that image (the pyramid is streamed exactly once).
 __global__ void __launch_bounds__(256)
-context_pool_kernel(const __half* __restrict__ pyramid, PyramidGeom pg, const int* __restrict__ roi_image,
-                    float* __restrict__ ctx /* [n_rois][49][256] */) {
+context_pool_kernel(const __half* __restrict__ pyramid, PyramidGeom pg, float* __restrict__ ctx /* [n_images][49][256] */) {
     ptx::griddep_launch();
     ptx::griddep_wait();
-    const int roi = blockIdx.x, bin = blockIdx.y, c = threadIdx.x;
+    const int n = blockIdx.x, bin = blockIdx.y, c = threadIdx.x;
     const int bi = bin / 7, bj = bin - bi * 7;
-    const int n = roi_image[roi];
     float total = 0.f;
 #pragma unroll 1
     for (int l = 0; l < 5; ++l) {
@@ -52,7 +51,7 @@ context_pool_kernel(const __half* __restrict__ pyramid, PyramidGeom pg, const in
         }
         total += s / static_cast<float>((y1 - y0) * (x1 - x0));
     }
-    ctx[(static_cast<size_t>(roi) * 49 + bin) * 256 + c] = total / 5.f;
+    ctx[(static_cast<size_t>(n) * 49 + bin) * 256 + c] = total / 5.f;
 }
 
 // ------------------------------------------------------------------------------------------------ MS_CAM
@@ -80,7 +79,8 @@ constexpr int kMsCamSmem = (49 * 256 + 256 * 64 + 49 * 64 + 256 + 64 + 64) * 4;
 // grid = n_rois, block = 256.  out = pooled * sigmoid(local_att(ctx) + global_att(ctx)) written as a zero-bordered
 // 9x9 fp16 plane (128 rows per ROI).
 __global__ void __launch_bounds__(256)
-ms_cam_kernel(const float* __restrict__ ctx, const __half* __restrict__ pooled, MsCamWeights w, __half* __restrict__ out) {
+ms_cam_kernel(const float* __restrict__ ctx, const int* __restrict__ roi_image, const __half* __restrict__ pooled,
+              MsCamWeights w, __half* __restrict__ out) {
     ptx::griddep_launch();
     ptx::griddep_wait();
     extern __shared__ uint8_t cam_smem_raw[];
@@ -91,7 +91,7 @@ ms_cam_kernel(const float* __restrict__ ctx, const __half* __restrict__ pooled, 
     float* s_g1 = s_g0 + 256;                 // [64]
     float* s_st = s_g1 + 64;                  // [32][2] GroupNorm(32, 64) statistics of the local branch
     const int roi = blockIdx.x, t = threadIdx.x, lane = t & 31, warp = t >> 5;
-    const float* cx = ctx + static_cast<size_t>(roi) * 49 * 256;
+    const float* cx = ctx + static_cast<size_t>(roi_image[roi]) * 49 * 256;
     for (int i = t; i < 49 * 256; i += 256) s_ctx[i] = cx[i];
     for (int i = t; i < 256 * 64; i += 256) s_w[i] = w.l_w1t[i];
     __syncthreads();

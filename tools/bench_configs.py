@@ -123,6 +123,34 @@ def main():
                                          "rois": n_cls * shots, "feature_pool_images": 16,
                                          "gflop": round(0.1736 * n_cls * shots, 1),
                                          "tflops": round(0.1736 * n_cls * shots / ms5, 1)}
+    del model, eng
+    torch.cuda.empty_cache()
+
+    # ---- cfg5 with the ROIEncoder generator ("roi_encoder only"): same 12 030 ROIs, EVAL_SHOT = 10
+    from sylph_few_shot_detection_b200.presets import lvis_roi_encoder_cfg
+    model = build(lvis_roi_encoder_cfg())
+    eng = model.engine
+    eng.extract_features(SLOT_SUPPORT, pool)
+
+    def sweep_re():
+        return eng.generate_codes(SLOT_SUPPORT, bx, roi_image, offsets)
+    ms5r = timed(sweep_re, warm=1, reps=3)
+    # per ROI: pool conv + 2 tokenizer convs 3 x 57.8 MMAC, fc1 3.2 MMAC, dense layers ~1.4 MMAC, MS_CAM 1.6 MMAC
+    gflop_roi = 2e-3 * (3 * 57.8 + 3.2 + 1.4 + 1.6)
+    res["cfg5_lvis_1203_class_sweep_roi_encoder"] = {"ms": round(ms5r, 3), "classes_per_s": round(1203 / (ms5r * 1e-3)),
+                                                     "rois": n_cls * shots, "feature_pool_images": 16,
+                                                     "gflop": round(gflop_roi * n_cls * shots, 1),
+                                                     "tflops": round(gflop_roi * n_cls * shots / ms5r, 1)}
+    eng.set_profiling(True)
+    sweep_re()
+    agg = {}
+    for name, t_ms, fl, by in eng.timings():
+        a = agg.setdefault(name, [0, 0.0])
+        a[0] += 1
+        a[1] += t_ms
+    eng.set_profiling(False)
+    res["cfg5_lvis_1203_class_sweep_roi_encoder"]["per_kernel_ms"] = {k: [v[0], round(v[1], 3)] for k, v in
+                                                                      sorted(agg.items(), key=lambda kv: -kv[1][1])}
     out = json.dumps(res, indent=1)
     print(out)
     if args.out:
