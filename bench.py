@@ -208,11 +208,17 @@ def main():
     offsets = list(range(0, N_WAY * N_SHOT + 1, N_SHOT))
     roi_image = list(range(N_WAY * N_SHOT))
 
+    merged_trunk = os.environ.get("SYLPH_BENCH_SPLIT_TRUNK", "0") != "1"
+
     def episode_device():
-        eng.extract_features(SLOT_SUPPORT, support_d)
+        if merged_trunk:   # support + query batches through one bottom-up trunk pass, FPN per slot
+            eng.extract_features_multi([(SLOT_SUPPORT, support_d), (SLOT_QUERY, query_d)])
+        else:
+            eng.extract_features(SLOT_SUPPORT, support_d)
         raw = eng.generate_codes(SLOT_SUPPORT, boxes, roi_image, offsets)
         codes = eng.normalize_codes(raw)
-        eng.extract_features(SLOT_QUERY, query_d)
+        if not merged_trunk:
+            eng.extract_features(SLOT_QUERY, query_d)
         return eng.detect(SLOT_QUERY, codes)
 
     def barrier():

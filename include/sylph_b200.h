@@ -87,6 +87,14 @@ int sylph_extract_features(sylph_ctx* ctx, int slot, int n_images, const float* 
 int sylph_extract_features_u8(sylph_ctx* ctx, int slot, int n_images, const uint8_t* const* images_dev,
                               const int* heights, const int* widths, void* stream);
 
+/* Several image batches through ONE bottom-up trunk pass (stem, res2..res5), then the FPN of each batch into its own
+ * slot: group g = images [sum(counts[0..g-1]), +counts[g]) -> slots[g].  Equivalent to n_groups sylph_extract_features
+ * calls; the groups share a trunk batch only when they pad to the same size (ImageList.from_tensors pads each reference
+ * call to its own batch maximum, meta_one_stage_detector.py:174-178), otherwise they run back to back.  The support and
+ * query batches of an episode (forward_class_code :245-247 + forward_instances :272-273) are the intended use. */
+int sylph_extract_features_multi(sylph_ctx* ctx, int n_groups, const int* slots, const int* counts,
+                                 const void* const* images_dev, int is_u8, const int* heights, const int* widths, void* stream);
+
 /* Plugin-level entry for features produced elsewhere (NCHW fp32 device tensors, one per level, (n, 256, H_l, W_l)):
  * the `features` argument of CodeGenerator.forward, sylph/modeling/code_generator/code_generator.py:1037-1053. */
 int sylph_import_features(sylph_ctx* ctx, int slot, int n_images, int padded_h, int padded_w,

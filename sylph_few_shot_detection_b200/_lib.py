@@ -88,6 +88,8 @@ def load() -> ctypes.CDLL:
     lib.sylph_extract_features.argtypes = [vp, c_int, c_int, POINTER(vp), ip, ip, vp]
     lib.sylph_extract_features_u8.restype = c_int
     lib.sylph_extract_features_u8.argtypes = [vp, c_int, c_int, POINTER(vp), ip, ip, vp]
+    lib.sylph_extract_features_multi.restype = c_int
+    lib.sylph_extract_features_multi.argtypes = [vp, c_int, ip, ip, POINTER(vp), c_int, ip, ip, vp]
     lib.sylph_import_features.restype = c_int
     lib.sylph_import_features.argtypes = [vp, c_int, c_int, c_int, c_int, POINTER(vp), ip, ip, vp]
     lib.sylph_feature_shape.restype = c_int
@@ -120,7 +122,7 @@ def load() -> ctypes.CDLL:
 
 EXPORTED_SYMBOLS = [
     "sylph_version", "sylph_create", "sylph_destroy", "sylph_last_error", "sylph_load_tensor",
-    "sylph_finalize_weights", "sylph_extract_features", "sylph_extract_features_u8", "sylph_import_features", "sylph_feature_shape",
+    "sylph_finalize_weights", "sylph_extract_features", "sylph_extract_features_u8", "sylph_extract_features_multi", "sylph_import_features", "sylph_feature_shape",
     "sylph_export_features", "sylph_generate_codes", "sylph_export_roi_features", "sylph_normalize_codes", "sylph_accumulate_codes", "sylph_reduce_codes",
     "sylph_detect", "sylph_export_head_output", "sylph_launch_count", "sylph_set_profiling", "sylph_get_timings",
 ]

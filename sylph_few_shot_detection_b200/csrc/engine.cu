@@ -789,25 +789,27 @@ static int setup_slot(sylph_ctx* c, int slot, int n, int hpad, int wpad, const i
     return 0;
 }
 
-static int run_backbone(sylph_ctx* c, int slot, int n, const void* const* images_dev, int is_u8, const int* hs,
-                        const int* ws, cudaStream_t st) {
+// Output of the bottom-up trunk (stem, res2..res5) over a batch of images: the res3..res5 activations stay in the
+// context buffers "bb.<key>.resN.x" (image-major planes) for the FPN of one or more pyramid slots.
+struct TrunkOut {
+    std::string key;
+    int n = 0, hpad = 0, wpad = 0;
+    PlaneGeom gs[4];
+};
+
+static int run_trunk(sylph_ctx* c, const std::string& key, int n, const void* const* images_dev, int is_u8, const int* hs,
+                     const int* ws, int hpad, int wpad, cudaStream_t st, TrunkOut* out) {
     const sylph_model_config& f = c->cfg;
     int hmax = 0, wmax = 0;
     for (int i = 0; i < n; ++i) { hmax = std::max(hmax, hs[i]); wmax = std::max(wmax, ws[i]); }
-    const int hpad = round_up(hmax, 32), wpad = round_up(wmax, 32);
     const std::string sig = std::to_string(n) + ":" + std::to_string(hpad) + "x" + std::to_string(wpad);
+    const std::string bb = "bb." + key + ".";
     // geometries
     const PlaneGeom g0 = regular_geom(0, hpad / 2, wpad / 2, 2);      // space-to-depth input / stem output
     PlaneGeom gs[4];                                                 // res2..res5
     for (int s = 0; s < 4; ++s) gs[s] = regular_geom(0, hpad >> (s + 2), wpad >> (s + 2), 1);
-    int lh[5], lw[5];
-    for (int l = 0; l < 3; ++l) { lh[l] = gs[l + 1].H; lw[l] = gs[l + 1].W; }
-    lh[3] = (lh[2] + 1) / 2; lw[3] = (lw[2] + 1) / 2;
-    lh[4] = (lh[3] + 1) / 2; lw[4] = (lw[3] + 1) / 2;
-    TRY(setup_slot(c, slot, n, hpad, wpad, lh, lw, st));
-    Slot& S = c->slots[slot];
-    S.img_h.assign(hs, hs + n);
-    S.img_w.assign(ws, ws + n);
+    out->key = key; out->n = n; out->hpad = hpad; out->wpad = wpad;
+    for (int s = 0; s < 4; ++s) out->gs[s] = gs[s];
 
     std::shared_ptr<PlaneSet> ps0, pss[4];
     TRY(make_plane_set(c, "stem:" + sig, geom_segs(g0, n), n * g0.rows_per_img, &ps0));
@@ -822,13 +824,13 @@ static int run_backbone(sylph_ctx* c, int slot, int n, const void* const* images
     };
     const long long rows0 = static_cast<long long>(n) * g0.rows_per_img;
     __half *S0, *S1;
-    TRY(buf("bb.s0", rows0, 16, true, &S0));
-    TRY(buf("bb.s1", rows0, 64, false, &S1));
+    TRY(buf(bb + "s0", rows0, 16, true, &S0));
+    TRY(buf(bb + "s1", rows0, 64, false, &S1));
     // ---- image descriptors
     std::vector<ImageDesc> descs(n);
     for (int i = 0; i < n; ++i) { descs[i].ptr = images_dev[i]; descs[i].h = hs[i]; descs[i].w = ws[i]; descs[i].is_u8 = is_u8; }
     void* d_desc;
-    TRY(ensure(c, "bb.desc", n * sizeof(ImageDesc), "", &d_desc, st, false));
+    TRY(ensure(c, bb + "desc", n * sizeof(ImageDesc), "", &d_desc, st, false));
     TRY(stage_h2d(c, d_desc, descs.data(), n * sizeof(ImageDesc), st));
     {
         StageTimer t(c, "prep_stem_input", st, static_cast<double>(n) * (3.0 * hmax * wmax + 32.0 * g0.H * g0.W));
@@ -855,7 +857,7 @@ static int run_backbone(sylph_ctx* c, int slot, int n, const void* const* images
         const int tiles = static_cast<int>(rows / kBlockM);
         const int out_ch = 256 << s, bott = 64 << s, in_ch = x_ch;
         __half *IN, *Y, *T1, *T2;
-        const std::string sn = "bb.res" + std::to_string(s + 2);
+        const std::string sn = bb + "res" + std::to_string(s + 2);
         TRY(buf(sn + ".in", rows, in_ch, true, &IN));
         TRY(buf(sn + ".x", rows, out_ch, false, &Y));
         TRY(buf(sn + ".t1", rows, bott, false, &T1));
@@ -904,21 +906,43 @@ static int run_backbone(sylph_ctx* c, int slot, int n, const void* const* images
         x_ch = out_ch;
         // lateral 1x1 for res3..res5 straight into the pyramid-indexed lateral buffer
     }
+    return 0;
+}
+
+// FPN + P6/P7 of `n` images of a trunk batch (images first .. first + n - 1) into pyramid slot `slot`.
+static int run_fpn(sylph_ctx* c, int slot, const TrunkOut& T, int first, int n, const int* hs, const int* ws, cudaStream_t st) {
+    const PlaneGeom* gs = T.gs;
+    int lh[5], lw[5];
+    for (int l = 0; l < 3; ++l) { lh[l] = gs[l + 1].H; lw[l] = gs[l + 1].W; }
+    lh[3] = (lh[2] + 1) / 2; lw[3] = (lw[2] + 1) / 2;
+    lh[4] = (lh[3] + 1) / 2; lw[4] = (lw[3] + 1) / 2;
+    TRY(setup_slot(c, slot, n, T.hpad, T.wpad, lh, lw, st));
+    Slot& S = c->slots[slot];
+    S.img_h.assign(hs, hs + n);
+    S.img_w.assign(ws, ws + n);
+    const std::string sig = std::to_string(n) + ":" + std::to_string(T.hpad) + "x" + std::to_string(T.wpad);
+    const std::string fb = "fpn" + std::to_string(slot) + ".";
+    auto buf = [&](const std::string& name, long long rows, int ch, bool zero, __half** out) -> int {
+        void* p;
+        TRY(ensure(c, name, (static_cast<size_t>(rows) + kBlockM) * ch * 2, sig, &p, st, zero));
+        *out = static_cast<__half*>(p);
+        return 0;
+    };
     // ---- FPN (top-down): lateral buffers share the pyramid row indexing
     __half* LAT;
     {
         void* p;
-        TRY(ensure(c, "bb.lat", (static_cast<size_t>(S.level_row0[5]) + kBlockM) * 256 * 2, S.ps ? ("pyr" + sig) : sig, &p, st, true));
+        TRY(ensure(c, fb + "lat", (static_cast<size_t>(S.level_row0[5]) + kBlockM) * 256 * 2, sig, &p, st, true));
         LAT = static_cast<__half*>(p);
     }
     for (int l = 2; l >= 0; --l) {
         const PlaneGeom& g = S.pg.lv[l];
         const long long rows = static_cast<long long>(n) * g.rows_per_img;
-        __half* XS = static_cast<__half*>(c->bufs["bb.res" + std::to_string(l + 3) + ".x"].p);
+        __half* XS = static_cast<__half*>(c->bufs["bb." + T.key + ".res" + std::to_string(l + 3) + ".x"].p);
         ConvCall k{};
-        k.W = &c->lat[l]; k.A = XS; k.a_rows = rows; k.a_cols = k.a_ld = 512 << l; k.ps = S.ps.get();
+        k.W = &c->lat[l]; k.A = XS; k.a_rows = static_cast<long long>(T.n) * g.rows_per_img; k.a_cols = k.a_ld = 512 << l; k.ps = S.ps.get();
         k.tile_begin = static_cast<int>(S.level_row0[l] / kBlockM); k.n_tiles = static_cast<int>(rows / kBlockM);
-        k.a_row_delta = -static_cast<int>(S.level_row0[l]); k.out = LAT; k.ldc = 256;
+        k.a_row_delta = -static_cast<int>(S.level_row0[l]) + first * g.rows_per_img; k.out = LAT; k.ldc = 256;
         k.flags = kEpiMask; k.name = "fpn.lateral1x1";
         TRY(run_conv(c, k, st));
         if (l < 2) {
@@ -937,8 +961,8 @@ static int run_backbone(sylph_ctx* c, int slot, int n, const void* const* images
         const PlaneGeom& g5 = S.pg.lv[2];
         const long long rows5 = static_cast<long long>(n) * g5.rows_per_img;
         __half *TMP, *R6;
-        TRY(buf("bb.p6tmp", S.level_row0[5], 256, false, &TMP));
-        TRY(buf("bb.p6relu", S.level_row0[5], 256, true, &R6));
+        TRY(buf(fb + "p6tmp", S.level_row0[5], 256, false, &TMP));
+        TRY(buf(fb + "p6relu", S.level_row0[5], 256, true, &R6));
         ConvCall k{};
         k.W = &c->p6; k.A = S.pyr; k.a_rows = S.level_row0[5]; k.a_cols = k.a_ld = 256; k.ps = S.ps.get();
         k.tile_begin = static_cast<int>(S.level_row0[2] / kBlockM); k.n_tiles = static_cast<int>(rows5 / kBlockM);
@@ -964,6 +988,15 @@ static int run_backbone(sylph_ctx* c, int slot, int n, const void* const* images
         c->launches++;
     }
     return 0;
+}
+
+static int run_backbone(sylph_ctx* c, int slot, int n, const void* const* images_dev, int is_u8, const int* hs,
+                        const int* ws, cudaStream_t st) {
+    int hmax = 0, wmax = 0;
+    for (int i = 0; i < n; ++i) { hmax = std::max(hmax, hs[i]); wmax = std::max(wmax, ws[i]); }
+    TrunkOut T;
+    TRY(run_trunk(c, "s" + std::to_string(slot), n, images_dev, is_u8, hs, ws, round_up(hmax, 32), round_up(wmax, 32), st, &T));
+    return run_fpn(c, slot, T, 0, n, hs, ws, st);
 }
 
 // conv3x3 + GroupNorm(32) + ReLU over `tiles` tiles of a plane set: conv epilogue accumulates the per-tile partial
@@ -1117,6 +1150,46 @@ int sylph_extract_features_u8(sylph_ctx* c, int slot, int n_images, const uint8_
     CU_TRY(c, cudaSetDevice(c->device));
     return run_backbone(c, slot, n_images, reinterpret_cast<const void* const*>(images_dev), 1, heights, widths,
                         static_cast<cudaStream_t>(stream));
+}
+
+int sylph_extract_features_multi(sylph_ctx* c, int n_groups, const int* slots, const int* counts,
+                                 const void* const* images_dev, int is_u8, const int* heights, const int* widths, void* stream) {
+    if (!c) return 1;
+    if (!c->finalized) return c->fail("weights not finalized");
+    if (n_groups <= 0 || n_groups > SYLPH_NUM_SLOTS || !slots || !counts) return c->fail("bad group list");
+    CU_TRY(c, cudaSetDevice(c->device));
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    int total = 0, hp = -1, wp = -1;
+    bool same = true;
+    for (int g = 0; g < n_groups; ++g) {
+        if (slots[g] < 0 || slots[g] >= SYLPH_NUM_SLOTS || counts[g] <= 0) return c->fail("bad slot / image count in group %d", g);
+        for (int h = 0; h < g; ++h)
+            if (slots[h] == slots[g]) return c->fail("slot %d listed twice", slots[g]);
+        int hmax = 0, wmax = 0;
+        for (int i = 0; i < counts[g]; ++i) { hmax = std::max(hmax, heights[total + i]); wmax = std::max(wmax, widths[total + i]); }
+        const int ghp = round_up(hmax, 32), gwp = round_up(wmax, 32);
+        if (g > 0 && (ghp != hp || gwp != wp)) same = false;
+        hp = ghp; wp = gwp;
+        total += counts[g];
+    }
+    // ImageList.from_tensors pads every reference call to ITS OWN batch maximum: the groups may only share one trunk
+    // batch when they pad to the same size; otherwise they run one after the other exactly like separate calls.
+    if (!same || n_groups == 1) {
+        int off = 0;
+        for (int g = 0; g < n_groups; ++g) {
+            TRY(run_backbone(c, slots[g], counts[g], images_dev + off, is_u8, heights + off, widths + off, st));
+            off += counts[g];
+        }
+        return 0;
+    }
+    TrunkOut T;
+    TRY(run_trunk(c, "m", total, images_dev, is_u8, heights, widths, hp, wp, st, &T));
+    int off = 0;
+    for (int g = 0; g < n_groups; ++g) {
+        TRY(run_fpn(c, slots[g], T, off, counts[g], heights + off, widths + off, st));
+        off += counts[g];
+    }
+    return 0;
 }
 
 int sylph_import_features(sylph_ctx* c, int slot, int n_images, int padded_h, int padded_w,

@@ -354,15 +354,18 @@ class MetaOneStageDetector(nn.Module):
         assert len(batched_inputs) == 1, f"batched_inputs has length: {len(batched_inputs)}"
         return self.forward_class_codes_batched(batched_inputs)[0]
 
-    def forward_class_codes_batched(self, batched_inputs: List[Dict[str, Any]]) -> List[Dict[str, torch.Tensor]]:
+    def forward_class_codes_batched(self, batched_inputs: List[Dict[str, Any]],
+                                    features_in_slot: bool = False) -> List[Dict[str, torch.Tensor]]:
         """B200-native extension: the support sets of MANY classes through one backbone batch and one code-generation
-        launch sequence; result[i] equals forward_class_code([batched_inputs[i]])."""
+        launch sequence; result[i] equals forward_class_code([batched_inputs[i]]).  `features_in_slot=True`: the
+        support pyramid of exactly these images already sits in SLOT_SUPPORT (Engine.extract_features_multi)."""
         records, offsets = [], [0]
         for item in batched_inputs:
             records.extend(item["support_set"])
             offsets.append(len(records))
         boxes = torch.cat([b.reshape(-1, 4)[:1].cpu() for b in select_a_mask([r["instances"] for r in records])], dim=0)
-        self.engine.extract_features(SLOT_SUPPORT, [r["image"] for r in records])
+        if not features_in_slot:
+            self.engine.extract_features(SLOT_SUPPORT, [r["image"] for r in records])
         if isinstance(self.code_generator, ROIEncoder):
             for a, b in zip(offsets[:-1], offsets[1:]):   # bs = 1 per call in the reference: N % EVAL_SHOT == 0
                 assert (b - a) % self.code_generator.eval_shot == 0 and b - a == self.code_generator.eval_shot, \
@@ -379,11 +382,13 @@ class MetaOneStageDetector(nn.Module):
         assert not self.training
         return self.code_generator(features=None, target_instances=None, cls_norm=True, class_codes=codes)
 
-    def forward_instances(self, batched_inputs: List[Dict[str, Any]], class_codes: Dict[str, torch.Tensor]):
+    def forward_instances(self, batched_inputs: List[Dict[str, Any]], class_codes: Dict[str, torch.Tensor],
+                          features_in_slot: bool = False):
         assert self.episodic_learning
         assert not self.training, "Not for training"
         images = [x["image"] for x in batched_inputs]
-        self.engine.extract_features(SLOT_QUERY, images)
+        if not features_in_slot:
+            self.engine.extract_features(SLOT_QUERY, images)
         sizes = [(int(im.shape[-2]), int(im.shape[-1])) for im in images]
         out_sizes = [(int(x.get("height", s[0])), int(x.get("width", s[1]))) for x, s in zip(batched_inputs, sizes)]
         results = self.proposal_generator.predict(class_codes, sizes, out_sizes)

@@ -33,13 +33,14 @@ def shard_range(n_items: int, world: int, rank: int) -> range:
     return range(begin, begin + base + (1 if rank < extra else 0))
 
 
-def inference_on_support_set(model: MetaOneStageDetector, support_items: Sequence[Dict[str, Any]]) -> List[Dict]:
+def inference_on_support_set(model: MetaOneStageDetector, support_items: Sequence[Dict[str, Any]],
+                             features_in_slot: bool = False) -> List[Dict]:
     """Step B for this rank's classes.  Each item: {"support_set": [K records], "support_set_target", "class_name"}.
     Returns the reference's list schema (meta_learn_evaluation.py:305-326) with RAW codes on the device."""
     if len(support_items) == 0:
         return []
     with torch.no_grad():
-        codes = model.forward_class_codes_batched(list(support_items))
+        codes = model.forward_class_codes_batched(list(support_items), features_in_slot=features_in_slot)
     out = []
     for item, code in zip(support_items, codes):
         out.append({"support_set_target": item["support_set_target"], "class_name": item.get("class_name", ""),
@@ -213,10 +214,14 @@ def format_class_codes_shared(all_class_codes: List[Dict], device=None) -> Dict[
 
 
 def inference_with_class_codes(model: MetaOneStageDetector, query_items: Sequence[Dict[str, Any]],
-                               class_codes: Dict[str, torch.Tensor], batch_size: int = 16) -> List[Dict]:
+                               class_codes: Dict[str, torch.Tensor], batch_size: int = 16,
+                               features_in_slot: bool = False) -> List[Dict]:
     """Step F for this rank's query images: [{"instances": Instances}] per image, in input order."""
     out: List[Dict] = []
     with torch.no_grad():
+        if features_in_slot:
+            assert len(query_items) <= batch_size
+            return model.forward_instances(list(query_items), class_codes, features_in_slot=True)
         for i in range(0, len(query_items), batch_size):
             out.extend(model(list(query_items[i:i + batch_size]), class_code=class_codes, run_type="meta_learn_test_instance"))
     return out
@@ -253,13 +258,23 @@ def run_episode(model: MetaOneStageDetector, support_items: Sequence[Dict[str, A
         ready = torch.cuda.Event()
         ready.record(side)
         my_query = staged
-    sub_codes = inference_on_support_set(model, my_support)
+    # support and query images already on the device: ONE bottom-up trunk pass for both batches (the FPN of each
+    # lands in its own slot); the engine falls back to two passes when the batches pad to different sizes
+    merged = False
+    if ready is None and my_support and 0 < len(my_query) <= 16 and torch.cuda.is_available():
+        sup_imgs = [r["image"] for it in my_support for r in it["support_set"]]
+        qry_imgs = [q["image"] for q in my_query]
+        if all(t.is_cuda for t in sup_imgs + qry_imgs) and len(sup_imgs) + len(qry_imgs) <= 64:
+            from .runtime import SLOT_QUERY, SLOT_SUPPORT
+            model.engine.extract_features_multi([(SLOT_SUPPORT, sup_imgs), (SLOT_QUERY, qry_imgs)])
+            merged = True
+    sub_codes = inference_on_support_set(model, my_support, features_in_slot=merged)
     all_codes = gather_class_code(sub_codes, group=group) if (world > 1 and shard) else sub_codes
     all_codes = inference_normalization(model, all_codes)
     packed = format_class_codes_shared(all_codes, device=model.device)
     if ready is not None:
         torch.cuda.current_stream().wait_event(ready)
-    return inference_with_class_codes(model, my_query, packed)
+    return inference_with_class_codes(model, my_query, packed, features_in_slot=merged)
 
 
 class EpisodePipeline:

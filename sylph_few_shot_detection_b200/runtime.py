@@ -125,6 +125,20 @@ class Engine:
         self._check(fn(self.h, slot, n, ptrs, hs, ws, self._stream()))
         self._keep = imgs  # keep inputs alive until the stream work is done
 
+    def extract_features_multi(self, groups: Sequence[Tuple[int, Sequence[torch.Tensor]]]) -> None:
+        """[(slot, images), ...] through one trunk pass when the groups pad to the same size (sylph_extract_features_multi)."""
+        flat = [im for _, ims in groups for im in ims]
+        u8 = all(im.dtype == torch.uint8 for im in flat)
+        imgs = [im.to(self.device, torch.uint8 if u8 else torch.float32, non_blocking=True).contiguous() for im in flat]
+        n = len(imgs)
+        slots = (c_int * len(groups))(*[int(s) for s, _ in groups])
+        counts = (c_int * len(groups))(*[len(ims) for _, ims in groups])
+        ptrs = (c_void_p * n)(*[im.data_ptr() for im in imgs])
+        hs = (c_int * n)(*[int(im.shape[-2]) for im in imgs])
+        ws = (c_int * n)(*[int(im.shape[-1]) for im in imgs])
+        self._check(self.lib.sylph_extract_features_multi(self.h, len(groups), slots, counts, ptrs, int(u8), hs, ws, self._stream()))
+        self._keep = imgs
+
     def import_features(self, slot: int, features: Sequence[torch.Tensor], padded_hw: Tuple[int, int]) -> None:
         feats = [f.to(self.device, torch.float32).contiguous() for f in features]
         assert len(feats) == NUM_LEVELS and all(f.shape[1] == 256 for f in feats)

@@ -248,3 +248,37 @@ def test_geometry_sweep_features_and_head_outputs(sizes):
         assert rel_err(model.engine.export_head_output(1, l, SLOT_QUERY, 3), inter["reg"][l]) < 4e-3, ("reg", l)
     for o, r in zip(out, ref):
         _match(o["instances"], r, frac=0.15)
+
+
+def test_merged_trunk_pass_is_bit_identical_to_separate_passes():
+    """sylph_extract_features_multi: support + query batches through ONE trunk pass give exactly the pyramids of two
+    separate calls (images are independent in the trunk); batches that pad to different sizes fall back to two passes
+    (each reference call pads to its own batch maximum), so results are identical there as well."""
+    from sylph_few_shot_detection_b200.runner import run_episode
+    from sylph_few_shot_detection_b200.runtime import SLOT_QUERY, SLOT_SUPPORT
+    cfg, state, model, orc = _setup(seed=6)
+    eng = model.engine
+    sup = [im.cuda() for im in _images(3, 160, 224, 5)]
+    for qry in ([im.cuda() for im in _images(2, 150, 200, 6)],       # pads to 160 x 224 as well -> shared trunk batch
+                [im.cuda() for im in _images(2, 96, 128, 7)]):       # pads to 96 x 128 -> fallback
+        eng.extract_features(SLOT_SUPPORT, sup)
+        eng.extract_features(SLOT_QUERY, qry)
+        want = [[eng.export_features(s, l).clone() for l in range(5)] for s in (SLOT_SUPPORT, SLOT_QUERY)]
+        eng.extract_features_multi([(SLOT_SUPPORT, sup), (SLOT_QUERY, qry)])
+        for si, s in enumerate((SLOT_SUPPORT, SLOT_QUERY)):
+            assert eng.feature_shape(s)[0] == (3 if s == SLOT_SUPPORT else 2)
+            for l in range(5):
+                assert torch.equal(eng.export_features(s, l), want[si][l])
+    with pytest.raises(RuntimeError, match="listed twice"):
+        eng.extract_features_multi([(SLOT_SUPPORT, sup), (SLOT_SUPPORT, sup)])
+    # run_episode takes the merged path for device-resident inputs and must equal the host-resident (two-pass) run
+    ims = _images(5, 160, 224, 9)
+    boxes = torch.tensor([[20.0, 30.0, 120.0, 140.0], [5.0, 5.0, 200.0, 150.0]])
+    np.random.seed(0)
+    host = run_episode(model, [_support_item(ims[0:2], boxes, 0), _support_item(ims[2:4], boxes, 1)],
+                       [{"image": ims[4], "height": 160, "width": 224}])
+    np.random.seed(0)
+    dev = run_episode(model, [_support_item([i.cuda() for i in ims[0:2]], boxes, 0), _support_item([i.cuda() for i in ims[2:4]], boxes, 1)],
+                      [{"image": ims[4].cuda(), "height": 160, "width": 224}])
+    assert torch.equal(host[0]["instances"].pred_boxes.tensor, dev[0]["instances"].pred_boxes.tensor)
+    assert torch.equal(host[0]["instances"].scores, dev[0]["instances"].scores)
