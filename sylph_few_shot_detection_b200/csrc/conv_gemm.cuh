@@ -81,6 +81,8 @@ struct GemmArgs {
     float* gn_partial;     // [absolute tile][32][2]
     int dbg_a_row_skew;    // experiment: load the A box `skew` rows early and start the MMA descriptor `skew` rows in
     int dbg_base_offset;   // experiment: matrix-descriptor base_offset field used with the skew
+    int dbg_skip;          // bring-up timing experiments (halo pipeline): 1 = no output stores, 2 = no MMAs issued,
+                           // 4 = no A loads (barriers only), 8 = no TMEM reads in the epilogue
 };
 
 // HALO > 0 selects the 3x3 "halo" pipeline: ONE A box of 130 rows (the 128 output rows plus one row on either side)
@@ -89,20 +91,29 @@ struct GemmArgs {
 // shared-memory address, so a row-shifted start needs no base-offset) -- while the per-tap B tiles cycle through their
 // own ring of STAGES slots.  A traffic from L2 drops 3x, which is what bounds the N <= 128 convolutions and most of
 // what bounds the N = 256 ones (profiles/r01_ncu_head_tower_kernel.md).
-template <int BN, int STAGES, int EPI_BUFS, int HALO>
+// STEM16 (with HALO slots): the 7x7/2 stem as a 4x4/1 convolution over 16 space-to-depth channels.  ONE A box of
+// 131 rows x 16 channels (32-byte rows, 32-byte swizzle) per vertical tap serves the four horizontal taps -- the
+// descriptor starts 0..3 rows into the tile and each tap is exactly one K = 16 tcgen05.mma -- against one 64 x 64 B tile
+// per vertical tap whose four 16-wide k sub-blocks are the horizontal taps.  A traffic from L2 is 17 KB per output tile
+// instead of 64 KB with 64-wide overlapped rows, which is what bounded the stem (profiles/r01_launches_s2.csv).
+// BRES (3x3 halo pipeline only): the 9 x kblocks weight tiles are the same for every output tile; when they fit in
+// shared memory (res2 conv2: 9 x 8 KB) they are loaded ONCE and stay resident in the STAGES slots (STAGES = 9 x kblocks),
+// so the per-tile TMA traffic is the three halo A boxes only.  A TMA unit retires roughly one <= 128-byte box row per
+// 5 clocks (~45 GB/s per SM): 9 x 64 weight rows per tile were 60 % of this kernel's row requests.
+template <int BN, int STAGES, int EPI_BUFS, int HALO, bool STEM16 = false, bool BRES = false>
 struct GemmSmem {
     static constexpr bool TMA_EPI = EPI_BUFS > 0;          // 0: direct epilogue, 1 / 2: staged epilogue buffers
     static constexpr int kABytes = kBlockM * kBlockK * 2;  // 16 KiB
     static constexpr int kAHaloRows = kBlockM + 2;
-    static constexpr int kAHaloTx = kAHaloRows * 128;       // bytes one halo box delivers
-    static constexpr int kAHaloBytes = 17 * 1024;           // slot size (multiple of the 1024-byte swizzle period)
+    static constexpr int kAHaloTx = STEM16 ? (kBlockM + 3) * 32 : kAHaloRows * 128;   // bytes one halo box delivers
+    static constexpr int kAHaloBytes = STEM16 ? 5 * 1024 : 17 * 1024;   // slot size (multiple of the 1024-byte swizzle period)
     static constexpr int kBBytes = BN * kBlockK * 2;
     static constexpr int kStageBytes = HALO ? kBBytes : kABytes + kBBytes;
     static constexpr int kRingOffset = HALO * kAHaloBytes;  // halo slots first, then the (B or A+B) stage ring
     static constexpr int kEpiBytes = TMA_EPI ? kBlockM * BN * 2 : 0;  // one staged output tile, BN/64 swizzled panels
     static constexpr int kEpiOffset = kRingOffset + STAGES * kStageBytes;
     static constexpr int kBarOffset = kEpiOffset + EPI_BUFS * kEpiBytes;
-    static constexpr int kGnOffset = kBarOffset + 512;
+    static constexpr int kGnOffset = kBarOffset + 1024;
     static constexpr int kTotal = kGnOffset + (TMA_EPI ? 0 : 4 * 32 * 2 * 4) + 1024;  // + alignment slack
     static constexpr int kThreads = TMA_EPI ? 352 : 320;
 };
@@ -115,20 +126,47 @@ __device__ __forceinline__ float2 unpack_half2(uint32_t u) {
     return __half22float2(*reinterpret_cast<const __half2*>(&u));
 }
 
-template <int BN, int STAGES, int EPI_BUFS, int HALO>
-__global__ void __launch_bounds__(GemmSmem<BN, STAGES, EPI_BUFS, HALO>::kThreads, 1)
+// tile -> (m_tile, n_tile) without an integer division in the common single-N-tile case
+__device__ __forceinline__ void split_tile(int tile, int num_n_tiles, int& m_tile, int& n_tile) {
+    if (num_n_tiles == 1) { m_tile = tile; n_tile = 0; }
+    else { m_tile = tile / num_n_tiles; n_tile = tile - m_tile * num_n_tiles; }
+}
+
+// Is `row` an interior pixel of plane `sg`?  (y, x) = divmod(local, Wp) through a float reciprocal with an exact fix-up
+// (local < 2^24): the 32-bit integer division cost ~30 dependent instructions per thread per tile.
+__device__ __forceinline__ bool row_is_interior(const Seg& sg, int row) {
+    const int local = row - sg.row0;
+    int y = __float2int_rz(__fdividef(static_cast<float>(local), static_cast<float>(sg.Wp)));
+    int x = local - y * sg.Wp;
+    if (x < 0) { --y; x += sg.Wp; }
+    else if (x >= sg.Wp) { ++y; x -= sg.Wp; }
+    return (local >= 0) && (local < sg.nrows) && (y >= sg.pad) && (y < sg.pad + sg.H) && (x >= sg.pad) && (x < sg.pad + sg.W);
+}
+
+template <int BN, int STAGES, int EPI_BUFS, int HALO, bool STEM16 = false, bool BRES = false>
+__global__ void __launch_bounds__(GemmSmem<BN, STAGES, EPI_BUFS, HALO, STEM16, BRES>::kThreads, 1)
 conv_gemm_f16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
                      const __grid_constant__ CUtensorMap tmap_res, const __grid_constant__ CUtensorMap tmap_out,
                      const GemmArgs p) {
-    using S = GemmSmem<BN, STAGES, EPI_BUFS, HALO>;
+    using S = GemmSmem<BN, STAGES, EPI_BUFS, HALO, STEM16, BRES>;
+    static_assert(!BRES || (HALO > 0 && !STEM16), "resident weights are implemented for the 3x3 halo pipeline");
     constexpr bool TMA_EPI = EPI_BUFS > 0;
     constexpr int kHalo = HALO > 0 ? HALO : 1;
-    static_assert(HALO == 0 || EPI_BUFS == 0, "the halo pipeline uses the direct epilogue");
+    static_assert(HALO == 0 || EPI_BUFS == 0 || STEM16, "the 3x3 halo pipeline uses the direct epilogue");
+    static_assert(!STEM16 || HALO > 0, "the stem variant uses the halo slots");
     constexpr int kBufs = EPI_BUFS > 0 ? EPI_BUFS : 1;
     constexpr int NH = BN >= 64 ? 2 : 1;       // epilogue warps per lane quadrant (column halves)
     constexpr int COLS = BN / NH;              // columns per epilogue warp
     constexpr int CH = COLS < 32 ? COLS : 32;  // epilogue column chunk
-    constexpr uint32_t kTmemCols = (2 * BN < 32) ? 32 : 2 * BN;
+    // accumulator buffers in TMEM: narrow tiles finish their MMAs in ~1 us while an epilogue takes 2-3 us from
+    // tcgen05.commit to the hand-back (barrier wake-up, tcgen05.ld, stores, arrive), so BN <= 128 uses four buffers
+    constexpr int kAcc = BN <= 128 ? 4 : 2;
+    // The CTA always takes ALL 512 TMEM columns (one CTA per SM anyway): the allocation then starts at column 0, the
+    // accumulator address is a compile-time expression, and ptxas keeps it in a uniform register instead of running an
+    // ELECT / R2UR.BROADCAST loop in front of every tcgen05.mma (the address read back from shared memory is not
+    // provably warp-uniform).  That loop cost ~40 issue clocks per MMA -- more than a whole N = 64 MMA (32 clocks).
+    constexpr uint32_t kTmemCols = 512;
+    static_assert(kAcc * BN <= 512, "accumulator buffers exceed TMEM");
     constexpr uint32_t kIdesc = ptx::make_idesc_f16(kBlockM, BN);
     static_assert(!TMA_EPI || BN % 64 == 0, "TMA epilogue works on 64-column panels");
 
@@ -137,8 +175,8 @@ conv_gemm_f16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_co
     uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + S::kBarOffset);
     uint64_t* empty_bar = full_bar + STAGES;
     uint64_t* tmem_full = empty_bar + STAGES;
-    uint64_t* tmem_empty = tmem_full + 2;
-    uint64_t* res_full = tmem_empty + 2;     // TMA_EPI: residual tile landed in epi buffer b
+    uint64_t* tmem_empty = tmem_full + 4;
+    uint64_t* res_full = tmem_empty + 4;     // TMA_EPI: residual tile landed in epi buffer b
     uint64_t* stage_ready = res_full + 2;    // TMA_EPI: epilogue finished writing epi buffer b
     uint64_t* epi_free = stage_ready + 2;    // TMA_EPI: TMA store finished reading epi buffer b
     uint64_t* a_full = epi_free + 2;         // HALO: halo A slot landed
@@ -168,11 +206,13 @@ conv_gemm_f16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_co
             ptx::mbar_init(&a_full[a], 1);
             ptx::mbar_init(&a_empty[a], 1);
         }
-        for (int a = 0; a < 2; ++a) {
+        for (int a = 0; a < kAcc; ++a) {
             ptx::mbar_init(&tmem_full[a], 1);
-            ptx::mbar_init(&tmem_empty[a], 128 * NH);
+            ptx::mbar_init(&tmem_empty[a], 4 * NH);     // one arrive per epilogue warp
+        }
+        for (int a = 0; a < 2; ++a) {
             ptx::mbar_init(&res_full[a], 1);
-            ptx::mbar_init(&stage_ready[a], 128 * NH);
+            ptx::mbar_init(&stage_ready[a], 4 * NH);    // one arrive per epilogue warp
             ptx::mbar_init(&epi_free[a], 1);
         }
         ptx::fence_barrier_init();
@@ -185,7 +225,8 @@ conv_gemm_f16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_co
     ptx::tc_fence_before();
     __syncthreads();
     ptx::tc_fence_after();
-    const uint32_t tmem_base = *tmem_slot;
+    if (*tmem_slot != 0u) __trap();   // a 512-column allocation can only start at column 0
+    constexpr uint32_t tmem_base = 0u;
     ptx::griddep_wait();     // PDL: everything above overlapped the previous kernel's tail; global memory from here on
 
     const int total_tiles = p.num_m_tiles * p.num_n_tiles;
@@ -200,12 +241,21 @@ conv_gemm_f16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_co
             int hs = 0;
             uint32_t hphase = 0;
             int it = 0;
+            // the padded width of the NEXT tile's plane is fetched one iteration ahead (two dependent global loads)
+            auto fetch_wp = [&](int t) -> int {
+                int m, n;
+                split_tile(t, p.num_n_tiles, m, n);
+                return p.segs[__ldg(p.tile_seg + p.tile_begin + m)].Wp;
+            };
+            int wp_next = (static_cast<int>(blockIdx.x) < total_tiles) ? fetch_wp(blockIdx.x) : 0;
             for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
-                const int m_tile = tile / p.num_n_tiles;
-                const int n_tile = tile - m_tile * p.num_n_tiles;
+                int m_tile, n_tile;
+                split_tile(tile, p.num_n_tiles, m_tile, n_tile);
                 const int out_row_base = (p.tile_begin + m_tile) * kBlockM;
                 const int a_row_base = out_row_base + p.a_row_delta;
                 const int b_row_base = n_tile * BN;
+                const int wp = wp_next;
+                if (tile + static_cast<int>(gridDim.x) < total_tiles) wp_next = fetch_wp(tile + gridDim.x);
                 if constexpr (TMA_EPI) {
                     if (use_res_tile) {
                         const int buf = it % kBufs;
@@ -217,16 +267,47 @@ conv_gemm_f16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_co
                                              n_tile * BN + pn * 64, out_row_base);
                     }
                 }
-                // planes of different FPN levels have different padded widths: the row shift of a tap is per tile
-                const int wp = p.segs[p.tile_seg[p.tile_begin + m_tile]].Wp;
-                if constexpr (HALO > 0) {
+                // planes of different FPN levels have different padded widths: the row shift of a tap is per tile (wp)
+                if constexpr (STEM16) {
+                    // the four 64 x 64 weight tiles (one per vertical tap) are the same for every output tile: they are
+                    // loaded once and stay resident; the ring only carries A boxes (4 per tile, several tiles ahead)
+                    if (it == 0) {
+                        for (int ty = 0; ty < 4; ++ty) {
+                            ptx::mbar_arrive_expect_tx(&full_bar[ty], S::kBBytes);
+                            ptx::tma_load_2d(smem + S::kRingOffset + ty * S::kStageBytes, &tmap_b, &full_bar[ty], 0,
+                                             ty * p.b_rows_per_tap + b_row_base);
+                        }
+                    }
+                    for (int ty = 0; ty < 4; ++ty) {
+                        ptx::mbar_wait(&a_empty[hs], hphase ^ 1u);
+                        ptx::mbar_arrive_expect_tx(&a_full[hs], S::kAHaloTx);
+                        ptx::tma_load_2d(smem + hs * S::kAHaloBytes, &tmap_a, &a_full[hs], 0, a_row_base + (ty - 2) * wp - 2);
+                        if (++hs == kHalo) { hs = 0; hphase ^= 1u; }
+                    }
+                    continue;
+                } else if constexpr (HALO > 0) {
+                    if constexpr (BRES) {
+                        if (it == 0) {   // resident weights: tile (tap, kb) -> slot tap * kblocks + kb, one barrier each
+                            for (int t = 0; t < 9 * p.kblocks_per_tap; ++t) {
+                                ptx::mbar_arrive_expect_tx(&full_bar[t], S::kBBytes);
+                                ptx::tma_load_2d(smem + S::kRingOffset + t * S::kStageBytes, &tmap_b, &full_bar[t],
+                                                 (t % p.kblocks_per_tap) * kBlockK,
+                                                 (t / p.kblocks_per_tap) * p.b_rows_per_tap + b_row_base);
+                            }
+                        }
+                    }
                     for (int dyi = 0; dyi < 3; ++dyi) {
                         for (int kb = 0; kb < p.kblocks_per_tap; ++kb) {
                             ptx::mbar_wait(&a_empty[hs], hphase ^ 1u);
-                            ptx::mbar_arrive_expect_tx(&a_full[hs], S::kAHaloTx);
-                            ptx::tma_load_2d(smem + hs * S::kAHaloBytes, &tmap_a, &a_full[hs], kb * kBlockK,
-                                             a_row_base + (dyi - 1) * wp - 1);
+                            if (p.dbg_skip & 4) {
+                                ptx::mbar_arrive(&a_full[hs]);
+                            } else {
+                                ptx::mbar_arrive_expect_tx(&a_full[hs], S::kAHaloTx);
+                                ptx::tma_load_2d(smem + hs * S::kAHaloBytes, &tmap_a, &a_full[hs], kb * kBlockK,
+                                                 a_row_base + (dyi - 1) * wp - 1);
+                            }
                             if (++hs == kHalo) { hs = 0; hphase ^= 1u; }
+                            if constexpr (BRES) continue;
                             for (int dxi = 0; dxi < 3; ++dxi) {
                                 ptx::mbar_wait(&empty_bar[stage], phase ^ 1u);
                                 ptx::mbar_arrive_expect_tx(&full_bar[stage], S::kBBytes);
@@ -262,25 +343,60 @@ conv_gemm_f16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_co
             uint32_t acc_phase = 0;
             int hs = 0;
             uint32_t hphase = 0;
+            [[maybe_unused]] bool b_resident = false;
             for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
                 ptx::mbar_wait(&tmem_empty[acc], acc_phase ^ 1u);
                 ptx::tc_fence_after();
                 const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(acc * BN);
-                if constexpr (HALO > 0) {
+                if constexpr (STEM16) {
+                    if (!b_resident) {
+                        for (int ty = 0; ty < 4; ++ty) ptx::mbar_wait(&full_bar[ty], 0);
+                        b_resident = true;
+                    }
+                    for (int ty = 0; ty < 4; ++ty) {
+                        ptx::mbar_wait(&a_full[hs], hphase);
+                        ptx::tc_fence_after();
+                        const uint32_t sa = ptx::smem_u32(smem + hs * S::kAHaloBytes);
+                        const uint64_t db = ptx::make_sw128_kmajor_desc(ptx::smem_u32(smem + S::kRingOffset + ty * S::kStageBytes));
+                        // horizontal tap tx: A starts tx rows (32 bytes) in, B advances 32 bytes of K
+                        ptx::umma_f16_x4(d_tmem, ptx::make_sw32_kmajor_desc(sa), db, kIdesc, ty ? 1u : 0u);
+                        ptx::umma_commit(&a_empty[hs]);
+                        if (++hs == kHalo) { hs = 0; hphase ^= 1u; }
+                    }
+                    ptx::umma_commit(&tmem_full[acc]);
+                    if (++acc == kAcc) { acc = 0; acc_phase ^= 1u; }
+                    continue;
+                } else if constexpr (HALO > 0) {
                     uint32_t first = 0;
+                    if constexpr (BRES) {
+                        if (!b_resident) {
+                            for (int t = 0; t < 9 * p.kblocks_per_tap; ++t) ptx::mbar_wait(&full_bar[t], 0);
+                            b_resident = true;
+                        }
+                    }
+                    int g_dy = 0, g_kb = 0;   // g = g_dy * kblocks_per_tap + g_kb, tracked without a division
                     for (int g = 0; g < 3 * p.kblocks_per_tap; ++g) {
                         ptx::mbar_wait(&a_full[hs], hphase);
                         const uint32_t sa = ptx::smem_u32(smem + hs * S::kAHaloBytes);
+                        const int dyi = g_dy, kb = g_kb;
+                        if (++g_kb == p.kblocks_per_tap) { g_kb = 0; ++g_dy; }
                         for (int dxi = 0; dxi < 3; ++dxi) {
+                            if constexpr (BRES) {
+                                ptx::tc_fence_after();
+                                const uint64_t da = ptx::make_sw128_kmajor_desc(sa + dxi * 128);
+                                const uint64_t db = ptx::make_sw128_kmajor_desc(ptx::smem_u32(
+                                    smem + S::kRingOffset + ((dyi * 3 + dxi) * p.kblocks_per_tap + kb) * S::kStageBytes));
+                                if (!(p.dbg_skip & 2)) ptx::umma_f16_x4(d_tmem, da, db, kIdesc, first);
+                                first = 1;
+                                continue;
+                            }
                             ptx::mbar_wait(&full_bar[stage], phase);
                             ptx::tc_fence_after();
                             // the tap's A tile is the halo tile started dxi rows in (address-based 128B swizzle)
                             const uint64_t da = ptx::make_sw128_kmajor_desc(sa + dxi * 128);
                             const uint64_t db = ptx::make_sw128_kmajor_desc(
                                 ptx::smem_u32(smem + S::kRingOffset + stage * S::kStageBytes));
-#pragma unroll
-                            for (int k = 0; k < kBlockK / kUmmaK; ++k)
-                                ptx::umma_f16(d_tmem, da + 2 * k, db + 2 * k, kIdesc, (first | k) ? 1u : 0u);
+                            ptx::umma_f16_x4(d_tmem, da, db, kIdesc, first);
                             first = 1;
                             ptx::umma_commit(&empty_bar[stage]);
                             if (++stage == STAGES) { stage = 0; phase ^= 1u; }
@@ -289,8 +405,7 @@ conv_gemm_f16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_co
                         if (++hs == kHalo) { hs = 0; hphase ^= 1u; }
                     }
                     ptx::umma_commit(&tmem_full[acc]);
-                    acc ^= 1;
-                    if (acc == 0) acc_phase ^= 1u;
+                    if (++acc == kAcc) { acc = 0; acc_phase ^= 1u; }
                     continue;
                 }
                 for (int ks = 0; ks < ksteps; ++ks) {
@@ -300,17 +415,13 @@ conv_gemm_f16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_co
                     const uint64_t da = ptx::make_sw128_kmajor_desc(sa + p.dbg_a_row_skew * 128) |
                                         (static_cast<uint64_t>(p.dbg_base_offset & 7) << 49);
                     const uint64_t db = ptx::make_sw128_kmajor_desc(sa + S::kABytes);
-#pragma unroll
-                    for (int k = 0; k < kBlockK / kUmmaK; ++k) {
-                        // advance 32 bytes of K inside the swizzle row: +2 in the (addr >> 4) field
-                        ptx::umma_f16(d_tmem, da + 2 * k, db + 2 * k, kIdesc, (ks | k) ? 1u : 0u);
-                    }
+                    // four K = 16 steps: +32 bytes of K inside the swizzle row = +2 in the (addr >> 4) field each
+                    ptx::umma_f16_x4(d_tmem, da, db, kIdesc, ks ? 1u : 0u);
                     ptx::umma_commit(&empty_bar[stage]);
                     if (++stage == STAGES) { stage = 0; phase ^= 1u; }
                 }
                 ptx::umma_commit(&tmem_full[acc]);
-                acc ^= 1;
-                if (acc == 0) acc_phase ^= 1u;
+                if (++acc == kAcc) { acc = 0; acc_phase ^= 1u; }
             }
         }
     } else if (warp - 2 < 4 * NH) {
@@ -323,20 +434,24 @@ conv_gemm_f16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_co
         int acc = 0;
         uint32_t acc_phase = 0;
         int it = 0;
+        // plane descriptor of the NEXT tile, fetched one iteration ahead: the two dependent global loads
+        // (tile -> plane index -> plane) otherwise sit on the critical path of every small tile's epilogue
+        const bool need_seg = (p.flags & (kEpiMask | kEpiGnStats)) != 0;
+        auto fetch_seg = [&](int t) -> Seg {
+            int m, n;
+            split_tile(t, p.num_n_tiles, m, n);
+            return p.segs[__ldg(p.tile_seg + p.tile_begin + m)];
+        };
+        Seg sg_next{};
+        if (need_seg && static_cast<int>(blockIdx.x) < total_tiles) sg_next = fetch_seg(blockIdx.x);
         for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
-            const int m_tile = tile / p.num_n_tiles;
-            const int n_tile = tile - m_tile * p.num_n_tiles;
+            int m_tile, n_tile;
+            split_tile(tile, p.num_n_tiles, m_tile, n_tile);
             const int abs_tile = p.tile_begin + m_tile;
             const int row = abs_tile * kBlockM + r_in_tile;
-            bool interior = true;
-            if (p.flags & (kEpiMask | kEpiGnStats)) {
-                const Seg sg = p.segs[p.tile_seg[abs_tile]];
-                const int local = row - sg.row0;
-                const int y = local / sg.Wp;
-                const int x = local - y * sg.Wp;
-                interior = (local < sg.nrows) && (y >= sg.pad) && (y < sg.pad + sg.H) && (x >= sg.pad) &&
-                           (x < sg.pad + sg.W);
-            }
+            const Seg sg = sg_next;
+            if (need_seg && tile + static_cast<int>(gridDim.x) < total_tiles) sg_next = fetch_seg(tile + gridDim.x);
+            const bool interior = need_seg ? row_is_interior(sg, row) : true;
             const bool keep = interior || !(p.flags & kEpiMask);
 
             if constexpr (TMA_EPI) {
@@ -399,9 +514,12 @@ conv_gemm_f16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_co
                                        pack_half2(f[8 * j + 4], f[8 * j + 5]), pack_half2(f[8 * j + 6], f[8 * j + 7]));
                 }
                 ptx::tc_fence_before();
-                ptx::mbar_arrive(&tmem_empty[acc]);
                 ptx::fence_proxy_async();          // generic-proxy smem writes -> visible to the TMA store
-                ptx::mbar_arrive(&stage_ready[buf]);
+                __syncwarp();
+                if (lane == 0) {                   // one arrive per warp (256 per-thread arrives serialise on the barrier)
+                    ptx::mbar_arrive(&tmem_empty[acc]);
+                    ptx::mbar_arrive(&stage_ready[buf]);
+                }
             } else {
                 // ======================================================= direct (register) epilogue
                 const size_t out_off = static_cast<size_t>(row) * p.ldc + static_cast<size_t>(n_tile) * BN + col_begin;
@@ -421,9 +539,14 @@ conv_gemm_f16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_co
 #pragma unroll
                 for (int c0 = 0; c0 < COLS; c0 += CH) {
                     uint32_t v[CH];
-                    if constexpr (CH == 32) ptx::tmem_ld_32x32b_x32(t_row + c0, v);
-                    else ptx::tmem_ld_32x32b_x16(t_row + c0, v);
-                    ptx::tmem_ld_wait();
+                    if (p.dbg_skip & 8) {
+#pragma unroll
+                        for (int j = 0; j < CH; ++j) v[j] = 0u;
+                    } else {
+                        if constexpr (CH == 32) ptx::tmem_ld_32x32b_x32(t_row + c0, v);
+                        else ptx::tmem_ld_32x32b_x16(t_row + c0, v);
+                        ptx::tmem_ld_wait();
+                    }
                     float f[CH];
 #pragma unroll
                     for (int j = 0; j < CH; ++j) f[j] = __uint_as_float(v[j]);
@@ -475,7 +598,9 @@ conv_gemm_f16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_co
 #pragma unroll
                         for (int j = 0; j < CH; ++j) f[j] = 0.f;
                     }
-                    if (p.flags & kEpiOutF32) {
+                    if (p.dbg_skip & 1) {
+                        if (f[0] == 12345.678f) static_cast<float*>(p.out)[0] = f[1];   // keep the math alive
+                    } else if (p.flags & kEpiOutF32) {
                         float4* op = reinterpret_cast<float4*>(static_cast<float*>(p.out) + out_off + c0);
 #pragma unroll
                         for (int j = 0; j < CH / 4; ++j) op[j] = make_float4(f[4 * j], f[4 * j + 1], f[4 * j + 2], f[4 * j + 3]);
@@ -487,9 +612,10 @@ conv_gemm_f16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_co
                                                pack_half2(f[8 * j + 4], f[8 * j + 5]), pack_half2(f[8 * j + 6], f[8 * j + 7]));
                     }
                 }
-                // accumulator buffer fully read: hand it back to the MMA warp
+                // accumulator buffer fully read: hand it back to the MMA warp (one arrive per warp)
                 ptx::tc_fence_before();
-                ptx::mbar_arrive(&tmem_empty[acc]);
+                __syncwarp();
+                if (lane == 0) ptx::mbar_arrive(&tmem_empty[acc]);
                 if constexpr (BN == 256) {
                     if (p.flags & kEpiGnStats) {
                         asm volatile("bar.sync 1, 256;" ::: "memory");
@@ -501,16 +627,15 @@ conv_gemm_f16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_co
                     }
                 }
             }
-            acc ^= 1;
-            if (acc == 0) acc_phase ^= 1u;
+            if (++acc == kAcc) { acc = 0; acc_phase ^= 1u; }
         }
     } else if (TMA_EPI && warp == 2 + 4 * NH) {
         // ------------------------------------------------------------ TMA store warp (staged epilogue only)
         if (lane == 0) {
             int it = 0;
             for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
-                const int m_tile = tile / p.num_n_tiles;
-                const int n_tile = tile - m_tile * p.num_n_tiles;
+                int m_tile, n_tile;
+                split_tile(tile, p.num_n_tiles, m_tile, n_tile);
                 const int out_row_base = (p.tile_begin + m_tile) * kBlockM;
                 const int buf = it % kBufs;
                 ptx::mbar_wait(&stage_ready[buf], (it / kBufs) & 1);

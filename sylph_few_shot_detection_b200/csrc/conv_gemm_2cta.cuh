@@ -71,6 +71,27 @@ __device__ __forceinline__ void umma_f16_pair(uint32_t tmem_d, uint64_t desc_a, 
         "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
         : "memory");
 }
+__device__ __forceinline__ void umma_f16_pair_x4(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc,
+                                                 uint32_t accumulate) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        ".reg .b64 a1, a2, a3, b1, b2, b3;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "add.s64 a1, %1, 2;\n\t"
+        "add.s64 b1, %2, 2;\n\t"
+        "add.s64 a2, %1, 4;\n\t"
+        "add.s64 b2, %2, 4;\n\t"
+        "add.s64 a3, %1, 6;\n\t"
+        "add.s64 b3, %2, 6;\n\t"
+        "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t"
+        "tcgen05.mma.cta_group::2.kind::f16 [%0], a1, b1, %3, 1;\n\t"
+        "tcgen05.mma.cta_group::2.kind::f16 [%0], a2, b2, %3, 1;\n\t"
+        "tcgen05.mma.cta_group::2.kind::f16 [%0], a3, b3, %3, 1;\n\t"
+        "}\n" ::"r"(tmem_d),
+        "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
 // arrive (when all MMAs issued so far retire) on the barrier at this offset in BOTH CTAs of the pair
 __device__ __forceinline__ void umma_commit_pair(uint64_t* bar) {
     asm volatile(
@@ -152,7 +173,8 @@ conv3x3_pair_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
     ptx::tc_fence_before();
     ptx::cluster_sync_all();   // barriers of BOTH CTAs are initialised before anyone signals across the pair
     ptx::tc_fence_after();
-    const uint32_t tmem_base = *tmem_slot;
+    if (*tmem_slot != 0u) __trap();   // all 512 columns: the allocation starts at column 0 (see conv_gemm.cuh)
+    constexpr uint32_t tmem_base = 0u;
     ptx::griddep_wait();
 
     const int pair_m_tiles = (p.num_m_tiles + 1) >> 1;
@@ -210,9 +232,7 @@ conv3x3_pair_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
                         ptx::tc_fence_after();
                         const uint64_t da = ptx::make_sw128_kmajor_desc(sa + dxi * 128);
                         const uint64_t db = ptx::make_sw128_kmajor_desc(ptx::smem_u32(smem + S::kRingOffset + sb * S::kBBytes));
-#pragma unroll
-                        for (int k = 0; k < kBlockK / kUmmaK; ++k)
-                            ptx::umma_f16_pair(d_tmem, da + 2 * k, db + 2 * k, kIdesc, (first | k) ? 1u : 0u);
+                        ptx::umma_f16_pair_x4(d_tmem, da, db, kIdesc, first);
                         first = 1;
                         ptx::umma_commit_pair(&empty_bar[sb]);
                         if (++sb == BSLOTS) { sb = 0; bphase ^= 1u; }
@@ -235,22 +255,25 @@ conv3x3_pair_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
         const int r_in_tile = quad * 32 + lane;
         int acc = 0;
         uint32_t acc_phase = 0;
+        const bool need_seg = (p.flags & (kEpiMask | kEpiGnStats)) != 0;
+        auto fetch_seg = [&](int t) -> Seg {   // plane of this CTA's M tile of pair tile t (clamped for the phantom tile)
+            int pm_, n_;
+            split_tile(t, p.num_n_tiles, pm_, n_);
+            const int m_ = 2 * pm_ + static_cast<int>(rank);
+            return p.segs[__ldg(p.tile_seg + p.tile_begin + (m_ < p.num_m_tiles ? m_ : p.num_m_tiles - 1))];
+        };
+        Seg sg_next{};
+        if (need_seg && cluster_id < total_pairs) sg_next = fetch_seg(cluster_id);
         for (int pt = cluster_id; pt < total_pairs; pt += num_clusters) {
-            const int pm = pt / p.num_n_tiles;
-            const int n_tile = pt - pm * p.num_n_tiles;
+            int pm, n_tile;
+            split_tile(pt, p.num_n_tiles, pm, n_tile);
             const int m_tile = 2 * pm + static_cast<int>(rank);
             const bool valid = m_tile < p.num_m_tiles;
             const int abs_tile = p.tile_begin + m_tile;
             const int row = abs_tile * kBlockM + r_in_tile;
-            bool interior = valid;
-            if (valid && (p.flags & (kEpiMask | kEpiGnStats))) {
-                const Seg sg = p.segs[p.tile_seg[abs_tile]];
-                const int local = row - sg.row0;
-                const int y = local / sg.Wp;
-                const int x = local - y * sg.Wp;
-                interior = (local < sg.nrows) && (y >= sg.pad) && (y < sg.pad + sg.H) && (x >= sg.pad) &&
-                           (x < sg.pad + sg.W);
-            }
+            const Seg sg = sg_next;
+            if (need_seg && pt + num_clusters < total_pairs) sg_next = fetch_seg(pt + num_clusters);
+            const bool interior = valid && (need_seg ? row_is_interior(sg, row) : true);
             const bool keep = interior || !(p.flags & kEpiMask);
             const size_t out_off = static_cast<size_t>(row) * p.ldc + static_cast<size_t>(n_tile) * BN + col_begin;
 

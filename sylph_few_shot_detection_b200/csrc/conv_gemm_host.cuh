@@ -49,13 +49,34 @@ inline int make_tmap_2d(CUtensorMap* m, const __half* base, uint64_t rows, uint6
     return 0;
 }
 
-template <int BN, int STAGES, int EPI_BUFS, int HALO = 0>
+// 2-D fp16 matrix [rows][16] (32-byte rows): box = [box_rows][16], 32-byte swizzle -- the stem's space-to-depth input.
+inline int make_tmap_2d_k16(CUtensorMap* m, const __half* base, uint64_t rows, uint32_t box_rows, std::string* err) {
+    PFN_tmapEncodeTiled enc = get_tmap_encode();
+    if (enc == nullptr) {
+        if (err) *err = "cuTensorMapEncodeTiled entry point unavailable";
+        return 1;
+    }
+    cuuint64_t dims[2] = {16, rows};
+    cuuint64_t strides[1] = {16 * sizeof(__half)};
+    cuuint32_t box[2] = {16, box_rows};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<__half*>(base), dims, strides, box, estr,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_32B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+        if (err) *err = "cuTensorMapEncodeTiled (k16) failed with CUresult " + std::to_string(static_cast<int>(r));
+        return 2;
+    }
+    return 0;
+}
+
+template <int BN, int STAGES, int EPI_BUFS, int HALO = 0, bool STEM16 = false, bool BRES = false>
 inline cudaError_t launch_conv_gemm_bn(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tres,
                                        const CUtensorMap& tout, const GemmArgs& args, int num_sms, cudaStream_t stream) {
-    using S = GemmSmem<BN, STAGES, EPI_BUFS, HALO>;
+    using S = GemmSmem<BN, STAGES, EPI_BUFS, HALO, STEM16, BRES>;
     static bool configured = false;
     if (!configured) {
-        cudaError_t e = cudaFuncSetAttribute(conv_gemm_f16_kernel<BN, STAGES, EPI_BUFS, HALO>,
+        cudaError_t e = cudaFuncSetAttribute(conv_gemm_f16_kernel<BN, STAGES, EPI_BUFS, HALO, STEM16, BRES>,
                                              cudaFuncAttributeMaxDynamicSharedMemorySize, S::kTotal);
         if (e != cudaSuccess) return e;
         configured = true;
@@ -63,7 +84,7 @@ inline cudaError_t launch_conv_gemm_bn(const CUtensorMap& ta, const CUtensorMap&
     const int total = args.num_m_tiles * args.num_n_tiles;
     if (total <= 0) return cudaSuccess;
     const int grid = total < num_sms ? total : num_sms;
-    return launch_k(conv_gemm_f16_kernel<BN, STAGES, EPI_BUFS, HALO>, dim3(grid), dim3(S::kThreads), S::kTotal, stream, ta, tb, tres, tout, args);
+    return launch_k(conv_gemm_f16_kernel<BN, STAGES, EPI_BUFS, HALO, STEM16, BRES>, dim3(grid), dim3(S::kThreads), S::kTotal, stream, ta, tb, tres, tout, args);
 }
 
 constexpr int kStagedTwoBufMaxKSteps = 8;
@@ -83,7 +104,10 @@ inline cudaError_t launch_conv_gemm(int bn, const CUtensorMap& ta, const CUtenso
 // 3x3 halo pipeline (taps in the standard (dy, dx) row-major order): `ta` must be a map whose box has kBlockM + 2 rows.
 // <BN, B slots, 0, A halo slots>: 3 x 17 KB + 5 x 32 KB = 211 KB for BN = 256.
 inline cudaError_t launch_conv_gemm_halo(int bn, const CUtensorMap& ta, const CUtensorMap& tb, const GemmArgs& args,
-                                         int num_sms, cudaStream_t stream) {
+                                         int num_sms, cudaStream_t stream, bool allow_resident = true) {
+    // 64 -> 64 channels (res2 conv2): all nine 8 KB weight tiles stay resident, 8 halo A slots (72 + 136 KB)
+    if (allow_resident && bn == 64 && args.kblocks_per_tap == 1 && args.num_n_tiles == 1)
+        return launch_conv_gemm_bn<64, 9, 0, 8, false, true>(ta, tb, ta, ta, args, num_sms, stream);
     switch (bn) {
         case 16: return launch_conv_gemm_bn<16, 12, 0, 4>(ta, tb, ta, ta, args, num_sms, stream);
         case 64: return launch_conv_gemm_bn<64, 12, 0, 4>(ta, tb, ta, ta, args, num_sms, stream);
@@ -123,6 +147,14 @@ inline cudaError_t launch_conv_gemm_staged(int bn, const CUtensorMap& ta, const 
     if (variant == 0) variant = (args.taps * args.kblocks_per_tap <= kStagedTwoBufMaxKSteps) ? 1 : 2;
     if (variant == 1) return launch_conv_gemm_bn<256, 2, 2>(ta, tb, tres, tout, args, num_sms, stream);
     return launch_conv_gemm_bn<256, 3, 1>(ta, tb, tres, tout, args, num_sms, stream);
+}
+
+// Stem: 4 vertical taps x (one 131 x 16 A box, 4 horizontal K = 16 MMAs), staged epilogue, Cout = 64; the weights
+// (4 x 8 KB) stay resident in shared memory and 16 A slots keep four output tiles of loads in flight.
+// `ta` from make_tmap_2d_k16 (box kBlockM + 3 rows), `tb` = [4 * 64][64] weights with 64-row boxes.
+inline cudaError_t launch_conv_gemm_stem16(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tout,
+                                           const GemmArgs& args, int num_sms, cudaStream_t stream) {
+    return launch_conv_gemm_bn<64, 4, 2, 16, true>(ta, tb, tout, tout, args, num_sms, stream);
 }
 
 // IEEE fp32 -> fp16, round to nearest even, saturating to the finite range (host-side weight preparation).

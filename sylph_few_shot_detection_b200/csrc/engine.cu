@@ -79,6 +79,7 @@ struct sylph_ctx {
     int staged_epilogue = 1;  // SYLPH_STAGED_EPILOGUE=0 falls back to the register epilogue for conv3
     int halo_pipeline = 1;    // SYLPH_HALO=0 falls back to one A box per tap for the 3x3 convolutions
     int pair_kernel = 1;      // SYLPH_PAIR=0 keeps the N = 256 3x3 convolutions on the single-CTA halo kernel
+    int stem16 = 1;           // SYLPH_STEM16=0 runs the stem over 64-wide overlapped rows instead of K = 16 taps
     std::vector<Timing> timings;
 
     // prepared weights
@@ -513,7 +514,11 @@ static int run_conv(sylph_ctx* c, const ConvCall& k, cudaStream_t st) {
     std::string err;
     const bool halo = c->halo_pipeline && W.taps == 9 && !k.stem && !k.staged;
     const bool pair = halo && c->pair_kernel && W.bn == 256 && !(k.flags & kEpiResidual);
-    if (make_tmap_2d(&ta, k.A, static_cast<uint64_t>(k.a_rows), k.a_cols, k.a_ld, halo ? kBlockM + 2 : kBlockM, &err))
+    const bool stem16 = k.stem && c->stem16 && k.staged && W.bn == 64 && W.taps == 4 && k.a_ld == 16;
+    if (stem16) {
+        if (make_tmap_2d_k16(&ta, k.A, static_cast<uint64_t>(k.a_rows), kBlockM + 3, &err))
+            return c->fail("A tensor map (%s): %s", k.name, err.c_str());
+    } else if (make_tmap_2d(&ta, k.A, static_cast<uint64_t>(k.a_rows), k.a_cols, k.a_ld, halo ? kBlockM + 2 : kBlockM, &err))
         return c->fail("A tensor map (%s): %s", k.name, err.c_str());
     if (make_tmap_2d(&tb, k.w_override ? k.w_override : W.w, static_cast<uint64_t>(W.taps) * W.cout_pad, W.k_per_tap,
                      W.k_per_tap, pair ? 128 : W.bn, &err))
@@ -560,7 +565,8 @@ static int run_conv(sylph_ctx* c, const ConvCall& k, cudaStream_t st) {
                          (k.flags & kEpiResidual) ? k.ld_res : k.ldc, kBlockM, &err) ||
             make_tmap_2d(&tout, static_cast<const __half*>(k.out), static_cast<uint64_t>(k.out_rows), k.ldc, k.ldc, kBlockM, &err))
             return c->fail("epilogue tensor maps (%s): %s", k.name, err.c_str());
-        CU_TRY(c, launch_conv_gemm_staged(W.bn, ta, tb, tres, tout, g, c->num_sms, st));
+        if (stem16) CU_TRY(c, launch_conv_gemm_stem16(ta, tb, tout, g, c->num_sms, st));
+        else CU_TRY(c, launch_conv_gemm_staged(W.bn, ta, tb, tres, tout, g, c->num_sms, st));
     } else if (pair) {
         CU_TRY(c, launch_conv3x3_pair(ta, tb, g, c->num_sms, st));
     } else if (halo) {
@@ -622,6 +628,7 @@ int sylph_create(sylph_ctx** out, int device, const sylph_model_config* cfg) {
     if (const char* e = getenv("SYLPH_STAGED_EPILOGUE")) c->staged_epilogue = atoi(e);
     if (const char* e = getenv("SYLPH_HALO")) c->halo_pipeline = atoi(e);
     if (const char* e = getenv("SYLPH_PAIR")) c->pair_kernel = atoi(e);
+    if (const char* e = getenv("SYLPH_STEM16")) c->stem16 = atoi(e);
     *out = c;
     if (cfg->pre_nms_topk * 5 > 8192) { c->fail("pre_nms_topk * 5 must be <= 8192"); }
     return 0;

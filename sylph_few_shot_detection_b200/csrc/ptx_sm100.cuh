@@ -129,6 +129,31 @@ __device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t desc_a, uint6
         "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
         : "memory");
 }
+// The four K = 16 steps of one 64-wide k-block in ONE asm block: descriptors advance by 32 bytes (2 x 16-byte units) per
+// step.  Issued separately, ptxas re-materialises the TMEM address into a uniform register (ELECT / R2UR.BROADCAST
+// loop) before EVERY tcgen05.mma -- ~60 clocks of issue latency per instruction, which starves the tensor pipe when an
+// MMA only takes 32 clocks (N = 64).  `accumulate` applies to the first step; the other three always accumulate.
+__device__ __forceinline__ void umma_f16_x4(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc,
+                                            uint32_t accumulate) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        ".reg .b64 a1, a2, a3, b1, b2, b3;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "add.s64 a1, %1, 2;\n\t"
+        "add.s64 b1, %2, 2;\n\t"
+        "add.s64 a2, %1, 4;\n\t"
+        "add.s64 b2, %2, 4;\n\t"
+        "add.s64 a3, %1, 6;\n\t"
+        "add.s64 b3, %2, 6;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], a1, b1, %3, 1;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], a2, b2, %3, 1;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], a3, b3, %3, 1;\n\t"
+        "}\n" ::"r"(tmem_d),
+        "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
 // Arrive on an mbarrier when all previously issued tcgen05.mma of this thread have completed.
 __device__ __forceinline__ void umma_commit(uint64_t* bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
@@ -170,6 +195,19 @@ __device__ __forceinline__ uint64_t make_sw128_kmajor_desc(uint32_t smem_addr) {
     d |= static_cast<uint64_t>(1024 >> 4) << 32;
     d |= static_cast<uint64_t>(1) << 46;
     d |= static_cast<uint64_t>(2) << 61;
+    return d;
+}
+
+// Same for a K-major tile whose rows are ONE 32-byte swizzle atom wide (16 fp16), written by TMA with
+// CU_TENSOR_MAP_SWIZZLE_32B: SBO = 256 B (8 rows x 32 B), layout type 6 (SWIZZLE_32B).  One tcgen05.mma (K = 16) consumes
+// the whole row; used by the stem convolution, whose K per (vertical, horizontal) tap is exactly 16 channels.
+__device__ __forceinline__ uint64_t make_sw32_kmajor_desc(uint32_t smem_addr) {
+    uint64_t d = 0;
+    d |= static_cast<uint64_t>((smem_addr & 0x3FFFF) >> 4);
+    d |= static_cast<uint64_t>(1) << 16;
+    d |= static_cast<uint64_t>(256 >> 4) << 32;
+    d |= static_cast<uint64_t>(1) << 46;
+    d |= static_cast<uint64_t>(6) << 61;
     return d;
 }
 

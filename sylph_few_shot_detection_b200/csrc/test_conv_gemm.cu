@@ -59,6 +59,7 @@ struct Case {
     bool pair = false;    // CTA-pair (cta_group::2) halo kernel
     bool halo = false;    // 3x3 halo pipeline (one 130-row A box per vertical tap and k-block)
     bool staged = false;  // TMA-in / TMA-out epilogue, run IN PLACE (out == residual buffer) like the bottleneck conv3
+    bool stem16 = false;  // stem as K = 16 taps: A map = [rows][16] with 32-byte swizzle, 131-row boxes (same math as a_ld = 16)
 };
 
 static int run_case(const Case& c, int num_sms) {
@@ -106,7 +107,8 @@ static int run_case(const Case& c, int num_sms) {
     const uint64_t a_rows_dim = (c.a_ld < c.cin_cols) ? static_cast<uint64_t>(M) - (c.cin_cols / c.a_ld - 1) : M;
     CUtensorMap ta, tb;
     std::string err;
-    if (make_tmap_2d(&ta, dA, a_rows_dim, c.cin_cols, c.a_ld, (c.halo || c.pair) ? 130 : 128, &err) ||
+    if ((c.stem16 ? make_tmap_2d_k16(&ta, dA, M, 131, &err)
+                  : make_tmap_2d(&ta, dA, a_rows_dim, c.cin_cols, c.a_ld, (c.halo || c.pair) ? 130 : 128, &err)) ||
         make_tmap_2d(&tb, dW, static_cast<uint64_t>(c.taps) * c.cout, Kt, Kt, c.pair ? 128 : c.bn, &err)) {
         printf("[%s] FAIL tensor map: %s\n", c.name, err.c_str());
         return 1;
@@ -139,7 +141,8 @@ static int run_case(const Case& c, int num_sms) {
             printf("[%s] FAIL epilogue tensor map: %s\n", c.name, err.c_str());
             return 1;
         }
-        CK(launch_conv_gemm_staged(c.bn, ta, tb, tio, tio, g, num_sms, 0));
+        if (c.stem16) CK(launch_conv_gemm_stem16(ta, tb, tio, g, num_sms, 0));
+        else CK(launch_conv_gemm_staged(c.bn, ta, tb, tio, tio, g, num_sms, 0));
     } else if (c.pair) {
         CK(launch_conv3x3_pair(ta, tb, g, num_sms, 0));
     } else if (c.halo) {
@@ -215,6 +218,7 @@ static Seg mk_seg(int row0, int H, int W, int pad) {
 }
 static int round128(int x) { return (x + 127) / 128 * 128; }
 
+static int g_dbg_skip = 0;
 static void bench_shape(const char* name, int bn, int m_tiles, int cin, int cout, int taps, int flags, int num_sms, int staged = 0, bool halo = false, bool pair = false) {
     const int M = m_tiles * 128;
     const int osz = (flags & kEpiOutF32) ? 4 : 2;
@@ -256,6 +260,7 @@ static void bench_shape(const char* name, int bn, int m_tiles, int cin, int cout
     g.num_m_tiles = m_tiles; g.num_n_tiles = cout / bn; g.taps = taps; g.kblocks_per_tap = cin / kBlockK; g.b_rows_per_tap = cout;
     for (int t = 0; t < taps; ++t) { g.tap_dy[t] = taps == 9 ? (t / 3) - 1 : 0; g.tap_dx[t] = taps == 9 ? (t % 3) - 1 : 0; }
     g.bias = dB; g.residual = dR; g.ld_res = cout; g.out = dO; g.ldc = cout; g.flags = flags; g.tile_seg = dTS; g.segs = dS; g.gn_partial = dG;
+    g.dbg_skip = g_dbg_skip;
     cudaEvent_t e0, e1;
     CK(cudaEventCreate(&e0)); CK(cudaEventCreate(&e1));
     CUtensorMap tio = ta;
@@ -290,6 +295,18 @@ int main(int argc, char** argv) {
     printf("device %s sm_%d%d SMs=%d\n", prop.name, prop.major, prop.minor, prop.multiProcessorCount);
     const int sms = prop.multiProcessorCount;
     int fails = 0;
+    if (argc > 2 && std::string(argv[1]) == "only") {   // one shape only (ncu captures): ./test_conv_gemm only <name>
+        const std::string n = argv[2];
+        if (argc > 3) g_dbg_skip = atoi(argv[3]);
+        printf("dbg_skip=%d ", g_dbg_skip);
+        if (n == "res2_conv2") bench_shape("res2_conv2_3x3_64_64_HALO", 64, 4272, 64, 64, 9, kEpiRelu | kEpiMask, sms, 0, true);
+        else if (n == "res3_conv2") bench_shape("res3_conv2_3x3_128_128_HALO", 128, 1088, 128, 128, 9, kEpiRelu | kEpiMask, sms, 0, true);
+        else if (n == "res2_conv1") bench_shape("res2_conv1_1x1_256_64_STAGED", 64, 4272, 256, 64, 1, kEpiRelu | kEpiMask, sms, 1);
+        else if (n == "res2_conv3") bench_shape("res2_conv3_1x1_64_256_res_STAGED_2x2", 256, 4272, 64, 256, 1, kEpiResidual | kEpiRelu | kEpiMask, sms, 1);
+        else if (n == "res4_conv3") bench_shape("res4_conv3_1x1_256_1024_res_STAGED_2x2", 256, 280, 256, 1024, 1, kEpiResidual | kEpiRelu | kEpiMask, sms, 1);
+        else printf("unknown shape %s\n", n.c_str());
+        return 0;
+    }
     {   // host fp32 -> fp16 conversion against the CUDA reference conversion
         int bad = 0;
         for (int i = 0; i < 2000000; ++i) {
@@ -375,6 +392,13 @@ int main(int argc, char** argv) {
         printf("bn=%d ", bnv);
         fails += run_case(c, sms);
     }
+    {   // halo pipeline with RESIDENT weights (64 -> 64 channels, res2 conv2), two planes, many tiles per CTA
+        Seg s0 = mk_seg(0, 140, 168, 1);
+        Seg s1 = mk_seg(round128(s0.nrows), 37, 41, 1);
+        Case c{"HALO_BRES_conv3x3_64_64", 64, {s0, s1}, s1.row0 + round128(s1.nrows), 64, 64, 64, 9, 1, dy9, dx9, kEpiMask | kEpiRelu, true};
+        c.halo = true;
+        fails += run_case(c, sms);
+    }
     {   // CTA pair, ODD number of M tiles (phantom tile), two planes, two N tiles, masked, fp16 out
         Seg s0 = mk_seg(0, 140, 168, 1);
         Seg s1 = mk_seg(round128(s0.nrows), 37, 41, 1);
@@ -409,6 +433,14 @@ int main(int argc, char** argv) {
         Seg s0 = mk_seg(0, 60, 70, 2);
         Case c{"STAGED_stem_overlapped_rows_bn64", 64, {s0}, round128(s0.nrows), 64, 16, 64, 4, 1, dy4, dx4, kEpiMask | kEpiRelu, true};
         c.staged = true;
+        fails += run_case(c, sms);
+    }
+    {   // stem as 16 K = 16 taps over a 32-byte-swizzled [rows][16] map; many tiles per CTA, two planes
+        Seg s0 = mk_seg(0, 150, 170, 2);
+        Seg s1 = mk_seg(round128(s0.nrows), 37, 45, 2);
+        Case c{"STEM16_sw32_k16_taps_bn64", 64, {s0, s1}, s1.row0 + round128(s1.nrows), 64, 16, 64, 4, 1, dy4, dx4, kEpiMask | kEpiRelu, true};
+        c.staged = true;
+        c.stem16 = true;
         fails += run_case(c, sms);
     }
     for (int bnv : {64, 128}) {   // staged epilogue for the narrow 1x1 convolutions (bottleneck conv1), many tiles per CTA
