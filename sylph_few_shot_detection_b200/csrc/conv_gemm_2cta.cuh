@@ -103,10 +103,13 @@ __device__ __forceinline__ void umma_commit_pair(uint64_t* bar) {
 
 }  // namespace ptx
 
-template <int HALO, int BSLOTS>
+// BN < 256 (res2 / res3 conv2): every tcgen05.mma carries ~90 clocks of fixed cost on top of its N / 2 clocks of math
+// (profiles/r01_mma_issue_experiments.md), so a single-CTA N = 64 instruction runs the tensor pipe at ~25 %; one pair
+// instruction covers 256 rows, halving the instruction count per output tile.
+template <int HALO, int BSLOTS, int BN_ = 256>
 struct Gemm2Smem {
-    static constexpr int kBN = 256;                      // output channels of the pair tile
-    static constexpr int kBHalf = 128;                   // B rows held by each CTA
+    static constexpr int kBN = BN_;                      // output channels of the pair tile
+    static constexpr int kBHalf = BN_ / 2;               // B rows held by each CTA
     static constexpr int kAHaloTx = (kBlockM + 2) * 128;
     static constexpr int kAHaloBytes = 17 * 1024;
     static constexpr int kBBytes = kBHalf * kBlockK * 2;  // 16 KiB
@@ -119,14 +122,16 @@ struct Gemm2Smem {
 
 // Tiles: pair tile index pt -> (pm, n_tile); CTA r handles output M tile 2 * pm + r.  p.num_m_tiles may be odd: the
 // phantom tile of the last pair loads zero-filled rows and stores nothing.
-template <int HALO, int BSLOTS>
+template <int HALO, int BSLOTS, int BN_ = 256>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(320, 1)
 conv3x3_pair_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
                     const GemmArgs p) {
-    using S = Gemm2Smem<HALO, BSLOTS>;
+    using S = Gemm2Smem<HALO, BSLOTS, BN_>;
     constexpr int BN = S::kBN;
     constexpr int COLS = BN / 2;
     constexpr int CH = 32;
+    constexpr int kAcc = BN <= 128 ? 4 : 2;              // accumulator buffers (see conv_gemm.cuh)
+    static_assert(BN == 64 || BN == 128 || BN == 256, "pair tile widths");
     constexpr uint32_t kTmemCols = 512;
     constexpr uint32_t kIdesc = ptx::make_idesc_f16(256, BN);
 
@@ -137,8 +142,8 @@ conv3x3_pair_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
     uint64_t* a_full = empty_bar + BSLOTS;                                    // leader only
     uint64_t* a_empty = a_full + HALO;                                        // local
     uint64_t* tmem_full = a_empty + HALO;                                     // local
-    uint64_t* tmem_empty = tmem_full + 2;                                     // leader only (count: both CTAs)
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+    uint64_t* tmem_empty = tmem_full + 4;                                     // leader only (count: both CTAs)
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + 4);
     float* gn_smem = reinterpret_cast<float*>(smem + S::kGnOffset);
 
     const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0);
@@ -159,7 +164,7 @@ conv3x3_pair_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
             ptx::mbar_init(&a_full[a], 1);
             ptx::mbar_init(&a_empty[a], 1);
         }
-        for (int a = 0; a < 2; ++a) {
+        for (int a = 0; a < kAcc; ++a) {
             ptx::mbar_init(&tmem_full[a], 1);
             ptx::mbar_init(&tmem_empty[a], 2 * 256);
         }
@@ -241,8 +246,7 @@ conv3x3_pair_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
                     if (++hs == HALO) { hs = 0; hphase ^= 1u; }
                 }
                 ptx::umma_commit_pair(&tmem_full[acc]);
-                acc ^= 1;
-                if (acc == 0) acc_phase ^= 1u;
+                if (++acc == kAcc) { acc = 0; acc_phase ^= 1u; }
             }
         }
         __syncwarp();
@@ -298,7 +302,7 @@ conv3x3_pair_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
                             f[4 * j + 0] += b.x; f[4 * j + 1] += b.y; f[4 * j + 2] += b.z; f[4 * j + 3] += b.w;
                         }
                     }
-                    if (p.flags & kEpiGnStats) {
+                    if (BN == 256 && (p.flags & kEpiGnStats)) {
 #pragma unroll
                         for (int g = 0; g < 4; ++g) {
                             float s = 0.f, ss = 0.f;
@@ -342,7 +346,7 @@ conv3x3_pair_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
             // accumulator drained: tell the leader's MMA warp (remote arrive for the second CTA of the pair)
             ptx::tc_fence_before();
             ptx::mbar_arrive_cluster(ptx::mapa_shared(ptx::smem_u32(&tmem_empty[acc]), 0));
-            if (p.flags & kEpiGnStats) {
+            if (BN == 256 && (p.flags & kEpiGnStats)) {
                 asm volatile("bar.sync 1, 256;" ::: "memory");
                 if (valid && et < 64) {
                     const float t = gn_smem[et] + gn_smem[64 + et] + gn_smem[128 + et] + gn_smem[192 + et];
@@ -350,8 +354,7 @@ conv3x3_pair_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
                 }
                 asm volatile("bar.sync 1, 256;" ::: "memory");
             }
-            acc ^= 1;
-            if (acc == 0) acc_phase ^= 1u;
+            if (++acc == kAcc) { acc = 0; acc_phase ^= 1u; }
         }
     }
 

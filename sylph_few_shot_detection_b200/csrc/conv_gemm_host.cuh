@@ -117,20 +117,34 @@ inline cudaError_t launch_conv_gemm_halo(int bn, const CUtensorMap& ta, const CU
     }
 }
 
-// CTA-pair (cta_group::2) 3x3 halo convolution, N tiles of 256: `ta` box = kBlockM + 2 rows, `tb` box = 128 rows.
-inline cudaError_t launch_conv3x3_pair(const CUtensorMap& ta, const CUtensorMap& tb, const GemmArgs& args, int num_sms,
-                                       cudaStream_t stream) {
-    using S = Gemm2Smem<3, 8>;
+// CTA-pair (cta_group::2) 3x3 halo convolution, N tiles of BN in {64, 128, 256}: `ta` box = kBlockM + 2 rows,
+// `tb` box = BN / 2 rows (each CTA of the pair holds half of the output channels of a B tile).
+template <int BN>
+inline cudaError_t launch_conv3x3_pair_bn(const CUtensorMap& ta, const CUtensorMap& tb, const GemmArgs& args, int num_sms,
+                                          cudaStream_t stream) {
+    constexpr int kHalo = BN == 256 ? 3 : 6;
+    constexpr int kBSlots = BN == 256 ? 8 : 12;
+    using S = Gemm2Smem<kHalo, kBSlots, BN>;
     static bool configured = false;
     if (!configured) {
-        cudaError_t e = cudaFuncSetAttribute(conv3x3_pair_kernel<3, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, S::kTotal);
+        cudaError_t e = cudaFuncSetAttribute(conv3x3_pair_kernel<kHalo, kBSlots, BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, S::kTotal);
         if (e != cudaSuccess) return e;
         configured = true;
     }
     const int pairs = ((args.num_m_tiles + 1) / 2) * args.num_n_tiles;
     if (pairs <= 0) return cudaSuccess;
     const int clusters = pairs < num_sms / 2 ? pairs : num_sms / 2;
-    return launch_k(conv3x3_pair_kernel<3, 8>, dim3(clusters * 2), dim3(S::kThreads), S::kTotal, stream, ta, tb, args);
+    return launch_k(conv3x3_pair_kernel<kHalo, kBSlots, BN>, dim3(clusters * 2), dim3(S::kThreads), S::kTotal, stream, ta, tb, args);
+}
+
+inline cudaError_t launch_conv3x3_pair(const CUtensorMap& ta, const CUtensorMap& tb, const GemmArgs& args, int num_sms,
+                                       cudaStream_t stream, int bn = 256) {
+    switch (bn) {
+        case 64: return launch_conv3x3_pair_bn<64>(ta, tb, args, num_sms, stream);
+        case 128: return launch_conv3x3_pair_bn<128>(ta, tb, args, num_sms, stream);
+        case 256: return launch_conv3x3_pair_bn<256>(ta, tb, args, num_sms, stream);
+        default: return cudaErrorInvalidValue;
+    }
 }
 
 // Staged (TMA in / TMA out) epilogue, fp16 output: `tres` / `tout` are [rows][C] maps with 128 x 64 boxes.

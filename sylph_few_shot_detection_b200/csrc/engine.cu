@@ -78,7 +78,8 @@ struct sylph_ctx {
     bool profiling = false;
     int staged_epilogue = 1;  // SYLPH_STAGED_EPILOGUE=0 falls back to the register epilogue for conv3
     int halo_pipeline = 1;    // SYLPH_HALO=0 falls back to one A box per tap for the 3x3 convolutions
-    int pair_kernel = 1;      // SYLPH_PAIR=0 keeps the N = 256 3x3 convolutions on the single-CTA halo kernel
+    int pair_kernel = 1;      // SYLPH_PAIR: bit 0 = CTA-pair kernel for the N = 256 3x3 convolutions, bit 1 = also for N = 64 /
+                              // 128 (measured SLOWER than the single-CTA halo kernel: profiles/r01_mma_issue_experiments.md)
     int stem16 = 1;           // SYLPH_STEM16=0 runs the stem over 64-wide overlapped rows instead of K = 16 taps
     std::vector<Timing> timings;
 
@@ -513,7 +514,7 @@ static int run_conv(sylph_ctx* c, const ConvCall& k, cudaStream_t st) {
     CUtensorMap ta, tb;
     std::string err;
     const bool halo = c->halo_pipeline && W.taps == 9 && !k.stem && !k.staged;
-    const bool pair = halo && c->pair_kernel && W.bn == 256 && !(k.flags & kEpiResidual);
+    const bool pair = halo && c->pair_kernel && (W.bn == 256 || ((c->pair_kernel & 2) && W.bn >= 64)) && !(k.flags & kEpiResidual);
     const bool stem16 = k.stem && c->stem16 && k.staged && W.bn == 64 && W.taps == 4 && k.a_ld == 16;
     if (stem16) {
         if (make_tmap_2d_k16(&ta, k.A, static_cast<uint64_t>(k.a_rows), kBlockM + 3, &err))
@@ -521,7 +522,7 @@ static int run_conv(sylph_ctx* c, const ConvCall& k, cudaStream_t st) {
     } else if (make_tmap_2d(&ta, k.A, static_cast<uint64_t>(k.a_rows), k.a_cols, k.a_ld, halo ? kBlockM + 2 : kBlockM, &err))
         return c->fail("A tensor map (%s): %s", k.name, err.c_str());
     if (make_tmap_2d(&tb, k.w_override ? k.w_override : W.w, static_cast<uint64_t>(W.taps) * W.cout_pad, W.k_per_tap,
-                     W.k_per_tap, pair ? 128 : W.bn, &err))
+                     W.k_per_tap, pair ? W.bn / 2 : W.bn, &err))
         return c->fail("B tensor map (%s): %s", k.name, err.c_str());
     GemmArgs g{};
     g.tile_begin = k.tile_begin;
@@ -568,7 +569,7 @@ static int run_conv(sylph_ctx* c, const ConvCall& k, cudaStream_t st) {
         if (stem16) CU_TRY(c, launch_conv_gemm_stem16(ta, tb, tout, g, c->num_sms, st));
         else CU_TRY(c, launch_conv_gemm_staged(W.bn, ta, tb, tres, tout, g, c->num_sms, st));
     } else if (pair) {
-        CU_TRY(c, launch_conv3x3_pair(ta, tb, g, c->num_sms, st));
+        CU_TRY(c, launch_conv3x3_pair(ta, tb, g, c->num_sms, st, W.bn));
     } else if (halo) {
         CU_TRY(c, launch_conv_gemm_halo(W.bn, ta, tb, g, c->num_sms, st));
     } else {

@@ -109,7 +109,7 @@ static int run_case(const Case& c, int num_sms) {
     std::string err;
     if ((c.stem16 ? make_tmap_2d_k16(&ta, dA, M, 131, &err)
                   : make_tmap_2d(&ta, dA, a_rows_dim, c.cin_cols, c.a_ld, (c.halo || c.pair) ? 130 : 128, &err)) ||
-        make_tmap_2d(&tb, dW, static_cast<uint64_t>(c.taps) * c.cout, Kt, Kt, c.pair ? 128 : c.bn, &err)) {
+        make_tmap_2d(&tb, dW, static_cast<uint64_t>(c.taps) * c.cout, Kt, Kt, c.pair ? c.bn / 2 : c.bn, &err)) {
         printf("[%s] FAIL tensor map: %s\n", c.name, err.c_str());
         return 1;
     }
@@ -144,7 +144,7 @@ static int run_case(const Case& c, int num_sms) {
         if (c.stem16) CK(launch_conv_gemm_stem16(ta, tb, tio, g, num_sms, 0));
         else CK(launch_conv_gemm_staged(c.bn, ta, tb, tio, tio, g, num_sms, 0));
     } else if (c.pair) {
-        CK(launch_conv3x3_pair(ta, tb, g, num_sms, 0));
+        CK(launch_conv3x3_pair(ta, tb, g, num_sms, 0, c.bn));
     } else if (c.halo) {
         CK(launch_conv_gemm_halo(c.bn, ta, tb, g, num_sms, 0));
     } else {
@@ -252,7 +252,7 @@ static void bench_shape(const char* name, int bn, int m_tiles, int cin, int cout
     }
     CUtensorMap ta, tb;
     std::string err;
-    if (make_tmap_2d(&ta, dA, M, cin, cin, (halo || pair) ? 130 : 128, &err) || make_tmap_2d(&tb, dW, static_cast<uint64_t>(taps) * cout, cin, cin, pair ? 128 : bn, &err)) {
+    if (make_tmap_2d(&ta, dA, M, cin, cin, (halo || pair) ? 130 : 128, &err) || make_tmap_2d(&tb, dW, static_cast<uint64_t>(taps) * cout, cin, cin, pair ? bn / 2 : bn, &err)) {
         printf("[%s] tensor map failed: %s\n", name, err.c_str());
         return;
     }
@@ -268,7 +268,7 @@ static void bench_shape(const char* name, int bn, int m_tiles, int cin, int cout
         g.residual = static_cast<const __half*>(dO);
         if (make_tmap_2d(&tio, static_cast<const __half*>(dO), M, cout, cout, 128, &err)) { printf("tmap failed\n"); return; }
     }
-    auto launch = [&]() { return staged ? launch_conv_gemm_staged(bn, ta, tb, tio, tio, g, num_sms, 0, staged) : (pair ? launch_conv3x3_pair(ta, tb, g, num_sms, 0) : (halo ? launch_conv_gemm_halo(bn, ta, tb, g, num_sms, 0) : launch_conv_gemm(bn, ta, tb, g, num_sms, 0))); };
+    auto launch = [&]() { return staged ? launch_conv_gemm_staged(bn, ta, tb, tio, tio, g, num_sms, 0, staged) : (pair ? launch_conv3x3_pair(ta, tb, g, num_sms, 0, bn) : (halo ? launch_conv_gemm_halo(bn, ta, tb, g, num_sms, 0) : launch_conv_gemm(bn, ta, tb, g, num_sms, 0))); };
     for (int i = 0; i < 3; ++i) CK(launch());
     CK(cudaDeviceSynchronize());
     const int iters = 10;
@@ -300,6 +300,8 @@ int main(int argc, char** argv) {
         if (argc > 3) g_dbg_skip = atoi(argv[3]);
         printf("dbg_skip=%d ", g_dbg_skip);
         if (n == "res2_conv2") bench_shape("res2_conv2_3x3_64_64_HALO", 64, 4272, 64, 64, 9, kEpiRelu | kEpiMask, sms, 0, true);
+        else if (n == "res2_conv2_pair") bench_shape("res2_conv2_3x3_64_64_PAIR", 64, 4272, 64, 64, 9, kEpiRelu | kEpiMask, sms, 0, false, true);
+        else if (n == "res3_conv2_pair") bench_shape("res3_conv2_3x3_128_128_PAIR", 128, 1088, 128, 128, 9, kEpiRelu | kEpiMask, sms, 0, false, true);
         else if (n == "res3_conv2") bench_shape("res3_conv2_3x3_128_128_HALO", 128, 1088, 128, 128, 9, kEpiRelu | kEpiMask, sms, 0, true);
         else if (n == "res2_conv1") bench_shape("res2_conv1_1x1_256_64_STAGED", 64, 4272, 256, 64, 1, kEpiRelu | kEpiMask, sms, 1);
         else if (n == "res2_conv3") bench_shape("res2_conv3_1x1_64_256_res_STAGED_2x2", 256, 4272, 64, 256, 1, kEpiResidual | kEpiRelu | kEpiMask, sms, 1);
@@ -406,6 +408,16 @@ int main(int argc, char** argv) {
         if ((total / 128) % 2 == 0) total += 128;
         Case c{"PAIR_conv3x3_n512_mask_relu", 256, {s0, s1}, total, 128, 128, 512, 9, 2, dy9, dx9, kEpiMask | kEpiRelu, true};
         c.pair = true;
+        fails += run_case(c, sms);
+    }
+    for (int bnv : {64, 128}) {   // narrow CTA-pair tiles (res2 / res3 conv2): odd tile count, two planes, many tiles per pair
+        Seg s0 = mk_seg(0, 140, 168, 1);
+        Seg s1 = mk_seg(round128(s0.nrows), 37, 41, 1);
+        int total = s1.row0 + round128(s1.nrows);
+        if ((total / 128) % 2 == 0) total += 128;
+        Case c{"PAIR_conv3x3_narrow_mask_relu", bnv, {s0, s1}, total, bnv, bnv, bnv, 9, bnv / 64, dy9, dx9, kEpiMask | kEpiRelu, true};
+        c.pair = true;
+        printf("bn=%d ", bnv);
         fails += run_case(c, sms);
     }
     {   // CTA pair + GroupNorm statistics + fp32 output (the tower configuration)
