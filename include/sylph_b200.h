@@ -116,7 +116,7 @@ int sylph_export_features(sylph_ctx* ctx, int slot, int level, float* out_dev, v
  * ROIAlign -> conv3x3+GN+ReLU -> MS_CAM context gate -> tokenizer -> transformer encoder -> class-token mean ->
  * weight / bias hyper-network heads; a row is then the FINAL code (bias includes the -log((1-p)/p) prior) and
  * sylph_normalize_codes is not applicable. */
-int sylph_generate_codes(sylph_ctx* ctx, int slot, int n_rois, const float* boxes_host, const int* roi_image,
+int sylph_generate_codes(sylph_ctx* ctx, int slot, int n_rois, const float* boxes_host /* host OR device pointer */, const int* roi_image,
                          int n_classes, const int* class_offsets, float* codes_out_dev, int64_t* levels_out_dev,
                          void* stream);
 

@@ -115,6 +115,8 @@ struct sylph_ctx {
     // point has to drain the stream (a pageable cudaMemcpyAsync synchronises the stream first)
     uint8_t* pinned = nullptr;
     size_t pinned_cap = 0, pinned_head = 0;
+    uint8_t* graph_arena = nullptr;  // pinned argument blocks referenced by captured CUDA graphs (bump-allocated)
+    size_t graph_arena_cap = 0, graph_arena_head = 0;
     std::map<std::string, std::shared_ptr<PlaneSet>> plane_sets;
     Slot slots[SYLPH_NUM_SLOTS];
     // state of the last generate_codes / detect call (for exports)
@@ -167,9 +169,25 @@ static int ensure(sylph_ctx* c, const std::string& name, size_t bytes, const std
 }
 
 // Copy `bytes` of host data to device memory through the pinned ring, stream-ordered, without blocking the host.
+// While the stream is being CAPTURED into a CUDA graph the copy node would re-read the ring slot at every replay, so
+// captured copies take a block of a separate pinned arena that is never reused (released with the context).
 static int stage_h2d(sylph_ctx* c, void* dst_dev, const void* src_host, size_t bytes, cudaStream_t st) {
     if (bytes == 0) return 0;
     const size_t need = (bytes + 255) & ~size_t(255);
+    cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
+    if (c->graph_arena == nullptr) {   // allocated outside any capture (allocation calls are illegal while capturing)
+        c->graph_arena_cap = size_t(2) << 20;
+        CU_TRY(c, cudaMallocHost(reinterpret_cast<void**>(&c->graph_arena), c->graph_arena_cap));
+    }
+    if (cudaStreamIsCapturing(st, &cap) == cudaSuccess && cap == cudaStreamCaptureStatusActive) {
+        if (c->graph_arena_head + need > c->graph_arena_cap)
+            return c->fail("pinned argument arena for captured CUDA graphs is exhausted (%zu bytes)", c->graph_arena_cap);
+        uint8_t* block = c->graph_arena + c->graph_arena_head;   // never reused: the graph re-reads it at every replay
+        c->graph_arena_head += need;
+        memcpy(block, src_host, bytes);
+        CU_TRY(c, cudaMemcpyAsync(dst_dev, block, bytes, cudaMemcpyHostToDevice, st));
+        return 0;
+    }
     if (c->pinned == nullptr || need > c->pinned_cap) {
         if (c->pinned) { CU_TRY(c, cudaDeviceSynchronize()); CU_TRY(c, cudaFreeHost(c->pinned)); }
         c->pinned_cap = std::max<size_t>(need * 2, size_t(4) << 20);
@@ -641,6 +659,7 @@ void sylph_destroy(sylph_ctx* c) {
     cudaDeviceSynchronize();
     for (auto& kv : c->bufs) if (kv.second.p) cudaFree(kv.second.p);
     if (c->pinned) cudaFreeHost(c->pinned);
+    if (c->graph_arena) cudaFreeHost(c->graph_arena);
     for (auto& kv : c->plane_sets) { cudaFree(kv.second->d_segs); cudaFree(kv.second->d_tile_seg); }
     delete c;  // prepared weights are released with the CUDA context
 }
@@ -1273,7 +1292,13 @@ int sylph_generate_codes(sylph_ctx* c, int slot, int n_rois, const float* boxes_
     TRY(ensure(c, "cg.gn_partial", static_cast<size_t>(n_rois) * 64 * 4, "", &gp, st, false));
     TRY(ensure(c, "cg.gn_stats", static_cast<size_t>(n_rois) * 64 * 4, "", &gs, st, false));
     TRY(ensure(c, "cg.shot", static_cast<size_t>(n_rois) * 257 * 4, "", &sc, st, false));
-    TRY(stage_h2d(c, pb, boxes_host, static_cast<size_t>(n_rois) * 16, st));
+    {   // the boxes may already live on the device (a static buffer refreshed between CUDA-graph replays)
+        cudaPointerAttributes pa{};
+        const bool on_device = cudaPointerGetAttributes(&pa, boxes_host) == cudaSuccess && pa.type == cudaMemoryTypeDevice;
+        if (!on_device) cudaGetLastError();   // plain host memory is reported as an error by older drivers: clear it
+        if (on_device) pb = const_cast<float*>(boxes_host);
+        else TRY(stage_h2d(c, pb, boxes_host, static_cast<size_t>(n_rois) * 16, st));
+    }
     TRY(stage_h2d(c, pi, roi_image, static_cast<size_t>(n_rois) * 4, st));
     TRY(stage_h2d(c, po, class_offsets, static_cast<size_t>(n_classes + 1) * 4, st));
     // plane set of the ROI planes (one 9x9 plane = one tile per ROI); grows with the largest ROI count seen

@@ -320,6 +320,56 @@ class EpisodePipeline:
         return out
 
 
+class EpisodeGraph:
+    """One meta-test episode of FIXED shape (classes x shots, query count, image size) captured into a CUDA graph: the
+    ~125 kernel launches of support backbone + code generation + normalisation + query backbone + head + proposals
+    replay as ONE graph launch, programmatic-dependent-launch edges included.  Inputs live in static device buffers:
+
+        g = EpisodeGraph(model, n_way=5, n_shot=5, n_query=8, image_hw=(800, 1333))
+        g.support[i].copy_(img); g.query[j].copy_(img); g.boxes.copy_(boxes_xyxy)     # any stream-ordered writes
+        dets, counts = g.replay()          # (n_query, max_dets, 9) detections and per-image counts, device tensors
+
+    Results are bit-identical to the eager calls (same kernels, same order; tests/test_gpu_cases.py)."""
+
+    def __init__(self, model: MetaOneStageDetector, n_way: int, n_shot: int, n_query: int, image_hw, warmup: int = 2):
+        from .runtime import SLOT_QUERY, SLOT_SUPPORT
+        self.model, self.eng = model, model.engine
+        dev = model.device
+        h, w = image_hw
+        self.support = [torch.zeros((3, h, w), dtype=torch.uint8, device=dev) for _ in range(n_way * n_shot)]
+        self.query = [torch.zeros((3, h, w), dtype=torch.uint8, device=dev) for _ in range(n_query)]
+        self.boxes = torch.tensor([[0.25 * w, 0.25 * h, 0.75 * w, 0.75 * h]] * (n_way * n_shot), dtype=torch.float32, device=dev)
+        self._roi_image = list(range(n_way * n_shot))
+        self._offsets = list(range(0, n_way * n_shot + 1, n_shot))
+        self._slots = (SLOT_SUPPORT, SLOT_QUERY)
+        side = torch.cuda.Stream(device=dev)
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            for _ in range(max(warmup, 1)):      # allocations, plane tables and kernel attributes settle before capture
+                self._run()
+        torch.cuda.current_stream().wait_stream(side)
+        torch.cuda.synchronize()
+        self.graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self.graph):
+            self.dets, self.counts = self._run()
+
+    def _run(self):
+        sup_slot, qry_slot = self._slots
+        self.eng.extract_features_multi([(sup_slot, self.support), (qry_slot, self.query)])
+        raw = self.eng.generate_codes(sup_slot, self.boxes, self._roi_image, self._offsets)
+        self.codes = self.eng.normalize_codes(raw) if not isinstance(self.model.code_generator, _roi_encoder_type()) else raw
+        return self.eng.detect(qry_slot, self.codes)
+
+    def replay(self):
+        self.graph.replay()
+        return self.dets, self.counts
+
+
+def _roi_encoder_type():
+    from .modeling import ROIEncoder
+    return ROIEncoder
+
+
 class MetaFCOSRunner:
     """The d2go-runner surface the reference CLI drives (`create_runner("sylph.runner.MetaFCOSRunner")`,
     sylph/runner/meta_fcos_runner.py:92-114, 381-382, 674-701), reduced to the inference hot path."""

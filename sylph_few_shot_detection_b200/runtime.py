@@ -165,7 +165,8 @@ class Engine:
     # ------------------------------------------------------------------ class codes
     def generate_codes(self, slot: int, boxes: torch.Tensor, roi_image: Sequence[int], class_offsets: Sequence[int],
                        want_levels: bool = False):
-        boxes = boxes.detach().to("cpu", torch.float32).contiguous()
+        # host boxes are staged through the pinned ring; a CUDA tensor is read in place (static buffer of a CUDA graph)
+        boxes = boxes.detach().to(torch.float32).contiguous()
         n_rois, n_classes = boxes.shape[0], len(class_offsets) - 1
         codes = torch.empty((n_classes, CODE_STRIDE), device=self.device, dtype=torch.float32)
         levels = torch.empty((n_rois,), device=self.device, dtype=torch.int64) if want_levels else None
@@ -174,6 +175,7 @@ class Engine:
         self._check(self.lib.sylph_generate_codes(
             self.h, slot, n_rois, ctypes.cast(c_void_p(boxes.data_ptr()), POINTER(c_float)), ri, n_classes, co,
             c_void_p(codes.data_ptr()), c_void_p(levels.data_ptr()) if want_levels else None, self._stream()))
+        self._keep_boxes = boxes   # keep the argument alive until the stream work has run
         return (codes, levels) if want_levels else codes
 
     def export_roi_features(self, n_rois: int) -> torch.Tensor:

@@ -282,3 +282,32 @@ def test_merged_trunk_pass_is_bit_identical_to_separate_passes():
                       [{"image": ims[4].cuda(), "height": 160, "width": 224}])
     assert torch.equal(host[0]["instances"].pred_boxes.tensor, dev[0]["instances"].pred_boxes.tensor)
     assert torch.equal(host[0]["instances"].scores, dev[0]["instances"].scores)
+
+
+def test_cuda_graph_episode_replays_bit_identically():
+    """runner.EpisodeGraph: the whole episode captured into one CUDA graph (PDL edges included); replays with new
+    images / boxes written into the static buffers equal the eager calls bit for bit."""
+    from sylph_few_shot_detection_b200.runner import EpisodeGraph
+    from sylph_few_shot_detection_b200.runtime import SLOT_QUERY, SLOT_SUPPORT
+    cfg, state, model, orc = _setup(seed=4)
+    eng = model.engine
+    g = EpisodeGraph(model, n_way=2, n_shot=2, n_query=2, image_hw=(160, 224))
+    for rep, seed in enumerate((3, 8)):
+        ims = [im.cuda() for im in _images(6, 160, 224, seed)]
+        boxes = torch.tensor([[20.0, 30.0, 120.0, 140.0], [5.0, 5.0, 200.0, 150.0], [40.0, 20.0, 180.0, 100.0],
+                              [60.0 + 5 * rep, 50.0, 140.0, 150.0]])
+        for dst, src in zip(g.support, ims[:4]):
+            dst.copy_(src)
+        for dst, src in zip(g.query, ims[4:]):
+            dst.copy_(src)
+        g.boxes.copy_(boxes)
+        dets, counts = g.replay()
+        dets, counts = dets.clone(), counts.clone()
+        eng.extract_features(SLOT_SUPPORT, ims[:4])
+        raw = eng.generate_codes(SLOT_SUPPORT, boxes, [0, 1, 2, 3], [0, 2, 4])
+        codes = eng.normalize_codes(raw)
+        assert torch.equal(codes, g.codes)
+        eng.extract_features(SLOT_QUERY, ims[4:])
+        d2, c2 = eng.detect(SLOT_QUERY, codes)
+        assert torch.equal(counts, c2) and torch.equal(dets, d2)
+        assert int(counts.sum()) > 0
