@@ -970,7 +970,7 @@ static int run_fpn(sylph_ctx* c, int slot, const TrunkOut& T, int first, int n, 
         k.W = &c->lat[l]; k.A = XS; k.a_rows = static_cast<long long>(T.n) * g.rows_per_img; k.a_cols = k.a_ld = 512 << l; k.ps = S.ps.get();
         k.tile_begin = static_cast<int>(S.level_row0[l] / kBlockM); k.n_tiles = static_cast<int>(rows / kBlockM);
         k.a_row_delta = -static_cast<int>(S.level_row0[l]) + first * g.rows_per_img; k.out = LAT; k.ldc = 256;
-        k.flags = kEpiMask; k.name = "fpn.lateral1x1";
+        k.flags = kEpiMask; k.name = "fpn.lateral1x1";   // direct epilogue: the staged variant measured slower here (K >= 512)
         TRY(run_conv(c, k, st));
         if (l < 2) {
             StageTimer t(c, "fpn.upsample_add", st, static_cast<double>(n) * g.H * g.W * 256 * 2 * 2.25);

@@ -176,15 +176,15 @@ fcos_nms_kernel(const unsigned long long* __restrict__ sel, const int* __restric
     }
     __syncthreads();
     // ---- bitonic sort, descending
+    // every thread owns whole compare-exchange pairs (q -> i with bit j clear, partner i | j): no idle half
     for (int k = 2; k <= sort_n; k <<= 1) {
         for (int j = k >> 1; j > 0; j >>= 1) {
-            for (int i = tid; i < sort_n; i += blockDim.x) {
-                const int ixj = i ^ j;
-                if (ixj > i) {
-                    const unsigned long long a = keys[i], b = keys[ixj];
-                    const bool desc = (i & k) == 0;
-                    if (desc ? (a < b) : (a > b)) { keys[i] = b; keys[ixj] = a; }
-                }
+            for (int q = tid; q < (sort_n >> 1); q += blockDim.x) {
+                const int i = ((q & ~(j - 1)) << 1) | (q & (j - 1));
+                const int ixj = i | j;
+                const unsigned long long a = keys[i], b = keys[ixj];
+                const bool desc = (i & k) == 0;
+                if (desc ? (a < b) : (a > b)) { keys[i] = b; keys[ixj] = a; }
             }
             __syncthreads();
         }
