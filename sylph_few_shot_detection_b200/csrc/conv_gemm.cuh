@@ -118,9 +118,26 @@ struct GemmSmem {
     static constexpr int kThreads = TMA_EPI ? 352 : 320;
 };
 
+// fp32 pair -> packed fp16x2 (a in the low half), round to nearest, saturating to +-65504: ONE F2FP.SATFINITE
+// instruction instead of four clamps and a convert -- the epilogue of a narrow tile is instruction-bound.
 __device__ __forceinline__ uint32_t pack_half2(float a, float b) {
-    const __half2 h = __floats2half2_rn(fminf(fmaxf(a, -kHalfMax), kHalfMax), fminf(fmaxf(b, -kHalfMax), kHalfMax));
-    return *reinterpret_cast<const uint32_t*>(&h);
+    uint32_t r;
+    asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(b), "f"(a));
+    return r;
+}
+// same with the ReLU folded into the conversion
+__device__ __forceinline__ uint32_t pack_half2_relu(float a, float b) {
+    uint32_t r;
+    asm("cvt.rn.relu.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(b), "f"(a));
+    return r;
+}
+// 8 fp32 -> uint4 of fp16 with optional ReLU; zero when the row is masked out
+__device__ __forceinline__ uint4 pack8(const float* f, bool relu, bool keep) {
+    uint4 o;
+    if (relu) { o.x = pack_half2_relu(f[0], f[1]); o.y = pack_half2_relu(f[2], f[3]); o.z = pack_half2_relu(f[4], f[5]); o.w = pack_half2_relu(f[6], f[7]); }
+    else { o.x = pack_half2(f[0], f[1]); o.y = pack_half2(f[2], f[3]); o.z = pack_half2(f[4], f[5]); o.w = pack_half2(f[6], f[7]); }
+    if (!keep) o = make_uint4(0u, 0u, 0u, 0u);
+    return o;
 }
 __device__ __forceinline__ float2 unpack_half2(uint32_t u) {
     return __half22float2(*reinterpret_cast<const __half2*>(&u));
@@ -499,19 +516,12 @@ conv_gemm_f16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_co
                             f[8 * j + 4] += c.x; f[8 * j + 5] += c.y; f[8 * j + 6] += d.x; f[8 * j + 7] += d.y;
                         }
                     }
-                    if (p.flags & kEpiRelu) {
+                    {
+                        const bool relu = (p.flags & kEpiRelu) != 0;
 #pragma unroll
-                        for (int j = 0; j < CH; ++j) f[j] = fmaxf(f[j], 0.f);
+                        for (int j = 0; j < CH / 8; ++j)
+                            *reinterpret_cast<uint4*>(panel + (((ch16 + j) ^ (r_in_tile & 7)) << 4)) = pack8(f + 8 * j, relu, keep);
                     }
-                    if (!keep) {
-#pragma unroll
-                        for (int j = 0; j < CH; ++j) f[j] = 0.f;
-                    }
-#pragma unroll
-                    for (int j = 0; j < CH / 8; ++j)
-                        *reinterpret_cast<uint4*>(panel + (((ch16 + j) ^ (r_in_tile & 7)) << 4)) =
-                            make_uint4(pack_half2(f[8 * j], f[8 * j + 1]), pack_half2(f[8 * j + 2], f[8 * j + 3]),
-                                       pack_half2(f[8 * j + 4], f[8 * j + 5]), pack_half2(f[8 * j + 6], f[8 * j + 7]));
                 }
                 ptx::tc_fence_before();
                 ptx::fence_proxy_async();          // generic-proxy smem writes -> visible to the TMA store
@@ -590,26 +600,25 @@ conv_gemm_f16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_co
                             f[8 * j + 4] += c.x; f[8 * j + 5] += c.y; f[8 * j + 6] += d.x; f[8 * j + 7] += d.y;
                         }
                     }
-                    if (p.flags & kEpiRelu) {
-#pragma unroll
-                        for (int j = 0; j < CH; ++j) f[j] = fmaxf(f[j], 0.f);
-                    }
-                    if (!keep) {
-#pragma unroll
-                        for (int j = 0; j < CH; ++j) f[j] = 0.f;
-                    }
                     if (p.dbg_skip & 1) {
                         if (f[0] == 12345.678f) static_cast<float*>(p.out)[0] = f[1];   // keep the math alive
                     } else if (p.flags & kEpiOutF32) {
+                        if (p.flags & kEpiRelu) {
+#pragma unroll
+                            for (int j = 0; j < CH; ++j) f[j] = fmaxf(f[j], 0.f);
+                        }
+                        if (!keep) {
+#pragma unroll
+                            for (int j = 0; j < CH; ++j) f[j] = 0.f;
+                        }
                         float4* op = reinterpret_cast<float4*>(static_cast<float*>(p.out) + out_off + c0);
 #pragma unroll
                         for (int j = 0; j < CH / 4; ++j) op[j] = make_float4(f[4 * j], f[4 * j + 1], f[4 * j + 2], f[4 * j + 3]);
                     } else {
+                        const bool relu = (p.flags & kEpiRelu) != 0;
                         uint4* op = reinterpret_cast<uint4*>(static_cast<__half*>(p.out) + out_off + c0);
 #pragma unroll
-                        for (int j = 0; j < CH / 8; ++j)
-                            op[j] = make_uint4(pack_half2(f[8 * j], f[8 * j + 1]), pack_half2(f[8 * j + 2], f[8 * j + 3]),
-                                               pack_half2(f[8 * j + 4], f[8 * j + 5]), pack_half2(f[8 * j + 6], f[8 * j + 7]));
+                        for (int j = 0; j < CH / 8; ++j) op[j] = pack8(f + 8 * j, relu, keep);
                     }
                 }
                 // accumulator buffer fully read: hand it back to the MMA warp (one arrive per warp)

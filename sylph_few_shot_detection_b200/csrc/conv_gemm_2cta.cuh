@@ -322,24 +322,23 @@ conv3x3_pair_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
                             }
                         }
                     }
-                    if (p.flags & kEpiRelu) {
-#pragma unroll
-                        for (int j = 0; j < CH; ++j) f[j] = fmaxf(f[j], 0.f);
-                    }
-                    if (!keep) {
-#pragma unroll
-                        for (int j = 0; j < CH; ++j) f[j] = 0.f;
-                    }
                     if (p.flags & kEpiOutF32) {
+                        if (p.flags & kEpiRelu) {
+#pragma unroll
+                            for (int j = 0; j < CH; ++j) f[j] = fmaxf(f[j], 0.f);
+                        }
+                        if (!keep) {
+#pragma unroll
+                            for (int j = 0; j < CH; ++j) f[j] = 0.f;
+                        }
                         float4* op = reinterpret_cast<float4*>(static_cast<float*>(p.out) + out_off + c0);
 #pragma unroll
                         for (int j = 0; j < CH / 4; ++j) op[j] = make_float4(f[4 * j], f[4 * j + 1], f[4 * j + 2], f[4 * j + 3]);
                     } else {
+                        const bool relu = (p.flags & kEpiRelu) != 0;
                         uint4* op = reinterpret_cast<uint4*>(static_cast<__half*>(p.out) + out_off + c0);
 #pragma unroll
-                        for (int j = 0; j < CH / 8; ++j)
-                            op[j] = make_uint4(pack_half2(f[8 * j], f[8 * j + 1]), pack_half2(f[8 * j + 2], f[8 * j + 3]),
-                                               pack_half2(f[8 * j + 4], f[8 * j + 5]), pack_half2(f[8 * j + 6], f[8 * j + 7]));
+                        for (int j = 0; j < CH / 8; ++j) op[j] = pack8(f + 8 * j, relu, keep);
                     }
                 }
             }

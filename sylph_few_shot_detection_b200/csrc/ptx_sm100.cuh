@@ -49,15 +49,36 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
         : "memory");
     return ok != 0;
 }
+// try_wait with a suspend-time hint: the hardware parks the thread until the phase completes or ~`ns` elapse, instead
+// of returning at once -- a spinning producer / MMA thread otherwise burns the issue slots (and the power budget) of the
+// epilogue warps that share its scheduler.
+__device__ __forceinline__ bool mbar_try_wait_hint(uint64_t* bar, uint32_t parity, uint32_t ns) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t"
+        "}\n"
+        : "=r"(ok)
+        : "r"(smem_u32(bar)), "r"(parity), "r"(ns)
+        : "memory");
+    return ok != 0;
+}
 // Bounded wait: a descriptor / phase bug must surface as a trapped kernel, never as a hung GPU.
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
     if (mbar_try_wait(bar, parity)) return;
-    long long t0 = clock64();
-    while (!mbar_try_wait(bar, parity)) {
-        if (clock64() - t0 > 4000000000LL) {  // ~2 s at 2 GHz
-            printf("sylph: mbarrier wait timeout block %d thread %d bar %u parity %u\n", blockIdx.x, threadIdx.x,
-                   smem_u32(bar), parity);
-            __trap();
+    uint32_t spins = 0;
+    long long t0 = 0;
+    while (!mbar_try_wait_hint(bar, parity, 20000u)) {
+        if ((++spins & 63u) == 0u) {   // look at the clock only every 64 parked waits
+            const long long now = clock64();
+            if (t0 == 0) t0 = now;
+            if (now - t0 > 4000000000LL) {  // ~2 s at 2 GHz
+                printf("sylph: mbarrier wait timeout block %d thread %d bar %u parity %u\n", blockIdx.x, threadIdx.x,
+                       smem_u32(bar), parity);
+                __trap();
+            }
         }
     }
 }

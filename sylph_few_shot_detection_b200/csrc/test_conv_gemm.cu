@@ -62,7 +62,9 @@ struct Case {
     bool stem16 = false;  // stem as K = 16 taps: A map = [rows][16] with 32-byte swizzle, 131-row boxes (same math as a_ld = 16)
 };
 
+static std::string g_case_filter;   // ./test_conv_gemm case <substring>: run only the matching correctness cases
 static int run_case(const Case& c, int num_sms) {
+    if (!g_case_filter.empty() && std::string(c.name).find(g_case_filter) == std::string::npos) return 0;
     const int M = c.total_rows;
     const int Kt = c.kpt * kBlockK;
     const size_t a_elems = static_cast<size_t>(M) * c.a_ld + 128;
@@ -295,6 +297,7 @@ int main(int argc, char** argv) {
     printf("device %s sm_%d%d SMs=%d\n", prop.name, prop.major, prop.minor, prop.multiProcessorCount);
     const int sms = prop.multiProcessorCount;
     int fails = 0;
+    if (argc > 2 && std::string(argv[1]) == "case") g_case_filter = argv[2];
     if (argc > 2 && std::string(argv[1]) == "only") {   // one shape only (ncu captures): ./test_conv_gemm only <name>
         const std::string n = argv[2];
         if (argc > 3) g_dbg_skip = atoi(argv[3]);
