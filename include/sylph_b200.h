@@ -154,6 +154,43 @@ int sylph_detect(sylph_ctx* ctx, int slot, const float* codes_dev, int n_classes
  * 1 bbox_reg after scale+ReLU (n, 4, H, W), 2 ctrness (n, 1, H, W), 3 iou (n, 1, H, W). */
 int sylph_export_head_output(sylph_ctx* ctx, int which, int level, float* out_dev, void* stream);
 
+/* ---- Episodic TRAINING forward of the proposal generator: losses only, no backward. ---- */
+
+/* The loss hyper-parameters FCOSOutputs._init_fcos reads (sylph/modeling/meta_fcos/fcos_outputs.py:70-102). */
+typedef struct sylph_loss_config {
+    float focal_alpha;         /* MODEL.FCOS.LOSS_ALPHA */
+    float focal_gamma;         /* MODEL.FCOS.LOSS_GAMMA */
+    int center_sample;         /* MODEL.FCOS.CENTER_SAMPLE */
+    float pos_radius;          /* MODEL.FCOS.POS_RADIUS */
+    int loc_loss_type;         /* MODEL.FCOS.LOC_LOSS_TYPE: 0 "iou", 1 "linear_iou", 2 "giou" */
+    int sizes_of_interest[4];  /* MODEL.FCOS.SIZES_OF_INTEREST */
+} sylph_loss_config;
+
+#define SYLPH_LOSS_SUMS 5      /* focal-loss sum, positives, sum of centre-ness targets, sum of IoU-loss x target, centre-ness BCE sum */
+#define SYLPH_BACKGROUND_ID 100000  /* FCOSOutputs.back_ground_id, fcos_outputs.py:101 */
+
+/* Head forward on the query slot with (n_classes, 257) FINAL codes, ground-truth assignment of every location and the
+ * per-rank loss sums.  The ground truths are ALREADY filtered to the episode's classes (MetaProposalNetwork._get_gt,
+ * meta_one_stage_detector.py:184-221): gt_boxes_host (n_gt, 4) XYXY absolute pixels, gt_classes_host (n_gt) class
+ * ids, gt_offsets_host (n_images + 1) prefix offsets per query image; support_targets_host (n_classes) = the class id
+ * of every code row.  sums_out_dev receives SYLPH_LOSS_SUMS doubles.  Optional per-location outputs in the reference's
+ * level-first order (level, image, y, x): labels (int64, SYLPH_BACKGROUND_ID for background), target_inds (int64, index
+ * into the concatenated ground truths, -1 for an image without any) and reg_targets (fp32 l, t, r, b divided by the
+ * level stride); pass NULL to skip.  Replaces MetaFCOS.forward (training branch, fcos.py:184-246) + FCOSOutputs.losses /
+ * _get_ground_truth / compute_targets_for_locations / fcos_losses_episodic_learning, fcos_outputs.py:140-349, 351-592,
+ * for CODE_GENERATOR.BOX_ON == False and DISTILLATION_LOSS_WEIGHT == 0 (the shipped configs). */
+int sylph_fcos_loss_sums(sylph_ctx* ctx, int slot, const float* codes_dev, int n_classes,
+                         const int64_t* support_targets_host, const sylph_loss_config* lc, int n_gt,
+                         const float* gt_boxes_host, const int64_t* gt_classes_host, const int* gt_offsets_host,
+                         double* sums_out_dev, int64_t* labels_out_dev, int64_t* target_inds_out_dev,
+                         float* reg_targets_out_dev, void* stream);
+
+/* losses_out_dev[0..2] = loss_fcos_cls, loss_fcos_loc, loss_fcos_ctr from this rank's sums.  global_pos_ctr_dev holds
+ * {positives, centre-ness target sum} summed over ALL ranks -- the two reduce_sum calls of
+ * fcos_losses_episodic_learning, fcos_outputs.py:520-523 and :557-558 -- or NULL for a single process. */
+int sylph_fcos_loss_finalize(sylph_ctx* ctx, const double* local_sums_dev, const double* global_pos_ctr_dev,
+                             int world_size, float* losses_out_dev, void* stream);
+
 /* Number of kernels this library launched on the context since creation (bench.py's gpu_launches). */
 int64_t sylph_launch_count(const sylph_ctx* ctx);
 

@@ -207,6 +207,116 @@ def build_base_reduce_golden():
     print(f"[base_reduce] wrote {path} ({os.path.getsize(path) / 1e3:.1f} kB)")
 
 
+# ---------------------------------------------------------------------------------------------------------------
+# Training forward: forward_few_shot_detector_training of the REFERENCE model in train() mode.
+TRAIN_CASES = {
+    # name: (config, seed, class ids, shots, query images per class, cfg overrides)
+    "coco_train_2way_2shot": ("coco", 11, [7, 3], 2, 2,
+                              ["MODEL.META_LEARN.SHOT", 2, "MODEL.META_LEARN.QUERY_SHOT", 2,
+                               "MODEL.PROPOSAL_GENERATOR.FREEZE_BBOX_BRANCH", False, "MODEL.PROPOSAL_GENERATOR.FREEZE", False]),
+    # the shipped finetune setting: box branch frozen -> only loss_fcos_cls is returned (fcos_outputs.py:87-92,626-632)
+    "lvis_train_3way_1shot_cls_only": ("lvis", 12, [40, 2, 17], 1, 1,
+                                       ["MODEL.META_LEARN.SHOT", 1, "MODEL.META_LEARN.QUERY_SHOT", 1]),
+}
+
+
+def build_train_case(name: str):
+    cfg_name, seed, ids, n_shot, n_query, opts = TRAIN_CASES[name]
+    g = torch.Generator().manual_seed(2000 + seed)
+    sizes = [(256, 320), (240, 300), (224, 288), (200, 352)]
+    items = []
+    k = 0
+    for ci, cid in enumerate(ids):
+        sup, qry = [], []
+        for s in range(n_shot):
+            h, w = sizes[k % len(sizes)]; k += 1
+            sup.append({"image": synth_image(g, h, w), "boxes": synth_box(g, h, w, big=(s % 2 == 1))[None],
+                        "classes": torch.tensor([cid])})
+        for q in range(n_query):
+            h, w = sizes[k % len(sizes)]; k += 1
+            # a mix of wanted classes, an unrelated class (dropped by _get_gt) and nested boxes (min-area rule);
+            # the LAST query image of the episode holds no wanted class at all (the "no gt" branch)
+            last = ci == len(ids) - 1 and q == n_query - 1
+            boxes = [synth_box(g, h, w, big=True), synth_box(g, h, w, big=False), synth_box(g, h, w, big=False),
+                     synth_box(g, h, w, big=True)]
+            classes = [cid, ids[(ci + 1) % len(ids)], 59, cid]
+            if last:
+                classes = [58, 59, 57, 56]
+            qry.append({"image": synth_image(g, h, w), "boxes": torch.stack(boxes), "classes": torch.tensor(classes)})
+        items.append({"support_set": sup, "query_set": qry, "support_set_target": cid})
+    return cfg_name, seed, opts, items
+
+
+def to_records(items):
+    """golden item -> the reference's batched_inputs (data/build.py:271-282)."""
+    def rec(r):
+        h, w = r["image"].shape[-2:]
+        inst = up.Instances((h, w))
+        inst.gt_boxes = up.Boxes(r["boxes"].clone())
+        inst.gt_classes = r["classes"].clone()
+        return {"image": r["image"].to(torch.float32), "instances": inst, "height": h, "width": w}
+    return [{"support_set": [rec(r) for r in it["support_set"]], "query_set": [rec(r) for r in it["query_set"]],
+             "support_set_target": torch.tensor(it["support_set_target"])} for it in items]
+
+
+def run_reference_training(cfg, state, items):
+    with contextlib.redirect_stdout(io.StringIO()):
+        model = reference_loader.build_reference_model(cfg)
+    W.load_into_module(model, state)
+    model.train()
+    np.random.seed(0)
+    batched = to_records(items)
+    with torch.no_grad(), contextlib.redirect_stdout(io.StringIO()), warnings_off():
+        losses = model(batched)
+        # ground-truth assignment straight from the reference's FCOSOutputs
+        query = [r for x in batched for r in x["query_set"]]
+        targets = [x["support_set_target"] for x in batched]
+        gts = model._get_gt(query, support_set_targets=targets)
+        il = model.convert_batched_inputs_to_image_list(query)
+        feats = model.backbone(il.tensor)
+        feats = [feats[f] for f in cfg.MODEL.FCOS.IN_FEATURES]
+        locations = model.proposal_generator.compute_locations(feats)
+        tt = model.proposal_generator.fcos_outputs._get_ground_truth(locations, gts)
+    return {"losses": {k: v.clone() for k, v in losses.items()},
+            "labels": torch.cat([x.reshape(-1) for x in tt["labels"]]),
+            "target_inds": torch.cat([x.reshape(-1) for x in tt["target_inds"]]),
+            "reg_targets": torch.cat([x.reshape(-1, 4) for x in tt["reg_targets"]]),
+            "fpn_levels": torch.cat([x.reshape(-1) for x in tt["fpn_levels"]]),
+            "gt_counts": [len(g) for g in gts]}
+
+
+def build_training_goldens():
+    for name in TRAIN_CASES:
+        cfg_name, seed, opts, items = build_train_case(name)
+        cfg = load_cfg(os.path.join(reference_loader.REFERENCE_ROOT, "configs", CONFIGS[cfg_name]), ["MODEL.DEVICE", "cpu"] + opts)
+        state = W.synthetic_state_dict(cfg, seed)
+        ref = run_reference_training(cfg, state, items)
+        orc = build_oracle(cfg, state)
+        losses, ex = orc.training_forward(to_records(items))
+        print(f"[{name}] reference losses {({k: float(v) for k, v in ref['losses'].items()})}; positives "
+              f"{int((ref['labels'] != 100000).sum())} of {ref['labels'].numel()}; gts per query image {ref['gt_counts']}")
+        assert set(losses) == set(ref["losses"]), (set(losses), set(ref["losses"]))
+        worst = 0.0
+        for k in ref["losses"]:
+            worst = max(worst, compare(k, losses[k].reshape(1), ref["losses"][k].reshape(1)))
+        assert torch.equal(ex["labels"], ref["labels"]) and torch.equal(ex["target_inds"], ref["target_inds"])
+        assert torch.equal(ex["fpn_levels"], ref["fpn_levels"])
+        assert torch.equal(ex["reg_targets"], ref["reg_targets"]), (ex["reg_targets"] - ref["reg_targets"]).abs().max()
+        print(f"[{name}] labels / target_inds / reg_targets bit-exact; worst loss deviation {worst:.3e}")
+        golden = {"case": name, "config": CONFIGS[cfg_name], "seed": seed, "opts": opts,
+                  "items": [{"support_set": [{"image": r["image"].to(torch.uint8), "boxes": r["boxes"], "classes": r["classes"]}
+                                             for r in it["support_set"]],
+                             "query_set": [{"image": r["image"].to(torch.uint8), "boxes": r["boxes"], "classes": r["classes"]}
+                                           for r in it["query_set"]],
+                             "support_set_target": it["support_set_target"]} for it in items],
+                  "losses": ref["losses"], "labels": ref["labels"].to(torch.int32), "target_inds": ref["target_inds"].to(torch.int32),
+                  "reg_targets": ref["reg_targets"], "fpn_levels": ref["fpn_levels"].to(torch.int8), "gt_counts": ref["gt_counts"],
+                  "torch_version": torch.__version__}
+        path = os.path.join(GOLDEN_DIR, f"{name}.pt")
+        torch.save(golden, path)
+        print(f"[{name}] wrote {path} ({os.path.getsize(path) / 1e6:.2f} MB)")
+
+
 @contextlib.contextmanager
 def warnings_off():
     import warnings
@@ -220,6 +330,10 @@ def main():
     if "--base-only" in sys.argv or "--all" in sys.argv or len(sys.argv) == 1:
         build_base_reduce_golden()
     if "--base-only" in sys.argv:
+        return
+    if "--train-only" in sys.argv or "--all" in sys.argv or len(sys.argv) == 1:
+        build_training_goldens()
+    if "--train-only" in sys.argv:
         return
     for name in CASES:
         cfg_name, seed, support, query = build_case(name)

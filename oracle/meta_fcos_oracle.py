@@ -297,3 +297,189 @@ class MetaFCOSOracle:
             return results, {"features": feats, "logits": logits, "reg": regs, "ctr": ctrs, "iou": ious,
                              "pre_nms": pre_nms, "image_sizes": il.image_sizes}
         return results
+
+    # -------------------------------------------------------------------------------- training forward
+    INF = 100000000          # fcos_outputs.py:29
+    BACKGROUND_ID = 100000   # fcos_outputs.py:101
+
+    @staticmethod
+    def filter_gt(query_records: Sequence[Dict], support_targets: Sequence[int]):
+        """MetaProposalNetwork._get_gt (meta_one_stage_detector.py:184-221): keep the ground truths of a query image
+        whose class is one of the episode's support classes, in their original order."""
+        keep_ids = [int(t) for t in support_targets]
+        out = []
+        for rec in query_records:
+            boxes = rec["instances"].gt_boxes.tensor
+            classes = rec["instances"].gt_classes
+            sel = [i for i in range(len(classes)) if int(classes[i]) in keep_ids]
+            out.append((boxes[sel].reshape(-1, 4).to(torch.float32), classes[sel].reshape(-1).to(torch.int64)))
+        return out
+
+    def fcos_targets(self, level_sizes: Sequence[Tuple[int, int]], gts):
+        """FCOSOutputs._get_ground_truth / compute_targets_for_locations / get_sample_region
+        (fcos_outputs.py:140-349).  Returns level-first flattened (L, N, H, W order, :125-138) labels (int64),
+        target_inds (int64), reg_targets (fp32, divided by the level stride, :186-189) and the per-location level."""
+        C = self.cfg.MODEL.FCOS
+        soi = [-1] + list(C.SIZES_OF_INTEREST) + [self.INF]
+        locs, ranges, num_loc = [], [], []
+        for l, (h, w) in enumerate(level_sizes):
+            loc = up.compute_locations(h, w, self.strides[l], torch.device("cpu")).to(torch.float32)
+            locs.append(loc)
+            num_loc.append(loc.shape[0])
+            ranges.append(torch.tensor([soi[l], soi[l + 1]], dtype=torch.float32)[None].expand(loc.shape[0], 2))
+        locations, ranges = torch.cat(locs), torch.cat(ranges)
+        xs, ys = locations[:, 0], locations[:, 1]
+        K = locations.shape[0]
+        labels, regs, inds = [], [], []
+        num_targets = 0
+        for boxes, classes in gts:
+            if boxes.numel() == 0:                                       # :274-281
+                labels.append(torch.full((K,), self.BACKGROUND_ID, dtype=torch.int64))
+                regs.append(torch.zeros(K, 4))
+                inds.append(torch.full((K,), -1, dtype=torch.int64))
+                continue
+            area = (boxes[:, 2] - boxes[:, 0]) * (boxes[:, 3] - boxes[:, 1])
+            l = xs[:, None] - boxes[:, 0][None]
+            t = ys[:, None] - boxes[:, 1][None]
+            r = boxes[:, 2][None] - xs[:, None]
+            b = boxes[:, 3][None] - ys[:, None]
+            reg = torch.stack([l, t, r, b], dim=2)
+            if C.CENTER_SAMPLE:                                          # get_sample_region, :193-248
+                cx = (boxes[:, 0] + boxes[:, 2]) * 0.5
+                cy = (boxes[:, 1] + boxes[:, 3]) * 0.5
+                if float(cx[0]) * K == 0:                                # ":213" quirk: first centre at x == 0
+                    inside = torch.zeros(K, boxes.shape[0], dtype=torch.bool)
+                else:
+                    rad = torch.cat([torch.full((n,), float(self.strides[i] * C.POS_RADIUS))
+                                     for i, n in enumerate(num_loc)])[:, None]
+                    x0 = torch.maximum(cx[None] - rad, boxes[:, 0][None])
+                    y0 = torch.maximum(cy[None] - rad, boxes[:, 1][None])
+                    x1 = torch.minimum(cx[None] + rad, boxes[:, 2][None])
+                    y1 = torch.minimum(cy[None] + rad, boxes[:, 3][None])
+                    inside = torch.stack([xs[:, None] - x0, ys[:, None] - y0, x1 - xs[:, None], y1 - ys[:, None]],
+                                         -1).min(-1)[0] > 0
+            else:
+                inside = reg.min(dim=2)[0] > 0
+            mx = reg.max(dim=2)[0]
+            cared = (mx >= ranges[:, [0]]) & (mx <= ranges[:, [1]])
+            a = area[None].repeat(K, 1)
+            a[~inside] = self.INF
+            a[~cared] = self.INF
+            amin, gi = a.min(dim=1)                                      # first minimum on ties
+            lab = classes[gi].clone()
+            lab[amin == self.INF] = self.BACKGROUND_ID
+            labels.append(lab)
+            regs.append(reg[torch.arange(K), gi])
+            inds.append(gi + num_targets)
+            num_targets += boxes.shape[0]
+
+        def level_first(per_image):
+            split = [torch.split(x, num_loc, dim=0) for x in per_image]
+            return [torch.cat(lv, dim=0) for lv in zip(*split)]
+        lab_l, reg_l, ind_l = level_first(labels), level_first(regs), level_first(inds)
+        reg_l = [r / float(self.strides[i]) for i, r in enumerate(reg_l)]
+        lvl = torch.cat([torch.full((x.shape[0],), i, dtype=torch.int64) for i, x in enumerate(lab_l)])
+        return torch.cat(lab_l), torch.cat(ind_l), torch.cat(reg_l), lvl
+
+    @staticmethod
+    def iou_terms(pred: torch.Tensor, target: torch.Tensor):
+        """IOULoss.compute_ious (sylph/modeling/meta_fcos/iou_loss.py:26-65) on (l, t, r, b) pairs."""
+        ta = (target[:, 0] + target[:, 2]) * (target[:, 1] + target[:, 3])
+        pa = (pred[:, 0] + pred[:, 2]) * (pred[:, 1] + pred[:, 3])
+        wi = torch.min(pred[:, 0], target[:, 0]) + torch.min(pred[:, 2], target[:, 2])
+        hi = torch.min(pred[:, 3], target[:, 3]) + torch.min(pred[:, 1], target[:, 1])
+        gw = torch.max(pred[:, 0], target[:, 0]) + torch.max(pred[:, 2], target[:, 2])
+        gh = torch.max(pred[:, 3], target[:, 3]) + torch.max(pred[:, 1], target[:, 1])
+        ac = gw * gh
+        inter = wi * hi
+        union = ta + pa - inter
+        ious = (inter + 1.0) / (union + 1.0)
+        return ious, ious - (ac - union) / ac
+
+    def fcos_losses(self, logits, regs, ctrs, gts, support_targets: Sequence[int], world_size: int = 1,
+                    reduce=None) -> Tuple[Dict[str, torch.Tensor], Dict[str, torch.Tensor]]:
+        """FCOSOutputs.losses -> fcos_losses_episodic_learning (fcos_outputs.py:351-637) for box_on == False.
+        `reduce` stands for adet's reduce_sum (identity for one process)."""
+        C = self.cfg.MODEL.FCOS
+        reduce = reduce or (lambda t: t)
+        labels, gt_inds, reg_targets, lvl = self.fcos_targets([tuple(x.shape[-2:]) for x in logits], gts)
+        flat = lambda xs, c: torch.cat([x.permute(0, 2, 3, 1).reshape(-1, c) for x in xs], dim=0)
+        NC = logits[0].shape[1]
+        logits_pred = flat(logits, NC)
+        reg_pred = flat(regs, 4)
+        ctr_pred = flat(ctrs, 1).reshape(-1)
+        st = torch.tensor([int(t) for t in support_targets], dtype=torch.int64).view(1, -1)
+        pos = torch.nonzero(labels != self.BACKGROUND_ID).squeeze(1)
+        total_pos = float(reduce(torch.tensor([pos.numel()], dtype=torch.int64)).item())
+        num_pos_avg = max(total_pos / world_size, 1.0)
+        class_target = (st == labels[:, None]).to(torch.float32)
+        loss_cls = up.sigmoid_focal_loss(logits_pred, class_target, alpha=C.LOSS_ALPHA, gamma=C.LOSS_GAMMA,
+                                         reduction="sum") / num_pos_avg
+        rt = reg_targets[pos]
+        lr, tb = rt[:, [0, 2]], rt[:, [1, 3]]
+        if rt.shape[0]:
+            ctr_t = torch.sqrt((lr.min(dim=-1)[0] / lr.max(dim=-1)[0]) * (tb.min(dim=-1)[0] / tb.max(dim=-1)[0]))
+        else:
+            ctr_t = rt.new_zeros(0)
+        denorm = max(float(reduce(ctr_t.sum()).item()) / world_size, 1e-6)
+        ious, gious = self.iou_terms(reg_pred[pos], rt)
+        if pos.numel() > 0:
+            kind = C.LOC_LOSS_TYPE
+            per = -torch.log(ious) if kind == "iou" else (1 - ious) if kind == "linear_iou" else (1 - gious)
+            loss_loc = (per * ctr_t).sum() / denorm
+            loss_ctr = F.binary_cross_entropy_with_logits(ctr_pred[pos], ctr_t, reduction="sum") / num_pos_avg
+        else:
+            loss_loc = reg_pred[pos].sum() * 0
+            loss_ctr = ctr_pred[pos].sum() * 0
+        losses = {"loss_fcos_cls": loss_cls}
+        P = self.cfg.MODEL.PROPOSAL_GENERATOR
+        if not (P.FREEZE_BBOX_BRANCH or P.FREEZE):                       # box_branch_loss_on, fcos_outputs.py:87-92
+            losses.update({"loss_fcos_loc": loss_loc, "loss_fcos_ctr": loss_ctr})
+        extras = {"labels": labels, "target_inds": gt_inds, "reg_targets": reg_targets, "fpn_levels": lvl,
+                  "num_pos": torch.tensor(pos.numel()), "ctr_targets_sum": ctr_t.sum(), "loss_denorm": torch.tensor(denorm)}
+        return losses, extras
+
+    @torch.no_grad()
+    def training_forward(self, batched_inputs: Sequence[Dict], world_size: int = 1, reduce=None):
+        """forward_few_shot_detector_training (meta_one_stage_detector.py:325-388): one item per class with
+        "support_set" (SHOT records, one selected box each), "query_set" and "support_set_target"."""
+        shot = int(self.cfg.MODEL.META_LEARN.SHOT)
+        support = [r for x in batched_inputs for r in x["support_set"]]
+        targets = [int(x["support_set_target"]) for x in batched_inputs]
+        query = [r for x in batched_inputs for r in x["query_set"]]
+        assert len(support) % shot == 0, f"Total size {len(support)} must be divisible by number of shot {shot}"
+        q_il = self.preprocess([r["image"] for r in query])
+        q_feats = self.features(q_il.tensor)
+        s_il = self.preprocess([r["image"] for r in support])
+        s_feats = self.features(s_il.tensor)
+        gts = self.filter_gt(query, targets)
+        boxes = torch.stack([r["instances"].gt_boxes.tensor[0] for r in support])   # one GT per support image
+        roi, _ = self.roi_features(s_feats, boxes)
+        w, b = self.per_shot_codes(roi)
+        n_cls = w.shape[0] // shot
+        weight = torch.full((n_cls, shot, 1, 1, 1), 1.0 / shot, dtype=w.dtype)      # code_generator.py:805-817
+        cls_conv = (weight * w.view(n_cls, shot, *w.shape[1:])).sum(dim=1)
+        cls_bias = (weight * b.view(n_cls, shot, 1, 1, 1)).sum(dim=1) if b is not None else torch.zeros(n_cls, 1, 1, 1)
+        cls_conv, cls_bias = self.process_codes_training(cls_conv, cls_bias)        # :993-994
+        codes = {"cls_conv": cls_conv, "cls_bias": cls_bias}
+        logits, regs, ctrs, ious = self.head(q_feats, codes)
+        losses, extras = self.fcos_losses(logits, regs, ctrs, gts, targets, world_size, reduce)
+        extras.update({"codes": codes, "gts": gts})
+        return losses, extras
+
+    def process_codes_training(self, cls_conv: torch.Tensor, cls_bias: torch.Tensor):
+        """code_process_module on the whole (C, 256, 1, 1) batch (code_generator.py:864-875; the `size(0) == 1`
+        assert of process_bias, :850-851, only applies in eval mode)."""
+        w = cls_conv
+        if self.G.POST_NORM != "" and w.size(1) % 32 == 0:
+            w = _gn(w, self._cg("post_norm.weight"), self._cg("post_norm.bias"), 1 if self.G.POST_NORM == "LN" else 32)
+        if self.G.CONV_L2_NORM:
+            w = F.normalize(w, p=2, dim=1)
+        key = "code_generator.code_generator_head.conv_scale.scale"
+        if key in self.sd:
+            w = w * self.sd[key]
+        b = cls_bias.reshape(cls_bias.numel())
+        key = "code_generator.code_generator_head.bias_scale.scale"
+        if key in self.sd:
+            b = b * self.sd[key]
+        return w, b + self.bias_value.to(b.dtype)

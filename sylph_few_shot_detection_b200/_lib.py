@@ -35,6 +35,16 @@ class ModelConfig(Structure):
     ]
 
 
+class LossConfig(Structure):
+    """Mirror of `sylph_loss_config` (training forward)."""
+    _fields_ = [("focal_alpha", c_float), ("focal_gamma", c_float), ("center_sample", c_int), ("pos_radius", c_float),
+                ("loc_loss_type", c_int), ("sizes_of_interest", c_int * 4)]
+
+
+LOSS_SUMS = 5
+BACKGROUND_ID = 100000
+
+
 def _sources():
     return sorted(os.path.join(_CSRC, f) for f in os.listdir(_CSRC) if f.endswith((".cu", ".cuh"))) + \
         [os.path.join(os.path.dirname(_PKG), "include", "sylph_b200.h")]
@@ -110,6 +120,11 @@ def load() -> ctypes.CDLL:
     lib.sylph_detect.argtypes = [vp, c_int, vp, c_int, ip, vp, vp, c_int, vp]
     lib.sylph_export_head_output.restype = c_int
     lib.sylph_export_head_output.argtypes = [vp, c_int, c_int, vp, vp]
+    lib.sylph_fcos_loss_sums.restype = c_int
+    lib.sylph_fcos_loss_sums.argtypes = [vp, c_int, vp, c_int, POINTER(c_int64), POINTER(LossConfig), c_int, fp,
+                                         POINTER(c_int64), ip, vp, vp, vp, vp, vp]
+    lib.sylph_fcos_loss_finalize.restype = c_int
+    lib.sylph_fcos_loss_finalize.argtypes = [vp, vp, vp, c_int, vp, vp]
     lib.sylph_launch_count.restype = c_int64
     lib.sylph_launch_count.argtypes = [vp]
     lib.sylph_set_profiling.restype = c_int
@@ -124,5 +139,5 @@ EXPORTED_SYMBOLS = [
     "sylph_version", "sylph_create", "sylph_destroy", "sylph_last_error", "sylph_load_tensor",
     "sylph_finalize_weights", "sylph_extract_features", "sylph_extract_features_u8", "sylph_extract_features_multi", "sylph_import_features", "sylph_feature_shape",
     "sylph_export_features", "sylph_generate_codes", "sylph_export_roi_features", "sylph_normalize_codes", "sylph_accumulate_codes", "sylph_reduce_codes",
-    "sylph_detect", "sylph_export_head_output", "sylph_launch_count", "sylph_set_profiling", "sylph_get_timings",
+    "sylph_detect", "sylph_export_head_output", "sylph_fcos_loss_sums", "sylph_fcos_loss_finalize", "sylph_launch_count", "sylph_set_profiling", "sylph_get_timings",
 ]

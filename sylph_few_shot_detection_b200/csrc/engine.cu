@@ -14,6 +14,7 @@
 #include "conv_gemm_host.cuh"
 #include "kernels_detect.cuh"
 #include "kernels_roi_encoder.cuh"
+#include "kernels_loss.cuh"
 
 namespace sylph {
 
@@ -1157,6 +1158,73 @@ static int roi_encoder_codes(sylph_ctx* c, const Slot& S, int n_rois, int n_clas
 
 }  // namespace sylph
 
+// Towers + code-conditioned classifier + box / centre-ness / IoU predictors on a feature slot (MetaFCOSHead.forward,
+// fcos.py:582-667): fills the "det.logits" ([rows][cout_pad] fp32) and "det.pred" ([rows][16] fp32) buffers.
+struct HeadOut { float* logits; float* pred; int logit_stride; };
+
+static int run_head(sylph_ctx* c, int slot, const float* codes_dev, int n_classes, cudaStream_t st, HeadOut* out) {
+    const sylph_model_config& f = c->cfg;
+    const Slot& S = c->slots[slot];
+    const long long rows = S.level_row0[5];
+    const int tiles = static_cast<int>(rows / kBlockM);
+    const int n_segs = 5 * S.n;
+    // ---- code-conditioned classifier weights
+    ConvW CW;
+    CW.taps = 1; CW.ksize = 1; CW.k_per_tap = 256; CW.cout = n_classes; CW.bn = pick_bn(n_classes);
+    CW.cout_pad = round_up(n_classes, CW.bn);
+    void *cw, *cb, *ta, *tb, *rawp, *lg, *pr, *gp, *gs;
+    TRY(ensure(c, "det.code_w", static_cast<size_t>(CW.cout_pad) * 256 * 2, "", &cw, st, false));
+    TRY(ensure(c, "det.code_b", static_cast<size_t>(CW.cout_pad) * 4, "", &cb, st, false));
+    TRY(ensure(c, "det.ta", (static_cast<size_t>(rows) + kBlockM) * 256 * 2, "", &ta, st, false));
+    TRY(ensure(c, "det.tb", (static_cast<size_t>(rows) + kBlockM) * 256 * 2, "", &tb, st, false));
+    TRY(ensure(c, "det.raw", (static_cast<size_t>(rows) + kBlockM) * 256 * 4, "", &rawp, st, false));
+    TRY(ensure(c, "det.logits", (static_cast<size_t>(rows) + kBlockM) * CW.cout_pad * 4, "", &lg, st, false));
+    TRY(ensure(c, "det.pred", (static_cast<size_t>(rows) + kBlockM) * 16 * 4, "", &pr, st, false));
+    TRY(ensure(c, "det.gn_partial", static_cast<size_t>(tiles) * 64 * 4, "", &gp, st, false));
+    TRY(ensure(c, "det.gn_stats", static_cast<size_t>(n_segs) * 64 * 4, "", &gs, st, false));
+    CW.w = static_cast<__half*>(cw);
+    CW.bias = static_cast<float*>(cb);
+    CU_TRY(c, launch_k(pack_code_weights_kernel, dim3(ceil_div(static_cast<long long>(CW.cout_pad) * 256, 256)), dim3(256), 0, st, 
+        codes_dev, n_classes, CW.cout_pad, f.generator == 1 ? 1 : f.cg_use_bias, f.generator == 1 ? c->cond_scale : 1.f, CW.w, CW.bias));
+    CU_TRY(c, cudaGetLastError());
+    c->launches++;
+    auto tower = [&](const std::vector<ConvW>& tw, const std::vector<float*>& gw, const std::vector<float*>& gb,
+                     const char* name, __half** result) -> int {
+        const __half* cur = S.pyr;
+        __half* bufs2[2] = {static_cast<__half*>(ta), static_cast<__half*>(tb)};
+        for (size_t i = 0; i < tw.size(); ++i) {
+            __half* o = bufs2[i & 1];
+            TRY(conv_gn_relu(c, tw[i], gw[i], gb[i], cur, rows, static_cast<float*>(rawp), o, S.ps.get(), 0, tiles, 0, n_segs,
+                             static_cast<float*>(gp), static_cast<float*>(gs), name, st));
+            cur = o;
+        }
+        *result = const_cast<__half*>(cur);
+        return 0;
+    };
+    __half* x;
+    TRY(tower(c->cls_tower, c->cls_gn_w, c->cls_gn_b, "head.cls_tower3x3", &x));
+    {
+        ConvCall k{};
+        k.W = &CW; k.A = x; k.a_rows = rows; k.a_cols = k.a_ld = 256; k.ps = S.ps.get(); k.tile_begin = 0; k.n_tiles = tiles;
+        k.a_row_delta = 0; k.out = lg; k.ldc = CW.cout_pad; k.flags = kEpiOutF32; k.name = "head.cond_cls1x1";
+        TRY(run_conv(c, k, st));
+    }
+    TRY(tower(c->box_tower, c->box_gn_w, c->box_gn_b, "head.bbox_tower3x3", &x));
+    {
+        ConvCall k{};
+        k.W = &c->pred; k.A = x; k.a_rows = rows; k.a_cols = k.a_ld = 256; k.ps = S.ps.get(); k.tile_begin = 0; k.n_tiles = tiles;
+        k.a_row_delta = 0; k.out = pr; k.ldc = 16; k.flags = kEpiOutF32; k.name = "head.pred3x3";
+        TRY(run_conv(c, k, st));
+    }
+    c->last_detect_slot = slot;
+    c->last_detect_classes = n_classes;
+    c->last_logit_stride = CW.cout_pad;
+    out->logits = static_cast<float*>(lg);
+    out->pred = static_cast<float*>(pr);
+    out->logit_stride = CW.cout_pad;
+    return 0;
+}
+
 extern "C" {
 
 int sylph_extract_features(sylph_ctx* c, int slot, int n_images, const float* const* images_dev, const int* heights,
@@ -1421,60 +1489,12 @@ int sylph_detect(sylph_ctx* c, int slot, const float* codes_dev, int n_classes, 
     CU_TRY(c, cudaSetDevice(c->device));
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     const Slot& S = c->slots[slot];
-    const long long rows = S.level_row0[5];
-    const int tiles = static_cast<int>(rows / kBlockM);
     const int n_segs = 5 * S.n;
-    // ---- code-conditioned classifier weights
-    ConvW CW;
-    CW.taps = 1; CW.ksize = 1; CW.k_per_tap = 256; CW.cout = n_classes; CW.bn = pick_bn(n_classes);
-    CW.cout_pad = round_up(n_classes, CW.bn);
-    void *cw, *cb, *ta, *tb, *rawp, *lg, *pr, *gp, *gs;
-    TRY(ensure(c, "det.code_w", static_cast<size_t>(CW.cout_pad) * 256 * 2, "", &cw, st, false));
-    TRY(ensure(c, "det.code_b", static_cast<size_t>(CW.cout_pad) * 4, "", &cb, st, false));
-    TRY(ensure(c, "det.ta", (static_cast<size_t>(rows) + kBlockM) * 256 * 2, "", &ta, st, false));
-    TRY(ensure(c, "det.tb", (static_cast<size_t>(rows) + kBlockM) * 256 * 2, "", &tb, st, false));
-    TRY(ensure(c, "det.raw", (static_cast<size_t>(rows) + kBlockM) * 256 * 4, "", &rawp, st, false));
-    TRY(ensure(c, "det.logits", (static_cast<size_t>(rows) + kBlockM) * CW.cout_pad * 4, "", &lg, st, false));
-    TRY(ensure(c, "det.pred", (static_cast<size_t>(rows) + kBlockM) * 16 * 4, "", &pr, st, false));
-    TRY(ensure(c, "det.gn_partial", static_cast<size_t>(tiles) * 64 * 4, "", &gp, st, false));
-    TRY(ensure(c, "det.gn_stats", static_cast<size_t>(n_segs) * 64 * 4, "", &gs, st, false));
-    CW.w = static_cast<__half*>(cw);
-    CW.bias = static_cast<float*>(cb);
-    CU_TRY(c, launch_k(pack_code_weights_kernel, dim3(ceil_div(static_cast<long long>(CW.cout_pad) * 256, 256)), dim3(256), 0, st, 
-        codes_dev, n_classes, CW.cout_pad, f.generator == 1 ? 1 : f.cg_use_bias, f.generator == 1 ? c->cond_scale : 1.f, CW.w, CW.bias));
-    CU_TRY(c, cudaGetLastError());
-    c->launches++;
-    auto tower = [&](const std::vector<ConvW>& tw, const std::vector<float*>& gw, const std::vector<float*>& gb,
-                     const char* name, __half** result) -> int {
-        const __half* cur = S.pyr;
-        __half* bufs2[2] = {static_cast<__half*>(ta), static_cast<__half*>(tb)};
-        for (size_t i = 0; i < tw.size(); ++i) {
-            __half* o = bufs2[i & 1];
-            TRY(conv_gn_relu(c, tw[i], gw[i], gb[i], cur, rows, static_cast<float*>(rawp), o, S.ps.get(), 0, tiles, 0, n_segs,
-                             static_cast<float*>(gp), static_cast<float*>(gs), name, st));
-            cur = o;
-        }
-        *result = const_cast<__half*>(cur);
-        return 0;
-    };
-    __half* x;
-    TRY(tower(c->cls_tower, c->cls_gn_w, c->cls_gn_b, "head.cls_tower3x3", &x));
-    {
-        ConvCall k{};
-        k.W = &CW; k.A = x; k.a_rows = rows; k.a_cols = k.a_ld = 256; k.ps = S.ps.get(); k.tile_begin = 0; k.n_tiles = tiles;
-        k.a_row_delta = 0; k.out = lg; k.ldc = CW.cout_pad; k.flags = kEpiOutF32; k.name = "head.cond_cls1x1";
-        TRY(run_conv(c, k, st));
-    }
-    TRY(tower(c->box_tower, c->box_gn_w, c->box_gn_b, "head.bbox_tower3x3", &x));
-    {
-        ConvCall k{};
-        k.W = &c->pred; k.A = x; k.a_rows = rows; k.a_cols = k.a_ld = 256; k.ps = S.ps.get(); k.tile_begin = 0; k.n_tiles = tiles;
-        k.a_row_delta = 0; k.out = pr; k.ldc = 16; k.flags = kEpiOutF32; k.name = "head.pred3x3";
-        TRY(run_conv(c, k, st));
-    }
-    c->last_detect_slot = slot;
-    c->last_detect_classes = n_classes;
-    c->last_logit_stride = CW.cout_pad;
+    HeadOut H{};
+    TRY(run_head(c, slot, codes_dev, n_classes, st, &H));
+    float* lg = H.logits;
+    float* pr = H.pred;
+    struct { int cout_pad; } CW{H.logit_stride};
     // ---- proposals
     DetectParams P{};
     P.pg = S.pg;
@@ -1557,6 +1577,83 @@ int sylph_export_head_output(sylph_ctx* c, int which, int level, float* out_dev,
     else { coff = 5; }
     const long long work = static_cast<long long>(S.n) * C * S.lh[level] * S.lw[level];
     CU_TRY(c, launch_k(export_nchw_kernel<float>, dim3(grid_for(work, 256, c->num_sms)), dim3(256), 0, st, src, out_dev, S.pg.lv[level], S.n, C, cstride, coff, scale, relu));
+    CU_TRY(c, cudaGetLastError());
+    c->launches++;
+    return 0;
+}
+
+int sylph_fcos_loss_sums(sylph_ctx* c, int slot, const float* codes_dev, int n_classes, const int64_t* support_targets_host,
+                         const sylph_loss_config* lc, int n_gt, const float* gt_boxes_host, const int64_t* gt_classes_host,
+                         const int* gt_offsets_host, double* sums_out_dev, int64_t* labels_out_dev,
+                         int64_t* target_inds_out_dev, float* reg_targets_out_dev, void* stream) {
+    if (!c) return 1;
+    if (!c->finalized) return c->fail("weights not finalized");
+    if (slot < 0 || slot >= SYLPH_NUM_SLOTS || !c->slots[slot].valid) return c->fail("slot %d holds no features", slot);
+    if (n_classes <= 0 || !support_targets_host) return c->fail("no class codes / support_set_targets");
+    if (!lc || !gt_offsets_host || !sums_out_dev) return c->fail("null argument");
+    if (lc->loc_loss_type < 0 || lc->loc_loss_type > 2) return c->fail("LOC_LOSS_TYPE must be iou | linear_iou | giou");
+    if (n_gt < 0 || (n_gt > 0 && (!gt_boxes_host || !gt_classes_host))) return c->fail("ground-truth arrays missing");
+    CU_TRY(c, cudaSetDevice(c->device));
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    const Slot& S = c->slots[slot];
+    if (gt_offsets_host[0] != 0 || gt_offsets_host[S.n] != n_gt) return c->fail("gt_offsets must run from 0 to n_gt over %d images", S.n);
+    for (int i = 0; i < S.n; ++i)
+        if (gt_offsets_host[i + 1] < gt_offsets_host[i]) return c->fail("gt_offsets must be non-decreasing");
+    HeadOut H{};
+    TRY(run_head(c, slot, codes_dev, n_classes, st, &H));
+    LossParams P{};
+    P.pg = S.pg;
+    P.n_images = S.n;
+    P.n_classes = n_classes;
+    P.logit_stride = H.logit_stride;
+    long long total_px = 0;
+    for (int l = 0; l < 5; ++l) {
+        P.stride[l] = 8 << l;
+        P.level_scale[l] = c->level_scale[l];
+        P.soi_lo[l] = l == 0 ? -1.f : static_cast<float>(lc->sizes_of_interest[l - 1]);
+        P.soi_hi[l] = l == 4 ? kFcosInf : static_cast<float>(lc->sizes_of_interest[l]);
+        P.radius[l] = static_cast<float>(static_cast<double>(P.stride[l]) * static_cast<double>(lc->pos_radius));
+        total_px += static_cast<long long>(S.n) * S.lh[l] * S.lw[l];
+    }
+    P.center_sample = lc->center_sample;
+    P.alpha = lc->focal_alpha;
+    P.gamma = lc->focal_gamma;
+    P.loc_loss_type = lc->loc_loss_type;
+    const int blocks = grid_for(total_px, 256, c->num_sms);
+    void *gb, *gc, *go, *stg, *part;
+    TRY(ensure(c, "loss.gt_boxes", static_cast<size_t>(std::max(n_gt, 1)) * 16, "", &gb, st, false));
+    TRY(ensure(c, "loss.gt_classes", static_cast<size_t>(std::max(n_gt, 1)) * 8, "", &gc, st, false));
+    TRY(ensure(c, "loss.gt_offsets", static_cast<size_t>(S.n + 1) * 4, "", &go, st, false));
+    TRY(ensure(c, "loss.support_targets", static_cast<size_t>(n_classes) * 8, "", &stg, st, false));
+    TRY(ensure(c, "loss.partials", static_cast<size_t>(blocks) * kLossSums * 8, "", &part, st, false));
+    TRY(stage_h2d(c, gb, gt_boxes_host, static_cast<size_t>(n_gt) * 16, st));
+    TRY(stage_h2d(c, gc, gt_classes_host, static_cast<size_t>(n_gt) * 8, st));
+    TRY(stage_h2d(c, go, gt_offsets_host, static_cast<size_t>(S.n + 1) * 4, st));
+    TRY(stage_h2d(c, stg, support_targets_host, static_cast<size_t>(n_classes) * 8, st));
+    {
+        StageTimer t(c, "loss.targets+sums", st, static_cast<double>(total_px) * (H.logit_stride + 16) * 4);
+        CU_TRY(c, launch_k(fcos_targets_loss_kernel, dim3(blocks), dim3(256), 0, st, static_cast<const float*>(H.logits),
+                           static_cast<const float*>(H.pred), P, static_cast<const float*>(gb), static_cast<const long long*>(gc),
+                           static_cast<const int*>(go), static_cast<const long long*>(stg), static_cast<double*>(part),
+                           reinterpret_cast<long long*>(labels_out_dev), reinterpret_cast<long long*>(target_inds_out_dev),
+                           reg_targets_out_dev));
+        CU_TRY(c, cudaGetLastError());
+        CU_TRY(c, launch_k(fcos_loss_reduce_kernel, dim3(1), dim3(256), 0, st, static_cast<const double*>(part), blocks, sums_out_dev));
+        CU_TRY(c, cudaGetLastError());
+        c->launches += 2;
+    }
+    return 0;
+}
+
+int sylph_fcos_loss_finalize(sylph_ctx* c, const double* local_sums_dev, const double* global_pos_ctr_dev, int world_size,
+                             float* losses_out_dev, void* stream) {
+    if (!c) return 1;
+    if (!local_sums_dev || !losses_out_dev) return c->fail("null argument");
+    if (world_size < 1) return c->fail("world_size must be >= 1");
+    CU_TRY(c, cudaSetDevice(c->device));
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    CU_TRY(c, launch_k(fcos_loss_finalize_kernel, dim3(1), dim3(32), 0, st, local_sums_dev,
+                       global_pos_ctr_dev ? global_pos_ctr_dev : local_sums_dev + 1, world_size, losses_out_dev));
     CU_TRY(c, cudaGetLastError());
     c->launches++;
     return 0;

@@ -212,7 +212,15 @@ class MetaFCOS(_EngineBound):
 
     def forward(self, images, features, gt_instances=None, top_module=None, support_set_per_class_code=None,
                 support_set_targets=None):
-        assert not self.training, "the B200 path implements inference only"
+        if self.training:
+            # training branch of MetaFCOS.forward (fcos.py:217-246): (results, losses); no proposals are yielded
+            assert support_set_per_class_code is not None and support_set_targets is not None, \
+                "only the episodic (code-conditioned) losses are implemented on the B200 path"
+            if features is not None:
+                feats = [features[f] for f in self.in_features]
+                h, w = feats[0].shape[-2:]
+                self.engine.import_features(SLOT_QUERY, feats, (h * self.fpn_strides[0], w * self.fpn_strides[0]))
+            return {}, self.losses(support_set_per_class_code, support_set_targets, gt_instances)
         if support_set_per_class_code is None:
             raise NotImplementedError("base-detector inference (cls_logits) is not implemented on the B200 path")
         image_sizes = images.image_sizes if hasattr(images, "image_sizes") else images
@@ -237,6 +245,55 @@ class MetaFCOS(_EngineBound):
             inst.fpn_levels = d[:, 8].to(torch.int64)
             results.append(inst)
         return results
+
+
+def _box_branch_loss_on(cfg) -> bool:
+    P = cfg.MODEL.PROPOSAL_GENERATOR
+    return not (P.FREEZE_BBOX_BRANCH or P.FREEZE)                       # fcos_outputs.py:87-92
+
+
+def _reduce_sum(t: torch.Tensor) -> torch.Tensor:
+    """adet.utils.comm.reduce_sum (fcos_outputs.py:522,558): all-reduce SUM, identity for one process."""
+    import torch.distributed as dist
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size() < 2:
+        return t
+    t = t.clone()
+    dist.all_reduce(t, op=dist.ReduceOp.SUM)
+    return t
+
+
+def _world_size() -> int:
+    import torch.distributed as dist
+    return dist.get_world_size() if dist.is_available() and dist.is_initialized() else 1
+
+
+def _meta_fcos_losses(self, class_codes: Dict[str, torch.Tensor], support_set_targets: Sequence[Any],
+                      gt_instances: Sequence[Any], want_targets: bool = False):
+    """FCOSOutputs.losses -> fcos_losses_episodic_learning (fcos_outputs.py:351-637) on the features in SLOT_QUERY:
+    one fused kernel assigns every location its ground truth and accumulates the loss sums; the two `reduce_sum`
+    scalars (positives, centre-ness target sum) travel as ONE 2-element all-reduce of a device tensor."""
+    assert support_set_targets is not None
+    assert gt_instances is not None and len(gt_instances) > 0
+    eng = self.engine
+    codes = pack_code_rows(class_codes).to(eng.device)
+    targets = [int(t) for t in support_set_targets]
+    boxes = [g.gt_boxes.tensor.reshape(-1, 4).cpu().float() for g in gt_instances]
+    classes = [g.gt_classes.reshape(-1).cpu().to(torch.int64) for g in gt_instances]
+    offsets = [0]
+    for b in boxes:
+        offsets.append(offsets[-1] + b.shape[0])
+    res = eng.fcos_loss_sums(SLOT_QUERY, codes, targets, torch.cat(boxes), torch.cat(classes), offsets, want_targets)
+    sums, extra = res if want_targets else (res, None)
+    world = _world_size()
+    glob = _reduce_sum(sums[1:3]) if world > 1 else None
+    out = eng.fcos_loss_finalize(sums, glob, world)
+    losses = {"loss_fcos_cls": out[0]}
+    if _box_branch_loss_on(self.cfg):
+        losses.update({"loss_fcos_loc": out[1], "loss_fcos_ctr": out[2]})
+    return (losses, {"sums": sums, "labels": extra[0], "target_inds": extra[1], "reg_targets": extra[2]}) if want_targets else losses
+
+
+MetaFCOS.losses = _meta_fcos_losses
 
 
 def pack_code_rows(class_codes: Dict[str, torch.Tensor]) -> torch.Tensor:
@@ -336,8 +393,13 @@ class MetaOneStageDetector(nn.Module):
 
     # ------------------------------------------------------------------ run_type protocol
     def forward(self, batched_inputs, class_code=None, run_type=None):
+        if run_type is None and self.training:
+            # MetaProposalNetwork.forward (meta_one_stage_detector.py:388-412): losses of one training episode batch
+            if not self.episodic_learning:
+                raise NotImplementedError("base-detector pre-training forward is not implemented on the B200 path")
+            return self.forward_few_shot_detector_training(batched_inputs)
         if self.training:
-            raise NotImplementedError("training forward is outside the B200 inference path")
+            raise NotImplementedError(f"not support this forward type: {run_type}, class_code: {class_code}")
         if run_type is None:
             raise NotImplementedError("base-detector inference (run_type=None) is not implemented on the B200 path")
         if run_type == "meta_learn_test_support":
@@ -376,6 +438,52 @@ class MetaOneStageDetector(nn.Module):
                     for i in range(len(batched_inputs))]
         return [{"cls_conv": raw[i:i + 1, :256].reshape(1, 256, 1, 1), "cls_bias": raw[i:i + 1, 256:].reshape(1, 1, 1, 1)}
                 for i in range(len(batched_inputs))]
+
+    # ------------------------------------------------------------------ training forward (losses only, no backward)
+    def _get_gt(self, batched_inputs: List[Dict[str, Any]], support_set_targets=None):
+        """meta_one_stage_detector.py:184-221: keep the ground truths whose class is one of the episode's classes."""
+        if "instances" not in batched_inputs[0]:
+            if "targets" in batched_inputs[0]:
+                raise NotImplementedError("targets are not supported")
+            return None
+        if support_set_targets is None:
+            return [x["instances"] for x in batched_inputs]
+        assert isinstance(support_set_targets, list), "support_set_targets is not list"
+        wanted = [int(t) for t in support_set_targets]
+        out = []
+        for x in batched_inputs:
+            boxes = x["instances"].gt_boxes.tensor.reshape(-1, 4)
+            classes = x["instances"].gt_classes.reshape(-1)
+            keep = [i for i in range(len(classes)) if int(classes[i]) in wanted]
+            inst = Instances(tuple(x["instances"].image_size))
+            inst.gt_boxes = Boxes(boxes[keep].reshape(-1, 4).to(torch.float32))
+            inst.gt_classes = classes[keep].to(torch.int64)
+            out.append(inst)
+        return out
+
+    def forward_few_shot_detector_training(self, batched_inputs: List[Dict[str, Any]], want_targets: bool = False):
+        """meta_one_stage_detector.py:325-388: each item = the query + support set of one class.  Returns the loss dict
+        (`loss_fcos_cls` [, `loss_fcos_loc`, `loss_fcos_ctr`]) as device scalars.  Forward only: this build has no
+        backward kernels, so the result serves validation-loss / loss-curve evaluation of a checkpoint."""
+        assert self.training
+        assert "support_set" in batched_inputs[0]
+        assert "query_set" in batched_inputs[0]
+        if isinstance(self.code_generator, ROIEncoder):
+            raise NotImplementedError("ROIEncoder training forward (transformer dropout) is not implemented")
+        support = [r for x in batched_inputs for r in x["support_set"]]
+        targets = [x["support_set_target"] for x in batched_inputs]
+        query = [r for x in batched_inputs for r in x["query_set"]]
+        shot = int(self.cfg.MODEL.META_LEARN.SHOT)
+        assert len(support) % shot == 0, \
+            f"Total size {len(support)} must be divisible by number of shot {shot}"     # code_generator.py:787-789
+        gts = self._get_gt(query, support_set_targets=targets)
+        boxes = torch.cat([b.reshape(-1, 4)[:1].cpu() for b in select_a_mask([r["instances"] for r in support])], dim=0)
+        self.engine.extract_features_multi([(SLOT_QUERY, [r["image"] for r in query]),
+                                            (SLOT_SUPPORT, [r["image"] for r in support])])
+        raw = self.engine.generate_codes(SLOT_SUPPORT, boxes, list(range(len(support))), list(range(0, len(support) + 1, shot)))
+        codes = self.engine.normalize_codes(raw)                                        # code_generator.py:993-994
+        class_codes = {"cls_conv": codes[:, :256].reshape(-1, 256, 1, 1), "cls_bias": codes[:, 256].reshape(-1)}
+        return self.proposal_generator.losses(class_codes, targets, gts, want_targets)
 
     def normalize_class_code(self, codes: List[Dict]):
         assert self.episodic_learning

@@ -8,7 +8,7 @@ from typing import Dict, List, Optional, Sequence, Tuple
 import torch
 
 from . import _lib
-from ._lib import CODE_STRIDE, DET_STRIDE, NUM_LEVELS, SLOT_QUERY, SLOT_SUPPORT, ModelConfig
+from ._lib import CODE_STRIDE, DET_STRIDE, LOSS_SUMS, NUM_LEVELS, SLOT_QUERY, SLOT_SUPPORT, LossConfig, ModelConfig
 
 
 def model_config_from_cfg(cfg) -> ModelConfig:
@@ -68,6 +68,30 @@ def model_config_from_cfg(cfg) -> ModelConfig:
         mc.re_layers = int(G.TRANSFORMER_ENCODER.LAYERS)
         mc.re_head_fcs, mc.re_head_dim = int(G.HEAD.NUM_FC), int(G.HEAD.FC_DIM)
     return mc
+
+
+def loss_config_from_cfg(cfg) -> LossConfig:
+    """The keys FCOSOutputs._init_fcos / _init_code_generator read for the training losses
+    (sylph/modeling/meta_fcos/fcos_outputs.py:70-123)."""
+    F, G = cfg.MODEL.FCOS, cfg.MODEL.META_LEARN.CODE_GENERATOR
+    kinds = {"iou": 0, "linear_iou": 1, "giou": 2}
+    if F.LOC_LOSS_TYPE not in kinds:
+        raise NotImplementedError(F.LOC_LOSS_TYPE)                      # IOULoss.forward, iou_loss.py:80-81
+    if G.NAME == "CodeGenerator" and G.BOX_ON:
+        raise NotImplementedError("CODE_GENERATOR.BOX_ON (per-class box regression) is not implemented")
+    if float(G.DISTILLATION_LOSS_WEIGHT) != 0.0:
+        raise NotImplementedError("DISTILLATION_LOSS_WEIGHT > 0 is not implemented (0.0 in the shipped configs)")
+    if G.CONTRASTIVE_LOSS not in ("", None):
+        raise NotImplementedError("CONTRASTIVE_LOSS (snnl) is not implemented ('' in the shipped configs)")
+    if len(F.SIZES_OF_INTEREST) != 4:
+        raise NotImplementedError("SIZES_OF_INTEREST must have 4 entries (5 FPN levels)")
+    lc = LossConfig()
+    lc.focal_alpha, lc.focal_gamma = float(F.LOSS_ALPHA), float(F.LOSS_GAMMA)
+    lc.center_sample, lc.pos_radius = int(bool(F.CENTER_SAMPLE)), float(F.POS_RADIUS)
+    lc.loc_loss_type = kinds[F.LOC_LOSS_TYPE]
+    for i in range(4):
+        lc.sizes_of_interest[i] = int(F.SIZES_OF_INTEREST[i])
+    return lc
 
 
 class Engine:
@@ -234,6 +258,47 @@ class Engine:
         ch = {0: n_classes, 1: 4, 2: 1, 3: 1}[which]
         out = torch.empty((n, ch, lh[level], lw[level]), device=self.device, dtype=torch.float32)
         self._check(self.lib.sylph_export_head_output(self.h, which, level, c_void_p(out.data_ptr()), self._stream()))
+        return out
+
+    # ------------------------------------------------------------------ training forward (losses only)
+    def fcos_loss_sums(self, slot: int, codes: torch.Tensor, support_targets: Sequence[int], gt_boxes: torch.Tensor,
+                       gt_classes: torch.Tensor, gt_offsets: Sequence[int], want_targets: bool = False):
+        """Head + ground-truth assignment + per-rank loss sums (sylph_fcos_loss_sums).  Returns the (5,) float64 sums
+        on the device and, with want_targets, (labels, target_inds, reg_targets) in level-first order."""
+        codes = codes.to(self.device, torch.float32).contiguous()
+        n, _, _, lh, lw = self.feature_shape(slot)
+        total = n * sum(h * w for h, w in zip(lh, lw))
+        n_cls = codes.shape[0]
+        gt_boxes = gt_boxes.detach().to("cpu", torch.float32).reshape(-1, 4).contiguous()
+        gt_classes = gt_classes.detach().to("cpu", torch.int64).reshape(-1).contiguous()
+        n_gt = gt_boxes.shape[0]
+        assert gt_classes.numel() == n_gt and len(gt_offsets) == n + 1 and len(support_targets) == n_cls
+        st = (c_int64 * n_cls)(*[int(t) for t in support_targets])
+        off = (c_int * (n + 1))(*[int(o) for o in gt_offsets])
+        sums = torch.empty((LOSS_SUMS,), device=self.device, dtype=torch.float64)
+        labels = inds = regs = None
+        if want_targets:
+            labels = torch.empty((total,), device=self.device, dtype=torch.int64)
+            inds = torch.empty((total,), device=self.device, dtype=torch.int64)
+            regs = torch.empty((total, 4), device=self.device, dtype=torch.float32)
+        if not hasattr(self, "_lc"):
+            self._lc = loss_config_from_cfg(self.cfg)
+        ptr = lambda t: c_void_p(t.data_ptr()) if t is not None else None
+        self._check(self.lib.sylph_fcos_loss_sums(
+            self.h, slot, ptr(codes), n_cls, st, byref(self._lc), n_gt,
+            ctypes.cast(c_void_p(gt_boxes.data_ptr()), POINTER(c_float)) if n_gt else None,
+            ctypes.cast(c_void_p(gt_classes.data_ptr()), POINTER(c_int64)) if n_gt else None, off,
+            ptr(sums), ptr(labels), ptr(inds), ptr(regs), self._stream()))
+        return (sums, (labels, inds, regs)) if want_targets else sums
+
+    def fcos_loss_finalize(self, sums: torch.Tensor, global_pos_ctr: Optional[torch.Tensor] = None, world_size: int = 1) -> torch.Tensor:
+        """(loss_fcos_cls, loss_fcos_loc, loss_fcos_ctr) as a (3,) fp32 device tensor (sylph_fcos_loss_finalize)."""
+        out = torch.empty((3,), device=self.device, dtype=torch.float32)
+        if global_pos_ctr is not None:
+            assert global_pos_ctr.is_cuda and global_pos_ctr.dtype == torch.float64 and global_pos_ctr.numel() == 2
+        self._check(self.lib.sylph_fcos_loss_finalize(
+            self.h, c_void_p(sums.data_ptr()), c_void_p(global_pos_ctr.data_ptr()) if global_pos_ctr is not None else None,
+            int(world_size), c_void_p(out.data_ptr()), self._stream()))
         return out
 
     # ------------------------------------------------------------------ instrumentation

@@ -38,6 +38,16 @@ def test_model_config_struct_layout_matches_header():
     assert ctypes.sizeof(_lib.ModelConfig) == 4 * (8 + 3 + 6 + 7 + 6)
 
 
+def test_loss_config_struct_layout_matches_header():
+    text = open(os.path.join(REPO, "include", "sylph_b200.h")).read()
+    body = text[text.index("typedef struct sylph_loss_config {"):text.index("} sylph_loss_config;")]
+    body = re.sub(r"/\*.*?\*/", "", body, flags=re.S)
+    fields = re.findall(r"\b(?:int|float)\s+([a-z_0-9]+)(?:\[4\])?;", body)
+    assert fields == [f[0] for f in _lib.LossConfig._fields_]
+    assert ctypes.sizeof(_lib.LossConfig) == 4 * (5 + 4)
+    assert f"#define SYLPH_LOSS_SUMS {_lib.LOSS_SUMS}" in text and f"#define SYLPH_BACKGROUND_ID {_lib.BACKGROUND_ID}" in text
+
+
 def test_create_fails_loudly_without_a_device():
     import torch
     if torch.cuda.is_available():

@@ -109,3 +109,60 @@ def test_gather_class_code_world2_with_an_empty_rank():
 def test_gather_is_identity_without_a_process_group():
     codes = [{"support_set_target": 0, "class_code": {"cls_conv": torch.zeros(1, 256, 1, 1), "cls_bias": torch.zeros(1, 1, 1, 1)}}]
     assert gather_class_code(codes) is codes
+
+
+def _worker_losses(rank, world, port, q):
+    """Training forward on 2 ranks: each rank holds its own query images; the positives and the
+    centre-ness target sum are all-reduced (fcos_outputs.py:520-523, 557-558) -- the mirror's `_reduce_sum` /
+    `_world_size` on a float64 pair, and the oracle's reduce hook, against a single-process recomputation."""
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from oracle import upstream as up
+        from oracle.meta_fcos_oracle import MetaFCOSOracle
+        from sylph_few_shot_detection_b200 import modeling as M
+        from sylph_few_shot_detection_b200 import weights as W
+        from tests.cases import cfg_for
+        cfg = cfg_for("COCO-Detection/Meta-FCOS/Meta-FCOS-finetune.yaml", ["MODEL.PROPOSAL_GENERATOR.FREEZE_BBOX_BRANCH", False,
+                                                                           "MODEL.PROPOSAL_GENERATOR.FREEZE", False])
+        orc = MetaFCOSOracle(cfg, {"pixel_mean": torch.zeros(3, 1, 1), "pixel_std": torch.ones(3, 1, 1),
+                                   **{k: v for k, v in W.synthetic_state_dict(cfg, 1).items() if k.startswith("backbone.")}})
+        g = torch.Generator().manual_seed(40 + rank)
+        sizes = [(12, 16), (6, 8), (3, 4), (2, 2), (1, 1)]
+        logits = [torch.randn(1, 2, h, w, generator=g) - 2 for h, w in sizes]
+        regs = [torch.rand(1, 4, h, w, generator=g) * 4 for h, w in sizes]
+        ctrs = [torch.randn(1, 1, h, w, generator=g) for h, w in sizes]
+        gts = [(torch.tensor([[8.0, 8.0, 90.0, 70.0], [30.0, 20.0, 60.0, 50.0]]) + 10 * rank, torch.tensor([3, 5]))]
+        losses, ex = orc.fcos_losses(logits, regs, ctrs, gts, [3, 5], world_size=up.get_world_size(), reduce=up.reduce_sum)
+        local, _ = orc.fcos_losses(logits, regs, ctrs, gts, [3, 5])            # world 1: local normalisers
+        pair = torch.tensor([float(ex["num_pos"]), float(ex["ctr_targets_sum"])], dtype=torch.float64)
+        total = M._reduce_sum(pair)
+        q.put((rank, M._world_size(), {k: float(v) for k, v in losses.items()}, {k: float(v) for k, v in local.items()},
+               pair.tolist(), total.tolist()))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_training_loss_normalisers_are_reduced_over_ranks():
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker_losses, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    out = sorted([q.get(timeout=180) for _ in range(2)])
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    pos = [o[4][0] for o in out]
+    ctr = [o[4][1] for o in out]
+    assert all(p > 0 for p in pos) and pos[0] != pos[1] or ctr[0] != ctr[1]
+    for rank, world, losses, local, pair, total in out:
+        assert world == 2
+        assert total[0] == pos[0] + pos[1] and abs(total[1] - (ctr[0] + ctr[1])) < 1e-9
+        avg_pos, avg_ctr = max(total[0] / 2, 1.0), max(total[1] / 2, 1e-6)
+        # same sums, other normalisers: loss_world2 = loss_local * local_norm / global_norm
+        assert abs(losses["loss_fcos_cls"] - local["loss_fcos_cls"] * max(pair[0], 1.0) / avg_pos) < 1e-5 * abs(losses["loss_fcos_cls"])
+        assert abs(losses["loss_fcos_ctr"] - local["loss_fcos_ctr"] * max(pair[0], 1.0) / avg_pos) < 1e-5 * abs(losses["loss_fcos_ctr"])
+        assert abs(losses["loss_fcos_loc"] - local["loss_fcos_loc"] * max(pair[1], 1e-6) / avg_ctr) < 1e-5 * abs(losses["loss_fcos_loc"])

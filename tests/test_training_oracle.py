@@ -1,0 +1,88 @@
+"""Training forward, CPU side: the oracle's restatement of `_get_gt`, the FCOS ground-truth
+assignment and `fcos_losses_episodic_learning` against golden vectors produced by the REFERENCE model in train() mode
+(oracle/make_golden.py --train-only), plus the host logic of the plugin mirror."""
+import pytest
+import torch
+
+from oracle.make_golden import to_records
+from oracle.meta_fcos_oracle import MetaFCOSOracle
+from sylph_few_shot_detection_b200 import weights as W
+from tests.cases import cfg_for, load_golden
+
+CASES = ["coco_train_2way_2shot", "lvis_train_3way_1shot_cls_only"]
+
+
+@pytest.mark.parametrize("case", CASES)
+def test_oracle_training_forward_reproduces_reference(case):
+    g = load_golden(case)
+    cfg = cfg_for(g["config"], g["opts"])
+    orc = MetaFCOSOracle(cfg, W.synthetic_state_dict(cfg, g["seed"]))
+    losses, ex = orc.training_forward(to_records(g["items"]))
+    assert set(losses) == set(g["losses"])
+    for k, v in g["losses"].items():
+        assert abs(float(losses[k]) - float(v)) <= 2e-5 * abs(float(v)), (k, float(losses[k]), float(v))
+    # integer / index outputs and the regression targets: bit-exact
+    assert torch.equal(ex["labels"], g["labels"].to(torch.int64))
+    assert torch.equal(ex["target_inds"], g["target_inds"].to(torch.int64))
+    assert torch.equal(ex["fpn_levels"], g["fpn_levels"].to(torch.int64))
+    assert torch.equal(ex["reg_targets"], g["reg_targets"])
+    assert [b.shape[0] for b, _ in ex["gts"]] == g["gt_counts"]
+
+
+def test_training_goldens_cover_the_interesting_regimes():
+    g = load_golden("coco_train_2way_2shot")
+    lab = g["labels"].to(torch.int64)
+    pos = lab != MetaFCOSOracle.BACKGROUND_ID
+    assert 0 < int(pos.sum()) < lab.numel()
+    assert g["gt_counts"][-1] == 0 and min(g["gt_counts"][:-1]) > 0          # an image without ground truth
+    assert int((g["target_inds"] == -1).sum()) > 0                           # ... marks its locations with -1
+    assert len(set(lab[pos].tolist())) == 2                                  # both episode classes are hit
+    assert len(set(g["fpn_levels"][pos].tolist())) >= 2                      # positives on several FPN levels
+    assert set(g["losses"]) == {"loss_fcos_cls", "loss_fcos_loc", "loss_fcos_ctr"}
+    assert set(load_golden("lvis_train_3way_1shot_cls_only")["losses"]) == {"loss_fcos_cls"}
+
+
+def test_targets_quirks_of_the_reference():
+    """First box centred on x == 0 disables centre sampling for the whole image (fcos_outputs.py:213); ties of the
+    minimal area go to the first ground truth; a location outside every size range is background but still carries the
+    regression target of ground truth 0."""
+    cfg = cfg_for("COCO-Detection/Meta-FCOS/Meta-FCOS-finetune.yaml")
+    orc = MetaFCOSOracle(cfg, W.synthetic_state_dict(cfg, 1))
+    sizes = [(8, 8), (4, 4), (2, 2), (1, 1), (1, 1)]
+    box = torch.tensor([[10.0, 10.0, 50.0, 50.0]])
+    lab, ind, reg, lvl = orc.fcos_targets(sizes, [(torch.cat([box, box]), torch.tensor([5, 9]))])
+    assert set(lab.tolist()) == {5, MetaFCOSOracle.BACKGROUND_ID}            # tie -> first ground truth
+    assert set(ind.tolist()) == {0}
+    bg = lab == MetaFCOSOracle.BACKGROUND_ID
+    assert bool((reg[bg].abs().sum(dim=1) > 0).all())
+    lab2, _, _, _ = orc.fcos_targets(sizes, [(torch.tensor([[-20.0, 4.0, 20.0, 44.0], [10.0, 10.0, 50.0, 50.0]]), torch.tensor([5, 9]))])
+    assert set(lab2.tolist()) == {MetaFCOSOracle.BACKGROUND_ID}
+
+
+def test_plugin_training_forward_host_logic():
+    """The mirror keeps the reference's dispatch and asserts without touching the GPU."""
+    from sylph_few_shot_detection_b200 import modeling as M
+    from sylph_few_shot_detection_b200.structures import Boxes, Instances
+    cfg = cfg_for("COCO-Detection/Meta-FCOS/Meta-FCOS-finetune.yaml", ["MODEL.META_LEARN.SHOT", 2])
+    model = M.build_model(cfg)
+    model.train()
+    with pytest.raises(AssertionError):
+        model([{"support_set": []}])                                          # no "query_set"
+    with pytest.raises(NotImplementedError):
+        model([], run_type="meta_learn_test_support")                         # run types are eval-only
+    inst = Instances((10, 10))
+    inst.gt_boxes = Boxes(torch.tensor([[1.0, 1.0, 5.0, 5.0], [2.0, 2.0, 6.0, 6.0], [0.0, 0.0, 3.0, 3.0]]))
+    inst.gt_classes = torch.tensor([4, 9, 4])
+    gts = model._get_gt([{"instances": inst}], support_set_targets=[torch.tensor(4), torch.tensor(7)])
+    assert gts[0].gt_classes.tolist() == [4, 4] and gts[0].gt_boxes.tensor.shape == (2, 4)
+    gts = model._get_gt([{"instances": inst}], support_set_targets=[torch.tensor(1)])
+    assert len(gts[0].gt_boxes) == 0 and gts[0].gt_boxes.tensor.shape == (0, 4)
+    rec = {"image": torch.zeros(3, 32, 32), "instances": inst, "height": 32, "width": 32}
+    with pytest.raises(AssertionError, match="divisible by number of shot"):
+        model([{"support_set": [rec], "query_set": [rec], "support_set_target": torch.tensor(4)}])
+    from sylph_few_shot_detection_b200.runtime import loss_config_from_cfg
+    lc = loss_config_from_cfg(cfg)
+    assert (lc.loc_loss_type, lc.center_sample, list(lc.sizes_of_interest)) == (2, 1, [64, 128, 256, 512])
+    bad = cfg_for("COCO-Detection/Meta-FCOS/Meta-FCOS-finetune.yaml", ["MODEL.META_LEARN.CODE_GENERATOR.BOX_ON", True])
+    with pytest.raises(NotImplementedError):
+        loss_config_from_cfg(bad)
