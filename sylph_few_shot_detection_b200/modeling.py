@@ -119,18 +119,19 @@ class CodeGenerator(_EngineBound):
         assert codes is not None
         if len(codes) == 0:
             return codes
-        rows = []
+        convs, biases = [], []
+        dev = self.engine.device  # codes normally already live on the device: no host round trip, no sync
         for code in codes:
             assert "class_code" in code, "class_code is not in code"
             assert "cls_conv" in code["class_code"], "class_conv is not in class_code"
             if "cls_weight_norm" in code["class_code"]:
                 raise NotImplementedError("cls_weight_norm (SCALE_LAYER) is not supported")
-            w = code["class_code"]["cls_conv"]
             b = code["class_code"]["cls_bias"]
             assert b.numel() == 1, "predicted bias should only have batch size 1"
-            dev = self.engine.device  # codes normally already live on the device: no host round trip, no sync
-            rows.append(torch.cat([w.reshape(-1).to(dev, torch.float32), b.reshape(-1).to(dev, torch.float32)]))
-        raw = torch.stack(rows)
+            convs.append(code["class_code"]["cls_conv"].reshape(1, 256).to(dev, torch.float32))
+            biases.append(b.reshape(1, 1).to(dev, torch.float32))
+        # three concatenations whatever the number of classes (was two small kernels per class)
+        raw = torch.cat([torch.cat(convs, dim=0), torch.cat(biases, dim=0)], dim=1)
         normed = self.engine.normalize_codes(raw)
         for i, code in enumerate(codes):
             code["class_code"]["cls_conv"] = normed[i, :256].reshape(1, 256, 1, 1)

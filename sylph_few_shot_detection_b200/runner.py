@@ -14,7 +14,7 @@ pickled CPU tensors through all_gather_object.
 """
 from __future__ import annotations
 
-from typing import Any, Dict, List, Optional, Sequence
+from typing import Any, Dict, List, Optional, Sequence, Tuple
 
 import torch
 import torch.distributed as dist
@@ -150,6 +150,46 @@ def replace_class_code(support_set_class_code: List[Dict], target_class_codes: L
     return results
 
 
+def _code_rows(codes: List[Dict], device) -> torch.Tensor:
+    """(n, 257) rows from the list schema with three concatenations (no per-class kernels, no host sync)."""
+    conv = torch.cat([c["class_code"]["cls_conv"].reshape(1, 256) for c in codes], dim=0).to(device, torch.float32)
+    bias = torch.cat([c["class_code"]["cls_bias"].reshape(1, 1) for c in codes], dim=0).to(device, torch.float32)
+    return torch.cat([conv, bias], dim=1)
+
+
+def gather_class_code_known_shards(sub_class_codes: List[Dict], counts: Sequence[int], meta: Sequence[Tuple[Any, str]],
+                                   group=None, device: Optional[torch.device] = None) -> List[Dict]:
+    """Step C when every rank already knows the shard sizes and the (support_set_target, class_name) of every class --
+    the case of `run_episode`, where the class list is global and only the CODES are produced per rank.  Exactly ONE
+    collective (all_gather_into_tensor of a fixed-stride [max_shard, 257] fp32 device buffer) and no host
+    synchronisation: the returned dicts hold views of the gathered buffer, the stream keeps running ahead.
+    Same result as `gather_class_code` (tests/test_runner_dist.py)."""
+    world = dist.get_world_size(group)
+    rank = dist.get_rank(group)
+    assert len(counts) == world and len(sub_class_codes) == counts[rank] and len(meta) == sum(counts)
+    if device is None:
+        device = (torch.device("cuda", torch.cuda.current_device()) if dist.get_backend(group) == "nccl"
+                  else torch.device("cpu"))
+    max_n = max(max(counts), 1)
+    if len(sub_class_codes) == max_n:
+        buf = _code_rows(sub_class_codes, device).contiguous()
+    else:
+        buf = torch.zeros((max_n, CODE_STRIDE), dtype=torch.float32, device=device)
+        if len(sub_class_codes):
+            buf[:len(sub_class_codes)] = _code_rows(sub_class_codes, device)
+    gathered = torch.empty((world * max_n, CODE_STRIDE), dtype=torch.float32, device=device)
+    dist.all_gather_into_tensor(gathered, buf, group=group)
+    out, k = [], 0
+    for r in range(world):
+        for i in range(counts[r]):
+            row = gathered[r * max_n + i]
+            target, name = meta[k]
+            k += 1
+            out.append({"support_set_target": target, "class_name": name,
+                        "class_code": {"cls_conv": row[:256].reshape(1, 256, 1, 1), "cls_bias": row[256:257].reshape(1, 1, 1, 1)}})
+    return out
+
+
 def gather_class_code(sub_class_codes: List[Dict], group=None, device: Optional[torch.device] = None,
                       reduce: bool = False, engine=None) -> List[Dict]:
     """Step C: all ranks end up with the codes of ALL classes, ordered by rank then local order (what concatenating
@@ -269,7 +309,13 @@ def run_episode(model: MetaOneStageDetector, support_items: Sequence[Dict[str, A
             model.engine.extract_features_multi([(SLOT_SUPPORT, sup_imgs), (SLOT_QUERY, qry_imgs)])
             merged = True
     sub_codes = inference_on_support_set(model, my_support, features_in_slot=merged)
-    all_codes = gather_class_code(sub_codes, group=group) if (world > 1 and shard) else sub_codes
+    if world > 1 and shard:
+        # the class list is global: shard sizes, ids and names are known everywhere, only the codes travel
+        counts = [len(shard_range(len(support_items), world, r)) for r in range(world)]
+        meta = [(it["support_set_target"], it.get("class_name", "")) for it in support_items]
+        all_codes = gather_class_code_known_shards(sub_codes, counts, meta, group=group)
+    else:
+        all_codes = sub_codes
     all_codes = inference_normalization(model, all_codes)
     packed = format_class_codes_shared(all_codes, device=model.device)
     if ready is not None:

@@ -7,7 +7,8 @@ import torch
 import torch.distributed as dist
 import torch.multiprocessing as mp
 
-from sylph_few_shot_detection_b200.runner import format_class_codes_shared, gather_class_code, shard_range
+from sylph_few_shot_detection_b200.runner import (format_class_codes_shared, gather_class_code,
+                                                   gather_class_code_known_shards, shard_range)
 
 
 def _free_port():
@@ -31,6 +32,15 @@ def _worker(rank, world, port, n_classes, q):
                                         "cls_bias": torch.randn(1, 1, 1, 1, generator=g)}})
         allc = gather_class_code(mine)
         packed = format_class_codes_shared(allc)
+        # the one-collective fast path of run_episode (shard sizes / ids / names known on every rank) must agree
+        counts = [len(shard_range(n_classes, world, r)) for r in range(world)]
+        meta = [(torch.tensor(c), f"class{c}") for c in range(n_classes)]
+        fast = gather_class_code_known_shards(mine, counts, meta)
+        assert [int(c["support_set_target"]) for c in fast] == [int(c["support_set_target"]) for c in allc]
+        assert [c["class_name"] for c in fast] == [c["class_name"] for c in allc]
+        for a, b in zip(fast, allc):
+            assert torch.equal(a["class_code"]["cls_conv"], b["class_code"]["cls_conv"])
+            assert torch.equal(a["class_code"]["cls_bias"], b["class_code"]["cls_bias"])
         q.put((rank, [int(c["support_set_target"]) for c in allc], [c["class_name"] for c in allc],
                packed["cls_conv"].clone(), packed["cls_bias"].clone()))
     finally:
