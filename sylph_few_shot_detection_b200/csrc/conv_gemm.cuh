@@ -82,7 +82,8 @@ struct GemmArgs {
     int dbg_a_row_skew;    // experiment: load the A box `skew` rows early and start the MMA descriptor `skew` rows in
     int dbg_base_offset;   // experiment: matrix-descriptor base_offset field used with the skew
     int dbg_skip;          // bring-up timing experiments (halo pipeline): 1 = no output stores, 2 = no MMAs issued,
-                           // 4 = no A loads (barriers only), 8 = no TMEM reads in the epilogue
+                           // 4 = no A loads (barriers only), 8 = no TMEM reads in the epilogue;
+                           // 16 (generic pipeline) = reload the weight tile of a ring slot even when it is already there
 };
 
 // HALO > 0 selects the 3x3 "halo" pipeline: ONE A box of 130 rows (the 128 output rows plus one row on either side)
@@ -258,6 +259,9 @@ conv_gemm_f16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_co
             int hs = 0;
             uint32_t hphase = 0;
             int it = 0;
+            [[maybe_unused]] int b_tag[STAGES];   // id of the weight tile each ring slot holds (generic pipeline)
+#pragma unroll
+            for (int s = 0; s < STAGES; ++s) b_tag[s] = 0;
             // the padded width of the NEXT tile's plane is fetched one iteration ahead (two dependent global loads)
             auto fetch_wp = [&](int t) -> int {
                 int m, n;
@@ -339,13 +343,23 @@ conv_gemm_f16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_co
                 int tap = 0, kb = 0;
                 for (int ks = 0; ks < ksteps; ++ks) {
                     ptx::mbar_wait(&empty_bar[stage], phase ^ 1u);
-                    ptx::mbar_arrive_expect_tx(&full_bar[stage], S::kStageBytes);
+                    // Weight tile already in this slot?  When the number of k-steps divides STAGES and the CTA keeps its
+                    // N tile (grid % num_n_tiles == 0, see launch_conv_gemm_bn), slot s always carries the same B tile:
+                    // it is loaded once and only the A half of the slot is refilled (the MMAs have retired -- the empty
+                    // barrier above -- and nothing else writes the B half).  B rows were 20-40 % of the TMA row requests
+                    // of the bottleneck 1x1 convolutions (profiles/r01_mma_issue_experiments.md, "TMA request rate").
+                    const int b_id = ks * p.num_n_tiles + n_tile + 1;
+                    const bool keep_b = !(p.dbg_skip & 16) && b_tag[stage] == b_id;
+                    ptx::mbar_arrive_expect_tx(&full_bar[stage], keep_b ? S::kABytes : S::kStageBytes);
                     uint8_t* sa = smem + S::kRingOffset + stage * S::kStageBytes;
                     ptx::tma_load_2d(sa, &tmap_a, &full_bar[stage], kb * kBlockK,
                                      a_row_base + static_cast<int>(p.tap_dy[tap]) * wp + static_cast<int>(p.tap_dx[tap]) -
                                          p.dbg_a_row_skew);
-                    ptx::tma_load_2d(sa + S::kABytes, &tmap_b, &full_bar[stage], kb * kBlockK,
-                                     tap * p.b_rows_per_tap + b_row_base);
+                    if (!keep_b) {
+                        ptx::tma_load_2d(sa + S::kABytes, &tmap_b, &full_bar[stage], kb * kBlockK,
+                                         tap * p.b_rows_per_tap + b_row_base);
+                        b_tag[stage] = b_id;
+                    }
                     if (++kb == p.kblocks_per_tap) { kb = 0; ++tap; }
                     if (++stage == STAGES) { stage = 0; phase ^= 1u; }
                 }

@@ -83,11 +83,19 @@ inline cudaError_t launch_conv_gemm_bn(const CUtensorMap& ta, const CUtensorMap&
     }
     const int total = args.num_m_tiles * args.num_n_tiles;
     if (total <= 0) return cudaSuccess;
-    const int grid = total < num_sms ? total : num_sms;
+    int grid = total < num_sms ? total : num_sms;
+    // Generic pipeline with k-steps | STAGES: ring slot s always carries k-step (s mod ksteps), so a CTA that also keeps
+    // its N tile never reloads a weight tile.  tile = blockIdx + j * grid and n_tile = tile mod num_n_tiles: the N tile
+    // is fixed per CTA iff grid is a multiple of num_n_tiles -- give up at most num_n_tiles - 1 SMs for that.
+    const int ksteps = args.taps * args.kblocks_per_tap;
+    if (HALO == 0 && !STEM16 && args.num_n_tiles > 1 && ksteps <= STAGES && STAGES % ksteps == 0 && grid == num_sms &&
+        grid > 4 * args.num_n_tiles && !(args.dbg_skip & 16))
+        grid -= grid % args.num_n_tiles;
     return launch_k(conv_gemm_f16_kernel<BN, STAGES, EPI_BUFS, HALO, STEM16, BRES>, dim3(grid), dim3(S::kThreads), S::kTotal, stream, ta, tb, tres, tout, args);
 }
 
 constexpr int kStagedTwoBufMaxKSteps = 8;
+constexpr bool kStagedConv1EightSlots = true;   // res2 conv1 (K = 256): 8 ring slots so that weight tiles stay put
 
 // Direct-epilogue variants: BN in {16, 64, 128, 256}.
 inline cudaError_t launch_conv_gemm(int bn, const CUtensorMap& ta, const CUtensorMap& tb, const GemmArgs& args,
@@ -155,7 +163,12 @@ inline cudaError_t launch_conv_gemm_staged(int bn, const CUtensorMap& ta, const 
                                            cudaStream_t stream, int variant = 0) {
     // BN = 256, variant 1: 2 mainloop stages + 2 staging buffers (the residual of tile i+1 streams in during the
     // epilogue of tile i); variant 2: 3 stages + 1 staging buffer for long K.  0 = pick by the number of k-steps.
-    if (bn == 64) return launch_conv_gemm_bn<64, 6, 2>(ta, tb, tres, tout, args, num_sms, stream);
+    if (bn == 64) {
+        // K = 256 (bottleneck conv1 of res2): 4 k-steps; 8 slots = two tiles in flight with resident weight tiles
+        if (variant == 3 || (variant == 0 && args.taps * args.kblocks_per_tap == 4 && kStagedConv1EightSlots))
+            return launch_conv_gemm_bn<64, 8, 2>(ta, tb, tres, tout, args, num_sms, stream);
+        return launch_conv_gemm_bn<64, 6, 2>(ta, tb, tres, tout, args, num_sms, stream);
+    }
     if (bn == 128) return launch_conv_gemm_bn<128, 4, 2>(ta, tb, tres, tout, args, num_sms, stream);
     if (bn != 256) return cudaErrorInvalidValue;
     if (variant == 0) variant = (args.taps * args.kblocks_per_tap <= kStagedTwoBufMaxKSteps) ? 1 : 2;

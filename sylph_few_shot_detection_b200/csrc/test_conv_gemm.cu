@@ -312,6 +312,26 @@ int main(int argc, char** argv) {
         else printf("unknown shape %s\n", n.c_str());
         return 0;
     }
+    if (argc > 1 && std::string(argv[1]) == "bskip") {
+        // A/B of the weight-tile reuse (dbg_skip bit 16 = always reload) on the bottleneck 1x1 shapes of one 33-image
+        // 800x1344 trunk pass (25 support + 8 query images of the headline episode)
+        for (int skip : {16, 0}) {
+            g_dbg_skip = skip;
+            printf("---- weight tiles %s\n", skip ? "reloaded for every output tile" : "kept in their ring slot");
+            bench_shape("res2_conv3_1x1_64_256_res_STAGED_2x2", 256, 17622, 64, 256, 1, kEpiResidual | kEpiRelu | kEpiMask, sms, 1);
+            bench_shape("res3_conv3_1x1_128_512_res_STAGED_2x2", 256, 4488, 128, 512, 1, kEpiResidual | kEpiRelu | kEpiMask, sms, 1);
+            bench_shape("res3_conv3_1x1_128_512_res_STAGED_bn128", 128, 4488, 128, 512, 1, kEpiResidual | kEpiRelu | kEpiMask, sms, 1);
+            bench_shape("res4_conv3_1x1_256_1024_res_STAGED_2x2", 256, 1155, 256, 1024, 1, kEpiResidual | kEpiRelu | kEpiMask, sms, 1);
+            bench_shape("res4_conv3_1x1_256_1024_res_STAGED_bn128", 128, 1155, 256, 1024, 1, kEpiResidual | kEpiRelu | kEpiMask, sms, 1);
+            bench_shape("res5_conv3_1x1_512_2048_res_STAGED_2x2", 256, 330, 512, 2048, 1, kEpiResidual | kEpiRelu | kEpiMask, sms, 1);
+            bench_shape("res2_conv1_1x1_256_64_STAGED_6slots", 64, 17622, 256, 64, 1, kEpiRelu | kEpiMask, sms, 1);
+            bench_shape("res2_conv1_1x1_256_64_STAGED_8slots", 64, 17622, 256, 64, 1, kEpiRelu | kEpiMask, sms, 3);
+            bench_shape("res3_conv1_1x1_512_128_STAGED", 128, 4488, 512, 128, 1, kEpiRelu | kEpiMask, sms, 1);
+            bench_shape("res3_shortcut_1x1_256_512_STAGED_2x2", 256, 4488, 256, 512, 1, kEpiMask, sms, 1);
+            bench_shape("res3_shortcut_1x1_256_512_STAGED_bn128", 128, 4488, 256, 512, 1, kEpiMask, sms, 1);
+        }
+        return 0;
+    }
     {   // host fp32 -> fp16 conversion against the CUDA reference conversion
         int bad = 0;
         for (int i = 0; i < 2000000; ++i) {
