@@ -7,6 +7,7 @@
 
 #include "conv_gemm.cuh"
 #include "conv_gemm_2cta.cuh"
+#include "conv1x1_pair.cuh"
 
 namespace sylph {
 
@@ -174,6 +175,25 @@ inline cudaError_t launch_conv_gemm_staged(int bn, const CUtensorMap& ta, const 
     if (variant == 0) variant = (args.taps * args.kblocks_per_tap <= kStagedTwoBufMaxKSteps) ? 1 : 2;
     if (variant == 1) return launch_conv_gemm_bn<256, 2, 2>(ta, tb, tres, tout, args, num_sms, stream);
     return launch_conv_gemm_bn<256, 3, 1>(ta, tb, tres, tout, args, num_sms, stream);
+}
+
+// CTA-pair 1x1 convolution with the staged epilogue (BN = 256, taps = 1): `tb` box = 128 rows (each CTA of the pair holds
+// half of the 256 output channels of a B tile), `ta` / `tres` / `tout` as for launch_conv_gemm_staged.
+// 3 ring slots x 32 KB + 2 staging buffers x 64 KB = 224 KB.
+inline cudaError_t launch_conv1x1_pair_staged(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tres,
+                                              const CUtensorMap& tout, const GemmArgs& args, int num_sms, cudaStream_t stream) {
+    using S = Pair1x1Smem<3, 2>;
+    static bool configured = false;
+    if (!configured) {
+        cudaError_t e = cudaFuncSetAttribute(conv1x1_pair_staged_kernel<3, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, S::kTotal);
+        if (e != cudaSuccess) return e;
+        configured = true;
+    }
+    if (args.taps != 1) return cudaErrorInvalidValue;
+    const int pairs = ((args.num_m_tiles + 1) / 2) * args.num_n_tiles;
+    if (pairs <= 0) return cudaSuccess;
+    const int clusters = pairs < num_sms / 2 ? pairs : num_sms / 2;
+    return launch_k(conv1x1_pair_staged_kernel<3, 2>, dim3(clusters * 2), dim3(S::kThreads), S::kTotal, stream, ta, tb, tres, tout, args);
 }
 
 // Stem: 4 vertical taps x (one 131 x 16 A box, 4 horizontal K = 16 MMAs), staged epilogue, Cout = 64; the weights

@@ -81,6 +81,8 @@ struct sylph_ctx {
     int halo_pipeline = 1;    // SYLPH_HALO=0 falls back to one A box per tap for the 3x3 convolutions
     int pair_kernel = 1;      // SYLPH_PAIR: bit 0 = CTA-pair kernel for the N = 256 3x3 convolutions, bit 1 = also for N = 64 /
                               // 128 (measured SLOWER than the single-CTA halo kernel: profiles/r01_mma_issue_experiments.md)
+    int pair1x1 = 1;          // SYLPH_PAIR1X1=0 keeps the single-CTA staged kernel for every 1x1 convolution; 2 = pair kernel
+                              // for every staged 1x1 convolution with 256-channel N tiles and K >= 256 (experiments)
     int stem16 = 1;           // SYLPH_STEM16=0 runs the stem over 64-wide overlapped rows instead of K = 16 taps
     std::vector<Timing> timings;
 
@@ -535,13 +537,20 @@ static int run_conv(sylph_ctx* c, const ConvCall& k, cudaStream_t st) {
     const bool halo = c->halo_pipeline && W.taps == 9 && !k.stem && !k.staged;
     const bool pair = halo && c->pair_kernel && (W.bn == 256 || ((c->pair_kernel & 2) && W.bn >= 64)) && !(k.flags & kEpiResidual);
     const bool stem16 = k.stem && c->stem16 && k.staged && W.bn == 64 && W.taps == 4 && k.a_ld == 16;
+    // Staged 1x1 convolutions with 256-channel N tiles: the CTA-pair kernel where it measured faster on the 33-image
+    // shapes (profiles/r01_pair1x1_shapes.log): shortcut convolutions (no residual, K >= 256, N >= 512: res4 0.205 ->
+    // 0.161 ms) and conv3 with K >= 512 (res5 0.126 -> 0.111 ms); res3 / res4 conv3 and the conv1 layers stay single-CTA
+    // (lock-stepped epilogues of the pair cost more than the halved weight traffic buys there).
+    const bool has_res = (k.flags & kEpiResidual) != 0;
+    const bool pair1x1 = k.staged && !k.stem && W.taps == 1 && W.bn == 256 && k.n_tiles >= 2 && W.k_per_tap >= 256 &&
+                         (c->pair1x1 == 2 || (c->pair1x1 == 1 && (has_res ? W.k_per_tap >= 512 : W.cout_pad >= 512)));
     if (stem16) {
         if (make_tmap_2d_k16(&ta, k.A, static_cast<uint64_t>(k.a_rows), kBlockM + 3, &err))
             return c->fail("A tensor map (%s): %s", k.name, err.c_str());
     } else if (make_tmap_2d(&ta, k.A, static_cast<uint64_t>(k.a_rows), k.a_cols, k.a_ld, halo ? kBlockM + 2 : kBlockM, &err))
         return c->fail("A tensor map (%s): %s", k.name, err.c_str());
     if (make_tmap_2d(&tb, k.w_override ? k.w_override : W.w, static_cast<uint64_t>(W.taps) * W.cout_pad, W.k_per_tap,
-                     W.k_per_tap, pair ? W.bn / 2 : W.bn, &err))
+                     W.k_per_tap, (pair || pair1x1) ? W.bn / 2 : W.bn, &err))
         return c->fail("B tensor map (%s): %s", k.name, err.c_str());
     GemmArgs g{};
     g.tile_begin = k.tile_begin;
@@ -586,6 +595,7 @@ static int run_conv(sylph_ctx* c, const ConvCall& k, cudaStream_t st) {
             make_tmap_2d(&tout, static_cast<const __half*>(k.out), static_cast<uint64_t>(k.out_rows), k.ldc, k.ldc, kBlockM, &err))
             return c->fail("epilogue tensor maps (%s): %s", k.name, err.c_str());
         if (stem16) CU_TRY(c, launch_conv_gemm_stem16(ta, tb, tout, g, c->num_sms, st));
+        else if (pair1x1) CU_TRY(c, launch_conv1x1_pair_staged(ta, tb, tres, tout, g, c->num_sms, st));
         else CU_TRY(c, launch_conv_gemm_staged(W.bn, ta, tb, tres, tout, g, c->num_sms, st));
     } else if (pair) {
         CU_TRY(c, launch_conv3x3_pair(ta, tb, g, c->num_sms, st, W.bn));
@@ -649,6 +659,7 @@ int sylph_create(sylph_ctx** out, int device, const sylph_model_config* cfg) {
     if (const char* e = getenv("SYLPH_HALO")) c->halo_pipeline = atoi(e);
     if (const char* e = getenv("SYLPH_PAIR")) c->pair_kernel = atoi(e);
     if (const char* e = getenv("SYLPH_STEM16")) c->stem16 = atoi(e);
+    if (const char* e = getenv("SYLPH_PAIR1X1")) c->pair1x1 = atoi(e);
     *out = c;
     if (cfg->pre_nms_topk * 5 > 8192) { c->fail("pre_nms_topk * 5 must be <= 8192"); }
     return 0;

@@ -59,6 +59,7 @@ struct Case {
     bool pair = false;    // CTA-pair (cta_group::2) halo kernel
     bool halo = false;    // 3x3 halo pipeline (one 130-row A box per vertical tap and k-block)
     bool staged = false;  // TMA-in / TMA-out epilogue, run IN PLACE (out == residual buffer) like the bottleneck conv3
+    bool pair1x1 = false; // CTA-pair 1x1 convolution with the staged epilogue (conv1x1_pair.cuh)
     bool stem16 = false;  // stem as K = 16 taps: A map = [rows][16] with 32-byte swizzle, 131-row boxes (same math as a_ld = 16)
 };
 
@@ -111,7 +112,7 @@ static int run_case(const Case& c, int num_sms) {
     std::string err;
     if ((c.stem16 ? make_tmap_2d_k16(&ta, dA, M, 131, &err)
                   : make_tmap_2d(&ta, dA, a_rows_dim, c.cin_cols, c.a_ld, (c.halo || c.pair) ? 130 : 128, &err)) ||
-        make_tmap_2d(&tb, dW, static_cast<uint64_t>(c.taps) * c.cout, Kt, Kt, c.pair ? c.bn / 2 : c.bn, &err)) {
+        make_tmap_2d(&tb, dW, static_cast<uint64_t>(c.taps) * c.cout, Kt, Kt, (c.pair || c.pair1x1) ? c.bn / 2 : c.bn, &err)) {
         printf("[%s] FAIL tensor map: %s\n", c.name, err.c_str());
         return 1;
     }
@@ -144,6 +145,7 @@ static int run_case(const Case& c, int num_sms) {
             return 1;
         }
         if (c.stem16) CK(launch_conv_gemm_stem16(ta, tb, tio, g, num_sms, 0));
+        else if (c.pair1x1) CK(launch_conv1x1_pair_staged(ta, tb, tio, tio, g, num_sms, 0));
         else CK(launch_conv_gemm_staged(c.bn, ta, tb, tio, tio, g, num_sms, 0));
     } else if (c.pair) {
         CK(launch_conv3x3_pair(ta, tb, g, num_sms, 0, c.bn));
@@ -254,7 +256,8 @@ static void bench_shape(const char* name, int bn, int m_tiles, int cin, int cout
     }
     CUtensorMap ta, tb;
     std::string err;
-    if (make_tmap_2d(&ta, dA, M, cin, cin, (halo || pair) ? 130 : 128, &err) || make_tmap_2d(&tb, dW, static_cast<uint64_t>(taps) * cout, cin, cin, pair ? bn / 2 : bn, &err)) {
+    const bool pair1x1 = staged == 9;   // CTA-pair 1x1 kernel with the staged epilogue
+    if (make_tmap_2d(&ta, dA, M, cin, cin, (halo || pair) ? 130 : 128, &err) || make_tmap_2d(&tb, dW, static_cast<uint64_t>(taps) * cout, cin, cin, (pair || pair1x1) ? bn / 2 : bn, &err)) {
         printf("[%s] tensor map failed: %s\n", name, err.c_str());
         return;
     }
@@ -270,7 +273,7 @@ static void bench_shape(const char* name, int bn, int m_tiles, int cin, int cout
         g.residual = static_cast<const __half*>(dO);
         if (make_tmap_2d(&tio, static_cast<const __half*>(dO), M, cout, cout, 128, &err)) { printf("tmap failed\n"); return; }
     }
-    auto launch = [&]() { return staged ? launch_conv_gemm_staged(bn, ta, tb, tio, tio, g, num_sms, 0, staged) : (pair ? launch_conv3x3_pair(ta, tb, g, num_sms, 0, bn) : (halo ? launch_conv_gemm_halo(bn, ta, tb, g, num_sms, 0) : launch_conv_gemm(bn, ta, tb, g, num_sms, 0))); };
+    auto launch = [&]() { return pair1x1 ? launch_conv1x1_pair_staged(ta, tb, tio, tio, g, num_sms, 0) : staged ? launch_conv_gemm_staged(bn, ta, tb, tio, tio, g, num_sms, 0, staged == 100 ? 0 : staged) : (pair ? launch_conv3x3_pair(ta, tb, g, num_sms, 0, bn) : (halo ? launch_conv_gemm_halo(bn, ta, tb, g, num_sms, 0) : launch_conv_gemm(bn, ta, tb, g, num_sms, 0))); };
     for (int i = 0; i < 3; ++i) CK(launch());
     CK(cudaDeviceSynchronize());
     const int iters = 10;
@@ -310,6 +313,22 @@ int main(int argc, char** argv) {
         else if (n == "res2_conv3") bench_shape("res2_conv3_1x1_64_256_res_STAGED_2x2", 256, 4272, 64, 256, 1, kEpiResidual | kEpiRelu | kEpiMask, sms, 1);
         else if (n == "res4_conv3") bench_shape("res4_conv3_1x1_256_1024_res_STAGED_2x2", 256, 280, 256, 1024, 1, kEpiResidual | kEpiRelu | kEpiMask, sms, 1);
         else printf("unknown shape %s\n", n.c_str());
+        return 0;
+    }
+    if (argc > 1 && std::string(argv[1]) == "pair1x1") {
+        // single-CTA staged kernels against the CTA-pair 1x1 kernel on the res3..res5 shapes of a 33-image trunk pass
+        struct Sh { const char* name; int m_tiles, cin, cout, flags; };
+        const int RES = kEpiResidual | kEpiRelu | kEpiMask, C1 = kEpiRelu | kEpiMask, SC = kEpiMask;
+        const Sh shapes[] = {{"res3_conv3_128_512", 4488, 128, 512, RES},   {"res4_conv3_256_1024", 1155, 256, 1024, RES},
+                             {"res5_conv3_512_2048", 330, 512, 2048, RES},  {"res4_conv1_1024_256", 1155, 1024, 256, C1},
+                             {"res5_conv1_2048_512", 330, 2048, 512, C1},   {"res3_shortcut_256_512", 4488, 256, 512, SC},
+                             {"res4_shortcut_512_1024", 1155, 512, 1024, SC}, {"res5_shortcut_1024_2048", 330, 1024, 2048, SC},
+                             {"res3_conv1_512_128(bn256)", 4488, 512, 256, C1}};
+        for (const Sh& sh : shapes) {
+            std::string a = std::string(sh.name) + "_SINGLE", b = std::string(sh.name) + "_PAIR";
+            bench_shape(a.c_str(), 256, sh.m_tiles, sh.cin, sh.cout, 1, sh.flags, sms, 0 + 100);   // 100 -> variant 0 (auto)
+            bench_shape(b.c_str(), 256, sh.m_tiles, sh.cin, sh.cout, 1, sh.flags, sms, 9);
+        }
         return 0;
     }
     if (argc > 1 && std::string(argv[1]) == "bskip") {
@@ -483,6 +502,29 @@ int main(int argc, char** argv) {
         Case c{"STAGED_conv1_1x1_relu_mask", bnv, {s0}, round128(s0.nrows), 256, 256, bnv, 1, 4, z1, z1, kEpiRelu | kEpiMask, true};
         c.staged = true;
         printf("bn=%d ", bnv);
+        fails += run_case(c, sms);
+    }
+    {   // CTA-pair 1x1 kernel, staged epilogue in place: residual + ReLU + mask, 4 N tiles, ODD number of M tiles
+        // (phantom tile in the last pair), many pair tiles per cluster (ring / staging-buffer phase cycling), K = 256
+        Seg s0 = mk_seg(0, 151, 168, 1);
+        Case c{"PAIR1x1_staged_inplace_res_relu_mask_n1024", 256, {s0}, round128(s0.nrows), 256, 256, 1024, 1, 4, z1, z1, kEpiRelu | kEpiResidual | kEpiMask, true};
+        c.staged = true;
+        c.pair1x1 = true;
+        fails += run_case(c, sms);
+    }
+    {   // same kernel without residual (conv1 / shortcut use), one N tile, K = 512, even M tiles, two planes
+        Seg s0 = mk_seg(0, 30, 40, 1);
+        Seg s1 = mk_seg(round128(s0.nrows), 13, 21, 1);
+        Case c{"PAIR1x1_staged_noresidual_n256_k512", 256, {s0, s1}, s1.row0 + round128(s1.nrows), 512, 512, 256, 1, 8, z1, z1, kEpiRelu | kEpiMask, true};
+        c.staged = true;
+        c.pair1x1 = true;
+        fails += run_case(c, sms);
+    }
+    {   // a single M tile (one real + one phantom tile in the only pair), 2 N tiles
+        Seg s0 = mk_seg(0, 8, 10, 1);
+        Case c{"PAIR1x1_single_tile_n512", 256, {s0}, round128(s0.nrows), 256, 256, 512, 1, 4, z1, z1, kEpiResidual | kEpiMask, true};
+        c.staged = true;
+        c.pair1x1 = true;
         fails += run_case(c, sms);
     }
     printf("correctness: %d failing case(s)\n", fails);
