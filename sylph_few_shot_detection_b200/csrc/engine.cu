@@ -873,9 +873,14 @@ static int run_trunk(sylph_ctx* c, const std::string& key, int n, const void* co
     TRY(stage_h2d(c, d_desc, descs.data(), n * sizeof(ImageDesc), st));
     {
         StageTimer t(c, "prep_stem_input", st, static_cast<double>(n) * (3.0 * hmax * wmax + 32.0 * g0.H * g0.W));
-        CU_TRY(c, launch_k(prep_stem_input_kernel, dim3(grid_for(static_cast<long long>(n) * g0.H * g0.W, 256, c->num_sms)), dim3(256), 0, st, 
-            static_cast<const ImageDesc*>(d_desc), S0, g0, n, f.pixel_mean[0], f.pixel_mean[1], f.pixel_mean[2],
-            f.pixel_std[0], f.pixel_std[1], f.pixel_std[2]));
+        if (is_u8)
+            CU_TRY(c, launch_k(prep_stem_input_u8_kernel, dim3((g0.W + 255) / 256, std::min(n * g0.H, c->num_sms * 8)), dim3(256), 0, st,
+                static_cast<const ImageDesc*>(d_desc), S0, g0, n, f.pixel_mean[0], f.pixel_mean[1], f.pixel_mean[2],
+                f.pixel_std[0], f.pixel_std[1], f.pixel_std[2]));
+        else
+            CU_TRY(c, launch_k(prep_stem_input_kernel, dim3(grid_for(static_cast<long long>(n) * g0.H * g0.W, 256, c->num_sms)), dim3(256), 0, st,
+                static_cast<const ImageDesc*>(d_desc), S0, g0, n, f.pixel_mean[0], f.pixel_mean[1], f.pixel_mean[2],
+                f.pixel_std[0], f.pixel_std[1], f.pixel_std[2]));
         CU_TRY(c, cudaGetLastError());
         c->launches++;
     }
@@ -1052,8 +1057,8 @@ static int conv_gn_relu(sylph_ctx* c, const ConvW& W, const float* gn_w, const f
     {
         const long long rows = static_cast<long long>(tiles) * kBlockM;
         StageTimer t(c, "gn_apply_relu", st, static_cast<double>(rows) * 256 * 6);
-        CU_TRY(c, launch_k(gn_apply_relu_kernel, dim3(grid_for(rows * 32, 256, c->num_sms)), dim3(256), 0, st, 
-            raw, out, gn_stats, gn_w, gn_b, ps->d_tile_seg, ps->d_segs, tile_begin * kBlockM, rows, 1));
+        CU_TRY(c, launch_k(gn_apply_relu_kernel, dim3(std::max(1, std::min(tiles, c->num_sms * 8))), dim3(256), 0, st,
+            raw, out, gn_stats, gn_w, gn_b, ps->d_tile_seg, ps->d_segs, tile_begin, tiles, 1));
         CU_TRY(c, cudaGetLastError());
     }
     c->launches += 2;

@@ -76,6 +76,88 @@ __global__ void prep_stem_input_kernel(const ImageDesc* __restrict__ imgs, __hal
     }
 }
 
+// uint8 images (what the data mapper hands over): the same arithmetic through a 3 x 256 table of the fp16 results
+// ((v - mean) / std rounded to nearest -- bit-identical to the kernel above, no divisions in the pixel loop), and the
+// six input rows of a 256-pixel output segment staged in shared memory with aligned 4-byte loads (3 coalesced word
+// loads per thread instead of 12 scattered byte loads: the byte loads, not HBM, bounded the kernel at 1.8 TB/s).
+// grid = (ceil(W2 / 256), rows of work); block = 256.
+__global__ void __launch_bounds__(256)
+prep_stem_input_u8_kernel(const ImageDesc* __restrict__ imgs, __half* __restrict__ out, PlaneGeom g, int n_images,
+                          float m0, float m1, float m2, float s0, float s1, float s2) {
+    ptx::griddep_launch();
+    __shared__ unsigned short lut[3][256];
+    __shared__ __align__(16) unsigned char rows[6][528];   // 512 pixels + up to 3 bytes of misalignment, padded
+    {
+        const float mean[3] = {m0, m1, m2};
+        const float stdv[3] = {s0, s1, s2};
+        for (int i = threadIdx.x; i < 768; i += 256) {
+            const int c = i >> 8, v = i & 255;
+            lut[c][v] = static_cast<unsigned short>(pack_half2((static_cast<float>(v) - mean[c]) / stdv[c], 0.f) & 0xFFFFu);
+        }
+    }
+    ptx::griddep_wait();
+    const int x0 = blockIdx.x * 256;              // first output pixel of this block's segment
+    const int n_rows = n_images * g.H;
+    for (int ry = blockIdx.y; ry < n_rows; ry += gridDim.y) {
+        const int n = ry / g.H, y2 = ry - n * g.H;
+        const ImageDesc im = imgs[n];
+        const unsigned char* base = static_cast<const unsigned char*>(im.ptr);
+        const size_t img_bytes = static_cast<size_t>(3) * im.h * im.w;
+        const int px0 = 2 * x0;                   // first input pixel
+        const int npx = min(512, im.w - px0);     // input pixels of this segment that exist
+        __syncthreads();                          // previous iteration's readers are done with `rows` (and the table is built)
+        int shift[6];
+#pragma unroll
+        for (int r = 0; r < 6; ++r) {
+            const int c = r >> 1, iy = 2 * y2 + (r & 1);
+            shift[r] = 0;
+            if (iy < im.h && npx > 0) {
+                const size_t a = (static_cast<size_t>(c) * im.h + iy) * im.w + px0;
+                const size_t a4 = (reinterpret_cast<size_t>(base) + a) & ~static_cast<size_t>(3);
+                shift[r] = static_cast<int>(reinterpret_cast<size_t>(base) + a - a4);
+                const int nwords = (shift[r] + npx + 3) >> 2;
+                const size_t lo = reinterpret_cast<size_t>(base), hi = lo + img_bytes;
+                for (int wd = threadIdx.x; wd < nwords; wd += 256) {
+                    const size_t wa = a4 + 4 * static_cast<size_t>(wd);
+                    uint32_t word;
+                    if (wa >= lo && wa + 4 <= hi) {
+                        word = __ldg(reinterpret_cast<const uint32_t*>(wa));
+                    } else {   // the aligned word straddles an end of the image tensor: byte loads of what exists
+                        word = 0;
+                        for (int b = 0; b < 4; ++b) {
+                            const size_t ba = wa + b;
+                            if (ba >= lo && ba < hi)
+                                word |= static_cast<uint32_t>(__ldg(reinterpret_cast<const unsigned char*>(ba))) << (8 * b);
+                        }
+                    }
+                    *reinterpret_cast<uint32_t*>(&rows[r][4 * wd]) = word;
+                }
+            }
+        }
+        __syncthreads();
+        const int x2 = x0 + threadIdx.x;
+        if (x2 < g.W) {
+            unsigned short h[12];
+#pragma unroll
+            for (int dy = 0; dy < 2; ++dy)
+#pragma unroll
+                for (int dx = 0; dx < 2; ++dx) {
+                    const int iy = 2 * y2 + dy, ix = 2 * x2 + dx;
+                    const bool in = iy < im.h && ix < im.w;
+#pragma unroll
+                    for (int c = 0; c < 3; ++c) {
+                        const int r = c * 2 + dy;
+                        h[(dy * 2 + dx) * 3 + c] = in ? lut[c][rows[r][shift[r] + 2 * threadIdx.x + dx]] : static_cast<unsigned short>(0);
+                    }
+                }
+            uint4* o = reinterpret_cast<uint4*>(out + plane_row(g, n, y2, x2) * 16);
+            auto pk = [](unsigned short lo, unsigned short hi) { return static_cast<uint32_t>(lo) | (static_cast<uint32_t>(hi) << 16); };
+            o[0] = make_uint4(pk(h[0], h[1]), pk(h[2], h[3]), pk(h[4], h[5]), pk(h[6], h[7]));
+            o[1] = make_uint4(pk(h[8], h[9]), pk(h[10], h[11]), 0u, 0u);
+        }
+    }
+}
+
 // ------------------------------------------------------------------------------------------------ max-pool 3x3 / 2
 // detectron2 BasicStem max_pool2d(kernel 3, stride 2, padding 1) on post-ReLU (>= 0) activations: the zero border of
 // the input plane stands in for the -inf padding.
@@ -198,42 +280,39 @@ gn_finalize_kernel(const float* __restrict__ partial, const Seg* __restrict__ se
 }
 
 // Apply: y = relu((x - mean) * rstd * gamma + beta) on interior pixels, 0 elsewhere; reads the fp32 conv output,
-// writes the fp16 activation the next convolution consumes.  One thread per (row, group of 8 channels).
-__global__ void gn_apply_relu_kernel(const float* __restrict__ x, __half* __restrict__ y, const float* __restrict__ stats,
-                                     const float* __restrict__ gamma, const float* __restrict__ beta,
-                                     const int* __restrict__ tile_seg, const Seg* __restrict__ segs, int row_begin,
-                                     long long n_rows, int relu) {
+// writes the fp16 activation the next convolution consumes.  One CTA per 128-row tile at a time: the plane descriptor
+// and the (plane, group) statistics are looked up once per tile (they were a three-deep dependent load chain in front
+// of every row), lane = group of 8 channels, warp w takes rows w, w + 8, ... with four rows of loads in flight.
+__global__ void __launch_bounds__(256)
+gn_apply_relu_kernel(const float* __restrict__ x, __half* __restrict__ y, const float* __restrict__ stats,
+                     const float* __restrict__ gamma, const float* __restrict__ beta, const int* __restrict__ tile_seg,
+                     const Seg* __restrict__ segs, int tile_begin, int n_tiles, int relu) {
     ptx::griddep_launch();
+    const int g = threadIdx.x & 31, w = threadIdx.x >> 5;
+    const float4 ga = __ldg(reinterpret_cast<const float4*>(gamma) + 2 * g), gb = __ldg(reinterpret_cast<const float4*>(gamma) + 2 * g + 1);
+    const float4 ba = __ldg(reinterpret_cast<const float4*>(beta) + 2 * g), bb = __ldg(reinterpret_cast<const float4*>(beta) + 2 * g + 1);
     ptx::griddep_wait();
-    const long long total = n_rows * 32;
-    for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
-         i += static_cast<long long>(gridDim.x) * blockDim.x) {
-        const int g = static_cast<int>(i & 31);
-        const long long row = row_begin + (i >> 5);
-        const int s = tile_seg[row / kBlockM];
+    for (int t = blockIdx.x; t < n_tiles; t += gridDim.x) {
+        const int tile = tile_begin + t;
+        const int s = __ldg(tile_seg + tile);
         const Seg sg = segs[s];
-        const int local = static_cast<int>(row - sg.row0);
-        const int yy = local / sg.Wp, xx = local - yy * sg.Wp;
-        const bool interior = local < sg.nrows && yy >= sg.pad && yy < sg.pad + sg.H && xx >= sg.pad && xx < sg.pad + sg.W;
-        uint4 o = make_uint4(0u, 0u, 0u, 0u);
-        if (interior) {
-            const float4* p = reinterpret_cast<const float4*>(x + row * 256) + 2 * g;
-            const float4 a = __ldg(p), b = __ldg(p + 1);
-            const float mean = stats[(static_cast<size_t>(s) * 32 + g) * 2];
-            const float rstd = stats[(static_cast<size_t>(s) * 32 + g) * 2 + 1];
-            const float4 ga = __ldg(reinterpret_cast<const float4*>(gamma) + 2 * g), gb = __ldg(reinterpret_cast<const float4*>(gamma) + 2 * g + 1);
-            const float4 ba = __ldg(reinterpret_cast<const float4*>(beta) + 2 * g), bb = __ldg(reinterpret_cast<const float4*>(beta) + 2 * g + 1);
-            float v[8] = {(a.x - mean) * rstd * ga.x + ba.x, (a.y - mean) * rstd * ga.y + ba.y,
-                          (a.z - mean) * rstd * ga.z + ba.z, (a.w - mean) * rstd * ga.w + ba.w,
-                          (b.x - mean) * rstd * gb.x + bb.x, (b.y - mean) * rstd * gb.y + bb.y,
-                          (b.z - mean) * rstd * gb.z + bb.z, (b.w - mean) * rstd * gb.w + bb.w};
-            if (relu) {
-#pragma unroll
-                for (int j = 0; j < 8; ++j) v[j] = fmaxf(v[j], 0.f);
+        const float2 st = *reinterpret_cast<const float2*>(stats + (static_cast<size_t>(s) * 32 + g) * 2);
+        const float mean = st.x, rstd = st.y;
+#pragma unroll 4
+        for (int r = w; r < kBlockM; r += 8) {
+            const int row = tile * kBlockM + r;
+            uint4 o = make_uint4(0u, 0u, 0u, 0u);
+            if (row_is_interior(sg, row)) {
+                const float4* p = reinterpret_cast<const float4*>(x + static_cast<size_t>(row) * 256) + 2 * g;
+                const float4 a = __ldg(p), b = __ldg(p + 1);
+                float v[8] = {(a.x - mean) * rstd * ga.x + ba.x, (a.y - mean) * rstd * ga.y + ba.y,
+                              (a.z - mean) * rstd * ga.z + ba.z, (a.w - mean) * rstd * ga.w + ba.w,
+                              (b.x - mean) * rstd * gb.x + bb.x, (b.y - mean) * rstd * gb.y + bb.y,
+                              (b.z - mean) * rstd * gb.z + bb.z, (b.w - mean) * rstd * gb.w + bb.w};
+                o = pack8(v, relu != 0, true);
             }
-            o = make_uint4(pack_half2(v[0], v[1]), pack_half2(v[2], v[3]), pack_half2(v[4], v[5]), pack_half2(v[6], v[7]));
+            reinterpret_cast<uint4*>(y + static_cast<size_t>(row) * 256)[g] = o;
         }
-        reinterpret_cast<uint4*>(y + row * 256)[g] = o;
     }
 }
 

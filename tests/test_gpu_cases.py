@@ -311,3 +311,25 @@ def test_cuda_graph_episode_replays_bit_identically():
         d2, c2 = eng.detect(SLOT_QUERY, codes)
         assert torch.equal(counts, c2) and torch.equal(dets, d2)
         assert int(counts.sum()) > 0
+
+
+def test_uint8_images_give_bit_identical_features_to_fp32_images():
+    """The uint8 prep kernel (table lookup + shared-memory staging with aligned word loads) against the fp32 prep
+    kernel on the same pixel values: ragged sizes in one batch, odd widths (row starts at every byte alignment),
+    a width beyond one 512-pixel segment, and images that are unaligned VIEWS into a larger byte buffer (first and
+    last word straddle the tensor ends)."""
+    from sylph_few_shot_detection_b200.runtime import SLOT_QUERY
+    cfg, state, model, _ = _setup()
+    eng = model.engine
+    g = torch.Generator().manual_seed(77)
+    sizes = [(97, 131), (64, 1333), (130, 257), (33, 70)]
+    ims = []
+    for k, (h, w) in enumerate(sizes):
+        raw = torch.randint(0, 256, (3 * h * w + 16,), generator=g, dtype=torch.uint8).cuda()
+        ims.append(raw[k + 1:k + 1 + 3 * h * w].view(3, h, w))      # storage offset 1, 2, 3, 4 bytes: unaligned views
+    eng.extract_features(SLOT_QUERY, ims)
+    a = [eng.export_features(SLOT_QUERY, l).clone() for l in range(5)]
+    eng.extract_features(SLOT_QUERY, [im.float() for im in ims])
+    b = [eng.export_features(SLOT_QUERY, l) for l in range(5)]
+    for x, y in zip(a, b):
+        assert torch.equal(x, y)
