@@ -356,7 +356,8 @@ def main():
             achieved = conv3_bytes_img * n_img / (tot_ms * 1e-3) * 1e-9
             peak = float(peaks["hbm_gbs"])
             roofline = {"kernel": "conv_gemm_f16_kernel<256,2,2,0> -- staged TMA-in/TMA-out 1x1 conv + residual + ReLU "
-                                  "(bottleneck conv3, res2..res5), the largest share of the step",
+                                  "(bottleneck conv3, res2..res5; the 3 res5 launches run its CTA-pair variant conv1x1_pair_staged_kernel), "
+                                  "the largest share of the step",
                         "bound": "hbm", "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s",
                         "frac": round(achieved / peak, 4), "traffic": ncu_traffic("conv_gemm_f16_kernel<256,2,2,0>.res2_conv3"),
                         "avg_launch_ms": round(tot_ms / len(conv3), 4), "launches_timed": len(conv3),
