@@ -231,21 +231,30 @@ class MetaFCOS(_EngineBound):
             self.engine.import_features(SLOT_QUERY, feats, (h * self.fpn_strides[0], w * self.fpn_strides[0]))
         return self.predict(support_set_per_class_code, image_sizes, image_sizes), {}
 
-    def predict(self, class_codes: Dict[str, torch.Tensor], image_sizes, out_sizes) -> List[Any]:
+    def predict_device(self, class_codes: Dict[str, torch.Tensor], out_sizes):
+        """Head + proposals + NMS + postprocess, everything left on the device and nothing synchronised:
+        (dets (n, max_dets, 9) fp32, counts (n,) int32) -- rows in descending score order, see SYLPH_DET_STRIDE."""
         codes = pack_code_rows(class_codes).to(self.engine.device)
-        dets, counts = self.engine.detect(SLOT_QUERY, codes, out_sizes)
-        counts = counts.cpu().tolist()
-        results = []
-        for i, n in enumerate(counts):
-            d = dets[i, :n]
-            inst = Instances(tuple(int(v) for v in out_sizes[i]))
-            inst.pred_boxes = Boxes(d[:, 0:4])
-            inst.scores = d[:, 4]
-            inst.pred_classes = d[:, 5].to(torch.int64)
-            inst.locations = d[:, 6:8]
-            inst.fpn_levels = d[:, 8].to(torch.int64)
-            results.append(inst)
-        return results
+        return self.engine.detect(SLOT_QUERY, codes, out_sizes)
+
+    def predict(self, class_codes: Dict[str, torch.Tensor], image_sizes, out_sizes) -> List[Any]:
+        dets, counts = self.predict_device(class_codes, out_sizes)
+        return instances_from_detections(dets, counts.cpu().tolist(), out_sizes)
+
+
+def instances_from_detections(dets: torch.Tensor, counts: Sequence[int], out_sizes) -> List[Any]:
+    """(n, max_dets, 9) detection rows -> the reference's `Instances` fields (fcos_outputs.py:986-1006)."""
+    results = []
+    for i, n in enumerate(counts):
+        d = dets[i, :n]
+        inst = Instances(tuple(int(v) for v in out_sizes[i]))
+        inst.pred_boxes = Boxes(d[:, 0:4])
+        inst.scores = d[:, 4]
+        inst.pred_classes = d[:, 5].to(torch.int64)
+        inst.locations = d[:, 6:8]
+        inst.fpn_levels = d[:, 8].to(torch.int64)
+        results.append(inst)
+    return results
 
 
 def _box_branch_loss_on(cfg) -> bool:
@@ -502,6 +511,21 @@ class MetaOneStageDetector(nn.Module):
         out_sizes = [(int(x.get("height", s[0])), int(x.get("width", s[1]))) for x, s in zip(batched_inputs, sizes)]
         results = self.proposal_generator.predict(class_codes, sizes, out_sizes)
         return [{"instances": r} for r in results]
+
+    def forward_instances_device(self, batched_inputs: List[Dict[str, Any]], class_codes: Dict[str, torch.Tensor],
+                                 features_in_slot: bool = False):
+        """`forward_instances` without the final device-to-host synchronisation: returns (dets, counts, out_sizes) with
+        the detections still on the device (`instances_from_detections` turns them into Instances).  Lets a caller
+        enqueue the next episode before it reads this one's results (runner.EpisodePipeline.run_async)."""
+        assert self.episodic_learning
+        assert not self.training, "Not for training"
+        images = [x["image"] for x in batched_inputs]
+        if not features_in_slot:
+            self.engine.extract_features(SLOT_QUERY, images)
+        sizes = [(int(im.shape[-2]), int(im.shape[-1])) for im in images]
+        out_sizes = [(int(x.get("height", s[0])), int(x.get("width", s[1]))) for x, s in zip(batched_inputs, sizes)]
+        dets, counts = self.proposal_generator.predict_device(class_codes, out_sizes)
+        return dets, counts, out_sizes
 
 
 def build_model(cfg) -> MetaOneStageDetector:

@@ -278,7 +278,7 @@ def _copy_stream(device):
 
 
 def run_episode(model: MetaOneStageDetector, support_items: Sequence[Dict[str, Any]], query_items: Sequence[Dict[str, Any]],
-                group=None, shard: bool = True) -> List[Dict]:
+                group=None, shard: bool = True, return_device: bool = False) -> List[Dict]:
     """One meta-test episode (steps B-F).  With a process group and `shard=True`, classes and query images are split
     contiguously over the ranks (InferenceSampler semantics) with ONE collective in between; each rank returns the
     detections of its own query shard."""
@@ -320,7 +320,27 @@ def run_episode(model: MetaOneStageDetector, support_items: Sequence[Dict[str, A
     packed = format_class_codes_shared(all_codes, device=model.device)
     if ready is not None:
         torch.cuda.current_stream().wait_event(ready)
+    if return_device:
+        assert len(my_query) <= 16
+        with torch.no_grad():
+            return model.forward_instances_device(list(my_query), packed, features_in_slot=merged)
     return inference_with_class_codes(model, my_query, packed, features_in_slot=merged)
+
+
+class EpisodeFuture:
+    """Detections of an episode enqueued with `EpisodePipeline.run_async`: `result()` waits for the device-to-host copy
+    and returns the reference's schema `[{"instances": Instances}]` with HOST tensors (what the evaluators consume,
+    sylph/evaluation/meta_learn_evaluation.py:430-437).  At most 4 futures may be outstanding (pinned ring)."""
+
+    def __init__(self, dets_host: torch.Tensor, counts_host: torch.Tensor, out_sizes, done):
+        self._dets, self._counts, self._out_sizes, self._done = dets_host, counts_host, out_sizes, done
+
+    def result(self) -> List[Dict]:
+        from .modeling import instances_from_detections
+        self._done.synchronize()
+        counts = self._counts.tolist()
+        dets = self._dets.clone()    # the pinned ring slot is reused by a later episode
+        return [{"instances": r} for r in instances_from_detections(dets, counts, self._out_sizes)]
 
 
 class EpisodePipeline:
@@ -337,6 +357,8 @@ class EpisodePipeline:
 
     def __init__(self, model: MetaOneStageDetector):
         self.model = model
+        self._ring: List[Any] = []   # pinned (dets, counts) host buffers of the last 4 asynchronous episodes
+        self._ring_pos = 0
 
     def submit(self, support_items: Sequence[Dict[str, Any]], query_items: Sequence[Dict[str, Any]]):
         dev = self.model.device
@@ -350,6 +372,35 @@ class EpisodePipeline:
         ev = torch.cuda.Event()
         ev.record(side)
         return sup, qry, ev
+
+    def run_async(self, handle) -> "EpisodeFuture":
+        """Enqueue the episode and an asynchronous copy of its detections into pinned host memory; nothing is
+        synchronised, so the caller can submit / enqueue the NEXT episode before it reads this one's results
+        (`future.result()`): the device never waits for the host between episodes."""
+        sup, qry, ev = handle
+        cur = torch.cuda.current_stream()
+        cur.wait_event(ev)
+        dets, counts, out_sizes = run_episode(self.model, sup, qry, shard=False, return_device=True)
+        def fresh():
+            return (torch.empty(dets.shape, dtype=dets.dtype, pin_memory=True),
+                    torch.empty(counts.shape, dtype=counts.dtype, pin_memory=True))
+        k = self._ring_pos % 4
+        self._ring_pos += 1
+        if k >= len(self._ring):
+            self._ring.append(fresh())            # the first four episodes allocate the ring
+        elif self._ring[k][0].shape != dets.shape:
+            self._ring[k] = fresh()               # another batch size: replace the slot (its old future was 4 episodes ago)
+        slot = self._ring[k]
+        slot[0].copy_(dets, non_blocking=True)
+        slot[1].copy_(counts, non_blocking=True)
+        done = torch.cuda.Event()
+        done.record(cur)
+        for item in sup:
+            for r in item["support_set"]:
+                r["image"].record_stream(cur)
+        for q in qry:
+            q["image"].record_stream(cur)
+        return EpisodeFuture(slot[0], slot[1], out_sizes, done)
 
     def run(self, handle) -> List[Dict]:
         sup, qry, ev = handle

@@ -333,3 +333,30 @@ def test_uint8_images_give_bit_identical_features_to_fp32_images():
     b = [eng.export_features(SLOT_QUERY, l) for l in range(5)]
     for x, y in zip(a, b):
         assert torch.equal(x, y)
+
+
+def test_async_episode_pipeline_returns_the_same_detections():
+    """EpisodePipeline.run_async / EpisodeFuture.result (no host synchronisation between episodes, detections copied
+    to pinned memory) against the synchronous EpisodePipeline.run on the same host-resident episodes."""
+    from sylph_few_shot_detection_b200.runner import EpisodePipeline
+    cfg, state, model, _ = _setup()
+    ims = _images(7, 160, 224, 5)
+    boxes = torch.tensor([[20.0, 30.0, 150.0, 120.0], [5.0, 10.0, 200.0, 150.0]])
+    episodes = []
+    for e in range(3):
+        support = [_support_item(ims[e:e + 2], boxes, 0), _support_item(ims[e + 2:e + 4], boxes, 1)]
+        query = [{"image": ims[(e + 4) % 7], "height": 160, "width": 224}, {"image": ims[(e + 5) % 7], "height": 80, "width": 112}]
+        episodes.append((support, query))
+    pipe = EpisodePipeline(model)
+    want = [pipe.run(pipe.submit(s, q)) for s, q in episodes]
+    futures = [pipe.run_async(pipe.submit(s, q)) for s, q in episodes]      # all three enqueued before any result is read
+    got = [f.result() for f in futures]
+    for w_ep, g_ep in zip(want, got):
+        assert len(w_ep) == len(g_ep) == 2
+        for w, gi in zip(w_ep, g_ep):
+            wi, gg = w["instances"], gi["instances"]
+            assert not gg.scores.is_cuda and gg.image_size == wi.image_size
+            assert torch.equal(wi.pred_boxes.tensor.cpu(), gg.pred_boxes.tensor)
+            assert torch.equal(wi.scores.cpu(), gg.scores)
+            assert torch.equal(wi.pred_classes.cpu(), gg.pred_classes)
+            assert torch.equal(wi.fpn_levels.cpu(), gg.fpn_levels)
