@@ -224,40 +224,142 @@ fcos_nms_kernel(const unsigned long long* __restrict__ sel, const int* __restric
     for (int i = tid; i < (n_max + 31) / 32; i += blockDim.x) supp[i] = 0u;
     if (tid == 0) n_kept_s = 0;
     __syncthreads();
-    // ---- greedy NMS in score order; stops once POST_NMS_TOPK survivors (plus score ties, `>=`) are found
+    // ---- greedy NMS in score order; stops once POST_NMS_TOPK survivors (plus score ties, `>=`) are found.
+    // Exactly the sequential greedy algorithm, evaluated 32 candidates at a time: (1) warp 0 collects the next <= 32
+    // candidates that no earlier survivor suppressed, (2) the 32 x 32 IoU matrix of the chunk is one comparison per
+    // thread (warp m ballots row m), (3) warp 0 resolves the chunk in order with bit operations and applies the stop
+    // rules per survivor, (4) all threads test the remaining candidates against the chunk's survivors.  Four barriers per
+    // chunk instead of one per survivor (the loop was barrier- and latency-bound: 0.22 ms for 8 images).
     const int keep_cap = min(max_dets, 1024);
-    float last_score = 0.f;
-    int n_kept = 0;
-    for (int i = 0; i < total; ++i) {
-        // next unsuppressed candidate: 32 flags per word (uniform: the bitmap was last written before a barrier)
-        const unsigned alive = ~supp[i >> 5] & (0xFFFFFFFFu << (i & 31));
-        if (alive == 0u) { i |= 31; continue; }
-        i = (i & ~31) + __ffs(alive) - 1;
-        if (i >= total) break;
-        const float sc = sqrtf(__uint_as_float(static_cast<unsigned>(keys[i] >> 32)));
-        if (p.post_topk > 0 && n_kept >= p.post_topk && sc < last_score) break;
-        if (n_kept >= keep_cap) break;
-        if (tid == 0) kept_idx[n_kept] = i;
-        ++n_kept;
-        last_score = sc;
-        const float oa = boff[i];
-        float4 a = rbox[i];
-        a.x += oa; a.y += oa; a.z += oa; a.w += oa;
-        const float area_a = (a.z - a.x) * (a.w - a.y);
-        for (int j = i + 1 + tid; j < total; j += blockDim.x) {
-            if ((supp[j >> 5] >> (j & 31)) & 1u) continue;
-            const float ob = boff[j];
-            float4 b = rbox[j];
-            b.x += ob; b.y += ob; b.z += ob; b.w += ob;
-            const float w = fmaxf(fminf(a.z, b.z) - fmaxf(a.x, b.x), 0.f);
-            const float h = fmaxf(fminf(a.w, b.w) - fmaxf(a.y, b.y), 0.f);
-            const float inter = w * h;
-            const float area_b = (b.z - b.x) * (b.w - b.y);
-            if (inter / (area_a + area_b - inter) > p.nms_thresh) atomicOr(&supp[j >> 5], 1u << (j & 31));
+    __shared__ int chunk_idx[32];
+    __shared__ unsigned chunk_row[32];
+    __shared__ int chunk_n_s, next_pos_s, done_s;
+    __shared__ unsigned surv_s;
+    __shared__ float last_score_s;
+    if (tid == 0) { done_s = 0; last_score_s = 0.f; }
+    int pos = 0;
+    const int warp_id = tid >> 5, lane = tid & 31;
+    while (true) {
+        // (1) next chunk: the alive candidates among the 1024 positions from pos on, the first 32 of them
+        if (warp_id == 0) {
+            const int w = (pos >> 5) + lane;
+            unsigned alive = 0u;
+            if (w * 32 < total) {
+                alive = ~supp[w];
+                if (w == (pos >> 5)) alive &= 0xFFFFFFFFu << (pos & 31);
+                if (w * 32 + 32 > total) alive &= (total & 31) ? ((1u << (total & 31)) - 1u) : 0xFFFFFFFFu;
+            }
+            const int cnt = __popc(alive);
+            int incl = cnt;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const int v = __shfl_up_sync(0xffffffffu, incl, o);
+                if (lane >= o) incl += v;
+            }
+            int excl = incl - cnt;
+            const int all = __shfl_sync(0xffffffffu, incl, 31);
+            // lane's alive bits fill chunk slots excl, excl + 1, ... while < 32
+            unsigned a = alive;
+            int last_taken = -1;
+            while (a != 0u && excl < 32) {
+                const int b = __ffs(a) - 1;
+                a &= a - 1u;
+                chunk_idx[excl++] = w * 32 + b;
+                last_taken = w * 32 + b;
+            }
+            // next scan position: one past the last candidate taken when the chunk is full, else the end of the window
+            int np = last_taken + 1;
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) np = max(np, __shfl_xor_sync(0xffffffffu, np, o));
+            if (lane == 0) {
+                chunk_n_s = min(all, 32);
+                next_pos_s = all >= 32 ? np : min(total, ((pos >> 5) + 32) * 32);
+            }
         }
+        __syncthreads();
+        const int cn = chunk_n_s;
+        const int next_pos = next_pos_s;
+        if (cn == 0) {
+            if (next_pos >= total) break;
+            pos = next_pos;
+            __syncthreads();   // chunk_n_s / next_pos_s are rewritten by warp 0 in the next round
+            continue;
+        }
+        // (2) IoU matrix of the chunk: thread (m, k) = (warp, lane); row m = candidates k > m that m would suppress
+        {
+            bool hit = false;
+            if (warp_id < cn && lane < cn && lane > warp_id) {
+                const int ia = chunk_idx[warp_id], ib = chunk_idx[lane];
+                const float oa = boff[ia], ob = boff[ib];
+                float4 a = rbox[ia], b = rbox[ib];
+                a.x += oa; a.y += oa; a.z += oa; a.w += oa;
+                b.x += ob; b.y += ob; b.z += ob; b.w += ob;
+                const float area_a = (a.z - a.x) * (a.w - a.y);
+                const float w = fmaxf(fminf(a.z, b.z) - fmaxf(a.x, b.x), 0.f);
+                const float h = fmaxf(fminf(a.w, b.w) - fmaxf(a.y, b.y), 0.f);
+                const float inter = w * h;
+                const float area_b = (b.z - b.x) * (b.w - b.y);
+                hit = inter / (area_a + area_b - inter) > p.nms_thresh;
+            }
+            const unsigned row = __ballot_sync(0xffffffffu, hit);
+            if (lane == 0) chunk_row[warp_id] = row;
+        }
+        __syncthreads();
+        // (3) resolve the chunk in score order (warp 0, every lane runs the same uniform loop)
+        if (warp_id == 0) {
+            unsigned removed = 0u, surv = 0u;
+            int nk = n_kept_s;
+            float last_score = last_score_s;
+            int done = 0;
+            for (int k = 0; k < cn; ++k) {
+                if ((removed >> k) & 1u) continue;
+                const int i = chunk_idx[k];
+                const float sc = sqrtf(__uint_as_float(static_cast<unsigned>(keys[i] >> 32)));
+                if ((p.post_topk > 0 && nk >= p.post_topk && sc < last_score) || nk >= keep_cap) { done = 1; break; }
+                if (lane == 0) kept_idx[nk] = i;
+                ++nk;
+                last_score = sc;
+                surv |= 1u << k;
+                removed |= chunk_row[k];
+            }
+            if (lane == 0) { n_kept_s = nk; last_score_s = last_score; done_s = done; surv_s = surv; }
+        }
+        __syncthreads();
+        if (done_s) break;
+        if (next_pos >= total) break;
+        // (4) the chunk's survivors suppress the candidates after the chunk
+        {
+            const unsigned surv = surv_s;
+            for (int j = next_pos + tid; j < total; j += blockDim.x) {
+                if ((supp[j >> 5] >> (j & 31)) & 1u) continue;
+                const float ob = boff[j];
+                float4 b = rbox[j];
+                b.x += ob; b.y += ob; b.z += ob; b.w += ob;
+                const float area_b = (b.z - b.x) * (b.w - b.y);
+                unsigned m = surv;
+                while (m != 0u) {
+                    const int k = __ffs(m) - 1;
+                    m &= m - 1u;
+                    const int ia = chunk_idx[k];
+                    const float oa = boff[ia];
+                    float4 a = rbox[ia];
+                    a.x += oa; a.y += oa; a.z += oa; a.w += oa;
+                    const float area_a = (a.z - a.x) * (a.w - a.y);
+                    const float w = fmaxf(fminf(a.z, b.z) - fmaxf(a.x, b.x), 0.f);
+                    const float h = fmaxf(fminf(a.w, b.w) - fmaxf(a.y, b.y), 0.f);
+                    const float inter = w * h;
+                    if (inter / (area_a + area_b - inter) > p.nms_thresh) {
+                        atomicOr(&supp[j >> 5], 1u << (j & 31));
+                        break;
+                    }
+                }
+            }
+        }
+        pos = next_pos;
         __syncthreads();
     }
     __syncthreads();
+    const int n_kept = n_kept_s;
     // ---- detector_postprocess: scale, clip, drop empty; one warp compacts in order
     if (tid < 32) {
         const NmsImageArgs ia = img_args[n];

@@ -78,6 +78,26 @@ def main():
     def step():
         return run_episode(model, support, query)
 
+    # throughput mode: the detections of episode i travel to pinned memory asynchronously and are read on the host
+    # while episode i+1 is already enqueued (runner.EpisodeFuture) -- no host synchronisation between episodes
+    from sylph_few_shot_detection_b200.runner import EpisodeFuture
+    ring, futures = [], []
+
+    def step_async():
+        dets, counts, out_sizes = run_episode(model, support, query, return_device=True)
+        if len(ring) < 4:
+            ring.append((torch.empty(dets.shape, dtype=dets.dtype, pin_memory=True),
+                         torch.empty(counts.shape, dtype=counts.dtype, pin_memory=True)))
+        slot = ring[step_async.k % len(ring)] if len(ring) == 4 else ring[-1]
+        step_async.k += 1
+        slot[0].copy_(dets, non_blocking=True)
+        slot[1].copy_(counts, non_blocking=True)
+        ev = torch.cuda.Event()
+        ev.record()
+        futures.append(EpisodeFuture(slot[0], slot[1], out_sizes, ev))
+        return futures.pop(0).result() if len(futures) > 1 else None
+    step_async.k = 0
+
     def timed(fn, warm, reps):
         for _ in range(warm):
             fn()
@@ -98,11 +118,15 @@ def main():
         return float(t)
 
     ms = timed(step, args.warmup, args.steps)
+    ms_async = timed(step_async, args.warmup, args.steps)
+    while futures:
+        futures.pop(0).result()
     res = step()
     n_det = [int(len(r["instances"])) for r in res]
     out = {"config": f"{args.way}-way {args.shot}-shot COCO-novel episode, {args.queries} query images 800x1333, classes and "
                      f"queries sharded over {world} GPU(s), one NCCL all-gather of the class codes",
            "n_gpus": world, "ms_per_episode": round(ms, 3), "episodes_per_s": round(1000.0 / ms, 2),
+           "ms_per_episode_async_results": round(ms_async, 3), "episodes_per_s_async_results": round(1000.0 / ms_async, 2),
            "episode_gflop": 23251, "tflops_all_gpus": round(23251 / ms, 1),
            "classes_on_rank0": len(my_cls), "queries_on_rank0": len(my_q), "detections_rank0": n_det,
            "steps": args.steps, "warmup": args.warmup, "timing": "CUDA events, max over ranks"}
