@@ -166,7 +166,8 @@ conv3x3_pair_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
         }
         for (int a = 0; a < kAcc; ++a) {
             ptx::mbar_init(&tmem_full[a], 1);
-            ptx::mbar_init(&tmem_empty[a], 2 * 256);
+            ptx::mbar_init(&tmem_empty[a], 2 * 8);   // one arrive per epilogue warp of both CTAs (512 per-thread
+                                                     // arrivals, half of them remote, serialised on one barrier)
         }
         ptx::fence_barrier_init();
     }
@@ -344,7 +345,8 @@ conv3x3_pair_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
             }
             // accumulator drained: tell the leader's MMA warp (remote arrive for the second CTA of the pair)
             ptx::tc_fence_before();
-            ptx::mbar_arrive_cluster(ptx::mapa_shared(ptx::smem_u32(&tmem_empty[acc]), 0));
+            __syncwarp();
+            if (lane == 0) ptx::mbar_arrive_cluster(ptx::mapa_shared(ptx::smem_u32(&tmem_empty[acc]), 0));
             if (BN == 256 && (p.flags & kEpiGnStats)) {
                 asm volatile("bar.sync 1, 256;" ::: "memory");
                 if (valid && et < 64) {

@@ -315,6 +315,18 @@ int main(int argc, char** argv) {
         else printf("unknown shape %s\n", n.c_str());
         return 0;
     }
+    if (argc > 1 && std::string(argv[1]) == "pairnarrow") {
+        // 3x3 convolutions at the 33-image sizes: single-CTA halo pipeline against the CTA-pair kernel
+        const int F = kEpiRelu | kEpiMask;
+        bench_shape("res2_conv2_3x3_64_64_HALO_BRES", 64, 17622, 64, 64, 9, F, sms, 0, true);
+        bench_shape("res2_conv2_3x3_64_64_PAIR", 64, 17622, 64, 64, 9, F, sms, 0, false, true);
+        bench_shape("res3_conv2_3x3_128_128_HALO", 128, 4488, 128, 128, 9, F, sms, 0, true);
+        bench_shape("res3_conv2_3x3_128_128_PAIR", 128, 4488, 128, 128, 9, F, sms, 0, false, true);
+        bench_shape("res4_conv2_3x3_256_256_PAIR", 256, 1155, 256, 256, 9, F, sms, 0, false, true);
+        bench_shape("res5_conv2_3x3_512_512_PAIR", 256, 330, 512, 512, 9, F, sms, 0, false, true);
+        bench_shape("tower3x3_256_gn_f32out_PAIR", 256, 1480, 256, 256, 9, kEpiMask | kEpiGnStats | kEpiOutF32, sms, 0, false, true);
+        return 0;
+    }
     if (argc > 1 && std::string(argv[1]) == "pair1x1") {
         // single-CTA staged kernels against the CTA-pair 1x1 kernel on the res3..res5 shapes of a 33-image trunk pass
         struct Sh { const char* name; int m_tiles, cin, cout, flags; };
