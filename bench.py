@@ -215,10 +215,11 @@ def main():
             eng.extract_features_multi([(SLOT_SUPPORT, support_d), (SLOT_QUERY, query_d)])
         else:
             eng.extract_features(SLOT_SUPPORT, support_d)
+        if merged_trunk:   # codes on the engine's side stream while the towers run (SYLPH_OVERLAP_CODEGEN=0: one stream)
+            return eng.generate_and_detect(SLOT_SUPPORT, SLOT_QUERY, boxes, roi_image, offsets)[0]
         raw = eng.generate_codes(SLOT_SUPPORT, boxes, roi_image, offsets)
         codes = eng.normalize_codes(raw)
-        if not merged_trunk:
-            eng.extract_features(SLOT_QUERY, query_d)
+        eng.extract_features(SLOT_QUERY, query_d)
         return eng.detect(SLOT_QUERY, codes)
 
     def barrier():

@@ -150,6 +150,14 @@ int sylph_reduce_codes(sylph_ctx* ctx, const float* parts_dev, int n_parts, int 
 int sylph_detect(sylph_ctx* ctx, int slot, const float* codes_dev, int n_classes, const int* out_sizes_host,
                  float* dets_out_dev, int* counts_out_dev, int max_dets, void* stream);
 
+/* sylph_detect for callers that produce the class codes on ANOTHER stream.  The class / box towers and the box
+ * predictors do not depend on the codes and are enqueued first; `stream` then waits on `codes_ready_event` (a cudaEvent_t
+ * cast to void*, recorded by the caller after the last write of codes_dev; NULL = no wait) right before the
+ * code-conditioned classifier (CondConvBasic, head_utils.py:60-81) reads codes_dev.  Code generation (ROIAlign, code
+ * tower, K-shot mean, normalisation, the all-gather) thereby overlaps the 9 tensor-bound tower launches. */
+int sylph_detect_after(sylph_ctx* ctx, int slot, const float* codes_dev, int n_classes, const int* out_sizes_host,
+                       float* dets_out_dev, int* counts_out_dev, int max_dets, void* codes_ready_event, void* stream);
+
 /* Head intermediates of the last sylph_detect call, NCHW fp32: which = 0 logits (n, n_classes, H, W),
  * 1 bbox_reg after scale+ReLU (n, 4, H, W), 2 ctrness (n, 1, H, W), 3 iou (n, 1, H, W). */
 int sylph_export_head_output(sylph_ctx* ctx, int which, int level, float* out_dev, void* stream);

@@ -118,6 +118,8 @@ def load() -> ctypes.CDLL:
     lib.sylph_reduce_codes.argtypes = [vp, vp, c_int, c_int, fp, vp, vp]
     lib.sylph_detect.restype = c_int
     lib.sylph_detect.argtypes = [vp, c_int, vp, c_int, ip, vp, vp, c_int, vp]
+    lib.sylph_detect_after.restype = c_int
+    lib.sylph_detect_after.argtypes = [vp, c_int, vp, c_int, ip, vp, vp, c_int, vp, vp]
     lib.sylph_export_head_output.restype = c_int
     lib.sylph_export_head_output.argtypes = [vp, c_int, c_int, vp, vp]
     lib.sylph_fcos_loss_sums.restype = c_int
@@ -139,5 +141,5 @@ EXPORTED_SYMBOLS = [
     "sylph_version", "sylph_create", "sylph_destroy", "sylph_last_error", "sylph_load_tensor",
     "sylph_finalize_weights", "sylph_extract_features", "sylph_extract_features_u8", "sylph_extract_features_multi", "sylph_import_features", "sylph_feature_shape",
     "sylph_export_features", "sylph_generate_codes", "sylph_export_roi_features", "sylph_normalize_codes", "sylph_accumulate_codes", "sylph_reduce_codes",
-    "sylph_detect", "sylph_export_head_output", "sylph_fcos_loss_sums", "sylph_fcos_loss_finalize", "sylph_launch_count", "sylph_set_profiling", "sylph_get_timings",
+    "sylph_detect", "sylph_detect_after", "sylph_export_head_output", "sylph_fcos_loss_sums", "sylph_fcos_loss_finalize", "sylph_launch_count", "sylph_set_profiling", "sylph_get_timings",
 ]

@@ -198,7 +198,7 @@ static int stage_h2d(sylph_ctx* c, void* dst_dev, const void* src_host, size_t b
         c->pinned_head = 0;
     }
     if (c->pinned_head + need > c->pinned_cap) {
-        CU_TRY(c, cudaStreamSynchronize(st));  // wrap-around: earlier copies out of the ring must have executed
+        CU_TRY(c, cudaDeviceSynchronize());  // wrap-around: earlier copies out of the ring (on ANY stream) must have executed
         c->pinned_head = 0;
     }
     uint8_t* slot = c->pinned + c->pinned_head;
@@ -1178,7 +1178,8 @@ static int roi_encoder_codes(sylph_ctx* c, const Slot& S, int n_rois, int n_clas
 // fcos.py:582-667): fills the "det.logits" ([rows][cout_pad] fp32) and "det.pred" ([rows][16] fp32) buffers.
 struct HeadOut { float* logits; float* pred; int logit_stride; };
 
-static int run_head(sylph_ctx* c, int slot, const float* codes_dev, int n_classes, cudaStream_t st, HeadOut* out) {
+static int run_head(sylph_ctx* c, int slot, const float* codes_dev, int n_classes, cudaStream_t st, HeadOut* out,
+                    cudaEvent_t codes_ready = nullptr) {
     const sylph_model_config& f = c->cfg;
     const Slot& S = c->slots[slot];
     const long long rows = S.level_row0[5];
@@ -1200,10 +1201,6 @@ static int run_head(sylph_ctx* c, int slot, const float* codes_dev, int n_classe
     TRY(ensure(c, "det.gn_stats", static_cast<size_t>(n_segs) * 64 * 4, "", &gs, st, false));
     CW.w = static_cast<__half*>(cw);
     CW.bias = static_cast<float*>(cb);
-    CU_TRY(c, launch_k(pack_code_weights_kernel, dim3(ceil_div(static_cast<long long>(CW.cout_pad) * 256, 256)), dim3(256), 0, st, 
-        codes_dev, n_classes, CW.cout_pad, f.generator == 1 ? 1 : f.cg_use_bias, f.generator == 1 ? c->cond_scale : 1.f, CW.w, CW.bias));
-    CU_TRY(c, cudaGetLastError());
-    c->launches++;
     auto tower = [&](const std::vector<ConvW>& tw, const std::vector<float*>& gw, const std::vector<float*>& gb,
                      const char* name, __half** result) -> int {
         const __half* cur = S.pyr;
@@ -1217,19 +1214,26 @@ static int run_head(sylph_ctx* c, int slot, const float* codes_dev, int n_classe
         *result = const_cast<__half*>(cur);
         return 0;
     };
+    // Everything that does not depend on the class codes first (box tower + predictors, class tower): a caller that
+    // generates the codes on another stream overlaps that work with these 9 tensor-bound launches (sylph_detect_after).
     __half* x;
-    TRY(tower(c->cls_tower, c->cls_gn_w, c->cls_gn_b, "head.cls_tower3x3", &x));
-    {
-        ConvCall k{};
-        k.W = &CW; k.A = x; k.a_rows = rows; k.a_cols = k.a_ld = 256; k.ps = S.ps.get(); k.tile_begin = 0; k.n_tiles = tiles;
-        k.a_row_delta = 0; k.out = lg; k.ldc = CW.cout_pad; k.flags = kEpiOutF32; k.name = "head.cond_cls1x1";
-        TRY(run_conv(c, k, st));
-    }
     TRY(tower(c->box_tower, c->box_gn_w, c->box_gn_b, "head.bbox_tower3x3", &x));
     {
         ConvCall k{};
         k.W = &c->pred; k.A = x; k.a_rows = rows; k.a_cols = k.a_ld = 256; k.ps = S.ps.get(); k.tile_begin = 0; k.n_tiles = tiles;
         k.a_row_delta = 0; k.out = pr; k.ldc = 16; k.flags = kEpiOutF32; k.name = "head.pred3x3";
+        TRY(run_conv(c, k, st));
+    }
+    TRY(tower(c->cls_tower, c->cls_gn_w, c->cls_gn_b, "head.cls_tower3x3", &x));
+    if (codes_ready != nullptr) CU_TRY(c, cudaStreamWaitEvent(st, codes_ready, 0));
+    CU_TRY(c, launch_k(pack_code_weights_kernel, dim3(ceil_div(static_cast<long long>(CW.cout_pad) * 256, 256)), dim3(256), 0, st,
+        codes_dev, n_classes, CW.cout_pad, f.generator == 1 ? 1 : f.cg_use_bias, f.generator == 1 ? c->cond_scale : 1.f, CW.w, CW.bias));
+    CU_TRY(c, cudaGetLastError());
+    c->launches++;
+    {
+        ConvCall k{};
+        k.W = &CW; k.A = x; k.a_rows = rows; k.a_cols = k.a_ld = 256; k.ps = S.ps.get(); k.tile_begin = 0; k.n_tiles = tiles;
+        k.a_row_delta = 0; k.out = lg; k.ldc = CW.cout_pad; k.flags = kEpiOutF32; k.name = "head.cond_cls1x1";
         TRY(run_conv(c, k, st));
     }
     c->last_detect_slot = slot;
@@ -1496,6 +1500,11 @@ int sylph_reduce_codes(sylph_ctx* c, const float* parts_dev, int n_parts, int n_
 
 int sylph_detect(sylph_ctx* c, int slot, const float* codes_dev, int n_classes, const int* out_sizes_host,
                  float* dets_out_dev, int* counts_out_dev, int max_dets, void* stream) {
+    return sylph_detect_after(c, slot, codes_dev, n_classes, out_sizes_host, dets_out_dev, counts_out_dev, max_dets, nullptr, stream);
+}
+
+int sylph_detect_after(sylph_ctx* c, int slot, const float* codes_dev, int n_classes, const int* out_sizes_host,
+                       float* dets_out_dev, int* counts_out_dev, int max_dets, void* codes_ready_event, void* stream) {
     if (!c) return 1;
     if (!c->finalized) return c->fail("weights not finalized");
     if (slot < 0 || slot >= SYLPH_NUM_SLOTS || !c->slots[slot].valid) return c->fail("slot %d holds no features", slot);
@@ -1507,7 +1516,7 @@ int sylph_detect(sylph_ctx* c, int slot, const float* codes_dev, int n_classes, 
     const Slot& S = c->slots[slot];
     const int n_segs = 5 * S.n;
     HeadOut H{};
-    TRY(run_head(c, slot, codes_dev, n_classes, st, &H));
+    TRY(run_head(c, slot, codes_dev, n_classes, st, &H, static_cast<cudaEvent_t>(codes_ready_event)));
     float* lg = H.logits;
     float* pr = H.pred;
     struct { int cout_pad; } CW{H.logit_stride};

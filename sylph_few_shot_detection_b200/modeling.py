@@ -231,9 +231,13 @@ class MetaFCOS(_EngineBound):
             self.engine.import_features(SLOT_QUERY, feats, (h * self.fpn_strides[0], w * self.fpn_strides[0]))
         return self.predict(support_set_per_class_code, image_sizes, image_sizes), {}
 
-    def predict_device(self, class_codes: Dict[str, torch.Tensor], out_sizes):
+    def predict_device(self, class_codes: Dict[str, torch.Tensor], out_sizes, code_rows: Optional[torch.Tensor] = None,
+                       codes_ready=None):
         """Head + proposals + NMS + postprocess, everything left on the device and nothing synchronised:
-        (dets (n, max_dets, 9) fp32, counts (n,) int32) -- rows in descending score order, see SYLPH_DET_STRIDE."""
+        (dets (n, max_dets, 9) fp32, counts (n,) int32) -- rows in descending score order, see SYLPH_DET_STRIDE.
+        `code_rows` + `codes_ready`: (C, 257) rows packed on ANOTHER stream and the event recorded there."""
+        if code_rows is not None:
+            return self.engine.detect(SLOT_QUERY, code_rows, out_sizes, codes_ready=codes_ready)
         codes = pack_code_rows(class_codes).to(self.engine.device)
         return self.engine.detect(SLOT_QUERY, codes, out_sizes)
 
@@ -513,7 +517,7 @@ class MetaOneStageDetector(nn.Module):
         return [{"instances": r} for r in results]
 
     def forward_instances_device(self, batched_inputs: List[Dict[str, Any]], class_codes: Dict[str, torch.Tensor],
-                                 features_in_slot: bool = False):
+                                 features_in_slot: bool = False, code_rows: Optional[torch.Tensor] = None, codes_ready=None):
         """`forward_instances` without the final device-to-host synchronisation: returns (dets, counts, out_sizes) with
         the detections still on the device (`instances_from_detections` turns them into Instances).  Lets a caller
         enqueue the next episode before it reads this one's results (runner.EpisodePipeline.run_async)."""
@@ -524,7 +528,7 @@ class MetaOneStageDetector(nn.Module):
             self.engine.extract_features(SLOT_QUERY, images)
         sizes = [(int(im.shape[-2]), int(im.shape[-1])) for im in images]
         out_sizes = [(int(x.get("height", s[0])), int(x.get("width", s[1]))) for x, s in zip(batched_inputs, sizes)]
-        dets, counts = self.proposal_generator.predict_device(class_codes, out_sizes)
+        dets, counts = self.proposal_generator.predict_device(class_codes, out_sizes, code_rows, codes_ready)
         return dets, counts, out_sizes
 
 

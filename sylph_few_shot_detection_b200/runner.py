@@ -308,16 +308,19 @@ def run_episode(model: MetaOneStageDetector, support_items: Sequence[Dict[str, A
             from .runtime import SLOT_QUERY, SLOT_SUPPORT
             model.engine.extract_features_multi([(SLOT_SUPPORT, sup_imgs), (SLOT_QUERY, qry_imgs)])
             merged = True
-    sub_codes = inference_on_support_set(model, my_support, features_in_slot=merged)
-    if world > 1 and shard:
-        # the class list is global: shard sizes, ids and names are known everywhere, only the codes travel
-        counts = [len(shard_range(len(support_items), world, r)) for r in range(world)]
-        meta = [(it["support_set_target"], it.get("class_name", "")) for it in support_items]
-        all_codes = gather_class_code_known_shards(sub_codes, counts, meta, group=group)
-    else:
-        all_codes = sub_codes
-    all_codes = inference_normalization(model, all_codes)
-    packed = format_class_codes_shared(all_codes, device=model.device)
+    def codes_phase():
+        sub_codes = inference_on_support_set(model, my_support, features_in_slot=merged)
+        if world > 1 and shard:
+            # the class list is global: shard sizes, ids and names are known everywhere, only the codes travel
+            counts = [len(shard_range(len(support_items), world, r)) for r in range(world)]
+            meta = [(it["support_set_target"], it.get("class_name", "")) for it in support_items]
+            all_codes = gather_class_code_known_shards(sub_codes, counts, meta, group=group)
+        else:
+            all_codes = sub_codes
+        all_codes = inference_normalization(model, all_codes)
+        return format_class_codes_shared(all_codes, device=model.device)
+
+    packed = codes_phase()
     if ready is not None:
         torch.cuda.current_stream().wait_event(ready)
     if return_device:
@@ -453,9 +456,10 @@ class EpisodeGraph:
     def _run(self):
         sup_slot, qry_slot = self._slots
         self.eng.extract_features_multi([(sup_slot, self.support), (qry_slot, self.query)])
-        raw = self.eng.generate_codes(sup_slot, self.boxes, self._roi_image, self._offsets)
-        self.codes = self.eng.normalize_codes(raw) if not isinstance(self.model.code_generator, _roi_encoder_type()) else raw
-        return self.eng.detect(qry_slot, self.codes)
+        out, self.codes = self.eng.generate_and_detect(
+            sup_slot, qry_slot, self.boxes, self._roi_image, self._offsets,
+            normalize=not isinstance(self.model.code_generator, _roi_encoder_type()))
+        return out
 
     def replay(self):
         self.graph.replay()

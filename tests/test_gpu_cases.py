@@ -360,3 +360,21 @@ def test_async_episode_pipeline_returns_the_same_detections():
             assert torch.equal(wi.scores.cpu(), gg.scores)
             assert torch.equal(wi.pred_classes.cpu(), gg.pred_classes)
             assert torch.equal(wi.fpn_levels.cpu(), gg.fpn_levels)
+
+
+def test_codes_on_a_side_stream_give_identical_detections():
+    """sylph_detect_after: code generation on the engine's side stream, towers on the current stream, joined by an event
+    right before the code-conditioned classifier -- against the single-stream order, bit for bit."""
+    from sylph_few_shot_detection_b200.runtime import SLOT_QUERY, SLOT_SUPPORT
+    cfg, state, model, _ = _setup()
+    eng = model.engine
+    ims = [im.cuda() for im in _images(6, 192, 256, 9)]
+    boxes = torch.tensor([[20.0, 30.0, 150.0, 120.0], [5.0, 10.0, 200.0, 150.0], [40.0, 40.0, 120.0, 160.0], [60.0, 20.0, 250.0, 100.0]])
+    eng.extract_features_multi([(SLOT_SUPPORT, ims[:4]), (SLOT_QUERY, ims[4:])])
+    (d0, c0), codes0 = eng.generate_and_detect(SLOT_SUPPORT, SLOT_QUERY, boxes, [0, 1, 2, 3], [0, 2, 4], overlap=False)
+    d0, c0, codes0 = d0.clone(), c0.clone(), codes0.clone()
+    for _ in range(3):
+        (d1, c1), codes1 = eng.generate_and_detect(SLOT_SUPPORT, SLOT_QUERY, boxes, [0, 1, 2, 3], [0, 2, 4], overlap=True)
+        torch.cuda.synchronize()
+        assert torch.equal(codes0, codes1) and torch.equal(c0, c1) and torch.equal(d0, d1)
+    assert int(c0.sum()) > 0
