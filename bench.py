@@ -318,6 +318,17 @@ def main():
 
     for _ in range(3):
         episode_e2e()
+    # diagnostic: pinned-host -> device bandwidth of one episode's images on this box / NUMA placement (when it drops
+    # below h2d_bytes_per_step / ms_per_step the end-to-end number is bound by the copy, not by the kernels)
+    torch.cuda.synchronize()
+    c0, c1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    c0.record()
+    _tmp = [t.to(dev, non_blocking=True) for t in support_h + query_h]
+    c1.record()
+    torch.cuda.synchronize()
+    h2d_gbs = sum(t.numel() for t in support_h + query_h) / (c0.elapsed_time(c1) * 1e-3) * 1e-9
+    pinned_ok = all(t.is_pinned() for t in support_h + query_h)
+    del _tmp
     ms_e2e, res = timed(episode_e2e, args.steps)
     while in_flight:
         in_flight.pop(0).result()
@@ -415,7 +426,7 @@ def main():
                "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f16",
                "data": "synthetic", "config": config,
                "e2e": {"value": round(e2e_value, 3), "unit": "episodes/s", "h2d_bytes_per_step": int(h2d),
-                       "d2h_bytes_per_step": int(d2h), "ms_per_step": round(ms_e2e / args.steps, 3)},
+                       "d2h_bytes_per_step": int(d2h), "h2d_copy_gbs": round(h2d_gbs, 1), "inputs_pinned": pinned_ok, "ms_per_step": round(ms_e2e / args.steps, 3)},
                "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline, "roofline_tensor": roofline_tensor, "cpu_baseline": cpu,
                "episode_tflops": round(EPISODE_GFLOP * 1e-3 * value / world, 1),
                "detections_per_image": [int(c) for c in counts.cpu().tolist()],

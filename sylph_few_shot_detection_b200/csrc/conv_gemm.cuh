@@ -58,6 +58,9 @@ enum EpilogueFlags : int {
     kEpiMask = 4,       // zero rows that are not interior pixels of their plane
     kEpiOutF32 = 8,     // store fp32 instead of fp16 (pre-GroupNorm tower outputs, logits, predictor outputs)
     kEpiGnStats = 16,   // per-tile GroupNorm partial sums (32 groups of 8 channels; needs BN == 256)
+    kEpiUpsample = 32,  // with kEpiResidual (direct epilogue): the residual row of output pixel (y, x) is pixel
+                        // (y / 2, x / 2) of the plane `up_seg_delta` segments further on -- the FPN top-down
+                        // `lateral + F.interpolate(coarser, scale_factor=2, mode="nearest")`, summed in fp32
 };
 
 struct GemmArgs {
@@ -79,6 +82,7 @@ struct GemmArgs {
     const int* tile_seg;   // [absolute tile] -> segment index
     const Seg* segs;
     float* gn_partial;     // [absolute tile][32][2]
+    int up_seg_delta;      // kEpiUpsample: segment index of the coarser plane = segment of the output tile + up_seg_delta
     int dbg_a_row_skew;    // experiment: load the A box `skew` rows early and start the MMA descriptor `skew` rows in
     int dbg_base_offset;   // experiment: matrix-descriptor base_offset field used with the skew
     int dbg_skip;          // bring-up timing experiments (halo pipeline): 1 = no output stores, 2 = no MMAs issued,
@@ -467,11 +471,15 @@ conv_gemm_f16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_co
         int it = 0;
         // plane descriptor of the NEXT tile, fetched one iteration ahead: the two dependent global loads
         // (tile -> plane index -> plane) otherwise sit on the critical path of every small tile's epilogue
-        const bool need_seg = (p.flags & (kEpiMask | kEpiGnStats)) != 0;
+        const bool upsample = !TMA_EPI && (p.flags & kEpiUpsample) && (p.flags & kEpiResidual);
+        const bool need_seg = (p.flags & (kEpiMask | kEpiGnStats)) != 0 || upsample;
+        Seg cg_next{};   // kEpiUpsample: the coarser plane of the NEXT tile
         auto fetch_seg = [&](int t) -> Seg {
             int m, n;
             split_tile(t, p.num_n_tiles, m, n);
-            return p.segs[__ldg(p.tile_seg + p.tile_begin + m)];
+            const int si = __ldg(p.tile_seg + p.tile_begin + m);
+            if (upsample) cg_next = p.segs[si + p.up_seg_delta];
+            return p.segs[si];
         };
         Seg sg_next{};
         if (need_seg && static_cast<int>(blockIdx.x) < total_tiles) sg_next = fetch_seg(blockIdx.x);
@@ -481,6 +489,7 @@ conv_gemm_f16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_co
             const int abs_tile = p.tile_begin + m_tile;
             const int row = abs_tile * kBlockM + r_in_tile;
             const Seg sg = sg_next;
+            const Seg cg = cg_next;
             if (need_seg && tile + static_cast<int>(gridDim.x) < total_tiles) sg_next = fetch_seg(tile + gridDim.x);
             const bool interior = need_seg ? row_is_interior(sg, row) : true;
             const bool keep = interior || !(p.flags & kEpiMask);
@@ -551,8 +560,18 @@ conv_gemm_f16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_co
                 uint4 res[COLS / 8 > 0 ? COLS / 8 : 1];
                 const bool use_res = (p.flags & kEpiResidual) && keep;
                 if (use_res) {
+                    size_t res_row = static_cast<size_t>(row);
+                    if (upsample) {   // interior pixel (y, x) of plane sg -> pixel (y / 2, x / 2) of the coarser plane cg
+                        const int local = row - sg.row0;
+                        int y = __float2int_rz(__fdividef(static_cast<float>(local), static_cast<float>(sg.Wp)));
+                        int x = local - y * sg.Wp;
+                        if (x < 0) { --y; x += sg.Wp; }
+                        else if (x >= sg.Wp) { ++y; x -= sg.Wp; }
+                        res_row = static_cast<size_t>(cg.row0) + static_cast<size_t>(((y - sg.pad) >> 1) + cg.pad) * cg.Wp +
+                                  (((x - sg.pad) >> 1) + cg.pad);
+                    }
                     const uint4* rp = reinterpret_cast<const uint4*>(
-                        p.residual + static_cast<size_t>(row) * p.ld_res + static_cast<size_t>(n_tile) * BN + col_begin);
+                        p.residual + res_row * p.ld_res + static_cast<size_t>(n_tile) * BN + col_begin);
 #pragma unroll
                     for (int j = 0; j < COLS / 8; ++j) res[j] = __ldg(rp + j);
                 }

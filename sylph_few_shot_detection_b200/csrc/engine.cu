@@ -81,6 +81,7 @@ struct sylph_ctx {
     int halo_pipeline = 1;    // SYLPH_HALO=0 falls back to one A box per tap for the 3x3 convolutions
     int pair_kernel = 1;      // SYLPH_PAIR: bit 0 = CTA-pair kernel for the N = 256 3x3 convolutions, bit 1 = also for N = 64 /
                               // 128 (measured SLOWER than the single-CTA halo kernel: profiles/r01_mma_issue_experiments.md)
+    int fuse_upsample = 1;    // SYLPH_FUSE_UPSAMPLE=0: separate upsample_add kernels after the FPN lateral convolutions
     int pair1x1 = 1;          // SYLPH_PAIR1X1=0 keeps the single-CTA staged kernel for every 1x1 convolution; 2 = pair kernel
                               // for every staged 1x1 convolution with 256-channel N tiles and K >= 256 (experiments)
     int stem16 = 1;           // SYLPH_STEM16=0 runs the stem over 64-wide overlapped rows instead of K = 16 taps
@@ -525,6 +526,7 @@ struct ConvCall {
     const float* bias_override = nullptr;
     const __half* w_override = nullptr;
     int stem = 0;
+    int up_seg_delta = 0;    // kEpiUpsample: coarser plane = segment of the output tile + this
     int staged = 0;          // TMA-in / TMA-out epilogue (fp16 output, BN = 256); needs out_rows
     long long out_rows = 0;  // rows of the output (and residual) buffer, for the staged epilogue's tensor maps
     const char* name = "conv";
@@ -574,6 +576,7 @@ static int run_conv(sylph_ctx* c, const ConvCall& k, cudaStream_t st) {
     g.tile_seg = k.ps->d_tile_seg;
     g.segs = k.ps->d_segs;
     g.gn_partial = k.gn_partial;
+    g.up_seg_delta = k.up_seg_delta;
     Timing tm;
     if (c->profiling) {
         tm.name = k.name;
@@ -660,6 +663,7 @@ int sylph_create(sylph_ctx** out, int device, const sylph_model_config* cfg) {
     if (const char* e = getenv("SYLPH_PAIR")) c->pair_kernel = atoi(e);
     if (const char* e = getenv("SYLPH_STEM16")) c->stem16 = atoi(e);
     if (const char* e = getenv("SYLPH_PAIR1X1")) c->pair1x1 = atoi(e);
+    if (const char* e = getenv("SYLPH_FUSE_UPSAMPLE")) c->fuse_upsample = atoi(e);
     *out = c;
     if (cfg->pre_nms_topk * 5 > 8192) { c->fail("pre_nms_topk * 5 must be <= 8192"); }
     return 0;
@@ -988,8 +992,14 @@ static int run_fpn(sylph_ctx* c, int slot, const TrunkOut& T, int first, int n, 
         k.tile_begin = static_cast<int>(S.level_row0[l] / kBlockM); k.n_tiles = static_cast<int>(rows / kBlockM);
         k.a_row_delta = -static_cast<int>(S.level_row0[l]) + first * g.rows_per_img; k.out = LAT; k.ldc = 256;
         k.flags = kEpiMask; k.name = "fpn.lateral1x1";   // direct epilogue: the staged variant measured slower here (K >= 512)
+        const bool fuse_up = c->fuse_upsample && l < 2;
+        if (fuse_up) {   // top-down add in the lateral convolution's epilogue: + LAT(level l + 1)(y / 2, x / 2), summed in fp32
+            k.flags |= kEpiResidual | kEpiUpsample;
+            k.residual = LAT; k.ld_res = 256; k.up_seg_delta = n;
+        }
         TRY(run_conv(c, k, st));
-        if (l < 2) {
+        k.flags = kEpiMask; k.residual = nullptr; k.up_seg_delta = 0;
+        if (l < 2 && !fuse_up) {
             StageTimer t(c, "fpn.upsample_add", st, static_cast<double>(n) * g.H * g.W * 256 * 2 * 2.25);
             CU_TRY(c, launch_k(upsample_add_kernel, dim3(grid_for(static_cast<long long>(n) * g.H * g.W * 32, 256, c->num_sms)), dim3(256), 0, st, 
                 LAT, LAT, g, S.pg.lv[l + 1], n, 256));

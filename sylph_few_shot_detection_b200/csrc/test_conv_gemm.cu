@@ -60,11 +60,13 @@ struct Case {
     bool halo = false;    // 3x3 halo pipeline (one 130-row A box per vertical tap and k-block)
     bool staged = false;  // TMA-in / TMA-out epilogue, run IN PLACE (out == residual buffer) like the bottleneck conv3
     bool pair1x1 = false; // CTA-pair 1x1 convolution with the staged epilogue (conv1x1_pair.cuh)
+    int sms_override = 0; // pretend the device has this many SMs: many tiles per CTA on a problem the CPU reference finishes quickly
     bool stem16 = false;  // stem as K = 16 taps: A map = [rows][16] with 32-byte swizzle, 131-row boxes (same math as a_ld = 16)
 };
 
 static std::string g_case_filter;   // ./test_conv_gemm case <substring>: run only the matching correctness cases
 static int run_case(const Case& c, int num_sms) {
+    if (c.sms_override > 0) num_sms = c.sms_override;
     if (!g_case_filter.empty() && std::string(c.name).find(g_case_filter) == std::string::npos) return 0;
     const int M = c.total_rows;
     const int Kt = c.kpt * kBlockK;
@@ -518,10 +520,11 @@ int main(int argc, char** argv) {
     }
     {   // CTA-pair 1x1 kernel, staged epilogue in place: residual + ReLU + mask, 4 N tiles, ODD number of M tiles
         // (phantom tile in the last pair), many pair tiles per cluster (ring / staging-buffer phase cycling), K = 256
-        Seg s0 = mk_seg(0, 151, 168, 1);
+        Seg s0 = mk_seg(0, 30, 40, 1);   // 1344 rows = 11 M tiles (odd) -> 6 pair tiles x 4 N tiles on 8 clusters: 3 per cluster
         Case c{"PAIR1x1_staged_inplace_res_relu_mask_n1024", 256, {s0}, round128(s0.nrows), 256, 256, 1024, 1, 4, z1, z1, kEpiRelu | kEpiResidual | kEpiMask, true};
         c.staged = true;
         c.pair1x1 = true;
+        c.sms_override = 16;
         fails += run_case(c, sms);
     }
     {   // same kernel without residual (conv1 / shortcut use), one N tile, K = 512, even M tiles, two planes
