@@ -33,6 +33,22 @@ def shard_range(n_items: int, world: int, rank: int) -> range:
     return range(begin, begin + base + (1 if rank < extra else 0))
 
 
+def balanced_query_assignment(support_images_per_rank: Sequence[int], n_query: int, query_cost: float = 1.7) -> List[List[int]]:
+    """Query image -> rank assignment for ONE episode whose classes are already sharded: every query image goes, in
+    order, to the rank with the smallest load so far (support images + `query_cost` image-equivalents per query image it
+    already holds: a query image pays the backbone AND the FCOS towers); ties go to the lowest rank.  Deterministic,
+    computed identically on every rank.  The reference shards query images contiguously with `InferenceSampler`
+    (sylph/data/build.py:749-755) whatever the class shards cost; with 20 classes on 8 GPUs that leaves the ranks that
+    hold 3 classes (15 support images) with a query image on top while the ranks with 2 classes wait in the all-gather."""
+    load = [float(v) for v in support_images_per_rank]
+    out: List[List[int]] = [[] for _ in load]
+    for q in range(n_query):
+        r = min(range(len(load)), key=lambda i: (load[i], i))
+        out[r].append(q)
+        load[r] += query_cost
+    return out
+
+
 def inference_on_support_set(model: MetaOneStageDetector, support_items: Sequence[Dict[str, Any]],
                              features_in_slot: bool = False) -> List[Dict]:
     """Step B for this rank's classes.  Each item: {"support_set": [K records], "support_set_target", "class_name"}.
@@ -277,16 +293,26 @@ def _copy_stream(device):
     return _COPY_STREAMS[key]
 
 
+def query_indices_of_rank(support_items: Sequence[Dict[str, Any]], n_query: int, world: int, rank: int,
+                          balance_queries: bool = False) -> List[int]:
+    """Indices (into the episode's query list) of the query images rank `rank` detects on in `run_episode`."""
+    if not balance_queries:
+        return list(shard_range(n_query, world, rank))
+    per_rank = [sum(len(support_items[i]["support_set"]) for i in shard_range(len(support_items), world, r)) for r in range(world)]
+    return balanced_query_assignment(per_rank, n_query)[rank]
+
+
 def run_episode(model: MetaOneStageDetector, support_items: Sequence[Dict[str, Any]], query_items: Sequence[Dict[str, Any]],
-                group=None, shard: bool = True, return_device: bool = False) -> List[Dict]:
+                group=None, shard: bool = True, return_device: bool = False, balance_queries: bool = False) -> List[Dict]:
     """One meta-test episode (steps B-F).  With a process group and `shard=True`, classes and query images are split
     contiguously over the ranks (InferenceSampler semantics) with ONE collective in between; each rank returns the
-    detections of its own query shard."""
+    detections of its own query shard.  `balance_queries=True` hands the query images to the least-loaded ranks instead
+    (`balanced_query_assignment`; the rank's query indices are `query_indices_of_rank(...)`)."""
     world = dist.get_world_size(group) if (dist.is_available() and dist.is_initialized()) else 1
     rank = dist.get_rank(group) if world > 1 else 0
     if world > 1 and shard:
         my_support = [support_items[i] for i in shard_range(len(support_items), world, rank)]
-        my_query = [query_items[i] for i in shard_range(len(query_items), world, rank)]
+        my_query = [query_items[i] for i in query_indices_of_rank(support_items, len(query_items), world, rank, balance_queries)]
     else:
         my_support, my_query = list(support_items), list(query_items)
     # host-resident query images start their H2D copy on a side stream now, so it overlaps the support pass
@@ -324,6 +350,8 @@ def run_episode(model: MetaOneStageDetector, support_items: Sequence[Dict[str, A
     if ready is not None:
         torch.cuda.current_stream().wait_event(ready)
     if return_device:
+        if not my_query:            # a rank without query images (more ranks than images, or balance_queries)
+            return None, None, []
         assert len(my_query) <= 16
         with torch.no_grad():
             return model.forward_instances_device(list(my_query), packed, features_in_slot=merged)

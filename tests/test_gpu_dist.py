@@ -31,12 +31,12 @@ def _episode_inputs():
     return support, query
 
 
-def _worker(rank, world, port, q):
+def _worker(rank, world, port, q, balance=False):
     import torch.distributed as dist
     from sylph_few_shot_detection_b200 import weights as W
     from sylph_few_shot_detection_b200.modeling import build_model
     from sylph_few_shot_detection_b200.presets import coco_meta_fcos_cfg
-    from sylph_few_shot_detection_b200.runner import run_episode, shard_range
+    from sylph_few_shot_detection_b200.runner import query_indices_of_rank, run_episode
     os.environ["MASTER_ADDR"] = "127.0.0.1"
     os.environ["MASTER_PORT"] = str(port)
     torch.cuda.set_device(rank)
@@ -47,15 +47,16 @@ def _worker(rank, world, port, q):
         model.pixel_mean = model.pixel_mean.to(torch.device("cuda", rank))
         model.load_state_dict(W.synthetic_state_dict(cfg, 13))
         support, query = _episode_inputs()
-        res = run_episode(model, support, query)
-        mine = list(shard_range(len(query), world, rank))
+        res = run_episode(model, support, query, balance_queries=balance)
+        mine = query_indices_of_rank(support, len(query), world, rank, balance)
         q.put((rank, mine, [(r["instances"].pred_boxes.tensor.cpu(), r["instances"].scores.cpu(),
                              r["instances"].pred_classes.cpu()) for r in res]))
     finally:
         dist.destroy_process_group()
 
 
-def test_sharded_episode_matches_single_gpu():
+@pytest.mark.parametrize("balance", [False, True])
+def test_sharded_episode_matches_single_gpu(balance):
     if torch.cuda.device_count() < 2:
         pytest.skip("needs 2 GPUs")
     from sylph_few_shot_detection_b200 import weights as W
@@ -65,7 +66,7 @@ def test_sharded_episode_matches_single_gpu():
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
     port = _free_port()
-    procs = [ctx.Process(target=_worker, args=(r, 2, port, q)) for r in range(2)]
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, q, balance)) for r in range(2)]
     for p in procs:
         p.start()
     out = [q.get(timeout=300) for _ in range(2)]

@@ -87,3 +87,18 @@ def test_shard_range_is_contiguous_balanced_and_complete():
         sizes = [len(p) for p in parts]
         assert max(sizes) - min(sizes) <= 1 and sizes == sorted(sizes, reverse=True)
     assert [len(shard_range(20, 8, r)) for r in range(8)] == [3, 3, 3, 3, 2, 2, 2, 2]
+
+
+def test_balanced_query_assignment_fills_the_lightest_ranks_first():
+    from sylph_few_shot_detection_b200.runner import balanced_query_assignment, query_indices_of_rank
+    # BASELINE configs[3]: 20 classes x 5 shots on 8 ranks (15,15,15,15,10,10,10,10 support images), 8 query images
+    a = balanced_query_assignment([15, 15, 15, 15, 10, 10, 10, 10], 8)
+    assert a == [[], [], [], [], [0, 4], [1, 5], [2, 6], [3, 7]]
+    assert sorted(q for r in a for q in r) == list(range(8))
+    # equal loads: round-robin from rank 0, i.e. one image per rank like the contiguous shards
+    assert balanced_query_assignment([5, 5, 5, 5], 4) == [[0], [1], [2], [3]]
+    assert balanced_query_assignment([3], 2) == [[0, 1]]
+    support = [{"support_set": [None] * 5} for _ in range(20)]
+    got = [query_indices_of_rank(support, 8, 8, r, balance_queries=True) for r in range(8)]
+    assert got == a
+    assert [query_indices_of_rank(support, 8, 8, r) for r in range(8)] == [[r] for r in range(8)]

@@ -119,6 +119,15 @@ def main():
 
     ms = timed(step, args.warmup, args.steps)
     ms_async = timed(step_async, args.warmup, args.steps)
+    ms_balanced = None
+    if world > 1:
+        # query images to the least-loaded ranks (runner.balanced_query_assignment) instead of contiguous shards
+        from sylph_few_shot_detection_b200.runner import query_indices_of_rank
+        mine_b = set(query_indices_of_rank(support, args.queries, world, rank, balance_queries=True))
+        g2 = torch.Generator().manual_seed(99)
+        for i in mine_b - my_q:      # this rank needs images it did not keep on the device
+            query[i] = dict(query[i], image=torch.randint(0, 256, (3, h, w), generator=g2, dtype=torch.uint8).to(dev))
+        ms_balanced = timed(lambda: run_episode(model, support, query, balance_queries=True), args.warmup, args.steps)
     while futures:
         futures.pop(0).result()
     res = step()
@@ -126,6 +135,7 @@ def main():
     out = {"config": f"{args.way}-way {args.shot}-shot COCO-novel episode, {args.queries} query images 800x1333, classes and "
                      f"queries sharded over {world} GPU(s), one NCCL all-gather of the class codes",
            "n_gpus": world, "ms_per_episode": round(ms, 3), "episodes_per_s": round(1000.0 / ms, 2),
+           "ms_per_episode_balanced_queries": round(ms_balanced, 3) if ms_balanced else None,
            "ms_per_episode_async_results": round(ms_async, 3), "episodes_per_s_async_results": round(1000.0 / ms_async, 2),
            "episode_gflop": 23251, "tflops_all_gpus": round(23251 / ms, 1),
            "classes_on_rank0": len(my_cls), "queries_on_rank0": len(my_q), "detections_rank0": n_det,
