@@ -317,6 +317,41 @@ def build_training_goldens():
         print(f"[{name}] wrote {path} ({os.path.getsize(path) / 1e6:.2f} MB)")
 
 
+# Loss-configuration variants on the inputs of "coco_train_2way_2shot": other IoU losses, no centre sampling, a wider
+# sampling radius, other focal-loss parameters.  Only the outputs are stored (inputs = the base case's).
+TRAIN_VARIANTS = {
+    "iou_loss": ["MODEL.FCOS.LOC_LOSS_TYPE", "iou"],
+    "linear_iou_loss": ["MODEL.FCOS.LOC_LOSS_TYPE", "linear_iou"],
+    "no_center_sample": ["MODEL.FCOS.CENTER_SAMPLE", False],
+    "radius_2p5_sizes": ["MODEL.FCOS.POS_RADIUS", 2.5, "MODEL.FCOS.SIZES_OF_INTEREST", [32, 64, 128, 256]],
+    "focal_alpha_gamma": ["MODEL.FCOS.LOSS_ALPHA", 0.4, "MODEL.FCOS.LOSS_GAMMA", 1.5],
+    "focal_no_alpha": ["MODEL.FCOS.LOSS_ALPHA", -1.0],
+}
+
+
+def build_training_variant_goldens():
+    base = "coco_train_2way_2shot"
+    cfg_name, seed, opts, items = build_train_case(base)
+    out = {"base_case": base, "variants": {}, "torch_version": torch.__version__}
+    for vname, vopts in TRAIN_VARIANTS.items():
+        cfg = load_cfg(os.path.join(reference_loader.REFERENCE_ROOT, "configs", CONFIGS[cfg_name]),
+                       ["MODEL.DEVICE", "cpu"] + opts + vopts)
+        state = W.synthetic_state_dict(cfg, seed)
+        ref = run_reference_training(cfg, state, items)
+        losses, ex = build_oracle(cfg, state).training_forward(to_records(items))
+        worst = max(abs(float(losses[k]) - float(v)) / max(abs(float(v)), 1e-12) for k, v in ref["losses"].items())
+        assert set(losses) == set(ref["losses"])
+        assert torch.equal(ex["labels"], ref["labels"]) and torch.equal(ex["target_inds"], ref["target_inds"])
+        assert torch.equal(ex["reg_targets"], ref["reg_targets"])
+        print(f"[train variant {vname}] reference losses {({k: round(float(v), 5) for k, v in ref['losses'].items()})}; "
+              f"positives {int((ref['labels'] != 100000).sum())}; oracle deviation {worst:.2e}, targets bit-exact")
+        out["variants"][vname] = {"opts": opts + vopts, "losses": ref["losses"], "labels": ref["labels"].to(torch.int32),
+                                  "target_inds": ref["target_inds"].to(torch.int32), "reg_targets": ref["reg_targets"].to(torch.float32)}
+    path = os.path.join(GOLDEN_DIR, "coco_train_variants.pt")
+    torch.save(out, path)
+    print(f"[train variants] wrote {path} ({os.path.getsize(path) / 1e6:.2f} MB)")
+
+
 @contextlib.contextmanager
 def warnings_off():
     import warnings
@@ -331,8 +366,12 @@ def main():
         build_base_reduce_golden()
     if "--base-only" in sys.argv:
         return
+    if "--train-variants-only" in sys.argv:
+        build_training_variant_goldens()
+        return
     if "--train-only" in sys.argv or "--all" in sys.argv or len(sys.argv) == 1:
         build_training_goldens()
+        build_training_variant_goldens()
     if "--train-only" in sys.argv:
         return
     for name in CASES:

@@ -111,3 +111,41 @@ def test_loss_sums_c_abi_edge_cases():
             assert float(sums[1]) > 0
     with pytest.raises(RuntimeError, match="gt_offsets"):
         eng.fcos_loss_sums(SLOT_QUERY, codes, [7, 8, 9], torch.zeros(1, 4), torch.zeros(1, dtype=torch.int64), [0, 0, 0])
+
+
+@pytest.mark.parametrize("variant", ["iou_loss", "linear_iou_loss", "no_center_sample", "radius_2p5_sizes",
+                                     "focal_alpha_gamma", "focal_no_alpha"])
+def test_training_forward_loss_configurations(variant):
+    """Every branch of the fused target-assignment + loss kernel (IoU / linear IoU / GIoU, centre sampling on / off, another
+    radius and size-of-interest table, focal alpha / gamma incl. alpha < 0) against the REFERENCE model run with the
+    same config overrides (oracle/make_golden.py --train-variants-only): targets bit-exact, losses as above."""
+    from oracle.meta_fcos_oracle import MetaFCOSOracle
+    from sylph_few_shot_detection_b200 import weights as W
+    from sylph_few_shot_detection_b200.modeling import build_model
+    from sylph_few_shot_detection_b200.runtime import SLOT_QUERY
+    base = load_golden("coco_train_2way_2shot")
+    v = load_golden("coco_train_variants")["variants"][variant]
+    cfg = cfg_for(base["config"], v["opts"])
+    state = W.synthetic_state_dict(cfg, base["seed"])
+    model = build_model(cfg)
+    model.load_state_dict(state)
+    model.train()
+    batched = _records(base["items"])
+    losses, ex = model.forward_few_shot_detector_training(batched, want_targets=True)
+    assert torch.equal(ex["labels"].cpu(), v["labels"].to(torch.int64))
+    assert torch.equal(ex["target_inds"].cpu(), v["target_inds"].to(torch.int64))
+    assert torch.equal(ex["reg_targets"].cpu(), v["reg_targets"])
+    orc = MetaFCOSOracle(cfg, state)
+    eng = model.engine
+    n_cls = len(base["items"])
+    logits = [eng.export_head_output(0, l, SLOT_QUERY, n_cls).cpu() for l in range(5)]
+    regs = [eng.export_head_output(1, l, SLOT_QUERY, n_cls).cpu() for l in range(5)]
+    ctrs = [eng.export_head_output(2, l, SLOT_QUERY, n_cls).cpu() for l in range(5)]
+    query = [r for x in batched for r in x["query_set"]]
+    targets = [int(x["support_set_target"]) for x in batched]
+    ref_losses, _ = orc.fcos_losses(logits, regs, ctrs, orc.filter_gt(query, targets), targets)
+    assert set(losses) == set(v["losses"]) == set(ref_losses)
+    for k in losses:
+        got = float(losses[k])
+        assert abs(got - float(ref_losses[k])) <= KERNEL_TOL * max(abs(float(ref_losses[k])), 1e-3), (k, got, float(ref_losses[k]))
+        assert abs(got - float(v["losses"][k])) <= LOSS_TOL * max(abs(float(v["losses"][k])), 1e-3), (k, got, float(v["losses"][k]))

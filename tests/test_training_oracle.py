@@ -86,3 +86,23 @@ def test_plugin_training_forward_host_logic():
     bad = cfg_for("COCO-Detection/Meta-FCOS/Meta-FCOS-finetune.yaml", ["MODEL.META_LEARN.CODE_GENERATOR.BOX_ON", True])
     with pytest.raises(NotImplementedError):
         loss_config_from_cfg(bad)
+
+
+VARIANTS = ["iou_loss", "linear_iou_loss", "no_center_sample", "radius_2p5_sizes", "focal_alpha_gamma", "focal_no_alpha"]
+
+
+@pytest.mark.parametrize("variant", VARIANTS)
+def test_oracle_training_forward_loss_configurations(variant):
+    """Other LOC_LOSS_TYPE / CENTER_SAMPLE / POS_RADIUS / SIZES_OF_INTEREST / focal-loss settings on the inputs of
+    coco_train_2way_2shot, against the reference model run with the same overrides."""
+    base = load_golden("coco_train_2way_2shot")
+    v = load_golden("coco_train_variants")["variants"][variant]
+    cfg = cfg_for(base["config"], v["opts"])
+    orc = MetaFCOSOracle(cfg, W.synthetic_state_dict(cfg, base["seed"]))
+    losses, ex = orc.training_forward(to_records(base["items"]))
+    assert set(losses) == set(v["losses"])
+    for k, ref in v["losses"].items():
+        assert abs(float(losses[k]) - float(ref)) <= 2e-5 * abs(float(ref)), (k, float(losses[k]), float(ref))
+    assert torch.equal(ex["labels"], v["labels"].to(torch.int64))
+    assert torch.equal(ex["target_inds"], v["target_inds"].to(torch.int64))
+    assert torch.equal(ex["reg_targets"], v["reg_targets"])
