@@ -359,7 +359,8 @@ def main():
             a[0] += 1; a[1] += t_ms; a[2] += fl; a[3] += by
         total_ms = sum(a[1] for a in agg.values())
         breakdown = {k: {"launches": a[0], "ms": round(a[1], 4), "share": round(a[1] / total_ms, 4),
-                         "tflops_padded": round(a[2] / a[1] * 1e-9, 1) if a[1] > 0 else None} for k, a in
+                         "tflops_padded": round(a[2] / a[1] * 1e-9, 1) if a[1] > 0 else None,
+                         "gbs_algorithmic": round(a[3] / a[1] * 1e-6, 1) if a[1] > 0 and a[3] > 0 else None} for k, a in
                      sorted(agg.items(), key=lambda kv: -kv[1][1])}
         traffic = {}
         try:
