@@ -334,19 +334,16 @@ def run_episode(model: MetaOneStageDetector, support_items: Sequence[Dict[str, A
             from .runtime import SLOT_QUERY, SLOT_SUPPORT
             model.engine.extract_features_multi([(SLOT_SUPPORT, sup_imgs), (SLOT_QUERY, qry_imgs)])
             merged = True
-    def codes_phase():
-        sub_codes = inference_on_support_set(model, my_support, features_in_slot=merged)
-        if world > 1 and shard:
-            # the class list is global: shard sizes, ids and names are known everywhere, only the codes travel
-            counts = [len(shard_range(len(support_items), world, r)) for r in range(world)]
-            meta = [(it["support_set_target"], it.get("class_name", "")) for it in support_items]
-            all_codes = gather_class_code_known_shards(sub_codes, counts, meta, group=group)
-        else:
-            all_codes = sub_codes
-        all_codes = inference_normalization(model, all_codes)
-        return format_class_codes_shared(all_codes, device=model.device)
-
-    packed = codes_phase()
+    sub_codes = inference_on_support_set(model, my_support, features_in_slot=merged)
+    if world > 1 and shard:
+        # the class list is global: shard sizes, ids and names are known everywhere, only the codes travel
+        counts = [len(shard_range(len(support_items), world, r)) for r in range(world)]
+        meta = [(it["support_set_target"], it.get("class_name", "")) for it in support_items]
+        all_codes = gather_class_code_known_shards(sub_codes, counts, meta, group=group)
+    else:
+        all_codes = sub_codes
+    all_codes = inference_normalization(model, all_codes)
+    packed = format_class_codes_shared(all_codes, device=model.device)
     if ready is not None:
         torch.cuda.current_stream().wait_event(ready)
     if return_device:
