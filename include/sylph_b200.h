@@ -127,6 +127,36 @@ int sylph_export_roi_features(sylph_ctx* ctx, float* out_dev, void* stream);
  * Replaces forward_normalize_code / code_process_module, code_generator.py:864-897. */
 int sylph_normalize_codes(sylph_ctx* ctx, const float* raw_codes_dev, float* out_codes_dev, int n_classes, void* stream);
 
+/* ---- Class-code exchange over NVLink peer memory: normalisation fused with the all-gather. ----
+ * In the sharded episode every rank generates the raw codes of a contiguous class shard; all ranks need the NORMALISED
+ * codes of all classes before detection.  The reference moves pickled code dicts with all_gather_object
+ * (MetaFCOSRunner._gather_class_code, sylph/runner/meta_fcos_runner.py:381-396) and then normalises every class on
+ * every rank (inference_normalization, sylph/evaluation/meta_learn_evaluation.py:105-116 ->
+ * forward_normalize_code, code_generator.py:877-897).  Here the normalisation kernel stores each finished row directly
+ * into the exchange buffer of EVERY rank of the box (peer memory mapped through CUDA IPC, stores travel over
+ * NVLink / NVSwitch) and publishes it with a system-scope atomic; a one-block kernel on each rank waits for the rows of
+ * the episode and hands them to the caller.  Two launches, no NCCL call, no host synchronisation.
+ *
+ * Setup (once per process group, all ranks of ONE box): sylph_exchange_create on every rank -> exchange the 64-byte
+ * handles by any means (the Python layer uses one all_gather) -> sylph_exchange_connect with the handles of all ranks in
+ * rank order.  world == 1 needs no handle exchange (handles_all may be NULL).  All ranks must then make the same
+ * sequence of sylph_normalize_codes_exchange calls (same n_total per call). */
+#define SYLPH_IPC_HANDLE_BYTES 64
+int sylph_exchange_create(sylph_ctx* ctx, int world, int rank, int max_classes, uint8_t* handle_out /* 64 bytes */);
+int sylph_exchange_connect(sylph_ctx* ctx, const uint8_t* handles_all /* world x 64 bytes, rank order */);
+
+/* Normalise this rank's n_local raw codes (rows class_offset .. class_offset + n_local - 1 of the episode's n_total
+ * classes; n_local may be 0), deliver them to every rank, wait for the rows of all other ranks and write the
+ * (n_total, 257) normalised codes to all_codes_out_dev.  Same arithmetic as sylph_normalize_codes (bit-identical rows);
+ * with generator == 1 (ROIEncoder, final codes) the rows travel unchanged.  A rank that waits longer than
+ * SYLPH_EXCHANGE_TIMEOUT_MS (default 5000) gives up and raises the flag sylph_exchange_status reports. */
+int sylph_normalize_codes_exchange(sylph_ctx* ctx, const float* raw_codes_dev, int n_local, int class_offset, int n_total,
+                                   float* all_codes_out_dev, void* stream);
+
+/* Synchronous: *timed_out = 1 if any exchange of this context gave up waiting; *rows_arrived = rows received so far. */
+int sylph_exchange_status(sylph_ctx* ctx, int* timed_out, int64_t* rows_arrived);
+void sylph_exchange_destroy(sylph_ctx* ctx);
+
 /* Base-class "all ground truths" path (MODEL.META_LEARN.USE_ALL_GTS_IN_BASE_CLASSES): a class arrives as several
  * chunks of <= 10 support boxes.  acc[class_of(k)] += chunk_codes[k] * chunk_weight[k] for k = 0..n_chunks-1 in order,
  * with the reference's fp32 rounding sequence (multiply, then add; no FMA).  acc_dev is [n_classes][257], zeroed by the

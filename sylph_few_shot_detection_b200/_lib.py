@@ -17,6 +17,7 @@ NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", 
 
 CODE_STRIDE = 257
 DET_STRIDE = 9
+IPC_HANDLE_BYTES = 64
 NUM_LEVELS = 5
 SLOT_SUPPORT, SLOT_QUERY = 0, 1
 
@@ -112,6 +113,16 @@ def load() -> ctypes.CDLL:
     lib.sylph_export_roi_features.argtypes = [vp, vp, vp]
     lib.sylph_normalize_codes.restype = c_int
     lib.sylph_normalize_codes.argtypes = [vp, vp, vp, c_int, vp]
+    lib.sylph_exchange_create.restype = c_int
+    lib.sylph_exchange_create.argtypes = [vp, c_int, c_int, c_int, vp]
+    lib.sylph_exchange_connect.restype = c_int
+    lib.sylph_exchange_connect.argtypes = [vp, vp]
+    lib.sylph_normalize_codes_exchange.restype = c_int
+    lib.sylph_normalize_codes_exchange.argtypes = [vp, vp, c_int, c_int, c_int, vp, vp]
+    lib.sylph_exchange_status.restype = c_int
+    lib.sylph_exchange_status.argtypes = [vp, ip, POINTER(c_int64)]
+    lib.sylph_exchange_destroy.restype = None
+    lib.sylph_exchange_destroy.argtypes = [vp]
     lib.sylph_accumulate_codes.restype = c_int
     lib.sylph_accumulate_codes.argtypes = [vp, vp, c_int, ip, fp, vp, c_int, vp]
     lib.sylph_reduce_codes.restype = c_int
@@ -140,6 +151,7 @@ def load() -> ctypes.CDLL:
 EXPORTED_SYMBOLS = [
     "sylph_version", "sylph_create", "sylph_destroy", "sylph_last_error", "sylph_load_tensor",
     "sylph_finalize_weights", "sylph_extract_features", "sylph_extract_features_u8", "sylph_extract_features_multi", "sylph_import_features", "sylph_feature_shape",
-    "sylph_export_features", "sylph_generate_codes", "sylph_export_roi_features", "sylph_normalize_codes", "sylph_accumulate_codes", "sylph_reduce_codes",
+    "sylph_export_features", "sylph_generate_codes", "sylph_export_roi_features", "sylph_normalize_codes", "sylph_exchange_create", "sylph_exchange_connect",
+    "sylph_normalize_codes_exchange", "sylph_exchange_status", "sylph_exchange_destroy", "sylph_accumulate_codes", "sylph_reduce_codes",
     "sylph_detect", "sylph_detect_after", "sylph_export_head_output", "sylph_fcos_loss_sums", "sylph_fcos_loss_finalize", "sylph_launch_count", "sylph_set_profiling", "sylph_get_timings",
 ]

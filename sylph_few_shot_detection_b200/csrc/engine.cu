@@ -114,6 +114,15 @@ struct sylph_ctx {
     std::vector<Dense> re_whead, re_bhead;
     float cond_scale = 1.f;            // fcos_head.cond_cls_logits.scales.0.scale (CondConvBlock, head_utils.py:121-162)
 
+    // class-code exchange over NVLink peer memory (sylph_exchange_*): one allocation per rank, mapped by all ranks
+    struct Exchange {
+        int world = 0, rank = 0, max_classes = 0;
+        void* local = nullptr;                       // ExchangeState header + [2][max_classes][257] floats
+        void* peer_base[sylph::kMaxExchangePeers] = {};
+        sylph::ExchangePeers peers{};
+        bool connected = false;
+        unsigned long long timeout_ns = 5000000000ull;   // SYLPH_EXCHANGE_TIMEOUT_MS
+    } xch;
     std::map<std::string, Buffer> bufs;
     // pinned host ring for small host->device argument arrays: copies from it are truly asynchronous, so no entry
     // point has to drain the stream (a pageable cudaMemcpyAsync synchronises the stream first)
@@ -673,6 +682,7 @@ void sylph_destroy(sylph_ctx* c) {
     if (!c) return;
     cudaSetDevice(c->device);
     cudaDeviceSynchronize();
+    sylph_exchange_destroy(c);
     for (auto& kv : c->bufs) if (kv.second.p) cudaFree(kv.second.p);
     if (c->pinned) cudaFreeHost(c->pinned);
     if (c->graph_arena) cudaFreeHost(c->graph_arena);
@@ -1468,6 +1478,120 @@ int sylph_normalize_codes(sylph_ctx* c, const float* raw_codes_dev, float* out_c
     CU_TRY(c, cudaGetLastError());
     c->launches++;
     return 0;
+}
+
+// ------------------------------------------------------------------------------------------------ code exchange
+static size_t exchange_bytes(int max_classes) {
+    return sizeof(ExchangeState) + static_cast<size_t>(2) * max_classes * SYLPH_CODE_STRIDE * sizeof(float);
+}
+
+int sylph_exchange_create(sylph_ctx* c, int world, int rank, int max_classes, uint8_t* handle_out) {
+    if (!c) return 1;
+    static_assert(sizeof(cudaIpcMemHandle_t) == SYLPH_IPC_HANDLE_BYTES, "IPC handle size");
+    if (world < 1 || world > kMaxExchangePeers) return c->fail("exchange: world size %d outside 1..%d", world, kMaxExchangePeers);
+    if (rank < 0 || rank >= world || max_classes < 1 || !handle_out) return c->fail("exchange: bad arguments");
+    if (c->xch.local) return c->fail("exchange: already created (sylph_exchange_destroy first)");
+    CU_TRY(c, cudaSetDevice(c->device));
+    void* p = nullptr;
+    CU_TRY(c, cudaMalloc(&p, exchange_bytes(max_classes)));   // cudaMalloc (not a pool) so that the block can be IPC-exported
+    CU_TRY(c, cudaMemset(p, 0, exchange_bytes(max_classes)));
+    CU_TRY(c, cudaDeviceSynchronize());
+    memset(handle_out, 0, SYLPH_IPC_HANDLE_BYTES);
+    if (world > 1) {
+        cudaIpcMemHandle_t h;
+        cudaError_t e = cudaIpcGetMemHandle(&h, p);
+        if (e != cudaSuccess) {
+            cudaFree(p);
+            return c->fail("cudaIpcGetMemHandle failed: %s", cudaGetErrorString(e));
+        }
+        memcpy(handle_out, &h, SYLPH_IPC_HANDLE_BYTES);
+    }
+    c->xch = sylph_ctx::Exchange();
+    c->xch.world = world;
+    c->xch.rank = rank;
+    c->xch.max_classes = max_classes;
+    c->xch.local = p;
+    if (const char* e = getenv("SYLPH_EXCHANGE_TIMEOUT_MS")) c->xch.timeout_ns = static_cast<unsigned long long>(atoll(e)) * 1000000ull;
+    return 0;
+}
+
+int sylph_exchange_connect(sylph_ctx* c, const uint8_t* handles_all) {
+    if (!c) return 1;
+    sylph_ctx::Exchange& x = c->xch;
+    if (!x.local) return c->fail("exchange: sylph_exchange_create first");
+    if (x.connected) return c->fail("exchange: already connected");
+    if (x.world > 1 && !handles_all) return c->fail("exchange: handles of all ranks required");
+    CU_TRY(c, cudaSetDevice(c->device));
+    for (int r = 0; r < x.world; ++r) {
+        void* base = x.local;
+        if (r != x.rank) {
+            cudaIpcMemHandle_t h;
+            memcpy(&h, handles_all + static_cast<size_t>(r) * SYLPH_IPC_HANDLE_BYTES, SYLPH_IPC_HANDLE_BYTES);
+            cudaError_t e = cudaIpcOpenMemHandle(&base, h, cudaIpcMemLazyEnablePeerAccess);
+            if (e != cudaSuccess) {
+                for (int q = 0; q < r; ++q)
+                    if (q != x.rank && x.peer_base[q]) { cudaIpcCloseMemHandle(x.peer_base[q]); x.peer_base[q] = nullptr; }
+                return c->fail("cudaIpcOpenMemHandle(rank %d) failed: %s (ranks must be GPUs of one box with peer access)", r,
+                               cudaGetErrorString(e));
+            }
+        }
+        x.peer_base[r] = base;
+        x.peers.arrived[r] = &reinterpret_cast<ExchangeState*>(base)->arrived;
+        x.peers.codes[r] = reinterpret_cast<float*>(static_cast<uint8_t*>(base) + sizeof(ExchangeState));
+    }
+    x.peers.world = x.world;
+    x.connected = true;
+    return 0;
+}
+
+int sylph_normalize_codes_exchange(sylph_ctx* c, const float* raw_codes_dev, int n_local, int class_offset, int n_total,
+                                   float* all_codes_out_dev, void* stream) {
+    if (!c) return 1;
+    if (!c->finalized) return c->fail("weights not finalized");
+    sylph_ctx::Exchange& x = c->xch;
+    if (!x.connected) return c->fail("exchange: not connected");
+    if (n_local < 0 || class_offset < 0 || n_total < 1 || class_offset + n_local > n_total || n_total > x.max_classes)
+        return c->fail("exchange: shard [%d, %d) of %d classes does not fit max_classes %d", class_offset, class_offset + n_local,
+                       n_total, x.max_classes);
+    if (!all_codes_out_dev || (n_local > 0 && !raw_codes_dev)) return c->fail("exchange: null buffer");
+    const sylph_model_config& f = c->cfg;
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    ExchangeState* state = reinterpret_cast<ExchangeState*>(x.local);
+    const float* local_codes = reinterpret_cast<const float*>(static_cast<uint8_t*>(x.local) + sizeof(ExchangeState));
+    if (n_local > 0) {
+        CU_TRY(c, launch_k(normalize_scatter_codes_kernel, dim3(n_local), dim3(256), 0, st, raw_codes_dev, x.peers,
+                           static_cast<const ExchangeState*>(state), class_offset, x.max_classes, f.generator == 0 ? 1 : 0,
+                           static_cast<const float*>(c->post_gn_w), static_cast<const float*>(c->post_gn_b), f.cg_post_norm,
+                           f.cg_conv_l2_norm, c->conv_scale, c->bias_scale, c->bias_value));
+        c->launches++;
+    }
+    const int collect_blocks = std::max(1, std::min(32, ceil_div(static_cast<long long>(n_total) * SYLPH_CODE_STRIDE, 4096)));
+    CU_TRY(c, launch_k(collect_codes_kernel, dim3(collect_blocks), dim3(1024), 0, st, state, local_codes, x.max_classes, n_total,
+                       all_codes_out_dev, x.timeout_ns));
+    CU_TRY(c, cudaGetLastError());
+    c->launches++;
+    return 0;
+}
+
+int sylph_exchange_status(sylph_ctx* c, int* timed_out, int64_t* rows_arrived) {
+    if (!c) return 1;
+    if (!c->xch.local) return c->fail("exchange: not created");
+    ExchangeState h;
+    CU_TRY(c, cudaSetDevice(c->device));
+    CU_TRY(c, cudaMemcpy(&h, c->xch.local, sizeof(h), cudaMemcpyDeviceToHost));   // synchronous: drains the device first
+    if (timed_out) *timed_out = static_cast<int>(h.error);
+    if (rows_arrived) *rows_arrived = static_cast<int64_t>(h.arrived);
+    return 0;
+}
+
+void sylph_exchange_destroy(sylph_ctx* c) {
+    if (!c || !c->xch.local) return;
+    cudaSetDevice(c->device);
+    cudaDeviceSynchronize();
+    for (int r = 0; r < c->xch.world; ++r)
+        if (r != c->xch.rank && c->xch.peer_base[r]) cudaIpcCloseMemHandle(c->xch.peer_base[r]);
+    cudaFree(c->xch.local);
+    c->xch = sylph_ctx::Exchange();
 }
 
 int sylph_accumulate_codes(sylph_ctx* c, const float* chunk_codes_dev, int n_chunks, const int* chunk_class_host,

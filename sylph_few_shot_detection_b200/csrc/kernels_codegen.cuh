@@ -180,19 +180,12 @@ reduce_codes_kernel(const float* __restrict__ parts, int n_parts, int n_classes,
     out[static_cast<size_t>(cls) * 257 + t] = d != 0.f ? __fdiv_rn(s, d) : s;
 }
 
-// Code normalisation, one 256-thread block per class (code_process_module, code_generator.py:832-875):
-// GroupNorm(32, 256) on the 1x1 map (8-lane shuffles) -> L2 normalise over the 256 channels -> x conv_scale;
-// bias x bias_scale + (-log((1 - p) / p)).
-__global__ void __launch_bounds__(256)
-normalize_codes_kernel(const float* __restrict__ raw, float* __restrict__ out, const float* __restrict__ gn_w,
-                       const float* __restrict__ gn_b, int post_norm, int l2_norm, float conv_scale, float bias_scale,
-                       float bias_value) {
-    ptx::griddep_launch();
-    ptx::griddep_wait();
-    __shared__ float red[8];
-    const int cls = blockIdx.x, t = threadIdx.x, lane = t & 31, warp = t >> 5;
-    float x = raw[static_cast<size_t>(cls) * 257 + t];
-    const float b = raw[static_cast<size_t>(cls) * 257 + 256];
+// Code normalisation of one channel, called by all 256 threads of a block (code_process_module,
+// code_generator.py:832-875): GroupNorm(32, 256) on the 1x1 map (8-lane shuffles) -> L2 normalise over the 256 channels.
+// `red` is an 8-float shared scratch.
+__device__ __forceinline__ float normalize_code_channel(float x, const float* __restrict__ gn_w, const float* __restrict__ gn_b,
+                                                        int post_norm, int l2_norm, float* red, int t) {
+    const int lane = t & 31, warp = t >> 5;
     if (post_norm) {
         float s = x;
         s += __shfl_xor_sync(0xffffffffu, s, 1);
@@ -217,8 +210,139 @@ normalize_codes_kernel(const float* __restrict__ raw, float* __restrict__ out, c
         for (int i = 0; i < 8; ++i) tot += red[i];
         x = x / fmaxf(sqrtf(tot), 1e-12f);
     }
+    return x;
+}
+
+// Code normalisation, one 256-thread block per class: normalised channel x conv_scale;
+// bias x bias_scale + (-log((1 - p) / p)).
+__global__ void __launch_bounds__(256)
+normalize_codes_kernel(const float* __restrict__ raw, float* __restrict__ out, const float* __restrict__ gn_w,
+                       const float* __restrict__ gn_b, int post_norm, int l2_norm, float conv_scale, float bias_scale,
+                       float bias_value) {
+    ptx::griddep_launch();
+    ptx::griddep_wait();
+    __shared__ float red[8];
+    const int cls = blockIdx.x, t = threadIdx.x;
+    float x = raw[static_cast<size_t>(cls) * 257 + t];
+    const float b = raw[static_cast<size_t>(cls) * 257 + 256];
+    x = normalize_code_channel(x, gn_w, gn_b, post_norm, l2_norm, red, t);
     out[static_cast<size_t>(cls) * 257 + t] = x * conv_scale;
     if (t == 0) out[static_cast<size_t>(cls) * 257 + 256] = b * bias_scale + bias_value;
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// Class-code exchange over NVLink peer memory: the normalisation kernel IS the all-gather.  Every rank owns one
+// exchange allocation (ExchangeState + two code buffers of max_classes rows, double-buffered by episode parity) that
+// all ranks of the box map through CUDA IPC.  The producer normalises the rank's class shard and stores every row
+// straight into ALL ranks' buffers (coalesced 1 KB rows over NVLink), then publishes the row with one system-scope
+// atomic per peer; the consumer waits until the rows of all classes of this episode have landed locally and hands
+// them to the caller.  Replaces MetaFCOSRunner._gather_class_code (sylph/runner/meta_fcos_runner.py:381-396:
+// all_gather_object of pickled code dicts) + inference_normalization (meta_learn_evaluation.py:105-116) for the
+// sharded episode; no NCCL call, no host synchronisation, two launches.
+struct ExchangeState {
+    unsigned long long arrived;      // rows that have landed in THIS rank's buffers, all episodes (remote atomics)
+    unsigned long long pad0[15];     // keep the remotely updated word in its own 128-byte line
+    unsigned long long expected;     // rows consumed by this rank so far (local; advanced by the collect kernel)
+    unsigned int parity;             // buffer half of the CURRENT episode (local; same value on every rank)
+    unsigned int error;              // sticky: a collect kernel gave up waiting (local)
+    unsigned int blocks_done;        // blocks of the running collect kernel that have finished (local)
+    unsigned int pad1[27];
+};
+static_assert(sizeof(ExchangeState) == 256, "ExchangeState is the 256-byte header of the exchange allocation");
+
+constexpr int kMaxExchangePeers = 16;
+struct ExchangePeers {
+    float* codes[kMaxExchangePeers];                 // peer r's code buffers: [2][max_classes][257]
+    unsigned long long* arrived[kMaxExchangePeers];  // &peer r's ExchangeState::arrived
+    int world;
+};
+
+__device__ __forceinline__ unsigned long long ld_acquire_sys_u64(const unsigned long long* p) {
+    unsigned long long v;
+    asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ unsigned long long global_timer_ns() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+    return t;
+}
+
+// One 256-thread block per local class.  do_norm = 0 forwards the rows unchanged (ROIEncoder codes are final).
+__global__ void __launch_bounds__(256)
+normalize_scatter_codes_kernel(const float* __restrict__ raw, ExchangePeers peers, const ExchangeState* self_state,
+                               int class_offset, int max_classes, int do_norm, const float* __restrict__ gn_w,
+                               const float* __restrict__ gn_b, int post_norm, int l2_norm, float conv_scale,
+                               float bias_scale, float bias_value) {
+    ptx::griddep_launch();
+    ptx::griddep_wait();
+    __shared__ float red[8];
+    const int cls = blockIdx.x, t = threadIdx.x;
+    float x = raw[static_cast<size_t>(cls) * 257 + t];
+    float b = raw[static_cast<size_t>(cls) * 257 + 256];
+    if (do_norm) {
+        x = normalize_code_channel(x, gn_w, gn_b, post_norm, l2_norm, red, t) * conv_scale;
+        b = b * bias_scale + bias_value;
+    }
+    const unsigned int parity = self_state->parity;   // written by the previous collect kernel of this stream
+    const size_t row = (static_cast<size_t>(parity) * max_classes + class_offset + cls) * 257;
+    for (int r = 0; r < peers.world; ++r) {
+        peers.codes[r][row + t] = x;
+        if (t == 0) peers.codes[r][row + 256] = b;
+    }
+    __syncthreads();
+    // release: the block's stores (ordered before the barrier) become visible system-wide before the row is counted
+    if (t < peers.world) {
+        __threadfence_system();
+        atomicAdd_system(peers.arrived[t], 1ULL);
+    }
+}
+
+// Wait (bounded) until n_total rows of this episode have landed, copy them to the caller's buffer, then advance the
+// rank's episode state.  A few blocks share the copy (grid-stride); each waits on the counter by itself and the last
+// block to finish advances the state, so no block depends on another being resident.  The timeout only guards against
+// ranks that disagree on the call sequence.
+__global__ void __launch_bounds__(1024)
+collect_codes_kernel(ExchangeState* state, const float* local_codes, int max_classes, int n_total, float* __restrict__ out,
+                     unsigned long long timeout_ns) {
+    ptx::griddep_launch();
+    ptx::griddep_wait();
+    __shared__ unsigned int s_parity;
+    __shared__ unsigned long long s_want;
+    if (threadIdx.x == 0) {
+        const unsigned long long want = state->expected + static_cast<unsigned long long>(n_total);
+        const unsigned long long t0 = global_timer_ns();
+        while (ld_acquire_sys_u64(&state->arrived) < want) {
+            if (global_timer_ns() - t0 > timeout_ns) {
+                state->error = 1u;
+                break;
+            }
+            __nanosleep(200);
+        }
+        s_parity = state->parity;
+        s_want = want;
+    }
+    __syncthreads();
+    const float* src = local_codes + static_cast<size_t>(s_parity) * max_classes * 257;
+    const int n = n_total * 257, step = gridDim.x * blockDim.x;
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    for (; i + 3 * step < n; i += 4 * step) {   // L2 is the coherence point for peer writes: ld.cg
+        const float a = __ldcg(src + i), b = __ldcg(src + i + step), c = __ldcg(src + i + 2 * step), d = __ldcg(src + i + 3 * step);
+        out[i] = a;
+        out[i + step] = b;
+        out[i + 2 * step] = c;
+        out[i + 3 * step] = d;
+    }
+    for (; i < n; i += step) out[i] = __ldcg(src + i);
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        __threadfence();
+        if (atomicAdd(&state->blocks_done, 1u) == gridDim.x - 1) {   // every block has read expected / parity by now
+            state->blocks_done = 0u;
+            state->expected = s_want;
+            state->parity = s_parity ^ 1u;
+        }
+    }
 }
 
 // Expand (n_classes, 257) codes into the K-major weight matrix [n_pad][256] + bias [n_pad] the logits GEMM reads

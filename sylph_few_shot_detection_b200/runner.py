@@ -14,6 +14,7 @@ pickled CPU tensors through all_gather_object.
 """
 from __future__ import annotations
 
+import os
 from typing import Any, Dict, List, Optional, Sequence, Tuple
 
 import torch
@@ -302,12 +303,39 @@ def query_indices_of_rank(support_items: Sequence[Dict[str, Any]], n_query: int,
     return balanced_query_assignment(per_rank, n_query)[rank]
 
 
+def exchange_codes_peer(model: MetaOneStageDetector, sub_class_codes: List[Dict], counts: Sequence[int],
+                        meta: Sequence[Tuple[Any, str]], group=None) -> List[Dict]:
+    """Steps C + D of the sharded episode in one fused device step: this rank's raw codes are normalised and stored
+    straight into every rank's exchange buffer over NVLink (`Engine.normalize_codes_exchange`), replacing
+    `_gather_class_code` (meta_fcos_runner.py:381-396) + `inference_normalization` (meta_learn_evaluation.py:105-116).
+    Returns the NORMALISED codes of all classes in the list schema (views of one (classes, 257) device buffer); same
+    values as `gather_class_code_known_shards` followed by `inference_normalization`."""
+    world = dist.get_world_size(group) if (dist.is_available() and dist.is_initialized()) else 1
+    rank = dist.get_rank(group) if world > 1 else 0
+    assert len(counts) == world and len(sub_class_codes) == counts[rank] and len(meta) == sum(counts)
+    engine = model.engine
+    engine.exchange_setup(group, max_classes=max(2048, sum(counts)))
+    raw = _code_rows(sub_class_codes, engine.device) if sub_class_codes else None
+    rows = engine.normalize_codes_exchange(raw, sum(counts[:rank]), sum(counts))
+    return [{"support_set_target": target, "class_name": name,
+             "class_code": {"cls_conv": rows[k, :256].reshape(1, 256, 1, 1), "cls_bias": rows[k, 256:257].reshape(1)}}
+            for k, (target, name) in enumerate(meta)]
+
+
+def code_exchange_mode() -> str:
+    """"nccl" (one all_gather_into_tensor, then normalisation on every rank) or "peer" (normalisation fused with the
+    all-gather over NVLink peer memory); SYLPH_CODE_EXCHANGE overrides the default."""
+    return os.environ.get("SYLPH_CODE_EXCHANGE", "nccl")
+
+
 def run_episode(model: MetaOneStageDetector, support_items: Sequence[Dict[str, Any]], query_items: Sequence[Dict[str, Any]],
-                group=None, shard: bool = True, return_device: bool = False, balance_queries: bool = False) -> List[Dict]:
+                group=None, shard: bool = True, return_device: bool = False, balance_queries: bool = False,
+                exchange: Optional[str] = None) -> List[Dict]:
     """One meta-test episode (steps B-F).  With a process group and `shard=True`, classes and query images are split
-    contiguously over the ranks (InferenceSampler semantics) with ONE collective in between; each rank returns the
+    contiguously over the ranks (InferenceSampler semantics) with ONE exchange step in between; each rank returns the
     detections of its own query shard.  `balance_queries=True` hands the query images to the least-loaded ranks instead
-    (`balanced_query_assignment`; the rank's query indices are `query_indices_of_rank(...)`)."""
+    (`balanced_query_assignment`; the rank's query indices are `query_indices_of_rank(...)`).  `exchange`: "nccl" = one
+    all_gather_into_tensor of the raw codes, "peer" = `exchange_codes_peer` (default: `code_exchange_mode()`)."""
     world = dist.get_world_size(group) if (dist.is_available() and dist.is_initialized()) else 1
     rank = dist.get_rank(group) if world > 1 else 0
     if world > 1 and shard:
@@ -339,10 +367,12 @@ def run_episode(model: MetaOneStageDetector, support_items: Sequence[Dict[str, A
         # the class list is global: shard sizes, ids and names are known everywhere, only the codes travel
         counts = [len(shard_range(len(support_items), world, r)) for r in range(world)]
         meta = [(it["support_set_target"], it.get("class_name", "")) for it in support_items]
-        all_codes = gather_class_code_known_shards(sub_codes, counts, meta, group=group)
+        if (exchange or code_exchange_mode()) == "peer":
+            all_codes = exchange_codes_peer(model, sub_codes, counts, meta, group=group)    # already normalised
+        else:
+            all_codes = inference_normalization(model, gather_class_code_known_shards(sub_codes, counts, meta, group=group))
     else:
-        all_codes = sub_codes
-    all_codes = inference_normalization(model, all_codes)
+        all_codes = inference_normalization(model, sub_codes)
     packed = format_class_codes_shared(all_codes, device=model.device)
     if ready is not None:
         torch.cuda.current_stream().wait_event(ready)

@@ -9,7 +9,7 @@ from typing import Dict, List, Optional, Sequence, Tuple
 import torch
 
 from . import _lib
-from ._lib import CODE_STRIDE, DET_STRIDE, LOSS_SUMS, NUM_LEVELS, SLOT_QUERY, SLOT_SUPPORT, LossConfig, ModelConfig
+from ._lib import CODE_STRIDE, DET_STRIDE, IPC_HANDLE_BYTES, LOSS_SUMS, NUM_LEVELS, SLOT_QUERY, SLOT_SUPPORT, LossConfig, ModelConfig
 
 
 def model_config_from_cfg(cfg) -> ModelConfig:
@@ -214,6 +214,61 @@ class Engine:
         self._check(self.lib.sylph_normalize_codes(self.h, c_void_p(raw.data_ptr()), c_void_p(out.data_ptr()),
                                                    raw.shape[0], self._stream()))
         return out
+
+    # ------------------------------------------------------------------ class-code exchange over NVLink peer memory
+    def exchange_setup(self, group=None, max_classes: int = 2048) -> None:
+        """Create this rank's exchange buffer, swap the CUDA IPC handles of all ranks of the group (ONE all-gather of
+        64 bytes, at setup only) and map the peers' buffers (sylph_exchange_create / _connect).  All ranks must be GPUs
+        of one box.  Idempotent for the same group size."""
+        import torch.distributed as dist
+        world = dist.get_world_size(group) if (dist.is_available() and dist.is_initialized()) else 1
+        rank = dist.get_rank(group) if world > 1 else 0
+        if getattr(self, "_xch", None) == (world, rank, max_classes):
+            return
+        if getattr(self, "_xch", None) is not None:
+            self.exchange_teardown(group)
+        handle = (ctypes.c_uint8 * IPC_HANDLE_BYTES)()
+        self._check(self.lib.sylph_exchange_create(self.h, world, rank, int(max_classes), handle))
+        handles = None
+        if world > 1:
+            dev = self.device if dist.get_backend(group) == "nccl" else torch.device("cpu")
+            mine = torch.tensor(list(handle), dtype=torch.uint8, device=dev)
+            everyone = torch.empty((world * IPC_HANDLE_BYTES,), dtype=torch.uint8, device=dev)
+            dist.all_gather_into_tensor(everyone, mine, group=group)
+            handles = (ctypes.c_uint8 * (world * IPC_HANDLE_BYTES))(*everyone.cpu().tolist())
+        self._check(self.lib.sylph_exchange_connect(self.h, handles))
+        self._xch = (world, rank, max_classes)
+
+    def normalize_codes_exchange(self, raw_local: Optional[torch.Tensor], class_offset: int, n_total: int) -> torch.Tensor:
+        """Normalise this rank's (n_local, 257) raw codes = classes [class_offset, class_offset + n_local) of the episode,
+        deliver them to every rank and return the (n_total, 257) normalised codes of ALL classes
+        (sylph_normalize_codes_exchange: two kernels, the stores travel over NVLink; no NCCL call, no host sync)."""
+        assert getattr(self, "_xch", None) is not None, "call exchange_setup(group) first"
+        n_local = 0 if raw_local is None else int(raw_local.shape[0])
+        raw = raw_local.to(self.device, torch.float32).contiguous() if n_local else None
+        out = torch.empty((n_total, CODE_STRIDE), device=self.device, dtype=torch.float32)
+        self._check(self.lib.sylph_normalize_codes_exchange(self.h, c_void_p(raw.data_ptr()) if n_local else None, n_local,
+                                                            int(class_offset), int(n_total), c_void_p(out.data_ptr()),
+                                                            self._stream()))
+        self._keep_raw = raw
+        return out
+
+    def exchange_status(self) -> Tuple[bool, int]:
+        """(timed_out, rows_arrived) -- synchronises the device."""
+        flag, rows = c_int(), c_int64()
+        self._check(self.lib.sylph_exchange_status(self.h, byref(flag), byref(rows)))
+        return bool(flag.value), int(rows.value)
+
+    def exchange_teardown(self, group=None) -> None:
+        """Unmap the peers and free the buffer; the barrier keeps a fast rank from freeing memory a peer still writes."""
+        import torch.distributed as dist
+        if getattr(self, "_xch", None) is None:
+            return
+        if self._xch[0] > 1 and dist.is_initialized():
+            torch.cuda.synchronize(self.device)
+            dist.barrier(group=group)
+        self.lib.sylph_exchange_destroy(self.h)
+        self._xch = None
 
     # ------------------------------------------------------------------ base-class accumulation / reduction
     def accumulate_codes(self, chunk_codes: torch.Tensor, chunk_class: Sequence[int], chunk_weight: Sequence[float],

@@ -176,3 +176,71 @@ def test_training_loss_normalisers_are_reduced_over_ranks():
         assert abs(losses["loss_fcos_cls"] - local["loss_fcos_cls"] * max(pair[0], 1.0) / avg_pos) < 1e-5 * abs(losses["loss_fcos_cls"])
         assert abs(losses["loss_fcos_ctr"] - local["loss_fcos_ctr"] * max(pair[0], 1.0) / avg_pos) < 1e-5 * abs(losses["loss_fcos_ctr"])
         assert abs(losses["loss_fcos_loc"] - local["loss_fcos_loc"] * max(pair[1], 1e-6) / avg_ctr) < 1e-5 * abs(losses["loss_fcos_loc"])
+
+
+class _StandInExchangeEngine:
+    """Host-side stand-in for Engine.exchange_setup / normalize_codes_exchange (the real one stores rows into peer GPU
+    memory, tests/test_gpu_zexchange.py): rows x 2 as the "normalisation", delivery through a gloo all-reduce of
+    disjoint row ranges.  What is under test is `exchange_codes_peer`'s shard arithmetic and output schema."""
+    device = torch.device("cpu")
+
+    def __init__(self):
+        self.calls = []
+
+    def exchange_setup(self, group, max_classes):
+        self.max_classes = max_classes
+
+    def normalize_codes_exchange(self, raw, class_offset, n_total):
+        self.calls.append((0 if raw is None else raw.shape[0], class_offset, n_total))
+        rows = torch.zeros((n_total, 257))
+        if raw is not None:
+            rows[class_offset:class_offset + raw.shape[0]] = raw * 2
+        dist.all_reduce(rows)
+        return rows
+
+
+def _worker_peer(rank, world, port, n_classes, q):
+    import types
+
+    from sylph_few_shot_detection_b200.runner import exchange_codes_peer
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        mine = []
+        for c in shard_range(n_classes, world, rank):
+            g = torch.Generator().manual_seed(100 + c)
+            mine.append({"support_set_target": torch.tensor(c), "class_name": f"class{c}",
+                         "class_code": {"cls_conv": torch.randn(1, 256, 1, 1, generator=g),
+                                        "cls_bias": torch.randn(1, 1, 1, 1, generator=g)}})
+        counts = [len(shard_range(n_classes, world, r)) for r in range(world)]
+        meta = [(torch.tensor(c), f"class{c}") for c in range(n_classes)]
+        eng = _StandInExchangeEngine()
+        allc = exchange_codes_peer(types.SimpleNamespace(engine=eng), mine, counts, meta)
+        packed = format_class_codes_shared(allc)
+        q.put((rank, eng.calls, [int(c["support_set_target"]) for c in allc], [c["class_name"] for c in allc],
+               [tuple(c["class_code"]["cls_bias"].shape) for c in allc], packed["cls_conv"].clone(), packed["cls_bias"].clone()))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_exchange_codes_peer_world2_shards_offsets_and_schema():
+    n = 5
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker_peer, args=(r, 2, port, n, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    out = sorted([q.get(timeout=120) for _ in range(2)], key=lambda t: t[0])
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    gens = [torch.Generator().manual_seed(100 + c) for c in range(n)]
+    conv = torch.cat([torch.randn(1, 256, 1, 1, generator=g) for g in gens]) * 2
+    bias = torch.cat([torch.randn(1, 1, 1, 1, generator=g).reshape(1) for g in gens]) * 2
+    assert out[0][1] == [(3, 0, 5)] and out[1][1] == [(2, 3, 5)]            # (n_local, class_offset, n_total) per rank
+    for rank, calls, ids, names, bias_shapes, got_conv, got_bias in out:
+        assert ids == list(range(n)) and names == [f"class{c}" for c in range(n)]
+        assert bias_shapes == [(1,)] * n                                   # process_bias output shape, code_generator.py:853
+        assert torch.equal(got_conv, conv) and torch.equal(got_bias, bias)

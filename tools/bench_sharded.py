@@ -150,6 +150,22 @@ def main():
         out["all_gather_general_ms"] = round(timed(lambda: gather_class_code(codes), 5, 50), 4)   # reference-shaped: 4 collectives + syncs
         out["all_gather_ms"] = round(timed(lambda: gather_class_code_known_shards(codes, counts, meta), 5, 50), 4)  # run_episode's path
         out["all_gather_bytes"] = args.way * 257 * 4
+        # the same step with the normalisation fused into a peer-memory all-gather (sylph_normalize_codes_exchange):
+        # exchange alone (against all-gather + normalisation of all classes), then the whole episode
+        from sylph_few_shot_detection_b200.runner import exchange_codes_peer, inference_normalization
+        try:
+            out["nccl_gather_plus_normalize_ms"] = round(timed(lambda: inference_normalization(
+                model, gather_class_code_known_shards(codes, counts, meta)), 5, 50), 4)
+            out["peer_exchange_ms"] = round(timed(lambda: exchange_codes_peer(model, codes, counts, meta), 5, 50), 4)
+            out["ms_per_episode_peer_exchange"] = round(timed(lambda: run_episode(model, support, query, exchange="peer"),
+                                                              args.warmup, args.steps), 3)
+            if ms_balanced:
+                out["ms_per_episode_balanced_peer_exchange"] = round(timed(
+                    lambda: run_episode(model, support, query, balance_queries=True, exchange="peer"), args.warmup, args.steps), 3)
+            out["peer_exchange_timed_out"] = model.engine.exchange_status()[0]
+            model.engine.exchange_teardown(None)
+        except RuntimeError as e:   # e.g. no peer access between the GPUs of this box
+            out["peer_exchange_error"] = str(e)[:300]
     if rank == 0:
         # ---- episodic training forward (losses only): 5-way 5-shot, 8 query images with 4 ground truths each
         tcfg = coco_meta_fcos_cfg(["MODEL.META_LEARN.SHOT", 5, "MODEL.PROPOSAL_GENERATOR.FREEZE_BBOX_BRANCH", False,
