@@ -89,3 +89,107 @@ def test_detector_postprocess_scales_clips_and_drops_empty():
     out = up.detector_postprocess(inst, 50, 100)
     assert len(out) == 2 and out.image_size == (50, 100)
     assert out.pred_boxes.tensor.tolist() == [[5.0, 5.0, 25.0, 30.0], [95.0, 45.0, 100.0, 50.0]]
+
+
+# ---- The restated bottom-up / top-down graphs against torchvision's INDEPENDENT implementations of the same published
+# architectures (ResNet bottleneck stages with frozen BN; FPN with nearest top-down + lateral + 3x3 output convs;
+# LastLevelP6P7 on p5).  detectron2 / AdelaiDet themselves are not installed, so this is the strongest
+# pin available offline for the graph structure: any mistake in block counts, strides, shortcut placement, the residual
+# add / ReLU order, the top-down order or the P6/P7 inputs shows up as a mismatch here.
+def _fill_frozen_bn(bn, g):
+    bn.weight.copy_(torch.rand(bn.weight.shape, generator=g) + 0.5)
+    bn.bias.copy_(torch.randn(bn.bias.shape, generator=g) * 0.1)
+    bn.running_mean.copy_(torch.randn(bn.running_mean.shape, generator=g) * 0.1)
+    bn.running_var.copy_(torch.rand(bn.running_var.shape, generator=g) + 0.5)
+
+
+def _copy_conv_bn(dst_conv, src_conv, src_bn):
+    dst_conv.weight.data.copy_(src_conv.weight.data)
+    for name in ("weight", "bias", "running_mean", "running_var"):
+        getattr(dst_conv.norm, name).copy_(getattr(src_bn, name))
+
+
+@pytest.mark.parametrize("depth", [50, 101])
+def test_resnet_restatement_matches_torchvision_resnet(depth):
+    import torchvision
+    from torchvision.ops.misc import FrozenBatchNorm2d as TvFrozenBN
+    g = torch.Generator().manual_seed(depth)
+    tv = getattr(torchvision.models, f"resnet{depth}")(weights=None, norm_layer=TvFrozenBN).eval()
+    with torch.no_grad():
+        for m in tv.modules():
+            if isinstance(m, torch.nn.Conv2d):
+                m.weight.copy_(torch.randn(m.weight.shape, generator=g) * (2.0 / (m.weight[0].numel())) ** 0.5)
+            elif isinstance(m, TvFrozenBN):
+                _fill_frozen_bn(m, g)
+        # torchvision strides the 3x3 convolution: the restatement's stride_in_1x1=False variant (the shipped configs use
+        # True, which moves the SAME stride to conv1 / keeps it on the shortcut -- one line in BottleneckBlock.__init__)
+        ours = up.ResNet(depth=depth, norm="FrozenBN", out_features=("res2", "res3", "res4", "res5"), stride_in_1x1=False).eval()
+        _copy_conv_bn(ours.stem.conv1, tv.conv1, tv.bn1)
+        for i in range(4):
+            theirs, mine = getattr(tv, f"layer{i + 1}"), getattr(ours, f"res{i + 2}")
+            assert len(theirs) == len(mine)
+            for tb, ob in zip(theirs, mine):
+                _copy_conv_bn(ob.conv1, tb.conv1, tb.bn1)
+                _copy_conv_bn(ob.conv2, tb.conv2, tb.bn2)
+                _copy_conv_bn(ob.conv3, tb.conv3, tb.bn3)
+                assert (tb.downsample is None) == (ob.shortcut is None)
+                if tb.downsample is not None:
+                    _copy_conv_bn(ob.shortcut, tb.downsample[0], tb.downsample[1])
+                assert ob.conv2.stride == tb.conv2.stride and ob.conv1.stride == tb.conv1.stride
+        x = torch.randn(2, 3, 64, 96, generator=g)
+        got = ours(x)
+        t = tv.maxpool(tv.relu(tv.bn1(tv.conv1(x))))
+        for i in range(4):
+            t = getattr(tv, f"layer{i + 1}")(t)
+            ref = got[f"res{i + 2}"]
+            assert ref.shape == t.shape
+            assert float((ref - t).abs().max()) <= 1e-4 * float(t.abs().max()), f"res{i + 2}"
+    shapes = ours.output_shape()
+    assert [shapes[f"res{i}"].stride for i in (2, 3, 4, 5)] == [4, 8, 16, 32]
+    assert [shapes[f"res{i}"].channels for i in (2, 3, 4, 5)] == [256, 512, 1024, 2048]
+
+
+def test_stride_in_1x1_moves_the_stride_to_the_first_convolution_only():
+    a = up.BottleneckBlock(256, 512, bottleneck_channels=128, stride=2, stride_in_1x1=True)
+    b = up.BottleneckBlock(256, 512, bottleneck_channels=128, stride=2, stride_in_1x1=False)
+    assert (a.conv1.stride, a.conv2.stride, a.conv3.stride, a.shortcut.stride) == ((2, 2), (1, 1), (1, 1), (2, 2))
+    assert (b.conv1.stride, b.conv2.stride, b.conv3.stride, b.shortcut.stride) == ((1, 1), (2, 2), (1, 1), (2, 2))
+
+
+def test_fpn_p6p7_restatement_matches_torchvision_fpn():
+    from collections import OrderedDict
+
+    from torchvision.ops import FeaturePyramidNetwork
+    from torchvision.ops.feature_pyramid_network import LastLevelP6P7 as TvP6P7
+    g = torch.Generator().manual_seed(9)
+
+    class _BottomUp(torch.nn.Module):
+        def output_shape(self):
+            return {"res3": up.ShapeSpec(channels=32, stride=8), "res4": up.ShapeSpec(channels=48, stride=16),
+                    "res5": up.ShapeSpec(channels=64, stride=32)}
+
+        def forward(self, x):
+            return x
+
+    with torch.no_grad():
+        ours = up.FPN(_BottomUp(), ["res3", "res4", "res5"], 16, top_block=up.LastLevelP6P7(16, 16, "p5")).eval()
+        tv = FeaturePyramidNetwork([32, 48, 64], 16, extra_blocks=TvP6P7(16, 16)).eval()
+        for m in tv.modules():
+            if isinstance(m, torch.nn.Conv2d):
+                m.weight.copy_(torch.randn(m.weight.shape, generator=g) * 0.1)
+                m.bias.copy_(torch.randn(m.bias.shape, generator=g) * 0.1)
+        for i, stage in enumerate((3, 4, 5)):
+            getattr(ours, f"fpn_lateral{stage}").load_state_dict(tv.inner_blocks[i][0].state_dict())
+            getattr(ours, f"fpn_output{stage}").load_state_dict(tv.layer_blocks[i][0].state_dict())
+        ours.top_block.p6.load_state_dict(tv.extra_blocks.p6.state_dict())
+        ours.top_block.p7.load_state_dict(tv.extra_blocks.p7.state_dict())
+        feats = {"res3": torch.randn(2, 32, 16, 24, generator=g), "res4": torch.randn(2, 48, 8, 12, generator=g),
+                 "res5": torch.randn(2, 64, 4, 6, generator=g)}
+        got = ours(feats)
+        ref = tv(OrderedDict((k, v) for k, v in feats.items()))
+    assert list(got.keys()) == ["p3", "p4", "p5", "p6", "p7"]
+    for (name, a), (_, b) in zip(got.items(), ref.items()):
+        assert a.shape == b.shape, name
+        assert float((a - b).abs().max()) <= 1e-5 * max(1.0, float(b.abs().max())), name
+    assert ours.size_divisibility == 32
+    assert [ours.output_shape()[f"p{i}"].stride for i in range(3, 8)] == [8, 16, 32, 64, 128]
