@@ -85,6 +85,9 @@ struct sylph_ctx {
     int pair1x1 = 1;          // SYLPH_PAIR1X1=0 keeps the single-CTA staged kernel for every 1x1 convolution; 2 = pair kernel
                               // for every staged 1x1 convolution with 256-channel N tiles and K >= 256 (experiments)
     int stem16 = 1;           // SYLPH_STEM16=0 runs the stem over 64-wide overlapped rows instead of K = 16 taps
+    int trunk_chunk[4] = {0, 0, 0, 0};  // SYLPH_TRUNK_CHUNK="a,b,c,d": images per pass through res2..res5 (0 = whole batch).
+                              // A small chunk keeps a stage's block-to-block activations (35 MB per image in res2) inside the
+                              // 126 MB L2 instead of streaming the whole batch (1.1 GB at 33 images) through HBM per layer.
     std::vector<Timing> timings;
 
     // prepared weights
@@ -673,6 +676,11 @@ int sylph_create(sylph_ctx** out, int device, const sylph_model_config* cfg) {
     if (const char* e = getenv("SYLPH_STEM16")) c->stem16 = atoi(e);
     if (const char* e = getenv("SYLPH_PAIR1X1")) c->pair1x1 = atoi(e);
     if (const char* e = getenv("SYLPH_FUSE_UPSAMPLE")) c->fuse_upsample = atoi(e);
+    if (const char* e = getenv("SYLPH_TRUNK_CHUNK")) {
+        int v[4] = {0, 0, 0, 0};
+        const int got = sscanf(e, "%d,%d,%d,%d", &v[0], &v[1], &v[2], &v[3]);
+        for (int i = 0; i < 4; ++i) c->trunk_chunk[i] = std::max(0, i < got ? v[i] : (got > 0 ? v[got - 1] : 0));
+    }
     *out = c;
     if (cfg->pre_nms_topk * 5 > 8192) { c->fail("pre_nms_topk * 5 must be <= 8192"); }
     return 0;
@@ -912,7 +920,6 @@ static int run_trunk(sylph_ctx* c, const std::string& key, int n, const void* co
     for (int s = 0; s < 4; ++s) {
         const PlaneGeom& g = gs[s];
         const long long rows = static_cast<long long>(n) * g.rows_per_img;
-        const int tiles = static_cast<int>(rows / kBlockM);
         const int out_ch = 256 << s, bott = 64 << s, in_ch = x_ch;
         __half *IN, *Y, *T1, *T2;
         const std::string sn = bb + "res" + std::to_string(s + 2);
@@ -930,12 +937,18 @@ static int run_trunk(sylph_ctx* c, const std::string& key, int n, const void* co
             c->launches++;
         }
         const auto& blocks = c->stages[s];
+        // all blocks of the stage over `chunk` images at a time (the planes of an image are whole 128-row tiles, and no
+        // layer of a stage reads another image's rows): same kernels, same tiles, bit-identical results in any order
+        const int chunk = (c->trunk_chunk[s] > 0 && c->trunk_chunk[s] < n) ? c->trunk_chunk[s] : n;
+        const int tiles_per_img = g.rows_per_img / kBlockM;
+        for (int i0 = 0; i0 < n; i0 += chunk)
         for (size_t b = 0; b < blocks.size(); ++b) {
             const sylph_ctx::Block& B = blocks[b];
             const __half* bin = (b == 0) ? IN : Y;
             const int bin_ch = (b == 0) ? in_ch : out_ch;
             ConvCall k{};
-            k.ps = pss[s].get(); k.tile_begin = 0; k.n_tiles = tiles; k.a_row_delta = 0; k.a_rows = rows;
+            k.ps = pss[s].get(); k.tile_begin = i0 * tiles_per_img; k.n_tiles = std::min(chunk, n - i0) * tiles_per_img;
+            k.a_row_delta = 0; k.a_rows = rows;
             if (B.has_sc) {
                 if (b != 0) return c->fail("shortcut conv on a non-first block is not supported");
                 k.W = &B.sc; k.A = bin; k.a_cols = k.a_ld = bin_ch; k.out = Y; k.ldc = out_ch; k.flags = kEpiMask;

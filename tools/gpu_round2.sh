@@ -1,0 +1,24 @@
+#!/bin/bash
+# First GPU call(s) of the next round: everything that was built after round 1's GPU budget ended.
+#   gpurun --timeout 900 -- 'bash tools/gpu_round2.sh one'          (1 GPU)
+#   gpurun --gpus 2 --timeout 600 -- 'bash tools/gpu_round2.sh two' (2 GPUs)
+set -u
+mkdir -p gpurun_out
+case "${1:-one}" in
+one)
+  # 1. opt-in experiment parity (chunked trunk)
+  SYLPH_RUN_UNVERIFIED=1 timeout 300 python -m pytest tests/test_gpu_zz_experiments.py tests/test_gpu_zexchange.py -x -q 2>&1 | tail -15
+  # 2. A/B of the L2-chunked trunk on the headline config (value only; 20 steps each)
+  for ch in "" "1,2,4,0" "2,4,8,0" "1,1,2,4" "3,6,0,0"; do
+    echo "== SYLPH_TRUNK_CHUNK='$ch'"
+    SYLPH_TRUNK_CHUNK="$ch" timeout 200 python bench.py --steps 20 --warmup 3 --no-cpu-baseline 2>/dev/null | tail -1 \
+      | python -c "import json,sys; d=json.loads(sys.stdin.readline()); print({k: d[k] for k in ('value','ms_per_step','gpu_launches')}, d['e2e']['value'], d['clocks'], {k: v['ms'] for k, v in list(d['per_kernel'].items())[:6]})" \
+      | tee -a gpurun_out/r02_trunk_chunk_ab.log
+  done
+  ;;
+two)
+  timeout 300 python -m pytest tests/test_gpu_dist.py tests/test_gpu_zexchange.py -x -q 2>&1 | tail -15
+  timeout 300 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511 \
+    tools/bench_sharded.py --steps 10 --out gpurun_out/r02_cfg4_sharded_n2.json 2>&1 | tail -3
+  ;;
+esac
