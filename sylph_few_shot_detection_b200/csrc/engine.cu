@@ -85,6 +85,7 @@ struct sylph_ctx {
     int pair1x1 = 1;          // SYLPH_PAIR1X1=0 keeps the single-CTA staged kernel for every 1x1 convolution; 2 = pair kernel
                               // for every staged 1x1 convolution with 256-channel N tiles and K >= 256 (experiments)
     int stem16 = 1;           // SYLPH_STEM16=0 runs the stem over 64-wide overlapped rows instead of K = 16 taps
+    int trunk_interleave = 0; // SYLPH_TRUNK_INTERLEAVE=k: stem + the first k stages image-major in chunks of trunk_chunk[0] images
     int trunk_chunk[4] = {0, 0, 0, 0};  // SYLPH_TRUNK_CHUNK="a,b,c,d": images per pass through res2..res5 (0 = whole batch).
                               // A small chunk keeps a stage's block-to-block activations (35 MB per image in res2) inside the
                               // 126 MB L2 instead of streaming the whole batch (1.1 GB at 33 images) through HBM per layer.
@@ -676,6 +677,7 @@ int sylph_create(sylph_ctx** out, int device, const sylph_model_config* cfg) {
     if (const char* e = getenv("SYLPH_STEM16")) c->stem16 = atoi(e);
     if (const char* e = getenv("SYLPH_PAIR1X1")) c->pair1x1 = atoi(e);
     if (const char* e = getenv("SYLPH_FUSE_UPSAMPLE")) c->fuse_upsample = atoi(e);
+    if (const char* e = getenv("SYLPH_TRUNK_INTERLEAVE")) c->trunk_interleave = atoi(e);
     if (const char* e = getenv("SYLPH_TRUNK_CHUNK")) {
         int v[4] = {0, 0, 0, 0};
         const int got = sscanf(e, "%d,%d,%d,%d", &v[0], &v[1], &v[2], &v[3]);
@@ -893,65 +895,161 @@ static int run_trunk(sylph_ctx* c, const std::string& key, int n, const void* co
     void* d_desc;
     TRY(ensure(c, bb + "desc", n * sizeof(ImageDesc), "", &d_desc, st, false));
     TRY(stage_h2d(c, d_desc, descs.data(), n * sizeof(ImageDesc), st));
-    {
-        StageTimer t(c, "prep_stem_input", st, static_cast<double>(n) * (3.0 * hmax * wmax + 32.0 * g0.H * g0.W));
-        if (is_u8)
-            CU_TRY(c, launch_k(prep_stem_input_u8_kernel, dim3((g0.W + 255) / 256, std::min(n * g0.H, c->num_sms * 8)), dim3(256), 0, st,
-                static_cast<const ImageDesc*>(d_desc), S0, g0, n, f.pixel_mean[0], f.pixel_mean[1], f.pixel_mean[2],
-                f.pixel_std[0], f.pixel_std[1], f.pixel_std[2]));
-        else
-            CU_TRY(c, launch_k(prep_stem_input_kernel, dim3(grid_for(static_cast<long long>(n) * g0.H * g0.W, 256, c->num_sms)), dim3(256), 0, st,
-                static_cast<const ImageDesc*>(d_desc), S0, g0, n, f.pixel_mean[0], f.pixel_mean[1], f.pixel_mean[2],
-                f.pixel_std[0], f.pixel_std[1], f.pixel_std[2]));
-        CU_TRY(c, cudaGetLastError());
-        c->launches++;
-    }
-    {   // stem: 7x7/2 conv + FrozenBN + ReLU as a 4-tap GEMM over overlapped 64-float rows
-        ConvCall k{};
-        k.W = &c->stem; k.A = S0; k.a_rows = rows0; k.a_cols = 64; k.a_ld = 16; k.ps = ps0.get();
-        k.tile_begin = 0; k.n_tiles = static_cast<int>(rows0 / kBlockM); k.a_row_delta = 0; k.out = S1; k.ldc = 64;
-        k.flags = kEpiRelu | kEpiMask; k.stem = 1; k.name = "stem7x7";
-        k.staged = c->staged_epilogue; k.out_rows = rows0;
-        TRY(run_conv(c, k, st));
-    }
-    // ---- res2..res5
-    __half* X = nullptr;  // running stage output
-    int x_ch = 64;
-    for (int s = 0; s < 4; ++s) {
-        const PlaneGeom& g = gs[s];
-        const long long rows = static_cast<long long>(n) * g.rows_per_img;
-        const int out_ch = 256 << s, bott = 64 << s, in_ch = x_ch;
-        __half *IN, *Y, *T1, *T2;
-        const std::string sn = bb + "res" + std::to_string(s + 2);
-        TRY(buf(sn + ".in", rows, in_ch, true, &IN));
-        TRY(buf(sn + ".x", rows, out_ch, false, &Y));
-        TRY(buf(sn + ".t1", rows, bott, false, &T1));
-        TRY(buf(sn + ".t2", rows, bott, false, &T2));
+    const bool image_major = c->trunk_interleave > 0 || c->trunk_chunk[0] > 0 || c->trunk_chunk[1] > 0 || c->trunk_chunk[2] > 0 ||
+                             c->trunk_chunk[3] > 0;
+    if (!image_major) {   // default: every layer over the whole batch
         {
-            StageTimer t(c, s == 0 ? "maxpool3x3s2" : "subsample2", st,
-                         static_cast<double>(n) * g.H * g.W * in_ch * 2 * (s == 0 ? 5.0 : 2.0));
-            const long long work = static_cast<long long>(n) * g.H * g.W * (in_ch / 8);
-            if (s == 0) CU_TRY(c, launch_k(maxpool3x3s2_kernel, dim3(grid_for(work, 256, c->num_sms)), dim3(256), 0, st, S1, IN, g0, g, n, in_ch));
-            else CU_TRY(c, launch_k(subsample2_kernel, dim3(grid_for(work, 256, c->num_sms)), dim3(256), 0, st, X, IN, gs[s - 1], g, n, in_ch));
+            StageTimer t(c, "prep_stem_input", st, static_cast<double>(n) * (3.0 * hmax * wmax + 32.0 * g0.H * g0.W));
+            if (is_u8)
+                CU_TRY(c, launch_k(prep_stem_input_u8_kernel, dim3((g0.W + 255) / 256, std::min(n * g0.H, c->num_sms * 8)), dim3(256), 0, st,
+                    static_cast<const ImageDesc*>(d_desc), S0, g0, n, f.pixel_mean[0], f.pixel_mean[1], f.pixel_mean[2],
+                    f.pixel_std[0], f.pixel_std[1], f.pixel_std[2]));
+            else
+                CU_TRY(c, launch_k(prep_stem_input_kernel, dim3(grid_for(static_cast<long long>(n) * g0.H * g0.W, 256, c->num_sms)), dim3(256), 0, st,
+                    static_cast<const ImageDesc*>(d_desc), S0, g0, n, f.pixel_mean[0], f.pixel_mean[1], f.pixel_mean[2],
+                    f.pixel_std[0], f.pixel_std[1], f.pixel_std[2]));
             CU_TRY(c, cudaGetLastError());
             c->launches++;
         }
-        const auto& blocks = c->stages[s];
-        // all blocks of the stage over `chunk` images at a time (the planes of an image are whole 128-row tiles, and no
-        // layer of a stage reads another image's rows): same kernels, same tiles, bit-identical results in any order
-        const int chunk = (c->trunk_chunk[s] > 0 && c->trunk_chunk[s] < n) ? c->trunk_chunk[s] : n;
+        {   // stem: 7x7/2 conv + FrozenBN + ReLU as a 4-tap GEMM over overlapped 64-float rows
+            ConvCall k{};
+            k.W = &c->stem; k.A = S0; k.a_rows = rows0; k.a_cols = 64; k.a_ld = 16; k.ps = ps0.get();
+            k.tile_begin = 0; k.n_tiles = static_cast<int>(rows0 / kBlockM); k.a_row_delta = 0; k.out = S1; k.ldc = 64;
+            k.flags = kEpiRelu | kEpiMask; k.stem = 1; k.name = "stem7x7";
+            k.staged = c->staged_epilogue; k.out_rows = rows0;
+            TRY(run_conv(c, k, st));
+        }
+        // ---- res2..res5
+        __half* X = nullptr;  // running stage output
+        int x_ch = 64;
+        for (int s = 0; s < 4; ++s) {
+            const PlaneGeom& g = gs[s];
+            const long long rows = static_cast<long long>(n) * g.rows_per_img;
+            const int tiles = static_cast<int>(rows / kBlockM);
+            const int out_ch = 256 << s, bott = 64 << s, in_ch = x_ch;
+            __half *IN, *Y, *T1, *T2;
+            const std::string sn = bb + "res" + std::to_string(s + 2);
+            TRY(buf(sn + ".in", rows, in_ch, true, &IN));
+            TRY(buf(sn + ".x", rows, out_ch, false, &Y));
+            TRY(buf(sn + ".t1", rows, bott, false, &T1));
+            TRY(buf(sn + ".t2", rows, bott, false, &T2));
+            {
+                StageTimer t(c, s == 0 ? "maxpool3x3s2" : "subsample2", st,
+                             static_cast<double>(n) * g.H * g.W * in_ch * 2 * (s == 0 ? 5.0 : 2.0));
+                const long long work = static_cast<long long>(n) * g.H * g.W * (in_ch / 8);
+                if (s == 0) CU_TRY(c, launch_k(maxpool3x3s2_kernel, dim3(grid_for(work, 256, c->num_sms)), dim3(256), 0, st, S1, IN, g0, g, n, in_ch));
+                else CU_TRY(c, launch_k(subsample2_kernel, dim3(grid_for(work, 256, c->num_sms)), dim3(256), 0, st, X, IN, gs[s - 1], g, n, in_ch));
+                CU_TRY(c, cudaGetLastError());
+                c->launches++;
+            }
+            const auto& blocks = c->stages[s];
+            for (size_t b = 0; b < blocks.size(); ++b) {
+                const sylph_ctx::Block& B = blocks[b];
+                const __half* bin = (b == 0) ? IN : Y;
+                const int bin_ch = (b == 0) ? in_ch : out_ch;
+                ConvCall k{};
+                k.ps = pss[s].get(); k.tile_begin = 0; k.n_tiles = tiles; k.a_row_delta = 0; k.a_rows = rows;
+                if (B.has_sc) {
+                    if (b != 0) return c->fail("shortcut conv on a non-first block is not supported");
+                    k.W = &B.sc; k.A = bin; k.a_cols = k.a_ld = bin_ch; k.out = Y; k.ldc = out_ch; k.flags = kEpiMask;
+                    k.name = "res.shortcut1x1";
+                    k.staged = c->staged_epilogue; k.out_rows = rows;
+                    TRY(run_conv(c, k, st));
+                    k.staged = 0;
+                } else if (b == 0) {
+                    return c->fail("identity shortcut on the first block of a stage is not supported");
+                }
+                k.residual = nullptr;
+                k.W = &B.c1; k.A = bin; k.a_cols = k.a_ld = bin_ch; k.out = T1; k.ldc = bott;
+                k.flags = kEpiRelu | kEpiMask; k.name = "res.conv1_1x1";
+                k.staged = c->staged_epilogue; k.out_rows = rows;
+                TRY(run_conv(c, k, st));
+                k.staged = 0;
+                k.W = &B.c2; k.A = T1; k.a_cols = k.a_ld = bott; k.out = T2; k.ldc = bott; k.name = "res.conv2_3x3";
+                TRY(run_conv(c, k, st));
+                k.W = &B.c3; k.A = T2; k.a_cols = k.a_ld = bott; k.out = Y; k.ldc = out_ch; k.residual = Y; k.ld_res = out_ch;
+                k.flags = kEpiRelu | kEpiMask | kEpiResidual; k.name = "res.conv3_1x1";
+                k.staged = c->staged_epilogue; k.out_rows = rows;
+                TRY(run_conv(c, k, st));
+                k.staged = 0;
+            }
+            X = Y;
+            x_ch = out_ch;
+            // lateral 1x1 for res3..res5 straight into the pyramid-indexed lateral buffer
+        }
+        return 0;
+    }
+    // Every step below takes an image range [i0, i0 + ni): the planes of an image are whole 128-row tiles and no layer
+    // reads another image's rows, so any order over the images runs the same kernels over the same tiles (bit-identical
+    // results).  SYLPH_TRUNK_CHUNK / SYLPH_TRUNK_INTERLEAVE (experiments, not yet measured) walk a few images at a time
+    // through several layers so that their activations are still in L2 when the next layer reads them.
+    auto shifted = [](PlaneGeom g, int i0) { g.row_base += i0 * g.rows_per_img; return g; };
+    const int tiles_per_img0 = g0.rows_per_img / kBlockM;
+    auto stem_group = [&](int i0, int ni) -> int {
+        {
+            StageTimer t(c, "prep_stem_input", st, static_cast<double>(ni) * (3.0 * hmax * wmax + 32.0 * g0.H * g0.W));
+            const ImageDesc* dd = static_cast<const ImageDesc*>(d_desc) + i0;
+            const PlaneGeom gg = shifted(g0, i0);
+            if (is_u8)
+                CU_TRY(c, launch_k(prep_stem_input_u8_kernel, dim3((g0.W + 255) / 256, std::min(ni * g0.H, c->num_sms * 8)), dim3(256), 0, st,
+                    dd, S0, gg, ni, f.pixel_mean[0], f.pixel_mean[1], f.pixel_mean[2],
+                    f.pixel_std[0], f.pixel_std[1], f.pixel_std[2]));
+            else
+                CU_TRY(c, launch_k(prep_stem_input_kernel, dim3(grid_for(static_cast<long long>(ni) * g0.H * g0.W, 256, c->num_sms)), dim3(256), 0, st,
+                    dd, S0, gg, ni, f.pixel_mean[0], f.pixel_mean[1], f.pixel_mean[2],
+                    f.pixel_std[0], f.pixel_std[1], f.pixel_std[2]));
+            CU_TRY(c, cudaGetLastError());
+            c->launches++;
+        }
+        // stem: 7x7/2 conv + FrozenBN + ReLU as a 4-tap GEMM over overlapped 64-float rows
+        ConvCall k{};
+        k.W = &c->stem; k.A = S0; k.a_rows = rows0; k.a_cols = 64; k.a_ld = 16; k.ps = ps0.get();
+        k.tile_begin = i0 * tiles_per_img0; k.n_tiles = ni * tiles_per_img0; k.a_row_delta = 0; k.out = S1; k.ldc = 64;
+        k.flags = kEpiRelu | kEpiMask; k.stem = 1; k.name = "stem7x7";
+        k.staged = c->staged_epilogue; k.out_rows = rows0;
+        return run_conv(c, k, st);
+    };
+    // ---- res2..res5: buffers of all stages first (allocation may synchronise; the launches below never do)
+    __half *IN[4], *Y[4], *T1[4], *T2[4];
+    for (int s = 0; s < 4; ++s) {
+        const long long rows = static_cast<long long>(n) * gs[s].rows_per_img;
+        const std::string sn = bb + "res" + std::to_string(s + 2);
+        TRY(buf(sn + ".in", rows, s == 0 ? 64 : 128 << s, true, &IN[s]));
+        TRY(buf(sn + ".x", rows, 256 << s, false, &Y[s]));
+        TRY(buf(sn + ".t1", rows, 64 << s, false, &T1[s]));
+        TRY(buf(sn + ".t2", rows, 64 << s, false, &T2[s]));
+    }
+    // input of stage s: 3x3/2 max-pool of the stem output (res2) or the even positions of the previous stage (STRIDE_IN_1X1)
+    auto downsample = [&](int s, int i0, int ni) -> int {
+        const PlaneGeom& g = gs[s];
+        const int in_ch = s == 0 ? 64 : 128 << s;
+        StageTimer t(c, s == 0 ? "maxpool3x3s2" : "subsample2", st,
+                     static_cast<double>(ni) * g.H * g.W * in_ch * 2 * (s == 0 ? 5.0 : 2.0));
+        const long long work = static_cast<long long>(ni) * g.H * g.W * (in_ch / 8);
+        if (s == 0) CU_TRY(c, launch_k(maxpool3x3s2_kernel, dim3(grid_for(work, 256, c->num_sms)), dim3(256), 0, st,
+                                       static_cast<const __half*>(S1), IN[0], shifted(g0, i0), shifted(g, i0), ni, in_ch));
+        else CU_TRY(c, launch_k(subsample2_kernel, dim3(grid_for(work, 256, c->num_sms)), dim3(256), 0, st,
+                                static_cast<const __half*>(Y[s - 1]), IN[s], shifted(gs[s - 1], i0), shifted(g, i0), ni, in_ch));
+        CU_TRY(c, cudaGetLastError());
+        c->launches++;
+        return 0;
+    };
+    auto stage_blocks = [&](int s, int i0, int ni) -> int {
+        const PlaneGeom& g = gs[s];
+        const long long rows = static_cast<long long>(n) * g.rows_per_img;
+        const int out_ch = 256 << s, bott = 64 << s, in_ch = s == 0 ? 64 : 128 << s;
         const int tiles_per_img = g.rows_per_img / kBlockM;
-        for (int i0 = 0; i0 < n; i0 += chunk)
+        const auto& blocks = c->stages[s];
         for (size_t b = 0; b < blocks.size(); ++b) {
             const sylph_ctx::Block& B = blocks[b];
-            const __half* bin = (b == 0) ? IN : Y;
+            const __half* bin = (b == 0) ? IN[s] : Y[s];
             const int bin_ch = (b == 0) ? in_ch : out_ch;
             ConvCall k{};
-            k.ps = pss[s].get(); k.tile_begin = i0 * tiles_per_img; k.n_tiles = std::min(chunk, n - i0) * tiles_per_img;
+            k.ps = pss[s].get(); k.tile_begin = i0 * tiles_per_img; k.n_tiles = ni * tiles_per_img;
             k.a_row_delta = 0; k.a_rows = rows;
             if (B.has_sc) {
                 if (b != 0) return c->fail("shortcut conv on a non-first block is not supported");
-                k.W = &B.sc; k.A = bin; k.a_cols = k.a_ld = bin_ch; k.out = Y; k.ldc = out_ch; k.flags = kEpiMask;
+                k.W = &B.sc; k.A = bin; k.a_cols = k.a_ld = bin_ch; k.out = Y[s]; k.ldc = out_ch; k.flags = kEpiMask;
                 k.name = "res.shortcut1x1";
                 k.staged = c->staged_epilogue; k.out_rows = rows;
                 TRY(run_conv(c, k, st));
@@ -960,22 +1058,42 @@ static int run_trunk(sylph_ctx* c, const std::string& key, int n, const void* co
                 return c->fail("identity shortcut on the first block of a stage is not supported");
             }
             k.residual = nullptr;
-            k.W = &B.c1; k.A = bin; k.a_cols = k.a_ld = bin_ch; k.out = T1; k.ldc = bott;
+            k.W = &B.c1; k.A = bin; k.a_cols = k.a_ld = bin_ch; k.out = T1[s]; k.ldc = bott;
             k.flags = kEpiRelu | kEpiMask; k.name = "res.conv1_1x1";
             k.staged = c->staged_epilogue; k.out_rows = rows;
             TRY(run_conv(c, k, st));
             k.staged = 0;
-            k.W = &B.c2; k.A = T1; k.a_cols = k.a_ld = bott; k.out = T2; k.ldc = bott; k.name = "res.conv2_3x3";
+            k.W = &B.c2; k.A = T1[s]; k.a_cols = k.a_ld = bott; k.out = T2[s]; k.ldc = bott; k.name = "res.conv2_3x3";
             TRY(run_conv(c, k, st));
-            k.W = &B.c3; k.A = T2; k.a_cols = k.a_ld = bott; k.out = Y; k.ldc = out_ch; k.residual = Y; k.ld_res = out_ch;
+            k.W = &B.c3; k.A = T2[s]; k.a_cols = k.a_ld = bott; k.out = Y[s]; k.ldc = out_ch; k.residual = Y[s]; k.ld_res = out_ch;
             k.flags = kEpiRelu | kEpiMask | kEpiResidual; k.name = "res.conv3_1x1";
             k.staged = c->staged_epilogue; k.out_rows = rows;
             TRY(run_conv(c, k, st));
             k.staged = 0;
         }
-        X = Y;
-        x_ch = out_ch;
-        // lateral 1x1 for res3..res5 straight into the pyramid-indexed lateral buffer
+        return 0;
+    };
+    auto chunk_of = [&](int s) { return (c->trunk_chunk[s] > 0 && c->trunk_chunk[s] < n) ? c->trunk_chunk[s] : n; };
+    // front: stem group + the first `front` stages image-major in chunks of trunk_chunk[0] images (0 stages = stem over the batch)
+    const int front = std::max(0, std::min(4, c->trunk_interleave));
+    if (front == 0) {
+        TRY(stem_group(0, n));
+    } else {
+        const int fc = chunk_of(0);
+        for (int i0 = 0; i0 < n; i0 += fc) {
+            const int ni = std::min(fc, n - i0);
+            TRY(stem_group(i0, ni));
+            for (int s = 0; s < front; ++s) {
+                TRY(downsample(s, i0, ni));
+                TRY(stage_blocks(s, i0, ni));
+            }
+        }
+    }
+    // back: each remaining stage over the batch, its blocks in chunks of trunk_chunk[s] images
+    for (int s = front; s < 4; ++s) {
+        TRY(downsample(s, 0, n));
+        const int ch = chunk_of(s);
+        for (int i0 = 0; i0 < n; i0 += ch) TRY(stage_blocks(s, i0, std::min(ch, n - i0)));
     }
     return 0;
 }

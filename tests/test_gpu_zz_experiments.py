@@ -13,19 +13,28 @@ pytestmark = [pytest.mark.gpu,
               pytest.mark.skipif(os.environ.get("SYLPH_RUN_UNVERIFIED") != "1", reason="unverified experiment: set SYLPH_RUN_UNVERIFIED=1")]
 
 
-@pytest.mark.parametrize("chunks", ["1", "2,3,1,0", "1,1,2,4"])
-def test_chunked_trunk_pass_is_bit_identical(chunks, monkeypatch):
-    """SYLPH_TRUNK_CHUNK: the blocks of a ResNet stage over a few images at a time (L2-resident activations) instead of
-    the whole batch per layer.  Same kernels over the same tiles: the pyramids must be bit-identical."""
+@pytest.mark.parametrize("chunks,interleave", [("1", 0), ("2,3,1,0", 0), ("1,1,2,4", 0), ("1", 1), ("2", 2), ("2,0,1,0", 4),
+                                               ("0", 3)])
+def test_chunked_trunk_pass_is_bit_identical(chunks, interleave, monkeypatch):
+    """SYLPH_TRUNK_CHUNK / SYLPH_TRUNK_INTERLEAVE: the layers of the trunk over a few images at a time (L2-resident
+    activations; with INTERLEAVE=k the stem group and the first k stages image-major) instead of the whole batch per
+    layer.  Same kernels over the same tiles: the pyramids must be bit-identical -- for fp32 and uint8 inputs."""
     from sylph_few_shot_detection_b200.runtime import SLOT_SUPPORT
     ims = [im.cuda() for im in _images(5, 160, 224, 41)]
     monkeypatch.delenv("SYLPH_TRUNK_CHUNK", raising=False)
+    monkeypatch.delenv("SYLPH_TRUNK_INTERLEAVE", raising=False)
     _, _, model, _ = _setup(seed=8)
-    model.engine.extract_features(SLOT_SUPPORT, ims)
-    want = [model.engine.export_features(SLOT_SUPPORT, l).clone() for l in range(5)]
-    monkeypatch.setenv("SYLPH_TRUNK_CHUNK", chunks)          # read by sylph_create
+    want = {}
+    for kind, batch in (("u8", ims), ("f32", [im.float() for im in ims])):
+        model.engine.extract_features(SLOT_SUPPORT, batch)
+        want[kind] = [model.engine.export_features(SLOT_SUPPORT, l).clone() for l in range(5)]
+    before = model.engine.launch_count()
+    monkeypatch.setenv("SYLPH_TRUNK_CHUNK", chunks)          # both read by sylph_create
+    monkeypatch.setenv("SYLPH_TRUNK_INTERLEAVE", str(interleave))
     _, _, chunked, _ = _setup(seed=8)
-    chunked.engine.extract_features(SLOT_SUPPORT, ims)
-    for l in range(5):
-        assert torch.equal(chunked.engine.export_features(SLOT_SUPPORT, l), want[l]), f"p{l + 3}"
-    assert chunked.engine.launch_count() > model.engine.launch_count()
+    for kind, batch in (("u8", ims), ("f32", [im.float() for im in ims])):
+        chunked.engine.extract_features(SLOT_SUPPORT, batch)
+        for l in range(5):
+            assert torch.equal(chunked.engine.export_features(SLOT_SUPPORT, l), want[kind][l]), f"{kind} p{l + 3}"
+    if chunks != "0":
+        assert chunked.engine.launch_count() > before
