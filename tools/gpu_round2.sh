@@ -16,10 +16,16 @@ one)
       | python -c "import json,sys; d=json.loads(sys.stdin.readline()); print({k: d[k] for k in ('value','ms_per_step','gpu_launches')}, d['e2e']['value'], d['clocks'], {k: v['ms'] for k, v in list(d['per_kernel'].items())[:8]})" \
       | tee -a gpurun_out/r02_trunk_chunk_ab.log
   done
+  # 3. configs[4] (LVIS 1203-class sweep) on one GPU with both exchange forms (world 1: the peer form is the two kernels alone)
+  timeout 300 python tools/bench_sweep_sharded.py --out gpurun_out/r02_cfg5_CodeGenerator_n1.json 2>&1 | tail -2
   ;;
 two)
   timeout 300 python -m pytest tests/test_gpu_dist.py tests/test_gpu_zexchange.py -x -q 2>&1 | tail -15
   timeout 300 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511 \
     tools/bench_sharded.py --steps 10 --out gpurun_out/r02_cfg4_sharded_n2.json 2>&1 | tail -3
+  for gen in CodeGenerator ROIEncoder; do
+    timeout 300 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29512 \
+      tools/bench_sweep_sharded.py --generator $gen --out gpurun_out/r02_cfg5_${gen}_n2.json 2>&1 | tail -2
+  done
   ;;
 esac
