@@ -62,3 +62,26 @@ def test_create_fails_loudly_without_a_device():
     from sylph_few_shot_detection_b200.runtime import Engine
     with pytest.raises(RuntimeError):
         Engine(coco_meta_fcos_cfg(), 0)
+
+
+def test_plain_c_client_compiles_against_the_header_and_runs(tmp_path):
+    """include/sylph_b200.h is valid C99 (-pedantic -Werror) and the library links from a plain-C host
+    (examples/c_client.c): without a device the client reports the failed sylph_create and exits 0."""
+    import shutil
+    import subprocess
+    import torch
+    if shutil.which("gcc") is None:
+        import pytest
+        pytest.skip("no gcc")
+    _lib.build()
+    exe = str(tmp_path / "c_client")
+    libdir = os.path.dirname(_lib.LIB_PATH)
+    subprocess.run(["gcc", "-std=c99", "-Wall", "-Wextra", "-pedantic", "-Werror", "-I", os.path.join(REPO, "include"),
+                    os.path.join(REPO, "examples", "c_client.c"), "-L", libdir, "-lsylph_b200", f"-Wl,-rpath,{libdir}", "-o", exe],
+                   check=True)
+    out = subprocess.run([exe], check=True, capture_output=True, text=True).stdout
+    assert "sm_100a" in out and f"IPC handle: {_lib.IPC_HANDLE_BYTES} bytes" in out
+    if not torch.cuda.is_available():
+        assert "no CPU fallback" in out
+    else:
+        assert "weights not finalized" in out and "single-rank exchange: status 0, timed_out 0, rows 0" in out
