@@ -153,6 +153,11 @@ int sylph_exchange_connect(sylph_ctx* ctx, const uint8_t* handles_all /* world x
 int sylph_normalize_codes_exchange(sylph_ctx* ctx, const float* raw_codes_dev, int n_local, int class_offset, int n_total,
                                    float* all_codes_out_dev, void* stream);
 
+/* Non-blocking: non-zero (with a message) once an exchange of this context has given up waiting.  The flag travels to
+ * pinned host memory behind every exchange, so it is current for every episode whose results the caller has already
+ * synchronised on; sylph_normalize_codes_exchange checks it on entry as well. */
+int sylph_exchange_poll(sylph_ctx* ctx);
+
 /* Synchronous: *timed_out = 1 if any exchange of this context gave up waiting; *rows_arrived = rows received so far. */
 int sylph_exchange_status(sylph_ctx* ctx, int* timed_out, int64_t* rows_arrived);
 void sylph_exchange_destroy(sylph_ctx* ctx);

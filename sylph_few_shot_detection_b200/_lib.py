@@ -119,6 +119,8 @@ def load() -> ctypes.CDLL:
     lib.sylph_exchange_connect.argtypes = [vp, vp]
     lib.sylph_normalize_codes_exchange.restype = c_int
     lib.sylph_normalize_codes_exchange.argtypes = [vp, vp, c_int, c_int, c_int, vp, vp]
+    lib.sylph_exchange_poll.restype = c_int
+    lib.sylph_exchange_poll.argtypes = [vp]
     lib.sylph_exchange_status.restype = c_int
     lib.sylph_exchange_status.argtypes = [vp, ip, POINTER(c_int64)]
     lib.sylph_exchange_destroy.restype = None
@@ -152,6 +154,6 @@ EXPORTED_SYMBOLS = [
     "sylph_version", "sylph_create", "sylph_destroy", "sylph_last_error", "sylph_load_tensor",
     "sylph_finalize_weights", "sylph_extract_features", "sylph_extract_features_u8", "sylph_extract_features_multi", "sylph_import_features", "sylph_feature_shape",
     "sylph_export_features", "sylph_generate_codes", "sylph_export_roi_features", "sylph_normalize_codes", "sylph_exchange_create", "sylph_exchange_connect",
-    "sylph_normalize_codes_exchange", "sylph_exchange_status", "sylph_exchange_destroy", "sylph_accumulate_codes", "sylph_reduce_codes",
+    "sylph_normalize_codes_exchange", "sylph_exchange_poll", "sylph_exchange_status", "sylph_exchange_destroy", "sylph_accumulate_codes", "sylph_reduce_codes",
     "sylph_detect", "sylph_detect_after", "sylph_export_head_output", "sylph_fcos_loss_sums", "sylph_fcos_loss_finalize", "sylph_launch_count", "sylph_set_profiling", "sylph_get_timings",
 ]

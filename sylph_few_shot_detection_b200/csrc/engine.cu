@@ -126,6 +126,7 @@ struct sylph_ctx {
         sylph::ExchangePeers peers{};
         bool connected = false;
         unsigned long long timeout_ns = 5000000000ull;   // SYLPH_EXCHANGE_TIMEOUT_MS
+        unsigned int* host_err = nullptr;            // pinned copy of ExchangeState::error, refreshed after every collect
     } xch;
     std::map<std::string, Buffer> bufs;
     // pinned host ring for small host->device argument arrays: copies from it are truly asynchronous, so no entry
@@ -1637,11 +1638,18 @@ int sylph_exchange_create(sylph_ctx* c, int world, int rank, int max_classes, ui
         }
         memcpy(handle_out, &h, SYLPH_IPC_HANDLE_BYTES);
     }
+    unsigned int* host_err = nullptr;
+    if (cudaHostAlloc(reinterpret_cast<void**>(&host_err), sizeof(unsigned int), cudaHostAllocDefault) != cudaSuccess) {
+        cudaFree(p);
+        return c->fail("exchange: cudaHostAlloc failed");
+    }
+    *host_err = 0u;
     c->xch = sylph_ctx::Exchange();
     c->xch.world = world;
     c->xch.rank = rank;
     c->xch.max_classes = max_classes;
     c->xch.local = p;
+    c->xch.host_err = host_err;
     if (const char* e = getenv("SYLPH_EXCHANGE_TIMEOUT_MS")) c->xch.timeout_ns = static_cast<unsigned long long>(atoll(e)) * 1000000ull;
     return 0;
 }
@@ -1685,6 +1693,7 @@ int sylph_normalize_codes_exchange(sylph_ctx* c, const float* raw_codes_dev, int
         return c->fail("exchange: shard [%d, %d) of %d classes does not fit max_classes %d", class_offset, class_offset + n_local,
                        n_total, x.max_classes);
     if (!all_codes_out_dev || (n_local > 0 && !raw_codes_dev)) return c->fail("exchange: null buffer");
+    TRY(sylph_exchange_poll(c));
     const sylph_model_config& f = c->cfg;
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     ExchangeState* state = reinterpret_cast<ExchangeState*>(x.local);
@@ -1701,6 +1710,19 @@ int sylph_normalize_codes_exchange(sylph_ctx* c, const float* raw_codes_dev, int
                        all_codes_out_dev, x.timeout_ns));
     CU_TRY(c, cudaGetLastError());
     c->launches++;
+    // the sticky error word follows the rows to the host (asynchronous 4-byte copy): sylph_exchange_poll reads it without
+    // touching the device, so a caller that has synchronised on the episode's results knows whether the codes were complete
+    CU_TRY(c, cudaMemcpyAsync(x.host_err, &state->error, sizeof(unsigned int), cudaMemcpyDeviceToHost, st));
+    return 0;
+}
+
+int sylph_exchange_poll(sylph_ctx* c) {
+    if (!c) return 1;
+    if (!c->xch.local || !c->xch.host_err) return c->fail("exchange: not created");
+    if (*static_cast<volatile unsigned int*>(c->xch.host_err) != 0u)
+        return c->fail("exchange: a rank waited longer than %llu ms for the class codes of its peers and gave up (ranks out of "
+                       "step, or SYLPH_EXCHANGE_TIMEOUT_MS too small): the codes of that episode were incomplete",
+                       c->xch.timeout_ns / 1000000ull);
     return 0;
 }
 
@@ -1722,6 +1744,7 @@ void sylph_exchange_destroy(sylph_ctx* c) {
     for (int r = 0; r < c->xch.world; ++r)
         if (r != c->xch.rank && c->xch.peer_base[r]) cudaIpcCloseMemHandle(c->xch.peer_base[r]);
     cudaFree(c->xch.local);
+    if (c->xch.host_err) cudaFreeHost(c->xch.host_err);
     c->xch = sylph_ctx::Exchange();
 }
 

@@ -382,7 +382,10 @@ def run_episode(model: MetaOneStageDetector, support_items: Sequence[Dict[str, A
         assert len(my_query) <= 16
         with torch.no_grad():
             return model.forward_instances_device(list(my_query), packed, features_in_slot=merged)
-    return inference_with_class_codes(model, my_query, packed, features_in_slot=merged)
+    results = inference_with_class_codes(model, my_query, packed, features_in_slot=merged)
+    if world > 1 and shard and (exchange or code_exchange_mode()) == "peer" and my_query:
+        model.engine.exchange_poll()   # the results above are on the host, so the flag of this episode is too: incomplete codes raise
+    return results
 
 
 class EpisodeFuture:

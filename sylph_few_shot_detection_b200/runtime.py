@@ -253,6 +253,11 @@ class Engine:
         self._keep_raw = raw
         return out
 
+    def exchange_poll(self) -> None:
+        """Raise RuntimeError if an exchange of this context gave up waiting for its peers (non-blocking: reads the pinned
+        copy of the flag, which is current for every episode whose results have been synchronised on)."""
+        self._check(self.lib.sylph_exchange_poll(self.h))
+
     def exchange_status(self) -> Tuple[bool, int]:
         """(timed_out, rows_arrived) -- synchronises the device."""
         flag, rows = c_int(), c_int64()

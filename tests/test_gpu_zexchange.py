@@ -27,6 +27,7 @@ def test_exchange_kernels_match_normalize_codes_one_rank():
             total += n
         timed_out, rows = eng.exchange_status()
         assert not timed_out and rows == total
+        eng.exchange_poll()                    # nothing to report
         with pytest.raises(RuntimeError):
             eng.normalize_codes_exchange(torch.zeros((65, 257)).cuda(), 0, 65)     # more classes than the buffer holds
         with pytest.raises(RuntimeError):
@@ -45,6 +46,10 @@ def test_exchange_times_out_instead_of_hanging(monkeypatch):
         eng.normalize_codes_exchange(torch.zeros((2, 257)).cuda(), 0, 3)   # 3 classes announced, 2 delivered
         timed_out, rows = eng.exchange_status()
         assert timed_out and rows == 2
+        with pytest.raises(RuntimeError, match="gave up"):
+            eng.exchange_poll()                # the flag has followed the rows to pinned host memory
+        with pytest.raises(RuntimeError, match="gave up"):
+            eng.normalize_codes_exchange(torch.zeros((1, 257)).cuda(), 0, 1)   # and the next exchange refuses to run
     finally:
         eng.exchange_teardown(None)
 
