@@ -34,7 +34,7 @@ ncu)
   for cfg in "|0" "1,2,4,0|0" "1,2,4,0|2"; do
     ch="${cfg%%|*}"; il="${cfg##*|}"; tag="chunk_${ch//,/_}_il${il}"
     SYLPH_TRUNK_CHUNK="$ch" SYLPH_TRUNK_INTERLEAVE="$il" timeout 600 ncu --metrics dram__bytes_read.sum,dram__bytes_write.sum,gpu__time_duration.sum \
-      --cache-control none --clock-control none --kernel-name-base demangled -k "regex:conv_gemm|conv1x1_pair|conv3x3_pair" -c 900 --csv \
+      --cache-control none --clock-control none --print-units base --kernel-name-base demangled -k "regex:conv_gemm|conv1x1_pair|conv3x3_pair" -c 900 --csv \
       --log-file gpurun_out/r02_trunk_dram_${tag}.csv python tools/profile_head.py 1 > gpurun_out/r02_trunk_dram_${tag}.log 2>&1
     python - "$tag" <<'PY'
 import csv, sys
@@ -46,7 +46,7 @@ agg, launches = {}, set()
 for r in rows[1:]:
     agg[r[i_metric]] = agg.get(r[i_metric], 0.0) + float(r[i_val].replace(",", ""))
     launches.add(r[i_id])
-print(tag, "GEMM launches", len(launches), {k: round(v / 1e9, 3) for k, v in agg.items()}, "(bytes -> GB, time -> s)")
+print(tag, "GEMM launches", len(launches), {k: round(v / 1e9, 3) for k, v in agg.items()}, "(bytes -> GB, ns -> s)")
 PY
   done
   ;;
