@@ -85,6 +85,9 @@ struct sylph_ctx {
     int pair1x1 = 1;          // SYLPH_PAIR1X1=0 keeps the single-CTA staged kernel for every 1x1 convolution; 2 = pair kernel
                               // for every staged 1x1 convolution with 256-channel N tiles and K >= 256 (experiments)
     int stem16 = 1;           // SYLPH_STEM16=0 runs the stem over 64-wide overlapped rows instead of K = 16 taps
+    int l2_persist_mb = 0;    // SYLPH_L2_PERSIST_MB=n (with the image-major trunk schedule): n MB of L2 set aside for persisting lines and
+                              // an access-policy window over the stage output of the chunk in flight (the residual the next block
+                              // re-reads), everything else streaming
     int trunk_interleave = 0; // SYLPH_TRUNK_INTERLEAVE=k: stem + the first k stages image-major in chunks of trunk_chunk[0] images
     int trunk_chunk[4] = {0, 0, 0, 0};  // SYLPH_TRUNK_CHUNK="a,b,c,d": images per pass through res2..res5 (0 = whole batch).
                               // A small chunk keeps a stage's block-to-block activations (35 MB per image in res2) inside the
@@ -679,6 +682,14 @@ int sylph_create(sylph_ctx** out, int device, const sylph_model_config* cfg) {
     if (const char* e = getenv("SYLPH_PAIR1X1")) c->pair1x1 = atoi(e);
     if (const char* e = getenv("SYLPH_FUSE_UPSAMPLE")) c->fuse_upsample = atoi(e);
     if (const char* e = getenv("SYLPH_TRUNK_INTERLEAVE")) c->trunk_interleave = atoi(e);
+    if (const char* e = getenv("SYLPH_L2_PERSIST_MB")) {
+        c->l2_persist_mb = std::max(0, atoi(e));
+        if (c->l2_persist_mb > 0 &&
+            cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, static_cast<size_t>(c->l2_persist_mb) << 20) != cudaSuccess) {
+            cudaGetLastError();
+            c->l2_persist_mb = 0;   // not supported here: run without the window
+        }
+    }
     if (const char* e = getenv("SYLPH_TRUNK_CHUNK")) {
         int v[4] = {0, 0, 0, 0};
         const int got = sscanf(e, "%d,%d,%d,%d", &v[0], &v[1], &v[2], &v[3]);
@@ -1035,11 +1046,25 @@ static int run_trunk(sylph_ctx* c, const std::string& key, int n, const void* co
         c->launches++;
         return 0;
     };
+    // optional L2 access-policy window over the stage output of the chunk in flight (SYLPH_L2_PERSIST_MB)
+    auto set_window = [&](void* base, size_t bytes) {
+        if (c->l2_persist_mb <= 0) return;
+        int max_win = 0;
+        cudaDeviceGetAttribute(&max_win, cudaDevAttrMaxAccessPolicyWindowSize, c->device);
+        cudaStreamAttrValue v{};
+        v.accessPolicyWindow.base_ptr = base;
+        v.accessPolicyWindow.num_bytes = std::min(bytes, static_cast<size_t>(std::max(max_win, 0)));
+        v.accessPolicyWindow.hitRatio = 1.0f;
+        v.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
+        v.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
+        if (cudaStreamSetAttribute(st, cudaStreamAttributeAccessPolicyWindow, &v) != cudaSuccess) cudaGetLastError();
+    };
     auto stage_blocks = [&](int s, int i0, int ni) -> int {
         const PlaneGeom& g = gs[s];
         const long long rows = static_cast<long long>(n) * g.rows_per_img;
         const int out_ch = 256 << s, bott = 64 << s, in_ch = s == 0 ? 64 : 128 << s;
         const int tiles_per_img = g.rows_per_img / kBlockM;
+        set_window(Y[s] + static_cast<size_t>(i0) * g.rows_per_img * out_ch, static_cast<size_t>(ni) * g.rows_per_img * out_ch * 2);
         const auto& blocks = c->stages[s];
         for (size_t b = 0; b < blocks.size(); ++b) {
             const sylph_ctx::Block& B = blocks[b];
@@ -1095,6 +1120,11 @@ static int run_trunk(sylph_ctx* c, const std::string& key, int n, const void* co
         TRY(downsample(s, 0, n));
         const int ch = chunk_of(s);
         for (int i0 = 0; i0 < n; i0 += ch) TRY(stage_blocks(s, i0, std::min(ch, n - i0)));
+    }
+    if (c->l2_persist_mb > 0) {   // leave the caller's stream as it was found
+        cudaStreamAttrValue v{};
+        v.accessPolicyWindow.num_bytes = 0;
+        if (cudaStreamSetAttribute(st, cudaStreamAttributeAccessPolicyWindow, &v) != cudaSuccess) cudaGetLastError();
     }
     return 0;
 }

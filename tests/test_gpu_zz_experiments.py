@@ -13,9 +13,9 @@ pytestmark = [pytest.mark.gpu,
               pytest.mark.skipif(os.environ.get("SYLPH_RUN_UNVERIFIED") != "1", reason="unverified experiment: set SYLPH_RUN_UNVERIFIED=1")]
 
 
-@pytest.mark.parametrize("chunks,interleave", [("1", 0), ("2,3,1,0", 0), ("1,1,2,4", 0), ("1", 1), ("2", 2), ("2,0,1,0", 4),
-                                               ("0", 3)])
-def test_chunked_trunk_pass_is_bit_identical(chunks, interleave, monkeypatch):
+@pytest.mark.parametrize("chunks,interleave,persist_mb", [("1", 0, 0), ("2,3,1,0", 0, 0), ("1,1,2,4", 0, 0), ("1", 1, 0), ("2", 2, 0),
+                                                          ("2,0,1,0", 4, 0), ("0", 3, 0), ("1,2,4,0", 0, 64), ("2", 2, 32)])
+def test_chunked_trunk_pass_is_bit_identical(chunks, interleave, persist_mb, monkeypatch):
     """SYLPH_TRUNK_CHUNK / SYLPH_TRUNK_INTERLEAVE: the layers of the trunk over a few images at a time (L2-resident
     activations; with INTERLEAVE=k the stem group and the first k stages image-major) instead of the whole batch per
     layer.  Same kernels over the same tiles: the pyramids must be bit-identical -- for fp32 and uint8 inputs."""
@@ -23,6 +23,7 @@ def test_chunked_trunk_pass_is_bit_identical(chunks, interleave, monkeypatch):
     ims = [im.cuda() for im in _images(5, 160, 224, 41)]
     monkeypatch.delenv("SYLPH_TRUNK_CHUNK", raising=False)
     monkeypatch.delenv("SYLPH_TRUNK_INTERLEAVE", raising=False)
+    monkeypatch.delenv("SYLPH_L2_PERSIST_MB", raising=False)
     _, _, model, _ = _setup(seed=8)
     want = {}
     for kind, batch in (("u8", ims), ("f32", [im.float() for im in ims])):
@@ -31,6 +32,7 @@ def test_chunked_trunk_pass_is_bit_identical(chunks, interleave, monkeypatch):
     before = model.engine.launch_count()
     monkeypatch.setenv("SYLPH_TRUNK_CHUNK", chunks)          # both read by sylph_create
     monkeypatch.setenv("SYLPH_TRUNK_INTERLEAVE", str(interleave))
+    monkeypatch.setenv("SYLPH_L2_PERSIST_MB", str(persist_mb))   # L2 access-policy window over the chunk's stage output
     _, _, chunked, _ = _setup(seed=8)
     for kind, batch in (("u8", ims), ("f32", [im.float() for im in ims])):
         chunked.engine.extract_features(SLOT_SUPPORT, batch)

@@ -9,10 +9,10 @@ one)
   # 1. opt-in experiment parity (chunked trunk)
   SYLPH_RUN_UNVERIFIED=1 timeout 300 python -m pytest tests/test_gpu_zz_experiments.py tests/test_gpu_zexchange.py -x -q 2>&1 | tail -15
   # 2. A/B of the L2-chunked trunk on the headline config (value only; 20 steps each)
-  for cfg in "|0" "1,2,4,0|0" "2,4,8,0|0" "1,1,2,4|0" "1,2,4,0|1" "1,2,4,0|2" "2,2,4,0|2" "3,6,0,0|2"; do
-    ch="${cfg%%|*}"; il="${cfg##*|}"
-    echo "== SYLPH_TRUNK_CHUNK='$ch' SYLPH_TRUNK_INTERLEAVE=$il" | tee -a gpurun_out/r02_trunk_chunk_ab.log
-    SYLPH_TRUNK_CHUNK="$ch" SYLPH_TRUNK_INTERLEAVE="$il" timeout 200 python bench.py --steps 20 --warmup 3 --no-cpu-baseline 2>/dev/null | tail -1 \
+  for cfg in "|0|0" "1,2,4,0|0|0" "2,4,8,0|0|0" "1,1,2,4|0|0" "1,2,4,0|1|0" "1,2,4,0|2|0" "2,2,4,0|2|0" "3,6,0,0|2|0" "1,2,4,0|0|64" "2,4,8,0|0|96"; do
+    ch="${cfg%%|*}"; rest="${cfg#*|}"; il="${rest%%|*}"; pm="${rest##*|}"
+    echo "== SYLPH_TRUNK_CHUNK='$ch' SYLPH_TRUNK_INTERLEAVE=$il SYLPH_L2_PERSIST_MB=$pm" | tee -a gpurun_out/r02_trunk_chunk_ab.log
+    SYLPH_TRUNK_CHUNK="$ch" SYLPH_TRUNK_INTERLEAVE="$il" SYLPH_L2_PERSIST_MB="$pm" timeout 200 python bench.py --steps 20 --warmup 3 --no-cpu-baseline 2>/dev/null | tail -1 \
       | python -c "import json,sys; d=json.loads(sys.stdin.readline()); print({k: d[k] for k in ('value','ms_per_step','gpu_launches')}, d['e2e']['value'], d['clocks'], {k: v['ms'] for k, v in list(d['per_kernel'].items())[:8]})" \
       | tee -a gpurun_out/r02_trunk_chunk_ab.log
   done
