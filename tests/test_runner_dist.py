@@ -244,3 +244,63 @@ def test_exchange_codes_peer_world2_shards_offsets_and_schema():
         assert ids == list(range(n)) and names == [f"class{c}" for c in range(n)]
         assert bias_shapes == [(1,)] * n                                   # process_bias output shape, code_generator.py:853
         assert torch.equal(got_conv, conv) and torch.equal(got_bias, bias)
+
+
+class _RecordingLib:
+    """Stands in for libsylph_b200.so in `Engine.exchange_setup`: hands out a recognisable 64-byte handle per rank and
+    records what `sylph_exchange_connect` receives (the real calls need a GPU: tests/test_gpu_zexchange.py)."""
+
+    def __init__(self):
+        self.created, self.connected, self.destroyed = None, None, 0
+
+    def sylph_exchange_create(self, h, world, rank, max_classes, handle):
+        self.created = (world, rank, max_classes)
+        for i in range(64):
+            handle[i] = (rank * 64 + i) % 251
+        return 0
+
+    def sylph_exchange_connect(self, h, handles):
+        self.connected = None if handles is None else bytes(handles)
+        return 0
+
+    def sylph_exchange_destroy(self, h):
+        self.destroyed += 1
+
+    def sylph_last_error(self, h):
+        return b""
+
+
+def _worker_handles(rank, world, port, q):
+    from sylph_few_shot_detection_b200.runtime import Engine
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        eng = Engine.__new__(Engine)            # no device here: only the handle exchange of exchange_setup is under test
+        eng.lib, eng.h, eng.device = _RecordingLib(), 1, torch.device("cpu")
+        eng.exchange_setup(None, max_classes=77)
+        first = (eng.lib.created, eng.lib.connected)
+        eng.exchange_setup(None, max_classes=77)            # idempotent for the same geometry
+        assert eng.lib.created == first[0] and eng.lib.destroyed == 0
+        # (exchange_teardown synchronises a CUDA device first: exercised by the GPU tests only)
+        q.put((rank, first[0], first[1]))
+        eng.h = None                                         # nothing for __del__ to destroy
+    finally:
+        dist.destroy_process_group()
+
+
+def test_exchange_setup_swaps_the_ipc_handles_in_rank_order():
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker_handles, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    out = sorted([q.get(timeout=120) for _ in range(2)], key=lambda t: t[0])
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    want = bytes((r * 64 + i) % 251 for r in range(2) for i in range(64))
+    for rank, created, connected in out:
+        assert created == (2, rank, 77)
+        assert connected == want and len(connected) == 128
