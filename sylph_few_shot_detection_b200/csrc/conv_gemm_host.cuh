@@ -146,6 +146,37 @@ inline cudaError_t launch_conv3x3_pair_bn(const CUtensorMap& ta, const CUtensorM
     return launch_k(conv3x3_pair_kernel<kHalo, kBSlots, BN>, dim3(clusters * 2), dim3(S::kThreads), S::kTotal, stream, ta, tb, args);
 }
 
+// Resident-weight form of the narrow pair kernel (experiment, SYLPH_PAIR_BRES): BN == Cin == 64 (res2 conv2, 9 slots of
+// 4 KB) or 128 (res3 conv2, 18 slots of 8 KB), one N tile.  Shared memory: 6 x 17 KB + 36 KB = 138 KB / 4 x 17 KB + 144 KB = 212 KB.
+template <int BN>
+inline cudaError_t launch_conv3x3_pair_bres_bn(const CUtensorMap& ta, const CUtensorMap& tb, const GemmArgs& args, int num_sms,
+                                               cudaStream_t stream) {
+    constexpr int kHalo = BN == 64 ? 6 : 4;
+    constexpr int kBSlots = 9 * (BN / kBlockK);
+    using S = Gemm2Smem<kHalo, kBSlots, BN>;
+    static_assert(S::kTotal <= 227 * 1024, "resident weights + A ring must fit the 227 KB of a CTA");
+    if (args.num_n_tiles != 1 || args.taps != 9 || args.kblocks_per_tap * 9 != kBSlots) return cudaErrorInvalidValue;
+    static bool configured = false;
+    if (!configured) {
+        cudaError_t e = cudaFuncSetAttribute(conv3x3_pair_kernel<kHalo, kBSlots, BN, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, S::kTotal);
+        if (e != cudaSuccess) return e;
+        configured = true;
+    }
+    const int pairs = (args.num_m_tiles + 1) / 2;
+    if (pairs <= 0) return cudaSuccess;
+    const int clusters = pairs < num_sms / 2 ? pairs : num_sms / 2;
+    return launch_k(conv3x3_pair_kernel<kHalo, kBSlots, BN, true>, dim3(clusters * 2), dim3(S::kThreads), S::kTotal, stream, ta, tb, args);
+}
+
+inline cudaError_t launch_conv3x3_pair_bres(const CUtensorMap& ta, const CUtensorMap& tb, const GemmArgs& args, int num_sms,
+                                            cudaStream_t stream, int bn) {
+    switch (bn) {
+        case 64: return launch_conv3x3_pair_bres_bn<64>(ta, tb, args, num_sms, stream);
+        case 128: return launch_conv3x3_pair_bres_bn<128>(ta, tb, args, num_sms, stream);
+        default: return cudaErrorInvalidValue;
+    }
+}
+
 inline cudaError_t launch_conv3x3_pair(const CUtensorMap& ta, const CUtensorMap& tb, const GemmArgs& args, int num_sms,
                                        cudaStream_t stream, int bn = 256) {
     switch (bn) {

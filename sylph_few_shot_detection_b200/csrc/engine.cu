@@ -85,6 +85,8 @@ struct sylph_ctx {
     int pair1x1 = 1;          // SYLPH_PAIR1X1=0 keeps the single-CTA staged kernel for every 1x1 convolution; 2 = pair kernel
                               // for every staged 1x1 convolution with 256-channel N tiles and K >= 256 (experiments)
     int stem16 = 1;           // SYLPH_STEM16=0 runs the stem over 64-wide overlapped rows instead of K = 16 taps
+    int pair_bres = 0;        // SYLPH_PAIR_BRES=1 (experiment): res2 / res3 conv2 (Cin == Cout == 64 / 128) on the CTA-pair kernel with
+                              // RESIDENT weights -- the combination DESIGN.md section 9 lists as untested
     int l2_persist_mb = 0;    // SYLPH_L2_PERSIST_MB=n (with the image-major trunk schedule): n MB of L2 set aside for persisting lines and
                               // an access-policy window over the stage output of the chunk in flight (the residual the next block
                               // re-reads), everything else streaming
@@ -554,7 +556,9 @@ static int run_conv(sylph_ctx* c, const ConvCall& k, cudaStream_t st) {
     CUtensorMap ta, tb;
     std::string err;
     const bool halo = c->halo_pipeline && W.taps == 9 && !k.stem && !k.staged;
-    const bool pair = halo && c->pair_kernel && (W.bn == 256 || ((c->pair_kernel & 2) && W.bn >= 64)) && !(k.flags & kEpiResidual);
+    const bool pair_bres = halo && c->pair_bres && (W.bn == 64 || W.bn == 128) && W.k_per_tap == W.bn && W.cout_pad == W.bn &&
+                           !(k.flags & (kEpiResidual | kEpiGnStats | kEpiOutF32));
+    const bool pair = pair_bres || (halo && c->pair_kernel && (W.bn == 256 || ((c->pair_kernel & 2) && W.bn >= 64)) && !(k.flags & kEpiResidual));
     const bool stem16 = k.stem && c->stem16 && k.staged && W.bn == 64 && W.taps == 4 && k.a_ld == 16;
     // Staged 1x1 convolutions with 256-channel N tiles: the CTA-pair kernel where it measured faster on the 33-image
     // shapes (profiles/r01_pair1x1_shapes.log): shortcut convolutions (no residual, K >= 256, N >= 512: res4 0.205 ->
@@ -617,6 +621,8 @@ static int run_conv(sylph_ctx* c, const ConvCall& k, cudaStream_t st) {
         if (stem16) CU_TRY(c, launch_conv_gemm_stem16(ta, tb, tout, g, c->num_sms, st));
         else if (pair1x1) CU_TRY(c, launch_conv1x1_pair_staged(ta, tb, tres, tout, g, c->num_sms, st));
         else CU_TRY(c, launch_conv_gemm_staged(W.bn, ta, tb, tres, tout, g, c->num_sms, st));
+    } else if (pair_bres) {
+        CU_TRY(c, launch_conv3x3_pair_bres(ta, tb, g, c->num_sms, st, W.bn));
     } else if (pair) {
         CU_TRY(c, launch_conv3x3_pair(ta, tb, g, c->num_sms, st, W.bn));
     } else if (halo) {
@@ -682,6 +688,7 @@ int sylph_create(sylph_ctx** out, int device, const sylph_model_config* cfg) {
     if (const char* e = getenv("SYLPH_PAIR1X1")) c->pair1x1 = atoi(e);
     if (const char* e = getenv("SYLPH_FUSE_UPSAMPLE")) c->fuse_upsample = atoi(e);
     if (const char* e = getenv("SYLPH_TRUNK_INTERLEAVE")) c->trunk_interleave = atoi(e);
+    if (const char* e = getenv("SYLPH_PAIR_BRES")) c->pair_bres = atoi(e);
     if (const char* e = getenv("SYLPH_L2_PERSIST_MB")) {
         c->l2_persist_mb = std::max(0, atoi(e));
         if (c->l2_persist_mb > 0 &&

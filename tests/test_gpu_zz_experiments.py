@@ -40,3 +40,28 @@ def test_chunked_trunk_pass_is_bit_identical(chunks, interleave, persist_mb, mon
             assert torch.equal(chunked.engine.export_features(SLOT_SUPPORT, l), want[kind][l]), f"{kind} p{l + 3}"
     if chunks != "0":
         assert chunked.engine.launch_count() > before
+
+
+def test_pair_kernel_with_resident_weights_matches_the_ring_streamed_pair_kernel(monkeypatch):
+    """SYLPH_PAIR_BRES=1: res2 / res3 conv2 on the CTA-pair kernel with all weight tiles resident.  Same MMA order as the
+    ring-streamed narrow pair kernel (SYLPH_PAIR=3, verified on hardware in round 1), so the pyramids must be bit-identical
+    to that build; against the default (single-CTA kernel for these layers) only the fp32 accumulation order differs."""
+    from sylph_few_shot_detection_b200.runtime import SLOT_SUPPORT
+    from tests.cases import rel_l2
+    ims = [im.cuda() for im in _images(3, 160, 224, 43)]       # 3 images: odd tile counts -> phantom tile of the last pair
+
+    def pyramids(env):
+        for k in ("SYLPH_PAIR", "SYLPH_PAIR_BRES"):
+            monkeypatch.delenv(k, raising=False)
+        for k, v in env.items():
+            monkeypatch.setenv(k, v)
+        _, _, model, _ = _setup(seed=8)
+        model.engine.extract_features(SLOT_SUPPORT, ims)
+        return [model.engine.export_features(SLOT_SUPPORT, l).clone() for l in range(5)]
+
+    default = pyramids({})
+    ring = pyramids({"SYLPH_PAIR": "3"})
+    resident = pyramids({"SYLPH_PAIR_BRES": "1"})
+    for l in range(5):
+        assert torch.equal(resident[l], ring[l]), f"p{l + 3}"
+        assert rel_l2(resident[l], default[l]) < 1e-3, f"p{l + 3}"

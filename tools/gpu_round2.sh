@@ -16,6 +16,13 @@ one)
       | python -c "import json,sys; d=json.loads(sys.stdin.readline()); print({k: d[k] for k in ('value','ms_per_step','gpu_launches')}, d['e2e']['value'], d['clocks'], {k: v['ms'] for k, v in list(d['per_kernel'].items())[:8]})" \
       | tee -a gpurun_out/r02_trunk_chunk_ab.log
   done
+  # 2b. res2 / res3 conv2 on the CTA-pair kernel with resident weights
+  for pb in 0 1; do
+    echo "== SYLPH_PAIR_BRES=$pb" | tee -a gpurun_out/r02_trunk_chunk_ab.log
+    SYLPH_PAIR_BRES=$pb timeout 200 python bench.py --steps 20 --warmup 3 --no-cpu-baseline 2>/dev/null | tail -1 \
+      | python -c "import json,sys; d=json.loads(sys.stdin.readline()); print({k: d[k] for k in ('value','ms_per_step')}, d['clocks'], d['per_kernel'].get('res.conv2_3x3'))" \
+      | tee -a gpurun_out/r02_trunk_chunk_ab.log
+  done
   # 3. configs[4] (LVIS 1203-class sweep) on one GPU with both exchange forms (world 1: the peer form is the two kernels alone)
   timeout 300 python tools/bench_sweep_sharded.py --out gpurun_out/r02_cfg5_CodeGenerator_n1.json 2>&1 | tail -2
   ;;
