@@ -1,0 +1,215 @@
+"""Drop-in check of the plugin mirror under the REFERENCE's OWN evaluation loops (build container only: needs
+/root/reference).  `sylph/evaluation/meta_learn_evaluation.py` is imported unmodified -- `inference_on_support_set_dataset`
+(:256-365), `inference_normalization` (:105-116), `format_class_codes_shared` (:71-103),
+`inference_on_dataset_with_class_codes` (:367-470) -- and drives `sylph_few_shot_detection_b200.modeling.MetaOneStageDetector`
+exactly as `MetaFCOSRunner._do_test_meta_learning` drives the reference model (meta_fcos_runner.py:451-672).
+
+There is no GPU here, so the engine behind the mirror is a TEST DOUBLE built on the CPU oracle (test infrastructure; the
+product has no CPU path).  The oracle reproduces the reference model with 0.0 deviation (tests/test_oracle.py), so any
+difference from the golden outputs of the reference model would be a bug in the host mirror: run_type dispatch, record
+schemas, select_a_mask, code dict shapes, code packing, detection unpacking into Instances."""
+import contextlib
+import sys
+import types
+
+import numpy as np
+import pytest
+import torch
+
+from tests.cases import cfg_for, load_golden
+
+pytestmark = pytest.mark.reference
+
+
+class OracleBackedEngine:
+    """Stands in for runtime.Engine (same method names / argument meaning), computing with the CPU oracle."""
+
+    def __init__(self, cfg, state):
+        from oracle.meta_fcos_oracle import MetaFCOSOracle
+        self.orc = MetaFCOSOracle(cfg, state)
+        self.device = torch.device("cpu")
+        self.post_nms_topk = cfg.MODEL.FCOS.POST_NMS_TOPK_TEST
+        self.slots = {}
+        self.calls = []
+
+    def extract_features(self, slot, images):
+        self.calls.append(("extract_features", slot, len(images)))
+        self.slots[slot] = [im.float() for im in images]
+
+    def generate_codes(self, slot, boxes, roi_image, class_offsets, want_levels=False):
+        self.calls.append(("generate_codes", slot, len(roi_image), len(class_offsets) - 1))
+        rows = []
+        for a, b in zip(class_offsets[:-1], class_offsets[1:]):
+            code = self.orc.class_code([self.slots[slot][roi_image[i]] for i in range(a, b)], boxes[a:b])
+            rows.append(torch.cat([code["cls_conv"].reshape(1, 256), code["cls_bias"].reshape(1, 1)], dim=1))
+        return torch.cat(rows, dim=0)
+
+    def normalize_codes(self, raw):
+        self.calls.append(("normalize_codes", raw.shape[0]))
+        rows = []
+        for r in raw:
+            w, b = self.orc.normalize_code(r[:256].reshape(1, 256, 1, 1), r[256:].reshape(1, 1, 1, 1))
+            rows.append(torch.cat([w.reshape(1, 256), b.reshape(1, 1)], dim=1))
+        return torch.cat(rows, dim=0)
+
+    def detect(self, slot, codes, out_sizes=None, max_dets=None, codes_ready=None):
+        self.calls.append(("detect", slot, codes.shape[0]))
+        res = self.orc.detect(self.slots[slot], {"cls_conv": codes[:, :256].reshape(-1, 256, 1, 1), "cls_bias": codes[:, 256]},
+                              out_sizes)
+        max_dets = max_dets or max(2 * self.post_nms_topk, 128)
+        dets = torch.zeros((len(res), max_dets, 9))
+        counts = torch.zeros((len(res),), dtype=torch.int32)
+        for i, r in enumerate(res):
+            order = torch.argsort(r["scores"], descending=True, stable=True)
+            n = int(order.numel())
+            dets[i, :n, 0:4] = r["boxes"][order]
+            dets[i, :n, 4] = r["scores"][order]
+            dets[i, :n, 5] = r["classes"][order].float()
+            dets[i, :n, 6:8] = r["locations"][order]
+            dets[i, :n, 8] = r["levels"][order].float()
+            counts[i] = n
+        return dets, counts
+
+
+def _reference_evaluation_module():
+    """Import sylph/evaluation/meta_learn_evaluation.py unmodified; its evaluator-side dependencies (pycocotools,
+    detectron2.evaluation, d2go) are replaced by empty stand-ins -- only the inference loops are exercised."""
+    from oracle import reference_loader
+    reference_loader.load()
+
+    def stub(name, **attrs):
+        m = types.ModuleType(name)
+        for k, v in attrs.items():
+            setattr(m, k, v)
+        sys.modules.setdefault(name, m)
+        return sys.modules[name]
+
+    class _Unused:
+        def __init__(self, *a, **k):
+            pass
+
+    @contextlib.contextmanager
+    def inference_context(model):           # detectron2.evaluation.evaluator.inference_context
+        was = model.training
+        model.eval()
+        yield
+        model.train(was)
+
+    class DatasetEvaluators:
+        def __init__(self, evaluators):
+            self.evaluators = evaluators
+
+        def reset(self):
+            pass
+
+        def process(self, inputs, outputs):
+            pass
+
+        def evaluate(self):
+            return {}
+
+    stub("pycocotools")
+    stub("pycocotools.cocoeval", COCOeval=_Unused)
+    stub("pycocotools.coco", COCO=_Unused)
+    stub("detectron2.evaluation")
+    stub("detectron2.evaluation.coco_evaluation", COCOEvaluator=_Unused, COCOevalMaxDets=_Unused,
+         _evaluate_predictions_on_coco=lambda *a, **k: None)
+    stub("detectron2.evaluation.evaluator", inference_context=inference_context, DatasetEvaluators=DatasetEvaluators)
+    stub("detectron2.evaluation.fast_eval_api", COCOeval_opt=_Unused)
+    stub("detectron2.utils.logger", create_small_table=lambda d: str(d), log_every_n_seconds=lambda *a, **k: None)
+    stub("d2go")
+    stub("d2go.utils")
+    stub("d2go.utils.misc", tabulate=lambda *a, **k: "")
+    import os
+    for pkg, path in (("sylph.data", "sylph/data"), ("sylph.data.data_injection", "sylph/data/data_injection")):
+        if pkg not in sys.modules:      # their __init__ files pull in the dataset catalogs (out of scope)
+            m = types.ModuleType(pkg)
+            m.__path__ = [os.path.join(reference_loader.REFERENCE_ROOT, path)]
+            sys.modules[pkg] = m
+    stub("sylph.data.data_injection.classes", COCO_BASE_CLASSES=[], COCO_NOVEL_CLASSES=[])
+    import importlib
+    return importlib.import_module("sylph.evaluation.meta_learn_evaluation")
+
+
+class _CollectingEvaluator:
+    def __init__(self):
+        self.seen = []
+
+    def reset(self):
+        self.seen = []
+
+    def process(self, inputs, outputs):
+        assert len(inputs) == len(outputs)
+        self.seen.extend(outputs)
+
+    def evaluate(self):
+        return {"n": len(self.seen)}
+
+
+@pytest.mark.parametrize("case", ["coco_2way_2shot", "lvis_1way_3shot"])
+def test_reference_evaluation_loops_drive_the_mirror_to_the_reference_results(case, tmp_path):
+    from sylph_few_shot_detection_b200 import modeling as M
+    from sylph_few_shot_detection_b200 import weights as W
+    from sylph_few_shot_detection_b200.structures import Boxes, Instances
+    ev = _reference_evaluation_module()
+    g = load_golden(case)
+    cfg = cfg_for(g["config"])
+    state = W.synthetic_state_dict(cfg, g["seed"])
+    model = M.build_model(cfg)
+    engine = OracleBackedEngine(cfg, state)
+    model._state, model._engine = state, engine          # what load_state_dict does, minus the CUDA context
+    for m in (model.backbone, model.proposal_generator, model.code_generator):
+        m.bind_engine(engine)
+
+    # the loaders of _do_test_meta_learning: one support set per item (batch size 1), query images batched
+    support_loader = []
+    for c, shots in enumerate(g["support"]):
+        records = []
+        for s in shots:
+            h, w = s["image"].shape[-2:]
+            inst = Instances((h, w))
+            inst.gt_boxes = Boxes(s["box"][None])
+            inst.gt_classes = torch.tensor([c])
+            records.append({"image": s["image"], "instances": inst, "height": h, "width": w})
+        support_loader.append([{"support_set": records, "support_set_target": torch.tensor(c), "class_name": f"class{c}"}])
+    query_loader = [[{"image": q, "height": q.shape[-2], "width": q.shape[-1]} for q in g["query"]]]
+
+    np.random.seed(0)
+    out_dir = str(tmp_path / "codes")
+    codes = ev.inference_on_support_set_dataset(model, support_loader, output_dir=out_dir)        # step B
+    assert [c["class_name"] for c in codes] == [f"class{c}" for c in range(len(g["support"]))]
+    for c, ref in zip(codes, g["raw_codes"]):
+        assert c["class_code"]["cls_conv"].shape == (1, 256, 1, 1) and c["class_code"]["cls_bias"].shape == (1, 1, 1, 1)
+        assert torch.equal(c["class_code"]["cls_conv"], ref["cls_conv"]) and torch.equal(c["class_code"]["cls_bias"], ref["cls_bias"])
+    # the reference loop also wrote <class_name>.pth files (meta_learn_evaluation.py:316-325): our store reads them
+    from sylph_few_shot_detection_b200.predictor import load_class_code_list
+    stored = load_class_code_list(out_dir, [c["class_name"] for c in codes])
+    assert all(torch.equal(a["class_code"]["cls_conv"], b["class_code"]["cls_conv"]) for a, b in zip(stored, codes))
+
+    codes = ev.inference_normalization(model, codes)                                              # step D
+    for c, ref in zip(codes, g["norm_codes"]):
+        assert c["class_code"]["cls_bias"].shape == (1,)
+        assert torch.equal(c["class_code"]["cls_conv"], ref["cls_conv"]) and torch.equal(c["class_code"]["cls_bias"], ref["cls_bias"])
+    packed = ev.format_class_codes_shared(codes, torch.device("cpu"))                             # step E
+    assert torch.equal(packed["cls_conv"], g["packed"]["cls_conv"]) and torch.equal(packed["cls_bias"], g["packed"]["cls_bias"])
+
+    evaluator = _CollectingEvaluator()
+    res = ev.inference_on_dataset_with_class_codes(model, query_loader, evaluator, packed)        # step F
+    assert res == {"n": len(g["query"])}
+    for out, ref, q in zip(evaluator.seen, g["detections"], g["query"]):
+        inst = out["instances"]
+        assert inst.image_size == (q.shape[-2], q.shape[-1])
+        got = {(int(l), int(x), int(y), int(c)): (b, float(s)) for b, s, c, (x, y), l in
+               zip(inst.pred_boxes.tensor, inst.scores, inst.pred_classes, inst.locations, inst.fpn_levels)}
+        want = {(int(l), int(loc[0]), int(loc[1]), int(c)): (b, float(s)) for b, s, c, loc, l in
+                zip(ref["boxes"], ref["scores"], ref["classes"], ref["locations"], ref["levels"])}
+        assert set(got) == set(want) and len(inst) == len(ref["scores"])
+        for k in want:
+            assert torch.equal(got[k][0], want[k][0]) and got[k][1] == want[k][1]
+        assert inst.pred_classes.dtype == torch.int64 and inst.fpn_levels.dtype == torch.int64
+        assert bool((inst.scores[:-1] >= inst.scores[1:]).all())          # rows arrive in descending score order
+    # the mirror made exactly the engine calls the C ABI offers for this loop: per class extract + generate, one
+    # normalisation of all classes, one extract + detect for the query batch
+    kinds = [c[0] for c in engine.calls]
+    n_cls = len(g["support"])
+    assert kinds == ["extract_features", "generate_codes"] * n_cls + ["normalize_codes", "extract_features", "detect"]
