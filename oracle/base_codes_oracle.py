@@ -2,8 +2,9 @@
 
 CPU restatement of the base-class "all ground truths" code path of the reference:
   * accumulate_base_codes ... the per-chunk weighted accumulation inside inference_on_support_set_dataset_base,
-                              sylph/evaluation/meta_learn_evaluation.py:190-203 (that file cannot be imported here: it
-                              needs pycocotools / detectron2.evaluation), restated line for line;
+                              sylph/evaluation/meta_learn_evaluation.py:190-203, restated line for line; pinned against the
+                              reference's real loop (imported unmodified on evaluator stand-ins) by
+                              tests/test_reference_loops_dropin.py: bit-equal codes and acc_weight;
   * reduce_class_code ....... sylph/modeling/code_generator/utils.py:397-427 (+ convert_list_to_dict :340-374);
   * replace_class_code ...... sylph/modeling/code_generator/utils.py:376-394.
 Pinned: `oracle/make_golden.py` runs the reference's own reduce_class_code / replace_class_code (imported unmodified

@@ -213,3 +213,30 @@ def test_reference_evaluation_loops_drive_the_mirror_to_the_reference_results(ca
     kinds = [c[0] for c in engine.calls]
     n_cls = len(g["support"])
     assert kinds == ["extract_features", "generate_codes"] * n_cls + ["normalize_codes", "extract_features", "detect"]
+
+
+def test_reference_base_class_loop_equals_the_golden_accumulation():
+    """`inference_on_support_set_dataset_base` (meta_learn_evaluation.py:118-254), imported unmodified, fed the seeded
+    chunk codes of tests/golden/base_reduce.pt through a stand-in model: its per-rank accumulators (codes AND the
+    Python-float acc_weight) equal the golden's `per_rank` entries bit for bit.  Those entries were produced by the
+    RESTATED loop (oracle/base_codes_oracle.accumulate_base_codes), so this pins the restatement -- and with it the
+    accumulate kernel the GPU tests compare with the same golden -- to the reference's real loop."""
+    import copy
+    ev = _reference_evaluation_module()
+    g = load_golden("base_reduce")
+    for chunks, ref in zip(g["chunks_per_rank"], g["per_rank"]):
+        served = iter(chunks)
+
+        def model(inputs, run_type=None):                 # not an nn.Module: the loop skips inference_context for it
+            assert run_type == "meta_learn_test_support" and len(inputs) == 1
+            return copy.deepcopy(next(served)["code"])
+
+        loader = [[{"support_set": [], "support_set_target": torch.tensor(c["cid"]), "class_name": c["name"], "len": c["len"],
+                    "total_len": c["total_len"]}] for c in chunks]
+        got = ev.inference_on_support_set_dataset_base(model, loader, all_id_map={}, base_id_map={})
+        assert [c["support_set_target"] for c in got] == [c["support_set_target"] for c in ref]
+        for a, b in zip(got, ref):
+            assert a["class_name"] == b["class_name"]
+            assert torch.equal(a["class_code"]["cls_conv"], b["class_code"]["cls_conv"])
+            assert torch.equal(a["class_code"]["cls_bias"], b["class_code"]["cls_bias"])
+            assert a["class_code"]["acc_weight"] == b["class_code"]["acc_weight"]
