@@ -57,6 +57,7 @@ struct Case {
     bool bias;
     int skew = 0, base_offset = 0;  // experiment: A box loaded `skew` rows early, descriptor started `skew` rows in
     bool pair = false;    // CTA-pair (cta_group::2) halo kernel
+    bool pair_bres = false; // ... with RESIDENT weights (conv3x3_pair_kernel<.., true>, bn == cin == cout in {64, 128})
     bool halo = false;    // 3x3 halo pipeline (one 130-row A box per vertical tap and k-block)
     bool staged = false;  // TMA-in / TMA-out epilogue, run IN PLACE (out == residual buffer) like the bottleneck conv3
     bool pair1x1 = false; // CTA-pair 1x1 convolution with the staged epilogue (conv1x1_pair.cuh)
@@ -149,6 +150,8 @@ static int run_case(const Case& c, int num_sms) {
         if (c.stem16) CK(launch_conv_gemm_stem16(ta, tb, tio, g, num_sms, 0));
         else if (c.pair1x1) CK(launch_conv1x1_pair_staged(ta, tb, tio, tio, g, num_sms, 0));
         else CK(launch_conv_gemm_staged(c.bn, ta, tb, tio, tio, g, num_sms, 0));
+    } else if (c.pair && c.pair_bres) {
+        CK(launch_conv3x3_pair_bres(ta, tb, g, num_sms, 0, c.bn));
     } else if (c.pair) {
         CK(launch_conv3x3_pair(ta, tb, g, num_sms, 0, c.bn));
     } else if (c.halo) {
@@ -225,7 +228,7 @@ static Seg mk_seg(int row0, int H, int W, int pad) {
 static int round128(int x) { return (x + 127) / 128 * 128; }
 
 static int g_dbg_skip = 0;
-static void bench_shape(const char* name, int bn, int m_tiles, int cin, int cout, int taps, int flags, int num_sms, int staged = 0, bool halo = false, bool pair = false) {
+static void bench_shape(const char* name, int bn, int m_tiles, int cin, int cout, int taps, int flags, int num_sms, int staged = 0, bool halo = false, bool pair = false, bool pair_bres = false) {
     const int M = m_tiles * 128;
     const int osz = (flags & kEpiOutF32) ? 4 : 2;
     __half *dA, *dW, *dR = nullptr;
@@ -275,7 +278,7 @@ static void bench_shape(const char* name, int bn, int m_tiles, int cin, int cout
         g.residual = static_cast<const __half*>(dO);
         if (make_tmap_2d(&tio, static_cast<const __half*>(dO), M, cout, cout, 128, &err)) { printf("tmap failed\n"); return; }
     }
-    auto launch = [&]() { return pair1x1 ? launch_conv1x1_pair_staged(ta, tb, tio, tio, g, num_sms, 0) : staged ? launch_conv_gemm_staged(bn, ta, tb, tio, tio, g, num_sms, 0, staged == 100 ? 0 : staged) : (pair ? launch_conv3x3_pair(ta, tb, g, num_sms, 0, bn) : (halo ? launch_conv_gemm_halo(bn, ta, tb, g, num_sms, 0) : launch_conv_gemm(bn, ta, tb, g, num_sms, 0))); };
+    auto launch = [&]() { return pair1x1 ? launch_conv1x1_pair_staged(ta, tb, tio, tio, g, num_sms, 0) : staged ? launch_conv_gemm_staged(bn, ta, tb, tio, tio, g, num_sms, 0, staged == 100 ? 0 : staged) : (pair ? (pair_bres ? launch_conv3x3_pair_bres(ta, tb, g, num_sms, 0, bn) : launch_conv3x3_pair(ta, tb, g, num_sms, 0, bn)) : (halo ? launch_conv_gemm_halo(bn, ta, tb, g, num_sms, 0) : launch_conv_gemm(bn, ta, tb, g, num_sms, 0))); };
     for (int i = 0; i < 3; ++i) CK(launch());
     CK(cudaDeviceSynchronize());
     const int iters = 10;
@@ -322,8 +325,10 @@ int main(int argc, char** argv) {
         const int F = kEpiRelu | kEpiMask;
         bench_shape("res2_conv2_3x3_64_64_HALO_BRES", 64, 17622, 64, 64, 9, F, sms, 0, true);
         bench_shape("res2_conv2_3x3_64_64_PAIR", 64, 17622, 64, 64, 9, F, sms, 0, false, true);
+        bench_shape("res2_conv2_3x3_64_64_PAIR_BRES", 64, 17622, 64, 64, 9, F, sms, 0, false, true, true);
         bench_shape("res3_conv2_3x3_128_128_HALO", 128, 4488, 128, 128, 9, F, sms, 0, true);
         bench_shape("res3_conv2_3x3_128_128_PAIR", 128, 4488, 128, 128, 9, F, sms, 0, false, true);
+        bench_shape("res3_conv2_3x3_128_128_PAIR_BRES", 128, 4488, 128, 128, 9, F, sms, 0, false, true, true);
         bench_shape("res4_conv2_3x3_256_256_PAIR", 256, 1155, 256, 256, 9, F, sms, 0, false, true);
         bench_shape("res5_conv2_3x3_512_512_PAIR", 256, 330, 512, 512, 9, F, sms, 0, false, true);
         bench_shape("tower3x3_256_gn_f32out_PAIR", 256, 1480, 256, 256, 9, kEpiMask | kEpiGnStats | kEpiOutF32, sms, 0, false, true);
@@ -475,6 +480,15 @@ int main(int argc, char** argv) {
         c.pair = true;
         printf("bn=%d ", bnv);
         fails += run_case(c, sms);
+        Case r = c;                      // the same problem on the resident-weight variant (experiment, SYLPH_PAIR_BRES)
+        r.name = "PAIR_BRES_conv3x3_narrow_mask_relu";
+        r.pair_bres = true;
+        printf("bn=%d ", bnv);
+        fails += run_case(r, sms);
+        r.name = "PAIR_BRES_conv3x3_narrow_many_tiles_per_cluster";
+        r.sms_override = 4;              // two clusters: every pair walks many tiles with the weights loaded once
+        printf("bn=%d ", bnv);
+        fails += run_case(r, sms);
     }
     {   // CTA pair + GroupNorm statistics + fp32 output (the tower configuration)
         Seg s0 = mk_seg(0, 13, 21, 1);

@@ -8,6 +8,9 @@ case "${1:-one}" in
 one)
   # 1. opt-in experiment parity (chunked trunk)
   SYLPH_RUN_UNVERIFIED=1 timeout 300 python -m pytest tests/test_gpu_zz_experiments.py tests/test_gpu_zexchange.py -x -q 2>&1 | tail -15
+  # 1b. the resident-weight pair kernel in the kernel harness: bit-check against the CPU reference, then the 33-image shapes
+  timeout 300 ./build/test_conv_gemm case PAIR_BRES 2>&1 | tail -8
+  timeout 300 ./build/test_conv_gemm pairnarrow 2>&1 | tee gpurun_out/r02_pairnarrow_bres.log | tail -12
   # 2. A/B of the L2-chunked trunk on the headline config (value only; 20 steps each)
   for cfg in "|0|0" "1,2,4,0|0|0" "2,4,8,0|0|0" "1,1,2,4|0|0" "1,2,4,0|1|0" "1,2,4,0|2|0" "2,2,4,0|2|0" "3,6,0,0|2|0" "1,2,4,0|0|64" "2,4,8,0|0|96"; do
     ch="${cfg%%|*}"; rest="${cfg#*|}"; il="${rest%%|*}"; pm="${rest##*|}"
