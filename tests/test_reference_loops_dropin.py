@@ -331,3 +331,62 @@ def test_gather_class_code_equals_the_reference_classmethod_on_two_ranks():
         p.join(timeout=60)
         assert p.exitcode == 0
     assert out == [(0, 5, 4), (1, 5, 4)]
+
+
+def test_select_a_mask_equals_the_reference_function_draw_for_draw():
+    """`select_a_mask` (sylph/modeling/code_generator/utils.py:27-47) next to the mirror's: same boxes for the same global
+    NumPy seed over several calls (the RNG state advances identically), same all-masks mode, same ValueError on empty."""
+    from oracle import reference_loader
+    from oracle import upstream as up
+    from sylph_few_shot_detection_b200 import modeling as M
+    from sylph_few_shot_detection_b200.structures import Boxes, Instances
+    ref_fn = reference_loader.load().cg_utils.select_a_mask
+    g = torch.Generator().manual_seed(2)
+
+    def make(n_boxes, kinds):
+        out = []
+        for cls_boxes, cls_inst in kinds:
+            inst = cls_inst((64, 64))
+            xy = torch.rand(n_boxes, 2, generator=torch.Generator().manual_seed(n_boxes)) * 30
+            inst.gt_boxes = cls_boxes(torch.cat([xy, xy + 10], dim=1))
+            out.append(inst)
+        return out
+    sizes = [1, 4, 2, 7, 3]
+    mine_in = [make(n, [(Boxes, Instances)])[0] for n in sizes]
+    ref_in = [make(n, [(up.Boxes, up.Instances)])[0] for n in sizes]
+    for use_all in (False, True):
+        np.random.seed(11)
+        got = [M.select_a_mask(mine_in, use_all_masks=use_all) for _ in range(3)]
+        np.random.seed(11)
+        want = [ref_fn(ref_in, use_all_masks=use_all) for _ in range(3)]
+        for a_call, b_call in zip(got, want):
+            assert len(a_call) == len(b_call) == len(sizes)
+            for a, b in zip(a_call, b_call):
+                # the reference wraps the single box in Boxes and returns the raw tensor in all-masks mode (:41-45); the
+                # mirror hands plain (k, 4) tensors to the engine either way
+                assert torch.equal(a, b.tensor if hasattr(b, "tensor") else b)
+    empty_mine, empty_ref = Instances((8, 8)), up.Instances((8, 8))
+    empty_mine.gt_boxes, empty_ref.gt_boxes = Boxes(torch.zeros(0, 4)), up.Boxes(torch.zeros(0, 4))
+    with pytest.raises(ValueError):
+        ref_fn([empty_ref])
+    with pytest.raises(ValueError):
+        M.select_a_mask([empty_mine])
+    del g
+
+
+def test_format_class_codes_shared_equals_the_reference_function():
+    """runner.format_class_codes_shared next to meta_learn_evaluation.format_class_codes_shared (:71-103) on code lists
+    in shuffled order (the reference places class c at list index c; the mirror sorts by id: same packing)."""
+    from sylph_few_shot_detection_b200.runner import format_class_codes_shared
+    ev = _reference_evaluation_module()
+    g = torch.Generator().manual_seed(5)
+    for n, order in ((1, [0]), (5, [3, 0, 4, 1, 2]), (20, list(reversed(range(20))))):
+        codes = [{"support_set_target": torch.tensor(c), "class_name": f"c{c}",
+                  "class_code": {"cls_conv": torch.randn(1, 256, 1, 1, generator=g), "cls_bias": torch.randn(1, generator=g)}}
+                 for c in order]
+        want = ev.format_class_codes_shared(codes, torch.device("cpu"))
+        got = format_class_codes_shared(codes, device=torch.device("cpu"))
+        assert set(got) == set(want) == {"cls_conv", "cls_bias"}
+        assert got["cls_conv"].shape == (n, 256, 1, 1) and got["cls_bias"].shape == (n,)
+        assert torch.equal(got["cls_conv"], want["cls_conv"]) and torch.equal(got["cls_bias"], want["cls_bias"])
+    assert ev.format_class_codes_shared([], torch.device("cpu")) == []
