@@ -85,6 +85,9 @@ struct sylph_ctx {
     int pair1x1 = 1;          // SYLPH_PAIR1X1=0 keeps the single-CTA staged kernel for every 1x1 convolution; 2 = pair kernel
                               // for every staged 1x1 convolution with 256-channel N tiles and K >= 256 (experiments)
     int stem16 = 1;           // SYLPH_STEM16=0 runs the stem over 64-wide overlapped rows instead of K = 16 taps
+    int lateral_mode = 0;     // SYLPH_LATERAL (experiment): FPN lateral 1x1 convolutions (K = 512..2048 -> 256, today 36 % of the tensor
+                              // peak on the direct-epilogue single-CTA kernel) through 1 = the CTA-pair staged 1x1 kernel, 2 = the
+                              // single-CTA staged kernel; the top-down add then runs as its own kernel
     int pair_bres = 0;        // SYLPH_PAIR_BRES=1 (experiment): res2 / res3 conv2 (Cin == Cout == 64 / 128) on the CTA-pair kernel with
                               // RESIDENT weights -- the combination DESIGN.md section 9 lists as untested
     int l2_persist_mb = 0;    // SYLPH_L2_PERSIST_MB=n (with the image-major trunk schedule): n MB of L2 set aside for persisting lines and
@@ -547,6 +550,7 @@ struct ConvCall {
     int stem = 0;
     int up_seg_delta = 0;    // kEpiUpsample: coarser plane = segment of the output tile + this
     int staged = 0;          // TMA-in / TMA-out epilogue (fp16 output, BN = 256); needs out_rows
+    int force_pair1x1 = 0;   // staged 1x1 convolution on the CTA-pair kernel whatever the shape table says (experiments)
     long long out_rows = 0;  // rows of the output (and residual) buffer, for the staged epilogue's tensor maps
     const char* name = "conv";
 };
@@ -566,7 +570,7 @@ static int run_conv(sylph_ctx* c, const ConvCall& k, cudaStream_t st) {
     // (lock-stepped epilogues of the pair cost more than the halved weight traffic buys there).
     const bool has_res = (k.flags & kEpiResidual) != 0;
     const bool pair1x1 = k.staged && !k.stem && W.taps == 1 && W.bn == 256 && k.n_tiles >= 2 && W.k_per_tap >= 256 &&
-                         (c->pair1x1 == 2 || (c->pair1x1 == 1 && (has_res ? W.k_per_tap >= 512 : W.cout_pad >= 512)));
+                         (k.force_pair1x1 || c->pair1x1 == 2 || (c->pair1x1 == 1 && (has_res ? W.k_per_tap >= 512 : W.cout_pad >= 512)));
     if (stem16) {
         if (make_tmap_2d_k16(&ta, k.A, static_cast<uint64_t>(k.a_rows), kBlockM + 3, &err))
             return c->fail("A tensor map (%s): %s", k.name, err.c_str());
@@ -689,6 +693,7 @@ int sylph_create(sylph_ctx** out, int device, const sylph_model_config* cfg) {
     if (const char* e = getenv("SYLPH_FUSE_UPSAMPLE")) c->fuse_upsample = atoi(e);
     if (const char* e = getenv("SYLPH_TRUNK_INTERLEAVE")) c->trunk_interleave = atoi(e);
     if (const char* e = getenv("SYLPH_PAIR_BRES")) c->pair_bres = atoi(e);
+    if (const char* e = getenv("SYLPH_LATERAL")) c->lateral_mode = atoi(e);
     if (const char* e = getenv("SYLPH_L2_PERSIST_MB")) {
         c->l2_persist_mb = std::max(0, atoi(e));
         if (c->l2_persist_mb > 0 &&
@@ -1171,13 +1176,16 @@ static int run_fpn(sylph_ctx* c, int slot, const TrunkOut& T, int first, int n, 
         k.tile_begin = static_cast<int>(S.level_row0[l] / kBlockM); k.n_tiles = static_cast<int>(rows / kBlockM);
         k.a_row_delta = -static_cast<int>(S.level_row0[l]) + first * g.rows_per_img; k.out = LAT; k.ldc = 256;
         k.flags = kEpiMask; k.name = "fpn.lateral1x1";   // direct epilogue: the staged variant measured slower here (K >= 512)
-        const bool fuse_up = c->fuse_upsample && l < 2;
+        const bool fuse_up = c->fuse_upsample && l < 2 && c->lateral_mode == 0;
+        if (c->lateral_mode != 0) {   // experiment: staged (TMA-out) epilogue, CTA pair for mode 1
+            k.staged = 1; k.out_rows = S.level_row0[5]; k.force_pair1x1 = c->lateral_mode == 1;
+        }
         if (fuse_up) {   // top-down add in the lateral convolution's epilogue: + LAT(level l + 1)(y / 2, x / 2), summed in fp32
             k.flags |= kEpiResidual | kEpiUpsample;
             k.residual = LAT; k.ld_res = 256; k.up_seg_delta = n;
         }
         TRY(run_conv(c, k, st));
-        k.flags = kEpiMask; k.residual = nullptr; k.up_seg_delta = 0;
+        k.flags = kEpiMask; k.residual = nullptr; k.up_seg_delta = 0; k.staged = 0; k.force_pair1x1 = 0;
         if (l < 2 && !fuse_up) {
             StageTimer t(c, "fpn.upsample_add", st, static_cast<double>(n) * g.H * g.W * 256 * 2 * 2.25);
             CU_TRY(c, launch_k(upsample_add_kernel, dim3(grid_for(static_cast<long long>(n) * g.H * g.W * 32, 256, c->num_sms)), dim3(256), 0, st, 

@@ -65,3 +65,28 @@ def test_pair_kernel_with_resident_weights_matches_the_ring_streamed_pair_kernel
     for l in range(5):
         assert torch.equal(resident[l], ring[l]), f"p{l + 3}"
         assert rel_l2(resident[l], default[l]) < 1e-3, f"p{l + 3}"
+
+
+def test_fpn_laterals_on_the_staged_kernels_match_the_unfused_default(monkeypatch):
+    """SYLPH_LATERAL=2 / 1: FPN lateral 1x1 convolutions through the single-CTA / CTA-pair staged (TMA-out) kernels with
+    the top-down add as its own kernel.  Reference point: SYLPH_FUSE_UPSAMPLE=0 (direct epilogue, separate add), where the
+    lateral is rounded to fp16 before the add exactly like here."""
+    from sylph_few_shot_detection_b200.runtime import SLOT_SUPPORT
+    from tests.cases import rel_l2
+    ims = [im.cuda() for im in _images(3, 160, 224, 47)]
+
+    def pyramids(env):
+        for k in ("SYLPH_LATERAL", "SYLPH_FUSE_UPSAMPLE"):
+            monkeypatch.delenv(k, raising=False)
+        for k, v in env.items():
+            monkeypatch.setenv(k, v)
+        _, _, model, _ = _setup(seed=8)
+        model.engine.extract_features(SLOT_SUPPORT, ims)
+        return [model.engine.export_features(SLOT_SUPPORT, l).clone() for l in range(5)]
+
+    unfused = pyramids({"SYLPH_FUSE_UPSAMPLE": "0"})
+    staged = pyramids({"SYLPH_LATERAL": "2"})
+    pair = pyramids({"SYLPH_LATERAL": "1"})
+    for l in range(5):
+        assert torch.equal(staged[l], unfused[l]), f"p{l + 3}"        # same k-loop, same rounding points
+        assert rel_l2(pair[l], unfused[l]) < 1e-4, f"p{l + 3}"

@@ -26,6 +26,13 @@ one)
       | python -c "import json,sys; d=json.loads(sys.stdin.readline()); print({k: d[k] for k in ('value','ms_per_step')}, d['clocks'], d['per_kernel'].get('res.conv2_3x3'))" \
       | tee -a gpurun_out/r02_trunk_chunk_ab.log
   done
+  # 2c. FPN laterals on the staged kernels (1 = CTA pair, 2 = single CTA), against the fused default
+  for lm in 0 1 2; do
+    echo "== SYLPH_LATERAL=$lm" | tee -a gpurun_out/r02_trunk_chunk_ab.log
+    SYLPH_LATERAL=$lm timeout 200 python bench.py --steps 20 --warmup 3 --no-cpu-baseline 2>/dev/null | tail -1 \
+      | python -c "import json,sys; d=json.loads(sys.stdin.readline()); print({k: d[k] for k in ('value','ms_per_step')}, d['clocks'], d['per_kernel'].get('fpn.lateral1x1'), d['per_kernel'].get('fpn.upsample_add'))" \
+      | tee -a gpurun_out/r02_trunk_chunk_ab.log
+  done
   # 3. configs[4] (LVIS 1203-class sweep) on one GPU with both exchange forms (world 1: the peer form is the two kernels alone)
   timeout 300 python tools/bench_sweep_sharded.py --out gpurun_out/r02_cfg5_CodeGenerator_n1.json 2>&1 | tail -2
   ;;
