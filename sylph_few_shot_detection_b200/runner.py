@@ -550,6 +550,94 @@ class MetaFCOSRunner:
         """meta_fcos_runner.py:381-439; `reduce=True` is the base-class all-GT path (reduce_class_code)."""
         return gather_class_code(sub_class_codes, reduce=reduce, engine=cls._model.engine if cls._model is not None else None)
 
-    def do_test(self, cfg, model, support_items, query_items):
-        """Episode-level equivalent of `_do_test_meta_learning` for in-memory loaders."""
-        return run_episode(model, support_items, query_items)
+    # ---- loaders and evaluators are the caller's (datasets, mappers and COCO / LVIS evaluators are outside the hot path):
+    # subclass and override, exactly the methods the reference runner defines (meta_fcos_runner.py:163-230, 232-300).
+    def build_episodic_learning_detection_test_support_set_loader(self, cfg, dataset_name: str, seed: int):
+        """Iterable of batches `[item]` (batch size 1): item = {"support_set": [K records], "support_set_target", "class_name"}."""
+        raise NotImplementedError("dataset loaders are outside the B200 hot path: override this builder (see INTEGRATION.md)")
+
+    def build_episodic_learning_detection_test_support_set_base_loader(self, cfg, dataset_name: str):
+        """Iterable of batches `[chunk]`: the items above plus "len" / "total_len" (<= 10 boxes per chunk, meta_lvis.py:303-306)."""
+        raise NotImplementedError("dataset loaders are outside the B200 hot path: override this builder (see INTEGRATION.md)")
+
+    def build_episodic_learning_detection_test_query_loader(self, cfg, dataset_name: str):
+        """Iterable of batches of query records {"image", "height", "width"[, "instances"]}."""
+        raise NotImplementedError("dataset loaders are outside the B200 hot path: override this builder (see INTEGRATION.md)")
+
+    def get_evaluator(self, cfg, dataset_name: str, output_folder: Optional[str] = None):
+        """An object with reset() / process(inputs, outputs) / evaluate() (detectron2 DatasetEvaluator protocol)."""
+        raise NotImplementedError("evaluators are outside the B200 hot path: override get_evaluator (see INTEGRATION.md)")
+
+    def thing_classes(self, cfg, dataset_name: str) -> Optional[Sequence[str]]:
+        """`MetadataCatalog.get(dataset_name).thing_classes` (:501); None skips the class-count assert (:540-542)."""
+        return None
+
+    def _do_test_meta_learning(self, cfg, model, train_iter=None, model_tag: str = "default"):
+        """`MetaFCOSRunner._do_test_meta_learning` (meta_fcos_runner.py:451-672), the evaluation sequence of the reference:
+        per test repetition (`TEST.REPEAT_TEST` at the final iteration) and dataset -- class codes from the support-set
+        loader (B), gather (C), optionally the base-class all-GT codes (gather with reduce, `replace_class_code`),
+        normalisation (D), packing (E), detection over the query loader into the evaluator (F).  Steps B and F go
+        through the batched entry points (all classes of the rank in one backbone batch; query batches as they come),
+        everything else is the reference's own sequence.  Returns {model_tag: {}, "seed<k>": {dataset: evaluator results}}."""
+        from collections import OrderedDict
+        assert len(cfg.DATASETS.TEST)
+        max_iter = (cfg.get("SOLVER") or {}).get("MAX_ITER")          # solver keys are not part of the inference config tree
+        is_final = (train_iter is None) or (max_iter is not None and train_iter == max_iter - 1)
+        type(self)._model = model
+        results = OrderedDict()
+        results[model_tag] = OrderedDict()
+        num_repeat_test = cfg.TEST.REPEAT_TEST if is_final else 1
+        for seed in range(num_repeat_test):
+            results[f"seed{seed}"] = OrderedDict()
+            for dataset_name in cfg.DATASETS.TEST:
+                if "base" in dataset_name and cfg.MODEL.META_LEARN.EVAL_WITH_PRETRAINED_CODE:
+                    raise NotImplementedError("inference with the pretrained class logits (base detector) is not on the B200 path")
+                output_folder = None
+                if cfg.get("OUTPUT_DIR", ""):
+                    output_folder = os.path.join(cfg.OUTPUT_DIR, "inference", model_tag,
+                                                 str(train_iter) if train_iter is not None else "final", dataset_name, str(seed))
+                support_loader = self.build_episodic_learning_detection_test_support_set_loader(cfg, dataset_name, seed)
+                items = []
+                for inputs in support_loader:
+                    assert len(inputs) == 1, "inputs' batch size is not 1"          # meta_learn_evaluation.py:299
+                    items.append(inputs[0])
+                sub_class_codes = inference_on_support_set(model, items)
+                if output_folder is not None:                                        # :316-325, raw codes, one file per class
+                    from .predictor import save_class_codes
+                    save_class_codes(sub_class_codes, output_folder)
+                few_shot_class_codes = self._gather_class_code(sub_class_codes)
+                if cfg.MODEL.META_LEARN.USE_ALL_GTS_IN_BASE_CLASSES:
+                    base_loader = self.build_episodic_learning_detection_test_support_set_base_loader(cfg, dataset_name)
+                    chunks = []
+                    for inputs in base_loader:
+                        assert len(inputs) == 1, "inputs' batch size is not 1"      # :163
+                        chunks.append(inputs[0])
+                    base_class_codes = self._gather_class_code(inference_on_support_set_base(model, chunks), reduce=True)
+                    class_codes = replace_class_code(few_shot_class_codes, base_class_codes, device=model.device)
+                else:
+                    class_codes = few_shot_class_codes
+                class_codes = inference_normalization(model, class_codes)
+                classes = self.thing_classes(cfg, dataset_name)
+                if classes is not None:
+                    assert len(class_codes) == len(classes), \
+                        f"Got {len(class_codes)} class codes for prediction, but expect to be {len(classes)}."
+                packed = format_class_codes_shared(class_codes, device=model.device)
+                query_loader = self.build_episodic_learning_detection_test_query_loader(cfg, dataset_name)
+                evaluator = self.get_evaluator(cfg, dataset_name, output_folder=output_folder)
+                evaluator.reset()
+                for inputs in query_loader:                                          # inference_on_dataset_with_class_codes :367-470
+                    outputs = inference_with_class_codes(model, list(inputs), packed, batch_size=max(len(inputs), 1))
+                    evaluator.process(inputs, outputs)
+                res = evaluator.evaluate()
+                results[f"seed{seed}"][dataset_name] = {} if res is None else res
+        return results
+
+    def do_test(self, cfg, model, train_iter=None, support_items=None, query_items=None):
+        """`do_test(cfg, model, train_iter=None)` (meta_fcos_runner.py:674-701): the meta-learning evaluation when
+        `MODEL.META_LEARN.EPISODIC_LEARNING` is on.  With in-memory `support_items` / `query_items` instead of loader
+        builders it runs ONE episode (`run_episode`) and returns its detections."""
+        if support_items is not None or query_items is not None:
+            return run_episode(model, support_items or [], query_items or [])
+        if not cfg.MODEL.META_LEARN.EPISODIC_LEARNING:
+            raise NotImplementedError("base-detector evaluation (non-episodic do_test) is not on the B200 path")
+        return self._do_test_meta_learning(cfg, model, train_iter=train_iter)

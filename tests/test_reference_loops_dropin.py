@@ -390,3 +390,80 @@ def test_format_class_codes_shared_equals_the_reference_function():
         assert got["cls_conv"].shape == (n, 256, 1, 1) and got["cls_bias"].shape == (n,)
         assert torch.equal(got["cls_conv"], want["cls_conv"]) and torch.equal(got["cls_bias"], want["cls_bias"])
     assert ev.format_class_codes_shared([], torch.device("cpu")) == []
+
+
+def test_runner_do_test_follows_the_reference_sequence_with_injected_loaders(tmp_path):
+    """`MetaFCOSRunner.do_test(cfg, model, train_iter=None)` -> `_do_test_meta_learning` (meta_fcos_runner.py:451-672,
+    674-701) with the loader / evaluator builders overridden by in-memory ones (what a deployment overrides): the
+    detections the evaluator receives equal the reference model's goldens; the class codes land in
+    OUTPUT_DIR/inference/default/final/<dataset>/<seed>/<class_name>.pth like the reference's."""
+    import os
+
+    from sylph_few_shot_detection_b200 import modeling as M
+    from sylph_few_shot_detection_b200 import weights as W
+    from sylph_few_shot_detection_b200.predictor import load_class_code_list
+    from sylph_few_shot_detection_b200.runner import MetaFCOSRunner
+    from sylph_few_shot_detection_b200.structures import Boxes, Instances
+    g = load_golden("coco_2way_2shot")
+    cfg = cfg_for(g["config"], ["DATASETS.TEST", ("coco_meta_val_novel",), "MODEL.META_LEARN.USE_ALL_GTS_IN_BASE_CLASSES", False,
+                                "TEST.REPEAT_TEST", 2])
+    cfg.OUTPUT_DIR = str(tmp_path)
+    state = W.synthetic_state_dict(cfg, g["seed"])
+    model = M.build_model(cfg)
+    engine = OracleBackedEngine(cfg, state)
+    model._state, model._engine = state, engine
+    for m in (model.backbone, model.proposal_generator, model.code_generator):
+        m.bind_engine(engine)
+
+    class Runner(MetaFCOSRunner):
+        def __init__(self):
+            self.evaluators = []
+
+        def build_episodic_learning_detection_test_support_set_loader(self, cfg, dataset_name, seed):
+            loader = []
+            for c, shots in enumerate(g["support"]):
+                records = []
+                for s in shots:
+                    h, w = s["image"].shape[-2:]
+                    inst = Instances((h, w))
+                    inst.gt_boxes = Boxes(s["box"][None])
+                    inst.gt_classes = torch.tensor([c])
+                    records.append({"image": s["image"], "instances": inst, "height": h, "width": w})
+                loader.append([{"support_set": records, "support_set_target": torch.tensor(c), "class_name": f"class{c}"}])
+            return loader
+
+        def build_episodic_learning_detection_test_query_loader(self, cfg, dataset_name):
+            return [[{"image": q, "height": q.shape[-2], "width": q.shape[-1]} for q in g["query"]]]
+
+        def get_evaluator(self, cfg, dataset_name, output_folder=None):
+            self.evaluators.append(_CollectingEvaluator())
+            return self.evaluators[-1]
+
+        def thing_classes(self, cfg, dataset_name):
+            return [f"class{c}" for c in range(len(g["support"]))]
+
+    runner = Runner()
+    np.random.seed(0)
+    results = runner.do_test(cfg, model)
+    assert list(results) == ["default", "seed0", "seed1"]                    # REPEAT_TEST repetitions at the final iteration
+    assert results["seed0"] == {"coco_meta_val_novel": {"n": len(g["query"])}}
+    for ev_ in runner.evaluators:
+        for out, ref in zip(ev_.seen, g["detections"]):
+            inst = out["instances"]
+            got = {(int(l), int(x), int(y), int(c)): float(s) for s, c, (x, y), l in
+                   zip(inst.scores, inst.pred_classes, inst.locations, inst.fpn_levels)}
+            want = {(int(l), int(loc[0]), int(loc[1]), int(c)): float(s) for s, c, loc, l in
+                    zip(ref["scores"], ref["classes"], ref["locations"], ref["levels"])}
+            assert got == want
+    folder = os.path.join(str(tmp_path), "inference", "default", "final", "coco_meta_val_novel", "1")
+    stored = load_class_code_list(folder, ["class0", "class1"])
+    for s_, ref in zip(stored, g["raw_codes"]):
+        assert torch.equal(s_["class_code"]["cls_conv"], ref["cls_conv"])     # RAW codes are what is stored (:316-325)
+    # the default builders say what to override instead of failing somewhere inside
+    with pytest.raises(NotImplementedError, match="override"):
+        MetaFCOSRunner().do_test(cfg, model)
+    # in-memory episode form
+    np.random.seed(0)
+    res = MetaFCOSRunner().do_test(cfg, model, support_items=[b[0] for b in runner.build_episodic_learning_detection_test_support_set_loader(cfg, "", 0)],
+                                   query_items=runner.build_episodic_learning_detection_test_query_loader(cfg, "")[0])
+    assert [len(r["instances"]) for r in res] == [int(d["scores"].numel()) for d in g["detections"]]
