@@ -33,3 +33,23 @@ def rel_l2(a: torch.Tensor, b: torch.Tensor) -> float:
     if b.numel() == 0:
         return 0.0 if a.numel() == 0 else float("inf")
     return float((a - b).norm() / (b.norm() + 1e-30))
+
+
+def fresh_rendezvous() -> str:
+    """Path of a not-yet-existing file for a torch.distributed FileStore rendezvous.  The multi-process CPU tests use it
+    instead of a TCP port picked with bind(0): such a port can be taken (or still be in TIME_WAIT) by the time the
+    workers listen on it, which showed up as a rare failure of the gloo tests."""
+    import os
+    import tempfile
+    fd, path = tempfile.mkstemp(prefix="sylph_rdzv_")
+    os.close(fd)
+    os.remove(path)
+    return path
+
+
+def init_gloo(rank: int, world: int, rendezvous: str) -> None:
+    import os
+
+    import torch.distributed as dist
+    os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+    dist.init_process_group("gloo", init_method="file://" + rendezvous, rank=rank, world_size=world)

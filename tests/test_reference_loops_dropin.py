@@ -272,9 +272,8 @@ def _worker_gather(rank, world, port, q):
     import torch.distributed as dist
     from oracle import base_codes_oracle as bo
     from sylph_few_shot_detection_b200.runner import gather_class_code
-    os.environ["MASTER_ADDR"] = "127.0.0.1"
-    os.environ["MASTER_PORT"] = str(port)
-    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from tests.cases import init_gloo
+    init_gloo(rank, world, port)          # `port` is a FileStore path (tests/cases.fresh_rendezvous)
     try:
         ref_gather = _reference_gather_class_code()
         g = torch.Generator().manual_seed(700 + rank)
@@ -314,13 +313,9 @@ def _worker_gather(rank, world, port, q):
 
 
 def test_gather_class_code_equals_the_reference_classmethod_on_two_ranks():
-    import socket
-
     import torch.multiprocessing as mp
-    s = socket.socket()
-    s.bind(("127.0.0.1", 0))
-    port = s.getsockname()[1]
-    s.close()
+    from tests.cases import fresh_rendezvous
+    port = fresh_rendezvous()
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
     procs = [ctx.Process(target=_worker_gather, args=(r, 2, port, q)) for r in range(2)]

@@ -1,7 +1,6 @@
 """N > 1 host logic on CPU: world_size-2 gloo process group, class-code all-gather (the one collective of the path,
 sylph/runner/meta_fcos_runner.py:381-396) and the sharding arithmetic."""
 import os
-import socket
 
 import torch
 import torch.distributed as dist
@@ -12,17 +11,13 @@ from sylph_few_shot_detection_b200.runner import (format_class_codes_shared, gat
 
 
 def _free_port():
-    s = socket.socket()
-    s.bind(("127.0.0.1", 0))
-    p = s.getsockname()[1]
-    s.close()
-    return p
+    from tests.cases import fresh_rendezvous
+    return fresh_rendezvous()
 
 
 def _worker(rank, world, port, n_classes, q):
-    os.environ["MASTER_ADDR"] = "127.0.0.1"
-    os.environ["MASTER_PORT"] = str(port)
-    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from tests.cases import init_gloo
+    init_gloo(rank, world, port)          # `port` is a FileStore path (tests/cases.fresh_rendezvous)
     try:
         mine = []
         for c in shard_range(n_classes, world, rank):
@@ -49,9 +44,8 @@ def _worker(rank, world, port, n_classes, q):
 
 def _worker_base(rank, world, port, q):
     """Base-class path: both ranks hold a PARTIAL sum of class 7 (acc_weight 0.4 / 0.6); rank 1 also holds class 3."""
-    os.environ["MASTER_ADDR"] = "127.0.0.1"
-    os.environ["MASTER_PORT"] = str(port)
-    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from tests.cases import init_gloo
+    init_gloo(rank, world, port)          # `port` is a FileStore path (tests/cases.fresh_rendezvous)
     try:
         g = torch.Generator().manual_seed(500 + rank)
         mine = [{"support_set_target": 7, "class_name": "seven",
@@ -125,9 +119,8 @@ def _worker_losses(rank, world, port, q):
     """Training forward on 2 ranks: each rank holds its own query images; the positives and the
     centre-ness target sum are all-reduced (fcos_outputs.py:520-523, 557-558) -- the mirror's `_reduce_sum` /
     `_world_size` on a float64 pair, and the oracle's reduce hook, against a single-process recomputation."""
-    os.environ["MASTER_ADDR"] = "127.0.0.1"
-    os.environ["MASTER_PORT"] = str(port)
-    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from tests.cases import init_gloo
+    init_gloo(rank, world, port)          # `port` is a FileStore path (tests/cases.fresh_rendezvous)
     try:
         from oracle import upstream as up
         from oracle.meta_fcos_oracle import MetaFCOSOracle
@@ -203,9 +196,8 @@ def _worker_peer(rank, world, port, n_classes, q):
     import types
 
     from sylph_few_shot_detection_b200.runner import exchange_codes_peer
-    os.environ["MASTER_ADDR"] = "127.0.0.1"
-    os.environ["MASTER_PORT"] = str(port)
-    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from tests.cases import init_gloo
+    init_gloo(rank, world, port)          # `port` is a FileStore path (tests/cases.fresh_rendezvous)
     try:
         mine = []
         for c in shard_range(n_classes, world, rank):
@@ -272,9 +264,8 @@ class _RecordingLib:
 
 def _worker_handles(rank, world, port, q):
     from sylph_few_shot_detection_b200.runtime import Engine
-    os.environ["MASTER_ADDR"] = "127.0.0.1"
-    os.environ["MASTER_PORT"] = str(port)
-    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from tests.cases import init_gloo
+    init_gloo(rank, world, port)          # `port` is a FileStore path (tests/cases.fresh_rendezvous)
     try:
         eng = Engine.__new__(Engine)            # no device here: only the handle exchange of exchange_setup is under test
         eng.lib, eng.h, eng.device = _RecordingLib(), 1, torch.device("cpu")
