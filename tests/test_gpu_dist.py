@@ -2,7 +2,6 @@
 the codes of its class shard, one all_gather_into_tensor, every rank detects on its query shard with ALL codes.
 Results must equal the single-GPU episode.  Skipped with fewer than 2 devices."""
 import os
-import socket
 
 import pytest
 import torch
@@ -12,11 +11,8 @@ pytestmark = pytest.mark.gpu
 
 
 def _free_port():
-    s = socket.socket()
-    s.bind(("127.0.0.1", 0))
-    p = s.getsockname()[1]
-    s.close()
-    return p
+    from tests.cases import fresh_rendezvous      # a FileStore path: no TCP port to race for
+    return fresh_rendezvous()
 
 
 def _episode_inputs():
@@ -38,9 +34,8 @@ def _worker(rank, world, port, q, balance=False):
     from sylph_few_shot_detection_b200.presets import coco_meta_fcos_cfg
     from sylph_few_shot_detection_b200.runner import query_indices_of_rank, run_episode
     os.environ["MASTER_ADDR"] = "127.0.0.1"
-    os.environ["MASTER_PORT"] = str(port)
     torch.cuda.set_device(rank)
-    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
+    dist.init_process_group("nccl", init_method="file://" + port, rank=rank, world_size=world, device_id=torch.device("cuda", rank))
     try:
         cfg = coco_meta_fcos_cfg()
         model = build_model(cfg)

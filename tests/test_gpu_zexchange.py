@@ -64,9 +64,8 @@ def _worker(rank, world, port, q):
     from sylph_few_shot_detection_b200.runner import query_indices_of_rank, run_episode
     from tests.test_gpu_dist import _episode_inputs
     os.environ["MASTER_ADDR"] = "127.0.0.1"
-    os.environ["MASTER_PORT"] = str(port)
     torch.cuda.set_device(rank)
-    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
+    dist.init_process_group("nccl", init_method="file://" + port, rank=rank, world_size=world, device_id=torch.device("cuda", rank))
     try:
         cfg = coco_meta_fcos_cfg()
         model = build_model(cfg)
