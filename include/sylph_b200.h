@@ -66,8 +66,22 @@ int sylph_create(sylph_ctx** ctx, int device, const sylph_model_config* cfg);
 void sylph_destroy(sylph_ctx* ctx);
 const char* sylph_last_error(const sylph_ctx* ctx);
 
+/* Operand precision of every tensor-core convolution; call before sylph_finalize_weights (the weights are prepared for
+ * one mode).  The reference computes in fp32 everywhere (sylph/modeling/meta_fcos/fcos.py:582-667,
+ * fcos_outputs.py:904-1008; torch CPU kernels).
+ *   exact = 1 (default): split-fp16 operands -- every activation and weight is a (hi, lo) fp16 pair with hi = rn(x),
+ *       lo = rn(x - hi), every product is a_hi*w_hi + a_lo*w_hi + a_hi*w_lo accumulated in fp32 in the tensor core
+ *       (three tcgen05.mma per k-step); outputs agree with the fp32 reference to ~1e-5 (max-norm), i.e. well inside
+ *       the 1e-3 bar of the path.
+ *   exact = 0: single fp16 operands (10-bit mantissa), one tcgen05.mma per k-step, half the activation bytes;
+ *       deep activations / logits carry 1-2.5e-3 (max-norm) of accumulated operand rounding.
+ * The environment variable SYLPH_PRECISION=fast|exact sets the default of new contexts. */
+int sylph_set_precision(sylph_ctx* ctx, int exact);
+int sylph_get_precision(const sylph_ctx* ctx);
+
 /* Stage one state-dict tensor (host fp32, contiguous) under its reference key, then
- * finalize: fold FrozenBN into the convolutions, reorder to tap-major K-major, round to TF32, upload.
+ * finalize: fold FrozenBN into the convolutions, reorder to tap-major K-major, round to fp16 (or split into
+ * fp16 hi/lo pairs), upload.
  * Replaces DetectionCheckpointer.load into the module tree (tools/train_net.py:51-61). Synchronous. */
 int sylph_load_tensor(sylph_ctx* ctx, const char* key, const float* host_data, const int64_t* shape, int ndim);
 int sylph_finalize_weights(sylph_ctx* ctx);

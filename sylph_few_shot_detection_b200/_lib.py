@@ -82,6 +82,9 @@ def load() -> ctypes.CDLL:
     if not os.path.exists(LIB_PATH):
         build()
     lib = ctypes.CDLL(LIB_PATH)
+    if not hasattr(lib, "sylph_set_precision"):   # a stale in-tree build from before the precision modes
+        build(force=True)
+        lib = ctypes.CDLL(LIB_PATH)
     vp, ip, fp = c_void_p, POINTER(c_int), POINTER(c_float)
     lib.sylph_version.restype = c_char_p
     lib.sylph_version.argtypes = []
@@ -91,6 +94,10 @@ def load() -> ctypes.CDLL:
     lib.sylph_destroy.argtypes = [vp]
     lib.sylph_last_error.restype = c_char_p
     lib.sylph_last_error.argtypes = [vp]
+    lib.sylph_set_precision.restype = c_int
+    lib.sylph_set_precision.argtypes = [vp, c_int]
+    lib.sylph_get_precision.restype = c_int
+    lib.sylph_get_precision.argtypes = [vp]
     lib.sylph_load_tensor.restype = c_int
     lib.sylph_load_tensor.argtypes = [vp, c_char_p, vp, POINTER(c_int64), c_int]
     lib.sylph_finalize_weights.restype = c_int
@@ -151,7 +158,7 @@ def load() -> ctypes.CDLL:
 
 
 EXPORTED_SYMBOLS = [
-    "sylph_version", "sylph_create", "sylph_destroy", "sylph_last_error", "sylph_load_tensor",
+    "sylph_version", "sylph_create", "sylph_destroy", "sylph_last_error", "sylph_set_precision", "sylph_get_precision", "sylph_load_tensor",
     "sylph_finalize_weights", "sylph_extract_features", "sylph_extract_features_u8", "sylph_extract_features_multi", "sylph_import_features", "sylph_feature_shape",
     "sylph_export_features", "sylph_generate_codes", "sylph_export_roi_features", "sylph_normalize_codes", "sylph_exchange_create", "sylph_exchange_connect",
     "sylph_normalize_codes_exchange", "sylph_exchange_poll", "sylph_exchange_status", "sylph_exchange_destroy", "sylph_accumulate_codes", "sylph_reduce_codes",

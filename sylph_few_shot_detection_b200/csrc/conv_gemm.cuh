@@ -83,6 +83,12 @@ struct GemmArgs {
     const Seg* segs;
     float* gn_partial;     // [absolute tile][32][2]
     int up_seg_delta;      // kEpiUpsample: segment index of the coarser plane = segment of the output tile + up_seg_delta
+    // Split-operand ("exact", f16x3) mode: every activation row is [C hi | C lo] fp16 with hi = rn(x), lo = rn(x - hi),
+    // every weight matrix is [w_hi | w_hi | w_lo] along K (K' = 3C), so that the k loop computes
+    // a_hi.w_hi + a_lo.w_hi + a_hi.w_lo in the fp32 accumulator: the A column of k-block kb is (kb * 64) mod 2C.
+    int a_wrap;            // SPLIT: 2C of the A operand (elements); a k-block column >= a_wrap wraps back by a_wrap
+    int out_lo;            // SPLIT: element offset of the lo half of an fp16 output row (= Cout of the whole layer)
+    int res_lo;            // SPLIT: element offset of the lo half of a residual row
     int dbg_a_row_skew;    // experiment: load the A box `skew` rows early and start the MMA descriptor `skew` rows in
     int dbg_base_offset;   // experiment: matrix-descriptor base_offset field used with the skew
     int dbg_skip;          // bring-up timing experiments (halo pipeline): 1 = no output stores, 2 = no MMAs issued,
@@ -105,7 +111,7 @@ struct GemmArgs {
 // shared memory (res2 conv2: 9 x 8 KB) they are loaded ONCE and stay resident in the STAGES slots (STAGES = 9 x kblocks),
 // so the per-tile TMA traffic is the three halo A boxes only.  A TMA unit retires roughly one <= 128-byte box row per
 // 5 clocks (~45 GB/s per SM): 9 x 64 weight rows per tile were 60 % of this kernel's row requests.
-template <int BN, int STAGES, int EPI_BUFS, int HALO, bool STEM16 = false, bool BRES = false>
+template <int BN, int STAGES, int EPI_BUFS, int HALO, bool STEM16 = false, bool BRES = false, bool SPLIT = false>
 struct GemmSmem {
     static constexpr bool TMA_EPI = EPI_BUFS > 0;          // 0: direct epilogue, 1 / 2: staged epilogue buffers
     static constexpr int kABytes = kBlockM * kBlockK * 2;  // 16 KiB
@@ -115,7 +121,8 @@ struct GemmSmem {
     static constexpr int kBBytes = BN * kBlockK * 2;
     static constexpr int kStageBytes = HALO ? kBBytes : kABytes + kBBytes;
     static constexpr int kRingOffset = HALO * kAHaloBytes;  // halo slots first, then the (B or A+B) stage ring
-    static constexpr int kEpiBytes = TMA_EPI ? kBlockM * BN * 2 : 0;  // one staged output tile, BN/64 swizzled panels
+    // one staged output tile, BN/64 swizzled panels (SPLIT: the hi panels, then as many lo panels)
+    static constexpr int kEpiBytes = TMA_EPI ? kBlockM * BN * 2 * (SPLIT ? 2 : 1) : 0;
     static constexpr int kEpiOffset = kRingOffset + STAGES * kStageBytes;
     static constexpr int kBarOffset = kEpiOffset + EPI_BUFS * kEpiBytes;
     static constexpr int kGnOffset = kBarOffset + 1024;
@@ -148,6 +155,22 @@ __device__ __forceinline__ float2 unpack_half2(uint32_t u) {
     return __half22float2(*reinterpret_cast<const __half2*>(&u));
 }
 
+// SPLIT storage: 8 fp32 -> hi = rn16(x) and lo = rn16(x - hi) (hi + lo carries ~22 mantissa bits of x)
+__device__ __forceinline__ void split8(const float* f, bool relu, bool keep, uint4& hi, uint4& lo) {
+    float r[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) r[j] = relu ? fmaxf(f[j], 0.f) : f[j];
+    hi = pack8(r, false, keep);
+    const float2 a = unpack_half2(hi.x), b = unpack_half2(hi.y), c = unpack_half2(hi.z), d = unpack_half2(hi.w);
+    float l[8] = {r[0] - a.x, r[1] - a.y, r[2] - b.x, r[3] - b.y, r[4] - c.x, r[5] - c.y, r[6] - d.x, r[7] - d.y};
+    lo = pack8(l, false, keep);
+}
+// f[0..7] += the 8 fp16 values of v
+__device__ __forceinline__ void add8(float* f, const uint4& v) {
+    const float2 a = unpack_half2(v.x), b = unpack_half2(v.y), c = unpack_half2(v.z), d = unpack_half2(v.w);
+    f[0] += a.x; f[1] += a.y; f[2] += b.x; f[3] += b.y; f[4] += c.x; f[5] += c.y; f[6] += d.x; f[7] += d.y;
+}
+
 // tile -> (m_tile, n_tile) without an integer division in the common single-N-tile case
 __device__ __forceinline__ void split_tile(int tile, int num_n_tiles, int& m_tile, int& n_tile) {
     if (num_n_tiles == 1) { m_tile = tile; n_tile = 0; }
@@ -165,13 +188,15 @@ __device__ __forceinline__ bool row_is_interior(const Seg& sg, int row) {
     return (local >= 0) && (local < sg.nrows) && (y >= sg.pad) && (y < sg.pad + sg.H) && (x >= sg.pad) && (x < sg.pad + sg.W);
 }
 
-template <int BN, int STAGES, int EPI_BUFS, int HALO, bool STEM16 = false, bool BRES = false>
-__global__ void __launch_bounds__(GemmSmem<BN, STAGES, EPI_BUFS, HALO, STEM16, BRES>::kThreads, 1)
+template <int BN, int STAGES, int EPI_BUFS, int HALO, bool STEM16 = false, bool BRES = false, bool SPLIT = false>
+__global__ void __launch_bounds__(GemmSmem<BN, STAGES, EPI_BUFS, HALO, STEM16, BRES, SPLIT>::kThreads, 1)
 conv_gemm_f16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
                      const __grid_constant__ CUtensorMap tmap_res, const __grid_constant__ CUtensorMap tmap_out,
                      const GemmArgs p) {
-    using S = GemmSmem<BN, STAGES, EPI_BUFS, HALO, STEM16, BRES>;
+    using S = GemmSmem<BN, STAGES, EPI_BUFS, HALO, STEM16, BRES, SPLIT>;
     static_assert(!BRES || (HALO > 0 && !STEM16), "resident weights are implemented for the 3x3 halo pipeline");
+    static_assert(!(BRES && SPLIT), "split operands triple the weight tiles: no resident-weight variant");
+    constexpr int kPanels = BN / 64;   // 64-column panels of one staged tile half
     constexpr bool TMA_EPI = EPI_BUFS > 0;
     constexpr int kHalo = HALO > 0 ? HALO : 1;
     static_assert(HALO == 0 || EPI_BUFS == 0 || STEM16, "the 3x3 halo pipeline uses the direct epilogue");
@@ -290,24 +315,38 @@ conv_gemm_f16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_co
                         for (int pn = 0; pn < BN / 64; ++pn)
                             ptx::tma_load_2d(epi_smem + buf * S::kEpiBytes + pn * (kBlockM * 128), &tmap_res, &res_full[buf],
                                              n_tile * BN + pn * 64, out_row_base);
+                        if constexpr (SPLIT) {
+#pragma unroll
+                            for (int pn = 0; pn < BN / 64; ++pn)
+                                ptx::tma_load_2d(epi_smem + buf * S::kEpiBytes + (kPanels + pn) * (kBlockM * 128), &tmap_res,
+                                                 &res_full[buf], p.res_lo + n_tile * BN + pn * 64, out_row_base);
+                        }
                     }
                 }
                 // planes of different FPN levels have different padded widths: the row shift of a tap is per tile (wp)
                 if constexpr (STEM16) {
                     // the four 64 x 64 weight tiles (one per vertical tap) are the same for every output tile: they are
                     // loaded once and stay resident; the ring only carries A boxes (4 per tile, several tiles ahead)
+                    // SPLIT: eight resident tiles (w_hi of the four vertical taps, then w_lo) and per vertical tap three A
+                    // boxes: columns 0..15 (hi) against w_hi, 16..31 (lo) against w_hi, 0..15 (hi) against w_lo
+                    constexpr int kStemB = SPLIT ? 8 : 4;
+                    static_assert(!STEM16 || STAGES >= kStemB, "stem: one ring slot per resident weight tile");
                     if (it == 0) {
-                        for (int ty = 0; ty < 4; ++ty) {
+                        for (int ty = 0; ty < kStemB; ++ty) {
                             ptx::mbar_arrive_expect_tx(&full_bar[ty], S::kBBytes);
                             ptx::tma_load_2d(smem + S::kRingOffset + ty * S::kStageBytes, &tmap_b, &full_bar[ty], 0,
                                              ty * p.b_rows_per_tap + b_row_base);
                         }
                     }
                     for (int ty = 0; ty < 4; ++ty) {
-                        ptx::mbar_wait(&a_empty[hs], hphase ^ 1u);
-                        ptx::mbar_arrive_expect_tx(&a_full[hs], S::kAHaloTx);
-                        ptx::tma_load_2d(smem + hs * S::kAHaloBytes, &tmap_a, &a_full[hs], 0, a_row_base + (ty - 2) * wp - 2);
-                        if (++hs == kHalo) { hs = 0; hphase ^= 1u; }
+#pragma unroll
+                        for (int pass = 0; pass < (SPLIT ? 3 : 1); ++pass) {
+                            ptx::mbar_wait(&a_empty[hs], hphase ^ 1u);
+                            ptx::mbar_arrive_expect_tx(&a_full[hs], S::kAHaloTx);
+                            ptx::tma_load_2d(smem + hs * S::kAHaloBytes, &tmap_a, &a_full[hs], pass == 1 ? 16 : 0,
+                                             a_row_base + (ty - 2) * wp - 2);
+                            if (++hs == kHalo) { hs = 0; hphase ^= 1u; }
+                        }
                     }
                     continue;
                 } else if constexpr (HALO > 0) {
@@ -328,7 +367,9 @@ conv_gemm_f16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_co
                                 ptx::mbar_arrive(&a_full[hs]);
                             } else {
                                 ptx::mbar_arrive_expect_tx(&a_full[hs], S::kAHaloTx);
-                                ptx::tma_load_2d(smem + hs * S::kAHaloBytes, &tmap_a, &a_full[hs], kb * kBlockK,
+                                int acol = kb * kBlockK;
+                                if constexpr (SPLIT) { if (acol >= p.a_wrap) acol -= p.a_wrap; }
+                                ptx::tma_load_2d(smem + hs * S::kAHaloBytes, &tmap_a, &a_full[hs], acol,
                                                  a_row_base + (dyi - 1) * wp - 1);
                             }
                             if (++hs == kHalo) { hs = 0; hphase ^= 1u; }
@@ -356,7 +397,9 @@ conv_gemm_f16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_co
                     const bool keep_b = !(p.dbg_skip & 16) && b_tag[stage] == b_id;
                     ptx::mbar_arrive_expect_tx(&full_bar[stage], keep_b ? S::kABytes : S::kStageBytes);
                     uint8_t* sa = smem + S::kRingOffset + stage * S::kStageBytes;
-                    ptx::tma_load_2d(sa, &tmap_a, &full_bar[stage], kb * kBlockK,
+                    int acol = kb * kBlockK;
+                    if constexpr (SPLIT) { if (acol >= p.a_wrap) acol -= p.a_wrap; }
+                    ptx::tma_load_2d(sa, &tmap_a, &full_bar[stage], acol,
                                      a_row_base + static_cast<int>(p.tap_dy[tap]) * wp + static_cast<int>(p.tap_dx[tap]) -
                                          p.dbg_a_row_skew);
                     if (!keep_b) {
@@ -385,18 +428,22 @@ conv_gemm_f16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_co
                 const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(acc * BN);
                 if constexpr (STEM16) {
                     if (!b_resident) {
-                        for (int ty = 0; ty < 4; ++ty) ptx::mbar_wait(&full_bar[ty], 0);
+                        for (int ty = 0; ty < (SPLIT ? 8 : 4); ++ty) ptx::mbar_wait(&full_bar[ty], 0);
                         b_resident = true;
                     }
                     for (int ty = 0; ty < 4; ++ty) {
-                        ptx::mbar_wait(&a_full[hs], hphase);
-                        ptx::tc_fence_after();
-                        const uint32_t sa = ptx::smem_u32(smem + hs * S::kAHaloBytes);
-                        const uint64_t db = ptx::make_sw128_kmajor_desc(ptx::smem_u32(smem + S::kRingOffset + ty * S::kStageBytes));
-                        // horizontal tap tx: A starts tx rows (32 bytes) in, B advances 32 bytes of K
-                        ptx::umma_f16_x4(d_tmem, ptx::make_sw32_kmajor_desc(sa), db, kIdesc, ty ? 1u : 0u);
-                        ptx::umma_commit(&a_empty[hs]);
-                        if (++hs == kHalo) { hs = 0; hphase ^= 1u; }
+#pragma unroll
+                        for (int pass = 0; pass < (SPLIT ? 3 : 1); ++pass) {
+                            ptx::mbar_wait(&a_full[hs], hphase);
+                            ptx::tc_fence_after();
+                            const uint32_t sa = ptx::smem_u32(smem + hs * S::kAHaloBytes);
+                            const uint64_t db = ptx::make_sw128_kmajor_desc(
+                                ptx::smem_u32(smem + S::kRingOffset + (ty + (pass == 2 ? 4 : 0)) * S::kStageBytes));
+                            // horizontal tap tx: A starts tx rows (32 bytes) in, B advances 32 bytes of K
+                            ptx::umma_f16_x4(d_tmem, ptx::make_sw32_kmajor_desc(sa), db, kIdesc, (ty | pass) ? 1u : 0u);
+                            ptx::umma_commit(&a_empty[hs]);
+                            if (++hs == kHalo) { hs = 0; hphase ^= 1u; }
+                        }
                     }
                     ptx::umma_commit(&tmem_full[acc]);
                     if (++acc == kAcc) { acc = 0; acc_phase ^= 1u; }
@@ -511,12 +558,17 @@ conv_gemm_f16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_co
                     ptx::tmem_ld_32x32b_x32(t_row + c0, v);
                     const int col = col_begin + c0;                 // first column of this chunk inside the tile
                     uint8_t* panel = tile_smem + (col >> 6) * (kBlockM * 128) + r_in_tile * 128;
+                    [[maybe_unused]] uint8_t* panel_lo = panel + kPanels * (kBlockM * 128);   // SPLIT: lo half of the tile
                     const int ch16 = (col & 63) >> 3;               // first 16-byte chunk inside the panel row
                     uint4 rr[CH / 8];
+                    [[maybe_unused]] uint4 rl[CH / 8];
                     if (use_res_tile) {
 #pragma unroll
-                        for (int j = 0; j < CH / 8; ++j)
+                        for (int j = 0; j < CH / 8; ++j) {
                             rr[j] = *reinterpret_cast<const uint4*>(panel + (((ch16 + j) ^ (r_in_tile & 7)) << 4));
+                            if constexpr (SPLIT)
+                                rl[j] = *reinterpret_cast<const uint4*>(panel_lo + (((ch16 + j) ^ (r_in_tile & 7)) << 4));
+                        }
                     }
                     ptx::tmem_ld_wait();
                     float f[CH];
@@ -533,17 +585,30 @@ conv_gemm_f16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_co
                     if (use_res_tile) {
 #pragma unroll
                         for (int j = 0; j < CH / 8; ++j) {
-                            const float2 a = unpack_half2(rr[j].x), b = unpack_half2(rr[j].y), c = unpack_half2(rr[j].z),
-                                         d = unpack_half2(rr[j].w);
-                            f[8 * j + 0] += a.x; f[8 * j + 1] += a.y; f[8 * j + 2] += b.x; f[8 * j + 3] += b.y;
-                            f[8 * j + 4] += c.x; f[8 * j + 5] += c.y; f[8 * j + 6] += d.x; f[8 * j + 7] += d.y;
+                            if constexpr (SPLIT) {   // (hi + lo) is exact in fp32; one rounding when it meets the accumulator
+                                float r8[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+                                add8(r8, rr[j]);
+                                add8(r8, rl[j]);
+#pragma unroll
+                                for (int q = 0; q < 8; ++q) f[8 * j + q] += r8[q];
+                            } else {
+                                add8(f + 8 * j, rr[j]);
+                            }
                         }
                     }
                     {
                         const bool relu = (p.flags & kEpiRelu) != 0;
 #pragma unroll
-                        for (int j = 0; j < CH / 8; ++j)
-                            *reinterpret_cast<uint4*>(panel + (((ch16 + j) ^ (r_in_tile & 7)) << 4)) = pack8(f + 8 * j, relu, keep);
+                        for (int j = 0; j < CH / 8; ++j) {
+                            if constexpr (SPLIT) {
+                                uint4 hi, lo;
+                                split8(f + 8 * j, relu, keep, hi, lo);
+                                *reinterpret_cast<uint4*>(panel + (((ch16 + j) ^ (r_in_tile & 7)) << 4)) = hi;
+                                *reinterpret_cast<uint4*>(panel_lo + (((ch16 + j) ^ (r_in_tile & 7)) << 4)) = lo;
+                            } else {
+                                *reinterpret_cast<uint4*>(panel + (((ch16 + j) ^ (r_in_tile & 7)) << 4)) = pack8(f + 8 * j, relu, keep);
+                            }
+                        }
                     }
                 }
                 ptx::tc_fence_before();
@@ -558,6 +623,7 @@ conv_gemm_f16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_co
                 const size_t out_off = static_cast<size_t>(row) * p.ldc + static_cast<size_t>(n_tile) * BN + col_begin;
                 // residual prefetch for this warp's whole column range, issued before the accumulator is ready
                 uint4 res[COLS / 8 > 0 ? COLS / 8 : 1];
+                [[maybe_unused]] uint4 res_l[SPLIT ? (COLS / 8 > 0 ? COLS / 8 : 1) : 1];
                 const bool use_res = (p.flags & kEpiResidual) && keep;
                 if (use_res) {
                     size_t res_row = static_cast<size_t>(row);
@@ -574,6 +640,12 @@ conv_gemm_f16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_co
                         p.residual + res_row * p.ld_res + static_cast<size_t>(n_tile) * BN + col_begin);
 #pragma unroll
                     for (int j = 0; j < COLS / 8; ++j) res[j] = __ldg(rp + j);
+                    if constexpr (SPLIT) {
+                        const uint4* rq = reinterpret_cast<const uint4*>(
+                            p.residual + res_row * p.ld_res + p.res_lo + static_cast<size_t>(n_tile) * BN + col_begin);
+#pragma unroll
+                        for (int j = 0; j < COLS / 8; ++j) res_l[j] = __ldg(rq + j);
+                    }
                 }
                 ptx::mbar_wait(&tmem_full[acc], acc_phase);
                 ptx::tc_fence_after();
@@ -627,10 +699,15 @@ conv_gemm_f16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_co
                     if (use_res) {
 #pragma unroll
                         for (int j = 0; j < CH / 8; ++j) {
-                            const uint4 r = res[c0 / 8 + j];
-                            const float2 a = unpack_half2(r.x), b = unpack_half2(r.y), c = unpack_half2(r.z), d = unpack_half2(r.w);
-                            f[8 * j + 0] += a.x; f[8 * j + 1] += a.y; f[8 * j + 2] += b.x; f[8 * j + 3] += b.y;
-                            f[8 * j + 4] += c.x; f[8 * j + 5] += c.y; f[8 * j + 6] += d.x; f[8 * j + 7] += d.y;
+                            if constexpr (SPLIT) {
+                                float r8[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+                                add8(r8, res[c0 / 8 + j]);
+                                add8(r8, res_l[c0 / 8 + j]);
+#pragma unroll
+                                for (int q = 0; q < 8; ++q) f[8 * j + q] += r8[q];
+                            } else {
+                                add8(f + 8 * j, res[c0 / 8 + j]);
+                            }
                         }
                     }
                     if (p.dbg_skip & 1) {
@@ -650,8 +727,19 @@ conv_gemm_f16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_co
                     } else {
                         const bool relu = (p.flags & kEpiRelu) != 0;
                         uint4* op = reinterpret_cast<uint4*>(static_cast<__half*>(p.out) + out_off + c0);
+                        if constexpr (SPLIT) {
+                            uint4* oq = reinterpret_cast<uint4*>(static_cast<__half*>(p.out) + out_off + p.out_lo + c0);
 #pragma unroll
-                        for (int j = 0; j < CH / 8; ++j) op[j] = pack8(f + 8 * j, relu, keep);
+                            for (int j = 0; j < CH / 8; ++j) {
+                                uint4 hi, lo;
+                                split8(f + 8 * j, relu, keep, hi, lo);
+                                op[j] = hi;
+                                oq[j] = lo;
+                            }
+                        } else {
+#pragma unroll
+                            for (int j = 0; j < CH / 8; ++j) op[j] = pack8(f + 8 * j, relu, keep);
+                        }
                     }
                 }
                 // accumulator buffer fully read: hand it back to the MMA warp (one arrive per warp)
@@ -685,6 +773,12 @@ conv_gemm_f16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_co
                 for (int pn = 0; pn < BN / 64; ++pn)
                     ptx::tma_store_2d(&tmap_out, epi_smem + buf * S::kEpiBytes + pn * (kBlockM * 128), n_tile * BN + pn * 64,
                                       out_row_base);
+                if constexpr (SPLIT) {
+#pragma unroll
+                    for (int pn = 0; pn < BN / 64; ++pn)
+                        ptx::tma_store_2d(&tmap_out, epi_smem + buf * S::kEpiBytes + (kPanels + pn) * (kBlockM * 128),
+                                          p.out_lo + n_tile * BN + pn * 64, out_row_base);
+                }
                 ptx::bulk_commit_group();
                 ptx::bulk_wait_read_all();
                 ptx::mbar_arrive(&epi_free[buf]);

@@ -122,11 +122,7 @@ struct Gemm2Smem {
 
 // Tiles: pair tile index pt -> (pm, n_tile); CTA r handles output M tile 2 * pm + r.  p.num_m_tiles may be odd: the
 // phantom tile of the last pair loads zero-filled rows and stores nothing.
-//
-// BRES (experiment, SYLPH_PAIR_BRES): RESIDENT weights -- all 9 * kblocks weight half-tiles are loaded once per CTA into
-// their own slot (BSLOTS == 9 * kblocks, one N tile: res2 / res3 conv2) and never recycled, so the per-tap B refill, its
-// full-barrier wait on fresh data and the per-tap commit disappear from the loop that is bound by instruction issue.
-template <int HALO, int BSLOTS, int BN_ = 256, bool BRES = false>
+template <int HALO, int BSLOTS, int BN_ = 256, bool SPLIT = false>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(320, 1)
 conv3x3_pair_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
                     const GemmArgs p) {
@@ -205,24 +201,15 @@ conv3x3_pair_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
                 const int a_row_base = (p.tile_begin + m_tile) * kBlockM + p.a_row_delta;
                 const int wp = p.segs[p.tile_seg[p.tile_begin + m_seg]].Wp;
                 const int b_row_base = n_tile * BN + static_cast<int>(rank) * S::kBHalf;
-                if constexpr (BRES) {
-                    if (pt == cluster_id) {   // first tile of this pair: weight tile (tap, kb) -> slot tap * kblocks + kb, for good
-                        for (int t = 0; t < 9 * p.kblocks_per_tap; ++t) {
-                            if (rank == 0) ptx::mbar_arrive_expect_tx(&full_bar[t], 2 * S::kBBytes);
-                            ptx::tma_load_2d_pair(smem + S::kRingOffset + t * S::kBBytes, &tmap_b, &full_bar[t],
-                                                  (t % p.kblocks_per_tap) * kBlockK,
-                                                  (t / p.kblocks_per_tap) * p.b_rows_per_tap + b_row_base);
-                        }
-                    }
-                }
                 for (int dyi = 0; dyi < 3; ++dyi) {
                     for (int kb = 0; kb < p.kblocks_per_tap; ++kb) {
                         ptx::mbar_wait(&a_empty[hs], hphase ^ 1u);
                         if (rank == 0) ptx::mbar_arrive_expect_tx(&a_full[hs], 2 * S::kAHaloTx);
-                        ptx::tma_load_2d_pair(smem + hs * S::kAHaloBytes, &tmap_a, &a_full[hs], kb * kBlockK,
+                        int acol = kb * kBlockK;   // SPLIT: [hi | lo] rows against [w_hi | w_hi | w_lo] (see GemmArgs::a_wrap)
+                        if constexpr (SPLIT) { if (acol >= p.a_wrap) acol -= p.a_wrap; }
+                        ptx::tma_load_2d_pair(smem + hs * S::kAHaloBytes, &tmap_a, &a_full[hs], acol,
                                               a_row_base + (dyi - 1) * wp - 1);
                         if (++hs == HALO) { hs = 0; hphase ^= 1u; }
-                        if constexpr (BRES) continue;
                         for (int dxi = 0; dxi < 3; ++dxi) {
                             ptx::mbar_wait(&empty_bar[sb], bphase ^ 1u);
                             if (rank == 0) ptx::mbar_arrive_expect_tx(&full_bar[sb], 2 * S::kBBytes);
@@ -249,17 +236,6 @@ conv3x3_pair_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
                     ptx::mbar_wait(&a_full[hs], hphase);
                     const uint32_t sa = ptx::smem_u32(smem + hs * S::kAHaloBytes);
                     for (int dxi = 0; dxi < 3; ++dxi) {
-                        if constexpr (BRES) {
-                            // g = dyi * kblocks + kb (the producer's order); the slot's only phase (parity 0) completes once
-                            const int t = ((g / p.kblocks_per_tap) * 3 + dxi) * p.kblocks_per_tap + g % p.kblocks_per_tap;
-                            ptx::mbar_wait(&full_bar[t], 0u);
-                            ptx::tc_fence_after();
-                            const uint64_t da = ptx::make_sw128_kmajor_desc(sa + dxi * 128);
-                            const uint64_t db = ptx::make_sw128_kmajor_desc(ptx::smem_u32(smem + S::kRingOffset + t * S::kBBytes));
-                            ptx::umma_f16_pair_x4(d_tmem, da, db, kIdesc, first);
-                            first = 1;
-                            continue;
-                        }
                         ptx::mbar_wait(&full_bar[sb], bphase);
                         ptx::tc_fence_after();
                         const uint64_t da = ptx::make_sw128_kmajor_desc(sa + dxi * 128);
@@ -364,8 +340,19 @@ conv3x3_pair_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
                     } else {
                         const bool relu = (p.flags & kEpiRelu) != 0;
                         uint4* op = reinterpret_cast<uint4*>(static_cast<__half*>(p.out) + out_off + c0);
+                        if constexpr (SPLIT) {
+                            uint4* oq = reinterpret_cast<uint4*>(static_cast<__half*>(p.out) + out_off + p.out_lo + c0);
 #pragma unroll
-                        for (int j = 0; j < CH / 8; ++j) op[j] = pack8(f + 8 * j, relu, keep);
+                            for (int j = 0; j < CH / 8; ++j) {
+                                uint4 hi, lo;
+                                split8(f + 8 * j, relu, keep, hi, lo);
+                                op[j] = hi;
+                                oq[j] = lo;
+                            }
+                        } else {
+#pragma unroll
+                            for (int j = 0; j < CH / 8; ++j) op[j] = pack8(f + 8 * j, relu, keep);
+                        }
                     }
                 }
             }

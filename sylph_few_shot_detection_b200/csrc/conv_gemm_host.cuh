@@ -51,14 +51,16 @@ inline int make_tmap_2d(CUtensorMap* m, const __half* base, uint64_t rows, uint6
 }
 
 // 2-D fp16 matrix [rows][16] (32-byte rows): box = [box_rows][16], 32-byte swizzle -- the stem's space-to-depth input.
-inline int make_tmap_2d_k16(CUtensorMap* m, const __half* base, uint64_t rows, uint32_t box_rows, std::string* err) {
+// `cols` = 32 for the split-operand layout ([16 hi | 16 lo] per row): the box stays 16 wide and starts at column 0 or 16.
+inline int make_tmap_2d_k16(CUtensorMap* m, const __half* base, uint64_t rows, uint32_t box_rows, std::string* err,
+                            uint64_t cols = 16) {
     PFN_tmapEncodeTiled enc = get_tmap_encode();
     if (enc == nullptr) {
         if (err) *err = "cuTensorMapEncodeTiled entry point unavailable";
         return 1;
     }
-    cuuint64_t dims[2] = {16, rows};
-    cuuint64_t strides[1] = {16 * sizeof(__half)};
+    cuuint64_t dims[2] = {cols, rows};
+    cuuint64_t strides[1] = {cols * sizeof(__half)};
     cuuint32_t box[2] = {16, box_rows};
     cuuint32_t estr[2] = {1, 1};
     CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<__half*>(base), dims, strides, box, estr,
@@ -71,16 +73,35 @@ inline int make_tmap_2d_k16(CUtensorMap* m, const __half* base, uint64_t rows, u
     return 0;
 }
 
-template <int BN, int STAGES, int EPI_BUFS, int HALO = 0, bool STEM16 = false, bool BRES = false>
+// cudaFuncSetAttribute(MaxDynamicSharedMemorySize) is per device: one flag per (kernel instantiation, device), so a
+// second context on another GPU of the same process opts in as well.
+struct PerDeviceOnce {
+    bool done[64] = {};
+    template <typename F>
+    cudaError_t run(F&& f) {
+        int dev = 0;
+        cudaError_t e = cudaGetDevice(&dev);
+        if (e != cudaSuccess) return e;
+        if (dev < 0 || dev >= 64) return f();
+        if (done[dev]) return cudaSuccess;
+        e = f();
+        if (e == cudaSuccess) done[dev] = true;
+        return e;
+    }
+};
+
+template <int BN, int STAGES, int EPI_BUFS, int HALO = 0, bool STEM16 = false, bool BRES = false, bool SPLIT = false>
 inline cudaError_t launch_conv_gemm_bn(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tres,
                                        const CUtensorMap& tout, const GemmArgs& args, int num_sms, cudaStream_t stream) {
-    using S = GemmSmem<BN, STAGES, EPI_BUFS, HALO, STEM16, BRES>;
-    static bool configured = false;
-    if (!configured) {
-        cudaError_t e = cudaFuncSetAttribute(conv_gemm_f16_kernel<BN, STAGES, EPI_BUFS, HALO, STEM16, BRES>,
-                                             cudaFuncAttributeMaxDynamicSharedMemorySize, S::kTotal);
+    using S = GemmSmem<BN, STAGES, EPI_BUFS, HALO, STEM16, BRES, SPLIT>;
+    static_assert(S::kTotal <= 227 * 1024, "shared memory of this instantiation exceeds the 227 KB of a CTA");
+    static PerDeviceOnce once;
+    {
+        cudaError_t e = once.run([] {
+            return cudaFuncSetAttribute(conv_gemm_f16_kernel<BN, STAGES, EPI_BUFS, HALO, STEM16, BRES, SPLIT>,
+                                        cudaFuncAttributeMaxDynamicSharedMemorySize, S::kTotal);
+        });
         if (e != cudaSuccess) return e;
-        configured = true;
     }
     const int total = args.num_m_tiles * args.num_n_tiles;
     if (total <= 0) return cudaSuccess;
@@ -92,7 +113,7 @@ inline cudaError_t launch_conv_gemm_bn(const CUtensorMap& ta, const CUtensorMap&
     if (HALO == 0 && !STEM16 && args.num_n_tiles > 1 && ksteps <= STAGES && STAGES % ksteps == 0 && grid == num_sms &&
         grid > 4 * args.num_n_tiles && !(args.dbg_skip & 16))
         grid -= grid % args.num_n_tiles;
-    return launch_k(conv_gemm_f16_kernel<BN, STAGES, EPI_BUFS, HALO, STEM16, BRES>, dim3(grid), dim3(S::kThreads), S::kTotal, stream, ta, tb, tres, tout, args);
+    return launch_k(conv_gemm_f16_kernel<BN, STAGES, EPI_BUFS, HALO, STEM16, BRES, SPLIT>, dim3(grid), dim3(S::kThreads), S::kTotal, stream, ta, tb, tres, tout, args);
 }
 
 constexpr int kStagedTwoBufMaxKSteps = 8;
@@ -100,7 +121,16 @@ constexpr bool kStagedConv1EightSlots = true;   // res2 conv1 (K = 256): 8 ring 
 
 // Direct-epilogue variants: BN in {16, 64, 128, 256}.
 inline cudaError_t launch_conv_gemm(int bn, const CUtensorMap& ta, const CUtensorMap& tb, const GemmArgs& args,
-                                    int num_sms, cudaStream_t stream) {
+                                    int num_sms, cudaStream_t stream, bool split = false) {
+    if (split) {
+        switch (bn) {
+            case 16: return launch_conv_gemm_bn<16, 8, 0, 0, false, false, true>(ta, tb, ta, ta, args, num_sms, stream);
+            case 64: return launch_conv_gemm_bn<64, 8, 0, 0, false, false, true>(ta, tb, ta, ta, args, num_sms, stream);
+            case 128: return launch_conv_gemm_bn<128, 6, 0, 0, false, false, true>(ta, tb, ta, ta, args, num_sms, stream);
+            case 256: return launch_conv_gemm_bn<256, 4, 0, 0, false, false, true>(ta, tb, ta, ta, args, num_sms, stream);
+            default: return cudaErrorInvalidValue;
+        }
+    }
     switch (bn) {
         case 16: return launch_conv_gemm_bn<16, 8, 0>(ta, tb, ta, ta, args, num_sms, stream);
         case 64: return launch_conv_gemm_bn<64, 8, 0>(ta, tb, ta, ta, args, num_sms, stream);
@@ -113,7 +143,16 @@ inline cudaError_t launch_conv_gemm(int bn, const CUtensorMap& ta, const CUtenso
 // 3x3 halo pipeline (taps in the standard (dy, dx) row-major order): `ta` must be a map whose box has kBlockM + 2 rows.
 // <BN, B slots, 0, A halo slots>: 3 x 17 KB + 5 x 32 KB = 211 KB for BN = 256.
 inline cudaError_t launch_conv_gemm_halo(int bn, const CUtensorMap& ta, const CUtensorMap& tb, const GemmArgs& args,
-                                         int num_sms, cudaStream_t stream, bool allow_resident = true) {
+                                         int num_sms, cudaStream_t stream, bool allow_resident = true, bool split = false) {
+    if (split) {
+        switch (bn) {
+            case 16: return launch_conv_gemm_bn<16, 12, 0, 4, false, false, true>(ta, tb, ta, ta, args, num_sms, stream);
+            case 64: return launch_conv_gemm_bn<64, 12, 0, 4, false, false, true>(ta, tb, ta, ta, args, num_sms, stream);
+            case 128: return launch_conv_gemm_bn<128, 8, 0, 4, false, false, true>(ta, tb, ta, ta, args, num_sms, stream);
+            case 256: return launch_conv_gemm_bn<256, 5, 0, 3, false, false, true>(ta, tb, ta, ta, args, num_sms, stream);
+            default: return cudaErrorInvalidValue;
+        }
+    }
     // 64 -> 64 channels (res2 conv2): all nine 8 KB weight tiles stay resident, 8 halo A slots (72 + 136 KB)
     if (allow_resident && bn == 64 && args.kblocks_per_tap == 1 && args.num_n_tiles == 1)
         return launch_conv_gemm_bn<64, 9, 0, 8, false, true>(ta, tb, ta, ta, args, num_sms, stream);
@@ -128,57 +167,36 @@ inline cudaError_t launch_conv_gemm_halo(int bn, const CUtensorMap& ta, const CU
 
 // CTA-pair (cta_group::2) 3x3 halo convolution, N tiles of BN in {64, 128, 256}: `ta` box = kBlockM + 2 rows,
 // `tb` box = BN / 2 rows (each CTA of the pair holds half of the output channels of a B tile).
-template <int BN>
+template <int BN, bool SPLIT = false>
 inline cudaError_t launch_conv3x3_pair_bn(const CUtensorMap& ta, const CUtensorMap& tb, const GemmArgs& args, int num_sms,
                                           cudaStream_t stream) {
     constexpr int kHalo = BN == 256 ? 3 : 6;
     constexpr int kBSlots = BN == 256 ? 8 : 12;
     using S = Gemm2Smem<kHalo, kBSlots, BN>;
-    static bool configured = false;
-    if (!configured) {
-        cudaError_t e = cudaFuncSetAttribute(conv3x3_pair_kernel<kHalo, kBSlots, BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, S::kTotal);
+    static PerDeviceOnce once;
+    {
+        cudaError_t e = once.run([] {
+            return cudaFuncSetAttribute(conv3x3_pair_kernel<kHalo, kBSlots, BN, SPLIT>,
+                                        cudaFuncAttributeMaxDynamicSharedMemorySize, S::kTotal);
+        });
         if (e != cudaSuccess) return e;
-        configured = true;
     }
     const int pairs = ((args.num_m_tiles + 1) / 2) * args.num_n_tiles;
     if (pairs <= 0) return cudaSuccess;
     const int clusters = pairs < num_sms / 2 ? pairs : num_sms / 2;
-    return launch_k(conv3x3_pair_kernel<kHalo, kBSlots, BN>, dim3(clusters * 2), dim3(S::kThreads), S::kTotal, stream, ta, tb, args);
-}
-
-// Resident-weight form of the narrow pair kernel (experiment, SYLPH_PAIR_BRES): BN == Cin == 64 (res2 conv2, 9 slots of
-// 4 KB) or 128 (res3 conv2, 18 slots of 8 KB), one N tile.  Shared memory: 6 x 17 KB + 36 KB = 138 KB / 4 x 17 KB + 144 KB = 212 KB.
-template <int BN>
-inline cudaError_t launch_conv3x3_pair_bres_bn(const CUtensorMap& ta, const CUtensorMap& tb, const GemmArgs& args, int num_sms,
-                                               cudaStream_t stream) {
-    constexpr int kHalo = BN == 64 ? 6 : 4;
-    constexpr int kBSlots = 9 * (BN / kBlockK);
-    using S = Gemm2Smem<kHalo, kBSlots, BN>;
-    static_assert(S::kTotal <= 227 * 1024, "resident weights + A ring must fit the 227 KB of a CTA");
-    if (args.num_n_tiles != 1 || args.taps != 9 || args.kblocks_per_tap * 9 != kBSlots) return cudaErrorInvalidValue;
-    static bool configured = false;
-    if (!configured) {
-        cudaError_t e = cudaFuncSetAttribute(conv3x3_pair_kernel<kHalo, kBSlots, BN, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, S::kTotal);
-        if (e != cudaSuccess) return e;
-        configured = true;
-    }
-    const int pairs = (args.num_m_tiles + 1) / 2;
-    if (pairs <= 0) return cudaSuccess;
-    const int clusters = pairs < num_sms / 2 ? pairs : num_sms / 2;
-    return launch_k(conv3x3_pair_kernel<kHalo, kBSlots, BN, true>, dim3(clusters * 2), dim3(S::kThreads), S::kTotal, stream, ta, tb, args);
-}
-
-inline cudaError_t launch_conv3x3_pair_bres(const CUtensorMap& ta, const CUtensorMap& tb, const GemmArgs& args, int num_sms,
-                                            cudaStream_t stream, int bn) {
-    switch (bn) {
-        case 64: return launch_conv3x3_pair_bres_bn<64>(ta, tb, args, num_sms, stream);
-        case 128: return launch_conv3x3_pair_bres_bn<128>(ta, tb, args, num_sms, stream);
-        default: return cudaErrorInvalidValue;
-    }
+    return launch_k(conv3x3_pair_kernel<kHalo, kBSlots, BN, SPLIT>, dim3(clusters * 2), dim3(S::kThreads), S::kTotal, stream, ta, tb, args);
 }
 
 inline cudaError_t launch_conv3x3_pair(const CUtensorMap& ta, const CUtensorMap& tb, const GemmArgs& args, int num_sms,
-                                       cudaStream_t stream, int bn = 256) {
+                                       cudaStream_t stream, int bn = 256, bool split = false) {
+    if (split) {
+        switch (bn) {
+            case 64: return launch_conv3x3_pair_bn<64, true>(ta, tb, args, num_sms, stream);
+            case 128: return launch_conv3x3_pair_bn<128, true>(ta, tb, args, num_sms, stream);
+            case 256: return launch_conv3x3_pair_bn<256, true>(ta, tb, args, num_sms, stream);
+            default: return cudaErrorInvalidValue;
+        }
+    }
     switch (bn) {
         case 64: return launch_conv3x3_pair_bn<64>(ta, tb, args, num_sms, stream);
         case 128: return launch_conv3x3_pair_bn<128>(ta, tb, args, num_sms, stream);
@@ -192,7 +210,14 @@ inline cudaError_t launch_conv3x3_pair(const CUtensorMap& ta, const CUtensorMap&
 // near 1.3 TB/s of write bandwidth; staging the tile in swizzled shared memory and leaving by TMA writes full lines.
 inline cudaError_t launch_conv_gemm_staged(int bn, const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tres,
                                            const CUtensorMap& tout, const GemmArgs& args, int num_sms,
-                                           cudaStream_t stream, int variant = 0) {
+                                           cudaStream_t stream, int variant = 0, bool split = false) {
+    // Split-operand mode: a staged tile is a hi half and a lo half, so N tiles are at most 128 channels wide
+    // (2 buffers x 64 KB next to a 3-stage ring) and the epilogue moves 4 B per output element either way.
+    if (split) {
+        if (bn == 64) return launch_conv_gemm_bn<64, 6, 2, 0, false, false, true>(ta, tb, tres, tout, args, num_sms, stream);
+        if (bn == 128) return launch_conv_gemm_bn<128, 3, 2, 0, false, false, true>(ta, tb, tres, tout, args, num_sms, stream);
+        return cudaErrorInvalidValue;
+    }
     // BN = 256, variant 1: 2 mainloop stages + 2 staging buffers (the residual of tile i+1 streams in during the
     // epilogue of tile i); variant 2: 3 stages + 1 staging buffer for long K.  0 = pick by the number of k-steps.
     if (bn == 64) {
@@ -214,11 +239,12 @@ inline cudaError_t launch_conv_gemm_staged(int bn, const CUtensorMap& ta, const 
 inline cudaError_t launch_conv1x1_pair_staged(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tres,
                                               const CUtensorMap& tout, const GemmArgs& args, int num_sms, cudaStream_t stream) {
     using S = Pair1x1Smem<3, 2>;
-    static bool configured = false;
-    if (!configured) {
-        cudaError_t e = cudaFuncSetAttribute(conv1x1_pair_staged_kernel<3, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, S::kTotal);
+    static PerDeviceOnce once;
+    {
+        cudaError_t e = once.run([] {
+            return cudaFuncSetAttribute(conv1x1_pair_staged_kernel<3, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, S::kTotal);
+        });
         if (e != cudaSuccess) return e;
-        configured = true;
     }
     if (args.taps != 1) return cudaErrorInvalidValue;
     const int pairs = ((args.num_m_tiles + 1) / 2) * args.num_n_tiles;
@@ -231,7 +257,9 @@ inline cudaError_t launch_conv1x1_pair_staged(const CUtensorMap& ta, const CUten
 // (4 x 8 KB) stay resident in shared memory and 16 A slots keep four output tiles of loads in flight.
 // `ta` from make_tmap_2d_k16 (box kBlockM + 3 rows), `tb` = [4 * 64][64] weights with 64-row boxes.
 inline cudaError_t launch_conv_gemm_stem16(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tout,
-                                           const GemmArgs& args, int num_sms, cudaStream_t stream) {
+                                           const GemmArgs& args, int num_sms, cudaStream_t stream, bool split = false) {
+    // split: 8 resident weight tiles (w_hi, w_lo of the four vertical taps), three A boxes per vertical tap
+    if (split) return launch_conv_gemm_bn<64, 8, 2, 16, true, false, true>(ta, tb, tout, tout, args, num_sms, stream);
     return launch_conv_gemm_bn<64, 4, 2, 16, true>(ta, tb, tout, tout, args, num_sms, stream);
 }
 
@@ -254,6 +282,29 @@ inline uint16_t float_to_half_bits(float f) {
     uint32_t h = base + q;
     if (rem > halfway || (rem == halfway && (h & 1u))) ++h;
     return static_cast<uint16_t>(sign | h);
+}
+
+// fp16 bits -> fp32 (exact), for the lo half of split weights: w_lo = rn16(w - float(w_hi)).
+inline float half_bits_to_float(uint16_t h) {
+    const uint32_t sign = static_cast<uint32_t>(h & 0x8000u) << 16;
+    const uint32_t e = (h >> 10) & 0x1Fu, m = h & 0x3FFu;
+    uint32_t x;
+    if (e == 0) {
+        if (m == 0) { x = sign; }
+        else {   // subnormal half: normalise
+            int sh = 0;
+            uint32_t mm = m;
+            while (!(mm & 0x400u)) { mm <<= 1; ++sh; }
+            x = sign | (static_cast<uint32_t>(127 - 15 - sh + 1) << 23) | ((mm & 0x3FFu) << 13);
+        }
+    } else if (e == 31) {
+        x = sign | 0x7F800000u | (m << 13);
+    } else {
+        x = sign | ((e + 112u) << 23) | (m << 13);
+    }
+    float f;
+    memcpy(&f, &x, 4);
+    return f;
 }
 
 }  // namespace sylph

@@ -27,11 +27,14 @@ struct HostTensor {
     std::vector<float> data;
 };
 
-// A convolution prepared for conv_gemm: weights [taps][cout_pad][k_per_tap] (TF32-rounded), bias [cout_pad].
+// A convolution prepared for conv_gemm: fp16 weights [taps][cout_pad][k_per_tap], fp32 bias [cout_pad].
+// Fast mode: k_per_tap = cin, one fp16 value per weight.  Split-operand (exact) mode: k_per_tap = 3 * cin, every row is
+// [w_hi | w_hi | w_lo] with w_hi = rn16(w), w_lo = rn16(w - w_hi) (conv_gemm.cuh, GemmArgs::a_wrap).
 struct ConvW {
     __half* w = nullptr;
     float* bias = nullptr;
-    int taps = 0, k_per_tap = 0, cout = 0, cout_pad = 0, bn = 0, ksize = 0;
+    int taps = 0, k_per_tap = 0, cin = 0, cout = 0, cout_pad = 0, bn = 0, ksize = 0;
+    int b_rows = 0;   // rows of the weight matrix (taps * cout_pad; the split-mode stem has 2 x 4 tiles)
 };
 
 struct PlaneSet {
@@ -85,18 +88,11 @@ struct sylph_ctx {
     int pair1x1 = 1;          // SYLPH_PAIR1X1=0 keeps the single-CTA staged kernel for every 1x1 convolution; 2 = pair kernel
                               // for every staged 1x1 convolution with 256-channel N tiles and K >= 256 (experiments)
     int stem16 = 1;           // SYLPH_STEM16=0 runs the stem over 64-wide overlapped rows instead of K = 16 taps
-    int lateral_mode = 0;     // SYLPH_LATERAL (experiment): FPN lateral 1x1 convolutions (K = 512..2048 -> 256, today 36 % of the tensor
-                              // peak on the direct-epilogue single-CTA kernel) through 1 = the CTA-pair staged 1x1 kernel, 2 = the
-                              // single-CTA staged kernel; the top-down add then runs as its own kernel
-    int pair_bres = 0;        // SYLPH_PAIR_BRES=1 (experiment): res2 / res3 conv2 (Cin == Cout == 64 / 128) on the CTA-pair kernel with
-                              // RESIDENT weights -- the combination DESIGN.md section 9 lists as untested
-    int l2_persist_mb = 0;    // SYLPH_L2_PERSIST_MB=n (with the image-major trunk schedule): n MB of L2 set aside for persisting lines and
-                              // an access-policy window over the stage output of the chunk in flight (the residual the next block
-                              // re-reads), everything else streaming
-    int trunk_interleave = 0; // SYLPH_TRUNK_INTERLEAVE=k: stem + the first k stages image-major in chunks of trunk_chunk[0] images
-    int trunk_chunk[4] = {0, 0, 0, 0};  // SYLPH_TRUNK_CHUNK="a,b,c,d": images per pass through res2..res5 (0 = whole batch).
-                              // A small chunk keeps a stage's block-to-block activations (35 MB per image in res2) inside the
-                              // 126 MB L2 instead of streaming the whole batch (1.1 GB at 33 images) through HBM per layer.
+    int split = 1;            // precision mode (sylph_set_precision / SYLPH_PRECISION): 1 = "exact", split fp16 operands
+                              // (hi + lo pairs, three tensor-core products per multiply: fp32-level results); 0 = "fast",
+                              // single fp16 operands (10-bit mantissa, 1-2.5e-3 max-norm error on deep activations)
+    int ld(int channels) const { return split ? 2 * channels : channels; }   // row pitch of an activation tensor
+    int lo(int channels) const { return split ? channels : 0; }             // offset of the lo half inside a row
     std::vector<Timing> timings;
 
     // prepared weights
@@ -339,18 +335,28 @@ static int prep_conv(sylph_ctx* c, const std::string& prefix, bool frozen_bn, bo
     }
     out->taps = kh * kw;
     out->ksize = kh;
-    out->k_per_tap = ci;
+    out->cin = ci;
+    out->k_per_tap = c->split ? 3 * ci : ci;
     out->cout = co;
     out->bn = pick_bn(co);
     out->cout_pad = round_up(co, out->bn);
-    std::vector<uint16_t> hw(static_cast<size_t>(out->taps) * out->cout_pad * ci, 0);
+    out->b_rows = out->taps * out->cout_pad;
+    const int kp = out->k_per_tap;
+    std::vector<uint16_t> hw(static_cast<size_t>(out->taps) * out->cout_pad * kp, 0);
     std::vector<float> hb(out->cout_pad, 0.f);
     for (int o = 0; o < co; ++o) {
         hb[o] = shift[o];
         for (int i = 0; i < ci; ++i)
-            for (int t = 0; t < out->taps; ++t)
-                hw[(static_cast<size_t>(t) * out->cout_pad + o) * ci + i] =
-                    float_to_half_bits(w->data[(static_cast<size_t>(o) * ci + i) * out->taps + t] * scale[o]);
+            for (int t = 0; t < out->taps; ++t) {
+                const float v = w->data[(static_cast<size_t>(o) * ci + i) * out->taps + t] * scale[o];
+                const uint16_t hi = float_to_half_bits(v);
+                uint16_t* row = &hw[(static_cast<size_t>(t) * out->cout_pad + o) * kp];
+                row[i] = hi;
+                if (c->split) {
+                    row[ci + i] = hi;
+                    row[2 * ci + i] = float_to_half_bits(v - half_bits_to_float(hi));
+                }
+            }
     }
     TRY(upload_half(c, hw, &out->w));
     TRY(upload(c, hb, &out->bias));
@@ -369,10 +375,14 @@ static int prep_stem(sylph_ctx* c, ConvW* out) {
     out->taps = 4;
     out->ksize = 7;
     out->k_per_tap = 64;
+    out->cin = 64;
     out->cout = co;
     out->bn = pick_bn(co);
     out->cout_pad = round_up(co, out->bn);
-    std::vector<uint16_t> hw(static_cast<size_t>(4) * out->cout_pad * 64, 0);
+    // split mode: tiles 0..3 = w_hi of the four vertical taps, tiles 4..7 = w_lo (conv_gemm.cuh, STEM16)
+    const int n_tiles = c->split ? 8 : 4;
+    out->b_rows = n_tiles * out->cout_pad;
+    std::vector<uint16_t> hw(static_cast<size_t>(n_tiles) * out->cout_pad * 64, 0);
     std::vector<float> hb(out->cout_pad, 0.f);
     for (int o = 0; o < co; ++o) {
         const float s = g->data[o] * (1.0f / std::sqrt(v->data[o] + 1e-5f));
@@ -385,8 +395,12 @@ static int prep_stem(sylph_ctx* c, ConvW* out) {
                         if (ky < 0 || ky > 6 || kx < 0 || kx > 6) continue;
                         for (int ch = 0; ch < 3; ++ch) {
                             const int k = tx * 16 + (dy * 2 + dx) * 3 + ch;
-                            hw[(static_cast<size_t>(ty) * out->cout_pad + o) * 64 + k] =
-                                float_to_half_bits(w->data[((static_cast<size_t>(o) * 3 + ch) * 7 + ky) * 7 + kx] * s);
+                            const float v = w->data[((static_cast<size_t>(o) * 3 + ch) * 7 + ky) * 7 + kx] * s;
+                            const uint16_t hi = float_to_half_bits(v);
+                            hw[(static_cast<size_t>(ty) * out->cout_pad + o) * 64 + k] = hi;
+                            if (c->split)
+                                hw[(static_cast<size_t>(4 + ty) * out->cout_pad + o) * 64 + k] =
+                                    float_to_half_bits(v - half_bits_to_float(hi));
                         }
                     }
     }
@@ -550,7 +564,6 @@ struct ConvCall {
     int stem = 0;
     int up_seg_delta = 0;    // kEpiUpsample: coarser plane = segment of the output tile + this
     int staged = 0;          // TMA-in / TMA-out epilogue (fp16 output, BN = 256); needs out_rows
-    int force_pair1x1 = 0;   // staged 1x1 convolution on the CTA-pair kernel whatever the shape table says (experiments)
     long long out_rows = 0;  // rows of the output (and residual) buffer, for the staged epilogue's tensor maps
     const char* name = "conv";
 };
@@ -559,34 +572,44 @@ static int run_conv(sylph_ctx* c, const ConvCall& k, cudaStream_t st) {
     const ConvW& W = *k.W;
     CUtensorMap ta, tb;
     std::string err;
+    const bool split = c->split != 0;
+    const bool out_f16 = !(k.flags & kEpiOutF32);
+    // Split-operand mode: a_cols / a_ld / ldc / ld_res are PHYSICAL pitches (2C: [C hi | C lo]); the weight matrix has
+    // K' = 3 cin per tap, the A column of a k-block wraps at 2 cin, fp16 outputs and residuals carry a lo half at +C.
+    if (split && !k.stem && (k.a_cols != 2 * W.cin || W.k_per_tap != 3 * W.cin))
+        return c->fail("split-operand convolution %s: A has %d columns, weights K' = %d for cin = %d", k.name, k.a_cols, W.k_per_tap, W.cin);
     const bool halo = c->halo_pipeline && W.taps == 9 && !k.stem && !k.staged;
-    const bool pair_bres = halo && c->pair_bres && (W.bn == 64 || W.bn == 128) && W.k_per_tap == W.bn && W.cout_pad == W.bn &&
-                           !(k.flags & (kEpiResidual | kEpiGnStats | kEpiOutF32));
-    const bool pair = pair_bres || (halo && c->pair_kernel && (W.bn == 256 || ((c->pair_kernel & 2) && W.bn >= 64)) && !(k.flags & kEpiResidual));
-    const bool stem16 = k.stem && c->stem16 && k.staged && W.bn == 64 && W.taps == 4 && k.a_ld == 16;
+    const bool pair = halo && c->pair_kernel && (W.bn == 256 || ((c->pair_kernel & 2) && W.bn >= 64)) && !(k.flags & kEpiResidual);
+    const bool stem16 = k.stem && c->stem16 && k.staged && W.bn == 64 && W.taps == 4 && k.a_ld == (split ? 32 : 16);
+    if (k.stem && split && !stem16) return c->fail("the split-operand stem needs SYLPH_STEM16=1 and the staged epilogue");
     // Staged 1x1 convolutions with 256-channel N tiles: the CTA-pair kernel where it measured faster on the 33-image
     // shapes (profiles/r01_pair1x1_shapes.log): shortcut convolutions (no residual, K >= 256, N >= 512: res4 0.205 ->
     // 0.161 ms) and conv3 with K >= 512 (res5 0.126 -> 0.111 ms); res3 / res4 conv3 and the conv1 layers stay single-CTA
     // (lock-stepped epilogues of the pair cost more than the halved weight traffic buys there).
     const bool has_res = (k.flags & kEpiResidual) != 0;
-    const bool pair1x1 = k.staged && !k.stem && W.taps == 1 && W.bn == 256 && k.n_tiles >= 2 && W.k_per_tap >= 256 &&
-                         (k.force_pair1x1 || c->pair1x1 == 2 || (c->pair1x1 == 1 && (has_res ? W.k_per_tap >= 512 : W.cout_pad >= 512)));
+    const bool pair1x1 = !split && k.staged && !k.stem && W.taps == 1 && W.bn == 256 && k.n_tiles >= 2 && W.k_per_tap >= 256 &&
+                         (c->pair1x1 == 2 || (c->pair1x1 == 1 && (has_res ? W.k_per_tap >= 512 : W.cout_pad >= 512)));
+    // N tile: a staged split tile holds a hi and a lo half, so it is at most 128 channels wide
+    const int bn = (split && k.staged && W.bn == 256) ? 128 : W.bn;
     if (stem16) {
-        if (make_tmap_2d_k16(&ta, k.A, static_cast<uint64_t>(k.a_rows), kBlockM + 3, &err))
+        if (make_tmap_2d_k16(&ta, k.A, static_cast<uint64_t>(k.a_rows), kBlockM + 3, &err, split ? 32 : 16))
             return c->fail("A tensor map (%s): %s", k.name, err.c_str());
     } else if (make_tmap_2d(&ta, k.A, static_cast<uint64_t>(k.a_rows), k.a_cols, k.a_ld, halo ? kBlockM + 2 : kBlockM, &err))
         return c->fail("A tensor map (%s): %s", k.name, err.c_str());
-    if (make_tmap_2d(&tb, k.w_override ? k.w_override : W.w, static_cast<uint64_t>(W.taps) * W.cout_pad, W.k_per_tap,
-                     W.k_per_tap, (pair || pair1x1) ? W.bn / 2 : W.bn, &err))
+    if (make_tmap_2d(&tb, k.w_override ? k.w_override : W.w, static_cast<uint64_t>(W.b_rows), W.k_per_tap,
+                     W.k_per_tap, (pair || pair1x1) ? bn / 2 : bn, &err))
         return c->fail("B tensor map (%s): %s", k.name, err.c_str());
     GemmArgs g{};
     g.tile_begin = k.tile_begin;
     g.num_m_tiles = k.n_tiles;
-    g.num_n_tiles = W.cout_pad / W.bn;
+    g.num_n_tiles = W.cout_pad / bn;
     g.a_row_delta = k.a_row_delta;
     g.taps = W.taps;
     g.kblocks_per_tap = W.k_per_tap / kBlockK;
     g.b_rows_per_tap = W.cout_pad;
+    g.a_wrap = split ? 2 * W.cin : 0;
+    g.out_lo = (split && out_f16) ? k.ldc / 2 : 0;
+    g.res_lo = split ? k.ld_res / 2 : 0;
     for (int t = 0; t < W.taps; ++t) {
         if (k.stem) { g.tap_dy[t] = static_cast<signed char>(t - 2); g.tap_dx[t] = -2; }
         else if (W.taps == 9) { g.tap_dy[t] = static_cast<signed char>(t / 3 - 1); g.tap_dx[t] = static_cast<signed char>(t % 3 - 1); }
@@ -608,13 +631,15 @@ static int run_conv(sylph_ctx* c, const ConvCall& k, cudaStream_t st) {
         cudaEventCreate(&tm.e0);
         cudaEventCreate(&tm.e1);
         const double rows = static_cast<double>(k.n_tiles) * kBlockM;
+        // executed tensor-core work (split mode: three products per multiply) and bytes of the padded planes moved
         tm.flops = 2.0 * rows * W.cout_pad * W.k_per_tap * W.taps;
-        tm.bytes = rows * (static_cast<double>(k.a_ld < k.a_cols ? k.a_ld : k.a_cols) + static_cast<double>(k.ldc < W.cout_pad ? k.ldc : W.cout_pad) *
-                           ((k.flags & kEpiResidual) ? 2.0 : 1.0)) * 2.0;
+        tm.bytes = rows * (static_cast<double>(k.a_ld < k.a_cols ? k.a_ld : k.a_cols) * 2.0 +
+                           static_cast<double>(out_f16 ? k.ldc * 2.0 : std::min(k.ldc, W.cout_pad) * 4.0) +
+                           ((k.flags & kEpiResidual) ? k.ld_res * 2.0 : 0.0));
         cudaEventRecord(tm.e0, st);
     }
     if (k.staged) {
-        if (W.bn < 64 || (k.flags & (kEpiOutF32 | kEpiGnStats)) || k.out_rows <= 0)
+        if (bn < 64 || (k.flags & (kEpiOutF32 | kEpiGnStats)) || k.out_rows <= 0)
             return c->fail("staged epilogue needs BN >= 64, fp16 output and out_rows (%s)", k.name);
         CUtensorMap tres, tout;
         const __half* rsrc = (k.flags & kEpiResidual) ? k.residual : static_cast<const __half*>(k.out);
@@ -622,17 +647,15 @@ static int run_conv(sylph_ctx* c, const ConvCall& k, cudaStream_t st) {
                          (k.flags & kEpiResidual) ? k.ld_res : k.ldc, kBlockM, &err) ||
             make_tmap_2d(&tout, static_cast<const __half*>(k.out), static_cast<uint64_t>(k.out_rows), k.ldc, k.ldc, kBlockM, &err))
             return c->fail("epilogue tensor maps (%s): %s", k.name, err.c_str());
-        if (stem16) CU_TRY(c, launch_conv_gemm_stem16(ta, tb, tout, g, c->num_sms, st));
+        if (stem16) CU_TRY(c, launch_conv_gemm_stem16(ta, tb, tout, g, c->num_sms, st, split));
         else if (pair1x1) CU_TRY(c, launch_conv1x1_pair_staged(ta, tb, tres, tout, g, c->num_sms, st));
-        else CU_TRY(c, launch_conv_gemm_staged(W.bn, ta, tb, tres, tout, g, c->num_sms, st));
-    } else if (pair_bres) {
-        CU_TRY(c, launch_conv3x3_pair_bres(ta, tb, g, c->num_sms, st, W.bn));
+        else CU_TRY(c, launch_conv_gemm_staged(bn, ta, tb, tres, tout, g, c->num_sms, st, 0, split));
     } else if (pair) {
-        CU_TRY(c, launch_conv3x3_pair(ta, tb, g, c->num_sms, st, W.bn));
+        CU_TRY(c, launch_conv3x3_pair(ta, tb, g, c->num_sms, st, bn, split));
     } else if (halo) {
-        CU_TRY(c, launch_conv_gemm_halo(W.bn, ta, tb, g, c->num_sms, st));
+        CU_TRY(c, launch_conv_gemm_halo(bn, ta, tb, g, c->num_sms, st, true, split));
     } else {
-        CU_TRY(c, launch_conv_gemm(W.bn, ta, tb, g, c->num_sms, st));
+        CU_TRY(c, launch_conv_gemm(bn, ta, tb, g, c->num_sms, st, split));
     }
     c->launches++;
     if (c->profiling) {
@@ -670,7 +693,7 @@ struct StageTimer {
 // ================================================================================================== C ABI
 extern "C" {
 
-const char* sylph_version(void) { return "sylph_b200 0.1 (sm_100a, tcgen05 FP16-operand / FP32-accumulate implicit-GEMM)"; }
+const char* sylph_version(void) { return "sylph_b200 0.2 (sm_100a, tcgen05 implicit-GEMM; split-fp16 x3 'exact' and single-fp16 'fast' operands, FP32 accumulate)"; }
 
 int sylph_create(sylph_ctx** out, int device, const sylph_model_config* cfg) {
     if (!out || !cfg) return 1;
@@ -691,22 +714,7 @@ int sylph_create(sylph_ctx** out, int device, const sylph_model_config* cfg) {
     if (const char* e = getenv("SYLPH_STEM16")) c->stem16 = atoi(e);
     if (const char* e = getenv("SYLPH_PAIR1X1")) c->pair1x1 = atoi(e);
     if (const char* e = getenv("SYLPH_FUSE_UPSAMPLE")) c->fuse_upsample = atoi(e);
-    if (const char* e = getenv("SYLPH_TRUNK_INTERLEAVE")) c->trunk_interleave = atoi(e);
-    if (const char* e = getenv("SYLPH_PAIR_BRES")) c->pair_bres = atoi(e);
-    if (const char* e = getenv("SYLPH_LATERAL")) c->lateral_mode = atoi(e);
-    if (const char* e = getenv("SYLPH_L2_PERSIST_MB")) {
-        c->l2_persist_mb = std::max(0, atoi(e));
-        if (c->l2_persist_mb > 0 &&
-            cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, static_cast<size_t>(c->l2_persist_mb) << 20) != cudaSuccess) {
-            cudaGetLastError();
-            c->l2_persist_mb = 0;   // not supported here: run without the window
-        }
-    }
-    if (const char* e = getenv("SYLPH_TRUNK_CHUNK")) {
-        int v[4] = {0, 0, 0, 0};
-        const int got = sscanf(e, "%d,%d,%d,%d", &v[0], &v[1], &v[2], &v[3]);
-        for (int i = 0; i < 4; ++i) c->trunk_chunk[i] = std::max(0, i < got ? v[i] : (got > 0 ? v[got - 1] : 0));
-    }
+    if (const char* e = getenv("SYLPH_PRECISION")) c->split = (strcmp(e, "fast") == 0 || strcmp(e, "0") == 0) ? 0 : 1;
     *out = c;
     if (cfg->pre_nms_topk * 5 > 8192) { c->fail("pre_nms_topk * 5 must be <= 8192"); }
     return 0;
@@ -725,6 +733,15 @@ void sylph_destroy(sylph_ctx* c) {
 }
 
 const char* sylph_last_error(const sylph_ctx* c) { return c ? c->err.c_str() : "null context"; }
+
+int sylph_set_precision(sylph_ctx* c, int exact) {
+    if (!c) return 1;
+    if (c->finalized || !c->bufs.empty()) return c->fail("sylph_set_precision must be called before sylph_finalize_weights");
+    c->split = exact ? 1 : 0;
+    return 0;
+}
+
+int sylph_get_precision(const sylph_ctx* c) { return c ? c->split : -1; }
 
 int sylph_load_tensor(sylph_ctx* c, const char* key, const float* host_data, const int64_t* shape, int ndim) {
     if (!c || !key || !host_data) return 1;
@@ -870,7 +887,7 @@ static int setup_slot(sylph_ctx* c, int slot, int n, int hpad, int wpad, const i
     for (int l = 0; l < 5; ++l) key += ":" + std::to_string(lh[l]) + "x" + std::to_string(lw[l]);
     TRY(make_plane_set(c, key, segs, row, &S.ps));
     void* p;
-    TRY(ensure(c, "pyr" + std::to_string(slot), (static_cast<size_t>(row) + kBlockM) * 256 * 2, key, &p, st, true));
+    TRY(ensure(c, "pyr" + std::to_string(slot), (static_cast<size_t>(row) + kBlockM) * c->ld(256) * 2, key, &p, st, true));
     S.pyr = static_cast<__half*>(p);
     S.valid = true;
     return 0;
@@ -905,7 +922,7 @@ static int run_trunk(sylph_ctx* c, const std::string& key, int n, const void* co
 
     auto buf = [&](const std::string& name, long long rows, int ch, bool zero, __half** out) -> int {
         void* p;
-        TRY(ensure(c, name, (static_cast<size_t>(rows) + kBlockM) * ch * 2, sig, &p, st, zero));
+        TRY(ensure(c, name, (static_cast<size_t>(rows) + kBlockM) * c->ld(ch) * 2, sig, &p, st, zero));
         *out = static_cast<__half*>(p);
         return 0;
     };
@@ -919,26 +936,24 @@ static int run_trunk(sylph_ctx* c, const std::string& key, int n, const void* co
     void* d_desc;
     TRY(ensure(c, bb + "desc", n * sizeof(ImageDesc), "", &d_desc, st, false));
     TRY(stage_h2d(c, d_desc, descs.data(), n * sizeof(ImageDesc), st));
-    const bool image_major = c->trunk_interleave > 0 || c->trunk_chunk[0] > 0 || c->trunk_chunk[1] > 0 || c->trunk_chunk[2] > 0 ||
-                             c->trunk_chunk[3] > 0;
-    if (!image_major) {   // default: every layer over the whole batch
+    {   // every layer over the whole batch
         {
             StageTimer t(c, "prep_stem_input", st, static_cast<double>(n) * (3.0 * hmax * wmax + 32.0 * g0.H * g0.W));
             if (is_u8)
                 CU_TRY(c, launch_k(prep_stem_input_u8_kernel, dim3((g0.W + 255) / 256, std::min(n * g0.H, c->num_sms * 8)), dim3(256), 0, st,
                     static_cast<const ImageDesc*>(d_desc), S0, g0, n, f.pixel_mean[0], f.pixel_mean[1], f.pixel_mean[2],
-                    f.pixel_std[0], f.pixel_std[1], f.pixel_std[2]));
+                    f.pixel_std[0], f.pixel_std[1], f.pixel_std[2], c->split));
             else
                 CU_TRY(c, launch_k(prep_stem_input_kernel, dim3(grid_for(static_cast<long long>(n) * g0.H * g0.W, 256, c->num_sms)), dim3(256), 0, st,
                     static_cast<const ImageDesc*>(d_desc), S0, g0, n, f.pixel_mean[0], f.pixel_mean[1], f.pixel_mean[2],
-                    f.pixel_std[0], f.pixel_std[1], f.pixel_std[2]));
+                    f.pixel_std[0], f.pixel_std[1], f.pixel_std[2], c->split));
             CU_TRY(c, cudaGetLastError());
             c->launches++;
         }
         {   // stem: 7x7/2 conv + FrozenBN + ReLU as a 4-tap GEMM over overlapped 64-float rows
             ConvCall k{};
-            k.W = &c->stem; k.A = S0; k.a_rows = rows0; k.a_cols = 64; k.a_ld = 16; k.ps = ps0.get();
-            k.tile_begin = 0; k.n_tiles = static_cast<int>(rows0 / kBlockM); k.a_row_delta = 0; k.out = S1; k.ldc = 64;
+            k.W = &c->stem; k.A = S0; k.a_rows = rows0; k.a_cols = 64; k.a_ld = c->ld(16); k.ps = ps0.get();
+            k.tile_begin = 0; k.n_tiles = static_cast<int>(rows0 / kBlockM); k.a_row_delta = 0; k.out = S1; k.ldc = c->ld(64);
             k.flags = kEpiRelu | kEpiMask; k.stem = 1; k.name = "stem7x7";
             k.staged = c->staged_epilogue; k.out_rows = rows0;
             TRY(run_conv(c, k, st));
@@ -961,8 +976,8 @@ static int run_trunk(sylph_ctx* c, const std::string& key, int n, const void* co
                 StageTimer t(c, s == 0 ? "maxpool3x3s2" : "subsample2", st,
                              static_cast<double>(n) * g.H * g.W * in_ch * 2 * (s == 0 ? 5.0 : 2.0));
                 const long long work = static_cast<long long>(n) * g.H * g.W * (in_ch / 8);
-                if (s == 0) CU_TRY(c, launch_k(maxpool3x3s2_kernel, dim3(grid_for(work, 256, c->num_sms)), dim3(256), 0, st, S1, IN, g0, g, n, in_ch));
-                else CU_TRY(c, launch_k(subsample2_kernel, dim3(grid_for(work, 256, c->num_sms)), dim3(256), 0, st, X, IN, gs[s - 1], g, n, in_ch));
+                if (s == 0) CU_TRY(c, launch_k(maxpool3x3s2_kernel, dim3(grid_for(work, 256, c->num_sms)), dim3(256), 0, st, S1, IN, g0, g, n, in_ch, c->lo(in_ch)));
+                else CU_TRY(c, launch_k(subsample2_kernel, dim3(grid_for(work * (c->split ? 2 : 1), 256, c->num_sms)), dim3(256), 0, st, X, IN, gs[s - 1], g, n, c->ld(in_ch)));
                 CU_TRY(c, cudaGetLastError());
                 c->launches++;
             }
@@ -975,7 +990,7 @@ static int run_trunk(sylph_ctx* c, const std::string& key, int n, const void* co
                 k.ps = pss[s].get(); k.tile_begin = 0; k.n_tiles = tiles; k.a_row_delta = 0; k.a_rows = rows;
                 if (B.has_sc) {
                     if (b != 0) return c->fail("shortcut conv on a non-first block is not supported");
-                    k.W = &B.sc; k.A = bin; k.a_cols = k.a_ld = bin_ch; k.out = Y; k.ldc = out_ch; k.flags = kEpiMask;
+                    k.W = &B.sc; k.A = bin; k.a_cols = k.a_ld = c->ld(bin_ch); k.out = Y; k.ldc = c->ld(out_ch); k.flags = kEpiMask;
                     k.name = "res.shortcut1x1";
                     k.staged = c->staged_epilogue; k.out_rows = rows;
                     TRY(run_conv(c, k, st));
@@ -984,14 +999,14 @@ static int run_trunk(sylph_ctx* c, const std::string& key, int n, const void* co
                     return c->fail("identity shortcut on the first block of a stage is not supported");
                 }
                 k.residual = nullptr;
-                k.W = &B.c1; k.A = bin; k.a_cols = k.a_ld = bin_ch; k.out = T1; k.ldc = bott;
+                k.W = &B.c1; k.A = bin; k.a_cols = k.a_ld = c->ld(bin_ch); k.out = T1; k.ldc = c->ld(bott);
                 k.flags = kEpiRelu | kEpiMask; k.name = "res.conv1_1x1";
                 k.staged = c->staged_epilogue; k.out_rows = rows;
                 TRY(run_conv(c, k, st));
                 k.staged = 0;
-                k.W = &B.c2; k.A = T1; k.a_cols = k.a_ld = bott; k.out = T2; k.ldc = bott; k.name = "res.conv2_3x3";
+                k.W = &B.c2; k.A = T1; k.a_cols = k.a_ld = c->ld(bott); k.out = T2; k.ldc = c->ld(bott); k.name = "res.conv2_3x3";
                 TRY(run_conv(c, k, st));
-                k.W = &B.c3; k.A = T2; k.a_cols = k.a_ld = bott; k.out = Y; k.ldc = out_ch; k.residual = Y; k.ld_res = out_ch;
+                k.W = &B.c3; k.A = T2; k.a_cols = k.a_ld = c->ld(bott); k.out = Y; k.ldc = c->ld(out_ch); k.residual = Y; k.ld_res = c->ld(out_ch);
                 k.flags = kEpiRelu | kEpiMask | kEpiResidual; k.name = "res.conv3_1x1";
                 k.staged = c->staged_epilogue; k.out_rows = rows;
                 TRY(run_conv(c, k, st));
@@ -999,146 +1014,9 @@ static int run_trunk(sylph_ctx* c, const std::string& key, int n, const void* co
             }
             X = Y;
             x_ch = out_ch;
-            // lateral 1x1 for res3..res5 straight into the pyramid-indexed lateral buffer
         }
         return 0;
     }
-    // Every step below takes an image range [i0, i0 + ni): the planes of an image are whole 128-row tiles and no layer
-    // reads another image's rows, so any order over the images runs the same kernels over the same tiles (bit-identical
-    // results).  SYLPH_TRUNK_CHUNK / SYLPH_TRUNK_INTERLEAVE (experiments, not yet measured) walk a few images at a time
-    // through several layers so that their activations are still in L2 when the next layer reads them.
-    auto shifted = [](PlaneGeom g, int i0) { g.row_base += i0 * g.rows_per_img; return g; };
-    const int tiles_per_img0 = g0.rows_per_img / kBlockM;
-    auto stem_group = [&](int i0, int ni) -> int {
-        {
-            StageTimer t(c, "prep_stem_input", st, static_cast<double>(ni) * (3.0 * hmax * wmax + 32.0 * g0.H * g0.W));
-            const ImageDesc* dd = static_cast<const ImageDesc*>(d_desc) + i0;
-            const PlaneGeom gg = shifted(g0, i0);
-            if (is_u8)
-                CU_TRY(c, launch_k(prep_stem_input_u8_kernel, dim3((g0.W + 255) / 256, std::min(ni * g0.H, c->num_sms * 8)), dim3(256), 0, st,
-                    dd, S0, gg, ni, f.pixel_mean[0], f.pixel_mean[1], f.pixel_mean[2],
-                    f.pixel_std[0], f.pixel_std[1], f.pixel_std[2]));
-            else
-                CU_TRY(c, launch_k(prep_stem_input_kernel, dim3(grid_for(static_cast<long long>(ni) * g0.H * g0.W, 256, c->num_sms)), dim3(256), 0, st,
-                    dd, S0, gg, ni, f.pixel_mean[0], f.pixel_mean[1], f.pixel_mean[2],
-                    f.pixel_std[0], f.pixel_std[1], f.pixel_std[2]));
-            CU_TRY(c, cudaGetLastError());
-            c->launches++;
-        }
-        // stem: 7x7/2 conv + FrozenBN + ReLU as a 4-tap GEMM over overlapped 64-float rows
-        ConvCall k{};
-        k.W = &c->stem; k.A = S0; k.a_rows = rows0; k.a_cols = 64; k.a_ld = 16; k.ps = ps0.get();
-        k.tile_begin = i0 * tiles_per_img0; k.n_tiles = ni * tiles_per_img0; k.a_row_delta = 0; k.out = S1; k.ldc = 64;
-        k.flags = kEpiRelu | kEpiMask; k.stem = 1; k.name = "stem7x7";
-        k.staged = c->staged_epilogue; k.out_rows = rows0;
-        return run_conv(c, k, st);
-    };
-    // ---- res2..res5: buffers of all stages first (allocation may synchronise; the launches below never do)
-    __half *IN[4], *Y[4], *T1[4], *T2[4];
-    for (int s = 0; s < 4; ++s) {
-        const long long rows = static_cast<long long>(n) * gs[s].rows_per_img;
-        const std::string sn = bb + "res" + std::to_string(s + 2);
-        TRY(buf(sn + ".in", rows, s == 0 ? 64 : 128 << s, true, &IN[s]));
-        TRY(buf(sn + ".x", rows, 256 << s, false, &Y[s]));
-        TRY(buf(sn + ".t1", rows, 64 << s, false, &T1[s]));
-        TRY(buf(sn + ".t2", rows, 64 << s, false, &T2[s]));
-    }
-    // input of stage s: 3x3/2 max-pool of the stem output (res2) or the even positions of the previous stage (STRIDE_IN_1X1)
-    auto downsample = [&](int s, int i0, int ni) -> int {
-        const PlaneGeom& g = gs[s];
-        const int in_ch = s == 0 ? 64 : 128 << s;
-        StageTimer t(c, s == 0 ? "maxpool3x3s2" : "subsample2", st,
-                     static_cast<double>(ni) * g.H * g.W * in_ch * 2 * (s == 0 ? 5.0 : 2.0));
-        const long long work = static_cast<long long>(ni) * g.H * g.W * (in_ch / 8);
-        if (s == 0) CU_TRY(c, launch_k(maxpool3x3s2_kernel, dim3(grid_for(work, 256, c->num_sms)), dim3(256), 0, st,
-                                       static_cast<const __half*>(S1), IN[0], shifted(g0, i0), shifted(g, i0), ni, in_ch));
-        else CU_TRY(c, launch_k(subsample2_kernel, dim3(grid_for(work, 256, c->num_sms)), dim3(256), 0, st,
-                                static_cast<const __half*>(Y[s - 1]), IN[s], shifted(gs[s - 1], i0), shifted(g, i0), ni, in_ch));
-        CU_TRY(c, cudaGetLastError());
-        c->launches++;
-        return 0;
-    };
-    // optional L2 access-policy window over the stage output of the chunk in flight (SYLPH_L2_PERSIST_MB)
-    auto set_window = [&](void* base, size_t bytes) {
-        if (c->l2_persist_mb <= 0) return;
-        int max_win = 0;
-        cudaDeviceGetAttribute(&max_win, cudaDevAttrMaxAccessPolicyWindowSize, c->device);
-        cudaStreamAttrValue v{};
-        v.accessPolicyWindow.base_ptr = base;
-        v.accessPolicyWindow.num_bytes = std::min(bytes, static_cast<size_t>(std::max(max_win, 0)));
-        v.accessPolicyWindow.hitRatio = 1.0f;
-        v.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
-        v.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
-        if (cudaStreamSetAttribute(st, cudaStreamAttributeAccessPolicyWindow, &v) != cudaSuccess) cudaGetLastError();
-    };
-    auto stage_blocks = [&](int s, int i0, int ni) -> int {
-        const PlaneGeom& g = gs[s];
-        const long long rows = static_cast<long long>(n) * g.rows_per_img;
-        const int out_ch = 256 << s, bott = 64 << s, in_ch = s == 0 ? 64 : 128 << s;
-        const int tiles_per_img = g.rows_per_img / kBlockM;
-        set_window(Y[s] + static_cast<size_t>(i0) * g.rows_per_img * out_ch, static_cast<size_t>(ni) * g.rows_per_img * out_ch * 2);
-        const auto& blocks = c->stages[s];
-        for (size_t b = 0; b < blocks.size(); ++b) {
-            const sylph_ctx::Block& B = blocks[b];
-            const __half* bin = (b == 0) ? IN[s] : Y[s];
-            const int bin_ch = (b == 0) ? in_ch : out_ch;
-            ConvCall k{};
-            k.ps = pss[s].get(); k.tile_begin = i0 * tiles_per_img; k.n_tiles = ni * tiles_per_img;
-            k.a_row_delta = 0; k.a_rows = rows;
-            if (B.has_sc) {
-                if (b != 0) return c->fail("shortcut conv on a non-first block is not supported");
-                k.W = &B.sc; k.A = bin; k.a_cols = k.a_ld = bin_ch; k.out = Y[s]; k.ldc = out_ch; k.flags = kEpiMask;
-                k.name = "res.shortcut1x1";
-                k.staged = c->staged_epilogue; k.out_rows = rows;
-                TRY(run_conv(c, k, st));
-                k.staged = 0;
-            } else if (b == 0) {
-                return c->fail("identity shortcut on the first block of a stage is not supported");
-            }
-            k.residual = nullptr;
-            k.W = &B.c1; k.A = bin; k.a_cols = k.a_ld = bin_ch; k.out = T1[s]; k.ldc = bott;
-            k.flags = kEpiRelu | kEpiMask; k.name = "res.conv1_1x1";
-            k.staged = c->staged_epilogue; k.out_rows = rows;
-            TRY(run_conv(c, k, st));
-            k.staged = 0;
-            k.W = &B.c2; k.A = T1[s]; k.a_cols = k.a_ld = bott; k.out = T2[s]; k.ldc = bott; k.name = "res.conv2_3x3";
-            TRY(run_conv(c, k, st));
-            k.W = &B.c3; k.A = T2[s]; k.a_cols = k.a_ld = bott; k.out = Y[s]; k.ldc = out_ch; k.residual = Y[s]; k.ld_res = out_ch;
-            k.flags = kEpiRelu | kEpiMask | kEpiResidual; k.name = "res.conv3_1x1";
-            k.staged = c->staged_epilogue; k.out_rows = rows;
-            TRY(run_conv(c, k, st));
-            k.staged = 0;
-        }
-        return 0;
-    };
-    auto chunk_of = [&](int s) { return (c->trunk_chunk[s] > 0 && c->trunk_chunk[s] < n) ? c->trunk_chunk[s] : n; };
-    // front: stem group + the first `front` stages image-major in chunks of trunk_chunk[0] images (0 stages = stem over the batch)
-    const int front = std::max(0, std::min(4, c->trunk_interleave));
-    if (front == 0) {
-        TRY(stem_group(0, n));
-    } else {
-        const int fc = chunk_of(0);
-        for (int i0 = 0; i0 < n; i0 += fc) {
-            const int ni = std::min(fc, n - i0);
-            TRY(stem_group(i0, ni));
-            for (int s = 0; s < front; ++s) {
-                TRY(downsample(s, i0, ni));
-                TRY(stage_blocks(s, i0, ni));
-            }
-        }
-    }
-    // back: each remaining stage over the batch, its blocks in chunks of trunk_chunk[s] images
-    for (int s = front; s < 4; ++s) {
-        TRY(downsample(s, 0, n));
-        const int ch = chunk_of(s);
-        for (int i0 = 0; i0 < n; i0 += ch) TRY(stage_blocks(s, i0, std::min(ch, n - i0)));
-    }
-    if (c->l2_persist_mb > 0) {   // leave the caller's stream as it was found
-        cudaStreamAttrValue v{};
-        v.accessPolicyWindow.num_bytes = 0;
-        if (cudaStreamSetAttribute(st, cudaStreamAttributeAccessPolicyWindow, &v) != cudaSuccess) cudaGetLastError();
-    }
-    return 0;
 }
 
 // FPN + P6/P7 of `n` images of a trunk batch (images first .. first + n - 1) into pyramid slot `slot`.
@@ -1156,7 +1034,7 @@ static int run_fpn(sylph_ctx* c, int slot, const TrunkOut& T, int first, int n, 
     const std::string fb = "fpn" + std::to_string(slot) + ".";
     auto buf = [&](const std::string& name, long long rows, int ch, bool zero, __half** out) -> int {
         void* p;
-        TRY(ensure(c, name, (static_cast<size_t>(rows) + kBlockM) * ch * 2, sig, &p, st, zero));
+        TRY(ensure(c, name, (static_cast<size_t>(rows) + kBlockM) * c->ld(ch) * 2, sig, &p, st, zero));
         *out = static_cast<__half*>(p);
         return 0;
     };
@@ -1164,7 +1042,7 @@ static int run_fpn(sylph_ctx* c, int slot, const TrunkOut& T, int first, int n, 
     __half* LAT;
     {
         void* p;
-        TRY(ensure(c, fb + "lat", (static_cast<size_t>(S.level_row0[5]) + kBlockM) * 256 * 2, sig, &p, st, true));
+        TRY(ensure(c, fb + "lat", (static_cast<size_t>(S.level_row0[5]) + kBlockM) * c->ld(256) * 2, sig, &p, st, true));
         LAT = static_cast<__half*>(p);
     }
     for (int l = 2; l >= 0; --l) {
@@ -1172,20 +1050,17 @@ static int run_fpn(sylph_ctx* c, int slot, const TrunkOut& T, int first, int n, 
         const long long rows = static_cast<long long>(n) * g.rows_per_img;
         __half* XS = static_cast<__half*>(c->bufs["bb." + T.key + ".res" + std::to_string(l + 3) + ".x"].p);
         ConvCall k{};
-        k.W = &c->lat[l]; k.A = XS; k.a_rows = static_cast<long long>(T.n) * g.rows_per_img; k.a_cols = k.a_ld = 512 << l; k.ps = S.ps.get();
+        k.W = &c->lat[l]; k.A = XS; k.a_rows = static_cast<long long>(T.n) * g.rows_per_img; k.a_cols = k.a_ld = c->ld(512 << l); k.ps = S.ps.get();
         k.tile_begin = static_cast<int>(S.level_row0[l] / kBlockM); k.n_tiles = static_cast<int>(rows / kBlockM);
-        k.a_row_delta = -static_cast<int>(S.level_row0[l]) + first * g.rows_per_img; k.out = LAT; k.ldc = 256;
+        k.a_row_delta = -static_cast<int>(S.level_row0[l]) + first * g.rows_per_img; k.out = LAT; k.ldc = c->ld(256);
         k.flags = kEpiMask; k.name = "fpn.lateral1x1";   // direct epilogue: the staged variant measured slower here (K >= 512)
-        const bool fuse_up = c->fuse_upsample && l < 2 && c->lateral_mode == 0;
-        if (c->lateral_mode != 0) {   // experiment: staged (TMA-out) epilogue, CTA pair for mode 1
-            k.staged = 1; k.out_rows = S.level_row0[5]; k.force_pair1x1 = c->lateral_mode == 1;
-        }
+        const bool fuse_up = (c->fuse_upsample || c->split) && l < 2;   // the separate add kernel exists for plain fp16 rows only
         if (fuse_up) {   // top-down add in the lateral convolution's epilogue: + LAT(level l + 1)(y / 2, x / 2), summed in fp32
             k.flags |= kEpiResidual | kEpiUpsample;
-            k.residual = LAT; k.ld_res = 256; k.up_seg_delta = n;
+            k.residual = LAT; k.ld_res = c->ld(256); k.up_seg_delta = n;
         }
         TRY(run_conv(c, k, st));
-        k.flags = kEpiMask; k.residual = nullptr; k.up_seg_delta = 0; k.staged = 0; k.force_pair1x1 = 0;
+        k.flags = kEpiMask; k.residual = nullptr; k.up_seg_delta = 0;
         if (l < 2 && !fuse_up) {
             StageTimer t(c, "fpn.upsample_add", st, static_cast<double>(n) * g.H * g.W * 256 * 2 * 2.25);
             CU_TRY(c, launch_k(upsample_add_kernel, dim3(grid_for(static_cast<long long>(n) * g.H * g.W * 32, 256, c->num_sms)), dim3(256), 0, st, 
@@ -1193,7 +1068,7 @@ static int run_fpn(sylph_ctx* c, int slot, const TrunkOut& T, int first, int n, 
             CU_TRY(c, cudaGetLastError());
             c->launches++;
         }
-        k.W = &c->outc[l]; k.A = LAT; k.a_rows = S.level_row0[5]; k.a_cols = k.a_ld = 256; k.a_row_delta = 0;
+        k.W = &c->outc[l]; k.A = LAT; k.a_rows = S.level_row0[5]; k.a_cols = k.a_ld = c->ld(256); k.a_row_delta = 0;
         k.out = S.pyr; k.name = "fpn.output3x3";
         TRY(run_conv(c, k, st));
     }
@@ -1205,26 +1080,31 @@ static int run_fpn(sylph_ctx* c, int slot, const TrunkOut& T, int first, int n, 
         TRY(buf(fb + "p6tmp", S.level_row0[5], 256, false, &TMP));
         TRY(buf(fb + "p6relu", S.level_row0[5], 256, true, &R6));
         ConvCall k{};
-        k.W = &c->p6; k.A = S.pyr; k.a_rows = S.level_row0[5]; k.a_cols = k.a_ld = 256; k.ps = S.ps.get();
+        k.W = &c->p6; k.A = S.pyr; k.a_rows = S.level_row0[5]; k.a_cols = k.a_ld = c->ld(256); k.ps = S.ps.get();
         k.tile_begin = static_cast<int>(S.level_row0[2] / kBlockM); k.n_tiles = static_cast<int>(rows5 / kBlockM);
-        k.a_row_delta = 0; k.out = TMP; k.ldc = 256; k.flags = kEpiMask; k.name = "fpn.p6_3x3";
+        k.a_row_delta = 0; k.out = TMP; k.ldc = c->ld(256); k.flags = kEpiMask; k.name = "fpn.p6_3x3";
         TRY(run_conv(c, k, st));
         const PlaneGeom& g6 = S.pg.lv[3];
-        CU_TRY(c, launch_k(subsample2_kernel, dim3(grid_for(static_cast<long long>(n) * g6.H * g6.W * 32, 256, c->num_sms)), dim3(256), 0, st, 
-            TMP, S.pyr, g5, g6, n, 256));
+        const int ld = c->ld(256);   // stride-2 gathers copy whole rows: the hi and lo halves travel together
+        CU_TRY(c, launch_k(subsample2_kernel, dim3(grid_for(static_cast<long long>(n) * g6.H * g6.W * (ld / 8), 256, c->num_sms)), dim3(256), 0, st,
+            TMP, S.pyr, g5, g6, n, ld));
         CU_TRY(c, cudaGetLastError());
         const long long rows6 = static_cast<long long>(n) * g6.rows_per_img;
-        CU_TRY(c, launch_k(relu_copy_kernel, dim3(grid_for(rows6 * 32, 256, c->num_sms)), dim3(256), 0, st, 
-            reinterpret_cast<const uint4*>(S.pyr + S.level_row0[3] * 256), reinterpret_cast<uint4*>(R6 + S.level_row0[3] * 256),
-            rows6 * 32));
+        if (c->split)
+            CU_TRY(c, launch_k(relu_copy_split_kernel, dim3(grid_for(rows6 * 32, 256, c->num_sms)), dim3(256), 0, st,
+                static_cast<const __half*>(S.pyr + S.level_row0[3] * ld), R6 + S.level_row0[3] * ld, rows6, 256));
+        else
+            CU_TRY(c, launch_k(relu_copy_kernel, dim3(grid_for(rows6 * 32, 256, c->num_sms)), dim3(256), 0, st,
+                reinterpret_cast<const uint4*>(S.pyr + S.level_row0[3] * 256), reinterpret_cast<uint4*>(R6 + S.level_row0[3] * 256),
+                rows6 * 32));
         CU_TRY(c, cudaGetLastError());
         c->launches += 2;
         k.W = &c->p7; k.A = R6; k.tile_begin = static_cast<int>(S.level_row0[3] / kBlockM);
         k.n_tiles = static_cast<int>(rows6 / kBlockM); k.name = "fpn.p7_3x3";
         TRY(run_conv(c, k, st));
         const PlaneGeom& g7 = S.pg.lv[4];
-        CU_TRY(c, launch_k(subsample2_kernel, dim3(grid_for(static_cast<long long>(n) * g7.H * g7.W * 32, 256, c->num_sms)), dim3(256), 0, st, 
-            TMP, S.pyr, g6, g7, n, 256));
+        CU_TRY(c, launch_k(subsample2_kernel, dim3(grid_for(static_cast<long long>(n) * g7.H * g7.W * (ld / 8), 256, c->num_sms)), dim3(256), 0, st,
+            TMP, S.pyr, g6, g7, n, ld));
         CU_TRY(c, cudaGetLastError());
         c->launches++;
     }
@@ -1246,7 +1126,7 @@ static int conv_gn_relu(sylph_ctx* c, const ConvW& W, const float* gn_w, const f
                         long long a_rows, float* raw, __half* out, const PlaneSet* ps, int tile_begin, int tiles,
                         int seg_begin, int n_segs, float* gn_partial, float* gn_stats, const char* name, cudaStream_t st) {
     ConvCall k{};
-    k.W = &W; k.A = in; k.a_rows = a_rows; k.a_cols = k.a_ld = 256; k.ps = ps; k.tile_begin = tile_begin; k.n_tiles = tiles;
+    k.W = &W; k.A = in; k.a_rows = a_rows; k.a_cols = k.a_ld = c->ld(256); k.ps = ps; k.tile_begin = tile_begin; k.n_tiles = tiles;
     k.a_row_delta = 0; k.out = raw; k.ldc = 256; k.flags = kEpiGnStats | kEpiOutF32; k.gn_partial = gn_partial; k.name = name;
     TRY(run_conv(c, k, st));
     CU_TRY(c, launch_k(gn_finalize_kernel, dim3(n_segs), dim3(256), 0, st, gn_partial, ps->d_segs, seg_begin, n_segs, gn_stats));
@@ -1255,7 +1135,7 @@ static int conv_gn_relu(sylph_ctx* c, const ConvW& W, const float* gn_w, const f
         const long long rows = static_cast<long long>(tiles) * kBlockM;
         StageTimer t(c, "gn_apply_relu", st, static_cast<double>(rows) * 256 * 6);
         CU_TRY(c, launch_k(gn_apply_relu_kernel, dim3(std::max(1, std::min(tiles, c->num_sms * 8))), dim3(256), 0, st,
-            raw, out, gn_stats, gn_w, gn_b, ps->d_tile_seg, ps->d_segs, tile_begin, tiles, 1));
+            raw, out, gn_stats, gn_w, gn_b, ps->d_tile_seg, ps->d_segs, tile_begin, tiles, 1, c->split));
         CU_TRY(c, cudaGetLastError());
     }
     c->launches += 2;
@@ -1384,13 +1264,14 @@ static int run_head(sylph_ctx* c, int slot, const float* codes_dev, int n_classe
     const int n_segs = 5 * S.n;
     // ---- code-conditioned classifier weights
     ConvW CW;
-    CW.taps = 1; CW.ksize = 1; CW.k_per_tap = 256; CW.cout = n_classes; CW.bn = pick_bn(n_classes);
+    CW.taps = 1; CW.ksize = 1; CW.cin = 256; CW.k_per_tap = c->split ? 768 : 256; CW.cout = n_classes; CW.bn = pick_bn(n_classes);
     CW.cout_pad = round_up(n_classes, CW.bn);
+    CW.b_rows = CW.cout_pad;
     void *cw, *cb, *ta, *tb, *rawp, *lg, *pr, *gp, *gs;
-    TRY(ensure(c, "det.code_w", static_cast<size_t>(CW.cout_pad) * 256 * 2, "", &cw, st, false));
+    TRY(ensure(c, "det.code_w", static_cast<size_t>(CW.cout_pad) * CW.k_per_tap * 2, "", &cw, st, false));
     TRY(ensure(c, "det.code_b", static_cast<size_t>(CW.cout_pad) * 4, "", &cb, st, false));
-    TRY(ensure(c, "det.ta", (static_cast<size_t>(rows) + kBlockM) * 256 * 2, "", &ta, st, false));
-    TRY(ensure(c, "det.tb", (static_cast<size_t>(rows) + kBlockM) * 256 * 2, "", &tb, st, false));
+    TRY(ensure(c, "det.ta", (static_cast<size_t>(rows) + kBlockM) * c->ld(256) * 2, "", &ta, st, false));
+    TRY(ensure(c, "det.tb", (static_cast<size_t>(rows) + kBlockM) * c->ld(256) * 2, "", &tb, st, false));
     TRY(ensure(c, "det.raw", (static_cast<size_t>(rows) + kBlockM) * 256 * 4, "", &rawp, st, false));
     TRY(ensure(c, "det.logits", (static_cast<size_t>(rows) + kBlockM) * CW.cout_pad * 4, "", &lg, st, false));
     TRY(ensure(c, "det.pred", (static_cast<size_t>(rows) + kBlockM) * 16 * 4, "", &pr, st, false));
@@ -1417,19 +1298,19 @@ static int run_head(sylph_ctx* c, int slot, const float* codes_dev, int n_classe
     TRY(tower(c->box_tower, c->box_gn_w, c->box_gn_b, "head.bbox_tower3x3", &x));
     {
         ConvCall k{};
-        k.W = &c->pred; k.A = x; k.a_rows = rows; k.a_cols = k.a_ld = 256; k.ps = S.ps.get(); k.tile_begin = 0; k.n_tiles = tiles;
+        k.W = &c->pred; k.A = x; k.a_rows = rows; k.a_cols = k.a_ld = c->ld(256); k.ps = S.ps.get(); k.tile_begin = 0; k.n_tiles = tiles;
         k.a_row_delta = 0; k.out = pr; k.ldc = 16; k.flags = kEpiOutF32; k.name = "head.pred3x3";
         TRY(run_conv(c, k, st));
     }
     TRY(tower(c->cls_tower, c->cls_gn_w, c->cls_gn_b, "head.cls_tower3x3", &x));
     if (codes_ready != nullptr) CU_TRY(c, cudaStreamWaitEvent(st, codes_ready, 0));
     CU_TRY(c, launch_k(pack_code_weights_kernel, dim3(ceil_div(static_cast<long long>(CW.cout_pad) * 256, 256)), dim3(256), 0, st,
-        codes_dev, n_classes, CW.cout_pad, f.generator == 1 ? 1 : f.cg_use_bias, f.generator == 1 ? c->cond_scale : 1.f, CW.w, CW.bias));
+        codes_dev, n_classes, CW.cout_pad, f.generator == 1 ? 1 : f.cg_use_bias, f.generator == 1 ? c->cond_scale : 1.f, CW.w, CW.bias, c->split));
     CU_TRY(c, cudaGetLastError());
     c->launches++;
     {
         ConvCall k{};
-        k.W = &CW; k.A = x; k.a_rows = rows; k.a_cols = k.a_ld = 256; k.ps = S.ps.get(); k.tile_begin = 0; k.n_tiles = tiles;
+        k.W = &CW; k.A = x; k.a_rows = rows; k.a_cols = k.a_ld = c->ld(256); k.ps = S.ps.get(); k.tile_begin = 0; k.n_tiles = tiles;
         k.a_row_delta = 0; k.out = lg; k.ldc = CW.cout_pad; k.flags = kEpiOutF32; k.name = "head.cond_cls1x1";
         TRY(run_conv(c, k, st));
     }
@@ -1516,7 +1397,7 @@ int sylph_import_features(sylph_ctx* c, int slot, int n_images, int padded_h, in
     S.img_w.assign(n_images, padded_w);
     for (int l = 0; l < 5; ++l) {
         const long long work = static_cast<long long>(n_images) * 256 * level_h[l] * level_w[l];
-        CU_TRY(c, launch_k(import_nchw_kernel, dim3(grid_for(work, 256, c->num_sms)), dim3(256), 0, st, level_ptrs_dev[l], S.pyr, S.pg.lv[l], n_images, 256));
+        CU_TRY(c, launch_k(import_nchw_kernel, dim3(grid_for(work, 256, c->num_sms)), dim3(256), 0, st, level_ptrs_dev[l], S.pyr, S.pg.lv[l], n_images, 256, c->lo(256)));
         CU_TRY(c, cudaGetLastError());
         c->launches++;
     }
@@ -1543,7 +1424,7 @@ int sylph_export_features(sylph_ctx* c, int slot, int level, float* out_dev, voi
     const Slot& S = c->slots[slot];
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     const long long work = static_cast<long long>(S.n) * 256 * S.lh[level] * S.lw[level];
-    CU_TRY(c, launch_k(export_nchw_kernel<__half>, dim3(grid_for(work, 256, c->num_sms)), dim3(256), 0, st, S.pyr, out_dev, S.pg.lv[level], S.n, 256, 256, 0, 1.f, 0));
+    CU_TRY(c, launch_k(export_nchw_kernel<__half>, dim3(grid_for(work, 256, c->num_sms)), dim3(256), 0, st, S.pyr, out_dev, S.pg.lv[level], S.n, 256, c->ld(256), 0, 1.f, 0, c->lo(256)));
     CU_TRY(c, cudaGetLastError());
     c->launches++;
     return 0;
@@ -1570,9 +1451,9 @@ int sylph_generate_codes(sylph_ctx* c, int slot, int n_rois, const float* boxes_
     TRY(ensure(c, "cg.boxes", n_rois * 16, "", &pb, st, false));
     TRY(ensure(c, "cg.roi_image", n_rois * 4, "", &pi, st, false));
     TRY(ensure(c, "cg.class_off", (n_classes + 1) * 4, "", &po, st, false));
-    TRY(ensure(c, "cg.r0", (rows + kBlockM) * 256 * 2, "roi", &r0, st, true));
-    TRY(ensure(c, "cg.r1", (rows + kBlockM) * 256 * 2, "roi", &r1, st, true));
-    TRY(ensure(c, "cg.r2", (rows + kBlockM) * 256 * 2, "roi", &r2, st, true));
+    TRY(ensure(c, "cg.r0", (rows + kBlockM) * c->ld(256) * 2, "roi", &r0, st, true));
+    TRY(ensure(c, "cg.r1", (rows + kBlockM) * c->ld(256) * 2, "roi", &r1, st, true));
+    TRY(ensure(c, "cg.r2", (rows + kBlockM) * c->ld(256) * 2, "roi", &r2, st, true));
     TRY(ensure(c, "cg.raw", (rows + kBlockM) * 256 * 4, "roi", &rawp, st, false));
     TRY(ensure(c, "cg.gn_partial", static_cast<size_t>(n_rois) * 64 * 4, "", &gp, st, false));
     TRY(ensure(c, "cg.gn_stats", static_cast<size_t>(n_rois) * 64 * 4, "", &gs, st, false));
@@ -1596,11 +1477,13 @@ int sylph_generate_codes(sylph_ctx* c, int slot, int n_rois, const float* boxes_
     {
         StageTimer t(c, "roi_align", st, static_cast<double>(n_rois) * (50176.0 + 0.5e6));
         CU_TRY(c, launch_k(roi_align_kernel, dim3(n_rois, 7), dim3(256), 0, st, S.pyr, S.pg, static_cast<const float*>(pb), static_cast<const int*>(pi),
-                                                         static_cast<__half*>(r0), reinterpret_cast<long long*>(levels_out_dev)));
+                                                         static_cast<__half*>(r0), reinterpret_cast<long long*>(levels_out_dev), c->split));
         CU_TRY(c, cudaGetLastError());
         c->launches++;
     }
     c->last_n_rois = n_rois;
+    if (f.generator == 1 && c->split)
+        return c->fail("the ROIEncoder generator runs in the fast precision mode only (sylph_set_precision(ctx, 0))");
     if (f.generator == 1)
         return roi_encoder_codes(c, S, n_rois, n_classes, static_cast<const int*>(pi), static_cast<const int*>(po), ps.get(),
                                  static_cast<__half*>(r0), static_cast<__half*>(r1), static_cast<__half*>(r2),
@@ -1616,14 +1499,14 @@ int sylph_generate_codes(sylph_ctx* c, int slot, int n_rois, const float* boxes_
     }
     {
         ConvCall k{};
-        k.W = &c->cg_cls; k.A = cur; k.a_rows = rows; k.a_cols = k.a_ld = 256; k.ps = ps.get(); k.tile_begin = 0;
+        k.W = &c->cg_cls; k.A = cur; k.a_rows = rows; k.a_cols = k.a_ld = c->ld(256); k.ps = ps.get(); k.tile_begin = 0;
         k.n_tiles = n_rois; k.a_row_delta = 0; k.out = raw; k.ldc = 256; k.flags = kEpiOutF32; k.name = "codegen.cls_conv3x3";
         TRY(run_conv(c, k, st));
     }
     {
         StageTimer t(c, "codegen.tail", st, static_cast<double>(n_rois) * 2 * 49 * 256 * 4);
         CU_TRY(c, launch_k(shot_code_kernel, dim3(n_rois), dim3(256), 0, st, raw, cur, c->cg_wbias, c->cg_bbias, f.cg_bias_layer, f.cg_bias_l2_norm,
-                                                 static_cast<float*>(sc)));
+                                                 static_cast<float*>(sc), c->split));
         CU_TRY(c, cudaGetLastError());
         CU_TRY(c, launch_k(class_mean_kernel, dim3(n_classes), dim3(288), 0, st, static_cast<const float*>(sc), static_cast<const int*>(po), codes_out_dev));
         CU_TRY(c, cudaGetLastError());
@@ -1637,7 +1520,7 @@ int sylph_export_roi_features(sylph_ctx* c, float* out_dev, void* stream) {
     if (c->last_n_rois <= 0) return c->fail("no ROI features: call sylph_generate_codes first");
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     CU_TRY(c, launch_k(export_roi_kernel, dim3(grid_for(static_cast<long long>(c->last_n_rois) * 256 * 49, 256, c->num_sms)), dim3(256), 0, st, 
-        static_cast<const __half*>(c->bufs["cg.r0"].p), out_dev, c->last_n_rois));
+        static_cast<const __half*>(c->bufs["cg.r0"].p), out_dev, c->last_n_rois, c->split));
     CU_TRY(c, cudaGetLastError());
     c->launches++;
     return 0;
@@ -1934,7 +1817,7 @@ int sylph_export_head_output(sylph_ctx* c, int which, int level, float* out_dev,
     else if (which == 2) { coff = 4; }
     else { coff = 5; }
     const long long work = static_cast<long long>(S.n) * C * S.lh[level] * S.lw[level];
-    CU_TRY(c, launch_k(export_nchw_kernel<float>, dim3(grid_for(work, 256, c->num_sms)), dim3(256), 0, st, src, out_dev, S.pg.lv[level], S.n, C, cstride, coff, scale, relu));
+    CU_TRY(c, launch_k(export_nchw_kernel<float>, dim3(grid_for(work, 256, c->num_sms)), dim3(256), 0, st, src, out_dev, S.pg.lv[level], S.n, C, cstride, coff, scale, relu, 0));
     CU_TRY(c, cudaGetLastError());
     c->launches++;
     return 0;

@@ -23,8 +23,9 @@ __device__ __forceinline__ int assign_level(float x0, float y0, float x1, float 
     return static_cast<int>(l) - 3;
 }
 
+// `ld` = row pitch, `lo` > 0 = offset of the lo half of a split-operand row (value = hi + lo, exact in fp32)
 __device__ __forceinline__ float bilinear_tap(const __half* __restrict__ feat, const PlaneGeom& g, int n, int H, int W,
-                                              float y, float x, int c) {
+                                              float y, float x, int c, int ld, int lo) {
     if (y < -1.f || y > static_cast<float>(H) || x < -1.f || x > static_cast<float>(W)) return 0.f;
     y = fmaxf(y, 0.f);
     x = fmaxf(x, 0.f);
@@ -32,10 +33,13 @@ __device__ __forceinline__ float bilinear_tap(const __half* __restrict__ feat, c
     if (y_low >= H - 1) { y_high = y_low = H - 1; y = static_cast<float>(y_low); } else { y_high = y_low + 1; }
     if (x_low >= W - 1) { x_high = x_low = W - 1; x = static_cast<float>(x_low); } else { x_high = x_low + 1; }
     const float ly = y - y_low, lx = x - x_low, hy = 1.f - ly, hx = 1.f - lx;
-    const float v1 = __half2float(__ldg(feat + plane_row(g, n, y_low, x_low) * 256 + c));
-    const float v2 = __half2float(__ldg(feat + plane_row(g, n, y_low, x_high) * 256 + c));
-    const float v3 = __half2float(__ldg(feat + plane_row(g, n, y_high, x_low) * 256 + c));
-    const float v4 = __half2float(__ldg(feat + plane_row(g, n, y_high, x_high) * 256 + c));
+    auto tap = [&](int yy, int xx) {
+        const __half* q = feat + plane_row(g, n, yy, xx) * ld + c;
+        float v = __half2float(__ldg(q));
+        if (lo) v += __half2float(__ldg(q + lo));
+        return v;
+    };
+    const float v1 = tap(y_low, x_low), v2 = tap(y_low, x_high), v3 = tap(y_high, x_low), v4 = tap(y_high, x_high);
     return hy * hx * v1 + hy * lx * v2 + ly * hx * v3 + ly * lx * v4;
 }
 
@@ -46,7 +50,8 @@ __device__ __forceinline__ float bilinear_tap(const __half* __restrict__ feat, c
 // reference call site sylph/modeling/code_generator/code_generator.py:930.
 __global__ void __launch_bounds__(256)
 roi_align_kernel(const __half* __restrict__ pyramid, PyramidGeom pg, const float* __restrict__ boxes,
-                 const int* __restrict__ roi_image, __half* __restrict__ roi_planes, long long* __restrict__ levels_out) {
+                 const int* __restrict__ roi_image, __half* __restrict__ roi_planes, long long* __restrict__ levels_out,
+                 int split) {
     ptx::griddep_launch();
     ptx::griddep_wait();
     const int roi = blockIdx.x, ph = blockIdx.y, c = threadIdx.x;
@@ -71,11 +76,18 @@ roi_align_kernel(const __half* __restrict__ pyramid, PyramidGeom pg, const float
             for (int ix = 0; ix < grid_w; ++ix) {
                 const float x = __fadd_rn(__fadd_rn(x0, __fmul_rn(static_cast<float>(pw), bin_w)),
                                           __fdiv_rn(__fmul_rn(static_cast<float>(ix) + 0.5f, bin_w), static_cast<float>(grid_w)));
-                acc += bilinear_tap(pyramid, g, n, g.H, g.W, y, x, c);
+                acc += bilinear_tap(pyramid, g, n, g.H, g.W, y, x, c, split ? 512 : 256, split ? 256 : 0);
             }
         }
         const size_t row = static_cast<size_t>(roi) * 128 + (ph + 1) * 9 + (pw + 1);
-        roi_planes[row * 256 + c] = __float2half_rn(fminf(fmaxf(acc / count, -kHalfMax), kHalfMax));
+        const float v = fminf(fmaxf(acc / count, -kHalfMax), kHalfMax);
+        const __half h = __float2half_rn(v);
+        if (split) {
+            roi_planes[row * 512 + c] = h;
+            roi_planes[row * 512 + 256 + c] = __float2half_rn(v - __half2float(h));
+        } else {
+            roi_planes[row * 256 + c] = h;
+        }
     }
 }
 
@@ -85,7 +97,7 @@ roi_align_kernel(const __half* __restrict__ pyramid, PyramidGeom pg, const float
 __global__ void __launch_bounds__(256)
 shot_code_kernel(const float* __restrict__ cls_raw, const __half* __restrict__ tower_out,
                  const float* __restrict__ w_bias /* [9][256] tap-major */, const float* __restrict__ b_bias,
-                 int has_bias_layer, int bias_l2_norm, float* __restrict__ shot_codes /* [n_rois][257] */) {
+                 int has_bias_layer, int bias_l2_norm, float* __restrict__ shot_codes /* [n_rois][257] */, int split) {
     ptx::griddep_launch();
     ptx::griddep_wait();
     __shared__ float pix[49];
@@ -107,10 +119,14 @@ shot_code_kernel(const float* __restrict__ cls_raw, const __half* __restrict__ t
 #pragma unroll
         for (int tap = 0; tap < 9; ++tap) {
             const int r2 = row + (tap / 3 - 1) * 9 + (tap % 3 - 1);  // zero border supplies the padding
-            const __half* a = tower_out + (base + r2) * 256;
+            const __half* a = tower_out + (base + r2) * (split ? 512 : 256);
             const float* w = w_bias + tap * 256;
 #pragma unroll
-            for (int j = 0; j < 8; ++j) acc += __half2float(a[lane + 32 * j]) * __ldg(w + lane + 32 * j);
+            for (int j = 0; j < 8; ++j) {
+                float av = __half2float(a[lane + 32 * j]);
+                if (split) av += __half2float(a[256 + lane + 32 * j]);
+                acc += av * __ldg(w + lane + 32 * j);
+            }
         }
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
@@ -349,20 +365,28 @@ collect_codes_kernel(ExchangeState* state, const float* local_codes, int max_cla
 // (rows >= n_classes are zero); weights are rounded to fp16 here.
 // `scale` is the learned output scale of CondConvBlock (head_utils.py:121-162, ROIEncoder head):
 // scale * (conv(x, W) + b) = conv(x, scale * W) + scale * b; 1 for CondConvBasic.
+// split mode: rows of [w_hi | w_hi | w_lo] (K' = 768) for the three-product k loop (GemmArgs::a_wrap).
 __global__ void pack_code_weights_kernel(const float* __restrict__ codes, int n_classes, int n_pad, int use_bias, float scale,
-                                         __half* __restrict__ w, float* __restrict__ bias) {
+                                         __half* __restrict__ w, float* __restrict__ bias, int split) {
     ptx::griddep_launch();
     ptx::griddep_wait();
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n_pad * 256) return;
     const int r = i >> 8, c = i & 255;
     const float v = r < n_classes ? codes[static_cast<size_t>(r) * 257 + c] * scale : 0.f;
-    w[i] = __float2half_rn(fminf(fmaxf(v, -kHalfMax), kHalfMax));
+    const __half h = __float2half_rn(fminf(fmaxf(v, -kHalfMax), kHalfMax));
+    if (split) {
+        w[r * 768 + c] = h;
+        w[r * 768 + 256 + c] = h;
+        w[r * 768 + 512 + c] = __float2half_rn(v - __half2float(h));
+    } else {
+        w[i] = h;
+    }
     if (c == 0) bias[r] = (r < n_classes && use_bias) ? codes[static_cast<size_t>(r) * 257 + 256] * scale : 0.f;
 }
 
 // (n_rois, 256, 7, 7) export of the pooled ROI planes (tests / plugin interop).
-__global__ void export_roi_kernel(const __half* __restrict__ roi_planes, float* __restrict__ out, int n_rois) {
+__global__ void export_roi_kernel(const __half* __restrict__ roi_planes, float* __restrict__ out, int n_rois, int split) {
     ptx::griddep_launch();
     ptx::griddep_wait();
     const long long total = static_cast<long long>(n_rois) * 256 * 49;
@@ -371,7 +395,9 @@ __global__ void export_roi_kernel(const __half* __restrict__ roi_planes, float* 
         const int p = static_cast<int>(i % 49);
         const int c = static_cast<int>((i / 49) % 256);
         const int r = static_cast<int>(i / (49 * 256));
-        out[i] = __half2float(roi_planes[(static_cast<size_t>(r) * 128 + (p / 7 + 1) * 9 + (p % 7 + 1)) * 256 + c]);
+        const size_t row = static_cast<size_t>(r) * 128 + (p / 7 + 1) * 9 + (p % 7 + 1);
+        out[i] = split ? __half2float(roi_planes[row * 512 + c]) + __half2float(roi_planes[row * 512 + 256 + c])
+                       : __half2float(roi_planes[row * 256 + c]);
     }
 }
 

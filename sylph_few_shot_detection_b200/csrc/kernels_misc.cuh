@@ -18,6 +18,26 @@ __device__ __forceinline__ size_t plane_row(const PlaneGeom& g, int n, int y, in
            static_cast<size_t>(y + g.pad) * g.Wp + (x + g.pad);
 }
 
+// Split-operand ("exact") storage: a row of C logical channels is [C hi | C lo] fp16 (pitch 2C).  Kernels below take
+// the row pitch `ld` and the offset `lo` of the lo half (0 = plain fp16 rows of the fast mode).
+__device__ __forceinline__ void load8f(const __half* row, int c, int lo, float* v) {
+    const uint4 h = __ldg(reinterpret_cast<const uint4*>(row + c));
+#pragma unroll
+    for (int j = 0; j < 8; ++j) v[j] = 0.f;
+    add8(v, h);
+    if (lo) add8(v, __ldg(reinterpret_cast<const uint4*>(row + lo + c)));   // hi + lo is exact in fp32
+}
+__device__ __forceinline__ void store8f(__half* row, int c, int lo, const float* v, bool relu) {
+    if (lo) {
+        uint4 h, l;
+        split8(v, relu, true, h, l);
+        *reinterpret_cast<uint4*>(row + c) = h;
+        *reinterpret_cast<uint4*>(row + lo + c) = l;
+    } else {
+        *reinterpret_cast<uint4*>(row + c) = pack8(v, relu, true);
+    }
+}
+
 __device__ __forceinline__ uint4 hmax8(uint4 a, uint4 b) {
     uint4 r;
     *reinterpret_cast<__half2*>(&r.x) = __hmax2(*reinterpret_cast<__half2*>(&a.x), *reinterpret_cast<__half2*>(&b.x));
@@ -38,7 +58,7 @@ struct ImageDesc {
 };
 
 __global__ void prep_stem_input_kernel(const ImageDesc* __restrict__ imgs, __half* __restrict__ out, PlaneGeom g,
-                                       int n_images, float m0, float m1, float m2, float s0, float s1, float s2) {
+                                       int n_images, float m0, float m1, float m2, float s0, float s1, float s2, int split) {
     ptx::griddep_launch();
     ptx::griddep_wait();
     const long long total = static_cast<long long>(n_images) * g.H * g.W;
@@ -70,6 +90,12 @@ __global__ void prep_stem_input_kernel(const ImageDesc* __restrict__ imgs, __hal
                 }
             }
         v[12] = v[13] = v[14] = v[15] = 0.f;
+        if (split) {   // rows of [16 hi | 16 lo]
+            __half* row = out + plane_row(g, n, y2, x2) * 32;
+            store8f(row, 0, 16, v, false);
+            store8f(row, 8, 16, v + 8, false);
+            continue;
+        }
         uint4* o = reinterpret_cast<uint4*>(out + plane_row(g, n, y2, x2) * 16);
         o[0] = make_uint4(pack_half2(v[0], v[1]), pack_half2(v[2], v[3]), pack_half2(v[4], v[5]), pack_half2(v[6], v[7]));
         o[1] = make_uint4(pack_half2(v[8], v[9]), pack_half2(v[10], v[11]), 0u, 0u);
@@ -83,16 +109,20 @@ __global__ void prep_stem_input_kernel(const ImageDesc* __restrict__ imgs, __hal
 // grid = (ceil(W2 / 256), rows of work); block = 256.
 __global__ void __launch_bounds__(256)
 prep_stem_input_u8_kernel(const ImageDesc* __restrict__ imgs, __half* __restrict__ out, PlaneGeom g, int n_images,
-                          float m0, float m1, float m2, float s0, float s1, float s2) {
+                          float m0, float m1, float m2, float s0, float s1, float s2, int split) {
     ptx::griddep_launch();
     __shared__ unsigned short lut[3][256];
+    __shared__ unsigned short lut_lo[3][256];   // split mode: rn16(x - hi), x = (v - mean) / std in fp32
     __shared__ __align__(16) unsigned char rows[6][528];   // 512 pixels + up to 3 bytes of misalignment, padded
     {
         const float mean[3] = {m0, m1, m2};
         const float stdv[3] = {s0, s1, s2};
         for (int i = threadIdx.x; i < 768; i += 256) {
             const int c = i >> 8, v = i & 255;
-            lut[c][v] = static_cast<unsigned short>(pack_half2((static_cast<float>(v) - mean[c]) / stdv[c], 0.f) & 0xFFFFu);
+            const float x = (static_cast<float>(v) - mean[c]) / stdv[c];
+            const uint32_t hi = pack_half2(x, 0.f);
+            lut[c][v] = static_cast<unsigned short>(hi & 0xFFFFu);
+            lut_lo[c][v] = static_cast<unsigned short>(pack_half2(x - unpack_half2(hi).x, 0.f) & 0xFFFFu);
         }
     }
     ptx::griddep_wait();
@@ -137,7 +167,7 @@ prep_stem_input_u8_kernel(const ImageDesc* __restrict__ imgs, __half* __restrict
         __syncthreads();
         const int x2 = x0 + threadIdx.x;
         if (x2 < g.W) {
-            unsigned short h[12];
+            unsigned short h[12], l[12];
 #pragma unroll
             for (int dy = 0; dy < 2; ++dy)
 #pragma unroll
@@ -147,13 +177,19 @@ prep_stem_input_u8_kernel(const ImageDesc* __restrict__ imgs, __half* __restrict
 #pragma unroll
                     for (int c = 0; c < 3; ++c) {
                         const int r = c * 2 + dy;
-                        h[(dy * 2 + dx) * 3 + c] = in ? lut[c][rows[r][shift[r] + 2 * threadIdx.x + dx]] : static_cast<unsigned short>(0);
+                        const int px = in ? rows[r][shift[r] + 2 * threadIdx.x + dx] : 0;
+                        h[(dy * 2 + dx) * 3 + c] = in ? lut[c][px] : static_cast<unsigned short>(0);
+                        l[(dy * 2 + dx) * 3 + c] = (in && split) ? lut_lo[c][px] : static_cast<unsigned short>(0);
                     }
                 }
-            uint4* o = reinterpret_cast<uint4*>(out + plane_row(g, n, y2, x2) * 16);
+            uint4* o = reinterpret_cast<uint4*>(out + plane_row(g, n, y2, x2) * (split ? 32 : 16));
             auto pk = [](unsigned short lo, unsigned short hi) { return static_cast<uint32_t>(lo) | (static_cast<uint32_t>(hi) << 16); };
             o[0] = make_uint4(pk(h[0], h[1]), pk(h[2], h[3]), pk(h[4], h[5]), pk(h[6], h[7]));
             o[1] = make_uint4(pk(h[8], h[9]), pk(h[10], h[11]), 0u, 0u);
+            if (split) {
+                o[2] = make_uint4(pk(l[0], l[1]), pk(l[2], l[3]), pk(l[4], l[5]), pk(l[6], l[7]));
+                o[3] = make_uint4(pk(l[8], l[9]), pk(l[10], l[11]), 0u, 0u);
+            }
         }
     }
 }
@@ -161,11 +197,40 @@ prep_stem_input_u8_kernel(const ImageDesc* __restrict__ imgs, __half* __restrict
 // ------------------------------------------------------------------------------------------------ max-pool 3x3 / 2
 // detectron2 BasicStem max_pool2d(kernel 3, stride 2, padding 1) on post-ReLU (>= 0) activations: the zero border of
 // the input plane stands in for the -inf padding.
+// `lo` > 0 (split mode): rows are [C hi | C lo]; the maximum is taken over hi + lo (exact in fp32) and split again.
 __global__ void maxpool3x3s2_kernel(const __half* __restrict__ in, __half* __restrict__ out, PlaneGeom gi, PlaneGeom go,
-                                    int n_images, int C) {
+                                    int n_images, int C, int lo) {
     ptx::griddep_launch();
     ptx::griddep_wait();
     const int c8n = C / 8;
+    if (lo) {
+        const int ld = 2 * C;
+        const long long total = static_cast<long long>(n_images) * go.H * go.W * c8n;
+        for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
+             i += static_cast<long long>(gridDim.x) * blockDim.x) {
+            const int c8 = static_cast<int>(i % c8n);
+            long long r = i / c8n;
+            const int ox = static_cast<int>(r % go.W);
+            r /= go.W;
+            const int oy = static_cast<int>(r % go.H);
+            const int n = static_cast<int>(r / go.H);
+            float m[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+            for (int ky = 0; ky < 3; ++ky)
+#pragma unroll
+                for (int kx = 0; kx < 3; ++kx) {
+                    const int iy = 2 * oy - 1 + ky, ix = 2 * ox - 1 + kx;
+                    if (iy < gi.H + gi.pad && ix < gi.W + gi.pad) {
+                        float v[8];
+                        load8f(in + plane_row(gi, n, iy, ix) * ld, c8 * 8, lo, v);
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) m[j] = fmaxf(m[j], v[j]);
+                    }
+                }
+            store8f(out + plane_row(go, n, oy, ox) * ld, c8 * 8, lo, m, false);
+        }
+        return;
+    }
     const long long total = static_cast<long long>(n_images) * go.H * go.W * c8n;
     for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
          i += static_cast<long long>(gridDim.x) * blockDim.x) {
@@ -244,6 +309,22 @@ __global__ void relu_copy_kernel(const uint4* __restrict__ in, uint4* __restrict
         out[i] = hmax8(__ldg(in + i), z);
 }
 
+// split mode: rows of [C hi | C lo]; relu(hi + lo) keeps both halves where the value is positive
+__global__ void relu_copy_split_kernel(const __half* __restrict__ in, __half* __restrict__ out, long long rows, int C) {
+    ptx::griddep_launch();
+    ptx::griddep_wait();
+    const int c8n = C / 8;
+    const long long total = rows * c8n;
+    for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
+         i += static_cast<long long>(gridDim.x) * blockDim.x) {
+        const int c8 = static_cast<int>(i % c8n);
+        const long long r = i / c8n;
+        float v[8];
+        load8f(in + r * 2 * C, c8 * 8, C, v);
+        store8f(out + r * 2 * C, c8 * 8, C, v, true);
+    }
+}
+
 // ------------------------------------------------------------------------------------------------ GroupNorm(32, 256)
 // Finalize: per (plane, group) reduce the per-tile partial sums the conv epilogue wrote, in double, in a fixed
 // order (deterministic).  stats[(seg * 32 + g) * 2] = mean, [+1] = rstd.   eps = 1e-5 (nn.GroupNorm default).
@@ -286,7 +367,7 @@ gn_finalize_kernel(const float* __restrict__ partial, const Seg* __restrict__ se
 __global__ void __launch_bounds__(256)
 gn_apply_relu_kernel(const float* __restrict__ x, __half* __restrict__ y, const float* __restrict__ stats,
                      const float* __restrict__ gamma, const float* __restrict__ beta, const int* __restrict__ tile_seg,
-                     const Seg* __restrict__ segs, int tile_begin, int n_tiles, int relu) {
+                     const Seg* __restrict__ segs, int tile_begin, int n_tiles, int relu, int split) {
     ptx::griddep_launch();
     const int g = threadIdx.x & 31, w = threadIdx.x >> 5;
     const float4 ga = __ldg(reinterpret_cast<const float4*>(gamma) + 2 * g), gb = __ldg(reinterpret_cast<const float4*>(gamma) + 2 * g + 1);
@@ -301,7 +382,7 @@ gn_apply_relu_kernel(const float* __restrict__ x, __half* __restrict__ y, const 
 #pragma unroll 4
         for (int r = w; r < kBlockM; r += 8) {
             const int row = tile * kBlockM + r;
-            uint4 o = make_uint4(0u, 0u, 0u, 0u);
+            uint4 o = make_uint4(0u, 0u, 0u, 0u), ol = make_uint4(0u, 0u, 0u, 0u);
             if (row_is_interior(sg, row)) {
                 const float4* p = reinterpret_cast<const float4*>(x + static_cast<size_t>(row) * 256) + 2 * g;
                 const float4 a = __ldg(p), b = __ldg(p + 1);
@@ -309,18 +390,25 @@ gn_apply_relu_kernel(const float* __restrict__ x, __half* __restrict__ y, const 
                               (a.z - mean) * rstd * ga.z + ba.z, (a.w - mean) * rstd * ga.w + ba.w,
                               (b.x - mean) * rstd * gb.x + bb.x, (b.y - mean) * rstd * gb.y + bb.y,
                               (b.z - mean) * rstd * gb.z + bb.z, (b.w - mean) * rstd * gb.w + bb.w};
-                o = pack8(v, relu != 0, true);
+                if (split) split8(v, relu != 0, true, o, ol);
+                else o = pack8(v, relu != 0, true);
             }
-            reinterpret_cast<uint4*>(y + static_cast<size_t>(row) * 256)[g] = o;
+            if (split) {   // rows of [256 hi | 256 lo]
+                reinterpret_cast<uint4*>(y + static_cast<size_t>(row) * 512)[g] = o;
+                reinterpret_cast<uint4*>(y + static_cast<size_t>(row) * 512 + 256)[g] = ol;
+            } else {
+                reinterpret_cast<uint4*>(y + static_cast<size_t>(row) * 256)[g] = o;
+            }
         }
     }
 }
 
 // ------------------------------------------------------------------------------------------------ NCHW <-> planes
 // (n, C, H, W) fp32 <-> plane rows; used by the plugin-level import and by tests/exports, not by the episode path.
+// `lo` > 0 (fp16 planes in split mode): the value is plane[.. + c] + plane[.. + lo + c].
 template <typename T>
 __global__ void export_nchw_kernel(const T* __restrict__ plane, float* __restrict__ out, PlaneGeom g, int n_images,
-                                   int C, int cstride, int coff, float scale, int relu) {
+                                   int C, int cstride, int coff, float scale, int relu, int lo) {
     ptx::griddep_launch();
     ptx::griddep_wait();
     const long long total = static_cast<long long>(n_images) * C * g.H * g.W;
@@ -332,14 +420,17 @@ __global__ void export_nchw_kernel(const T* __restrict__ plane, float* __restric
         r /= g.H;
         const int c = static_cast<int>(r % C);
         const int n = static_cast<int>(r / C);
-        float v = static_cast<float>(plane[plane_row(g, n, y, x) * cstride + coff + c]) * scale;
+        const size_t at = plane_row(g, n, y, x) * cstride + coff + c;
+        float v = static_cast<float>(plane[at]);
+        if (lo) v += static_cast<float>(plane[at + lo]);
+        v *= scale;
         if (relu) v = fmaxf(v, 0.f);
         out[i] = v;
     }
 }
 
 __global__ void import_nchw_kernel(const float* __restrict__ in, __half* __restrict__ plane, PlaneGeom g, int n_images,
-                                   int C) {
+                                   int C, int lo) {
     ptx::griddep_launch();
     ptx::griddep_wait();
     const long long total = static_cast<long long>(n_images) * C * g.H * g.W;
@@ -352,7 +443,13 @@ __global__ void import_nchw_kernel(const float* __restrict__ in, __half* __restr
         const int y = static_cast<int>(r % g.H);
         const int n = static_cast<int>(r / g.H);
         const float v = __ldg(in + ((static_cast<size_t>(n) * C + c) * g.H + y) * g.W + x);
-        plane[plane_row(g, n, y, x) * C + c] = __float2half_rn(fminf(fmaxf(v, -kHalfMax), kHalfMax));
+        const __half h = __float2half_rn(fminf(fmaxf(v, -kHalfMax), kHalfMax));
+        if (lo) {   // rows of [C hi | C lo]
+            plane[plane_row(g, n, y, x) * 2 * C + c] = h;
+            plane[plane_row(g, n, y, x) * 2 * C + lo + c] = __float2half_rn(v - __half2float(h));
+        } else {
+            plane[plane_row(g, n, y, x) * C + c] = h;
+        }
     }
 }
 

@@ -25,23 +25,6 @@ static float frand() {
     g_seed = g_seed * 1664525u + 1013904223u;
     return ((g_seed >> 8) & 0xFFFF) / 65536.0f * 2.f - 1.f;
 }
-static float half_bits_to_float(uint16_t h) {
-    const uint32_t sign = (h & 0x8000u) << 16;
-    uint32_t e = (h >> 10) & 0x1F, m = h & 0x3FF, x;
-    if (e == 0) {
-        if (m == 0) x = sign;
-        else {
-            int sh = 0;
-            while (!(m & 0x400)) { m <<= 1; ++sh; }
-            x = sign | ((113 - sh) << 23) | ((m & 0x3FF) << 13);
-        }
-    } else if (e == 31) x = sign | 0x7F800000u | (m << 13);
-    else x = sign | ((e + 112) << 23) | (m << 13);
-    float f;
-    memcpy(&f, &x, 4);
-    return f;
-}
-
 struct Case {
     const char* name;
     int bn;
@@ -57,7 +40,7 @@ struct Case {
     bool bias;
     int skew = 0, base_offset = 0;  // experiment: A box loaded `skew` rows early, descriptor started `skew` rows in
     bool pair = false;    // CTA-pair (cta_group::2) halo kernel
-    bool pair_bres = false; // ... with RESIDENT weights (conv3x3_pair_kernel<.., true>, bn == cin == cout in {64, 128})
+    bool split = false;   // split-operand ("exact") mode: A rows [C hi | C lo], weights [w_hi | w_hi | w_lo], fp16 outputs hi | lo
     bool halo = false;    // 3x3 halo pipeline (one 130-row A box per vertical tap and k-block)
     bool staged = false;  // TMA-in / TMA-out epilogue, run IN PLACE (out == residual buffer) like the bottleneck conv3
     bool pair1x1 = false; // CTA-pair 1x1 convolution with the staged epilogue (conv1x1_pair.cuh)
@@ -70,16 +53,60 @@ static int run_case(const Case& c, int num_sms) {
     if (c.sms_override > 0) num_sms = c.sms_override;
     if (!g_case_filter.empty() && std::string(c.name).find(g_case_filter) == std::string::npos) return 0;
     const int M = c.total_rows;
-    const int Kt = c.kpt * kBlockK;
-    const size_t a_elems = static_cast<size_t>(M) * c.a_ld + 128;
-    std::vector<uint16_t> hA(a_elems), hW(static_cast<size_t>(c.taps) * c.cout * Kt), hR;
+    const int Kt = c.kpt * kBlockK;             // logical K per tap
+    const bool sp = c.split;
+    const int a_ld = sp ? 2 * c.a_ld : c.a_ld;  // physical A pitch: [C hi | C lo] in split mode
+    const int lo_a = sp ? c.a_ld : 0;
+    const int Kp = sp ? 3 * Kt : Kt;            // physical K per tap of the weight rows: [w_hi | w_hi | w_lo]
+    const int ldc = (sp && !(c.flags & kEpiOutF32)) ? 2 * c.cout : c.cout;   // fp16 outputs carry a lo half
+    const int ld_r = sp ? 2 * c.cout : c.cout;
+    const size_t a_elems = static_cast<size_t>(M) * a_ld + 128;
+    const int w_tiles = (sp && c.stem16) ? 2 * c.taps : c.taps;   // split stem: tiles [hi taps | lo taps], K = 64 each
+    const int Kw = c.stem16 ? Kt : Kp;
+    std::vector<uint16_t> hA(a_elems, 0), hW(static_cast<size_t>(w_tiles) * c.cout * Kw, 0), hR;
+    // the values the kernel is expected to multiply: hi (+ lo) of every operand, as doubles
+    std::vector<double> vA(static_cast<size_t>(M) * c.a_ld + 128, 0.0), vW(static_cast<size_t>(c.taps) * c.cout * Kt, 0.0), vR;
     std::vector<float> hB(c.cout);
-    for (auto& v : hA) v = float_to_half_bits(frand());
-    for (auto& v : hW) v = float_to_half_bits(frand() * 0.1f);
+    auto put = [&](float v, uint16_t* hi_dst, uint16_t* lo_dst) -> double {
+        const uint16_t hi = float_to_half_bits(v);
+        *hi_dst = hi;
+        double val = half_bits_to_float(hi);
+        if (lo_dst) {
+            const uint16_t lo = float_to_half_bits(v - half_bits_to_float(hi));
+            *lo_dst = lo;
+            val += half_bits_to_float(lo);
+        }
+        return val;
+    };
+    for (size_t r = 0; r * c.a_ld + c.a_ld <= vA.size(); ++r)
+        for (int k = 0; k < c.a_ld; ++k) {
+            const size_t at = r * a_ld + k;
+            if (at + lo_a >= hA.size()) continue;
+            vA[r * c.a_ld + k] = put(frand() * 1.0003f, &hA[at], sp ? &hA[at + lo_a] : nullptr);
+        }
+    for (int t = 0; t < c.taps; ++t)
+        for (int n = 0; n < c.cout; ++n)
+            for (int k = 0; k < Kt; ++k) {
+                const float v = frand() * 0.10007f;
+                double& val = vW[(static_cast<size_t>(t) * c.cout + n) * Kt + k];
+                if (c.stem16 && sp) {
+                    val = put(v, &hW[(static_cast<size_t>(t) * c.cout + n) * Kt + k], &hW[(static_cast<size_t>(c.taps + t) * c.cout + n) * Kt + k]);
+                } else if (sp) {
+                    uint16_t* row = &hW[(static_cast<size_t>(t) * c.cout + n) * Kp];
+                    val = put(v, &row[k], &row[2 * Kt + k]);
+                    row[Kt + k] = row[k];
+                } else {
+                    val = put(v, &hW[(static_cast<size_t>(t) * c.cout + n) * Kt + k], nullptr);
+                }
+            }
     for (auto& v : hB) v = c.bias ? frand() : 0.f;
     if (c.flags & kEpiResidual) {
-        hR.resize(static_cast<size_t>(M) * c.cout);
-        for (auto& v : hR) v = float_to_half_bits(frand());
+        hR.assign(static_cast<size_t>(M) * ld_r, 0);
+        vR.assign(static_cast<size_t>(M) * c.cout, 0.0);
+        for (int r = 0; r < M; ++r)
+            for (int n = 0; n < c.cout; ++n)
+                vR[static_cast<size_t>(r) * c.cout + n] = put(frand() * 1.0003f, &hR[static_cast<size_t>(r) * ld_r + n],
+                                                              sp ? &hR[static_cast<size_t>(r) * ld_r + c.cout + n] : nullptr);
     }
     std::vector<int> tile_seg(M / 128, 0);
     for (size_t s = 0; s < c.segs.size(); ++s) {
@@ -87,7 +114,7 @@ static int run_case(const Case& c, int num_sms) {
         for (int t = t0; t < t1; ++t) tile_seg[t] = static_cast<int>(s);
     }
     const bool f32out = c.flags & kEpiOutF32;
-    const size_t out_bytes = static_cast<size_t>(M) * c.cout * (f32out ? 4 : 2);
+    const size_t out_bytes = static_cast<size_t>(M) * ldc * (f32out ? 4 : 2);
     __half *dA, *dW, *dR = nullptr;
     float *dB, *dG;
     void* dO;
@@ -113,9 +140,9 @@ static int run_case(const Case& c, int num_sms) {
     const uint64_t a_rows_dim = (c.a_ld < c.cin_cols) ? static_cast<uint64_t>(M) - (c.cin_cols / c.a_ld - 1) : M;
     CUtensorMap ta, tb;
     std::string err;
-    if ((c.stem16 ? make_tmap_2d_k16(&ta, dA, M, 131, &err)
-                  : make_tmap_2d(&ta, dA, a_rows_dim, c.cin_cols, c.a_ld, (c.halo || c.pair) ? 130 : 128, &err)) ||
-        make_tmap_2d(&tb, dW, static_cast<uint64_t>(c.taps) * c.cout, Kt, Kt, (c.pair || c.pair1x1) ? c.bn / 2 : c.bn, &err)) {
+    if ((c.stem16 ? make_tmap_2d_k16(&ta, dA, M, 131, &err, sp ? 32 : 16)
+                  : make_tmap_2d(&ta, dA, a_rows_dim, sp ? 2 * c.cin_cols : c.cin_cols, a_ld, (c.halo || c.pair) ? 130 : 128, &err)) ||
+        make_tmap_2d(&tb, dW, static_cast<uint64_t>(w_tiles) * c.cout, Kw, Kw, (c.pair || c.pair1x1) ? c.bn / 2 : c.bn, &err)) {
         printf("[%s] FAIL tensor map: %s\n", c.name, err.c_str());
         return 1;
     }
@@ -125,14 +152,17 @@ static int run_case(const Case& c, int num_sms) {
     g.num_n_tiles = c.cout / c.bn;
     g.a_row_delta = 0;
     g.taps = c.taps;
-    g.kblocks_per_tap = c.kpt;
+    g.kblocks_per_tap = Kw / kBlockK;
     g.b_rows_per_tap = c.cout;
+    g.a_wrap = sp ? 2 * Kt : 0;
+    g.out_lo = (sp && !f32out) ? c.cout : 0;
+    g.res_lo = sp ? c.cout : 0;
     for (int t = 0; t < c.taps; ++t) { g.tap_dy[t] = c.dys[t]; g.tap_dx[t] = c.dxs[t]; }
     g.bias = c.bias ? dB : nullptr;
     g.residual = dR;
-    g.ld_res = c.cout;
+    g.ld_res = ld_r;
     g.out = dO;
-    g.ldc = c.cout;
+    g.ldc = ldc;
     g.flags = c.flags;
     g.tile_seg = dTS;
     g.segs = dS;
@@ -143,21 +173,19 @@ static int run_case(const Case& c, int num_sms) {
         if (!hR.empty()) CK(cudaMemcpy(dO, hR.data(), hR.size() * 2, cudaMemcpyHostToDevice));  // in place: out starts as the residual
         g.residual = static_cast<const __half*>(dO);
         CUtensorMap tio;
-        if (make_tmap_2d(&tio, static_cast<const __half*>(dO), M, c.cout, c.cout, 128, &err)) {
+        if (make_tmap_2d(&tio, static_cast<const __half*>(dO), M, ldc, ldc, 128, &err)) {
             printf("[%s] FAIL epilogue tensor map: %s\n", c.name, err.c_str());
             return 1;
         }
-        if (c.stem16) CK(launch_conv_gemm_stem16(ta, tb, tio, g, num_sms, 0));
+        if (c.stem16) CK(launch_conv_gemm_stem16(ta, tb, tio, g, num_sms, 0, sp));
         else if (c.pair1x1) CK(launch_conv1x1_pair_staged(ta, tb, tio, tio, g, num_sms, 0));
-        else CK(launch_conv_gemm_staged(c.bn, ta, tb, tio, tio, g, num_sms, 0));
-    } else if (c.pair && c.pair_bres) {
-        CK(launch_conv3x3_pair_bres(ta, tb, g, num_sms, 0, c.bn));
+        else CK(launch_conv_gemm_staged(c.bn, ta, tb, tio, tio, g, num_sms, 0, 0, sp));
     } else if (c.pair) {
-        CK(launch_conv3x3_pair(ta, tb, g, num_sms, 0, c.bn));
+        CK(launch_conv3x3_pair(ta, tb, g, num_sms, 0, c.bn, sp));
     } else if (c.halo) {
-        CK(launch_conv_gemm_halo(c.bn, ta, tb, g, num_sms, 0));
+        CK(launch_conv_gemm_halo(c.bn, ta, tb, g, num_sms, 0, true, sp));
     } else {
-        CK(launch_conv_gemm(c.bn, ta, tb, g, num_sms, 0));
+        CK(launch_conv_gemm(c.bn, ta, tb, g, num_sms, 0, sp));
     }
     cudaError_t e = cudaDeviceSynchronize();
     if (e != cudaSuccess) {
@@ -172,7 +200,9 @@ static int run_case(const Case& c, int num_sms) {
     double max_err = 0, max_ref = 0;
     std::vector<double> gref(hG.size(), 0.0);
     int bad = 0;
-    const double tol = f32out ? 1e-4 : 1.5e-3;
+    // split: what is left is the tensor core's fp32 accumulation (it truncates when it aligns addends: up to ~7e-5 on
+    // K' = 3 x 2304 sums of magnitude 7, measured) and the dropped lo.lo products (2^-22 relative)
+    const double tol = sp ? 1e-4 : (f32out ? 1e-4 : 1.5e-3);
     for (int r = 0; r < M; ++r) {
         const Seg& sg = c.segs[tile_seg[r / 128]];
         int local = r - sg.row0, y = local / sg.Wp, x = local % sg.Wp;
@@ -183,21 +213,21 @@ static int run_case(const Case& c, int num_sms) {
             for (int t = 0; t < c.taps; ++t) {
                 long ar = static_cast<long>(r) + c.dys[t] * sg.Wp + c.dxs[t];
                 if (ar < 0 || ar >= static_cast<long>(a_rows_dim)) continue;
-                const uint16_t* arow = &hA[static_cast<size_t>(ar) * c.a_ld];
-                const uint16_t* wrow = &hW[(static_cast<size_t>(t) * c.cout + n) * Kt];
-                for (int k = 0; k < Kt && k < c.cin_cols; ++k)
-                    acc += static_cast<double>(half_bits_to_float(arow[k])) * half_bits_to_float(wrow[k]);
+                const double* arow = &vA[static_cast<size_t>(ar) * c.a_ld];   // overlapped rows (stem): arow[k] runs into the next rows
+                const double* wrow = &vW[(static_cast<size_t>(t) * c.cout + n) * Kt];
+                for (int k = 0; k < Kt && k < c.cin_cols; ++k) acc += arow[k] * wrow[k];
             }
             if ((c.flags & kEpiGnStats) && interior) {
                 gref[(r / 128) * 64 + (n / 8) * 2] += acc;
                 gref[(r / 128) * 64 + (n / 8) * 2 + 1] += acc * acc;
             }
-            if (c.flags & kEpiResidual) acc += half_bits_to_float(hR[static_cast<size_t>(r) * c.cout + n]);
+            if (c.flags & kEpiResidual) acc += vR[static_cast<size_t>(r) * c.cout + n];
             if (c.flags & kEpiRelu) acc = acc > 0 ? acc : 0;
             if (!keep) acc = 0;
-            const size_t idx = static_cast<size_t>(r) * c.cout + n;
+            const size_t idx = static_cast<size_t>(r) * ldc + n;
             double got = f32out ? reinterpret_cast<const float*>(hO.data())[idx]
                                 : half_bits_to_float(reinterpret_cast<const uint16_t*>(hO.data())[idx]);
+            if (sp && !f32out) got += half_bits_to_float(reinterpret_cast<const uint16_t*>(hO.data())[idx + c.cout]);
             double err2 = fabs(got - acc);
             if (!(err2 == err2)) err2 = 1e30;
             if (err2 > max_err) max_err = err2;
@@ -228,17 +258,22 @@ static Seg mk_seg(int row0, int H, int W, int pad) {
 static int round128(int x) { return (x + 127) / 128 * 128; }
 
 static int g_dbg_skip = 0;
-static void bench_shape(const char* name, int bn, int m_tiles, int cin, int cout, int taps, int flags, int num_sms, int staged = 0, bool halo = false, bool pair = false, bool pair_bres = false) {
+static void bench_shape(const char* name, int bn, int m_tiles, int cin, int cout, int taps, int flags, int num_sms, int staged = 0, bool halo = false, bool pair = false, bool split = false) {
+    // split: `cin` / `cout` stay the LOGICAL channel counts; the buffers hold [C hi | C lo] rows and [w_hi | w_hi | w_lo] weights
     const int M = m_tiles * 128;
     const int osz = (flags & kEpiOutF32) ? 4 : 2;
+    const int cin_l = cin, cout_l = cout;
+    const int ldo = (split && osz == 2) ? 2 * cout : cout;
+    const int kw = split ? 3 * cin : cin;
+    if (split) cin *= 2;   // physical A pitch
     __half *dA, *dW, *dR = nullptr;
     void* dO;
     float *dG, *dB;
     int* dTS;
     Seg* dS;
     CK(cudaMalloc(&dA, static_cast<size_t>(M) * cin * 2));
-    CK(cudaMalloc(&dW, static_cast<size_t>(taps) * cout * cin * 2));
-    CK(cudaMalloc(&dO, static_cast<size_t>(M) * cout * osz));
+    CK(cudaMalloc(&dW, static_cast<size_t>(taps) * cout * kw * 2));
+    CK(cudaMalloc(&dO, static_cast<size_t>(M) * ldo * osz));
     CK(cudaMalloc(&dB, cout * 4));
     CK(cudaMalloc(&dG, static_cast<size_t>(m_tiles) * 64 * 4));
     CK(cudaMalloc(&dTS, m_tiles * 4));
@@ -247,7 +282,7 @@ static void bench_shape(const char* name, int bn, int m_tiles, int cin, int cout
         std::vector<uint16_t> h(static_cast<size_t>(M) * cin);
         for (auto& v : h) v = float_to_half_bits(frand());
         CK(cudaMemcpy(dA, h.data(), h.size() * 2, cudaMemcpyHostToDevice));
-        std::vector<uint16_t> w(static_cast<size_t>(taps) * cout * cin);
+        std::vector<uint16_t> w(static_cast<size_t>(taps) * cout * kw);
         for (auto& v : w) v = float_to_half_bits(frand() * 0.05f);
         CK(cudaMemcpy(dW, w.data(), w.size() * 2, cudaMemcpyHostToDevice));
     }
@@ -256,29 +291,30 @@ static void bench_shape(const char* name, int bn, int m_tiles, int cin, int cout
     Seg s = mk_seg(0, M / 170 - 2, 168, 1);  // p3-like plane width
     CK(cudaMemcpy(dS, &s, sizeof(Seg), cudaMemcpyHostToDevice));
     if (flags & kEpiResidual) {
-        CK(cudaMalloc(&dR, static_cast<size_t>(M) * cout * 2));
-        CK(cudaMemset(dR, 0, static_cast<size_t>(M) * cout * 2));
+        CK(cudaMalloc(&dR, static_cast<size_t>(M) * ldo * 2));
+        CK(cudaMemset(dR, 0, static_cast<size_t>(M) * ldo * 2));
     }
     CUtensorMap ta, tb;
     std::string err;
     const bool pair1x1 = staged == 9;   // CTA-pair 1x1 kernel with the staged epilogue
-    if (make_tmap_2d(&ta, dA, M, cin, cin, (halo || pair) ? 130 : 128, &err) || make_tmap_2d(&tb, dW, static_cast<uint64_t>(taps) * cout, cin, cin, (pair || pair1x1) ? bn / 2 : bn, &err)) {
+    if (make_tmap_2d(&ta, dA, M, cin, cin, (halo || pair) ? 130 : 128, &err) || make_tmap_2d(&tb, dW, static_cast<uint64_t>(taps) * cout, kw, kw, (pair || pair1x1) ? bn / 2 : bn, &err)) {
         printf("[%s] tensor map failed: %s\n", name, err.c_str());
         return;
     }
     GemmArgs g{};
-    g.num_m_tiles = m_tiles; g.num_n_tiles = cout / bn; g.taps = taps; g.kblocks_per_tap = cin / kBlockK; g.b_rows_per_tap = cout;
+    g.num_m_tiles = m_tiles; g.num_n_tiles = cout / bn; g.taps = taps; g.kblocks_per_tap = kw / kBlockK; g.b_rows_per_tap = cout;
+    g.a_wrap = split ? 2 * cin_l : 0; g.out_lo = (split && osz == 2) ? cout_l : 0; g.res_lo = split ? cout_l : 0;
     for (int t = 0; t < taps; ++t) { g.tap_dy[t] = taps == 9 ? (t / 3) - 1 : 0; g.tap_dx[t] = taps == 9 ? (t % 3) - 1 : 0; }
-    g.bias = dB; g.residual = dR; g.ld_res = cout; g.out = dO; g.ldc = cout; g.flags = flags; g.tile_seg = dTS; g.segs = dS; g.gn_partial = dG;
+    g.bias = dB; g.residual = dR; g.ld_res = ldo; g.out = dO; g.ldc = ldo; g.flags = flags; g.tile_seg = dTS; g.segs = dS; g.gn_partial = dG;
     g.dbg_skip = g_dbg_skip;
     cudaEvent_t e0, e1;
     CK(cudaEventCreate(&e0)); CK(cudaEventCreate(&e1));
     CUtensorMap tio = ta;
     if (staged) {
         g.residual = static_cast<const __half*>(dO);
-        if (make_tmap_2d(&tio, static_cast<const __half*>(dO), M, cout, cout, 128, &err)) { printf("tmap failed\n"); return; }
+        if (make_tmap_2d(&tio, static_cast<const __half*>(dO), M, ldo, ldo, 128, &err)) { printf("tmap failed\n"); return; }
     }
-    auto launch = [&]() { return pair1x1 ? launch_conv1x1_pair_staged(ta, tb, tio, tio, g, num_sms, 0) : staged ? launch_conv_gemm_staged(bn, ta, tb, tio, tio, g, num_sms, 0, staged == 100 ? 0 : staged) : (pair ? (pair_bres ? launch_conv3x3_pair_bres(ta, tb, g, num_sms, 0, bn) : launch_conv3x3_pair(ta, tb, g, num_sms, 0, bn)) : (halo ? launch_conv_gemm_halo(bn, ta, tb, g, num_sms, 0) : launch_conv_gemm(bn, ta, tb, g, num_sms, 0))); };
+    auto launch = [&]() { return pair1x1 ? launch_conv1x1_pair_staged(ta, tb, tio, tio, g, num_sms, 0) : staged ? launch_conv_gemm_staged(bn, ta, tb, tio, tio, g, num_sms, 0, staged == 100 ? 0 : staged, split) : (pair ? launch_conv3x3_pair(ta, tb, g, num_sms, 0, bn, split) : (halo ? launch_conv_gemm_halo(bn, ta, tb, g, num_sms, 0, true, split) : launch_conv_gemm(bn, ta, tb, g, num_sms, 0, split))); };
     for (int i = 0; i < 3; ++i) CK(launch());
     CK(cudaDeviceSynchronize());
     const int iters = 10;
@@ -289,8 +325,8 @@ static void bench_shape(const char* name, int bn, int m_tiles, int cin, int cout
     float ms;
     CK(cudaEventElapsedTime(&ms, e0, e1));
     ms /= iters;
-    double flop = 2.0 * M * cout * static_cast<double>(cin) * taps;
-    double bytes = static_cast<double>(M) * cin * 2 + static_cast<double>(M) * cout * (osz + ((flags & kEpiResidual) ? 2 : 0));
+    double flop = 2.0 * M * cout * static_cast<double>(kw) * taps;   // executed (split: three products per multiply)
+    double bytes = static_cast<double>(M) * cin * 2 + static_cast<double>(M) * ldo * (osz + ((flags & kEpiResidual) ? 2 : 0));
     printf("[bench %s] M=%d K=%d N=%d : %.3f ms  %.1f TFLOP/s  %.1f GB/s (algorithmic)\n", name, M, cin * taps, cout, ms,
            flop / ms * 1e-9, bytes / ms * 1e-6);
     cudaFree(dA); cudaFree(dW); cudaFree(dO); cudaFree(dB); cudaFree(dG); cudaFree(dTS); cudaFree(dS);
@@ -325,10 +361,8 @@ int main(int argc, char** argv) {
         const int F = kEpiRelu | kEpiMask;
         bench_shape("res2_conv2_3x3_64_64_HALO_BRES", 64, 17622, 64, 64, 9, F, sms, 0, true);
         bench_shape("res2_conv2_3x3_64_64_PAIR", 64, 17622, 64, 64, 9, F, sms, 0, false, true);
-        bench_shape("res2_conv2_3x3_64_64_PAIR_BRES", 64, 17622, 64, 64, 9, F, sms, 0, false, true, true);
         bench_shape("res3_conv2_3x3_128_128_HALO", 128, 4488, 128, 128, 9, F, sms, 0, true);
         bench_shape("res3_conv2_3x3_128_128_PAIR", 128, 4488, 128, 128, 9, F, sms, 0, false, true);
-        bench_shape("res3_conv2_3x3_128_128_PAIR_BRES", 128, 4488, 128, 128, 9, F, sms, 0, false, true, true);
         bench_shape("res4_conv2_3x3_256_256_PAIR", 256, 1155, 256, 256, 9, F, sms, 0, false, true);
         bench_shape("res5_conv2_3x3_512_512_PAIR", 256, 330, 512, 512, 9, F, sms, 0, false, true);
         bench_shape("tower3x3_256_gn_f32out_PAIR", 256, 1480, 256, 256, 9, kEpiMask | kEpiGnStats | kEpiOutF32, sms, 0, false, true);
@@ -480,15 +514,6 @@ int main(int argc, char** argv) {
         c.pair = true;
         printf("bn=%d ", bnv);
         fails += run_case(c, sms);
-        Case r = c;                      // the same problem on the resident-weight variant (experiment, SYLPH_PAIR_BRES)
-        r.name = "PAIR_BRES_conv3x3_narrow_mask_relu";
-        r.pair_bres = true;
-        printf("bn=%d ", bnv);
-        fails += run_case(r, sms);
-        r.name = "PAIR_BRES_conv3x3_narrow_many_tiles_per_cluster";
-        r.sms_override = 4;              // two clusters: every pair walks many tiles with the weights loaded once
-        printf("bn=%d ", bnv);
-        fails += run_case(r, sms);
     }
     {   // CTA pair + GroupNorm statistics + fp32 output (the tower configuration)
         Seg s0 = mk_seg(0, 13, 21, 1);
@@ -556,7 +581,91 @@ int main(int argc, char** argv) {
         c.pair1x1 = true;
         fails += run_case(c, sms);
     }
+    // ---------------------------------------------------------------- split-operand ("exact") mode of every kernel family
+    {   // generic pipeline, direct epilogue: fp16 hi | lo output + residual, and fp32 output
+        Case c{"SPLIT_gemm_bn256_n1024_res", 256, {mk_seg(0, 1, 638, 1)}, 128 * 3, 128, 128, 1024, 1, 2, z1, z1, kEpiRelu | kEpiResidual, true};
+        c.segs[0].nrows = c.total_rows;
+        c.split = true;
+        fails += run_case(c, sms);
+        Case d{"SPLIT_gemm_bn64_k256_f32out", 64, {mk_seg(0, 1, 638, 1)}, 128 * 37, 256, 256, 64, 1, 4, z1, z1, kEpiOutF32, true};
+        d.segs[0].nrows = d.total_rows;
+        d.split = true;
+        fails += run_case(d, sms);
+    }
+    for (int bnv : {64, 128}) {   // staged epilogue, in place, residual, many tiles per CTA, several N tiles
+        Seg s0 = mk_seg(0, 150, 168, 1);
+        Case c{"SPLIT_staged_inplace_res_relu_mask", bnv, {s0}, round128(s0.nrows), 128, 128, bnv * 4, 1, 2, z1, z1, kEpiRelu | kEpiResidual | kEpiMask, true};
+        c.staged = true;
+        c.split = true;
+        printf("bn=%d ", bnv);
+        fails += run_case(c, sms);
+        Case d{"SPLIT_staged_noresidual_k256", bnv, {s0}, round128(s0.nrows), 256, 256, bnv, 1, 4, z1, z1, kEpiRelu | kEpiMask, true};
+        d.staged = true;
+        d.split = true;
+        printf("bn=%d ", bnv);
+        fails += run_case(d, sms);
+    }
+    for (int bnv : {256, 128, 64, 16}) {   // halo pipeline
+        Seg s0 = mk_seg(0, 70, 84, 1);
+        Seg s1 = mk_seg(round128(s0.nrows), 37, 41, 1);
+        int total = s1.row0 + round128(s1.nrows);
+        const int cout = bnv == 16 ? 16 : (bnv == 256 ? 512 : bnv);
+        Case c{"SPLIT_HALO_conv3x3", bnv, {s0, s1}, total, 128, 128, cout, 9, 2, dy9, dx9,
+               kEpiMask | (bnv == 256 ? 0 : kEpiRelu) | (bnv == 16 ? kEpiOutF32 : 0), true};
+        c.halo = true;
+        c.split = true;
+        printf("bn=%d ", bnv);
+        fails += run_case(c, sms);
+    }
+    {   // CTA pair: fp16 hi | lo output (odd tile count) and the tower configuration (GN statistics, fp32 output)
+        Seg s0 = mk_seg(0, 70, 84, 1);
+        Seg s1 = mk_seg(round128(s0.nrows), 37, 41, 1);
+        int total = s1.row0 + round128(s1.nrows);
+        if ((total / 128) % 2 == 0) total += 128;
+        Case c{"SPLIT_PAIR_conv3x3_n512_mask_relu", 256, {s0, s1}, total, 128, 128, 512, 9, 2, dy9, dx9, kEpiMask | kEpiRelu, true};
+        c.pair = true;
+        c.split = true;
+        fails += run_case(c, sms);
+        Seg t0 = mk_seg(0, 13, 21, 1);
+        Seg t1 = mk_seg(round128(t0.nrows), 7, 11, 1);
+        Case d{"SPLIT_PAIR_conv3x3_bn256_mask_gn_f32out", 256, {t0, t1}, t1.row0 + round128(t1.nrows), 256, 256, 256, 9, 4, dy9, dx9, kEpiMask | kEpiGnStats | kEpiOutF32, true};
+        d.pair = true;
+        d.split = true;
+        fails += run_case(d, sms);
+    }
+    {   // stem: [16 hi | 16 lo] rows, eight resident weight tiles, three A boxes per vertical tap
+        Seg s0 = mk_seg(0, 150, 170, 2);
+        Seg s1 = mk_seg(round128(s0.nrows), 37, 45, 2);
+        Case c{"SPLIT_STEM16", 64, {s0, s1}, s1.row0 + round128(s1.nrows), 64, 16, 64, 4, 1, dy4, dx4, kEpiMask | kEpiRelu, true};
+        c.staged = true;
+        c.stem16 = true;
+        c.split = true;
+        fails += run_case(c, sms);
+    }
     printf("correctness: %d failing case(s)\n", fails);
+    if (argc > 1 && std::string(argv[1]) == "split") {
+        // fast against split-operand mode on the shapes of a 33-image trunk pass and an 8-image head pass
+        const int RES = kEpiResidual | kEpiRelu | kEpiMask, C1 = kEpiRelu | kEpiMask, SC = kEpiMask;
+        for (int sp = 0; sp < 2; ++sp) {
+            printf("---- %s\n", sp ? "split fp16 x3 (exact)" : "single fp16 (fast)");
+            const bool b = sp != 0;
+            bench_shape("res2_conv1_1x1_256_64_STAGED", 64, 17622, 256, 64, 1, C1, sms, 100, false, false, b);
+            bench_shape("res2_conv2_3x3_64_64_HALO", 64, 17622, 64, 64, 9, C1, sms, 0, true, false, b);
+            bench_shape("res2_conv3_1x1_64_256_res_STAGED", b ? 128 : 256, 17622, 64, 256, 1, RES, sms, 100, false, false, b);
+            bench_shape("res3_conv1_1x1_512_128_STAGED", 128, 4488, 512, 128, 1, C1, sms, 100, false, false, b);
+            bench_shape("res3_conv2_3x3_128_128_HALO", 128, 4488, 128, 128, 9, C1, sms, 0, true, false, b);
+            bench_shape("res3_conv3_1x1_128_512_res_STAGED", b ? 128 : 256, 4488, 128, 512, 1, RES, sms, 100, false, false, b);
+            bench_shape("res3_shortcut_1x1_256_512_STAGED", b ? 128 : 256, 4488, 256, 512, 1, SC, sms, 100, false, false, b);
+            bench_shape("res4_conv1_1x1_1024_256_STAGED", b ? 128 : 256, 1155, 1024, 256, 1, C1, sms, 100, false, false, b);
+            bench_shape("res4_conv2_3x3_256_256_PAIR", 256, 1155, 256, 256, 9, C1, sms, 0, false, true, b);
+            bench_shape("res4_conv3_1x1_256_1024_res_STAGED", b ? 128 : 256, 1155, 256, 1024, 1, RES, sms, 100, false, false, b);
+            bench_shape("res5_conv2_3x3_512_512_PAIR", 256, 330, 512, 512, 9, C1, sms, 0, false, true, b);
+            bench_shape("res5_conv3_1x1_512_2048_res_STAGED", b ? 128 : 256, 330, 512, 2048, 1, RES, sms, 100, false, false, b);
+            bench_shape("tower3x3_256_gn_f32out_PAIR", 256, 1480, 256, 256, 9, kEpiMask | kEpiGnStats | kEpiOutF32, sms, 0, false, true, b);
+            bench_shape("fpn_lateral3_1x1_512_256", 256, 4488, 512, 256, 1, SC, sms, 0, false, false, b);
+        }
+        return 0;
+    }
     if (argc > 1 && std::string(argv[1]) == "bench") {
         bench_shape("tower3x3_256_gn_f32out", 256, 1480, 256, 256, 9, kEpiMask | kEpiGnStats | kEpiOutF32, sms);
         bench_shape("tower3x3_256_plain", 256, 1480, 256, 256, 9, 0, sms);

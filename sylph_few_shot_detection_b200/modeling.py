@@ -370,6 +370,9 @@ class MetaOneStageDetector(nn.Module):
         self.in_features = cfg.MODEL.FCOS.IN_FEATURES
         self._state: Dict[str, torch.Tensor] = {}
         self._engine: Optional[Engine] = None
+        # operand precision of the engine built by load_state_dict: None = $SYLPH_PRECISION, else "exact"
+        # (runtime.Engine); assign "fast" before loading the weights to trade the fp32-level agreement for speed
+        self.precision: Optional[str] = None
         self.eval()
 
     # ------------------------------------------------------------------ weights: reference key layout (Appendix C)
@@ -385,7 +388,7 @@ class MetaOneStageDetector(nn.Module):
         self._state = {k: state_dict[k].detach().cpu().float() for k in spec if k in state_dict}
         dev = self.pixel_mean.device
         index = dev.index if dev.type == "cuda" and dev.index is not None else (torch.cuda.current_device() if torch.cuda.is_available() else 0)
-        self._engine = Engine(self.cfg, index)
+        self._engine = Engine(self.cfg, index, self.precision)
         self._engine.load_state_dict(self._state)
         for m in (self.backbone, self.proposal_generator, self.code_generator):
             if m is not None:
@@ -532,6 +535,9 @@ class MetaOneStageDetector(nn.Module):
         return dets, counts, out_sizes
 
 
-def build_model(cfg) -> MetaOneStageDetector:
-    """`runner.build_model(cfg)` equivalent: META_ARCH_REGISTRY lookup by cfg.MODEL.META_ARCHITECTURE."""
-    return META_ARCH_REGISTRY.get(cfg.MODEL.META_ARCHITECTURE)(cfg)
+def build_model(cfg, precision: Optional[str] = None) -> MetaOneStageDetector:
+    """`runner.build_model(cfg)` equivalent: META_ARCH_REGISTRY lookup by cfg.MODEL.META_ARCHITECTURE.
+    `precision` ("exact" | "fast" | None) is handed to the engine when the weights are loaded."""
+    model = META_ARCH_REGISTRY.get(cfg.MODEL.META_ARCHITECTURE)(cfg)
+    model.precision = precision
+    return model

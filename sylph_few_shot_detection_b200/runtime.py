@@ -98,7 +98,9 @@ def loss_config_from_cfg(cfg) -> LossConfig:
 class Engine:
     """One context per device.  Raises RuntimeError with the library's message on any non-zero status."""
 
-    def __init__(self, cfg, device: int = 0):
+    def __init__(self, cfg, device: int = 0, precision: Optional[str] = None):
+        """`precision`: "exact" (split-fp16 operands, three tensor-core products per multiply: fp32-level agreement
+        with the reference) or "fast" (single fp16 operands).  None = $SYLPH_PRECISION, else "exact"."""
         if not torch.cuda.is_available():
             raise RuntimeError("sylph_b200 needs a CUDA device (sm_100a); there is no CPU fallback")
         self.lib = _lib.load()
@@ -106,11 +108,17 @@ class Engine:
         self.cfg = cfg
         self.mc = model_config_from_cfg(cfg)
         self.post_nms_topk = self.mc.post_nms_topk
+        if precision is None:
+            precision = os.environ.get("SYLPH_PRECISION", "exact")
+        if precision not in ("exact", "fast"):
+            raise ValueError(f"precision must be 'exact' or 'fast', got {precision!r}")
         h = c_void_p()
         rc = self.lib.sylph_create(byref(h), device, byref(self.mc))
         if rc != 0 or not h:
             raise RuntimeError(f"sylph_create failed with status {rc} (needs an sm_100 device)")
         self.h = h
+        self._check(self.lib.sylph_set_precision(self.h, 1 if precision == "exact" else 0))
+        self.precision = precision
         self._loaded = False
 
     def __del__(self):
