@@ -101,6 +101,13 @@ int sylph_extract_features(sylph_ctx* ctx, int slot, int n_images, const float* 
 int sylph_extract_features_u8(sylph_ctx* ctx, int slot, int n_images, const uint8_t* const* images_dev,
                               const int* heights, const int* widths, void* stream);
 
+/* The backbone as the reference calls it: `self.backbone(images.tensor)` on an ALREADY normalised, zero-padded
+ * (N, 3, H, W) fp32 batch (sylph/modeling/meta_arch/meta_one_stage_detector.py:174-182; build_fcos_resnet_fpn_backbone,
+ * configs/COCO-Detection/Meta-FCOS/Base-FCOS.yaml:3-11).  Same kernels as sylph_extract_features with mean 0 / std 1;
+ * H and W are padded up to multiples of 32 with zeros if they are not.  sylph_export_features returns p3..p7. */
+int sylph_extract_features_normalized(sylph_ctx* ctx, int slot, int n_images, const float* batch_dev, int height, int width,
+                                      void* stream);
+
 /* Several image batches through ONE bottom-up trunk pass (stem, res2..res5), then the FPN of each batch into its own
  * slot: group g = images [sum(counts[0..g-1]), +counts[g]) -> slots[g].  Equivalent to n_groups sylph_extract_features
  * calls; the groups share a trunk batch only when they pad to the same size (ImageList.from_tensors pads each reference
@@ -113,6 +120,13 @@ int sylph_extract_features_multi(sylph_ctx* ctx, int n_groups, const int* slots,
  * the `features` argument of CodeGenerator.forward, sylph/modeling/code_generator/code_generator.py:1037-1053. */
 int sylph_import_features(sylph_ctx* ctx, int slot, int n_images, int padded_h, int padded_w,
                           const float* const* level_ptrs_dev, const int* level_h, const int* level_w, void* stream);
+
+/* Original (un-padded) sizes of the images whose features were imported with sylph_import_features: the
+ * `image_sizes` of the ImageList handed to MetaFCOS.forward (sylph/modeling/meta_fcos/fcos.py:184-268).  Detection
+ * boxes are scaled by out_size / image_size (detector_postprocess, meta_one_stage_detector.py:288-295), so a caller
+ * that asks for out_sizes == image_sizes gets un-scaled proposals in the frame of the padded batch, as the reference's
+ * proposal generator returns them.  Without this call the imported images count as padded_h x padded_w. Host-only. */
+int sylph_set_image_sizes(sylph_ctx* ctx, int slot, int n_images, const int* heights, const int* widths);
 
 /* Geometry of a slot after extract/import: level_h/level_w receive SYLPH_NUM_LEVELS entries. */
 int sylph_feature_shape(sylph_ctx* ctx, int slot, int* n_images, int* padded_h, int* padded_w, int* level_h, int* level_w);

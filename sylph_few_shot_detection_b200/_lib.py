@@ -106,10 +106,14 @@ def load() -> ctypes.CDLL:
     lib.sylph_extract_features.argtypes = [vp, c_int, c_int, POINTER(vp), ip, ip, vp]
     lib.sylph_extract_features_u8.restype = c_int
     lib.sylph_extract_features_u8.argtypes = [vp, c_int, c_int, POINTER(vp), ip, ip, vp]
+    lib.sylph_extract_features_normalized.restype = c_int
+    lib.sylph_extract_features_normalized.argtypes = [vp, c_int, c_int, vp, c_int, c_int, vp]
     lib.sylph_extract_features_multi.restype = c_int
     lib.sylph_extract_features_multi.argtypes = [vp, c_int, ip, ip, POINTER(vp), c_int, ip, ip, vp]
     lib.sylph_import_features.restype = c_int
     lib.sylph_import_features.argtypes = [vp, c_int, c_int, c_int, c_int, POINTER(vp), ip, ip, vp]
+    lib.sylph_set_image_sizes.restype = c_int
+    lib.sylph_set_image_sizes.argtypes = [vp, c_int, c_int, ip, ip]
     lib.sylph_feature_shape.restype = c_int
     lib.sylph_feature_shape.argtypes = [vp, c_int, ip, ip, ip, ip, ip]
     lib.sylph_export_features.restype = c_int
@@ -159,7 +163,7 @@ def load() -> ctypes.CDLL:
 
 EXPORTED_SYMBOLS = [
     "sylph_version", "sylph_create", "sylph_destroy", "sylph_last_error", "sylph_set_precision", "sylph_get_precision", "sylph_load_tensor",
-    "sylph_finalize_weights", "sylph_extract_features", "sylph_extract_features_u8", "sylph_extract_features_multi", "sylph_import_features", "sylph_feature_shape",
+    "sylph_finalize_weights", "sylph_extract_features", "sylph_extract_features_u8", "sylph_extract_features_normalized", "sylph_extract_features_multi", "sylph_import_features", "sylph_set_image_sizes", "sylph_feature_shape",
     "sylph_export_features", "sylph_generate_codes", "sylph_export_roi_features", "sylph_normalize_codes", "sylph_exchange_create", "sylph_exchange_connect",
     "sylph_normalize_codes_exchange", "sylph_exchange_poll", "sylph_exchange_status", "sylph_exchange_destroy", "sylph_accumulate_codes", "sylph_reduce_codes",
     "sylph_detect", "sylph_detect_after", "sylph_export_head_output", "sylph_fcos_loss_sums", "sylph_fcos_loss_finalize", "sylph_launch_count", "sylph_set_profiling", "sylph_get_timings",

@@ -88,6 +88,7 @@ struct sylph_ctx {
     int pair1x1 = 1;          // SYLPH_PAIR1X1=0 keeps the single-CTA staged kernel for every 1x1 convolution; 2 = pair kernel
                               // for every staged 1x1 convolution with 256-channel N tiles and K >= 256 (experiments)
     int stem16 = 1;           // SYLPH_STEM16=0 runs the stem over 64-wide overlapped rows instead of K = 16 taps
+    int roi_separable = 1;    // SYLPH_ROI_ALIGN=sample: the per-sample ROIAlign kernel instead of the separable one
     int split = 1;            // precision mode (sylph_set_precision / SYLPH_PRECISION): 1 = "exact", split fp16 operands
                               // (hi + lo pairs, three tensor-core products per multiply: fp32-level results); 0 = "fast",
                               // single fp16 operands (10-bit mantissa, 1-2.5e-3 max-norm error on deep activations)
@@ -714,6 +715,7 @@ int sylph_create(sylph_ctx** out, int device, const sylph_model_config* cfg) {
     if (const char* e = getenv("SYLPH_STEM16")) c->stem16 = atoi(e);
     if (const char* e = getenv("SYLPH_PAIR1X1")) c->pair1x1 = atoi(e);
     if (const char* e = getenv("SYLPH_FUSE_UPSAMPLE")) c->fuse_upsample = atoi(e);
+    if (const char* e = getenv("SYLPH_ROI_ALIGN")) c->roi_separable = strcmp(e, "sample") == 0 ? 0 : 1;
     if (const char* e = getenv("SYLPH_PRECISION")) c->split = (strcmp(e, "fast") == 0 || strcmp(e, "0") == 0) ? 0 : 1;
     *out = c;
     if (cfg->pre_nms_topk * 5 > 8192) { c->fail("pre_nms_topk * 5 must be <= 8192"); }
@@ -902,8 +904,11 @@ struct TrunkOut {
 };
 
 static int run_trunk(sylph_ctx* c, const std::string& key, int n, const void* const* images_dev, int is_u8, const int* hs,
-                     const int* ws, int hpad, int wpad, cudaStream_t st, TrunkOut* out) {
-    const sylph_model_config& f = c->cfg;
+                     const int* ws, int hpad, int wpad, cudaStream_t st, TrunkOut* out, bool normalized = false) {
+    sylph_model_config f = c->cfg;
+    if (normalized) {   // the caller's batch is already (x - mean) / std: the fused preparation only re-lays it out
+        for (int i = 0; i < 3; ++i) { f.pixel_mean[i] = 0.f; f.pixel_std[i] = 1.f; }
+    }
     int hmax = 0, wmax = 0;
     for (int i = 0; i < n; ++i) { hmax = std::max(hmax, hs[i]); wmax = std::max(wmax, ws[i]); }
     const std::string sig = std::to_string(n) + ":" + std::to_string(hpad) + "x" + std::to_string(wpad);
@@ -1112,11 +1117,12 @@ static int run_fpn(sylph_ctx* c, int slot, const TrunkOut& T, int first, int n, 
 }
 
 static int run_backbone(sylph_ctx* c, int slot, int n, const void* const* images_dev, int is_u8, const int* hs,
-                        const int* ws, cudaStream_t st) {
+                        const int* ws, cudaStream_t st, bool normalized = false) {
     int hmax = 0, wmax = 0;
     for (int i = 0; i < n; ++i) { hmax = std::max(hmax, hs[i]); wmax = std::max(wmax, ws[i]); }
     TrunkOut T;
-    TRY(run_trunk(c, "s" + std::to_string(slot), n, images_dev, is_u8, hs, ws, round_up(hmax, 32), round_up(wmax, 32), st, &T));
+    TRY(run_trunk(c, "s" + std::to_string(slot), n, images_dev, is_u8, hs, ws, round_up(hmax, 32), round_up(wmax, 32), st, &T,
+                  normalized));
     return run_fpn(c, slot, T, 0, n, hs, ws, st);
 }
 
@@ -1161,7 +1167,7 @@ static int roi_encoder_codes(sylph_ctx* c, const Slot& S, int n_rois, int n_clas
     const int t_pad = round_up(n_rois, kBlockM);
     void *pctx, *ptok, *px0, *px1, *pxa, *ph, *pcls, *phd;
     TRY(ensure(c, "re.ctx", static_cast<size_t>(S.n) * 49 * 256 * 4, "", &pctx, st, false));
-    TRY(ensure(c, "re.tokens", (static_cast<size_t>(t_pad) + kBlockM) * 12544 * 2, "tok", &ptok, st, true));
+    TRY(ensure(c, "re.tokens", (static_cast<size_t>(t_pad) + kBlockM) * c->ld(12544) * 2, "tok", &ptok, st, true));
     TRY(ensure(c, "re.x0", static_cast<size_t>(t_pad) * 256 * 4, "", &px0, st, false));
     TRY(ensure(c, "re.x1", static_cast<size_t>(t_pad) * 256 * 4, "", &px1, st, false));
     TRY(ensure(c, "re.xa", static_cast<size_t>(t_pad) * 256 * 4, "", &pxa, st, false));
@@ -1174,19 +1180,20 @@ static int roi_encoder_codes(sylph_ctx* c, const Slot& S, int n_rois, int n_clas
     {
         StageTimer t(c, "roienc.context_pool", st, static_cast<double>(S.n) * 22400 * 256 * 2);
         CU_TRY(c, launch_k(context_pool_kernel, dim3(S.n, 49), dim3(256), 0, st, static_cast<const __half*>(S.pyr), S.pg,
-                           static_cast<float*>(pctx)));
+                           static_cast<float*>(pctx), c->split));
         c->launches++;
     }
     {
-        static bool attr_set = false;
-        if (!attr_set) {
-            CU_TRY(c, cudaFuncSetAttribute(ms_cam_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kMsCamSmem));
-            attr_set = true;
-        }
-        StageTimer t(c, "roienc.ms_cam", st, static_cast<double>(n_rois) * 49 * 256 * 8);
-        CU_TRY(c, launch_k(ms_cam_kernel, dim3(n_rois), dim3(256), static_cast<size_t>(kMsCamSmem), st,
-                           static_cast<const float*>(pctx), d_roi_image, static_cast<const __half*>(r1), c->re_cam, r2));
-        c->launches++;
+        static PerDeviceOnce once;
+        CU_TRY(c, once.run([] { return cudaFuncSetAttribute(ms_cam_gate_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kMsCamSmem); }));
+        void* pgate;
+        TRY(ensure(c, "re.gate", static_cast<size_t>(S.n) * 49 * 256 * 4, "", &pgate, st, false));
+        StageTimer t(c, "roienc.ms_cam", st, static_cast<double>(n_rois) * 49 * 256 * (c->split ? 8 : 4) + static_cast<double>(S.n) * 49 * 256 * 8);
+        CU_TRY(c, launch_k(ms_cam_gate_kernel, dim3(S.n), dim3(256), static_cast<size_t>(kMsCamSmem), st,
+                           static_cast<const float*>(pctx), c->re_cam, static_cast<float*>(pgate)));
+        CU_TRY(c, launch_k(ms_cam_apply_kernel, dim3(grid_for(static_cast<long long>(n_rois) * 128 * 32, 256, c->num_sms)), dim3(256), 0, st,
+                           static_cast<const float*>(pgate), d_roi_image, static_cast<const __half*>(r1), r2, n_rois, c->split));
+        c->launches += 2;
     }
     // Tokenizer: NUM_CONV x (conv3x3 + GN + ReLU), flatten, fc1 (tensor-core GEMM over K = 12544), fc2.. (+ ReLU)
     __half* cur = r2;
@@ -1199,11 +1206,11 @@ static int roi_encoder_codes(sylph_ctx* c, const Slot& S, int n_rois, int n_clas
         nxt = (done == r2) ? r1 : done;
     }
     CU_TRY(c, launch_k(gather_tokens_kernel, dim3(grid_for(static_cast<long long>(n_rois) * 49 * 32, 256, c->num_sms)), dim3(256),
-                       0, st, static_cast<const __half*>(cur), static_cast<__half*>(ptok), n_rois));
+                       0, st, static_cast<const __half*>(cur), static_cast<__half*>(ptok), n_rois, c->split));
     c->launches++;
     {
         ConvCall k{};
-        k.W = &c->re_fc1; k.A = static_cast<const __half*>(ptok); k.a_rows = t_pad; k.a_cols = k.a_ld = 12544; k.ps = ps;
+        k.W = &c->re_fc1; k.A = static_cast<const __half*>(ptok); k.a_rows = t_pad; k.a_cols = k.a_ld = c->ld(12544); k.ps = ps;
         k.tile_begin = 0; k.n_tiles = t_pad / kBlockM; k.a_row_delta = 0; k.out = px0; k.ldc = 256;
         k.flags = kEpiRelu | kEpiOutF32; k.name = "roienc.fc1_gemm";
         TRY(run_conv(c, k, st));
@@ -1345,6 +1352,19 @@ int sylph_extract_features_u8(sylph_ctx* c, int slot, int n_images, const uint8_
                         static_cast<cudaStream_t>(stream));
 }
 
+int sylph_extract_features_normalized(sylph_ctx* c, int slot, int n_images, const float* batch_dev, int height, int width,
+                                      void* stream) {
+    if (!c) return 1;
+    if (!c->finalized) return c->fail("weights not finalized");
+    if (slot < 0 || slot >= SYLPH_NUM_SLOTS || n_images <= 0 || !batch_dev || height <= 0 || width <= 0)
+        return c->fail("bad slot / batch");
+    CU_TRY(c, cudaSetDevice(c->device));
+    std::vector<const void*> ptrs(n_images);
+    std::vector<int> hs(n_images, height), ws(n_images, width);
+    for (int i = 0; i < n_images; ++i) ptrs[i] = batch_dev + static_cast<size_t>(i) * 3 * height * width;
+    return run_backbone(c, slot, n_images, ptrs.data(), 0, hs.data(), ws.data(), static_cast<cudaStream_t>(stream), true);
+}
+
 int sylph_extract_features_multi(sylph_ctx* c, int n_groups, const int* slots, const int* counts,
                                  const void* const* images_dev, int is_u8, const int* heights, const int* widths, void* stream) {
     if (!c) return 1;
@@ -1401,6 +1421,19 @@ int sylph_import_features(sylph_ctx* c, int slot, int n_images, int padded_h, in
         CU_TRY(c, cudaGetLastError());
         c->launches++;
     }
+    return 0;
+}
+
+int sylph_set_image_sizes(sylph_ctx* c, int slot, int n_images, const int* heights, const int* widths) {
+    if (!c) return 1;
+    if (slot < 0 || slot >= SYLPH_NUM_SLOTS || !c->slots[slot].valid) return c->fail("slot %d holds no features", slot);
+    Slot& S = c->slots[slot];
+    if (n_images != S.n || !heights || !widths) return c->fail("sylph_set_image_sizes: the slot holds %d images", S.n);
+    for (int i = 0; i < n_images; ++i)
+        if (heights[i] <= 0 || widths[i] <= 0 || heights[i] > S.hpad || widths[i] > S.wpad)
+            return c->fail("image %d: size %d x %d outside the padded batch %d x %d", i, heights[i], widths[i], S.hpad, S.wpad);
+    S.img_h.assign(heights, heights + n_images);
+    S.img_w.assign(widths, widths + n_images);
     return 0;
 }
 
@@ -1475,15 +1508,24 @@ int sylph_generate_codes(sylph_ctx* c, int slot, int n_rois, const float* boxes_
         TRY(make_plane_set(c, "roi:" + std::to_string(cap), geom_segs(g, cap), cap * 128, &ps));
     }
     {
-        StageTimer t(c, "roi_align", st, static_cast<double>(n_rois) * (50176.0 + 0.5e6));
-        CU_TRY(c, launch_k(roi_align_kernel, dim3(n_rois, 7), dim3(256), 0, st, S.pyr, S.pg, static_cast<const float*>(pb), static_cast<const int*>(pi),
-                                                         static_cast<__half*>(r0), reinterpret_cast<long long*>(levels_out_dev), c->split));
+        StageTimer t(c, "roi_align", st, static_cast<double>(n_rois) * (50176.0 + 0.5e6) * (c->split ? 2 : 1));
+        // separable form (every footprint pixel read once); SYLPH_ROI_ALIGN=sample keeps the per-sample kernel, which also
+        // serves planes wider than the separable kernel's weight tables
+        int span = 1;
+        for (int l = 0; l < 5; ++l) span = std::max(span, std::max(S.lh[l], S.lw[l]));
+        if (c->roi_separable && span <= kRoiSepMaxSpan) {
+            const size_t smem = static_cast<size_t>(14) * span * sizeof(float);
+            CU_TRY(c, launch_k(roi_align_separable_kernel, dim3(n_rois), dim3(256), smem, st, static_cast<const __half*>(S.pyr), S.pg,
+                               static_cast<const float*>(pb), static_cast<const int*>(pi), static_cast<__half*>(r0),
+                               reinterpret_cast<long long*>(levels_out_dev), c->split, span));
+        } else {
+            CU_TRY(c, launch_k(roi_align_kernel, dim3(n_rois, 7), dim3(256), 0, st, S.pyr, S.pg, static_cast<const float*>(pb), static_cast<const int*>(pi),
+                                                             static_cast<__half*>(r0), reinterpret_cast<long long*>(levels_out_dev), c->split));
+        }
         CU_TRY(c, cudaGetLastError());
         c->launches++;
     }
     c->last_n_rois = n_rois;
-    if (f.generator == 1 && c->split)
-        return c->fail("the ROIEncoder generator runs in the fast precision mode only (sylph_set_precision(ctx, 0))");
     if (f.generator == 1)
         return roi_encoder_codes(c, S, n_rois, n_classes, static_cast<const int*>(pi), static_cast<const int*>(po), ps.get(),
                                  static_cast<__half*>(r0), static_cast<__half*>(r1), static_cast<__half*>(r2),
@@ -1789,11 +1831,8 @@ int sylph_detect_after(sylph_ctx* c, int slot, const float* codes_dev, int n_cla
         int sort_n = 32;
         while (sort_n < n_max) sort_n <<= 1;
         const size_t smem = static_cast<size_t>(sort_n) * 8 + static_cast<size_t>(n_max) * 21 + 16;
-        static bool attr_set = false;
-        if (!attr_set) {
-            CU_TRY(c, cudaFuncSetAttribute(fcos_nms_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-            attr_set = true;
-        }
+        static PerDeviceOnce once;
+        CU_TRY(c, once.run([] { return cudaFuncSetAttribute(fcos_nms_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024); }));
         if (smem > 200 * 1024) return c->fail("NMS shared memory budget exceeded (pre_nms_topk too large)");
         CU_TRY(c, launch_k(fcos_nms_kernel, dim3(S.n), dim3(1024), smem, st, static_cast<const unsigned long long*>(sel), static_cast<const int*>(selc),
                                                  static_cast<const float*>(pr), P, static_cast<const NmsImageArgs*>(ia), sort_n,

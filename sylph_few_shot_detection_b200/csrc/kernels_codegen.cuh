@@ -91,6 +91,114 @@ roi_align_kernel(const __half* __restrict__ pyramid, PyramidGeom pg, const float
     }
 }
 
+// The same ROIAlign, SEPARABLE: the sampling points of a bin form a tensor-product grid and bilinear interpolation
+// factorises, so out(ph, pw) = sum_r Wy[ph][r] * sum_c Wx[pw][c] * f(r, c) with two small weight matrices per ROI
+// (bilinear taps, the "outside the map" rule and the edge clamps are all per-axis, and 1 / (grid_h * grid_w) splits into
+// the two factors).  Every pixel of the ROI footprint is then read about once (16-byte channel vectors) instead of
+// once per sample tap: the per-sample kernel above issues 16-64 two-byte loads per output value, which is what bounds
+// the 12 030-ROI class sweep of BASELINE configs[4] (4.0 ms, ~0.1 of HBM peak, profiles/r01_configs_3_4_5_s2.json).
+// Sample coordinates are computed with exactly the expressions of the per-sample kernel; only the fp32 summation order
+// differs (values agree to rounding; the FPN level per ROI stays bit-exact).
+// grid = n_rois, block = 256 = 32 channel groups of 8 x 8 row slots (slot ph < 7 owns output row ph).
+// Dynamic shared memory: 7 * (R + C) floats with R x C the footprint (rows x columns of the level the ROI reads).
+constexpr int kRoiSepMaxSpan = 512;   // footprint rows / columns the separable kernel accepts (else: per-sample kernel)
+
+__global__ void __launch_bounds__(256)
+roi_align_separable_kernel(const __half* __restrict__ pyramid, PyramidGeom pg, const float* __restrict__ boxes,
+                           const int* __restrict__ roi_image, __half* __restrict__ roi_planes,
+                           long long* __restrict__ levels_out, int split, int span_cap) {
+    ptx::griddep_launch();
+    ptx::griddep_wait();
+    extern __shared__ float roi_w[];
+    __shared__ int s_lo[14], s_hi[14];
+    const int roi = blockIdx.x, t = threadIdx.x;
+    const float bx0 = boxes[roi * 4 + 0], by0 = boxes[roi * 4 + 1], bx1 = boxes[roi * 4 + 2], by1 = boxes[roi * 4 + 3];
+    const int lvl = assign_level(bx0, by0, bx1, by1);
+    if (t == 0 && levels_out != nullptr) levels_out[roi] = lvl;
+    const PlaneGeom g = pg.lv[lvl];
+    const float sc = pg.scale[lvl];
+    const int n = roi_image[roi];
+    const float x0 = __fsub_rn(__fmul_rn(bx0, sc), 0.5f), y0 = __fsub_rn(__fmul_rn(by0, sc), 0.5f);
+    const float x1 = __fsub_rn(__fmul_rn(bx1, sc), 0.5f), y1 = __fsub_rn(__fmul_rn(by1, sc), 0.5f);
+    const float roi_w_ = __fsub_rn(x1, x0), roi_h = __fsub_rn(y1, y0);
+    const float bin_h = __fdiv_rn(roi_h, 7.f), bin_w = __fdiv_rn(roi_w_, 7.f);
+    const int grid_h = static_cast<int>(ceilf(__fdiv_rn(roi_h, 7.f)));
+    const int grid_w = static_cast<int>(ceilf(__fdiv_rn(roi_w_, 7.f)));
+    // footprint on the level: rows r0 .. r0 + R - 1, columns c0 .. c0 + C - 1 (clamped to the plane like the taps are)
+    const int r0 = min(max(static_cast<int>(floorf(y0)), 0), g.H - 1);
+    const int r1 = min(max(static_cast<int>(floorf(y1)) + 1, r0), g.H - 1);
+    const int c0 = min(max(static_cast<int>(floorf(x0)), 0), g.W - 1);
+    const int c1 = min(max(static_cast<int>(floorf(x1)) + 1, c0), g.W - 1);
+    const int R = min(r1 - r0 + 1, span_cap), C = min(c1 - c0 + 1, span_cap);
+    float* Wy = roi_w;            // [7][R]
+    float* Wx = roi_w + 7 * R;    // [7][C]
+    for (int i = t; i < 7 * (R + C); i += 256) roi_w[i] = 0.f;
+    __syncthreads();
+    if (t < 14) {   // thread = (axis, bin): accumulate the bilinear tap weights of the bin's sample rows / columns
+        const bool is_x = t >= 7;
+        const int b = is_x ? t - 7 : t;
+        const int grid = is_x ? grid_w : grid_h, size = is_x ? g.W : g.H, span = is_x ? C : R, first = is_x ? c0 : r0;
+        const float start = is_x ? x0 : y0, bin = is_x ? bin_w : bin_h;
+        float* w = (is_x ? Wx : Wy) + b * span;
+        const float inv = grid > 0 ? 1.f / static_cast<float>(grid) : 0.f;
+        int lo = span, hi = -1;
+        for (int i = 0; i < grid; ++i) {
+            float p = __fadd_rn(__fadd_rn(start, __fmul_rn(static_cast<float>(b), bin)),
+                                __fdiv_rn(__fmul_rn(static_cast<float>(i) + 0.5f, bin), static_cast<float>(grid)));
+            if (p < -1.f || p > static_cast<float>(size)) continue;    // the sample contributes zero
+            p = fmaxf(p, 0.f);
+            int low = static_cast<int>(p), high;
+            if (low >= size - 1) { high = low = size - 1; p = static_cast<float>(low); } else { high = low + 1; }
+            const float l = p - low, h = 1.f - l;
+            const int a = low - first, bb = high - first;
+            if (a >= 0 && a < span) { w[a] += h * inv; lo = min(lo, a); hi = max(hi, a); }
+            if (bb >= 0 && bb < span) { w[bb] += l * inv; lo = min(lo, bb); hi = max(hi, bb); }
+        }
+        s_lo[t] = lo;
+        s_hi[t] = hi;
+    }
+    __syncthreads();
+    const int cg = t & 31, ph = t >> 5;   // 8 channels starting at 8 * cg; output row ph (slot 7 idles)
+    const int ld = split ? 512 : 256, lo_off = split ? 256 : 0;
+    float acc[7][8];
+#pragma unroll
+    for (int pw = 0; pw < 7; ++pw)
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc[pw][j] = 0.f;
+    if (ph < 7 && s_hi[ph] >= s_lo[ph]) {
+        const int rlo = s_lo[ph], rhi = s_hi[ph];
+        const float* wy = Wy + ph * R;
+        for (int c = 0; c < C; ++c) {
+            float col[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+            const __half* p = pyramid + plane_row(g, n, r0 + rlo, c0 + c) * ld;
+            for (int r = rlo; r <= rhi; ++r) {
+                float v[8];
+                load8f(p, cg * 8, lo_off, v);
+                const float w = wy[r];
+#pragma unroll
+                for (int j = 0; j < 8; ++j) col[j] += w * v[j];
+                p += static_cast<size_t>(g.Wp) * ld;
+            }
+#pragma unroll
+            for (int pw = 0; pw < 7; ++pw) {
+                const float w = Wx[pw * C + c];
+#pragma unroll
+                for (int j = 0; j < 8; ++j) acc[pw][j] += w * col[j];
+            }
+        }
+    }
+    if (ph < 7) {
+#pragma unroll
+        for (int pw = 0; pw < 7; ++pw) {
+            float o[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) o[j] = fminf(fmaxf(acc[pw][j], -kHalfMax), kHalfMax);
+            const size_t row = static_cast<size_t>(roi) * 128 + (ph + 1) * 9 + (pw + 1);
+            store8f(roi_planes + row * ld, cg * 8, lo_off, o, false);
+        }
+    }
+}
+
 // Per support ROI ("shot"): global average pool of the cls-conv output (GlobalAdaptiveAvgPool2d, k_s = 1) and the
 // 256 -> 1 3x3 bias convolution on the tower output, optional L2 normalisation over the 49 positions, then its pool.
 // reference: code_generator.py:954-967, utils.py:51-67.   grid = n_rois, block = 256.

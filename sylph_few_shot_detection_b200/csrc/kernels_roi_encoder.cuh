@@ -26,12 +26,36 @@ namespace sylph {
 // bin (torch adaptive_avg_pool2d: rows floor(i*H/7) .. ceil((i+1)*H/7) - 1).  The context depends on the image only, so it
 // is computed once per support image and shared by all ROIs of that image (the pyramid is streamed exactly once).
 __global__ void __launch_bounds__(256)
-context_pool_kernel(const __half* __restrict__ pyramid, PyramidGeom pg, float* __restrict__ ctx /* [n_images][49][256] */) {
+context_pool_kernel(const __half* __restrict__ pyramid, PyramidGeom pg, float* __restrict__ ctx /* [n_images][49][256] */,
+                    int split) {
     ptx::griddep_launch();
     ptx::griddep_wait();
     const int n = blockIdx.x, bin = blockIdx.y, c = threadIdx.x;
     const int bi = bin / 7, bj = bin - bi * 7;
     float total = 0.f;
+    if (split) {   // rows of [256 hi | 256 lo]: the value of a channel is hi + lo (exact in fp32)
+#pragma unroll 1
+        for (int l = 0; l < 5; ++l) {
+            const PlaneGeom g = pg.lv[l];
+            const int y0 = (bi * g.H) / 7, y1 = ((bi + 1) * g.H + 6) / 7;
+            const int x0 = (bj * g.W) / 7, x1 = ((bj + 1) * g.W + 6) / 7;
+            float s = 0.f;
+            for (int y = y0; y < y1; ++y) {
+                const __half* row = pyramid + plane_row(g, n, y, x0) * 512 + c;
+                int x = x0;
+                for (; x + 2 <= x1; x += 2) {
+                    const float a = __half2float(__ldg(row)) + __half2float(__ldg(row + 256));
+                    const float b = __half2float(__ldg(row + 512)) + __half2float(__ldg(row + 768));
+                    s += a; s += b;
+                    row += 1024;
+                }
+                for (; x < x1; ++x) { s += __half2float(__ldg(row)) + __half2float(__ldg(row + 256)); row += 512; }
+            }
+            total += s / static_cast<float>((y1 - y0) * (x1 - x0));
+        }
+        ctx[(static_cast<size_t>(n) * 49 + bin) * 256 + c] = total / 5.f;
+        return;
+    }
 #pragma unroll 1
     for (int l = 0; l < 5; ++l) {
         const PlaneGeom g = pg.lv[l];
@@ -76,11 +100,12 @@ struct MsCamWeights {
 
 constexpr int kMsCamSmem = (49 * 256 + 256 * 64 + 49 * 64 + 256 + 64 + 64) * 4;
 
-// grid = n_rois, block = 256.  out = pooled * sigmoid(local_att(ctx) + global_att(ctx)) written as a zero-bordered
-// 9x9 fp16 plane (128 rows per ROI).
+// The attention gate sigmoid(local_att(ctx) + global_att(ctx)) depends on the IMAGE only (ctx is the image's pooled
+// context), so it is computed once per support image -- grid = n_images, block = 256, gate[image][49][256] fp32 -- and
+// applied to every ROI of that image by ms_cam_apply_kernel.  (Round 1 recomputed both branches per ROI: 6.6 ms of the
+// 19.4 ms LVIS class sweep, where 12 030 ROIs share 16 images.)
 __global__ void __launch_bounds__(256)
-ms_cam_kernel(const float* __restrict__ ctx, const int* __restrict__ roi_image, const __half* __restrict__ pooled,
-              MsCamWeights w, __half* __restrict__ out) {
+ms_cam_gate_kernel(const float* __restrict__ ctx, MsCamWeights w, float* __restrict__ gate) {
     ptx::griddep_launch();
     ptx::griddep_wait();
     extern __shared__ uint8_t cam_smem_raw[];
@@ -90,8 +115,8 @@ ms_cam_kernel(const float* __restrict__ ctx, const int* __restrict__ roi_image, 
     float* s_g0 = s_h1 + 49 * 64;             // [256]
     float* s_g1 = s_g0 + 256;                 // [64]
     float* s_st = s_g1 + 64;                  // [32][2] GroupNorm(32, 64) statistics of the local branch
-    const int roi = blockIdx.x, t = threadIdx.x, lane = t & 31, warp = t >> 5;
-    const float* cx = ctx + static_cast<size_t>(roi_image[roi]) * 49 * 256;
+    const int img = blockIdx.x, t = threadIdx.x, lane = t & 31, warp = t >> 5;
+    const float* cx = ctx + static_cast<size_t>(img) * 49 * 256;
     for (int i = t; i < 49 * 256; i += 256) s_ctx[i] = cx[i];
     for (int i = t; i < 256 * 64; i += 256) s_w[i] = w.l_w1t[i];
     __syncthreads();
@@ -189,24 +214,60 @@ ms_cam_kernel(const float* __restrict__ ctx, const int* __restrict__ roi_image, 
     const float mean = s / 392.f;
     const float rstd = rsqrtf(fmaxf(ss / 392.f - mean * mean, 0.f) + 1e-5f);
     const float gw = w.l_g2w[t], gb = w.l_g2b[t];
-    const size_t base = static_cast<size_t>(roi) * 128;
-    for (int r = 0; r < 128; ++r) out[(base + r) * 256 + t] = __float2half_rn(0.f);
 #pragma unroll
     for (int p = 0; p < 49; ++p) {
-        const int row = (p / 7 + 1) * 9 + (p % 7 + 1);
         const float lg = (h2[p] - mean) * rstd * gw + gb + gl;
-        const float wei = 1.f / (1.f + __expf(-lg));
-        const float x = __half2float(pooled[(base + row) * 256 + t]);
-        out[(base + row) * 256 + t] = __float2half_rn(fminf(fmaxf(x * wei, -kHalfMax), kHalfMax));
+        gate[(static_cast<size_t>(img) * 49 + p) * 256 + t] = 1.f / (1.f + __expf(-lg));
+    }
+}
+
+// out = pooled * gate[image of the ROI], written as a zero-bordered 9x9 plane (128 rows per ROI); one 8-channel vector
+// per thread.  (FeatureFusionModuleV2.forward, sylph/modeling/code_generator/utils.py:153-165.)
+__global__ void __launch_bounds__(256)
+ms_cam_apply_kernel(const float* __restrict__ gate, const int* __restrict__ roi_image, const __half* __restrict__ pooled,
+                    __half* __restrict__ out, int n_rois, int split) {
+    ptx::griddep_launch();
+    ptx::griddep_wait();
+    const int ld = split ? 512 : 256, lo = split ? 256 : 0;
+    const long long total = static_cast<long long>(n_rois) * 128 * 32;
+    for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
+         i += static_cast<long long>(gridDim.x) * blockDim.x) {
+        const int c8 = static_cast<int>(i & 31);
+        const long long row = i >> 5;
+        const int roi = static_cast<int>(row >> 7), r = static_cast<int>(row & 127);
+        const int y = r / 9, x = r - y * 9;
+        float v[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+        if (r < 81 && y >= 1 && y <= 7 && x >= 1 && x <= 7) {
+            load8f(pooled + row * ld, c8 * 8, lo, v);
+            const float4* gp = reinterpret_cast<const float4*>(gate + (static_cast<size_t>(__ldg(roi_image + roi)) * 49 + (y - 1) * 7 + (x - 1)) * 256) + 2 * c8;
+            const float4 a = __ldg(gp), b = __ldg(gp + 1);
+            v[0] *= a.x; v[1] *= a.y; v[2] *= a.z; v[3] *= a.w; v[4] *= b.x; v[5] *= b.y; v[6] *= b.z; v[7] *= b.w;
+        }
+        store8f(out + row * ld, c8 * 8, lo, v, false);
     }
 }
 
 // ------------------------------------------------------------------------------------------------ tokens
 // planes [n][128 rows][256] -> A[n][p * 256 + c] (p = 7 * y + x); one uint4 (8 channels) per thread.
-__global__ void gather_tokens_kernel(const __half* __restrict__ planes, __half* __restrict__ tokens, int n_rois) {
+// split mode: planes rows are [256 hi | 256 lo], token rows [12544 hi | 12544 lo].
+__global__ void gather_tokens_kernel(const __half* __restrict__ planes, __half* __restrict__ tokens, int n_rois, int split) {
     ptx::griddep_launch();
     ptx::griddep_wait();
     const long long total = static_cast<long long>(n_rois) * 49 * 32;
+    if (split) {
+        for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < 2 * total;
+             i += static_cast<long long>(gridDim.x) * blockDim.x) {
+            const int half_idx = static_cast<int>(i / total);           // 0 = hi, 1 = lo
+            const long long j = i - half_idx * total;
+            const int v = static_cast<int>(j & 31);
+            const int p = static_cast<int>((j >> 5) % 49);
+            const long long n = j / (49 * 32);
+            const int row = (p / 7 + 1) * 9 + (p % 7 + 1);
+            reinterpret_cast<uint4*>(tokens + n * 25088 + half_idx * 12544)[p * 32 + v] =
+                __ldg(reinterpret_cast<const uint4*>(planes + (n * 128 + row) * 512 + half_idx * 256) + v);
+        }
+        return;
+    }
     for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
          i += static_cast<long long>(gridDim.x) * blockDim.x) {
         const int v = static_cast<int>(i & 31);

@@ -81,7 +81,8 @@ class CodeGenerator(_EngineBound):
 
     def __init__(self, cfg, feature_channels: int, feature_levels: int, strides: Tuple[int]):
         super().__init__()
-        assert feature_channels == 256 and feature_levels == 5, "the B200 path is built for the 256-channel p3..p7 pyramid"
+        if feature_channels != 256 or feature_levels != 5:   # the reference accepts any (build.py:29-39)
+            raise NotImplementedError("the B200 path is built for the 256-channel p3..p7 pyramid of the shipped configs")
         self.in_features = cfg.MODEL.FCOS.IN_FEATURES
         self.strides = tuple(strides)
         self.all_mask = cfg.MODEL.META_LEARN.CODE_GENERATOR.ALL_MASK
@@ -152,7 +153,8 @@ class ROIEncoder(_EngineBound):
 
     def __init__(self, cfg, feature_channels: int, feature_levels: int, strides: Tuple[int]):
         super().__init__()
-        assert feature_channels == 256 and feature_levels == 5, "the B200 path is built for the 256-channel p3..p7 pyramid"
+        if feature_channels != 256 or feature_levels != 5:   # the reference accepts any (build.py:29-39)
+            raise NotImplementedError("the B200 path is built for the 256-channel p3..p7 pyramid of the shipped configs")
         self.cfg = cfg
         self.strides = tuple(strides)
         self.shot = cfg.MODEL.META_LEARN.SHOT
@@ -228,7 +230,10 @@ class MetaFCOS(_EngineBound):
         if features is not None:  # NCHW features from a foreign backbone
             feats = [features[f] for f in self.in_features]
             h, w = feats[0].shape[-2:]
-            self.engine.import_features(SLOT_QUERY, feats, (h * self.fpn_strides[0], w * self.fpn_strides[0]))
+            # the slot learns the true image sizes: with out_sizes == image_sizes the fused postprocess scales by exactly 1
+            # (the reference's proposal generator returns un-scaled boxes in the frame of the padded batch)
+            self.engine.import_features(SLOT_QUERY, feats, (h * self.fpn_strides[0], w * self.fpn_strides[0]),
+                                        image_sizes=[tuple(int(v) for v in s) for s in image_sizes])
         return self.predict(support_set_per_class_code, image_sizes, image_sizes), {}
 
     def predict_device(self, class_codes: Dict[str, torch.Tensor], out_sizes, code_rows: Optional[torch.Tensor] = None,
@@ -320,8 +325,10 @@ def pack_code_rows(class_codes: Dict[str, torch.Tensor]) -> torch.Tensor:
 
 
 class _BackboneHandle(_EngineBound):
-    """`build_fcos_resnet_fpn_backbone` stand-in: exposes `size_divisibility` / `output_shape()` and, when called with
-    a normalised (N, 3, H, W) batch, is not supported -- the fused prep+backbone entry takes raw images."""
+    """`build_fcos_resnet_fpn_backbone` drop-in: `size_divisibility`, `output_shape()` and `forward(x)` on a normalised,
+    zero-padded (N, 3, H, W) batch -> {"p3".."p7": (N, 256, H_l, W_l) fp32}, the call the reference makes at
+    meta_one_stage_detector.py:180-182.  (MetaOneStageDetector itself hands RAW images to the engine: the
+    normalisation is fused into the stem's input preparation.)"""
 
     size_divisibility = 32
 
@@ -333,7 +340,8 @@ class _BackboneHandle(_EngineBound):
         return self._out
 
     def forward(self, x):
-        raise NotImplementedError("call MetaOneStageDetector with raw images: normalisation is fused into the stem")
+        self.engine.extract_features_normalized(SLOT_SUPPORT, x)
+        return {f"p{3 + l}": self.engine.export_features(SLOT_SUPPORT, l) for l in range(5)}
 
 
 @BACKBONE_REGISTRY.register()
@@ -433,28 +441,68 @@ class MetaOneStageDetector(nn.Module):
         assert len(batched_inputs) == 1, f"batched_inputs has length: {len(batched_inputs)}"
         return self.forward_class_codes_batched(batched_inputs)[0]
 
+    # images of one trunk pass of the batched support path, in units of 800 x 1344 images (activation memory bound)
+    SUPPORT_PASS_IMAGE_BUDGET = 64
+
+    @staticmethod
+    def class_padded_size(item: Dict[str, Any], divisibility: int = 32) -> Tuple[int, int]:
+        """The size ImageList.from_tensors pads ONE reference call (= one class, meta_one_stage_detector.py:174-178) to."""
+        hs = [int(r["image"].shape[-2]) for r in item["support_set"]]
+        ws = [int(r["image"].shape[-1]) for r in item["support_set"]]
+        return (-(-max(hs) // divisibility) * divisibility, -(-max(ws) // divisibility) * divisibility)
+
     def forward_class_codes_batched(self, batched_inputs: List[Dict[str, Any]],
                                     features_in_slot: bool = False) -> List[Dict[str, torch.Tensor]]:
-        """B200-native extension: the support sets of MANY classes through one backbone batch and one code-generation
-        launch sequence; result[i] equals forward_class_code([batched_inputs[i]]).  `features_in_slot=True`: the
-        support pyramid of exactly these images already sits in SLOT_SUPPORT (Engine.extract_features_multi)."""
-        records, offsets = [], [0]
-        for item in batched_inputs:
-            records.extend(item["support_set"])
-            offsets.append(len(records))
-        boxes = torch.cat([b.reshape(-1, 4)[:1].cpu() for b in select_a_mask([r["instances"] for r in records])], dim=0)
-        if not features_in_slot:
-            self.engine.extract_features(SLOT_SUPPORT, [r["image"] for r in records])
-        if isinstance(self.code_generator, ROIEncoder):
-            for a, b in zip(offsets[:-1], offsets[1:]):   # bs = 1 per call in the reference: N % EVAL_SHOT == 0
-                assert (b - a) % self.code_generator.eval_shot == 0 and b - a == self.code_generator.eval_shot, \
-                    f"{b - a} % {self.code_generator.eval_shot}"
-        raw = self.engine.generate_codes(SLOT_SUPPORT, boxes, list(range(len(records))), offsets)
-        if isinstance(self.code_generator, ROIEncoder):
-            return [{"cls_conv": raw[i:i + 1, :256].reshape(1, 256, 1, 1), "cls_bias": raw[i, 256:].reshape(1)}
-                    for i in range(len(batched_inputs))]
-        return [{"cls_conv": raw[i:i + 1, :256].reshape(1, 256, 1, 1), "cls_bias": raw[i:i + 1, 256:].reshape(1, 1, 1, 1)}
-                for i in range(len(batched_inputs))]
+        """B200-native extension: the support sets of MANY classes through shared backbone batches and one
+        code-generation launch sequence per batch; result[i] equals forward_class_code([batched_inputs[i]]).
+        The reference runs one class per call and pads each call to ITS OWN maximum size, so only classes that pad to the
+        same size share a trunk pass (features near the right / bottom border and p6 / p7 depend on the padded size), and
+        a pass holds at most SUPPORT_PASS_IMAGE_BUDGET full-size images (LVIS-scale class lists do not fit one batch).
+        `features_in_slot=True`: the support pyramid of exactly these images already sits in SLOT_SUPPORT
+        (Engine.extract_features_multi; the caller has checked that all classes pad to one size)."""
+        roi_encoder = isinstance(self.code_generator, ROIEncoder)
+        if roi_encoder:
+            for item in batched_inputs:   # bs = 1 per call in the reference: N % EVAL_SHOT == 0
+                n = len(item["support_set"])
+                assert n % self.code_generator.eval_shot == 0 and n == self.code_generator.eval_shot, \
+                    f"{n} % {self.code_generator.eval_shot}"
+        # one host-RNG draw per support image, in the order of the reference's per-class calls (utils.py:27-47)
+        boxes_of = [torch.cat([b.reshape(-1, 4)[:1].cpu() for b in select_a_mask([r["instances"] for r in item["support_set"]])], dim=0)
+                    for item in batched_inputs]
+        if features_in_slot:
+            passes = [list(range(len(batched_inputs)))]
+        else:
+            by_size: Dict[Tuple[int, int], List[int]] = {}
+            for i, item in enumerate(batched_inputs):
+                by_size.setdefault(self.class_padded_size(item), []).append(i)
+            passes = []
+            for (hp, wp), idx in by_size.items():
+                per_image = (hp * wp) / float(800 * 1344)
+                cur, load = [], 0.0
+                for i in idx:
+                    cost = len(batched_inputs[i]["support_set"]) * per_image
+                    if cur and load + cost > self.SUPPORT_PASS_IMAGE_BUDGET:
+                        passes.append(cur)
+                        cur, load = [], 0.0
+                    cur.append(i)
+                    load += cost
+                if cur:
+                    passes.append(cur)
+        rows: List[Optional[torch.Tensor]] = [None] * len(batched_inputs)
+        for idx in passes:
+            records, offsets = [], [0]
+            for i in idx:
+                records.extend(batched_inputs[i]["support_set"])
+                offsets.append(len(records))
+            if not features_in_slot:
+                self.engine.extract_features(SLOT_SUPPORT, [r["image"] for r in records])
+            raw = self.engine.generate_codes(SLOT_SUPPORT, torch.cat([boxes_of[i] for i in idx], dim=0),
+                                             list(range(len(records))), offsets)
+            for k, i in enumerate(idx):
+                rows[i] = raw[k:k + 1]
+        if roi_encoder:
+            return [{"cls_conv": r[:, :256].reshape(1, 256, 1, 1), "cls_bias": r[0, 256:].reshape(1)} for r in rows]
+        return [{"cls_conv": r[:, :256].reshape(1, 256, 1, 1), "cls_bias": r[:, 256:].reshape(1, 1, 1, 1)} for r in rows]
 
     # ------------------------------------------------------------------ training forward (losses only, no backward)
     def _get_gt(self, batched_inputs: List[Dict[str, Any]], support_set_targets=None):

@@ -358,7 +358,9 @@ def run_episode(model: MetaOneStageDetector, support_items: Sequence[Dict[str, A
     if ready is None and my_support and 0 < len(my_query) <= 16 and torch.cuda.is_available():
         sup_imgs = [r["image"] for it in my_support for r in it["support_set"]]
         qry_imgs = [q["image"] for q in my_query]
-        if all(t.is_cuda for t in sup_imgs + qry_imgs) and len(sup_imgs) + len(qry_imgs) <= 64:
+        # one shared support batch only when every class pads to the same size (each reference call pads to its own maximum)
+        one_size = len({model.class_padded_size(it) for it in my_support}) == 1
+        if one_size and all(t.is_cuda for t in sup_imgs + qry_imgs) and len(sup_imgs) + len(qry_imgs) <= 64:
             from .runtime import SLOT_QUERY, SLOT_SUPPORT
             model.engine.extract_features_multi([(SLOT_SUPPORT, sup_imgs), (SLOT_QUERY, qry_imgs)])
             merged = True

@@ -172,7 +172,19 @@ class Engine:
         self._check(self.lib.sylph_extract_features_multi(self.h, len(groups), slots, counts, ptrs, int(u8), hs, ws, self._stream()))
         self._keep = imgs
 
-    def import_features(self, slot: int, features: Sequence[torch.Tensor], padded_hw: Tuple[int, int]) -> None:
+    def extract_features_normalized(self, slot: int, batch: torch.Tensor) -> None:
+        """The backbone on an already normalised, zero-padded (N, 3, H, W) batch (what the reference hands to
+        `self.backbone(images.tensor)`)."""
+        x = batch.to(self.device, torch.float32).contiguous()
+        assert x.dim() == 4 and x.shape[1] == 3, "expected a (N, 3, H, W) batch"
+        self._check(self.lib.sylph_extract_features_normalized(self.h, slot, x.shape[0], c_void_p(x.data_ptr()),
+                                                               int(x.shape[2]), int(x.shape[3]), self._stream()))
+        x.record_stream(torch.cuda.current_stream())
+
+    def import_features(self, slot: int, features: Sequence[torch.Tensor], padded_hw: Tuple[int, int],
+                        image_sizes: Optional[Sequence[Tuple[int, int]]] = None) -> None:
+        """`image_sizes`: the un-padded (h, w) of every image (ImageList.image_sizes); detection boxes are scaled by
+        out_size / image_size, so they must be known for proposals to come back un-scaled."""
         feats = [f.to(self.device, torch.float32).contiguous() for f in features]
         assert len(feats) == NUM_LEVELS and all(f.shape[1] == 256 for f in feats)
         n = feats[0].shape[0]
@@ -181,6 +193,10 @@ class Engine:
         lw = (c_int * NUM_LEVELS)(*[int(f.shape[3]) for f in feats])
         self._check(self.lib.sylph_import_features(self.h, slot, n, int(padded_hw[0]), int(padded_hw[1]), ptrs, lh, lw,
                                                    self._stream()))
+        if image_sizes is not None:
+            hs = (c_int * n)(*[int(s[0]) for s in image_sizes])
+            ws = (c_int * n)(*[int(s[1]) for s in image_sizes])
+            self._check(self.lib.sylph_set_image_sizes(self.h, slot, n, hs, ws))
         self._keep = feats
 
     def feature_shape(self, slot: int):

@@ -261,6 +261,50 @@ def synthetic_state_dict(cfg, seed: int = 0) -> "OrderedDict[str, torch.Tensor]"
     return OrderedDict((k, synthetic_tensor(cfg, k, shp, seed)) for k, shp in state_spec(cfg).items())
 
 
+def reference_init_state_dict(cfg, seed: int = 0) -> "OrderedDict[str, torch.Tensor]":
+    """The reference's own initialisers ("random-init weights" of BASELINE.json): c2_msra for the ResNet,
+    c2_xavier for FPN / P6P7, identity FrozenBN, N(0, 0.01) convolutions with zero bias in the FCOS head
+    (sylph/modeling/meta_fcos/fcos.py:445-461) and in the code generator (code_generator.py:400-415), GroupNorm affine
+    (1, 0), every `Scale` at its init value.  With these weights every class logit sits at the prior
+    (sigmoid(-4.595) = 0.01 < INFERENCE_TH_TEST): detection has ZERO candidates -- the bench reports this variant next to
+    the "trained-like" synthetic weights that exercise the proposal / NMS kernels."""
+    out: "OrderedDict[str, torch.Tensor]" = OrderedDict()
+    head_like = ("proposal_generator.fcos_head.", "code_generator.")
+    for key, shape in state_spec(cfg).items():
+        g = _gen(key, seed)
+        leaf = key.rsplit(".", 1)[-1]
+        if key in ("pixel_mean", "pixel_std"):
+            t = synthetic_tensor(cfg, key, shape, seed)
+        elif key.endswith(".scale"):
+            t = torch.full(shape, 1.0)
+        elif leaf == "running_mean":
+            t = torch.zeros(shape)
+        elif leaf == "running_var":
+            t = torch.full(shape, 1.0 - 1e-5)           # detectron2 FrozenBatchNorm2d default
+        elif len(shape) == 1:
+            is_norm = (".norm." in key) or ("init_norm" in key) or ("post_norm" in key) or _is_gn_key(key) or "norm" in key.split(".")[-2]
+            if key.endswith("cls_logits.bias"):
+                t = torch.full(shape, -math.log((1 - cfg.MODEL.FCOS.PRIOR_PROB) / cfg.MODEL.FCOS.PRIOR_PROB))
+            elif is_norm and leaf == "weight":
+                t = torch.ones(shape)
+            else:
+                t = torch.zeros(shape)                  # norm bias, conv bias
+        elif len(shape) == 2:
+            bound = math.sqrt(1.0 / shape[1])           # nn.Linear default (kaiming_uniform, a = sqrt(5))
+            t = (torch.rand(shape, generator=g) * 2 - 1) * bound
+        else:
+            cout, cin, kh, kw = shape
+            if key.startswith(head_like):
+                t = torch.randn(shape, generator=g) * 0.01
+            elif key.startswith("backbone.bottom_up"):
+                t = torch.randn(shape, generator=g) * math.sqrt(2.0 / (cout * kh * kw))     # c2_msra_fill
+            else:
+                bound = math.sqrt(3.0 / (cin * kh * kw))                                    # c2_xavier_fill
+                t = (torch.rand(shape, generator=g) * 2 - 1) * bound
+        out[key] = t.to(torch.float32)
+    return out
+
+
 def load_into_module(module: torch.nn.Module, state: Dict[str, torch.Tensor]) -> None:
     """Strict load: every key of the module must be present with the same shape (and vice versa)."""
     own = module.state_dict()

@@ -1,38 +1,27 @@
 """GPU parity tests: the CUDA path (through the C ABI) against the golden vectors produced by the REFERENCE modules
 and against the CPU oracle on the same seeded inputs.
 
-Tolerances.  The convolutions run on the tensor cores with fp16 operands (10-bit mantissa,
-round-to-nearest -- the same operand precision as the TF32 mode PyTorch/cuDNN use by default for fp32 convolutions on
-GPUs, i.e. what the reference itself runs on a GPU) and FP32 accumulation / epilogues.  BASELINE.json's north_star
-bar is 1e-3 relative to the fp32 CPU forward:
-  * OUTPUTS of the path -- class codes (raw and normalised) ..... CODE_TOL = 1e-3 (max-norm, measured 4-5e-4)
-                           detection boxes ........................ 0.5 px (1e-3 of a 500 px image; measured <= 0.35 px)
-                           detection scores ....................... GUARD = 5e-3 absolute (measured <= 2.2e-3)
-  * INTERMEDIATE tensors after ~50-70 convolution layers of 10-bit-mantissa operands accumulate 1-2.5e-3 (max-norm)
-    of rounding noise; they are held to DEEP_TOL = 3e-3 (feature maps, logits, box regression) and CTR_TOL = 6e-3
-    (centerness logits: a zero-mean 2304-term sum with heavy cancellation, so its error is large relative to its own
-    small magnitude), with the relative L2 error additionally held to L2_TOL.
-Integer outputs (FPN level of each ROI, (level, location, class) of each detection) must be exact, except for
-candidates whose oracle score lies within `GUARD` of a decision threshold ("hard parts").
+Bar (tests/parity.py): BASELINE.json's north_star -- 1e-3 relative to the fp32 CPU forward on every float tensor of
+the path (class codes, pyramid features, ROI features, logits, box regression, centre-ness, detection scores), boxes
+within 1e-3 of the image size, integer outputs exact (FPN level per ROI; (level, location, class) of every detection,
+where a key may differ only if the ORACLE's value behind it sits within the guard band of a decision threshold --
+proven per key by `check_detections`).  The default "exact" precision mode (split-fp16 operands, three tensor-core
+products per multiply, fp32 accumulation) is held to that bar; the "fast" mode (single fp16 operands) runs the same test
+against its measured error (FAST_*), reported in DESIGN.md section 5 -- it is not the parity claim.
 """
 import pytest
 import torch
 
 from tests.cases import cfg_for, load_golden, rel_err, rel_l2
+from tests.parity import FAST_CTR_TOL, FAST_GUARD, FAST_TOL, GUARD, TOL, check_detections, dets_to_keyed
 
 pytestmark = pytest.mark.gpu
 
-CODE_TOL = 1e-3         # class codes: max abs error relative to the tensor's max magnitude
-DEEP_TOL = 3e-3         # deep intermediate tensors, max-norm
-L2_TOL = 2e-3           # deep intermediate tensors, ||a-b|| / ||b||
-CTR_TOL = 6e-3          # centerness logits, max-norm
-GUARD = 5e-3            # guard band on scores around thresholds / NMS decisions
 
-
-def _engine(cfg, seed):
+def _engine(cfg, seed, precision="exact"):
     from sylph_few_shot_detection_b200 import weights as W
     from sylph_few_shot_detection_b200.runtime import Engine
-    eng = Engine(cfg, 0)
+    eng = Engine(cfg, 0, precision)
     state = W.synthetic_state_dict(cfg, seed)
     eng.load_state_dict(state)
     return eng, state
@@ -43,14 +32,20 @@ def _oracle(cfg, state):
     return MetaFCOSOracle(cfg, state)
 
 
+@pytest.mark.parametrize("precision", ["exact", "fast"])
 @pytest.mark.parametrize("case", ["coco_2way_2shot", "lvis_1way_3shot"])
-def test_episode_matches_reference_golden(case):
+def test_episode_matches_reference_golden(case, precision):
     from sylph_few_shot_detection_b200.runtime import SLOT_QUERY, SLOT_SUPPORT
     g = load_golden(case)
     cfg = cfg_for(g["config"])
-    eng, state = _engine(cfg, g["seed"])
+    eng, state = _engine(cfg, g["seed"], precision)
     orc = _oracle(cfg, state)
     report = []
+    exact = precision == "exact"
+    CODE_TOL = TOL                                   # class codes meet the bar in both modes
+    DEEP_TOL = L2_TOL = TOL if exact else FAST_TOL
+    CTR_TOL = TOL if exact else FAST_CTR_TOL
+    guard = GUARD if exact else FAST_GUARD
 
     # ---- support pass: all classes in one backbone batch
     images, boxes, roi_image, offsets = [], [], [], [0]
@@ -96,26 +91,21 @@ def test_episode_matches_reference_golden(case):
     for name, e, tol in report:
         print(f"  {name:28s} {e:.3e}  (tol {tol:.0e}) {'' if e <= tol else '<-- FAIL'}")
 
-    # ---- detections: keyed by (level, location, class); boxes/scores compared on matches
+    # ---- detections: keyed by (level, location, class); every key on one side only must be explained (tests/parity.py)
     dets, counts = dets.cpu(), counts.cpu()
+    codes = {"cls_conv": g["packed"]["cls_conv"], "cls_bias": g["packed"]["cls_bias"]}
+    ref_dets, inter = orc.detect(queries, codes, return_intermediate=True)
     for i, ref in enumerate(g["detections"]):
+        # the oracle reproduces the reference golden (0.0 deviation on the CPU that made it, tests/test_oracle.py; another
+        # host CPU may pick other fp32 kernels); its intermediates explain borderline keys
+        assert ref_dets[i]["scores"].shape == ref["scores"].shape and torch.allclose(ref_dets[i]["scores"], ref["scores"], atol=2e-5)
+        assert torch.equal(ref_dets[i]["classes"], ref["classes"]) and torch.allclose(ref_dets[i]["boxes"], ref["boxes"], atol=1e-2)
         n = int(counts[i])
         d = dets[i, :n]
-        got = {(int(r[8]), int(r[6]), int(r[7]), int(r[5])): r for r in d}
-        want = {(int(lv), int(loc[0]), int(loc[1]), int(cl)): (b, s) for b, s, cl, loc, lv in
-                zip(ref["boxes"], ref["scores"], ref["classes"], ref["locations"], ref["levels"])}
-        common = set(got) & set(want)
-        only_got, only_want = set(got) - set(want), set(want) - set(got)
-        print(f"  image {i}: {n} detections vs reference {len(want)}; common {len(common)}, "
-              f"extra {len(only_got)}, missing {len(only_want)}")
-        # scores must be non-increasing
-        assert all(float(d[k, 4]) >= float(d[k + 1, 4]) for k in range(n - 1))
-        box_err = max([float((got[k][:4] - want[k][0]).abs().max()) for k in common] or [0.0])
-        score_err = max([abs(float(got[k][4]) - float(want[k][1])) for k in common] or [0.0])
-        print(f"           max box err {box_err:.3e} px, max score err {score_err:.3e}")
-        assert box_err <= 0.5, "boxes of matched detections differ by more than half a pixel"
-        assert score_err <= GUARD
-        # set differences are allowed only for borderline detections (threshold / NMS / top-k guard band)
-        assert len(only_got) + len(only_want) <= max(2, int(0.1 * len(want))), (only_got, only_want)
+        assert all(float(d[k, 4]) >= float(d[k + 1, 4]) for k in range(n - 1)), "scores must be non-increasing"
+        st = check_detections(dets_to_keyed(dets[i], n), ref_dets[i], inter, i, cfg, guard=guard,
+                              score_tol=TOL if exact else FAST_GUARD, box_tol_px=None if exact else 0.5,
+                              name=f"{case} image {i} [{precision}]")
+        print(f"  image {i}: {st}")
     bad = [(n, e, t) for n, e, t in report if not e <= t]
     assert not bad, f"tensors outside tolerance: {bad}"

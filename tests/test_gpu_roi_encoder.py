@@ -1,19 +1,18 @@
 """GPU parity of the ROIEncoder code generator and the CondConvBlock classifier through the C
 ABI and the plugin API, against the golden vectors of the reference's own modules and the CPU oracle.
-Tolerances as in tests/test_gpu_parity.py; the generator adds two more fp16-operand 3x3 convolutions, a K = 12544
-fp16-operand GEMM and fp32 dense layers behind the ROI features, so its codes are held to RE_CODE_TOL = 2e-3."""
+Bar as in tests/parity.py (1e-3 relative on every float output, detection keys exact outside the guard band), in the
+default "exact" precision mode: the generator's extra 3x3 convolutions and its K = 12544 GEMM run with split-fp16
+operands like every other tensor-core product of the path."""
 import numpy as np
 import pytest
 import torch
 
 from tests.cases import cfg_for, load_golden, rel_err, rel_l2
+from tests.parity import TOL, check_detections, dets_to_keyed, instances_to_keyed
 
 pytestmark = pytest.mark.gpu
 
-RE_CODE_TOL = 2e-3
-DEEP_TOL = 3e-3
-L2_TOL = 2e-3
-GUARD = 5e-3
+RE_CODE_TOL = DEEP_TOL = L2_TOL = TOL
 
 
 def _setup():
@@ -48,7 +47,7 @@ def test_roi_encoder_codes_and_detections_match_reference_golden():
     for c, ref in enumerate(g["raw_codes"]):
         report.append((f"cls_conv[{c}]", rel_err(raw[c, :256], ref["cls_conv"].reshape(-1)), RE_CODE_TOL))
         report.append((f"cls_conv[{c}] (L2)", rel_l2(raw[c, :256], ref["cls_conv"].reshape(-1)), RE_CODE_TOL))
-        report.append((f"cls_bias[{c}] (abs)", abs(float(raw[c, 256]) - float(ref["cls_bias"].reshape(-1)[0])), 5e-3))
+        report.append((f"cls_bias[{c}] (abs)", abs(float(raw[c, 256]) - float(ref["cls_bias"].reshape(-1)[0])), TOL))
     with pytest.raises(RuntimeError, match="no code normalisation"):
         eng.normalize_codes(raw)
     # ---- query pass with the REFERENCE's packed codes: CondConvBlock scale folded into the logits GEMM
@@ -63,17 +62,12 @@ def test_roi_encoder_codes_and_detections_match_reference_golden():
     for name, e, tol in report:
         print(f"  {name:24s} {e:.3e}  (tol {tol:.0e}) {'' if e <= tol else '<-- FAIL'}")
     dets, counts = dets.cpu(), counts.cpu()
+    codes = {"cls_conv": g["packed"]["cls_conv"], "cls_bias": g["packed"]["cls_bias"]}
+    ref_dets, inter = orc.detect([q.float() for q in g["query"]], codes, return_intermediate=True)
     for i, ref in enumerate(g["detections"]):
-        n = int(counts[i])
-        got = {(int(r[8]), int(r[6]), int(r[7]), int(r[5])): r for r in dets[i, :n]}
-        want = {(int(lv), int(loc[0]), int(loc[1]), int(cl)): (b, s) for b, s, cl, loc, lv in
-                zip(ref["boxes"], ref["scores"], ref["classes"], ref["locations"], ref["levels"])}
-        common = set(got) & set(want)
-        diff = (set(got) - set(want)) | (set(want) - set(got))
-        print(f"  image {i}: {n} detections vs reference {len(want)}; common {len(common)}, differing {len(diff)}")
-        assert len(diff) <= max(2, int(0.1 * len(want)))
-        assert max([float((got[k][:4] - want[k][0]).abs().max()) for k in common] or [0.0]) <= 0.5
-        assert max([abs(float(got[k][4]) - float(want[k][1])) for k in common] or [0.0]) <= GUARD
+        assert ref_dets[i]["scores"].shape == ref["scores"].shape and torch.allclose(ref_dets[i]["scores"], ref["scores"], atol=2e-5)
+        st = check_detections(dets_to_keyed(dets[i], int(counts[i])), ref_dets[i], inter, i, cfg, name=f"roi encoder image {i}")
+        print(f"  image {i}: {st}")
     bad = [(n, e, t) for n, e, t in report if not e <= t]
     assert not bad, f"tensors outside tolerance: {bad}"
 
@@ -108,9 +102,10 @@ def test_roi_encoder_plugin_surface_and_episode():
     q = g["query"][0]
     res = run_episode(model, items, [{"image": q, "height": q.shape[-2], "width": q.shape[-1]}])
     inst = res[0]["instances"]
-    ref = g["detections"][0]
-    assert abs(len(inst) - int(ref["scores"].numel())) <= max(2, int(0.1 * ref["scores"].numel()))
-    assert abs(float(inst.scores[0]) - float(ref["scores"][0])) < GUARD
+    packed = {"cls_conv": g["packed"]["cls_conv"], "cls_bias": g["packed"]["cls_bias"]}
+    ref_dets, inter = orc.detect([q.float()], packed, return_intermediate=True)
+    # the episode's own codes (within 1e-3 of the golden's) move scores by up to ~1e-3: guard band of that width
+    check_detections(instances_to_keyed(inst), ref_dets[0], inter, 0, cfg, guard=2e-3, score_tol=2e-3, name="roi encoder episode")
 
 
 def test_roi_encoder_forward_on_foreign_nchw_features():
@@ -131,4 +126,4 @@ def test_roi_encoder_forward_on_foreign_nchw_features():
     assert out["cls_conv"].shape == (1, 256, 1, 1) and out["cls_bias"].shape == (1,)
     ref = g["raw_codes"][0]
     assert rel_err(out["cls_conv"], ref["cls_conv"]) < RE_CODE_TOL
-    assert abs(float(out["cls_bias"][0]) - float(ref["cls_bias"].reshape(-1)[0])) < 5e-3
+    assert abs(float(out["cls_bias"][0]) - float(ref["cls_bias"].reshape(-1)[0])) < TOL

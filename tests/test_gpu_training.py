@@ -4,15 +4,15 @@ sylph_fcos_loss_finalize) and the plugin mirror (`model.train(); model(batched_i
 Tolerances: labels, target_inds and reg_targets are bit-exact against the REFERENCE golden.  The loss arithmetic is
 checked twice: (a) TIGHT -- the oracle's loss restatement is fed the head outputs exported from the CUDA path, so only
 the loss kernels differ (fp32 terms, fp64 accumulation): 2e-5 relative; (b) END TO END against the reference's fp32
-losses: LOSS_TOL = 1e-2 relative -- the logits carry the 1-2.5e-3 noise of the fp16-operand backbone (DESIGN.md
-section 5) and the focal loss amplifies it through exp()."""
+losses: LOSS_TOL = 1e-3 relative (the north-star bar) in the default "exact" precision mode (split-fp16 operands; the
+single-fp16 "fast" mode measured up to 1e-2 here: the focal loss amplifies its 1-2.5e-3 logit noise through exp())."""
 import pytest
 import torch
 
 from tests.cases import cfg_for, load_golden
 
 pytestmark = pytest.mark.gpu
-LOSS_TOL = 1e-2
+LOSS_TOL = 1e-3
 KERNEL_TOL = 2e-5
 
 
