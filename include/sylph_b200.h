@@ -221,6 +221,12 @@ int sylph_detect(sylph_ctx* ctx, int slot, const float* codes_dev, int n_classes
 int sylph_detect_after(sylph_ctx* ctx, int slot, const float* codes_dev, int n_classes, const int* out_sizes_host,
                        float* dets_out_dev, int* counts_out_dev, int max_dets, void* codes_ready_event, void* stream);
 
+/* Health of the finished sylph_detect calls: non-zero (and a message) when an (image, level) candidate list overflowed its
+ * 2^22 slots, i.e. detections were dropped -- reachable only at LVIS scale (1203 classes on p3) with a very low threshold.
+ * The word travels to pinned host memory behind every detect call, so call this after synchronising on the detections;
+ * it never touches the device.  (The reference has no such limit: fcos_outputs.py:960-984 sorts whatever passes.) */
+int sylph_detect_poll(sylph_ctx* ctx);
+
 /* Head intermediates of the last sylph_detect call, NCHW fp32: which = 0 logits (n, n_classes, H, W),
  * 1 bbox_reg after scale+ReLU (n, 4, H, W), 2 ctrness (n, 1, H, W), 3 iou (n, 1, H, W). */
 int sylph_export_head_output(sylph_ctx* ctx, int which, int level, float* out_dev, void* stream);

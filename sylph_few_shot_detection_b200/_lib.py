@@ -144,6 +144,8 @@ def load() -> ctypes.CDLL:
     lib.sylph_detect.argtypes = [vp, c_int, vp, c_int, ip, vp, vp, c_int, vp]
     lib.sylph_detect_after.restype = c_int
     lib.sylph_detect_after.argtypes = [vp, c_int, vp, c_int, ip, vp, vp, c_int, vp, vp]
+    lib.sylph_detect_poll.restype = c_int
+    lib.sylph_detect_poll.argtypes = [vp]
     lib.sylph_export_head_output.restype = c_int
     lib.sylph_export_head_output.argtypes = [vp, c_int, c_int, vp, vp]
     lib.sylph_fcos_loss_sums.restype = c_int
@@ -166,5 +168,5 @@ EXPORTED_SYMBOLS = [
     "sylph_finalize_weights", "sylph_extract_features", "sylph_extract_features_u8", "sylph_extract_features_normalized", "sylph_extract_features_multi", "sylph_import_features", "sylph_set_image_sizes", "sylph_feature_shape",
     "sylph_export_features", "sylph_generate_codes", "sylph_export_roi_features", "sylph_normalize_codes", "sylph_exchange_create", "sylph_exchange_connect",
     "sylph_normalize_codes_exchange", "sylph_exchange_poll", "sylph_exchange_status", "sylph_exchange_destroy", "sylph_accumulate_codes", "sylph_reduce_codes",
-    "sylph_detect", "sylph_detect_after", "sylph_export_head_output", "sylph_fcos_loss_sums", "sylph_fcos_loss_finalize", "sylph_launch_count", "sylph_set_profiling", "sylph_get_timings",
+    "sylph_detect", "sylph_detect_after", "sylph_detect_poll", "sylph_export_head_output", "sylph_fcos_loss_sums", "sylph_fcos_loss_finalize", "sylph_launch_count", "sylph_set_profiling", "sylph_get_timings",
 ]

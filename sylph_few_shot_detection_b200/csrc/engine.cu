@@ -138,6 +138,7 @@ struct sylph_ctx {
     // point has to drain the stream (a pageable cudaMemcpyAsync synchronises the stream first)
     uint8_t* pinned = nullptr;
     size_t pinned_cap = 0, pinned_head = 0;
+    unsigned int* detect_overflow_host = nullptr;   // pinned copy of the candidate-overflow word of the last detect calls (sticky)
     uint8_t* graph_arena = nullptr;  // pinned argument blocks referenced by captured CUDA graphs (bump-allocated)
     size_t graph_arena_cap = 0, graph_arena_head = 0;
     std::map<std::string, std::shared_ptr<PlaneSet>> plane_sets;
@@ -730,6 +731,7 @@ void sylph_destroy(sylph_ctx* c) {
     for (auto& kv : c->bufs) if (kv.second.p) cudaFree(kv.second.p);
     if (c->pinned) cudaFreeHost(c->pinned);
     if (c->graph_arena) cudaFreeHost(c->graph_arena);
+    if (c->detect_overflow_host) cudaFreeHost(c->detect_overflow_host);
     for (auto& kv : c->plane_sets) { cudaFree(kv.second->d_segs); cudaFree(kv.second->d_tile_seg); }
     delete c;  // prepared weights are released with the CUDA context
 }
@@ -1787,6 +1789,10 @@ int sylph_detect_after(sylph_ctx* c, int slot, const float* codes_dev, int n_cla
     long long off = 0;
     for (int l = 0; l < 5; ++l) {
         const long long full = static_cast<long long>(S.lh[l]) * S.lw[l] * n_classes;
+        // the NMS key packs (level << 28 | location * classes + class): larger planes / class counts would corrupt it silently
+        if (full >= (1LL << 28))
+            return c->fail("level %d: %d x %d locations x %d classes = %lld candidate slots exceed the 2^28 key space of the "
+                           "proposal kernels (split the class list over several detect calls)", l, S.lh[l], S.lw[l], n_classes, full);
         P.cap[l] = static_cast<int>(std::min<long long>(full, 1 << 22));
         P.cand_off[l] = off;
         off += static_cast<long long>(S.n) * P.cap[l];
@@ -1839,6 +1845,30 @@ int sylph_detect_after(sylph_ctx* c, int slot, const float* codes_dev, int n_cla
                                                  n_max, dets_out_dev, counts_out_dev, max_dets));
         CU_TRY(c, cudaGetLastError());
         c->launches += 3;
+        // the overflow word (an (image, level) list had more candidates above the threshold than its 2^22 slots) follows the
+        // detections to pinned host memory: sylph_detect_poll reports it without touching the device.  Not while capturing
+        // a CUDA graph (the pinned word is allocated lazily, and allocation is illegal during capture).
+        cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
+        const bool capturing = cudaStreamIsCapturing(st, &cap) == cudaSuccess && cap == cudaStreamCaptureStatusActive;
+        if (!capturing) {
+            if (c->detect_overflow_host == nullptr) {
+                CU_TRY(c, cudaHostAlloc(reinterpret_cast<void**>(&c->detect_overflow_host), 2 * sizeof(unsigned int), cudaHostAllocDefault));
+                c->detect_overflow_host[0] = c->detect_overflow_host[1] = 0u;
+            }
+            CU_TRY(c, cudaMemcpyAsync(c->detect_overflow_host, static_cast<int*>(cnt) + n_segs, sizeof(unsigned int), cudaMemcpyDeviceToHost, st));
+        }
+    }
+    return 0;
+}
+
+int sylph_detect_poll(sylph_ctx* c) {
+    if (!c) return 1;
+    if (c->detect_overflow_host == nullptr) return 0;
+    if (*static_cast<volatile unsigned int*>(c->detect_overflow_host) != 0u) {
+        c->detect_overflow_host[1] = 1u;
+        c->detect_overflow_host[0] = 0u;
+        return c->fail("a detect call dropped candidates: more than 2^22 (location, class) pairs of one (image, level) passed "
+                       "INFERENCE_TH_TEST (lower the class count per call or raise the threshold)");
     }
     return 0;
 }

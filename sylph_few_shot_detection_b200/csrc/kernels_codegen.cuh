@@ -103,7 +103,7 @@ roi_align_kernel(const __half* __restrict__ pyramid, PyramidGeom pg, const float
 // Dynamic shared memory: 7 * (R + C) floats with R x C the footprint (rows x columns of the level the ROI reads).
 constexpr int kRoiSepMaxSpan = 512;   // footprint rows / columns the separable kernel accepts (else: per-sample kernel)
 
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, 2)
 roi_align_separable_kernel(const __half* __restrict__ pyramid, PyramidGeom pg, const float* __restrict__ boxes,
                            const int* __restrict__ roi_image, __half* __restrict__ roi_planes,
                            long long* __restrict__ levels_out, int split, int span_cap) {
@@ -171,13 +171,23 @@ roi_align_separable_kernel(const __half* __restrict__ pyramid, PyramidGeom pg, c
         for (int c = 0; c < C; ++c) {
             float col[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
             const __half* p = pyramid + plane_row(g, n, r0 + rlo, c0 + c) * ld;
-            for (int r = rlo; r <= rhi; ++r) {
+            const size_t pitch = static_cast<size_t>(g.Wp) * ld;
+            int r = rlo;
+            for (; r + 1 <= rhi; r += 2) {     // two rows of loads in flight per thread
+                float v[8], u[8];
+                load8f(p, cg * 8, lo_off, v);
+                load8f(p + pitch, cg * 8, lo_off, u);
+                const float w0 = wy[r], w1 = wy[r + 1];
+#pragma unroll
+                for (int j = 0; j < 8; ++j) col[j] += w0 * v[j] + w1 * u[j];
+                p += 2 * pitch;
+            }
+            if (r <= rhi) {
                 float v[8];
                 load8f(p, cg * 8, lo_off, v);
                 const float w = wy[r];
 #pragma unroll
                 for (int j = 0; j < 8; ++j) col[j] += w * v[j];
-                p += static_cast<size_t>(g.Wp) * ld;
             }
 #pragma unroll
             for (int pw = 0; pw < 7; ++pw) {

@@ -248,7 +248,9 @@ class MetaFCOS(_EngineBound):
 
     def predict(self, class_codes: Dict[str, torch.Tensor], image_sizes, out_sizes) -> List[Any]:
         dets, counts = self.predict_device(class_codes, out_sizes)
-        return instances_from_detections(dets, counts.cpu().tolist(), out_sizes)
+        counts = counts.cpu().tolist()      # synchronises: the overflow word of this call is on the host as well
+        self.engine.detect_poll()
+        return instances_from_detections(dets, counts, out_sizes)
 
 
 def instances_from_detections(dets: torch.Tensor, counts: Sequence[int], out_sizes) -> List[Any]:

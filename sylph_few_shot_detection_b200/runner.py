@@ -17,6 +17,8 @@ from __future__ import annotations
 import os
 from typing import Any, Dict, List, Optional, Sequence, Tuple
 
+import numpy as np
+
 import torch
 import torch.distributed as dist
 
@@ -259,12 +261,20 @@ def inference_normalization(model: MetaOneStageDetector, all_class_codes: List[D
 
 def format_class_codes_shared(all_class_codes: List[Dict], device=None) -> Dict[str, torch.Tensor]:
     """Step E (meta_learn_evaluation.py:71-103): index by support_set_target, concatenate, flatten the bias."""
-    by_id = {}
+    n = len(all_class_codes)
+    if n == 0:
+        return all_class_codes          # the reference returns the (empty) list itself (:86-87)
+    slots: List[Optional[Dict]] = [None] * n
     for c in all_class_codes:
-        by_id[_target_id(c["support_set_target"])] = c["class_code"]
-    ids = sorted(by_id)
-    conv = torch.cat([by_id[i]["cls_conv"] for i in ids], dim=0)
-    bias = torch.cat([by_id[i]["cls_bias"].reshape(-1) for i in ids], dim=0)
+        i = _target_id(c["support_set_target"])
+        if not 0 <= i < n:        # the reference indexes a list of n entries with the target id: IndexError
+            raise IndexError(f"support_set_target {i} outside [0, {n}): class ids must be 0..n-1 (meta_learn_evaluation.py:93-96)")
+        slots[i] = c["class_code"]
+    missing = [i for i, v in enumerate(slots) if v is None]
+    if missing:                   # ... and concatenates the list: a hole (duplicate / missing id) is a TypeError there
+        raise TypeError(f"no class code for class id(s) {missing[:8]}: ids must be exactly 0..{n - 1} without duplicates")
+    conv = torch.cat([v["cls_conv"] for v in slots], dim=0)
+    bias = torch.cat([v["cls_bias"].reshape(-1) for v in slots], dim=0)
     if device is not None:
         conv, bias = conv.to(device), bias.to(device)
     return {"cls_conv": conv, "cls_bias": bias}
@@ -526,6 +536,10 @@ class EpisodeGraph:
         return self.dets, self.counts
 
 
+def _is_main_process() -> bool:
+    return not (dist.is_available() and dist.is_initialized()) or dist.get_rank() == 0
+
+
 def _roi_encoder_type():
     from .modeling import ROIEncoder
     return ROIEncoder
@@ -579,8 +593,10 @@ class MetaFCOSRunner:
         per test repetition (`TEST.REPEAT_TEST` at the final iteration) and dataset -- class codes from the support-set
         loader (B), gather (C), optionally the base-class all-GT codes (gather with reduce, `replace_class_code`),
         normalisation (D), packing (E), detection over the query loader into the evaluator (F).  Steps B and F go
-        through the batched entry points (all classes of the rank in one backbone batch; query batches as they come),
-        everything else is the reference's own sequence.  Returns {model_tag: {}, "seed<k>": {dataset: evaluator results}}."""
+        through the batched entry points (the rank's classes in shared backbone batches, grouped by padded size and bounded
+        per pass; query batches as they come), everything else is the reference's own sequence.  On the main process:
+        {"seed<k>": {dataset: evaluator results}, model_tag: {dataset: bbox metrics averaged over the repetitions, plus
+        AP*_avg / AP*_std at the final iteration}} (meta_fcos_runner.py:602-634)."""
         from collections import OrderedDict
         assert len(cfg.DATASETS.TEST)
         max_iter = (cfg.get("SOLVER") or {}).get("MAX_ITER")          # solver keys are not part of the inference config tree
@@ -631,7 +647,29 @@ class MetaFCOSRunner:
                     outputs = inference_with_class_codes(model, list(inputs), packed, batch_size=max(len(inputs), 1))
                     evaluator.process(inputs, outputs)
                 res = evaluator.evaluate()
-                results[f"seed{seed}"][dataset_name] = {} if res is None else res
+                if not _is_main_process():
+                    continue                                                           # results live on the main process only
+                res = {} if res is None else res
+                results[f"seed{seed}"][dataset_name] = res
+                # running mean of the bbox metrics over the repetitions, AP(_r/c/f)_avg / _std at the end (:602-634)
+                if "bbox" in res:
+                    from copy import deepcopy
+                    if seed == 0:
+                        results[model_tag][dataset_name] = deepcopy(res)
+                    else:
+                        acc = results[model_tag][dataset_name]["bbox"]
+                        for k in acc:
+                            acc[k] += res["bbox"][k]
+                            if seed == num_repeat_test - 1:
+                                acc[k] /= num_repeat_test
+                    if is_final and seed == num_repeat_test - 1:
+                        for k in ("AP", "APr", "APc", "APf"):
+                            vals = [results[f"seed{s}"][dataset_name]["bbox"][k] for s in range(num_repeat_test)
+                                    if k in results[f"seed{s}"][dataset_name].get("bbox", {})]
+                            if vals:
+                                arr = np.array(vals, dtype=np.float64)
+                                results[model_tag][dataset_name]["bbox"][f"{k}_avg"] = float(arr.mean())
+                                results[model_tag][dataset_name]["bbox"][f"{k}_std"] = float(arr.std())
         return results
 
     def do_test(self, cfg, model, train_iter=None, support_items=None, query_items=None):

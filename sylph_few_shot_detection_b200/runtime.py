@@ -349,6 +349,10 @@ class Engine:
             codes.record_stream(torch.cuda.current_stream())
         return dets, counts
 
+    def detect_poll(self) -> None:
+        """Raises if a finished detect call dropped candidates (list overflow); call after synchronising on its results."""
+        self._check(self.lib.sylph_detect_poll(self.h))
+
     def side_stream(self) -> "torch.cuda.Stream":
         """Context-owned second stream: code generation runs here while the code-independent FCOS towers run on the
         caller's stream (generate_and_detect, runner.run_episode)."""

@@ -69,7 +69,7 @@ def test_select_a_mask_consumes_the_global_numpy_rng_and_rejects_empty():
 
 
 def test_pack_and_format_class_codes():
-    codes = [{"support_set_target": torch.tensor(2), "class_code": {"cls_conv": torch.full((1, 256, 1, 1), 2.0), "cls_bias": torch.tensor([0.2])}},
+    codes = [{"support_set_target": torch.tensor(1), "class_code": {"cls_conv": torch.full((1, 256, 1, 1), 2.0), "cls_bias": torch.tensor([0.2])}},
              {"support_set_target": 0, "class_code": {"cls_conv": torch.full((1, 256, 1, 1), 0.5), "cls_bias": torch.tensor([0.0])}}]
     packed = format_class_codes_shared(codes)
     assert packed["cls_conv"].shape == (2, 256, 1, 1) and packed["cls_bias"].shape == (2,)

@@ -52,6 +52,9 @@ class OracleBackedEngine:
             rows.append(torch.cat([w.reshape(1, 256), b.reshape(1, 1)], dim=1))
         return torch.cat(rows, dim=0)
 
+    def detect_poll(self):
+        pass          # the oracle never drops candidates
+
     def detect(self, slot, codes, out_sizes=None, max_dets=None, codes_ready=None):
         self.calls.append(("detect", slot, codes.shape[0]))
         res = self.orc.detect(self.slots[slot], {"cls_conv": codes[:, :256].reshape(-1, 256, 1, 1), "cls_bias": codes[:, 256]},
@@ -384,7 +387,16 @@ def test_format_class_codes_shared_equals_the_reference_function():
         assert set(got) == set(want) == {"cls_conv", "cls_bias"}
         assert got["cls_conv"].shape == (n, 256, 1, 1) and got["cls_bias"].shape == (n,)
         assert torch.equal(got["cls_conv"], want["cls_conv"]) and torch.equal(got["cls_bias"], want["cls_bias"])
-    assert ev.format_class_codes_shared([], torch.device("cpu")) == []
+    assert ev.format_class_codes_shared([], torch.device("cpu")) == [] and format_class_codes_shared([]) == []
+    # ids that are not exactly 0..n-1 fail loudly on both sides (the reference indexes a list of n slots, then concatenates)
+    def code(c):
+        return {"support_set_target": torch.tensor(c), "class_name": f"c{c}",
+                "class_code": {"cls_conv": torch.randn(1, 256, 1, 1, generator=g), "cls_bias": torch.randn(1, generator=g)}}
+    for bad, exc in (([code(0), code(2)], IndexError), ([code(0), code(0)], TypeError)):
+        with pytest.raises(exc):
+            ev.format_class_codes_shared(bad, torch.device("cpu"))
+        with pytest.raises(exc):
+            format_class_codes_shared(bad, device=torch.device("cpu"))
 
 
 def test_runner_do_test_follows_the_reference_sequence_with_injected_loaders(tmp_path):
