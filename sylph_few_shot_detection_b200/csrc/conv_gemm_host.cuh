@@ -216,6 +216,9 @@ inline cudaError_t launch_conv_gemm_staged(int bn, const CUtensorMap& ta, const 
     if (split) {
         if (bn == 64) return launch_conv_gemm_bn<64, 6, 2, 0, false, false, true>(ta, tb, tres, tout, args, num_sms, stream);
         if (bn == 128) return launch_conv_gemm_bn<128, 3, 2, 0, false, false, true>(ta, tb, tres, tout, args, num_sms, stream);
+        // 256-wide split tile: ONE 128 KB staging buffer (hi + lo) next to a 2-stage ring -- halves the A re-reads from L2 of
+        // the wide layers (N >= 512), at the price of no residual prefetch under the previous tile's epilogue
+        if (bn == 256) return launch_conv_gemm_bn<256, 2, 1, 0, false, false, true>(ta, tb, tres, tout, args, num_sms, stream);
         return cudaErrorInvalidValue;
     }
     // BN = 256, variant 1: 2 mainloop stages + 2 staging buffers (the residual of tile i+1 streams in during the

@@ -592,7 +592,11 @@ static int run_conv(sylph_ctx* c, const ConvCall& k, cudaStream_t st) {
     const bool pair1x1 = !split && k.staged && !k.stem && W.taps == 1 && W.bn == 256 && k.n_tiles >= 2 && W.k_per_tap >= 256 &&
                          (c->pair1x1 == 2 || (c->pair1x1 == 1 && (has_res ? W.k_per_tap >= 512 : W.cout_pad >= 512)));
     // N tile: a staged split tile holds a hi and a lo half, so it is at most 128 channels wide
-    const int bn = (split && k.staged && W.bn == 256) ? 128 : W.bn;
+    // (two 64 KB staging buffers); shortcut convolutions (no residual to prefetch, N >= 512) run 256-wide tiles over ONE 128 KB
+    // staging buffer, which halves their A re-reads from L2: 0.72 -> 0.64 / 0.60 -> 0.55 / 0.60 -> 0.54 ms on res3..res5 at 33
+    // images; every other staged layer measured slower that way (profiles/r02_split_tile_width_ab.log)
+    const bool wide_split = split && k.staged && W.bn == 256 && !has_res && !(k.flags & kEpiRelu) && W.cout_pad >= 512;
+    const int bn = (split && k.staged && W.bn == 256 && !wide_split) ? 128 : W.bn;
     if (stem16) {
         if (make_tmap_2d_k16(&ta, k.A, static_cast<uint64_t>(k.a_rows), kBlockM + 3, &err, split ? 32 : 16))
             return c->fail("A tensor map (%s): %s", k.name, err.c_str());

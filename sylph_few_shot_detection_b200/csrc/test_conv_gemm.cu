@@ -605,6 +605,17 @@ int main(int argc, char** argv) {
         printf("bn=%d ", bnv);
         fails += run_case(d, sms);
     }
+    {   // 256-wide staged split tile (one staging buffer), residual in place and store-only
+        Seg s0 = mk_seg(0, 150, 168, 1);
+        Case c{"SPLIT_staged_bn256_inplace_res_relu_mask", 256, {s0}, round128(s0.nrows), 128, 128, 1024, 1, 2, z1, z1, kEpiRelu | kEpiResidual | kEpiMask, true};
+        c.staged = true;
+        c.split = true;
+        fails += run_case(c, sms);
+        Case d{"SPLIT_staged_bn256_noresidual_k512", 256, {s0}, round128(s0.nrows), 512, 512, 512, 1, 8, z1, z1, kEpiMask, true};
+        d.staged = true;
+        d.split = true;
+        fails += run_case(d, sms);
+    }
     for (int bnv : {256, 128, 64, 16}) {   // halo pipeline
         Seg s0 = mk_seg(0, 70, 84, 1);
         Seg s1 = mk_seg(round128(s0.nrows), 37, 41, 1);
@@ -663,6 +674,18 @@ int main(int argc, char** argv) {
             bench_shape("res5_conv3_1x1_512_2048_res_STAGED", b ? 128 : 256, 330, 512, 2048, 1, RES, sms, 100, false, false, b);
             bench_shape("tower3x3_256_gn_f32out_PAIR", 256, 1480, 256, 256, 9, kEpiMask | kEpiGnStats | kEpiOutF32, sms, 0, false, true, b);
             bench_shape("fpn_lateral3_1x1_512_256", 256, 4488, 512, 256, 1, SC, sms, 0, false, false, b);
+        }
+        printf("---- split, staged 1x1 layers: 128-wide tiles (2 staging buffers) against 256-wide tiles (1 staging buffer)\n");
+        struct Sh { const char* name; int m_tiles, cin, cout, flags; };
+        const Sh shapes[] = {{"res3_shortcut_256_512", 4488, 256, 512, SC},     {"res4_shortcut_512_1024", 1155, 512, 1024, SC},
+                             {"res5_shortcut_1024_2048", 330, 1024, 2048, SC},  {"res4_conv1_1024_256", 1155, 1024, 256, C1},
+                             {"res5_conv1_2048_512", 330, 2048, 512, C1},       {"res2_conv3_64_256", 17622, 64, 256, RES},
+                             {"res3_conv3_128_512", 4488, 128, 512, RES},       {"res4_conv3_256_1024", 1155, 256, 1024, RES},
+                             {"res5_conv3_512_2048", 330, 512, 2048, RES}};
+        for (const Sh& sh : shapes) {
+            std::string a = std::string(sh.name) + "_bn128", c = std::string(sh.name) + "_bn256";
+            bench_shape(a.c_str(), 128, sh.m_tiles, sh.cin, sh.cout, 1, sh.flags, sms, 100, false, false, true);
+            bench_shape(c.c_str(), 256, sh.m_tiles, sh.cin, sh.cout, 1, sh.flags, sms, 100, false, false, true);
         }
         return 0;
     }

@@ -333,9 +333,39 @@ def exchange_codes_peer(model: MetaOneStageDetector, sub_class_codes: List[Dict]
 
 
 def code_exchange_mode() -> str:
-    """"nccl" (one all_gather_into_tensor, then normalisation on every rank) or "peer" (normalisation fused with the
-    all-gather over NVLink peer memory); SYLPH_CODE_EXCHANGE overrides the default."""
-    return os.environ.get("SYLPH_CODE_EXCHANGE", "nccl")
+    """"nccl" (one all_gather_into_tensor, then normalisation on every rank), "peer" (normalisation fused with the
+    all-gather over NVLink peer memory) or "auto" (default): peer when every rank of the group could map every other rank's
+    exchange buffer (GPUs of one box with peer access), the collective otherwise.  Measured on 8 B200s (profiles/r02_bench_n8.json,
+    r02_cfg5_*_n8.json): the exchange alone 0.21 ms (peer) against 0.49 ms (all-gather + normalisation of all classes), the
+    1203-class sweep 1.70 against 1.98 ms, the 20-way episode equal within noise.  SYLPH_CODE_EXCHANGE overrides."""
+    return os.environ.get("SYLPH_CODE_EXCHANGE", "auto")
+
+
+def _resolve_exchange(model: MetaOneStageDetector, mode: Optional[str], n_classes: int, group=None) -> str:
+    """"auto" -> "peer" / "nccl", decided ONCE per engine and agreed by all ranks (a MIN all-reduce of the local outcome of the
+    IPC set-up), so no rank can end up waiting in a collective the others do not enter."""
+    mode = mode or code_exchange_mode()
+    if mode != "auto":
+        return mode
+    engine = model.engine
+    cached = getattr(engine, "_auto_exchange", None)
+    if cached is not None:
+        return cached
+    decided = "nccl"
+    if dist.is_available() and dist.is_initialized() and dist.get_backend(group) == "nccl" and hasattr(engine, "exchange_setup"):
+        ok = 1
+        try:
+            engine.exchange_setup(group, max_classes=max(2048, n_classes))
+        except RuntimeError:
+            ok = 0
+        flag = torch.tensor([ok], device=engine.device, dtype=torch.int32)
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN, group=group)
+        if int(flag) == 1:
+            decided = "peer"
+        elif ok:
+            engine.exchange_teardown(group)
+    engine._auto_exchange = decided
+    return decided
 
 
 def run_episode(model: MetaOneStageDetector, support_items: Sequence[Dict[str, Any]], query_items: Sequence[Dict[str, Any]],
@@ -379,7 +409,8 @@ def run_episode(model: MetaOneStageDetector, support_items: Sequence[Dict[str, A
         # the class list is global: shard sizes, ids and names are known everywhere, only the codes travel
         counts = [len(shard_range(len(support_items), world, r)) for r in range(world)]
         meta = [(it["support_set_target"], it.get("class_name", "")) for it in support_items]
-        if (exchange or code_exchange_mode()) == "peer":
+        exchange = _resolve_exchange(model, exchange, len(support_items), group)
+        if exchange == "peer":
             all_codes = exchange_codes_peer(model, sub_codes, counts, meta, group=group)    # already normalised
         else:
             all_codes = inference_normalization(model, gather_class_code_known_shards(sub_codes, counts, meta, group=group))
@@ -395,7 +426,7 @@ def run_episode(model: MetaOneStageDetector, support_items: Sequence[Dict[str, A
         with torch.no_grad():
             return model.forward_instances_device(list(my_query), packed, features_in_slot=merged)
     results = inference_with_class_codes(model, my_query, packed, features_in_slot=merged)
-    if world > 1 and shard and (exchange or code_exchange_mode()) == "peer" and my_query:
+    if world > 1 and shard and exchange == "peer" and my_query:
         model.engine.exchange_poll()   # the results above are on the host, so the flag of this episode is too: incomplete codes raise
     return results
 
