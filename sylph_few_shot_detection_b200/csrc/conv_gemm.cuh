@@ -195,7 +195,8 @@ conv_gemm_f16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_co
                      const GemmArgs p) {
     using S = GemmSmem<BN, STAGES, EPI_BUFS, HALO, STEM16, BRES, SPLIT>;
     static_assert(!BRES || (HALO > 0 && !STEM16), "resident weights are implemented for the 3x3 halo pipeline");
-    static_assert(!(BRES && SPLIT), "split operands triple the weight tiles: no resident-weight variant");
+    // BRES + SPLIT (res2 conv2, 64 -> 64 channels): the k loop over K' = 3C visits [w_hi, w_hi, w_lo] per tap, i.e. only 18
+    // DISTINCT weight tiles (9 taps x {hi, lo}); slot tap holds w_hi, slot 9 + tap holds w_lo (STAGES = 18, 144 KB).
     constexpr int kPanels = BN / 64;   // 64-column panels of one staged tile half
     constexpr bool TMA_EPI = EPI_BUFS > 0;
     constexpr int kHalo = HALO > 0 ? HALO : 1;
@@ -350,7 +351,15 @@ conv_gemm_f16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_co
                     }
                     continue;
                 } else if constexpr (HALO > 0) {
-                    if constexpr (BRES) {
+                    if constexpr (BRES && SPLIT) {
+                        if (it == 0) {   // 18 resident tiles: slot t < 9 = w_hi of tap t (k-block 0), slot 9 + t = w_lo (k-block 2)
+                            for (int t = 0; t < 18; ++t) {
+                                ptx::mbar_arrive_expect_tx(&full_bar[t], S::kBBytes);
+                                ptx::tma_load_2d(smem + S::kRingOffset + t * S::kStageBytes, &tmap_b, &full_bar[t],
+                                                 t < 9 ? 0 : 2 * kBlockK, (t % 9) * p.b_rows_per_tap + b_row_base);
+                            }
+                        }
+                    } else if constexpr (BRES) {
                         if (it == 0) {   // resident weights: tile (tap, kb) -> slot tap * kblocks + kb, one barrier each
                             for (int t = 0; t < 9 * p.kblocks_per_tap; ++t) {
                                 ptx::mbar_arrive_expect_tx(&full_bar[t], S::kBBytes);
@@ -452,7 +461,7 @@ conv_gemm_f16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_co
                     uint32_t first = 0;
                     if constexpr (BRES) {
                         if (!b_resident) {
-                            for (int t = 0; t < 9 * p.kblocks_per_tap; ++t) ptx::mbar_wait(&full_bar[t], 0);
+                            for (int t = 0; t < (SPLIT ? 18 : 9 * p.kblocks_per_tap); ++t) ptx::mbar_wait(&full_bar[t], 0);
                             b_resident = true;
                         }
                     }
@@ -466,8 +475,8 @@ conv_gemm_f16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_co
                             if constexpr (BRES) {
                                 ptx::tc_fence_after();
                                 const uint64_t da = ptx::make_sw128_kmajor_desc(sa + dxi * 128);
-                                const uint64_t db = ptx::make_sw128_kmajor_desc(ptx::smem_u32(
-                                    smem + S::kRingOffset + ((dyi * 3 + dxi) * p.kblocks_per_tap + kb) * S::kStageBytes));
+                                const int slot = SPLIT ? (dyi * 3 + dxi) + (kb == 2 ? 9 : 0) : (dyi * 3 + dxi) * p.kblocks_per_tap + kb;
+                                const uint64_t db = ptx::make_sw128_kmajor_desc(ptx::smem_u32(smem + S::kRingOffset + slot * S::kStageBytes));
                                 if (!(p.dbg_skip & 2)) ptx::umma_f16_x4(d_tmem, da, db, kIdesc, first);
                                 first = 1;
                                 continue;

@@ -145,6 +145,10 @@ inline cudaError_t launch_conv_gemm(int bn, const CUtensorMap& ta, const CUtenso
 inline cudaError_t launch_conv_gemm_halo(int bn, const CUtensorMap& ta, const CUtensorMap& tb, const GemmArgs& args,
                                          int num_sms, cudaStream_t stream, bool allow_resident = true, bool split = false) {
     if (split) {
+        // 64 -> 64 channels (res2 conv2) in split mode: K' = 192 per tap = 3 k-blocks over 18 distinct weight tiles (w_hi, w_lo of
+        // the nine taps), all resident (144 KB) next to 4 halo A slots (68 KB)
+        if (allow_resident && bn == 64 && args.kblocks_per_tap == 3 && args.num_n_tiles == 1 && args.a_wrap == 128)
+            return launch_conv_gemm_bn<64, 18, 0, 4, false, true, true>(ta, tb, ta, ta, args, num_sms, stream);
         switch (bn) {
             case 16: return launch_conv_gemm_bn<16, 12, 0, 4, false, false, true>(ta, tb, ta, ta, args, num_sms, stream);
             case 64: return launch_conv_gemm_bn<64, 12, 0, 4, false, false, true>(ta, tb, ta, ta, args, num_sms, stream);

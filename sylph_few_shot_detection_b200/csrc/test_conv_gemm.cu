@@ -628,6 +628,14 @@ int main(int argc, char** argv) {
         printf("bn=%d ", bnv);
         fails += run_case(c, sms);
     }
+    {   // split halo pipeline with the 18 resident weight tiles (64 -> 64 channels, res2 conv2), two planes, many tiles per CTA
+        Seg s0 = mk_seg(0, 140, 168, 1);
+        Seg s1 = mk_seg(round128(s0.nrows), 37, 41, 1);
+        Case c{"SPLIT_HALO_BRES_conv3x3_64_64", 64, {s0, s1}, s1.row0 + round128(s1.nrows), 64, 64, 64, 9, 1, dy9, dx9, kEpiMask | kEpiRelu, true};
+        c.halo = true;
+        c.split = true;
+        fails += run_case(c, sms);
+    }
     {   // CTA pair: fp16 hi | lo output (odd tile count) and the tower configuration (GN statistics, fp32 output)
         Seg s0 = mk_seg(0, 70, 84, 1);
         Seg s1 = mk_seg(round128(s0.nrows), 37, 41, 1);

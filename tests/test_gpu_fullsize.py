@@ -157,3 +157,59 @@ def test_full_size_slice_matches_the_oracle(case):
     if not case.startswith("cfg1"):
         assert any(s["n_ref"] < cap for s in report["detections"] if s["pass"] != "codes as generated"), \
             "bias-shifted pass should leave at least one image below the post-NMS cap"
+
+
+def test_lvis_1203_class_sweep_matches_the_oracle_on_a_class_sample():
+    """BASELINE configs[4]: the 1203-class code-generation sweep (10 shots = 12 030 ROIs in ONE launch sequence over the
+    pyramids of a pool of full-size support images) against the oracle on a sample of 201 classes (every 6th): raw and
+    normalised codes within the bar, FPN levels of ALL 12 030 ROIs bit-exact.  The oracle pools from ITS OWN features of
+    the same images, so backbone, ROIAlign, tower and normalisation are all inside the comparison."""
+    from oracle import upstream as up
+    from oracle.meta_fcos_oracle import MetaFCOSOracle
+    from sylph_few_shot_detection_b200 import weights as Wt
+    from sylph_few_shot_detection_b200.presets import lvis_meta_fcos_cfg
+    from sylph_few_shot_detection_b200.runtime import SLOT_SUPPORT, Engine
+    cfg = lvis_meta_fcos_cfg()
+    state = Wt.synthetic_state_dict(cfg, 5)
+    eng = Engine(cfg, 0, "exact")
+    eng.load_state_dict(state)
+    orc = MetaFCOSOracle(cfg, state)
+    n_pool, n_cls, shots = 6, 1203, 10
+    g = torch.Generator().manual_seed(99)
+    pool = [torch.randint(0, 256, (3, H, W), generator=g, dtype=torch.uint8) for _ in range(n_pool)]
+    n = n_cls * shots
+    side = torch.exp(torch.empty(n).uniform_(math.log(24.0), math.log(1100.0), generator=g))
+    aspect = torch.exp(torch.empty(n).uniform_(-0.9, 0.9, generator=g))
+    bw, bh = (side * aspect.sqrt()).clamp(8.0, W - 1.0), (side / aspect.sqrt()).clamp(8.0, H - 1.0)
+    cx = torch.rand(n, generator=g) * (W - bw) + bw / 2
+    cy = torch.rand(n, generator=g) * (H - bh) + bh / 2
+    boxes = torch.stack([cx - bw / 2, cy - bh / 2, cx + bw / 2, cy + bh / 2], dim=1)
+    roi_image = [(7 * i + i // shots) % n_pool for i in range(n)]
+    offsets = list(range(0, n + 1, shots))
+    eng.extract_features(SLOT_SUPPORT, [p.cuda() for p in pool])
+    raw, levels = eng.generate_codes(SLOT_SUPPORT, boxes, roi_image, offsets, want_levels=True)
+    normed = eng.normalize_codes(raw)
+    lvl_ref = up.assign_boxes_to_levels([up.Boxes(b[None]) for b in boxes], 3, 7, 224, 4)
+    assert torch.equal(levels.cpu(), lvl_ref), "FPN level assignment must be bit-exact for all 12 030 ROIs"
+    assert len(set(lvl_ref.tolist())) >= 4
+    feats = orc.features(orc.preprocess([p.float() for p in pool]).tensor)
+    sample = list(range(0, n_cls, 6))
+    assert len(sample) >= 200
+    worst = {"raw cls_conv": 0.0, "raw cls_bias": 0.0, "norm cls_conv": 0.0, "norm cls_bias": 0.0}
+    for c in sample:
+        idx = list(range(offsets[c], offsets[c + 1]))
+        sub = [f[[roi_image[i] for i in idx]] for f in feats]
+        roi, _ = orc.roi_features(sub, boxes[idx])
+        w, b = orc.per_shot_codes(roi)
+        w_mean, b_mean = w.mean(0, keepdim=True), b.mean(0, keepdim=True)
+        wn, bn = orc.normalize_code(w_mean, b_mean)
+        worst["raw cls_conv"] = max(worst["raw cls_conv"], rel_err(raw[c, :256], w_mean.reshape(-1)))
+        worst["raw cls_bias"] = max(worst["raw cls_bias"], abs(float(raw[c, 256]) - float(b_mean)))
+        worst["norm cls_conv"] = max(worst["norm cls_conv"], rel_err(normed[c, :256], wn.reshape(-1)))
+        worst["norm cls_bias"] = max(worst["norm cls_bias"], abs(float(normed[c, 256]) - float(bn)) / abs(float(bn)))
+    print(f"\n  1203-class sweep, {len(sample)} classes checked: {worst}")
+    os.makedirs("gpurun_out", exist_ok=True)
+    with open(os.path.join("gpurun_out", "r02_fullsize_parity_cfg4_sweep.json"), "w") as f:
+        json.dump({"case": "configs[4] 1203-class sweep, 10 shots, pool of 6 images 800x1333", "classes_checked": len(sample),
+                   "levels_used": sorted(set(lvl_ref.tolist())), "worst": worst, "tolerance": TOL}, f, indent=1)
+    assert all(v <= TOL for v in worst.values()), worst
