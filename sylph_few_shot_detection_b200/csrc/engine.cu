@@ -570,16 +570,30 @@ struct ConvCall {
     const char* name = "conv";
 };
 
+static int run_conv_impl(sylph_ctx* c, const ConvCall& k, cudaStream_t st, const bool has_res);
+
 static int run_conv(sylph_ctx* c, const ConvCall& k, cudaStream_t st) {
+    const ConvW& W = *k.W;
+    // Split-operand mode: a_cols / a_ld / ldc / ld_res are PHYSICAL pitches (2C: [C hi | C lo]); the weight matrix has
+    // K' = 3 cin per tap, the A column of a k-block wraps at 2 cin, fp16 outputs and residuals carry a lo half at +C.
+    if (c->split && !k.stem && (k.a_cols != 2 * W.cin || W.k_per_tap != 3 * W.cin))
+        return c->fail("split-operand convolution %s: A has %d columns, weights K' = %d for cin = %d", k.name, k.a_cols, W.k_per_tap, W.cin);
+    const bool has_res = (k.flags & kEpiResidual) != 0;
+    // Split mode, deep 1x1 layers without a residual (conv1 of res4 / res5, the res5 shortcut: cin >= 1024, K' >= 3072): bound by
+    // L2->SM operand traffic, not by stores -- the 256-wide register-epilogue kernel (4-stage ring, half the A re-reads) beats the
+    // staged 128-wide one: 0.304 -> 0.253, 0.320 -> 0.247, 0.540 -> 0.486 ms (profiles/r02_split_tile_width_ab.log)
+    const bool deep_direct = c->split && k.staged && !k.stem && W.taps == 1 && !has_res && W.bn == 256 && W.cin >= 1024;
+    ConvCall kk = k;
+    if (deep_direct) kk.staged = 0;
+    return run_conv_impl(c, kk, st, has_res);
+}
+
+static int run_conv_impl(sylph_ctx* c, const ConvCall& k, cudaStream_t st, const bool has_res) {
     const ConvW& W = *k.W;
     CUtensorMap ta, tb;
     std::string err;
     const bool split = c->split != 0;
     const bool out_f16 = !(k.flags & kEpiOutF32);
-    // Split-operand mode: a_cols / a_ld / ldc / ld_res are PHYSICAL pitches (2C: [C hi | C lo]); the weight matrix has
-    // K' = 3 cin per tap, the A column of a k-block wraps at 2 cin, fp16 outputs and residuals carry a lo half at +C.
-    if (split && !k.stem && (k.a_cols != 2 * W.cin || W.k_per_tap != 3 * W.cin))
-        return c->fail("split-operand convolution %s: A has %d columns, weights K' = %d for cin = %d", k.name, k.a_cols, W.k_per_tap, W.cin);
     const bool halo = c->halo_pipeline && W.taps == 9 && !k.stem && !k.staged;
     const bool pair = halo && c->pair_kernel && (W.bn == 256 || ((c->pair_kernel & 2) && W.bn >= 64)) && !(k.flags & kEpiResidual);
     const bool stem16 = k.stem && c->stem16 && k.staged && W.bn == 64 && W.taps == 4 && k.a_ld == (split ? 32 : 16);
@@ -588,7 +602,6 @@ static int run_conv(sylph_ctx* c, const ConvCall& k, cudaStream_t st) {
     // shapes (profiles/r01_pair1x1_shapes.log): shortcut convolutions (no residual, K >= 256, N >= 512: res4 0.205 ->
     // 0.161 ms) and conv3 with K >= 512 (res5 0.126 -> 0.111 ms); res3 / res4 conv3 and the conv1 layers stay single-CTA
     // (lock-stepped epilogues of the pair cost more than the halved weight traffic buys there).
-    const bool has_res = (k.flags & kEpiResidual) != 0;
     const bool pair1x1 = !split && k.staged && !k.stem && W.taps == 1 && W.bn == 256 && k.n_tiles >= 2 && W.k_per_tap >= 256 &&
                          (c->pair1x1 == 2 || (c->pair1x1 == 1 && (has_res ? W.k_per_tap >= 512 : W.cout_pad >= 512)));
     // N tile: a staged split tile holds a hi and a lo half, so it is at most 128 channels wide

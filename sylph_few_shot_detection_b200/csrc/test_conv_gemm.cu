@@ -691,9 +691,10 @@ int main(int argc, char** argv) {
                              {"res3_conv3_128_512", 4488, 128, 512, RES},       {"res4_conv3_256_1024", 1155, 256, 1024, RES},
                              {"res5_conv3_512_2048", 330, 512, 2048, RES}};
         for (const Sh& sh : shapes) {
-            std::string a = std::string(sh.name) + "_bn128", c = std::string(sh.name) + "_bn256";
+            std::string a = std::string(sh.name) + "_bn128", c = std::string(sh.name) + "_bn256", d = std::string(sh.name) + "_DIRECT_bn256";
             bench_shape(a.c_str(), 128, sh.m_tiles, sh.cin, sh.cout, 1, sh.flags, sms, 100, false, false, true);
             bench_shape(c.c_str(), 256, sh.m_tiles, sh.cin, sh.cout, 1, sh.flags, sms, 100, false, false, true);
+            bench_shape(d.c_str(), 256, sh.m_tiles, sh.cin, sh.cout, 1, sh.flags, sms, 0, false, false, true);   // register epilogue
         }
         return 0;
     }
