@@ -165,15 +165,17 @@ def run_reference(args, cfg, config):
     from sylph_few_shot_detection_b200 import weights as W
     threads = os.cpu_count() or 1
     ref = CpuReference(cfg, W.synthetic_state_dict(cfg, 0), threads)
-    ref.warm()
-    for _ in range(args.warmup):
-        ref.episode()
+    # warm-up steps: one support image -> code and one query image -> detections each (thread pool, oneDNN primitive caches
+    # for every layer shape of the path); the --steps timed steps are WHOLE episodes
+    for _ in range(max(args.warmup, 1)):
+        ref.warm()
     secs = [ref.episode() for _ in range(args.steps)]
     total = sum(secs)
     v = len(secs) / total
     base = {"value": v, "unit": "episodes/s", "cores": threads, "kind": "port",
             "sample": f"{len(secs)} whole episodes (25 support images in 5 batches of K = 5, 8 batch-1 query calls, 800x1333, fp32), "
-                      f"{total / len(secs):.2f} s each; one CPU process on all {threads} host cores whatever --gpus says",
+                      f"{total / len(secs):.2f} s each (warm-up steps: 1 support + 1 query image passes); one CPU process on all {threads} host "
+                      f"cores whatever --gpus says",
             "episode_seconds": total / len(secs), "detections_per_episode": ref.last_detections}
     print(json.dumps({"impl": "reference", "metric": METRIC, "value": v, "unit": "episodes/s", "n_gpus": args.gpus,
                       "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1000.0 * total / len(secs),

@@ -49,7 +49,9 @@ typedef struct sylph_model_config {
     int cg_bias_l2_norm;       /* CODE_GENERATOR.BIAS_L2_NORM */
     int cg_use_bias;           /* CODE_GENERATOR.USE_BIAS (CondConvBasic use_bias) */
     int cg_has_conv_scale;     /* USE_WEIGHT_SCALE and (CONV_L2_NORM or POST_NORM) */
-    int generator;             /* CODE_GENERATOR.NAME: 0 = "CodeGenerator" / "CodeGeneratorHead", 1 = "ROIEncoder" */
+    int generator;             /* CODE_GENERATOR.NAME: 0 = "CodeGenerator" / "CodeGeneratorHead", 1 = "ROIEncoder";
+                                  2 = none: base detector (MODEL.META_LEARN.EPISODIC_LEARNING off, meta_one_stage_detector.py:298-323):
+                                  the rows handed to sylph_detect are cls_logits.weight / .bias (fcos.py:544-576) */
     int re_tok_convs;          /* ROIEncoder: CODE_GENERATOR.TOKENIZER.NUM_CONV (CONV_DIM 256, NORM "GN") */
     int re_tok_fcs;            /* ROIEncoder: CODE_GENERATOR.TOKENIZER.NUM_FC (FC_DIM 256 = transformer d_model) */
     int re_layers;             /* ROIEncoder: CODE_GENERATOR.TRANSFORMER_ENCODER.LAYERS (dim_feedforward = 4 x 256) */

@@ -352,6 +352,58 @@ def build_training_variant_goldens():
     print(f"[train variants] wrote {path} ({os.path.getsize(path) / 1e6:.2f} MB)")
 
 
+def base_detector_state(cfg, seed):
+    """Synthetic weights of the NON-episodic model with a class-logits convolution strong enough to fire (the synthetic
+    N(0, 0.01) initialiser leaves every logit at the prior)."""
+    state = W.synthetic_state_dict(cfg, seed)
+    k = "proposal_generator.fcos_head.cls_logits.weight"
+    g = torch.Generator().manual_seed(4242 + seed)
+    state[k] = torch.nn.functional.normalize(torch.randn(state[k].shape, generator=g), dim=1) * 5.0
+    state["proposal_generator.fcos_head.cls_logits.bias"] = torch.randn(state[k].shape[0], generator=g) * 0.3 - 4.2
+    return state
+
+
+def build_base_detector_golden():
+    """`run_type=None` on the reference's NON-episodic model (Meta-FCOS-pretrain.yaml: base detector inference,
+    meta_one_stage_detector.py:298-323, 435-441): the reference model's own detections and head outputs."""
+    name, seed = "coco_base_detector", 12
+    cfg = load_cfg(os.path.join(reference_loader.REFERENCE_ROOT, "configs", "COCO-Detection/Meta-FCOS/Meta-FCOS-pretrain.yaml"),
+                   ["MODEL.DEVICE", "cpu"])
+    state = base_detector_state(cfg, seed)
+    g = torch.Generator().manual_seed(2000 + seed)
+    query = [synth_image(g, 224, 288), synth_image(g, 200, 256)]
+    with contextlib.redirect_stdout(io.StringIO()):
+        model = reference_loader.build_reference_model(cfg)
+    W.load_into_module(model, state)
+    model.eval()
+    batched = [{"image": q, "height": q.shape[-2], "width": q.shape[-1]} for q in query]
+    with torch.no_grad():
+        res = model(batched)                                   # run_type=None
+        il = model.convert_batched_inputs_to_image_list(batched)
+        feats = model.backbone(il.tensor)
+        feats = [feats[f] for f in cfg.MODEL.FCOS.IN_FEATURES]
+        logits, regs, ctrs, ious, _, _ = model.proposal_generator.fcos_head(feats, None, False, None)
+    dets = [{"boxes": r["instances"].pred_boxes.tensor.clone(), "scores": r["instances"].scores.clone(),
+             "classes": r["instances"].pred_classes.clone(), "locations": r["instances"].locations.clone(),
+             "levels": r["instances"].fpn_levels.clone()} for r in res]
+    print(f"[{name}] reference detections per image: {[int(d['scores'].numel()) for d in dets]}")
+    orc = build_oracle(cfg, state)
+    codes = {"cls_conv": state["proposal_generator.fcos_head.cls_logits.weight"], "cls_bias": state["proposal_generator.fcos_head.cls_logits.bias"]}
+    mine, inter = orc.detect(query, codes, return_intermediate=True)
+    worst = 0.0
+    for l in range(5):
+        worst = max(worst, compare(f"logits p{l + 3}", inter["logits"][l], logits[l]))
+    for i, (d, r) in enumerate(zip(mine, dets)):
+        assert d["scores"].numel() == r["scores"].numel() and torch.equal(d["classes"], r["classes"]) and torch.equal(d["locations"], r["locations"])
+        worst = max(worst, compare(f"det boxes[{i}]", d["boxes"], r["boxes"]), compare(f"det scores[{i}]", d["scores"], r["scores"]))
+    print(f"[{name}] worst relative deviation oracle vs reference: {worst:.3e}")
+    path = os.path.join(GOLDEN_DIR, f"{name}.pt")
+    torch.save({"case": name, "config": "COCO-Detection/Meta-FCOS/Meta-FCOS-pretrain.yaml", "seed": seed,
+                "query": [q.to(torch.uint8) for q in query], "detections": dets, "logits": [t.clone() for t in logits],
+                "reg": [t.clone() for t in regs], "ctr": [t.clone() for t in ctrs], "torch_version": torch.__version__}, path)
+    print(f"[{name}] wrote {path} ({os.path.getsize(path) / 1e6:.2f} MB)")
+
+
 @contextlib.contextmanager
 def warnings_off():
     import warnings
@@ -362,9 +414,16 @@ def warnings_off():
 
 def main():
     os.makedirs(GOLDEN_DIR, exist_ok=True)
+    if "--base-detector-only" in sys.argv:
+        build_base_detector_golden()
+        return
     if "--base-only" in sys.argv or "--all" in sys.argv or len(sys.argv) == 1:
         build_base_reduce_golden()
     if "--base-only" in sys.argv:
+        return
+    if "--base-detector-only" in sys.argv or "--all" in sys.argv or len(sys.argv) == 1:
+        build_base_detector_golden()
+    if "--base-detector-only" in sys.argv:
         return
     if "--train-variants-only" in sys.argv:
         build_training_variant_goldens()

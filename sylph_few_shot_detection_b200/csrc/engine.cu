@@ -841,7 +841,9 @@ int sylph_finalize_weights(sylph_ctx* c) {
         c->level_scale[l] = 1.f;
         if (f.use_scale) TRY(scalar_of(c, head + "scales." + std::to_string(l) + ".scale", &c->level_scale[l]));
     }
-    if (f.generator == 1) {
+    if (f.generator == 2) {
+        // base detector (EPISODIC_LEARNING off): no code generator; the class codes of sylph_detect are cls_logits
+    } else if (f.generator == 1) {
         TRY(prep_roi_encoder(c));
     } else {
         const std::string cg = "code_generator.code_generator_head.";
@@ -1331,7 +1333,7 @@ static int run_head(sylph_ctx* c, int slot, const float* codes_dev, int n_classe
     TRY(tower(c->cls_tower, c->cls_gn_w, c->cls_gn_b, "head.cls_tower3x3", &x));
     if (codes_ready != nullptr) CU_TRY(c, cudaStreamWaitEvent(st, codes_ready, 0));
     CU_TRY(c, launch_k(pack_code_weights_kernel, dim3(ceil_div(static_cast<long long>(CW.cout_pad) * 256, 256)), dim3(256), 0, st,
-        codes_dev, n_classes, CW.cout_pad, f.generator == 1 ? 1 : f.cg_use_bias, f.generator == 1 ? c->cond_scale : 1.f, CW.w, CW.bias, c->split));
+        codes_dev, n_classes, CW.cout_pad, f.generator != 0 ? 1 : f.cg_use_bias, f.generator == 1 ? c->cond_scale : 1.f, CW.w, CW.bias, c->split));
     CU_TRY(c, cudaGetLastError());
     c->launches++;
     {
@@ -1488,6 +1490,7 @@ int sylph_generate_codes(sylph_ctx* c, int slot, int n_rois, const float* boxes_
     if (!c) return 1;
     if (!c->finalized) return c->fail("weights not finalized");
     if (slot < 0 || slot >= SYLPH_NUM_SLOTS || !c->slots[slot].valid) return c->fail("slot %d holds no features", slot);
+    if (c->cfg.generator == 2) return c->fail("this model has no code generator (MODEL.META_LEARN.EPISODIC_LEARNING is off)");
     if (n_rois <= 0 || n_classes <= 0) return c->fail("empty support set");  // select_a_mask raises ValueError
     const Slot& S = c->slots[slot];
     for (int i = 0; i < n_rois; ++i)
@@ -1593,6 +1596,7 @@ int sylph_normalize_codes(sylph_ctx* c, const float* raw_codes_dev, float* out_c
     if (n_classes <= 0) return 0;  // forward_normalize_code returns an empty list unchanged
     const sylph_model_config& f = c->cfg;
     if (f.generator == 1) return c->fail("ROIEncoder codes are final: there is no code normalisation for this generator");
+    if (f.generator == 2) return c->fail("this model has no code generator (MODEL.META_LEARN.EPISODIC_LEARNING is off)");
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     CU_TRY(c, launch_k(normalize_codes_kernel, dim3(n_classes), dim3(256), 0, st, raw_codes_dev, out_codes_dev, c->post_gn_w, c->post_gn_b, f.cg_post_norm,
                                                       f.cg_conv_l2_norm, c->conv_scale, c->bias_scale, c->bias_value));

@@ -428,7 +428,10 @@ class MetaOneStageDetector(nn.Module):
         if self.training:
             raise NotImplementedError(f"not support this forward type: {run_type}, class_code: {class_code}")
         if run_type is None:
-            raise NotImplementedError("base-detector inference (run_type=None) is not implemented on the B200 path")
+            # "a normal base detector inference" (meta_one_stage_detector.py:435-441 -> MetaProposalNetwork.forward :388-412)
+            processed_results = self.forward_base_detector(batched_inputs)
+            renamed = [{"instances": r["proposals"]} for r in processed_results]
+            return processed_results if len(renamed) == 0 else renamed
         if run_type == "meta_learn_test_support":
             return self.forward_class_code(batched_inputs)
         if run_type == "meta_learn_normalize_code":
@@ -436,6 +439,20 @@ class MetaOneStageDetector(nn.Module):
         if run_type == "meta_learn_test_instance":
             return self.forward_instances(batched_inputs, class_code)
         raise NotImplementedError(f"not support this forward type: {run_type}, class_code: {class_code}")
+
+    def forward_base_detector(self, batched_inputs: List[Dict[str, Any]]) -> List[Dict[str, Any]]:
+        """meta_one_stage_detector.py:298-323 in eval mode: backbone, FCOS head with the model's own `cls_logits` classifier
+        (MetaFCOSHead.forward_base_train, fcos.py:544-576), proposals, NMS, detector_postprocess -> [{"proposals": Instances}].
+        On the engine the `cls_logits` weights are simply the class-code rows of the code-conditioned classifier."""
+        if self.episodic_learning:   # MetaProposalNetwork.forward raises exactly this for an episodic model in eval mode
+            raise NotImplementedError("Episodic learning inferrence for image and features is not supported in forward.")
+        assert not self.training
+        k = int(self.cfg.MODEL.FCOS.CLS_LOGITS_KERNEL_SIZE)
+        if k != 1:
+            raise NotImplementedError("the B200 classifier is the 1x1 convolution of the shipped configs (CLS_LOGITS_KERNEL_SIZE 1)")
+        codes = {"cls_conv": self._state["proposal_generator.fcos_head.cls_logits.weight"],
+                 "cls_bias": self._state["proposal_generator.fcos_head.cls_logits.bias"]}
+        return [{"proposals": r["instances"]} for r in self._detect(batched_inputs, codes)]
 
     def forward_class_code(self, batched_inputs: List[Dict[str, Any]]) -> Dict[str, torch.Tensor]:
         """One class per call (assert at meta_one_stage_detector.py:238)."""
@@ -561,6 +578,9 @@ class MetaOneStageDetector(nn.Module):
                           features_in_slot: bool = False):
         assert self.episodic_learning
         assert not self.training, "Not for training"
+        return self._detect(batched_inputs, class_codes, features_in_slot)
+
+    def _detect(self, batched_inputs: List[Dict[str, Any]], class_codes: Dict[str, torch.Tensor], features_in_slot: bool = False):
         images = [x["image"] for x in batched_inputs]
         if not features_in_slot:
             self.engine.extract_features(SLOT_QUERY, images)

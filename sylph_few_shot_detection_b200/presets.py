@@ -39,6 +39,19 @@ OVERRIDES = {
         "MODEL.META_LEARN.CODE_GENERATOR.USE_PER_CLS_SCALE", True,
         "MODEL.TFA.USE_PRETRAINED_BASE_CLS_LOGITS", False,
     ],
+    # base detector (pre-training model, no code generator): `run_type=None` inference with the model's own cls_logits
+    "COCO-Detection/Meta-FCOS/Meta-FCOS-pretrain.yaml": [
+        "MODEL.META_ARCHITECTURE", "MetaOneStageDetector",
+        "MODEL.BACKBONE.NAME", "build_fcos_resnet_fpn_backbone",
+        "MODEL.BACKBONE.FREEZE", False,
+        "MODEL.RESNETS.OUT_FEATURES", ["res3", "res4", "res5"],
+        "MODEL.RESNETS.DEPTH", 50,
+        "MODEL.FPN.IN_FEATURES", ["res3", "res4", "res5"],
+        "MODEL.PROPOSAL_GENERATOR.NAME", "MetaFCOS",
+        "MODEL.META_LEARN.EPISODIC_LEARNING", False,
+        "MODEL.FCOS.NUM_CLASSES", 60,
+        "MODEL.DDP_FIND_UNUSED_PARAMETERS", True,
+    ],
     # ROIEncoder generator (transformer hyper-network); inherits Base-Meta-FCOS.yaml, not the CodeGenerator overrides
     "LVISv1-Detection/Meta-FCOS/Meta-FCOS-ROI-Encoder-finetune.yaml": [
         "MODEL.META_ARCHITECTURE", "MetaOneStageDetector",

@@ -24,13 +24,16 @@ def model_config_from_cfg(cfg) -> ModelConfig:
         raise NotImplementedError("only the p3..p7 pyramid (strides 8..128) is implemented")
     if cfg.MODEL.RESNETS.NORM != "FrozenBN" or not cfg.MODEL.RESNETS.STRIDE_IN_1X1:
         raise NotImplementedError("backbone must use FrozenBN and STRIDE_IN_1X1 (inference path)")
-    if roi_encoder:
+    episodic = bool(cfg.MODEL.META_LEARN.EPISODIC_LEARNING)
+    if not episodic:
+        roi_encoder = False              # base detector: no code generator is built, its config keys are not read
+    elif roi_encoder:
         T, E, H = G.TOKENIZER, G.TRANSFORMER_ENCODER, G.HEAD
         if int(T.CONV_DIM) != 256 or int(T.FC_DIM) != 256 or int(H.OUTPUT_DIM) != 256 or T.NORM != "GN":
             raise NotImplementedError("ROIEncoder: TOKENIZER.CONV_DIM / FC_DIM and HEAD.OUTPUT_DIM must be 256, TOKENIZER.NORM 'GN'")
         if int(T.NUM_CONV) < 1 or int(T.NUM_FC) < 1 or int(H.NUM_FC) < 1 or int(H.FC_DIM) > 1024 or 256 % int(E.HEADS):
             raise NotImplementedError("ROIEncoder: unsupported tokenizer / head depth or width")
-    else:
+    if episodic and not roi_encoder:
         for layer in G.TOWER_LAYERS:
             if list(layer) != ["GN", "ReLU"]:
                 raise NotImplementedError("CODE_GENERATOR.TOWER_LAYERS entries must be ['GN', 'ReLU']")
@@ -38,7 +41,7 @@ def model_config_from_cfg(cfg) -> ModelConfig:
             raise NotImplementedError("CODE_GENERATOR.CLS_LAYER must be ['', '', 1]")
         if len(G.WEIGHT_LAYER) or len(G.SCALE_LAYER) or G.COMPRESS_CODE_W_MAX or G.ROI_BOX.FPN_MULTILEVEL_FEATURE:
             raise NotImplementedError("WEIGHT_LAYER / SCALE_LAYER / COMPRESS_CODE_W_MAX / multilevel ROI are not implemented")
-    if G.ROI_BOX.POOLER_TYPE != "ROIAlignV2" or int(G.ROI_BOX.POOLER_RESOLUTION) != 7:
+    if episodic and (G.ROI_BOX.POOLER_TYPE != "ROIAlignV2" or int(G.ROI_BOX.POOLER_RESOLUTION) != 7):
         raise NotImplementedError("ROI pooler must be ROIAlignV2 at 7x7")
     if cfg.MODEL.PROPOSAL_GENERATOR.OWD:
         raise NotImplementedError("OWD scoring is not implemented")
@@ -56,14 +59,15 @@ def model_config_from_cfg(cfg) -> ModelConfig:
         mc.pixel_std[i] = float(cfg.MODEL.PIXEL_STD[i])
     mc.cg_tower_layers = len(G.TOWER_LAYERS)
     mc.cg_post_norm = int(G.POST_NORM == "GN")
-    if G.POST_NORM not in ("", "GN"):
+    if episodic and G.POST_NORM not in ("", "GN"):
         raise NotImplementedError("POST_NORM must be '' or 'GN'")
     mc.cg_conv_l2_norm = int(bool(G.CONV_L2_NORM))
     mc.cg_bias_layer = int(len(G.BIAS_LAYER) == 3)
     mc.cg_bias_l2_norm = int(bool(G.BIAS_L2_NORM))
     mc.cg_use_bias = int(bool(G.USE_BIAS))
     mc.cg_has_conv_scale = int(bool(G.USE_WEIGHT_SCALE and (G.CONV_L2_NORM or G.POST_NORM != "")))
-    mc.generator = int(roi_encoder)
+    # 0 = CodeGenerator, 1 = ROIEncoder, 2 = none (base detector: MODEL.META_LEARN.EPISODIC_LEARNING False, cls_logits classifier)
+    mc.generator = int(roi_encoder) if cfg.MODEL.META_LEARN.EPISODIC_LEARNING else 2
     if roi_encoder:
         mc.re_tok_convs, mc.re_tok_fcs = int(G.TOKENIZER.NUM_CONV), int(G.TOKENIZER.NUM_FC)
         mc.re_layers = int(G.TRANSFORMER_ENCODER.LAYERS)

@@ -89,7 +89,9 @@ def state_spec(cfg) -> "OrderedDict[str, Tuple[int, ...]]":
             spec[f"{head}.scales.{lvl}.scale"] = (1,)
 
     G = cfg.MODEL.META_LEARN.CODE_GENERATOR
-    if G.NAME == "ROIEncoder":
+    if not cfg.MODEL.META_LEARN.EPISODIC_LEARNING:
+        pass                                            # base detector: no code generator (meta_one_stage_detector.py:83-87)
+    elif G.NAME == "ROIEncoder":
         _roi_encoder_spec(cfg, spec, conv, gn)
         spec[f"{head}.cond_cls_logits.scales.0.scale"] = (1,)   # CondConvBlock(weight_len=256), head_utils.py:131-137
     else:

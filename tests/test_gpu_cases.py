@@ -187,6 +187,39 @@ def test_proposal_generator_on_foreign_features_returns_unscaled_proposals():
         _match(p, r, inter, i, cfg, name=f"foreign features image {i}")
 
 
+def test_base_detector_inference_matches_the_reference_golden():
+    """`model(batched_inputs)` with run_type=None on the NON-episodic model (Meta-FCOS-pretrain.yaml): the reference's
+    "normal base detector inference" (meta_one_stage_detector.py:298-323, 435-441) against the golden its own model produced;
+    an episodic model refuses the call with the reference's message."""
+    from oracle.meta_fcos_oracle import MetaFCOSOracle
+    from sylph_few_shot_detection_b200.modeling import build_model
+    from sylph_few_shot_detection_b200.runtime import SLOT_QUERY
+    from tests.cases import cfg_for, load_golden
+    from tests.test_oracle import base_detector_state
+    g = load_golden("coco_base_detector")
+    cfg = cfg_for(g["config"])
+    state = base_detector_state(cfg, g["seed"])
+    model = build_model(cfg)
+    assert model.code_generator is None
+    model.load_state_dict(state)
+    batched = [{"image": q, "height": q.shape[-2], "width": q.shape[-1]} for q in g["query"]]
+    out = model(batched)
+    assert len(out) == 2 and set(out[0]) == {"instances"}
+    orc = MetaFCOSOracle(cfg, state)
+    codes = {"cls_conv": state["proposal_generator.fcos_head.cls_logits.weight"], "cls_bias": state["proposal_generator.fcos_head.cls_logits.bias"]}
+    ref, inter = orc.detect([q.float() for q in g["query"]], codes, return_intermediate=True)
+    for l in range(5):
+        assert rel_err(model.engine.export_head_output(0, l, SLOT_QUERY, 60), g["logits"][l]) < TOL, l
+    for i, (o, r) in enumerate(zip(out, ref)):
+        assert r["scores"].numel() == g["detections"][i]["scores"].numel()
+        _match(o["instances"], r, inter, i, cfg, name=f"base detector image {i}")
+    with pytest.raises(RuntimeError, match="no code generator"):
+        model.engine.normalize_codes(torch.zeros(1, 257))
+    _, _, episodic, _ = _setup(seed=4)
+    with pytest.raises(NotImplementedError, match="Episodic learning inferrence"):
+        episodic(batched)
+
+
 def test_batched_class_codes_equal_per_class_calls_and_levels_are_exact():
     from sylph_few_shot_detection_b200.runtime import SLOT_SUPPORT
     from oracle import upstream as up

@@ -80,6 +80,36 @@ def test_roi_encoder_oracle_reproduces_reference_outputs():
         assert rel_err(d["boxes"], r["boxes"]) < TOL and rel_err(d["scores"], r["scores"]) < TOL
 
 
+def base_detector_state(cfg, seed):
+    """The weights oracle/make_golden.py::base_detector_state gave the reference model (class-logits conv that fires)."""
+    state = W.synthetic_state_dict(cfg, seed)
+    k = "proposal_generator.fcos_head.cls_logits.weight"
+    g = torch.Generator().manual_seed(4242 + seed)
+    state[k] = torch.nn.functional.normalize(torch.randn(state[k].shape, generator=g), dim=1) * 5.0
+    state["proposal_generator.fcos_head.cls_logits.bias"] = torch.randn(state[k].shape[0], generator=g) * 0.3 - 4.2
+    return state
+
+
+def test_oracle_reproduces_the_reference_base_detector():
+    """`run_type=None` on the NON-episodic reference model (Meta-FCOS-pretrain.yaml; meta_one_stage_detector.py:298-323):
+    the model's own `cls_logits` convolution is the classifier.  For the oracle these weights are simply the code rows."""
+    g = load_golden("coco_base_detector")
+    cfg = cfg_for(g["config"])
+    assert not cfg.MODEL.META_LEARN.EPISODIC_LEARNING
+    state = base_detector_state(cfg, g["seed"])
+    assert not any(k.startswith("code_generator.") for k in state)
+    orc = MetaFCOSOracle(cfg, state)
+    codes = {"cls_conv": state["proposal_generator.fcos_head.cls_logits.weight"],
+             "cls_bias": state["proposal_generator.fcos_head.cls_logits.bias"]}
+    dets, inter = orc.detect([q.float() for q in g["query"]], codes, return_intermediate=True)
+    for l in range(5):
+        assert rel_err(inter["logits"][l], g["logits"][l]) < TOL and rel_err(inter["reg"][l], g["reg"][l]) < TOL
+    for d, r in zip(dets, g["detections"]):
+        assert d["scores"].numel() == r["scores"].numel() > 0
+        assert torch.equal(d["classes"], r["classes"]) and torch.equal(d["locations"], r["locations"])
+        assert rel_err(d["boxes"], r["boxes"]) < TOL and rel_err(d["scores"], r["scores"]) < TOL
+
+
 def test_golden_vectors_cover_the_interesting_regimes():
     g = load_golden("coco_2way_2shot")
     # post-NMS top-k saturated on one image, not on the other; several FPN levels contribute
