@@ -42,7 +42,8 @@ def build_code_generator(cfg, feature_channels: int, feature_levels: Optional[in
 
 def select_a_mask(gt_instances: Sequence[Any], use_all_masks: bool = False) -> List[torch.Tensor]:
     """One GT box per support image, drawn with the global NumPy RNG exactly like the reference
-    (sylph/modeling/code_generator/utils.py:27-47); empty boxes raise ValueError."""
+    (sylph/modeling/code_generator/utils.py:27-47); empty boxes raise ValueError.  `use_all_masks`
+    (CODE_GENERATOR.ALL_MASK): every box of the image, no RNG draw."""
     out = []
     for inst in gt_instances:
         boxes = inst.gt_boxes.tensor
@@ -54,6 +55,16 @@ def select_a_mask(gt_instances: Sequence[Any], use_all_masks: bool = False) -> L
             idx = np.random.choice(range(len(boxes)), 1)
             out.append(boxes[idx])
     return out
+
+
+def support_boxes(gt_instances: Sequence[Any], use_all_masks: bool, total_shots: int) -> torch.Tensor:
+    """The (total_shots, 4) boxes the ROI pooler receives (code_generator.py:928-937): `select_a_mask`, then the reference's
+    own check that pooling returned exactly one ROI per support image -- which, with ALL_MASK, holds only when every image
+    carries a single box."""
+    boxes = torch.cat([b.reshape(-1, 4).cpu() for b in select_a_mask(gt_instances, use_all_masks)], dim=0)
+    assert boxes.shape[0] == total_shots, \
+        f"pooled_features.shape[0] {boxes.shape[0]} Vs batch_size * num_shots {total_shots}"
+    return boxes
 
 
 class _EngineBound(nn.Module):
@@ -87,8 +98,6 @@ class CodeGenerator(_EngineBound):
         self.strides = tuple(strides)
         self.all_mask = cfg.MODEL.META_LEARN.CODE_GENERATOR.ALL_MASK
         self.contrastive_loss = cfg.MODEL.META_LEARN.CODE_GENERATOR.CONTRASTIVE_LOSS
-        if self.all_mask:
-            raise NotImplementedError("ALL_MASK=True is not supported")
 
     def forward(self, features: Optional[List[torch.Tensor]], target_instances=None, cls_norm: bool = False,
                 class_codes: Optional[List[Dict]] = None):
@@ -102,7 +111,7 @@ class CodeGenerator(_EngineBound):
         assert not self.training, "the B200 path implements inference only"
         total_shots = features[0].size(0)
         assert len(gt_instances) == total_shots
-        boxes = torch.cat([b.reshape(-1, 4)[:1] for b in select_a_mask(gt_instances, self.all_mask)], dim=0)
+        boxes = support_boxes(gt_instances, self.all_mask, total_shots)
         h, w = features[0].shape[-2:]
         self.engine.import_features(SLOT_SUPPORT, features, (h * self.strides[0], w * self.strides[0]))
         return self._codes_of_one_class(boxes, list(range(total_shots)))
@@ -486,7 +495,8 @@ class MetaOneStageDetector(nn.Module):
                 assert n % self.code_generator.eval_shot == 0 and n == self.code_generator.eval_shot, \
                     f"{n} % {self.code_generator.eval_shot}"
         # one host-RNG draw per support image, in the order of the reference's per-class calls (utils.py:27-47)
-        boxes_of = [torch.cat([b.reshape(-1, 4)[:1].cpu() for b in select_a_mask([r["instances"] for r in item["support_set"]])], dim=0)
+        all_mask = bool(self.cfg.MODEL.META_LEARN.CODE_GENERATOR.ALL_MASK) and not roi_encoder
+        boxes_of = [support_boxes([r["instances"] for r in item["support_set"]], all_mask, len(item["support_set"]))
                     for item in batched_inputs]
         if features_in_slot:
             passes = [list(range(len(batched_inputs)))]

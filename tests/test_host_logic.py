@@ -68,6 +68,22 @@ def test_select_a_mask_consumes_the_global_numpy_rng_and_rejects_empty():
         M.select_a_mask([empty])
 
 
+def test_all_mask_takes_every_box_and_keeps_the_reference_shape_check():
+    """CODE_GENERATOR.ALL_MASK (utils.py:27-47, code_generator.py:928-937): no RNG draw; the pooler must still return one
+    ROI per support image, so an image with two boxes trips the reference's own assertion."""
+    def inst(n):
+        i = Instances((64, 64))
+        i.gt_boxes = Boxes(torch.arange(4.0 * n).reshape(n, 4) + 1.0)
+        return i
+    np.random.seed(3)
+    state = np.random.get_state()[1].copy()
+    got = M.support_boxes([inst(1), inst(1)], True, 2)
+    assert got.shape == (2, 4) and np.array_equal(np.random.get_state()[1], state)       # global RNG untouched
+    with pytest.raises(AssertionError, match="pooled_features.shape"):
+        M.support_boxes([inst(2), inst(1)], True, 2)
+    assert M.support_boxes([inst(3), inst(2)], False, 2).shape == (2, 4)                   # one drawn box per image
+
+
 def test_pack_and_format_class_codes():
     codes = [{"support_set_target": torch.tensor(1), "class_code": {"cls_conv": torch.full((1, 256, 1, 1), 2.0), "cls_bias": torch.tensor([0.2])}},
              {"support_set_target": 0, "class_code": {"cls_conv": torch.full((1, 256, 1, 1), 0.5), "cls_bias": torch.tensor([0.0])}}]
