@@ -89,6 +89,7 @@ struct GemmArgs {
     int a_wrap;            // SPLIT: 2C of the A operand (elements); a k-block column >= a_wrap wraps back by a_wrap
     int out_lo;            // SPLIT: element offset of the lo half of an fp16 output row (= Cout of the whole layer)
     int res_lo;            // SPLIT: element offset of the lo half of a residual row
+    int nm_lo_row;         // NM: row offset of the w_lo block inside a tap of the weight matrix (= cout_pad)
     int dbg_a_row_skew;    // experiment: load the A box `skew` rows early and start the MMA descriptor `skew` rows in
     int dbg_base_offset;   // experiment: matrix-descriptor base_offset field used with the skew
     int dbg_skip;          // bring-up timing experiments (halo pipeline): 1 = no output stores, 2 = no MMAs issued,
@@ -111,15 +112,23 @@ struct GemmArgs {
 // shared memory (res2 conv2: 9 x 8 KB) they are loaded ONCE and stay resident in the STAGES slots (STAGES = 9 x kblocks),
 // so the per-tile TMA traffic is the three halo A boxes only.  A TMA unit retires roughly one <= 128-byte box row per
 // 5 clocks (~45 GB/s per SM): 9 x 64 weight rows per tile were 60 % of this kernel's row requests.
-template <int BN, int STAGES, int EPI_BUFS, int HALO, bool STEM16 = false, bool BRES = false, bool SPLIT = false>
+// NM ("N-merged" split mode, narrow 3x3 layers): the weight matrix holds, per tap, the BN rows of w_hi followed by the BN rows
+// of w_lo (K = C per tap).  The a_hi pass multiplies a 2 BN-row B tile in ONE instruction -- accumulator columns [0, BN) get
+// a_hi.w_hi, [BN, 2 BN) get a_hi.w_lo -- and the a_lo pass the first BN rows into [0, BN); the epilogue adds the two column
+// halves.  Two tcgen05.mma per k-step instead of three: these layers (N = 64 / 128) are bound by instruction issue, not math.
+// QS ("quad stage", split mode, generic 1x1 pipeline): a ring stage holds the FOUR tiles of one 64-wide k-block -- a_hi, a_lo, w_hi,
+// w_lo -- and the issuer runs the three products a_hi.w_hi + a_lo.w_hi + a_hi.w_lo from them, so every operand tile crosses
+// L2 -> shared memory ONCE per k-block instead of 1.5 times (the K' = 3C loop loads [hi | lo | hi] against [w_hi | w_hi | w_lo]:
+// six tiles per k-block).  The deep 1x1 layers (res4 / res5) are bound by exactly that traffic.  args.kblocks_per_tap = C / 64.
+template <int BN, int STAGES, int EPI_BUFS, int HALO, bool STEM16 = false, bool BRES = false, bool SPLIT = false, bool NM = false, bool QS = false>
 struct GemmSmem {
     static constexpr bool TMA_EPI = EPI_BUFS > 0;          // 0: direct epilogue, 1 / 2: staged epilogue buffers
     static constexpr int kABytes = kBlockM * kBlockK * 2;  // 16 KiB
     static constexpr int kAHaloRows = kBlockM + 2;
     static constexpr int kAHaloTx = STEM16 ? (kBlockM + 3) * 32 : kAHaloRows * 128;   // bytes one halo box delivers
     static constexpr int kAHaloBytes = STEM16 ? 5 * 1024 : 17 * 1024;   // slot size (multiple of the 1024-byte swizzle period)
-    static constexpr int kBBytes = BN * kBlockK * 2;
-    static constexpr int kStageBytes = HALO ? kBBytes : kABytes + kBBytes;
+    static constexpr int kBBytes = BN * kBlockK * 2 * (NM ? 2 : 1);
+    static constexpr int kStageBytes = HALO ? kBBytes : (QS ? 2 * (kABytes + kBBytes) : kABytes + kBBytes);
     static constexpr int kRingOffset = HALO * kAHaloBytes;  // halo slots first, then the (B or A+B) stage ring
     // one staged output tile, BN/64 swizzled panels (SPLIT: the hi panels, then as many lo panels)
     static constexpr int kEpiBytes = TMA_EPI ? kBlockM * BN * 2 * (SPLIT ? 2 : 1) : 0;
@@ -188,13 +197,16 @@ __device__ __forceinline__ bool row_is_interior(const Seg& sg, int row) {
     return (local >= 0) && (local < sg.nrows) && (y >= sg.pad) && (y < sg.pad + sg.H) && (x >= sg.pad) && (x < sg.pad + sg.W);
 }
 
-template <int BN, int STAGES, int EPI_BUFS, int HALO, bool STEM16 = false, bool BRES = false, bool SPLIT = false>
-__global__ void __launch_bounds__(GemmSmem<BN, STAGES, EPI_BUFS, HALO, STEM16, BRES, SPLIT>::kThreads, 1)
+template <int BN, int STAGES, int EPI_BUFS, int HALO, bool STEM16 = false, bool BRES = false, bool SPLIT = false, bool NM = false, bool QS = false>
+__global__ void __launch_bounds__(GemmSmem<BN, STAGES, EPI_BUFS, HALO, STEM16, BRES, SPLIT, NM, QS>::kThreads, 1)
 conv_gemm_f16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
                      const __grid_constant__ CUtensorMap tmap_res, const __grid_constant__ CUtensorMap tmap_out,
                      const GemmArgs p) {
-    using S = GemmSmem<BN, STAGES, EPI_BUFS, HALO, STEM16, BRES, SPLIT>;
+    using S = GemmSmem<BN, STAGES, EPI_BUFS, HALO, STEM16, BRES, SPLIT, NM, QS>;
+    static_assert(!QS || (SPLIT && HALO == 0 && !STEM16 && !NM && !BRES), "quad stages: split mode, generic (1x1) pipeline");
     static_assert(!BRES || (HALO > 0 && !STEM16), "resident weights are implemented for the 3x3 halo pipeline");
+    static_assert(!NM || (SPLIT && HALO > 0 && BN <= 128 && (STEM16 || EPI_BUFS == 0)), "N-merged split mode: narrow 3x3 halo layers and the stem");
+    constexpr int kAccCols = NM ? 2 * BN : BN;   // TMEM columns of one accumulator buffer
     // BRES + SPLIT (res2 conv2, 64 -> 64 channels): the k loop over K' = 3C visits [w_hi, w_hi, w_lo] per tap, i.e. only 18
     // DISTINCT weight tiles (9 taps x {hi, lo}); slot tap holds w_hi, slot 9 + tap holds w_lo (STAGES = 18, 144 KB).
     constexpr int kPanels = BN / 64;   // 64-column panels of one staged tile half
@@ -208,14 +220,15 @@ conv_gemm_f16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_co
     constexpr int CH = COLS < 32 ? COLS : 32;  // epilogue column chunk
     // accumulator buffers in TMEM: narrow tiles finish their MMAs in ~1 us while an epilogue takes 2-3 us from
     // tcgen05.commit to the hand-back (barrier wake-up, tcgen05.ld, stores, arrive), so BN <= 128 uses four buffers
-    constexpr int kAcc = BN <= 128 ? 4 : 2;
+    constexpr int kAcc = kAccCols <= 128 ? 4 : 2;
     // The CTA always takes ALL 512 TMEM columns (one CTA per SM anyway): the allocation then starts at column 0, the
     // accumulator address is a compile-time expression, and ptxas keeps it in a uniform register instead of running an
     // ELECT / R2UR.BROADCAST loop in front of every tcgen05.mma (the address read back from shared memory is not
     // provably warp-uniform).  That loop cost ~40 issue clocks per MMA -- more than a whole N = 64 MMA (32 clocks).
     constexpr uint32_t kTmemCols = 512;
-    static_assert(kAcc * BN <= 512, "accumulator buffers exceed TMEM");
+    static_assert(kAcc * kAccCols <= 512, "accumulator buffers exceed TMEM");
     constexpr uint32_t kIdesc = ptx::make_idesc_f16(kBlockM, BN);
+    [[maybe_unused]] constexpr uint32_t kIdesc2 = ptx::make_idesc_f16(kBlockM, NM ? 2 * BN : BN);   // NM: the a_hi pass (N = 2 BN)
     static_assert(!TMA_EPI || BN % 64 == 0, "TMA epilogue works on 64-column panels");
 
     extern __shared__ uint8_t smem_raw[];
@@ -330,18 +343,21 @@ conv_gemm_f16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_co
                     // loaded once and stay resident; the ring only carries A boxes (4 per tile, several tiles ahead)
                     // SPLIT: eight resident tiles (w_hi of the four vertical taps, then w_lo) and per vertical tap three A
                     // boxes: columns 0..15 (hi) against w_hi, 16..31 (lo) against w_hi, 0..15 (hi) against w_lo
-                    constexpr int kStemB = SPLIT ? 8 : 4;
+                    // NM: four resident tiles of 2 x 64 rows ([w_hi ; w_lo] of a vertical tap) and two A boxes per tap (hi, lo)
+                    constexpr int kStemB = NM ? 4 : SPLIT ? 8 : 4;
                     static_assert(!STEM16 || STAGES >= kStemB, "stem: one ring slot per resident weight tile");
                     if (it == 0) {
                         for (int ty = 0; ty < kStemB; ++ty) {
                             ptx::mbar_arrive_expect_tx(&full_bar[ty], S::kBBytes);
-                            ptx::tma_load_2d(smem + S::kRingOffset + ty * S::kStageBytes, &tmap_b, &full_bar[ty], 0,
-                                             ty * p.b_rows_per_tap + b_row_base);
+                            uint8_t* dst = smem + S::kRingOffset + ty * S::kStageBytes;
+                            ptx::tma_load_2d(dst, &tmap_b, &full_bar[ty], 0, ty * p.b_rows_per_tap + b_row_base);
+                            if constexpr (NM)
+                                ptx::tma_load_2d(dst + S::kBBytes / 2, &tmap_b, &full_bar[ty], 0, ty * p.b_rows_per_tap + p.nm_lo_row + b_row_base);
                         }
                     }
                     for (int ty = 0; ty < 4; ++ty) {
 #pragma unroll
-                        for (int pass = 0; pass < (SPLIT ? 3 : 1); ++pass) {
+                        for (int pass = 0; pass < (NM ? 2 : SPLIT ? 3 : 1); ++pass) {
                             ptx::mbar_wait(&a_empty[hs], hphase ^ 1u);
                             ptx::mbar_arrive_expect_tx(&a_full[hs], S::kAHaloTx);
                             ptx::tma_load_2d(smem + hs * S::kAHaloBytes, &tmap_a, &a_full[hs], pass == 1 ? 16 : 0,
@@ -351,7 +367,16 @@ conv_gemm_f16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_co
                     }
                     continue;
                 } else if constexpr (HALO > 0) {
-                    if constexpr (BRES && SPLIT) {
+                    if constexpr (BRES && NM) {
+                        if (it == 0) {   // 9 resident tiles of 2 BN rows: slot = tap, rows [w_hi ; w_lo] (K = 64 = one k-block)
+                            for (int t = 0; t < 9; ++t) {
+                                ptx::mbar_arrive_expect_tx(&full_bar[t], S::kBBytes);
+                                uint8_t* dst = smem + S::kRingOffset + t * S::kStageBytes;
+                                ptx::tma_load_2d(dst, &tmap_b, &full_bar[t], 0, t * p.b_rows_per_tap + b_row_base);
+                                ptx::tma_load_2d(dst + S::kBBytes / 2, &tmap_b, &full_bar[t], 0, t * p.b_rows_per_tap + p.nm_lo_row + b_row_base);
+                            }
+                        }
+                    } else if constexpr (BRES && SPLIT) {
                         if (it == 0) {   // 18 resident tiles: slot t < 9 = w_hi of tap t (k-block 0), slot 9 + t = w_lo (k-block 2)
                             for (int t = 0; t < 18; ++t) {
                                 ptx::mbar_arrive_expect_tx(&full_bar[t], S::kBBytes);
@@ -377,7 +402,7 @@ conv_gemm_f16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_co
                             } else {
                                 ptx::mbar_arrive_expect_tx(&a_full[hs], S::kAHaloTx);
                                 int acol = kb * kBlockK;
-                                if constexpr (SPLIT) { if (acol >= p.a_wrap) acol -= p.a_wrap; }
+                                if constexpr (SPLIT && !NM) { if (acol >= p.a_wrap) acol -= p.a_wrap; }   // NM: [hi | lo] in order
                                 ptx::tma_load_2d(smem + hs * S::kAHaloBytes, &tmap_a, &a_full[hs], acol,
                                                  a_row_base + (dyi - 1) * wp - 1);
                             }
@@ -385,9 +410,21 @@ conv_gemm_f16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_co
                             if constexpr (BRES) continue;
                             for (int dxi = 0; dxi < 3; ++dxi) {
                                 ptx::mbar_wait(&empty_bar[stage], phase ^ 1u);
-                                ptx::mbar_arrive_expect_tx(&full_bar[stage], S::kBBytes);
-                                ptx::tma_load_2d(smem + S::kRingOffset + stage * S::kStageBytes, &tmap_b, &full_bar[stage],
-                                                 kb * kBlockK, (dyi * 3 + dxi) * p.b_rows_per_tap + b_row_base);
+                                uint8_t* dst = smem + S::kRingOffset + stage * S::kStageBytes;
+                                if constexpr (NM) {
+                                    // k-blocks [0, KB) pair a_hi with [w_hi ; w_lo] (2 BN rows), [KB, 2 KB) pair a_lo with w_hi
+                                    const int kbh = p.kblocks_per_tap >> 1;
+                                    const bool hi_pass = kb < kbh;
+                                    const int bcol = (hi_pass ? kb : kb - kbh) * kBlockK;
+                                    const int brow = (dyi * 3 + dxi) * p.b_rows_per_tap + b_row_base;
+                                    ptx::mbar_arrive_expect_tx(&full_bar[stage], hi_pass ? S::kBBytes : S::kBBytes / 2);
+                                    ptx::tma_load_2d(dst, &tmap_b, &full_bar[stage], bcol, brow);
+                                    if (hi_pass) ptx::tma_load_2d(dst + S::kBBytes / 2, &tmap_b, &full_bar[stage], bcol, brow + p.nm_lo_row);
+                                } else {
+                                    ptx::mbar_arrive_expect_tx(&full_bar[stage], S::kBBytes);
+                                    ptx::tma_load_2d(dst, &tmap_b, &full_bar[stage], kb * kBlockK,
+                                                     (dyi * 3 + dxi) * p.b_rows_per_tap + b_row_base);
+                                }
                                 if (++stage == STAGES) { stage = 0; phase ^= 1u; }
                             }
                         }
@@ -397,6 +434,21 @@ conv_gemm_f16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_co
                 int tap = 0, kb = 0;
                 for (int ks = 0; ks < ksteps; ++ks) {
                     ptx::mbar_wait(&empty_bar[stage], phase ^ 1u);
+                    if constexpr (QS) {
+                        // [a_hi | a_lo | w_hi | w_lo] of k-block kb: A columns kb * 64 and C + kb * 64, weight columns kb * 64 (w_hi)
+                        // and 2C + kb * 64 (w_lo) of the [w_hi | w_hi | w_lo] rows
+                        uint8_t* sq = smem + S::kRingOffset + stage * S::kStageBytes;
+                        const int arow = a_row_base + static_cast<int>(p.tap_dy[tap]) * wp + static_cast<int>(p.tap_dx[tap]);
+                        const int brow = tap * p.b_rows_per_tap + b_row_base;
+                        ptx::mbar_arrive_expect_tx(&full_bar[stage], S::kStageBytes);
+                        ptx::tma_load_2d(sq, &tmap_a, &full_bar[stage], kb * kBlockK, arow);
+                        ptx::tma_load_2d(sq + S::kABytes, &tmap_a, &full_bar[stage], (p.a_wrap >> 1) + kb * kBlockK, arow);
+                        ptx::tma_load_2d(sq + 2 * S::kABytes, &tmap_b, &full_bar[stage], kb * kBlockK, brow);
+                        ptx::tma_load_2d(sq + 2 * S::kABytes + S::kBBytes, &tmap_b, &full_bar[stage], p.a_wrap + kb * kBlockK, brow);
+                        if (++kb == p.kblocks_per_tap) { kb = 0; ++tap; }
+                        if (++stage == STAGES) { stage = 0; phase ^= 1u; }
+                        continue;
+                    }
                     // Weight tile already in this slot?  When the number of k-steps divides STAGES and the CTA keeps its
                     // N tile (grid % num_n_tiles == 0, see launch_conv_gemm_bn), slot s always carries the same B tile:
                     // it is loaded once and only the A half of the slot is refilled (the MMAs have retired -- the empty
@@ -434,22 +486,23 @@ conv_gemm_f16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_co
             for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
                 ptx::mbar_wait(&tmem_empty[acc], acc_phase ^ 1u);
                 ptx::tc_fence_after();
-                const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(acc * BN);
+                const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(acc * kAccCols);
                 if constexpr (STEM16) {
                     if (!b_resident) {
-                        for (int ty = 0; ty < (SPLIT ? 8 : 4); ++ty) ptx::mbar_wait(&full_bar[ty], 0);
+                        for (int ty = 0; ty < (NM ? 4 : SPLIT ? 8 : 4); ++ty) ptx::mbar_wait(&full_bar[ty], 0);
                         b_resident = true;
                     }
                     for (int ty = 0; ty < 4; ++ty) {
 #pragma unroll
-                        for (int pass = 0; pass < (SPLIT ? 3 : 1); ++pass) {
+                        for (int pass = 0; pass < (NM ? 2 : SPLIT ? 3 : 1); ++pass) {
                             ptx::mbar_wait(&a_full[hs], hphase);
                             ptx::tc_fence_after();
                             const uint32_t sa = ptx::smem_u32(smem + hs * S::kAHaloBytes);
                             const uint64_t db = ptx::make_sw128_kmajor_desc(
-                                ptx::smem_u32(smem + S::kRingOffset + (ty + (pass == 2 ? 4 : 0)) * S::kStageBytes));
+                                ptx::smem_u32(smem + S::kRingOffset + (ty + ((!NM && pass == 2) ? 4 : 0)) * S::kStageBytes));
                             // horizontal tap tx: A starts tx rows (32 bytes) in, B advances 32 bytes of K
-                            ptx::umma_f16_x4(d_tmem, ptx::make_sw32_kmajor_desc(sa), db, kIdesc, (ty | pass) ? 1u : 0u);
+                            // (NM: pass 0 = a_hi against the 128-row [w_hi ; w_lo] tile, pass 1 = a_lo against its first 64 rows)
+                            ptx::umma_f16_x4(d_tmem, ptx::make_sw32_kmajor_desc(sa), db, (NM && pass == 0) ? kIdesc2 : kIdesc, (ty | pass) ? 1u : 0u);
                             ptx::umma_commit(&a_empty[hs]);
                             if (++hs == kHalo) { hs = 0; hphase ^= 1u; }
                         }
@@ -461,7 +514,7 @@ conv_gemm_f16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_co
                     uint32_t first = 0;
                     if constexpr (BRES) {
                         if (!b_resident) {
-                            for (int t = 0; t < (SPLIT ? 18 : 9 * p.kblocks_per_tap); ++t) ptx::mbar_wait(&full_bar[t], 0);
+                            for (int t = 0; t < (NM ? 9 : SPLIT ? 18 : 9 * p.kblocks_per_tap); ++t) ptx::mbar_wait(&full_bar[t], 0);
                             b_resident = true;
                         }
                     }
@@ -475,9 +528,10 @@ conv_gemm_f16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_co
                             if constexpr (BRES) {
                                 ptx::tc_fence_after();
                                 const uint64_t da = ptx::make_sw128_kmajor_desc(sa + dxi * 128);
-                                const int slot = SPLIT ? (dyi * 3 + dxi) + (kb == 2 ? 9 : 0) : (dyi * 3 + dxi) * p.kblocks_per_tap + kb;
+                                const int slot = NM ? (dyi * 3 + dxi) : SPLIT ? (dyi * 3 + dxi) + (kb == 2 ? 9 : 0) : (dyi * 3 + dxi) * p.kblocks_per_tap + kb;
                                 const uint64_t db = ptx::make_sw128_kmajor_desc(ptx::smem_u32(smem + S::kRingOffset + slot * S::kStageBytes));
-                                if (!(p.dbg_skip & 2)) ptx::umma_f16_x4(d_tmem, da, db, kIdesc, first);
+                                // NM (one k-block per half): kb = 0 is the a_hi pass over the 2 BN-row tile, kb = 1 the a_lo pass over w_hi
+                                if (!(p.dbg_skip & 2)) ptx::umma_f16_x4(d_tmem, da, db, (NM && kb == 0) ? kIdesc2 : kIdesc, first);
                                 first = 1;
                                 continue;
                             }
@@ -487,7 +541,7 @@ conv_gemm_f16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_co
                             const uint64_t da = ptx::make_sw128_kmajor_desc(sa + dxi * 128);
                             const uint64_t db = ptx::make_sw128_kmajor_desc(
                                 ptx::smem_u32(smem + S::kRingOffset + stage * S::kStageBytes));
-                            ptx::umma_f16_x4(d_tmem, da, db, kIdesc, first);
+                            ptx::umma_f16_x4(d_tmem, da, db, (NM && kb < (p.kblocks_per_tap >> 1)) ? kIdesc2 : kIdesc, first);
                             first = 1;
                             ptx::umma_commit(&empty_bar[stage]);
                             if (++stage == STAGES) { stage = 0; phase ^= 1u; }
@@ -503,6 +557,17 @@ conv_gemm_f16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_co
                     ptx::mbar_wait(&full_bar[stage], phase);
                     ptx::tc_fence_after();
                     const uint32_t sa = ptx::smem_u32(smem + S::kRingOffset + stage * S::kStageBytes);
+                    if constexpr (QS) {
+                        const uint64_t da_hi = ptx::make_sw128_kmajor_desc(sa), da_lo = ptx::make_sw128_kmajor_desc(sa + S::kABytes);
+                        const uint64_t db_hi = ptx::make_sw128_kmajor_desc(sa + 2 * S::kABytes);
+                        const uint64_t db_lo = ptx::make_sw128_kmajor_desc(sa + 2 * S::kABytes + S::kBBytes);
+                        ptx::umma_f16_x4(d_tmem, da_hi, db_hi, kIdesc, ks ? 1u : 0u);
+                        ptx::umma_f16_x4(d_tmem, da_lo, db_hi, kIdesc, 1u);
+                        ptx::umma_f16_x4(d_tmem, da_hi, db_lo, kIdesc, 1u);
+                        ptx::umma_commit(&empty_bar[stage]);
+                        if (++stage == STAGES) { stage = 0; phase ^= 1u; }
+                        continue;
+                    }
                     const uint64_t da = ptx::make_sw128_kmajor_desc(sa + p.dbg_a_row_skew * 128) |
                                         (static_cast<uint64_t>(p.dbg_base_offset & 7) << 49);
                     const uint64_t db = ptx::make_sw128_kmajor_desc(sa + S::kABytes);
@@ -560,11 +625,13 @@ conv_gemm_f16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_co
                 else ptx::mbar_wait(&epi_free[buf], ph ^ 1u);
                 ptx::tc_fence_after();
                 const uint32_t t_row = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) +
-                                       static_cast<uint32_t>(acc * BN + col_begin);
+                                       static_cast<uint32_t>(acc * kAccCols + col_begin);
 #pragma unroll
                 for (int c0 = 0; c0 < COLS; c0 += CH) {
                     uint32_t v[CH];
+                    [[maybe_unused]] uint32_t v2[NM ? CH : 1];
                     ptx::tmem_ld_32x32b_x32(t_row + c0, v);
+                    if constexpr (NM) ptx::tmem_ld_32x32b_x32(t_row + BN + c0, v2);
                     const int col = col_begin + c0;                 // first column of this chunk inside the tile
                     uint8_t* panel = tile_smem + (col >> 6) * (kBlockM * 128) + r_in_tile * 128;
                     [[maybe_unused]] uint8_t* panel_lo = panel + kPanels * (kBlockM * 128);   // SPLIT: lo half of the tile
@@ -659,21 +726,32 @@ conv_gemm_f16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_co
                 ptx::mbar_wait(&tmem_full[acc], acc_phase);
                 ptx::tc_fence_after();
                 const uint32_t t_row = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) +
-                                       static_cast<uint32_t>(acc * BN + col_begin);
+                                       static_cast<uint32_t>(acc * kAccCols + col_begin);
 #pragma unroll
                 for (int c0 = 0; c0 < COLS; c0 += CH) {
                     uint32_t v[CH];
+                    [[maybe_unused]] uint32_t v2[NM ? CH : 1];
                     if (p.dbg_skip & 8) {
 #pragma unroll
                         for (int j = 0; j < CH; ++j) v[j] = 0u;
                     } else {
                         if constexpr (CH == 32) ptx::tmem_ld_32x32b_x32(t_row + c0, v);
                         else ptx::tmem_ld_32x32b_x16(t_row + c0, v);
+                        if constexpr (NM) {   // the a_hi.w_lo partial products sit BN columns further on
+                            if constexpr (CH == 32) ptx::tmem_ld_32x32b_x32(t_row + BN + c0, v2);
+                            else ptx::tmem_ld_32x32b_x16(t_row + BN + c0, v2);
+                        }
                         ptx::tmem_ld_wait();
                     }
                     float f[CH];
 #pragma unroll
                     for (int j = 0; j < CH; ++j) f[j] = __uint_as_float(v[j]);
+                    if constexpr (NM) {
+                        if (!(p.dbg_skip & 8)) {
+#pragma unroll
+                            for (int j = 0; j < CH; ++j) f[j] += __uint_as_float(v2[j]);
+                        }
+                    }
                     if (p.bias != nullptr) {
                         const float4* bp = reinterpret_cast<const float4*>(p.bias + n_tile * BN + col_begin + c0);
 #pragma unroll

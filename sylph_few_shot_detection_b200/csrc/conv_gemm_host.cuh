@@ -90,15 +90,15 @@ struct PerDeviceOnce {
     }
 };
 
-template <int BN, int STAGES, int EPI_BUFS, int HALO = 0, bool STEM16 = false, bool BRES = false, bool SPLIT = false>
+template <int BN, int STAGES, int EPI_BUFS, int HALO = 0, bool STEM16 = false, bool BRES = false, bool SPLIT = false, bool NM = false, bool QS = false>
 inline cudaError_t launch_conv_gemm_bn(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tres,
                                        const CUtensorMap& tout, const GemmArgs& args, int num_sms, cudaStream_t stream) {
-    using S = GemmSmem<BN, STAGES, EPI_BUFS, HALO, STEM16, BRES, SPLIT>;
+    using S = GemmSmem<BN, STAGES, EPI_BUFS, HALO, STEM16, BRES, SPLIT, NM, QS>;
     static_assert(S::kTotal <= 227 * 1024, "shared memory of this instantiation exceeds the 227 KB of a CTA");
     static PerDeviceOnce once;
     {
         cudaError_t e = once.run([] {
-            return cudaFuncSetAttribute(conv_gemm_f16_kernel<BN, STAGES, EPI_BUFS, HALO, STEM16, BRES, SPLIT>,
+            return cudaFuncSetAttribute(conv_gemm_f16_kernel<BN, STAGES, EPI_BUFS, HALO, STEM16, BRES, SPLIT, NM, QS>,
                                         cudaFuncAttributeMaxDynamicSharedMemorySize, S::kTotal);
         });
         if (e != cudaSuccess) return e;
@@ -110,10 +110,10 @@ inline cudaError_t launch_conv_gemm_bn(const CUtensorMap& ta, const CUtensorMap&
     // its N tile never reloads a weight tile.  tile = blockIdx + j * grid and n_tile = tile mod num_n_tiles: the N tile
     // is fixed per CTA iff grid is a multiple of num_n_tiles -- give up at most num_n_tiles - 1 SMs for that.
     const int ksteps = args.taps * args.kblocks_per_tap;
-    if (HALO == 0 && !STEM16 && args.num_n_tiles > 1 && ksteps <= STAGES && STAGES % ksteps == 0 && grid == num_sms &&
+    if (HALO == 0 && !STEM16 && !QS && args.num_n_tiles > 1 && ksteps <= STAGES && STAGES % ksteps == 0 && grid == num_sms &&
         grid > 4 * args.num_n_tiles && !(args.dbg_skip & 16))
         grid -= grid % args.num_n_tiles;
-    return launch_k(conv_gemm_f16_kernel<BN, STAGES, EPI_BUFS, HALO, STEM16, BRES, SPLIT>, dim3(grid), dim3(S::kThreads), S::kTotal, stream, ta, tb, tres, tout, args);
+    return launch_k(conv_gemm_f16_kernel<BN, STAGES, EPI_BUFS, HALO, STEM16, BRES, SPLIT, NM, QS>, dim3(grid), dim3(S::kThreads), S::kTotal, stream, ta, tb, tres, tout, args);
 }
 
 constexpr int kStagedTwoBufMaxKSteps = 8;
@@ -167,6 +167,38 @@ inline cudaError_t launch_conv_gemm_halo(int bn, const CUtensorMap& ta, const CU
         case 256: return launch_conv_gemm_bn<256, 5, 0, 3>(ta, tb, ta, ta, args, num_sms, stream);
         default: return cudaErrorInvalidValue;
     }
+}
+
+// N-merged split halo pipeline for the narrow 3x3 layers (conv_gemm.cuh, NM): `tb` is the map over the [taps][2 cout_pad][cin]
+// weight matrix with BN-row boxes, args.kblocks_per_tap = 2 cin / 64, args.nm_lo_row = cout_pad.
+// B slots hold 2 BN rows: BN = 64: 4 halo slots + 12 x 16 KB = 260 KB is too much -> 8 slots (196 KB); resident form for
+// 64 -> 64 channels: 9 x 16 KB + 4 halo slots = 212 KB; BN = 128: 4 x 17 KB + 4 x 32 KB = 196 KB; BN = 16: 12 x 4 KB.
+inline cudaError_t launch_conv_gemm_halo_nm(int bn, const CUtensorMap& ta, const CUtensorMap& tb, const GemmArgs& args,
+                                            int num_sms, cudaStream_t stream, bool allow_resident = true) {
+    if (allow_resident && bn == 64 && args.kblocks_per_tap == 2 && args.num_n_tiles == 1)
+        return launch_conv_gemm_bn<64, 9, 0, 4, false, true, true, true>(ta, tb, ta, ta, args, num_sms, stream);
+    switch (bn) {
+        case 16: return launch_conv_gemm_bn<16, 12, 0, 4, false, false, true, true>(ta, tb, ta, ta, args, num_sms, stream);
+        case 64: return launch_conv_gemm_bn<64, 8, 0, 4, false, false, true, true>(ta, tb, ta, ta, args, num_sms, stream);
+        case 128: return launch_conv_gemm_bn<128, 4, 0, 4, false, false, true, true>(ta, tb, ta, ta, args, num_sms, stream);
+        default: return cudaErrorInvalidValue;
+    }
+}
+
+// Quad-stage split 1x1 kernels (conv_gemm.cuh, QS): args.kblocks_per_tap = cin / 64 (LOGICAL k-blocks), args.a_wrap = 2 cin,
+// `tb` the usual map over the [w_hi | w_hi | w_lo] rows with BN-row boxes.  A stage is 32 KB of A + 2 BN x 128 B of weights:
+//   staged, BN = 128: 2 stages x 64 KB + ONE 64 KB staging buffer (192 KB); staged, BN = 256: 1 stage x 96 KB + 128 KB;
+//   register epilogue, BN = 256: 2 stages x 96 KB; BN = 128: 3 stages x 64 KB.
+inline cudaError_t launch_conv_gemm_qs(int bn, bool staged, const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tres,
+                                       const CUtensorMap& tout, const GemmArgs& args, int num_sms, cudaStream_t stream) {
+    if (staged) {
+        if (bn == 128) return launch_conv_gemm_bn<128, 2, 1, 0, false, false, true, false, true>(ta, tb, tres, tout, args, num_sms, stream);
+        if (bn == 256) return launch_conv_gemm_bn<256, 1, 1, 0, false, false, true, false, true>(ta, tb, tres, tout, args, num_sms, stream);
+        return cudaErrorInvalidValue;
+    }
+    if (bn == 128) return launch_conv_gemm_bn<128, 3, 0, 0, false, false, true, false, true>(ta, tb, ta, ta, args, num_sms, stream);
+    if (bn == 256) return launch_conv_gemm_bn<256, 2, 0, 0, false, false, true, false, true>(ta, tb, ta, ta, args, num_sms, stream);
+    return cudaErrorInvalidValue;
 }
 
 // CTA-pair (cta_group::2) 3x3 halo convolution, N tiles of BN in {64, 128, 256}: `ta` box = kBlockM + 2 rows,

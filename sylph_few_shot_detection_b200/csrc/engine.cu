@@ -32,6 +32,7 @@ struct HostTensor {
 // [w_hi | w_hi | w_lo] with w_hi = rn16(w), w_lo = rn16(w - w_hi) (conv_gemm.cuh, GemmArgs::a_wrap).
 struct ConvW {
     __half* w = nullptr;
+    __half* w_nm = nullptr;   // split mode, 3x3 layers with N <= 128: [taps][w_hi rows ; w_lo rows][cin] for the N-merged kernel
     float* bias = nullptr;
     int taps = 0, k_per_tap = 0, cin = 0, cout = 0, cout_pad = 0, bn = 0, ksize = 0;
     int b_rows = 0;   // rows of the weight matrix (taps * cout_pad; the split-mode stem has 2 x 4 tiles)
@@ -88,6 +89,8 @@ struct sylph_ctx {
     int pair1x1 = 1;          // SYLPH_PAIR1X1=0 keeps the single-CTA staged kernel for every 1x1 convolution; 2 = pair kernel
                               // for every staged 1x1 convolution with 256-channel N tiles and K >= 256 (experiments)
     int stem16 = 1;           // SYLPH_STEM16=0 runs the stem over 64-wide overlapped rows instead of K = 16 taps
+    int quad = 1;             // SYLPH_QS=0: K' = 3C loop for every split 1x1 layer instead of quad stages on the deep ones
+    int nmerge = 1;           // SYLPH_NM=0: three instructions per k-step for the narrow split 3x3 layers instead of the N-merged two
     int roi_separable = 1;    // SYLPH_ROI_ALIGN=sample: the per-sample ROIAlign kernel instead of the separable one
     int split = 1;            // precision mode (sylph_set_precision / SYLPH_PRECISION): 1 = "exact", split fp16 operands
                               // (hi + lo pairs, three tensor-core products per multiply: fp32-level results); 0 = "fast",
@@ -362,6 +365,17 @@ static int prep_conv(sylph_ctx* c, const std::string& prefix, bool frozen_bn, bo
     }
     TRY(upload_half(c, hw, &out->w));
     TRY(upload(c, hb, &out->bias));
+    if (c->split && out->taps == 9 && out->bn <= 128) {
+        // the same weights for the N-merged kernel (conv_gemm.cuh, NM): per tap the cout_pad rows of w_hi, then those of w_lo
+        std::vector<uint16_t> nm(static_cast<size_t>(out->taps) * 2 * out->cout_pad * ci, 0);
+        for (int t = 0; t < out->taps; ++t)
+            for (int o = 0; o < co; ++o) {
+                const uint16_t* src = &hw[(static_cast<size_t>(t) * out->cout_pad + o) * kp];
+                memcpy(&nm[(static_cast<size_t>(2 * t) * out->cout_pad + o) * ci], src, static_cast<size_t>(ci) * 2);
+                memcpy(&nm[(static_cast<size_t>(2 * t + 1) * out->cout_pad + o) * ci], src + 2 * ci, static_cast<size_t>(ci) * 2);
+            }
+        TRY(upload_half(c, nm, &out->w_nm));
+    }
     return 0;
 }
 
@@ -566,6 +580,7 @@ struct ConvCall {
     int stem = 0;
     int up_seg_delta = 0;    // kEpiUpsample: coarser plane = segment of the output tile + this
     int staged = 0;          // TMA-in / TMA-out epilogue (fp16 output, BN = 256); needs out_rows
+    int qs = 0;              // split mode: quad-stage 1x1 kernel (conv_gemm.cuh QS) with N tiles of this width (128 / 256), 0 = K' = 3C loop
     long long out_rows = 0;  // rows of the output (and residual) buffer, for the staged epilogue's tensor maps
     const char* name = "conv";
 };
@@ -585,6 +600,25 @@ static int run_conv(sylph_ctx* c, const ConvCall& k, cudaStream_t st) {
     const bool deep_direct = c->split && k.staged && !k.stem && W.taps == 1 && !has_res && W.bn == 256 && W.cin >= 1024;
     ConvCall kk = k;
     if (deep_direct) kk.staged = 0;
+    // Split mode, 1x1 layers with cin >= 512 (and the res3 / res4 shortcuts): quad stages -- a_hi, a_lo, w_hi, w_lo of a k-block are
+    // loaded once (four tiles instead of six per k-block).  Measured at the 33-image shapes (profiles/r02_quad_stage_ab.log):
+    // conv1 res3 0.344 -> 0.288, res4 0.256 -> 0.228, res5 0.251 -> 0.223; shortcut res3 0.639 -> 0.568, res4 0.542 -> 0.458,
+    // res5 0.495 -> 0.424; laterals 0.572 / 0.257 / 0.158 -> 0.512 / 0.229 / 0.125 ms.  conv3 (staged, residual) stays on the
+    // K' = 3C kernel: quad stages leave room for ONE staging buffer only, which costs more than the operand traffic saved
+    // (res4 0.404 -> 0.498), except on res5 (K = 512) where the register epilogue wins (0.359 -> 0.325).
+    if (c->split && c->quad && !k.stem && W.taps == 1 && k.w_override == nullptr && W.cout_pad % 128 == 0 && W.cin % 64 == 0 &&
+        !(k.flags & (kEpiOutF32 | kEpiGnStats))) {
+        const bool upsample = (k.flags & kEpiUpsample) != 0;
+        if (has_res && !upsample) {
+            if (W.cin >= 512) { kk.qs = 128; kk.staged = 0; }                                   // res5 conv3
+        } else if (k.staged && !(k.flags & kEpiRelu) && W.cout_pad >= 512) {                    // shortcut convolutions
+            if (W.cin >= 1024) { kk.qs = 256; kk.staged = 0; }
+            else if (W.cin >= 256) { kk.qs = 128; }
+        } else if (W.cin >= 512) {                                                              // conv1, FPN laterals
+            kk.qs = (W.cin == 512 && W.cout_pad % 256 == 0 && !k.staged) ? 256 : 128;
+            kk.staged = 0;
+        }
+    }
     return run_conv_impl(c, kk, st, has_res);
 }
 
@@ -609,14 +643,20 @@ static int run_conv_impl(sylph_ctx* c, const ConvCall& k, cudaStream_t st, const
     // staging buffer, which halves their A re-reads from L2: 0.72 -> 0.64 / 0.60 -> 0.55 / 0.60 -> 0.54 ms on res3..res5 at 33
     // images; every other staged layer measured slower that way (profiles/r02_split_tile_width_ab.log)
     const bool wide_split = split && k.staged && W.bn == 256 && !has_res && !(k.flags & kEpiRelu) && W.cout_pad >= 512;
-    const int bn = (split && k.staged && W.bn == 256 && !wide_split) ? 128 : W.bn;
+    const int bn = k.qs ? k.qs : (split && k.staged && W.bn == 256 && !wide_split) ? 128 : W.bn;
     if (stem16) {
         if (make_tmap_2d_k16(&ta, k.A, static_cast<uint64_t>(k.a_rows), kBlockM + 3, &err, split ? 32 : 16))
             return c->fail("A tensor map (%s): %s", k.name, err.c_str());
     } else if (make_tmap_2d(&ta, k.A, static_cast<uint64_t>(k.a_rows), k.a_cols, k.a_ld, halo ? kBlockM + 2 : kBlockM, &err))
         return c->fail("A tensor map (%s): %s", k.name, err.c_str());
-    if (make_tmap_2d(&tb, k.w_override ? k.w_override : W.w, static_cast<uint64_t>(W.b_rows), W.k_per_tap,
-                     W.k_per_tap, (pair || pair1x1) ? bn / 2 : bn, &err))
+    // narrow split 3x3 layers (res2 / res3 conv2, the predictor): N-merged kernel over the [taps][w_hi ; w_lo][cin] weights --
+    // res2 conv2 0.60 -> 0.47 ms, res3 conv2 0.47 -> 0.42 ms, predictor 0.26 -> 0.18 ms (test_conv_gemm split)
+    const bool nm = split && halo && !pair && c->nmerge && W.w_nm != nullptr && k.w_override == nullptr && W.cout_pad == bn;
+    if (nm) {
+        if (make_tmap_2d(&tb, W.w_nm, static_cast<uint64_t>(W.taps) * 2 * W.cout_pad, W.cin, W.cin, bn, &err))
+            return c->fail("B tensor map (%s): %s", k.name, err.c_str());
+    } else if (make_tmap_2d(&tb, k.w_override ? k.w_override : W.w, static_cast<uint64_t>(W.b_rows), W.k_per_tap,
+                            W.k_per_tap, (pair || pair1x1) ? bn / 2 : bn, &err))
         return c->fail("B tensor map (%s): %s", k.name, err.c_str());
     GemmArgs g{};
     g.tile_begin = k.tile_begin;
@@ -627,6 +667,12 @@ static int run_conv_impl(sylph_ctx* c, const ConvCall& k, cudaStream_t st, const
     g.kblocks_per_tap = W.k_per_tap / kBlockK;
     g.b_rows_per_tap = W.cout_pad;
     g.a_wrap = split ? 2 * W.cin : 0;
+    if (k.qs) g.kblocks_per_tap = W.cin / kBlockK;   // logical k-blocks: a stage carries a_hi, a_lo, w_hi, w_lo
+    if (nm) {
+        g.kblocks_per_tap = 2 * W.cin / kBlockK;
+        g.b_rows_per_tap = 2 * W.cout_pad;
+        g.nm_lo_row = W.cout_pad;
+    }
     g.out_lo = (split && out_f16) ? k.ldc / 2 : 0;
     g.res_lo = split ? k.ld_res / 2 : 0;
     for (int t = 0; t < W.taps; ++t) {
@@ -668,9 +714,14 @@ static int run_conv_impl(sylph_ctx* c, const ConvCall& k, cudaStream_t st, const
             return c->fail("epilogue tensor maps (%s): %s", k.name, err.c_str());
         if (stem16) CU_TRY(c, launch_conv_gemm_stem16(ta, tb, tout, g, c->num_sms, st, split));
         else if (pair1x1) CU_TRY(c, launch_conv1x1_pair_staged(ta, tb, tres, tout, g, c->num_sms, st));
+        else if (k.qs) CU_TRY(c, launch_conv_gemm_qs(bn, true, ta, tb, tres, tout, g, c->num_sms, st));
         else CU_TRY(c, launch_conv_gemm_staged(bn, ta, tb, tres, tout, g, c->num_sms, st, 0, split));
+    } else if (k.qs) {
+        CU_TRY(c, launch_conv_gemm_qs(bn, false, ta, tb, ta, ta, g, c->num_sms, st));
     } else if (pair) {
         CU_TRY(c, launch_conv3x3_pair(ta, tb, g, c->num_sms, st, bn, split));
+    } else if (nm) {
+        CU_TRY(c, launch_conv_gemm_halo_nm(bn, ta, tb, g, c->num_sms, st));
     } else if (halo) {
         CU_TRY(c, launch_conv_gemm_halo(bn, ta, tb, g, c->num_sms, st, true, split));
     } else {
@@ -733,6 +784,8 @@ int sylph_create(sylph_ctx** out, int device, const sylph_model_config* cfg) {
     if (const char* e = getenv("SYLPH_STEM16")) c->stem16 = atoi(e);
     if (const char* e = getenv("SYLPH_PAIR1X1")) c->pair1x1 = atoi(e);
     if (const char* e = getenv("SYLPH_FUSE_UPSAMPLE")) c->fuse_upsample = atoi(e);
+    if (const char* e = getenv("SYLPH_NM")) c->nmerge = atoi(e);
+    if (const char* e = getenv("SYLPH_QS")) c->quad = atoi(e);
     if (const char* e = getenv("SYLPH_ROI_ALIGN")) c->roi_separable = strcmp(e, "sample") == 0 ? 0 : 1;
     if (const char* e = getenv("SYLPH_PRECISION")) c->split = (strcmp(e, "fast") == 0 || strcmp(e, "0") == 0) ? 0 : 1;
     *out = c;

@@ -40,11 +40,13 @@ struct Case {
     bool bias;
     int skew = 0, base_offset = 0;  // experiment: A box loaded `skew` rows early, descriptor started `skew` rows in
     bool pair = false;    // CTA-pair (cta_group::2) halo kernel
+    bool nm = false;      // split mode, N-merged narrow 3x3 halo kernel: weights [taps][w_hi rows ; w_lo rows][cin]
     bool split = false;   // split-operand ("exact") mode: A rows [C hi | C lo], weights [w_hi | w_hi | w_lo], fp16 outputs hi | lo
     bool halo = false;    // 3x3 halo pipeline (one 130-row A box per vertical tap and k-block)
     bool staged = false;  // TMA-in / TMA-out epilogue, run IN PLACE (out == residual buffer) like the bottleneck conv3
     bool pair1x1 = false; // CTA-pair 1x1 convolution with the staged epilogue (conv1x1_pair.cuh)
     int sms_override = 0; // pretend the device has this many SMs: many tiles per CTA on a problem the CPU reference finishes quickly
+    bool qs = false;      // split mode, quad-stage 1x1 kernel (a_hi, a_lo, w_hi, w_lo of a k-block loaded once; conv_gemm.cuh QS)
     bool stem16 = false;  // stem as K = 16 taps: A map = [rows][16] with 32-byte swizzle, 131-row boxes (same math as a_ld = 16)
 };
 
@@ -61,8 +63,9 @@ static int run_case(const Case& c, int num_sms) {
     const int ldc = (sp && !(c.flags & kEpiOutF32)) ? 2 * c.cout : c.cout;   // fp16 outputs carry a lo half
     const int ld_r = sp ? 2 * c.cout : c.cout;
     const size_t a_elems = static_cast<size_t>(M) * a_ld + 128;
-    const int w_tiles = (sp && c.stem16) ? 2 * c.taps : c.taps;   // split stem: tiles [hi taps | lo taps], K = 64 each
-    const int Kw = c.stem16 ? Kt : Kp;
+    const bool nm = c.nm && sp && c.halo;
+    const int w_tiles = (sp && c.stem16) || nm ? 2 * c.taps : c.taps;   // split stem: tiles [hi taps | lo taps]; NM: [tap][hi ; lo]
+    const int Kw = (c.stem16 || nm) ? Kt : Kp;
     std::vector<uint16_t> hA(a_elems, 0), hW(static_cast<size_t>(w_tiles) * c.cout * Kw, 0), hR;
     // the values the kernel is expected to multiply: hi (+ lo) of every operand, as doubles
     std::vector<double> vA(static_cast<size_t>(M) * c.a_ld + 128, 0.0), vW(static_cast<size_t>(c.taps) * c.cout * Kt, 0.0), vR;
@@ -89,7 +92,9 @@ static int run_case(const Case& c, int num_sms) {
             for (int k = 0; k < Kt; ++k) {
                 const float v = frand() * 0.10007f;
                 double& val = vW[(static_cast<size_t>(t) * c.cout + n) * Kt + k];
-                if (c.stem16 && sp) {
+                if (nm) {
+                    val = put(v, &hW[(static_cast<size_t>(2 * t) * c.cout + n) * Kt + k], &hW[(static_cast<size_t>(2 * t + 1) * c.cout + n) * Kt + k]);
+                } else if (c.stem16 && sp) {
                     val = put(v, &hW[(static_cast<size_t>(t) * c.cout + n) * Kt + k], &hW[(static_cast<size_t>(c.taps + t) * c.cout + n) * Kt + k]);
                 } else if (sp) {
                     uint16_t* row = &hW[(static_cast<size_t>(t) * c.cout + n) * Kp];
@@ -152,8 +157,9 @@ static int run_case(const Case& c, int num_sms) {
     g.num_n_tiles = c.cout / c.bn;
     g.a_row_delta = 0;
     g.taps = c.taps;
-    g.kblocks_per_tap = Kw / kBlockK;
-    g.b_rows_per_tap = c.cout;
+    g.kblocks_per_tap = nm ? 2 * Kt / kBlockK : (c.qs ? Kt / kBlockK : Kw / kBlockK);
+    g.b_rows_per_tap = nm ? 2 * c.cout : c.cout;
+    g.nm_lo_row = c.cout;
     g.a_wrap = sp ? 2 * Kt : 0;
     g.out_lo = (sp && !f32out) ? c.cout : 0;
     g.res_lo = sp ? c.cout : 0;
@@ -179,11 +185,16 @@ static int run_case(const Case& c, int num_sms) {
         }
         if (c.stem16) CK(launch_conv_gemm_stem16(ta, tb, tio, g, num_sms, 0, sp));
         else if (c.pair1x1) CK(launch_conv1x1_pair_staged(ta, tb, tio, tio, g, num_sms, 0));
+        else if (c.qs) CK(launch_conv_gemm_qs(c.bn, true, ta, tb, tio, tio, g, num_sms, 0));
         else CK(launch_conv_gemm_staged(c.bn, ta, tb, tio, tio, g, num_sms, 0, 0, sp));
     } else if (c.pair) {
         CK(launch_conv3x3_pair(ta, tb, g, num_sms, 0, c.bn, sp));
+    } else if (nm) {
+        CK(launch_conv_gemm_halo_nm(c.bn, ta, tb, g, num_sms, 0));
     } else if (c.halo) {
         CK(launch_conv_gemm_halo(c.bn, ta, tb, g, num_sms, 0, true, sp));
+    } else if (c.qs) {
+        CK(launch_conv_gemm_qs(c.bn, false, ta, tb, ta, ta, g, num_sms, 0));
     } else {
         CK(launch_conv_gemm(c.bn, ta, tb, g, num_sms, 0, sp));
     }
@@ -258,13 +269,14 @@ static Seg mk_seg(int row0, int H, int W, int pad) {
 static int round128(int x) { return (x + 127) / 128 * 128; }
 
 static int g_dbg_skip = 0;
-static void bench_shape(const char* name, int bn, int m_tiles, int cin, int cout, int taps, int flags, int num_sms, int staged = 0, bool halo = false, bool pair = false, bool split = false) {
+static void bench_shape(const char* name, int bn, int m_tiles, int cin, int cout, int taps, int flags, int num_sms, int staged = 0, bool halo = false, bool pair = false, bool split = false, bool nm = false, bool qs = false) {
     // split: `cin` / `cout` stay the LOGICAL channel counts; the buffers hold [C hi | C lo] rows and [w_hi | w_hi | w_lo] weights
     const int M = m_tiles * 128;
     const int osz = (flags & kEpiOutF32) ? 4 : 2;
     const int cin_l = cin, cout_l = cout;
     const int ldo = (split && osz == 2) ? 2 * cout : cout;
-    const int kw = split ? 3 * cin : cin;
+    const int kw = nm ? cin : (split ? 3 * cin : cin);       // NM: [taps][2 cout][cin]
+    const int w_rows_per_tap = nm ? 2 * cout : cout;
     if (split) cin *= 2;   // physical A pitch
     __half *dA, *dW, *dR = nullptr;
     void* dO;
@@ -272,7 +284,7 @@ static void bench_shape(const char* name, int bn, int m_tiles, int cin, int cout
     int* dTS;
     Seg* dS;
     CK(cudaMalloc(&dA, static_cast<size_t>(M) * cin * 2));
-    CK(cudaMalloc(&dW, static_cast<size_t>(taps) * cout * kw * 2));
+    CK(cudaMalloc(&dW, static_cast<size_t>(taps) * w_rows_per_tap * kw * 2));
     CK(cudaMalloc(&dO, static_cast<size_t>(M) * ldo * osz));
     CK(cudaMalloc(&dB, cout * 4));
     CK(cudaMalloc(&dG, static_cast<size_t>(m_tiles) * 64 * 4));
@@ -282,7 +294,7 @@ static void bench_shape(const char* name, int bn, int m_tiles, int cin, int cout
         std::vector<uint16_t> h(static_cast<size_t>(M) * cin);
         for (auto& v : h) v = float_to_half_bits(frand());
         CK(cudaMemcpy(dA, h.data(), h.size() * 2, cudaMemcpyHostToDevice));
-        std::vector<uint16_t> w(static_cast<size_t>(taps) * cout * kw);
+        std::vector<uint16_t> w(static_cast<size_t>(taps) * w_rows_per_tap * kw);
         for (auto& v : w) v = float_to_half_bits(frand() * 0.05f);
         CK(cudaMemcpy(dW, w.data(), w.size() * 2, cudaMemcpyHostToDevice));
     }
@@ -297,12 +309,12 @@ static void bench_shape(const char* name, int bn, int m_tiles, int cin, int cout
     CUtensorMap ta, tb;
     std::string err;
     const bool pair1x1 = staged == 9;   // CTA-pair 1x1 kernel with the staged epilogue
-    if (make_tmap_2d(&ta, dA, M, cin, cin, (halo || pair) ? 130 : 128, &err) || make_tmap_2d(&tb, dW, static_cast<uint64_t>(taps) * cout, kw, kw, (pair || pair1x1) ? bn / 2 : bn, &err)) {
+    if (make_tmap_2d(&ta, dA, M, cin, cin, (halo || pair) ? 130 : 128, &err) || make_tmap_2d(&tb, dW, static_cast<uint64_t>(taps) * w_rows_per_tap, kw, kw, (pair || pair1x1) ? bn / 2 : bn, &err)) {
         printf("[%s] tensor map failed: %s\n", name, err.c_str());
         return;
     }
     GemmArgs g{};
-    g.num_m_tiles = m_tiles; g.num_n_tiles = cout / bn; g.taps = taps; g.kblocks_per_tap = kw / kBlockK; g.b_rows_per_tap = cout;
+    g.num_m_tiles = m_tiles; g.num_n_tiles = cout / bn; g.taps = taps; g.kblocks_per_tap = nm ? 2 * cin_l / kBlockK : (qs ? cin_l / kBlockK : kw / kBlockK); g.b_rows_per_tap = w_rows_per_tap; g.nm_lo_row = cout_l;
     g.a_wrap = split ? 2 * cin_l : 0; g.out_lo = (split && osz == 2) ? cout_l : 0; g.res_lo = split ? cout_l : 0;
     for (int t = 0; t < taps; ++t) { g.tap_dy[t] = taps == 9 ? (t / 3) - 1 : 0; g.tap_dx[t] = taps == 9 ? (t % 3) - 1 : 0; }
     g.bias = dB; g.residual = dR; g.ld_res = ldo; g.out = dO; g.ldc = ldo; g.flags = flags; g.tile_seg = dTS; g.segs = dS; g.gn_partial = dG;
@@ -314,7 +326,7 @@ static void bench_shape(const char* name, int bn, int m_tiles, int cin, int cout
         g.residual = static_cast<const __half*>(dO);
         if (make_tmap_2d(&tio, static_cast<const __half*>(dO), M, ldo, ldo, 128, &err)) { printf("tmap failed\n"); return; }
     }
-    auto launch = [&]() { return pair1x1 ? launch_conv1x1_pair_staged(ta, tb, tio, tio, g, num_sms, 0) : staged ? launch_conv_gemm_staged(bn, ta, tb, tio, tio, g, num_sms, 0, staged == 100 ? 0 : staged, split) : (pair ? launch_conv3x3_pair(ta, tb, g, num_sms, 0, bn, split) : (halo ? launch_conv_gemm_halo(bn, ta, tb, g, num_sms, 0, true, split) : launch_conv_gemm(bn, ta, tb, g, num_sms, 0, split))); };
+    auto launch = [&]() { return qs ? launch_conv_gemm_qs(bn, staged != 0, ta, tb, tio, tio, g, num_sms, 0) : pair1x1 ? launch_conv1x1_pair_staged(ta, tb, tio, tio, g, num_sms, 0) : staged ? launch_conv_gemm_staged(bn, ta, tb, tio, tio, g, num_sms, 0, staged == 100 ? 0 : staged, split) : (pair ? launch_conv3x3_pair(ta, tb, g, num_sms, 0, bn, split) : (nm ? launch_conv_gemm_halo_nm(bn, ta, tb, g, num_sms, 0) : halo ? launch_conv_gemm_halo(bn, ta, tb, g, num_sms, 0, true, split) : launch_conv_gemm(bn, ta, tb, g, num_sms, 0, split))); };
     for (int i = 0; i < 3; ++i) CK(launch());
     CK(cudaDeviceSynchronize());
     const int iters = 10;
@@ -325,7 +337,7 @@ static void bench_shape(const char* name, int bn, int m_tiles, int cin, int cout
     float ms;
     CK(cudaEventElapsedTime(&ms, e0, e1));
     ms /= iters;
-    double flop = 2.0 * M * cout * static_cast<double>(kw) * taps;   // executed (split: three products per multiply)
+    double flop = 2.0 * M * cout * static_cast<double>(split ? 3 * cin_l : cin_l) * taps;   // executed (split: three products per multiply)
     double bytes = static_cast<double>(M) * cin * 2 + static_cast<double>(M) * ldo * (osz + ((flags & kEpiResidual) ? 2 : 0));
     printf("[bench %s] M=%d K=%d N=%d : %.3f ms  %.1f TFLOP/s  %.1f GB/s (algorithmic)\n", name, M, cin * taps, cout, ms,
            flop / ms * 1e-9, bytes / ms * 1e-6);
@@ -616,6 +628,26 @@ int main(int argc, char** argv) {
         d.split = true;
         fails += run_case(d, sms);
     }
+    for (int bnv : {128, 256}) {   // quad-stage 1x1 kernels: staged in place with residual (many tiles per CTA), store-only, register epilogue
+        Seg s0 = mk_seg(0, 150, 168, 1);
+        Case c{"SPLIT_QS_staged_inplace_res_relu_mask_k256", bnv, {s0}, round128(s0.nrows), 256, 256, 1024, 1, 4, z1, z1, kEpiRelu | kEpiResidual | kEpiMask, true};
+        c.staged = true; c.split = true; c.qs = true;
+        printf("bn=%d ", bnv);
+        fails += run_case(c, sms);
+        Case d{"SPLIT_QS_staged_noresidual_k512", bnv, {s0}, round128(s0.nrows), 512, 512, 512, 1, 8, z1, z1, kEpiMask, true};
+        d.staged = true; d.split = true; d.qs = true;
+        printf("bn=%d ", bnv);
+        fails += run_case(d, sms);
+        Case e{"SPLIT_QS_direct_relu_mask_k1024", bnv, {s0}, round128(s0.nrows), 1024, 1024, 256, 1, 16, z1, z1, kEpiRelu | kEpiMask, true};
+        e.split = true; e.qs = true;
+        printf("bn=%d ", bnv);
+        fails += run_case(e, sms);
+        Case f{"SPLIT_QS_direct_f32out_k128", bnv, {mk_seg(0, 1, 638, 1)}, 128 * 5, 128, 128, 256, 1, 2, z1, z1, kEpiOutF32, true};
+        f.segs[0].nrows = f.total_rows;
+        f.split = true; f.qs = true;
+        printf("bn=%d ", bnv);
+        fails += run_case(f, sms);
+    }
     for (int bnv : {256, 128, 64, 16}) {   // halo pipeline
         Seg s0 = mk_seg(0, 70, 84, 1);
         Seg s1 = mk_seg(round128(s0.nrows), 37, 41, 1);
@@ -626,6 +658,26 @@ int main(int argc, char** argv) {
         c.halo = true;
         c.split = true;
         printf("bn=%d ", bnv);
+        fails += run_case(c, sms);
+    }
+    for (int bnv : {128, 64, 16}) {   // N-merged split halo pipeline (two instructions per k-step), ring-streamed weights
+        Seg s0 = mk_seg(0, 70, 84, 1);
+        Seg s1 = mk_seg(round128(s0.nrows), 37, 41, 1);
+        Case c{"SPLIT_NM_HALO_conv3x3", bnv, {s0, s1}, s1.row0 + round128(s1.nrows), 128, 128, bnv, 9, 2, dy9, dx9,
+               kEpiMask | kEpiRelu | (bnv == 16 ? kEpiOutF32 : 0), true};
+        c.halo = true;
+        c.split = true;
+        c.nm = true;
+        printf("bn=%d ", bnv);
+        fails += run_case(c, sms);
+    }
+    {   // N-merged with the nine resident 2 x 64-row weight tiles (64 -> 64 channels, res2 conv2)
+        Seg s0 = mk_seg(0, 140, 168, 1);
+        Seg s1 = mk_seg(round128(s0.nrows), 37, 41, 1);
+        Case c{"SPLIT_NM_HALO_BRES_conv3x3_64_64", 64, {s0, s1}, s1.row0 + round128(s1.nrows), 64, 64, 64, 9, 1, dy9, dx9, kEpiMask | kEpiRelu, true};
+        c.halo = true;
+        c.split = true;
+        c.nm = true;
         fails += run_case(c, sms);
     }
     {   // split halo pipeline with the 18 resident weight tiles (64 -> 64 channels, res2 conv2), two planes, many tiles per CTA
@@ -683,6 +735,13 @@ int main(int argc, char** argv) {
             bench_shape("tower3x3_256_gn_f32out_PAIR", 256, 1480, 256, 256, 9, kEpiMask | kEpiGnStats | kEpiOutF32, sms, 0, false, true, b);
             bench_shape("fpn_lateral3_1x1_512_256", 256, 4488, 512, 256, 1, SC, sms, 0, false, false, b);
         }
+        printf("---- split, narrow 3x3 layers: three instructions per k-step against the N-merged two\n");
+        bench_shape("res2_conv2_3x3_64_64_HALO_BRES", 64, 17622, 64, 64, 9, C1, sms, 0, true, false, true);
+        bench_shape("res2_conv2_3x3_64_64_NM_BRES", 64, 17622, 64, 64, 9, C1, sms, 0, true, false, true, true);
+        bench_shape("res3_conv2_3x3_128_128_HALO", 128, 4488, 128, 128, 9, C1, sms, 0, true, false, true);
+        bench_shape("res3_conv2_3x3_128_128_NM", 128, 4488, 128, 128, 9, C1, sms, 0, true, false, true, true);
+        bench_shape("pred3x3_256_16_f32out_HALO", 16, 1480, 256, 16, 9, kEpiOutF32, sms, 0, true, false, true);
+        bench_shape("pred3x3_256_16_f32out_NM", 16, 1480, 256, 16, 9, kEpiOutF32, sms, 0, true, false, true, true);
         printf("---- split, staged 1x1 layers: 128-wide tiles (2 staging buffers) against 256-wide tiles (1 staging buffer)\n");
         struct Sh { const char* name; int m_tiles, cin, cout, flags; };
         const Sh shapes[] = {{"res3_shortcut_256_512", 4488, 256, 512, SC},     {"res4_shortcut_512_1024", 1155, 512, 1024, SC},
@@ -697,6 +756,33 @@ int main(int argc, char** argv) {
             bench_shape(d.c_str(), 256, sh.m_tiles, sh.cin, sh.cout, 1, sh.flags, sms, 0, false, false, true);   // register epilogue
         }
         return 0;
+    }
+    if (argc > 1 && std::string(argv[1]) == "qs") {
+        // split mode, deep 1x1 layers at the 33-image shapes: K' = 3C loop (six tiles per k-block) against quad stages (four)
+        const int RES = kEpiResidual | kEpiRelu | kEpiMask, C1 = kEpiRelu | kEpiMask, SC = kEpiMask;
+        struct Sh { const char* name; int m_tiles, cin, cout, flags; };
+        const Sh shapes[] = {{"res3_conv3_128_512", 4488, 128, 512, RES},       {"res4_conv3_256_1024", 1155, 256, 1024, RES},
+                             {"res5_conv3_512_2048", 330, 512, 2048, RES},      {"res3_shortcut_256_512", 4488, 256, 512, SC},
+                             {"res4_shortcut_512_1024", 1155, 512, 1024, SC},   {"res5_shortcut_1024_2048", 330, 1024, 2048, SC},
+                             {"res3_conv1_512_128", 4488, 512, 128, C1},        {"res4_conv1_1024_256", 1155, 1024, 256, C1},
+                             {"res5_conv1_2048_512", 330, 2048, 512, C1},       {"fpn_lateral3_512_256", 4488, 512, 256, SC},
+                             {"fpn_lateral4_1024_256", 1155, 1024, 256, SC},    {"fpn_lateral5_2048_256", 330, 2048, 256, SC}};
+        for (const Sh& sh : shapes) {
+            const std::string n = sh.name;
+            const bool res = (sh.flags & kEpiResidual) != 0;
+            if (sh.cout >= 256) {
+                bench_shape((n + "_K3_staged_bn128").c_str(), 128, sh.m_tiles, sh.cin, sh.cout, 1, sh.flags, sms, 100, false, false, true);
+                if (!res) bench_shape((n + "_K3_staged_bn256").c_str(), 256, sh.m_tiles, sh.cin, sh.cout, 1, sh.flags, sms, 100, false, false, true);
+                if (!res) bench_shape((n + "_K3_direct_bn256").c_str(), 256, sh.m_tiles, sh.cin, sh.cout, 1, sh.flags, sms, 0, false, false, true);
+                bench_shape((n + "_QS_staged_bn256").c_str(), 256, sh.m_tiles, sh.cin, sh.cout, 1, sh.flags, sms, 100, false, false, true, false, true);
+                bench_shape((n + "_QS_direct_bn256").c_str(), 256, sh.m_tiles, sh.cin, sh.cout, 1, sh.flags, sms, 0, false, false, true, false, true);
+            } else {
+                bench_shape((n + "_K3_staged_bn128").c_str(), 128, sh.m_tiles, sh.cin, sh.cout, 1, sh.flags, sms, 100, false, false, true);
+            }
+            bench_shape((n + "_QS_staged_bn128").c_str(), 128, sh.m_tiles, sh.cin, sh.cout, 1, sh.flags, sms, 100, false, false, true, false, true);
+            bench_shape((n + "_QS_direct_bn128").c_str(), 128, sh.m_tiles, sh.cin, sh.cout, 1, sh.flags, sms, 0, false, false, true, false, true);
+        }
+        return fails ? 1 : 0;
     }
     if (argc > 1 && std::string(argv[1]) == "bench") {
         bench_shape("tower3x3_256_gn_f32out", 256, 1480, 256, 256, 9, kEpiMask | kEpiGnStats | kEpiOutF32, sms);
