@@ -8,6 +8,7 @@
 #include "conv_gemm.cuh"
 #include "conv_gemm_2cta.cuh"
 #include "conv1x1_pair.cuh"
+#include "conv1x1_pair_split.cuh"
 
 namespace sylph {
 
@@ -290,6 +291,34 @@ inline cudaError_t launch_conv1x1_pair_staged(const CUtensorMap& ta, const CUten
     if (pairs <= 0) return cudaSuccess;
     const int clusters = pairs < num_sms / 2 ? pairs : num_sms / 2;
     return launch_k(conv1x1_pair_staged_kernel<3, 2>, dim3(clusters * 2), dim3(S::kThreads), S::kTotal, stream, ta, tb, tres, tout, args);
+}
+
+// Split-mode CTA-pair 1x1 convolution with the chunked staged epilogue (conv1x1_pair_split.cuh; BN = 256, taps = 1): `tb` box =
+// 128 rows, `ta` / `tres` / `tout` as for launch_conv_gemm_staged.  qs = false: K' = 3C loop (args.kblocks_per_tap = 3C / 64),
+// 3 stages x 32 KB + 4 chunk buffers x 32 KB; qs = true: quad stages (args.kblocks_per_tap = C / 64), 2 x 64 KB + 3 x 32 KB.
+template <bool QS>
+inline cudaError_t launch_conv1x1_pair_split_t(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tres,
+                                               const CUtensorMap& tout, const GemmArgs& args, int num_sms, cudaStream_t stream) {
+    constexpr int kStages = QS ? 2 : 3, kChunkBufs = QS ? 3 : 4;
+    using S = PairSplitSmem<kStages, kChunkBufs, QS>;
+    static_assert(S::kTotal <= 227 * 1024, "shared memory of this instantiation exceeds the 227 KB of a CTA");
+    static PerDeviceOnce once;
+    {
+        cudaError_t e = once.run([] {
+            return cudaFuncSetAttribute(conv1x1_pair_split_kernel<kStages, kChunkBufs, QS>, cudaFuncAttributeMaxDynamicSharedMemorySize, S::kTotal);
+        });
+        if (e != cudaSuccess) return e;
+    }
+    if (args.taps != 1) return cudaErrorInvalidValue;
+    const int pairs = ((args.num_m_tiles + 1) / 2) * args.num_n_tiles;
+    if (pairs <= 0) return cudaSuccess;
+    const int clusters = pairs < num_sms / 2 ? pairs : num_sms / 2;
+    return launch_k(conv1x1_pair_split_kernel<kStages, kChunkBufs, QS>, dim3(clusters * 2), dim3(S::kThreads), S::kTotal, stream, ta, tb, tres, tout, args);
+}
+inline cudaError_t launch_conv1x1_pair_split(bool qs, const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tres,
+                                             const CUtensorMap& tout, const GemmArgs& args, int num_sms, cudaStream_t stream) {
+    return qs ? launch_conv1x1_pair_split_t<true>(ta, tb, tres, tout, args, num_sms, stream)
+              : launch_conv1x1_pair_split_t<false>(ta, tb, tres, tout, args, num_sms, stream);
 }
 
 // Stem: 4 vertical taps x (one 131 x 16 A box, 4 horizontal K = 16 MMAs), staged epilogue, Cout = 64; the weights

@@ -89,6 +89,7 @@ struct sylph_ctx {
     int pair1x1 = 1;          // SYLPH_PAIR1X1=0 keeps the single-CTA staged kernel for every 1x1 convolution; 2 = pair kernel
                               // for every staged 1x1 convolution with 256-channel N tiles and K >= 256 (experiments)
     int stem16 = 1;           // SYLPH_STEM16=0 runs the stem over 64-wide overlapped rows instead of K = 16 taps
+    int sync_each = 0;        // SYLPH_SYNC_EACH=1: synchronise after every convolution launch and name the one that faults
     int quad = 1;             // SYLPH_QS=0: K' = 3C loop for every split 1x1 layer instead of quad stages on the deep ones
     int nmerge = 1;           // SYLPH_NM=0: three instructions per k-step for the narrow split 3x3 layers instead of the N-merged two
     int roi_separable = 1;    // SYLPH_ROI_ALIGN=sample: the per-sample ROIAlign kernel instead of the separable one
@@ -580,6 +581,7 @@ struct ConvCall {
     int stem = 0;
     int up_seg_delta = 0;    // kEpiUpsample: coarser plane = segment of the output tile + this
     int staged = 0;          // TMA-in / TMA-out epilogue (fp16 output, BN = 256); needs out_rows
+    int pairsplit = 0;       // split mode: CTA-pair 1x1 kernel with the chunked staged epilogue and quad stages (conv1x1_pair_split.cuh)
     int qs = 0;              // split mode: quad-stage 1x1 kernel (conv_gemm.cuh QS) with N tiles of this width (128 / 256), 0 = K' = 3C loop
     long long out_rows = 0;  // rows of the output (and residual) buffer, for the staged epilogue's tensor maps
     const char* name = "conv";
@@ -609,14 +611,25 @@ static int run_conv(sylph_ctx* c, const ConvCall& k, cudaStream_t st) {
     if (c->split && c->quad && !k.stem && W.taps == 1 && k.w_override == nullptr && W.cout_pad % 128 == 0 && W.cin % 64 == 0 &&
         !(k.flags & (kEpiOutF32 | kEpiGnStats))) {
         const bool upsample = (k.flags & kEpiUpsample) != 0;
+        // CTA-pair kernel with the chunked staged epilogue (conv1x1_pair_split.cuh) wherever the output leaves by TMA in
+        // 256-channel tiles: one M = 256 instruction per k-step halves every SM's shared-memory operand reads -- at 33 images
+        // conv3 res4 0.406 -> 0.299, res5 0.360 -> 0.234; shortcut res3 0.639 -> 0.444, res4 0.542 -> 0.380, res5 0.495 -> 0.383;
+        // conv1 res4 0.256 -> 0.210, res5 0.251 -> 0.217 ms (profiles/r02_pair_split_ab.log); res3 conv3 (K = 128) is HBM-bound
+        // either way and stays on the single-CTA kernel.
+        const bool pair_ok = c->pair1x1 && k.staged && k.out_rows > 0 && W.cout_pad % 256 == 0 && !upsample;
         if (has_res && !upsample) {
-            if (W.cin >= 512) { kk.qs = 128; kk.staged = 0; }                                   // res5 conv3
+            if (pair_ok && W.cin >= 256) { kk.pairsplit = 1; kk.staged = 1; }                   // res4 / res5 conv3
+            else if (W.cin >= 512) { kk.qs = 128; kk.staged = 0; }
         } else if (k.staged && !(k.flags & kEpiRelu) && W.cout_pad >= 512) {                    // shortcut convolutions
-            if (W.cin >= 1024) { kk.qs = 256; kk.staged = 0; }
+            if (pair_ok && W.cin >= 256) { kk.pairsplit = 1; kk.staged = 1; }   // (deep_direct above may have cleared `staged`)
+            else if (W.cin >= 1024) { kk.qs = 256; kk.staged = 0; }
             else if (W.cin >= 256) { kk.qs = 128; }
         } else if (W.cin >= 512) {                                                              // conv1, FPN laterals
-            kk.qs = (W.cin == 512 && W.cout_pad % 256 == 0 && !k.staged) ? 256 : 128;
-            kk.staged = 0;
+            if (pair_ok) { kk.pairsplit = 1; kk.staged = 1; }
+            else {
+                kk.qs = (W.cin == 512 && W.cout_pad % 256 == 0 && !k.staged) ? 256 : 128;
+                kk.staged = 0;
+            }
         }
     }
     return run_conv_impl(c, kk, st, has_res);
@@ -643,7 +656,7 @@ static int run_conv_impl(sylph_ctx* c, const ConvCall& k, cudaStream_t st, const
     // staging buffer, which halves their A re-reads from L2: 0.72 -> 0.64 / 0.60 -> 0.55 / 0.60 -> 0.54 ms on res3..res5 at 33
     // images; every other staged layer measured slower that way (profiles/r02_split_tile_width_ab.log)
     const bool wide_split = split && k.staged && W.bn == 256 && !has_res && !(k.flags & kEpiRelu) && W.cout_pad >= 512;
-    const int bn = k.qs ? k.qs : (split && k.staged && W.bn == 256 && !wide_split) ? 128 : W.bn;
+    const int bn = k.pairsplit ? 256 : k.qs ? k.qs : (split && k.staged && W.bn == 256 && !wide_split) ? 128 : W.bn;
     if (stem16) {
         if (make_tmap_2d_k16(&ta, k.A, static_cast<uint64_t>(k.a_rows), kBlockM + 3, &err, split ? 32 : 16))
             return c->fail("A tensor map (%s): %s", k.name, err.c_str());
@@ -656,7 +669,7 @@ static int run_conv_impl(sylph_ctx* c, const ConvCall& k, cudaStream_t st, const
         if (make_tmap_2d(&tb, W.w_nm, static_cast<uint64_t>(W.taps) * 2 * W.cout_pad, W.cin, W.cin, bn, &err))
             return c->fail("B tensor map (%s): %s", k.name, err.c_str());
     } else if (make_tmap_2d(&tb, k.w_override ? k.w_override : W.w, static_cast<uint64_t>(W.b_rows), W.k_per_tap,
-                            W.k_per_tap, (pair || pair1x1) ? bn / 2 : bn, &err))
+                            W.k_per_tap, (pair || pair1x1 || k.pairsplit) ? bn / 2 : bn, &err))
         return c->fail("B tensor map (%s): %s", k.name, err.c_str());
     GemmArgs g{};
     g.tile_begin = k.tile_begin;
@@ -667,7 +680,7 @@ static int run_conv_impl(sylph_ctx* c, const ConvCall& k, cudaStream_t st, const
     g.kblocks_per_tap = W.k_per_tap / kBlockK;
     g.b_rows_per_tap = W.cout_pad;
     g.a_wrap = split ? 2 * W.cin : 0;
-    if (k.qs) g.kblocks_per_tap = W.cin / kBlockK;   // logical k-blocks: a stage carries a_hi, a_lo, w_hi, w_lo
+    if (k.qs || k.pairsplit) g.kblocks_per_tap = W.cin / kBlockK;   // logical k-blocks: a stage carries a_hi, a_lo, w_hi, w_lo
     if (nm) {
         g.kblocks_per_tap = 2 * W.cin / kBlockK;
         g.b_rows_per_tap = 2 * W.cout_pad;
@@ -714,6 +727,7 @@ static int run_conv_impl(sylph_ctx* c, const ConvCall& k, cudaStream_t st, const
             return c->fail("epilogue tensor maps (%s): %s", k.name, err.c_str());
         if (stem16) CU_TRY(c, launch_conv_gemm_stem16(ta, tb, tout, g, c->num_sms, st, split));
         else if (pair1x1) CU_TRY(c, launch_conv1x1_pair_staged(ta, tb, tres, tout, g, c->num_sms, st));
+        else if (k.pairsplit) CU_TRY(c, launch_conv1x1_pair_split(true, ta, tb, tres, tout, g, c->num_sms, st));
         else if (k.qs) CU_TRY(c, launch_conv_gemm_qs(bn, true, ta, tb, tres, tout, g, c->num_sms, st));
         else CU_TRY(c, launch_conv_gemm_staged(bn, ta, tb, tres, tout, g, c->num_sms, st, 0, split));
     } else if (k.qs) {
@@ -728,6 +742,12 @@ static int run_conv_impl(sylph_ctx* c, const ConvCall& k, cudaStream_t st, const
         CU_TRY(c, launch_conv_gemm(bn, ta, tb, g, c->num_sms, st, split));
     }
     c->launches++;
+    if (c->sync_each) {   // SYLPH_SYNC_EACH=1 (debugging): name the convolution whose kernel faults
+        const cudaError_t e = cudaStreamSynchronize(st);
+        if (e != cudaSuccess)
+            return c->fail("convolution %s (cin %d, cout %d, taps %d, tiles %d, staged %d, qs %d, pairsplit %d): %s", k.name, W.cin,
+                           W.cout, W.taps, k.n_tiles, k.staged, k.qs, k.pairsplit, cudaGetErrorString(e));
+    }
     if (c->profiling) {
         cudaEventRecord(tm.e1, st);
         c->timings.push_back(tm);
@@ -786,6 +806,7 @@ int sylph_create(sylph_ctx** out, int device, const sylph_model_config* cfg) {
     if (const char* e = getenv("SYLPH_FUSE_UPSAMPLE")) c->fuse_upsample = atoi(e);
     if (const char* e = getenv("SYLPH_NM")) c->nmerge = atoi(e);
     if (const char* e = getenv("SYLPH_QS")) c->quad = atoi(e);
+    if (const char* e = getenv("SYLPH_SYNC_EACH")) c->sync_each = atoi(e);
     if (const char* e = getenv("SYLPH_ROI_ALIGN")) c->roi_separable = strcmp(e, "sample") == 0 ? 0 : 1;
     if (const char* e = getenv("SYLPH_PRECISION")) c->split = (strcmp(e, "fast") == 0 || strcmp(e, "0") == 0) ? 0 : 1;
     *out = c;

@@ -46,6 +46,7 @@ struct Case {
     bool staged = false;  // TMA-in / TMA-out epilogue, run IN PLACE (out == residual buffer) like the bottleneck conv3
     bool pair1x1 = false; // CTA-pair 1x1 convolution with the staged epilogue (conv1x1_pair.cuh)
     int sms_override = 0; // pretend the device has this many SMs: many tiles per CTA on a problem the CPU reference finishes quickly
+    int pairsplit = 0;    // split mode, CTA-pair 1x1 kernel with the chunked staged epilogue: 1 = K' = 3C loop, 2 = quad stages
     bool qs = false;      // split mode, quad-stage 1x1 kernel (a_hi, a_lo, w_hi, w_lo of a k-block loaded once; conv_gemm.cuh QS)
     bool stem16 = false;  // stem as K = 16 taps: A map = [rows][16] with 32-byte swizzle, 131-row boxes (same math as a_ld = 16)
 };
@@ -147,7 +148,7 @@ static int run_case(const Case& c, int num_sms) {
     std::string err;
     if ((c.stem16 ? make_tmap_2d_k16(&ta, dA, M, 131, &err, sp ? 32 : 16)
                   : make_tmap_2d(&ta, dA, a_rows_dim, sp ? 2 * c.cin_cols : c.cin_cols, a_ld, (c.halo || c.pair) ? 130 : 128, &err)) ||
-        make_tmap_2d(&tb, dW, static_cast<uint64_t>(w_tiles) * c.cout, Kw, Kw, (c.pair || c.pair1x1) ? c.bn / 2 : c.bn, &err)) {
+        make_tmap_2d(&tb, dW, static_cast<uint64_t>(w_tiles) * c.cout, Kw, Kw, (c.pair || c.pair1x1 || c.pairsplit) ? c.bn / 2 : c.bn, &err)) {
         printf("[%s] FAIL tensor map: %s\n", c.name, err.c_str());
         return 1;
     }
@@ -157,7 +158,7 @@ static int run_case(const Case& c, int num_sms) {
     g.num_n_tiles = c.cout / c.bn;
     g.a_row_delta = 0;
     g.taps = c.taps;
-    g.kblocks_per_tap = nm ? 2 * Kt / kBlockK : (c.qs ? Kt / kBlockK : Kw / kBlockK);
+    g.kblocks_per_tap = nm ? 2 * Kt / kBlockK : ((c.qs || c.pairsplit == 2) ? Kt / kBlockK : Kw / kBlockK);
     g.b_rows_per_tap = nm ? 2 * c.cout : c.cout;
     g.nm_lo_row = c.cout;
     g.a_wrap = sp ? 2 * Kt : 0;
@@ -185,6 +186,7 @@ static int run_case(const Case& c, int num_sms) {
         }
         if (c.stem16) CK(launch_conv_gemm_stem16(ta, tb, tio, g, num_sms, 0, sp));
         else if (c.pair1x1) CK(launch_conv1x1_pair_staged(ta, tb, tio, tio, g, num_sms, 0));
+        else if (c.pairsplit) CK(launch_conv1x1_pair_split(c.pairsplit == 2, ta, tb, tio, tio, g, num_sms, 0));
         else if (c.qs) CK(launch_conv_gemm_qs(c.bn, true, ta, tb, tio, tio, g, num_sms, 0));
         else CK(launch_conv_gemm_staged(c.bn, ta, tb, tio, tio, g, num_sms, 0, 0, sp));
     } else if (c.pair) {
@@ -309,12 +311,13 @@ static void bench_shape(const char* name, int bn, int m_tiles, int cin, int cout
     CUtensorMap ta, tb;
     std::string err;
     const bool pair1x1 = staged == 9;   // CTA-pair 1x1 kernel with the staged epilogue
-    if (make_tmap_2d(&ta, dA, M, cin, cin, (halo || pair) ? 130 : 128, &err) || make_tmap_2d(&tb, dW, static_cast<uint64_t>(taps) * w_rows_per_tap, kw, kw, (pair || pair1x1) ? bn / 2 : bn, &err)) {
+    const int pairsplit = staged == 10 ? 1 : staged == 11 ? 2 : 0;   // split-mode CTA-pair 1x1 kernel (K' = 3C loop / quad stages)
+    if (make_tmap_2d(&ta, dA, M, cin, cin, (halo || pair) ? 130 : 128, &err) || make_tmap_2d(&tb, dW, static_cast<uint64_t>(taps) * w_rows_per_tap, kw, kw, (pair || pair1x1 || pairsplit) ? bn / 2 : bn, &err)) {
         printf("[%s] tensor map failed: %s\n", name, err.c_str());
         return;
     }
     GemmArgs g{};
-    g.num_m_tiles = m_tiles; g.num_n_tiles = cout / bn; g.taps = taps; g.kblocks_per_tap = nm ? 2 * cin_l / kBlockK : (qs ? cin_l / kBlockK : kw / kBlockK); g.b_rows_per_tap = w_rows_per_tap; g.nm_lo_row = cout_l;
+    g.num_m_tiles = m_tiles; g.num_n_tiles = cout / bn; g.taps = taps; g.kblocks_per_tap = nm ? 2 * cin_l / kBlockK : ((qs || pairsplit == 2) ? cin_l / kBlockK : kw / kBlockK); g.b_rows_per_tap = w_rows_per_tap; g.nm_lo_row = cout_l;
     g.a_wrap = split ? 2 * cin_l : 0; g.out_lo = (split && osz == 2) ? cout_l : 0; g.res_lo = split ? cout_l : 0;
     for (int t = 0; t < taps; ++t) { g.tap_dy[t] = taps == 9 ? (t / 3) - 1 : 0; g.tap_dx[t] = taps == 9 ? (t % 3) - 1 : 0; }
     g.bias = dB; g.residual = dR; g.ld_res = ldo; g.out = dO; g.ldc = ldo; g.flags = flags; g.tile_seg = dTS; g.segs = dS; g.gn_partial = dG;
@@ -326,7 +329,7 @@ static void bench_shape(const char* name, int bn, int m_tiles, int cin, int cout
         g.residual = static_cast<const __half*>(dO);
         if (make_tmap_2d(&tio, static_cast<const __half*>(dO), M, ldo, ldo, 128, &err)) { printf("tmap failed\n"); return; }
     }
-    auto launch = [&]() { return qs ? launch_conv_gemm_qs(bn, staged != 0, ta, tb, tio, tio, g, num_sms, 0) : pair1x1 ? launch_conv1x1_pair_staged(ta, tb, tio, tio, g, num_sms, 0) : staged ? launch_conv_gemm_staged(bn, ta, tb, tio, tio, g, num_sms, 0, staged == 100 ? 0 : staged, split) : (pair ? launch_conv3x3_pair(ta, tb, g, num_sms, 0, bn, split) : (nm ? launch_conv_gemm_halo_nm(bn, ta, tb, g, num_sms, 0) : halo ? launch_conv_gemm_halo(bn, ta, tb, g, num_sms, 0, true, split) : launch_conv_gemm(bn, ta, tb, g, num_sms, 0, split))); };
+    auto launch = [&]() { return pairsplit ? launch_conv1x1_pair_split(pairsplit == 2, ta, tb, tio, tio, g, num_sms, 0) : qs ? launch_conv_gemm_qs(bn, staged != 0, ta, tb, tio, tio, g, num_sms, 0) : pair1x1 ? launch_conv1x1_pair_staged(ta, tb, tio, tio, g, num_sms, 0) : staged ? launch_conv_gemm_staged(bn, ta, tb, tio, tio, g, num_sms, 0, staged == 100 ? 0 : staged, split) : (pair ? launch_conv3x3_pair(ta, tb, g, num_sms, 0, bn, split) : (nm ? launch_conv_gemm_halo_nm(bn, ta, tb, g, num_sms, 0) : halo ? launch_conv_gemm_halo(bn, ta, tb, g, num_sms, 0, true, split) : launch_conv_gemm(bn, ta, tb, g, num_sms, 0, split))); };
     for (int i = 0; i < 3; ++i) CK(launch());
     CK(cudaDeviceSynchronize());
     const int iters = 10;
@@ -628,6 +631,37 @@ int main(int argc, char** argv) {
         d.split = true;
         fails += run_case(d, sms);
     }
+    for (int mode : {1, 2}) {   // split CTA-pair 1x1 kernel, chunked staged epilogue: K' = 3C loop (1) and quad stages (2)
+        {   // residual in place + ReLU + mask, 4 N tiles, ODD number of M tiles (phantom tile), many pair tiles per cluster
+            Seg s0 = mk_seg(0, 30, 40, 1);   // 11 M tiles
+            Case c{"SPLIT_PAIR1x1_inplace_res_relu_mask_n1024", 256, {s0}, round128(s0.nrows), 256, 256, 1024, 1, 4, z1, z1, kEpiRelu | kEpiResidual | kEpiMask, true};
+            c.staged = true; c.split = true; c.pairsplit = mode; c.sms_override = 16;
+            printf("mode=%d ", mode);
+            fails += run_case(c, sms);
+        }
+        {   // no residual (conv1 / shortcut use), one N tile, K = 512, two planes, all SMs
+            Seg s0 = mk_seg(0, 150, 168, 1);
+            Seg s1 = mk_seg(round128(s0.nrows), 13, 21, 1);
+            Case c{"SPLIT_PAIR1x1_noresidual_n256_k512", 256, {s0, s1}, s1.row0 + round128(s1.nrows), 512, 512, 256, 1, 8, z1, z1, kEpiRelu | kEpiMask, true};
+            c.staged = true; c.split = true; c.pairsplit = mode;
+            printf("mode=%d ", mode);
+            fails += run_case(c, sms);
+        }
+        {   // a single M tile (one real + one phantom tile in the only pair), 2 N tiles, residual
+            Seg s0 = mk_seg(0, 8, 10, 1);
+            Case c{"SPLIT_PAIR1x1_single_tile_n512", 256, {s0}, round128(s0.nrows), 256, 256, 512, 1, 4, z1, z1, kEpiResidual | kEpiMask, true};
+            c.staged = true; c.split = true; c.pairsplit = mode;
+            printf("mode=%d ", mode);
+            fails += run_case(c, sms);
+        }
+        {   // many tiles per cluster without residual (buffer hand-back through epi_free), 2 N tiles
+            Seg s0 = mk_seg(0, 150, 168, 1);
+            Case c{"SPLIT_PAIR1x1_noresidual_n512_manytiles", 256, {s0}, round128(s0.nrows), 128, 128, 512, 1, 2, z1, z1, kEpiMask, true};
+            c.staged = true; c.split = true; c.pairsplit = mode; c.sms_override = 8;
+            printf("mode=%d ", mode);
+            fails += run_case(c, sms);
+        }
+    }
     for (int bnv : {128, 256}) {   // quad-stage 1x1 kernels: staged in place with residual (many tiles per CTA), store-only, register epilogue
         Seg s0 = mk_seg(0, 150, 168, 1);
         Case c{"SPLIT_QS_staged_inplace_res_relu_mask_k256", bnv, {s0}, round128(s0.nrows), 256, 256, 1024, 1, 4, z1, z1, kEpiRelu | kEpiResidual | kEpiMask, true};
@@ -778,6 +812,10 @@ int main(int argc, char** argv) {
                 bench_shape((n + "_QS_direct_bn256").c_str(), 256, sh.m_tiles, sh.cin, sh.cout, 1, sh.flags, sms, 0, false, false, true, false, true);
             } else {
                 bench_shape((n + "_K3_staged_bn128").c_str(), 128, sh.m_tiles, sh.cin, sh.cout, 1, sh.flags, sms, 100, false, false, true);
+            }
+            if (sh.cout % 256 == 0) {
+                bench_shape((n + "_PAIR_K3").c_str(), 256, sh.m_tiles, sh.cin, sh.cout, 1, sh.flags, sms, 10, false, false, true);
+                bench_shape((n + "_PAIR_QS").c_str(), 256, sh.m_tiles, sh.cin, sh.cout, 1, sh.flags, sms, 11, false, false, true);
             }
             bench_shape((n + "_QS_staged_bn128").c_str(), 128, sh.m_tiles, sh.cin, sh.cout, 1, sh.flags, sms, 100, false, false, true, false, true);
             bench_shape((n + "_QS_direct_bn128").c_str(), 128, sh.m_tiles, sh.cin, sh.cout, 1, sh.flags, sms, 0, false, false, true, false, true);
