@@ -369,27 +369,44 @@ def measure_mode(hz: Harness, cfg, state, precision: str, peaks, full: bool):
         elem = 4 if precision == "exact" else 2
         conv3 = [t for n, t, _, _ in tm if n == "res.conv3_1x1"]
         hp, wp = (IMG_H + 31) // 32 * 32, (IMG_W + 31) // 32 * 32
-        conv3_bytes_img = sum(nb * (hp >> (s + 2)) * (wp >> (s + 2)) * ((64 << s) + 2 * (256 << s)) * elem
-                              for s, nb in enumerate([3, 4, 6, 3]))
-        if conv3:
-            tot_ms = sum(conv3)
+        blocks = [3, 4, 6, 3]
+        stage_bytes_img = [nb * (hp >> (s + 2)) * (wp >> (s + 2)) * ((64 << s) + 2 * (256 << s)) * elem for s, nb in enumerate(blocks)]
+        if len(conv3) == sum(blocks):
+            # ONE kernel per roofline record: the single-CTA staged kernel runs conv3 of res2 + res3 in exact mode (res4 / res5 run
+            # the CTA-pair kernel, reported beside it) and of res2..res4 in fast mode (res5: conv1x1_pair_staged_kernel)
+            n_single = 2 if precision == "exact" else 3
+            n_launch = sum(blocks[:n_single])
+            tot_ms = sum(conv3[:n_launch])
             n_img = N_WAY * N_SHOT + N_QUERY
-            achieved = conv3_bytes_img * n_img / (tot_ms * 1e-3) * 1e-9
+            bytes_total = sum(stage_bytes_img[:n_single]) * n_img
+            achieved = bytes_total / (tot_ms * 1e-3) * 1e-9
             peak = float(peaks["hbm_gbs"])
-            kname = ("conv_gemm_f16_kernel<128,3,2,0,SPLIT> -- staged TMA-in/TMA-out 1x1 conv + residual + ReLU on hi|lo planes"
-                     if precision == "exact" else
-                     "conv_gemm_f16_kernel<256,2,2,0> -- staged TMA-in/TMA-out 1x1 conv + residual + ReLU (res5: conv1x1_pair_staged_kernel)")
-            out["roofline"] = {"kernel": kname + " (bottleneck conv3, res2..res5), the largest share of the step",
+            kname = ("conv_gemm_f16_kernel<128,3,2,0,SPLIT> -- staged TMA-in/TMA-out 1x1 conv + residual + ReLU on hi|lo planes "
+                     "(bottleneck conv3 of res2 + res3)" if precision == "exact" else
+                     "conv_gemm_f16_kernel<256,2,2,0> -- staged TMA-in/TMA-out 1x1 conv + residual + ReLU (bottleneck conv3 of res2..res4)")
+            out["roofline"] = {"kernel": kname + ", the kernel with the largest share of the step",
                                "bound": "hbm", "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s",
                                "frac": round(achieved / peak, 4),
                                "traffic": ncu_traffic("conv3_split.res2" if precision == "exact" else "conv_gemm_f16_kernel<256,2,2,0>.res2_conv3"),
-                               "avg_launch_ms": round(tot_ms / len(conv3), 4), "launches_timed": len(conv3),
-                               "share_of_step": breakdown["res.conv3_1x1"]["share"],
-                               "bytes_per_launch": conv3_bytes_img * n_img / len(conv3),
+                               "avg_launch_ms": round(tot_ms / n_launch, 4), "launches_timed": n_launch,
+                               "share_of_step": round(tot_ms / total_ms, 4),
+                               "bytes_per_launch": bytes_total / n_launch,
                                "peak_source": f"MEASURED_PEAKS.json hbm_gbs ({peaks['source']})",
                                "note": f"achieved = sum of algorithmic bytes ({elem} B per stored element) / sum of launch durations "
-                                       "over the 16 launches of one episode (shapes differ per stage); traffic = ncu DRAM bytes of "
-                                       "ONE res2 launch at 8 images (profiles/ncu_traffic.json)"}
+                                       f"over this kernel's {n_launch} conv3 launches of one episode (shapes differ per stage); traffic = "
+                                       "ncu DRAM bytes of ONE res2 launch at 8 images (profiles/ncu_traffic.json)"}
+            # the other conv3 kernel of the same stage group: CTA-pair 1x1 kernel (exact: res4 + res5, chunked staged epilogue)
+            rest_ms = sum(conv3[n_launch:])
+            rest_bytes = sum(stage_bytes_img[n_single:]) * n_img
+            rest_flop = sum(nb * (hp >> (s + 2)) * (wp >> (s + 2)) * 2.0 * (64 << s) * (256 << s)
+                            for s, nb in enumerate(blocks) if s >= n_single) * n_img * (3 if precision == "exact" else 1)
+            out["roofline_conv3_deep"] = {
+                "kernel": ("conv1x1_pair_split_kernel<2,3,QS> -- cta_group::2 1x1 conv, quad stages, chunked staged epilogue (conv3 of res4 + res5)"
+                           if precision == "exact" else "conv1x1_pair_staged_kernel<3,2> (conv3 of res5)"),
+                "launches_timed": len(conv3) - n_launch, "ms": round(rest_ms, 4), "share_of_step": round(rest_ms / total_ms, 4),
+                "hbm_gbs": round(rest_bytes / (rest_ms * 1e-3) * 1e-9, 1), "hbm_frac": round(rest_bytes / (rest_ms * 1e-3) * 1e-9 / peak, 4),
+                "tflops_executed": round(rest_flop / (rest_ms * 1e-3) * 1e-12, 1),
+                "tensor_frac": round(rest_flop / (rest_ms * 1e-3) * 1e-12 / float(peaks["bf16_tflops_sustained"]), 4)}
         # (2) the tensor-bound kernel: CTA-pair 3x3 convolution of the FCOS towers
         tower = [t for n, t, _, _ in tm if n in ("head.cls_tower3x3", "head.bbox_tower3x3")]
         if tower:
@@ -693,7 +710,8 @@ def main():
                "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": head["dtype"],
                "data": "synthetic", "config": dict(config, precision=head_mode, launch=head["launch"]),
                "e2e": head["e2e"], "gpu_launches": head["gpu_launches"], "clocks": head["clocks"],
-               "roofline": head.get("roofline"), "roofline_tensor": head.get("roofline_tensor"), "cpu_baseline": cpu,
+               "roofline": head.get("roofline"), "roofline_tensor": head.get("roofline_tensor"),
+               "roofline_conv3_deep": head.get("roofline_conv3_deep"), "cpu_baseline": cpu,
                "episode_tflops_algorithmic": round(EPISODE_GFLOP * 1e-3 * head["value"] / world, 1),
                "detections_per_image": head["detections_per_image"], "fast_mode": fast, "variants": variants, "sharded": sharded,
                "per_kernel": head.get("per_kernel")}

@@ -650,6 +650,10 @@ conv_gemm_f16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_co
                     float f[CH];
 #pragma unroll
                     for (int j = 0; j < CH; ++j) f[j] = __uint_as_float(v[j]);
+                    if constexpr (NM) {   // the a_hi.w_lo partial products sit BN columns further on
+#pragma unroll
+                        for (int j = 0; j < CH; ++j) f[j] += __uint_as_float(v2[j]);
+                    }
                     if (p.bias != nullptr) {
                         const float4* bp = reinterpret_cast<const float4*>(p.bias + n_tile * BN + col);
 #pragma unroll

@@ -325,7 +325,10 @@ inline cudaError_t launch_conv1x1_pair_split(bool qs, const CUtensorMap& ta, con
 // (4 x 8 KB) stay resident in shared memory and 16 A slots keep four output tiles of loads in flight.
 // `ta` from make_tmap_2d_k16 (box kBlockM + 3 rows), `tb` = [4 * 64][64] weights with 64-row boxes.
 inline cudaError_t launch_conv_gemm_stem16(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tout,
-                                           const GemmArgs& args, int num_sms, cudaStream_t stream, bool split = false) {
+                                           const GemmArgs& args, int num_sms, cudaStream_t stream, bool split = false, bool nm = false) {
+    // split + nm: four resident [w_hi ; w_lo] tiles of 128 rows, two A boxes (hi, lo) per vertical tap, 32 instead of 48
+    // instructions per tile (args.nm_lo_row = row offset of the w_lo tiles in the weight matrix)
+    if (split && nm) return launch_conv_gemm_bn<64, 4, 2, 16, true, false, true, true>(ta, tb, tout, tout, args, num_sms, stream);
     // split: 8 resident weight tiles (w_hi, w_lo of the four vertical taps), three A boxes per vertical tap
     if (split) return launch_conv_gemm_bn<64, 8, 2, 16, true, false, true>(ta, tb, tout, tout, args, num_sms, stream);
     return launch_conv_gemm_bn<64, 4, 2, 16, true>(ta, tb, tout, tout, args, num_sms, stream);

@@ -680,6 +680,7 @@ static int run_conv_impl(sylph_ctx* c, const ConvCall& k, cudaStream_t st, const
     g.kblocks_per_tap = W.k_per_tap / kBlockK;
     g.b_rows_per_tap = W.cout_pad;
     g.a_wrap = split ? 2 * W.cin : 0;
+    if (stem16 && split) g.nm_lo_row = 4 * W.cout_pad;   // stem weight matrix: the four w_hi tiles, then the four w_lo tiles
     if (k.qs || k.pairsplit) g.kblocks_per_tap = W.cin / kBlockK;   // logical k-blocks: a stage carries a_hi, a_lo, w_hi, w_lo
     if (nm) {
         g.kblocks_per_tap = 2 * W.cin / kBlockK;
@@ -725,7 +726,7 @@ static int run_conv_impl(sylph_ctx* c, const ConvCall& k, cudaStream_t st, const
                          (k.flags & kEpiResidual) ? k.ld_res : k.ldc, kBlockM, &err) ||
             make_tmap_2d(&tout, static_cast<const __half*>(k.out), static_cast<uint64_t>(k.out_rows), k.ldc, k.ldc, kBlockM, &err))
             return c->fail("epilogue tensor maps (%s): %s", k.name, err.c_str());
-        if (stem16) CU_TRY(c, launch_conv_gemm_stem16(ta, tb, tout, g, c->num_sms, st, split));
+        if (stem16) CU_TRY(c, launch_conv_gemm_stem16(ta, tb, tout, g, c->num_sms, st, split, split && c->nmerge));
         else if (pair1x1) CU_TRY(c, launch_conv1x1_pair_staged(ta, tb, tres, tout, g, c->num_sms, st));
         else if (k.pairsplit) CU_TRY(c, launch_conv1x1_pair_split(true, ta, tb, tres, tout, g, c->num_sms, st));
         else if (k.qs) CU_TRY(c, launch_conv_gemm_qs(bn, true, ta, tb, tres, tout, g, c->num_sms, st));

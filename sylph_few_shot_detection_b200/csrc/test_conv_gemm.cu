@@ -160,7 +160,7 @@ static int run_case(const Case& c, int num_sms) {
     g.taps = c.taps;
     g.kblocks_per_tap = nm ? 2 * Kt / kBlockK : ((c.qs || c.pairsplit == 2) ? Kt / kBlockK : Kw / kBlockK);
     g.b_rows_per_tap = nm ? 2 * c.cout : c.cout;
-    g.nm_lo_row = c.cout;
+    g.nm_lo_row = (c.stem16 && sp) ? c.taps * c.cout : c.cout;
     g.a_wrap = sp ? 2 * Kt : 0;
     g.out_lo = (sp && !f32out) ? c.cout : 0;
     g.res_lo = sp ? c.cout : 0;
@@ -184,7 +184,7 @@ static int run_case(const Case& c, int num_sms) {
             printf("[%s] FAIL epilogue tensor map: %s\n", c.name, err.c_str());
             return 1;
         }
-        if (c.stem16) CK(launch_conv_gemm_stem16(ta, tb, tio, g, num_sms, 0, sp));
+        if (c.stem16) CK(launch_conv_gemm_stem16(ta, tb, tio, g, num_sms, 0, sp, sp && c.nm));
         else if (c.pair1x1) CK(launch_conv1x1_pair_staged(ta, tb, tio, tio, g, num_sms, 0));
         else if (c.pairsplit) CK(launch_conv1x1_pair_split(c.pairsplit == 2, ta, tb, tio, tio, g, num_sms, 0));
         else if (c.qs) CK(launch_conv_gemm_qs(c.bn, true, ta, tb, tio, tio, g, num_sms, 0));
@@ -746,6 +746,10 @@ int main(int argc, char** argv) {
         c.stem16 = true;
         c.split = true;
         fails += run_case(c, sms);
+        Case d = c;   // N-merged: four resident [w_hi ; w_lo] tiles, two A boxes per vertical tap
+        d.name = "SPLIT_NM_STEM16";
+        d.nm = true;
+        fails += run_case(d, sms);
     }
     printf("correctness: %d failing case(s)\n", fails);
     if (argc > 1 && std::string(argv[1]) == "split") {
