@@ -90,6 +90,7 @@ struct GemmArgs {
     int out_lo;            // SPLIT: element offset of the lo half of an fp16 output row (= Cout of the whole layer)
     int res_lo;            // SPLIT: element offset of the lo half of a residual row
     int nm_lo_row;         // NM: row offset of the w_lo block inside a tap of the weight matrix (= cout_pad)
+    int nm_passes;         // NM stem: 1 = the a_lo pass is skipped (re-centred uint8 pixels are exact in fp16: a_lo == 0), else 2
     int dbg_a_row_skew;    // experiment: load the A box `skew` rows early and start the MMA descriptor `skew` rows in
     int dbg_base_offset;   // experiment: matrix-descriptor base_offset field used with the skew
     int dbg_skip;          // bring-up timing experiments (halo pipeline): 1 = no output stores, 2 = no MMAs issued,
@@ -355,9 +356,9 @@ conv_gemm_f16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_co
                                 ptx::tma_load_2d(dst + S::kBBytes / 2, &tmap_b, &full_bar[ty], 0, ty * p.b_rows_per_tap + p.nm_lo_row + b_row_base);
                         }
                     }
+                    const int npass = NM ? (p.nm_passes == 1 ? 1 : 2) : SPLIT ? 3 : 1;   // NM, nm_passes = 1: a_lo == 0 (uint8 images)
                     for (int ty = 0; ty < 4; ++ty) {
-#pragma unroll
-                        for (int pass = 0; pass < (NM ? 2 : SPLIT ? 3 : 1); ++pass) {
+                        for (int pass = 0; pass < npass; ++pass) {
                             ptx::mbar_wait(&a_empty[hs], hphase ^ 1u);
                             ptx::mbar_arrive_expect_tx(&a_full[hs], S::kAHaloTx);
                             ptx::tma_load_2d(smem + hs * S::kAHaloBytes, &tmap_a, &a_full[hs], pass == 1 ? 16 : 0,
@@ -492,9 +493,9 @@ conv_gemm_f16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_co
                         for (int ty = 0; ty < (NM ? 4 : SPLIT ? 8 : 4); ++ty) ptx::mbar_wait(&full_bar[ty], 0);
                         b_resident = true;
                     }
+                    const int npass = NM ? (p.nm_passes == 1 ? 1 : 2) : SPLIT ? 3 : 1;
                     for (int ty = 0; ty < 4; ++ty) {
-#pragma unroll
-                        for (int pass = 0; pass < (NM ? 2 : SPLIT ? 3 : 1); ++pass) {
+                        for (int pass = 0; pass < npass; ++pass) {
                             ptx::mbar_wait(&a_full[hs], hphase);
                             ptx::tc_fence_after();
                             const uint32_t sa = ptx::smem_u32(smem + hs * S::kAHaloBytes);

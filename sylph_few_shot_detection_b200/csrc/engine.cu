@@ -401,9 +401,39 @@ static int prep_stem(sylph_ctx* c, ConvW* out) {
     out->b_rows = n_tiles * out->cout_pad;
     std::vector<uint16_t> hw(static_cast<size_t>(n_tiles) * out->cout_pad * 64, 0);
     std::vector<float> hb(out->cout_pad, 0.f);
+    // Exact mode: the stem reads re-centred integer pixels u = (v - round(mean)) / 256 (kernels_misc.cuh, "image prep, exact
+    // mode"), so the weights carry 256 / std of their input channel and the bias the -(mean - round(mean)) / std term of all 49 taps;
+    // folded in double, then split into hi + lo.
+    const sylph_model_config& f = c->cfg;
     for (int o = 0; o < co; ++o) {
         const float s = g->data[o] * (1.0f / std::sqrt(v->data[o] + 1e-5f));
         hb[o] = b->data[o] - m->data[o] * s;
+        if (c->split) {
+            double corr = 0.0;
+            for (int ch = 0; ch < 3; ++ch) {
+                const double delta = static_cast<double>(f.pixel_mean[ch]) - std::nearbyint(static_cast<double>(f.pixel_mean[ch]));
+                for (int kk = 0; kk < 49; ++kk)
+                    corr += static_cast<double>(w->data[(static_cast<size_t>(o) * 3 + ch) * 49 + kk]) * s / f.pixel_std[ch] * delta;
+            }
+            hb[o] = static_cast<float>(static_cast<double>(b->data[o]) - static_cast<double>(m->data[o]) * s - corr);
+            for (int ty = 0; ty < 4; ++ty)
+                for (int tx = 0; tx < 4; ++tx)
+                    for (int dy = 0; dy < 2; ++dy)
+                        for (int dx = 0; dx < 2; ++dx) {
+                            const int ky = 2 * ty + dy - 1, kx = 2 * tx + dx - 1;
+                            if (ky < 0 || ky > 6 || kx < 0 || kx > 6) continue;
+                            for (int ch = 0; ch < 3; ++ch) {
+                                const int k = tx * 16 + (dy * 2 + dx) * 3 + ch;
+                                const double wv = static_cast<double>(w->data[((static_cast<size_t>(o) * 3 + ch) * 7 + ky) * 7 + kx]) * s *
+                                                  256.0 / f.pixel_std[ch];
+                                const uint16_t hi = float_to_half_bits(static_cast<float>(wv));
+                                hw[(static_cast<size_t>(ty) * out->cout_pad + o) * 64 + k] = hi;
+                                hw[(static_cast<size_t>(4 + ty) * out->cout_pad + o) * 64 + k] =
+                                    float_to_half_bits(static_cast<float>(wv - static_cast<double>(half_bits_to_float(hi))));
+                            }
+                        }
+            continue;
+        }
         for (int ty = 0; ty < 4; ++ty)
             for (int tx = 0; tx < 4; ++tx)
                 for (int dy = 0; dy < 2; ++dy)
@@ -578,7 +608,7 @@ struct ConvCall {
     float* gn_partial = nullptr;
     const float* bias_override = nullptr;
     const __half* w_override = nullptr;
-    int stem = 0;
+    int stem = 0;            // 1 = the stem convolution; 2 = exact mode with uint8 images (a_lo == 0: the a_lo pass is skipped)
     int up_seg_delta = 0;    // kEpiUpsample: coarser plane = segment of the output tile + this
     int staged = 0;          // TMA-in / TMA-out epilogue (fp16 output, BN = 256); needs out_rows
     int pairsplit = 0;       // split mode: CTA-pair 1x1 kernel with the chunked staged epilogue and quad stages (conv1x1_pair_split.cuh)
@@ -680,6 +710,7 @@ static int run_conv_impl(sylph_ctx* c, const ConvCall& k, cudaStream_t st, const
     g.kblocks_per_tap = W.k_per_tap / kBlockK;
     g.b_rows_per_tap = W.cout_pad;
     g.a_wrap = split ? 2 * W.cin : 0;
+    g.nm_passes = (k.stem == 2) ? 1 : 2;
     if (stem16 && split) g.nm_lo_row = 4 * W.cout_pad;   // stem weight matrix: the four w_hi tiles, then the four w_lo tiles
     if (k.qs || k.pairsplit) g.kblocks_per_tap = W.cin / kBlockK;   // logical k-blocks: a stage carries a_hi, a_lo, w_hi, w_lo
     if (nm) {
@@ -1002,6 +1033,14 @@ struct TrunkOut {
 static int run_trunk(sylph_ctx* c, const std::string& key, int n, const void* const* images_dev, int is_u8, const int* hs,
                      const int* ws, int hpad, int wpad, cudaStream_t st, TrunkOut* out, bool normalized = false) {
     sylph_model_config f = c->cfg;
+    CentreParams cp{};   // exact mode: re-centred integer pixels (kernels_misc.cuh); `normalized` input is de-normalised first
+    for (int i = 0; i < 3; ++i) {
+        cp.m_r[i] = std::nearbyint(f.pixel_mean[i]);
+        cp.mean[i] = f.pixel_mean[i];
+        cp.stdv[i] = f.pixel_std[i];
+        cp.pad[i] = static_cast<float>((static_cast<double>(f.pixel_mean[i]) - std::nearbyint(static_cast<double>(f.pixel_mean[i]))) / 256.0);
+    }
+    cp.denorm = normalized ? 1 : 0;
     if (normalized) {   // the caller's batch is already (x - mean) / std: the fused preparation only re-lays it out
         for (int i = 0; i < 3; ++i) { f.pixel_mean[i] = 0.f; f.pixel_std[i] = 1.f; }
     }
@@ -1040,7 +1079,13 @@ static int run_trunk(sylph_ctx* c, const std::string& key, int n, const void* co
     {   // every layer over the whole batch
         {
             StageTimer t(c, "prep_stem_input", st, static_cast<double>(n) * (3.0 * hmax * wmax + 32.0 * g0.H * g0.W));
-            if (is_u8)
+            if (c->split && is_u8)
+                CU_TRY(c, launch_k(prep_stem_centred_u8_kernel, dim3((g0.W + 255) / 256, std::min(n * g0.H, c->num_sms * 8)), dim3(256), 0, st,
+                    static_cast<const ImageDesc*>(d_desc), S0, g0, n, cp));
+            else if (c->split)
+                CU_TRY(c, launch_k(prep_stem_centred_kernel, dim3(grid_for(static_cast<long long>(n) * g0.H * g0.W, 256, c->num_sms)), dim3(256), 0, st,
+                    static_cast<const ImageDesc*>(d_desc), S0, g0, n, cp));
+            else if (is_u8)
                 CU_TRY(c, launch_k(prep_stem_input_u8_kernel, dim3((g0.W + 255) / 256, std::min(n * g0.H, c->num_sms * 8)), dim3(256), 0, st,
                     static_cast<const ImageDesc*>(d_desc), S0, g0, n, f.pixel_mean[0], f.pixel_mean[1], f.pixel_mean[2],
                     f.pixel_std[0], f.pixel_std[1], f.pixel_std[2], c->split));
@@ -1055,7 +1100,7 @@ static int run_trunk(sylph_ctx* c, const std::string& key, int n, const void* co
             ConvCall k{};
             k.W = &c->stem; k.A = S0; k.a_rows = rows0; k.a_cols = 64; k.a_ld = c->ld(16); k.ps = ps0.get();
             k.tile_begin = 0; k.n_tiles = static_cast<int>(rows0 / kBlockM); k.a_row_delta = 0; k.out = S1; k.ldc = c->ld(64);
-            k.flags = kEpiRelu | kEpiMask; k.stem = 1; k.name = "stem7x7";
+            k.flags = kEpiRelu | kEpiMask; k.stem = (c->split && is_u8) ? 2 : 1; k.name = "stem7x7";   // 2: a_lo == 0, one A pass
             k.staged = c->staged_epilogue; k.out_rows = rows0;
             TRY(run_conv(c, k, st));
         }

@@ -194,6 +194,169 @@ prep_stem_input_u8_kernel(const ImageDesc* __restrict__ imgs, __half* __restrict
     }
 }
 
+// ------------------------------------------------------------------------------------------------ image prep, exact mode
+// Exact (split-operand) mode feeds the stem with RE-CENTRED INTEGER pixels instead of normalised ones:
+//   u = (v - m_r) / 256,  m_r = round(pixel_mean)   -- for uint8 images an 8-bit integer times 2^-8: EXACT in one fp16, lo = 0
+//   y = sum_taps (256 w s / std) u + [b_bn - sum_taps (w s / std)(mean - m_r)]      (weights and bias folded in double, engine.cu)
+// which equals the reference's conv((v - mean) / std) up to the fp32 rounding of either side.  The reference pads the NORMALISED
+// image with zeros (ImageList.from_tensors + the convolution's own padding), i.e. with pixel value `mean`: every position outside
+// the image -- including the 2-pixel border ring of the plane that the convolution's padding reads -- holds
+// pad_c = rn16((mean_c - m_r_c) / 256) instead of 0, so no position-dependent correction is needed (the ring is written here on
+// every pass; the error of rounding pad_c to fp16 is < 3e-7 of the pixel range, at padded taps only).
+// The stem then needs ONE pass over a_hi for uint8 images (a_lo == 0): 16 instead of 32 instructions per tile.
+// Float images run both passes; integer-valued float images give bit-identical features (the a_lo pass adds exact zeros).
+struct CentreParams {
+    float m_r[3];     // round(pixel_mean)
+    float mean[3], stdv[3];
+    float pad[3];     // (mean - m_r) / 256
+    int denorm;       // float input is already (x - mean) / std (plugin boundary): v = x * std + mean first
+};
+
+__device__ __forceinline__ void write_ring_pixels(__half* __restrict__ out, const PlaneGeom& g, int n_images, const CentreParams& cp,
+                                                  long long first, long long stride) {
+    // border ring of every plane: (H + 4) x (W + 4) minus the interior, rows of [16 hi | 16 lo]
+    const int ring_w = g.W + 4, ring_h = g.H + 4;
+    const long long per_img = 2LL * 2 * ring_w + 2LL * 2 * g.H;   // two full rows above + below, two columns left + right
+    uint4 v0, v1;
+    {
+        const uint32_t p0 = pack_half2(cp.pad[0], cp.pad[1]) , p1 = pack_half2(cp.pad[2], cp.pad[0]), p2 = pack_half2(cp.pad[1], cp.pad[2]);
+        v0 = make_uint4(p0, p1, p2, p0);   // channels (dy, dx, c) = 12 values: c cycles 0 1 2 0 1 2 ...
+        v1 = make_uint4(p1, p2, 0u, 0u);
+    }
+    for (long long i = first; i < per_img * n_images; i += stride) {
+        const int n = static_cast<int>(i / per_img);
+        long long r = i - n * per_img;
+        int y, x;
+        if (r < 2LL * ring_w) { y = static_cast<int>(r / ring_w) - 2; x = static_cast<int>(r % ring_w) - 2; }
+        else if (r < 4LL * ring_w) { r -= 2LL * ring_w; y = g.H + static_cast<int>(r / ring_w); x = static_cast<int>(r % ring_w) - 2; }
+        else { r -= 4LL * ring_w; y = static_cast<int>(r / 4); const int q = static_cast<int>(r % 4); x = q < 2 ? q - 2 : g.W + q - 2; }
+        (void)ring_h;
+        uint4* o = reinterpret_cast<uint4*>(out + plane_row(g, n, y, x) * 32);
+        o[0] = v0; o[1] = v1;
+        o[2] = make_uint4(0u, 0u, 0u, 0u); o[3] = make_uint4(0u, 0u, 0u, 0u);
+    }
+}
+
+// float (or uint8 through the slow path) images -> [16 hi | 16 lo] rows of u = (v - m_r) / 256
+__global__ void prep_stem_centred_kernel(const ImageDesc* __restrict__ imgs, __half* __restrict__ out, PlaneGeom g, int n_images,
+                                         CentreParams cp) {
+    ptx::griddep_launch();
+    ptx::griddep_wait();
+    const long long total = static_cast<long long>(n_images) * g.H * g.W;
+    const long long tid = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
+    const long long nthreads = static_cast<long long>(gridDim.x) * blockDim.x;
+    for (long long i = tid; i < total; i += nthreads) {
+        const int x2 = static_cast<int>(i % g.W);
+        const int y2 = static_cast<int>((i / g.W) % g.H);
+        const int n = static_cast<int>(i / (static_cast<long long>(g.W) * g.H));
+        const ImageDesc im = imgs[n];
+        float v[16];
+#pragma unroll
+        for (int dy = 0; dy < 2; ++dy)
+#pragma unroll
+            for (int dx = 0; dx < 2; ++dx) {
+                const int iy = 2 * y2 + dy, ix = 2 * x2 + dx;
+                const bool in = iy < im.h && ix < im.w;
+#pragma unroll
+                for (int c = 0; c < 3; ++c) {
+                    float t = __half2float(__float2half_rn(cp.pad[c]));   // the fp16 pad value, lo = 0, as in the uint8 kernel
+                    if (in) {
+                        const size_t off = (static_cast<size_t>(c) * im.h + iy) * im.w + ix;
+                        float px = im.is_u8 ? static_cast<float>(__ldg(static_cast<const unsigned char*>(im.ptr) + off))
+                                            : __ldg(static_cast<const float*>(im.ptr) + off);
+                        if (cp.denorm) px = __fmaf_rn(px, cp.stdv[c], cp.mean[c]);
+                        t = (px - cp.m_r[c]) * (1.f / 256.f);
+                    }
+                    v[(dy * 2 + dx) * 3 + c] = t;
+                }
+            }
+        v[12] = v[13] = v[14] = v[15] = 0.f;
+        __half* row = out + plane_row(g, n, y2, x2) * 32;
+        store8f(row, 0, 16, v, false);
+        store8f(row, 8, 16, v + 8, false);
+    }
+    write_ring_pixels(out, g, n_images, cp, tid, nthreads);
+}
+
+// uint8 images: table of the (exact) fp16 values, six input rows of a 256-pixel output segment staged in shared memory (see
+// prep_stem_input_u8_kernel); writes the hi half of every row only -- the stem never reads the lo half on this path.
+__global__ void __launch_bounds__(256)
+prep_stem_centred_u8_kernel(const ImageDesc* __restrict__ imgs, __half* __restrict__ out, PlaneGeom g, int n_images, CentreParams cp) {
+    ptx::griddep_launch();
+    __shared__ unsigned short lut[3][256];
+    __shared__ unsigned short padv[3];
+    __shared__ __align__(16) unsigned char rows[6][528];
+    for (int i = threadIdx.x; i < 768; i += 256) {
+        const int c = i >> 8, v = i & 255;
+        lut[c][v] = static_cast<unsigned short>(pack_half2((static_cast<float>(v) - cp.m_r[c]) * (1.f / 256.f), 0.f) & 0xFFFFu);
+    }
+    if (threadIdx.x < 3) padv[threadIdx.x] = static_cast<unsigned short>(pack_half2(cp.pad[threadIdx.x], 0.f) & 0xFFFFu);
+    ptx::griddep_wait();
+    const int x0 = blockIdx.x * 256;
+    const int n_rows = n_images * g.H;
+    for (int ry = blockIdx.y; ry < n_rows; ry += gridDim.y) {
+        const int n = ry / g.H, y2 = ry - n * g.H;
+        const ImageDesc im = imgs[n];
+        const unsigned char* base = static_cast<const unsigned char*>(im.ptr);
+        const size_t img_bytes = static_cast<size_t>(3) * im.h * im.w;
+        const int px0 = 2 * x0;
+        const int npx = min(512, im.w - px0);
+        __syncthreads();
+        int shift[6];
+#pragma unroll
+        for (int r = 0; r < 6; ++r) {
+            const int c = r >> 1, iy = 2 * y2 + (r & 1);
+            shift[r] = 0;
+            if (iy < im.h && npx > 0) {
+                const size_t a = (static_cast<size_t>(c) * im.h + iy) * im.w + px0;
+                const size_t a4 = (reinterpret_cast<size_t>(base) + a) & ~static_cast<size_t>(3);
+                shift[r] = static_cast<int>(reinterpret_cast<size_t>(base) + a - a4);
+                const int nwords = (shift[r] + npx + 3) >> 2;
+                const size_t lo = reinterpret_cast<size_t>(base), hi = lo + img_bytes;
+                for (int wd = threadIdx.x; wd < nwords; wd += 256) {
+                    const size_t wa = a4 + 4 * static_cast<size_t>(wd);
+                    uint32_t word;
+                    if (wa >= lo && wa + 4 <= hi) {
+                        word = __ldg(reinterpret_cast<const uint32_t*>(wa));
+                    } else {
+                        word = 0;
+                        for (int b = 0; b < 4; ++b) {
+                            const size_t ba = wa + b;
+                            if (ba >= lo && ba < hi)
+                                word |= static_cast<uint32_t>(__ldg(reinterpret_cast<const unsigned char*>(ba))) << (8 * b);
+                        }
+                    }
+                    *reinterpret_cast<uint32_t*>(&rows[r][4 * wd]) = word;
+                }
+            }
+        }
+        __syncthreads();
+        const int x2 = x0 + threadIdx.x;
+        if (x2 < g.W) {
+            unsigned short h[12];
+#pragma unroll
+            for (int dy = 0; dy < 2; ++dy)
+#pragma unroll
+                for (int dx = 0; dx < 2; ++dx) {
+                    const int iy = 2 * y2 + dy, ix = 2 * x2 + dx;
+                    const bool in = iy < im.h && ix < im.w;
+#pragma unroll
+                    for (int c = 0; c < 3; ++c) {
+                        const int r = c * 2 + dy;
+                        const int px = in ? rows[r][shift[r] + 2 * threadIdx.x + dx] : 0;
+                        h[(dy * 2 + dx) * 3 + c] = in ? lut[c][px] : padv[c];
+                    }
+                }
+            uint4* o = reinterpret_cast<uint4*>(out + plane_row(g, n, y2, x2) * 32);
+            auto pk = [](unsigned short lo, unsigned short hi) { return static_cast<uint32_t>(lo) | (static_cast<uint32_t>(hi) << 16); };
+            o[0] = make_uint4(pk(h[0], h[1]), pk(h[2], h[3]), pk(h[4], h[5]), pk(h[6], h[7]));
+            o[1] = make_uint4(pk(h[8], h[9]), pk(h[10], h[11]), 0u, 0u);
+        }
+    }
+    const long long tid = (static_cast<long long>(blockIdx.y) * gridDim.x + blockIdx.x) * blockDim.x + threadIdx.x;
+    write_ring_pixels(out, g, n_images, cp, tid, static_cast<long long>(gridDim.x) * gridDim.y * blockDim.x);
+}
+
 // ------------------------------------------------------------------------------------------------ max-pool 3x3 / 2
 // detectron2 BasicStem max_pool2d(kernel 3, stride 2, padding 1) on post-ReLU (>= 0) activations: the zero border of
 // the input plane stands in for the -inf padding.
