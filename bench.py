@@ -387,7 +387,7 @@ def measure_mode(hz: Harness, cfg, state, precision: str, peaks, full: bool):
             out["roofline"] = {"kernel": kname + ", the kernel with the largest share of the step",
                                "bound": "hbm", "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s",
                                "frac": round(achieved / peak, 4),
-                               "traffic": ncu_traffic("conv3_split.res2" if precision == "exact" else "conv_gemm_f16_kernel<256,2,2,0>.res2_conv3"),
+                               "traffic": ncu_traffic("conv3_split.mean33" if precision == "exact" else "conv_gemm_f16_kernel<256,2,2,0>.res2_conv3"),
                                "avg_launch_ms": round(tot_ms / n_launch, 4), "launches_timed": n_launch,
                                "share_of_step": round(tot_ms / total_ms, 4),
                                "bytes_per_launch": bytes_total / n_launch,
