@@ -394,7 +394,8 @@ def measure_mode(hz: Harness, cfg, state, precision: str, peaks, full: bool):
                                "peak_source": f"MEASURED_PEAKS.json hbm_gbs ({peaks['source']})",
                                "note": f"achieved = sum of algorithmic bytes ({elem} B per stored element) / sum of launch durations "
                                        f"over this kernel's {n_launch} conv3 launches of one episode (shapes differ per stage); traffic = "
-                                       "ncu DRAM bytes of ONE res2 launch at 8 images (profiles/ncu_traffic.json)"}
+                                       "ncu DRAM bytes per launch of the same launches at 33 images, mean (exact) / of one res2 launch at 8 images (fast) "
+                                       "(profiles/ncu_traffic.json)"}
             # the other conv3 kernel of the same stage group: CTA-pair 1x1 kernel (exact: res4 + res5, chunked staged epilogue)
             rest_ms = sum(conv3[n_launch:])
             rest_bytes = sum(stage_bytes_img[n_single:]) * n_img
