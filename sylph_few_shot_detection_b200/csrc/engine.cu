@@ -1081,7 +1081,7 @@ static int run_trunk(sylph_ctx* c, const std::string& key, int n, const void* co
             StageTimer t(c, "prep_stem_input", st, static_cast<double>(n) * (3.0 * hmax * wmax + 32.0 * g0.H * g0.W));
             if (c->split && is_u8)
                 CU_TRY(c, launch_k(prep_stem_centred_u8_kernel, dim3((g0.W + 255) / 256, std::min(n * g0.H, c->num_sms * 8)), dim3(256), 0, st,
-                    static_cast<const ImageDesc*>(d_desc), S0, g0, n, cp));
+                    static_cast<const ImageDesc*>(d_desc), S0, g0, n, cp, c->nmerge ? 0 : 1));
             else if (c->split)
                 CU_TRY(c, launch_k(prep_stem_centred_kernel, dim3(grid_for(static_cast<long long>(n) * g0.H * g0.W, 256, c->num_sms)), dim3(256), 0, st,
                     static_cast<const ImageDesc*>(d_desc), S0, g0, n, cp));

@@ -281,7 +281,8 @@ __global__ void prep_stem_centred_kernel(const ImageDesc* __restrict__ imgs, __h
 // uint8 images: table of the (exact) fp16 values, six input rows of a 256-pixel output segment staged in shared memory (see
 // prep_stem_input_u8_kernel); writes the hi half of every row only -- the stem never reads the lo half on this path.
 __global__ void __launch_bounds__(256)
-prep_stem_centred_u8_kernel(const ImageDesc* __restrict__ imgs, __half* __restrict__ out, PlaneGeom g, int n_images, CentreParams cp) {
+prep_stem_centred_u8_kernel(const ImageDesc* __restrict__ imgs, __half* __restrict__ out, PlaneGeom g, int n_images, CentreParams cp,
+                            int zero_lo) {   // zero_lo: the stem variant in use reads the lo half (SYLPH_NM=0): keep it zero
     ptx::griddep_launch();
     __shared__ unsigned short lut[3][256];
     __shared__ unsigned short padv[3];
@@ -351,6 +352,7 @@ prep_stem_centred_u8_kernel(const ImageDesc* __restrict__ imgs, __half* __restri
             auto pk = [](unsigned short lo, unsigned short hi) { return static_cast<uint32_t>(lo) | (static_cast<uint32_t>(hi) << 16); };
             o[0] = make_uint4(pk(h[0], h[1]), pk(h[2], h[3]), pk(h[4], h[5]), pk(h[6], h[7]));
             o[1] = make_uint4(pk(h[8], h[9]), pk(h[10], h[11]), 0u, 0u);
+            if (zero_lo) { o[2] = make_uint4(0u, 0u, 0u, 0u); o[3] = make_uint4(0u, 0u, 0u, 0u); }
         }
     }
     const long long tid = (static_cast<long long>(blockIdx.y) * gridDim.x + blockIdx.x) * blockDim.x + threadIdx.x;

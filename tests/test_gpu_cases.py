@@ -486,3 +486,42 @@ def test_codes_on_a_side_stream_give_identical_detections():
         torch.cuda.synchronize()
         assert torch.equal(codes0, codes1) and torch.equal(c0, c1) and torch.equal(d0, d1)
     assert int(c0.sum()) > 0
+
+
+def test_non_integer_float_images_take_the_hi_lo_stem_path():
+    """Exact mode re-centres pixels on round(pixel_mean): uint8 images need one stem pass (a_lo == 0); float images with
+    fractional pixel values carry a lo half and run both passes -- features against the CPU oracle on the same float values,
+    ragged sizes in one batch (padding value rn16((mean - round(mean)) / 256) outside each image and in the border ring)."""
+    from sylph_few_shot_detection_b200.runtime import SLOT_QUERY
+    cfg, state, model, orc = _setup(seed=9)
+    g = torch.Generator().manual_seed(31)
+    ims = []
+    for i, (h, w) in enumerate([(120, 200), (96, 131), (160, 77)]):
+        ims.append((_images(1, h, w, 300 + i)[0].float() + torch.rand(3, h, w, generator=g) * 0.98 - 0.49).clamp(0, 255))
+    model.engine.extract_features(SLOT_QUERY, [im.cuda() for im in ims])
+    codes = {"cls_conv": torch.zeros(1, 256, 1, 1), "cls_bias": torch.tensor([-5.0])}
+    _, inter = orc.detect(ims, codes, return_intermediate=True)
+    feats = inter["features"]
+    for l in range(5):
+        got = model.engine.export_features(SLOT_QUERY, l)
+        assert got.shape == feats[l].shape
+        assert rel_err(got, feats[l]) < TOL, ("features", l, rel_err(got, feats[l]))
+
+
+@pytest.mark.parametrize("switch", ["SYLPH_NM", "SYLPH_QS", "SYLPH_PAIR1X1"])
+def test_exact_mode_kernel_switches_give_the_same_features(switch, monkeypatch):
+    """The exact-mode schedule switches (N-merged 3x3 / stem, quad stages, CTA-pair split 1x1 kernel) change which kernels run
+    and the order of fp32 additions, never the arithmetic: features with a switch off agree with the default build to 2e-5
+    (and both meet the 1e-3 bar against the oracle elsewhere in this suite)."""
+    from sylph_few_shot_detection_b200.runtime import SLOT_QUERY
+    ims = [im.cuda() for im in _images(2, 224, 320, 41)]
+    _, _, model, _ = _setup(seed=4)
+    model.engine.extract_features(SLOT_QUERY, ims)
+    ref = [model.engine.export_features(SLOT_QUERY, l).clone() for l in range(5)]
+    del model
+    monkeypatch.setenv(switch, "0")
+    _, _, model2, _ = _setup(seed=4)
+    model2.engine.extract_features(SLOT_QUERY, ims)
+    for l in range(5):
+        got = model2.engine.export_features(SLOT_QUERY, l)
+        assert rel_err(got, ref[l]) < 2e-5, (switch, l, rel_err(got, ref[l]))
