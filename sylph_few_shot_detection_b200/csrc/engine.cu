@@ -89,6 +89,7 @@ struct sylph_ctx {
     int pair1x1 = 1;          // SYLPH_PAIR1X1=0 keeps the single-CTA staged kernel for every 1x1 convolution; 2 = pair kernel
                               // for every staged 1x1 convolution with 256-channel N tiles and K >= 256 (experiments)
     int stem16 = 1;           // SYLPH_STEM16=0 runs the stem over 64-wide overlapped rows instead of K = 16 taps
+    int cls_pooled = 1;       // SYLPH_CLS_POOLED=0: per-pixel cls convolution over the ROI planes, pooled afterwards (round-1 form)
     int sync_each = 0;        // SYLPH_SYNC_EACH=1: synchronise after every convolution launch and name the one that faults
     int quad = 1;             // SYLPH_QS=0: K' = 3C loop for every split 1x1 layer instead of quad stages on the deep ones
     int nmerge = 1;           // SYLPH_NM=0: three instructions per k-step for the narrow split 3x3 layers instead of the N-merged two
@@ -107,7 +108,7 @@ struct sylph_ctx {
     ConvW lat[3], outc[3], p6, p7;
     std::vector<ConvW> cls_tower, box_tower, cg_tower;
     std::vector<float*> cls_gn_w, cls_gn_b, box_gn_w, box_gn_b, cg_gn_w, cg_gn_b;
-    ConvW pred, cg_cls;
+    ConvW pred, cg_cls, cg_cls_pooled;
     float level_scale[5] = {1, 1, 1, 1, 1};
     float* cg_wbias = nullptr;  // [9][256]
     float* cg_bbias = nullptr;  // [1]
@@ -839,6 +840,7 @@ int sylph_create(sylph_ctx** out, int device, const sylph_model_config* cfg) {
     if (const char* e = getenv("SYLPH_NM")) c->nmerge = atoi(e);
     if (const char* e = getenv("SYLPH_QS")) c->quad = atoi(e);
     if (const char* e = getenv("SYLPH_SYNC_EACH")) c->sync_each = atoi(e);
+    if (const char* e = getenv("SYLPH_CLS_POOLED")) c->cls_pooled = atoi(e);
     if (const char* e = getenv("SYLPH_ROI_ALIGN")) c->roi_separable = strcmp(e, "sample") == 0 ? 0 : 1;
     if (const char* e = getenv("SYLPH_PRECISION")) c->split = (strcmp(e, "fast") == 0 || strcmp(e, "0") == 0) ? 0 : 1;
     *out = c;
@@ -963,6 +965,20 @@ int sylph_finalize_weights(sylph_ctx* c) {
         }
         TRY(prep_conv(c, cg + "support_set_cls_conv.0", false, true, &c->cg_cls));
         if (c->cg_cls.cout != 256) return c->fail("CODE_GENERATOR.OUT_CHANNEL must be 256 on this path");
+        {   // the same layer as a [2304 -> 256] GEMM over the nine window means of a ROI (kernels_codegen.cuh, roi_window_means_kernel)
+            const HostTensor *w = find_t(c, cg + "support_set_cls_conv.0.weight"), *b = find_t(c, cg + "support_set_cls_conv.0.bias");
+            if (!w || !b || w->data.size() != static_cast<size_t>(256) * 256 * 9) return c->fail("support_set_cls_conv must be a 3x3 256 -> 256 convolution");
+            HostTensor pw;
+            pw.shape = {256, 2304, 1, 1};
+            pw.data.resize(w->data.size());
+            for (int o = 0; o < 256; ++o)
+                for (int ch = 0; ch < 256; ++ch)
+                    for (int tap = 0; tap < 9; ++tap)
+                        pw.data[static_cast<size_t>(o) * 2304 + tap * 256 + ch] = w->data[(static_cast<size_t>(o) * 256 + ch) * 9 + tap];
+            c->staged["__cg_cls_pooled.weight"] = std::move(pw);
+            c->staged["__cg_cls_pooled.bias"] = *b;
+            TRY(prep_conv(c, "__cg_cls_pooled", false, true, &c->cg_cls_pooled));
+        }
         if (f.cg_bias_layer) {
             const HostTensor *w = find_t(c, cg + "support_set_cls_bias.0.weight"), *b = find_t(c, cg + "support_set_cls_bias.0.bias");
             if (!w || !b || w->data.size() != 256 * 9) return c->fail("missing support_set_cls_bias tensors");
@@ -1681,7 +1697,27 @@ int sylph_generate_codes(sylph_ctx* c, int slot, int n_rois, const float* boxes_
         cur = nxt;
         nxt = (cur == r1) ? static_cast<__half*>(r2) : static_cast<__half*>(r1);
     }
-    {
+    const float* pooled = nullptr;
+    if (c->cls_pooled) {
+        // pool before the cls convolution (exact algebra, kernels_codegen.cuh): nine window means per ROI, then one GEMM with
+        // M = n_rois, K = 2304 -- the per-pixel convolution over one 128-row tile per ROI did 128x the tensor work
+        const int t_pad = round_up(n_rois, kBlockM);
+        void *pw, *pp;
+        TRY(ensure(c, "cg.win", static_cast<size_t>(t_pad + kBlockM) * c->ld(2304) * 2, "win", &pw, st, true));
+        TRY(ensure(c, "cg.pooled", static_cast<size_t>(t_pad + kBlockM) * 256 * 4, "", &pp, st, false));
+        {
+            StageTimer t(c, "codegen.window_means", st, static_cast<double>(n_rois) * (49.0 * 256 + 2304) * (c->split ? 4 : 2));
+            CU_TRY(c, launch_k(roi_window_means_kernel, dim3(n_rois), dim3(256), 0, st, static_cast<const __half*>(cur), static_cast<__half*>(pw), c->split));
+            CU_TRY(c, cudaGetLastError());
+            c->launches++;
+        }
+        ConvCall k{};
+        k.W = &c->cg_cls_pooled; k.A = static_cast<const __half*>(pw); k.a_rows = t_pad; k.a_cols = k.a_ld = c->ld(2304); k.ps = ps.get();
+        k.tile_begin = 0; k.n_tiles = t_pad / kBlockM; k.a_row_delta = 0; k.out = pp; k.ldc = 256; k.flags = kEpiOutF32;
+        k.name = "codegen.cls_gemm";
+        TRY(run_conv(c, k, st));
+        pooled = static_cast<const float*>(pp);
+    } else {
         ConvCall k{};
         k.W = &c->cg_cls; k.A = cur; k.a_rows = rows; k.a_cols = k.a_ld = c->ld(256); k.ps = ps.get(); k.tile_begin = 0;
         k.n_tiles = n_rois; k.a_row_delta = 0; k.out = raw; k.ldc = 256; k.flags = kEpiOutF32; k.name = "codegen.cls_conv3x3";
@@ -1690,7 +1726,7 @@ int sylph_generate_codes(sylph_ctx* c, int slot, int n_rois, const float* boxes_
     {
         StageTimer t(c, "codegen.tail", st, static_cast<double>(n_rois) * 2 * 49 * 256 * 4);
         CU_TRY(c, launch_k(shot_code_kernel, dim3(n_rois), dim3(256), 0, st, raw, cur, c->cg_wbias, c->cg_bbias, f.cg_bias_layer, f.cg_bias_l2_norm,
-                                                 static_cast<float*>(sc), c->split));
+                                                 static_cast<float*>(sc), c->split, pooled));
         CU_TRY(c, cudaGetLastError());
         CU_TRY(c, launch_k(class_mean_kernel, dim3(n_classes), dim3(288), 0, st, static_cast<const float*>(sc), static_cast<const int*>(po), codes_out_dev));
         CU_TRY(c, cudaGetLastError());

@@ -209,24 +209,69 @@ roi_align_separable_kernel(const __half* __restrict__ pyramid, PyramidGeom pg, c
     }
 }
 
+// Pool BEFORE the cls convolution: the reference's support_set_cls_conv is conv3x3(256 -> 256, bias) followed directly by a global
+// average pool (CLS_LAYER ["", "", 1]: no norm, no ReLU in between; code_generator.py:954, utils.py:51-67), and the mean over the 49
+// positions commutes with the convolution:  mean_p conv(x)[p] = sum_tap W_tap . (mean over the 7x7 window shifted by the tap) + b.
+// This kernel writes, per ROI, the nine window means of the tower output (zero padding = the plane's zero border) as one row of
+// 9 x 256 values (hi | lo halves in exact mode); the convolution becomes a [n_rois x 2304] x [2304 x 256] GEMM -- 1 / 128 of the
+// tensor work of the per-pixel convolution over 128-row ROI tiles.   grid = n_rois, block = 256 (one channel per thread).
+__global__ void __launch_bounds__(256)
+roi_window_means_kernel(const __half* __restrict__ tower_out, __half* __restrict__ win /* [rows][9 * 256 (x2)] */, int split) {
+    ptx::griddep_launch();
+    ptx::griddep_wait();
+    const int roi = blockIdx.x, t = threadIdx.x;
+    const int ld = split ? 512 : 256;
+    const __half* base = tower_out + static_cast<size_t>(roi) * 128 * ld;
+    float s[9];
+#pragma unroll
+    for (int k = 0; k < 9; ++k) s[k] = 0.f;
+#pragma unroll
+    for (int y = 1; y <= 7; ++y)
+#pragma unroll
+        for (int x = 1; x <= 7; ++x) {
+            const __half* a = base + static_cast<size_t>(y * 9 + x) * ld;
+            float v = __half2float(a[t]);
+            if (split) v += __half2float(a[256 + t]);
+            // pixel (y, x) lies in the window of tap (dy, dx) iff 1 + dy <= y <= 7 + dy and 1 + dx <= x <= 7 + dx
+#pragma unroll
+            for (int dy = -1; dy <= 1; ++dy)
+#pragma unroll
+                for (int dx = -1; dx <= 1; ++dx)
+                    if (y >= 1 + dy && y <= 7 + dy && x >= 1 + dx && x <= 7 + dx) s[(dy + 1) * 3 + (dx + 1)] += v;
+        }
+    __half* o = win + static_cast<size_t>(roi) * (split ? 4608 : 2304);
+#pragma unroll
+    for (int k = 0; k < 9; ++k) {
+        const float m = s[k] / 49.f;
+        const __half hi = __float2half_rn(m);
+        o[k * 256 + t] = hi;
+        if (split) o[2304 + k * 256 + t] = __float2half_rn(m - __half2float(hi));
+    }
+}
+
 // Per support ROI ("shot"): global average pool of the cls-conv output (GlobalAdaptiveAvgPool2d, k_s = 1) and the
 // 256 -> 1 3x3 bias convolution on the tower output, optional L2 normalisation over the 49 positions, then its pool.
 // reference: code_generator.py:954-967, utils.py:51-67.   grid = n_rois, block = 256.
 __global__ void __launch_bounds__(256)
 shot_code_kernel(const float* __restrict__ cls_raw, const __half* __restrict__ tower_out,
                  const float* __restrict__ w_bias /* [9][256] tap-major */, const float* __restrict__ b_bias,
-                 int has_bias_layer, int bias_l2_norm, float* __restrict__ shot_codes /* [n_rois][257] */, int split) {
+                 int has_bias_layer, int bias_l2_norm, float* __restrict__ shot_codes /* [n_rois][257] */, int split,
+                 const float* __restrict__ cls_pooled = nullptr /* [n_rois][256]: the pooled cls-conv output (pool-before-conv path) */) {
     ptx::griddep_launch();
     ptx::griddep_wait();
     __shared__ float pix[49];
     const int roi = blockIdx.x, t = threadIdx.x, warp = t >> 5, lane = t & 31;
     const size_t base = static_cast<size_t>(roi) * 128;
-    float s = 0.f;
-    for (int p = 0; p < 49; ++p) {
-        const int row = (p / 7 + 1) * 9 + (p % 7 + 1);
-        s += cls_raw[(base + row) * 256 + t];
+    if (cls_pooled != nullptr) {
+        shot_codes[static_cast<size_t>(roi) * 257 + t] = cls_pooled[static_cast<size_t>(roi) * 256 + t];
+    } else {
+        float s = 0.f;
+        for (int p = 0; p < 49; ++p) {
+            const int row = (p / 7 + 1) * 9 + (p % 7 + 1);
+            s += cls_raw[(base + row) * 256 + t];
+        }
+        shot_codes[static_cast<size_t>(roi) * 257 + t] = s / 49.f;
     }
-    shot_codes[static_cast<size_t>(roi) * 257 + t] = s / 49.f;
     if (!has_bias_layer) {
         if (t == 0) shot_codes[static_cast<size_t>(roi) * 257 + 256] = 0.f;
         return;
