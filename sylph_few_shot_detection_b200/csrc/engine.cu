@@ -89,6 +89,7 @@ struct sylph_ctx {
     int pair1x1 = 1;          // SYLPH_PAIR1X1=0 keeps the single-CTA staged kernel for every 1x1 convolution; 2 = pair kernel
                               // for every staged 1x1 convolution with 256-channel N tiles and K >= 256 (experiments)
     int stem16 = 1;           // SYLPH_STEM16=0 runs the stem over 64-wide overlapped rows instead of K = 16 taps
+    int linear_gemm_min = 512; // SYLPH_LINEAR_GEMM_MIN: dense layers of the ROIEncoder run as tensor-core GEMMs from this many rows on
     int cls_pooled = 1;       // SYLPH_CLS_POOLED=0: per-pixel cls convolution over the ROI planes, pooled afterwards (round-1 form)
     int sync_each = 0;        // SYLPH_SYNC_EACH=1: synchronise after every convolution launch and name the one that faults
     int quad = 1;             // SYLPH_QS=0: K' = 3C loop for every split 1x1 layer instead of quad stages on the deep ones
@@ -116,7 +117,7 @@ struct sylph_ctx {
     float* post_gn_b = nullptr;
     float conv_scale = 1.f, bias_scale = 1.f, bias_value = 0.f;
     // ROIEncoder generator (cfg.generator == 1)
-    struct Dense { float* w = nullptr; float* b = nullptr; int in = 0, out = 0; };
+    struct Dense { float* w = nullptr; float* b = nullptr; int in = 0, out = 0; ConvW gemm; bool has_gemm = false; };   // gemm: the same layer for the tensor cores (many rows)
     struct EncLayer { Dense attn, ff1, ff2; float *n1w = nullptr, *n1b = nullptr, *n2w = nullptr, *n2b = nullptr; };
     ConvW re_pool_conv, re_fc1;
     float *re_pool_gn_w = nullptr, *re_pool_gn_b = nullptr;
@@ -482,11 +483,30 @@ static int upload_t(sylph_ctx* c, const std::string& key, float** d, size_t expe
     return upload(c, h, d);
 }
 
+// The same dense layer as a 1x1 "convolution" for the tensor-core GEMM kernels ([rows][in] x [in][out], split operands in exact
+// mode): used when the layer runs over thousands of rows (class sweeps); `w` is [out][in] row-major.
+static int prep_dense_gemm(sylph_ctx* c, const std::string& tag, const std::vector<float>& w, const std::vector<float>& b,
+                           sylph_ctx::Dense* d) {
+    if (d->in % kBlockK != 0 || d->out < 16) return 0;
+    HostTensor hw, hb;
+    hw.shape = {d->out, d->in, 1, 1};
+    hw.data = w;
+    hb.shape = {d->out};
+    hb.data = b;
+    c->staged["__dense_" + tag + ".weight"] = std::move(hw);
+    c->staged["__dense_" + tag + ".bias"] = std::move(hb);
+    TRY(prep_conv(c, "__dense_" + tag, false, true, &d->gemm));
+    d->has_gemm = true;
+    return 0;
+}
+
 static int prep_dense(sylph_ctx* c, const std::string& prefix, int in, int out, sylph_ctx::Dense* d) {
     d->in = in;
     d->out = out;
     TRY(upload_t(c, prefix + ".weight", &d->w, static_cast<size_t>(in) * out));
     TRY(upload_t(c, prefix + ".bias", &d->b, static_cast<size_t>(out)));
+    const HostTensor *w = find_t(c, prefix + ".weight"), *b = find_t(c, prefix + ".bias");
+    if (w && b) TRY(prep_dense_gemm(c, prefix, w->data, b->data, d));
     return 0;
 }
 
@@ -569,6 +589,7 @@ static int prep_roi_encoder(sylph_ctx* c) {
         L.attn.in = L.attn.out = 256;
         TRY(upload(c, wf, &L.attn.w));
         TRY(upload(c, bf, &L.attn.b));
+        TRY(prep_dense_gemm(c, k + "attn_folded", wf, bf, &L.attn));
         TRY(prep_dense(c, k + "linear1", 256, 1024, &L.ff1));
         TRY(prep_dense(c, k + "linear2", 1024, 256, &L.ff2));
         TRY(upload_vec(c, k + "norm1.weight", &L.n1w, 256));
@@ -640,7 +661,7 @@ static int run_conv(sylph_ctx* c, const ConvCall& k, cudaStream_t st) {
     // K' = 3C kernel: quad stages leave room for ONE staging buffer only, which costs more than the operand traffic saved
     // (res4 0.404 -> 0.498), except on res5 (K = 512) where the register epilogue wins (0.359 -> 0.325).
     if (c->split && c->quad && !k.stem && W.taps == 1 && k.w_override == nullptr && W.cout_pad % 128 == 0 && W.cin % 64 == 0 &&
-        !(k.flags & (kEpiOutF32 | kEpiGnStats))) {
+        !(k.flags & kEpiGnStats)) {
         const bool upsample = (k.flags & kEpiUpsample) != 0;
         // CTA-pair kernel with the chunked staged epilogue (conv1x1_pair_split.cuh) wherever the output leaves by TMA in
         // 256-channel tiles: one M = 256 instruction per k-step halves every SM's shared-memory operand reads -- at 33 images
@@ -841,6 +862,7 @@ int sylph_create(sylph_ctx** out, int device, const sylph_model_config* cfg) {
     if (const char* e = getenv("SYLPH_QS")) c->quad = atoi(e);
     if (const char* e = getenv("SYLPH_SYNC_EACH")) c->sync_each = atoi(e);
     if (const char* e = getenv("SYLPH_CLS_POOLED")) c->cls_pooled = atoi(e);
+    if (const char* e = getenv("SYLPH_LINEAR_GEMM_MIN")) c->linear_gemm_min = atoi(e);
     if (const char* e = getenv("SYLPH_ROI_ALIGN")) c->roi_separable = strcmp(e, "sample") == 0 ? 0 : 1;
     if (const char* e = getenv("SYLPH_PRECISION")) c->split = (strcmp(e, "fast") == 0 || strcmp(e, "0") == 0) ? 0 : 1;
     *out = c;
@@ -1305,9 +1327,26 @@ static int conv_gn_relu(sylph_ctx* c, const ConvW& W, const float* gn_w, const f
     return 0;
 }
 
+static int run_conv(sylph_ctx* c, const ConvCall& k, cudaStream_t st);
+
 static int run_linear(sylph_ctx* c, const sylph_ctx::Dense& d, const float* x, int ldx, float* y, int ldy, int T, int relu,
-                      float add_const, cudaStream_t st) {
+                      float add_const, cudaStream_t st, const PlaneSet* ps = nullptr) {
     if (d.in > 1024) return c->fail("linear layer wider than 1024 inputs");
+    // Thousands of rows (class sweeps): fp32 rows -> fp16 (hi | lo) rows, then the tensor-core GEMM with an fp32 epilogue (bias,
+    // ReLU).  `y` must have room for T rounded up to 128 rows; `ps` supplies the tile -> plane table the kernel's producer reads.
+    if (ps != nullptr && d.has_gemm && T >= c->linear_gemm_min && add_const == 0.f && ldy == d.out && ldx == d.in) {
+        const int t_pad = round_up(T, kBlockM);
+        void* pa;
+        TRY(ensure(c, "re.lin_a", (static_cast<size_t>(t_pad) + kBlockM) * c->ld(1024) * 2, "lin", &pa, st, true));
+        const long long work = static_cast<long long>(T) * (d.in / 8);
+        CU_TRY(c, launch_k(split_rows_kernel, dim3(grid_for(work, 256, c->num_sms)), dim3(256), 0, st, x, static_cast<__half*>(pa), T, d.in, c->split));
+        c->launches++;
+        ConvCall k{};
+        k.W = &d.gemm; k.A = static_cast<const __half*>(pa); k.a_rows = t_pad; k.a_cols = k.a_ld = c->ld(d.in); k.ps = ps;
+        k.tile_begin = 0; k.n_tiles = t_pad / kBlockM; k.a_row_delta = 0; k.out = y; k.ldc = ldy;
+        k.flags = kEpiOutF32 | (relu ? kEpiRelu : 0); k.name = "roienc.dense_gemm";
+        return run_conv(c, k, st);
+    }
     CU_TRY(c, launch_k(linear_kernel, dim3(ceil_div(T, 8), ceil_div(d.out, 64)), dim3(256), 0, st, x, ldx,
                        static_cast<const float*>(d.w), static_cast<const float*>(d.b), y, ldy, T, d.in, d.out, relu, add_const));
     c->launches++;
@@ -1378,16 +1417,16 @@ static int roi_encoder_codes(sylph_ctx* c, const Slot& S, int n_rois, int n_clas
     float* h = static_cast<float*>(ph);
     StageTimer t(c, "roienc.token_mlp", st, 0);
     for (const auto& d : c->re_tok_fc) {
-        TRY(run_linear(c, d, x, 256, y, 256, n_rois, 1, 0.f, st));
+        TRY(run_linear(c, d, x, 256, y, 256, n_rois, 1, 0.f, st, ps));
         std::swap(x, y);
     }
     // TransformerEncoder, sequence length 1 per class (see kernels_roi_encoder.cuh)
     for (const auto& L : c->re_enc) {
-        TRY(run_linear(c, L.attn, x, 256, xa, 256, n_rois, 0, 0.f, st));
+        TRY(run_linear(c, L.attn, x, 256, xa, 256, n_rois, 0, 0.f, st, ps));
         CU_TRY(c, launch_k(add_layernorm_kernel, dim3(ceil_div(n_rois, 8)), dim3(256), 0, st, static_cast<const float*>(x),
                            static_cast<const float*>(xa), static_cast<const float*>(L.n1w), static_cast<const float*>(L.n1b), y, n_rois));
-        TRY(run_linear(c, L.ff1, y, 256, h, 1024, n_rois, 1, 0.f, st));
-        TRY(run_linear(c, L.ff2, h, 1024, xa, 256, n_rois, 0, 0.f, st));
+        TRY(run_linear(c, L.ff1, y, 256, h, 1024, n_rois, 1, 0.f, st, ps));
+        TRY(run_linear(c, L.ff2, h, 1024, xa, 256, n_rois, 0, 0.f, st, ps));
         CU_TRY(c, launch_k(add_layernorm_kernel, dim3(ceil_div(n_rois, 8)), dim3(256), 0, st, static_cast<const float*>(y),
                            static_cast<const float*>(xa), static_cast<const float*>(L.n2w), static_cast<const float*>(L.n2b), x, n_rois));
         c->launches += 2;

@@ -319,6 +319,25 @@ linear_kernel(const float* __restrict__ x, int ldx, const float* __restrict__ W,
     }
 }
 
+// fp32 rows [T][K] -> fp16 operand rows for the tensor-core GEMM: [K hi | K lo] (exact mode) or [K] (fast mode); 8 values per thread.
+__global__ void __launch_bounds__(256)
+split_rows_kernel(const float* __restrict__ x, __half* __restrict__ out, int T, int K, int split) {
+    ptx::griddep_launch();
+    ptx::griddep_wait();
+    const int k8n = K / 8;
+    const long long total = static_cast<long long>(T) * k8n;
+    for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
+         i += static_cast<long long>(gridDim.x) * blockDim.x) {
+        const int k8 = static_cast<int>(i % k8n);
+        const long long t = i / k8n;
+        const float4 a = __ldg(reinterpret_cast<const float4*>(x + t * K + k8 * 8));
+        const float4 b = __ldg(reinterpret_cast<const float4*>(x + t * K + k8 * 8) + 1);
+        const float v[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+        __half* row = out + t * (split ? 2 * K : K);
+        store8f(row, k8 * 8, split ? K : 0, v, false);
+    }
+}
+
 // out[t] = LayerNorm(x[t] + r[t]) * g + b over 256 features (eps = 1e-5), one warp per token.
 __global__ void __launch_bounds__(256)
 add_layernorm_kernel(const float* __restrict__ x, const float* __restrict__ r, const float* __restrict__ g,

@@ -127,3 +127,32 @@ def test_roi_encoder_forward_on_foreign_nchw_features():
     ref = g["raw_codes"][0]
     assert rel_err(out["cls_conv"], ref["cls_conv"]) < RE_CODE_TOL
     assert abs(float(out["cls_bias"][0]) - float(ref["cls_bias"].reshape(-1)[0])) < TOL
+
+
+def test_roi_encoder_dense_layers_on_the_tensor_cores_match_the_golden(monkeypatch):
+    """Class sweeps (thousands of ROIs) run the tokenizer's fc layers and the transformer's folded attention / FFN as tensor-core
+    GEMMs (fp32 rows -> hi | lo fp16 rows, fp32 epilogue) instead of the CUDA-core kernel: forced on for the 6-ROI golden here
+    (SYLPH_LINEAR_GEMM_MIN=1), codes against the reference's own ROIEncoder at the same bar."""
+    from sylph_few_shot_detection_b200.runtime import SLOT_SUPPORT
+    monkeypatch.setenv("SYLPH_LINEAR_GEMM_MIN", "1")
+    g, cfg, state, model, orc = _setup()
+    eng = model.engine
+    images, boxes, offsets = [], [], [0]
+    for shots in g["support"]:
+        for s in shots:
+            images.append(s["image"].float())
+            boxes.append(s["box"])
+        offsets.append(len(images))
+    eng.extract_features(SLOT_SUPPORT, [im.cuda() for im in images])
+    l0 = eng.launch_count()
+    raw = eng.generate_codes(SLOT_SUPPORT, torch.stack(boxes), list(range(len(images))), offsets)
+    monkeypatch.delenv("SYLPH_LINEAR_GEMM_MIN")
+    _, _, _, model2, _ = _setup()
+    model2.engine.extract_features(SLOT_SUPPORT, [im.cuda() for im in images])
+    l1 = model2.engine.launch_count()
+    raw2 = model2.engine.generate_codes(SLOT_SUPPORT, torch.stack(boxes), list(range(len(images))), offsets)
+    assert eng.launch_count() - l0 > model2.engine.launch_count() - l1, "the GEMM path adds one row-split launch per dense layer"
+    for c, ref in enumerate(g["raw_codes"]):
+        assert rel_err(raw[c, :256], ref["cls_conv"].reshape(-1)) <= RE_CODE_TOL
+        assert abs(float(raw[c, 256]) - float(ref["cls_bias"].reshape(-1)[0])) <= TOL
+    assert rel_err(raw, raw2) < 1e-4

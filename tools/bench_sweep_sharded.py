@@ -33,6 +33,7 @@ def main():
     ap.add_argument("--pool", type=int, default=16)
     ap.add_argument("--generator", default="CodeGenerator", choices=["CodeGenerator", "ROIEncoder"])
     ap.add_argument("--out", default="")
+    ap.add_argument("--profile", action="store_true", help="per-stage breakdown of one sweep (CUDA events around every launch)")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
@@ -98,6 +99,19 @@ def main():
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return float(t)
 
+    if args.profile and rank == 0:
+        generate()
+        eng.set_profiling(True)
+        generate()
+        torch.cuda.synchronize()
+        agg = {}
+        for name, t_ms, fl, by in eng.timings():
+            a = agg.setdefault(name, [0, 0.0, 0.0])
+            a[0] += 1; a[1] += t_ms; a[2] += fl
+        eng.set_profiling(False)
+        for k, a in sorted(agg.items(), key=lambda kv: -kv[1][1]):
+            print(f"  {k:28s} launches {a[0]:3d}  {a[1]:8.3f} ms  {a[2] / max(a[1], 1e-9) * 1e-9:8.1f} TFLOP/s executed", file=sys.stderr)
+        print(f"  sum of timed stages {sum(a[1] for a in agg.values()):.3f} ms", file=sys.stderr)
     ms_gen = timed(generate)
     ms_nccl = timed(sweep_nccl)
     out = {"config": f"LVIS {n_cls}-class code-generation sweep ({args.generator}), {shots} shots = {n_cls * shots} ROIs over a pool "
