@@ -89,6 +89,7 @@ struct sylph_ctx {
     int pair1x1 = 1;          // SYLPH_PAIR1X1=0 keeps the single-CTA staged kernel for every 1x1 convolution; 2 = pair kernel
                               // for every staged 1x1 convolution with 256-channel N tiles and K >= 256 (experiments)
     int stem16 = 1;           // SYLPH_STEM16=0 runs the stem over 64-wide overlapped rows instead of K = 16 taps
+    int roi_stride = 81;      // rows per ROI plane: 81 = packed 9x9 planes (SYLPH_ROI_PACKED=0: one 128-row tile per ROI, 37 % more conv tiles)
     int linear_gemm_min = 512; // SYLPH_LINEAR_GEMM_MIN: dense layers of the ROIEncoder run as tensor-core GEMMs from this many rows on
     int cls_pooled = 1;       // SYLPH_CLS_POOLED=0: per-pixel cls convolution over the ROI planes, pooled afterwards (round-1 form)
     int sync_each = 0;        // SYLPH_SYNC_EACH=1: synchronise after every convolution launch and name the one that faults
@@ -863,6 +864,7 @@ int sylph_create(sylph_ctx** out, int device, const sylph_model_config* cfg) {
     if (const char* e = getenv("SYLPH_SYNC_EACH")) c->sync_each = atoi(e);
     if (const char* e = getenv("SYLPH_CLS_POOLED")) c->cls_pooled = atoi(e);
     if (const char* e = getenv("SYLPH_LINEAR_GEMM_MIN")) c->linear_gemm_min = atoi(e);
+    if (const char* e = getenv("SYLPH_ROI_PACKED")) c->roi_stride = atoi(e) ? 81 : 128;
     if (const char* e = getenv("SYLPH_ROI_ALIGN")) c->roi_separable = strcmp(e, "sample") == 0 ? 0 : 1;
     if (const char* e = getenv("SYLPH_PRECISION")) c->split = (strcmp(e, "fast") == 0 || strcmp(e, "0") == 0) ? 0 : 1;
     *out = c;
@@ -1327,6 +1329,23 @@ static int conv_gn_relu(sylph_ctx* c, const ConvW& W, const float* gn_w, const f
     return 0;
 }
 
+// conv3x3 (256 -> 256) + GroupNorm + ReLU over ROI planes (code-generator tower, ROIEncoder pool / tokenizer convolutions).  The
+// planes are packed at c->roi_stride rows, so the convolution runs over ceil(n_rois * stride / 128) tiles without per-tile
+// GroupNorm sums (a tile holds rows of several ROIs) and roi_gn_relu_kernel normalises the 49 interior pixels of every ROI.
+static int roi_conv_gn_relu(sylph_ctx* c, const ConvW& W, const float* gn_w, const float* gn_b, const __half* in, long long a_rows,
+                            float* raw, __half* out, const PlaneSet* ps, int n_rois, const char* name, cudaStream_t st) {
+    ConvCall k{};
+    k.W = &W; k.A = in; k.a_rows = a_rows; k.a_cols = k.a_ld = c->ld(256); k.ps = ps; k.tile_begin = 0;
+    k.n_tiles = static_cast<int>((static_cast<long long>(n_rois) * c->roi_stride + kBlockM - 1) / kBlockM);
+    k.a_row_delta = 0; k.out = raw; k.ldc = 256; k.flags = kEpiOutF32; k.name = name;
+    TRY(run_conv(c, k, st));
+    StageTimer t(c, "roi_gn_relu", st, static_cast<double>(n_rois) * 49 * 256 * (4 + (c->split ? 4 : 2)));
+    CU_TRY(c, launch_k(roi_gn_relu_kernel, dim3(n_rois), dim3(256), 0, st, static_cast<const float*>(raw), out, gn_w, gn_b, c->split, c->roi_stride));
+    CU_TRY(c, cudaGetLastError());
+    c->launches++;
+    return 0;
+}
+
 static int run_conv(sylph_ctx* c, const ConvCall& k, cudaStream_t st);
 
 static int run_linear(sylph_ctx* c, const sylph_ctx::Dense& d, const float* x, int ldx, float* y, int ldy, int T, int relu,
@@ -1359,7 +1378,7 @@ static int roi_encoder_codes(sylph_ctx* c, const Slot& S, int n_rois, int n_clas
                              const int* d_class_off, const PlaneSet* ps, __half* r0, __half* r1, __half* r2, float* raw,
                              float* gp, float* gs, float* codes_out_dev, cudaStream_t st) {
     const sylph_model_config& f = c->cfg;
-    const long long rows = static_cast<long long>(n_rois) * 128;
+    const long long rows = round_up(static_cast<int>(static_cast<long long>(n_rois) * c->roi_stride), kBlockM);
     const int t_pad = round_up(n_rois, kBlockM);
     void *pctx, *ptok, *px0, *px1, *pxa, *ph, *pcls, *phd;
     TRY(ensure(c, "re.ctx", static_cast<size_t>(S.n) * 49 * 256 * 4, "", &pctx, st, false));
@@ -1371,8 +1390,7 @@ static int roi_encoder_codes(sylph_ctx* c, const Slot& S, int n_rois, int n_clas
     TRY(ensure(c, "re.cls", static_cast<size_t>(n_classes) * 256 * 4, "", &pcls, st, false));
     TRY(ensure(c, "re.hd", static_cast<size_t>(n_classes) * 1024 * 4 * 2, "", &phd, st, false));
     // FeatureFusionModuleV2: conv3x3 + GN + ReLU on the pooled features, then the MS_CAM context gate
-    TRY(conv_gn_relu(c, c->re_pool_conv, c->re_pool_gn_w, c->re_pool_gn_b, r0, rows, raw, r1, ps, 0, n_rois, 0, n_rois, gp, gs,
-                     "roienc.pool_conv3x3", st));
+    TRY(roi_conv_gn_relu(c, c->re_pool_conv, c->re_pool_gn_w, c->re_pool_gn_b, r0, rows, raw, r1, ps, n_rois, "roienc.pool_conv3x3", st));
     {
         StageTimer t(c, "roienc.context_pool", st, static_cast<double>(S.n) * 22400 * 256 * 2);
         CU_TRY(c, launch_k(context_pool_kernel, dim3(S.n, 49), dim3(256), 0, st, static_cast<const __half*>(S.pyr), S.pg,
@@ -1387,22 +1405,21 @@ static int roi_encoder_codes(sylph_ctx* c, const Slot& S, int n_rois, int n_clas
         StageTimer t(c, "roienc.ms_cam", st, static_cast<double>(n_rois) * 49 * 256 * (c->split ? 8 : 4) + static_cast<double>(S.n) * 49 * 256 * 8);
         CU_TRY(c, launch_k(ms_cam_gate_kernel, dim3(S.n), dim3(256), static_cast<size_t>(kMsCamSmem), st,
                            static_cast<const float*>(pctx), c->re_cam, static_cast<float*>(pgate)));
-        CU_TRY(c, launch_k(ms_cam_apply_kernel, dim3(grid_for(static_cast<long long>(n_rois) * 128 * 32, 256, c->num_sms)), dim3(256), 0, st,
-                           static_cast<const float*>(pgate), d_roi_image, static_cast<const __half*>(r1), r2, n_rois, c->split));
+        CU_TRY(c, launch_k(ms_cam_apply_kernel, dim3(grid_for(static_cast<long long>(n_rois) * c->roi_stride * 32, 256, c->num_sms)), dim3(256), 0, st,
+                           static_cast<const float*>(pgate), d_roi_image, static_cast<const __half*>(r1), r2, n_rois, c->split, c->roi_stride));
         c->launches += 2;
     }
     // Tokenizer: NUM_CONV x (conv3x3 + GN + ReLU), flatten, fc1 (tensor-core GEMM over K = 12544), fc2.. (+ ReLU)
     __half* cur = r2;
     __half* nxt = r0;
     for (int i = 0; i < f.re_tok_convs; ++i) {
-        TRY(conv_gn_relu(c, c->re_tok_conv[i], c->re_tok_gn_w[i], c->re_tok_gn_b[i], cur, rows, raw, nxt, ps, 0, n_rois, 0,
-                         n_rois, gp, gs, "roienc.tok_conv3x3", st));
+        TRY(roi_conv_gn_relu(c, c->re_tok_conv[i], c->re_tok_gn_w[i], c->re_tok_gn_b[i], cur, rows, raw, nxt, ps, n_rois, "roienc.tok_conv3x3", st));
         __half* done = cur;
         cur = nxt;
         nxt = (done == r2) ? r1 : done;
     }
     CU_TRY(c, launch_k(gather_tokens_kernel, dim3(grid_for(static_cast<long long>(n_rois) * 49 * 32, 256, c->num_sms)), dim3(256),
-                       0, st, static_cast<const __half*>(cur), static_cast<__half*>(ptok), n_rois, c->split));
+                       0, st, static_cast<const __half*>(cur), static_cast<__half*>(ptok), n_rois, c->split, c->roi_stride));
     c->launches++;
     {
         ConvCall k{};
@@ -1676,7 +1693,7 @@ int sylph_generate_codes(sylph_ctx* c, int slot, int n_rois, const float* boxes_
     CU_TRY(c, cudaSetDevice(c->device));
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     const sylph_model_config& f = c->cfg;
-    const long long rows = static_cast<long long>(n_rois) * 128;
+    const long long rows = round_up(static_cast<int>(static_cast<long long>(n_rois) * c->roi_stride), kBlockM);   // ROI planes, packed
     void *pb, *pi, *po, *r0, *r1, *r2, *rawp, *gp, *gs, *sc;
     TRY(ensure(c, "cg.boxes", n_rois * 16, "", &pb, st, false));
     TRY(ensure(c, "cg.roi_image", n_rois * 4, "", &pi, st, false));
@@ -1714,10 +1731,10 @@ int sylph_generate_codes(sylph_ctx* c, int slot, int n_rois, const float* boxes_
             const size_t smem = static_cast<size_t>(14) * span * sizeof(float);
             CU_TRY(c, launch_k(roi_align_separable_kernel, dim3(n_rois), dim3(256), smem, st, static_cast<const __half*>(S.pyr), S.pg,
                                static_cast<const float*>(pb), static_cast<const int*>(pi), static_cast<__half*>(r0),
-                               reinterpret_cast<long long*>(levels_out_dev), c->split, span));
+                               reinterpret_cast<long long*>(levels_out_dev), c->split, span, c->roi_stride));
         } else {
             CU_TRY(c, launch_k(roi_align_kernel, dim3(n_rois, 7), dim3(256), 0, st, S.pyr, S.pg, static_cast<const float*>(pb), static_cast<const int*>(pi),
-                                                             static_cast<__half*>(r0), reinterpret_cast<long long*>(levels_out_dev), c->split));
+                                                             static_cast<__half*>(r0), reinterpret_cast<long long*>(levels_out_dev), c->split, c->roi_stride));
         }
         CU_TRY(c, cudaGetLastError());
         c->launches++;
@@ -1731,8 +1748,7 @@ int sylph_generate_codes(sylph_ctx* c, int slot, int n_rois, const float* boxes_
     __half* nxt = static_cast<__half*>(r1);
     float* raw = static_cast<float*>(rawp);
     for (int i = 0; i < f.cg_tower_layers; ++i) {
-        TRY(conv_gn_relu(c, c->cg_tower[i], c->cg_gn_w[i], c->cg_gn_b[i], cur, rows, raw, nxt, ps.get(), 0, n_rois, 0, n_rois,
-                         static_cast<float*>(gp), static_cast<float*>(gs), "codegen.tower3x3", st));
+        TRY(roi_conv_gn_relu(c, c->cg_tower[i], c->cg_gn_w[i], c->cg_gn_b[i], cur, rows, raw, nxt, ps.get(), n_rois, "codegen.tower3x3", st));
         cur = nxt;
         nxt = (cur == r1) ? static_cast<__half*>(r2) : static_cast<__half*>(r1);
     }
@@ -1746,7 +1762,7 @@ int sylph_generate_codes(sylph_ctx* c, int slot, int n_rois, const float* boxes_
         TRY(ensure(c, "cg.pooled", static_cast<size_t>(t_pad + kBlockM) * 256 * 4, "", &pp, st, false));
         {
             StageTimer t(c, "codegen.window_means", st, static_cast<double>(n_rois) * (49.0 * 256 + 2304) * (c->split ? 4 : 2));
-            CU_TRY(c, launch_k(roi_window_means_kernel, dim3(n_rois), dim3(256), 0, st, static_cast<const __half*>(cur), static_cast<__half*>(pw), c->split));
+            CU_TRY(c, launch_k(roi_window_means_kernel, dim3(n_rois), dim3(256), 0, st, static_cast<const __half*>(cur), static_cast<__half*>(pw), c->split, c->roi_stride));
             CU_TRY(c, cudaGetLastError());
             c->launches++;
         }
@@ -1759,13 +1775,13 @@ int sylph_generate_codes(sylph_ctx* c, int slot, int n_rois, const float* boxes_
     } else {
         ConvCall k{};
         k.W = &c->cg_cls; k.A = cur; k.a_rows = rows; k.a_cols = k.a_ld = c->ld(256); k.ps = ps.get(); k.tile_begin = 0;
-        k.n_tiles = n_rois; k.a_row_delta = 0; k.out = raw; k.ldc = 256; k.flags = kEpiOutF32; k.name = "codegen.cls_conv3x3";
+        k.n_tiles = static_cast<int>(rows / kBlockM); k.a_row_delta = 0; k.out = raw; k.ldc = 256; k.flags = kEpiOutF32; k.name = "codegen.cls_conv3x3";
         TRY(run_conv(c, k, st));
     }
     {
         StageTimer t(c, "codegen.tail", st, static_cast<double>(n_rois) * 2 * 49 * 256 * 4);
         CU_TRY(c, launch_k(shot_code_kernel, dim3(n_rois), dim3(256), 0, st, raw, cur, c->cg_wbias, c->cg_bbias, f.cg_bias_layer, f.cg_bias_l2_norm,
-                                                 static_cast<float*>(sc), c->split, pooled));
+                                                 static_cast<float*>(sc), c->split, pooled, c->roi_stride));
         CU_TRY(c, cudaGetLastError());
         CU_TRY(c, launch_k(class_mean_kernel, dim3(n_classes), dim3(288), 0, st, static_cast<const float*>(sc), static_cast<const int*>(po), codes_out_dev));
         CU_TRY(c, cudaGetLastError());
@@ -1779,7 +1795,7 @@ int sylph_export_roi_features(sylph_ctx* c, float* out_dev, void* stream) {
     if (c->last_n_rois <= 0) return c->fail("no ROI features: call sylph_generate_codes first");
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     CU_TRY(c, launch_k(export_roi_kernel, dim3(grid_for(static_cast<long long>(c->last_n_rois) * 256 * 49, 256, c->num_sms)), dim3(256), 0, st, 
-        static_cast<const __half*>(c->bufs["cg.r0"].p), out_dev, c->last_n_rois, c->split));
+        static_cast<const __half*>(c->bufs["cg.r0"].p), out_dev, c->last_n_rois, c->split, c->roi_stride));
     CU_TRY(c, cudaGetLastError());
     c->launches++;
     return 0;

@@ -51,7 +51,7 @@ __device__ __forceinline__ float bilinear_tap(const __half* __restrict__ feat, c
 __global__ void __launch_bounds__(256)
 roi_align_kernel(const __half* __restrict__ pyramid, PyramidGeom pg, const float* __restrict__ boxes,
                  const int* __restrict__ roi_image, __half* __restrict__ roi_planes, long long* __restrict__ levels_out,
-                 int split) {
+                 int split, int roi_stride) {
     ptx::griddep_launch();
     ptx::griddep_wait();
     const int roi = blockIdx.x, ph = blockIdx.y, c = threadIdx.x;
@@ -79,7 +79,7 @@ roi_align_kernel(const __half* __restrict__ pyramid, PyramidGeom pg, const float
                 acc += bilinear_tap(pyramid, g, n, g.H, g.W, y, x, c, split ? 512 : 256, split ? 256 : 0);
             }
         }
-        const size_t row = static_cast<size_t>(roi) * 128 + (ph + 1) * 9 + (pw + 1);
+        const size_t row = static_cast<size_t>(roi) * roi_stride + (ph + 1) * 9 + (pw + 1);
         const float v = fminf(fmaxf(acc / count, -kHalfMax), kHalfMax);
         const __half h = __float2half_rn(v);
         if (split) {
@@ -106,7 +106,7 @@ constexpr int kRoiSepMaxSpan = 512;   // footprint rows / columns the separable 
 __global__ void __launch_bounds__(256, 2)
 roi_align_separable_kernel(const __half* __restrict__ pyramid, PyramidGeom pg, const float* __restrict__ boxes,
                            const int* __restrict__ roi_image, __half* __restrict__ roi_planes,
-                           long long* __restrict__ levels_out, int split, int span_cap) {
+                           long long* __restrict__ levels_out, int split, int span_cap, int roi_stride) {
     ptx::griddep_launch();
     ptx::griddep_wait();
     extern __shared__ float roi_w[];
@@ -203,9 +203,51 @@ roi_align_separable_kernel(const __half* __restrict__ pyramid, PyramidGeom pg, c
             float o[8];
 #pragma unroll
             for (int j = 0; j < 8; ++j) o[j] = fminf(fmaxf(acc[pw][j], -kHalfMax), kHalfMax);
-            const size_t row = static_cast<size_t>(roi) * 128 + (ph + 1) * 9 + (pw + 1);
+            const size_t row = static_cast<size_t>(roi) * roi_stride + (ph + 1) * 9 + (pw + 1);
             store8f(roi_planes + row * ld, cg * 8, lo_off, o, false);
         }
+    }
+}
+
+// GroupNorm(32, 256) + ReLU over the 7x7 interior of every ROI plane of a raw (fp32) convolution output, written as the fp16
+// (hi | lo) operand plane of the next layer.  One block per ROI, one channel per thread: a group is 8 consecutive lanes.  The ROI
+// planes are PACKED (roi_stride = 81 rows, no alignment to the 128-row tiles), so a convolution tile holds rows of 2-3 ROIs and
+// the per-tile GroupNorm partial sums of the big planes do not apply; 49 x 256 values per ROI need no partials anyway.
+// Two-pass statistics in fp32 (reference: torch.nn.GroupNorm, eps 1e-5, biased variance).  Border rows are never written: they
+// stay zero from the allocation.   grid = n_rois, block = 256.
+__global__ void __launch_bounds__(256)
+roi_gn_relu_kernel(const float* __restrict__ raw, __half* __restrict__ out, const float* __restrict__ gamma,
+                   const float* __restrict__ beta, int split, int roi_stride) {
+    ptx::griddep_launch();
+    ptx::griddep_wait();
+    const int roi = blockIdx.x, t = threadIdx.x;
+    const float* base = raw + static_cast<size_t>(roi) * roi_stride * 256;
+    float v[49];
+    float s = 0.f;
+#pragma unroll
+    for (int p = 0; p < 49; ++p) {
+        v[p] = base[static_cast<size_t>((p / 7 + 1) * 9 + (p % 7 + 1)) * 256 + t];
+        s += v[p];
+    }
+#pragma unroll
+    for (int o = 1; o < 8; o <<= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    const float mean = s / 392.f;
+    float q = 0.f;
+#pragma unroll
+    for (int p = 0; p < 49; ++p) { const float d = v[p] - mean; q += d * d; }
+#pragma unroll
+    for (int o = 1; o < 8; o <<= 1) q += __shfl_xor_sync(0xffffffffu, q, o);
+    const float rstd = rsqrtf(q / 392.f + 1e-5f);
+    const float g = gamma[t] * rstd, b = beta[t] - mean * g;
+    const int ld = split ? 512 : 256;
+    __half* ob = out + static_cast<size_t>(roi) * roi_stride * ld;
+#pragma unroll
+    for (int p = 0; p < 49; ++p) {
+        const float y = fminf(fmaxf(v[p] * g + b, 0.f), kHalfMax);
+        const __half hi = __float2half_rn(y);
+        __half* o = ob + static_cast<size_t>((p / 7 + 1) * 9 + (p % 7 + 1)) * ld;
+        o[t] = hi;
+        if (split) o[256 + t] = __float2half_rn(y - __half2float(hi));
     }
 }
 
@@ -216,12 +258,13 @@ roi_align_separable_kernel(const __half* __restrict__ pyramid, PyramidGeom pg, c
 // 9 x 256 values (hi | lo halves in exact mode); the convolution becomes a [n_rois x 2304] x [2304 x 256] GEMM -- 1 / 128 of the
 // tensor work of the per-pixel convolution over 128-row ROI tiles.   grid = n_rois, block = 256 (one channel per thread).
 __global__ void __launch_bounds__(256)
-roi_window_means_kernel(const __half* __restrict__ tower_out, __half* __restrict__ win /* [rows][9 * 256 (x2)] */, int split) {
+roi_window_means_kernel(const __half* __restrict__ tower_out, __half* __restrict__ win /* [rows][9 * 256 (x2)] */, int split,
+                        int roi_stride) {
     ptx::griddep_launch();
     ptx::griddep_wait();
     const int roi = blockIdx.x, t = threadIdx.x;
     const int ld = split ? 512 : 256;
-    const __half* base = tower_out + static_cast<size_t>(roi) * 128 * ld;
+    const __half* base = tower_out + static_cast<size_t>(roi) * roi_stride * ld;
     float s[9];
 #pragma unroll
     for (int k = 0; k < 9; ++k) s[k] = 0.f;
@@ -256,12 +299,13 @@ __global__ void __launch_bounds__(256)
 shot_code_kernel(const float* __restrict__ cls_raw, const __half* __restrict__ tower_out,
                  const float* __restrict__ w_bias /* [9][256] tap-major */, const float* __restrict__ b_bias,
                  int has_bias_layer, int bias_l2_norm, float* __restrict__ shot_codes /* [n_rois][257] */, int split,
-                 const float* __restrict__ cls_pooled = nullptr /* [n_rois][256]: the pooled cls-conv output (pool-before-conv path) */) {
+                 const float* __restrict__ cls_pooled = nullptr /* [n_rois][256]: the pooled cls-conv output (pool-before-conv path) */,
+                 int roi_stride = 128) {
     ptx::griddep_launch();
     ptx::griddep_wait();
     __shared__ float pix[49];
     const int roi = blockIdx.x, t = threadIdx.x, warp = t >> 5, lane = t & 31;
-    const size_t base = static_cast<size_t>(roi) * 128;
+    const size_t base = static_cast<size_t>(roi) * roi_stride;
     if (cls_pooled != nullptr) {
         shot_codes[static_cast<size_t>(roi) * 257 + t] = cls_pooled[static_cast<size_t>(roi) * 256 + t];
     } else {
@@ -549,7 +593,8 @@ __global__ void pack_code_weights_kernel(const float* __restrict__ codes, int n_
 }
 
 // (n_rois, 256, 7, 7) export of the pooled ROI planes (tests / plugin interop).
-__global__ void export_roi_kernel(const __half* __restrict__ roi_planes, float* __restrict__ out, int n_rois, int split) {
+__global__ void export_roi_kernel(const __half* __restrict__ roi_planes, float* __restrict__ out, int n_rois, int split,
+                                  int roi_stride) {
     ptx::griddep_launch();
     ptx::griddep_wait();
     const long long total = static_cast<long long>(n_rois) * 256 * 49;
@@ -558,7 +603,7 @@ __global__ void export_roi_kernel(const __half* __restrict__ roi_planes, float* 
         const int p = static_cast<int>(i % 49);
         const int c = static_cast<int>((i / 49) % 256);
         const int r = static_cast<int>(i / (49 * 256));
-        const size_t row = static_cast<size_t>(r) * 128 + (p / 7 + 1) * 9 + (p % 7 + 1);
+        const size_t row = static_cast<size_t>(r) * roi_stride + (p / 7 + 1) * 9 + (p % 7 + 1);
         out[i] = split ? __half2float(roi_planes[row * 512 + c]) + __half2float(roi_planes[row * 512 + 256 + c])
                        : __half2float(roi_planes[row * 256 + c]);
     }

@@ -225,16 +225,16 @@ ms_cam_gate_kernel(const float* __restrict__ ctx, MsCamWeights w, float* __restr
 // per thread.  (FeatureFusionModuleV2.forward, sylph/modeling/code_generator/utils.py:153-165.)
 __global__ void __launch_bounds__(256)
 ms_cam_apply_kernel(const float* __restrict__ gate, const int* __restrict__ roi_image, const __half* __restrict__ pooled,
-                    __half* __restrict__ out, int n_rois, int split) {
+                    __half* __restrict__ out, int n_rois, int split, int roi_stride) {
     ptx::griddep_launch();
     ptx::griddep_wait();
     const int ld = split ? 512 : 256, lo = split ? 256 : 0;
-    const long long total = static_cast<long long>(n_rois) * 128 * 32;
+    const long long total = static_cast<long long>(n_rois) * roi_stride * 32;
     for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
          i += static_cast<long long>(gridDim.x) * blockDim.x) {
         const int c8 = static_cast<int>(i & 31);
         const long long row = i >> 5;
-        const int roi = static_cast<int>(row >> 7), r = static_cast<int>(row & 127);
+        const int roi = static_cast<int>(row / roi_stride), r = static_cast<int>(row - static_cast<long long>(roi) * roi_stride);
         const int y = r / 9, x = r - y * 9;
         float v[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
         if (r < 81 && y >= 1 && y <= 7 && x >= 1 && x <= 7) {
@@ -250,7 +250,8 @@ ms_cam_apply_kernel(const float* __restrict__ gate, const int* __restrict__ roi_
 // ------------------------------------------------------------------------------------------------ tokens
 // planes [n][128 rows][256] -> A[n][p * 256 + c] (p = 7 * y + x); one uint4 (8 channels) per thread.
 // split mode: planes rows are [256 hi | 256 lo], token rows [12544 hi | 12544 lo].
-__global__ void gather_tokens_kernel(const __half* __restrict__ planes, __half* __restrict__ tokens, int n_rois, int split) {
+__global__ void gather_tokens_kernel(const __half* __restrict__ planes, __half* __restrict__ tokens, int n_rois, int split,
+                                     int roi_stride) {
     ptx::griddep_launch();
     ptx::griddep_wait();
     const long long total = static_cast<long long>(n_rois) * 49 * 32;
@@ -264,7 +265,7 @@ __global__ void gather_tokens_kernel(const __half* __restrict__ planes, __half* 
             const long long n = j / (49 * 32);
             const int row = (p / 7 + 1) * 9 + (p % 7 + 1);
             reinterpret_cast<uint4*>(tokens + n * 25088 + half_idx * 12544)[p * 32 + v] =
-                __ldg(reinterpret_cast<const uint4*>(planes + (n * 128 + row) * 512 + half_idx * 256) + v);
+                __ldg(reinterpret_cast<const uint4*>(planes + (n * roi_stride + row) * 512 + half_idx * 256) + v);
         }
         return;
     }
@@ -274,7 +275,7 @@ __global__ void gather_tokens_kernel(const __half* __restrict__ planes, __half* 
         const int p = static_cast<int>((i >> 5) % 49);
         const long long n = i / (49 * 32);
         const int row = (p / 7 + 1) * 9 + (p % 7 + 1);
-        reinterpret_cast<uint4*>(tokens)[i] = __ldg(reinterpret_cast<const uint4*>(planes + (n * 128 + row) * 256) + v);
+        reinterpret_cast<uint4*>(tokens)[i] = __ldg(reinterpret_cast<const uint4*>(planes + (n * roi_stride + row) * 256) + v);
     }
 }
 
