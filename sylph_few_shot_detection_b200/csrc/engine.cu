@@ -1162,7 +1162,9 @@ static int run_trunk(sylph_ctx* c, const std::string& key, int n, const void* co
                 StageTimer t(c, s == 0 ? "maxpool3x3s2" : "subsample2", st,
                              static_cast<double>(n) * g.H * g.W * in_ch * 2 * (s == 0 ? 5.0 : 2.0));
                 const long long work = static_cast<long long>(n) * g.H * g.W * (in_ch / 8);
-                if (s == 0) CU_TRY(c, launch_k(maxpool3x3s2_kernel, dim3(grid_for(work, 256, c->num_sms)), dim3(256), 0, st, S1, IN, g0, g, n, in_ch, c->lo(in_ch)));
+                // split mode: a thread walks a strip of 8 output rows (kernels_misc.cuh)
+                const long long work_mp = c->split ? static_cast<long long>(n) * ((g.H + 7) / 8) * g.W * (in_ch / 8) : work;
+                if (s == 0) CU_TRY(c, launch_k(maxpool3x3s2_kernel, dim3(grid_for(work_mp, 256, c->num_sms)), dim3(256), 0, st, S1, IN, g0, g, n, in_ch, c->lo(in_ch)));
                 else CU_TRY(c, launch_k(subsample2_kernel, dim3(grid_for(work * (c->split ? 2 : 1), 256, c->num_sms)), dim3(256), 0, st, X, IN, gs[s - 1], g, n, c->ld(in_ch)));
                 CU_TRY(c, cudaGetLastError());
                 c->launches++;

@@ -286,7 +286,7 @@ prep_stem_centred_u8_kernel(const ImageDesc* __restrict__ imgs, __half* __restri
     ptx::griddep_launch();
     __shared__ unsigned short lut[3][256];
     __shared__ unsigned short padv[3];
-    __shared__ __align__(16) unsigned char rows[6][528];
+    __shared__ __align__(16) unsigned char rows[2][6][528];   // double-buffered: the loads of segment i + 1 fly while i is converted
     for (int i = threadIdx.x; i < 768; i += 256) {
         const int c = i >> 8, v = i & 255;
         lut[c][v] = static_cast<unsigned short>(pack_half2((static_cast<float>(v) - cp.m_r[c]) * (1.f / 256.f), 0.f) & 0xFFFFu);
@@ -294,46 +294,73 @@ prep_stem_centred_u8_kernel(const ImageDesc* __restrict__ imgs, __half* __restri
     if (threadIdx.x < 3) padv[threadIdx.x] = static_cast<unsigned short>(pack_half2(cp.pad[threadIdx.x], 0.f) & 0xFFFFu);
     ptx::griddep_wait();
     const int x0 = blockIdx.x * 256;
+    const int px0 = 2 * x0;                           // first input pixel of this block's 512-pixel segment
     const int n_rows = n_images * g.H;
-    for (int ry = blockIdx.y; ry < n_rows; ry += gridDim.y) {
+    // input row r (0..5 = channel r / 2, image row 2 y2 + (r & 1)) of work item ry: aligned word range and byte shift
+    auto row_span = [&](int ry, int r, size_t& a4, int& shift, int& nwords, size_t& lo_b, size_t& hi_b) {
         const int n = ry / g.H, y2 = ry - n * g.H;
         const ImageDesc im = imgs[n];
-        const unsigned char* base = static_cast<const unsigned char*>(im.ptr);
-        const size_t img_bytes = static_cast<size_t>(3) * im.h * im.w;
-        const int px0 = 2 * x0;
+        const int c = r >> 1, iy = 2 * y2 + (r & 1);
         const int npx = min(512, im.w - px0);
-        __syncthreads();
-        int shift[6];
+        nwords = 0; shift = 0; a4 = 0;
+        lo_b = reinterpret_cast<size_t>(im.ptr);
+        hi_b = lo_b + static_cast<size_t>(3) * im.h * im.w;
+        if (iy < im.h && npx > 0) {
+            const size_t a = lo_b + (static_cast<size_t>(c) * im.h + iy) * im.w + px0;
+            a4 = a & ~static_cast<size_t>(3);
+            shift = static_cast<int>(a - a4);
+            nwords = (shift + npx + 3) >> 2;
+        }
+    };
+    // every row has at most (3 + 512 + 3) / 4 = 130 words: thread t < 130 carries word t of each of the six rows
+    auto fetch = [&](int ry, uint32_t* w) {
 #pragma unroll
         for (int r = 0; r < 6; ++r) {
-            const int c = r >> 1, iy = 2 * y2 + (r & 1);
-            shift[r] = 0;
-            if (iy < im.h && npx > 0) {
-                const size_t a = (static_cast<size_t>(c) * im.h + iy) * im.w + px0;
-                const size_t a4 = (reinterpret_cast<size_t>(base) + a) & ~static_cast<size_t>(3);
-                shift[r] = static_cast<int>(reinterpret_cast<size_t>(base) + a - a4);
-                const int nwords = (shift[r] + npx + 3) >> 2;
-                const size_t lo = reinterpret_cast<size_t>(base), hi = lo + img_bytes;
-                for (int wd = threadIdx.x; wd < nwords; wd += 256) {
-                    const size_t wa = a4 + 4 * static_cast<size_t>(wd);
-                    uint32_t word;
-                    if (wa >= lo && wa + 4 <= hi) {
-                        word = __ldg(reinterpret_cast<const uint32_t*>(wa));
-                    } else {
-                        word = 0;
-                        for (int b = 0; b < 4; ++b) {
-                            const size_t ba = wa + b;
-                            if (ba >= lo && ba < hi)
-                                word |= static_cast<uint32_t>(__ldg(reinterpret_cast<const unsigned char*>(ba))) << (8 * b);
-                        }
+            size_t a4, lo_b, hi_b;
+            int shift, nwords;
+            row_span(ry, r, a4, shift, nwords, lo_b, hi_b);
+            w[r] = 0;
+            if (static_cast<int>(threadIdx.x) < nwords) {
+                const size_t wa = a4 + 4 * static_cast<size_t>(threadIdx.x);
+                if (wa >= lo_b && wa + 4 <= hi_b) {
+                    w[r] = __ldg(reinterpret_cast<const uint32_t*>(wa));
+                } else {   // the aligned word straddles an end of the image tensor: byte loads of what exists
+                    for (int b = 0; b < 4; ++b) {
+                        const size_t ba = wa + b;
+                        if (ba >= lo_b && ba < hi_b)
+                            w[r] |= static_cast<uint32_t>(__ldg(reinterpret_cast<const unsigned char*>(ba))) << (8 * b);
                     }
-                    *reinterpret_cast<uint32_t*>(&rows[r][4 * wd]) = word;
                 }
             }
         }
-        __syncthreads();
+    };
+    auto stash = [&](int buf, const uint32_t* w) {
+        if (threadIdx.x < 132) {
+#pragma unroll
+            for (int r = 0; r < 6; ++r) *reinterpret_cast<uint32_t*>(&rows[buf][r][4 * threadIdx.x]) = w[r];
+        }
+    };
+    int cur = 0;
+    uint32_t w[6];
+    if (static_cast<int>(blockIdx.y) < n_rows) {
+        fetch(blockIdx.y, w);
+        stash(0, w);
+    }
+    __syncthreads();
+    for (int ry = blockIdx.y; ry < n_rows; ry += gridDim.y) {
+        const int nxt = ry + gridDim.y;
+        if (nxt < n_rows) fetch(nxt, w);              // global loads in flight during the conversion below
+        const int n = ry / g.H, y2 = ry - n * g.H;
+        const ImageDesc im = imgs[n];
         const int x2 = x0 + threadIdx.x;
         if (x2 < g.W) {
+            int shift[6];
+#pragma unroll
+            for (int r = 0; r < 6; ++r) {
+                size_t a4, lo_b, hi_b;
+                int nwords;
+                row_span(ry, r, a4, shift[r], nwords, lo_b, hi_b);
+            }
             unsigned short h[12];
 #pragma unroll
             for (int dy = 0; dy < 2; ++dy)
@@ -344,7 +371,7 @@ prep_stem_centred_u8_kernel(const ImageDesc* __restrict__ imgs, __half* __restri
 #pragma unroll
                     for (int c = 0; c < 3; ++c) {
                         const int r = c * 2 + dy;
-                        const int px = in ? rows[r][shift[r] + 2 * threadIdx.x + dx] : 0;
+                        const int px = in ? rows[cur][r][shift[r] + 2 * threadIdx.x + dx] : 0;
                         h[(dy * 2 + dx) * 3 + c] = in ? lut[c][px] : padv[c];
                     }
                 }
@@ -354,6 +381,9 @@ prep_stem_centred_u8_kernel(const ImageDesc* __restrict__ imgs, __half* __restri
             o[1] = make_uint4(pk(h[8], h[9]), pk(h[10], h[11]), 0u, 0u);
             if (zero_lo) { o[2] = make_uint4(0u, 0u, 0u, 0u); o[3] = make_uint4(0u, 0u, 0u, 0u); }
         }
+        if (nxt < n_rows) stash(cur ^ 1, w);          // the other buffer: its readers finished before the previous barrier
+        __syncthreads();
+        cur ^= 1;
     }
     const long long tid = (static_cast<long long>(blockIdx.y) * gridDim.x + blockIdx.x) * blockDim.x + threadIdx.x;
     write_ring_pixels(out, g, n_images, cp, tid, static_cast<long long>(gridDim.x) * gridDim.y * blockDim.x);
@@ -369,30 +399,50 @@ __global__ void maxpool3x3s2_kernel(const __half* __restrict__ in, __half* __res
     ptx::griddep_wait();
     const int c8n = C / 8;
     if (lo) {
+        // a thread walks a strip of kStrip output rows of one (column, 8-channel group): the horizontal 3-tap maximum of input row
+        // 2 oy + 1 is also the first row of output oy + 1, so an output costs 6 taps (12 loads) instead of 9 (18)
+        constexpr int kStrip = 8;
         const int ld = 2 * C;
-        const long long total = static_cast<long long>(n_images) * go.H * go.W * c8n;
+        const int strips = (go.H + kStrip - 1) / kStrip;
+        const long long total = static_cast<long long>(n_images) * strips * go.W * c8n;
+        auto rowmax = [&](int n, int iy, int ox, int c8, float* m) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) m[j] = 0.f;
+            if (iy >= gi.H + gi.pad) return;
+#pragma unroll
+            for (int kx = 0; kx < 3; ++kx) {
+                const int ix = 2 * ox - 1 + kx;
+                if (ix < gi.W + gi.pad) {
+                    float v[8];
+                    load8f(in + plane_row(gi, n, iy, ix) * ld, c8 * 8, lo, v);
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) m[j] = fmaxf(m[j], v[j]);
+                }
+            }
+        };
         for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
              i += static_cast<long long>(gridDim.x) * blockDim.x) {
             const int c8 = static_cast<int>(i % c8n);
             long long r = i / c8n;
             const int ox = static_cast<int>(r % go.W);
             r /= go.W;
-            const int oy = static_cast<int>(r % go.H);
-            const int n = static_cast<int>(r / go.H);
-            float m[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+            const int oy0 = static_cast<int>(r % strips) * kStrip;
+            const int n = static_cast<int>(r / strips);
+            float carry[8];
+            rowmax(n, 2 * oy0 - 1, ox, c8, carry);   // row -1 of the first strip is the zero border
+            for (int k = 0; k < kStrip; ++k) {
+                const int oy = oy0 + k;
+                if (oy >= go.H) break;
+                float a[8], b[8];
+                rowmax(n, 2 * oy, ox, c8, a);
+                rowmax(n, 2 * oy + 1, ox, c8, b);
+                float m[8];
 #pragma unroll
-            for (int ky = 0; ky < 3; ++ky)
+                for (int j = 0; j < 8; ++j) m[j] = fmaxf(fmaxf(carry[j], a[j]), b[j]);
+                store8f(out + plane_row(go, n, oy, ox) * ld, c8 * 8, lo, m, false);
 #pragma unroll
-                for (int kx = 0; kx < 3; ++kx) {
-                    const int iy = 2 * oy - 1 + ky, ix = 2 * ox - 1 + kx;
-                    if (iy < gi.H + gi.pad && ix < gi.W + gi.pad) {
-                        float v[8];
-                        load8f(in + plane_row(gi, n, iy, ix) * ld, c8 * 8, lo, v);
-#pragma unroll
-                        for (int j = 0; j < 8; ++j) m[j] = fmaxf(m[j], v[j]);
-                    }
-                }
-            store8f(out + plane_row(go, n, oy, ox) * ld, c8 * 8, lo, m, false);
+                for (int j = 0; j < 8; ++j) carry[j] = b[j];
+            }
         }
         return;
     }
