@@ -16,8 +16,10 @@ with its measured error.
   e2e          the same through the public plugin API (MetaOneStageDetector / EpisodePipeline), inputs in pinned HOST
                memory: H2D of every image and D2H of the detections inside the timed region; `latency_ms` is one episode
                submitted and read back synchronously
-  roofline     the kernel with the largest share of the step (staged 1x1 bottleneck conv + residual, HBM-bound);
-               roofline_tensor: the FCOS tower kernel (tensor-bound); both timed live with CUDA events
+  roofline     one kernel per record, timed live with CUDA events: `roofline` = the HBM-bound kernel with the largest share
+               (single-CTA staged 1x1 conv + residual: conv3 of res2 + res3), `roofline_tensor` = the CTA-pair 3x3 kernel
+               (largest share of the step; FCOS towers, and every launch of it), `roofline_conv3_deep` = the CTA-pair
+               split 1x1 kernel (conv3 of res4 + res5)
   cpu_baseline the CPU oracle (port of the reference forward) on this box's host cores: ONE whole episode with the
                reference's loop structure (rank 0, N = 1)
   variants     random-init weights (zero candidates), BASELINE configs[2] (R-101 10-shot) and configs[4] (1203-class
