@@ -43,8 +43,8 @@ def model_config_from_cfg(cfg) -> ModelConfig:
             raise NotImplementedError("WEIGHT_LAYER / SCALE_LAYER / COMPRESS_CODE_W_MAX / multilevel ROI are not implemented")
     if episodic and (G.ROI_BOX.POOLER_TYPE != "ROIAlignV2" or int(G.ROI_BOX.POOLER_RESOLUTION) != 7):
         raise NotImplementedError("ROI pooler must be ROIAlignV2 at 7x7")
-    if cfg.MODEL.PROPOSAL_GENERATOR.OWD:
-        raise NotImplementedError("OWD scoring is not implemented")
+    # MODEL.PROPOSAL_GENERATOR.OWD only selects the evaluator (meta_fcos_runner.py:121-126: COCO_OWD_Evaluator, class-agnostic
+    # matching); nothing under sylph/modeling reads it, so the forward path is the same either way.
     quality = sorted(F.BOX_QUALITY)
     mc = ModelConfig()
     mc.resnet_depth = int(cfg.MODEL.RESNETS.DEPTH)
