@@ -57,6 +57,8 @@ typedef struct sylph_model_config {
     int re_layers;             /* ROIEncoder: CODE_GENERATOR.TRANSFORMER_ENCODER.LAYERS (dim_feedforward = 4 x 256) */
     int re_head_fcs;           /* ROIEncoder: CODE_GENERATOR.HEAD.NUM_FC (OUTPUT_DIM 256) */
     int re_head_dim;           /* ROIEncoder: CODE_GENERATOR.HEAD.FC_DIM (<= 1024) */
+    int cg_weight_layer;       /* len(CODE_GENERATOR.WEIGHT_LAYER) == 3: per-shot weights = softmax over the shots of a 256 -> 1 3x3
+                                  convolution + global average pool (code_generator.py:583-612, 766-776, 969-981) instead of 1 / K */
 } sylph_model_config;
 
 /* Library / build identification (no GPU needed). */

@@ -33,13 +33,16 @@ CONFIGS = {
     "lvis_roienc": "LVISv1-Detection/Meta-FCOS/Meta-FCOS-ROI-Encoder-finetune.yaml",
 }
 # extra config overrides of a case (also applied by the tests that rebuild the cfg from the preset)
-CASE_OPTS = {"lvis_roienc_2way_3shot": ["MODEL.META_LEARN.EVAL_SHOT", 3]}
+CASE_OPTS = {"lvis_roienc_2way_3shot": ["MODEL.META_LEARN.EVAL_SHOT", 3],
+             # per-shot weight head (commented out in the shipped LVIS configs: "# WEIGHT_LAYER: [\"\", \"\", 1]")
+             "coco_weight_layer_2way_3shot": ["MODEL.META_LEARN.CODE_GENERATOR.WEIGHT_LAYER", ["", "", 1]]}
 # vendored copies of the two YAML trees are NOT kept; tests rebuild the cfg from these overrides on top of defaults
 CASES = {
     # name: (config, seed, classes, shots, support (H, W) list, query (H, W) list)
     "coco_2way_2shot": ("coco", 3, 2, 2, [(256, 320), (240, 300)], [(256, 320), (200, 288)]),
     "lvis_1way_3shot": ("lvis", 5, 1, 3, [(224, 256), (256, 224), (200, 240)], [(224, 288)]),
     "lvis_roienc_2way_3shot": ("lvis_roienc", 9, 2, 3, [(224, 256), (256, 224), (200, 240)], [(224, 288)]),
+    "coco_weight_layer_2way_3shot": ("coco", 13, 2, 3, [(224, 256), (256, 224), (200, 240)], [(224, 288)]),
 }
 
 

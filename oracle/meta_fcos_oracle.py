@@ -111,7 +111,20 @@ class MetaFCOSOracle:
                 shp = b.shape
                 b = F.normalize(b.reshape(shp[0], shp[1], -1), p=2, dim=2).reshape(shp)
             b = F.adaptive_avg_pool2d(b, (1, 1))
+        self._last_weight_logits = None
+        if len(self.G.WEIGHT_LAYER) == 3:
+            # support_set_cls_weight (code_generator.py:583-612, 969-973): conv 256 -> 1 (+ norm: none supported) + global pool
+            wl = F.conv2d(x, self._cg("support_set_cls_weight.0.weight"), self._cg("support_set_cls_weight.0.bias"), padding=1)
+            self._last_weight_logits = F.adaptive_avg_pool2d(wl, (1, 1))
         return w, b
+
+    def shot_weights(self, n_cls: int, shot: int, dtype) -> torch.Tensor:
+        """process_weight (code_generator.py:766-776) on the weight-head output of the LAST per_shot_codes call: softmax over the
+        shots of every class; uniform 1 / K without a WEIGHT_LAYER (:805-806)."""
+        wl = getattr(self, "_last_weight_logits", None)
+        if wl is None:
+            return torch.full((n_cls, shot, 1, 1, 1), 1.0 / shot, dtype=dtype)
+        return torch.softmax(wl.view(n_cls, shot, 1, 1, 1), dim=1)
 
     @torch.no_grad()
     def class_code(self, support_images: Sequence[torch.Tensor], boxes: torch.Tensor) -> Dict[str, torch.Tensor]:
@@ -123,7 +136,7 @@ class MetaFCOSOracle:
         roi, _ = self.roi_features(feats, boxes)
         w, b = self.per_shot_codes(roi)
         k = w.shape[0]
-        weight = torch.full((1, k, 1, 1, 1), 1.0 / k, dtype=w.dtype)
+        weight = self.shot_weights(1, k, w.dtype)
         cls_conv = (weight * w.view(1, k, *w.shape[1:])).sum(dim=1)
         if b is not None:
             cls_bias = (weight * b.view(1, k, 1, 1, 1)).sum(dim=1)
@@ -457,7 +470,7 @@ class MetaFCOSOracle:
         roi, _ = self.roi_features(s_feats, boxes)
         w, b = self.per_shot_codes(roi)
         n_cls = w.shape[0] // shot
-        weight = torch.full((n_cls, shot, 1, 1, 1), 1.0 / shot, dtype=w.dtype)      # code_generator.py:805-817
+        weight = self.shot_weights(n_cls, shot, w.dtype)                            # code_generator.py:766-776, 805-817
         cls_conv = (weight * w.view(n_cls, shot, *w.shape[1:])).sum(dim=1)
         cls_bias = (weight * b.view(n_cls, shot, 1, 1, 1)).sum(dim=1) if b is not None else torch.zeros(n_cls, 1, 1, 1)
         cls_conv, cls_bias = self.process_codes_training(cls_conv, cls_bias)        # :993-994

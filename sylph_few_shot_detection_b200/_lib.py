@@ -32,7 +32,7 @@ class ModelConfig(Structure):
         ("cg_tower_layers", c_int), ("cg_post_norm", c_int), ("cg_conv_l2_norm", c_int), ("cg_bias_layer", c_int),
         ("cg_bias_l2_norm", c_int), ("cg_use_bias", c_int), ("cg_has_conv_scale", c_int),
         ("generator", c_int), ("re_tok_convs", c_int), ("re_tok_fcs", c_int), ("re_layers", c_int),
-        ("re_head_fcs", c_int), ("re_head_dim", c_int),
+        ("re_head_fcs", c_int), ("re_head_dim", c_int), ("cg_weight_layer", c_int),
     ]
 
 

@@ -114,6 +114,8 @@ struct sylph_ctx {
     float level_scale[5] = {1, 1, 1, 1, 1};
     float* cg_wbias = nullptr;  // [9][256]
     float* cg_bbias = nullptr;  // [1]
+    float* cg_wweight = nullptr;  // [9][256]: per-shot weight head (CODE_GENERATOR.WEIGHT_LAYER), tap-major like cg_wbias
+    float* cg_bweight = nullptr;  // [1]
     float* post_gn_w = nullptr;
     float* post_gn_b = nullptr;
     float conv_scale = 1.f, bias_scale = 1.f, bias_value = 0.f;
@@ -1015,6 +1017,15 @@ int sylph_finalize_weights(sylph_ctx* c) {
         } else {
             c->bias_scale = 1.f;
         }
+        if (f.cg_weight_layer) {
+            const HostTensor *w = find_t(c, cg + "support_set_cls_weight.0.weight"), *b = find_t(c, cg + "support_set_cls_weight.0.bias");
+            if (!w || !b || w->data.size() != 256 * 9) return c->fail("missing support_set_cls_weight tensors");
+            std::vector<float> hw(9 * 256);
+            for (int ch = 0; ch < 256; ++ch)
+                for (int t = 0; t < 9; ++t) hw[t * 256 + ch] = w->data[ch * 9 + t];
+            TRY(upload(c, hw, &c->cg_wweight));
+            TRY(upload(c, b->data, &c->cg_bweight));
+        }
         if (f.cg_post_norm) {
             TRY(upload_vec(c, cg + "post_norm.weight", &c->post_gn_w, 256));
             TRY(upload_vec(c, cg + "post_norm.bias", &c->post_gn_b, 256));
@@ -1782,10 +1793,14 @@ int sylph_generate_codes(sylph_ctx* c, int slot, int n_rois, const float* boxes_
     }
     {
         StageTimer t(c, "codegen.tail", st, static_cast<double>(n_rois) * 2 * 49 * 256 * 4);
+        void* pwl = nullptr;   // per-shot weight logits (WEIGHT_LAYER): softmax over the shots of a class replaces 1 / K
+        if (f.cg_weight_layer) TRY(ensure(c, "cg.wlogit", static_cast<size_t>(n_rois) * 4, "", &pwl, st, false));
         CU_TRY(c, launch_k(shot_code_kernel, dim3(n_rois), dim3(256), 0, st, raw, cur, c->cg_wbias, c->cg_bbias, f.cg_bias_layer, f.cg_bias_l2_norm,
-                                                 static_cast<float*>(sc), c->split, pooled, c->roi_stride));
+                                                 static_cast<float*>(sc), c->split, pooled, c->roi_stride,
+                                                 static_cast<const float*>(c->cg_wweight), static_cast<const float*>(c->cg_bweight), static_cast<float*>(pwl)));
         CU_TRY(c, cudaGetLastError());
-        CU_TRY(c, launch_k(class_mean_kernel, dim3(n_classes), dim3(288), 0, st, static_cast<const float*>(sc), static_cast<const int*>(po), codes_out_dev));
+        CU_TRY(c, launch_k(class_mean_kernel, dim3(n_classes), dim3(288), 0, st, static_cast<const float*>(sc), static_cast<const int*>(po), codes_out_dev,
+                           static_cast<const float*>(pwl)));
         CU_TRY(c, cudaGetLastError());
         c->launches += 2;
     }

@@ -300,7 +300,9 @@ shot_code_kernel(const float* __restrict__ cls_raw, const __half* __restrict__ t
                  const float* __restrict__ w_bias /* [9][256] tap-major */, const float* __restrict__ b_bias,
                  int has_bias_layer, int bias_l2_norm, float* __restrict__ shot_codes /* [n_rois][257] */, int split,
                  const float* __restrict__ cls_pooled = nullptr /* [n_rois][256]: the pooled cls-conv output (pool-before-conv path) */,
-                 int roi_stride = 128) {
+                 int roi_stride = 128,
+                 const float* __restrict__ w_weight = nullptr /* [9][256]: WEIGHT_LAYER head */, const float* __restrict__ b_weight = nullptr,
+                 float* __restrict__ shot_wlogit = nullptr /* [n_rois]: pooled output of the weight head */) {
     ptx::griddep_launch();
     ptx::griddep_wait();
     __shared__ float pix[49];
@@ -316,30 +318,43 @@ shot_code_kernel(const float* __restrict__ cls_raw, const __half* __restrict__ t
         }
         shot_codes[static_cast<size_t>(roi) * 257 + t] = s / 49.f;
     }
+    // a 256 -> 1 3x3 convolution of the tower output at the 49 positions (bias head, weight head): pix[p]
+    auto head_conv = [&](const float* __restrict__ w9, const float* __restrict__ b1) {
+        for (int p = warp; p < 49; p += 8) {
+            const int row = (p / 7 + 1) * 9 + (p % 7 + 1);
+            float acc = 0.f;
+#pragma unroll
+            for (int tap = 0; tap < 9; ++tap) {
+                const int r2 = row + (tap / 3 - 1) * 9 + (tap % 3 - 1);  // zero border supplies the padding
+                const __half* a = tower_out + (base + r2) * (split ? 512 : 256);
+                const float* w = w9 + tap * 256;
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    float av = __half2float(a[lane + 32 * j]);
+                    if (split) av += __half2float(a[256 + lane + 32 * j]);
+                    acc += av * __ldg(w + lane + 32 * j);
+                }
+            }
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+            if (lane == 0) pix[p] = acc + b1[0];
+        }
+        __syncthreads();
+    };
+    if (shot_wlogit != nullptr) {   // weight head: conv + GlobalAdaptiveAvgPool2d (code_generator.py:583-612)
+        head_conv(w_weight, b_weight);
+        if (t == 0) {
+            float m = 0.f;
+            for (int p = 0; p < 49; ++p) m += pix[p];
+            shot_wlogit[roi] = m / 49.f;
+        }
+        __syncthreads();
+    }
     if (!has_bias_layer) {
         if (t == 0) shot_codes[static_cast<size_t>(roi) * 257 + 256] = 0.f;
         return;
     }
-    for (int p = warp; p < 49; p += 8) {
-        const int row = (p / 7 + 1) * 9 + (p % 7 + 1);
-        float acc = 0.f;
-#pragma unroll
-        for (int tap = 0; tap < 9; ++tap) {
-            const int r2 = row + (tap / 3 - 1) * 9 + (tap % 3 - 1);  // zero border supplies the padding
-            const __half* a = tower_out + (base + r2) * (split ? 512 : 256);
-            const float* w = w_bias + tap * 256;
-#pragma unroll
-            for (int j = 0; j < 8; ++j) {
-                float av = __half2float(a[lane + 32 * j]);
-                if (split) av += __half2float(a[256 + lane + 32 * j]);
-                acc += av * __ldg(w + lane + 32 * j);
-            }
-        }
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
-        if (lane == 0) pix[p] = acc + b_bias[0];
-    }
-    __syncthreads();
+    head_conv(w_bias, b_bias);
     if (t == 0) {
         float denom = 1.f;
         if (bias_l2_norm) {
@@ -353,18 +368,27 @@ shot_code_kernel(const float* __restrict__ cls_raw, const __half* __restrict__ t
     }
 }
 
-// K-shot mean per class with the reference's op order: sum_k (1/K) * x_k  (compute_code, code_generator.py:805-817).
+// K-shot combination per class with the reference's op order: sum_k w_k * x_k (compute_code, code_generator.py:805-817) with
+// w_k = 1 / K, or -- WEIGHT_LAYER -- w = softmax over the class's shots of the weight head's logits (process_weight, :766-776).
 __global__ void __launch_bounds__(288)
 class_mean_kernel(const float* __restrict__ shot_codes, const int* __restrict__ class_offsets,
-                  float* __restrict__ raw_codes) {
+                  float* __restrict__ raw_codes, const float* __restrict__ shot_wlogit = nullptr) {
     ptx::griddep_launch();
     ptx::griddep_wait();
     const int cls = blockIdx.x, t = threadIdx.x;
     if (t >= 257) return;
     const int k0 = class_offsets[cls], k1 = class_offsets[cls + 1];
-    const float w = 1.0f / static_cast<float>(k1 - k0);
     float s = 0.f;
-    for (int k = k0; k < k1; ++k) s += w * shot_codes[static_cast<size_t>(k) * 257 + t];
+    if (shot_wlogit != nullptr) {
+        float mx = -3.4e38f;
+        for (int k = k0; k < k1; ++k) mx = fmaxf(mx, shot_wlogit[k]);
+        float den = 0.f;
+        for (int k = k0; k < k1; ++k) den += expf(shot_wlogit[k] - mx);
+        for (int k = k0; k < k1; ++k) s += (expf(shot_wlogit[k] - mx) / den) * shot_codes[static_cast<size_t>(k) * 257 + t];
+    } else {
+        const float w = 1.0f / static_cast<float>(k1 - k0);
+        for (int k = k0; k < k1; ++k) s += w * shot_codes[static_cast<size_t>(k) * 257 + t];
+    }
     raw_codes[static_cast<size_t>(cls) * 257 + t] = s;
 }
 

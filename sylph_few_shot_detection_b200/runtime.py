@@ -39,8 +39,10 @@ def model_config_from_cfg(cfg) -> ModelConfig:
                 raise NotImplementedError("CODE_GENERATOR.TOWER_LAYERS entries must be ['GN', 'ReLU']")
         if list(G.CLS_LAYER) != ["", "", 1]:
             raise NotImplementedError("CODE_GENERATOR.CLS_LAYER must be ['', '', 1]")
-        if len(G.WEIGHT_LAYER) or len(G.SCALE_LAYER) or G.COMPRESS_CODE_W_MAX or G.ROI_BOX.FPN_MULTILEVEL_FEATURE:
-            raise NotImplementedError("WEIGHT_LAYER / SCALE_LAYER / COMPRESS_CODE_W_MAX / multilevel ROI are not implemented")
+        if len(G.WEIGHT_LAYER) not in (0, 3) or (len(G.WEIGHT_LAYER) == 3 and G.WEIGHT_LAYER[0] != ""):
+            raise NotImplementedError("CODE_GENERATOR.WEIGHT_LAYER must be [] or ['', <act>, <pool>] (no norm layer on the 1-channel head)")
+        if len(G.SCALE_LAYER) or G.COMPRESS_CODE_W_MAX or G.ROI_BOX.FPN_MULTILEVEL_FEATURE:
+            raise NotImplementedError("SCALE_LAYER / COMPRESS_CODE_W_MAX / multilevel ROI are not implemented")
     if episodic and (G.ROI_BOX.POOLER_TYPE != "ROIAlignV2" or int(G.ROI_BOX.POOLER_RESOLUTION) != 7):
         raise NotImplementedError("ROI pooler must be ROIAlignV2 at 7x7")
     # MODEL.PROPOSAL_GENERATOR.OWD only selects the evaluator (meta_fcos_runner.py:121-126: COCO_OWD_Evaluator, class-agnostic
@@ -63,6 +65,7 @@ def model_config_from_cfg(cfg) -> ModelConfig:
         raise NotImplementedError("POST_NORM must be '' or 'GN'")
     mc.cg_conv_l2_norm = int(bool(G.CONV_L2_NORM))
     mc.cg_bias_layer = int(len(G.BIAS_LAYER) == 3)
+    mc.cg_weight_layer = int(episodic and not roi_encoder and len(G.WEIGHT_LAYER) == 3)
     mc.cg_bias_l2_norm = int(bool(G.BIAS_L2_NORM))
     mc.cg_use_bias = int(bool(G.USE_BIAS))
     mc.cg_has_conv_scale = int(bool(G.USE_WEIGHT_SCALE and (G.CONV_L2_NORM or G.POST_NORM != "")))

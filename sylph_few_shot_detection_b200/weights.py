@@ -126,6 +126,8 @@ def _code_generator_spec(cfg, spec, conv, gn, fpn_c) -> None:
     if len(G.BIAS_LAYER) == 3:
         conv(f"{cg}.support_set_cls_bias.0", 1, 256, 3, True)
         spec[f"{cg}.bias_scale.scale"] = (1,)
+    if len(G.WEIGHT_LAYER) == 3:      # per-shot weight head (code_generator.py:583-612): conv 256 -> 1 (+ pool)
+        conv(f"{cg}.support_set_cls_weight.0", 1, 256, 3, True)
     if G.USE_WEIGHT_SCALE and (G.CONV_L2_NORM or G.POST_NORM != ""):
         spec[f"{cg}.conv_scale.scale"] = (1,)
 
@@ -237,6 +239,8 @@ def synthetic_tensor(cfg, key: str, shape: Tuple[int, ...], seed: int = 0) -> to
         return normal(0.01)
     if any(s in key for s in ("bbox_pred", "ctrness", "iou_overlap", "support_set_cls_bias")):
         return normal(0.03)
+    if "support_set_cls_weight" in key:   # per-shot weight head: logits that spread the softmax weights well away from 1 / K
+        return normal(0.3)
     return normal(math.sqrt(2.0 / (cin * kh * kw)))
 
 

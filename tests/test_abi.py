@@ -35,7 +35,7 @@ def test_model_config_struct_layout_matches_header():
     body = re.sub(r"/\*.*?\*/", "", body, flags=re.S)
     fields = re.findall(r"\b(?:int|float)\s+([a-z_0-9]+)(?:\[3\])?;", body)
     assert fields == [f[0] for f in _lib.ModelConfig._fields_]
-    assert ctypes.sizeof(_lib.ModelConfig) == 4 * (8 + 3 + 6 + 7 + 6)
+    assert ctypes.sizeof(_lib.ModelConfig) == 4 * (8 + 3 + 6 + 7 + 6 + 1)
 
 
 def test_loss_config_struct_layout_matches_header():

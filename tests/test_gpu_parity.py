@@ -33,11 +33,11 @@ def _oracle(cfg, state):
 
 
 @pytest.mark.parametrize("precision", ["exact", "fast"])
-@pytest.mark.parametrize("case", ["coco_2way_2shot", "lvis_1way_3shot"])
+@pytest.mark.parametrize("case", ["coco_2way_2shot", "lvis_1way_3shot", "coco_weight_layer_2way_3shot"])
 def test_episode_matches_reference_golden(case, precision):
     from sylph_few_shot_detection_b200.runtime import SLOT_QUERY, SLOT_SUPPORT
     g = load_golden(case)
-    cfg = cfg_for(g["config"])
+    cfg = cfg_for(g["config"], g.get("opts"))
     eng, state = _engine(cfg, g["seed"], precision)
     orc = _oracle(cfg, state)
     report = []

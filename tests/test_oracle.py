@@ -11,16 +11,19 @@ from tests.cases import cfg_for, load_golden, rel_err
 TOL = 2e-5
 
 
-@pytest.mark.parametrize("case", ["coco_2way_2shot", "lvis_1way_3shot"])
+@pytest.mark.parametrize("case", ["coco_2way_2shot", "lvis_1way_3shot", "coco_weight_layer_2way_3shot"])
 def test_oracle_reproduces_reference_outputs(case):
     g = load_golden(case)
-    cfg = cfg_for(g["config"])
+    cfg = cfg_for(g["config"], g.get("opts"))     # coco_weight_layer_*: CODE_GENERATOR.WEIGHT_LAYER ["", "", 1] (softmax shot weights)
     state = W.synthetic_state_dict(cfg, g["seed"])
     orc = MetaFCOSOracle(cfg, state)
     normed = []
     for c, shots in enumerate(g["support"]):
         code = orc.class_code([s["image"].float() for s in shots], torch.stack([s["box"] for s in shots]))
         assert code["cls_conv"].shape == (1, 256, 1, 1) and code["cls_bias"].shape == (1, 1, 1, 1)
+        if "weight_layer" in case:   # the weight head is live: softmax weights far from 1 / K
+            wts = orc.shot_weights(1, len(shots), torch.float32).reshape(-1)
+            assert abs(float(wts.sum()) - 1.0) < 1e-6 and float(wts.max() - wts.min()) > 0.05
         assert rel_err(code["cls_conv"], g["raw_codes"][c]["cls_conv"]) < TOL
         assert rel_err(code["cls_bias"], g["raw_codes"][c]["cls_bias"]) < TOL
         w, b = orc.normalize_code(code["cls_conv"], code["cls_bias"])
