@@ -235,7 +235,7 @@ int sylph_detect_poll(sylph_ctx* ctx);
  * 1 bbox_reg after scale+ReLU (n, 4, H, W), 2 ctrness (n, 1, H, W), 3 iou (n, 1, H, W). */
 int sylph_export_head_output(sylph_ctx* ctx, int which, int level, float* out_dev, void* stream);
 
-/* ---- Episodic TRAINING forward of the proposal generator: losses only, no backward. ---- */
+/* ---- Episodic TRAINING forward of the proposal generator: losses; the backward of the code generator follows below. ---- */
 
 /* The loss hyper-parameters FCOSOutputs._init_fcos reads (sylph/modeling/meta_fcos/fcos_outputs.py:70-102). */
 typedef struct sylph_loss_config {
@@ -271,6 +271,59 @@ int sylph_fcos_loss_sums(sylph_ctx* ctx, int slot, const float* codes_dev, int n
  * fcos_losses_episodic_learning, fcos_outputs.py:520-523 and :557-558 -- or NULL for a single process. */
 int sylph_fcos_loss_finalize(sylph_ctx* ctx, const double* local_sums_dev, const double* global_pos_ctr_dev,
                              int world_size, float* losses_out_dev, void* stream);
+
+/* ---- Backward of the episodic training step for the CODE GENERATOR. ----
+ * Scope: the meta-training configurations that freeze the detector and train the hyper-network
+ * (configs/COCO-Detection/Meta-FCOS/Meta-FCOS-finetune-lvis.yaml: BACKBONE.FREEZE, PROPOSAL_GENERATOR.FREEZE_CLS_TOWER,
+ * FREEZE_BBOX_BRANCH on, CODE_GENERATOR.FREEZE off).  The only loss that reaches the code generator is loss_fcos_cls
+ * (the box losses depend on the frozen box branch alone).  Gradients equal what the reference's
+ * `sum(model(batched_inputs).values()).backward()` leaves in `.grad` of every `code_generator.*` parameter
+ * (detectron2 SimpleTrainer.run_step on forward_few_shot_detector_training, meta_one_stage_detector.py:325-388).
+ * Not built: the backward of the FCOS class tower (FREEZE_CLS_TOWER: False) and of the backbone. */
+
+/* d loss_fcos_cls / d FINAL class codes, (n_classes, 257) fp32 rows [cls_conv 256 | cls_bias].  Call right after
+ * sylph_fcos_loss_sums on the same slot with the same codes (the head's logits and class-tower output of that call
+ * are read in place); labels_dev = that call's labels_out_dev; local_sums_dev / global_pos_ctr_dev / world_size as for
+ * sylph_fcos_loss_finalize (num_pos_avg, fcos_outputs.py:520-523).  grad_loss_dev: one float, the upstream gradient of the
+ * loss (NULL = 1).  Differentiates fvcore's sigmoid_focal_loss_jit (fcos_outputs.py:525-537) and CondConvBasic
+ * (sylph/modeling/meta_fcos/head_utils.py:60-81). */
+int sylph_fcos_cls_loss_backward(sylph_ctx* ctx, int slot, int n_classes, const int64_t* support_targets_host,
+                                 const sylph_loss_config* lc, const int64_t* labels_dev, const double* local_sums_dev,
+                                 const double* global_pos_ctr_dev, int world_size, const float* grad_loss_dev,
+                                 float* grad_codes_out_dev, void* stream);
+
+/* The code generator's trainable tensors, device fp32 in the reference's state_dict layouts
+ * (`code_generator.code_generator_head.*`); NULL where the configuration has no such tensor. */
+#define SYLPH_CG_MAX_TOWER 4
+typedef struct sylph_codegen_tensors {
+    float* tower_w[SYLPH_CG_MAX_TOWER];     /* support_set_shared_tower.{3i}.weight   (256, 256, 3, 3) */
+    float* tower_b[SYLPH_CG_MAX_TOWER];     /* support_set_shared_tower.{3i}.bias     (256) */
+    float* tower_gn_w[SYLPH_CG_MAX_TOWER];  /* support_set_shared_tower.{3i+1}.weight (256) */
+    float* tower_gn_b[SYLPH_CG_MAX_TOWER];  /* support_set_shared_tower.{3i+1}.bias   (256) */
+    float* cls_w;                           /* support_set_cls_conv.0.weight (256, 256, 3, 3) */
+    float* cls_b;                           /* support_set_cls_conv.0.bias   (256) */
+    float* bias_w;                          /* support_set_cls_bias.0.weight (1, 256, 3, 3) */
+    float* bias_b;                          /* support_set_cls_bias.0.bias   (1) */
+    float* post_norm_w;                     /* post_norm.weight (256) */
+    float* post_norm_b;                     /* post_norm.bias   (256) */
+    float* conv_scale;                      /* conv_scale.scale (1) */
+    float* bias_scale;                      /* bias_scale.scale (1) */
+} sylph_codegen_tensors;
+
+/* Backward through code_process_module, compute_code, the pools, support_set_cls_conv / support_set_cls_bias and
+ * support_set_shared_tower (sylph/modeling/code_generator/code_generator.py:648-688, 778-875, 941-994) for the ROIs of the last
+ * sylph_generate_codes call (n_rois, class_offsets as in that call; its pooled ROI features are read in place).
+ * raw_codes_dev = that call's output, grad_codes_dev = gradient with respect to the FINAL codes
+ * (sylph_normalize_codes of raw_codes_dev); `params` are read, every non-NULL tensor of `grads` is overwritten
+ * (not accumulated).  Deterministic (no atomics). */
+int sylph_codegen_backward(sylph_ctx* ctx, int n_rois, int n_classes, const int* class_offsets_host,
+                           const float* raw_codes_dev, const float* grad_codes_dev, const sylph_codegen_tensors* params,
+                           const sylph_codegen_tensors* grads, void* stream);
+
+/* Re-prepare the code generator's weights after an optimiser step: stage ALL `code_generator.*` tensors with
+ * sylph_load_tensor, then call this instead of sylph_finalize_weights (the rest of the model keeps its prepared
+ * weights; device buffers are reused).  Synchronises the device. */
+int sylph_update_code_generator(sylph_ctx* ctx);
 
 /* Number of kernels this library launched on the context since creation (bench.py's gpu_launches). */
 int64_t sylph_launch_count(const sylph_ctx* ctx);

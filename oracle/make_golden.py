@@ -355,6 +355,64 @@ def build_training_variant_goldens():
     print(f"[train variants] wrote {path} ({os.path.getsize(path) / 1e6:.2f} MB)")
 
 
+# Backward of the training step for the code generator: the REFERENCE model's own
+# `sum(model(batched).values()).backward()` (what detectron2's SimpleTrainer.run_step does), the `.grad` of every
+# code-generator parameter.  The 2.4 MB convolution gradients are stored as a strided sample (every GRAD_SAMPLE_STEP-th element of
+# the flattened tensor) plus float64 checksums (sum, sum of squares) of the whole tensor; small tensors in full.
+GRAD_SAMPLE_STEP = 7
+GRAD_CASES = ["lvis_train_3way_1shot_cls_only", "coco_train_2way_2shot"]
+
+
+def run_reference_training_grads(cfg, state, items):
+    with contextlib.redirect_stdout(io.StringIO()):
+        model = reference_loader.build_reference_model(cfg)
+    W.load_into_module(model, state)
+    model.train()
+    np.random.seed(0)
+    batched = to_records(items)
+    with contextlib.redirect_stdout(io.StringIO()), warnings_off():
+        losses = model(batched)
+        sum(losses.values()).backward()
+    pre = "code_generator."
+    grads = {n: p.grad.detach().clone() for n, p in model.named_parameters() if n.startswith(pre) and p.grad is not None}
+    return {k: v.detach().clone() for k, v in losses.items()}, grads
+
+
+def pack_grad(t: torch.Tensor):
+    flat = t.reshape(-1)
+    d = flat.double()
+    rec = {"shape": tuple(t.shape), "sum": float(d.sum()), "sumsq": float((d * d).sum()), "absmax": float(d.abs().max())}
+    if flat.numel() > 4096:
+        rec["sample_step"] = GRAD_SAMPLE_STEP
+        rec["sample"] = flat[::GRAD_SAMPLE_STEP].clone()
+    else:
+        rec["full"] = flat.clone()
+    return rec
+
+
+def build_training_grad_goldens():
+    out = {"cases": {}, "torch_version": torch.__version__, "sample_step": GRAD_SAMPLE_STEP}
+    for name in GRAD_CASES:
+        cfg_name, seed, opts, items = build_train_case(name)
+        cfg = load_cfg(os.path.join(reference_loader.REFERENCE_ROOT, "configs", CONFIGS[cfg_name]), ["MODEL.DEVICE", "cpu"] + opts)
+        state = W.synthetic_state_dict(cfg, seed)
+        ref_losses, ref_grads = run_reference_training_grads(cfg, state, items)
+        orc = build_oracle(cfg, state)
+        losses, grads, ex = orc.training_grads(to_records(items))
+        assert set(grads) == set(ref_grads), (sorted(set(grads) ^ set(ref_grads)))
+        worst = 0.0
+        for k in sorted(ref_grads):
+            worst = max(worst, compare(k.replace("code_generator.code_generator_head.", "d "), grads[k], ref_grads[k]))
+        print(f"[{name}] oracle autograd vs reference .grad: worst relative deviation {worst:.3e}")
+        assert worst < 2e-5, worst
+        out["cases"][name] = {"losses": ref_losses, "grads": {k: pack_grad(v) for k, v in ref_grads.items()},
+                              "grad_codes": {k: v.clone() for k, v in ex["grad_codes"].items()},
+                              "grad_codes_source": "oracle autograd (the reference does not expose the codes); pinned through the parameter gradients"}
+    path = os.path.join(GOLDEN_DIR, "train_grads.pt")
+    torch.save(out, path)
+    print(f"[train grads] wrote {path} ({os.path.getsize(path) / 1e6:.2f} MB)")
+
+
 def base_detector_state(cfg, seed):
     """Synthetic weights of the NON-episodic model with a class-logits convolution strong enough to fire (the synthetic
     N(0, 0.01) initialiser leaves every logit at the prior)."""
@@ -431,9 +489,13 @@ def main():
     if "--train-variants-only" in sys.argv:
         build_training_variant_goldens()
         return
+    if "--train-grads-only" in sys.argv:
+        build_training_grad_goldens()
+        return
     if "--train-only" in sys.argv or "--all" in sys.argv or len(sys.argv) == 1:
         build_training_goldens()
         build_training_variant_goldens()
+        build_training_grad_goldens()
     if "--train-only" in sys.argv:
         return
     for name in CASES:

@@ -456,29 +456,66 @@ class MetaFCOSOracle:
     def training_forward(self, batched_inputs: Sequence[Dict], world_size: int = 1, reduce=None):
         """forward_few_shot_detector_training (meta_one_stage_detector.py:325-388): one item per class with
         "support_set" (SHOT records, one selected box each), "query_set" and "support_set_target"."""
+        return self._training_forward(batched_inputs, world_size, reduce)
+
+    def _training_forward(self, batched_inputs: Sequence[Dict], world_size: int = 1, reduce=None):
+        """Body of training_forward without the no_grad guard (training_grads differentiates it).  The backbone runs under
+        no_grad either way: MODEL.BACKBONE.FREEZE is on in every shipped meta-training config."""
+        cls = type(self)
         shot = int(self.cfg.MODEL.META_LEARN.SHOT)
         support = [r for x in batched_inputs for r in x["support_set"]]
         targets = [int(x["support_set_target"]) for x in batched_inputs]
         query = [r for x in batched_inputs for r in x["query_set"]]
         assert len(support) % shot == 0, f"Total size {len(support)} must be divisible by number of shot {shot}"
-        q_il = self.preprocess([r["image"] for r in query])
-        q_feats = self.features(q_il.tensor)
-        s_il = self.preprocess([r["image"] for r in support])
-        s_feats = self.features(s_il.tensor)
+        with torch.no_grad():
+            q_il = self.preprocess([r["image"] for r in query])
+            q_feats = self.features(q_il.tensor)
+            s_il = self.preprocess([r["image"] for r in support])
+            s_feats = self.features(s_il.tensor)
         gts = self.filter_gt(query, targets)
         boxes = torch.stack([r["instances"].gt_boxes.tensor[0] for r in support])   # one GT per support image
         roi, _ = self.roi_features(s_feats, boxes)
-        w, b = self.per_shot_codes(roi)
+        w, b = cls.per_shot_codes.__wrapped__(self, roi)
         n_cls = w.shape[0] // shot
         weight = self.shot_weights(n_cls, shot, w.dtype)                            # code_generator.py:766-776, 805-817
-        cls_conv = (weight * w.view(n_cls, shot, *w.shape[1:])).sum(dim=1)
-        cls_bias = (weight * b.view(n_cls, shot, 1, 1, 1)).sum(dim=1) if b is not None else torch.zeros(n_cls, 1, 1, 1)
-        cls_conv, cls_bias = self.process_codes_training(cls_conv, cls_bias)        # :993-994
+        raw_conv = (weight * w.view(n_cls, shot, *w.shape[1:])).sum(dim=1)
+        raw_bias = (weight * b.view(n_cls, shot, 1, 1, 1)).sum(dim=1) if b is not None else torch.zeros(n_cls, 1, 1, 1)
+        cls_conv, cls_bias = self.process_codes_training(raw_conv, raw_bias)        # :993-994
         codes = {"cls_conv": cls_conv, "cls_bias": cls_bias}
-        logits, regs, ctrs, ious = self.head(q_feats, codes)
+        logits, regs, ctrs, ious = cls.head.__wrapped__(self, q_feats, codes)
         losses, extras = self.fcos_losses(logits, regs, ctrs, gts, targets, world_size, reduce)
-        extras.update({"codes": codes, "gts": gts})
+        extras.update({"codes": codes, "gts": gts, "raw_codes": {"cls_conv": raw_conv, "cls_bias": raw_bias}, "roi": roi})
         return losses, extras
+
+    # parameters of the code generator that receive a gradient in the reference's training step (the `init_norm.*` layers
+    # are registered but never called on this path)
+    def trainable_code_generator_keys(self) -> List[str]:
+        pre = "code_generator.code_generator_head."
+        return [k for k, v in self.sd.items() if k.startswith(pre) and torch.is_floating_point(v)
+                and not k.startswith(pre + "init_norm.")]
+
+    def training_grads(self, batched_inputs: Sequence[Dict], world_size: int = 1, reduce=None):
+        """Backward of the episodic training step for the CODE GENERATOR: autograd through the restated
+        forward.  d(sum of the returned losses) / d(parameter) for every code-generator tensor, as the reference's
+        `losses = model(batched); sum(losses.values()).backward()` leaves them in `.grad` (detectron2 SimpleTrainer.run_step),
+        plus the gradient with respect to the final class codes.  Returns (losses, {state_dict key: grad}, extras)."""
+        keys = self.trainable_code_generator_keys()
+        saved = {k: self.sd[k] for k in keys}
+        leaves = {k: saved[k].detach().clone().requires_grad_(True) for k in keys}
+        self.sd.update(leaves)
+        try:
+            with torch.enable_grad():
+                losses, extras = self._training_forward(batched_inputs, world_size, reduce)
+                for t in (extras["codes"]["cls_conv"], extras["codes"]["cls_bias"]):
+                    t.retain_grad()
+                total = sum(losses.values())
+                total.backward()
+            grads = {k: (leaves[k].grad if leaves[k].grad is not None else torch.zeros_like(leaves[k])).detach() for k in keys}
+            extras["grad_codes"] = {"cls_conv": extras["codes"]["cls_conv"].grad.detach(),
+                                    "cls_bias": extras["codes"]["cls_bias"].grad.detach()}
+        finally:
+            self.sd.update(saved)
+        return {k: v.detach() for k, v in losses.items()}, grads, extras
 
     def process_codes_training(self, cls_conv: torch.Tensor, cls_bias: torch.Tensor):
         """code_process_module on the whole (C, 256, 1, 1) batch (code_generator.py:864-875; the `size(0) == 1`

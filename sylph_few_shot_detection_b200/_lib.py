@@ -44,6 +44,15 @@ class LossConfig(Structure):
 
 LOSS_SUMS = 5
 BACKGROUND_ID = 100000
+CG_MAX_TOWER = 4
+
+
+class CodegenTensors(Structure):
+    """Mirror of `sylph_codegen_tensors`: device fp32 pointers of the code generator's trainable tensors (or their gradients)."""
+    _fields_ = [("tower_w", c_void_p * CG_MAX_TOWER), ("tower_b", c_void_p * CG_MAX_TOWER),
+                ("tower_gn_w", c_void_p * CG_MAX_TOWER), ("tower_gn_b", c_void_p * CG_MAX_TOWER),
+                ("cls_w", c_void_p), ("cls_b", c_void_p), ("bias_w", c_void_p), ("bias_b", c_void_p),
+                ("post_norm_w", c_void_p), ("post_norm_b", c_void_p), ("conv_scale", c_void_p), ("bias_scale", c_void_p)]
 
 
 def _sources():
@@ -82,7 +91,7 @@ def load() -> ctypes.CDLL:
     if not os.path.exists(LIB_PATH):
         build()
     lib = ctypes.CDLL(LIB_PATH)
-    if not hasattr(lib, "sylph_set_precision"):   # a stale in-tree build from before the precision modes
+    if not hasattr(lib, "sylph_codegen_backward"):   # a stale in-tree build from before the training backward
         build(force=True)
         lib = ctypes.CDLL(LIB_PATH)
     vp, ip, fp = c_void_p, POINTER(c_int), POINTER(c_float)
@@ -153,6 +162,12 @@ def load() -> ctypes.CDLL:
                                          POINTER(c_int64), ip, vp, vp, vp, vp, vp]
     lib.sylph_fcos_loss_finalize.restype = c_int
     lib.sylph_fcos_loss_finalize.argtypes = [vp, vp, vp, c_int, vp, vp]
+    lib.sylph_fcos_cls_loss_backward.restype = c_int
+    lib.sylph_fcos_cls_loss_backward.argtypes = [vp, c_int, c_int, POINTER(c_int64), POINTER(LossConfig), vp, vp, vp, c_int, vp, vp, vp]
+    lib.sylph_codegen_backward.restype = c_int
+    lib.sylph_codegen_backward.argtypes = [vp, c_int, c_int, ip, vp, vp, POINTER(CodegenTensors), POINTER(CodegenTensors), vp]
+    lib.sylph_update_code_generator.restype = c_int
+    lib.sylph_update_code_generator.argtypes = [vp]
     lib.sylph_launch_count.restype = c_int64
     lib.sylph_launch_count.argtypes = [vp]
     lib.sylph_set_profiling.restype = c_int
@@ -168,5 +183,6 @@ EXPORTED_SYMBOLS = [
     "sylph_finalize_weights", "sylph_extract_features", "sylph_extract_features_u8", "sylph_extract_features_normalized", "sylph_extract_features_multi", "sylph_import_features", "sylph_set_image_sizes", "sylph_feature_shape",
     "sylph_export_features", "sylph_generate_codes", "sylph_export_roi_features", "sylph_normalize_codes", "sylph_exchange_create", "sylph_exchange_connect",
     "sylph_normalize_codes_exchange", "sylph_exchange_poll", "sylph_exchange_status", "sylph_exchange_destroy", "sylph_accumulate_codes", "sylph_reduce_codes",
-    "sylph_detect", "sylph_detect_after", "sylph_detect_poll", "sylph_export_head_output", "sylph_fcos_loss_sums", "sylph_fcos_loss_finalize", "sylph_launch_count", "sylph_set_profiling", "sylph_get_timings",
+    "sylph_detect", "sylph_detect_after", "sylph_detect_poll", "sylph_export_head_output", "sylph_fcos_loss_sums", "sylph_fcos_loss_finalize",
+    "sylph_fcos_cls_loss_backward", "sylph_codegen_backward", "sylph_update_code_generator", "sylph_launch_count", "sylph_set_profiling", "sylph_get_timings",
 ]

@@ -15,6 +15,7 @@
 #include "kernels_detect.cuh"
 #include "kernels_roi_encoder.cuh"
 #include "kernels_loss.cuh"
+#include "kernels_backward.cuh"
 
 namespace sylph {
 
@@ -155,6 +156,9 @@ struct sylph_ctx {
     // state of the last generate_codes / detect call (for exports)
     int last_n_rois = 0;
     int last_detect_slot = -1, last_detect_classes = 0, last_logit_stride = 0;
+    const __half* last_cls_tower = nullptr;   // output planes of the class tower of the last head pass (backward of the cls loss)
+    bool weights_ready = false;               // sylph_finalize_weights has succeeded once (sylph_update_code_generator needs it)
+    bool inplace_uploads = false;             // sylph_update_code_generator: re-upload into the existing device buffers
 
     int fail(const char* fmt, ...) {
         char b[1024];
@@ -239,13 +243,13 @@ static int stage_h2d(sylph_ctx* c, void* dst_dev, const void* src_host, size_t b
 }
 
 static int upload(sylph_ctx* c, const std::vector<float>& h, float** d) {
-    CU_TRY(c, cudaMalloc(d, std::max<size_t>(h.size(), 1) * sizeof(float)));
+    if (!(c->inplace_uploads && *d != nullptr)) CU_TRY(c, cudaMalloc(d, std::max<size_t>(h.size(), 1) * sizeof(float)));
     CU_TRY(c, cudaMemcpy(*d, h.data(), h.size() * sizeof(float), cudaMemcpyHostToDevice));
     return 0;
 }
 
 static int upload_half(sylph_ctx* c, const std::vector<uint16_t>& h, __half** d) {
-    CU_TRY(c, cudaMalloc(d, std::max<size_t>(h.size(), 1) * sizeof(uint16_t)));
+    if (!(c->inplace_uploads && *d != nullptr)) CU_TRY(c, cudaMalloc(d, std::max<size_t>(h.size(), 1) * sizeof(uint16_t)));
     CU_TRY(c, cudaMemcpy(*d, h.data(), h.size() * sizeof(uint16_t), cudaMemcpyHostToDevice));
     return 0;
 }
@@ -909,6 +913,71 @@ int sylph_load_tensor(sylph_ctx* c, const char* key, const float* host_data, con
     return 0;
 }
 
+}  // extern "C"
+
+// CodeGenerator weights (code_generator.py:520-646).  With c->inplace_uploads the prepared tensors are refreshed in their
+// existing device buffers (sylph_update_code_generator: the weights after an optimiser step, same shapes).
+static int prep_code_generator(sylph_ctx* c) {
+    const sylph_model_config& f = c->cfg;
+    const std::string cg = "code_generator.code_generator_head.";
+    if (!c->inplace_uploads) {
+        c->cg_tower.assign(f.cg_tower_layers, ConvW());
+        c->cg_gn_w.assign(f.cg_tower_layers, nullptr);
+        c->cg_gn_b.assign(f.cg_tower_layers, nullptr);
+    }
+    for (int i = 0; i < f.cg_tower_layers; ++i) {
+        TRY(prep_conv(c, cg + "support_set_shared_tower." + std::to_string(3 * i), false, true, &c->cg_tower[i]));
+        TRY(upload_vec(c, cg + "support_set_shared_tower." + std::to_string(3 * i + 1) + ".weight", &c->cg_gn_w[i], 256));
+        TRY(upload_vec(c, cg + "support_set_shared_tower." + std::to_string(3 * i + 1) + ".bias", &c->cg_gn_b[i], 256));
+    }
+    TRY(prep_conv(c, cg + "support_set_cls_conv.0", false, true, &c->cg_cls));
+    if (c->cg_cls.cout != 256) return c->fail("CODE_GENERATOR.OUT_CHANNEL must be 256 on this path");
+    {   // the same layer as a [2304 -> 256] GEMM over the nine window means of a ROI (kernels_codegen.cuh, roi_window_means_kernel)
+        const HostTensor *w = find_t(c, cg + "support_set_cls_conv.0.weight"), *b = find_t(c, cg + "support_set_cls_conv.0.bias");
+        if (!w || !b || w->data.size() != static_cast<size_t>(256) * 256 * 9) return c->fail("support_set_cls_conv must be a 3x3 256 -> 256 convolution");
+        HostTensor pw;
+        pw.shape = {256, 2304, 1, 1};
+        pw.data.resize(w->data.size());
+        for (int o = 0; o < 256; ++o)
+            for (int ch = 0; ch < 256; ++ch)
+                for (int tap = 0; tap < 9; ++tap)
+                    pw.data[static_cast<size_t>(o) * 2304 + tap * 256 + ch] = w->data[(static_cast<size_t>(o) * 256 + ch) * 9 + tap];
+        c->staged["__cg_cls_pooled.weight"] = std::move(pw);
+        c->staged["__cg_cls_pooled.bias"] = *b;
+        TRY(prep_conv(c, "__cg_cls_pooled", false, true, &c->cg_cls_pooled));
+    }
+    if (f.cg_bias_layer) {
+        const HostTensor *w = find_t(c, cg + "support_set_cls_bias.0.weight"), *b = find_t(c, cg + "support_set_cls_bias.0.bias");
+        if (!w || !b || w->data.size() != 256 * 9) return c->fail("missing support_set_cls_bias tensors");
+        std::vector<float> hw(9 * 256);
+        for (int ch = 0; ch < 256; ++ch)
+            for (int t = 0; t < 9; ++t) hw[t * 256 + ch] = w->data[ch * 9 + t];
+        TRY(upload(c, hw, &c->cg_wbias));
+        TRY(upload(c, b->data, &c->cg_bbias));
+        TRY(scalar_of(c, cg + "bias_scale.scale", &c->bias_scale));
+    } else {
+        c->bias_scale = 1.f;
+    }
+    if (f.cg_weight_layer) {
+        const HostTensor *w = find_t(c, cg + "support_set_cls_weight.0.weight"), *b = find_t(c, cg + "support_set_cls_weight.0.bias");
+        if (!w || !b || w->data.size() != 256 * 9) return c->fail("missing support_set_cls_weight tensors");
+        std::vector<float> hw(9 * 256);
+        for (int ch = 0; ch < 256; ++ch)
+            for (int t = 0; t < 9; ++t) hw[t * 256 + ch] = w->data[ch * 9 + t];
+        TRY(upload(c, hw, &c->cg_wweight));
+        TRY(upload(c, b->data, &c->cg_bweight));
+    }
+    if (f.cg_post_norm) {
+        TRY(upload_vec(c, cg + "post_norm.weight", &c->post_gn_w, 256));
+        TRY(upload_vec(c, cg + "post_norm.bias", &c->post_gn_b, 256));
+    }
+    c->conv_scale = 1.f;
+    if (f.cg_has_conv_scale) TRY(scalar_of(c, cg + "conv_scale.scale", &c->conv_scale));
+    return 0;
+}
+
+extern "C" {
+
 int sylph_finalize_weights(sylph_ctx* c) {
     if (!c) return 1;
     CU_TRY(c, cudaSetDevice(c->device));
@@ -980,63 +1049,34 @@ int sylph_finalize_weights(sylph_ctx* c) {
     } else if (f.generator == 1) {
         TRY(prep_roi_encoder(c));
     } else {
-        const std::string cg = "code_generator.code_generator_head.";
-        c->cg_tower.assign(f.cg_tower_layers, ConvW());
-        c->cg_gn_w.assign(f.cg_tower_layers, nullptr);
-        c->cg_gn_b.assign(f.cg_tower_layers, nullptr);
-        for (int i = 0; i < f.cg_tower_layers; ++i) {
-            TRY(prep_conv(c, cg + "support_set_shared_tower." + std::to_string(3 * i), false, true, &c->cg_tower[i]));
-            TRY(upload_vec(c, cg + "support_set_shared_tower." + std::to_string(3 * i + 1) + ".weight", &c->cg_gn_w[i], 256));
-            TRY(upload_vec(c, cg + "support_set_shared_tower." + std::to_string(3 * i + 1) + ".bias", &c->cg_gn_b[i], 256));
-        }
-        TRY(prep_conv(c, cg + "support_set_cls_conv.0", false, true, &c->cg_cls));
-        if (c->cg_cls.cout != 256) return c->fail("CODE_GENERATOR.OUT_CHANNEL must be 256 on this path");
-        {   // the same layer as a [2304 -> 256] GEMM over the nine window means of a ROI (kernels_codegen.cuh, roi_window_means_kernel)
-            const HostTensor *w = find_t(c, cg + "support_set_cls_conv.0.weight"), *b = find_t(c, cg + "support_set_cls_conv.0.bias");
-            if (!w || !b || w->data.size() != static_cast<size_t>(256) * 256 * 9) return c->fail("support_set_cls_conv must be a 3x3 256 -> 256 convolution");
-            HostTensor pw;
-            pw.shape = {256, 2304, 1, 1};
-            pw.data.resize(w->data.size());
-            for (int o = 0; o < 256; ++o)
-                for (int ch = 0; ch < 256; ++ch)
-                    for (int tap = 0; tap < 9; ++tap)
-                        pw.data[static_cast<size_t>(o) * 2304 + tap * 256 + ch] = w->data[(static_cast<size_t>(o) * 256 + ch) * 9 + tap];
-            c->staged["__cg_cls_pooled.weight"] = std::move(pw);
-            c->staged["__cg_cls_pooled.bias"] = *b;
-            TRY(prep_conv(c, "__cg_cls_pooled", false, true, &c->cg_cls_pooled));
-        }
-        if (f.cg_bias_layer) {
-            const HostTensor *w = find_t(c, cg + "support_set_cls_bias.0.weight"), *b = find_t(c, cg + "support_set_cls_bias.0.bias");
-            if (!w || !b || w->data.size() != 256 * 9) return c->fail("missing support_set_cls_bias tensors");
-            std::vector<float> hw(9 * 256);
-            for (int ch = 0; ch < 256; ++ch)
-                for (int t = 0; t < 9; ++t) hw[t * 256 + ch] = w->data[ch * 9 + t];
-            TRY(upload(c, hw, &c->cg_wbias));
-            TRY(upload(c, b->data, &c->cg_bbias));
-            TRY(scalar_of(c, cg + "bias_scale.scale", &c->bias_scale));
-        } else {
-            c->bias_scale = 1.f;
-        }
-        if (f.cg_weight_layer) {
-            const HostTensor *w = find_t(c, cg + "support_set_cls_weight.0.weight"), *b = find_t(c, cg + "support_set_cls_weight.0.bias");
-            if (!w || !b || w->data.size() != 256 * 9) return c->fail("missing support_set_cls_weight tensors");
-            std::vector<float> hw(9 * 256);
-            for (int ch = 0; ch < 256; ++ch)
-                for (int t = 0; t < 9; ++t) hw[t * 256 + ch] = w->data[ch * 9 + t];
-            TRY(upload(c, hw, &c->cg_wweight));
-            TRY(upload(c, b->data, &c->cg_bweight));
-        }
-        if (f.cg_post_norm) {
-            TRY(upload_vec(c, cg + "post_norm.weight", &c->post_gn_w, 256));
-            TRY(upload_vec(c, cg + "post_norm.bias", &c->post_gn_b, 256));
-        }
-        c->conv_scale = 1.f;
-        if (f.cg_has_conv_scale) TRY(scalar_of(c, cg + "conv_scale.scale", &c->conv_scale));
+        TRY(prep_code_generator(c));
     }
     c->bias_value = -std::log((1.f - f.prior_prob) / f.prior_prob);
     c->staged.clear();
     c->finalized = true;
+    c->weights_ready = true;
     return 0;
+}
+
+int sylph_update_code_generator(sylph_ctx* c) {
+    if (!c) return 1;
+    if (!c->weights_ready) return c->fail("sylph_update_code_generator: call sylph_finalize_weights once first");
+    if (c->cfg.generator != 0) return c->fail("sylph_update_code_generator: only the CodeGenerator plugin is trainable on this path");
+    for (const auto& kv : c->staged)
+        if (kv.first.rfind("code_generator.", 0) != 0) {
+            c->staged.clear();   // the context keeps serving the weights it had
+            c->finalized = true;
+            return c->fail("sylph_update_code_generator: staged tensor %s is not a code-generator tensor "
+                           "(sylph_finalize_weights reloads a whole model)", kv.first.c_str());
+        }
+    CU_TRY(c, cudaSetDevice(c->device));
+    CU_TRY(c, cudaDeviceSynchronize());   // no launch may still read the tensors that are about to change
+    c->inplace_uploads = true;
+    const int rc = prep_code_generator(c);
+    c->inplace_uploads = false;
+    c->staged.clear();
+    c->finalized = true;
+    return rc;
 }
 
 }  // extern "C"
@@ -1550,6 +1590,7 @@ static int run_head(sylph_ctx* c, int slot, const float* codes_dev, int n_classe
     c->last_detect_slot = slot;
     c->last_detect_classes = n_classes;
     c->last_logit_stride = CW.cout_pad;
+    c->last_cls_tower = x;
     out->logits = static_cast<float*>(lg);
     out->pred = static_cast<float*>(pr);
     out->logit_stride = CW.cout_pad;
@@ -2215,6 +2256,190 @@ int sylph_fcos_loss_finalize(sylph_ctx* c, const double* local_sums_dev, const d
                        global_pos_ctr_dev ? global_pos_ctr_dev : local_sums_dev + 1, world_size, losses_out_dev));
     CU_TRY(c, cudaGetLastError());
     c->launches++;
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------------ training backward
+int sylph_fcos_cls_loss_backward(sylph_ctx* c, int slot, int n_classes, const int64_t* support_targets_host,
+                                 const sylph_loss_config* lc, const int64_t* labels_dev, const double* local_sums_dev,
+                                 const double* global_pos_ctr_dev, int world_size, const float* grad_loss_dev,
+                                 float* grad_codes_out_dev, void* stream) {
+    if (!c) return 1;
+    if (!c->finalized) return c->fail("weights not finalized");
+    if (slot < 0 || slot >= SYLPH_NUM_SLOTS || !c->slots[slot].valid) return c->fail("slot %d holds no features", slot);
+    if (!support_targets_host || !lc || !labels_dev || !local_sums_dev || !grad_codes_out_dev) return c->fail("null argument");
+    if (world_size < 1) return c->fail("world_size must be >= 1");
+    if (c->last_detect_slot != slot || c->last_detect_classes != n_classes || c->last_cls_tower == nullptr)
+        return c->fail("sylph_fcos_cls_loss_backward: the last head pass was not sylph_fcos_loss_sums on slot %d with %d classes", slot, n_classes);
+    CU_TRY(c, cudaSetDevice(c->device));
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    const Slot& S = c->slots[slot];
+    auto lg = c->bufs.find("det.logits");
+    if (lg == c->bufs.end() || !lg->second.p) return c->fail("no logits buffer");
+    void *stg, *part;
+    long long total_px = 0;
+    for (int l = 0; l < 5; ++l) total_px += static_cast<long long>(S.n) * S.lh[l] * S.lw[l];
+    const int blocks = static_cast<int>(std::min<long long>(2LL * c->num_sms, (total_px + kClsBwdRows - 1) / kClsBwdRows));
+    TRY(ensure(c, "bwd.support_targets", static_cast<size_t>(n_classes) * 8, "", &stg, st, false));
+    TRY(ensure(c, "bwd.code_partials", static_cast<size_t>(blocks) * n_classes * 257 * 4, "", &part, st, false));
+    TRY(stage_h2d(c, stg, support_targets_host, static_cast<size_t>(n_classes) * 8, st));
+    {
+        StageTimer t(c, "bwd.cls_loss_codes", st, static_cast<double>(total_px) * (c->ld(256) * 2 + c->last_logit_stride * 4));
+        CU_TRY(c, launch_k(fcos_cls_loss_bwd_kernel, dim3(blocks), dim3(256), 0, st, static_cast<const float*>(lg->second.p),
+                           c->last_logit_stride, c->last_cls_tower, c->ld(256), c->lo(256), S.pg, S.n,
+                           reinterpret_cast<const long long*>(labels_dev), static_cast<const long long*>(stg), n_classes,
+                           lc->focal_alpha, lc->focal_gamma, global_pos_ctr_dev ? global_pos_ctr_dev : local_sums_dev + 1,
+                           world_size, grad_loss_dev, static_cast<float*>(part)));
+        CU_TRY(c, cudaGetLastError());
+        const int n_elems = n_classes * 257;
+        CU_TRY(c, launch_k(fcos_code_grad_reduce_kernel, dim3(ceil_div(n_elems, 256)), dim3(256), 0, st,
+                           static_cast<const float*>(part), blocks, n_elems, grad_codes_out_dev));
+        CU_TRY(c, cudaGetLastError());
+        c->launches += 2;
+    }
+    return 0;
+}
+
+static int sgemm(sylph_ctx* c, cudaStream_t st, const float* A, long long sam, long long sak, const float* B, long long sbk,
+                 long long sbn, float* C, long long ldc, int M, int N, int K, const float* bias, int accumulate) {
+    CU_TRY(c, launch_k(sgemm_f32_kernel, dim3(ceil_div(N, kSgTile), ceil_div(M, kSgTile)), dim3(256), 0, st, A, sam, sak, B, sbk, sbn,
+                       C, ldc, M, N, K, bias, accumulate));
+    CU_TRY(c, cudaGetLastError());
+    c->launches++;
+    return 0;
+}
+
+int sylph_codegen_backward(sylph_ctx* c, int n_rois, int n_classes, const int* class_offsets_host, const float* raw_codes_dev,
+                           const float* grad_codes_dev, const sylph_codegen_tensors* params, const sylph_codegen_tensors* grads,
+                           void* stream) {
+    if (!c) return 1;
+    if (!c->finalized) return c->fail("weights not finalized");
+    const sylph_model_config& f = c->cfg;
+    if (f.generator != 0) return c->fail("sylph_codegen_backward: only the CodeGenerator plugin is trainable on this path");
+    if (f.cg_weight_layer) return c->fail("sylph_codegen_backward: CODE_GENERATOR.WEIGHT_LAYER is not differentiated on this path");
+    if (!class_offsets_host || !raw_codes_dev || !grad_codes_dev || !params || !grads) return c->fail("null argument");
+    if (n_rois <= 0 || n_rois != c->last_n_rois)
+        return c->fail("sylph_codegen_backward: %d ROIs, but the last sylph_generate_codes call pooled %d", n_rois, c->last_n_rois);
+    if (n_rois > 4096) return c->fail("sylph_codegen_backward: at most 4096 support ROIs per call");
+    if (f.cg_tower_layers > SYLPH_CG_MAX_TOWER) return c->fail("more than %d tower layers", SYLPH_CG_MAX_TOWER);
+    if (class_offsets_host[0] != 0 || class_offsets_host[n_classes] != n_rois) return c->fail("class_offsets must span all ROIs");
+    const int L = f.cg_tower_layers;
+    for (int i = 0; i < L; ++i)
+        if (!params->tower_w[i] || !params->tower_b[i] || !params->tower_gn_w[i] || !params->tower_gn_b[i] ||
+            !grads->tower_w[i] || !grads->tower_b[i] || !grads->tower_gn_w[i] || !grads->tower_gn_b[i])
+            return c->fail("tower layer %d: missing parameter / gradient tensor", i);
+    if (!params->cls_w || !params->cls_b || !grads->cls_w || !grads->cls_b) return c->fail("support_set_cls_conv tensors missing");
+    if (f.cg_bias_layer && (!params->bias_w || !params->bias_b || !grads->bias_w || !grads->bias_b))
+        return c->fail("support_set_cls_bias tensors missing");
+    if (f.cg_post_norm && (!params->post_norm_w || !params->post_norm_b || !grads->post_norm_w || !grads->post_norm_b))
+        return c->fail("post_norm tensors missing");
+    if (f.cg_has_conv_scale && (!params->conv_scale || !grads->conv_scale)) return c->fail("conv_scale tensors missing");
+    if (f.cg_bias_layer && (!params->bias_scale || !grads->bias_scale)) return c->fail("bias_scale tensors missing");
+    CU_TRY(c, cudaSetDevice(c->device));
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    std::vector<int> roi_class(n_rois);
+    for (int k = 0; k < n_classes; ++k) {
+        if (class_offsets_host[k + 1] <= class_offsets_host[k]) return c->fail("class %d has no support ROI", k);
+        for (int r = class_offsets_host[k]; r < class_offsets_host[k + 1]; ++r) roi_class[r] = k;
+    }
+    const int P = n_rois * 49;
+    const size_t act = static_cast<size_t>(P) * 256 * 4;
+    void *xbuf, *ybuf, *stats, *col, *dcol, *da, *db, *yc, *vb, *dv, *draw, *parts, *scal, *prc, *pco;
+    TRY(ensure(c, "bwd.x", act * (L + 1), "", &xbuf, st, false));              // inputs of every layer (X_0 .. X_L)
+    TRY(ensure(c, "bwd.y", act * std::max(L, 1), "", &ybuf, st, false));       // convolution outputs in front of the GroupNorms
+    TRY(ensure(c, "bwd.stats", static_cast<size_t>(std::max(L, 1)) * 2 * n_rois * 256 * 4, "", &stats, st, false));
+    TRY(ensure(c, "bwd.col", static_cast<size_t>(P) * 2304 * 4, "", &col, st, false));
+    TRY(ensure(c, "bwd.dcol", static_cast<size_t>(P) * 2304 * 4, "", &dcol, st, false));
+    TRY(ensure(c, "bwd.da", act, "", &da, st, false));
+    TRY(ensure(c, "bwd.db", act, "", &db, st, false));
+    TRY(ensure(c, "bwd.yc", act, "", &yc, st, false));
+    TRY(ensure(c, "bwd.vb", static_cast<size_t>(P) * 4, "", &vb, st, false));
+    TRY(ensure(c, "bwd.dv", static_cast<size_t>(P) * 4, "", &dv, st, false));
+    TRY(ensure(c, "bwd.draw", static_cast<size_t>(n_classes) * 257 * 4, "", &draw, st, false));
+    TRY(ensure(c, "bwd.parts", static_cast<size_t>(2) * n_rois * 256 * 4, "", &parts, st, false));
+    TRY(ensure(c, "bwd.scalars", 64, "", &scal, st, false));
+    TRY(ensure(c, "bwd.roi_class", static_cast<size_t>(n_rois) * 4, "", &prc, st, false));
+    TRY(ensure(c, "bwd.class_off", static_cast<size_t>(n_classes + 1) * 4, "", &pco, st, false));
+    TRY(stage_h2d(c, prc, roi_class.data(), static_cast<size_t>(n_rois) * 4, st));
+    TRY(stage_h2d(c, pco, class_offsets_host, static_cast<size_t>(n_classes + 1) * 4, st));
+    auto r0 = c->bufs.find("cg.r0");
+    if (r0 == c->bufs.end() || !r0->second.p) return c->fail("no ROI planes");
+    auto X = [&](int i) { return static_cast<float*>(xbuf) + static_cast<size_t>(i) * P * 256; };
+    auto Y = [&](int i) { return static_cast<float*>(ybuf) + static_cast<size_t>(i) * P * 256; };
+    auto MEAN = [&](int i) { return static_cast<float*>(stats) + static_cast<size_t>(2 * i) * n_rois * 256; };
+    auto RSTD = [&](int i) { return static_cast<float*>(stats) + static_cast<size_t>(2 * i + 1) * n_rois * 256; };
+    float* colp = static_cast<float*>(col);
+    float* dcolp = static_cast<float*>(dcol);
+    const int g_act = grid_for(static_cast<long long>(P) * 256, 256, c->num_sms);
+    const int g_col = grid_for(static_cast<long long>(P) * 2304, 256, c->num_sms);
+    StageTimer t(c, "bwd.code_generator", st, 0.0);
+    // ---- forward, fp32 (code_generator.py:941-967)
+    CU_TRY(c, launch_k(roi_planes_to_f32_kernel, dim3(g_act), dim3(256), 0, st, static_cast<const __half*>(r0->second.p), X(0), n_rois,
+                       c->split, c->roi_stride));
+    c->launches++;
+    for (int i = 0; i < L; ++i) {
+        CU_TRY(c, launch_k(im2col_roi_kernel, dim3(g_col), dim3(256), 0, st, static_cast<const float*>(X(i)), colp, n_rois));
+        c->launches++;
+        TRY(sgemm(c, st, colp, 2304, 1, params->tower_w[i], 1, 2304, Y(i), 256, P, 256, 2304, params->tower_b[i], 0));
+        CU_TRY(c, launch_k(roi_gn_relu_fwd_f32_kernel, dim3(n_rois), dim3(256), 0, st, static_cast<const float*>(Y(i)),
+                           static_cast<const float*>(params->tower_gn_w[i]), static_cast<const float*>(params->tower_gn_b[i]), X(i + 1),
+                           MEAN(i), RSTD(i)));
+        c->launches++;
+    }
+    CU_TRY(c, launch_k(im2col_roi_kernel, dim3(g_col), dim3(256), 0, st, static_cast<const float*>(X(L)), colp, n_rois));
+    c->launches++;
+    if (f.cg_bias_layer)   // v = support_set_cls_bias(x): one output channel
+        TRY(sgemm(c, st, colp, 2304, 1, params->bias_w, 1, 2304, static_cast<float*>(vb), 1, P, 1, 2304, params->bias_b, 0));
+    // ---- code processing, class mean, pools (code_generator.py:778-875)
+    CU_TRY(c, launch_k(normalize_codes_bwd_kernel, dim3(1), dim3(256), 0, st, raw_codes_dev, grad_codes_dev, n_classes,
+                       static_cast<const float*>(params->post_norm_w), static_cast<const float*>(params->post_norm_b), f.cg_post_norm,
+                       f.cg_conv_l2_norm, static_cast<const float*>(f.cg_has_conv_scale ? params->conv_scale : nullptr),
+                       static_cast<const float*>(f.cg_bias_layer ? params->bias_scale : nullptr), static_cast<float*>(draw),
+                       f.cg_post_norm ? grads->post_norm_w : nullptr, f.cg_post_norm ? grads->post_norm_b : nullptr,
+                       static_cast<float*>(scal)));
+    c->launches++;
+    if (f.cg_has_conv_scale) CU_TRY(c, cudaMemcpyAsync(grads->conv_scale, scal, 4, cudaMemcpyDeviceToDevice, st));
+    if (f.cg_bias_layer) CU_TRY(c, cudaMemcpyAsync(grads->bias_scale, static_cast<float*>(scal) + 1, 4, cudaMemcpyDeviceToDevice, st));
+    float* dyc = static_cast<float*>(da);
+    CU_TRY(c, launch_k(shot_code_bwd_kernel, dim3(n_rois), dim3(256), 0, st, static_cast<const float*>(draw), static_cast<const int*>(prc),
+                       static_cast<const int*>(pco), static_cast<const float*>(vb), f.cg_bias_layer, f.cg_bias_l2_norm, dyc,
+                       static_cast<float*>(dv)));
+    c->launches++;
+    // ---- support_set_cls_conv / support_set_cls_bias: weight, bias and input gradients
+    auto colsum = [&](const float* in, int ld_in, int rows, int cols, float* out) -> int {
+        CU_TRY(c, launch_k(colsum_f32_kernel, dim3(ceil_div(cols, 32)), dim3(256), 0, st, in, static_cast<long long>(ld_in), rows, cols, out));
+        c->launches++;
+        return 0;
+    };
+    TRY(sgemm(c, st, dyc, 1, 256, colp, 2304, 1, grads->cls_w, 2304, 256, 2304, P, nullptr, 0));          // dW = dY^T col
+    TRY(colsum(dyc, 256, P, 256, grads->cls_b));
+    if (L > 0) TRY(sgemm(c, st, dyc, 256, 1, params->cls_w, 2304, 1, dcolp, 2304, P, 2304, 256, nullptr, 0));  // dcol = dY W
+    if (f.cg_bias_layer) {
+        const float* dvp = static_cast<const float*>(dv);
+        TRY(sgemm(c, st, dvp, 1, 1, colp, 2304, 1, grads->bias_w, 2304, 1, 2304, P, nullptr, 0));
+        TRY(colsum(dvp, 1, P, 1, grads->bias_b));
+        if (L > 0) TRY(sgemm(c, st, dvp, 1, 1, params->bias_w, 2304, 1, dcolp, 2304, P, 2304, 1, nullptr, 1));
+    }
+    // ---- support_set_shared_tower, last layer first
+    float* dx = static_cast<float*>(db);
+    for (int i = L - 1; i >= 0; --i) {
+        CU_TRY(c, launch_k(col2im_roi_kernel, dim3(g_act), dim3(256), 0, st, static_cast<const float*>(dcolp), dx, n_rois));
+        c->launches++;
+        float* dgp = static_cast<float*>(parts);
+        float* dbp = dgp + static_cast<size_t>(n_rois) * 256;
+        CU_TRY(c, launch_k(roi_gn_relu_bwd_f32_kernel, dim3(n_rois), dim3(256), 0, st, static_cast<const float*>(dx),
+                           static_cast<const float*>(Y(i)), static_cast<const float*>(MEAN(i)), static_cast<const float*>(RSTD(i)),
+                           static_cast<const float*>(params->tower_gn_w[i]), static_cast<const float*>(params->tower_gn_b[i]), dx, dgp, dbp));
+        c->launches++;
+        TRY(colsum(dgp, 256, n_rois, 256, grads->tower_gn_w[i]));
+        TRY(colsum(dbp, 256, n_rois, 256, grads->tower_gn_b[i]));
+        CU_TRY(c, launch_k(im2col_roi_kernel, dim3(g_col), dim3(256), 0, st, static_cast<const float*>(X(i)), colp, n_rois));
+        c->launches++;
+        TRY(sgemm(c, st, dx, 1, 256, colp, 2304, 1, grads->tower_w[i], 2304, 256, 2304, P, nullptr, 0));
+        TRY(colsum(dx, 256, P, 256, grads->tower_b[i]));
+        if (i > 0) TRY(sgemm(c, st, dx, 256, 1, params->tower_w[i], 2304, 1, dcolp, 2304, P, 2304, 256, nullptr, 0));
+    }
+    CU_TRY(c, cudaGetLastError());
     return 0;
 }
 

@@ -1,0 +1,446 @@
+// Backward of the episodic TRAINING step for the part the shipped meta-training configs train with a frozen detector
+// (e.g. configs/COCO-Detection/Meta-FCOS/Meta-FCOS-finetune-lvis.yaml: BACKBONE.FREEZE, FREEZE_CLS_TOWER,
+// FREEZE_BBOX_BRANCH on, CODE_GENERATOR.FREEZE off): the classification loss -> the class codes -> the code generator.
+//   d loss_fcos_cls / d logits   sigmoid focal loss (fvcore sigmoid_focal_loss_jit, called at fcos_outputs.py:525-537)
+//   d / d codes                  CondConvBasic (meta_fcos/head_utils.py:60-81): logits = <tower output, cls_conv> + cls_bias
+//   d / d raw codes, post_norm, conv_scale, bias_scale     code_process_module (code_generator.py:833-875)
+//   d / d per-shot codes         compute_code (:778-831), uniform 1 / SHOT weights
+//   d / d support_set_cls_conv / support_set_cls_bias (+ F.normalize over the 49 positions) / support_set_shared_tower
+//                                (conv3x3 + GroupNorm(32) + ReLU per layer; :648-688, 941-967)
+// Everything here is fp32 on CUDA cores: 15-50 ROIs of 7x7 pixels are 0.9 GFLOP per convolution, the episode's time is in
+// the frozen detector's forward.  The code generator's forward is re-evaluated in fp32 from the pooled ROI features the
+// forward pass left in the ROI planes (no activations are kept by the tensor-core forward kernels).
+// Convolutions are GEMMs over an explicit im2col matrix whose K index is ci * 9 + tap, i.e. PyTorch's OIHW order: the
+// caller's parameter tensors are read, and the gradients written, in place in the state_dict layout.
+// No atomics: every reduction has a fixed order, so gradients are bit-reproducible run to run.
+#pragma once
+#include "kernels_loss.cuh"
+
+namespace sylph {
+
+// ------------------------------------------------------------------------------------------------ generic fp32 GEMM
+// C[M, N] (row-major, ldc) = (accumulate ? C : 0) + A'[M, K] * B'[K, N] (+ bias[n]);  A'(m, k) = A[m * sam + k * sak],
+// B'(k, n) = B[k * sbk + n * sbn].  64 x 64 x 16 tiles, 256 threads, 4 x 4 outputs per thread; any M, N, K.
+constexpr int kSgTile = 64, kSgK = 16;
+
+__global__ void __launch_bounds__(256)
+sgemm_f32_kernel(const float* __restrict__ A, long long sam, long long sak, const float* __restrict__ B, long long sbk,
+                 long long sbn, float* __restrict__ C, long long ldc, int M, int N, int K, const float* __restrict__ bias,
+                 int accumulate) {
+    ptx::griddep_launch();
+    ptx::griddep_wait();
+    __shared__ float As[kSgK][kSgTile + 4];
+    __shared__ float Bs[kSgK][kSgTile + 4];
+    const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
+    const int m0 = blockIdx.y * kSgTile, n0 = blockIdx.x * kSgTile;
+    float acc[4][4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+    for (int k0 = 0; k0 < K; k0 += kSgK) {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const int e = tid + i * 256;
+            int m, k;
+            if (sak == 1) { m = e >> 4; k = e & 15; } else { m = e & 63; k = e >> 6; }
+            const int gm = m0 + m, gk = k0 + k;
+            As[k][m] = (gm < M && gk < K) ? __ldg(A + gm * sam + gk * sak) : 0.f;
+            int n, kb;
+            if (sbn == 1) { n = e & 63; kb = e >> 6; } else { kb = e & 15; n = e >> 4; }
+            const int gn = n0 + n, gkb = k0 + kb;
+            Bs[kb][n] = (gn < N && gkb < K) ? __ldg(B + gkb * sbk + gn * sbn) : 0.f;
+        }
+        __syncthreads();
+#pragma unroll
+        for (int k = 0; k < kSgK; ++k) {
+            float a[4], b[4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) a[i] = As[k][ty * 4 + i];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) b[j] = Bs[k][tx * 4 + j];
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+#pragma unroll
+                for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
+        }
+        __syncthreads();
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const int gm = m0 + ty * 4 + i;
+        if (gm >= M) continue;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const int gn = n0 + tx * 4 + j;
+            if (gn >= N) continue;
+            float v = acc[i][j];
+            if (bias) v += bias[gn];
+            float* dst = C + gm * ldc + gn;
+            *dst = accumulate ? *dst + v : v;
+        }
+    }
+}
+
+// out[c] = sum over r < rows of in[r * ld + c], c < cols: one block per 32 columns, 8 row lanes, fixed order.
+__global__ void __launch_bounds__(256)
+colsum_f32_kernel(const float* __restrict__ in, long long ld, int rows, int cols, float* __restrict__ out) {
+    ptx::griddep_launch();
+    ptx::griddep_wait();
+    __shared__ float red[8][33];
+    const int lane = threadIdx.x & 31, rl = threadIdx.x >> 5;
+    const int c = blockIdx.x * 32 + lane;
+    float s = 0.f;
+    if (c < cols)
+        for (int r = rl; r < rows; r += 8) s += in[r * ld + c];
+    red[rl][lane] = s;
+    __syncthreads();
+    if (rl == 0 && c < cols) {
+        float t = 0.f;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) t += red[i][lane];
+        out[c] = t;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------ ROI planes <-> fp32
+// Interior 7x7 pixels of the pooled ROI planes (9x9 zero-bordered, `roi_stride` rows per ROI, rows [256 hi | 256 lo] in
+// exact mode) -> X[(roi * 49 + p) * 256 + c] fp32.
+__global__ void __launch_bounds__(256)
+roi_planes_to_f32_kernel(const __half* __restrict__ planes, float* __restrict__ X, int n_rois, int split, int roi_stride) {
+    ptx::griddep_launch();
+    ptx::griddep_wait();
+    const long long total = static_cast<long long>(n_rois) * 49 * 256;
+    for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
+         i += static_cast<long long>(gridDim.x) * blockDim.x) {
+        const int c = static_cast<int>(i & 255);
+        const long long rp = i >> 8;
+        const int p = static_cast<int>(rp % 49);
+        const int r = static_cast<int>(rp / 49);
+        const size_t row = static_cast<size_t>(r) * roi_stride + (p / 7 + 1) * 9 + (p % 7 + 1);
+        X[i] = split ? __half2float(planes[row * 512 + c]) + __half2float(planes[row * 512 + 256 + c])
+                     : __half2float(planes[row * 256 + c]);
+    }
+}
+
+// col[(roi * 49 + p) * 2304 + ci * 9 + tap] = X[roi, y + dy, x + dx, ci] (zero outside the 7x7 plane), tap = (dy+1)*3 + dx+1.
+__global__ void __launch_bounds__(256)
+im2col_roi_kernel(const float* __restrict__ X, float* __restrict__ col, int n_rois) {
+    ptx::griddep_launch();
+    ptx::griddep_wait();
+    const long long total = static_cast<long long>(n_rois) * 49 * 2304;
+    for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
+         i += static_cast<long long>(gridDim.x) * blockDim.x) {
+        const int k = static_cast<int>(i % 2304);
+        const long long rp = i / 2304;
+        const int p = static_cast<int>(rp % 49);
+        const long long r = rp / 49;
+        const int ci = k / 9, tap = k - ci * 9;
+        const int yy = p / 7 + tap / 3 - 1, xx = p % 7 + tap % 3 - 1;
+        col[i] = (yy >= 0 && yy < 7 && xx >= 0 && xx < 7) ? X[(r * 49 + yy * 7 + xx) * 256 + ci] : 0.f;
+    }
+}
+
+// dX[roi, y, x, ci] = sum over taps of dcol[(roi, y - dy, x - dx), ci * 9 + tap] (the transpose of im2col, as a gather).
+__global__ void __launch_bounds__(256)
+col2im_roi_kernel(const float* __restrict__ dcol, float* __restrict__ dX, int n_rois) {
+    ptx::griddep_launch();
+    ptx::griddep_wait();
+    const long long total = static_cast<long long>(n_rois) * 49 * 256;
+    for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
+         i += static_cast<long long>(gridDim.x) * blockDim.x) {
+        const int ci = static_cast<int>(i & 255);
+        const long long rp = i >> 8;
+        const int p = static_cast<int>(rp % 49);
+        const long long r = rp / 49;
+        const int y = p / 7, x = p % 7;
+        float s = 0.f;
+#pragma unroll
+        for (int tap = 0; tap < 9; ++tap) {
+            const int yo = y - (tap / 3 - 1), xo = x - (tap % 3 - 1);   // the output pixel whose tap reads (y, x)
+            if (yo >= 0 && yo < 7 && xo >= 0 && xo < 7) s += dcol[(r * 49 + yo * 7 + xo) * 2304 + ci * 9 + tap];
+        }
+        dX[i] = s;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------ GroupNorm(32) + ReLU
+__device__ __forceinline__ float group8_sum(float v) {   // sum over the 8 channels of a group = 8 consecutive lanes
+    v += __shfl_xor_sync(0xffffffffu, v, 1);
+    v += __shfl_xor_sync(0xffffffffu, v, 2);
+    v += __shfl_xor_sync(0xffffffffu, v, 4);
+    return v;
+}
+
+// One block per ROI, thread = channel.  Y, Xout: [(roi * 49 + p) * 256 + c].  mean / rstd: [roi * 256 + c] (the group's value,
+// replicated per channel).  Two-pass variance over the group's 8 x 49 values, eps 1e-5 (torch.nn.GroupNorm).
+__global__ void __launch_bounds__(256)
+roi_gn_relu_fwd_f32_kernel(const float* __restrict__ Y, const float* __restrict__ gamma, const float* __restrict__ beta,
+                           float* __restrict__ Xout, float* __restrict__ mean_out, float* __restrict__ rstd_out) {
+    ptx::griddep_launch();
+    ptx::griddep_wait();
+    const int r = blockIdx.x, c = threadIdx.x;
+    const float* y = Y + static_cast<size_t>(r) * 49 * 256 + c;
+    float s = 0.f;
+    for (int p = 0; p < 49; ++p) s += y[p * 256];
+    const float mean = group8_sum(s) / 392.f;
+    float v = 0.f;
+    for (int p = 0; p < 49; ++p) { const float d = y[p * 256] - mean; v = fmaf(d, d, v); }
+    const float rstd = 1.f / sqrtf(group8_sum(v) / 392.f + 1e-5f);
+    const float g = gamma[c], b = beta[c];
+    float* xo = Xout + static_cast<size_t>(r) * 49 * 256 + c;
+    for (int p = 0; p < 49; ++p) xo[p * 256] = fmaxf(fmaf((y[p * 256] - mean) * rstd, g, b), 0.f);
+    mean_out[r * 256 + c] = mean;
+    rstd_out[r * 256 + c] = rstd;
+}
+
+// dXn: gradient with respect to the ReLU output.  dY receives the gradient with respect to the convolution output;
+// dgamma_part / dbeta_part [roi * 256 + c] are summed over ROIs by colsum_f32_kernel.  dY may alias dXn.
+__global__ void __launch_bounds__(256)
+roi_gn_relu_bwd_f32_kernel(const float* dXn, const float* __restrict__ Y, const float* __restrict__ mean_in,
+                           const float* __restrict__ rstd_in, const float* __restrict__ gamma, const float* __restrict__ beta,
+                           float* dY, float* __restrict__ dgamma_part, float* __restrict__ dbeta_part) {
+    ptx::griddep_launch();
+    ptx::griddep_wait();
+    const int r = blockIdx.x, c = threadIdx.x;
+    const size_t base = static_cast<size_t>(r) * 49 * 256 + c;
+    const float mean = mean_in[r * 256 + c], rstd = rstd_in[r * 256 + c], g = gamma[c], b = beta[c];
+    float dg = 0.f, db = 0.f, sa = 0.f, sb = 0.f;
+    for (int p = 0; p < 49; ++p) {
+        const float yh = (Y[base + p * 256] - mean) * rstd;
+        const float dz = fmaf(yh, g, b) > 0.f ? dXn[base + p * 256] : 0.f;
+        dg = fmaf(dz, yh, dg);
+        db += dz;
+        sa = fmaf(dz, g, sa);
+        sb = fmaf(dz * g, yh, sb);
+    }
+    const float a = group8_sum(sa) / 392.f, bb = group8_sum(sb) / 392.f;
+    for (int p = 0; p < 49; ++p) {
+        const float yh = (Y[base + p * 256] - mean) * rstd;
+        const float dz = fmaf(yh, g, b) > 0.f ? dXn[base + p * 256] : 0.f;
+        dY[base + p * 256] = rstd * (dz * g - a - yh * bb);
+    }
+    dgamma_part[r * 256 + c] = dg;
+    dbeta_part[r * 256 + c] = db;
+}
+
+// ------------------------------------------------------------------------------------------------ code processing
+// Backward of code_process_module over all classes (code_generator.py:833-875): one block, classes in order, so the
+// parameter gradients (post_norm weight / bias, conv_scale, bias_scale) have a fixed summation order.
+//   raw[cls * 257 + k]: codes in front of the normalisation (k < 256 cls_conv, k == 256 cls_bias)
+//   gout[cls * 257 + k]: gradient with respect to the FINAL codes;   draw: gradient with respect to raw.
+// scalars_out[0] = d conv_scale, scalars_out[1] = d bias_scale.
+__global__ void __launch_bounds__(256)
+normalize_codes_bwd_kernel(const float* __restrict__ raw, const float* __restrict__ gout, int n_classes,
+                           const float* __restrict__ gn_w, const float* __restrict__ gn_b, int post_norm, int l2_norm,
+                           const float* __restrict__ conv_scale, const float* __restrict__ bias_scale,
+                           float* __restrict__ draw, float* __restrict__ d_gn_w, float* __restrict__ d_gn_b,
+                           float* __restrict__ scalars_out) {
+    ptx::griddep_launch();
+    ptx::griddep_wait();
+    __shared__ float red[8];
+    __shared__ float tot_s;
+    const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
+    auto block_sum = [&](float v) -> float {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+        __syncthreads();                       // red / tot_s of the previous call have been read by everyone
+        if (lane == 0) red[warp] = v;
+        __syncthreads();
+        if (t == 0) {
+            float s = 0.f;
+#pragma unroll
+            for (int i = 0; i < 8; ++i) s += red[i];
+            tot_s = s;
+        }
+        __syncthreads();
+        return tot_s;
+    };
+    const float cs = conv_scale ? conv_scale[0] : 1.f, bs = bias_scale ? bias_scale[0] : 1.f;
+    const float gw = post_norm ? gn_w[t] : 1.f, gb = post_norm ? gn_b[t] : 0.f;
+    float acc_gw = 0.f, acc_gb = 0.f, acc_cs = 0.f, acc_bs = 0.f;
+    for (int cls = 0; cls < n_classes; ++cls) {
+        const float x = raw[static_cast<size_t>(cls) * 257 + t];
+        float gh = x, rstd8 = 1.f, g = x;
+        if (post_norm) {
+            const float mean = group8_sum(x) / 8.f;
+            const float d = x - mean;
+            rstd8 = rsqrtf(group8_sum(d * d) / 8.f + 1e-5f);
+            gh = d * rstd8;
+            g = fmaf(gh, gw, gb);
+        }
+        float nrm = 1.f, l = g;
+        if (l2_norm) {
+            nrm = fmaxf(sqrtf(block_sum(g * g)), 1e-12f);
+            l = g / nrm;
+        }
+        const float go = gout[static_cast<size_t>(cls) * 257 + t];
+        acc_cs = fmaf(go, l, acc_cs);                      // summed over the block at the end
+        const float dl = go * cs;
+        float dg = dl;
+        if (l2_norm) dg = (dl - l * block_sum(l * dl)) / nrm;
+        float dx = dg;
+        if (post_norm) {
+            acc_gw = fmaf(dg, gh, acc_gw);
+            acc_gb += dg;
+            const float dgh = dg * gw;
+            const float m1 = group8_sum(dgh) / 8.f, m2 = group8_sum(dgh * gh) / 8.f;
+            dx = rstd8 * (dgh - m1 - gh * m2);
+        }
+        draw[static_cast<size_t>(cls) * 257 + t] = dx;
+        if (t == 0) {
+            const float gbias = gout[static_cast<size_t>(cls) * 257 + 256];
+            acc_bs = fmaf(gbias, raw[static_cast<size_t>(cls) * 257 + 256], acc_bs);
+            draw[static_cast<size_t>(cls) * 257 + 256] = gbias * bs;
+        }
+    }
+    if (post_norm && d_gn_w) { d_gn_w[t] = acc_gw; d_gn_b[t] = acc_gb; }
+    const float dcs = block_sum(acc_cs);
+    if (t == 0) { scalars_out[0] = dcs; scalars_out[1] = acc_bs; }
+}
+
+// ------------------------------------------------------------------------------------------------ class mean + pools
+// One block per ROI.  draw[cls * 257 + k]: gradient with respect to the raw class codes; the class of ROI r is
+// roi_class[r] with K = shots_of_class.  Writes the gradient with respect to the cls convolution's output
+// dYc[(r * 49 + p) * 256 + co] = draw / (K * 49) (uniform shot weights, global average pool) and, with a bias layer, the gradient
+// dv[r * 49 + p] with respect to the bias convolution's output v (49 values per ROI):
+//   BIAS_L2_NORM: u = v / max(|v|, 1e-12), b = mean(u)  ->  dv = (du - u <u, du>) / |v|,  du = draw_bias / (K * 49).
+__global__ void __launch_bounds__(256)
+shot_code_bwd_kernel(const float* __restrict__ draw, const int* __restrict__ roi_class, const int* __restrict__ class_off,
+                     const float* __restrict__ v_bias, int bias_layer, int bias_l2_norm, float* __restrict__ dYc,
+                     float* __restrict__ dv) {
+    ptx::griddep_launch();
+    ptx::griddep_wait();
+    __shared__ float sv[49];
+    __shared__ float s_nrm, s_dot;
+    const int r = blockIdx.x, t = threadIdx.x;
+    const int cls = roi_class[r];
+    const float inv = 1.f / (static_cast<float>(class_off[cls + 1] - class_off[cls]) * 49.f);
+    const float g = draw[static_cast<size_t>(cls) * 257 + t] * inv;
+    float* dst = dYc + static_cast<size_t>(r) * 49 * 256 + t;
+    for (int p = 0; p < 49; ++p) dst[p * 256] = g;
+    if (!bias_layer) return;
+    const float du = draw[static_cast<size_t>(cls) * 257 + 256] * inv;
+    if (!bias_l2_norm) {
+        if (t < 49) dv[r * 49 + t] = du;
+        return;
+    }
+    if (t < 49) sv[t] = v_bias[r * 49 + t];
+    __syncthreads();
+    if (t == 0) {
+        float ss = 0.f;
+        for (int p = 0; p < 49; ++p) ss = fmaf(sv[p], sv[p], ss);
+        const float nrm = fmaxf(sqrtf(ss), 1e-12f);
+        float dot = 0.f;
+        for (int p = 0; p < 49; ++p) dot += (sv[p] / nrm) * du;
+        s_nrm = nrm;
+        s_dot = dot;
+    }
+    __syncthreads();
+    if (t < 49) {
+        const float u = sv[t] / s_nrm;
+        dv[r * 49 + t] = (du - u * s_dot) / s_nrm;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------ classification loss
+// d loss_fcos_cls / d codes.  Locations in the level-first order of fcos_targets_loss_kernel; `labels` are that kernel's
+// labels_out.  Per location and class: g = focal'(logit, target) * upstream / num_pos_avg; the block accumulates
+// dcode[c][k] += g * tower[row][k] (thread = channel k) and dbias[c] += g over its share of the locations, then writes
+// partials[block][c][257]; fcos_code_grad_reduce_kernel sums the blocks in order.
+constexpr int kClsBwdRows = 32;   // locations per staging round
+constexpr int kClsBwdTile = 8;    // classes per pass over the locations
+
+__global__ void __launch_bounds__(256)
+fcos_cls_loss_bwd_kernel(const float* __restrict__ logits, int logit_stride, const __half* __restrict__ tower, int ld, int lo,
+                         PyramidGeom pg, int n_images, const long long* __restrict__ labels,
+                         const long long* __restrict__ support_targets, int n_classes, float alpha, float gamma,
+                         const double* __restrict__ global_pos, int world, const float* __restrict__ upstream,
+                         float* __restrict__ partials) {
+    ptx::griddep_launch();
+    ptx::griddep_wait();
+    __shared__ float sg[kClsBwdRows][kClsBwdTile];
+    __shared__ unsigned long long srow[kClsBwdRows];
+    const int t = threadIdx.x;
+    long long total = 0;
+    long long lvl_start[6];
+    for (int l = 0; l < 5; ++l) { lvl_start[l] = total; total += static_cast<long long>(n_images) * pg.lv[l].H * pg.lv[l].W; }
+    lvl_start[5] = total;
+    const float num_pos_avg = fmaxf(static_cast<float>(global_pos[0] / world), 1.0f);
+    const float scale = (upstream ? upstream[0] : 1.f) / num_pos_avg;
+    const long long rounds = (total + kClsBwdRows - 1) / kClsBwdRows;
+    for (int c0 = 0; c0 < n_classes; c0 += kClsBwdTile) {
+        const int nc = min(kClsBwdTile, n_classes - c0);
+        float acc[kClsBwdTile];
+#pragma unroll
+        for (int c = 0; c < kClsBwdTile; ++c) acc[c] = 0.f;
+        float accb = 0.f;                                           // threads t < nc: bias gradient of class c0 + t
+        for (long long rd = blockIdx.x; rd < rounds; rd += gridDim.x) {
+            const long long i0 = rd * kClsBwdRows;
+            __syncthreads();                                        // the previous round's sg / srow have been consumed
+            {
+                const int rr = t / kClsBwdTile, cc = t % kClsBwdTile;   // 32 x 8 = 256 (row, class) pairs
+                const long long i = i0 + rr;
+                float gval = 0.f;
+                unsigned long long row = 0;
+                if (i < total) {
+                    int l = 0;
+                    while (i >= lvl_start[l + 1]) ++l;
+                    const PlaneGeom g = pg.lv[l];
+                    const long long j = i - lvl_start[l];
+                    const int hw = g.H * g.W;
+                    const int n = static_cast<int>(j / hw);
+                    const int loc = static_cast<int>(j - static_cast<long long>(n) * hw);
+                    const int y = loc / g.W, x = loc - y * g.W;
+                    row = plane_row(g, n, y, x);
+                    if (cc < nc) {
+                        const float v = logits[row * logit_stride + c0 + cc];
+                        const bool pos = support_targets[c0 + cc] == labels[i];
+                        const float p = 1.f / (1.f + expf(-v));
+                        const float ce = bce_with_logits(v, pos ? 1.f : 0.f);
+                        float gr;
+                        if (pos) {
+                            const float om = 1.f - p;
+                            gr = (gamma == 2.f ? om * om : powf(om, gamma)) * (-gamma * p * ce - om);
+                            if (alpha >= 0.f) gr *= alpha;
+                        } else {
+                            gr = (gamma == 2.f ? p * p : powf(p, gamma)) * (gamma * (1.f - p) * ce + p);
+                            if (alpha >= 0.f) gr *= 1.f - alpha;
+                        }
+                        gval = gr * scale;
+                    }
+                }
+                sg[rr][cc] = gval;
+                if (cc == 0) srow[rr] = (i < total) ? row : ~0ull;
+            }
+            __syncthreads();
+            for (int rr = 0; rr < kClsBwdRows; ++rr) {
+                const unsigned long long row = srow[rr];
+                if (row == ~0ull) break;
+                const __half* px = tower + row * ld;
+                float x = __half2float(px[t]);
+                if (lo) x += __half2float(px[lo + t]);
+#pragma unroll
+                for (int c = 0; c < kClsBwdTile; ++c) acc[c] = fmaf(sg[rr][c], x, acc[c]);
+                if (t < nc) accb += sg[rr][t];
+            }
+        }
+        float* out = partials + (static_cast<size_t>(blockIdx.x) * n_classes + c0) * 257;
+        for (int c = 0; c < nc; ++c) out[static_cast<size_t>(c) * 257 + t] = acc[c];
+        if (t < nc) out[static_cast<size_t>(t) * 257 + 256] = accb;
+    }
+}
+
+// out[e] = sum over blocks (in order, fp64) of partials[b * n_elems + e].
+__global__ void __launch_bounds__(256)
+fcos_code_grad_reduce_kernel(const float* __restrict__ partials, int n_blocks, int n_elems, float* __restrict__ out) {
+    ptx::griddep_launch();
+    ptx::griddep_wait();
+    const int e = blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= n_elems) return;
+    double s = 0.0;
+    for (int b = 0; b < n_blocks; ++b) s += static_cast<double>(partials[static_cast<size_t>(b) * n_elems + e]);
+    out[e] = static_cast<float>(s);
+}
+
+}  // namespace sylph

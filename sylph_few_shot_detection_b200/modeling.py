@@ -368,6 +368,33 @@ def build_proposal_generator(cfg, input_shape):
     return PROPOSAL_GENERATOR_REGISTRY.get(cfg.MODEL.PROPOSAL_GENERATOR.NAME)(cfg, input_shape)
 
 
+class _CodeGeneratorGrad(torch.autograd.Function):
+    """Ties the loss value the engine computed to the code generator's parameters: backward runs the engine's backward
+    kernels (sylph_fcos_cls_loss_backward + sylph_codegen_backward) and hands every parameter its gradient, so that
+    `sum(losses.values()).backward()` fills `.grad` like the reference's autograd graph does."""
+
+    @staticmethod
+    def forward(ctx, loss_value, closure, *params):
+        ctx.closure = closure
+        return loss_value.detach().clone()
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        return (None, None) + tuple(ctx.closure(grad_out))
+
+
+def _register_parameter_tree(root: nn.Module, dotted: str, param: nn.Parameter) -> None:
+    """Register `param` under its dotted state_dict name below `root` (plain container modules for the inner names),
+    so that named_parameters() yields the reference's keys."""
+    parts = dotted.split(".")
+    m = root
+    for name in parts[:-1]:
+        if name not in m._modules:
+            m.add_module(name, nn.Module())
+        m = m._modules[name]
+    m.register_parameter(parts[-1], param)
+
+
 @META_ARCH_REGISTRY.register()
 class MetaOneStageDetector(nn.Module):
     """Drop-in for the reference meta-architecture in eval mode (meta_one_stage_detector.py:415-455)."""
@@ -389,6 +416,9 @@ class MetaOneStageDetector(nn.Module):
         self.in_features = cfg.MODEL.FCOS.IN_FEATURES
         self._state: Dict[str, torch.Tensor] = {}
         self._engine: Optional[Engine] = None
+        self._trainable: Dict[str, nn.Parameter] = {}      # code-generator parameters (enable_code_generator_training)
+        self._synced_versions: Tuple[int, ...] = ()
+        self._train_step = 0
         # operand precision of the engine built by load_state_dict: None = $SYLPH_PRECISION, else "exact"
         # (runtime.Engine); assign "fast" before loading the weights to trade the fp32-level agreement for speed
         self.precision: Optional[str] = None
@@ -412,10 +442,64 @@ class MetaOneStageDetector(nn.Module):
         for m in (self.backbone, self.proposal_generator, self.code_generator):
             if m is not None:
                 m.bind_engine(self._engine)
+        if self._trainable:                                  # reloaded weights: the parameters follow
+            with torch.no_grad():
+                for k, p in self._trainable.items():
+                    p.copy_(self._state[k].to(p.device))
+            self._synced_versions = tuple(p._version for p in self._trainable.values())
+        elif self.training:
+            self.enable_code_generator_training()
         return self
 
     def state_dict(self, *args, **kwargs):  # type: ignore[override]
-        return dict(self._state)
+        out = dict(self._state)
+        for k, p in self._trainable.items():        # the live values of the parameters an optimiser may have stepped
+            out[k] = p.detach().cpu().float().clone()
+        return out
+
+    # ------------------------------------------------------------------ trainable code generator (meta-training)
+    def train(self, mode: bool = True):  # type: ignore[override]
+        super().train(mode)
+        if mode and self._engine is not None:
+            self.enable_code_generator_training()
+        return self
+
+    def enable_code_generator_training(self) -> List[nn.Parameter]:
+        """Register every `code_generator.*` tensor as an nn.Parameter on the device under its reference name (the
+        reference's CodeGenerator owns them as module parameters, code_generator.py:520-646), so that an optimiser built
+        from `model.parameters()` trains the hyper-network.  Called by `train()` once weights are loaded.  The detector
+        itself stays frozen on this path: there are no backward kernels for the backbone or the FCOS towers, which is the
+        shipped hyper-network stage (configs/COCO-Detection/Meta-FCOS/Meta-FCOS-finetune-lvis.yaml)."""
+        if self._trainable or not self.episodic_learning or isinstance(self.code_generator, ROIEncoder):
+            return list(self._trainable.values())
+        if self.cfg.MODEL.META_LEARN.CODE_GENERATOR.FREEZE:
+            return []
+        P = self.cfg.MODEL.PROPOSAL_GENERATOR
+        if not (self.cfg.MODEL.BACKBONE.FREEZE and P.FREEZE_CLS_TOWER and P.FREEZE_BBOX_BRANCH) and not P.FREEZE:
+            import logging
+            logging.getLogger(__name__).warning(
+                "the configuration leaves parts of the detector trainable (BACKBONE.FREEZE / FREEZE_CLS_TOWER / FREEZE_BBOX_BRANCH); "
+                "the B200 path has backward kernels for the code generator only -- the detector stays frozen")
+        dev = self.engine.device
+        for k, v in self._state.items():
+            if k.startswith("code_generator.") and torch.is_floating_point(v):
+                p = nn.Parameter(v.to(dev, torch.float32).contiguous().clone())
+                _register_parameter_tree(self.code_generator, k[len("code_generator."):], p)
+                self._trainable[k] = p
+        self._synced_versions = tuple(p._version for p in self._trainable.values())
+        return list(self._trainable.values())
+
+    def _sync_code_generator(self) -> None:
+        """Hand the engine the parameters' current values when an optimiser (or anything else) has changed them in place."""
+        if not self._trainable:
+            return
+        versions = tuple(p._version for p in self._trainable.values())
+        if versions != self._synced_versions:
+            live = {k: p.detach() for k, p in self._trainable.items()}
+            self.engine.update_code_generator(live)
+            for k, v in live.items():
+                self._state[k] = v.cpu().float().clone()
+            self._synced_versions = versions
 
     @property
     def device(self):
@@ -533,7 +617,7 @@ class MetaOneStageDetector(nn.Module):
             return [{"cls_conv": r[:, :256].reshape(1, 256, 1, 1), "cls_bias": r[0, 256:].reshape(1)} for r in rows]
         return [{"cls_conv": r[:, :256].reshape(1, 256, 1, 1), "cls_bias": r[:, 256:].reshape(1, 1, 1, 1)} for r in rows]
 
-    # ------------------------------------------------------------------ training forward (losses only, no backward)
+    # ------------------------------------------------------------------ training forward + code-generator backward
     def _get_gt(self, batched_inputs: List[Dict[str, Any]], support_set_targets=None):
         """meta_one_stage_detector.py:184-221: keep the ground truths whose class is one of the episode's classes."""
         if "instances" not in batched_inputs[0]:
@@ -557,8 +641,10 @@ class MetaOneStageDetector(nn.Module):
 
     def forward_few_shot_detector_training(self, batched_inputs: List[Dict[str, Any]], want_targets: bool = False):
         """meta_one_stage_detector.py:325-388: each item = the query + support set of one class.  Returns the loss dict
-        (`loss_fcos_cls` [, `loss_fcos_loc`, `loss_fcos_ctr`]) as device scalars.  Forward only: this build has no
-        backward kernels, so the result serves validation-loss / loss-curve evaluation of a checkpoint."""
+        (`loss_fcos_cls` [, `loss_fcos_loc`, `loss_fcos_ctr`]) as device scalars.  With the code generator's parameters
+        registered (`model.train()` after load_state_dict) and autograd enabled, `loss_fcos_cls` carries a backward hook:
+        `sum(losses.values()).backward()` fills `.grad` of every `code_generator.*` parameter like the reference's
+        autograd graph (the detector is frozen on this path)."""
         assert self.training
         assert "support_set" in batched_inputs[0]
         assert "query_set" in batched_inputs[0]
@@ -574,10 +660,40 @@ class MetaOneStageDetector(nn.Module):
         boxes = torch.cat([b.reshape(-1, 4)[:1].cpu() for b in select_a_mask([r["instances"] for r in support])], dim=0)
         self.engine.extract_features_multi([(SLOT_QUERY, [r["image"] for r in query]),
                                             (SLOT_SUPPORT, [r["image"] for r in support])])
-        raw = self.engine.generate_codes(SLOT_SUPPORT, boxes, list(range(len(support))), list(range(0, len(support) + 1, shot)))
+        self._sync_code_generator()
+        class_offsets = list(range(0, len(support) + 1, shot))
+        raw = self.engine.generate_codes(SLOT_SUPPORT, boxes, list(range(len(support))), class_offsets)
         codes = self.engine.normalize_codes(raw)                                        # code_generator.py:993-994
         class_codes = {"cls_conv": codes[:, :256].reshape(-1, 256, 1, 1), "cls_bias": codes[:, 256].reshape(-1)}
-        return self.proposal_generator.losses(class_codes, targets, gts, want_targets)
+        differentiable = bool(self._trainable) and torch.is_grad_enabled()
+        res = self.proposal_generator.losses(class_codes, targets, gts, want_targets or differentiable)
+        if not differentiable:
+            return res
+        losses, extra = res
+        # ---- backward hook: loss_fcos_cls is the only loss that depends on the code generator (the box losses read the
+        # frozen box branch alone); its gradient runs through the engine's backward kernels
+        self._train_step += 1
+        step, eng = self._train_step, self.engine
+        keys = [k for k, p in self._trainable.items() if p.requires_grad]
+        params = [self._trainable[k] for k in keys]
+        live = {k: self._trainable[k].detach() for k in self._trainable}
+        tgt = [int(t) for t in targets]
+        world = _world_size()
+        glob = _reduce_sum(extra["sums"][1:3]) if world > 1 else None
+
+        def closure(grad_out):
+            if self._train_step != step:
+                raise RuntimeError("backward() of a training episode must run before the next forward: the engine's activation "
+                                   "buffers of that episode have been overwritten")
+            g_codes = eng.fcos_cls_loss_backward(SLOT_QUERY, len(tgt), tgt, extra["labels"], extra["sums"], glob, world, grad_out)
+            grads = eng.codegen_backward(class_offsets, raw, g_codes, live)
+            self._last_grad_codes = g_codes
+            return [grads[k] if k in grads and not k.startswith("code_generator.code_generator_head.init_norm.") else None
+                    for k in keys]
+
+        losses = dict(losses)
+        losses["loss_fcos_cls"] = _CodeGeneratorGrad.apply(losses["loss_fcos_cls"], closure, *params)
+        return (losses, extra) if want_targets else losses
 
     def normalize_class_code(self, codes: List[Dict]):
         assert self.episodic_learning

@@ -9,7 +9,8 @@ from typing import Dict, List, Optional, Sequence, Tuple
 import torch
 
 from . import _lib
-from ._lib import CODE_STRIDE, DET_STRIDE, IPC_HANDLE_BYTES, LOSS_SUMS, NUM_LEVELS, SLOT_QUERY, SLOT_SUPPORT, LossConfig, ModelConfig
+from ._lib import (CG_MAX_TOWER, CODE_STRIDE, DET_STRIDE, IPC_HANDLE_BYTES, LOSS_SUMS, NUM_LEVELS, SLOT_QUERY, SLOT_SUPPORT, CodegenTensors,
+                   LossConfig, ModelConfig)
 
 
 def model_config_from_cfg(cfg) -> ModelConfig:
@@ -443,6 +444,74 @@ class Engine:
             self.h, c_void_p(sums.data_ptr()), c_void_p(global_pos_ctr.data_ptr()) if global_pos_ctr is not None else None,
             int(world_size), c_void_p(out.data_ptr()), self._stream()))
         return out
+
+    # ------------------------------------------------------------------ training backward (code generator)
+    CG_PREFIX = "code_generator.code_generator_head."
+
+    def fcos_cls_loss_backward(self, slot: int, n_classes: int, support_targets: Sequence[int], labels: torch.Tensor,
+                               sums: torch.Tensor, global_pos_ctr: Optional[torch.Tensor] = None, world_size: int = 1,
+                               grad_loss: Optional[torch.Tensor] = None) -> torch.Tensor:
+        """d loss_fcos_cls / d FINAL codes, (n_classes, 257) on the device (sylph_fcos_cls_loss_backward); call right after
+        fcos_loss_sums(..., want_targets=True) on the same slot: `labels` and `sums` are that call's outputs."""
+        assert labels.is_cuda and labels.dtype == torch.int64 and sums.is_cuda and sums.dtype == torch.float64
+        st = (c_int64 * n_classes)(*[int(t) for t in support_targets])
+        out = torch.empty((n_classes, CODE_STRIDE), device=self.device, dtype=torch.float32)
+        if grad_loss is not None:
+            grad_loss = grad_loss.detach().to(self.device, torch.float32).reshape(1).contiguous()
+        if not hasattr(self, "_lc"):
+            self._lc = loss_config_from_cfg(self.cfg)
+        self._check(self.lib.sylph_fcos_cls_loss_backward(
+            self.h, slot, n_classes, st, byref(self._lc), c_void_p(labels.data_ptr()), c_void_p(sums.data_ptr()),
+            c_void_p(global_pos_ctr.data_ptr()) if global_pos_ctr is not None else None, int(world_size),
+            c_void_p(grad_loss.data_ptr()) if grad_loss is not None else None, c_void_p(out.data_ptr()), self._stream()))
+        return out
+
+    def _codegen_tensor_struct(self, tensors: Dict[str, torch.Tensor]) -> CodegenTensors:
+        """state_dict-keyed device fp32 tensors -> sylph_codegen_tensors (missing keys stay NULL)."""
+        ct = CodegenTensors()
+        def ptr(name):
+            t = tensors.get(self.CG_PREFIX + name)
+            if t is None:
+                return None
+            assert t.is_cuda and t.dtype == torch.float32 and t.is_contiguous(), name
+            return t.data_ptr()
+        for i in range(min(int(self.mc.cg_tower_layers), CG_MAX_TOWER)):
+            ct.tower_w[i] = ptr(f"support_set_shared_tower.{3 * i}.weight")
+            ct.tower_b[i] = ptr(f"support_set_shared_tower.{3 * i}.bias")
+            ct.tower_gn_w[i] = ptr(f"support_set_shared_tower.{3 * i + 1}.weight")
+            ct.tower_gn_b[i] = ptr(f"support_set_shared_tower.{3 * i + 1}.bias")
+        ct.cls_w, ct.cls_b = ptr("support_set_cls_conv.0.weight"), ptr("support_set_cls_conv.0.bias")
+        ct.bias_w, ct.bias_b = ptr("support_set_cls_bias.0.weight"), ptr("support_set_cls_bias.0.bias")
+        ct.post_norm_w, ct.post_norm_b = ptr("post_norm.weight"), ptr("post_norm.bias")
+        ct.conv_scale, ct.bias_scale = ptr("conv_scale.scale"), ptr("bias_scale.scale")
+        return ct
+
+    def codegen_backward(self, class_offsets: Sequence[int], raw_codes: torch.Tensor, grad_codes: torch.Tensor,
+                         params: Dict[str, torch.Tensor]) -> Dict[str, torch.Tensor]:
+        """Gradients of the code generator's tensors for the ROIs of the last generate_codes call (sylph_codegen_backward).
+        `params`: {state_dict key: device fp32 tensor}; returns {key: gradient} for the same keys."""
+        n_classes = len(class_offsets) - 1
+        n_rois = int(class_offsets[-1])
+        raw_codes = raw_codes.to(self.device, torch.float32).contiguous()
+        grad_codes = grad_codes.to(self.device, torch.float32).contiguous()
+        assert raw_codes.shape == (n_classes, CODE_STRIDE) and grad_codes.shape == (n_classes, CODE_STRIDE)
+        grads = {k: torch.zeros_like(v) for k, v in params.items()}
+        co = (c_int * (n_classes + 1))(*[int(i) for i in class_offsets])
+        p_struct, g_struct = self._codegen_tensor_struct(params), self._codegen_tensor_struct(grads)
+        self._check(self.lib.sylph_codegen_backward(self.h, n_rois, n_classes, co, c_void_p(raw_codes.data_ptr()),
+                                                    c_void_p(grad_codes.data_ptr()), byref(p_struct), byref(g_struct), self._stream()))
+        self._keep_bwd = (raw_codes, grad_codes, params)   # alive until the stream work has run
+        return grads
+
+    def update_code_generator(self, state: Dict[str, torch.Tensor]) -> None:
+        """Re-prepare the code generator's weights from `state` (every `code_generator.*` tensor) after an optimiser step."""
+        for k, v in state.items():
+            if not k.startswith("code_generator."):
+                continue
+            t = v.detach().to("cpu", torch.float32).contiguous()
+            shape = (c_int64 * max(t.dim(), 1))(*t.shape)
+            self._check(self.lib.sylph_load_tensor(self.h, k.encode(), c_void_p(t.data_ptr()), shape, t.dim()))
+        self._check(self.lib.sylph_update_code_generator(self.h))
 
     # ------------------------------------------------------------------ instrumentation
     def launch_count(self) -> int:

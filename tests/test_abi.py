@@ -48,6 +48,16 @@ def test_loss_config_struct_layout_matches_header():
     assert f"#define SYLPH_LOSS_SUMS {_lib.LOSS_SUMS}" in text and f"#define SYLPH_BACKGROUND_ID {_lib.BACKGROUND_ID}" in text
 
 
+def test_codegen_tensors_struct_layout_matches_header():
+    text = open(os.path.join(REPO, "include", "sylph_b200.h")).read()
+    body = text[text.index("typedef struct sylph_codegen_tensors {"):text.index("} sylph_codegen_tensors;")]
+    body = re.sub(r"/\*.*?\*/", "", body, flags=re.S)
+    fields = re.findall(r"\bfloat\*\s+([a-z_0-9]+)(?:\[SYLPH_CG_MAX_TOWER\])?;", body)
+    assert fields == [f[0] for f in _lib.CodegenTensors._fields_]
+    assert f"#define SYLPH_CG_MAX_TOWER {_lib.CG_MAX_TOWER}" in text
+    assert ctypes.sizeof(_lib.CodegenTensors) == 8 * (4 * _lib.CG_MAX_TOWER + 8)
+
+
 def test_create_fails_loudly_without_a_device():
     import torch
     if torch.cuda.is_available():

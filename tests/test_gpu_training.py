@@ -149,3 +149,120 @@ def test_training_forward_loss_configurations(variant):
         got = float(losses[k])
         assert abs(got - float(ref_losses[k])) <= KERNEL_TOL * max(abs(float(ref_losses[k])), 1e-3), (k, got, float(ref_losses[k]))
         assert abs(got - float(v["losses"][k])) <= LOSS_TOL * max(abs(float(v["losses"][k])), 1e-3), (k, got, float(v["losses"][k]))
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# Backward of the training step for the code generator (sylph_fcos_cls_loss_backward + sylph_codegen_backward behind the
+# plugin's autograd hook).  GRAD_TOL: max-norm error of a gradient tensor relative to its largest entry, against the
+# REFERENCE model's own `.grad` (tests/golden/train_grads.pt) and, tensor for tensor in full, against the oracle's
+# autograd (pinned to that golden at 0.0 deviation by tests/test_training_oracle.py).
+GRAD_TOL = 1e-3
+
+
+def _train_model(case):
+    from sylph_few_shot_detection_b200 import weights as W
+    from sylph_few_shot_detection_b200.modeling import build_model
+    g = load_golden(case)
+    cfg = cfg_for(g["config"], g["opts"])
+    state = W.synthetic_state_dict(cfg, g["seed"])
+    model = build_model(cfg)
+    model.load_state_dict(state)
+    model.train()
+    return g, cfg, state, model
+
+
+@pytest.mark.parametrize("case", ["lvis_train_3way_1shot_cls_only", "coco_train_2way_2shot"])
+def test_code_generator_gradients_match_reference(case):
+    from oracle.make_golden import to_records
+    from oracle.meta_fcos_oracle import MetaFCOSOracle
+    from tests.test_training_oracle import check_grads_against_golden
+    g, cfg, state, model = _train_model(case)
+    gg = load_golden("train_grads")["cases"][case]
+    names = dict(model.named_parameters())
+    pre = "code_generator.code_generator_head."
+    assert set(gg["grads"]) <= set(names) and all(p.is_cuda for p in names.values())
+    assert all(k.startswith("code_generator.") for k in names)                 # the detector is frozen on this path
+    losses = model(_records(g["items"]))
+    assert set(losses) == set(gg["losses"])
+    sum(losses.values()).backward()
+    grads = {k: p.grad for k, p in names.items() if p.grad is not None}
+    assert set(grads) == set(gg["grads"])                                      # init_norm.* get none, like the reference
+    worst = check_grads_against_golden(grads, gg["grads"], GRAD_TOL, case)
+    # gradient with respect to the final class codes
+    gc = model._last_grad_codes.cpu()
+    ref_w = gg["grad_codes"]["cls_conv"].reshape(-1, 256)
+    ref_b = gg["grad_codes"]["cls_bias"].reshape(-1)
+    assert float((gc[:, :256] - ref_w).abs().max()) <= GRAD_TOL * float(ref_w.abs().max())
+    assert float((gc[:, 256] - ref_b).abs().max()) <= GRAD_TOL * float(ref_b.abs().max())
+    # every tensor in full against the oracle's autograd
+    orc = MetaFCOSOracle(cfg, state)
+    _, ograds, _ = orc.training_grads(to_records(g["items"]))
+    for k, v in ograds.items():
+        err = float((grads[k].cpu() - v).abs().max()) / max(float(v.abs().max()), 1e-12)
+        assert err <= GRAD_TOL, (k, err)
+        worst = max(worst, err)
+    print(f"[{case}] worst relative gradient error {worst:.2e}")
+
+
+def test_code_generator_backward_is_deterministic_and_guards_stale_buffers():
+    g, cfg, state, model = _train_model("lvis_train_3way_1shot_cls_only")
+    batched = _records(g["items"])
+    runs = []
+    for _ in range(2):
+        model.zero_grad(set_to_none=True)
+        losses = model(batched)
+        sum(losses.values()).backward()
+        runs.append({k: p.grad.clone() for k, p in model.named_parameters() if p.grad is not None})
+    assert runs[0].keys() == runs[1].keys() and len(runs[0]) == 16
+    for k in runs[0]:
+        assert torch.equal(runs[0][k], runs[1][k]), k                          # fixed-order reductions, no atomics
+    # an upstream factor scales every gradient (the hook receives d total / d loss_fcos_cls on the device)
+    model.zero_grad(set_to_none=True)
+    (2.0 * model(batched)["loss_fcos_cls"]).backward()
+    k = "code_generator.code_generator_head.support_set_cls_conv.0.weight"
+    got = dict(model.named_parameters())[k].grad
+    assert float((got - 2.0 * runs[0][k]).abs().max()) <= 1e-5 * float(runs[0][k].abs().max())
+    # backward of an episode whose engine buffers a later forward has overwritten must fail loudly
+    first = model(batched)
+    model(batched)
+    with pytest.raises(RuntimeError, match="before the next forward"):
+        first["loss_fcos_cls"].backward()
+    # no_grad forward: plain loss tensors, no hook
+    with torch.no_grad():
+        assert not model(batched)["loss_fcos_cls"].requires_grad
+
+
+def test_optimizer_step_reaches_the_engine():
+    """One SGD step on the plugin's parameters: the next forward runs with the stepped weights (sylph_update_code_generator)
+    and agrees with the oracle evaluated on the stepped state_dict; state_dict() returns the live values."""
+    from oracle.make_golden import to_records
+    from oracle.meta_fcos_oracle import MetaFCOSOracle
+    g, cfg, state, model = _train_model("lvis_train_3way_1shot_cls_only")
+    batched = _records(g["items"])
+    opt = torch.optim.SGD(model.parameters(), lr=1e-4)   # the oracle's loss on this episode: 1.692 -> 1.583 at this step size
+    l0 = model(batched)["loss_fcos_cls"]
+    l0.backward()
+    opt.step()
+    l1 = float(model(batched)["loss_fcos_cls"])
+    assert l1 != float(l0)
+    stepped = model.state_dict()
+    k = "code_generator.code_generator_head.support_set_cls_conv.0.weight"
+    assert not torch.equal(stepped[k], state[k])
+    assert all(torch.equal(stepped[q], state[q]) for q in state if not q.startswith("code_generator."))
+    orc = MetaFCOSOracle(cfg, {q: v.clone() for q, v in stepped.items()})
+    ref, _ = orc.training_forward(to_records(g["items"]))
+    assert abs(l1 - float(ref["loss_fcos_cls"])) <= LOSS_TOL * abs(float(ref["loss_fcos_cls"])), (l1, float(ref["loss_fcos_cls"]))
+    # the plain SGD step lowers this episode's loss (sanity of the gradient's sign)
+    assert l1 < float(l0), (l1, float(l0))
+
+
+def test_backward_c_abi_validation():
+    from sylph_few_shot_detection_b200.runtime import SLOT_QUERY
+    g, cfg, state, model = _train_model("lvis_train_3way_1shot_cls_only")
+    eng = model.engine
+    labels = torch.zeros(10, dtype=torch.int64, device="cuda")
+    sums = torch.zeros(5, dtype=torch.float64, device="cuda")
+    with pytest.raises(RuntimeError, match="last head pass"):
+        eng.fcos_cls_loss_backward(SLOT_QUERY, 3, [1, 2, 3], labels, sums)
+    with pytest.raises(RuntimeError, match="last sylph_generate_codes"):
+        eng.codegen_backward([0, 1, 2], torch.zeros(2, 257), torch.zeros(2, 257), {})

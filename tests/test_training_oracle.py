@@ -106,3 +106,76 @@ def test_oracle_training_forward_loss_configurations(variant):
     assert torch.equal(ex["labels"], v["labels"].to(torch.int64))
     assert torch.equal(ex["target_inds"], v["target_inds"].to(torch.int64))
     assert torch.equal(ex["reg_targets"], v["reg_targets"])
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# Backward of the training step for the code generator: tests/golden/train_grads.pt holds the REFERENCE
+# model's own `.grad` after `sum(model(batched).values()).backward()` (oracle/make_golden.py --train-grads-only).
+def check_grads_against_golden(grads, packed, tol, what=""):
+    """`grads`: {state_dict key: tensor}; `packed`: the golden's per-tensor record (full tensor, or strided sample + float64
+    checksums of the whole tensor).  Max-norm error relative to the tensor's largest gradient <= tol."""
+    assert set(grads) >= set(packed), sorted(set(packed) - set(grads))
+    worst = 0.0
+    for k, rec in packed.items():
+        g = grads[k].detach().cpu().float().reshape(-1)
+        assert tuple(grads[k].shape) == tuple(rec["shape"]), k
+        scale = max(rec["absmax"], 1e-12)
+        ref = rec["full"] if "full" in rec else rec["sample"]
+        got = g if "full" in rec else g[::rec["sample_step"]]
+        err = float((got - ref).abs().max()) / scale
+        assert err <= tol, (what, k, err)
+        # whole-tensor checksums: the sum moves by at most numel * tol * absmax, the L2 norm by a relative tol
+        d = g.double()
+        assert abs(float(d.sum()) - rec["sum"]) <= tol * scale * g.numel() ** 0.5 * 4 + 1e-12, (what, k, "sum")
+        assert abs(float((d * d).sum()) ** 0.5 - rec["sumsq"] ** 0.5) <= tol * max(rec["sumsq"] ** 0.5, 1e-12) * 2 + 1e-12, (what, k, "norm")
+        worst = max(worst, err)
+    return worst
+
+
+@pytest.mark.parametrize("case", ["lvis_train_3way_1shot_cls_only", "coco_train_2way_2shot"])
+def test_oracle_training_grads_reproduce_reference(case):
+    g = load_golden(case)
+    gg = load_golden("train_grads")["cases"][case]
+    cfg = cfg_for(g["config"], g["opts"])
+    orc = MetaFCOSOracle(cfg, W.synthetic_state_dict(cfg, g["seed"]))
+    before = {k: v.clone() for k, v in orc.sd.items() if k.startswith("code_generator.")}
+    losses, grads, ex = orc.training_grads(to_records(g["items"]))
+    for k, v in gg["losses"].items():
+        assert abs(float(losses[k]) - float(v)) <= 2e-5 * abs(float(v)), k
+    assert set(grads) == set(gg["grads"])
+    worst = check_grads_against_golden(grads, gg["grads"], 2e-5, case)
+    assert worst <= 2e-5
+    assert torch.allclose(ex["grad_codes"]["cls_conv"], gg["grad_codes"]["cls_conv"], rtol=0, atol=2e-5 * float(gg["grad_codes"]["cls_conv"].abs().max()))
+    # the oracle's weights are untouched and detached again
+    for k, v in before.items():
+        assert torch.equal(orc.sd[k], v) and not orc.sd[k].requires_grad
+    # every code-generator tensor except the never-called init_norm layers receives a gradient
+    assert all(float(v.abs().max()) > 0 for v in grads.values())
+    assert not any("init_norm" in k for k in grads)
+
+
+def test_parameter_tree_and_backward_hook_plumbing():
+    """Host logic of the plugin's training mode without a device: parameters appear under the reference's names, the
+    autograd hook hands each parameter the gradient its closure returns, and None leaves `.grad` unset."""
+    from torch import nn
+    from sylph_few_shot_detection_b200 import modeling as M
+    root = nn.Module()
+    names = ["code_generator_head.support_set_shared_tower.0.weight", "code_generator_head.support_set_shared_tower.1.bias",
+             "code_generator_head.conv_scale.scale", "code_generator_head.init_norm.0.weight"]
+    params = [nn.Parameter(torch.full((3,), float(i + 1))) for i in range(len(names))]
+    for n, p in zip(names, params):
+        M._register_parameter_tree(root, n, p)
+    assert [n for n, _ in root.named_parameters()] == names
+    seen = {}
+
+    def closure(grad_out):
+        seen["grad_out"] = float(grad_out)
+        return [torch.full((3,), 10.0 * (i + 1)) * grad_out if i < 3 else None for i in range(4)]
+
+    loss = M._CodeGeneratorGrad.apply(torch.tensor(2.5), closure, *params)
+    assert float(loss) == 2.5 and loss.requires_grad
+    (3.0 * loss + torch.tensor(1.0)).backward()
+    assert seen["grad_out"] == 3.0
+    for i in range(3):
+        assert torch.equal(params[i].grad, torch.full((3,), 30.0 * (i + 1)))
+    assert params[3].grad is None
