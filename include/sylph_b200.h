@@ -325,6 +325,11 @@ int sylph_codegen_backward(sylph_ctx* ctx, int n_rois, int n_classes, const int*
  * weights; device buffers are reused).  Synchronises the device. */
 int sylph_update_code_generator(sylph_ctx* ctx);
 
+/* The same refresh from DEVICE tensors (the optimiser's parameters), prepared by kernels on `stream`: fp32 OIHW -> the
+ * tap-major fp16 (hi | hi | lo in exact mode) operand layout, bit-identical to the host preparation.  Only conv_scale /
+ * bias_scale travel to the host (8 bytes; the call waits for the stream). */
+int sylph_update_code_generator_device(sylph_ctx* ctx, const sylph_codegen_tensors* params, void* stream);
+
 /* Number of kernels this library launched on the context since creation (bench.py's gpu_launches). */
 int64_t sylph_launch_count(const sylph_ctx* ctx);
 

@@ -2443,6 +2443,60 @@ int sylph_codegen_backward(sylph_ctx* c, int n_rois, int n_classes, const int* c
     return 0;
 }
 
+int sylph_update_code_generator_device(sylph_ctx* c, const sylph_codegen_tensors* params, void* stream) {
+    if (!c) return 1;
+    if (!c->weights_ready || !c->finalized) return c->fail("sylph_update_code_generator_device: call sylph_finalize_weights once first");
+    const sylph_model_config& f = c->cfg;
+    if (f.generator != 0) return c->fail("sylph_update_code_generator_device: only the CodeGenerator plugin is trainable on this path");
+    if (f.cg_weight_layer) return c->fail("sylph_update_code_generator_device: CODE_GENERATOR.WEIGHT_LAYER is not covered");
+    if (!params) return c->fail("null argument");
+    const int L = f.cg_tower_layers;
+    if (L > SYLPH_CG_MAX_TOWER) return c->fail("more than %d tower layers", SYLPH_CG_MAX_TOWER);
+    for (int i = 0; i < L; ++i)
+        if (!params->tower_w[i] || !params->tower_b[i] || !params->tower_gn_w[i] || !params->tower_gn_b[i])
+            return c->fail("tower layer %d: missing parameter tensor", i);
+    if (!params->cls_w || !params->cls_b) return c->fail("support_set_cls_conv tensors missing");
+    if (f.cg_bias_layer && (!params->bias_w || !params->bias_b || !params->bias_scale)) return c->fail("support_set_cls_bias / bias_scale tensors missing");
+    if (f.cg_post_norm && (!params->post_norm_w || !params->post_norm_b)) return c->fail("post_norm tensors missing");
+    if (f.cg_has_conv_scale && !params->conv_scale) return c->fail("conv_scale tensor missing");
+    CU_TRY(c, cudaSetDevice(c->device));
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    auto pack = [&](const float* w, const float* b, ConvW& W, int pooled) -> int {
+        if (W.w_nm != nullptr) return c->fail("N-merged weight copies are not refreshed on the device");
+        const int ci = pooled ? W.cin / 9 : W.cin;
+        CU_TRY(c, launch_k(pack_oihw_weights_kernel, dim3(grid_for(static_cast<long long>(W.cout) * ci * 9, 256, c->num_sms)), dim3(256), 0, st,
+                           w, W.w, W.cout, ci, 9, W.cout_pad, c->split, pooled));
+        CU_TRY(c, cudaMemcpyAsync(W.bias, b, static_cast<size_t>(W.cout) * 4, cudaMemcpyDeviceToDevice, st));
+        c->launches++;
+        return 0;
+    };
+    for (int i = 0; i < L; ++i) {
+        if (c->cg_tower[i].taps != 9 || c->cg_tower[i].cin != 256) return c->fail("tower layer %d is not a 3x3 256-channel convolution", i);
+        TRY(pack(params->tower_w[i], params->tower_b[i], c->cg_tower[i], 0));
+        CU_TRY(c, cudaMemcpyAsync(c->cg_gn_w[i], params->tower_gn_w[i], 1024, cudaMemcpyDeviceToDevice, st));
+        CU_TRY(c, cudaMemcpyAsync(c->cg_gn_b[i], params->tower_gn_b[i], 1024, cudaMemcpyDeviceToDevice, st));
+    }
+    TRY(pack(params->cls_w, params->cls_b, c->cg_cls, 0));
+    TRY(pack(params->cls_w, params->cls_b, c->cg_cls_pooled, 1));
+    if (f.cg_bias_layer) {
+        CU_TRY(c, launch_k(transpose_taps_kernel, dim3(9), dim3(256), 0, st, static_cast<const float*>(params->bias_w), c->cg_wbias, 256, 9));
+        c->launches++;
+        CU_TRY(c, cudaMemcpyAsync(c->cg_bbias, params->bias_b, 4, cudaMemcpyDeviceToDevice, st));
+    }
+    if (f.cg_post_norm) {
+        CU_TRY(c, cudaMemcpyAsync(c->post_gn_w, params->post_norm_w, 1024, cudaMemcpyDeviceToDevice, st));
+        CU_TRY(c, cudaMemcpyAsync(c->post_gn_b, params->post_norm_b, 1024, cudaMemcpyDeviceToDevice, st));
+    }
+    // the two scalars are kernel arguments of the normalisation kernels: 8 bytes back to the host (waits for the stream)
+    float cs = 1.f, bs = 1.f;
+    if (f.cg_has_conv_scale) CU_TRY(c, cudaMemcpyAsync(&cs, params->conv_scale, 4, cudaMemcpyDeviceToHost, st));
+    if (f.cg_bias_layer) CU_TRY(c, cudaMemcpyAsync(&bs, params->bias_scale, 4, cudaMemcpyDeviceToHost, st));
+    CU_TRY(c, cudaStreamSynchronize(st));
+    c->conv_scale = cs;
+    c->bias_scale = bs;
+    return 0;
+}
+
 int64_t sylph_launch_count(const sylph_ctx* c) { return c ? c->launches : 0; }
 
 int sylph_set_profiling(sylph_ctx* c, int enabled) {

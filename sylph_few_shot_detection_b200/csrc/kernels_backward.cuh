@@ -443,4 +443,46 @@ fcos_code_grad_reduce_kernel(const float* __restrict__ partials, int n_blocks, i
     out[e] = static_cast<float>(s);
 }
 
+// ------------------------------------------------------------------------------------------------ weight refresh
+// The code generator's weights after an optimiser step, prepared on the device in the layouts engine.cu prep_conv builds on
+// the host: fp32 OIHW [co][ci][taps] -> rows [(tap * cout_pad + o)][kp] of fp16, kp = ci (fast) or [w_hi | w_hi | w_lo] = 3 ci
+// (exact: hi = rn16(w), lo = rn16(w - hi)).  pooled != 0: the same 3x3 layer as ONE [co][taps * ci] GEMM (K index tap * ci +
+// ch; engine.cu "__cg_cls_pooled").
+__global__ void __launch_bounds__(256)
+pack_oihw_weights_kernel(const float* __restrict__ w, __half* __restrict__ out, int co, int ci, int taps, int cout_pad, int split,
+                         int pooled) {
+    ptx::griddep_launch();
+    ptx::griddep_wait();
+    const long long total = static_cast<long long>(co) * ci * taps;
+    for (long long e = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; e < total;
+         e += static_cast<long long>(gridDim.x) * blockDim.x) {
+        // e enumerates the OUTPUT order (tap, o, i) so that stores are contiguous along i
+        const int i = static_cast<int>(e % ci);
+        const int o = static_cast<int>((e / ci) % co);
+        const int t = static_cast<int>(e / (static_cast<long long>(ci) * co));
+        const float v = w[(static_cast<size_t>(o) * ci + i) * taps + t];
+        const __half hi = __float2half_rn(v);
+        size_t row, k, kdim;
+        if (pooled) { row = o; k = static_cast<size_t>(t) * ci + i; kdim = static_cast<size_t>(taps) * ci; }
+        else { row = static_cast<size_t>(t) * cout_pad + o; k = i; kdim = ci; }
+        __half* dst = out + row * (split ? 3 * kdim : kdim);
+        dst[k] = hi;
+        if (split) {
+            dst[kdim + k] = hi;
+            dst[2 * kdim + k] = __float2half_rn(v - __half2float(hi));
+        }
+    }
+}
+
+// [1][256][9] bias / weight-head convolution -> tap-major [9][256] fp32 (shot_code_kernel's layout).
+__global__ void __launch_bounds__(256)
+transpose_taps_kernel(const float* __restrict__ w, float* __restrict__ out, int ci, int taps) {
+    ptx::griddep_launch();
+    ptx::griddep_wait();
+    const int e = blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= ci * taps) return;
+    const int t = e / ci, ch = e - t * ci;
+    out[e] = w[ch * taps + t];
+}
+
 }  // namespace sylph

@@ -495,10 +495,8 @@ class MetaOneStageDetector(nn.Module):
             return
         versions = tuple(p._version for p in self._trainable.values())
         if versions != self._synced_versions:
-            live = {k: p.detach() for k, p in self._trainable.items()}
-            self.engine.update_code_generator(live)
-            for k, v in live.items():
-                self._state[k] = v.cpu().float().clone()
+            # device-side refresh (sylph_update_code_generator_device); state_dict() reads the live parameters
+            self.engine.update_code_generator_device({k: p.detach() for k, p in self._trainable.items()})
             self._synced_versions = versions
 
     @property

@@ -513,6 +513,12 @@ class Engine:
             self._check(self.lib.sylph_load_tensor(self.h, k.encode(), c_void_p(t.data_ptr()), shape, t.dim()))
         self._check(self.lib.sylph_update_code_generator(self.h))
 
+    def update_code_generator_device(self, params: Dict[str, torch.Tensor]) -> None:
+        """The same refresh straight from the optimiser's DEVICE tensors (sylph_update_code_generator_device): the operand
+        layouts are packed by kernels on the current stream, nothing but the two scale scalars touches the host."""
+        p_struct = self._codegen_tensor_struct(params)
+        self._check(self.lib.sylph_update_code_generator_device(self.h, byref(p_struct), self._stream()))
+
     # ------------------------------------------------------------------ instrumentation
     def launch_count(self) -> int:
         return int(self.lib.sylph_launch_count(self.h))

@@ -113,23 +113,24 @@ def test_oracle_training_forward_loss_configurations(variant):
 # model's own `.grad` after `sum(model(batched).values()).backward()` (oracle/make_golden.py --train-grads-only).
 def check_grads_against_golden(grads, packed, tol, what=""):
     """`grads`: {state_dict key: tensor}; `packed`: the golden's per-tensor record (full tensor, or strided sample + float64
-    checksums of the whole tensor).  Max-norm error relative to the tensor's largest gradient <= tol."""
+    checksums of the whole tensor).  Max-norm error relative to the tensor's largest gradient <= tol for every tensor;
+    returns the worst one."""
     assert set(grads) >= set(packed), sorted(set(packed) - set(grads))
-    worst = 0.0
+    errs = {}
     for k, rec in packed.items():
         g = grads[k].detach().cpu().float().reshape(-1)
         assert tuple(grads[k].shape) == tuple(rec["shape"]), k
         scale = max(rec["absmax"], 1e-12)
         ref = rec["full"] if "full" in rec else rec["sample"]
         got = g if "full" in rec else g[::rec["sample_step"]]
-        err = float((got - ref).abs().max()) / scale
-        assert err <= tol, (what, k, err)
-        # whole-tensor checksums: the sum moves by at most numel * tol * absmax, the L2 norm by a relative tol
+        errs[k] = float((got - ref).abs().max()) / scale
+        # whole-tensor checksums: the sum moves by at most ~sqrt(numel) * tol * absmax, the L2 norm by a relative tol
         d = g.double()
         assert abs(float(d.sum()) - rec["sum"]) <= tol * scale * g.numel() ** 0.5 * 4 + 1e-12, (what, k, "sum")
         assert abs(float((d * d).sum()) ** 0.5 - rec["sumsq"] ** 0.5) <= tol * max(rec["sumsq"] ** 0.5, 1e-12) * 2 + 1e-12, (what, k, "norm")
-        worst = max(worst, err)
-    return worst
+    bad = {k: round(v, 6) for k, v in errs.items() if v > tol}
+    assert not bad, (what, tol, bad)
+    return max(errs.values())
 
 
 @pytest.mark.parametrize("case", ["lvis_train_3way_1shot_cls_only", "coco_train_2way_2shot"])
