@@ -330,6 +330,10 @@ int sylph_update_code_generator(sylph_ctx* ctx);
  * bias_scale travel to the host (8 bytes; the call waits for the stream). */
 int sylph_update_code_generator_device(sylph_ctx* ctx, const sylph_codegen_tensors* params, void* stream);
 
+/* Debugging aid: copy the first `bytes` of one of the context's named scratch buffers (engine.cu `ensure` names, e.g.
+ * "bwd.x", "det.logits") to out_dev.  Not part of the reference-facing surface. */
+int sylph_debug_read_buffer(sylph_ctx* ctx, const char* name, void* out_dev, size_t bytes, void* stream);
+
 /* Number of kernels this library launched on the context since creation (bench.py's gpu_launches). */
 int64_t sylph_launch_count(const sylph_ctx* ctx);
 

@@ -360,7 +360,11 @@ def build_training_variant_goldens():
 # code-generator parameter.  The 2.4 MB convolution gradients are stored as a strided sample (every GRAD_SAMPLE_STEP-th element of
 # the flattened tensor) plus float64 checksums (sum, sum of squares) of the whole tensor; small tensors in full.
 GRAD_SAMPLE_STEP = 7
-GRAD_CASES = ["lvis_train_3way_1shot_cls_only", "coco_train_2way_2shot"]
+GRAD_CASES = ["lvis_train_3way_1shot_cls_only", "coco_train_2way_2shot", "coco_train_2way_2shot_mild"]
+# "coco_train_2way_2shot" saturates the classifier with its synthetic weights (loss_fcos_cls = 92.9); the "_mild" variant is the
+# same episode with conv_scale = 0.5 instead of 6 (logits of order 1, the regime of a trained model)
+GRAD_STATE_OVERRIDES = {"coco_train_2way_2shot_mild": {"code_generator.code_generator_head.conv_scale.scale": 0.5}}
+GRAD_BASE_CASE = {"coco_train_2way_2shot_mild": "coco_train_2way_2shot"}
 
 
 def run_reference_training_grads(cfg, state, items):
@@ -393,9 +397,11 @@ def pack_grad(t: torch.Tensor):
 def build_training_grad_goldens():
     out = {"cases": {}, "torch_version": torch.__version__, "sample_step": GRAD_SAMPLE_STEP}
     for name in GRAD_CASES:
-        cfg_name, seed, opts, items = build_train_case(name)
+        cfg_name, seed, opts, items = build_train_case(GRAD_BASE_CASE.get(name, name))
         cfg = load_cfg(os.path.join(reference_loader.REFERENCE_ROOT, "configs", CONFIGS[cfg_name]), ["MODEL.DEVICE", "cpu"] + opts)
         state = W.synthetic_state_dict(cfg, seed)
+        for k, v in GRAD_STATE_OVERRIDES.get(name, {}).items():
+            state[k] = torch.full_like(state[k], v)
         ref_losses, ref_grads = run_reference_training_grads(cfg, state, items)
         orc = build_oracle(cfg, state)
         losses, grads, ex = orc.training_grads(to_records(items))
@@ -405,7 +411,8 @@ def build_training_grad_goldens():
             worst = max(worst, compare(k.replace("code_generator.code_generator_head.", "d "), grads[k], ref_grads[k]))
         print(f"[{name}] oracle autograd vs reference .grad: worst relative deviation {worst:.3e}")
         assert worst < 2e-5, worst
-        out["cases"][name] = {"losses": ref_losses, "grads": {k: pack_grad(v) for k, v in ref_grads.items()},
+        out["cases"][name] = {"base_case": GRAD_BASE_CASE.get(name, name), "state_overrides": GRAD_STATE_OVERRIDES.get(name, {}),
+                              "losses": ref_losses, "grads": {k: pack_grad(v) for k, v in ref_grads.items()},
                               "grad_codes": {k: v.clone() for k, v in ex["grad_codes"].items()},
                               "grad_codes_source": "oracle autograd (the reference does not expose the codes); pinned through the parameter gradients"}
     path = os.path.join(GOLDEN_DIR, "train_grads.pt")

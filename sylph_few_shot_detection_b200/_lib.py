@@ -170,6 +170,8 @@ def load() -> ctypes.CDLL:
     lib.sylph_update_code_generator.argtypes = [vp]
     lib.sylph_update_code_generator_device.restype = c_int
     lib.sylph_update_code_generator_device.argtypes = [vp, POINTER(CodegenTensors), vp]
+    lib.sylph_debug_read_buffer.restype = c_int
+    lib.sylph_debug_read_buffer.argtypes = [vp, c_char_p, vp, ctypes.c_size_t, vp]
     lib.sylph_launch_count.restype = c_int64
     lib.sylph_launch_count.argtypes = [vp]
     lib.sylph_set_profiling.restype = c_int
@@ -186,5 +188,5 @@ EXPORTED_SYMBOLS = [
     "sylph_export_features", "sylph_generate_codes", "sylph_export_roi_features", "sylph_normalize_codes", "sylph_exchange_create", "sylph_exchange_connect",
     "sylph_normalize_codes_exchange", "sylph_exchange_poll", "sylph_exchange_status", "sylph_exchange_destroy", "sylph_accumulate_codes", "sylph_reduce_codes",
     "sylph_detect", "sylph_detect_after", "sylph_detect_poll", "sylph_export_head_output", "sylph_fcos_loss_sums", "sylph_fcos_loss_finalize",
-    "sylph_fcos_cls_loss_backward", "sylph_codegen_backward", "sylph_update_code_generator", "sylph_update_code_generator_device", "sylph_launch_count", "sylph_set_profiling", "sylph_get_timings",
+    "sylph_fcos_cls_loss_backward", "sylph_codegen_backward", "sylph_update_code_generator", "sylph_update_code_generator_device", "sylph_debug_read_buffer", "sylph_launch_count", "sylph_set_profiling", "sylph_get_timings",
 ]

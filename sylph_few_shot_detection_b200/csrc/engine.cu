@@ -2422,15 +2422,19 @@ int sylph_codegen_backward(sylph_ctx* c, int n_rois, int n_classes, const int* c
     }
     // ---- support_set_shared_tower, last layer first
     float* dx = static_cast<float*>(db);
+    const char* dbg = getenv("SYLPH_BWD_DEBUG_STOP");   // debugging aid: return with the intermediates of this layer in place
+    const int dbg_stop = dbg ? atoi(dbg) : -1;
     for (int i = L - 1; i >= 0; --i) {
         CU_TRY(c, launch_k(col2im_roi_kernel, dim3(g_act), dim3(256), 0, st, static_cast<const float*>(dcolp), dx, n_rois));
         c->launches++;
+        if (dbg_stop == 10 + i) return 0;
         float* dgp = static_cast<float*>(parts);
         float* dbp = dgp + static_cast<size_t>(n_rois) * 256;
         CU_TRY(c, launch_k(roi_gn_relu_bwd_f32_kernel, dim3(n_rois), dim3(256), 0, st, static_cast<const float*>(dx),
                            static_cast<const float*>(Y(i)), static_cast<const float*>(MEAN(i)), static_cast<const float*>(RSTD(i)),
                            static_cast<const float*>(params->tower_gn_w[i]), static_cast<const float*>(params->tower_gn_b[i]), dx, dgp, dbp));
         c->launches++;
+        if (dbg_stop == i) return 0;
         TRY(colsum(dgp, 256, n_rois, 256, grads->tower_gn_w[i]));
         TRY(colsum(dbp, 256, n_rois, 256, grads->tower_gn_b[i]));
         CU_TRY(c, launch_k(im2col_roi_kernel, dim3(g_col), dim3(256), 0, st, static_cast<const float*>(X(i)), colp, n_rois));
@@ -2494,6 +2498,15 @@ int sylph_update_code_generator_device(sylph_ctx* c, const sylph_codegen_tensors
     CU_TRY(c, cudaStreamSynchronize(st));
     c->conv_scale = cs;
     c->bias_scale = bs;
+    return 0;
+}
+
+int sylph_debug_read_buffer(sylph_ctx* c, const char* name, void* out_dev, size_t bytes, void* stream) {
+    if (!c || !name || !out_dev) return 1;
+    auto it = c->bufs.find(name);
+    if (it == c->bufs.end() || !it->second.p) return c->fail("no buffer named %s", name);
+    if (bytes > it->second.cap) return c->fail("buffer %s holds %zu bytes, %zu requested", name, it->second.cap, bytes);
+    CU_TRY(c, cudaMemcpyAsync(out_dev, it->second.p, bytes, cudaMemcpyDeviceToDevice, static_cast<cudaStream_t>(stream)));
     return 0;
 }
 

@@ -519,6 +519,13 @@ class Engine:
         p_struct = self._codegen_tensor_struct(params)
         self._check(self.lib.sylph_update_code_generator_device(self.h, byref(p_struct), self._stream()))
 
+    def debug_read_buffer(self, name: str, shape, dtype=torch.float32) -> torch.Tensor:
+        """Copy of one of the engine's named scratch buffers (debugging aid, sylph_debug_read_buffer)."""
+        out = torch.empty(shape, device=self.device, dtype=dtype)
+        self._check(self.lib.sylph_debug_read_buffer(self.h, name.encode(), c_void_p(out.data_ptr()), out.numel() * out.element_size(),
+                                                     self._stream()))
+        return out
+
     # ------------------------------------------------------------------ instrumentation
     def launch_count(self) -> int:
         return int(self.lib.sylph_launch_count(self.h))

@@ -156,29 +156,31 @@ def test_training_forward_loss_configurations(variant):
 # plugin's autograd hook).  GRAD_TOL: max-norm error of a gradient tensor relative to its largest entry, against the
 # REFERENCE model's own `.grad` (tests/golden/train_grads.pt) and, tensor for tensor in full, against the oracle's
 # autograd (pinned to that golden at 0.0 deviation by tests/test_training_oracle.py).
-# End to end the gradient inherits the forward's operand error THROUGH the focal loss: d loss / d logit = f(sigmoid(logit)), so a
-# logit error of 1e-4 x |logit| moves it by that many parts of itself.  "lvis_train_3way_1shot_cls_only" (loss 1.7, logits of
-# order 1: the regime of a trained model) measures 2e-4 and is held to GRAD_TOL; "coco_train_2way_2shot" is a deliberately hot
-# case (synthetic weights that saturate the classifier: loss_fcos_cls = 92.9, |logit| up to ~40) and measures 1.8e-3.  The
-# kernels themselves are held to KERNEL_GRAD_TOL by the two tests below that feed them fp32 inputs.
+# The gradient of a ReLU network is a DISCONTINUOUS function of its input: an element whose pre-activation crosses 0 switches its
+# whole contribution on or off.  The reference's own autograd moves by 1.6e-3 .. 2.1e-3 (max-norm per tensor) when its pooled ROI
+# features move by 1e-4 relative, and by 5e-7 when they move by 1e-6 (test_reference_gradient_conditioning, CPU) -- and 1e-4 is
+# what the exact-mode forward delivers (section 5 of DESIGN.md).  So end to end, against the reference model's `.grad`:
+#   * tensors behind no ReLU (cls / bias convolution, post_norm, scales): GRAD_TOL = 1e-3 max-norm (measured 1e-5 .. 2e-4);
+#   * the tower's tensors: relative L2 error <= GRAD_L2_TOL = 2e-3 (measured 1.4e-4 .. 1.3e-3) and max-norm <= GRAD_TOL_KINK = 1e-2
+#     (measured up to 4.2e-3 on single entries of the hot case "coco_train_2way_2shot", loss_fcos_cls = 92.9).
+# The kernels themselves are held to KERNEL_GRAD_TOL by the two tests below, which feed them fp32 inputs and pin the ReLU pattern.
 GRAD_TOL = 1e-3
-GRAD_TOL_SATURATED = 4e-3
+GRAD_L2_TOL = 2e-3
+GRAD_TOL_KINK = 1e-2
 KERNEL_GRAD_TOL = 5e-5
 
 
 def _train_model(case):
-    from sylph_few_shot_detection_b200 import weights as W
     from sylph_few_shot_detection_b200.modeling import build_model
-    g = load_golden(case)
-    cfg = cfg_for(g["config"], g["opts"])
-    state = W.synthetic_state_dict(cfg, g["seed"])
+    from tests.test_training_oracle import grad_case
+    g, _, cfg, state = grad_case(case)
     model = build_model(cfg)
     model.load_state_dict(state)
     model.train()
     return g, cfg, state, model
 
 
-@pytest.mark.parametrize("case", ["lvis_train_3way_1shot_cls_only", "coco_train_2way_2shot"])
+@pytest.mark.parametrize("case", ["lvis_train_3way_1shot_cls_only", "coco_train_2way_2shot_mild", "coco_train_2way_2shot"])
 def test_code_generator_gradients_match_reference(case):
     from oracle.make_golden import to_records
     from oracle.meta_fcos_oracle import MetaFCOSOracle
@@ -194,33 +196,49 @@ def test_code_generator_gradients_match_reference(case):
     sum(losses.values()).backward()
     grads = {k: p.grad for k, p in names.items() if p.grad is not None}
     assert set(grads) == set(gg["grads"])                                      # init_norm.* get none, like the reference
-    tol = GRAD_TOL if case.startswith("lvis") else GRAD_TOL_SATURATED
-    worst = check_grads_against_golden(grads, gg["grads"], tol, case)
+    tol = GRAD_TOL_KINK
+    smooth = {k: v for k, v in gg["grads"].items() if "support_set_shared_tower" not in k}
+    check_grads_against_golden(grads, smooth, GRAD_TOL, case + " (no ReLU behind)", GRAD_TOL)
+    worst, _ = check_grads_against_golden(grads, gg["grads"], GRAD_TOL_KINK, case, GRAD_L2_TOL)
     # gradient with respect to the final class codes
     gc = model._last_grad_codes.cpu()
     ref_w = gg["grad_codes"]["cls_conv"].reshape(-1, 256)
     ref_b = gg["grad_codes"]["cls_bias"].reshape(-1)
-    assert float((gc[:, :256] - ref_w).abs().max()) <= tol * float(ref_w.abs().max())
-    assert float((gc[:, 256] - ref_b).abs().max()) <= tol * float(ref_b.abs().max())
+    assert float((gc[:, :256] - ref_w).abs().max()) <= GRAD_TOL * float(ref_w.abs().max())      # no ReLU between the loss and the codes
+    assert float((gc[:, 256] - ref_b).abs().max()) <= GRAD_TOL * float(ref_b.abs().max())
     # every tensor in full against the oracle's autograd
     orc = MetaFCOSOracle(cfg, state)
     _, ograds, _ = orc.training_grads(to_records(g["items"]))
     for k, v in ograds.items():
         err = float((grads[k].cpu() - v).abs().max()) / max(float(v.abs().max()), 1e-12)
-        assert err <= tol, (k, err)
+        l2 = float((grads[k].cpu() - v).norm()) / max(float(v.norm()), 1e-30)
+        assert err <= tol and l2 <= GRAD_L2_TOL, (k, err, l2)
         worst = max(worst, err)
     print(f"[{case}] worst relative gradient error {worst:.2e}")
 
 
-@pytest.mark.parametrize("case", ["lvis_train_3way_1shot_cls_only", "coco_train_2way_2shot"])
-def test_codegen_backward_kernels_alone(case):
+@pytest.mark.parametrize("case,opts", [
+    ("lvis_train_3way_1shot_cls_only", []),
+    ("coco_train_2way_2shot", []),
+    ("coco_train_2way_2shot", ["MODEL.META_LEARN.CODE_GENERATOR.BIAS_L2_NORM", True]),
+    ("coco_train_2way_2shot", ["MODEL.META_LEARN.SHOT", 1]),
+    ("coco_train_2way_2shot", ["MODEL.META_LEARN.SHOT", 4, "MODEL.META_LEARN.CODE_GENERATOR.POST_NORM", ""]),
+])
+def test_codegen_backward_kernels_alone(case, opts):
     """sylph_codegen_backward against autograd through the oracle's code generator on the SAME fp32 inputs: the pooled ROI
     features exported from the engine, the oracle's raw codes and a random upstream gradient -- only the backward kernels
-    (fp32 re-evaluation of the tower, GroupNorm / ReLU / pool / L2 / normalisation backward, the three GEMM forms) differ."""
-    import torch.nn.functional as F  # noqa: F401
+    (fp32 re-evaluation of the tower, GroupNorm / ReLU / pool / L2 / normalisation backward, the three GEMM forms) differ.
+    Configuration variants: BIAS_L2_NORM on / off, 1 / 2 / 4 shots per class, POST_NORM on / off."""
+    import torch.nn.functional as F
     from oracle.meta_fcos_oracle import MetaFCOSOracle
+    from sylph_few_shot_detection_b200 import weights as W
+    from sylph_few_shot_detection_b200.modeling import build_model
     from sylph_few_shot_detection_b200.runtime import SLOT_SUPPORT
-    g, cfg, state, model = _train_model(case)
+    g = load_golden(case)
+    cfg = cfg_for(g["config"], list(g["opts"]) + list(opts))
+    state = W.synthetic_state_dict(cfg, g["seed"])
+    model = build_model(cfg)
+    model.load_state_dict(state)
     eng = model.engine
     batched = _records(g["items"])
     support = [r for x in batched for r in x["support_set"]]
@@ -233,30 +251,64 @@ def test_codegen_backward_kernels_alone(case):
     roi = eng.export_roi_features(n).cpu()
     orc = MetaFCOSOracle(cfg, state)
     keys = orc.trainable_code_generator_keys()
-    leaves = {k: orc.sd[k].detach().clone().requires_grad_(True) for k in keys}
-    saved = {k: orc.sd[k] for k in keys}
-    orc.sd.update(leaves)
-    try:
-        with torch.enable_grad():
-            w, b = MetaFCOSOracle.per_shot_codes.__wrapped__(orc, roi)
-            raw_w = w.view(n_cls, shot, *w.shape[1:]).mean(dim=1)
-            raw_b = b.view(n_cls, shot, 1, 1, 1).mean(dim=1)
-            fw, fb = orc.process_codes_training(raw_w, raw_b)
-            gen = torch.Generator().manual_seed(7)
-            G = torch.randn(n_cls, 257, generator=gen)
-            ((fw.reshape(n_cls, 256) * G[:, :256]).sum() + (fb.reshape(-1) * G[:, 256]).sum()).backward()
-        ref = {k: leaves[k].grad.detach() for k in keys}
-    finally:
-        orc.sd.update(saved)
-    raw = torch.cat([raw_w.detach().reshape(n_cls, 256), raw_b.detach().reshape(n_cls, 1)], dim=1)
     params = {k: state[k].cuda().float().contiguous() for k in keys}
+    gen = torch.Generator().manual_seed(7)
+    G = torch.randn(n_cls, 257, generator=gen)
+    L = len(cfg.MODEL.META_LEARN.CODE_GENERATOR.TOWER_LAYERS)
+
+    def oracle_grads(masks):
+        """autograd through per_shot_codes -> class mean -> process_codes_training; `masks` (one (n, 256, 7, 7) bool tensor per tower
+        layer) pins every ReLU to x * mask, None = the plain ReLU."""
+        leaves = {k: orc.sd[k].detach().clone().requires_grad_(True) for k in keys}
+        saved = {k: orc.sd[k] for k in keys}
+        orc.sd.update(leaves)
+        pre = {}
+        if masks is not None:
+            def tower(x):
+                for i in range(L):
+                    x = F.conv2d(x, orc._cg(f"support_set_shared_tower.{3 * i}.weight"), orc._cg(f"support_set_shared_tower.{3 * i}.bias"), padding=1)
+                    x = F.group_norm(x, 32, orc._cg(f"support_set_shared_tower.{3 * i + 1}.weight"), orc._cg(f"support_set_shared_tower.{3 * i + 1}.bias"), 1e-5)
+                    pre[i] = x.detach()
+                    x = x * masks[i]
+                return x
+            orc._cg_tower = tower
+        try:
+            with torch.enable_grad():
+                w, b = MetaFCOSOracle.per_shot_codes.__wrapped__(orc, roi)
+                raw_w = w.view(n_cls, shot, *w.shape[1:]).mean(dim=1)
+                raw_b = b.view(n_cls, shot, 1, 1, 1).mean(dim=1)
+                fw, fb = orc.process_codes_training(raw_w, raw_b)
+                ((fw.reshape(n_cls, 256) * G[:, :256]).sum() + (fb.reshape(-1) * G[:, 256]).sum()).backward()
+            grads = {k: leaves[k].grad.detach() for k in keys if leaves[k].grad is not None}
+        finally:
+            orc.sd.update(saved)
+            if masks is not None:
+                del orc._cg_tower
+        raw = torch.cat([raw_w.detach().reshape(n_cls, 256), raw_b.detach().reshape(n_cls, 1)], dim=1)
+        return grads, raw, pre
+
+    _, raw, _ = oracle_grads(None)
     got = eng.codegen_backward(offsets, raw, G, params)
-    worst = 0.0
-    for k in keys:
-        err = float((got[k].cpu() - ref[k]).abs().max()) / max(float(ref[k].abs().max()), 1e-12)
-        assert err <= KERNEL_GRAD_TOL, (k, err)
-        worst = max(worst, err)
-    print(f"[{case}] codegen backward kernels vs fp32 autograd: worst {worst:.2e}")
+    # A ReLU is not differentiable at 0: two fp32 evaluations of the same tower that differ in the last bits may put an element
+    # on different sides, and ONE such element moves single gradient entries by ~4e-3 of the largest (measured; the reference's
+    # own autograd moves by 2e-3 when its input moves by 1e-4, tests/test_training_oracle.py).  So the reference is
+    # evaluated with the ReLU pattern of the engine's fp32 re-evaluation (its layer inputs X_1 .. X_L, read back), and the
+    # patterns themselves may only differ where the pre-activation is within rounding distance of 0.
+    xs = eng.debug_read_buffer("bwd.x", (L + 1, n, 7, 7, 256)).cpu()
+    masks = [(xs[i + 1] > 0).permute(0, 3, 1, 2) for i in range(L)]
+    ref, _, pre = oracle_grads(masks)
+    flips = 0
+    for i in range(L):
+        differ = masks[i] != (pre[i] > 0)
+        flips += int(differ.sum())
+        assert float(pre[i][differ].abs().max()) < 1e-4 if differ.any() else True, "ReLU patterns differ away from 0"
+    assert flips <= 8, flips
+    errs = {k.split("head.")[1]: (float((got[k].cpu() - ref[k]).abs().max()) / max(float(ref[k].abs().max()), 1e-12),
+                                  float((got[k].cpu() - ref[k]).norm()) / max(float(ref[k].norm()), 1e-30)) for k in ref}
+    print(f"[{case} {opts}] codegen backward kernels vs fp32 autograd ({flips} ReLU ties), max-norm / rel-L2: " +
+          ", ".join(f"{k} {a:.1e}/{b:.1e}" for k, (a, b) in errs.items()))
+    bad = {k: v for k, v in errs.items() if v[0] > KERNEL_GRAD_TOL}
+    assert not bad, bad
 
 
 def test_cls_loss_backward_kernel_alone():
@@ -368,6 +420,9 @@ def test_backward_c_abi_validation():
     eng = model.engine
     labels = torch.zeros(10, dtype=torch.int64, device="cuda")
     sums = torch.zeros(5, dtype=torch.float64, device="cuda")
+    with pytest.raises(RuntimeError, match="holds no features"):
+        eng.fcos_cls_loss_backward(SLOT_QUERY, 3, [1, 2, 3], labels, sums)
+    eng.extract_features(SLOT_QUERY, [torch.zeros(3, 64, 64, dtype=torch.uint8, device="cuda")])
     with pytest.raises(RuntimeError, match="last head pass"):
         eng.fcos_cls_loss_backward(SLOT_QUERY, 3, [1, 2, 3], labels, sums)
     with pytest.raises(RuntimeError, match="last sylph_generate_codes"):

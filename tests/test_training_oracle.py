@@ -111,12 +111,12 @@ def test_oracle_training_forward_loss_configurations(variant):
 # ---------------------------------------------------------------------------------------------------------------
 # Backward of the training step for the code generator: tests/golden/train_grads.pt holds the REFERENCE
 # model's own `.grad` after `sum(model(batched).values()).backward()` (oracle/make_golden.py --train-grads-only).
-def check_grads_against_golden(grads, packed, tol, what=""):
+def check_grads_against_golden(grads, packed, tol, what="", l2_tol=None):
     """`grads`: {state_dict key: tensor}; `packed`: the golden's per-tensor record (full tensor, or strided sample + float64
-    checksums of the whole tensor).  Max-norm error relative to the tensor's largest gradient <= tol for every tensor;
-    returns the worst one."""
+    checksums of the whole tensor).  Per tensor: max-norm error relative to the tensor's largest gradient <= tol and
+    (l2_tol) relative L2 error <= l2_tol; returns (worst max-norm, worst L2)."""
     assert set(grads) >= set(packed), sorted(set(packed) - set(grads))
-    errs = {}
+    errs, l2s = {}, {}
     for k, rec in packed.items():
         g = grads[k].detach().cpu().float().reshape(-1)
         assert tuple(grads[k].shape) == tuple(rec["shape"]), k
@@ -124,28 +124,47 @@ def check_grads_against_golden(grads, packed, tol, what=""):
         ref = rec["full"] if "full" in rec else rec["sample"]
         got = g if "full" in rec else g[::rec["sample_step"]]
         errs[k] = float((got - ref).abs().max()) / scale
+        l2s[k] = float((got - ref).double().norm()) / max(float(ref.double().norm()), 1e-30)
         # whole-tensor checksums: the sum moves by at most ~sqrt(numel) * tol * absmax, the L2 norm by a relative tol
         d = g.double()
         assert abs(float(d.sum()) - rec["sum"]) <= tol * scale * g.numel() ** 0.5 * 4 + 1e-12, (what, k, "sum")
         assert abs(float((d * d).sum()) ** 0.5 - rec["sumsq"] ** 0.5) <= tol * max(rec["sumsq"] ** 0.5, 1e-12) * 2 + 1e-12, (what, k, "norm")
-    bad = {k: round(v, 6) for k, v in errs.items() if v > tol}
-    assert not bad, (what, tol, bad)
-    return max(errs.values())
+    short = lambda k: k.replace("code_generator.code_generator_head.", "")
+    print(f"[{what}] max-norm / rel-L2 per tensor: " + ", ".join(f"{short(k)} {errs[k]:.1e}/{l2s[k]:.1e}" for k in errs))
+    bad = {short(k): round(v, 6) for k, v in errs.items() if v > tol}
+    assert not bad, (what, "max-norm", tol, bad)
+    if l2_tol is not None:
+        bad = {short(k): round(v, 6) for k, v in l2s.items() if v > l2_tol}
+        assert not bad, (what, "rel-L2", l2_tol, bad)
+    return max(errs.values()), max(l2s.values())
 
 
-@pytest.mark.parametrize("case", ["lvis_train_3way_1shot_cls_only", "coco_train_2way_2shot"])
-def test_oracle_training_grads_reproduce_reference(case):
-    g = load_golden(case)
+GRAD_CASES = ["lvis_train_3way_1shot_cls_only", "coco_train_2way_2shot", "coco_train_2way_2shot_mild"]
+
+
+def grad_case(case):
+    """(episode golden, gradient golden, cfg, state_dict) of a gradient case: the episode of its base case, the synthetic
+    weights of that case's seed with the case's overrides (oracle/make_golden.py GRAD_STATE_OVERRIDES)."""
     gg = load_golden("train_grads")["cases"][case]
+    g = load_golden(gg["base_case"])
     cfg = cfg_for(g["config"], g["opts"])
-    orc = MetaFCOSOracle(cfg, W.synthetic_state_dict(cfg, g["seed"]))
+    state = W.synthetic_state_dict(cfg, g["seed"])
+    for k, v in gg["state_overrides"].items():
+        state[k] = torch.full_like(state[k], v)
+    return g, gg, cfg, state
+
+
+@pytest.mark.parametrize("case", GRAD_CASES)
+def test_oracle_training_grads_reproduce_reference(case):
+    g, gg, cfg, state = grad_case(case)
+    orc = MetaFCOSOracle(cfg, state)
     before = {k: v.clone() for k, v in orc.sd.items() if k.startswith("code_generator.")}
     losses, grads, ex = orc.training_grads(to_records(g["items"]))
     for k, v in gg["losses"].items():
         assert abs(float(losses[k]) - float(v)) <= 2e-5 * abs(float(v)), k
     assert set(grads) == set(gg["grads"])
-    worst = check_grads_against_golden(grads, gg["grads"], 2e-5, case)
-    assert worst <= 2e-5
+    worst, worst_l2 = check_grads_against_golden(grads, gg["grads"], 2e-5, case, 2e-5)
+    assert worst <= 2e-5 and worst_l2 <= 2e-5
     assert torch.allclose(ex["grad_codes"]["cls_conv"], gg["grad_codes"]["cls_conv"], rtol=0, atol=2e-5 * float(gg["grad_codes"]["cls_conv"].abs().max()))
     # the oracle's weights are untouched and detached again
     for k, v in before.items():
@@ -180,3 +199,45 @@ def test_parameter_tree_and_backward_hook_plumbing():
     for i in range(3):
         assert torch.equal(params[i].grad, torch.full((3,), 30.0 * (i + 1)))
     assert params[3].grad is None
+
+
+def test_reference_gradient_conditioning():
+    """Why the end-to-end gradient tolerances of tests/test_gpu_training.py are what they are: the gradient of the code generator's
+    ReLU tower is discontinuous in its input.  The restated reference's own autograd (fp32) moves by ~2e-3 of a tensor's
+    largest entry when the pooled ROI features move by 1e-4 relative -- the accuracy of the exact-mode forward -- and by < 5e-6 when
+    they move by 1e-6; tensors with no ReLU behind them (the cls convolution) move by the perturbation itself."""
+    g, gg, cfg, state = grad_case("coco_train_2way_2shot_mild")
+    orc = MetaFCOSOracle(cfg, state)
+    support = [r for x in to_records(g["items"]) for r in x["support_set"]]
+    shot = int(cfg.MODEL.META_LEARN.SHOT)
+    with torch.no_grad():
+        feats = orc.features(orc.preprocess([r["image"] for r in support]).tensor)
+    roi, _ = orc.roi_features(feats, torch.stack([r["instances"].gt_boxes.tensor[0] for r in support]))
+    n_cls = roi.shape[0] // shot
+    keys = orc.trainable_code_generator_keys()
+    gen = torch.Generator().manual_seed(7)
+    G = torch.randn(n_cls, 257, generator=gen)
+
+    def grads_for(r):
+        saved = {k: orc.sd[k] for k in keys}
+        leaves = {k: saved[k].detach().clone().requires_grad_(True) for k in keys}
+        orc.sd.update(leaves)
+        try:
+            with torch.enable_grad():
+                w, b = MetaFCOSOracle.per_shot_codes.__wrapped__(orc, r)
+                fw, fb = orc.process_codes_training(w.view(n_cls, shot, *w.shape[1:]).mean(1), b.view(n_cls, shot, 1, 1, 1).mean(1))
+                ((fw.reshape(n_cls, 256) * G[:, :256]).sum() + (fb.reshape(-1) * G[:, 256]).sum()).backward()
+            return {k: leaves[k].grad.detach() for k in keys}
+        finally:
+            orc.sd.update(saved)
+
+    base = grads_for(roi)
+    moved = {}
+    for eps in (1e-6, 1e-4):
+        other = grads_for(roi * (1 + eps * torch.randn(roi.shape, generator=gen)))
+        moved[eps] = {k: float((other[k] - base[k]).abs().max() / base[k].abs().max()) for k in keys}
+    tower = [k for k in keys if "support_set_shared_tower" in k]
+    cls_w = "code_generator.code_generator_head.support_set_cls_conv.0.weight"
+    assert max(moved[1e-6][k] for k in tower) < 5e-6
+    assert max(moved[1e-4][k] for k in tower) > 5e-4            # an order of magnitude more than the perturbation
+    assert moved[1e-4][cls_w] < 2e-4
