@@ -22,8 +22,8 @@ with its measured error.
                split 1x1 kernel (conv3 of res4 + res5)
   cpu_baseline the CPU oracle (port of the reference forward) on this box's host cores: ONE whole episode with the
                reference's loop structure (rank 0, N = 1)
-  variants     random-init weights (zero candidates), BASELINE configs[2] (R-101 10-shot) and configs[4] (1203-class
-               code-generation sweep) on one GPU
+  variants     random-init weights (zero candidates), BASELINE configs[2] (R-101 10-shot), configs[4] (1203-class
+               code-generation sweep) and one meta-training iteration of the code generator on one GPU
   sharded      N > 1: BASELINE configs[3] (20-way 5-shot, 8 queries) with classes and queries sharded over the ranks and
                the class-code exchange inside the timed region, against the same episode on one GPU (strong scaling)
 
@@ -525,6 +525,47 @@ def measure_variants(hz: Harness, cfg, dev):
                                      "classes_per_s": round(1203 / (ms * 1e-3))}
         del model, eng
         torch.cuda.empty_cache()
+    # (d) one meta-training iteration of the hyper-network stage: 3 classes x 5 support images + 3 query images
+    # (the per-GPU batch of the shipped meta-training configs), detector frozen, code generator trained
+    from sylph_few_shot_detection_b200.structures import Boxes, Instances
+    tc = cfg.clone()
+    tc.defrost()
+    tc.MODEL.META_LEARN.SHOT, tc.MODEL.META_LEARN.QUERY_SHOT = 5, 1
+    tc.freeze()
+    model = build_model_for(tc, W.synthetic_state_dict(tc, 0), dev, "exact")
+    model.train()
+    sup, bx3, qry = synth_episode(21, n_way=3, n_shot=5, n_query=3)
+    gq = synth_episode(22, n_way=3, n_shot=2, n_query=1)[1]
+
+    def record(img, boxes, classes):
+        inst = Instances((IMG_H, IMG_W))
+        inst.gt_boxes = Boxes(boxes.reshape(-1, 4).clone())
+        inst.gt_classes = torch.tensor(classes)
+        return {"image": img.to(dev), "instances": inst, "height": IMG_H, "width": IMG_W}
+    batched = [{"support_set": [record(sup[c * 5 + s], bx3[c * 5 + s], [c]) for s in range(5)],
+                "query_set": [record(qry[c], gq[2 * c:2 * c + 2], [c, (c + 1) % 3])], "support_set_target": torch.tensor(c)} for c in range(3)]
+    opt = torch.optim.SGD(model.parameters(), lr=1e-6)
+
+    def forward_only():
+        with torch.no_grad():
+            return model(batched)
+
+    def iteration():
+        model.zero_grad(set_to_none=True)
+        losses = model(batched)
+        sum(losses.values()).backward()
+        opt.step()
+        return losses
+    ms_f, _ = timed(forward_only, warm=2, reps=4)
+    ms_it, losses = timed(iteration, warm=2, reps=4)
+    out["training_iteration"] = {"workload": "hyper-network meta-training iteration: 3 classes x 5 support images + 3 query images 800x1333, "
+                                             "R-50 FPN, detector frozen, code generator trained; forward (losses) + backward "
+                                             "(sylph_fcos_cls_loss_backward + sylph_codegen_backward) + SGD step + device-side weight refresh",
+                                 "ms_forward_losses": round(ms_f, 3), "ms_per_iteration": round(ms_it, 3),
+                                 "loss_fcos_cls": round(float(losses["loss_fcos_cls"].detach()), 5),
+                                 "trainable_tensors": sum(1 for p in model.parameters() if p.grad is not None)}
+    del model
+    torch.cuda.empty_cache()
     return out
 
 
