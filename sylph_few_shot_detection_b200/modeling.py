@@ -320,7 +320,8 @@ def _meta_fcos_losses(self, class_codes: Dict[str, torch.Tensor], support_set_ta
     losses = {"loss_fcos_cls": out[0]}
     if _box_branch_loss_on(self.cfg):
         losses.update({"loss_fcos_loc": out[1], "loss_fcos_ctr": out[2]})
-    return (losses, {"sums": sums, "labels": extra[0], "target_inds": extra[1], "reg_targets": extra[2]}) if want_targets else losses
+    return (losses, {"sums": sums, "labels": extra[0], "target_inds": extra[1], "reg_targets": extra[2],
+                     "global_pos_ctr": glob}) if want_targets else losses
 
 
 MetaFCOS.losses = _meta_fcos_losses
@@ -677,7 +678,7 @@ class MetaOneStageDetector(nn.Module):
         live = {k: self._trainable[k].detach() for k in self._trainable}
         tgt = [int(t) for t in targets]
         world = _world_size()
-        glob = _reduce_sum(extra["sums"][1:3]) if world > 1 else None
+        glob = extra["global_pos_ctr"]      # {positives, centre-ness target sum} over all ranks (None for one process)
 
         def closure(grad_out):
             if self._train_step != step:
