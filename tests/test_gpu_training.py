@@ -223,6 +223,8 @@ def test_code_generator_gradients_match_reference(case):
     ("coco_train_2way_2shot", ["MODEL.META_LEARN.CODE_GENERATOR.BIAS_L2_NORM", True]),
     ("coco_train_2way_2shot", ["MODEL.META_LEARN.SHOT", 1]),
     ("coco_train_2way_2shot", ["MODEL.META_LEARN.SHOT", 4, "MODEL.META_LEARN.CODE_GENERATOR.POST_NORM", ""]),
+    ("synthetic_15_rois", ["MODEL.META_LEARN.SHOT", 5]),
+    ("synthetic_15_rois", ["MODEL.META_LEARN.SHOT", 3, "MODEL.META_LEARN.CODE_GENERATOR.TOWER_LAYERS", [["GN", "ReLU"], ["GN", "ReLU"], ["GN", "ReLU"]]]),
 ])
 def test_codegen_backward_kernels_alone(case, opts):
     """sylph_codegen_backward against autograd through the oracle's code generator on the SAME fp32 inputs: the pooled ROI
@@ -234,18 +236,27 @@ def test_codegen_backward_kernels_alone(case, opts):
     from sylph_few_shot_detection_b200 import weights as W
     from sylph_few_shot_detection_b200.modeling import build_model
     from sylph_few_shot_detection_b200.runtime import SLOT_SUPPORT
-    g = load_golden(case)
-    cfg = cfg_for(g["config"], list(g["opts"]) + list(opts))
-    state = W.synthetic_state_dict(cfg, g["seed"])
+    if case == "synthetic_15_rois":      # the ROI count of a meta-training batch (3 classes x 5 shots): 735 pixel rows, 12 GEMM row tiles
+        cfg = cfg_for("COCO-Detection/Meta-FCOS/Meta-FCOS-finetune.yaml", list(opts))
+        state = W.synthetic_state_dict(cfg, 3)
+        gi = torch.Generator().manual_seed(15)
+        images = [torch.randint(0, 256, (3, 160, 224), generator=gi, dtype=torch.uint8) for _ in range(15)]
+        x0 = torch.rand(15, generator=gi) * 100
+        y0 = torch.rand(15, generator=gi) * 60
+        boxes = torch.stack([x0, y0, x0 + 20 + torch.rand(15, generator=gi) * 100, y0 + 20 + torch.rand(15, generator=gi) * 70], dim=1)
+    else:
+        g = load_golden(case)
+        cfg = cfg_for(g["config"], list(g["opts"]) + list(opts))
+        state = W.synthetic_state_dict(cfg, g["seed"])
+        support = [r for x in _records(g["items"]) for r in x["support_set"]]
+        images = [r["image"] for r in support]
+        boxes = torch.stack([r["instances"].gt_boxes.tensor[0] for r in support])
     model = build_model(cfg)
     model.load_state_dict(state)
     eng = model.engine
-    batched = _records(g["items"])
-    support = [r for x in batched for r in x["support_set"]]
     shot = int(cfg.MODEL.META_LEARN.SHOT)
-    n, n_cls = len(support), len(support) // shot
-    boxes = torch.stack([r["instances"].gt_boxes.tensor[0] for r in support])
-    eng.extract_features(SLOT_SUPPORT, [r["image"].cuda() for r in support])
+    n, n_cls = len(images), len(images) // shot
+    eng.extract_features(SLOT_SUPPORT, [im.cuda() for im in images])
     offsets = list(range(0, n + 1, shot))
     eng.generate_codes(SLOT_SUPPORT, boxes, list(range(n)), offsets)
     roi = eng.export_roi_features(n).cpu()
