@@ -2279,7 +2279,7 @@ int sylph_fcos_cls_loss_backward(sylph_ctx* c, int slot, int n_classes, const in
     void *stg, *part;
     long long total_px = 0;
     for (int l = 0; l < 5; ++l) total_px += static_cast<long long>(S.n) * S.lh[l] * S.lw[l];
-    const int blocks = static_cast<int>(std::min<long long>(2LL * c->num_sms, (total_px + kClsBwdRows - 1) / kClsBwdRows));
+    const int blocks = static_cast<int>(std::min<long long>(8LL * c->num_sms, (total_px + kClsBwdRows - 1) / kClsBwdRows));
     TRY(ensure(c, "bwd.support_targets", static_cast<size_t>(n_classes) * 8, "", &stg, st, false));
     TRY(ensure(c, "bwd.code_partials", static_cast<size_t>(blocks) * n_classes * 257 * 4, "", &part, st, false));
     TRY(stage_h2d(c, stg, support_targets_host, static_cast<size_t>(n_classes) * 8, st));
@@ -2302,8 +2302,13 @@ int sylph_fcos_cls_loss_backward(sylph_ctx* c, int slot, int n_classes, const in
 
 static int sgemm(sylph_ctx* c, cudaStream_t st, const float* A, long long sam, long long sak, const float* B, long long sbk,
                  long long sbn, float* C, long long ldc, int M, int N, int K, const float* bias, int accumulate) {
-    CU_TRY(c, launch_k(sgemm_f32_kernel, dim3(ceil_div(N, kSgTile), ceil_div(M, kSgTile)), dim3(256), 0, st, A, sam, sak, B, sbk, sbn,
-                       C, ldc, M, N, K, bias, accumulate));
+    // 64 x 64 tiles when they fill the machine, 32 x 32 tiles otherwise (the forward re-evaluation of 15 ROIs is 12 x 4 large tiles)
+    if (static_cast<long long>(ceil_div(N, 64)) * ceil_div(M, 64) >= 2LL * c->num_sms)
+        CU_TRY(c, launch_k(sgemm_f32_kernel<4, 4>, dim3(ceil_div(N, 64), ceil_div(M, 64)), dim3(256), 0, st, A, sam, sak, B, sbk, sbn,
+                           C, ldc, M, N, K, bias, accumulate));
+    else
+        CU_TRY(c, launch_k(sgemm_f32_kernel<2, 2>, dim3(ceil_div(N, 32), ceil_div(M, 32)), dim3(256), 0, st, A, sam, sak, B, sbk, sbn,
+                           C, ldc, M, N, K, bias, accumulate));
     CU_TRY(c, cudaGetLastError());
     c->launches++;
     return 0;

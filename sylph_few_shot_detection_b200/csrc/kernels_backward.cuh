@@ -20,59 +20,66 @@ namespace sylph {
 
 // ------------------------------------------------------------------------------------------------ generic fp32 GEMM
 // C[M, N] (row-major, ldc) = (accumulate ? C : 0) + A'[M, K] * B'[K, N] (+ bias[n]);  A'(m, k) = A[m * sam + k * sak],
-// B'(k, n) = B[k * sbk + n * sbn].  64 x 64 x 16 tiles, 256 threads, 4 x 4 outputs per thread; any M, N, K.
-constexpr int kSgTile = 64, kSgK = 16;
+// B'(k, n) = B[k * sbk + n * sbn].  (16 TM) x (16 TN) x 16 tiles, 256 threads, TM x TN outputs per thread; any M, N, K.
+// <4, 4> = 64 x 64 tiles; <2, 2> = 32 x 32 tiles for problems whose 64 x 64 grid would leave most SMs idle.
+constexpr int kSgK = 16;
 
+template <int TM, int TN>
 __global__ void __launch_bounds__(256)
 sgemm_f32_kernel(const float* __restrict__ A, long long sam, long long sak, const float* __restrict__ B, long long sbk,
                  long long sbn, float* __restrict__ C, long long ldc, int M, int N, int K, const float* __restrict__ bias,
                  int accumulate) {
+    constexpr int BM = 16 * TM, BN = 16 * TN;
     ptx::griddep_launch();
     ptx::griddep_wait();
-    __shared__ float As[kSgK][kSgTile + 4];
-    __shared__ float Bs[kSgK][kSgTile + 4];
+    __shared__ float As[kSgK][BM + 4];
+    __shared__ float Bs[kSgK][BN + 4];
     const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
-    const int m0 = blockIdx.y * kSgTile, n0 = blockIdx.x * kSgTile;
-    float acc[4][4];
+    const int m0 = blockIdx.y * BM, n0 = blockIdx.x * BN;
+    float acc[TM][TN];
 #pragma unroll
-    for (int i = 0; i < 4; ++i)
+    for (int i = 0; i < TM; ++i)
 #pragma unroll
-        for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+        for (int j = 0; j < TN; ++j) acc[i][j] = 0.f;
     for (int k0 = 0; k0 < K; k0 += kSgK) {
 #pragma unroll
-        for (int i = 0; i < 4; ++i) {
+        for (int i = 0; i < TM; ++i) {
             const int e = tid + i * 256;
             int m, k;
-            if (sak == 1) { m = e >> 4; k = e & 15; } else { m = e & 63; k = e >> 6; }
+            if (sak == 1) { m = e >> 4; k = e & 15; } else { m = e % BM; k = e / BM; }
             const int gm = m0 + m, gk = k0 + k;
             As[k][m] = (gm < M && gk < K) ? __ldg(A + gm * sam + gk * sak) : 0.f;
+        }
+#pragma unroll
+        for (int i = 0; i < TN; ++i) {
+            const int e = tid + i * 256;
             int n, kb;
-            if (sbn == 1) { n = e & 63; kb = e >> 6; } else { kb = e & 15; n = e >> 4; }
+            if (sbn == 1) { n = e % BN; kb = e / BN; } else { kb = e & 15; n = e >> 4; }
             const int gn = n0 + n, gkb = k0 + kb;
             Bs[kb][n] = (gn < N && gkb < K) ? __ldg(B + gkb * sbk + gn * sbn) : 0.f;
         }
         __syncthreads();
 #pragma unroll
         for (int k = 0; k < kSgK; ++k) {
-            float a[4], b[4];
+            float a[TM], b[TN];
 #pragma unroll
-            for (int i = 0; i < 4; ++i) a[i] = As[k][ty * 4 + i];
+            for (int i = 0; i < TM; ++i) a[i] = As[k][ty * TM + i];
 #pragma unroll
-            for (int j = 0; j < 4; ++j) b[j] = Bs[k][tx * 4 + j];
+            for (int j = 0; j < TN; ++j) b[j] = Bs[k][tx * TN + j];
 #pragma unroll
-            for (int i = 0; i < 4; ++i)
+            for (int i = 0; i < TM; ++i)
 #pragma unroll
-                for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
+                for (int j = 0; j < TN; ++j) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
         }
         __syncthreads();
     }
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
-        const int gm = m0 + ty * 4 + i;
+    for (int i = 0; i < TM; ++i) {
+        const int gm = m0 + ty * TM + i;
         if (gm >= M) continue;
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-            const int gn = n0 + tx * 4 + j;
+        for (int j = 0; j < TN; ++j) {
+            const int gn = n0 + tx * TN + j;
             if (gn >= N) continue;
             float v = acc[i][j];
             if (bias) v += bias[gn];
@@ -414,10 +421,11 @@ fcos_cls_loss_bwd_kernel(const float* __restrict__ logits, int logit_stride, con
                 if (cc == 0) srow[rr] = (i < total) ? row : ~0ull;
             }
             __syncthreads();
+            // rows past the end carry g = 0 and read row 0: no branch, so that the loads of several rows are in flight together
+#pragma unroll 8
             for (int rr = 0; rr < kClsBwdRows; ++rr) {
                 const unsigned long long row = srow[rr];
-                if (row == ~0ull) break;
-                const __half* px = tower + row * ld;
+                const __half* px = tower + (row == ~0ull ? 0ull : row) * ld;
                 float x = __half2float(px[t]);
                 if (lo) x += __half2float(px[lo + t]);
 #pragma unroll
