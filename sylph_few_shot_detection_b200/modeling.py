@@ -512,6 +512,7 @@ class MetaOneStageDetector(nn.Module):
 
     # ------------------------------------------------------------------ run_type protocol
     def forward(self, batched_inputs, class_code=None, run_type=None):
+        self._sync_code_generator()      # parameters an optimiser has stepped since the last call reach the engine first
         if run_type is None and self.training:
             # MetaProposalNetwork.forward (meta_one_stage_detector.py:388-412): losses of one training episode batch
             if not self.episodic_learning:

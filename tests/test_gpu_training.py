@@ -423,6 +423,24 @@ def test_optimizer_step_reaches_the_engine():
     assert abs(l1 - float(ref["loss_fcos_cls"])) <= LOSS_TOL * abs(float(ref["loss_fcos_cls"])), (l1, float(ref["loss_fcos_cls"]))
     # the plain SGD step lowers this episode's loss (sanity of the gradient's sign)
     assert l1 < float(l0), (l1, float(l0))
+    # a second step, then straight to eval: the inference entry points see the stepped weights too
+    model.zero_grad(set_to_none=True)
+    model(batched)["loss_fcos_cls"].backward()
+    opt.step()
+    model.eval()
+    item = {"support_set": batched[0]["support_set"], "support_set_target": batched[0]["support_set_target"]}
+    import numpy as np
+    np.random.seed(0)
+    code = model([item], run_type="meta_learn_test_support")
+    orc2 = MetaFCOSOracle(cfg, {q: v.clone() for q, v in model.state_dict().items()})
+    ref_code = orc2.class_code([r["image"] for r in item["support_set"]],
+                               torch.stack([r["instances"].gt_boxes.tensor[0] for r in item["support_set"]]))
+    got_w = code["cls_conv"].cpu().reshape(-1)
+    assert float((got_w - ref_code["cls_conv"].reshape(-1)).abs().max()) <= 1e-3 * float(ref_code["cls_conv"].abs().max())
+    orc1 = MetaFCOSOracle(cfg, {q: v.clone() for q, v in stepped.items()})
+    old_code = orc1.class_code([r["image"] for r in item["support_set"]],
+                               torch.stack([r["instances"].gt_boxes.tensor[0] for r in item["support_set"]]))
+    assert float((got_w - old_code["cls_conv"].reshape(-1)).abs().max()) > 1e-3 * float(ref_code["cls_conv"].abs().max())   # not the weights of one step ago
 
 
 def test_backward_c_abi_validation():
