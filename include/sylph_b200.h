@@ -279,7 +279,7 @@ int sylph_fcos_loss_finalize(sylph_ctx* ctx, const double* local_sums_dev, const
  * (the box losses depend on the frozen box branch alone).  Gradients equal what the reference's
  * `sum(model(batched_inputs).values()).backward()` leaves in `.grad` of every `code_generator.*` parameter
  * (detectron2 SimpleTrainer.run_step on forward_few_shot_detector_training, meta_one_stage_detector.py:325-388).
- * Not built: the backward of the FCOS class tower (FREEZE_CLS_TOWER: False) and of the backbone. */
+ * The class tower's backward (FREEZE_CLS_TOWER: False) follows further below; the backbone and the box branch have none. */
 
 /* d loss_fcos_cls / d FINAL class codes, (n_classes, 257) fp32 rows [cls_conv 256 | cls_bias].  Call right after
  * sylph_fcos_loss_sums on the same slot with the same codes (the head's logits and class-tower output of that call
@@ -329,6 +329,39 @@ int sylph_update_code_generator(sylph_ctx* ctx);
  * tap-major fp16 (hi | hi | lo in exact mode) operand layout, bit-identical to the host preparation.  Only conv_scale /
  * bias_scale travel to the host (8 bytes; the call waits for the stream). */
 int sylph_update_code_generator_device(sylph_ctx* ctx, const sylph_codegen_tensors* params, void* stream);
+
+/* ---- Backward of the FCOS class tower (PROPOSAL_GENERATOR.FREEZE_CLS_TOWER: False, the shipped Meta-FCOS-finetune.yaml
+ * configurations of COCO and LVIS train the code generator AND the class tower; the backbone and the box branch stay frozen). ----
+ * Reference: autograd of MetaFCOSHead.cls_tower (sylph/modeling/meta_fcos/fcos.py:72-122, 582-667: NUM_CLS_CONVS x
+ * [conv3x3 + GroupNorm(32) + ReLU], shared by the five levels) under loss_fcos_cls. */
+
+/* Keep the class tower's activations during the head pass of sylph_fcos_loss_sums (every layer's input planes, pre-GroupNorm
+ * output and GroupNorm statistics stay in their own buffers instead of two ping-pong buffers).  Off by default. */
+int sylph_set_training(sylph_ctx* ctx, int enabled);
+
+/* The class tower's tensors, device fp32 in the state_dict layouts (`proposal_generator.fcos_head.cls_tower.*`). */
+typedef struct sylph_tower_tensors {
+    float* conv_w[SYLPH_CG_MAX_TOWER];      /* cls_tower.{3i}.weight   (256, 256, 3, 3) */
+    float* conv_b[SYLPH_CG_MAX_TOWER];      /* cls_tower.{3i}.bias     (256) */
+    float* gn_w[SYLPH_CG_MAX_TOWER];        /* cls_tower.{3i+1}.weight (256) */
+    float* gn_b[SYLPH_CG_MAX_TOWER];        /* cls_tower.{3i+1}.bias   (256) */
+} sylph_tower_tensors;
+
+/* Gradients of loss_fcos_cls with respect to the class tower's tensors.  Call after sylph_fcos_loss_sums (training mode on) on
+ * the same slot with the same FINAL codes; labels_dev / local_sums_dev / global_pos_ctr_dev / world_size / grad_loss_dev as
+ * for sylph_fcos_cls_loss_backward.  Per layer, last first: ReLU + GroupNorm backward over the planes, the weight gradient
+ * by a tcgen05 kernel that reads both operands MN-major straight from the planes (csrc/wgrad3x3.cuh), the input gradient
+ * by the forward convolution kernel on the transposed, tap-reversed weights.  Every non-NULL tensor of `grads` is
+ * overwritten.  Deterministic. */
+int sylph_cls_tower_backward(sylph_ctx* ctx, int slot, int n_classes, const float* codes_dev,
+                             const int64_t* support_targets_host, const sylph_loss_config* lc, const int64_t* labels_dev,
+                             const double* local_sums_dev, const double* global_pos_ctr_dev, int world_size,
+                             const float* grad_loss_dev, const sylph_tower_tensors* params,
+                             const sylph_tower_tensors* grads, void* stream);
+
+/* Re-prepare the class tower's weights (forward operands and the transposed copies of the backward) from the optimiser's
+ * device tensors, by kernels on `stream`. */
+int sylph_update_cls_tower_device(sylph_ctx* ctx, const sylph_tower_tensors* params, void* stream);
 
 /* Debugging aid: copy the first `bytes` of one of the context's named scratch buffers (engine.cu `ensure` names, e.g.
  * "bwd.x", "det.logits") to out_dev.  Not part of the reference-facing surface. */

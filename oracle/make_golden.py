@@ -377,18 +377,18 @@ def run_reference_training_grads(cfg, state, items):
     with contextlib.redirect_stdout(io.StringIO()), warnings_off():
         losses = model(batched)
         sum(losses.values()).backward()
-    pre = "code_generator."
+    pre = ("code_generator.", "proposal_generator.fcos_head.cls_tower.")
     grads = {n: p.grad.detach().clone() for n, p in model.named_parameters() if n.startswith(pre) and p.grad is not None}
     return {k: v.detach().clone() for k, v in losses.items()}, grads
 
 
-def pack_grad(t: torch.Tensor):
+def pack_grad(t: torch.Tensor, step: int = GRAD_SAMPLE_STEP):
     flat = t.reshape(-1)
     d = flat.double()
     rec = {"shape": tuple(t.shape), "sum": float(d.sum()), "sumsq": float((d * d).sum()), "absmax": float(d.abs().max())}
     if flat.numel() > 4096:
-        rec["sample_step"] = GRAD_SAMPLE_STEP
-        rec["sample"] = flat[::GRAD_SAMPLE_STEP].clone()
+        rec["sample_step"] = step
+        rec["sample"] = flat[::step].clone()
     else:
         rec["full"] = flat.clone()
     return rec
@@ -408,11 +408,12 @@ def build_training_grad_goldens():
         assert set(grads) == set(ref_grads), (sorted(set(grads) ^ set(ref_grads)))
         worst = 0.0
         for k in sorted(ref_grads):
-            worst = max(worst, compare(k.replace("code_generator.code_generator_head.", "d "), grads[k], ref_grads[k]))
+            worst = max(worst, compare(k.replace("code_generator.code_generator_head.", "d ").replace("proposal_generator.fcos_head.", "d "), grads[k], ref_grads[k]))
         print(f"[{name}] oracle autograd vs reference .grad: worst relative deviation {worst:.3e}")
         assert worst < 2e-5, worst
         out["cases"][name] = {"base_case": GRAD_BASE_CASE.get(name, name), "state_overrides": GRAD_STATE_OVERRIDES.get(name, {}),
-                              "losses": ref_losses, "grads": {k: pack_grad(v) for k, v in ref_grads.items()},
+                              "losses": ref_losses, "grads": {k: pack_grad(v, GRAD_SAMPLE_STEP if k.startswith("code_generator.") else 23)
+                                                                for k, v in ref_grads.items()},
                               "grad_codes": {k: v.clone() for k, v in ex["grad_codes"].items()},
                               "grad_codes_source": "oracle autograd (the reference does not expose the codes); pinned through the parameter gradients"}
     path = os.path.join(GOLDEN_DIR, "train_grads.pt")

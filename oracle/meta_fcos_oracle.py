@@ -494,12 +494,21 @@ class MetaFCOSOracle:
         return [k for k, v in self.sd.items() if k.startswith(pre) and torch.is_floating_point(v)
                 and not k.startswith(pre + "init_norm.")]
 
+    def trainable_keys(self) -> List[str]:
+        """Code generator + (unless FREEZE_CLS_TOWER / FREEZE) the FCOS class tower: the tensors the B200 path has backward
+        kernels for; the reference additionally trains whatever else the configuration leaves unfrozen."""
+        keys = self.trainable_code_generator_keys()
+        P = self.cfg.MODEL.PROPOSAL_GENERATOR
+        if not (P.FREEZE_CLS_TOWER or P.FREEZE):
+            keys += [k for k in self.sd if k.startswith("proposal_generator.fcos_head.cls_tower.")]
+        return keys
+
     def training_grads(self, batched_inputs: Sequence[Dict], world_size: int = 1, reduce=None):
-        """Backward of the episodic training step for the CODE GENERATOR: autograd through the restated
-        forward.  d(sum of the returned losses) / d(parameter) for every code-generator tensor, as the reference's
+        """Backward of the episodic training step for the CODE GENERATOR and the FCOS CLASS TOWER: autograd through
+        the restated forward.  d(sum of the returned losses) / d(parameter) for every tensor of `trainable_keys`, as the reference's
         `losses = model(batched); sum(losses.values()).backward()` leaves them in `.grad` (detectron2 SimpleTrainer.run_step),
         plus the gradient with respect to the final class codes.  Returns (losses, {state_dict key: grad}, extras)."""
-        keys = self.trainable_code_generator_keys()
+        keys = self.trainable_keys()
         saved = {k: self.sd[k] for k in keys}
         leaves = {k: saved[k].detach().clone().requires_grad_(True) for k in keys}
         self.sd.update(leaves)

@@ -16,6 +16,7 @@
 #include "kernels_roi_encoder.cuh"
 #include "kernels_loss.cuh"
 #include "kernels_backward.cuh"
+#include "wgrad3x3.cuh"
 
 namespace sylph {
 
@@ -158,6 +159,13 @@ struct sylph_ctx {
     int last_detect_slot = -1, last_detect_classes = 0, last_logit_stride = 0;
     const __half* last_cls_tower = nullptr;   // output planes of the class tower of the last head pass (backward of the cls loss)
     bool weights_ready = false;               // sylph_finalize_weights has succeeded once (sylph_update_code_generator needs it)
+    // training of the FCOS class tower (sylph_set_training): the head pass keeps every layer's input planes, pre-GroupNorm
+    // convolution output and GroupNorm statistics for sylph_cls_tower_backward
+    bool train_save = false;
+    std::vector<const __half*> saved_x;       // input planes of class-tower layer i
+    std::vector<const float*> saved_raw, saved_stats;
+    std::vector<ConvW> cls_tower_t;           // transposed, tap-reversed class-tower weights (input-gradient convolutions)
+    bool cls_tower_t_ready = false;
     bool inplace_uploads = false;             // sylph_update_code_generator: re-upload into the existing device buffers
 
     int fail(const char* fmt, ...) {
@@ -1553,13 +1561,33 @@ static int run_head(sylph_ctx* c, int slot, const float* codes_dev, int n_classe
     CW.w = static_cast<__half*>(cw);
     CW.bias = static_cast<float*>(cb);
     auto tower = [&](const std::vector<ConvW>& tw, const std::vector<float*>& gw, const std::vector<float*>& gb,
-                     const char* name, __half** result) -> int {
+                     const char* name, __half** result, bool save = false) -> int {
         const __half* cur = S.pyr;
         __half* bufs2[2] = {static_cast<__half*>(ta), static_cast<__half*>(tb)};
+        if (save) {
+            c->saved_x.assign(tw.size(), nullptr);
+            c->saved_raw.assign(tw.size(), nullptr);
+            c->saved_stats.assign(tw.size(), nullptr);
+        }
         for (size_t i = 0; i < tw.size(); ++i) {
             __half* o = bufs2[i & 1];
-            TRY(conv_gn_relu(c, tw[i], gw[i], gb[i], cur, rows, static_cast<float*>(rawp), o, S.ps.get(), 0, tiles, 0, n_segs,
-                             static_cast<float*>(gp), static_cast<float*>(gs), name, st));
+            float* raw_i = static_cast<float*>(rawp);
+            float* gs_i = static_cast<float*>(gs);
+            if (save) {   // training: every layer keeps its own output planes, convolution output and statistics
+                void *po, *pr, *pg;
+                const std::string tag = std::to_string(i);
+                TRY(ensure(c, "det.cls_x" + tag, (static_cast<size_t>(rows) + kBlockM) * c->ld(256) * 2, "", &po, st, false));
+                TRY(ensure(c, "det.cls_raw" + tag, (static_cast<size_t>(rows) + kBlockM) * 256 * 4, "", &pr, st, false));
+                TRY(ensure(c, "det.cls_gs" + tag, static_cast<size_t>(n_segs) * 64 * 4, "", &pg, st, false));
+                o = static_cast<__half*>(po);
+                raw_i = static_cast<float*>(pr);
+                gs_i = static_cast<float*>(pg);
+                c->saved_x[i] = cur;
+                c->saved_raw[i] = raw_i;
+                c->saved_stats[i] = gs_i;
+            }
+            TRY(conv_gn_relu(c, tw[i], gw[i], gb[i], cur, rows, raw_i, o, S.ps.get(), 0, tiles, 0, n_segs,
+                             static_cast<float*>(gp), gs_i, name, st));
             cur = o;
         }
         *result = const_cast<__half*>(cur);
@@ -1575,7 +1603,7 @@ static int run_head(sylph_ctx* c, int slot, const float* codes_dev, int n_classe
         k.a_row_delta = 0; k.out = pr; k.ldc = 16; k.flags = kEpiOutF32; k.name = "head.pred3x3";
         TRY(run_conv(c, k, st));
     }
-    TRY(tower(c->cls_tower, c->cls_gn_w, c->cls_gn_b, "head.cls_tower3x3", &x));
+    TRY(tower(c->cls_tower, c->cls_gn_w, c->cls_gn_b, "head.cls_tower3x3", &x, c->train_save));
     if (codes_ready != nullptr) CU_TRY(c, cudaStreamWaitEvent(st, codes_ready, 0));
     CU_TRY(c, launch_k(pack_code_weights_kernel, dim3(ceil_div(static_cast<long long>(CW.cout_pad) * 256, 256)), dim3(256), 0, st,
         codes_dev, n_classes, CW.cout_pad, f.generator != 0 ? 1 : f.cg_use_bias, f.generator == 1 ? c->cond_scale : 1.f, CW.w, CW.bias, c->split));
@@ -2503,6 +2531,170 @@ int sylph_update_code_generator_device(sylph_ctx* c, const sylph_codegen_tensors
     CU_TRY(c, cudaStreamSynchronize(st));
     c->conv_scale = cs;
     c->bias_scale = bs;
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------------ class-tower training
+int sylph_set_training(sylph_ctx* c, int enabled) {
+    if (!c) return 1;
+    c->train_save = enabled != 0;
+    if (!c->train_save) { c->saved_x.clear(); c->saved_raw.clear(); c->saved_stats.clear(); }
+    return 0;
+}
+
+// Transposed, tap-reversed copies of the class-tower weights for the input-gradient convolutions (device-side packing).
+static int prep_cls_tower_transposed(sylph_ctx* c, const sylph_tower_tensors* params, cudaStream_t st) {
+    const int L = static_cast<int>(c->cls_tower.size());
+    if (static_cast<int>(c->cls_tower_t.size()) != L) c->cls_tower_t.assign(L, ConvW());
+    for (int i = 0; i < L; ++i) {
+        const ConvW& F = c->cls_tower[i];
+        if (F.taps != 9 || F.cin != 256 || F.cout != 256 || F.w_nm != nullptr) return c->fail("class-tower layer %d is not a 3x3 256 -> 256 convolution", i);
+        ConvW& T = c->cls_tower_t[i];
+        if (T.w == nullptr) {
+            T = F;
+            T.w = nullptr; T.bias = nullptr; T.w_nm = nullptr;
+            CU_TRY(c, cudaMalloc(&T.w, static_cast<size_t>(F.b_rows) * F.k_per_tap * 2));
+            CU_TRY(c, cudaMalloc(&T.bias, static_cast<size_t>(F.cout_pad) * 4));
+            CU_TRY(c, cudaMemsetAsync(T.bias, 0, static_cast<size_t>(F.cout_pad) * 4, st));
+        }
+        CU_TRY(c, launch_k(pack_oihw_weights_transposed_kernel, dim3(grid_for(256 * 256 * 9, 256, c->num_sms)), dim3(256), 0, st,
+                           static_cast<const float*>(params->conv_w[i]), T.w, c->split));
+        c->launches++;
+    }
+    c->cls_tower_t_ready = true;
+    return 0;
+}
+
+int sylph_update_cls_tower_device(sylph_ctx* c, const sylph_tower_tensors* params, void* stream) {
+    if (!c) return 1;
+    if (!c->weights_ready || !c->finalized) return c->fail("sylph_update_cls_tower_device: call sylph_finalize_weights once first");
+    if (!params) return c->fail("null argument");
+    const int L = static_cast<int>(c->cls_tower.size());
+    if (L > SYLPH_CG_MAX_TOWER) return c->fail("more than %d class-tower layers", SYLPH_CG_MAX_TOWER);
+    for (int i = 0; i < L; ++i)
+        if (!params->conv_w[i] || !params->conv_b[i] || !params->gn_w[i] || !params->gn_b[i]) return c->fail("class-tower layer %d: missing parameter tensor", i);
+    CU_TRY(c, cudaSetDevice(c->device));
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    for (int i = 0; i < L; ++i) {
+        ConvW& W = c->cls_tower[i];
+        if (W.taps != 9 || W.cin != 256 || W.cout != 256 || W.w_nm != nullptr) return c->fail("class-tower layer %d is not a 3x3 256 -> 256 convolution", i);
+        CU_TRY(c, launch_k(pack_oihw_weights_kernel, dim3(grid_for(256 * 256 * 9, 256, c->num_sms)), dim3(256), 0, st,
+                           static_cast<const float*>(params->conv_w[i]), W.w, 256, 256, 9, W.cout_pad, c->split, 0));
+        CU_TRY(c, cudaMemcpyAsync(W.bias, params->conv_b[i], 1024, cudaMemcpyDeviceToDevice, st));
+        CU_TRY(c, cudaMemcpyAsync(c->cls_gn_w[i], params->gn_w[i], 1024, cudaMemcpyDeviceToDevice, st));
+        CU_TRY(c, cudaMemcpyAsync(c->cls_gn_b[i], params->gn_b[i], 1024, cudaMemcpyDeviceToDevice, st));
+        c->launches++;
+    }
+    return prep_cls_tower_transposed(c, params, st);
+}
+
+int sylph_cls_tower_backward(sylph_ctx* c, int slot, int n_classes, const float* codes_dev, const int64_t* support_targets_host,
+                             const sylph_loss_config* lc, const int64_t* labels_dev, const double* local_sums_dev,
+                             const double* global_pos_ctr_dev, int world_size, const float* grad_loss_dev,
+                             const sylph_tower_tensors* params, const sylph_tower_tensors* grads, void* stream) {
+    if (!c) return 1;
+    if (!c->finalized) return c->fail("weights not finalized");
+    if (slot < 0 || slot >= SYLPH_NUM_SLOTS || !c->slots[slot].valid) return c->fail("slot %d holds no features", slot);
+    if (!codes_dev || !support_targets_host || !lc || !labels_dev || !local_sums_dev || !params || !grads) return c->fail("null argument");
+    if (world_size < 1) return c->fail("world_size must be >= 1");
+    const int L = static_cast<int>(c->cls_tower.size());
+    if (L < 1 || L > SYLPH_CG_MAX_TOWER) return c->fail("class tower of %d layers", L);
+    if (c->last_detect_slot != slot || c->last_detect_classes != n_classes || static_cast<int>(c->saved_x.size()) != L || !c->train_save)
+        return c->fail("sylph_cls_tower_backward: the last head pass was not sylph_fcos_loss_sums on slot %d with %d classes in training mode "
+                       "(sylph_set_training)", slot, n_classes);
+    for (int i = 0; i < L; ++i)
+        if (!params->conv_w[i] || !params->gn_w[i] || !params->gn_b[i] || !grads->conv_w[i] || !grads->conv_b[i] || !grads->gn_w[i] || !grads->gn_b[i])
+            return c->fail("class-tower layer %d: missing parameter / gradient tensor", i);
+    CU_TRY(c, cudaSetDevice(c->device));
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    const Slot& S = c->slots[slot];
+    if (!c->cls_tower_t_ready) TRY(prep_cls_tower_transposed(c, params, st));
+    auto lg = c->bufs.find("det.logits");
+    if (lg == c->bufs.end() || !lg->second.p) return c->fail("no logits buffer");
+    const long long rows = S.level_row0[5];
+    const int tiles = static_cast<int>(rows / kBlockM);
+    const int n_segs = 5 * S.n;
+    long long total_px = 0;
+    for (int l = 0; l < 5; ++l) total_px += static_cast<long long>(S.n) * S.lh[l] * S.lw[l];
+    const std::string sig = std::to_string(rows) + ":" + std::to_string(S.n) + ":" + std::to_string(S.hpad) + "x" + std::to_string(S.wpad);
+    void *stg, *dxa, *dxb, *dyp, *part, *segsum, *ab, *segmax, *scales, *biasp, *wpart;
+    const int splits = std::max(1, c->num_sms / 18);
+    TRY(ensure(c, "tbw.support_targets", static_cast<size_t>(n_classes) * 8, "", &stg, st, false));
+    TRY(ensure(c, "tbw.dx_a", (static_cast<size_t>(rows) + kBlockM) * 256 * 4, sig, &dxa, st, true));   // gradient entering a layer's ReLU (fp32)
+    TRY(ensure(c, "tbw.dx_b", (static_cast<size_t>(rows) + kBlockM) * 256 * 4, sig, &dxb, st, true));
+    TRY(ensure(c, "tbw.dy", (static_cast<size_t>(rows) + kBlockM) * c->ld(256) * 2, sig, &dyp, st, true));  // scaled dY planes
+    TRY(ensure(c, "tbw.partial", static_cast<size_t>(tiles) * kGnBwdPartial * 4, "", &part, st, false));
+    TRY(ensure(c, "tbw.seg_sums", static_cast<size_t>(n_segs) * 2 * 256 * 4, "", &segsum, st, false));
+    TRY(ensure(c, "tbw.ab", static_cast<size_t>(n_segs) * 64 * 4, "", &ab, st, false));
+    TRY(ensure(c, "tbw.seg_max", static_cast<size_t>(n_segs) * 4, "", &segmax, st, false));
+    TRY(ensure(c, "tbw.scales", static_cast<size_t>(SYLPH_CG_MAX_TOWER) * 2 * 4, "", &scales, st, false));
+    TRY(ensure(c, "tbw.bias_partial", static_cast<size_t>(tiles) * 256 * 4, "", &biasp, st, false));
+    TRY(ensure(c, "tbw.wgrad_partial", static_cast<size_t>(splits) * 9 * 256 * 256 * 4, "", &wpart, st, false));
+    TRY(stage_h2d(c, stg, support_targets_host, static_cast<size_t>(n_classes) * 8, st));
+    StageTimer timer(c, "bwd.cls_tower", st, 0.0);
+    // ---- gradient of the loss with respect to the tower's output (through the conditional convolution)
+    {
+        const int blocks = static_cast<int>(std::min<long long>(8LL * c->num_sms, (total_px + kClsBwdRows - 1) / kClsBwdRows));
+        CU_TRY(c, launch_k(tower_out_grad_kernel, dim3(blocks), dim3(256), 0, st, static_cast<const float*>(lg->second.p), c->last_logit_stride,
+                           codes_dev, S.pg, S.n, reinterpret_cast<const long long*>(labels_dev), static_cast<const long long*>(stg), n_classes,
+                           lc->focal_alpha, lc->focal_gamma, global_pos_ctr_dev ? global_pos_ctr_dev : local_sums_dev + 1, world_size,
+                           grad_loss_dev, static_cast<float*>(dxa)));
+        c->launches++;
+    }
+    static bool attr_set[2] = {false, false};
+    float* dx_in = static_cast<float*>(dxa);
+    float* dx_out = static_cast<float*>(dxb);
+    const float* in_scale = nullptr;          // the scale of the gradient in dx_in (NULL = 1)
+    const int g_tiles = std::max(1, std::min(tiles, c->num_sms * 8));
+    for (int i = L - 1; i >= 0; --i) {
+        float* sc = static_cast<float*>(scales) + 2 * i;
+        CU_TRY(c, launch_k(gn_bwd_partial_kernel, dim3(g_tiles), dim3(256), 0, st, static_cast<const float*>(dx_in), in_scale, c->saved_raw[i],
+                           c->saved_stats[i], static_cast<const float*>(params->gn_w[i]), static_cast<const float*>(params->gn_b[i]),
+                           static_cast<const int*>(S.ps->d_tile_seg), static_cast<const Seg*>(S.ps->d_segs), tiles, static_cast<float*>(part)));
+        CU_TRY(c, launch_k(gn_bwd_finalize_kernel, dim3(n_segs), dim3(256), 0, st, static_cast<const float*>(part), static_cast<const Seg*>(S.ps->d_segs),
+                           static_cast<const float*>(params->gn_w[i]), static_cast<float*>(segsum), static_cast<float*>(ab), static_cast<float*>(segmax)));
+        CU_TRY(c, launch_k(gn_bwd_scale_kernel, dim3(1), dim3(256), 0, st, static_cast<const float*>(segmax), c->saved_stats[i], n_segs,
+                           static_cast<const float*>(params->gn_w[i]), sc));
+        CU_TRY(c, launch_k(gn_bwd_apply_kernel, dim3(g_tiles), dim3(256), 0, st, static_cast<const float*>(dx_in), in_scale, c->saved_raw[i],
+                           c->saved_stats[i], static_cast<const float*>(ab), static_cast<const float*>(params->gn_w[i]),
+                           static_cast<const float*>(params->gn_b[i]), static_cast<const float*>(sc), static_cast<const int*>(S.ps->d_tile_seg),
+                           static_cast<const Seg*>(S.ps->d_segs), tiles, static_cast<__half*>(dyp), c->split, static_cast<float*>(biasp)));
+        CU_TRY(c, launch_k(tower_param_grad_reduce_kernel, dim3(3), dim3(256), 0, st, static_cast<const float*>(segsum), n_segs,
+                           static_cast<const float*>(biasp), tiles, grads->gn_w[i], grads->gn_b[i], grads->conv_b[i]));
+        CU_TRY(c, cudaGetLastError());
+        c->launches += 5;
+        // ---- weight gradient: dW = dY^T X_i per tap, straight from the planes (wgrad3x3.cuh)
+        {
+            CUtensorMap tdy, tx;
+            std::string err;
+            if (make_tmap_2d(&tdy, static_cast<const __half*>(dyp), static_cast<uint64_t>(rows), c->ld(256), c->ld(256), kWgTileK, &err) ||
+                make_tmap_2d(&tx, c->saved_x[i], static_cast<uint64_t>(rows), c->ld(256), c->ld(256), kWgTileK, &err))
+                return c->fail("wgrad tensor maps: %s", err.c_str());
+            WgradArgs wa{static_cast<const Seg*>(S.ps->d_segs), static_cast<const int*>(S.ps->d_tile_seg), static_cast<int>(rows / kWgTileK),
+                         static_cast<float*>(wpart)};
+            if (c->split) {
+                if (!attr_set[1]) { CU_TRY(c, cudaFuncSetAttribute(wgrad3x3_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, WgradSmem<true>::kTotal)); attr_set[1] = true; }
+                CU_TRY(c, launch_k(wgrad3x3_kernel<true>, dim3(splits, 9, 2), dim3(kWgThreads), WgradSmem<true>::kTotal, st, tdy, tx, wa));
+            } else {
+                if (!attr_set[0]) { CU_TRY(c, cudaFuncSetAttribute(wgrad3x3_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, WgradSmem<false>::kTotal)); attr_set[0] = true; }
+                CU_TRY(c, launch_k(wgrad3x3_kernel<false>, dim3(splits, 9, 2), dim3(kWgThreads), WgradSmem<false>::kTotal, st, tdy, tx, wa));
+            }
+            CU_TRY(c, launch_k(wgrad_reduce_scaled_kernel, dim3(9 * 256), dim3(256), 0, st, static_cast<const float*>(wpart), splits,
+                               static_cast<const float*>(sc), grads->conv_w[i]));
+            CU_TRY(c, cudaGetLastError());
+            c->launches += 2;
+        }
+        // ---- input gradient: the forward convolution kernel on dY with the transposed, tap-reversed weights -> fp32, still scaled
+        if (i > 0) {
+            ConvCall k{};
+            k.W = &c->cls_tower[i]; k.w_override = c->cls_tower_t[i].w; k.bias_override = c->cls_tower_t[i].bias;
+            k.A = static_cast<const __half*>(dyp); k.a_rows = rows; k.a_cols = k.a_ld = c->ld(256); k.ps = S.ps.get(); k.tile_begin = 0;
+            k.n_tiles = tiles; k.a_row_delta = 0; k.out = dx_out; k.ldc = 256; k.flags = kEpiOutF32; k.name = "bwd.cls_tower_dgrad3x3";
+            TRY(run_conv(c, k, st));
+            std::swap(dx_in, dx_out);
+            in_scale = sc;
+        }
+    }
     return 0;
 }
 

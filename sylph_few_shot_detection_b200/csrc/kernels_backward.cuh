@@ -355,6 +355,23 @@ shot_code_bwd_kernel(const float* __restrict__ draw, const int* __restrict__ roi
 // labels_out.  Per location and class: g = focal'(logit, target) * upstream / num_pos_avg; the block accumulates
 // dcode[c][k] += g * tower[row][k] (thread = channel k) and dbias[c] += g over its share of the locations, then writes
 // partials[block][c][257]; fcos_code_grad_reduce_kernel sums the blocks in order.
+// d sigmoid_focal_loss / d logit (fvcore sigmoid_focal_loss_jit): with p = sigmoid(v), ce = softplus(-v) (target 1) or softplus(v)
+// (target 0):  target 1: alpha (1 - p)^gamma (-gamma p ce - (1 - p));  target 0: (1 - alpha) p^gamma (gamma (1 - p) ce + p).
+__device__ __forceinline__ float focal_grad(float v, bool pos, float alpha, float gamma) {
+    const float p = 1.f / (1.f + expf(-v));
+    const float ce = bce_with_logits(v, pos ? 1.f : 0.f);
+    float gr;
+    if (pos) {
+        const float om = 1.f - p;
+        gr = (gamma == 2.f ? om * om : powf(om, gamma)) * (-gamma * p * ce - om);
+        if (alpha >= 0.f) gr *= alpha;
+    } else {
+        gr = (gamma == 2.f ? p * p : powf(p, gamma)) * (gamma * (1.f - p) * ce + p);
+        if (alpha >= 0.f) gr *= 1.f - alpha;
+    }
+    return gr;
+}
+
 constexpr int kClsBwdRows = 32;   // locations per staging round
 constexpr int kClsBwdTile = 8;    // classes per pass over the locations
 
@@ -402,19 +419,7 @@ fcos_cls_loss_bwd_kernel(const float* __restrict__ logits, int logit_stride, con
                     row = plane_row(g, n, y, x);
                     if (cc < nc) {
                         const float v = logits[row * logit_stride + c0 + cc];
-                        const bool pos = support_targets[c0 + cc] == labels[i];
-                        const float p = 1.f / (1.f + expf(-v));
-                        const float ce = bce_with_logits(v, pos ? 1.f : 0.f);
-                        float gr;
-                        if (pos) {
-                            const float om = 1.f - p;
-                            gr = (gamma == 2.f ? om * om : powf(om, gamma)) * (-gamma * p * ce - om);
-                            if (alpha >= 0.f) gr *= alpha;
-                        } else {
-                            gr = (gamma == 2.f ? p * p : powf(p, gamma)) * (gamma * (1.f - p) * ce + p);
-                            if (alpha >= 0.f) gr *= 1.f - alpha;
-                        }
-                        gval = gr * scale;
+                        gval = focal_grad(v, support_targets[c0 + cc] == labels[i], alpha, gamma) * scale;
                     }
                 }
                 sg[rr][cc] = gval;
@@ -491,6 +496,332 @@ transpose_taps_kernel(const float* __restrict__ w, float* __restrict__ out, int 
     if (e >= ci * taps) return;
     const int t = e / ci, ch = e - t * ci;
     out[e] = w[ch * taps + t];
+}
+
+// ------------------------------------------------------------------------------------------------ FCOS class tower
+// Backward of the class tower over the query pyramid (fcos.py:72-122: NUM_CLS_CONVS x [conv3x3 + GroupNorm(32) + ReLU], weights
+// shared by the levels, GroupNorm statistics per (image, level) plane), SURVEY.md 8f-4 with FREEZE_CLS_TOWER: False.
+//   d loss / d tower output        = sum over classes of d loss / d logit[c] * cls_conv[c]   (tower_out_grad_kernel)
+//   per layer, last first:  ReLU + GroupNorm backward over the planes (three kernels below) -> dY as fp16 (hi | lo) planes,
+//   weight gradient = wgrad3x3_kernel(dY, layer input), input gradient = the FORWARD convolution kernel on dY with the
+//   transposed, tap-reversed weights.
+// Gradients span many orders of magnitude, fp16 does not: every layer's dY is stored as s * dY with a power of two s picked on
+// the device from the largest |dz| of the layer (gn_bwd_scale_kernel); consumers divide by s in fp32 (the next layer's first
+// pass, the weight-gradient reduce).
+
+// dX[row][k] = sum_c g[row][c] * codes[c][k] on interior pixels (fp32, [rows][256]); thread = channel k.
+__global__ void __launch_bounds__(256)
+tower_out_grad_kernel(const float* __restrict__ logits, int logit_stride, const float* __restrict__ codes, PyramidGeom pg,
+                      int n_images, const long long* __restrict__ labels, const long long* __restrict__ support_targets,
+                      int n_classes, float alpha, float gamma, const double* __restrict__ global_pos, int world,
+                      const float* __restrict__ upstream, float* __restrict__ dX) {
+    ptx::griddep_launch();
+    ptx::griddep_wait();
+    __shared__ float sg[kClsBwdRows][kClsBwdTile];
+    __shared__ unsigned long long srow[kClsBwdRows];
+    const int t = threadIdx.x;
+    long long total = 0;
+    long long lvl_start[6];
+    for (int l = 0; l < 5; ++l) { lvl_start[l] = total; total += static_cast<long long>(n_images) * pg.lv[l].H * pg.lv[l].W; }
+    lvl_start[5] = total;
+    const float num_pos_avg = fmaxf(static_cast<float>(global_pos[0] / world), 1.0f);
+    const float scale = (upstream ? upstream[0] : 1.f) / num_pos_avg;
+    const long long rounds = (total + kClsBwdRows - 1) / kClsBwdRows;
+    for (long long rd = blockIdx.x; rd < rounds; rd += gridDim.x) {
+        const long long i0 = rd * kClsBwdRows;
+        float acc[kClsBwdRows];
+#pragma unroll
+        for (int rr = 0; rr < kClsBwdRows; ++rr) acc[rr] = 0.f;
+        for (int c0 = 0; c0 < n_classes; c0 += kClsBwdTile) {
+            const int nc = min(kClsBwdTile, n_classes - c0);
+            __syncthreads();
+            {
+                const int rr = t / kClsBwdTile, cc = t % kClsBwdTile;
+                const long long i = i0 + rr;
+                float gval = 0.f;
+                unsigned long long row = ~0ull;
+                if (i < total) {
+                    int l = 0;
+                    while (i >= lvl_start[l + 1]) ++l;
+                    const PlaneGeom g = pg.lv[l];
+                    const long long j = i - lvl_start[l];
+                    const int hw = g.H * g.W;
+                    const int n = static_cast<int>(j / hw);
+                    const int loc = static_cast<int>(j - static_cast<long long>(n) * hw);
+                    const int y = loc / g.W, x = loc - y * g.W;
+                    row = plane_row(g, n, y, x);
+                    if (cc < nc)
+                        gval = focal_grad(logits[row * logit_stride + c0 + cc], support_targets[c0 + cc] == labels[i], alpha, gamma) * scale;
+                }
+                sg[rr][cc] = gval;
+                if (cc == 0) srow[rr] = row;
+            }
+            __syncthreads();
+            float w[kClsBwdTile];
+#pragma unroll
+            for (int c = 0; c < kClsBwdTile; ++c) w[c] = c < nc ? codes[static_cast<size_t>(c0 + c) * 257 + t] : 0.f;
+#pragma unroll
+            for (int rr = 0; rr < kClsBwdRows; ++rr)
+#pragma unroll
+                for (int c = 0; c < kClsBwdTile; ++c) acc[rr] = fmaf(sg[rr][c], w[c], acc[rr]);
+        }
+#pragma unroll
+        for (int rr = 0; rr < kClsBwdRows; ++rr) {
+            const unsigned long long row = srow[rr];
+            if (row != ~0ull) dX[row * 256 + t] = acc[rr];
+        }
+    }
+}
+
+constexpr int kGnBwdPartial = 3 * 256;   // per tile: sum dz [256], sum dz * yhat [256], max |dz| (replicated over the row)
+
+// Pass 1, one CTA per 128-row tile at a time (lane = group of 8 channels, warp w takes rows w, w + 8, ...): per channel
+// sum dz and sum dz * yhat over the tile's interior pixels, dz = (dX / in_scale) where the forward's pre-activation is > 0.
+__global__ void __launch_bounds__(256)
+gn_bwd_partial_kernel(const float* __restrict__ dX, const float* __restrict__ in_scale, const float* __restrict__ Y,
+                      const float* __restrict__ stats, const float* __restrict__ gamma, const float* __restrict__ beta,
+                      const int* __restrict__ tile_seg, const Seg* __restrict__ segs, int n_tiles, float* __restrict__ partial) {
+    ptx::griddep_launch();
+    ptx::griddep_wait();
+    __shared__ float red[8][2][256];
+    __shared__ float redmax[8];
+    const int g = threadIdx.x & 31, w = threadIdx.x >> 5;
+    float ga[8], be[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) { ga[j] = gamma[8 * g + j]; be[j] = beta[8 * g + j]; }
+    const float inv_in = in_scale ? 1.f / in_scale[0] : 1.f;
+    for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+        const int s = __ldg(tile_seg + tile);
+        const Seg sgm = segs[s];
+        const float2 st = *reinterpret_cast<const float2*>(stats + (static_cast<size_t>(s) * 32 + g) * 2);
+        float a0[8], a1[8], mx = 0.f;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) { a0[j] = 0.f; a1[j] = 0.f; }
+        for (int r = w; r < kBlockM; r += 8) {
+            const int row = tile * kBlockM + r;
+            if (!row_is_interior(sgm, row)) continue;
+            const float4* py = reinterpret_cast<const float4*>(Y + static_cast<size_t>(row) * 256) + 2 * g;
+            const float4* pd = reinterpret_cast<const float4*>(dX + static_cast<size_t>(row) * 256) + 2 * g;
+            const float4 ya = __ldg(py), yb = __ldg(py + 1), da = __ldg(pd), db = __ldg(pd + 1);
+            const float yv[8] = {ya.x, ya.y, ya.z, ya.w, yb.x, yb.y, yb.z, yb.w};
+            const float dv[8] = {da.x, da.y, da.z, da.w, db.x, db.y, db.z, db.w};
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                const float yh = (yv[j] - st.x) * st.y;
+                const float dz = ((yv[j] - st.x) * st.y * ga[j] + be[j]) > 0.f ? dv[j] * inv_in : 0.f;   // the forward's expression
+                a0[j] += dz;
+                a1[j] = fmaf(dz, yh, a1[j]);
+                mx = fmaxf(mx, fabsf(dz));
+            }
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+        __syncthreads();                      // red of the previous tile has been read
+#pragma unroll
+        for (int j = 0; j < 8; ++j) { red[w][0][8 * g + j] = a0[j]; red[w][1][8 * g + j] = a1[j]; }
+        if (g == 0) redmax[w] = mx;
+        __syncthreads();
+        const int c = threadIdx.x;
+        float s0 = 0.f, s1 = 0.f, m = 0.f;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) { s0 += red[k][0][c]; s1 += red[k][1][c]; m = fmaxf(m, redmax[k]); }
+        float* dst = partial + static_cast<size_t>(tile) * kGnBwdPartial;
+        dst[c] = s0;
+        dst[256 + c] = s1;
+        dst[512 + c] = m;
+    }
+}
+
+// Per plane (one block, thread = channel): tile partials summed in order (fp64) -> seg_sums[seg][2][256] (sum dz, sum dz yhat) and
+// the two group means of GroupNorm's backward, ab[(seg * 32 + g) * 2] = mean(dz gamma), [+1] = mean(dz gamma yhat) over the
+// group's 8 x H x W values; seg_max[seg] = max |dz| of the plane.
+__global__ void __launch_bounds__(256)
+gn_bwd_finalize_kernel(const float* __restrict__ partial, const Seg* __restrict__ segs, const float* __restrict__ gamma,
+                       float* __restrict__ seg_sums, float* __restrict__ ab, float* __restrict__ seg_max) {
+    ptx::griddep_launch();
+    ptx::griddep_wait();
+    const int s = blockIdx.x, c = threadIdx.x;
+    const Seg sg = segs[s];
+    const int t0 = sg.row0 / kBlockM, t1 = (sg.row0 + sg.nrows + kBlockM - 1) / kBlockM;
+    double s0 = 0.0, s1 = 0.0;
+    float m = 0.f;
+    for (int t = t0; t < t1; ++t) {
+        const float* src = partial + static_cast<size_t>(t) * kGnBwdPartial;
+        s0 += static_cast<double>(src[c]);
+        s1 += static_cast<double>(src[256 + c]);
+        m = fmaxf(m, src[512 + c]);
+    }
+    seg_sums[(static_cast<size_t>(s) * 2) * 256 + c] = static_cast<float>(s0);
+    seg_sums[(static_cast<size_t>(s) * 2 + 1) * 256 + c] = static_cast<float>(s1);
+    const double gm = static_cast<double>(gamma[c]);
+    double a = gm * s0, b = gm * s1;
+#pragma unroll
+    for (int o = 1; o < 8; o <<= 1) {
+        a += __shfl_xor_sync(0xffffffffu, a, o);
+        b += __shfl_xor_sync(0xffffffffu, b, o);
+    }
+    const double cnt = static_cast<double>(sg.H) * sg.W * 8.0;
+    if ((c & 7) == 0) {
+        ab[(static_cast<size_t>(s) * 32 + (c >> 3)) * 2] = static_cast<float>(a / cnt);
+        ab[(static_cast<size_t>(s) * 32 + (c >> 3)) * 2 + 1] = static_cast<float>(b / cnt);
+    }
+    if (c == 0) seg_max[s] = m;
+}
+
+// scale[0] = the power of two s with s * max|dz| * max(rstd) * max|gamma| ~ 256 (1 when the layer's gradient is all zero),
+// scale[1] = 1 / s.  One block.
+__global__ void __launch_bounds__(256)
+gn_bwd_scale_kernel(const float* __restrict__ seg_max, const float* __restrict__ stats, int n_segs, const float* __restrict__ gamma,
+                    float* __restrict__ scale) {
+    ptx::griddep_launch();
+    ptx::griddep_wait();
+    __shared__ float red[256];
+    const int t = threadIdx.x;
+    float m = 0.f, r = 0.f;
+    for (int i = t; i < n_segs; i += 256) m = fmaxf(m, seg_max[i]);
+    for (int i = t; i < n_segs * 32; i += 256) r = fmaxf(r, stats[2 * i + 1]);
+    const float gmx = fabsf(gamma[t]);
+    auto block_max = [&](float v) -> float {
+        __syncthreads();
+        red[t] = v;
+        __syncthreads();
+        for (int o = 128; o > 0; o >>= 1) {
+            if (t < o) red[t] = fmaxf(red[t], red[t + o]);
+            __syncthreads();
+        }
+        return red[0];
+    };
+    const float mm = block_max(m), rr = block_max(r), gg = block_max(gmx);
+    if (t == 0) {
+        const float bound = mm * rr * gg;
+        float s = 1.f;
+        if (bound > 0.f && isfinite(bound)) {
+            int e = static_cast<int>(floorf(log2f(256.f / bound)));
+            e = max(-40, min(60, e));
+            s = exp2f(static_cast<float>(e));
+        }
+        scale[0] = s;
+        scale[1] = 1.f / s;
+    }
+}
+
+// Pass 2: dY = rstd * (dz gamma - a - yhat b) on interior pixels, stored as scale * dY in fp16 (hi | lo) planes (0 elsewhere);
+// per tile the channel sums of the UNscaled dY (the convolution bias gradient) go to bias_partial[tile][256].
+__global__ void __launch_bounds__(256)
+gn_bwd_apply_kernel(const float* __restrict__ dX, const float* __restrict__ in_scale, const float* __restrict__ Y,
+                    const float* __restrict__ stats, const float* __restrict__ ab, const float* __restrict__ gamma,
+                    const float* __restrict__ beta, const float* __restrict__ out_scale, const int* __restrict__ tile_seg,
+                    const Seg* __restrict__ segs, int n_tiles, __half* __restrict__ dY, int split, float* __restrict__ bias_partial) {
+    ptx::griddep_launch();
+    ptx::griddep_wait();
+    __shared__ float red[8][256];
+    const int g = threadIdx.x & 31, w = threadIdx.x >> 5;
+    float ga[8], be[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) { ga[j] = gamma[8 * g + j]; be[j] = beta[8 * g + j]; }
+    const float inv_in = in_scale ? 1.f / in_scale[0] : 1.f;
+    const float osc = out_scale[0];
+    for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+        const int s = __ldg(tile_seg + tile);
+        const Seg sgm = segs[s];
+        const float2 st = *reinterpret_cast<const float2*>(stats + (static_cast<size_t>(s) * 32 + g) * 2);
+        const float2 abv = *reinterpret_cast<const float2*>(ab + (static_cast<size_t>(s) * 32 + g) * 2);
+        float bs[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) bs[j] = 0.f;
+        for (int r = w; r < kBlockM; r += 8) {
+            const int row = tile * kBlockM + r;
+            uint4 o = make_uint4(0u, 0u, 0u, 0u), ol = make_uint4(0u, 0u, 0u, 0u);
+            if (row_is_interior(sgm, row)) {
+                const float4* py = reinterpret_cast<const float4*>(Y + static_cast<size_t>(row) * 256) + 2 * g;
+                const float4* pd = reinterpret_cast<const float4*>(dX + static_cast<size_t>(row) * 256) + 2 * g;
+                const float4 ya = __ldg(py), yb = __ldg(py + 1), da = __ldg(pd), db = __ldg(pd + 1);
+                const float yv[8] = {ya.x, ya.y, ya.z, ya.w, yb.x, yb.y, yb.z, yb.w};
+                const float dv[8] = {da.x, da.y, da.z, da.w, db.x, db.y, db.z, db.w};
+                float v[8];
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    const float yh = (yv[j] - st.x) * st.y;
+                    const float dz = ((yv[j] - st.x) * st.y * ga[j] + be[j]) > 0.f ? dv[j] * inv_in : 0.f;
+                    const float dy = st.y * (dz * ga[j] - abv.x - yh * abv.y);
+                    bs[j] += dy;
+                    v[j] = dy * osc;
+                }
+                if (split) split8(v, false, true, o, ol);
+                else o = pack8(v, false, true);
+            }
+            if (split) {
+                reinterpret_cast<uint4*>(dY + static_cast<size_t>(row) * 512)[g] = o;
+                reinterpret_cast<uint4*>(dY + static_cast<size_t>(row) * 512 + 256)[g] = ol;
+            } else {
+                reinterpret_cast<uint4*>(dY + static_cast<size_t>(row) * 256)[g] = o;
+            }
+        }
+        __syncthreads();
+#pragma unroll
+        for (int j = 0; j < 8; ++j) red[w][8 * g + j] = bs[j];
+        __syncthreads();
+        float t = 0.f;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) t += red[k][threadIdx.x];
+        bias_partial[static_cast<size_t>(tile) * 256 + threadIdx.x] = t;
+    }
+}
+
+// d gamma[c] = sum over planes of sum dz yhat, d beta[c] = sum over planes of sum dz, d conv bias[c] = sum over tiles of sum dY:
+// fixed order, fp64.  grid 3 (which = blockIdx.x), thread = channel.
+__global__ void __launch_bounds__(256)
+tower_param_grad_reduce_kernel(const float* __restrict__ seg_sums, int n_segs, const float* __restrict__ bias_partial, int n_tiles,
+                               float* __restrict__ d_gamma, float* __restrict__ d_beta, float* __restrict__ d_bias) {
+    ptx::griddep_launch();
+    ptx::griddep_wait();
+    const int c = threadIdx.x;
+    double s = 0.0;
+    if (blockIdx.x == 0) {
+        for (int i = 0; i < n_segs; ++i) s += static_cast<double>(seg_sums[(static_cast<size_t>(i) * 2 + 1) * 256 + c]);
+        d_gamma[c] = static_cast<float>(s);
+    } else if (blockIdx.x == 1) {
+        for (int i = 0; i < n_segs; ++i) s += static_cast<double>(seg_sums[(static_cast<size_t>(i) * 2) * 256 + c]);
+        d_beta[c] = static_cast<float>(s);
+    } else {
+        for (int t = 0; t < n_tiles; ++t) s += static_cast<double>(bias_partial[static_cast<size_t>(t) * 256 + c]);
+        d_bias[c] = static_cast<float>(s);
+    }
+}
+
+// fp32 OIHW [co][ci][9] -> the operand rows of the INPUT-gradient convolution: Wt[o' = ci][i' = co][tap] = W[co][ci][8 - tap]
+// in the layout of pack_oihw_weights_kernel (tap-major rows [(tap * 256 + o')][k], [hi | hi | lo] in exact mode).
+__global__ void __launch_bounds__(256)
+pack_oihw_weights_transposed_kernel(const float* __restrict__ w, __half* __restrict__ out, int split) {
+    ptx::griddep_launch();
+    ptx::griddep_wait();
+    const int total = 256 * 256 * 9;
+    for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < total; e += gridDim.x * blockDim.x) {
+        const int i = e & 255;            // input channel of the gradient convolution = co of the forward weights
+        const int o = (e >> 8) & 255;     // output channel = ci of the forward weights
+        const int t = e >> 16;
+        const float v = w[(static_cast<size_t>(i) * 256 + o) * 9 + (8 - t)];
+        const __half hi = __float2half_rn(v);
+        __half* dst = out + (static_cast<size_t>(t) * 256 + o) * (split ? 768 : 256);
+        dst[i] = hi;
+        if (split) {
+            dst[256 + i] = hi;
+            dst[512 + i] = __float2half_rn(v - __half2float(hi));
+        }
+    }
+}
+
+// Scaled weight-gradient reduce: dW = (sum over splits of partial) * inv_scale[1] (wgrad_reduce_kernel with the layer's scale).
+__global__ void __launch_bounds__(256)
+wgrad_reduce_scaled_kernel(const float* __restrict__ partial, int splits, const float* __restrict__ scale, float* __restrict__ dW) {
+    ptx::griddep_launch();
+    ptx::griddep_wait();
+    const int e = blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= 9 * 256 * 256) return;
+    const int ci = e & 255, co = (e >> 8) & 255, tap = e >> 16;
+    double s = 0.0;
+    for (int k = 0; k < splits; ++k) s += static_cast<double>(partial[(static_cast<size_t>(k * 9 + tap) * 256 + co) * 256 + ci]);
+    dW[(co * 256 + ci) * 9 + tap] = static_cast<float>(s * static_cast<double>(scale[1]));
 }
 
 }  // namespace sylph

@@ -476,19 +476,34 @@ class MetaOneStageDetector(nn.Module):
         if self.cfg.MODEL.META_LEARN.CODE_GENERATOR.FREEZE:
             return []
         P = self.cfg.MODEL.PROPOSAL_GENERATOR
-        if not (self.cfg.MODEL.BACKBONE.FREEZE and P.FREEZE_CLS_TOWER and P.FREEZE_BBOX_BRANCH) and not P.FREEZE:
+        if not (self.cfg.MODEL.BACKBONE.FREEZE and P.FREEZE_BBOX_BRANCH) and not P.FREEZE:
             import logging
             logging.getLogger(__name__).warning(
-                "the configuration leaves parts of the detector trainable (BACKBONE.FREEZE / FREEZE_CLS_TOWER / FREEZE_BBOX_BRANCH); "
-                "the B200 path has backward kernels for the code generator only -- the detector stays frozen")
+                "the configuration leaves the backbone / the box branch trainable (BACKBONE.FREEZE / FREEZE_BBOX_BRANCH); the B200 path "
+                "has backward kernels for the code generator and the FCOS class tower only -- those parts stay frozen")
         dev = self.engine.device
         for k, v in self._state.items():
             if k.startswith("code_generator.") and torch.is_floating_point(v):
                 p = nn.Parameter(v.to(dev, torch.float32).contiguous().clone())
                 _register_parameter_tree(self.code_generator, k[len("code_generator."):], p)
                 self._trainable[k] = p
+        if self.trains_cls_tower:
+            pre = "proposal_generator.fcos_head.cls_tower."
+            for k, v in self._state.items():
+                if k.startswith(pre):
+                    p = nn.Parameter(v.to(dev, torch.float32).contiguous().clone())
+                    _register_parameter_tree(self.proposal_generator, k[len("proposal_generator."):], p)
+                    self._trainable[k] = p
+            self.engine.set_training(True)
         self._synced_versions = tuple(p._version for p in self._trainable.values())
         return list(self._trainable.values())
+
+    @property
+    def trains_cls_tower(self) -> bool:
+        """The class tower trains with the code generator unless PROPOSAL_GENERATOR.FREEZE_CLS_TOWER / FREEZE (the reference freezes
+        by `requires_grad = False`, meta_one_stage_detector.py:117-155)."""
+        P = self.cfg.MODEL.PROPOSAL_GENERATOR
+        return not (P.FREEZE_CLS_TOWER or P.FREEZE)
 
     def _sync_code_generator(self) -> None:
         """Hand the engine the parameters' current values when an optimiser (or anything else) has changed them in place."""
@@ -496,8 +511,12 @@ class MetaOneStageDetector(nn.Module):
             return
         versions = tuple(p._version for p in self._trainable.values())
         if versions != self._synced_versions:
-            # device-side refresh (sylph_update_code_generator_device); state_dict() reads the live parameters
-            self.engine.update_code_generator_device({k: p.detach() for k, p in self._trainable.items()})
+            # device-side refresh (sylph_update_code_generator_device / sylph_update_cls_tower_device); state_dict() reads the
+            # live parameters
+            live = {k: p.detach() for k, p in self._trainable.items()}
+            self.engine.update_code_generator_device(live)
+            if self.trains_cls_tower:
+                self.engine.update_cls_tower_device(live)
             self._synced_versions = versions
 
     @property
@@ -687,6 +706,8 @@ class MetaOneStageDetector(nn.Module):
                                    "buffers of that episode have been overwritten")
             g_codes = eng.fcos_cls_loss_backward(SLOT_QUERY, len(tgt), tgt, extra["labels"], extra["sums"], glob, world, grad_out)
             grads = eng.codegen_backward(class_offsets, raw, g_codes, live)
+            if self.trains_cls_tower:
+                grads.update(eng.cls_tower_backward(SLOT_QUERY, codes, tgt, extra["labels"], extra["sums"], live, glob, world, grad_out))
             self._last_grad_codes = g_codes
             return [grads[k] if k in grads and not k.startswith("code_generator.code_generator_head.init_norm.") else None
                     for k in keys]

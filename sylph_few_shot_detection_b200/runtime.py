@@ -10,7 +10,7 @@ import torch
 
 from . import _lib
 from ._lib import (CG_MAX_TOWER, CODE_STRIDE, DET_STRIDE, IPC_HANDLE_BYTES, LOSS_SUMS, NUM_LEVELS, SLOT_QUERY, SLOT_SUPPORT, CodegenTensors,
-                   LossConfig, ModelConfig)
+                   LossConfig, ModelConfig, TowerTensors)
 
 
 def model_config_from_cfg(cfg) -> ModelConfig:
@@ -495,6 +495,7 @@ class Engine:
         raw_codes = raw_codes.to(self.device, torch.float32).contiguous()
         grad_codes = grad_codes.to(self.device, torch.float32).contiguous()
         assert raw_codes.shape == (n_classes, CODE_STRIDE) and grad_codes.shape == (n_classes, CODE_STRIDE)
+        params = {k: v for k, v in params.items() if k.startswith("code_generator.")}
         grads = {k: torch.zeros_like(v) for k, v in params.items()}
         co = (c_int * (n_classes + 1))(*[int(i) for i in class_offsets])
         p_struct, g_struct = self._codegen_tensor_struct(params), self._codegen_tensor_struct(grads)
@@ -518,6 +519,53 @@ class Engine:
         layouts are packed by kernels on the current stream, nothing but the two scale scalars touches the host."""
         p_struct = self._codegen_tensor_struct(params)
         self._check(self.lib.sylph_update_code_generator_device(self.h, byref(p_struct), self._stream()))
+
+    # ------------------------------------------------------------------ training backward (FCOS class tower)
+    TOWER_PREFIX = "proposal_generator.fcos_head.cls_tower."
+
+    def set_training(self, on: bool) -> None:
+        """Keep the class tower's activations during the head pass of fcos_loss_sums (sylph_set_training)."""
+        self._check(self.lib.sylph_set_training(self.h, 1 if on else 0))
+
+    def _tower_tensor_struct(self, tensors: Dict[str, torch.Tensor]) -> TowerTensors:
+        tt = TowerTensors()
+        def ptr(name):
+            t = tensors.get(self.TOWER_PREFIX + name)
+            if t is None:
+                return None
+            assert t.is_cuda and t.dtype == torch.float32 and t.is_contiguous(), name
+            return t.data_ptr()
+        for i in range(min(int(self.mc.num_cls_convs), CG_MAX_TOWER)):
+            tt.conv_w[i], tt.conv_b[i] = ptr(f"{3 * i}.weight"), ptr(f"{3 * i}.bias")
+            tt.gn_w[i], tt.gn_b[i] = ptr(f"{3 * i + 1}.weight"), ptr(f"{3 * i + 1}.bias")
+        return tt
+
+    def cls_tower_backward(self, slot: int, codes: torch.Tensor, support_targets: Sequence[int], labels: torch.Tensor,
+                           sums: torch.Tensor, params: Dict[str, torch.Tensor], global_pos_ctr: Optional[torch.Tensor] = None,
+                           world_size: int = 1, grad_loss: Optional[torch.Tensor] = None) -> Dict[str, torch.Tensor]:
+        """Gradients of loss_fcos_cls with respect to the class tower's tensors (sylph_cls_tower_backward); call after
+        fcos_loss_sums(..., want_targets=True) with training mode on.  `codes`: the FINAL (C, 257) rows of that call."""
+        codes = codes.to(self.device, torch.float32).contiguous()
+        n_classes = codes.shape[0]
+        st = (c_int64 * n_classes)(*[int(t) for t in support_targets])
+        if grad_loss is not None:
+            grad_loss = grad_loss.detach().to(self.device, torch.float32).reshape(1).contiguous()
+        if not hasattr(self, "_lc"):
+            self._lc = loss_config_from_cfg(self.cfg)
+        params = {k: v for k, v in params.items() if k.startswith(self.TOWER_PREFIX)}
+        grads = {k: torch.zeros_like(v) for k, v in params.items()}
+        p_struct, g_struct = self._tower_tensor_struct(params), self._tower_tensor_struct(grads)
+        self._check(self.lib.sylph_cls_tower_backward(
+            self.h, slot, n_classes, c_void_p(codes.data_ptr()), st, byref(self._lc), c_void_p(labels.data_ptr()),
+            c_void_p(sums.data_ptr()), c_void_p(global_pos_ctr.data_ptr()) if global_pos_ctr is not None else None, int(world_size),
+            c_void_p(grad_loss.data_ptr()) if grad_loss is not None else None, byref(p_struct), byref(g_struct), self._stream()))
+        self._keep_tbw = (codes, grad_loss, params)
+        return grads
+
+    def update_cls_tower_device(self, params: Dict[str, torch.Tensor]) -> None:
+        """Re-prepare the class tower's weights from the optimiser's device tensors (sylph_update_cls_tower_device)."""
+        p_struct = self._tower_tensor_struct(params)
+        self._check(self.lib.sylph_update_cls_tower_device(self.h, byref(p_struct), self._stream()))
 
     def debug_read_buffer(self, name: str, shape, dtype=torch.float32) -> torch.Tensor:
         """Copy of one of the engine's named scratch buffers (debugging aid, sylph_debug_read_buffer)."""

@@ -58,6 +58,15 @@ def test_codegen_tensors_struct_layout_matches_header():
     assert ctypes.sizeof(_lib.CodegenTensors) == 8 * (4 * _lib.CG_MAX_TOWER + 8)
 
 
+def test_tower_tensors_struct_layout_matches_header():
+    text = open(os.path.join(REPO, "include", "sylph_b200.h")).read()
+    body = text[text.index("typedef struct sylph_tower_tensors {"):text.index("} sylph_tower_tensors;")]
+    body = re.sub(r"/\*.*?\*/", "", body, flags=re.S)
+    fields = re.findall(r"\bfloat\*\s+([a-z_0-9]+)\[SYLPH_CG_MAX_TOWER\];", body)
+    assert fields == [f[0] for f in _lib.TowerTensors._fields_]
+    assert ctypes.sizeof(_lib.TowerTensors) == 8 * 4 * _lib.CG_MAX_TOWER
+
+
 def test_create_fails_loudly_without_a_device():
     import torch
     if torch.cuda.is_available():

@@ -190,14 +190,16 @@ def test_code_generator_gradients_match_reference(case):
     names = dict(model.named_parameters())
     pre = "code_generator.code_generator_head."
     assert set(gg["grads"]) <= set(names) and all(p.is_cuda for p in names.values())
-    assert all(k.startswith("code_generator.") for k in names)                 # the detector is frozen on this path
+    # the code generator and (FREEZE_CLS_TOWER: False in these configurations) the FCOS class tower train; the rest is frozen
+    assert all(k.startswith(("code_generator.", "proposal_generator.fcos_head.cls_tower.")) for k in names)
+    assert any(k.startswith("proposal_generator.fcos_head.cls_tower.") for k in names)
     losses = model(_records(g["items"]))
     assert set(losses) == set(gg["losses"])
     sum(losses.values()).backward()
     grads = {k: p.grad for k, p in names.items() if p.grad is not None}
     assert set(grads) == set(gg["grads"])                                      # init_norm.* get none, like the reference
     tol = GRAD_TOL_KINK
-    smooth = {k: v for k, v in gg["grads"].items() if "support_set_shared_tower" not in k}
+    smooth = {k: v for k, v in gg["grads"].items() if "support_set_shared_tower" not in k and "cls_tower" not in k}
     check_grads_against_golden(grads, smooth, GRAD_TOL, case + " (no ReLU behind)", GRAD_TOL)
     worst, _ = check_grads_against_golden(grads, gg["grads"], GRAD_TOL_KINK, case, GRAD_L2_TOL)
     # gradient with respect to the final class codes
@@ -382,7 +384,7 @@ def test_code_generator_backward_is_deterministic_and_guards_stale_buffers():
         losses = model(batched)
         sum(losses.values()).backward()
         runs.append({k: p.grad.clone() for k, p in model.named_parameters() if p.grad is not None})
-    assert runs[0].keys() == runs[1].keys() and len(runs[0]) == 16
+    assert runs[0].keys() == runs[1].keys() and len(runs[0]) == 32      # 16 code-generator + 16 class-tower tensors
     for k in runs[0]:
         assert torch.equal(runs[0][k], runs[1][k]), k                          # fixed-order reductions, no atomics
     # an upstream factor scales every gradient (the hook receives d total / d loss_fcos_cls on the device)

@@ -129,7 +129,7 @@ def check_grads_against_golden(grads, packed, tol, what="", l2_tol=None):
         d = g.double()
         assert abs(float(d.sum()) - rec["sum"]) <= tol * scale * g.numel() ** 0.5 * 4 + 1e-12, (what, k, "sum")
         assert abs(float((d * d).sum()) ** 0.5 - rec["sumsq"] ** 0.5) <= tol * max(rec["sumsq"] ** 0.5, 1e-12) * 2 + 1e-12, (what, k, "norm")
-    short = lambda k: k.replace("code_generator.code_generator_head.", "")
+    short = lambda k: k.replace("code_generator.code_generator_head.", "").replace("proposal_generator.fcos_head.", "")
     print(f"[{what}] max-norm / rel-L2 per tensor: " + ", ".join(f"{short(k)} {errs[k]:.1e}/{l2s[k]:.1e}" for k in errs))
     bad = {short(k): round(v, 6) for k, v in errs.items() if v > tol}
     assert not bad, (what, "max-norm", tol, bad)
