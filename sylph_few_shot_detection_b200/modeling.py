@@ -708,7 +708,7 @@ class MetaOneStageDetector(nn.Module):
             grads = eng.codegen_backward(class_offsets, raw, g_codes, live)
             if self.trains_cls_tower:
                 grads.update(eng.cls_tower_backward(SLOT_QUERY, codes, tgt, extra["labels"], extra["sums"], live, glob, world, grad_out))
-            self._last_grad_codes = g_codes
+            self._last_grad_codes, self._last_final_codes = g_codes, codes
             return [grads[k] if k in grads and not k.startswith("code_generator.code_generator_head.init_norm.") else None
                     for k in keys]
 

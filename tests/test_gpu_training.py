@@ -164,9 +164,14 @@ def test_training_forward_loss_configurations(variant):
 #   * the tower's tensors: relative L2 error <= GRAD_L2_TOL = 2e-3 (measured 1.4e-4 .. 1.3e-3) and max-norm <= GRAD_TOL_KINK = 1e-2
 #     (measured up to 4.2e-3 on single entries of the hot case "coco_train_2way_2shot", loss_fcos_cls = 92.9).
 # The kernels themselves are held to KERNEL_GRAD_TOL by the two tests below, which feed them fp32 inputs and pin the ReLU pattern.
+#   * the FCOS class tower's tensors (four ReLU layers over every pyramid location; the reference's autograd moves by rel-L2 4e-3 .. 8e-3 and
+#     max-norm up to 2.4e-2 under the same 1e-4 feature noise, test_reference_gradient_conditioning_class_tower): relative L2 error
+#     <= TOWER_L2_TOL = 8e-3 (measured 1.6e-4 .. 2.1e-3), max-norm <= TOWER_TOL_KINK = 3e-2 (measured up to 7e-3).
 GRAD_TOL = 1e-3
 GRAD_L2_TOL = 2e-3
 GRAD_TOL_KINK = 1e-2
+TOWER_L2_TOL = 8e-3
+TOWER_TOL_KINK = 3e-2
 KERNEL_GRAD_TOL = 5e-5
 
 
@@ -201,7 +206,11 @@ def test_code_generator_gradients_match_reference(case):
     tol = GRAD_TOL_KINK
     smooth = {k: v for k, v in gg["grads"].items() if "support_set_shared_tower" not in k and "cls_tower" not in k}
     check_grads_against_golden(grads, smooth, GRAD_TOL, case + " (no ReLU behind)", GRAD_TOL)
-    worst, _ = check_grads_against_golden(grads, gg["grads"], GRAD_TOL_KINK, case, GRAD_L2_TOL)
+    cg = {k: v for k, v in gg["grads"].items() if "cls_tower" not in k}
+    tw = {k: v for k, v in gg["grads"].items() if "cls_tower" in k}
+    worst, _ = check_grads_against_golden(grads, cg, GRAD_TOL_KINK, case, GRAD_L2_TOL)
+    worst_tower, _ = check_grads_against_golden(grads, tw, TOWER_TOL_KINK, case + " (class tower)", TOWER_L2_TOL)
+    worst = max(worst, worst_tower)
     # gradient with respect to the final class codes
     gc = model._last_grad_codes.cpu()
     ref_w = gg["grad_codes"]["cls_conv"].reshape(-1, 256)
@@ -214,7 +223,10 @@ def test_code_generator_gradients_match_reference(case):
     for k, v in ograds.items():
         err = float((grads[k].cpu() - v).abs().max()) / max(float(v.abs().max()), 1e-12)
         l2 = float((grads[k].cpu() - v).norm()) / max(float(v.norm()), 1e-30)
-        assert err <= tol and l2 <= GRAD_L2_TOL, (k, err, l2)
+        if "cls_tower" in k:
+            assert err <= TOWER_TOL_KINK and l2 <= TOWER_L2_TOL, (k, err, l2)
+        else:
+            assert err <= tol and l2 <= GRAD_L2_TOL, (k, err, l2)
         worst = max(worst, err)
     print(f"[{case}] worst relative gradient error {worst:.2e}")
 
@@ -495,3 +507,73 @@ def test_device_weight_refresh_is_bit_identical_to_host_preparation(precision):
     assert torch.equal(codes(), c0)
     eng.update_code_generator(stepped)
     assert torch.equal(codes(), c_dev)
+
+
+def test_cls_tower_backward_kernels_alone():
+    """sylph_cls_tower_backward against fp32 autograd on the engine's OWN inputs and ReLU pattern: the pyramid exported from the
+    engine feeds a torch class tower whose ReLUs are pinned to the pattern of the engine's saved activations, the engine's final
+    codes condition the classifier, the focal loss is differentiated by autograd.  What is left are the kernels: tower-output
+    gradient, GroupNorm / ReLU backward over the planes, the scaled fp16 (hi | lo) dY, the MN-major tcgen05 weight gradient, the
+    input-gradient convolutions (three products per multiply)."""
+    import torch.nn.functional as F
+    from oracle import upstream as up
+    from oracle.meta_fcos_oracle import MetaFCOSOracle
+    from sylph_few_shot_detection_b200.runtime import SLOT_QUERY
+    g, cfg, state, model = _train_model("lvis_train_3way_1shot_cls_only")
+    eng = model.engine
+    batched = _records(g["items"])
+    losses = model(batched)
+    sum(losses.values()).backward()
+    pre = "proposal_generator.fcos_head.cls_tower."
+    got = {k: p.grad.cpu() for k, p in model.named_parameters() if k.startswith(pre)}
+    assert len(got) == 16
+    n, _, _, lh, lw = eng.feature_shape(SLOT_QUERY)
+    feats = [eng.export_features(SLOT_QUERY, l).cpu() for l in range(5)]
+    codes = model._last_final_codes.cpu()
+    n_cls = codes.shape[0]
+    # ReLU pattern of the engine's saved layer outputs (planes "det.cls_x<i>": rows [256 hi | 256 lo], level-major, 1-pixel border)
+    r128 = lambda v: (v + 127) // 128 * 128
+    rows_per = [r128((h + 2) * (w + 2)) for h, w in zip(lh, lw)]
+    level_row0 = [0]
+    for rp in rows_per:
+        level_row0.append(level_row0[-1] + n * rp)
+    L = int(cfg.MODEL.FCOS.NUM_CLS_CONVS)
+    masks = []
+    for i in range(L):
+        planes = eng.debug_read_buffer(f"det.cls_x{i}", (level_row0[5], 512), torch.float16).cpu().float()
+        val = planes[:, :256] + planes[:, 256:]
+        per_level = []
+        for l, (h, w) in enumerate(zip(lh, lw)):
+            blk = val[level_row0[l]:level_row0[l + 1]].reshape(n, rows_per[l], 256)[:, :(h + 2) * (w + 2)].reshape(n, h + 2, w + 2, 256)
+            per_level.append((blk[:, 1:h + 1, 1:w + 1] > 0).permute(0, 3, 1, 2))
+        masks.append(per_level)
+    orc = MetaFCOSOracle(cfg, state)
+    leaves = {k: state[k].detach().clone().requires_grad_(True) for k in got}
+    query = [r for x in batched for r in x["query_set"]]
+    targets = [int(x["support_set_target"]) for x in batched]
+    gts = orc.filter_gt(query, targets)
+    labels, _, _, _ = orc.fcos_targets([(h, w) for h, w in zip(lh, lw)], gts)
+    flips = 0
+    logits = []
+    with torch.enable_grad():
+        for l in range(5):
+            x = feats[l]
+            for i in range(L):
+                x = F.conv2d(x, leaves[f"{pre}{3 * i}.weight"], leaves[f"{pre}{3 * i}.bias"], padding=1)
+                x = F.group_norm(x, 32, leaves[f"{pre}{3 * i + 1}.weight"], leaves[f"{pre}{3 * i + 1}.bias"], 1e-5)
+                flips += int(((x.detach() > 0) != masks[i][l]).sum())
+                x = x * masks[i][l]
+            logits.append(F.conv2d(x, codes[:, :256].reshape(n_cls, 256, 1, 1), codes[:, 256]))
+        pred = torch.cat([t.permute(0, 2, 3, 1).reshape(-1, n_cls) for t in logits])
+        tgt = (torch.tensor(targets).view(1, -1) == labels[:, None]).float()
+        n_pos = max(float((labels != MetaFCOSOracle.BACKGROUND_ID).sum()), 1.0)
+        C = cfg.MODEL.FCOS
+        (up.sigmoid_focal_loss(pred, tgt, alpha=C.LOSS_ALPHA, gamma=C.LOSS_GAMMA, reduction="sum") / n_pos).backward()
+    total = sum(m.numel() for per in masks for m in per)
+    assert flips <= 2e-3 * total, (flips, total)           # the patterns differ only near 0 (forward noise of 1e-4)
+    errs = {k[len(pre):]: (float((got[k] - leaves[k].grad).abs().max() / leaves[k].grad.abs().max()),
+                           float((got[k] - leaves[k].grad).norm() / leaves[k].grad.norm())) for k in got}
+    print(f"[class tower kernels alone, {flips} of {total} ReLU decisions differ from torch's own forward] max-norm / rel-L2: " +
+          ", ".join(f"{k} {a:.1e}/{b:.1e}" for k, (a, b) in errs.items()))
+    bad = {k: v for k, v in errs.items() if v[0] > 5e-4 or v[1] > 5e-4}
+    assert not bad, bad

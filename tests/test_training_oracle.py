@@ -241,3 +241,25 @@ def test_reference_gradient_conditioning():
     assert max(moved[1e-6][k] for k in tower) < 5e-6
     assert max(moved[1e-4][k] for k in tower) > 5e-4            # an order of magnitude more than the perturbation
     assert moved[1e-4][cls_w] < 2e-4
+
+
+def test_reference_gradient_conditioning_class_tower():
+    """The same measurement for the FCOS class tower (four ReLU layers over every pyramid location): the restated reference's
+    autograd moves by several 1e-3 of a tensor's norm when the pyramid features move by 1e-4 relative -- the bars of
+    tests/test_gpu_training.py for `cls_tower.*` (rel-L2 8e-3, max-norm 3e-2) sit at that level, the CUDA path measures 2e-4 .. 2e-3."""
+    g, gg, cfg, state = grad_case("lvis_train_3way_1shot_cls_only")
+    orc = MetaFCOSOracle(cfg, state)
+    items = to_records(g["items"])
+    _, base, _ = orc.training_grads(items)
+    plain = orc.features
+    gen = torch.Generator().manual_seed(1)
+    orc.features = lambda b: [f * (1 + 1e-4 * torch.randn(f.shape, generator=gen)) for f in plain(b)]
+    try:
+        _, moved, _ = orc.training_grads(items)
+    finally:
+        del orc.features
+    tower = [k for k in base if "cls_tower" in k]
+    assert len(tower) == 16
+    l2 = {k: float((moved[k] - base[k]).norm() / base[k].norm()) for k in tower}
+    assert max(l2.values()) > 2e-3, l2            # an order of magnitude above the perturbation
+    assert max(l2.values()) < 5e-2, l2
