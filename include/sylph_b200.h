@@ -273,7 +273,7 @@ int sylph_fcos_loss_finalize(sylph_ctx* ctx, const double* local_sums_dev, const
                              int world_size, float* losses_out_dev, void* stream);
 
 /* ---- Backward of the episodic training step for the CODE GENERATOR. ----
- * Scope: the meta-training configurations that freeze the detector and train the hyper-network
+ * Scope: the meta-training configurations that train the hyper-network (the class tower's backward follows further below)
  * (configs/COCO-Detection/Meta-FCOS/Meta-FCOS-finetune-lvis.yaml: BACKBONE.FREEZE, PROPOSAL_GENERATOR.FREEZE_CLS_TOWER,
  * FREEZE_BBOX_BRANCH on, CODE_GENERATOR.FREEZE off).  The only loss that reaches the code generator is loss_fcos_cls
  * (the box losses depend on the frozen box branch alone).  Gradients equal what the reference's

@@ -431,7 +431,9 @@ def test_optimizer_step_reaches_the_engine():
     stepped = model.state_dict()
     k = "code_generator.code_generator_head.support_set_cls_conv.0.weight"
     assert not torch.equal(stepped[k], state[k])
-    assert all(torch.equal(stepped[q], state[q]) for q in state if not q.startswith("code_generator."))
+    trained = ("code_generator.", "proposal_generator.fcos_head.cls_tower.")
+    assert all(torch.equal(stepped[q], state[q]) for q in state if not q.startswith(trained))       # the rest of the detector is frozen
+    assert not torch.equal(stepped["proposal_generator.fcos_head.cls_tower.0.weight"], state["proposal_generator.fcos_head.cls_tower.0.weight"])
     orc = MetaFCOSOracle(cfg, {q: v.clone() for q, v in stepped.items()})
     ref, _ = orc.training_forward(to_records(g["items"]))
     assert abs(l1 - float(ref["loss_fcos_cls"])) <= LOSS_TOL * abs(float(ref["loss_fcos_cls"])), (l1, float(ref["loss_fcos_cls"]))
