@@ -379,6 +379,7 @@ def run_reference_training_grads(cfg, state, items):
         sum(losses.values()).backward()
     pre = ("code_generator.", "proposal_generator.fcos_head.cls_tower.")
     grads = {n: p.grad.detach().clone() for n, p in model.named_parameters() if n.startswith(pre) and p.grad is not None}
+    grads["__all_keys_with_grad__"] = sorted(n for n, p in model.named_parameters() if p.grad is not None)
     return {k: v.detach().clone() for k, v in losses.items()}, grads
 
 
@@ -403,6 +404,7 @@ def build_training_grad_goldens():
         for k, v in GRAD_STATE_OVERRIDES.get(name, {}).items():
             state[k] = torch.full_like(state[k], v)
         ref_losses, ref_grads = run_reference_training_grads(cfg, state, items)
+        all_with_grad = ref_grads.pop("__all_keys_with_grad__")
         orc = build_oracle(cfg, state)
         losses, grads, ex = orc.training_grads(to_records(items))
         assert set(grads) == set(ref_grads), (sorted(set(grads) ^ set(ref_grads)))
@@ -412,6 +414,7 @@ def build_training_grad_goldens():
         print(f"[{name}] oracle autograd vs reference .grad: worst relative deviation {worst:.3e}")
         assert worst < 2e-5, worst
         out["cases"][name] = {"base_case": GRAD_BASE_CASE.get(name, name), "state_overrides": GRAD_STATE_OVERRIDES.get(name, {}),
+                              "reference_keys_with_grad": all_with_grad,     # EVERY parameter the reference's backward reaches
                               "losses": ref_losses, "grads": {k: pack_grad(v, GRAD_SAMPLE_STEP if k.startswith("code_generator.") else 23)
                                                                 for k, v in ref_grads.items()},
                               "grad_codes": {k: v.clone() for k, v in ex["grad_codes"].items()},

@@ -263,3 +263,17 @@ def test_reference_gradient_conditioning_class_tower():
     l2 = {k: float((moved[k] - base[k]).norm() / base[k].norm()) for k in tower}
     assert max(l2.values()) > 2e-3, l2            # an order of magnitude above the perturbation
     assert max(l2.values()) < 5e-2, l2
+
+
+def test_shipped_finetune_configuration_is_covered_completely():
+    """configs/LVISv1-Detection/Meta-FCOS/Meta-FCOS-finetune.yaml (backbone and box branch frozen, code generator and class tower trained): the
+    parameters the REFERENCE's backward reaches are exactly the 32 tensors the B200 path differentiates -- nothing the reference trains in
+    the shipped hyper-network stage is left without a gradient.  The COCO training golden unfreezes the box branch on purpose
+    (FREEZE_BBOX_BRANCH: False, to exercise all three losses): there the reference also reaches the box branch, which stays frozen here."""
+    cases = load_golden("train_grads")["cases"]
+    lvis = cases["lvis_train_3way_1shot_cls_only"]
+    assert set(lvis["reference_keys_with_grad"]) == set(lvis["grads"]) and len(lvis["grads"]) == 32
+    coco = cases["coco_train_2way_2shot"]
+    extra = set(coco["reference_keys_with_grad"]) - set(coco["grads"])
+    assert extra and all(k.startswith(("proposal_generator.fcos_head.bbox_", "proposal_generator.fcos_head.ctrness",
+                                       "proposal_generator.fcos_head.scales", "proposal_generator.fcos_head.iou_overlap")) for k in extra), extra
