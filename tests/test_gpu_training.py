@@ -175,11 +175,12 @@ TOWER_TOL_KINK = 3e-2
 KERNEL_GRAD_TOL = 5e-5
 
 
-def _train_model(case):
+def _train_model(case, precision=None):
     from sylph_few_shot_detection_b200.modeling import build_model
     from tests.test_training_oracle import grad_case
     g, _, cfg, state = grad_case(case)
     model = build_model(cfg)
+    model.precision = precision
     model.load_state_dict(state)
     model.train()
     return g, cfg, state, model
@@ -511,18 +512,20 @@ def test_device_weight_refresh_is_bit_identical_to_host_preparation(precision):
     assert torch.equal(codes(), c_dev)
 
 
-def test_cls_tower_backward_kernels_alone():
+@pytest.mark.parametrize("precision,tol", [("exact", 5e-4), ("fast", 1e-2)])
+def test_cls_tower_backward_kernels_alone(precision, tol):
     """sylph_cls_tower_backward against fp32 autograd on the engine's OWN inputs and ReLU pattern: the pyramid exported from the
     engine feeds a torch class tower whose ReLUs are pinned to the pattern of the engine's saved activations, the engine's final
     codes condition the classifier, the focal loss is differentiated by autograd.  What is left are the kernels: tower-output
     gradient, GroupNorm / ReLU backward over the planes, the scaled fp16 (hi | lo) dY, the MN-major tcgen05 weight gradient, the
-    input-gradient convolutions (three products per multiply)."""
+    input-gradient convolutions (three products per multiply).  "fast": single fp16 operands (11-bit dY, one product)."""
     import torch.nn.functional as F
     from oracle import upstream as up
     from oracle.meta_fcos_oracle import MetaFCOSOracle
     from sylph_few_shot_detection_b200.runtime import SLOT_QUERY
-    g, cfg, state, model = _train_model("lvis_train_3way_1shot_cls_only")
+    g, cfg, state, model = _train_model("lvis_train_3way_1shot_cls_only", precision)
     eng = model.engine
+    assert eng.precision == precision
     batched = _records(g["items"])
     losses = model(batched)
     sum(losses.values()).backward()
@@ -542,8 +545,9 @@ def test_cls_tower_backward_kernels_alone():
     L = int(cfg.MODEL.FCOS.NUM_CLS_CONVS)
     masks = []
     for i in range(L):
-        planes = eng.debug_read_buffer(f"det.cls_x{i}", (level_row0[5], 512), torch.float16).cpu().float()
-        val = planes[:, :256] + planes[:, 256:]
+        ld = 512 if precision == "exact" else 256
+        planes = eng.debug_read_buffer(f"det.cls_x{i}", (level_row0[5], ld), torch.float16).cpu().float()
+        val = planes[:, :256] + planes[:, 256:] if precision == "exact" else planes
         per_level = []
         for l, (h, w) in enumerate(zip(lh, lw)):
             blk = val[level_row0[l]:level_row0[l + 1]].reshape(n, rows_per[l], 256)[:, :(h + 2) * (w + 2)].reshape(n, h + 2, w + 2, 256)
@@ -572,10 +576,10 @@ def test_cls_tower_backward_kernels_alone():
         C = cfg.MODEL.FCOS
         (up.sigmoid_focal_loss(pred, tgt, alpha=C.LOSS_ALPHA, gamma=C.LOSS_GAMMA, reduction="sum") / n_pos).backward()
     total = sum(m.numel() for per in masks for m in per)
-    assert flips <= 2e-3 * total, (flips, total)           # the patterns differ only near 0 (forward noise of 1e-4)
+    assert flips <= (2e-3 if precision == "exact" else 2e-2) * total, (flips, total)   # the patterns differ only near 0 (forward noise)
     errs = {k[len(pre):]: (float((got[k] - leaves[k].grad).abs().max() / leaves[k].grad.abs().max()),
                            float((got[k] - leaves[k].grad).norm() / leaves[k].grad.norm())) for k in got}
-    print(f"[class tower kernels alone, {flips} of {total} ReLU decisions differ from torch's own forward] max-norm / rel-L2: " +
+    print(f"[class tower kernels alone, {precision}, {flips} of {total} ReLU decisions differ from torch's own forward] max-norm / rel-L2: " +
           ", ".join(f"{k} {a:.1e}/{b:.1e}" for k, (a, b) in errs.items()))
-    bad = {k: v for k, v in errs.items() if v[0] > 5e-4 or v[1] > 5e-4}
+    bad = {k: v for k, v in errs.items() if v[0] > tol or v[1] > tol}
     assert not bad, bad
