@@ -1063,6 +1063,7 @@ int sylph_finalize_weights(sylph_ctx* c) {
     c->staged.clear();
     c->finalized = true;
     c->weights_ready = true;
+    c->cls_tower_t_ready = false;   // the transposed class-tower copies of the backward follow the new weights at their next use
     return 0;
 }
 
@@ -2641,7 +2642,6 @@ int sylph_cls_tower_backward(sylph_ctx* c, int slot, int n_classes, const float*
                            grad_loss_dev, static_cast<float*>(dxa)));
         c->launches++;
     }
-    static bool attr_set[2] = {false, false};
     float* dx_in = static_cast<float*>(dxa);
     float* dx_out = static_cast<float*>(dxb);
     const float* in_scale = nullptr;          // the scale of the gradient in dx_in (NULL = 1)
@@ -2673,10 +2673,10 @@ int sylph_cls_tower_backward(sylph_ctx* c, int slot, int n_classes, const float*
             WgradArgs wa{static_cast<const Seg*>(S.ps->d_segs), static_cast<const int*>(S.ps->d_tile_seg), static_cast<int>(rows / kWgTileK),
                          static_cast<float*>(wpart)};
             if (c->split) {
-                if (!attr_set[1]) { CU_TRY(c, cudaFuncSetAttribute(wgrad3x3_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, WgradSmem<true>::kTotal)); attr_set[1] = true; }
+                CU_TRY(c, cudaFuncSetAttribute(wgrad3x3_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, WgradSmem<true>::kTotal));   // per device: set on every call
                 CU_TRY(c, launch_k(wgrad3x3_kernel<true>, dim3(splits, 9, 2), dim3(kWgThreads), WgradSmem<true>::kTotal, st, tdy, tx, wa));
             } else {
-                if (!attr_set[0]) { CU_TRY(c, cudaFuncSetAttribute(wgrad3x3_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, WgradSmem<false>::kTotal)); attr_set[0] = true; }
+                CU_TRY(c, cudaFuncSetAttribute(wgrad3x3_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, WgradSmem<false>::kTotal));
                 CU_TRY(c, launch_k(wgrad3x3_kernel<false>, dim3(splits, 9, 2), dim3(kWgThreads), WgradSmem<false>::kTotal, st, tdy, tx, wa));
             }
             CU_TRY(c, launch_k(wgrad_reduce_scaled_kernel, dim3(9 * 256), dim3(256), 0, st, static_cast<const float*>(wpart), splits,

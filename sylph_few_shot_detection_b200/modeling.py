@@ -463,6 +463,9 @@ class MetaOneStageDetector(nn.Module):
         super().train(mode)
         if mode and self._engine is not None:
             self.enable_code_generator_training()
+        if self._engine is not None and self._trainable:
+            # the head keeps the class tower's activations only while training (eval passes stay on the two ping-pong buffers)
+            self._engine.set_training(bool(mode) and self.trains_cls_tower)
         return self
 
     def enable_code_generator_training(self) -> List[nn.Parameter]:
@@ -494,7 +497,7 @@ class MetaOneStageDetector(nn.Module):
                     p = nn.Parameter(v.to(dev, torch.float32).contiguous().clone())
                     _register_parameter_tree(self.proposal_generator, k[len("proposal_generator."):], p)
                     self._trainable[k] = p
-            self.engine.set_training(True)
+            self.engine.set_training(self.training)
         self._synced_versions = tuple(p._version for p in self._trainable.values())
         return list(self._trainable.values())
 
