@@ -526,7 +526,7 @@ def measure_variants(hz: Harness, cfg, dev):
         del model, eng
         torch.cuda.empty_cache()
     # (d) one meta-training iteration of the hyper-network stage: 3 classes x 5 support images + 3 query images
-    # (the per-GPU batch of the shipped meta-training configs), detector frozen, code generator trained
+    # (the per-GPU batch of the shipped meta-training configs), backbone and box branch frozen, code generator and class tower trained
     from sylph_few_shot_detection_b200.structures import Boxes, Instances
     tc = cfg.clone()
     tc.defrost()
@@ -558,9 +558,10 @@ def measure_variants(hz: Harness, cfg, dev):
         return losses
     ms_f, _ = timed(forward_only, warm=2, reps=4)
     ms_it, losses = timed(iteration, warm=2, reps=4)
-    out["training_iteration"] = {"workload": "hyper-network meta-training iteration: 3 classes x 5 support images + 3 query images 800x1333, "
-                                             "R-50 FPN, detector frozen, code generator trained; forward (losses) + backward "
-                                             "(sylph_fcos_cls_loss_backward + sylph_codegen_backward) + SGD step + device-side weight refresh",
+    out["training_iteration"] = {"workload": "hyper-network meta-training iteration (Meta-FCOS-finetune.yaml): 3 classes x 5 support images + 3 query images "
+                                             "800x1333, R-50 FPN, backbone and box branch frozen, code generator and FCOS class tower trained; forward "
+                                             "(losses) + backward (sylph_fcos_cls_loss_backward + sylph_codegen_backward + sylph_cls_tower_backward) + SGD "
+                                             "step + device-side weight refresh",
                                  "ms_forward_losses": round(ms_f, 3), "ms_per_iteration": round(ms_it, 3),
                                  "loss_fcos_cls": round(float(losses["loss_fcos_cls"].detach()), 5),
                                  "trainable_tensors": sum(1 for p in model.parameters() if p.grad is not None)}

@@ -1,12 +1,12 @@
 #!/usr/bin/env python
 """One meta-training iteration of the hyper-network stage on one GPU: the per-GPU batch of the shipped
 meta-training configs (MODEL.META_LEARN.CLASS 3 x SHOT 5 support images + QUERY_SHOT 1 query image per class, 800x1333),
-detector frozen, code generator trained.
+backbone and box branch frozen, code generator and FCOS class tower trained (Meta-FCOS-finetune.yaml).
 
     python tools/bench_training.py [--steps 10] [--classes 3] [--shot 5] [--out profiles/rNN_training_step.json]
 
 Reports ms per iteration for (a) the training forward alone (losses), (b) forward + backward of the code generator
-(sylph_fcos_cls_loss_backward + sylph_codegen_backward behind `sum(losses.values()).backward()`), (c) forward + backward +
+(sylph_fcos_cls_loss_backward + sylph_codegen_backward + sylph_cls_tower_backward behind `sum(losses.values()).backward()`), (c) forward + backward +
 an SGD step + the weight refresh of the engine (sylph_update_code_generator), and the per-stage device times of the
 backward kernels.  CUDA events, inputs resident on the device (uint8), synthetic weights and images."""
 import argparse
@@ -101,7 +101,7 @@ def main():
             stages[name] = round(stages.get(name, 0.0) + ms, 4)
     eng.set_profiling(False)
     out = {"workload": f"{args.classes} classes x {args.shot} support images + {args.classes * args.query_shot} query images, 800x1333, "
-                       "R-50 FPN, detector frozen, code generator trained (per-GPU batch of the shipped meta-training configs)",
+                       "R-50 FPN, backbone and box branch frozen, code generator + FCOS class tower trained (per-GPU batch of the shipped meta-training configs)",
            "precision": eng.precision, "ms_forward_losses": round(ms_fwd, 3), "ms_forward_backward": round(ms_fb, 3),
            "ms_forward_backward_sgd_refresh": round(ms_full, 3), "backward_stage_ms": stages,
            "loss_fcos_cls": float(losses["loss_fcos_cls"]), "steps": args.steps, "warmup": args.warmup}
