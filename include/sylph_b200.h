@@ -266,6 +266,11 @@ int sylph_fcos_loss_sums(sylph_ctx* ctx, int slot, const float* codes_dev, int n
                          double* sums_out_dev, int64_t* labels_out_dev, int64_t* target_inds_out_dev,
                          float* reg_targets_out_dev, void* stream);
 
+/* enabled = 0: sylph_fcos_loss_sums skips the box tower and the box / centre-ness predictors and leaves the three box sums at 0
+ * (only the positives are counted) -- the reference returns loss_fcos_cls alone when the box branch is frozen
+ * (box_branch_loss_on, fcos_outputs.py:87-92, 626-632), so its outputs are never looked at.  Default 1.  sylph_detect is not affected. */
+int sylph_set_loss_box_branch(sylph_ctx* ctx, int enabled);
+
 /* losses_out_dev[0..2] = loss_fcos_cls, loss_fcos_loc, loss_fcos_ctr from this rank's sums.  global_pos_ctr_dev holds
  * {positives, centre-ness target sum} summed over ALL ranks -- the two reduce_sum calls of
  * fcos_losses_episodic_learning, fcos_outputs.py:520-523 and :557-558 -- or NULL for a single process. */

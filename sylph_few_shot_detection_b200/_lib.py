@@ -97,7 +97,7 @@ def load() -> ctypes.CDLL:
     if not os.path.exists(LIB_PATH):
         build()
     lib = ctypes.CDLL(LIB_PATH)
-    if not hasattr(lib, "sylph_cls_tower_backward"):   # a stale in-tree build from before the training backward
+    if not hasattr(lib, "sylph_set_loss_box_branch"):   # a stale in-tree build from before the training backward
         build(force=True)
         lib = ctypes.CDLL(LIB_PATH)
     vp, ip, fp = c_void_p, POINTER(c_int), POINTER(c_float)
@@ -176,6 +176,8 @@ def load() -> ctypes.CDLL:
     lib.sylph_update_code_generator.argtypes = [vp]
     lib.sylph_update_code_generator_device.restype = c_int
     lib.sylph_update_code_generator_device.argtypes = [vp, POINTER(CodegenTensors), vp]
+    lib.sylph_set_loss_box_branch.restype = c_int
+    lib.sylph_set_loss_box_branch.argtypes = [vp, c_int]
     lib.sylph_set_training.restype = c_int
     lib.sylph_set_training.argtypes = [vp, c_int]
     lib.sylph_cls_tower_backward.restype = c_int
@@ -201,6 +203,6 @@ EXPORTED_SYMBOLS = [
     "sylph_export_features", "sylph_generate_codes", "sylph_export_roi_features", "sylph_normalize_codes", "sylph_exchange_create", "sylph_exchange_connect",
     "sylph_normalize_codes_exchange", "sylph_exchange_poll", "sylph_exchange_status", "sylph_exchange_destroy", "sylph_accumulate_codes", "sylph_reduce_codes",
     "sylph_detect", "sylph_detect_after", "sylph_detect_poll", "sylph_export_head_output", "sylph_fcos_loss_sums", "sylph_fcos_loss_finalize",
-    "sylph_fcos_cls_loss_backward", "sylph_codegen_backward", "sylph_update_code_generator", "sylph_update_code_generator_device", "sylph_set_training", "sylph_cls_tower_backward",
+    "sylph_fcos_cls_loss_backward", "sylph_codegen_backward", "sylph_update_code_generator", "sylph_update_code_generator_device", "sylph_set_training", "sylph_set_loss_box_branch", "sylph_cls_tower_backward",
     "sylph_update_cls_tower_device", "sylph_debug_read_buffer", "sylph_launch_count", "sylph_set_profiling", "sylph_get_timings",
 ]

@@ -162,6 +162,7 @@ struct sylph_ctx {
     // training of the FCOS class tower (sylph_set_training): the head pass keeps every layer's input planes, pre-GroupNorm
     // convolution output and GroupNorm statistics for sylph_cls_tower_backward
     bool train_save = false;
+    bool loss_box_branch = true;              // sylph_set_loss_box_branch(0): the training forward skips the box tower and its predictors
     std::vector<const __half*> saved_x;       // input planes of class-tower layer i
     std::vector<const float*> saved_raw, saved_stats;
     std::vector<ConvW> cls_tower_t;           // transposed, tap-reversed class-tower weights (input-gradient convolutions)
@@ -1538,7 +1539,7 @@ static int roi_encoder_codes(sylph_ctx* c, const Slot& S, int n_rois, int n_clas
 struct HeadOut { float* logits; float* pred; int logit_stride; };
 
 static int run_head(sylph_ctx* c, int slot, const float* codes_dev, int n_classes, cudaStream_t st, HeadOut* out,
-                    cudaEvent_t codes_ready = nullptr) {
+                    cudaEvent_t codes_ready = nullptr, bool with_box_branch = true) {
     const sylph_model_config& f = c->cfg;
     const Slot& S = c->slots[slot];
     const long long rows = S.level_row0[5];
@@ -1597,8 +1598,8 @@ static int run_head(sylph_ctx* c, int slot, const float* codes_dev, int n_classe
     // Everything that does not depend on the class codes first (box tower + predictors, class tower): a caller that
     // generates the codes on another stream overlaps that work with these 9 tensor-bound launches (sylph_detect_after).
     __half* x;
-    TRY(tower(c->box_tower, c->box_gn_w, c->box_gn_b, "head.bbox_tower3x3", &x));
-    {
+    if (with_box_branch) {   // skipped by the training forward when the box losses are off (FREEZE_BBOX_BRANCH, sylph_set_loss_box_branch)
+        TRY(tower(c->box_tower, c->box_gn_w, c->box_gn_b, "head.bbox_tower3x3", &x));
         ConvCall k{};
         k.W = &c->pred; k.A = x; k.a_rows = rows; k.a_cols = k.a_ld = c->ld(256); k.ps = S.ps.get(); k.tile_begin = 0; k.n_tiles = tiles;
         k.a_row_delta = 0; k.out = pr; k.ldc = 16; k.flags = kEpiOutF32; k.name = "head.pred3x3";
@@ -1621,7 +1622,7 @@ static int run_head(sylph_ctx* c, int slot, const float* codes_dev, int n_classe
     c->last_logit_stride = CW.cout_pad;
     c->last_cls_tower = x;
     out->logits = static_cast<float*>(lg);
-    out->pred = static_cast<float*>(pr);
+    out->pred = with_box_branch ? static_cast<float*>(pr) : nullptr;
     out->logit_stride = CW.cout_pad;
     return 0;
 }
@@ -2229,7 +2230,7 @@ int sylph_fcos_loss_sums(sylph_ctx* c, int slot, const float* codes_dev, int n_c
     for (int i = 0; i < S.n; ++i)
         if (gt_offsets_host[i + 1] < gt_offsets_host[i]) return c->fail("gt_offsets must be non-decreasing");
     HeadOut H{};
-    TRY(run_head(c, slot, codes_dev, n_classes, st, &H));
+    TRY(run_head(c, slot, codes_dev, n_classes, st, &H, nullptr, c->loss_box_branch));
     LossParams P{};
     P.pg = S.pg;
     P.n_images = S.n;
@@ -2536,6 +2537,12 @@ int sylph_update_code_generator_device(sylph_ctx* c, const sylph_codegen_tensors
 }
 
 // ------------------------------------------------------------------------------------------------ class-tower training
+int sylph_set_loss_box_branch(sylph_ctx* c, int enabled) {
+    if (!c) return 1;
+    c->loss_box_branch = enabled != 0;
+    return 0;
+}
+
 int sylph_set_training(sylph_ctx* c, int enabled) {
     if (!c) return 1;
     c->train_save = enabled != 0;

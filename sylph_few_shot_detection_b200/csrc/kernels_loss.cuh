@@ -121,7 +121,9 @@ fcos_targets_loss_kernel(const float* __restrict__ logits, const float* __restri
             acc[0] += static_cast<double>(loss);
         }
         // ---- positives: centre-ness target, IoU loss, centre-ness BCE (:550-592)
-        if (label != kBackgroundId) {
+        if (label != kBackgroundId && pred == nullptr) {
+            acc[1] += 1.0;                                                     // box branch skipped: positives only
+        } else if (label != kBackgroundId) {
             const float lr_min = fminf(rt[0], rt[2]), lr_max = fmaxf(rt[0], rt[2]);
             const float tb_min = fminf(rt[1], rt[3]), tb_max = fmaxf(rt[1], rt[3]);
             const float ctr_t = sqrtf(__fmul_rn(lr_min / lr_max, tb_min / tb_max));

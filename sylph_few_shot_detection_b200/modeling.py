@@ -312,6 +312,10 @@ def _meta_fcos_losses(self, class_codes: Dict[str, torch.Tensor], support_set_ta
     offsets = [0]
     for b in boxes:
         offsets.append(offsets[-1] + b.shape[0])
+    box_on = _box_branch_loss_on(self.cfg)
+    if getattr(eng, "_loss_box_branch", True) != box_on:      # box losses off (FREEZE_BBOX_BRANCH): the head skips the box branch
+        eng.set_loss_box_branch(box_on)
+        eng._loss_box_branch = box_on
     res = eng.fcos_loss_sums(SLOT_QUERY, codes, targets, torch.cat(boxes), torch.cat(classes), offsets, want_targets)
     sums, extra = res if want_targets else (res, None)
     world = _world_size()

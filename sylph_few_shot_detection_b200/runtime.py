@@ -523,6 +523,10 @@ class Engine:
     # ------------------------------------------------------------------ training backward (FCOS class tower)
     TOWER_PREFIX = "proposal_generator.fcos_head.cls_tower."
 
+    def set_loss_box_branch(self, on: bool) -> None:
+        """Off: fcos_loss_sums skips the box tower / predictors (the reference returns loss_fcos_cls alone when the box branch is frozen)."""
+        self._check(self.lib.sylph_set_loss_box_branch(self.h, 1 if on else 0))
+
     def set_training(self, on: bool) -> None:
         """Keep the class tower's activations during the head pass of fcos_loss_sums (sylph_set_training)."""
         self._check(self.lib.sylph_set_training(self.h, 1 if on else 0))
