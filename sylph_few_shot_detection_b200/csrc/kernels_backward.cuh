@@ -1,18 +1,21 @@
-// Backward of the episodic TRAINING step for the part the shipped meta-training configs train with a frozen detector
-// (e.g. configs/COCO-Detection/Meta-FCOS/Meta-FCOS-finetune-lvis.yaml: BACKBONE.FREEZE, FREEZE_CLS_TOWER,
-// FREEZE_BBOX_BRANCH on, CODE_GENERATOR.FREEZE off): the classification loss -> the class codes -> the code generator.
+// Backward of the episodic TRAINING step for what the shipped meta-training configurations train (SURVEY.md 8f-4;
+// configs/{COCO,LVISv1}-Detection/Meta-FCOS/Meta-FCOS-finetune.yaml: BACKBONE.FREEZE and FREEZE_BBOX_BRANCH on, CODE_GENERATOR.FREEZE and
+// FREEZE_CLS_TOWER off): the classification loss -> {the class codes -> the code generator} and {the FCOS class tower}.
 //   d loss_fcos_cls / d logits   sigmoid focal loss (fvcore sigmoid_focal_loss_jit, called at fcos_outputs.py:525-537)
 //   d / d codes                  CondConvBasic (meta_fcos/head_utils.py:60-81): logits = <tower output, cls_conv> + cls_bias
 //   d / d raw codes, post_norm, conv_scale, bias_scale     code_process_module (code_generator.py:833-875)
 //   d / d per-shot codes         compute_code (:778-831), uniform 1 / SHOT weights
 //   d / d support_set_cls_conv / support_set_cls_bias (+ F.normalize over the 49 positions) / support_set_shared_tower
 //                                (conv3x3 + GroupNorm(32) + ReLU per layer; :648-688, 941-967)
-// Everything here is fp32 on CUDA cores: 15-50 ROIs of 7x7 pixels are 0.9 GFLOP per convolution, the episode's time is in
-// the frozen detector's forward.  The code generator's forward is re-evaluated in fp32 from the pooled ROI features the
-// forward pass left in the ROI planes (no activations are kept by the tensor-core forward kernels).
-// Convolutions are GEMMs over an explicit im2col matrix whose K index is ci * 9 + tap, i.e. PyTorch's OIHW order: the
-// caller's parameter tensors are read, and the gradients written, in place in the state_dict layout.
-// No atomics: every reduction has a fixed order, so gradients are bit-reproducible run to run.
+//   d / d cls_tower              (fcos.py:72-122; second half of this file + wgrad3x3.cuh)
+// CODE GENERATOR (first half): fp32 on CUDA cores -- 15-50 ROIs of 7x7 pixels are 0.9 GFLOP per convolution and do not fill a tensor-core
+// tile pipeline.  Its forward is re-evaluated in fp32 from the pooled ROI features the forward pass left in the ROI planes (the tensor-core
+// forward kernels keep no activations of the ROI tower).  Convolutions are GEMMs over an explicit im2col matrix whose K index is
+// ci * 9 + tap, i.e. PyTorch's OIHW order: the caller's parameter tensors are read, and the gradients written, in place in the
+// state_dict layout.
+// CLASS TOWER (second half): the convolutions' weight and input gradients run on the tensor cores (wgrad3x3.cuh; the forward convolution
+// kernel on transposed weights); the kernels here are the GroupNorm / ReLU backward over the planes and the glue around them.
+// No atomics anywhere: every reduction has a fixed order, so gradients are bit-reproducible run to run.
 #pragma once
 #include "kernels_loss.cuh"
 
