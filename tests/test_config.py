@@ -75,3 +75,18 @@ def test_state_spec_equals_reference_model_state_dict(name):
         model = reference_loader.build_reference_model(cfg)
     ref = {k: tuple(v.shape) for k, v in model.state_dict().items()}
     assert ref == dict(W.state_spec(cfg))
+
+
+def test_unsupported_training_variants_fail_loudly():
+    """SURVEY K9 (soft-nearest-neighbour loss), per-class box regression and distillation are outside the path: the loss
+    configuration refuses them instead of computing something else."""
+    import pytest
+    from sylph_few_shot_detection_b200.presets import coco_meta_fcos_cfg
+    from sylph_few_shot_detection_b200.runtime import loss_config_from_cfg
+    loss_config_from_cfg(coco_meta_fcos_cfg())
+    for opts in (["MODEL.META_LEARN.CODE_GENERATOR.CONTRASTIVE_LOSS", "snnl"],
+                 ["MODEL.META_LEARN.CODE_GENERATOR.BOX_ON", True],
+                 ["MODEL.META_LEARN.CODE_GENERATOR.DISTILLATION_LOSS_WEIGHT", 0.5],
+                 ["MODEL.FCOS.LOC_LOSS_TYPE", "diou"]):
+        with pytest.raises(NotImplementedError):
+            loss_config_from_cfg(coco_meta_fcos_cfg(opts))
