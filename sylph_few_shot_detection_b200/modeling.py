@@ -452,6 +452,7 @@ class MetaOneStageDetector(nn.Module):
                 for k, p in self._trainable.items():
                     p.copy_(self._state[k].to(p.device))
             self._synced_versions = tuple(p._version for p in self._trainable.values())
+            self._engine.set_training(self.training and self.trains_cls_tower)   # a fresh engine: re-apply the training mode
         elif self.training:
             self.enable_code_generator_training()
         return self

@@ -414,6 +414,15 @@ def test_code_generator_backward_is_deterministic_and_guards_stale_buffers():
     # no_grad forward: plain loss tensors, no hook
     with torch.no_grad():
         assert not model(batched)["loss_fcos_cls"].requires_grad
+    # reloading a checkpoint into the training model (a fresh engine underneath) keeps the parameters and the training mode
+    ids = [id(p) for p in model.parameters()]
+    model.load_state_dict(state)
+    assert [id(p) for p in model.parameters()] == ids
+    model.zero_grad(set_to_none=True)
+    sum(model(batched).values()).backward()
+    for k, p in model.named_parameters():
+        if k in runs[0]:
+            assert torch.equal(p.grad, runs[0][k]), k
 
 
 def test_optimizer_step_reaches_the_engine():
