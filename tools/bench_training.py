@@ -4,6 +4,9 @@ meta-training configs (MODEL.META_LEARN.CLASS 3 x SHOT 5 support images + QUERY_
 backbone and box branch frozen, code generator and FCOS class tower trained (Meta-FCOS-finetune.yaml).
 
     python tools/bench_training.py [--steps 10] [--classes 3] [--shot 5] [--out profiles/rNN_training_step.json]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 tools/bench_training.py   # data parallel:
+        every rank trains on its own episode batch, the model is wrapped in DistributedDataParallel (gradient all-reduce over NCCL), the loss
+        normalisers are summed over the ranks; time = max over ranks
 
 Reports ms per iteration for (a) the training forward alone (losses), (b) forward + backward of the code generator
 (sylph_fcos_cls_loss_backward + sylph_codegen_backward + sylph_cls_tower_backward behind `sum(losses.values()).backward()`), (c) forward + backward +
@@ -29,7 +32,14 @@ def main():
     ap.add_argument("--query-shot", type=int, default=1)
     ap.add_argument("--out", default="")
     args = ap.parse_args()
-    dev = torch.device("cuda", 0)
+    rank, world = int(os.environ.get("RANK", "0")), int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        import torch.distributed as dist
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
     from sylph_few_shot_detection_b200 import weights as W
     from sylph_few_shot_detection_b200.modeling import build_model
     from sylph_few_shot_detection_b200.presets import coco_meta_fcos_cfg
@@ -38,12 +48,12 @@ def main():
 
     cfg = coco_meta_fcos_cfg(["MODEL.META_LEARN.SHOT", args.shot, "MODEL.META_LEARN.QUERY_SHOT", args.query_shot])
     model = build_model(cfg)
-    model.pixel_mean = model.pixel_mean.to(dev)
+    model.to(dev)
     model.load_state_dict(W.synthetic_state_dict(cfg, 0))
     model.train()
     h, w = 800, 1333
-    g = torch.Generator().manual_seed(4321)
-    bx = synth_boxes(args.classes * (args.shot + 2 * args.query_shot), 4322, h, w)
+    g = torch.Generator().manual_seed(4321 + rank)                 # every rank its own episode batch
+    bx = synth_boxes(args.classes * (args.shot + 2 * args.query_shot), 4322 + rank, h, w)
     k = 0
     batched = []
     for c in range(args.classes):
@@ -62,6 +72,10 @@ def main():
                         "height": h, "width": w})
         batched.append({"support_set": sup, "query_set": qry, "support_set_target": torch.tensor(c)})
     opt = torch.optim.SGD(model.parameters(), lr=1e-6)
+    net = model
+    if world > 1:
+        from torch.nn.parallel import DistributedDataParallel as DDP
+        net = DDP(model, device_ids=[local], find_unused_parameters=True)   # DDP_FIND_UNUSED_PARAMETERS: True in the shipped configs
 
     def fwd():
         with torch.no_grad():
@@ -69,7 +83,7 @@ def main():
 
     def fwd_bwd():
         model.zero_grad(set_to_none=True)
-        losses = model(batched)
+        losses = net(batched)
         sum(losses.values()).backward()
         return losses
 
@@ -88,7 +102,11 @@ def main():
             fn()
         e1.record()
         torch.cuda.synchronize()
-        return e0.elapsed_time(e1) / args.steps
+        t = torch.tensor([e0.elapsed_time(e1) / args.steps], device=dev, dtype=torch.float64)
+        if world > 1:
+            dist.barrier()
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t)
 
     ms_fwd, ms_fb, ms_full = timed(fwd), timed(fwd_bwd), timed(full)
     eng = model.engine
@@ -104,7 +122,14 @@ def main():
                        "R-50 FPN, backbone and box branch frozen, code generator + FCOS class tower trained (per-GPU batch of the shipped meta-training configs)",
            "precision": eng.precision, "ms_forward_losses": round(ms_fwd, 3), "ms_forward_backward": round(ms_fb, 3),
            "ms_forward_backward_sgd_refresh": round(ms_full, 3), "backward_stage_ms": stages,
-           "loss_fcos_cls": float(losses["loss_fcos_cls"]), "steps": args.steps, "warmup": args.warmup}
+           "loss_fcos_cls": float(losses["loss_fcos_cls"].detach()), "steps": args.steps, "warmup": args.warmup, "n_gpus": world,
+           "iterations_per_s_all_gpus": round(world * 1000.0 / ms_full, 2),
+           "episode_batches": "one per rank (data parallel, DistributedDataParallel gradient all-reduce)" if world > 1 else "one"}
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+    if rank != 0:
+        return
     print(json.dumps(out))
     if args.out:
         with open(args.out, "w") as f:
