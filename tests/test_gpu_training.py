@@ -482,6 +482,19 @@ def test_backward_c_abi_validation():
         eng.fcos_cls_loss_backward(SLOT_QUERY, 3, [1, 2, 3], labels, sums)
     with pytest.raises(RuntimeError, match="last sylph_generate_codes"):
         eng.codegen_backward([0, 1, 2], torch.zeros(2, 257), torch.zeros(2, 257), {})
+    # the class tower's backward needs the activations of a head pass in training mode
+    live = {k: p.detach() for k, p in model.named_parameters()}
+    eng.set_training(False)
+    batched = _records(g["items"])
+    with torch.no_grad():
+        model(batched)
+    with pytest.raises(RuntimeError, match="training mode"):
+        eng.cls_tower_backward(SLOT_QUERY, torch.zeros(3, 257), [40, 2, 17], labels, sums, live)
+    eng.set_training(True)
+    with pytest.raises(RuntimeError, match="missing parameter"):
+        with torch.no_grad():
+            losses, ex = model.forward_few_shot_detector_training(batched, want_targets=True)
+        eng.cls_tower_backward(SLOT_QUERY, torch.zeros(3, 257), [40, 2, 17], ex["labels"], ex["sums"], {})
 
 
 @pytest.mark.parametrize("precision", ["exact", "fast"])
