@@ -31,6 +31,8 @@ def main():
     ap.add_argument("--shot", type=int, default=5)
     ap.add_argument("--query-shot", type=int, default=1)
     ap.add_argument("--out", default="")
+    ap.add_argument("--precision", default="exact", choices=["exact", "fast"],
+                    help="operand scheme of the tensor-core kernels, forward and backward (DESIGN.md section 5)")
     args = ap.parse_args()
     rank, world = int(os.environ.get("RANK", "0")), int(os.environ.get("WORLD_SIZE", "1"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
@@ -47,7 +49,7 @@ def main():
     from tools.bench_configs import boxes as synth_boxes
 
     cfg = coco_meta_fcos_cfg(["MODEL.META_LEARN.SHOT", args.shot, "MODEL.META_LEARN.QUERY_SHOT", args.query_shot])
-    model = build_model(cfg)
+    model = build_model(cfg, args.precision)
     model.to(dev)
     model.load_state_dict(W.synthetic_state_dict(cfg, 0))
     model.train()
