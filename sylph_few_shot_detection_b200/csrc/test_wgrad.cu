@@ -116,7 +116,8 @@ static int run(const std::vector<std::pair<int, int>>& hw, bool split, int split
     return ok ? 0 : 1;
 }
 
-int main() {
+int main(int argc, char** argv) {
+    const bool quick = argc > 1 && std::string(argv[1]) == "quick";   // correctness cases only (compute-sanitizer runs)
     int fails = 0;
     const std::vector<std::pair<int, int>> small = {{20, 24}, {9, 11}};
     fails += run(small, false, 3, false);
@@ -127,7 +128,7 @@ int main() {
     // FCOS class tower, 3 query images at 800 x 1333: p3..p7 planes of each image
     std::vector<std::pair<int, int>> tower;
     for (int n = 0; n < 3; ++n) { tower.push_back({100, 168}); tower.push_back({50, 84}); tower.push_back({25, 42}); tower.push_back({13, 21}); tower.push_back({7, 11}); }
-    if (fails == 0) { run(tower, true, 8, true); run(tower, true, 16, true); run(tower, false, 8, true); }
+    if (fails == 0 && !quick) { run(tower, true, 8, true); run(tower, true, 16, true); run(tower, false, 8, true); }
     printf("%s\n", fails == 0 ? "ALL PASS" : "FAILURES");
     return fails;
 }
