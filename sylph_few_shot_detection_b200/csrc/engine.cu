@@ -2322,7 +2322,7 @@ int sylph_fcos_cls_loss_backward(sylph_ctx* c, int slot, int n_classes, const in
                            world_size, grad_loss_dev, static_cast<float*>(part)));
         CU_TRY(c, cudaGetLastError());
         const int n_elems = n_classes * 257;
-        CU_TRY(c, launch_k(fcos_code_grad_reduce_kernel, dim3(ceil_div(n_elems, 256)), dim3(256), 0, st,
+        CU_TRY(c, launch_k(fcos_code_grad_reduce_kernel, dim3(ceil_div(static_cast<long long>(n_elems) * 32, 256)), dim3(256), 0, st,
                            static_cast<const float*>(part), blocks, n_elems, grad_codes_out_dev));
         CU_TRY(c, cudaGetLastError());
         c->launches += 2;
@@ -2658,7 +2658,7 @@ int sylph_cls_tower_backward(sylph_ctx* c, int slot, int n_classes, const float*
         CU_TRY(c, launch_k(gn_bwd_partial_kernel, dim3(g_tiles), dim3(256), 0, st, static_cast<const float*>(dx_in), in_scale, c->saved_raw[i],
                            c->saved_stats[i], static_cast<const float*>(params->gn_w[i]), static_cast<const float*>(params->gn_b[i]),
                            static_cast<const int*>(S.ps->d_tile_seg), static_cast<const Seg*>(S.ps->d_segs), tiles, static_cast<float*>(part)));
-        CU_TRY(c, launch_k(gn_bwd_finalize_kernel, dim3(n_segs), dim3(256), 0, st, static_cast<const float*>(part), static_cast<const Seg*>(S.ps->d_segs),
+        CU_TRY(c, launch_k(gn_bwd_finalize_kernel, dim3(n_segs), dim3(1024), 0, st, static_cast<const float*>(part), static_cast<const Seg*>(S.ps->d_segs),
                            static_cast<const float*>(params->gn_w[i]), static_cast<float*>(segsum), static_cast<float*>(ab), static_cast<float*>(segmax)));
         CU_TRY(c, launch_k(gn_bwd_scale_kernel, dim3(1), dim3(256), 0, st, static_cast<const float*>(segmax), c->saved_stats[i], n_segs,
                            static_cast<const float*>(params->gn_w[i]), sc));
@@ -2666,7 +2666,7 @@ int sylph_cls_tower_backward(sylph_ctx* c, int slot, int n_classes, const float*
                            c->saved_stats[i], static_cast<const float*>(ab), static_cast<const float*>(params->gn_w[i]),
                            static_cast<const float*>(params->gn_b[i]), static_cast<const float*>(sc), static_cast<const int*>(S.ps->d_tile_seg),
                            static_cast<const Seg*>(S.ps->d_segs), tiles, static_cast<__half*>(dyp), c->split, static_cast<float*>(biasp)));
-        CU_TRY(c, launch_k(tower_param_grad_reduce_kernel, dim3(3), dim3(256), 0, st, static_cast<const float*>(segsum), n_segs,
+        CU_TRY(c, launch_k(tower_param_grad_reduce_kernel, dim3(3), dim3(1024), 0, st, static_cast<const float*>(segsum), n_segs,
                            static_cast<const float*>(biasp), tiles, grads->gn_w[i], grads->gn_b[i], grads->conv_b[i]));
         CU_TRY(c, cudaGetLastError());
         c->launches += 5;

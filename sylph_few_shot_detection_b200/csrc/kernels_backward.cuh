@@ -447,16 +447,19 @@ fcos_cls_loss_bwd_kernel(const float* __restrict__ logits, int logit_stride, con
     }
 }
 
-// out[e] = sum over blocks (in order, fp64) of partials[b * n_elems + e].
+// out[e] = sum over blocks of partials[b * n_elems + e], fp64: one warp per element, lane l sums blocks l, l + 32, ... in order, then a fixed
+// shuffle tree (deterministic for a given grid size).
 __global__ void __launch_bounds__(256)
 fcos_code_grad_reduce_kernel(const float* __restrict__ partials, int n_blocks, int n_elems, float* __restrict__ out) {
     ptx::griddep_launch();
     ptx::griddep_wait();
-    const int e = blockIdx.x * blockDim.x + threadIdx.x;
-    if (e >= n_elems) return;
+    const int e = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    if (e >= n_elems) return;                       // whole warps leave together
     double s = 0.0;
-    for (int b = 0; b < n_blocks; ++b) s += static_cast<double>(partials[static_cast<size_t>(b) * n_elems + e]);
-    out[e] = static_cast<float>(s);
+    for (int b = lane; b < n_blocks; b += 32) s += static_cast<double>(partials[static_cast<size_t>(b) * n_elems + e]);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    if (lane == 0) out[e] = static_cast<float>(s);
 }
 
 // ------------------------------------------------------------------------------------------------ weight refresh
@@ -638,22 +641,32 @@ gn_bwd_partial_kernel(const float* __restrict__ dX, const float* __restrict__ in
 // Per plane (one block, thread = channel): tile partials summed in order (fp64) -> seg_sums[seg][2][256] (sum dz, sum dz yhat) and
 // the two group means of GroupNorm's backward, ab[(seg * 32 + g) * 2] = mean(dz gamma), [+1] = mean(dz gamma yhat) over the
 // group's 8 x H x W values; seg_max[seg] = max |dz| of the plane.
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(1024)
 gn_bwd_finalize_kernel(const float* __restrict__ partial, const Seg* __restrict__ segs, const float* __restrict__ gamma,
                        float* __restrict__ seg_sums, float* __restrict__ ab, float* __restrict__ seg_max) {
     ptx::griddep_launch();
     ptx::griddep_wait();
-    const int s = blockIdx.x, c = threadIdx.x;
+    // 1024 threads: channel c = thread & 255, quarter q = thread >> 8 takes the plane's tiles t0 + q, t0 + q + 4, ...; the four partial sums
+    // are combined in the order q = 0..3 (a p3 plane has 136 tiles: one thread walking them all was latency-bound)
+    __shared__ double rs0[4][256], rs1[4][256];
+    __shared__ float rm[4][256];
+    const int s = blockIdx.x, c = threadIdx.x & 255, q = threadIdx.x >> 8;
     const Seg sg = segs[s];
     const int t0 = sg.row0 / kBlockM, t1 = (sg.row0 + sg.nrows + kBlockM - 1) / kBlockM;
     double s0 = 0.0, s1 = 0.0;
     float m = 0.f;
-    for (int t = t0; t < t1; ++t) {
+    for (int t = t0 + q; t < t1; t += 4) {
         const float* src = partial + static_cast<size_t>(t) * kGnBwdPartial;
         s0 += static_cast<double>(src[c]);
         s1 += static_cast<double>(src[256 + c]);
         m = fmaxf(m, src[512 + c]);
     }
+    rs0[q][c] = s0; rs1[q][c] = s1; rm[q][c] = m;
+    __syncthreads();
+    if (q != 0) return;                              // warps 0..7 go on, complete
+    s0 = rs0[0][c] + rs0[1][c] + rs0[2][c] + rs0[3][c];
+    s1 = rs1[0][c] + rs1[1][c] + rs1[2][c] + rs1[3][c];
+    m = fmaxf(fmaxf(rm[0][c], rm[1][c]), fmaxf(rm[2][c], rm[3][c]));
     seg_sums[(static_cast<size_t>(s) * 2) * 256 + c] = static_cast<float>(s0);
     seg_sums[(static_cast<size_t>(s) * 2 + 1) * 256 + c] = static_cast<float>(s1);
     const double gm = static_cast<double>(gamma[c]);
@@ -773,23 +786,29 @@ gn_bwd_apply_kernel(const float* __restrict__ dX, const float* __restrict__ in_s
 
 // d gamma[c] = sum over planes of sum dz yhat, d beta[c] = sum over planes of sum dz, d conv bias[c] = sum over tiles of sum dY:
 // fixed order, fp64.  grid 3 (which = blockIdx.x), thread = channel.
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(1024)
 tower_param_grad_reduce_kernel(const float* __restrict__ seg_sums, int n_segs, const float* __restrict__ bias_partial, int n_tiles,
                                float* __restrict__ d_gamma, float* __restrict__ d_beta, float* __restrict__ d_bias) {
     ptx::griddep_launch();
     ptx::griddep_wait();
-    const int c = threadIdx.x;
+    // 1024 threads: channel c = thread & 255, quarter q = thread >> 8 sums items q, q + 4, ...; quarters combined in the order 0..3
+    __shared__ double red[4][256];
+    const int c = threadIdx.x & 255, q = threadIdx.x >> 8;
     double s = 0.0;
     if (blockIdx.x == 0) {
-        for (int i = 0; i < n_segs; ++i) s += static_cast<double>(seg_sums[(static_cast<size_t>(i) * 2 + 1) * 256 + c]);
-        d_gamma[c] = static_cast<float>(s);
+        for (int i = q; i < n_segs; i += 4) s += static_cast<double>(seg_sums[(static_cast<size_t>(i) * 2 + 1) * 256 + c]);
     } else if (blockIdx.x == 1) {
-        for (int i = 0; i < n_segs; ++i) s += static_cast<double>(seg_sums[(static_cast<size_t>(i) * 2) * 256 + c]);
-        d_beta[c] = static_cast<float>(s);
+        for (int i = q; i < n_segs; i += 4) s += static_cast<double>(seg_sums[(static_cast<size_t>(i) * 2) * 256 + c]);
     } else {
-        for (int t = 0; t < n_tiles; ++t) s += static_cast<double>(bias_partial[static_cast<size_t>(t) * 256 + c]);
-        d_bias[c] = static_cast<float>(s);
+        for (int t = q; t < n_tiles; t += 4) s += static_cast<double>(bias_partial[static_cast<size_t>(t) * 256 + c]);
     }
+    red[q][c] = s;
+    __syncthreads();
+    if (q != 0) return;
+    const float v = static_cast<float>(red[0][c] + red[1][c] + red[2][c] + red[3][c]);
+    if (blockIdx.x == 0) d_gamma[c] = v;
+    else if (blockIdx.x == 1) d_beta[c] = v;
+    else d_bias[c] = v;
 }
 
 // fp32 OIHW [co][ci][9] -> the operand rows of the INPUT-gradient convolution: Wt[o' = ci][i' = co][tap] = W[co][ci][8 - tap]
